@@ -1,0 +1,66 @@
+"""Import shim for the UNMODIFIED reference package at /root/reference.
+
+TEST INFRASTRUCTURE ONLY.  Used in the build container (where /root/reference
+exists) by `tests/golden/make_golden.py` and by the optional live-reference
+tests.  Nothing on the product path, and nothing that runs on the GPU box,
+may import this module.
+
+The reference's `scnym/__init__.py` imports `anndata`, `scanpy` and
+`tensorboardX`, none of which are installed.  The shim
+registers the reference directory as a namespace package under the private
+name `scnym_ref` so that it can coexist with `scnym_b200` in one process,
+stubbing the three missing third-party modules.
+"""
+import importlib
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("SCNYM_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "scnym"))
+
+
+def _stub(name, **attrs):
+    if name in sys.modules:
+        return sys.modules[name]
+    m = types.ModuleType(name)
+    for k, v in attrs.items():
+        setattr(m, k, v)
+    sys.modules[name] = m
+    return m
+
+
+def load_reference(modules=("model", "dataprep", "losses", "utils", "trainer", "predict", "main")):
+    """Return the reference package (modules loaded unmodified from disk)."""
+    if not reference_available():
+        raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
+    if "scnym" in sys.modules and getattr(sys.modules["scnym"], "__scnym_ref__", False):
+        return sys.modules["scnym"]
+    try:
+        import anndata  # noqa: F401
+    except Exception:
+        _stub("anndata", AnnData=type("AnnData", (), {}))
+    try:
+        import scanpy  # noqa: F401
+    except Exception:
+        _stub("scanpy")
+    try:
+        import tensorboardX  # noqa: F401
+    except Exception:
+        _stub("tensorboardX", SummaryWriter=type("SummaryWriter", (), {}))
+    try:
+        import configargparse  # noqa: F401
+    except Exception:
+        _stub("configargparse")
+    # the reference uses absolute-relative imports (`from .model import ...`)
+    # so it must be registered under its own package name `scnym`.
+    pkg = types.ModuleType("scnym")
+    pkg.__path__ = [os.path.join(REFERENCE_ROOT, "scnym")]
+    pkg.__scnym_ref__ = True
+    sys.modules["scnym"] = pkg
+    for n in modules:
+        setattr(pkg, n, importlib.import_module("scnym." + n))
+    return pkg
