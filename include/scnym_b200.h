@@ -1,0 +1,135 @@
+/*
+ * libscnym_b200 -- C ABI of the B200-native scNym hot path (MixMatch+DAN train step, batched predict).
+ *
+ * The reference (calico/scnym v0.4.0) has no FFI/plugin layer: its hot path is Python calling
+ * PyTorch ops.  This header is the boundary introduced directly UNDER the reference's Python
+ * surfaces (scnym.model / losses / trainer / predict); each entry point names the reference code
+ * (file:line under /root/reference) whose arithmetic it replaces.  INTEGRATION.md shows the ctypes
+ * binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a BORROWED device pointer (e.g. torch.Tensor.data_ptr()); the library
+ *    allocates nothing and keeps no global state besides a thread-local error string;
+ *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it, performs no
+ *    host synchronisation and is CUDA-graph capturable;
+ *  - return 0 on success, negative on error (scnb_last_error() has the message);
+ *  - all floating point is fp32, column indices int32, dataset indptr int64, batch indptr int32;
+ *  - row-major matrices; W1T is the first-layer weight stored gene-major [G, H0]
+ *    (== embed.0.weight.t().contiguous()).
+ *  - `*_dev` arguments are device-resident scalars/arrays so that data-dependent sizes
+ *    (pseudolabel confidence thresholding) never reach the host.
+ *  - dropout: `keep_mask` (uint8, 1 = keep) injects the Bernoulli draw for parity tests; when NULL
+ *    the kernel draws Philox4x32-10(seed = rng[0], stream = rng[1]*64 + stream_id, index).
+ */
+#ifndef SCNYM_B200_H
+#define SCNYM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* scnb_last_error(void);
+int scnb_version(void);
+int scnb_device_arch(void);
+
+/* ---- K0/K1: batch assembly.  Replaces SingleCellDS.__getitem__ + default collate
+ *      (scnym/dataprep.py:114-168: per-cell CSR row -> dense fp32 vector, stacked) and the
+ *      `log1p_drop` augmentation ExpMinusOne -> InputDropout(0.1) -> LibrarySizeNormalize
+ *      (scnym/dataprep.py:257-274, 468-496, 213-254, 720-729), applied on stored nnz only. ---- */
+int scnb_csr_row_offsets(const int64_t* indptr, const int64_t* rows /*NULL: row0+i*/, int64_t row0, int n,
+                         int32_t* b_indptr /*[n+1]*/, const int32_t* carry_in_dev /*NULL: 0*/, void* stream);
+int scnb_gather_i32(const int32_t* table, const int64_t* rows, int n, int32_t fill, int32_t* out, void* stream);
+int scnb_csr_gather_rows(const int64_t* indptr, const int32_t* indices, const float* data, const int64_t* rows,
+                         int64_t row0, int n, const int32_t* b_indptr, int32_t* b_idx, float* b_val, int augment,
+                         int aug_row_begin, int aug_row_end, const uint8_t* keep_mask /*per batch nnz*/,
+                         const uint64_t* rng, uint32_t stream_id, float p_drop, void* stream);
+
+/* ---- K2a/K8: first layer nn.Linear(n_genes, n_hidden_init) (scnym/model.py:211) on CSR input.
+ *      fwd: Z = X W1T + b1.   bwd: dW1T += X^T dZ (caller zeroes dW1T).  dX is never formed: the
+ *      reference computes it only because inputs carry requires_grad (scnym/trainer.py:596-599)
+ *      and never reads it. ---- */
+int scnb_csr_linear_fwd(const int32_t* b_indptr, const int32_t* b_idx, const float* b_val, int n, const float* W1T,
+                        const float* b1, int H0, float* Z, void* stream);
+int scnb_csr_linear_fwd_i64(const int64_t* indptr /*first row of the range*/, const int32_t* indices, const float* data,
+                            int n, const float* W1T, const float* b1, int H0, float* Z, void* stream);
+int scnb_csr_linear_bwd_dw(const int32_t* b_indptr, const int32_t* b_idx, const float* b_val, int n, const float* dZ,
+                           int H0, float* dW1T, void* stream);
+
+/* ---- K5: hidden nn.Linear layers, classifier and DAN head (scnym/model.py:218,170,229,377-383)
+ *      and their backward GEMMs.  C = alpha*op(A)op(B) + beta*C (+bias[N]) (+ReLU). ---- */
+int scnb_sgemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+               int ldc, float alpha, float beta, const float* bias, int relu, const float* gate /*ReLU-bwd mask, C layout*/,
+               void* stream);
+int scnb_colsum(const float* A, int M, int N, int lda, float* out, int accumulate, void* stream);
+int scnb_relu_bwd(const float* g, const float* y, float* out, long long n, void* stream);
+
+/* ---- K4: nn.BatchNorm1d -> nn.Dropout -> nn.ReLU (scnym/model.py:212-217, 219-224, 173-182),
+ *      train mode with per-segment batch statistics or eval mode with running statistics.
+ *      stats: [n_seg][3][H] = mean, biased var, invstd.  pre_out (optional) receives the
+ *      pre-ReLU value (api.py:700 embedding = last BN output). ---- */
+int scnb_bn_act_fwd(const float* Z, float* A, float* pre_out, int H, int n_seg, const int32_t* seg_off_dev, int max_rows,
+                    int train, const float* gamma, const float* beta, const float* running_mean,
+                    const float* running_var, float* stats, const uint8_t* keep_mask, const uint64_t* rng,
+                    uint32_t stream_id, float p_drop, int relu, void* stream);
+int scnb_bn_act_bwd(const float* dA, const float* Z, const float* A, int H, int n_seg, const int32_t* seg_off_dev,
+                    int max_rows, const float* gamma, const float* stats, const uint8_t* keep_mask, const uint64_t* rng,
+                    uint32_t stream_id, float p_drop, int relu, float* dZ, float* dgamma /*+=*/, float* dbeta /*+=*/,
+                    void* stream);
+int scnb_bn_eval_bwd(const float* dA, const float* A, int relu, int rows, int H, const float* gamma,
+                     const float* running_var, float* dZ, void* stream);
+int scnb_bn_running_update(float* running_mean, float* running_var, int64_t* num_batches_tracked, const float* stats0,
+                           const float* stats1, const float* stats2, const float* stats3 /*shared block: one per application*/,
+                           const int32_t* seg_off_dev, int n_seg, int H, float momentum, void* stream);
+
+/* ---- K3: SampleMixUp (scnym/dataprep.py:638-705) folded behind the first layer (linearity):
+ *      out[i] = gam[i] Z[srcA[i]] + (1-gam[i]) Z[srcB[i]];  adjoint gathers through inverse maps. ---- */
+int scnb_mix_rows(const float* Z, int H, const int32_t* srcA, const int32_t* srcB, const float* gam,
+                  const int32_t* n_active_dev, int max_rows, float* out, void* stream);
+int scnb_unmix_rows(const float* dOut, int H, const int32_t* inv3 /*[3][n_base]*/, const float* coef3, int n_base,
+                    float* dZ, void* stream);
+
+/* ---- K6: MixMatchLoss._generate_labels + sharpen_labels (scnym/losses.py:660-737, 529-573) and
+ *      the confident/unconfident split, MixUp permutation and DAN row selection
+ *      (scnym/losses.py:811-875, 1195-1213).  perm_keys stand in for torch.randperm
+ *      (ridx = stable argsort(keys[:n_conf+L])), gamma_raw for Beta(alpha,alpha).sample(). ---- */
+int scnb_pseudolabel(const float* teacher_logits /*[K][U][C]*/, int K, int U, int C, float T, int sharpen,
+                     float min_confidence, float* q, float* conf, uint8_t* confident, float* scratch_UC, void* stream);
+int scnb_mixmatch_plan(const uint8_t* confident, const float* perm_keys, const float* gamma_raw, int U, int L, int use_dan,
+                       int dan_conf_only, int mixup_on, int32_t* counts8, int32_t* seg_off4,
+                       int32_t* work_i /*[U + 3(U+L)]*/, int32_t* srcA, int32_t* srcB, float* gam, int Rmax, int32_t* inv3,
+                       float* coef3, float* pconf1, void* stream);
+
+/* ---- K7: losses with fused dLogits.  cross_entropy (scnym/losses.py:67-151; supervised call
+ *      :920-923, domain call :1224-1243), MSE on probabilities with confidence masking
+ *      (scnym/main.py:504-505, scnym/losses.py:880-913).  loss_out[0] += loss, loss_out[1] += hits. ---- */
+int scnb_soft_ce_fwd_bwd(const float* logits, int n_max, int C, const int32_t* n_rows_dev, const float* Y,
+                         const int32_t* mapA, const int32_t* mapB, const float* gam, int map_off,
+                         const float* class_weight, const int32_t* n_norm_dev, int n_norm, float grad_scale,
+                         const float* loss_scale_dev, float* dlogits, float* loss_out2, int count_acc, void* stream);
+int scnb_softmax_mse_fwd_bwd(const float* logits, int n_max, int C, const int32_t* n_conf_dev, const float* Y,
+                             const int32_t* mapA, const int32_t* mapB, const float* gam, int map_off, int n_norm,
+                             const float* weight_dev, float weight, float* dlogits, float* loss_out, void* stream);
+int scnb_onehot_rows(const int32_t* ids, const int32_t* src, int src_off, int n, int C, float* out, void* stream);
+
+/* ---- K9/K10: optimizer.step() (scnym/trainer.py:234,671,1089; torch.optim.{Adadelta,Adam,AdamW,SGD}
+ *      selected at scnym/main.py:36-41,374-396) over the flat parameter arena, and the mean-teacher
+ *      EMA (scnym/losses.py:382-406).  opt: 0 adadelta, 1 adam, 2 adamw, 3 sgd(momentum).
+ *      hp8 = [lr, weight_decay, beta1, beta2, eps, rho, momentum, 0] (device);
+ *      state4 = [t, rng_seed, rng_counter, mixmatch_step] (device int64). ---- */
+int scnb_step_begin(int64_t* state4, void* stream);
+int scnb_mm_step_inc(int64_t* state4, void* stream);
+int scnb_optim_step(int opt, float* params, const float* grads, float* state1, float* state2, long long n,
+                    const float* hp8, const int64_t* state4, void* stream);
+int scnb_ema_update(float* teacher, const float* params, long long n, float decay, const int64_t* state4, void* stream);
+
+/* ---- Predict head: Predicter.predict (scnym/predict.py:178-192): ensemble-mean logits,
+ *      argmax, softmax. ---- */
+int scnb_predict_head(const float* logits_sum, int n_models, int n, int C, int64_t* pred, float* prob, float* score,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCNYM_B200_H */

@@ -1,0 +1,73 @@
+// Shared device/host helpers for libscnym_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define SCNB_OK 0
+#define SCNB_ERR_ARG -1
+#define SCNB_ERR_CUDA -2
+#define SCNB_ERR_UNSUPPORTED -3
+
+void scnb_set_error(const char* fmt, ...);
+
+#define SCNB_CHECK_ARG(cond, ...)          \
+  do {                                     \
+    if (!(cond)) {                         \
+      scnb_set_error(__VA_ARGS__);         \
+      return SCNB_ERR_ARG;                 \
+    }                                      \
+  } while (0)
+
+// Launch errors only (no sync: every entry point is asynchronous and graph-capturable).
+#define SCNB_CHECK_LAUNCH(name)                                              \
+  do {                                                                       \
+    cudaError_t e__ = cudaGetLastError();                                    \
+    if (e__ != cudaSuccess) {                                                \
+      scnb_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+      return SCNB_ERR_CUDA;                                                  \
+    }                                                                        \
+  } while (0)
+
+static inline int scnb_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Philox4x32-10 counter RNG (Salmon et al. 2011), used for in-kernel dropout masks when no
+// mask pointer is injected.  ctr = (idx_lo, idx_hi, stream, 0), key = seed.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+// Uniform in [0,1) for element `idx` of logical stream `stream` (one Philox call per 4 elements).
+__device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t stream, uint64_t idx) {
+  uint64_t blk = idx >> 2;
+  uint4 r = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)),
+                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  uint32_t v = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
+  return (float)(v >> 8) * (1.0f / 16777216.0f);
+}
+// keep decision for dropout: injected mask wins; else Philox(seed, stream, idx) >= p.
+__device__ __forceinline__ bool dropout_keep(const uint8_t* mask, uint64_t idx, uint64_t seed, uint64_t stream, float p) {
+  if (mask) return mask[idx] != 0;
+  return philox_uniform(seed, stream, idx) >= p;
+}
+#endif

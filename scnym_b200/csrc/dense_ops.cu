@@ -1,0 +1,527 @@
+// Dense hidden-stack kernels of the scNym hot path (sm_100a), v1 SIMT fp32.
+//   scnb_sgemm            C = op(A) op(B) (+beta C) (+bias) (+relu)           (nn.Linear fwd / dA / dW)
+//   scnb_colsum           out[N] (+)= sum_rows A[M,N]                          (bias gradients)
+//   scnb_bn_act_fwd/bwd   segmented BatchNorm1d -> Dropout -> ReLU             (model.py:212-217 etc.)
+//   scnb_mix_rows / scnb_unmix_rows   hidden-space MixUp and its adjoint        (dataprep.py:665-689)
+//   scnb_bn_running_update            running_mean / running_var / num_batches_tracked
+// "Segments" are the row ranges of the student super-batch [U-mixed | L-mixed | DAN] that need
+// separate batch statistics; seg_off lives in device memory because the DAN segment length is
+// data dependent when pseudolabel thresholding is on.  Rows >= seg_off[n_seg] are written as 0.
+#include "common.cuh"
+
+#define BN_EPS 1e-5f
+
+// ---------------------------------------------------------------------------------------------
+// SGEMM: 64x64x16 tiles, 256 threads, 4x4 register micro-tile, register-prefetched double buffer.
+// Row-major.  op(A)[m,k] = TA ? A[k*lda+m] : A[m*lda+k];  op(B)[k,n] = TB ? B[n*ldb+k] : B[k*ldb+n].
+// ---------------------------------------------------------------------------------------------
+#define GBM 64
+#define GBN 64
+#define GBK 16
+#define GPAD 4
+
+template <bool TA, bool VEC>
+__device__ __forceinline__ void load_a_frag(const float* __restrict__ A, int lda, int M, int K, int m0, int k0, int tid,
+                                            float (&r)[4]) {
+  if (!TA) {  // contiguous along k: thread -> (m = tid/4, k = (tid%4)*4 .. +3)
+    const int m = m0 + (tid >> 2), k = k0 + ((tid & 3) << 2);
+    if (VEC) {
+      if (m < M && k < K) {
+        const float4 v = *reinterpret_cast<const float4*>(A + (size_t)m * lda + k);
+        r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+      } else { r[0] = r[1] = r[2] = r[3] = 0.f; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[i] = (m < M && k + i < K) ? A[(size_t)m * lda + k + i] : 0.f;
+    }
+  } else {  // contiguous along m: thread -> (k = tid/16, m = (tid%16)*4 .. +3)
+    const int k = k0 + (tid >> 4), m = m0 + ((tid & 15) << 2);
+    if (VEC) {
+      if (k < K && m < M) {
+        const float4 v = *reinterpret_cast<const float4*>(A + (size_t)k * lda + m);
+        r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+      } else { r[0] = r[1] = r[2] = r[3] = 0.f; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[i] = (k < K && m + i < M) ? A[(size_t)k * lda + m + i] : 0.f;
+    }
+  }
+}
+template <bool TA>
+__device__ __forceinline__ void store_a_frag(float (*As)[GBM + GPAD], int tid, const float (&r)[4]) {
+  if (!TA) {
+    const int m = tid >> 2, k = (tid & 3) << 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) As[k + i][m] = r[i];
+  } else {
+    const int k = tid >> 4, m = (tid & 15) << 2;
+    *reinterpret_cast<float4*>(&As[k][m]) = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+template <bool TB, bool VEC>
+__device__ __forceinline__ void load_b_frag(const float* __restrict__ B, int ldb, int N, int K, int n0, int k0, int tid,
+                                            float (&r)[4]) {
+  if (!TB) {  // B stored [K,N], contiguous along n: thread -> (k = tid/16, n = (tid%16)*4)
+    const int k = k0 + (tid >> 4), n = n0 + ((tid & 15) << 2);
+    if (VEC) {
+      if (k < K && n < N) {
+        const float4 v = *reinterpret_cast<const float4*>(B + (size_t)k * ldb + n);
+        r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+      } else { r[0] = r[1] = r[2] = r[3] = 0.f; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[i] = (k < K && n + i < N) ? B[(size_t)k * ldb + n + i] : 0.f;
+    }
+  } else {  // B stored [N,K], contiguous along k: thread -> (n = tid/4, k = (tid%4)*4)
+    const int n = n0 + (tid >> 2), k = k0 + ((tid & 3) << 2);
+    if (VEC) {
+      if (n < N && k < K) {
+        const float4 v = *reinterpret_cast<const float4*>(B + (size_t)n * ldb + k);
+        r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+      } else { r[0] = r[1] = r[2] = r[3] = 0.f; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[i] = (n < N && k + i < K) ? B[(size_t)n * ldb + k + i] : 0.f;
+    }
+  }
+}
+template <bool TB>
+__device__ __forceinline__ void store_b_frag(float (*Bs)[GBN + GPAD], int tid, const float (&r)[4]) {
+  if (!TB) {
+    const int k = tid >> 4, n = (tid & 15) << 2;
+    *reinterpret_cast<float4*>(&Bs[k][n]) = make_float4(r[0], r[1], r[2], r[3]);
+  } else {
+    const int n = tid >> 2, k = (tid & 3) << 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) Bs[k + i][n] = r[i];
+  }
+}
+
+template <bool TA, bool TB, bool VEC>
+__global__ void __launch_bounds__(256) k_sgemm(int M, int N, int K, const float* __restrict__ A, int lda,
+                                               const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
+                                               float alpha, float beta, const float* __restrict__ bias, int relu,
+                                               const float* __restrict__ gate) {
+  __shared__ __align__(16) float As[2][GBK][GBM + GPAD];
+  __shared__ __align__(16) float Bs[2][GBK][GBN + GPAD];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float ra[4], rb[4];
+  load_a_frag<TA, VEC>(A, lda, M, K, m0, 0, tid, ra);
+  load_b_frag<TB, VEC>(B, ldb, N, K, n0, 0, tid, rb);
+  store_a_frag<TA>(As[0], tid, ra);
+  store_b_frag<TB>(Bs[0], tid, rb);
+  __syncthreads();
+  const int nk = (K + GBK - 1) / GBK;
+  for (int kt = 0; kt < nk; ++kt) {
+    const int cur = kt & 1;
+    if (kt + 1 < nk) {
+      load_a_frag<TA, VEC>(A, lda, M, K, m0, (kt + 1) * GBK, tid, ra);
+      load_b_frag<TB, VEC>(B, ldb, N, K, n0, (kt + 1) * GBK, tid, rb);
+    }
+#pragma unroll
+    for (int k = 0; k < GBK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[cur][k][ty << 2]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[cur][k][tx << 2]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      store_a_frag<TA>(As[cur ^ 1], tid, ra);
+      store_b_frag<TB>(Bs[cur ^ 1], tid, rb);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + (ty << 2) + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + (tx << 2) + j;
+      if (n >= N) continue;
+      float v = alpha * acc[i][j];
+      if (beta != 0.f) v += beta * C[(size_t)m * ldc + n];
+      if (bias) v += bias[n];
+      if (relu) v = fmaxf(v, 0.f);
+      if (gate && !(gate[(size_t)m * ldc + n] > 0.f)) v = 0.f;  // ReLU backward gate (same layout as C)
+      C[(size_t)m * ldc + n] = v;
+    }
+  }
+}
+
+extern "C" int scnb_sgemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                          float* C, int ldc, float alpha, float beta, const float* bias, int relu, const float* gate,
+                          void* stream) {
+  SCNB_CHECK_ARG(M >= 0 && N >= 0 && K >= 0 && A && B && C, "sgemm: bad arguments");
+  if (M == 0 || N == 0) return SCNB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(scnb_cdiv(N, GBN), scnb_cdiv(M, GBM)), block(256);
+  const bool vec = (lda % 4 == 0) && (ldb % 4 == 0) && (((uintptr_t)A | (uintptr_t)B) % 16 == 0) &&
+                   (transA ? (M % 4 == 0) : (K % 4 == 0)) && (transB ? (K % 4 == 0) : (N % 4 == 0));
+#define SCNB_LAUNCH_SGEMM(TA, TB, V) \
+  k_sgemm<TA, TB, V><<<grid, block, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate)
+  if (!transA && !transB) { if (vec) SCNB_LAUNCH_SGEMM(false, false, true); else SCNB_LAUNCH_SGEMM(false, false, false); }
+  else if (!transA && transB) { if (vec) SCNB_LAUNCH_SGEMM(false, true, true); else SCNB_LAUNCH_SGEMM(false, true, false); }
+  else if (transA && !transB) { if (vec) SCNB_LAUNCH_SGEMM(true, false, true); else SCNB_LAUNCH_SGEMM(true, false, false); }
+  else { if (vec) SCNB_LAUNCH_SGEMM(true, true, true); else SCNB_LAUNCH_SGEMM(true, true, false); }
+#undef SCNB_LAUNCH_SGEMM
+  SCNB_CHECK_LAUNCH("sgemm");
+  return SCNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Column sums (bias gradients).  Block = 32 columns x 32 row lanes; deterministic tree.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_colsum(const float* __restrict__ A, int M, int N, int lda, float* __restrict__ out,
+                                                 int accumulate) {
+  __shared__ float red[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (c < N)
+    for (int r = ty; r < M; r += 32) s += A[(size_t)r * lda + c];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t += red[i][tx];
+    if (c < N) out[c] = accumulate ? out[c] + t : t;
+  }
+}
+
+extern "C" int scnb_colsum(const float* A, int M, int N, int lda, float* out, int accumulate, void* stream) {
+  SCNB_CHECK_ARG(A && out && M >= 0 && N > 0, "colsum: bad arguments");
+  k_colsum<<<scnb_cdiv(N, 32), 1024, 0, (cudaStream_t)stream>>>(A, M, N, lda, out, accumulate);
+  SCNB_CHECK_LAUNCH("colsum");
+  return SCNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Segmented BatchNorm1d -> Dropout -> ReLU.
+// Block = 8 columns x 128 row lanes (a warp reads 4 rows x 32 B); grid = ceil(H/8); the block walks
+// the segments in order, so gamma/beta gradients are accumulated deterministically.
+// stats layout: [n_seg][3][H] = mean, biased var, invstd.
+// ---------------------------------------------------------------------------------------------
+#define BN_CW 8
+#define BN_RL 128
+
+__device__ __forceinline__ float bn_block_colsum(float v, float (*red)[BN_CW], int cx, int ry) {
+  // reduce over the 128 row lanes of each of the 8 columns; result broadcast to every thread of the column
+  red[ry][cx] = v;
+  __syncthreads();
+  for (int s = BN_RL / 2; s > 0; s >>= 1) {
+    if (ry < s) red[ry][cx] += red[ry + s][cx];
+    __syncthreads();
+  }
+  float out = red[0][cx];
+  __syncthreads();
+  return out;
+}
+
+__global__ void __launch_bounds__(1024) k_bn_act_fwd(const float* __restrict__ Z, float* __restrict__ Aout,
+                                                     float* __restrict__ pre_out, int H, int n_seg,
+                                                     const int32_t* __restrict__ seg_off, int max_rows, int train,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                     const float* __restrict__ rmean, const float* __restrict__ rvar,
+                                                     float* __restrict__ stats, const uint8_t* __restrict__ keep_mask,
+                                                     const uint64_t* __restrict__ rng, uint32_t stream_id, float p_drop,
+                                                     int relu) {
+  __shared__ float red[BN_RL][BN_CW];
+  const int cx = threadIdx.x & (BN_CW - 1), ry = threadIdx.x / BN_CW;
+  const int c = blockIdx.x * BN_CW + cx;
+  const bool cok = c < H;
+  const float g = cok ? gamma[c] : 1.f, b = cok ? beta[c] : 0.f;
+  uint64_t seed = 0, strm = 0;
+  if (train && p_drop > 0.f && !keep_mask) {
+    seed = rng[0];
+    strm = rng[1] * 64ull + stream_id;
+  }
+  const float drop_scale = 1.0f / (1.0f - p_drop);
+  for (int s = 0; s < n_seg; ++s) {
+    const int r0 = seg_off[s], r1 = min(seg_off[s + 1], max_rows);
+    const int n = r1 - r0;
+    float mean, invstd;
+    if (train) {
+      float acc = 0.f;
+      if (cok)
+        for (int r = r0 + ry; r < r1; r += BN_RL) acc += Z[(size_t)r * H + c];
+      mean = bn_block_colsum(acc, red, cx, ry) / (float)max(n, 1);
+      acc = 0.f;
+      if (cok)
+        for (int r = r0 + ry; r < r1; r += BN_RL) {
+          const float d = Z[(size_t)r * H + c] - mean;
+          acc = fmaf(d, d, acc);
+        }
+      const float var = bn_block_colsum(acc, red, cx, ry) / (float)max(n, 1);
+      invstd = 1.0f / sqrtf(var + BN_EPS);
+      if (cok && ry == 0 && stats) {
+        stats[((size_t)s * 3 + 0) * H + c] = mean;
+        stats[((size_t)s * 3 + 1) * H + c] = var;
+        stats[((size_t)s * 3 + 2) * H + c] = invstd;
+      }
+    } else {
+      mean = cok ? rmean[c] : 0.f;
+      invstd = cok ? 1.0f / sqrtf(rvar[c] + BN_EPS) : 1.f;
+    }
+    if (cok)
+      for (int r = r0 + ry; r < r1; r += BN_RL) {
+        const size_t o = (size_t)r * H + c;
+        float y = (Z[o] - mean) * invstd * g + b;
+        if (train && p_drop > 0.f) y = dropout_keep(keep_mask, o, seed, strm, p_drop) ? y * drop_scale : 0.f;
+        if (pre_out) pre_out[o] = y;
+        Aout[o] = relu ? fmaxf(y, 0.f) : y;
+      }
+  }
+  // inactive tail rows
+  if (cok)
+    for (int r = min(seg_off[n_seg], max_rows) + ry; r < max_rows; r += BN_RL) {
+      Aout[(size_t)r * H + c] = 0.f;
+      if (pre_out) pre_out[(size_t)r * H + c] = 0.f;
+    }
+}
+
+extern "C" int scnb_bn_act_fwd(const float* Z, float* A, float* pre_out, int H, int n_seg, const int32_t* seg_off_dev,
+                               int max_rows, int train, const float* gamma, const float* beta, const float* running_mean,
+                               const float* running_var, float* stats, const uint8_t* keep_mask, const uint64_t* rng,
+                               uint32_t stream_id, float p_drop, int relu, void* stream) {
+  SCNB_CHECK_ARG(Z && A && gamma && beta && seg_off_dev && H > 0 && n_seg > 0 && max_rows >= 0, "bn_act_fwd: bad arguments");
+  SCNB_CHECK_ARG(train || (running_mean && running_var), "bn_act_fwd: eval mode needs running statistics");
+  SCNB_CHECK_ARG(!(train && p_drop > 0.f) || keep_mask || rng, "bn_act_fwd: dropout needs keep_mask or rng state");
+  SCNB_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "bn_act_fwd: p_drop out of range");
+  k_bn_act_fwd<<<scnb_cdiv(H, BN_CW), 1024, 0, (cudaStream_t)stream>>>(Z, A, pre_out, H, n_seg, seg_off_dev, max_rows, train,
+                                                                        gamma, beta, running_mean, running_var, stats,
+                                                                        keep_mask, rng, stream_id, p_drop, relu);
+  SCNB_CHECK_LAUNCH("bn_act_fwd");
+  return SCNB_OK;
+}
+
+// Backward (train mode).  dA is the gradient w.r.t. the post-ReLU activation A.
+//   dd = dA*[A>0]; dy = dd*keep/(1-p); dbeta += sum dy; dgamma += sum dy*zhat;
+//   dz = gamma*invstd*(dy - mean(dy) - zhat*mean(dy*zhat))
+__global__ void __launch_bounds__(1024) k_bn_act_bwd(const float* __restrict__ dA, const float* __restrict__ Z,
+                                                     const float* __restrict__ Aact, int H, int n_seg,
+                                                     const int32_t* __restrict__ seg_off, int max_rows,
+                                                     const float* __restrict__ gamma, const float* __restrict__ stats,
+                                                     const uint8_t* __restrict__ keep_mask, const uint64_t* __restrict__ rng,
+                                                     uint32_t stream_id, float p_drop, int relu, float* __restrict__ dZ,
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float red[BN_RL][BN_CW];
+  const int cx = threadIdx.x & (BN_CW - 1), ry = threadIdx.x / BN_CW;
+  const int c = blockIdx.x * BN_CW + cx;
+  const bool cok = c < H;
+  const float g = cok ? gamma[c] : 1.f;
+  uint64_t seed = 0, strm = 0;
+  if (p_drop > 0.f && !keep_mask) {
+    seed = rng[0];
+    strm = rng[1] * 64ull + stream_id;
+  }
+  const float drop_scale = 1.0f / (1.0f - p_drop);
+  float dg_tot = 0.f, db_tot = 0.f;
+  for (int s = 0; s < n_seg; ++s) {
+    const int r0 = seg_off[s], r1 = min(seg_off[s + 1], max_rows);
+    const int n = r1 - r0;
+    const float mean = cok ? stats[((size_t)s * 3 + 0) * H + c] : 0.f;
+    const float invstd = cok ? stats[((size_t)s * 3 + 2) * H + c] : 1.f;
+    float s1 = 0.f, s2 = 0.f;
+    if (cok)
+      for (int r = r0 + ry; r < r1; r += BN_RL) {
+        const size_t o = (size_t)r * H + c;
+        float dy = dA[o];
+        if (relu && !(Aact[o] > 0.f)) dy = 0.f;
+        if (p_drop > 0.f) dy = dropout_keep(keep_mask, o, seed, strm, p_drop) ? dy * drop_scale : 0.f;
+        s1 += dy;
+        s2 = fmaf(dy, (Z[o] - mean) * invstd, s2);
+      }
+    s1 = bn_block_colsum(s1, red, cx, ry);
+    s2 = bn_block_colsum(s2, red, cx, ry);
+    dg_tot += s2;
+    db_tot += s1;
+    const float inv_n = 1.0f / (float)max(n, 1);
+    const float m1 = s1 * inv_n, m2 = s2 * inv_n, k = g * invstd;
+    if (cok)
+      for (int r = r0 + ry; r < r1; r += BN_RL) {
+        const size_t o = (size_t)r * H + c;
+        float dy = dA[o];
+        if (relu && !(Aact[o] > 0.f)) dy = 0.f;
+        if (p_drop > 0.f) dy = dropout_keep(keep_mask, o, seed, strm, p_drop) ? dy * drop_scale : 0.f;
+        const float zh = (Z[o] - mean) * invstd;
+        dZ[o] = k * (dy - m1 - zh * m2);
+      }
+  }
+  if (cok) {
+    for (int r = min(seg_off[n_seg], max_rows) + ry; r < max_rows; r += BN_RL) dZ[(size_t)r * H + c] = 0.f;
+    if (ry == 0) {
+      dgamma[c] += dg_tot;
+      dbeta[c] += db_tot;
+    }
+  }
+}
+
+extern "C" int scnb_bn_act_bwd(const float* dA, const float* Z, const float* A, int H, int n_seg, const int32_t* seg_off_dev,
+                               int max_rows, const float* gamma, const float* stats, const uint8_t* keep_mask,
+                               const uint64_t* rng, uint32_t stream_id, float p_drop, int relu, float* dZ, float* dgamma,
+                               float* dbeta, void* stream) {
+  SCNB_CHECK_ARG(dA && Z && A && gamma && stats && dZ && dgamma && dbeta && seg_off_dev && H > 0 && n_seg > 0,
+                 "bn_act_bwd: bad arguments");
+  SCNB_CHECK_ARG(!(p_drop > 0.f) || keep_mask || rng, "bn_act_bwd: dropout needs keep_mask or rng state");
+  k_bn_act_bwd<<<scnb_cdiv(H, BN_CW), 1024, 0, (cudaStream_t)stream>>>(dA, Z, A, H, n_seg, seg_off_dev, max_rows, gamma, stats,
+                                                                        keep_mask, rng, stream_id, p_drop, relu, dZ, dgamma,
+                                                                        dbeta);
+  SCNB_CHECK_LAUNCH("bn_act_bwd");
+  return SCNB_OK;
+}
+
+// running statistics: one update per (segment, application), segment-major -- the order in which
+// the reference's three forwards touch a BatchNorm module; a block shared by several applications
+// (n_layers >= 3, model.py:207) passes one stats pointer per application.  SURVEY A2: momentum 0.1,
+// unbiased variance in the running estimate.  nbt += number of updates applied.
+struct StatsList { const float* p[4]; };
+__global__ void k_bn_running_update(float* __restrict__ rmean, float* __restrict__ rvar, int64_t* __restrict__ nbt,
+                                    StatsList sl, int n_stats, const int32_t* __restrict__ seg_off, int n_seg, int H,
+                                    float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  int applied = 0;
+  float rm = 0.f, rv = 0.f;
+  if (c < H) {
+    rm = rmean[c];
+    rv = rvar[c];
+  }
+  for (int s = 0; s < n_seg; ++s) {
+    const int n = seg_off[s + 1] - seg_off[s];
+    if (n <= 0) continue;
+    for (int a = 0; a < n_stats; ++a) {
+      ++applied;
+      if (c < H) {
+        const float mean = sl.p[a][((size_t)s * 3 + 0) * H + c];
+        const float var = sl.p[a][((size_t)s * 3 + 1) * H + c];
+        const float unb = var * ((float)n / (float)max(n - 1, 1));
+        rm = (1.f - momentum) * rm + momentum * mean;
+        rv = (1.f - momentum) * rv + momentum * unb;
+      }
+    }
+  }
+  if (c < H) {
+    rmean[c] = rm;
+    rvar[c] = rv;
+  }
+  if (c == 0 && nbt) *nbt += applied;
+}
+
+extern "C" int scnb_bn_running_update(float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                                      const float* stats0, const float* stats1, const float* stats2, const float* stats3,
+                                      const int32_t* seg_off_dev, int n_seg, int H, float momentum, void* stream) {
+  SCNB_CHECK_ARG(running_mean && running_var && stats0 && seg_off_dev && n_seg > 0 && H > 0, "bn_running_update: bad arguments");
+  StatsList sl;
+  sl.p[0] = stats0; sl.p[1] = stats1; sl.p[2] = stats2; sl.p[3] = stats3;
+  int n_stats = 1;
+  while (n_stats < 4 && sl.p[n_stats]) ++n_stats;
+  k_bn_running_update<<<scnb_cdiv(H, 256), 256, 0, (cudaStream_t)stream>>>(running_mean, running_var, num_batches_tracked, sl,
+                                                                            n_stats, seg_off_dev, n_seg, H, momentum);
+  SCNB_CHECK_LAUNCH("bn_running_update");
+  return SCNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Hidden-space MixUp: out[i,:] = gam[i]*Z[srcA[i],:] + (1-gam[i])*Z[srcB[i],:], i < *n_active;
+// zero rows after.  Adjoint: dZ[r,:] = sum_{k<3} coef[k][r] * dOut[inv[k][r],:]  (inv = -1 -> none).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_mix_rows(const float* __restrict__ Z, int H, const int32_t* __restrict__ srcA,
+                                                  const int32_t* __restrict__ srcB, const float* __restrict__ gam,
+                                                  const int32_t* __restrict__ n_active, int max_rows, float* __restrict__ out) {
+  const int i = blockIdx.x;
+  const int na = n_active ? min(*n_active, max_rows) : max_rows;
+  float* o = out + (size_t)i * H;
+  if (i >= na) {
+    for (int h = threadIdx.x; h < H; h += blockDim.x) o[h] = 0.f;
+    return;
+  }
+  const int a = srcA[i], b = srcB ? srcB[i] : a;
+  const float g = gam ? gam[i] : 1.f;
+  const float* za = Z + (size_t)a * H;
+  const float* zb = Z + (size_t)b * H;
+  if (a == b || g == 1.f) {
+    for (int h = threadIdx.x; h < H; h += blockDim.x) o[h] = za[h];
+  } else {
+    const float g1 = 1.f - g;
+    for (int h = threadIdx.x; h < H; h += blockDim.x) o[h] = g * za[h] + g1 * zb[h];
+  }
+}
+
+extern "C" int scnb_mix_rows(const float* Z, int H, const int32_t* srcA, const int32_t* srcB, const float* gam,
+                             const int32_t* n_active_dev, int max_rows, float* out, void* stream) {
+  SCNB_CHECK_ARG(Z && srcA && out && H > 0 && max_rows >= 0, "mix_rows: bad arguments");
+  if (max_rows == 0) return SCNB_OK;
+  k_mix_rows<<<max_rows, 256, 0, (cudaStream_t)stream>>>(Z, H, srcA, srcB, gam, n_active_dev, max_rows, out);
+  SCNB_CHECK_LAUNCH("mix_rows");
+  return SCNB_OK;
+}
+
+__global__ void __launch_bounds__(256) k_unmix_rows(const float* __restrict__ dOut, int H, const int32_t* __restrict__ inv,
+                                                    const float* __restrict__ coef, int n_base, float* __restrict__ dZ) {
+  const int r = blockIdx.x;
+  int i0 = inv[r], i1 = inv[n_base + r], i2 = inv[2 * n_base + r];
+  float c0 = coef[r], c1 = coef[n_base + r], c2 = coef[2 * n_base + r];
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    float v = 0.f;
+    if (i0 >= 0) v = fmaf(c0, dOut[(size_t)i0 * H + h], v);
+    if (i1 >= 0) v = fmaf(c1, dOut[(size_t)i1 * H + h], v);
+    if (i2 >= 0) v = fmaf(c2, dOut[(size_t)i2 * H + h], v);
+    dZ[(size_t)r * H + h] = v;
+  }
+}
+
+extern "C" int scnb_unmix_rows(const float* dOut, int H, const int32_t* inv3, const float* coef3, int n_base, float* dZ,
+                               void* stream) {
+  SCNB_CHECK_ARG(dOut && inv3 && coef3 && dZ && H > 0 && n_base >= 0, "unmix_rows: bad arguments");
+  if (n_base == 0) return SCNB_OK;
+  k_unmix_rows<<<n_base, 256, 0, (cudaStream_t)stream>>>(dOut, H, inv3, coef3, n_base, dZ);
+  SCNB_CHECK_LAUNCH("unmix_rows");
+  return SCNB_OK;
+}
+
+// out = g * [y > 0]   (backward of a ReLU fused into a Linear epilogue)
+__global__ void k_relu_bwd(const float* __restrict__ g, const float* __restrict__ y, float* __restrict__ out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = y[i] > 0.f ? g[i] : 0.f;
+}
+
+extern "C" int scnb_relu_bwd(const float* g, const float* y, float* out, long long n, void* stream) {
+  SCNB_CHECK_ARG(g && y && out && n >= 0, "relu_bwd: bad arguments");
+  if (n == 0) return SCNB_OK;
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  k_relu_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, y, out, (size_t)n);
+  SCNB_CHECK_LAUNCH("relu_bwd");
+  return SCNB_OK;
+}
+
+// Eval-mode BatchNorm backward w.r.t. its input: dz = dy * gamma / sqrt(running_var + eps) (optionally ReLU-gated by A).
+__global__ void k_bn_eval_bwd(const float* __restrict__ dA, const float* __restrict__ Aact, int relu, size_t n, int H,
+                              const float* __restrict__ gamma, const float* __restrict__ rvar, float* __restrict__ dZ) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % H);
+    float dy = dA[i];
+    if (relu && !(Aact[i] > 0.f)) dy = 0.f;
+    dZ[i] = dy * gamma[c] / sqrtf(rvar[c] + BN_EPS);
+  }
+}
+
+extern "C" int scnb_bn_eval_bwd(const float* dA, const float* A, int relu, int rows, int H, const float* gamma,
+                                const float* running_var, float* dZ, void* stream) {
+  SCNB_CHECK_ARG(dA && A && gamma && running_var && dZ && rows >= 0 && H > 0, "bn_eval_bwd: bad arguments");
+  const size_t n = (size_t)rows * H;
+  if (n == 0) return SCNB_OK;
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  k_bn_eval_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(dA, A, relu, n, H, gamma, running_var, dZ);
+  SCNB_CHECK_LAUNCH("bn_eval_bwd");
+  return SCNB_OK;
+}

@@ -1,0 +1,549 @@
+// Pseudolabel, MixUp planning and loss kernels of the scNym hot path (sm_100a).
+//   scnb_pseudolabel        K-view softmax mean, confidence, sharpening        (losses.py:660-737, 529-573)
+//   scnb_mixmatch_plan      confident/unconfident compaction, injected-key permutation, Beta gamma,
+//                           row maps of the student super-batch and their inverses
+//                           (losses.py:811-875, dataprep.py:665-689, losses.py:1195-1213)
+//   scnb_soft_ce_fwd_bwd    soft-target CE + dLogits                            (losses.py:67-151)
+//   scnb_softmax_mse_fwd_bwd  sum_c (softmax(z)-y)^2 masked mean + dLogits      (losses.py:880-913)
+//   scnb_predict_head       ensemble-mean logits -> argmax / softmax            (predict.py:178-192)
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// Pseudolabels.  One warp per unlabeled row.  logits: [K][U][C].
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pseudolabel(const float* __restrict__ logits, int K, int U, int C, float T,
+                                                     int sharpen, float min_conf, float* __restrict__ q,
+                                                     float* __restrict__ conf, uint8_t* __restrict__ confident,
+                                                     float* __restrict__ scratch) {
+  const int lane = threadIdx.x & 31;
+  const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (u >= U) return;
+  float* qb = scratch + (size_t)u * C;  // mean probabilities
+  for (int c = lane; c < C; c += 32) qb[c] = 0.f;
+  __syncwarp();
+  const float invK = 1.0f / (float)K;
+  for (int k = 0; k < K; ++k) {
+    const float* z = logits + ((size_t)k * U + u) * C;
+    float m = -INFINITY;
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, z[c]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += expf(z[c] - m);
+    s = warp_sum(s);
+    for (int c = lane; c < C; c += 32) qb[c] += expf(z[c] - m) / s;
+  }
+  __syncwarp();
+  // mean over K, max/argmax (first maximal index, as torch.max)
+  float best = -INFINITY;
+  int besti = 0x7fffffff;
+  for (int c = lane; c < C; c += 32) {
+    const float v = qb[c] * invK;
+    qb[c] = v;
+    if (v > best) { best = v; besti = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+  }
+  if (lane == 0) {
+    conf[u] = best;
+    confident[u] = best >= min_conf ? 1 : 0;
+  }
+  __syncwarp();
+  float* qo = q + (size_t)u * C;
+  if (!sharpen || T == 1.0f) {
+    for (int c = lane; c < C; c += 32) qo[c] = qb[c];
+  } else if (T == 0.0f) {
+    for (int c = lane; c < C; c += 32) qo[c] = (c == besti) ? 1.f : 0.f;
+  } else {
+    const float e = 1.0f / T;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += powf(qb[c], e);
+    s = warp_sum(s);
+    for (int c = lane; c < C; c += 32) qo[c] = powf(qb[c], e) / s;
+  }
+}
+
+extern "C" int scnb_pseudolabel(const float* teacher_logits, int K, int U, int C, float T, int sharpen, float min_confidence,
+                                float* q, float* conf, uint8_t* confident, float* scratch_UC, void* stream) {
+  SCNB_CHECK_ARG(teacher_logits && q && conf && confident && scratch_UC && K > 0 && U >= 0 && C > 0, "pseudolabel: bad arguments");
+  if (U == 0) return SCNB_OK;
+  k_pseudolabel<<<scnb_cdiv(U, 8), 256, 0, (cudaStream_t)stream>>>(teacher_logits, K, U, C, T, sharpen, min_confidence, q, conf,
+                                                                     confident, scratch_UC);
+  SCNB_CHECK_LAUNCH("pseudolabel");
+  return SCNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MixMatch plan.  Base rows: [0,U) unlabeled (raw), [U,U+L) labeled (augmented).
+// Super-batch rows: [0,U) U-pass = [mixed confident ; raw unconfident], [U,U+L) L-pass (mixed),
+// [U+L, U+L+n_dan) DAN = [labeled ; unlabeled (all or confident only)].
+// plan_i layout (int32): see offsets below.  All of it lives in device memory.
+// ---------------------------------------------------------------------------------------------
+struct PlanPtrs {
+  int32_t* counts;    // [8]: n_conf, n_mm, n_dan, R_active, U, L, n_dan_unl, 0
+  float* pconf;       // [1]: n_dan_unl / max(U,1)  (losses.py:1203)
+  int32_t* seg_off;   // [4]
+  int32_t* cpos;      // [U]   position among confident (or among unconfident) rows
+  int32_t* cat2base;  // [U+L]
+  int32_t* rank;      // [U+L]
+  int32_t* ridx;      // [U+L]
+  int32_t* srcA;      // [Rmax]
+  int32_t* srcB;      // [Rmax]
+  float* gam;         // [Rmax]
+  int32_t* inv3;      // [3][U+L]
+  float* coef3;       // [3][U+L]
+};
+
+__global__ void __launch_bounds__(1024) k_plan_compact(const uint8_t* __restrict__ confident, int U, int L, int use_dan,
+                                                       int dan_conf_only, PlanPtrs P) {
+  __shared__ int wtot[32];
+  __shared__ int carry_s;
+  __shared__ int n_conf_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  // exclusive scan of the confident flags
+  for (int base = 0; base < U; base += 1024) {
+    const int i = base + tid;
+    const int f = (i < U && confident[i]) ? 1 : 0;
+    int x = f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wtot[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      int t = wtot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      wtot[lane] = t;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int excl = carry + (wid ? wtot[wid - 1] : 0) + x - f;
+    if (i < U) P.cpos[i] = f ? excl : (i - excl);  // rank among confident, or among unconfident
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + wtot[31];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const int n_conf = carry_s;
+    n_conf_s = n_conf;
+    const int n_dan_unl = use_dan ? (dan_conf_only ? n_conf : U) : 0;
+    const int n_dan = use_dan ? L + n_dan_unl : 0;
+    P.counts[0] = n_conf;
+    P.counts[1] = n_conf + L;
+    P.counts[2] = n_dan;
+    P.counts[3] = U + L + n_dan;
+    P.counts[4] = U;
+    P.counts[5] = L;
+    P.counts[6] = n_dan_unl;
+    P.counts[7] = 0;
+    if (P.pconf) P.pconf[0] = (float)n_dan_unl / (float)max(U, 1);
+    P.seg_off[0] = 0;
+    P.seg_off[1] = U;
+    P.seg_off[2] = U + L;
+    P.seg_off[3] = U + L + n_dan;
+  }
+  __syncthreads();
+  const int n_conf = n_conf_s;
+  for (int i = tid; i < U; i += 1024)
+    if (confident[i]) P.cat2base[P.cpos[i]] = i;
+  for (int i = tid; i < L; i += 1024) P.cat2base[n_conf + i] = U + i;
+}
+
+// rank[j] = #{k < n_mm : key[k] < key[j] or (key[k]==key[j] and k<j)};  ridx[rank[j]] = j
+// (== torch.argsort(keys[:n_mm], stable=True), standing in for torch.randperm(n_mm)).
+__global__ void __launch_bounds__(256) k_plan_rank(const float* __restrict__ keys, PlanPtrs P, int n_max) {
+  __shared__ float tile[256];
+  const int n = P.counts[1];
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (blockIdx.x * 256 >= n) return;
+  const float kj = j < n ? keys[j] : 0.f;
+  int r = 0;
+  for (int base = 0; base < n; base += 256) {
+    const int k = base + threadIdx.x;
+    tile[threadIdx.x] = k < n ? keys[k] : INFINITY;
+    __syncthreads();
+    const int lim = min(256, n - base);
+    for (int t = 0; t < lim; ++t) {
+      const float kv = tile[t];
+      r += (kv < kj || (kv == kj && base + t < j)) ? 1 : 0;
+    }
+    __syncthreads();
+  }
+  if (j < n) {
+    P.rank[j] = r;
+    P.ridx[r] = j;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_plan_maps(const uint8_t* __restrict__ confident, const float* __restrict__ gamma_raw,
+                                                   int U, int L, int use_dan, int dan_conf_only, int mixup_on, int Rmax,
+                                                   PlanPtrs P) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int n_conf = P.counts[0], n_dan_unl = P.counts[6];
+  const int nb = U + L;
+  // ---- forward maps over super-batch rows ----
+  if (i < Rmax) {
+    int a = 0, b = 0;
+    float g = 1.f;
+    if (i < U) {                       // U-pass
+      if (i < n_conf) {
+        a = P.cat2base[i];
+        if (mixup_on) {
+          b = P.cat2base[P.ridx[i]];
+          const float gr = gamma_raw[i];
+          g = fmaxf(gr, 1.f - gr);
+        } else b = a;
+      } else {                         // unconfident rows appended un-mixed, original order
+        a = -1;                        // filled below from the inverse side
+        b = -1;
+      }
+    } else if (i < U + L) {            // L-pass
+      const int j = n_conf + (i - U);
+      a = i;                           // base row U + (i-U)
+      if (mixup_on) {
+        b = P.cat2base[P.ridx[j]];
+        const float gr = gamma_raw[j];
+        g = fmaxf(gr, 1.f - gr);
+      } else b = a;
+    } else {                           // DAN
+      const int k = i - U - L;
+      if (k < L) a = U + k;
+      else if (k - L < n_dan_unl) a = dan_conf_only ? P.cat2base[k - L] : (k - L);
+      else a = 0;                      // inactive tail
+      b = a;
+    }
+    if (a >= 0) {
+      P.srcA[i] = a;
+      P.srcB[i] = b;
+      P.gam[i] = g;
+    }
+  }
+  // ---- inverse maps over base rows (and the unconfident forward rows) ----
+  if (i < nb) {
+    int iA, iB = -1, iD = -1;
+    float cA, cB = 0.f, cD = 0.f;
+    if (i < U) {
+      if (confident[i]) {
+        const int j = P.cpos[i];
+        iA = j;
+        float g = 1.f;
+        if (mixup_on) { const float gr = gamma_raw[j]; g = fmaxf(gr, 1.f - gr); }
+        cA = g;
+        if (mixup_on) {
+          const int jp = P.rank[j];    // cat row whose partner is j
+          iB = jp < n_conf ? jp : U + (jp - n_conf);
+          const float gr = gamma_raw[jp];
+          cB = 1.f - fmaxf(gr, 1.f - gr);
+        }
+        if (use_dan) { iD = U + L + L + (dan_conf_only ? j : i); cD = 1.f; }
+      } else {
+        const int row = n_conf + P.cpos[i];
+        iA = row;
+        cA = 1.f;
+        P.srcA[row] = i;
+        P.srcB[row] = i;
+        P.gam[row] = 1.f;
+        if (use_dan && !dan_conf_only) { iD = U + L + L + i; cD = 1.f; }
+      }
+    } else {
+      const int l = i - U, j = n_conf + l;
+      iA = U + l;
+      float g = 1.f;
+      if (mixup_on) { const float gr = gamma_raw[j]; g = fmaxf(gr, 1.f - gr); }
+      cA = g;
+      if (mixup_on) {
+        const int jp = P.rank[j];
+        iB = jp < n_conf ? jp : U + (jp - n_conf);
+        const float gr = gamma_raw[jp];
+        cB = 1.f - fmaxf(gr, 1.f - gr);
+      }
+      if (use_dan) { iD = U + L + l; cD = 1.f; }
+    }
+    P.inv3[i] = iA;            P.coef3[i] = cA;
+    P.inv3[nb + i] = iB;       P.coef3[nb + i] = cB;
+    P.inv3[2 * nb + i] = iD;   P.coef3[2 * nb + i] = cD;
+  }
+}
+
+extern "C" int scnb_mixmatch_plan(const uint8_t* confident, const float* perm_keys, const float* gamma_raw, int U, int L,
+                                  int use_dan, int dan_conf_only, int mixup_on, int32_t* counts8, int32_t* seg_off4,
+                                  int32_t* work_i /* [U + 3*(U+L)] */, int32_t* srcA, int32_t* srcB, float* gam, int Rmax,
+                                  int32_t* inv3, float* coef3, float* pconf1, void* stream) {
+  SCNB_CHECK_ARG(confident && perm_keys && gamma_raw && counts8 && seg_off4 && work_i && srcA && srcB && gam && inv3 && coef3,
+                 "mixmatch_plan: null pointer");
+  SCNB_CHECK_ARG(U >= 0 && L >= 1 && Rmax >= U + L + (use_dan ? U + L : 0), "mixmatch_plan: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = U + L;
+  PlanPtrs P;
+  P.counts = counts8;
+  P.pconf = pconf1;
+  P.seg_off = seg_off4;
+  P.cpos = work_i;
+  P.cat2base = work_i + U;
+  P.rank = work_i + U + nb;
+  P.ridx = work_i + U + 2 * nb;
+  P.srcA = srcA;
+  P.srcB = srcB;
+  P.gam = gam;
+  P.inv3 = inv3;
+  P.coef3 = coef3;
+  k_plan_compact<<<1, 1024, 0, st>>>(confident, U, L, use_dan, dan_conf_only, P);
+  SCNB_CHECK_LAUNCH("mixmatch_plan/compact");
+  if (mixup_on) {
+    k_plan_rank<<<scnb_cdiv(nb, 256), 256, 0, st>>>(perm_keys, P, nb);
+    SCNB_CHECK_LAUNCH("mixmatch_plan/rank");
+  }
+  k_plan_maps<<<scnb_cdiv(Rmax > nb ? Rmax : nb, 256), 256, 0, st>>>(confident, gamma_raw, U, L, use_dan, dan_conf_only,
+                                                                      mixup_on, Rmax, P);
+  SCNB_CHECK_LAUNCH("mixmatch_plan/maps");
+  return SCNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Soft-target cross entropy, mean over `n_norm` rows, with dLogits.  One warp per row.
+//   label row i = gam[i]*Y[mapA[i]] + (1-gam[i])*Y[mapB[i]]   (maps optional -> Y[i])
+//   loss_i = -w_i * sum_c y_c * log_softmax(z)_c ;  w_i = max_c(cw_c*y_c) if class weights
+//   dz = grad_scale * (w_i/n_norm) * (softmax(z)*sum_c y_c - y)
+// Rows >= *n_rows_dev are inactive: dz = 0.  loss_out[0] += loss (atomic); loss_out[1] += #argmax hits.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_soft_ce(const float* __restrict__ Zl, int n_max, int C,
+                                                 const int32_t* __restrict__ n_rows_dev, const float* __restrict__ Y,
+                                                 const int32_t* __restrict__ mapA, const int32_t* __restrict__ mapB,
+                                                 const float* __restrict__ gam, int map_off,
+                                                 const float* __restrict__ class_weight, const int32_t* __restrict__ n_norm_dev,
+                                                 int n_norm, float grad_scale, const float* __restrict__ loss_scale_dev,
+                                                 float* __restrict__ dZ, float* __restrict__ loss_out, int count_acc) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n_max) return;
+  const int n_rows = n_rows_dev ? min(*n_rows_dev, n_max) : n_max;
+  float* dz = dZ ? dZ + (size_t)i * C : nullptr;
+  if (i >= n_rows) {
+    if (dz)
+      for (int c = lane; c < C; c += 32) dz[c] = 0.f;
+    return;
+  }
+  const float nn = (float)(n_norm_dev ? max(*n_norm_dev, 1) : max(n_norm, 1));
+  const float ls = loss_scale_dev ? *loss_scale_dev : 1.f;
+  const float* z = Zl + (size_t)i * C;
+  int a = i, b = i;
+  float g = 1.f;
+  if (mapA) {
+    a = mapA[map_off + i];
+    b = mapB ? mapB[map_off + i] : a;
+    g = gam ? gam[map_off + i] : 1.f;
+  }
+  const float* ya = Y + (size_t)a * C;
+  const float* yb = Y + (size_t)b * C;
+  const float g1 = 1.f - g;
+  float m = -INFINITY;
+  int am = 0x7fffffff;
+  for (int c = lane; c < C; c += 32) {
+    const float v = z[c];
+    if (v > m) { m = v; am = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, am, o);
+    if (om > m || (om == m && oi < am)) { m = om; am = oi; }
+  }
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += expf(z[c] - m);
+  s = warp_sum(s);
+  const float lse = logf(s);
+  float dot = 0.f, ysum = 0.f, w = -INFINITY;
+  float ym = -INFINITY;  // argmax of the dominant label row (the original, un-mixed label)
+  int yam = 0x7fffffff;
+  for (int c = lane; c < C; c += 32) {
+    const float y = (a == b) ? ya[c] : g * ya[c] + g1 * yb[c];
+    dot += y * ((z[c] - m) - lse);
+    ysum += y;
+    if (class_weight) w = fmaxf(w, class_weight[c] * y);
+    if (ya[c] > ym) { ym = ya[c]; yam = c; }
+  }
+  if (count_acc) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, ym, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, yam, o);
+      if (om > ym || (om == ym && oi < yam)) { ym = om; yam = oi; }
+    }
+  }
+  dot = warp_sum(dot);
+  ysum = warp_sum(ysum);
+  w = class_weight ? warp_max(w) : 1.f;
+  const float li = -dot * w;
+  if (dz) {
+    const float k = grad_scale * ls * w / nn;
+    for (int c = lane; c < C; c += 32) {
+      const float y = (a == b) ? ya[c] : g * ya[c] + g1 * yb[c];
+      const float p = expf(z[c] - m) / s;
+      dz[c] = k * (p * ysum - y);
+    }
+  }
+  if (lane == 0) {
+    atomicAdd(loss_out, li * ls / nn);
+    if (count_acc && yam == am) atomicAdd(loss_out + 1, 1.0f);
+  }
+}
+
+extern "C" int scnb_soft_ce_fwd_bwd(const float* logits, int n_max, int C, const int32_t* n_rows_dev, const float* Y,
+                                    const int32_t* mapA, const int32_t* mapB, const float* gam, int map_off,
+                                    const float* class_weight, const int32_t* n_norm_dev, int n_norm, float grad_scale,
+                                    const float* loss_scale_dev, float* dlogits, float* loss_out2, int count_acc,
+                                    void* stream) {
+  SCNB_CHECK_ARG(logits && Y && loss_out2 && n_max >= 0 && C > 0, "soft_ce_fwd_bwd: bad arguments");
+  if (n_max == 0) return SCNB_OK;
+  k_soft_ce<<<scnb_cdiv(n_max, 8), 256, 0, (cudaStream_t)stream>>>(logits, n_max, C, n_rows_dev, Y, mapA, mapB, gam, map_off,
+                                                                     class_weight, n_norm_dev, n_norm, grad_scale,
+                                                                     loss_scale_dev, dlogits, loss_out2, count_acc);
+  SCNB_CHECK_LAUNCH("soft_ce_fwd_bwd");
+  return SCNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Interpolation-consistency MSE on probabilities (losses.py:880-913):
+//   L_u = (1/n_norm) sum_{i < n_conf} sum_c (softmax(z_i)_c - y'_ic)^2 ;  rows >= n_conf get zero loss/grad.
+//   dz = p * (g - sum_c g_c p_c),  g = 2 (p - y') * weight / n_norm
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_softmax_mse(const float* __restrict__ Zl, int n_max, int C,
+                                                     const int32_t* __restrict__ n_conf_dev, const float* __restrict__ Y,
+                                                     const int32_t* __restrict__ mapA, const int32_t* __restrict__ mapB,
+                                                     const float* __restrict__ gam, int map_off, int n_norm,
+                                                     const float* __restrict__ weight_dev, float weight,
+                                                     float* __restrict__ dZ, float* __restrict__ loss_out) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n_max) return;
+  const int n_conf = n_conf_dev ? min(*n_conf_dev, n_max) : n_max;
+  float* dz = dZ ? dZ + (size_t)i * C : nullptr;
+  if (i >= n_conf) {
+    if (dz)
+      for (int c = lane; c < C; c += 32) dz[c] = 0.f;
+    return;
+  }
+  const float wgt = weight_dev ? *weight_dev : weight;
+  const float* z = Zl + (size_t)i * C;
+  int a = i, b = i;
+  float g = 1.f;
+  if (mapA) {
+    a = mapA[map_off + i];
+    b = mapB ? mapB[map_off + i] : a;
+    g = gam ? gam[map_off + i] : 1.f;
+  }
+  const float* ya = Y + (size_t)a * C;
+  const float* yb = Y + (size_t)b * C;
+  const float g1 = 1.f - g;
+  float m = -INFINITY;
+  for (int c = lane; c < C; c += 32) m = fmaxf(m, z[c]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += expf(z[c] - m);
+  s = warp_sum(s);
+  float sq = 0.f, gp = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float y = (a == b) ? ya[c] : g * ya[c] + g1 * yb[c];
+    const float p = expf(z[c] - m) / s;
+    const float d = p - y;
+    sq = fmaf(d, d, sq);
+    gp = fmaf(d, p, gp);
+  }
+  sq = warp_sum(sq);
+  gp = warp_sum(gp);
+  const float inv_n = 1.0f / (float)max(n_norm, 1);
+  if (dz) {
+    const float k = 2.0f * wgt * inv_n;
+    for (int c = lane; c < C; c += 32) {
+      const float y = (a == b) ? ya[c] : g * ya[c] + g1 * yb[c];
+      const float p = expf(z[c] - m) / s;
+      dz[c] = k * p * ((p - y) - gp);
+    }
+  }
+  if (lane == 0) atomicAdd(loss_out, sq * inv_n);
+}
+
+extern "C" int scnb_softmax_mse_fwd_bwd(const float* logits, int n_max, int C, const int32_t* n_conf_dev, const float* Y,
+                                        const int32_t* mapA, const int32_t* mapB, const float* gam, int map_off, int n_norm,
+                                        const float* weight_dev, float weight, float* dlogits, float* loss_out, void* stream) {
+  SCNB_CHECK_ARG(logits && Y && loss_out && n_max >= 0 && C > 0, "softmax_mse_fwd_bwd: bad arguments");
+  if (n_max == 0) return SCNB_OK;
+  k_softmax_mse<<<scnb_cdiv(n_max, 8), 256, 0, (cudaStream_t)stream>>>(logits, n_max, C, n_conf_dev, Y, mapA, mapB, gam, map_off,
+                                                                         n_norm, weight_dev, weight, dlogits, loss_out);
+  SCNB_CHECK_LAUNCH("softmax_mse_fwd_bwd");
+  return SCNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One-hot gather:  out[i, :] = onehot(ids[src[i]])  (domain targets of the DAN rows), zeros when id < 0.
+// Also usable to build label matrices from integer labels.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_onehot_rows(const int32_t* __restrict__ ids, const int32_t* __restrict__ src, int src_off, int n, int C,
+                              float* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * C) return;
+  const int i = t / C, c = t - i * C;
+  const int r = src ? src[src_off + i] : i;
+  out[t] = (ids[r] == c) ? 1.f : 0.f;
+}
+
+extern "C" int scnb_onehot_rows(const int32_t* ids, const int32_t* src, int src_off, int n, int C, float* out, void* stream) {
+  SCNB_CHECK_ARG(ids && out && n >= 0 && C > 0, "onehot_rows: bad arguments");
+  if (n == 0) return SCNB_OK;
+  k_onehot_rows<<<scnb_cdiv((long long)n * C, 256), 256, 0, (cudaStream_t)stream>>>(ids, src, src_off, n, C, out);
+  SCNB_CHECK_LAUNCH("onehot_rows");
+  return SCNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Predict head: score = logits_sum / n_models; pred = argmax; prob = softmax(score).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_predict_head(const float* __restrict__ logits_sum, float inv_models, int n, int C,
+                                                      int64_t* __restrict__ pred, float* __restrict__ prob,
+                                                      float* __restrict__ score) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const float* z = logits_sum + (size_t)i * C;
+  float m = -INFINITY;
+  int am = 0x7fffffff;
+  for (int c = lane; c < C; c += 32) {
+    const float v = z[c] * inv_models;
+    if (v > m) { m = v; am = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, am, o);
+    if (om > m || (om == m && oi < am)) { m = om; am = oi; }
+  }
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += expf(z[c] * inv_models - m);
+  s = warp_sum(s);
+  for (int c = lane; c < C; c += 32) {
+    const float v = z[c] * inv_models;
+    if (score) score[(size_t)i * C + c] = v;
+    if (prob) prob[(size_t)i * C + c] = expf(v - m) / s;
+  }
+  if (lane == 0 && pred) pred[i] = am;
+}
+
+extern "C" int scnb_predict_head(const float* logits_sum, int n_models, int n, int C, int64_t* pred, float* prob, float* score,
+                                 void* stream) {
+  SCNB_CHECK_ARG(logits_sum && n_models > 0 && n >= 0 && C > 0, "predict_head: bad arguments");
+  if (n == 0) return SCNB_OK;
+  k_predict_head<<<scnb_cdiv(n, 8), 256, 0, (cudaStream_t)stream>>>(logits_sum, 1.0f / (float)n_models, n, C, pred, prob, score);
+  SCNB_CHECK_LAUNCH("predict_head");
+  return SCNB_OK;
+}

@@ -1,0 +1,118 @@
+// Fused optimizer / teacher kernels over the flat parameter arena (sm_100a).
+//   scnb_step_begin   advance the device-side step counters (optimizer t, RNG counter, MixMatch step)
+//   scnb_optim_step   Adadelta / Adam / AdamW / SGD-momentum, one elementwise pass over the arena
+//                     (torch.optim single-tensor rules; reference call sites main.py:36-41,374-396)
+//   scnb_ema_update   mean-teacher EMA t <- a t + (1-a) p, a = min(1 - 1/(step+1), decay)   (losses.py:382-406)
+// Hyper-parameters live in a small device buffer so that a captured CUDA graph can be replayed
+// while lr / weights change:  hp = [lr, weight_decay, beta1, beta2, eps, rho, momentum, 0]
+// state (int64): st = [t (optimizer steps taken), rng_seed, rng_counter, mm_step]
+#include "common.cuh"
+
+enum { OPT_ADADELTA = 0, OPT_ADAM = 1, OPT_ADAMW = 2, OPT_SGD = 3 };
+
+__global__ void k_step_begin(int64_t* st) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    st[0] += 1;  // optimizer step index t (1-based when read by optim_step)
+    st[2] += 1;  // RNG counter
+  }
+}
+
+extern "C" int scnb_step_begin(int64_t* state4, void* stream) {
+  SCNB_CHECK_ARG(state4, "step_begin: null state");
+  k_step_begin<<<1, 32, 0, (cudaStream_t)stream>>>(state4);
+  SCNB_CHECK_LAUNCH("step_begin");
+  return SCNB_OK;
+}
+
+__global__ void k_mm_step_inc(int64_t* st) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) st[3] += 1;
+}
+
+template <int OPT>
+__global__ void __launch_bounds__(256) k_optim(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ s1,
+                                               float* __restrict__ s2, size_t n, const float* __restrict__ hp,
+                                               const int64_t* __restrict__ st) {
+  __shared__ float sh[4];
+  const float lr = hp[0], wd = hp[1], b1 = hp[2], b2 = hp[3], eps = hp[4], rho = hp[5], mom = hp[6];
+  if (threadIdx.x == 0) {
+    const double t = (double)st[0];
+    const double bc1 = 1.0 - pow((double)b1, t), bc2 = 1.0 - pow((double)b2, t);
+    sh[0] = (float)((double)lr / bc1);  // step_size
+    sh[1] = (float)sqrt(bc2);
+    sh[2] = (st[0] <= 1) ? 1.f : 0.f;   // first step (SGD momentum buffer init)
+  }
+  __syncthreads();
+  const float step_size = sh[0], bc2_sqrt = sh[1];
+  const bool first = sh[2] != 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float pi = p[i], gi = g[i];
+    if (OPT == OPT_ADADELTA) {
+      gi = fmaf(wd, pi, gi);
+      float sq = rho * s1[i] + (1.f - rho) * gi * gi;
+      float acc = s2[i];
+      const float delta = sqrtf(acc + eps) / sqrtf(sq + eps) * gi;
+      acc = rho * acc + (1.f - rho) * delta * delta;
+      s1[i] = sq;
+      s2[i] = acc;
+      p[i] = pi - lr * delta;
+    } else if (OPT == OPT_ADAM || OPT == OPT_ADAMW) {
+      if (OPT == OPT_ADAMW) pi = pi * (1.f - lr * wd);
+      else gi = fmaf(wd, pi, gi);
+      float m = s1[i], v = s2[i];
+      m = m + (1.f - b1) * (gi - m);
+      v = b2 * v + (1.f - b2) * gi * gi;
+      const float denom = sqrtf(v) / bc2_sqrt + eps;
+      s1[i] = m;
+      s2[i] = v;
+      p[i] = pi - step_size * (m / denom);
+    } else {  // SGD with momentum (dampening 0, no nesterov)
+      gi = fmaf(wd, pi, gi);
+      float buf = first ? gi : mom * s1[i] + gi;
+      s1[i] = buf;
+      p[i] = pi - lr * buf;
+    }
+  }
+}
+
+extern "C" int scnb_optim_step(int opt, float* params, const float* grads, float* state1, float* state2, long long n,
+                               const float* hp8, const int64_t* state4, void* stream) {
+  SCNB_CHECK_ARG(params && grads && state1 && hp8 && state4 && n >= 0, "optim_step: bad arguments");
+  SCNB_CHECK_ARG(opt == OPT_SGD || state2, "optim_step: second state buffer required");
+  if (n == 0) return SCNB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  switch (opt) {
+    case OPT_ADADELTA: k_optim<OPT_ADADELTA><<<blocks, 256, 0, st>>>(params, grads, state1, state2, (size_t)n, hp8, state4); break;
+    case OPT_ADAM: k_optim<OPT_ADAM><<<blocks, 256, 0, st>>>(params, grads, state1, state2, (size_t)n, hp8, state4); break;
+    case OPT_ADAMW: k_optim<OPT_ADAMW><<<blocks, 256, 0, st>>>(params, grads, state1, state2, (size_t)n, hp8, state4); break;
+    case OPT_SGD: k_optim<OPT_SGD><<<blocks, 256, 0, st>>>(params, grads, state1, state2, (size_t)n, hp8, state4); break;
+    default: scnb_set_error("optim_step: unknown optimizer %d", opt); return SCNB_ERR_ARG;
+  }
+  SCNB_CHECK_LAUNCH("optim_step");
+  return SCNB_OK;
+}
+
+__global__ void __launch_bounds__(256) k_ema(float* __restrict__ t, const float* __restrict__ p, size_t n, float decay,
+                                             const int64_t* __restrict__ st) {
+  const double step = (double)st[3];
+  const float a = fminf((float)(1.0 - 1.0 / (step + 1.0)), decay);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    t[i] = t[i] * a + (1.f - a) * p[i];
+}
+
+extern "C" int scnb_ema_update(float* teacher, const float* params, long long n, float decay, const int64_t* state4,
+                               void* stream) {
+  SCNB_CHECK_ARG(teacher && params && state4 && n >= 0, "ema_update: bad arguments");
+  if (n == 0) return SCNB_OK;
+  const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  k_ema<<<blocks, 256, 0, (cudaStream_t)stream>>>(teacher, params, (size_t)n, decay, state4);
+  SCNB_CHECK_LAUNCH("ema_update");
+  return SCNB_OK;
+}
+
+extern "C" int scnb_mm_step_inc(int64_t* state4, void* stream) {
+  SCNB_CHECK_ARG(state4, "mm_step_inc: null state");
+  k_mm_step_inc<<<1, 32, 0, (cudaStream_t)stream>>>(state4);
+  SCNB_CHECK_LAUNCH("mm_step_inc");
+  return SCNB_OK;
+}

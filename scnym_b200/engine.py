@@ -1,0 +1,580 @@
+"""Fused MixMatch(+DAN) / supervised training engine.
+
+One `step()` is the body of the reference's minibatch loop
+(scnym/trainer.py:575-671 `SemiSupervisedTrainer.train_epoch`, :189-256 `Trainer.train_epoch`):
+batch assembly, `log1p_drop`, teacher pseudolabels, MixUp, the three student forwards, the
+three losses, backward and `optimizer.step()` -- as a fixed sequence of libscnym_b200 kernels
+on device-resident CSR data, with no host synchronisation, replayable as one CUDA graph.
+
+Algebra exploited:
+  * the first Linear is applied ONCE per step to the rows [U_raw ; L_aug]; MixUp is applied to
+    its output (linearity), and the same product feeds the eval-mode teacher (when the teacher
+    is the current student and pseudolabels are not augmented) and the DAN pass;
+  * the three student forwards run as one "super-batch" [U-mixed | L-mixed | DAN] whose
+    BatchNorm layers keep per-segment statistics; Linear layers and all weight gradients see
+    one tall matrix;
+  * dW1 is one transposed sparse product from the un-mixed, summed dZ1.
+"""
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import call, ptr, OPTIMIZER_CODES
+from .dataprep import DeviceCSR
+from .model import CellTypeCLF, DANN
+
+# Philox stream ids (one logical random stream per use inside a step)
+SID_IN_L = 0          # input dropout, labelled rows
+SID_IN_U = 1          # + k : input dropout of teacher view k
+SID_HID = 16          # + application index : hidden dropout of the student super-batch
+
+
+@dataclass
+class EngineConfig:
+    # MixMatchLoss (losses.py:603-610) / fit_model defaults (main.py:511-524, api.py:71-105)
+    n_augmentations: int = 1
+    T: float = 0.5
+    augment_pseudolabels: bool = False
+    pseudolabel_min_confidence: float = 0.0
+    mixup_alpha: float = 0.3
+    mean_teacher: bool = False
+    decay_coef: float = 0.997
+    p_in_drop: float = 0.1
+    # DANLoss (losses.py:1043-1105)
+    use_dan: bool = True
+    dan_use_conf_pseudolabels: bool = False
+    dan_scale_loss_pseudoconf: bool = False
+    # optimizer (main.py:36-41, 374-396)
+    optimizer: str = "adadelta"
+    lr: float = 1.0
+    weight_decay: float = 1e-4
+    betas: tuple = (0.9, 0.999)
+    eps: Optional[float] = None
+    rho: float = 0.9
+    momentum: float = 0.9
+    class_weight: Optional[List[float]] = None
+    seed: int = 0
+    use_cuda_graph: bool = True
+
+
+class ParamArena(object):
+    """All trainable parameters in one flat fp32 buffer (+ grads and optimizer state).
+
+    Parameters keep their nn.Module identity: each `p.data` becomes a view into the arena and
+    `p.grad` a view into the gradient arena, so `state_dict()` / `load_state_dict()` /
+    `torch.save` behave as before while the optimizer is one elementwise kernel.
+    """
+
+    def __init__(self, named_params: List, device) -> None:
+        self.names, self.params, self.offsets, self.sizes = [], [], {}, {}
+        total = 0
+        seen = set()
+        for name, p in named_params:
+            if id(p) in seen:
+                continue
+            seen.add(id(p))
+            n = p.numel()
+            self.names.append(name)
+            self.params.append(p)
+            self.offsets[name] = total
+            self.sizes[name] = n
+            total += (n + 3) // 4 * 4  # keep every tensor 16-byte aligned
+        self.total = total
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=device)
+        self.state1 = torch.zeros(total, dtype=torch.float32, device=device)
+        self.state2 = torch.zeros(total, dtype=torch.float32, device=device)
+        self._views, self._gviews = {}, {}
+        for name, p in zip(self.names, self.params):
+            o, n = self.offsets[name], self.sizes[name]
+            if p.dim() == 2 and not p.data.is_contiguous() and p.data.t().is_contiguous():
+                shp = p.data.t().shape  # gene-major first layer: arena holds [G, H0]
+                v = self.flat[o:o + n].view(shp)
+                v.copy_(p.data.t())
+                gv = self.grad[o:o + n].view(shp)
+                p.data = v.t()
+                p.grad = gv.t()
+            else:
+                v = self.flat[o:o + n].view(p.shape)
+                v.copy_(p.data)
+                gv = self.grad[o:o + n].view(p.shape)
+                p.data = v
+                p.grad = gv
+            self._views[name], self._gviews[name] = v, gv
+
+    def w(self, name):  # storage-layout view of a parameter
+        return self._views[name]
+
+    def g(self, name):
+        return self._gviews[name]
+
+    def check_aliasing(self):
+        """Raise if something re-pointed a parameter away from the arena (e.g. `.cuda()`)."""
+        for name, p in zip(self.names, self.params):
+            base = self._views[name]
+            if p.data.untyped_storage().data_ptr() != base.untyped_storage().data_ptr():
+                raise RuntimeError(f"parameter {name} no longer aliases the engine arena; rebuild the engine")
+
+
+class TrainEngine(object):
+    """Device-resident training step for `CellTypeCLF` (+ `DANN` head).
+
+    mode "mixmatch": SemiSupervisedTrainer step (MixMatchLoss + optional DANLoss)
+    mode "supervised": Trainer step (cross_entropy on raw batches)
+    """
+
+    def __init__(self, model: CellTypeCLF, cfg: EngineConfig, labeled: DeviceCSR, labeled_y, batch_size: int,
+                 unlabeled: Optional[DeviceCSR] = None, unlabeled_batch_size: Optional[int] = None,
+                 dann: Optional[DANN] = None, labeled_domain=None, unlabeled_domain=None, mode: str = "mixmatch",
+                 extra_named_params: Optional[List] = None) -> None:
+        if not torch.cuda.is_available():
+            raise _lib.ScnbError("TrainEngine needs a CUDA device (no CPU fallback)")
+        _lib.lib()
+        self.model, self.cfg, self.mode = model, cfg, mode
+        self.dev = labeled.device
+        dev = self.dev
+        self.lab, self.unl = labeled, unlabeled
+        self.L = int(batch_size)
+        self.U = int(unlabeled_batch_size if unlabeled_batch_size is not None else batch_size) if mode == "mixmatch" else 0
+        if mode == "mixmatch" and unlabeled is None:
+            raise ValueError("mixmatch mode needs unlabeled data")
+        self.use_dan = bool(cfg.use_dan and dann is not None and mode == "mixmatch")
+        self.dann = dann if self.use_dan else None
+        self.G, self.C = model.n_genes, model.n_cell_types
+        blocks = model.block_modules()
+        self.n_app = len(blocks)
+        self.widths = [blk[0].out_features for blk in blocks]
+        self.H = self.widths[-1]
+        self.D = int(dann.n_domains) if self.use_dan else 0
+        L, U = self.L, self.U
+        self.nb = U + L
+        self.Rd = (U + L) if self.use_dan else 0
+        self.Rmax = self.nb + self.Rd
+        self.K_eff = cfg.n_augmentations if cfg.augment_pseudolabels else 1
+        self.teacher_own_spmm = bool(cfg.mean_teacher or cfg.augment_pseudolabels)
+
+        # ---- parameters -> arena (optimizer order: model.parameters(), then the DAN head group,
+        #      main.py:374-381, 582-587) ----
+        if next(model.parameters()).device != dev:
+            model.to(dev)
+        named = [("model." + n, p) for n, p in model.named_parameters()]
+        if self.use_dan:
+            self.dann.domain_clf.to(dev)
+            named += [("dan." + n, p) for n, p in self.dann.domain_clf.named_parameters()]
+        if extra_named_params:
+            named += list(extra_named_params)
+        self.arena = ParamArena(named, dev)
+        self.n_model_params = sum(((p.numel() + 3) // 4 * 4) for n, p in zip(self.arena.names, self.arena.params)
+                                  if n.startswith("model."))
+        # block application -> parameter names
+        mods = list(model.embed)
+        self._blk = []
+        for a in range(self.n_app):
+            lin, bn = mods[4 * a], mods[4 * a + 1]
+            li = [i for i, m in enumerate(mods) if m is lin][0]
+            bi = [i for i, m in enumerate(mods) if m is bn][0]
+            self._blk.append(dict(lin=lin, bn=bn, drop=mods[4 * a + 2], W=f"model.embed.{li}.weight", b=f"model.embed.{li}.bias",
+                                  g=f"model.embed.{bi}.weight", beta=f"model.embed.{bi}.bias", bn_key=bi))
+        self._dan_lin = [m for m in self.dann.domain_clf if isinstance(m, nn.Linear)] if self.use_dan else []
+        if self.use_dan and len(self._dan_lin) != 2:
+            raise NotImplementedError("engine supports DANN(n_layers=1) (the only configuration fit_model builds)")
+
+        # ---- labels / domains ----
+        self.lab_y = torch.as_tensor(np.asarray(labeled_y), dtype=torch.int32).to(dev)
+        self.lab_dom = None if labeled_domain is None else torch.as_tensor(np.asarray(labeled_domain), dtype=torch.int32).to(dev)
+        self.unl_dom = None if unlabeled_domain is None else torch.as_tensor(np.asarray(unlabeled_domain), dtype=torch.int32).to(dev)
+        self.class_weight = None if cfg.class_weight is None else torch.tensor(cfg.class_weight, dtype=torch.float32, device=dev)
+
+        f32 = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        i32 = lambda *s: torch.zeros(*s, dtype=torch.int32, device=dev)
+        # ---- per-step inputs (host writes, graph reads) ----
+        self.l_rows = torch.zeros(L, dtype=torch.int64, device=dev)
+        self.u_rows = torch.zeros(max(U, 1), dtype=torch.int64, device=dev)
+        self.perm_keys = f32(max(self.nb, 1))
+        self.gamma_raw = f32(max(self.nb, 1)) + 1.0
+        self.hp = f32(8)
+        self.state = torch.zeros(4, dtype=torch.int64, device=dev)  # t, seed, rng counter, mm step
+        self.state[1] = int(cfg.seed)
+        self.set_hyper(lr=cfg.lr)
+        self.unsup_weight, self.dan_weight = 1.0, 1.0
+        # ---- batch CSR ----
+        maxnnz = max(labeled.max_row_nnz, unlabeled.max_row_nnz if unlabeled is not None else 0, 1)
+        cap = self.nb * maxnnz
+        self.cap = cap
+        self.b_indptr, self.b_idx, self.b_val = i32(self.nb + 1), i32(cap), f32(cap)
+        H0 = self.widths[0]
+        self.Z1 = f32(self.nb, H0)
+        # injected randomness (tests); None -> Philox in-kernel
+        self.inj_in_keep_L = None     # uint8 [cap] aligned with batch nnz positions
+        self.inj_in_keep_U = None     # list of K uint8 [U*maxnnz]
+        self.inj_hidden_keep = None   # list over applications of uint8 [Rmax, H_a]
+        if mode == "mixmatch":
+            K = self.K_eff
+            if self.teacher_own_spmm:
+                self.tb_indptr, self.tb_idx, self.tb_val = i32(U + 1), i32(U * maxnnz), f32(U * maxnnz)
+                self.TZ1 = f32(K * U, H0)
+            self.TA = [f32(K * U, w) for w in self.widths]
+            self.TZ = [None] + [f32(K * U, w) for w in self.widths[1:]]
+            self.t_logits = f32(K * U, self.C)
+            self.Ycat = f32(self.nb, self.C)
+            self.conf = f32(U)
+            self.confident = torch.zeros(U, dtype=torch.uint8, device=dev)
+            self.pl_scratch = f32(U, self.C)
+            self.lab_ids = i32(L)
+            self.base_dom = i32(self.nb)
+            self.counts, self.seg_off = i32(8), i32(4)
+            self.plan_work = i32(U + 3 * self.nb)
+            self.srcA, self.srcB, self.gam = i32(self.Rmax), i32(self.Rmax), f32(self.Rmax)
+            self.inv3, self.coef3 = i32(3, self.nb), f32(3, self.nb)
+            self.pconf = f32(1)
+            self.n_seg = 3 if self.use_dan else 2
+            if cfg.mean_teacher:
+                self.teacher_flat = self.arena.flat[: self.n_model_params].clone()
+                self.teacher_bn = None  # snapshot of BN buffers taken at the first step (losses.py:343-348)
+        else:
+            self.Rmax = L
+            self.n_seg = 1
+            self.seg_off = torch.tensor([0, L], dtype=torch.int32, device=dev)
+            self.Ycat = f32(L, self.C)
+            self.lab_ids = i32(L)
+        R = self.Rmax
+        self.Zs = [f32(R, w) for w in self.widths]
+        self.As = [f32(R, w) for w in self.widths]
+        self.stats = [f32(3, 3, w) for w in self.widths]
+        self.logits = f32(self.nb if mode == "mixmatch" else L, self.C)
+        self.dlogits = torch.zeros_like(self.logits)
+        wmax = max(self.widths)
+        self.dA, self.dZ = f32(R, wmax), f32(R, wmax)
+        self.dZ1 = f32(self.nb, H0) if mode == "mixmatch" else None
+        if self.use_dan:
+            self.Hd, self.dHd = f32(self.Rd, self.H), f32(self.Rd, self.H)
+            self.dlog, self.ddlog = f32(self.Rd, self.D), f32(self.Rd, self.D)
+            self.dlabel = f32(self.Rd, self.D)
+        if mode == "mixmatch":
+            self._const_seg(self.K_eff * U)  # created here: no H2D copies may happen during graph capture
+        self.loss_buf = f32(8)       # [sup, sup_hits, unsup, -, dan, dan_hits, -, -]
+        self.loss_hist = None
+        self._graph = None
+        self._graph_key = None
+        self.steps_done = 0
+        self.kernels_per_step = None
+
+    # ------------------------------------------------------------------------------------
+    def set_hyper(self, lr=None, weight_decay=None):
+        c = self.cfg
+        if lr is not None:
+            c.lr = float(lr)
+        if weight_decay is not None:
+            c.weight_decay = float(weight_decay)
+        eps = c.eps if c.eps is not None else (1e-6 if c.optimizer == "adadelta" else 1e-8)
+        vals = [c.lr, c.weight_decay, c.betas[0], c.betas[1], eps, c.rho, c.momentum, 0.0]
+        self.hp.copy_(torch.tensor(vals, dtype=torch.float32), non_blocking=False)
+
+    def set_weights(self, unsup_weight: float, dan_weight: float = 0.0):
+        """ICLWeight(epoch) values (trainer.py:628,654); changing them re-captures the graph."""
+        self.unsup_weight, self.dan_weight = float(unsup_weight), float(dan_weight)
+
+    def P(self, name):
+        return ptr(self.arena.w(name))
+
+    def Gp(self, name):
+        return ptr(self.arena.g(name))
+
+    # ------------------------------------------------------------------------------------
+    def _teacher_ptrs(self):
+        """(weights, BN buffers) the eval-mode teacher reads."""
+        if self.cfg.mean_teacher:
+            off = self.arena.offsets
+            tw = lambda name: self.teacher_flat[off[name]: off[name] + self.arena.sizes[name]]
+            bn = self.teacher_bn
+            return tw, (lambda a: (bn[a][0], bn[a][1]))
+        return (lambda name: self.arena.w(name)), (lambda a: (self._blk[a]["bn"].running_mean, self._blk[a]["bn"].running_var))
+
+    def _launch_mixmatch(self):
+        c, st = self.cfg, torch.cuda.current_stream().cuda_stream
+        L, U, nb, R, C, H0 = self.L, self.U, self.nb, self.Rmax, self.C, self.widths[0]
+        rng = ptr(self.state[1:3])
+        blk = self._blk
+        call("scnb_step_begin", ptr(self.state), st)
+        self.arena.grad.zero_()
+        self.loss_buf.zero_()
+        # -- ids of the sampled rows
+        call("scnb_gather_i32", ptr(self.lab_y), ptr(self.l_rows), L, 0, ptr(self.lab_ids), st)
+        if self.use_dan:
+            call("scnb_gather_i32", ptr(self.unl_dom), ptr(self.u_rows), U, 1, ptr(self.base_dom), st)
+            call("scnb_gather_i32", ptr(self.lab_dom), ptr(self.l_rows), L, 0, ptr(self.base_dom[U:]), st)
+        # -- batch CSR [U_raw ; L_aug]
+        call("scnb_csr_row_offsets", ptr(self.unl.indptr), ptr(self.u_rows), 0, U, ptr(self.b_indptr), None, st)
+        call("scnb_csr_row_offsets", ptr(self.lab.indptr), ptr(self.l_rows), 0, L, ptr(self.b_indptr[U:]), ptr(self.b_indptr[U:]), st)
+        call("scnb_csr_gather_rows", ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data), ptr(self.u_rows), 0, U,
+             ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), 0, 0, 0, None, None, 0, 0.0, st)
+        call("scnb_csr_gather_rows", ptr(self.lab.indptr), ptr(self.lab.indices), ptr(self.lab.data), ptr(self.l_rows), 0, L,
+             ptr(self.b_indptr[U:]), ptr(self.b_idx), ptr(self.b_val), 1, 0, L, ptr(self.inj_in_keep_L), rng, SID_IN_L,
+             c.p_in_drop, st)
+        # -- first layer, once
+        call("scnb_csr_linear_fwd", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), nb, self.P(blk[0]["W"]),
+             self.P(blk[0]["b"]), H0, ptr(self.Z1), st)
+        # -- teacher (eval mode, losses.py:660-737)
+        tw, tbn = self._teacher_ptrs()
+        if c.mean_teacher:
+            call("scnb_ema_update", ptr(self.teacher_flat), ptr(self.arena.flat), self.n_model_params, c.decay_coef,
+                 ptr(self.state), st)
+        K = self.K_eff
+        if self.teacher_own_spmm:
+            for k in range(K):
+                if c.augment_pseudolabels:
+                    call("scnb_csr_row_offsets", ptr(self.unl.indptr), ptr(self.u_rows), 0, U, ptr(self.tb_indptr), None, st)
+                    km = self.inj_in_keep_U[k] if self.inj_in_keep_U is not None else None
+                    call("scnb_csr_gather_rows", ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data),
+                         ptr(self.u_rows), 0, U, ptr(self.tb_indptr), ptr(self.tb_idx), ptr(self.tb_val), 1, 0, U, ptr(km), rng,
+                         SID_IN_U + k, c.p_in_drop, st)
+                    ip, ix, vv = self.tb_indptr, self.tb_idx, self.tb_val
+                else:
+                    ip, ix, vv = self.b_indptr, self.b_idx, self.b_val
+                call("scnb_csr_linear_fwd", ptr(ip), ptr(ix), ptr(vv), U, ptr(tw(blk[0]["W"])), ptr(tw(blk[0]["b"])), H0,
+                     ptr(self.TZ1[k * U:]), st)
+            tz = self.TZ1
+        else:
+            tz = self.Z1  # rows [0, U)
+        KU = K * U
+        seg_t = self._const_seg(KU)
+        for a in range(self.n_app):
+            rm, rv = tbn(a)
+            call("scnb_bn_act_fwd", ptr(tz), ptr(self.TA[a]), None, self.widths[a], 1, ptr(seg_t), KU, 0, ptr(tw(blk[a]["g"])),
+                 ptr(tw(blk[a]["beta"])), ptr(rm), ptr(rv), None, None, None, 0, 0.0, 1, st)
+            if a + 1 < self.n_app:
+                call("scnb_sgemm", 0, 1, KU, self.widths[a + 1], self.widths[a], ptr(self.TA[a]), self.widths[a],
+                     ptr(tw(blk[a + 1]["W"])), self.widths[a], ptr(self.TZ[a + 1]), self.widths[a + 1], 1.0, 0.0,
+                     ptr(tw(blk[a + 1]["b"])), 0, None, st)
+                tz = self.TZ[a + 1]
+        call("scnb_sgemm", 0, 1, KU, C, self.H, ptr(self.TA[-1]), self.H, ptr(tw("model.classif.0.weight")), self.H,
+             ptr(self.t_logits), C, 1.0, 0.0, ptr(tw("model.classif.0.bias")), 0, None, st)
+        call("scnb_pseudolabel", ptr(self.t_logits), K, U, C, float(c.T if c.T is not None else 1.0), int(c.T is not None),
+             float(c.pseudolabel_min_confidence), ptr(self.Ycat), ptr(self.conf), ptr(self.confident), ptr(self.pl_scratch), st)
+        call("scnb_onehot_rows", ptr(self.lab_ids), None, 0, L, C, ptr(self.Ycat[U:]), st)
+        # -- MixUp plan + hidden-space MixUp (losses.py:811-875)
+        call("scnb_mixmatch_plan", ptr(self.confident), ptr(self.perm_keys), ptr(self.gamma_raw), U, L, int(self.use_dan),
+             int(c.dan_use_conf_pseudolabels), int(c.mixup_alpha > 0.0), ptr(self.counts), ptr(self.seg_off),
+             ptr(self.plan_work), ptr(self.srcA), ptr(self.srcB), ptr(self.gam), R, ptr(self.inv3), ptr(self.coef3),
+             ptr(self.pconf), st)
+        call("scnb_mix_rows", ptr(self.Z1), H0, ptr(self.srcA), ptr(self.srcB), ptr(self.gam), ptr(self.counts[3:]), R,
+             ptr(self.Zs[0]), st)
+        # -- student super-batch forward
+        self._student_forward(st, rng)
+        call("scnb_sgemm", 0, 1, nb, C, self.H, ptr(self.As[-1]), self.H, self.P("model.classif.0.weight"), self.H,
+             ptr(self.logits), C, 1.0, 0.0, self.P("model.classif.0.bias"), 0, None, st)
+        if self.use_dan:
+            d0, d1 = self._dan_names()
+            Ae = self.As[-1][nb:]
+            call("scnb_sgemm", 0, 1, self.Rd, self.H, self.H, ptr(Ae), self.H, self.P(d0 + ".weight"), self.H, ptr(self.Hd),
+                 self.H, 1.0, 0.0, self.P(d0 + ".bias"), 1, None, st)
+            call("scnb_sgemm", 0, 1, self.Rd, self.D, self.H, ptr(self.Hd), self.H, self.P(d1 + ".weight"), self.H,
+                 ptr(self.dlog), self.D, 1.0, 0.0, self.P(d1 + ".bias"), 0, None, st)
+            call("scnb_onehot_rows", ptr(self.base_dom), ptr(self.srcA), nb, self.Rd, self.D, ptr(self.dlabel), st)
+        # -- losses + dLogits (losses.py:896-923, 1224-1243; trainer.py:651-656)
+        call("scnb_softmax_mse_fwd_bwd", ptr(self.logits), U, C, ptr(self.counts), ptr(self.Ycat), ptr(self.srcA),
+             ptr(self.srcB), ptr(self.gam), 0, U, None, self.unsup_weight, ptr(self.dlogits), ptr(self.loss_buf[2:]), st)
+        call("scnb_soft_ce_fwd_bwd", ptr(self.logits[U:]), L, C, None, ptr(self.Ycat), ptr(self.srcA), ptr(self.srcB),
+             ptr(self.gam), U, ptr(self.class_weight), None, L, 1.0, None, ptr(self.dlogits[U:]), ptr(self.loss_buf), 1, st)
+        if self.use_dan:
+            call("scnb_soft_ce_fwd_bwd", ptr(self.dlog), self.Rd, self.D, ptr(self.counts[2:]), ptr(self.dlabel), None, None,
+                 None, 0, None, ptr(self.counts[2:]), 0, 1.0, ptr(self.pconf) if c.dan_scale_loss_pseudoconf else None,
+                 ptr(self.ddlog), ptr(self.loss_buf[4:]), 1, st)
+        # -- backward
+        Hh = self.H
+        dA_last = self._view(self.dA, R, Hh)
+        call("scnb_sgemm", 0, 0, nb, Hh, C, ptr(self.dlogits), C, self.P("model.classif.0.weight"), Hh, ptr(dA_last), Hh, 1.0,
+             0.0, None, 0, None, st)
+        call("scnb_sgemm", 1, 0, C, Hh, nb, ptr(self.dlogits), C, ptr(self.As[-1]), Hh, self.Gp("model.classif.0.weight"), Hh,
+             1.0, 1.0, None, 0, None, st)
+        call("scnb_colsum", ptr(self.dlogits), nb, C, C, self.Gp("model.classif.0.bias"), 1, st)
+        if self.use_dan:
+            d0, d1 = self._dan_names()
+            Ae = self.As[-1][nb:]
+            call("scnb_sgemm", 1, 0, self.D, Hh, self.Rd, ptr(self.ddlog), self.D, ptr(self.Hd), Hh, self.Gp(d1 + ".weight"), Hh,
+                 1.0, 1.0, None, 0, None, st)
+            call("scnb_colsum", ptr(self.ddlog), self.Rd, self.D, self.D, self.Gp(d1 + ".bias"), 1, st)
+            call("scnb_sgemm", 0, 0, self.Rd, Hh, self.D, ptr(self.ddlog), self.D, self.P(d1 + ".weight"), Hh, ptr(self.dHd), Hh,
+                 1.0, 0.0, None, 0, ptr(self.Hd), st)
+            call("scnb_sgemm", 1, 0, Hh, Hh, self.Rd, ptr(self.dHd), Hh, ptr(Ae), Hh, self.Gp(d0 + ".weight"), Hh, 1.0, 1.0, None,
+                 0, None, st)
+            call("scnb_colsum", ptr(self.dHd), self.Rd, Hh, Hh, self.Gp(d0 + ".bias"), 1, st)
+            # gradient reversal: dEmbed = -w * dHd W  (model.py:338)
+            call("scnb_sgemm", 0, 0, self.Rd, Hh, Hh, ptr(self.dHd), Hh, self.P(d0 + ".weight"), Hh, ptr(dA_last[nb:]), Hh,
+                 -self.dan_weight, 0.0, None, 0, None, st)
+        dZ_first = self._student_backward(st, rng, dA_last)
+        call("scnb_unmix_rows", ptr(dZ_first), H0, ptr(self.inv3), ptr(self.coef3), nb, ptr(self.dZ1), st)
+        call("scnb_colsum", ptr(self.dZ1), nb, H0, H0, self.Gp(blk[0]["b"]), 1, st)
+        call("scnb_csr_linear_bwd_dw", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), nb, ptr(self.dZ1), H0,
+             self.Gp(blk[0]["W"]), st)
+        self._finish_step(st)
+        call("scnb_mm_step_inc", ptr(self.state), st)
+
+    def _view(self, buf, rows, width):
+        """[rows, width] contiguous view at the start of a scratch buffer."""
+        return buf.view(-1)[: rows * width].view(rows, width)
+
+    def _const_seg(self, n):
+        key = ("seg", n)
+        if not hasattr(self, "_cseg"):
+            self._cseg = {}
+        if key not in self._cseg:
+            self._cseg[key] = torch.tensor([0, n], dtype=torch.int32, device=self.dev)
+        return self._cseg[key]
+
+    def _dan_names(self):
+        names = [n for n in self.arena.names if n.startswith("dan.") and n.endswith(".weight")]
+        return names[0][: -len(".weight")], names[1][: -len(".weight")]
+
+    def _hidden_keep(self, a):
+        return ptr(self.inj_hidden_keep[a]) if self.inj_hidden_keep is not None else None
+
+    def _student_forward(self, st, rng):
+        blk, R = self._blk, self.Rmax
+        for a in range(self.n_app):
+            w = self.widths[a]
+            p = float(blk[a]["drop"].p)
+            call("scnb_bn_act_fwd", ptr(self.Zs[a]), ptr(self.As[a]), None, w, self.n_seg, ptr(self.seg_off), R, 1,
+                 self.P(blk[a]["g"]), self.P(blk[a]["beta"]), None, None, ptr(self.stats[a]), self._hidden_keep(a), rng,
+                 SID_HID + a, p, 1, st)
+            if a + 1 < self.n_app:
+                w2 = self.widths[a + 1]
+                call("scnb_sgemm", 0, 1, R, w2, w, ptr(self.As[a]), w, self.P(blk[a + 1]["W"]), w, ptr(self.Zs[a + 1]), w2, 1.0,
+                     0.0, self.P(blk[a + 1]["b"]), 0, None, st)
+
+    def _student_backward(self, st, rng, dA):
+        """dA: gradient w.r.t. As[-1].  Returns dZ of the first application ([R, H0])."""
+        blk, R = self._blk, self.Rmax
+        for a in range(self.n_app - 1, -1, -1):
+            w = self.widths[a]
+            p = float(blk[a]["drop"].p)
+            dZ = self._view(self.dZ, R, w)
+            call("scnb_bn_act_bwd", ptr(dA), ptr(self.Zs[a]), ptr(self.As[a]), w, self.n_seg, ptr(self.seg_off), R,
+                 self.P(blk[a]["g"]), ptr(self.stats[a]), self._hidden_keep(a), rng, SID_HID + a, p, 1, ptr(dZ),
+                 self.Gp(blk[a]["g"]), self.Gp(blk[a]["beta"]), st)
+            if a == 0:
+                return dZ
+            wp = self.widths[a - 1]
+            call("scnb_sgemm", 1, 0, w, wp, R, ptr(dZ), w, ptr(self.As[a - 1]), wp, self.Gp(blk[a]["W"]), wp, 1.0, 1.0, None, 0,
+                 None, st)
+            call("scnb_colsum", ptr(dZ), R, w, w, self.Gp(blk[a]["b"]), 1, st)
+            dA = self._view(self.dA, R, wp)
+            call("scnb_sgemm", 0, 0, R, wp, w, ptr(dZ), w, self.P(blk[a]["W"]), wp, ptr(dA), wp, 1.0, 0.0, None, 0, None, st)
+        return None
+
+    def _finish_step(self, st):
+        """optimizer.step() + BatchNorm running statistics in the reference's update order."""
+        c = self.cfg
+        call("scnb_optim_step", OPTIMIZER_CODES[c.optimizer], ptr(self.arena.flat), ptr(self.arena.grad),
+             ptr(self.arena.state1), ptr(self.arena.state2), self.arena.total, ptr(self.hp), ptr(self.state), st)
+        done = set()
+        for a in range(self.n_app):
+            bn = self._blk[a]["bn"]
+            if id(bn) in done:
+                continue
+            done.add(id(bn))
+            apps = [b for b in range(self.n_app) if self._blk[b]["bn"] is bn]
+            if len(apps) > 4:
+                raise NotImplementedError("a BatchNorm module shared by more than 4 applications (n_layers > 5)")
+            sp = [ptr(self.stats[b]) for b in apps] + [None] * (4 - len(apps))
+            call("scnb_bn_running_update", ptr(bn.running_mean), ptr(bn.running_var), ptr(bn.num_batches_tracked), sp[0], sp[1],
+                 sp[2], sp[3], ptr(self.seg_off), self.n_seg, self.widths[a], float(bn.momentum), st)
+
+    # ------------------------------------------------------------------------------------
+    def _launch_supervised(self):
+        """Trainer.train_epoch body (trainer.py:189-256): raw batch -> model -> CE -> backward -> step."""
+        st = torch.cuda.current_stream().cuda_stream
+        L, C, H0 = self.L, self.C, self.widths[0]
+        rng = ptr(self.state[1:3])
+        blk = self._blk
+        call("scnb_step_begin", ptr(self.state), st)
+        self.arena.grad.zero_()
+        self.loss_buf.zero_()
+        call("scnb_gather_i32", ptr(self.lab_y), ptr(self.l_rows), L, 0, ptr(self.lab_ids), st)
+        call("scnb_csr_row_offsets", ptr(self.lab.indptr), ptr(self.l_rows), 0, L, ptr(self.b_indptr), None, st)
+        call("scnb_csr_gather_rows", ptr(self.lab.indptr), ptr(self.lab.indices), ptr(self.lab.data), ptr(self.l_rows), 0, L,
+             ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), 0, 0, 0, None, None, 0, 0.0, st)
+        call("scnb_csr_linear_fwd", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), L, self.P(blk[0]["W"]),
+             self.P(blk[0]["b"]), H0, ptr(self.Zs[0]), st)
+        self._student_forward(st, rng)
+        call("scnb_sgemm", 0, 1, L, C, self.H, ptr(self.As[-1]), self.H, self.P("model.classif.0.weight"), self.H,
+             ptr(self.logits), C, 1.0, 0.0, self.P("model.classif.0.bias"), 0, None, st)
+        call("scnb_onehot_rows", ptr(self.lab_ids), None, 0, L, C, ptr(self.Ycat), st)
+        call("scnb_soft_ce_fwd_bwd", ptr(self.logits), L, C, None, ptr(self.Ycat), None, None, None, 0, ptr(self.class_weight),
+             None, L, 1.0, None, ptr(self.dlogits), ptr(self.loss_buf), 1, st)
+        Hh = self.H
+        dA_last = self._view(self.dA, L, Hh)
+        call("scnb_sgemm", 0, 0, L, Hh, C, ptr(self.dlogits), C, self.P("model.classif.0.weight"), Hh, ptr(dA_last), Hh, 1.0, 0.0,
+             None, 0, None, st)
+        call("scnb_sgemm", 1, 0, C, Hh, L, ptr(self.dlogits), C, ptr(self.As[-1]), Hh, self.Gp("model.classif.0.weight"), Hh, 1.0,
+             1.0, None, 0, None, st)
+        call("scnb_colsum", ptr(self.dlogits), L, C, C, self.Gp("model.classif.0.bias"), 1, st)
+        dZ1 = self._student_backward(st, rng, dA_last)
+        call("scnb_colsum", ptr(dZ1), L, H0, H0, self.Gp(blk[0]["b"]), 1, st)
+        call("scnb_csr_linear_bwd_dw", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), L, ptr(dZ1), H0,
+             self.Gp(blk[0]["W"]), st)
+        self._finish_step(st)
+
+    # ------------------------------------------------------------------------------------
+    def _launch(self):
+        if self.mode == "mixmatch":
+            self._launch_mixmatch()
+        else:
+            self._launch_supervised()
+
+    def load_batch(self, l_rows, u_rows=None, perm_keys=None, gamma_raw=None):
+        """Stage one step's sampled rows / MixUp randomness into the device input buffers."""
+        self.l_rows.copy_(torch.as_tensor(l_rows, dtype=torch.int64), non_blocking=True)
+        if self.mode == "mixmatch":
+            self.u_rows.copy_(torch.as_tensor(u_rows, dtype=torch.int64), non_blocking=True)
+            if perm_keys is not None:
+                self.perm_keys.copy_(torch.as_tensor(perm_keys, dtype=torch.float32), non_blocking=True)
+            if gamma_raw is not None:
+                self.gamma_raw.copy_(torch.as_tensor(gamma_raw, dtype=torch.float32), non_blocking=True)
+
+    def step(self):
+        """Run one training step on whatever is staged in the input buffers."""
+        if self.mode == "mixmatch" and self.cfg.mean_teacher and self.teacher_bn is None:
+            self.teacher_bn = [(b["bn"].running_mean.clone(), b["bn"].running_var.clone()) for b in self._blk]
+        injected = any(x is not None for x in (self.inj_in_keep_L, self.inj_in_keep_U, self.inj_hidden_keep))
+        if self.cfg.use_cuda_graph and not injected:
+            key = (self.unsup_weight, self.dan_weight)
+            if self._graph is None or self._graph_key != key:
+                self._capture(key)
+            self._graph.replay()
+        else:
+            before = _lib.launch_count
+            self._launch()
+            self.kernels_per_step = _lib.launch_count - before
+        self.steps_done += 1
+
+    def _capture(self, key):
+        # warm-up on a side stream is not needed: the library allocates nothing; but the first
+        # eager pass must not double-apply a step, so capture directly.
+        self.arena.check_aliasing()
+        g = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        before = _lib.launch_count
+        with torch.cuda.graph(g):
+            self._launch()
+        self.kernels_per_step = _lib.launch_count - before
+        self._graph, self._graph_key = g, key
+
+    def losses(self) -> Dict[str, float]:
+        """Read the last step's scalars (one D2H copy; the only host sync the engine exposes)."""
+        v = self.loss_buf.cpu().tolist()
+        out = {"sup_loss": v[0], "sup_acc": v[1] / max(self.L, 1)}
+        if self.mode == "mixmatch":
+            out["unsup_loss"] = v[2]
+            if self.use_dan:
+                n_dan = int(self.counts[2].item())
+                out["dan_loss"] = v[4]
+                out["dan_acc"] = v[5] / max(n_dan, 1)
+            out["loss"] = v[0] + self.unsup_weight * v[2] + (v[4] if self.use_dan else 0.0)
+        else:
+            out["loss"] = v[0]
+        return out

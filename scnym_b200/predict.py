@@ -1,0 +1,147 @@
+"""`Predicter` -- batched inference (reference surface: scnym/predict.py:12-216).
+
+The reference densifies each cell on the host, copies [1024, G] dense batches to the GPU and
+runs a second full pass for the embedding (scnym/api.py:692-708).  Here the atlas stays in HBM
+as CSR and one pass of kernels per row chunk emits argmax, probabilities/scores and the
+`X_scnym` embedding (last BatchNorm output, eval mode, pre-ReLU).
+"""
+import os
+from typing import Optional, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call, ptr
+from .dataprep import DeviceCSR
+from .model import CellTypeCLF
+
+CHUNK_ROWS = 65536  # rows per kernel launch; eval-mode results do not depend on it
+
+
+class EvalRunner(object):
+    """Eval-mode forward of `CellTypeCLF` over row ranges of a DeviceCSR (no autograd)."""
+
+    def __init__(self, models, chunk_rows: int = CHUNK_ROWS) -> None:
+        self.models = list(models)
+        m0 = self.models[0]
+        self.dev = next(m0.parameters()).device
+        if self.dev.type != "cuda":
+            raise _lib.ScnbError("scnym_b200 inference needs the models on a CUDA device (no CPU fallback)")
+        self.widths = [b[0].out_features for b in m0.block_modules()]
+        self.C = m0.n_cell_types
+        self.chunk = int(chunk_rows)
+        f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.dev)
+        self.Z = [f32(self.chunk, w) for w in self.widths]
+        self.A = [f32(self.chunk, w) for w in self.widths]
+        self.logits = f32(self.chunk, self.C)
+        self.seg = torch.zeros(2, dtype=torch.int32, device=self.dev)
+        self._seg_n = -1
+
+    def _set_seg(self, n):
+        if n != self._seg_n:
+            self.seg.copy_(torch.tensor([0, n], dtype=torch.int32))
+            self._seg_n = n
+
+    def run_chunk(self, ds: DeviceCSR, row0: int, n: int, pred, prob, score, embed):
+        """Rows [row0, row0+n) -> writes pred[n], prob[n,C], score[n,C], embed[n,H] (any may be None)."""
+        st = torch.cuda.current_stream().cuda_stream
+        self._set_seg(n)
+        for mi, model in enumerate(self.models):
+            blocks = model.block_modules()
+            for a, (lin, bn, _) in enumerate(blocks):
+                w = self.widths[a]
+                if a == 0:
+                    wt = lin.weight_t()
+                    call("scnb_csr_linear_fwd_i64", ptr(ds.indptr[row0:]), ptr(ds.indices), ptr(ds.data), n, ptr(wt),
+                         ptr(lin.bias), w, ptr(self.Z[0]), st)
+                else:
+                    wp = self.widths[a - 1]
+                    call("scnb_sgemm", 0, 1, n, w, wp, ptr(self.A[a - 1]), wp, ptr(lin.weight), wp, ptr(self.Z[a]), w, 1.0, 0.0,
+                         ptr(lin.bias), 0, None, st)
+                last = a == len(blocks) - 1
+                pre = embed if (last and mi == 0 and embed is not None) else None
+                call("scnb_bn_act_fwd", ptr(self.Z[a]), ptr(self.A[a]), ptr(pre), w, 1, ptr(self.seg), n, 0, ptr(bn.weight),
+                     ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var), None, None, None, 0, 0.0, 1, st)
+            clf = model.classif[0]
+            H = self.widths[-1]
+            call("scnb_sgemm", 0, 1, n, self.C, H, ptr(self.A[-1]), H, ptr(clf.weight), H, ptr(self.logits), self.C, 1.0,
+                 0.0 if mi == 0 else 1.0, ptr(clf.bias), 0, None, st)
+        call("scnb_predict_head", ptr(self.logits), len(self.models), n, self.C, ptr(pred), ptr(prob), ptr(score), st)
+
+    def run(self, ds: DeviceCSR, want_prob=True, want_score=False, want_embed=False, row0: int = 0, n_rows: Optional[int] = None):
+        N = ds.n_rows - row0 if n_rows is None else n_rows
+        dev = self.dev
+        pred = torch.empty(N, dtype=torch.int64, device=dev)
+        prob = torch.empty((N, self.C), dtype=torch.float32, device=dev) if want_prob else None
+        score = torch.empty((N, self.C), dtype=torch.float32, device=dev) if want_score else None
+        embed = torch.empty((N, self.widths[-1]), dtype=torch.float32, device=dev) if want_embed else None
+        for s in range(0, N, self.chunk):
+            n = min(self.chunk, N - s)
+            self.run_chunk(ds, row0 + s, n, pred[s:], prob[s:] if prob is not None else None,
+                           score[s:] if score is not None else None, embed[s:] if embed is not None else None)
+        return pred, prob, score, embed
+
+
+class Predicter(object):
+    """Predict cell types from expression data using `CellTypeCLF` (scnym/predict.py:12-216)."""
+
+    def __init__(self, model_weights: Union[str, list, tuple], n_genes: int = None, n_cell_types: int = None,
+                 labels: list = None, **kwargs) -> None:
+        self.model_weights = [model_weights] if type(model_weights) == str else model_weights
+        self.labels = labels
+        if n_cell_types is None:
+            print("Assuming `n_cell_types` is the same as in the pretrained model weights.")
+            params = torch.load(self.model_weights[0], map_location="cpu")
+            fkey = list(params.keys())[-1]
+            self.n_cell_types = len(params[fkey])
+        else:
+            self.n_cell_types = n_cell_types
+        for weights in self.model_weights:
+            if not os.path.exists(weights):
+                raise FileNotFoundError()
+        if n_genes is None:
+            print("Assuming `n_genes` is the same as in the pretrained model weights.")
+            params = torch.load(self.model_weights[0], map_location="cpu")
+            fkey = list(params.keys())[0]
+            self.n_genes = params[fkey].shape[1]
+        else:
+            self.n_genes = n_genes
+        if not torch.cuda.is_available():
+            raise _lib.ScnbError("scnym_b200.Predicter needs a CUDA device (no CPU fallback)")
+        self.models = []
+        for weights in self.model_weights:
+            model = CellTypeCLF(n_genes=self.n_genes, n_cell_types=self.n_cell_types, **kwargs)
+            model.load_state_dict(torch.load(weights, map_location="cpu"))
+            self.models.append(model.cuda().eval())
+        self._runner = None
+
+    def predict(self, X, output: str = None, batch_size: int = 1024, **kwargs):
+        """Returns (predictions int[N], names list|None[, prob-or-score float32 [N, C]])."""
+        if not X.shape[1] == self.n_genes:
+            gs = (X.shape[1], self.n_genes)
+            raise ValueError("%d genes in X, %d genes in model." % gs)
+        return_prob = kwargs.get("return_prob", None)
+        if output not in ["prob", "score"] and output is not None:
+            raise ValueError(f"{output} is not a valid additional output.")
+        pred, prob, score, _ = self.predict_device(X, want_prob=True, want_score=(output == "score"), want_embed=False)
+        predictions = pred.cpu().numpy()
+        names = [self.labels[p] for p in predictions] if self.labels is not None else None
+        if return_prob is True:
+            return predictions, names, prob.cpu().numpy()
+        elif output is not None:
+            if output == "prob":
+                return predictions, names, prob.cpu().numpy()
+            return predictions, names, score.cpu().numpy()
+        return predictions, names
+
+    def predict_device(self, X, want_prob=True, want_score=False, want_embed=False):
+        """Device-resident results (torch CUDA tensors); X may be ndarray, scipy CSR, dense torch or DeviceCSR."""
+        if isinstance(X, torch.Tensor):
+            X = X.detach().cpu().numpy()
+        ds = DeviceCSR.from_any(X, device=next(self.models[0].parameters()).device)
+        if self._runner is None:
+            self._runner = EvalRunner(self.models, chunk_rows=min(CHUNK_ROWS, max(ds.n_rows, 1)))
+        elif self._runner.chunk < min(CHUNK_ROWS, ds.n_rows):
+            self._runner = EvalRunner(self.models, chunk_rows=min(CHUNK_ROWS, ds.n_rows))
+        return self._runner.run(ds, want_prob, want_score, want_embed)

@@ -1,0 +1,364 @@
+"""GPU unit tests of individual C-ABI entry points against fp64 torch-CPU restatements."""
+import numpy as np
+import pytest
+import torch
+
+from tests import golden_util as GU
+
+pytestmark = pytest.mark.gpu
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(name, got, want, tol=1e-5):
+    e = GU.rel_err(got, want)
+    assert e <= tol, f"{name}: rel err {e:.3e} > {tol}"
+
+
+@pytest.mark.parametrize("tA", [0, 1])
+@pytest.mark.parametrize("tB", [0, 1])
+@pytest.mark.parametrize("M,N,K", [(64, 64, 64), (130, 70, 50), (33, 5, 17), (1, 256, 256), (512, 16, 256), (7, 3, 1)])
+def test_sgemm(tA, tB, M, N, K):
+    from scnym_b200._lib import call, ptr
+    torch.manual_seed(M * 7 + N * 3 + K + tA * 2 + tB)
+    A = torch.randn((K, M) if tA else (M, K))
+    B = torch.randn((N, K) if tB else (K, N))
+    C0 = torch.randn(M, N)
+    bias = torch.randn(N)
+    gate = torch.randn(M, N)
+    opA = A.t() if tA else A
+    opB = B.t() if tB else B
+    for (alpha, beta, use_bias, relu, use_gate) in [(1.0, 0.0, False, 0, False), (-0.3, 1.0, True, 0, False),
+                                                     (1.0, 0.0, True, 1, False), (1.0, 0.0, False, 0, True)]:
+        want = alpha * (opA.double() @ opB.double()) + beta * C0.double()
+        if use_bias:
+            want = want + bias.double()
+        if relu:
+            want = want.clamp_min(0)
+        if use_gate:
+            want = want * (gate > 0)
+        Cd = C0.cuda().clone()
+        Ad, Bd = A.cuda(), B.cuda()
+        bd, gd = bias.cuda(), gate.cuda()
+        call("scnb_sgemm", tA, tB, M, N, K, ptr(Ad), Ad.shape[1], ptr(Bd), Bd.shape[1], ptr(Cd), N, alpha, beta,
+             ptr(bd) if use_bias else None, relu, ptr(gd) if use_gate else None, _st())
+        _chk(f"sgemm {tA}{tB} {M}x{N}x{K}", Cd.cpu(), want.float(), tol=2e-5)
+
+
+def test_colsum_and_relu_bwd():
+    from scnym_b200._lib import call, ptr
+    A = torch.randn(300, 70)
+    out = torch.ones(70).cuda()
+    call("scnb_colsum", ptr(A.cuda()), 300, 70, 70, ptr(out), 1, _st())
+    _chk("colsum", out.cpu(), 1 + A.double().sum(0), tol=1e-5)
+    g, y = torch.randn(1000), torch.randn(1000)
+    o = torch.empty(1000).cuda()
+    call("scnb_relu_bwd", ptr(g.cuda()), ptr(y.cuda()), ptr(o), 1000, _st())
+    assert torch.equal(o.cpu(), g * (y > 0))
+
+
+@pytest.mark.parametrize("H0", [128, 256, 512, 96, 33])
+def test_csr_linear_fwd_bwd(H0):
+    from oracle import scnym_oracle as O
+    from scnym_b200._lib import call, ptr
+    from scnym_b200.dataprep import DeviceCSR, gather_rows
+    G, n = 500, 37
+    ip, ii, dd, _ = O.synth_csr(n + 10, G, 0.08, 3, seed=H0)
+    rows = torch.randperm(n + 10)[:n]
+    X = O.csr_to_dense(ip, ii, dd, G, rows.numpy())
+    ds = DeviceCSR.from_arrays(ip, ii, dd, G)
+    b = gather_rows(ds, rows.cuda())
+    torch.manual_seed(H0)
+    WT, b1 = torch.randn(G, H0) * 0.1, torch.randn(H0)
+    Z = torch.empty(n, H0).cuda()
+    call("scnb_csr_linear_fwd", ptr(b.indptr), ptr(b.indices), ptr(b.data), n, ptr(WT.cuda()), ptr(b1.cuda()), H0, ptr(Z), _st())
+    _chk("csr fwd", Z.cpu(), X.double() @ WT.double() + b1.double())
+    _chk("to_dense", b.to_dense().cpu(), X, tol=0)
+    dZ = torch.randn(n, H0)
+    dW = torch.zeros(G, H0).cuda()
+    call("scnb_csr_linear_bwd_dw", ptr(b.indptr), ptr(b.indices), ptr(b.data), n, ptr(dZ.cuda()), H0, ptr(dW), _st())
+    _chk("csr bwd", dW.cpu(), X.double().t() @ dZ.double())
+    # dataset-CSR (int64 indptr) variant on a contiguous row range
+    Z2 = torch.empty(9, H0).cuda()
+    call("scnb_csr_linear_fwd_i64", ptr(ds.indptr[5:]), ptr(ds.indices), ptr(ds.data), 9, ptr(WT.cuda()), None, H0, ptr(Z2), _st())
+    _chk("csr fwd i64", Z2.cpu(), O.csr_to_dense(ip, ii, dd, G, np.arange(5, 14)).double() @ WT.double())
+
+
+def test_gather_rows_log1p_drop_matches_oracle():
+    from oracle import scnym_oracle as O
+    from scnym_b200.dataprep import DeviceCSR, gather_rows
+    G, n = 400, 25
+    ip, ii, dd, _ = O.synth_csr(n, G, 0.1, 3, seed=4)
+    rows = np.random.default_rng(0).permutation(n)
+    X = O.csr_to_dense(ip, ii, dd, G, rows)
+    keep = (torch.rand(n, G) < 0.9)
+    want = O.log1p_drop(X, keep)
+    ds = DeviceCSR.from_arrays(ip, ii, dd, G)
+    km = np.concatenate([keep[i, ii[ip[r]:ip[r + 1]]].numpy() for i, r in enumerate(rows)]).astype(np.uint8)
+    buf = np.ones(n * ds.max_row_nnz, dtype=np.uint8)
+    buf[:km.size] = km
+    b = gather_rows(ds, torch.from_numpy(rows).cuda(), augment=True, keep_mask=torch.from_numpy(buf).cuda())
+    _chk("log1p_drop", b.to_dense().cpu(), want, tol=2e-6)
+    # Philox path: ~10% dropped, rows renormalised to 1e6
+    rng = torch.tensor([123, 7], dtype=torch.int64).cuda()
+    b2 = gather_rows(ds, torch.from_numpy(rows).cuda(), augment=True, rng=rng, stream_id=3)
+    D2 = b2.to_dense().cpu()
+    frac = float(((D2 == 0) & (X > 0)).sum()) / float((X > 0).sum())
+    assert 0.05 < frac < 0.15
+    _chk("row sums", torch.expm1(D2.double()).sum(1), torch.full((n,), 1e6, dtype=torch.float64), tol=1e-4)
+    b3 = gather_rows(ds, torch.from_numpy(rows).cuda(), augment=True, rng=rng, stream_id=3)
+    assert torch.equal(b3.to_dense(), b2.to_dense())  # counter-based: same (seed, counter, stream) -> same mask
+
+
+def _bn_ref(Z, segs, g, b, keep, p):
+    """fp64 autograd restatement of segmented BN -> dropout -> relu."""
+    outs = []
+    for (r0, r1) in segs:
+        z = Z[r0:r1]
+        mu = z.mean(0)
+        var = ((z - mu) ** 2).mean(0)
+        y = (z - mu) / torch.sqrt(var + 1e-5) * g + b
+        y = y * keep[r0:r1].double() / (1 - p)
+        outs.append(torch.relu(y))
+    return torch.cat(outs, 0)
+
+
+@pytest.mark.parametrize("H,segs,maxr", [(64, [(0, 40), (40, 70), (70, 130)], 150), (37, [(0, 5), (5, 300)], 300),
+                                         (256, [(0, 256), (256, 512), (512, 1024)], 1024)])
+def test_bn_act_fwd_bwd(H, segs, maxr):
+    from scnym_b200._lib import call, ptr
+    torch.manual_seed(H)
+    Z = (torch.randn(maxr, H) * 2 + 0.5)
+    g, b = torch.rand(H) + 0.5, torch.randn(H) * 0.1
+    keep = (torch.rand(maxr, H) < 0.5).to(torch.uint8)
+    dA = torch.randn(maxr, H)
+    Zd = Z.double().requires_grad_(True)
+    gd, bd = g.double().requires_grad_(True), b.double().requires_grad_(True)
+    A_ref = _bn_ref(Zd, segs, gd, bd, keep, 0.5)
+    n_act = segs[-1][1]
+    (A_ref * dA[:n_act].double()).sum().backward()
+    seg = torch.tensor([s[0] for s in segs] + [n_act], dtype=torch.int32).cuda()
+    A = torch.full((maxr, H), 7.0).cuda()
+    stats = torch.zeros(len(segs), 3, H).cuda()
+    Zc, gc, bc, kc = Z.cuda(), g.cuda(), b.cuda(), keep.cuda()
+    call("scnb_bn_act_fwd", ptr(Zc), ptr(A), None, H, len(segs), ptr(seg), maxr, 1, ptr(gc), ptr(bc), None, None, ptr(stats),
+         ptr(kc), None, 0, 0.5, 1, _st())
+    _chk("bn fwd", A[:n_act].cpu(), A_ref.detach())
+    assert float(A[n_act:].abs().sum()) == 0.0
+    dZ = torch.full((maxr, H), 7.0).cuda()
+    dg, db = torch.zeros(H).cuda(), torch.zeros(H).cuda()
+    call("scnb_bn_act_bwd", ptr(dA.cuda()), ptr(Zc), ptr(A), H, len(segs), ptr(seg), maxr, ptr(gc), ptr(stats), ptr(kc), None, 0,
+         0.5, 1, ptr(dZ), ptr(dg), ptr(db), _st())
+    _chk("bn dZ", dZ[:n_act].cpu(), Zd.grad[:n_act], tol=2e-5)
+    _chk("bn dgamma", dg.cpu(), gd.grad, tol=2e-5)
+    _chk("bn dbeta", db.cpu(), bd.grad, tol=2e-5)
+    assert float(dZ[n_act:].abs().sum()) == 0.0
+    # running statistics, segment order, unbiased variance
+    rm, rv = torch.zeros(H), torch.ones(H)
+    for (r0, r1) in segs:
+        z = Z[r0:r1].double()
+        rm = 0.9 * rm + 0.1 * z.mean(0)
+        rv = 0.9 * rv + 0.1 * z.var(0, unbiased=True)
+    rmc, rvc = torch.zeros(H).cuda(), torch.ones(H).cuda()
+    nbt = torch.zeros((), dtype=torch.int64).cuda()
+    call("scnb_bn_running_update", ptr(rmc), ptr(rvc), ptr(nbt), ptr(stats), None, None, None, ptr(seg), len(segs), H, 0.1, _st())
+    _chk("running_mean", rmc.cpu(), rm)
+    _chk("running_var", rvc.cpu(), rv)
+    assert int(nbt) == len(segs)
+    # eval mode
+    Ae = torch.empty(maxr, H).cuda()
+    pre = torch.empty(maxr, H).cuda()
+    call("scnb_bn_act_fwd", ptr(Zc), ptr(Ae), ptr(pre), H, 1, ptr(torch.tensor([0, maxr], dtype=torch.int32).cuda()), maxr, 0,
+         ptr(gc), ptr(bc), ptr(rmc), ptr(rvc), None, None, None, 0, 0.0, 1, _st())
+    want = (Z.double() - rmc.cpu().double()) / torch.sqrt(rvc.cpu().double() + 1e-5) * g.double() + b.double()
+    _chk("bn eval pre", pre.cpu(), want)
+    _chk("bn eval", Ae.cpu(), want.clamp_min(0))
+
+
+def test_bn_act_philox_dropout_consistent_between_fwd_and_bwd():
+    from scnym_b200._lib import call, ptr
+    H, n = 128, 512
+    Z = torch.randn(n, H).cuda()
+    g, b = torch.ones(H).cuda(), torch.full((H,), 3.0).cuda()   # beta=3 -> almost all pre-dropout values positive
+    seg = torch.tensor([0, n], dtype=torch.int32).cuda()
+    rng = torch.tensor([42, 5], dtype=torch.int64).cuda()
+    A, stats = torch.empty(n, H).cuda(), torch.zeros(1, 3, H).cuda()
+    call("scnb_bn_act_fwd", ptr(Z), ptr(A), None, H, 1, ptr(seg), n, 1, ptr(g), ptr(b), None, None, ptr(stats), None, ptr(rng), 17,
+         0.5, 1, _st())
+    frac = float((A == 0).float().mean())
+    assert 0.47 < frac < 0.53
+    dZ, dg, db = torch.empty(n, H).cuda(), torch.zeros(H).cuda(), torch.zeros(H).cuda()
+    ones = torch.ones(n, H).cuda()
+    call("scnb_bn_act_bwd", ptr(ones), ptr(Z), ptr(A), H, 1, ptr(seg), n, ptr(g), ptr(stats), None, ptr(rng), 17, 0.5, 1, ptr(dZ),
+         ptr(dg), ptr(db), _st())
+    # dbeta = sum of dy = 2 * (#kept and positive) per column
+    _chk("dbeta", db.cpu(), 2.0 * (A > 0).float().sum(0).cpu(), tol=1e-6)
+    A2 = torch.empty(n, H).cuda()
+    rng2 = torch.tensor([42, 6], dtype=torch.int64).cuda()
+    call("scnb_bn_act_fwd", ptr(Z), ptr(A2), None, H, 1, ptr(seg), n, 1, ptr(g), ptr(b), None, None, ptr(stats), None, ptr(rng2),
+         17, 0.5, 1, _st())
+    assert not torch.equal(A2 == 0, A == 0)  # next step counter -> fresh mask
+
+
+@pytest.mark.parametrize("K,T,C", [(1, 0.5, 7), (3, 0.5, 40), (2, 0.0, 5), (1, 1.0, 5), (2, 2.0, 33)])
+def test_pseudolabel(K, T, C):
+    from oracle import scnym_oracle as O
+    from scnym_b200._lib import call, ptr
+    torch.manual_seed(K * 10 + C)
+    U = 50
+    logits = torch.randn(K, U, C) * 2
+    qbar = torch.stack([O.softmax(logits[k]) for k in range(K)]).mean(0)
+    conf = qbar.max(1).values
+    tau = float(conf.median())
+    want_q = O.sharpen_labels(qbar.clone(), T).float()
+    q, cf = torch.empty(U, C).cuda(), torch.empty(U).cuda()
+    flag = torch.empty(U, dtype=torch.uint8).cuda()
+    call("scnb_pseudolabel", ptr(logits.cuda()), K, U, C, T, 1, tau, ptr(q), ptr(cf), ptr(flag), ptr(torch.empty(U, C).cuda()), _st())
+    _chk("q", q.cpu(), want_q)
+    _chk("conf", cf.cpu(), conf)
+    exact = (conf - tau).abs() > 1e-6
+    assert torch.equal(flag.cpu().bool()[exact], (conf >= tau)[exact])
+
+
+def _plan(confident, keys, graw, U, L, use_dan, dan_conf, mixup_on=1):
+    from scnym_b200._lib import call, ptr
+    nb = U + L
+    R = nb + (nb if use_dan else 0)
+    i32 = lambda *s: torch.full(s, -7, dtype=torch.int32).cuda()
+    out = dict(counts=i32(8), seg=i32(4), work=i32(U + 3 * nb), srcA=i32(R), srcB=i32(R), gam=torch.zeros(R).cuda(),
+               inv3=i32(3, nb), coef3=torch.zeros(3, nb).cuda(), pconf=torch.zeros(1).cuda())
+    call("scnb_mixmatch_plan", ptr(confident.cuda()), ptr(keys.cuda()), ptr(graw.cuda()), U, L, use_dan, dan_conf, mixup_on,
+         ptr(out["counts"]), ptr(out["seg"]), ptr(out["work"]), ptr(out["srcA"]), ptr(out["srcB"]), ptr(out["gam"]), R,
+         ptr(out["inv3"]), ptr(out["coef3"]), ptr(out["pconf"]), _st())
+    torch.cuda.synchronize()
+    return {k: v.cpu() for k, v in out.items()}, R
+
+
+@pytest.mark.parametrize("U,L,frac,use_dan,dan_conf", [(40, 24, 0.5, 1, 1), (40, 24, 0.5, 1, 0), (33, 17, 0.0, 1, 1),
+                                                       (16, 16, 1.0, 0, 0), (300, 260, 0.3, 1, 1), (1500, 1100, 0.7, 1, 0)])
+def test_mixmatch_plan_and_mix_adjoint(U, L, frac, use_dan, dan_conf):
+    from oracle import scnym_oracle as O
+    from scnym_b200._lib import call, ptr
+    torch.manual_seed(U + L)
+    confident = (torch.rand(U) < frac).to(torch.uint8)
+    keys, graw = torch.rand(U + L), torch.distributions.Beta(0.3, 0.3).sample((U + L,))
+    out, R = _plan(confident, keys, graw, U, L, use_dan, dan_conf)
+    nb = U + L
+    cidx = torch.where(confident.bool())[0]
+    uidx = torch.where(~confident.bool())[0]
+    n_conf = cidx.numel()
+    ridx, gam = O.mixup_indices(keys, graw, n_conf + L)
+    cat2base = torch.cat([cidx, U + torch.arange(L)])
+    n_dan_unl = (n_conf if dan_conf else U) if use_dan else 0
+    n_dan = L + n_dan_unl if use_dan else 0
+    assert out["counts"][:4].tolist() == [n_conf, n_conf + L, n_dan, nb + n_dan]
+    assert out["seg"].tolist() == [0, U, nb, nb + n_dan]
+    assert abs(float(out["pconf"]) - n_dan_unl / max(U, 1)) < 1e-7
+    # expected forward maps
+    eA = torch.cat([cat2base[:n_conf], uidx, U + torch.arange(L)])
+    eB = torch.cat([cat2base[ridx[:n_conf]], uidx, cat2base[ridx[n_conf:]]])
+    eG = torch.cat([gam[:n_conf, 0], torch.ones(uidx.numel()), gam[n_conf:, 0]])
+    if use_dan:
+        dan_rows = torch.cat([U + torch.arange(L), cidx if dan_conf else torch.arange(U)])
+        eA, eB, eG = torch.cat([eA, dan_rows]), torch.cat([eB, dan_rows]), torch.cat([eG, torch.ones(dan_rows.numel())])
+    na = nb + n_dan
+    assert torch.equal(out["srcA"][:na].long(), eA)
+    assert torch.equal(out["srcB"][:na].long(), eB)
+    assert torch.allclose(out["gam"][:na], eG.float(), rtol=0, atol=0)
+    # mix / unmix are adjoint:  <mix(Z), dOut> == <Z, unmix(dOut)>
+    H = 24
+    Z, dOut = torch.randn(nb, H), torch.randn(R, H)
+    dOut[na:] = 0
+    mixed = torch.empty(R, H).cuda()
+    call("scnb_mix_rows", ptr(Z.cuda()), H, ptr(out["srcA"].cuda()), ptr(out["srcB"].cuda()), ptr(out["gam"].cuda()),
+         ptr(out["counts"][3:].cuda()), R, ptr(mixed), _st())
+    want = eG[:, None].double() * Z[eA].double() + (1 - eG[:, None].double()) * Z[eB].double()
+    _chk("mix", mixed[:na].cpu(), want)
+    assert float(mixed[na:].abs().sum()) == 0
+    dZ = torch.empty(nb, H).cuda()
+    call("scnb_unmix_rows", ptr(dOut.cuda()), H, ptr(out["inv3"].cuda()), ptr(out["coef3"].cuda()), nb, ptr(dZ), _st())
+    lhs = float((want * dOut[:na].double()).sum())
+    rhs = float((Z.double() * dZ.cpu().double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), 1.0)
+    Zd = Z.double().requires_grad_(True)
+    ((eG[:, None].double() * Zd[eA] + (1 - eG[:, None].double()) * Zd[eB]) * dOut[:na].double()).sum().backward()
+    _chk("unmix", dZ.cpu(), Zd.grad, tol=2e-5)
+
+
+def test_losses_match_oracle_autograd():
+    from oracle import scnym_oracle as O
+    from scnym_b200._lib import call, ptr
+    torch.manual_seed(0)
+    n, C = 45, 9
+    z = (torch.randn(n, C) * 2).double().requires_grad_(True)
+    Y = torch.softmax(torch.randn(n, C) * 2, 1)
+    cw = torch.rand(C) + 0.5
+    loss = O.cross_entropy(z, Y.double(), class_weight=cw.double())
+    loss.backward()
+    dz, lo = torch.empty(n, C).cuda(), torch.zeros(2).cuda()
+    call("scnb_soft_ce_fwd_bwd", ptr(z.detach().float().cuda()), n, C, None, ptr(Y.cuda()), None, None, None, 0, ptr(cw.cuda()),
+         None, n, 1.0, None, ptr(dz), ptr(lo), 1, _st())
+    _chk("ce loss", lo[0].cpu(), loss.detach())
+    _chk("ce grad", dz.cpu(), z.grad, tol=2e-5)
+    assert int(lo[1]) == int((z.argmax(1) == Y.argmax(1)).sum())
+    # masked MSE on probabilities with mixed labels, weight 0.7, n_conf < n
+    z2 = (torch.randn(n, C) * 2).double().requires_grad_(True)
+    a, b = torch.randint(0, n, (n,)), torch.randint(0, n, (n,))
+    g = torch.rand(n) * 0.5 + 0.5
+    n_conf = 30
+    Ym = g[:, None].double() * Y[a].double() + (1 - g[:, None].double()) * Y[b].double()
+    per = ((O.softmax(z2) - Ym) ** 2).sum(1)
+    mask = torch.zeros(n, dtype=torch.float64)
+    mask[:n_conf] = 1
+    l2 = (per * mask).mean()
+    (0.7 * l2).backward()
+    dz2, lo2 = torch.empty(n, C).cuda(), torch.zeros(1).cuda()
+    call("scnb_softmax_mse_fwd_bwd", ptr(z2.detach().float().cuda()), n, C, ptr(torch.tensor([n_conf], dtype=torch.int32).cuda()),
+         ptr(Y.cuda()), ptr(a.int().cuda()), ptr(b.int().cuda()), ptr(g.cuda()), 0, n, None, 0.7, ptr(dz2), ptr(lo2), _st())
+    _chk("mse loss", lo2[0].cpu(), l2.detach())
+    _chk("mse grad", dz2.cpu(), z2.grad, tol=2e-5)
+
+
+@pytest.mark.parametrize("name", ["adadelta", "adam", "adamw", "sgd"])
+def test_optim_step_matches_torch_optim(name):
+    from scnym_b200._lib import call, ptr, OPTIMIZER_CODES
+    torch.manual_seed(1)
+    n = 5000
+    p0 = torch.randn(n)
+    rp = p0.clone().requires_grad_(True)
+    kw = dict(lr=1.0 if name == "adadelta" else 0.01, weight_decay=1e-2)
+    cls = {"adadelta": torch.optim.Adadelta, "adam": torch.optim.Adam, "adamw": torch.optim.AdamW, "sgd": torch.optim.SGD}[name]
+    ropt = cls([rp], momentum=0.9, **kw) if name == "sgd" else cls([rp], **kw)
+    p, s1, s2 = p0.cuda(), torch.zeros(n).cuda(), torch.zeros(n).cuda()
+    eps = 1e-6 if name == "adadelta" else 1e-8
+    hp = torch.tensor([kw["lr"], kw["weight_decay"], 0.9, 0.999, eps, 0.9, 0.9, 0.0]).cuda()
+    state = torch.zeros(4, dtype=torch.int64).cuda()
+    for t in range(4):
+        g = torch.randn(n)
+        rp.grad = g.clone()
+        ropt.step()
+        call("scnb_step_begin", ptr(state), _st())
+        call("scnb_optim_step", OPTIMIZER_CODES[name], ptr(p), ptr(g.cuda()), ptr(s1), ptr(s2), n, ptr(hp), ptr(state), _st())
+        _chk(f"{name} t={t}", p.cpu(), rp.detach(), tol=2e-6)
+
+
+def test_ema_update_and_counters():
+    from scnym_b200._lib import call, ptr
+    t, p = torch.randn(1000), torch.randn(1000)
+    td, state = t.cuda(), torch.zeros(4, dtype=torch.int64).cuda()
+    call("scnb_ema_update", ptr(td), ptr(p.cuda()), 1000, 0.997, ptr(state), _st())
+    _chk("ema step0 == copy", td.cpu(), p, tol=0)
+    for _ in range(5):
+        call("scnb_mm_step_inc", ptr(state), _st())
+    td = t.cuda()
+    call("scnb_ema_update", ptr(td), ptr(p.cuda()), 1000, 0.997, ptr(state), _st())
+    a = min(1 - 1 / 6, 0.997)
+    _chk("ema step5", td.cpu(), a * t + (1 - a) * p, tol=1e-6)
+
+
+def test_bad_arguments_raise():
+    from scnym_b200._lib import call, ScnbError
+    with pytest.raises(ScnbError):
+        call("scnb_sgemm", 0, 0, 4, 4, 4, None, 4, None, 4, None, 4, 1.0, 0.0, None, 0, None, _st())
