@@ -258,8 +258,11 @@ __global__ void __launch_bounds__(256) k_csr_linear_bwd_dw_v4(const int32_t* __r
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
   const int s = indptr[row], e = indptr[row + 1];
-  for (int hv = lane; hv < H0v; hv += 32) {
-    const float4 g = dZ[(size_t)row * H0v + hv];
+  // hv0 loop bounds are warp-uniform so that every lane takes part in the shuffles
+  for (int hv0 = 0; hv0 < H0v; hv0 += 32) {
+    const int hv = hv0 + lane;
+    const bool ok = hv < H0v;
+    const float4 g = ok ? dZ[(size_t)row * H0v + hv] : make_float4(0.f, 0.f, 0.f, 0.f);
     for (int base = s; base < e; base += 32) {
       const int cnt = min(32, e - base);
       int c = 0;
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(256) k_csr_linear_bwd_dw_v4(const int32_t* __r
       for (int k = 0; k < cnt; ++k) {
         const int ck = __shfl_sync(0xffffffffu, c, k);
         const float vk = __shfl_sync(0xffffffffu, v, k);
-        if (vk != 0.f) atomicAdd(dW1T + (size_t)ck * H0v + hv, make_float4(vk * g.x, vk * g.y, vk * g.z, vk * g.w));
+        if (ok && vk != 0.f) atomicAdd(dW1T + (size_t)ck * H0v + hv, make_float4(vk * g.x, vk * g.y, vk * g.z, vk * g.w));
       }
     }
   }

@@ -12,6 +12,23 @@ def _st():
     return torch.cuda.current_stream().cuda_stream
 
 
+_keep = []
+
+
+def D(t):
+    """Move to the GPU and keep the tensor alive until the test ends (raw pointers are borrowed)."""
+    t = t.cuda()
+    _keep.append(t)
+    return t
+
+
+@pytest.fixture(autouse=True)
+def _release_device_tensors():
+    yield
+    torch.cuda.synchronize()
+    _keep.clear()
+
+
 def _chk(name, got, want, tol=1e-5):
     e = GU.rel_err(got, want)
     assert e <= tol, f"{name}: rel err {e:.3e} > {tol}"
@@ -51,11 +68,11 @@ def test_colsum_and_relu_bwd():
     from scnym_b200._lib import call, ptr
     A = torch.randn(300, 70)
     out = torch.ones(70).cuda()
-    call("scnb_colsum", ptr(A.cuda()), 300, 70, 70, ptr(out), 1, _st())
+    call("scnb_colsum", ptr(D(A)), 300, 70, 70, ptr(out), 1, _st())
     _chk("colsum", out.cpu(), 1 + A.double().sum(0), tol=1e-5)
     g, y = torch.randn(1000), torch.randn(1000)
     o = torch.empty(1000).cuda()
-    call("scnb_relu_bwd", ptr(g.cuda()), ptr(y.cuda()), ptr(o), 1000, _st())
+    call("scnb_relu_bwd", ptr(D(g)), ptr(D(y)), ptr(o), 1000, _st())
     assert torch.equal(o.cpu(), g * (y > 0))
 
 
@@ -73,16 +90,16 @@ def test_csr_linear_fwd_bwd(H0):
     torch.manual_seed(H0)
     WT, b1 = torch.randn(G, H0) * 0.1, torch.randn(H0)
     Z = torch.empty(n, H0).cuda()
-    call("scnb_csr_linear_fwd", ptr(b.indptr), ptr(b.indices), ptr(b.data), n, ptr(WT.cuda()), ptr(b1.cuda()), H0, ptr(Z), _st())
+    call("scnb_csr_linear_fwd", ptr(b.indptr), ptr(b.indices), ptr(b.data), n, ptr(D(WT)), ptr(D(b1)), H0, ptr(Z), _st())
     _chk("csr fwd", Z.cpu(), X.double() @ WT.double() + b1.double())
     _chk("to_dense", b.to_dense().cpu(), X, tol=0)
     dZ = torch.randn(n, H0)
     dW = torch.zeros(G, H0).cuda()
-    call("scnb_csr_linear_bwd_dw", ptr(b.indptr), ptr(b.indices), ptr(b.data), n, ptr(dZ.cuda()), H0, ptr(dW), _st())
+    call("scnb_csr_linear_bwd_dw", ptr(b.indptr), ptr(b.indices), ptr(b.data), n, ptr(D(dZ)), H0, ptr(dW), _st())
     _chk("csr bwd", dW.cpu(), X.double().t() @ dZ.double())
     # dataset-CSR (int64 indptr) variant on a contiguous row range
     Z2 = torch.empty(9, H0).cuda()
-    call("scnb_csr_linear_fwd_i64", ptr(ds.indptr[5:]), ptr(ds.indices), ptr(ds.data), 9, ptr(WT.cuda()), None, H0, ptr(Z2), _st())
+    call("scnb_csr_linear_fwd_i64", ptr(ds.indptr[5:]), ptr(ds.indices), ptr(ds.data), 9, ptr(D(WT)), None, H0, ptr(Z2), _st())
     _chk("csr fwd i64", Z2.cpu(), O.csr_to_dense(ip, ii, dd, G, np.arange(5, 14)).double() @ WT.double())
 
 
@@ -149,7 +166,7 @@ def test_bn_act_fwd_bwd(H, segs, maxr):
     assert float(A[n_act:].abs().sum()) == 0.0
     dZ = torch.full((maxr, H), 7.0).cuda()
     dg, db = torch.zeros(H).cuda(), torch.zeros(H).cuda()
-    call("scnb_bn_act_bwd", ptr(dA.cuda()), ptr(Zc), ptr(A), H, len(segs), ptr(seg), maxr, ptr(gc), ptr(stats), ptr(kc), None, 0,
+    call("scnb_bn_act_bwd", ptr(D(dA)), ptr(Zc), ptr(A), H, len(segs), ptr(seg), maxr, ptr(gc), ptr(stats), ptr(kc), None, 0,
          0.5, 1, ptr(dZ), ptr(dg), ptr(db), _st())
     _chk("bn dZ", dZ[:n_act].cpu(), Zd.grad[:n_act], tol=2e-5)
     _chk("bn dgamma", dg.cpu(), gd.grad, tol=2e-5)
@@ -170,7 +187,7 @@ def test_bn_act_fwd_bwd(H, segs, maxr):
     # eval mode
     Ae = torch.empty(maxr, H).cuda()
     pre = torch.empty(maxr, H).cuda()
-    call("scnb_bn_act_fwd", ptr(Zc), ptr(Ae), ptr(pre), H, 1, ptr(torch.tensor([0, maxr], dtype=torch.int32).cuda()), maxr, 0,
+    call("scnb_bn_act_fwd", ptr(Zc), ptr(Ae), ptr(pre), H, 1, ptr(D(torch.tensor([0, maxr], dtype=torch.int32))), maxr, 0,
          ptr(gc), ptr(bc), ptr(rmc), ptr(rvc), None, None, None, 0, 0.0, 1, _st())
     want = (Z.double() - rmc.cpu().double()) / torch.sqrt(rvc.cpu().double() + 1e-5) * g.double() + b.double()
     _chk("bn eval pre", pre.cpu(), want)
@@ -215,7 +232,7 @@ def test_pseudolabel(K, T, C):
     want_q = O.sharpen_labels(qbar.clone(), T).float()
     q, cf = torch.empty(U, C).cuda(), torch.empty(U).cuda()
     flag = torch.empty(U, dtype=torch.uint8).cuda()
-    call("scnb_pseudolabel", ptr(logits.cuda()), K, U, C, T, 1, tau, ptr(q), ptr(cf), ptr(flag), ptr(torch.empty(U, C).cuda()), _st())
+    call("scnb_pseudolabel", ptr(D(logits)), K, U, C, T, 1, tau, ptr(q), ptr(cf), ptr(flag), ptr(D(torch.empty(U, C))), _st())
     _chk("q", q.cpu(), want_q)
     _chk("conf", cf.cpu(), conf)
     exact = (conf - tau).abs() > 1e-6
@@ -229,7 +246,7 @@ def _plan(confident, keys, graw, U, L, use_dan, dan_conf, mixup_on=1):
     i32 = lambda *s: torch.full(s, -7, dtype=torch.int32).cuda()
     out = dict(counts=i32(8), seg=i32(4), work=i32(U + 3 * nb), srcA=i32(R), srcB=i32(R), gam=torch.zeros(R).cuda(),
                inv3=i32(3, nb), coef3=torch.zeros(3, nb).cuda(), pconf=torch.zeros(1).cuda())
-    call("scnb_mixmatch_plan", ptr(confident.cuda()), ptr(keys.cuda()), ptr(graw.cuda()), U, L, use_dan, dan_conf, mixup_on,
+    call("scnb_mixmatch_plan", ptr(D(confident)), ptr(D(keys)), ptr(D(graw)), U, L, use_dan, dan_conf, mixup_on,
          ptr(out["counts"]), ptr(out["seg"]), ptr(out["work"]), ptr(out["srcA"]), ptr(out["srcB"]), ptr(out["gam"]), R,
          ptr(out["inv3"]), ptr(out["coef3"]), ptr(out["pconf"]), _st())
     torch.cuda.synchronize()
@@ -272,13 +289,13 @@ def test_mixmatch_plan_and_mix_adjoint(U, L, frac, use_dan, dan_conf):
     Z, dOut = torch.randn(nb, H), torch.randn(R, H)
     dOut[na:] = 0
     mixed = torch.empty(R, H).cuda()
-    call("scnb_mix_rows", ptr(Z.cuda()), H, ptr(out["srcA"].cuda()), ptr(out["srcB"].cuda()), ptr(out["gam"].cuda()),
-         ptr(out["counts"][3:].cuda()), R, ptr(mixed), _st())
+    call("scnb_mix_rows", ptr(D(Z)), H, ptr(D(out["srcA"])), ptr(D(out["srcB"])), ptr(D(out["gam"])),
+         ptr(D(out["counts"][3:])), R, ptr(mixed), _st())
     want = eG[:, None].double() * Z[eA].double() + (1 - eG[:, None].double()) * Z[eB].double()
     _chk("mix", mixed[:na].cpu(), want)
     assert float(mixed[na:].abs().sum()) == 0
     dZ = torch.empty(nb, H).cuda()
-    call("scnb_unmix_rows", ptr(dOut.cuda()), H, ptr(out["inv3"].cuda()), ptr(out["coef3"].cuda()), nb, ptr(dZ), _st())
+    call("scnb_unmix_rows", ptr(D(dOut)), H, ptr(D(out["inv3"])), ptr(D(out["coef3"])), nb, ptr(dZ), _st())
     lhs = float((want * dOut[:na].double()).sum())
     rhs = float((Z.double() * dZ.cpu().double()).sum())
     assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), 1.0)
@@ -298,7 +315,7 @@ def test_losses_match_oracle_autograd():
     loss = O.cross_entropy(z, Y.double(), class_weight=cw.double())
     loss.backward()
     dz, lo = torch.empty(n, C).cuda(), torch.zeros(2).cuda()
-    call("scnb_soft_ce_fwd_bwd", ptr(z.detach().float().cuda()), n, C, None, ptr(Y.cuda()), None, None, None, 0, ptr(cw.cuda()),
+    call("scnb_soft_ce_fwd_bwd", ptr(D(z.detach().float())), n, C, None, ptr(D(Y)), None, None, None, 0, ptr(D(cw)),
          None, n, 1.0, None, ptr(dz), ptr(lo), 1, _st())
     _chk("ce loss", lo[0].cpu(), loss.detach())
     _chk("ce grad", dz.cpu(), z.grad, tol=2e-5)
@@ -315,8 +332,8 @@ def test_losses_match_oracle_autograd():
     l2 = (per * mask).mean()
     (0.7 * l2).backward()
     dz2, lo2 = torch.empty(n, C).cuda(), torch.zeros(1).cuda()
-    call("scnb_softmax_mse_fwd_bwd", ptr(z2.detach().float().cuda()), n, C, ptr(torch.tensor([n_conf], dtype=torch.int32).cuda()),
-         ptr(Y.cuda()), ptr(a.int().cuda()), ptr(b.int().cuda()), ptr(g.cuda()), 0, n, None, 0.7, ptr(dz2), ptr(lo2), _st())
+    call("scnb_softmax_mse_fwd_bwd", ptr(D(z2.detach().float())), n, C, ptr(D(torch.tensor([n_conf], dtype=torch.int32))),
+         ptr(D(Y)), ptr(D(a.int())), ptr(D(b.int())), ptr(D(g)), 0, n, None, 0.7, ptr(dz2), ptr(lo2), _st())
     _chk("mse loss", lo2[0].cpu(), l2.detach())
     _chk("mse grad", dz2.cpu(), z2.grad, tol=2e-5)
 
@@ -340,7 +357,7 @@ def test_optim_step_matches_torch_optim(name):
         rp.grad = g.clone()
         ropt.step()
         call("scnb_step_begin", ptr(state), _st())
-        call("scnb_optim_step", OPTIMIZER_CODES[name], ptr(p), ptr(g.cuda()), ptr(s1), ptr(s2), n, ptr(hp), ptr(state), _st())
+        call("scnb_optim_step", OPTIMIZER_CODES[name], ptr(p), ptr(D(g)), ptr(s1), ptr(s2), n, ptr(hp), ptr(state), _st())
         _chk(f"{name} t={t}", p.cpu(), rp.detach(), tol=2e-6)
 
 
@@ -348,12 +365,12 @@ def test_ema_update_and_counters():
     from scnym_b200._lib import call, ptr
     t, p = torch.randn(1000), torch.randn(1000)
     td, state = t.cuda(), torch.zeros(4, dtype=torch.int64).cuda()
-    call("scnb_ema_update", ptr(td), ptr(p.cuda()), 1000, 0.997, ptr(state), _st())
+    call("scnb_ema_update", ptr(td), ptr(D(p)), 1000, 0.997, ptr(state), _st())
     _chk("ema step0 == copy", td.cpu(), p, tol=0)
     for _ in range(5):
         call("scnb_mm_step_inc", ptr(state), _st())
     td = t.cuda()
-    call("scnb_ema_update", ptr(td), ptr(p.cuda()), 1000, 0.997, ptr(state), _st())
+    call("scnb_ema_update", ptr(td), ptr(D(p)), 1000, 0.997, ptr(state), _st())
     a = min(1 - 1 / 6, 0.997)
     _chk("ema step5", td.cpu(), a * t + (1 - a) * p, tol=1e-6)
 
