@@ -46,6 +46,17 @@ int scnb_csr_gather_rows(const int64_t* indptr, const int32_t* indices, const fl
                          int aug_row_begin, int aug_row_end, const uint8_t* keep_mask /*per batch nnz*/,
                          const uint64_t* rng, uint32_t stream_id, float p_drop, void* stream);
 
+/* Device-resident sampler hand-off (replaces DataLoader iteration, scnym/trainer.py:574-582):
+ * copies the row ids / MixUp randomness of step (state4[0] % n_tab) from per-epoch tables. */
+int scnb_fetch_step(const int64_t* l_tab, const int64_t* u_tab, const float* key_tab, const float* gam_tab, int L, int U,
+                    int n_tab, const int64_t* state4, int64_t* l_rows, int64_t* u_rows, float* keys, float* gam,
+                    void* stream);
+/* HOST function (no stream): gather CSR rows of a host-resident matrix into (pinned) staging
+ * buffers for the host-buffer entry; replaces per-cell densify + collate (dataprep.py:114-168). */
+int scnb_host_gather_rows(const int64_t* indptr, const int32_t* indices, const float* data, const int64_t* rows, int n,
+                          int64_t* out_indptr, int32_t* out_indices, float* out_data, long long out_capacity,
+                          int n_threads);
+
 /* ---- K2a/K8: first layer nn.Linear(n_genes, n_hidden_init) (scnym/model.py:211) on CSR input.
  *      fwd: Z = X W1T + b1.   bwd: dW1T += X^T dZ (caller zeroes dW1T).  dX is never formed: the
  *      reference computes it only because inputs carry requires_grad (scnym/trainer.py:596-599)

@@ -17,6 +17,8 @@ SIGNATURES = {
     "scnb_csr_row_offsets": [P, P, L, I, P, P, P],
     "scnb_gather_i32": [P, P, I, I, P, P],
     "scnb_csr_gather_rows": [P, P, P, P, L, I, P, P, P, I, I, I, P, P, U32, F, P],
+    "scnb_fetch_step": [P, P, P, P, I, I, I, P, P, P, P, P, P],
+    "scnb_host_gather_rows": [P, P, P, P, I, P, P, P, L, I],
     "scnb_csr_linear_fwd": [P, P, P, I, P, P, I, P, P],
     "scnb_csr_linear_fwd_i64": [P, P, P, I, P, P, I, P, P],
     "scnb_csr_linear_bwd_dw": [P, P, P, I, P, I, P, P],

@@ -323,3 +323,34 @@ extern "C" int scnb_gather_i32(const int32_t* table, const int64_t* rows, int n,
   SCNB_CHECK_LAUNCH("gather_i32");
   return SCNB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Device-resident sampler hand-off: copy row ids / MixUp randomness of step (state4[0] % n_tab)
+// from per-epoch tables into the engine's input buffers, so that an epoch is pure graph replay.
+// Replaces the host DataLoader iteration of scnym/trainer.py:574-582 (+ main.py:48-68 `repeater`).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_fetch_step(const int64_t* __restrict__ l_tab, const int64_t* __restrict__ u_tab,
+                             const float* __restrict__ key_tab, const float* __restrict__ gam_tab, int L, int U, int n_tab,
+                             const int64_t* __restrict__ state4, int64_t* __restrict__ l_rows, int64_t* __restrict__ u_rows,
+                             float* __restrict__ keys, float* __restrict__ gam) {
+  const int64_t s = state4[0] % (int64_t)n_tab;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < L) l_rows[i] = l_tab[s * L + i];
+  if (u_tab && i < U) u_rows[i] = u_tab[s * U + i];
+  if (key_tab && i < L + U) {
+    keys[i] = key_tab[s * (L + U) + i];
+    gam[i] = gam_tab[s * (L + U) + i];
+  }
+}
+
+extern "C" int scnb_fetch_step(const int64_t* l_tab, const int64_t* u_tab, const float* key_tab, const float* gam_tab, int L,
+                               int U, int n_tab, const int64_t* state4, int64_t* l_rows, int64_t* u_rows, float* keys,
+                               float* gam, void* stream) {
+  SCNB_CHECK_ARG(l_tab && state4 && l_rows && L > 0 && U >= 0 && n_tab > 0, "fetch_step: bad arguments");
+  SCNB_CHECK_ARG(!u_tab || u_rows, "fetch_step: u_rows missing");
+  SCNB_CHECK_ARG(!key_tab || (gam_tab && keys && gam), "fetch_step: key/gamma buffers missing");
+  k_fetch_step<<<scnb_cdiv(L + U, 256), 256, 0, (cudaStream_t)stream>>>(l_tab, u_tab, key_tab, gam_tab, L, U, n_tab, state4, l_rows,
+                                                                        u_rows, keys, gam);
+  SCNB_CHECK_LAUNCH("fetch_step");
+  return SCNB_OK;
+}

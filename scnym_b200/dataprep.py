@@ -128,3 +128,64 @@ def gather_rows(ds: DeviceCSR, rows: Optional[torch.Tensor] = None, row0: int = 
     call("scnb_csr_gather_rows", ptr(ds.indptr), ptr(ds.indices), ptr(ds.data), ptr(rows), row0, n, ptr(out.indptr),
          ptr(out.indices), ptr(out.data), int(augment), 0, n, ptr(keep_mask), ptr(rng), stream_id, float(p_drop), st)
     return out
+
+
+class HostBatchFeeder(object):
+    """Host-buffer entry: assembles one minibatch from a HOST-resident CSR matrix into pinned
+    staging buffers (C threads, `scnb_host_gather_rows`) and copies it to fixed device staging
+    tensors that a `TrainEngine` reads as a tiny DeviceCSR (rows 0..B-1).
+
+    This is the path a caller takes when the expression matrix does not live in HBM; it is
+    what `bench.py` times as `e2e` (host->device copies inside the timed region).
+    """
+
+    def __init__(self, indptr, indices, data, n_cols: int, batch: int, device="cuda", labels=None, domains=None,
+                 n_threads: int = 4) -> None:
+        self.indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        self.indices = np.ascontiguousarray(indices, dtype=np.int32)
+        self.data = np.ascontiguousarray(data, dtype=np.float32)
+        self.labels = None if labels is None else np.ascontiguousarray(labels, dtype=np.int32)
+        self.domains = None if domains is None else np.ascontiguousarray(domains, dtype=np.int32)
+        self.n_cols, self.B, self.n_threads = int(n_cols), int(batch), int(n_threads)
+        self.max_row_nnz = int(np.diff(self.indptr).max()) if len(self.indptr) > 1 else 1
+        self.cap = self.B * max(self.max_row_nnz, 1)
+        pin = lambda n, dt: torch.empty(n, dtype=dt).pin_memory()
+        self.p_indptr, self.p_idx, self.p_val = pin(self.B + 1, torch.int64), pin(self.cap, torch.int32), pin(self.cap, torch.float32)
+        self.p_y, self.p_dom = pin(self.B, torch.int32), pin(self.B, torch.int32)
+        dev = torch.device(device)
+        self.d_indptr = torch.zeros(self.B + 1, dtype=torch.int64, device=dev)
+        self.d_idx = torch.zeros(self.cap, dtype=torch.int32, device=dev)
+        self.d_val = torch.zeros(self.cap, dtype=torch.float32, device=dev)
+        self.d_y = torch.zeros(self.B, dtype=torch.int32, device=dev)
+        self.d_dom = torch.zeros(self.B, dtype=torch.int32, device=dev)
+        self.csr = DeviceCSR(self.d_indptr, self.d_idx, self.d_val, self.n_cols, self.max_row_nnz)
+        self.csr.n_rows = self.B
+        self.bytes_last = 0
+
+    def feed(self, rows) -> int:
+        """Gather `rows` (int64 numpy, len B) and enqueue the H2D copies on the current stream.
+        Returns the number of bytes copied host->device."""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        if rows.shape[0] != self.B:
+            raise ValueError(f"expected {self.B} rows, got {rows.shape[0]}")
+        h = _lib.lib()
+        rc = h.scnb_host_gather_rows(self.indptr.ctypes.data, self.indices.ctypes.data, self.data.ctypes.data,
+                                     rows.ctypes.data, self.B, self.p_indptr.data_ptr(), self.p_idx.data_ptr(),
+                                     self.p_val.data_ptr(), self.cap, self.n_threads)
+        if rc != 0:
+            raise _lib.ScnbError(h.scnb_last_error().decode())
+        nnz = int(self.p_indptr[self.B])
+        self.d_indptr.copy_(self.p_indptr, non_blocking=True)
+        self.d_idx[:nnz].copy_(self.p_idx[:nnz], non_blocking=True)
+        self.d_val[:nnz].copy_(self.p_val[:nnz], non_blocking=True)
+        nbytes = (self.B + 1) * 8 + nnz * 8
+        if self.labels is not None:
+            self.p_y.copy_(torch.from_numpy(self.labels[rows]))
+            self.d_y.copy_(self.p_y, non_blocking=True)
+            nbytes += self.B * 4
+        if self.domains is not None:
+            self.p_dom.copy_(torch.from_numpy(self.domains[rows]))
+            self.d_dom.copy_(self.p_dom, non_blocking=True)
+            nbytes += self.B * 4
+        self.bytes_last = nbytes
+        return nbytes

@@ -184,9 +184,16 @@ class TrainEngine(object):
             raise NotImplementedError("engine supports DANN(n_layers=1) (the only configuration fit_model builds)")
 
         # ---- labels / domains ----
-        self.lab_y = torch.as_tensor(np.asarray(labeled_y), dtype=torch.int32).to(dev)
-        self.lab_dom = None if labeled_domain is None else torch.as_tensor(np.asarray(labeled_domain), dtype=torch.int32).to(dev)
-        self.unl_dom = None if unlabeled_domain is None else torch.as_tensor(np.asarray(unlabeled_domain), dtype=torch.int32).to(dev)
+        def ids(x):
+            # device int32 tensors are borrowed as they are (host-batch staging buffers are rewritten every step)
+            if x is None:
+                return None
+            if isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.int32:
+                return x
+            if isinstance(x, torch.Tensor):
+                return x.to(device=dev, dtype=torch.int32)
+            return torch.as_tensor(np.asarray(x), dtype=torch.int32).to(dev)
+        self.lab_y, self.lab_dom, self.unl_dom = ids(labeled_y), ids(labeled_domain), ids(unlabeled_domain)
         self.class_weight = None if cfg.class_weight is None else torch.tensor(cfg.class_weight, dtype=torch.float32, device=dev)
 
         f32 = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
@@ -258,6 +265,7 @@ class TrainEngine(object):
             self._const_seg(self.K_eff * U)  # created here: no H2D copies may happen during graph capture
         self.loss_buf = f32(8)       # [sup, sup_hits, unsup, -, dan, dan_hits, -, -]
         self.loss_hist = None
+        self._tabs = None            # per-epoch sampler tables (device); see set_epoch_tables
         self._graph = None
         self._graph_key = None
         self.steps_done = 0
@@ -299,6 +307,7 @@ class TrainEngine(object):
         L, U, nb, R, C, H0 = self.L, self.U, self.nb, self.Rmax, self.C, self.widths[0]
         rng = ptr(self.state[1:3])
         blk = self._blk
+        self._fetch(st)
         call("scnb_step_begin", ptr(self.state), st)
         self.arena.grad.zero_()
         self.loss_buf.zero_()
@@ -491,6 +500,7 @@ class TrainEngine(object):
         L, C, H0 = self.L, self.C, self.widths[0]
         rng = ptr(self.state[1:3])
         blk = self._blk
+        self._fetch(st)
         call("scnb_step_begin", ptr(self.state), st)
         self.arena.grad.zero_()
         self.loss_buf.zero_()
@@ -525,6 +535,66 @@ class TrainEngine(object):
             self._launch_mixmatch()
         else:
             self._launch_supervised()
+
+    def _fetch(self, st):
+        if self._tabs is None:
+            return
+        t = self._tabs
+        call("scnb_fetch_step", ptr(t["l"]), ptr(t.get("u")), ptr(t.get("k")), ptr(t.get("g")), self.L, self.U, t["n"],
+             ptr(self.state), ptr(self.l_rows), ptr(self.u_rows), ptr(self.perm_keys), ptr(self.gamma_raw), st)
+
+    def set_epoch_tables(self, l_tab, u_tab=None, key_tab=None, gam_tab=None):
+        """Device-resident sampler: row ids (and MixUp randomness) for `n` consecutive steps.
+        Step s reads row `(steps_taken % n)`; tables are copied into persistent buffers so a
+        captured graph stays valid across epochs (same n) -- replaces DataLoader iteration
+        (scnym/trainer.py:574-582) and the `repeater` around the unlabeled loader (main.py:48-68)."""
+        n = int(l_tab.shape[0])
+        mk = lambda t, dt: None if t is None else torch.as_tensor(t).to(device=self.dev, dtype=dt).contiguous()
+        new = dict(n=n, l=mk(l_tab, torch.int64), u=mk(u_tab, torch.int64), k=mk(key_tab, torch.float32),
+                   g=mk(gam_tab, torch.float32))
+        if self.mode == "mixmatch" and (new["u"] is None or new["k"] is None or new["g"] is None):
+            raise ValueError("mixmatch tables need unlabeled rows, permutation keys and gamma draws")
+        old = self._tabs
+        if old is not None and old["n"] == n and all((old[k] is None) == (new[k] is None) for k in "lukg"):
+            for k in "lukg":
+                if new[k] is not None:
+                    old[k].copy_(new[k])
+        else:
+            self._tabs = new
+            self._graph = None  # pointers changed: re-capture
+
+    def sample_epoch_tables(self, n_steps: int, generator: Optional[torch.Generator] = None):
+        """Draw one epoch of batches on the device: shuffled labeled rows without replacement
+        (DataLoader(shuffle=True, drop_last=True), main.py:317-323), unlabeled rows likewise with
+        wrap-around, uniform permutation keys and Beta(alpha, alpha) MixUp draws."""
+        dev, L, U = self.dev, self.L, self.U
+        def draw(n_rows, per):
+            need = n_steps * per
+            chunks, have = [], 0
+            while have < need:
+                chunks.append(torch.randperm(n_rows, device=dev, generator=generator))
+                have += n_rows
+            flat = torch.cat(chunks)
+            # drop_last semantics inside each pass over the data
+            usable = (n_rows // per) * per
+            if usable >= need or usable == 0:
+                return flat[:need].view(n_steps, per)
+            out = torch.cat([c[:usable] for c in chunks])
+            while out.numel() < need:
+                out = torch.cat([out, torch.randperm(n_rows, device=dev, generator=generator)[:usable]])
+            return out[:need].view(n_steps, per)
+        l_tab = draw(self.lab.n_rows, L)
+        if self.mode != "mixmatch":
+            self.set_epoch_tables(l_tab)
+            return
+        u_tab = draw(self.unl.n_rows, U)
+        keys = torch.rand((n_steps, L + U), device=dev, generator=generator)
+        a = max(float(self.cfg.mixup_alpha), 1e-3)
+        conc = torch.full((n_steps, L + U), a, device=dev)
+        g1 = torch._standard_gamma(conc, generator=generator)
+        g2 = torch._standard_gamma(conc, generator=generator)
+        gam = g1 / (g1 + g2).clamp_min(1e-30)      # Beta(a, a) as a ratio of Gammas
+        self.set_epoch_tables(l_tab, u_tab, keys, gam)
 
     def load_batch(self, l_rows, u_rows=None, perm_keys=None, gamma_raw=None):
         """Stage one step's sampled rows / MixUp randomness into the device input buffers."""
