@@ -118,7 +118,8 @@ int scnb_mixmatch_plan(const uint8_t* confident, const float* perm_keys, const f
 int scnb_soft_ce_fwd_bwd(const float* logits, int n_max, int C, const int32_t* n_rows_dev, const float* Y,
                          const int32_t* mapA, const int32_t* mapB, const float* gam, int map_off,
                          const float* class_weight, const int32_t* n_norm_dev, int n_norm, float grad_scale,
-                         const float* loss_scale_dev, float* dlogits, float* loss_out2, int count_acc, void* stream);
+                         const float* loss_scale_dev, float* dlogits, float* loss_out2, int count_acc,
+                         float* row_loss_out /*optional [n_max]: unreduced losses*/, void* stream);
 int scnb_softmax_mse_fwd_bwd(const float* logits, int n_max, int C, const int32_t* n_conf_dev, const float* Y,
                              const int32_t* mapA, const int32_t* mapB, const float* gam, int map_off, int n_norm,
                              const float* weight_dev, float weight, float* dlogits, float* loss_out, void* stream);
@@ -133,6 +134,8 @@ int scnb_step_begin(int64_t* state4, void* stream);
 int scnb_mm_step_inc(int64_t* state4, void* stream);
 int scnb_optim_step(int opt, float* params, const float* grads, float* state1, float* state2, long long n,
                     const float* hp8, const int64_t* state4, void* stream);
+int scnb_record_step(const float* loss8, float* hist, int hist_cap, const float* conf, int U, float* conf_ring, int ring_cap,
+                     const int64_t* state4, void* stream);
 int scnb_ema_update(float* teacher, const float* params, long long n, float decay, const int64_t* state4, void* stream);
 
 /* ---- Predict head: Predicter.predict (scnym/predict.py:178-192): ensemble-mean logits,

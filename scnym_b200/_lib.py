@@ -33,13 +33,14 @@ SIGNATURES = {
     "scnb_unmix_rows": [P, I, P, P, I, P, P],
     "scnb_pseudolabel": [P, I, I, I, F, I, F, P, P, P, P, P],
     "scnb_mixmatch_plan": [P, P, P, I, I, I, I, I, P, P, P, P, P, P, I, P, P, P, P],
-    "scnb_soft_ce_fwd_bwd": [P, I, I, P, P, P, P, P, I, P, P, I, F, P, P, P, I, P],
+    "scnb_soft_ce_fwd_bwd": [P, I, I, P, P, P, P, P, I, P, P, I, F, P, P, P, I, P, P],
     "scnb_softmax_mse_fwd_bwd": [P, I, I, P, P, P, P, P, I, I, P, F, P, P, P],
     "scnb_onehot_rows": [P, P, I, I, I, P, P],
     "scnb_step_begin": [P, P],
     "scnb_mm_step_inc": [P, P],
     "scnb_optim_step": [I, P, P, P, P, L, P, P, P],
     "scnb_ema_update": [P, P, L, F, P, P],
+    "scnb_record_step": [P, P, I, P, I, P, I, P, P],
     "scnb_predict_head": [P, I, I, I, P, P, P, P],
 }
 

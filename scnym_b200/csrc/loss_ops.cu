@@ -323,7 +323,8 @@ __global__ void __launch_bounds__(256) k_soft_ce(const float* __restrict__ Zl, i
                                                  const float* __restrict__ gam, int map_off,
                                                  const float* __restrict__ class_weight, const int32_t* __restrict__ n_norm_dev,
                                                  int n_norm, float grad_scale, const float* __restrict__ loss_scale_dev,
-                                                 float* __restrict__ dZ, float* __restrict__ loss_out, int count_acc) {
+                                                 float* __restrict__ dZ, float* __restrict__ loss_out, int count_acc,
+                                                 float* __restrict__ row_loss) {
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= n_max) return;
@@ -332,6 +333,7 @@ __global__ void __launch_bounds__(256) k_soft_ce(const float* __restrict__ Zl, i
   if (i >= n_rows) {
     if (dz)
       for (int c = lane; c < C; c += 32) dz[c] = 0.f;
+    if (row_loss && lane == 0) row_loss[i] = 0.f;
     return;
   }
   const float nn = (float)(n_norm_dev ? max(*n_norm_dev, 1) : max(n_norm, 1));
@@ -394,6 +396,7 @@ __global__ void __launch_bounds__(256) k_soft_ce(const float* __restrict__ Zl, i
     }
   }
   if (lane == 0) {
+    if (row_loss) row_loss[i] = li * ls;
     atomicAdd(loss_out, li * ls / nn);
     if (count_acc && yam == am) atomicAdd(loss_out + 1, 1.0f);
   }
@@ -403,12 +406,12 @@ extern "C" int scnb_soft_ce_fwd_bwd(const float* logits, int n_max, int C, const
                                     const int32_t* mapA, const int32_t* mapB, const float* gam, int map_off,
                                     const float* class_weight, const int32_t* n_norm_dev, int n_norm, float grad_scale,
                                     const float* loss_scale_dev, float* dlogits, float* loss_out2, int count_acc,
-                                    void* stream) {
+                                    float* row_loss_out, void* stream) {
   SCNB_CHECK_ARG(logits && Y && loss_out2 && n_max >= 0 && C > 0, "soft_ce_fwd_bwd: bad arguments");
   if (n_max == 0) return SCNB_OK;
   k_soft_ce<<<scnb_cdiv(n_max, 8), 256, 0, (cudaStream_t)stream>>>(logits, n_max, C, n_rows_dev, Y, mapA, mapB, gam, map_off,
                                                                      class_weight, n_norm_dev, n_norm, grad_scale,
-                                                                     loss_scale_dev, dlogits, loss_out2, count_acc);
+                                                                     loss_scale_dev, dlogits, loss_out2, count_acc, row_loss_out);
   SCNB_CHECK_LAUNCH("soft_ce_fwd_bwd");
   return SCNB_OK;
 }

@@ -116,3 +116,24 @@ extern "C" int scnb_mm_step_inc(int64_t* state4, void* stream) {
   SCNB_CHECK_LAUNCH("mm_step_inc");
   return SCNB_OK;
 }
+
+// Per-step bookkeeping without host syncs: loss scalars of step t go to hist[(t-1) % hist_cap],
+// pseudolabel confidences to conf_ring[(t-1) % ring_cap] (replaces the per-step .item()/.cpu()
+// reads of scnym/trainer.py:666-681 and losses.py:714-725; read back once per epoch).
+__global__ void k_record_step(const float* __restrict__ loss8, float* __restrict__ hist, int hist_cap,
+                              const float* __restrict__ conf, int U, float* __restrict__ conf_ring, int ring_cap,
+                              const int64_t* __restrict__ st) {
+  const int64_t t = st[0] - 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (hist && i < 8) hist[(t % hist_cap) * 8 + i] = loss8[i];
+  if (conf_ring && i < U) conf_ring[(t % ring_cap) * U + i] = conf[i];
+}
+
+extern "C" int scnb_record_step(const float* loss8, float* hist, int hist_cap, const float* conf, int U, float* conf_ring,
+                                int ring_cap, const int64_t* state4, void* stream) {
+  SCNB_CHECK_ARG(loss8 && state4 && (!hist || hist_cap > 0) && (!conf_ring || (conf && ring_cap > 0)), "record_step: bad arguments");
+  const int n = U > 8 ? U : 8;
+  k_record_step<<<scnb_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(loss8, hist, hist_cap, conf, U, conf_ring, ring_cap, state4);
+  SCNB_CHECK_LAUNCH("record_step");
+  return SCNB_OK;
+}

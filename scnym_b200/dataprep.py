@@ -189,3 +189,269 @@ class HostBatchFeeder(object):
             nbytes += self.B * 4
         self.bytes_last = nbytes
         return nbytes
+
+
+# =================================================================================================
+# Reference-compatible surface (scnym/dataprep.py): SingleCellDS, SampleMixUp, augmentations
+# =================================================================================================
+class SingleCellDS(torch.utils.data.Dataset):
+    """Dataset of single cell profiles (scnym/dataprep.py:12-168).
+
+    Same constructor, attributes (`X`, `y_labels`, `y`, `dom_labels`, `dom`, `transform`) and
+    `__getitem__` contract as the reference, so foreign code can still index it on the host;
+    the scnym_b200 trainers never do -- they call `device_csr()` once and sample rows on the GPU.
+    """
+
+    def __init__(self, X, y, domain=None, transform=None, num_classes: int = -1, num_domains: int = -1) -> None:
+        from scipy import sparse
+        super().__init__()
+        if type(X) not in (np.ndarray, sparse.csr_matrix):
+            raise TypeError(f"X is type {type(X)}, must `np.ndarray` or `sparse.csr_matrix`")
+        if type(y) not in (np.ndarray, sparse.csr_matrix):
+            raise TypeError(f"X is type {type(y)}, must `np.ndarray` or `sparse.csr_matrix`")
+        if type(y) != np.ndarray:
+            y = y.toarray()
+        self.X = X
+        self.y_labels = torch.from_numpy(y).long()
+        self.y = torch.nn.functional.one_hot(self.y_labels, num_classes=num_classes).float()
+        self.num_classes = int(self.y.shape[1]) if self.y.dim() > 1 else num_classes
+        self.dom_labels = domain
+        self.num_domains = num_domains
+        if self.dom_labels is not None:
+            self.dom = torch.nn.functional.one_hot(torch.from_numpy(np.asarray(self.dom_labels)).long(),
+                                                   num_classes=num_domains).float()
+        else:
+            self.dom = np.zeros_like(self.y) - 1
+        self.transform = transform
+        if not self.X.shape[0] == self.y.shape[0]:
+            raise ValueError("X rows %d not equal to y rows %d." % (self.X.shape[0], self.y.shape[0]))
+        self._dev = None
+
+    def __len__(self) -> int:
+        return self.X.shape[0]
+
+    def __getitem__(self, idx: int) -> dict:
+        if type(idx) != int:
+            raise TypeError(f"indices must be int, you passed {type(idx)}, {idx}")
+        if idx < 0 or idx > len(self):
+            raise ValueError("idx %d is invalid for dataset with %d examples." % (idx, len(self)))
+        input_ = self.X[idx, ...]
+        if type(input_) != np.ndarray:
+            input_ = input_.toarray()
+        input_ = torch.from_numpy(np.asarray(input_)).float()
+        if input_.dim() > 1 and input_.size(0) == 1:
+            input_ = input_.squeeze()
+        sample = {"input": input_, "output": self.y[idx], "domain": self.dom[idx]}
+        if self.transform is not None:
+            sample = self.transform(sample)
+        return sample
+
+    def device_csr(self, device="cuda") -> DeviceCSR:
+        """The expression matrix resident in HBM as CSR (uploaded once, cached)."""
+        if self._dev is None or self._dev.device != torch.device(device):
+            self._dev = DeviceCSR.from_any(self.X, device)
+        return self._dev
+
+
+class DeviceLoader(object):
+    """Stand-in for `torch.utils.data.DataLoader(SingleCellDS, ...)` whose batches are drawn on
+    the GPU.  Exposes `.dataset`, `.batch_size`, `.sampler`, `__len__` (read by
+    `Trainer.__init__`, scnym/trainer.py:157-171) and iterates sample dicts
+    {"input": CSRBatch, "output": one-hot [B, C], "domain": one-hot [B, D] or -1} for criteria
+    that consume batches one by one; the fused trainers bypass iteration entirely."""
+
+    def __init__(self, dataset: SingleCellDS, batch_size: int, shuffle: bool = False, drop_last: bool = False,
+                 sampler=None, device="cuda") -> None:
+        self.dataset, self.batch_size, self.shuffle, self.drop_last = dataset, int(batch_size), shuffle, drop_last
+        self.sampler = sampler if sampler is not None else ("RandomSampler" if shuffle else "SequentialSampler")
+        self.weights = None
+        if sampler is not None and hasattr(sampler, "weights"):
+            self.weights = torch.as_tensor(sampler.weights, dtype=torch.float64)
+            self.num_samples = int(sampler.num_samples)
+        self.device = torch.device(device)
+
+    def __len__(self) -> int:
+        n = len(self.dataset) if self.weights is None else self.num_samples
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def epoch_order(self) -> torch.Tensor:
+        """Row order of one epoch, on the device (shuffle / weighted sampling / sequential)."""
+        n = len(self.dataset)
+        if self.weights is not None:  # WeightedRandomSampler (main.py:229-232): with replacement
+            return torch.multinomial(self.weights.to(self.device).float(), self.num_samples, replacement=True)
+        if self.shuffle:
+            return torch.randperm(n, device=self.device)
+        return torch.arange(n, device=self.device)
+
+    def __iter__(self):
+        ds = self.dataset.device_csr(self.device)
+        order = self.epoch_order()
+        y = self.dataset.y.to(self.device)
+        dom = torch.as_tensor(self.dataset.dom).to(self.device)
+        for b in range(len(self)):
+            rows = order[b * self.batch_size:(b + 1) * self.batch_size]
+            yield {"input": gather_rows(ds, rows), "output": y[rows], "domain": dom[rows], "rows": rows}
+
+
+def balance_classes(y: np.ndarray, class_min: int = 256) -> np.ndarray:
+    """Class balancing by under/over-sampling (scnym/dataprep.py:171-210)."""
+    classes, counts = np.unique(y, return_counts=True)
+    min_count = max(int(np.min(counts)), class_min)
+    all_idx = []
+    for i, c in enumerate(classes):
+        class_idx = np.where(y == c)[0].astype("int")
+        rep = counts[i] < min_count
+        if rep:
+            print("Count for class %s is %d. Oversampling." % (c, counts[i]))
+        all_idx += [np.random.choice(class_idx, size=min_count, replace=rep)]
+    return np.concatenate(all_idx).astype("int")
+
+
+def _dense_as_csr(x: torch.Tensor) -> DeviceCSR:
+    """View a dense CUDA [B, G] tensor as a CSR matrix that stores every entry."""
+    B, G = x.shape
+    key = (x.device, B, G)
+    cache = _dense_as_csr.cache
+    if key not in cache:
+        cache[key] = (torch.arange(B + 1, device=x.device, dtype=torch.int64) * G,
+                      torch.arange(G, device=x.device, dtype=torch.int32).repeat(B))
+    ip, ix = cache[key]
+    return DeviceCSR(ip, ix, x.contiguous().view(-1).float(), G, G)
+
+
+_dense_as_csr.cache = {}
+
+
+class Log1pDrop(object):
+    """`log1p_drop` = ExpMinusOne -> InputDropout(0.1) -> LibrarySizeNormalize(log1p)
+    (scnym/dataprep.py:721-729) as ONE device kernel over the stored entries.  Accepts a sample
+    dict whose "input" is a CSRBatch or a dense CUDA tensor and replaces it, as the reference
+    Compose does.  `KEEP_INJECT` (test hook) supplies the Bernoulli keep mask."""
+    KEEP_INJECT = []
+
+    def __init__(self, p_drop: float = 0.1) -> None:
+        self.p_drop = p_drop
+        # mimic torchvision.transforms.Compose.transforms for code that introspects the scheme
+        self.transforms = [ExpMinusOne(), InputDropout(p_drop=p_drop), LibrarySizeNormalize(log1p=True)]
+
+    def __call__(self, sample: dict) -> dict:
+        x = sample["input"]
+        dense = isinstance(x, torch.Tensor)
+        if dense:
+            _lib.require_cuda(x)
+            ds = _dense_as_csr(x.detach())
+        else:
+            ds = DeviceCSR(x.indptr.to(torch.int64), x.indices, x.data, x.n_cols, max(int(x.indices.numel() // max(x.n_rows, 1)), 1))
+        keep = None
+        if Log1pDrop.KEEP_INJECT:
+            keep = Log1pDrop.KEEP_INJECT.pop(0)
+            if dense:
+                keep = keep.to(device=x.device, dtype=torch.uint8).contiguous().view(-1)
+        n = ds.n_rows
+        nnz_cap = int(ds.data.numel())
+        out = CSRBatch(torch.empty(n + 1, dtype=torch.int32, device=ds.device), torch.empty(max(nnz_cap, 1), dtype=torch.int32, device=ds.device),
+                       torch.empty(max(nnz_cap, 1), dtype=torch.float32, device=ds.device), n, ds.n_cols)
+        if keep is None:
+            keep = (torch.rand(max(nnz_cap, 1), device=ds.device) >= self.p_drop).to(torch.uint8)
+        st = _stream()
+        call("scnb_csr_row_offsets", ptr(ds.indptr), None, 0, n, ptr(out.indptr), None, st)
+        call("scnb_csr_gather_rows", ptr(ds.indptr), ptr(ds.indices), ptr(ds.data), None, 0, n, ptr(out.indptr), ptr(out.indices),
+             ptr(out.data), 1, 0, n, ptr(keep), None, 0, float(self.p_drop), st)
+        sample["input"] = out.data[: n * ds.n_cols].view(n, ds.n_cols) if dense else out
+        return sample
+
+
+class LibrarySizeNormalize(object):
+    """Host-tensor restatement kept for API compatibility (scnym/dataprep.py:213-254); the
+    device path uses `Log1pDrop`."""
+
+    def __init__(self, counts_per_cell_after: int = int(1e6), log1p: bool = True) -> None:
+        self.counts_per_cell_after, self.log1p = counts_per_cell_after, log1p
+
+    def __call__(self, sample: dict) -> dict:
+        x = sample["input"]
+        x = x / torch.sum(x, dim=1).reshape(-1, 1) * self.counts_per_cell_after
+        sample["input"] = torch.log1p(x) if self.log1p else x
+        return sample
+
+
+class ExpMinusOne(object):
+    def __call__(self, sample: dict) -> dict:
+        sample["input"] = torch.expm1(sample["input"])
+        return sample
+
+
+class InputDropout(object):
+    def __init__(self, p_drop: float = 0.1) -> None:
+        self.p_drop = p_drop
+
+    def __call__(self, sample: dict) -> dict:
+        sample["input"] = torch.nn.functional.dropout(sample["input"], p=self.p_drop, inplace=False)
+        return sample
+
+
+def mixup(a, b, gamma):
+    """gamma * a + (1 - gamma) * b (scnym/dataprep.py:571-594)."""
+    return gamma * a + (1 - gamma) * b
+
+
+class SampleMixUp(object):
+    """MixUp on a sample batch (scnym/dataprep.py:597-705): `ridx = randperm(n)`,
+    `gamma ~ Beta(alpha, alpha)` (max(gamma, 1-gamma) if keep_dominant_obs), every tensor in
+    the dict mixed, `random_idx` recorded.  Used by the module-level path on dense tensors; the
+    fused engine performs the same mix behind the first layer (`scnb_mix_rows`)."""
+    INJECT = []  # test hook: (perm_keys, gamma_raw) tuples
+
+    def __init__(self, alpha: float = 0.2, keep_dominant_obs: bool = False) -> None:
+        self.alpha = alpha
+        if alpha > 0.0:
+            self.beta = torch.distributions.beta.Beta(self.alpha, self.alpha)
+        self.keep_dominant_obs = keep_dominant_obs
+
+    def __call__(self, sample: dict) -> dict:
+        if self.alpha == 0.0:
+            return sample
+        input_, output = sample["input"], sample["output"]
+        n = input_.size(0)
+        if SampleMixUp.INJECT:
+            keys, graw = SampleMixUp.INJECT.pop(0)
+            ridx = torch.argsort(keys[:n], stable=True)
+            gamma = graw[:n].clone()
+        else:
+            ridx = torch.randperm(n)
+            gamma = self.beta.sample((n,))
+        if self.keep_dominant_obs:
+            gamma = torch.maximum(gamma, 1 - gamma)
+        gamma = gamma.reshape(-1, 1).to(device=input_.device)
+        ridx_d = ridx.to(input_.device)
+        sample["input"] = mixup(input_, input_[ridx_d], gamma)
+        sample["output"] = mixup(output, output[ridx_d], gamma)
+        for k in [k for k in sample.keys() if k not in ("input", "output")]:
+            if type(sample[k]) == torch.Tensor:
+                sample[k] = mixup(sample[k], sample[k][ridx_d], gamma=gamma)
+        sample["random_idx"] = ridx
+        return sample
+
+
+def identity(x):
+    return x
+
+
+def _unsupported_scheme(name):
+    def f(sample):
+        raise NotImplementedError(
+            f"augmentation scheme {name!r} is outside the scnym_api configurations (api.py:87 fixes 'log1p_drop'); "
+            "SURVEY.md §2 row 16")
+    return f
+
+
+AUGMENTATION_SCHEMES = {
+    "log1p_drop": Log1pDrop(p_drop=0.1),
+    "log1p_mask": _unsupported_scheme("log1p_mask"),
+    "log1p_poisson": _unsupported_scheme("log1p_poisson"),
+    "log1p_poisson_drop": _unsupported_scheme("log1p_poisson_drop"),
+    "count_poisson": _unsupported_scheme("count_poisson"),
+    "None": identity,
+    "none": identity,
+    None: identity,
+}

@@ -388,11 +388,11 @@ class TrainEngine(object):
         call("scnb_softmax_mse_fwd_bwd", ptr(self.logits), U, C, ptr(self.counts), ptr(self.Ycat), ptr(self.srcA),
              ptr(self.srcB), ptr(self.gam), 0, U, None, self.unsup_weight, ptr(self.dlogits), ptr(self.loss_buf[2:]), st)
         call("scnb_soft_ce_fwd_bwd", ptr(self.logits[U:]), L, C, None, ptr(self.Ycat), ptr(self.srcA), ptr(self.srcB),
-             ptr(self.gam), U, ptr(self.class_weight), None, L, 1.0, None, ptr(self.dlogits[U:]), ptr(self.loss_buf), 1, st)
+             ptr(self.gam), U, ptr(self.class_weight), None, L, 1.0, None, ptr(self.dlogits[U:]), ptr(self.loss_buf), 1, None, st)
         if self.use_dan:
             call("scnb_soft_ce_fwd_bwd", ptr(self.dlog), self.Rd, self.D, ptr(self.counts[2:]), ptr(self.dlabel), None, None,
                  None, 0, None, ptr(self.counts[2:]), 0, 1.0, ptr(self.pconf) if c.dan_scale_loss_pseudoconf else None,
-                 ptr(self.ddlog), ptr(self.loss_buf[4:]), 1, st)
+                 ptr(self.ddlog), ptr(self.loss_buf[4:]), 1, None, st)
         # -- backward
         Hh = self.H
         dA_last = self._view(self.dA, R, Hh)
@@ -492,6 +492,35 @@ class TrainEngine(object):
             sp = [ptr(self.stats[b]) for b in apps] + [None] * (4 - len(apps))
             call("scnb_bn_running_update", ptr(bn.running_mean), ptr(bn.running_var), ptr(bn.num_batches_tracked), sp[0], sp[1],
                  sp[2], sp[3], ptr(self.seg_off), self.n_seg, self.widths[a], float(bn.momentum), st)
+        if self.loss_hist is not None:
+            mm = self.mode == "mixmatch"
+            call("scnb_record_step", ptr(self.loss_buf), ptr(self.loss_hist), int(self.loss_hist.shape[0]),
+                 ptr(self.conf) if mm else None, self.U if mm else 0, ptr(self.conf_ring) if mm else None,
+                 int(self.conf_ring.shape[0]) if mm else 0, ptr(self.state), st)
+
+    def enable_history(self, capacity: int, ring: int = 64):
+        """Keep per-step loss scalars (and the last `ring` steps' pseudolabel confidences) on the
+        device; `history()` reads them back once (epoch end) instead of the reference's per-step
+        `.item()` / `.cpu()` synchronisations (trainer.py:666-681, losses.py:714-725)."""
+        if self.loss_hist is None or self.loss_hist.shape[0] != capacity:
+            self.loss_hist = torch.zeros((capacity, 8), dtype=torch.float32, device=self.dev)
+            self.conf_ring = torch.zeros((ring, max(self.U, 1)), dtype=torch.float32, device=self.dev)
+            self._graph = None
+        self._hist_t0 = int(self.steps_done)
+
+    def history(self):
+        """(losses [n,8] numpy in step order since enable_history, confidences [(<=ring), U])."""
+        torch.cuda.synchronize()
+        n = int(self.steps_done) - self._hist_t0
+        cap = self.loss_hist.shape[0]
+        t_first = int(self.state[0].item()) - n
+        idx = [(t_first + i) % cap for i in range(n)]
+        h = self.loss_hist.cpu().numpy()[idx]
+        ring = self.conf_ring.shape[0]
+        m = min(n, ring)
+        t_end = int(self.state[0].item())
+        ridx = [(t_end - m + i) % ring for i in range(m)]
+        return h, self.conf_ring.cpu().numpy()[ridx]
 
     # ------------------------------------------------------------------------------------
     def _launch_supervised(self):
@@ -515,7 +544,7 @@ class TrainEngine(object):
              ptr(self.logits), C, 1.0, 0.0, self.P("model.classif.0.bias"), 0, None, st)
         call("scnb_onehot_rows", ptr(self.lab_ids), None, 0, L, C, ptr(self.Ycat), st)
         call("scnb_soft_ce_fwd_bwd", ptr(self.logits), L, C, None, ptr(self.Ycat), None, None, None, 0, ptr(self.class_weight),
-             None, L, 1.0, None, ptr(self.dlogits), ptr(self.loss_buf), 1, st)
+             None, L, 1.0, None, ptr(self.dlogits), ptr(self.loss_buf), 1, None, st)
         Hh = self.H
         dA_last = self._view(self.dA, L, Hh)
         call("scnb_sgemm", 0, 0, L, Hh, C, ptr(self.dlogits), C, self.P("model.classif.0.weight"), Hh, ptr(dA_last), Hh, 1.0, 0.0,

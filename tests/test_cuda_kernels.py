@@ -316,7 +316,7 @@ def test_losses_match_oracle_autograd():
     loss.backward()
     dz, lo = torch.empty(n, C).cuda(), torch.zeros(2).cuda()
     call("scnb_soft_ce_fwd_bwd", ptr(D(z.detach().float())), n, C, None, ptr(D(Y)), None, None, None, 0, ptr(D(cw)),
-         None, n, 1.0, None, ptr(dz), ptr(lo), 1, _st())
+         None, n, 1.0, None, ptr(dz), ptr(lo), 1, None, _st())
     _chk("ce loss", lo[0].cpu(), loss.detach())
     _chk("ce grad", dz.cpu(), z.grad, tol=2e-5)
     assert int(lo[1]) == int((z.argmax(1) == Y.argmax(1)).sum())
