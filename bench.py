@@ -107,7 +107,7 @@ def time_device_resident(args, device, rank, world):
     from scnym_b200.engine import TrainEngine
     model, dann, cfg, lab, y, unl = build_train(device, rank)
     eng = TrainEngine(model.to(device), cfg, lab, y.to(torch.int32), CFG["L"], unlabeled=unl, unlabeled_batch_size=CFG["U"],
-                      dann=dann, mode="mixmatch")
+                      dann=dann, mode="mixmatch", comm=make_comm(world))
     eng.set_weights(unsup_weight=1.0, dan_weight=0.1)
     n_tab = args.steps + args.warmup
     gen = torch.Generator(device=device)
@@ -198,7 +198,7 @@ def time_e2e(args, device, rank, world):
     fu = HostBatchFeeder(unl.indptr.cpu().numpy(), unl.indices.cpu().numpy(), unl.data.cpu().numpy(), c["G"], c["U"], device)
     del lab, unl
     eng = TrainEngine(model.to(device), cfg, fl.csr, fl.d_y, c["L"], unlabeled=fu.csr, unlabeled_batch_size=c["U"], dann=dann,
-                      mode="mixmatch")
+                      mode="mixmatch", comm=make_comm(world))
     eng.set_weights(1.0, 0.1)
     eng.l_rows.copy_(torch.arange(c["L"]))
     eng.u_rows.copy_(torch.arange(c["U"]))
@@ -317,6 +317,14 @@ def cpu_reference_step_time(n_steps, warmup, budget_s=25.0, seed=0):
         if s >= warmup and time.perf_counter() - t_start > budget_s:
             break
     return t_all / done, t_comp / done, done
+
+
+def make_comm(world):
+    """Data-parallel communicator (NCCL) when launched under torchrun; None for a single process."""
+    if world <= 1:
+        return None
+    from scnym_b200.parallel import TorchDistComm
+    return TorchDistComm()
 
 
 def barrier(world):

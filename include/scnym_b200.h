@@ -83,16 +83,19 @@ int scnb_relu_bwd(const float* g, const float* y, float* out, long long n, void*
 int scnb_bn_act_fwd(const float* Z, float* A, float* pre_out, int H, int n_seg, const int32_t* seg_off_dev, int max_rows,
                     int train, const float* gamma, const float* beta, const float* running_mean,
                     const float* running_var, float* stats, const uint8_t* keep_mask, const uint64_t* rng,
-                    uint32_t stream_id, float p_drop, int relu, void* stream);
+                    uint32_t stream_id, float p_drop, int relu,
+                    float* dp_partial_out /*[n_seg*2*H + n_seg]: local sum z, sum z^2, row counts; no apply*/,
+                    const float* dp_sums /*same layout after the cross-rank all-reduce*/, void* stream);
 int scnb_bn_act_bwd(const float* dA, const float* Z, const float* A, int H, int n_seg, const int32_t* seg_off_dev,
                     int max_rows, const float* gamma, const float* stats, const uint8_t* keep_mask, const uint64_t* rng,
                     uint32_t stream_id, float p_drop, int relu, float* dZ, float* dgamma /*+=*/, float* dbeta /*+=*/,
-                    void* stream);
+                    float* dp_partial_out /*local sum dy, sum dy*zhat, counts*/, const float* dp_sums, void* stream);
 int scnb_bn_eval_bwd(const float* dA, const float* A, int relu, int rows, int H, const float* gamma,
                      const float* running_var, float* dZ, void* stream);
 int scnb_bn_running_update(float* running_mean, float* running_var, int64_t* num_batches_tracked, const float* stats0,
                            const float* stats1, const float* stats2, const float* stats3 /*shared block: one per application*/,
-                           const int32_t* seg_off_dev, int n_seg, int H, float momentum, void* stream);
+                           const int32_t* seg_off_dev, int n_seg, int H, float momentum,
+                           const float* dp_cnt /*NULL or global rows per segment*/, void* stream);
 
 /* ---- K3: SampleMixUp (scnym/dataprep.py:638-705) folded behind the first layer (linearity):
  *      out[i] = gam[i] Z[srcA[i]] + (1-gam[i]) Z[srcB[i]];  adjoint gathers through inverse maps. ---- */

@@ -26,9 +26,9 @@ SIGNATURES = {
     "scnb_colsum": [P, I, I, I, P, I, P],
     "scnb_relu_bwd": [P, P, P, L, P],
     "scnb_bn_eval_bwd": [P, P, I, I, I, P, P, P, P],
-    "scnb_bn_act_fwd": [P, P, P, I, I, P, I, I, P, P, P, P, P, P, P, U32, F, I, P],
-    "scnb_bn_act_bwd": [P, P, P, I, I, P, I, P, P, P, P, U32, F, I, P, P, P, P],
-    "scnb_bn_running_update": [P, P, P, P, P, P, P, P, I, I, F, P],
+    "scnb_bn_act_fwd": [P, P, P, I, I, P, I, I, P, P, P, P, P, P, P, U32, F, I, P, P, P],
+    "scnb_bn_act_bwd": [P, P, P, I, I, P, I, P, P, P, P, U32, F, I, P, P, P, P, P, P],
+    "scnb_bn_running_update": [P, P, P, P, P, P, P, P, I, I, F, P, P],
     "scnb_mix_rows": [P, I, P, P, P, P, I, P, P],
     "scnb_unmix_rows": [P, I, P, P, I, P, P],
     "scnb_pseudolabel": [P, I, I, I, F, I, F, P, P, P, P, P],

@@ -235,7 +235,12 @@ __global__ void __launch_bounds__(1024) k_bn_act_fwd(const float* __restrict__ Z
                                                      const float* __restrict__ rmean, const float* __restrict__ rvar,
                                                      float* __restrict__ stats, const uint8_t* __restrict__ keep_mask,
                                                      const uint64_t* __restrict__ rng, uint32_t stream_id, float p_drop,
-                                                     int relu) {
+                                                     int relu, float* __restrict__ partial_out,
+                                                     const float* __restrict__ ext_sums, const float* __restrict__ ext_cnt) {
+  // Data-parallel (cross-rank BatchNorm statistics) protocol:
+  //   pass 1  partial_out != NULL : write local [seg][0]=sum z, [seg][1]=sum z^2, [n_seg*2*H + seg]=row count; no apply
+  //   (all-reduce SUM of that buffer over ranks)
+  //   pass 2  ext_sums != NULL    : statistics from the reduced sums / counts (ext_cnt), then apply
   __shared__ float red[BN_RL][BN_CW];
   const int cx = threadIdx.x & (BN_CW - 1), ry = threadIdx.x / BN_CW;
   const int c = blockIdx.x * BN_CW + cx;
@@ -251,18 +256,42 @@ __global__ void __launch_bounds__(1024) k_bn_act_fwd(const float* __restrict__ Z
     const int r0 = seg_off[s], r1 = min(seg_off[s + 1], max_rows);
     const int n = r1 - r0;
     float mean, invstd;
-    if (train) {
-      float acc = 0.f;
-      if (cok)
-        for (int r = r0 + ry; r < r1; r += BN_RL) acc += Z[(size_t)r * H + c];
-      mean = bn_block_colsum(acc, red, cx, ry) / (float)max(n, 1);
-      acc = 0.f;
+    if (train && partial_out) {
+      float a1 = 0.f, a2 = 0.f;
       if (cok)
         for (int r = r0 + ry; r < r1; r += BN_RL) {
-          const float d = Z[(size_t)r * H + c] - mean;
-          acc = fmaf(d, d, acc);
+          const float z = Z[(size_t)r * H + c];
+          a1 += z;
+          a2 = fmaf(z, z, a2);
         }
-      const float var = bn_block_colsum(acc, red, cx, ry) / (float)max(n, 1);
+      a1 = bn_block_colsum(a1, red, cx, ry);
+      a2 = bn_block_colsum(a2, red, cx, ry);
+      if (cok && ry == 0) {
+        partial_out[((size_t)s * 2 + 0) * H + c] = a1;
+        partial_out[((size_t)s * 2 + 1) * H + c] = a2;
+      }
+      if (blockIdx.x == 0 && threadIdx.x == 0) partial_out[(size_t)n_seg * 2 * H + s] = (float)n;
+      continue;
+    }
+    if (train) {
+      float var;
+      if (ext_sums) {
+        const float ng = fmaxf(ext_cnt[s], 1.f);
+        mean = cok ? ext_sums[((size_t)s * 2 + 0) * H + c] / ng : 0.f;
+        var = cok ? fmaxf(ext_sums[((size_t)s * 2 + 1) * H + c] / ng - mean * mean, 0.f) : 1.f;
+      } else {
+        float acc = 0.f;
+        if (cok)
+          for (int r = r0 + ry; r < r1; r += BN_RL) acc += Z[(size_t)r * H + c];
+        mean = bn_block_colsum(acc, red, cx, ry) / (float)max(n, 1);
+        acc = 0.f;
+        if (cok)
+          for (int r = r0 + ry; r < r1; r += BN_RL) {
+            const float d = Z[(size_t)r * H + c] - mean;
+            acc = fmaf(d, d, acc);
+          }
+        var = bn_block_colsum(acc, red, cx, ry) / (float)max(n, 1);
+      }
       invstd = 1.0f / sqrtf(var + BN_EPS);
       if (cok && ry == 0 && stats) {
         stats[((size_t)s * 3 + 0) * H + c] = mean;
@@ -283,7 +312,7 @@ __global__ void __launch_bounds__(1024) k_bn_act_fwd(const float* __restrict__ Z
       }
   }
   // inactive tail rows
-  if (cok)
+  if (cok && !(train && partial_out))
     for (int r = min(seg_off[n_seg], max_rows) + ry; r < max_rows; r += BN_RL) {
       Aout[(size_t)r * H + c] = 0.f;
       if (pre_out) pre_out[(size_t)r * H + c] = 0.f;
@@ -293,14 +322,18 @@ __global__ void __launch_bounds__(1024) k_bn_act_fwd(const float* __restrict__ Z
 extern "C" int scnb_bn_act_fwd(const float* Z, float* A, float* pre_out, int H, int n_seg, const int32_t* seg_off_dev,
                                int max_rows, int train, const float* gamma, const float* beta, const float* running_mean,
                                const float* running_var, float* stats, const uint8_t* keep_mask, const uint64_t* rng,
-                               uint32_t stream_id, float p_drop, int relu, void* stream) {
+                               uint32_t stream_id, float p_drop, int relu, float* dp_partial_out, const float* dp_sums,
+                               void* stream) {
   SCNB_CHECK_ARG(Z && A && gamma && beta && seg_off_dev && H > 0 && n_seg > 0 && max_rows >= 0, "bn_act_fwd: bad arguments");
   SCNB_CHECK_ARG(train || (running_mean && running_var), "bn_act_fwd: eval mode needs running statistics");
   SCNB_CHECK_ARG(!(train && p_drop > 0.f) || keep_mask || rng, "bn_act_fwd: dropout needs keep_mask or rng state");
   SCNB_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "bn_act_fwd: p_drop out of range");
+  SCNB_CHECK_ARG(!(dp_partial_out && dp_sums), "bn_act_fwd: partial and reduced statistics are exclusive");
+  const float* ext_cnt = dp_sums ? dp_sums + (size_t)n_seg * 2 * H : nullptr;
   k_bn_act_fwd<<<scnb_cdiv(H, BN_CW), 1024, 0, (cudaStream_t)stream>>>(Z, A, pre_out, H, n_seg, seg_off_dev, max_rows, train,
                                                                         gamma, beta, running_mean, running_var, stats,
-                                                                        keep_mask, rng, stream_id, p_drop, relu);
+                                                                        keep_mask, rng, stream_id, p_drop, relu,
+                                                                        dp_partial_out, dp_sums, ext_cnt);
   SCNB_CHECK_LAUNCH("bn_act_fwd");
   return SCNB_OK;
 }
@@ -314,7 +347,12 @@ __global__ void __launch_bounds__(1024) k_bn_act_bwd(const float* __restrict__ d
                                                      const float* __restrict__ gamma, const float* __restrict__ stats,
                                                      const uint8_t* __restrict__ keep_mask, const uint64_t* __restrict__ rng,
                                                      uint32_t stream_id, float p_drop, int relu, float* __restrict__ dZ,
-                                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                     float* __restrict__ partial_out, const float* __restrict__ ext_sums,
+                                                     const float* __restrict__ ext_cnt) {
+  // Data-parallel protocol as in the forward: pass 1 (partial_out) writes the local column sums
+  // [seg][0]=sum dy, [seg][1]=sum dy*zhat and accumulates the local dgamma/dbeta; after the
+  // all-reduce, pass 2 (ext_sums) forms dZ from the global sums and global row counts.
   __shared__ float red[BN_RL][BN_CW];
   const int cx = threadIdx.x & (BN_CW - 1), ry = threadIdx.x / BN_CW;
   const int c = blockIdx.x * BN_CW + cx;
@@ -333,20 +371,34 @@ __global__ void __launch_bounds__(1024) k_bn_act_bwd(const float* __restrict__ d
     const float mean = cok ? stats[((size_t)s * 3 + 0) * H + c] : 0.f;
     const float invstd = cok ? stats[((size_t)s * 3 + 2) * H + c] : 1.f;
     float s1 = 0.f, s2 = 0.f;
-    if (cok)
-      for (int r = r0 + ry; r < r1; r += BN_RL) {
-        const size_t o = (size_t)r * H + c;
-        float dy = dA[o];
-        if (relu && !(Aact[o] > 0.f)) dy = 0.f;
-        if (p_drop > 0.f) dy = dropout_keep(keep_mask, o, seed, strm, p_drop) ? dy * drop_scale : 0.f;
-        s1 += dy;
-        s2 = fmaf(dy, (Z[o] - mean) * invstd, s2);
+    float inv_n = 1.0f / (float)max(n, 1);
+    if (ext_sums) {
+      s1 = cok ? ext_sums[((size_t)s * 2 + 0) * H + c] : 0.f;
+      s2 = cok ? ext_sums[((size_t)s * 2 + 1) * H + c] : 0.f;
+      inv_n = 1.0f / fmaxf(ext_cnt[s], 1.f);
+    } else {
+      if (cok)
+        for (int r = r0 + ry; r < r1; r += BN_RL) {
+          const size_t o = (size_t)r * H + c;
+          float dy = dA[o];
+          if (relu && !(Aact[o] > 0.f)) dy = 0.f;
+          if (p_drop > 0.f) dy = dropout_keep(keep_mask, o, seed, strm, p_drop) ? dy * drop_scale : 0.f;
+          s1 += dy;
+          s2 = fmaf(dy, (Z[o] - mean) * invstd, s2);
+        }
+      s1 = bn_block_colsum(s1, red, cx, ry);
+      s2 = bn_block_colsum(s2, red, cx, ry);
+      dg_tot += s2;
+      db_tot += s1;
+      if (partial_out) {
+        if (cok && ry == 0) {
+          partial_out[((size_t)s * 2 + 0) * H + c] = s1;
+          partial_out[((size_t)s * 2 + 1) * H + c] = s2;
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) partial_out[(size_t)n_seg * 2 * H + s] = (float)n;
+        continue;
       }
-    s1 = bn_block_colsum(s1, red, cx, ry);
-    s2 = bn_block_colsum(s2, red, cx, ry);
-    dg_tot += s2;
-    db_tot += s1;
-    const float inv_n = 1.0f / (float)max(n, 1);
+    }
     const float m1 = s1 * inv_n, m2 = s2 * inv_n, k = g * invstd;
     if (cok)
       for (int r = r0 + ry; r < r1; r += BN_RL) {
@@ -359,8 +411,9 @@ __global__ void __launch_bounds__(1024) k_bn_act_bwd(const float* __restrict__ d
       }
   }
   if (cok) {
-    for (int r = min(seg_off[n_seg], max_rows) + ry; r < max_rows; r += BN_RL) dZ[(size_t)r * H + c] = 0.f;
-    if (ry == 0) {
+    if (!partial_out)
+      for (int r = min(seg_off[n_seg], max_rows) + ry; r < max_rows; r += BN_RL) dZ[(size_t)r * H + c] = 0.f;
+    if (ry == 0 && !ext_sums) {
       dgamma[c] += dg_tot;
       dbeta[c] += db_tot;
     }
@@ -370,13 +423,15 @@ __global__ void __launch_bounds__(1024) k_bn_act_bwd(const float* __restrict__ d
 extern "C" int scnb_bn_act_bwd(const float* dA, const float* Z, const float* A, int H, int n_seg, const int32_t* seg_off_dev,
                                int max_rows, const float* gamma, const float* stats, const uint8_t* keep_mask,
                                const uint64_t* rng, uint32_t stream_id, float p_drop, int relu, float* dZ, float* dgamma,
-                               float* dbeta, void* stream) {
+                               float* dbeta, float* dp_partial_out, const float* dp_sums, void* stream) {
   SCNB_CHECK_ARG(dA && Z && A && gamma && stats && dZ && dgamma && dbeta && seg_off_dev && H > 0 && n_seg > 0,
                  "bn_act_bwd: bad arguments");
   SCNB_CHECK_ARG(!(p_drop > 0.f) || keep_mask || rng, "bn_act_bwd: dropout needs keep_mask or rng state");
+  SCNB_CHECK_ARG(!(dp_partial_out && dp_sums), "bn_act_bwd: partial and reduced sums are exclusive");
+  const float* ext_cnt = dp_sums ? dp_sums + (size_t)n_seg * 2 * H : nullptr;
   k_bn_act_bwd<<<scnb_cdiv(H, BN_CW), 1024, 0, (cudaStream_t)stream>>>(dA, Z, A, H, n_seg, seg_off_dev, max_rows, gamma, stats,
                                                                         keep_mask, rng, stream_id, p_drop, relu, dZ, dgamma,
-                                                                        dbeta);
+                                                                        dbeta, dp_partial_out, dp_sums, ext_cnt);
   SCNB_CHECK_LAUNCH("bn_act_bwd");
   return SCNB_OK;
 }
@@ -388,7 +443,7 @@ extern "C" int scnb_bn_act_bwd(const float* dA, const float* Z, const float* A, 
 struct StatsList { const float* p[4]; };
 __global__ void k_bn_running_update(float* __restrict__ rmean, float* __restrict__ rvar, int64_t* __restrict__ nbt,
                                     StatsList sl, int n_stats, const int32_t* __restrict__ seg_off, int n_seg, int H,
-                                    float momentum) {
+                                    float momentum, const float* __restrict__ dp_cnt) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   int applied = 0;
   float rm = 0.f, rv = 0.f;
@@ -397,7 +452,7 @@ __global__ void k_bn_running_update(float* __restrict__ rmean, float* __restrict
     rv = rvar[c];
   }
   for (int s = 0; s < n_seg; ++s) {
-    const int n = seg_off[s + 1] - seg_off[s];
+    const int n = dp_cnt ? (int)dp_cnt[s] : seg_off[s + 1] - seg_off[s];  // global rows under data parallelism
     if (n <= 0) continue;
     for (int a = 0; a < n_stats; ++a) {
       ++applied;
@@ -419,14 +474,15 @@ __global__ void k_bn_running_update(float* __restrict__ rmean, float* __restrict
 
 extern "C" int scnb_bn_running_update(float* running_mean, float* running_var, int64_t* num_batches_tracked,
                                       const float* stats0, const float* stats1, const float* stats2, const float* stats3,
-                                      const int32_t* seg_off_dev, int n_seg, int H, float momentum, void* stream) {
+                                      const int32_t* seg_off_dev, int n_seg, int H, float momentum, const float* dp_cnt,
+                                      void* stream) {
   SCNB_CHECK_ARG(running_mean && running_var && stats0 && seg_off_dev && n_seg > 0 && H > 0, "bn_running_update: bad arguments");
   StatsList sl;
   sl.p[0] = stats0; sl.p[1] = stats1; sl.p[2] = stats2; sl.p[3] = stats3;
   int n_stats = 1;
   while (n_stats < 4 && sl.p[n_stats]) ++n_stats;
   k_bn_running_update<<<scnb_cdiv(H, 256), 256, 0, (cudaStream_t)stream>>>(running_mean, running_var, num_batches_tracked, sl,
-                                                                            n_stats, seg_off_dev, n_seg, H, momentum);
+                                                                            n_stats, seg_off_dev, n_seg, H, momentum, dp_cnt);
   SCNB_CHECK_LAUNCH("bn_running_update");
   return SCNB_OK;
 }

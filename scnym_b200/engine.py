@@ -130,11 +130,12 @@ class TrainEngine(object):
     def __init__(self, model: CellTypeCLF, cfg: EngineConfig, labeled: DeviceCSR, labeled_y, batch_size: int,
                  unlabeled: Optional[DeviceCSR] = None, unlabeled_batch_size: Optional[int] = None,
                  dann: Optional[DANN] = None, labeled_domain=None, unlabeled_domain=None, mode: str = "mixmatch",
-                 extra_named_params: Optional[List] = None) -> None:
+                 extra_named_params: Optional[List] = None, comm=None) -> None:
         if not torch.cuda.is_available():
             raise _lib.ScnbError("TrainEngine needs a CUDA device (no CPU fallback)")
         _lib.lib()
         self.model, self.cfg, self.mode = model, cfg, mode
+        self.comm = comm if (comm is not None and comm.world > 1) else None
         self.dev = labeled.device
         dev = self.dev
         self.lab, self.unl = labeled, unlabeled
@@ -252,6 +253,14 @@ class TrainEngine(object):
         self.Zs = [f32(R, w) for w in self.widths]
         self.As = [f32(R, w) for w in self.widths]
         self.stats = [f32(3, 3, w) for w in self.widths]
+        if self.comm is not None:
+            # cross-rank exchange buffers per application: [n_seg][2][w] sums + [n_seg] row counts
+            self.dp_fwd = [f32(self.n_seg * 2 * w + self.n_seg) for w in self.widths]
+            self.dp_bwd = [f32(self.n_seg * 2 * w + self.n_seg) for w in self.widths]
+            self.comm.broadcast(self.arena.flat)  # identical replicas to start from
+            for b in self._blk:
+                self.comm.broadcast(b["bn"].running_mean)
+                self.comm.broadcast(b["bn"].running_var)
         self.logits = f32(self.nb if mode == "mixmatch" else L, self.C)
         self.dlogits = torch.zeros_like(self.logits)
         wmax = max(self.widths)
@@ -354,7 +363,7 @@ class TrainEngine(object):
         for a in range(self.n_app):
             rm, rv = tbn(a)
             call("scnb_bn_act_fwd", ptr(tz), ptr(self.TA[a]), None, self.widths[a], 1, ptr(seg_t), KU, 0, ptr(tw(blk[a]["g"])),
-                 ptr(tw(blk[a]["beta"])), ptr(rm), ptr(rv), None, None, None, 0, 0.0, 1, st)
+                 ptr(tw(blk[a]["beta"])), ptr(rm), ptr(rv), None, None, None, 0, 0.0, 1, None, None, st)
             if a + 1 < self.n_app:
                 call("scnb_sgemm", 0, 1, KU, self.widths[a + 1], self.widths[a], ptr(self.TA[a]), self.widths[a],
                      ptr(tw(blk[a + 1]["W"])), self.widths[a], ptr(self.TZ[a + 1]), self.widths[a + 1], 1.0, 0.0,
@@ -447,9 +456,16 @@ class TrainEngine(object):
         for a in range(self.n_app):
             w = self.widths[a]
             p = float(blk[a]["drop"].p)
-            call("scnb_bn_act_fwd", ptr(self.Zs[a]), ptr(self.As[a]), None, w, self.n_seg, ptr(self.seg_off), R, 1,
-                 self.P(blk[a]["g"]), self.P(blk[a]["beta"]), None, None, ptr(self.stats[a]), self._hidden_keep(a), rng,
-                 SID_HID + a, p, 1, st)
+            fwd = lambda part, sums: call(
+                "scnb_bn_act_fwd", ptr(self.Zs[a]), ptr(self.As[a]), None, w, self.n_seg, ptr(self.seg_off), R, 1,
+                self.P(blk[a]["g"]), self.P(blk[a]["beta"]), None, None, ptr(self.stats[a]), self._hidden_keep(a), rng,
+                SID_HID + a, p, 1, part, sums, st)
+            if self.comm is None:
+                fwd(None, None)
+            else:  # cross-rank BatchNorm statistics: local sums -> all-reduce -> apply
+                fwd(ptr(self.dp_fwd[a]), None)
+                self.comm.all_reduce_sum(self.dp_fwd[a])
+                fwd(None, ptr(self.dp_fwd[a]))
             if a + 1 < self.n_app:
                 w2 = self.widths[a + 1]
                 call("scnb_sgemm", 0, 1, R, w2, w, ptr(self.As[a]), w, self.P(blk[a + 1]["W"]), w, ptr(self.Zs[a + 1]), w2, 1.0,
@@ -462,9 +478,16 @@ class TrainEngine(object):
             w = self.widths[a]
             p = float(blk[a]["drop"].p)
             dZ = self._view(self.dZ, R, w)
-            call("scnb_bn_act_bwd", ptr(dA), ptr(self.Zs[a]), ptr(self.As[a]), w, self.n_seg, ptr(self.seg_off), R,
-                 self.P(blk[a]["g"]), ptr(self.stats[a]), self._hidden_keep(a), rng, SID_HID + a, p, 1, ptr(dZ),
-                 self.Gp(blk[a]["g"]), self.Gp(blk[a]["beta"]), st)
+            bwd = lambda part, sums: call(
+                "scnb_bn_act_bwd", ptr(dA), ptr(self.Zs[a]), ptr(self.As[a]), w, self.n_seg, ptr(self.seg_off), R,
+                self.P(blk[a]["g"]), ptr(self.stats[a]), self._hidden_keep(a), rng, SID_HID + a, p, 1, ptr(dZ),
+                self.Gp(blk[a]["g"]), self.Gp(blk[a]["beta"]), part, sums, st)
+            if self.comm is None:
+                bwd(None, None)
+            else:
+                bwd(ptr(self.dp_bwd[a]), None)
+                self.comm.all_reduce_sum(self.dp_bwd[a])
+                bwd(None, ptr(self.dp_bwd[a]))
             if a == 0:
                 return dZ
             wp = self.widths[a - 1]
@@ -478,6 +501,8 @@ class TrainEngine(object):
     def _finish_step(self, st):
         """optimizer.step() + BatchNorm running statistics in the reference's update order."""
         c = self.cfg
+        if self.comm is not None:
+            self.comm.all_reduce_avg(self.arena.grad)  # data-parallel gradient exchange (NCCL over NVLink)
         call("scnb_optim_step", OPTIMIZER_CODES[c.optimizer], ptr(self.arena.flat), ptr(self.arena.grad),
              ptr(self.arena.state1), ptr(self.arena.state2), self.arena.total, ptr(self.hp), ptr(self.state), st)
         done = set()
@@ -491,7 +516,8 @@ class TrainEngine(object):
                 raise NotImplementedError("a BatchNorm module shared by more than 4 applications (n_layers > 5)")
             sp = [ptr(self.stats[b]) for b in apps] + [None] * (4 - len(apps))
             call("scnb_bn_running_update", ptr(bn.running_mean), ptr(bn.running_var), ptr(bn.num_batches_tracked), sp[0], sp[1],
-                 sp[2], sp[3], ptr(self.seg_off), self.n_seg, self.widths[a], float(bn.momentum), st)
+                 sp[2], sp[3], ptr(self.seg_off), self.n_seg, self.widths[a], float(bn.momentum),
+                 ptr(self.dp_fwd[a][self.n_seg * 2 * self.widths[a]:]) if self.comm is not None else None, st)
         if self.loss_hist is not None:
             mm = self.mode == "mixmatch"
             call("scnb_record_step", ptr(self.loss_buf), ptr(self.loss_hist), int(self.loss_hist.shape[0]),

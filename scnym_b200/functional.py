@@ -179,12 +179,12 @@ class _BnActFn(torch.autograd.Function):
         stats = torch.empty((1, 3, H), device=z.device, dtype=torch.float32) if training else None
         call("scnb_bn_act_fwd", ptr(z), ptr(a), None, H, 1, ptr(seg), n, int(training), ptr(gamma), ptr(beta),
              ptr(bn.running_mean), ptr(bn.running_var), ptr(stats), ptr(keep), None, 0,
-             float(p_drop if training else 0.0), int(relu), _stream())
+             float(p_drop if training else 0.0), int(relu), None, None, _stream())
         if training:
             if n < 2:
                 raise ValueError("Expected more than 1 value per channel when training")
             call("scnb_bn_running_update", ptr(bn.running_mean), ptr(bn.running_var), ptr(bn.num_batches_tracked), ptr(stats),
-                 None, None, None, ptr(seg), 1, H, float(bn.momentum), _stream())
+                 None, None, None, ptr(seg), 1, H, float(bn.momentum), None, _stream())
         ctx.training, ctx.p_drop, ctx.relu, ctx.bn = training, float(p_drop if training else 0.0), relu, bn
         ctx.save_for_backward(z, a, gamma, stats, keep, seg)
         return a
@@ -199,7 +199,7 @@ class _BnActFn(torch.autograd.Function):
             dgamma = torch.zeros((H,), device=z.device, dtype=torch.float32)
             dbeta = torch.zeros((H,), device=z.device, dtype=torch.float32)
             call("scnb_bn_act_bwd", ptr(g), ptr(z), ptr(a), H, 1, ptr(seg), n, ptr(gamma), ptr(stats), ptr(keep), None, 0,
-                 ctx.p_drop, int(ctx.relu), ptr(dz), ptr(dgamma), ptr(dbeta), _stream())
+                 ctx.p_drop, int(ctx.relu), ptr(dz), ptr(dgamma), ptr(dbeta), None, None, _stream())
         else:
             call("scnb_bn_eval_bwd", ptr(g), ptr(a), int(ctx.relu), n, H, ptr(gamma), ptr(ctx.bn.running_var), ptr(dz), _stream())
             dgamma = dbeta = None

@@ -62,7 +62,7 @@ class EvalRunner(object):
                 last = a == len(blocks) - 1
                 pre = embed if (last and mi == 0 and embed is not None) else None
                 call("scnb_bn_act_fwd", ptr(self.Z[a]), ptr(self.A[a]), ptr(pre), w, 1, ptr(self.seg), n, 0, ptr(bn.weight),
-                     ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var), None, None, None, 0, 0.0, 1, st)
+                     ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var), None, None, None, 0, 0.0, 1, None, None, st)
             clf = model.classif[0]
             H = self.widths[-1]
             call("scnb_sgemm", 0, 1, n, self.C, H, ptr(self.A[-1]), H, ptr(clf.weight), H, ptr(self.logits), self.C, 1.0,

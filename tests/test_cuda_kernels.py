@@ -161,13 +161,13 @@ def test_bn_act_fwd_bwd(H, segs, maxr):
     stats = torch.zeros(len(segs), 3, H).cuda()
     Zc, gc, bc, kc = Z.cuda(), g.cuda(), b.cuda(), keep.cuda()
     call("scnb_bn_act_fwd", ptr(Zc), ptr(A), None, H, len(segs), ptr(seg), maxr, 1, ptr(gc), ptr(bc), None, None, ptr(stats),
-         ptr(kc), None, 0, 0.5, 1, _st())
+         ptr(kc), None, 0, 0.5, 1, None, None, _st())
     _chk("bn fwd", A[:n_act].cpu(), A_ref.detach())
     assert float(A[n_act:].abs().sum()) == 0.0
     dZ = torch.full((maxr, H), 7.0).cuda()
     dg, db = torch.zeros(H).cuda(), torch.zeros(H).cuda()
     call("scnb_bn_act_bwd", ptr(D(dA)), ptr(Zc), ptr(A), H, len(segs), ptr(seg), maxr, ptr(gc), ptr(stats), ptr(kc), None, 0,
-         0.5, 1, ptr(dZ), ptr(dg), ptr(db), _st())
+         0.5, 1, ptr(dZ), ptr(dg), ptr(db), None, None, _st())
     _chk("bn dZ", dZ[:n_act].cpu(), Zd.grad[:n_act], tol=2e-5)
     _chk("bn dgamma", dg.cpu(), gd.grad, tol=2e-5)
     _chk("bn dbeta", db.cpu(), bd.grad, tol=2e-5)
@@ -180,7 +180,7 @@ def test_bn_act_fwd_bwd(H, segs, maxr):
         rv = 0.9 * rv + 0.1 * z.var(0, unbiased=True)
     rmc, rvc = torch.zeros(H).cuda(), torch.ones(H).cuda()
     nbt = torch.zeros((), dtype=torch.int64).cuda()
-    call("scnb_bn_running_update", ptr(rmc), ptr(rvc), ptr(nbt), ptr(stats), None, None, None, ptr(seg), len(segs), H, 0.1, _st())
+    call("scnb_bn_running_update", ptr(rmc), ptr(rvc), ptr(nbt), ptr(stats), None, None, None, ptr(seg), len(segs), H, 0.1, None, _st())
     _chk("running_mean", rmc.cpu(), rm)
     _chk("running_var", rvc.cpu(), rv)
     assert int(nbt) == len(segs)
@@ -188,7 +188,7 @@ def test_bn_act_fwd_bwd(H, segs, maxr):
     Ae = torch.empty(maxr, H).cuda()
     pre = torch.empty(maxr, H).cuda()
     call("scnb_bn_act_fwd", ptr(Zc), ptr(Ae), ptr(pre), H, 1, ptr(D(torch.tensor([0, maxr], dtype=torch.int32))), maxr, 0,
-         ptr(gc), ptr(bc), ptr(rmc), ptr(rvc), None, None, None, 0, 0.0, 1, _st())
+         ptr(gc), ptr(bc), ptr(rmc), ptr(rvc), None, None, None, 0, 0.0, 1, None, None, _st())
     want = (Z.double() - rmc.cpu().double()) / torch.sqrt(rvc.cpu().double() + 1e-5) * g.double() + b.double()
     _chk("bn eval pre", pre.cpu(), want)
     _chk("bn eval", Ae.cpu(), want.clamp_min(0))
@@ -203,19 +203,19 @@ def test_bn_act_philox_dropout_consistent_between_fwd_and_bwd():
     rng = torch.tensor([42, 5], dtype=torch.int64).cuda()
     A, stats = torch.empty(n, H).cuda(), torch.zeros(1, 3, H).cuda()
     call("scnb_bn_act_fwd", ptr(Z), ptr(A), None, H, 1, ptr(seg), n, 1, ptr(g), ptr(b), None, None, ptr(stats), None, ptr(rng), 17,
-         0.5, 1, _st())
+         0.5, 1, None, None, _st())
     frac = float((A == 0).float().mean())
     assert 0.47 < frac < 0.53
     dZ, dg, db = torch.empty(n, H).cuda(), torch.zeros(H).cuda(), torch.zeros(H).cuda()
     ones = torch.ones(n, H).cuda()
     call("scnb_bn_act_bwd", ptr(ones), ptr(Z), ptr(A), H, 1, ptr(seg), n, ptr(g), ptr(stats), None, ptr(rng), 17, 0.5, 1, ptr(dZ),
-         ptr(dg), ptr(db), _st())
+         ptr(dg), ptr(db), None, None, _st())
     # dbeta = sum of dy = 2 * (#kept and positive) per column
     _chk("dbeta", db.cpu(), 2.0 * (A > 0).float().sum(0).cpu(), tol=1e-6)
     A2 = torch.empty(n, H).cuda()
     rng2 = torch.tensor([42, 6], dtype=torch.int64).cuda()
     call("scnb_bn_act_fwd", ptr(Z), ptr(A2), None, H, 1, ptr(seg), n, 1, ptr(g), ptr(b), None, None, ptr(stats), None, ptr(rng2),
-         17, 0.5, 1, _st())
+         17, 0.5, 1, None, None, _st())
     assert not torch.equal(A2 == 0, A == 0)  # next step counter -> fresh mask
 
 
