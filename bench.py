@@ -433,7 +433,13 @@ def main():
                 "predict": predict, "losses_last_step": {k: round(float(v), 6) for k, v in losses.items()}}
         print(json.dumps(line))
     if world > 1:
-        torch.distributed.destroy_process_group()
+        # Captured CUDA graphs hold NCCL kernels; tearing the communicator down underneath them can
+        # block forever, so synchronise, flush and leave without destroy_process_group().
+        torch.cuda.synchronize()
+        barrier(world)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
