@@ -181,7 +181,8 @@ def algorithmic_bytes(eng, name):
     table = {
         "scnb_csr_linear_fwd": 8 * nnz + 4 * G * H0 + 4 * nb * H0,          # CSR stream + W1T once + Z
         "scnb_csr_linear_bwd_dw": 8 * nnz + 4 * nb * H0 + 4 * G * H0,       # CSR stream + dZ + dW1T written once
-        "scnb_optim_step": 28 * P,                                          # read p,g,m,v / write p,m,v
+        "scnb_csr_w1_bwd_optim": 8 * nnz + 4 * nb * H0 + 24 * G * H0,       # batch entries + dZ + read p,m,v / write p,m,v of W1T
+        "scnb_optim_step": 28 * (P - G * H0 if getattr(eng, "fused_w1", False) else P),   # read p,g,m,v / write p,m,v
     }
     return table.get(name)
 

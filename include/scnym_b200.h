@@ -44,7 +44,9 @@ int scnb_gather_i32(const int32_t* table, const int64_t* rows, int n, int32_t fi
 int scnb_csr_gather_rows(const int64_t* indptr, const int32_t* indices, const float* data, const int64_t* rows,
                          int64_t row0, int n, const int32_t* b_indptr, int32_t* b_idx, float* b_val, int augment,
                          int aug_row_begin, int aug_row_end, const uint8_t* keep_mask /*per batch nnz*/,
-                         const uint64_t* rng, uint32_t stream_id, float p_drop, void* stream);
+                         const uint64_t* rng, uint32_t stream_id, float p_drop,
+                         int32_t* gene_cnt /*NULL or [G]: += per-gene count of non-zero entries (for scnb_csr_to_csc)*/,
+                         void* stream);
 
 /* Device-resident sampler hand-off (replaces DataLoader iteration, scnym/trainer.py:574-582):
  * copies the row ids / MixUp randomness of step (state4[0] % n_tab) from per-epoch tables. */
@@ -67,6 +69,22 @@ int scnb_csr_linear_fwd_i64(const int64_t* indptr /*first row of the range*/, co
                             int n, const float* W1T, const float* b1, int H0, float* Z, void* stream);
 int scnb_csr_linear_bwd_dw(const int32_t* b_indptr, const int32_t* b_idx, const float* b_val, int n, const float* dZ,
                            int H0, float* dW1T, void* stream);
+
+/* ---- K8+K9 fused: first-layer weight gradient AND optimizer.step() for W1T in one pass
+ *      (scnym/model.py:211 backward + scnym/trainer.py:671 / torch.optim rules, scnym/main.py:36-41,374-396).
+ *      The batch is first transposed to gene-major order ("batch CSC"): gene_cnt[G] is the histogram
+ *      accumulated by scnb_csr_gather_rows (or scnb_csc_count); scnb_csr_to_csc scans it into
+ *      c_ptr[G+1], resets gene_cnt to 0 and fills c_ent[nnz] = {int32 row, fp32 value} pairs.
+ *      scnb_csr_w1_bwd_optim then computes, per gene g, grad = sum v*dZ[row,:] and applies optimizer
+ *      `opt` to W1T[g,:], state1[g,:], state2[g,:] (opt = -1: gradient only, written to grad_out).
+ *      grad_out may be NULL when opt >= 0 (the gradient then never reaches HBM).  Requires H0 % 64 == 0. ---- */
+int scnb_csc_count(const int32_t* b_idx, const float* b_val, int nnz, int32_t* gene_cnt, void* stream);
+int scnb_csr_to_csc(const int32_t* b_indptr, const int32_t* b_idx, const float* b_val, int n, int G, int32_t* gene_cnt,
+                    int32_t* c_ptr /*[G+1]*/, int32_t* cursor /*[G] scratch*/, void* c_ent /*[nnz] 8-byte pairs*/,
+                    void* stream);
+int scnb_csr_w1_bwd_optim(int opt, const int32_t* c_ptr, const void* c_ent, const float* dZ /*[nb,H0]*/, int nb, int H0,
+                          int G, float* W1T, float* grad_out, float* state1, float* state2, const float* hp8,
+                          const int64_t* state4, void* stream);
 
 /* ---- K5: hidden nn.Linear layers, classifier and DAN head (scnym/model.py:218,170,229,377-383)
  *      and their backward GEMMs.  C = alpha*op(A)op(B) + beta*C (+bias[N]) (+ReLU). ---- */

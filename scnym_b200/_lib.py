@@ -16,12 +16,15 @@ P, I, L, F, U32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_flo
 SIGNATURES = {
     "scnb_csr_row_offsets": [P, P, L, I, P, P, P],
     "scnb_gather_i32": [P, P, I, I, P, P],
-    "scnb_csr_gather_rows": [P, P, P, P, L, I, P, P, P, I, I, I, P, P, U32, F, P],
+    "scnb_csr_gather_rows": [P, P, P, P, L, I, P, P, P, I, I, I, P, P, U32, F, P, P],
     "scnb_fetch_step": [P, P, P, P, I, I, I, P, P, P, P, P, P],
     "scnb_host_gather_rows": [P, P, P, P, I, P, P, P, L, I],
     "scnb_csr_linear_fwd": [P, P, P, I, P, P, I, P, P],
     "scnb_csr_linear_fwd_i64": [P, P, P, I, P, P, I, P, P],
     "scnb_csr_linear_bwd_dw": [P, P, P, I, P, I, P, P],
+    "scnb_csc_count": [P, P, I, P, P],
+    "scnb_csr_to_csc": [P, P, P, I, I, P, P, P, P, P],
+    "scnb_csr_w1_bwd_optim": [I, P, P, P, I, I, I, P, P, P, P, P, P, P],
     "scnb_sgemm": [I, I, I, I, I, P, I, P, I, P, I, F, F, P, I, P, P],
     "scnb_colsum": [P, I, I, I, P, I, P],
     "scnb_relu_bwd": [P, P, P, L, P],
@@ -44,7 +47,7 @@ SIGNATURES = {
     "scnb_predict_head": [P, I, I, I, P, P, P, P],
 }
 
-OPTIMIZER_CODES = {"adadelta": 0, "adam": 1, "adamw": 2, "sgd": 3}
+OPTIMIZER_CODES = {"none": -1, "adadelta": 0, "adam": 1, "adamw": 2, "sgd": 3}
 
 _lib = None
 _lock = threading.Lock()

@@ -4,7 +4,7 @@
 //   K8     scnb_csr_linear_bwd_dw                      : dW1T += X_csr^T * dZ   (vector atomics, v1)
 // Reference semantics: scnym/dataprep.py:143-155 (row densify), :721-729 (log1p_drop),
 // scnym/model.py:211 (first nn.Linear).  The dense [B,G] batch of the reference is never formed.
-#include "common.cuh"
+#include "optim.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // Row offsets: b_indptr[i] = sum_{j<i} len(rows[j]);  single CTA, n up to a few 100k.
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) k_gather_rows(const int64_t* __restrict__
                                                      int32_t* __restrict__ b_idx, float* __restrict__ b_val, int augment,
                                                      int aug_row_begin, int aug_row_end, const uint8_t* __restrict__ keep_mask,
                                                      const uint64_t* __restrict__ rng, uint32_t stream_id, float p_drop,
-                                                     float target_sum) {
+                                                     float target_sum, int32_t* __restrict__ gene_cnt) {
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= n) return;
@@ -82,8 +82,11 @@ __global__ void __launch_bounds__(256) k_gather_rows(const int64_t* __restrict__
   const bool aug = augment && i >= aug_row_begin && i < aug_row_end;
   if (!aug) {
     for (int j = lane; j < len; j += 32) {
-      b_idx[d + j] = indices[s + j];
-      b_val[d + j] = data[s + j];
+      const int c = indices[s + j];
+      const float v = data[s + j];
+      b_idx[d + j] = c;
+      b_val[d + j] = v;
+      if (gene_cnt && v != 0.f) atomicAdd(gene_cnt + c, 1);
     }
     return;
   }
@@ -106,63 +109,96 @@ __global__ void __launch_bounds__(256) k_gather_rows(const int64_t* __restrict__
     bool keep = dropout_keep(keep_mask, (uint64_t)(d + j), seed, strm, p_drop);
     e = e * (keep ? inv_keep : 0.f);
     float v = log1pf((e / sum) * target_sum);  // NaN if every entry of the row was dropped, as in the reference
-    b_idx[d + j] = indices[s + j];
+    const int c = indices[s + j];
+    b_idx[d + j] = c;
     b_val[d + j] = v;
+    if (gene_cnt && v != 0.f) atomicAdd(gene_cnt + c, 1);
   }
 }
 
 extern "C" int scnb_csr_gather_rows(const int64_t* indptr, const int32_t* indices, const float* data, const int64_t* rows,
                                     int64_t row0, int n, const int32_t* b_indptr, int32_t* b_idx, float* b_val, int augment,
                                     int aug_row_begin, int aug_row_end, const uint8_t* keep_mask, const uint64_t* rng,
-                                    uint32_t stream_id, float p_drop, void* stream) {
+                                    uint32_t stream_id, float p_drop, int32_t* gene_cnt, void* stream) {
   SCNB_CHECK_ARG(indptr && indices && data && b_indptr && b_idx && b_val && n >= 0, "csr_gather_rows: bad arguments");
   SCNB_CHECK_ARG(!augment || keep_mask || rng, "csr_gather_rows: augmentation needs keep_mask or rng state");
   if (n == 0) return SCNB_OK;
   k_gather_rows<<<scnb_cdiv(n, 8), 256, 0, (cudaStream_t)stream>>>(indptr, indices, data, rows, row0, n, b_indptr, b_idx,
                                                                      b_val, augment, aug_row_begin, aug_row_end, keep_mask,
-                                                                     rng, stream_id, p_drop, 1e6f);
+                                                                     rng, stream_id, p_drop, 1e6f, gene_cnt);
   SCNB_CHECK_LAUNCH("csr_gather_rows");
   return SCNB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2a  Z[n,H0] = X_csr[n,G] * W1T[G,H0] + b1.   One warp per row; lane owns NV float4 column
-// groups (h = (i*32+lane)*4); the (col,val) stream is loaded coalesced 32 at a time and
-// broadcast by shuffle; W1T rows are read as 512-byte coalesced segments.
+// K2a  Z[n,H0] = X_csr[n,G] * W1T[G,H0] + b1.   WPR warps per row (the row's nnz are split in WPR
+// contiguous chunks; partial sums meet in shared memory and are added in a fixed order, so the
+// result does not depend on timing).  A lane owns NV float4 column groups (h = (i*32+lane)*4); the
+// (col,val) stream is loaded coalesced 32 at a time and broadcast by shuffle; W1T rows are read as
+// 512-byte coalesced segments.  Small batches (train: 512 rows) use WPR=8 so that the launch covers
+// every SM; large row ranges (predict) use WPR=1, where the 8 rows of a CTA walk the gene axis
+// together and share W1T rows through L1.
 // ---------------------------------------------------------------------------------------------
-template <int NV, typename IdxT>
+template <int NV, int WPR, typename IdxT>
 __global__ void __launch_bounds__(256) k_csr_linear_fwd(const IdxT* __restrict__ indptr, const int32_t* __restrict__ idx,
                                                         const float* __restrict__ val, int n, const float4* __restrict__ W1T,
                                                         const float4* __restrict__ b1, int H0v, float4* __restrict__ Z) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= n) return;
-  const long long s = (long long)indptr[row], e = (long long)indptr[row + 1];
+  constexpr int RPC = 8 / WPR;  // rows per CTA
+  __shared__ float4 part[WPR > 1 ? 8 : 1][NV * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * RPC + warp / WPR;
+  const int sub = warp % WPR;
   float4 acc[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (long long base = s; base < e; base += 32) {
-    const int cnt = (int)min((long long)32, e - base);
-    int c = 0;
-    float v = 0.f;
-    if (lane < cnt) {
-      c = idx[base + lane];
-      v = val[base + lane];
+  if (row < n) {
+    long long s = (long long)indptr[row], e = (long long)indptr[row + 1];
+    if (WPR > 1) {
+      const long long chunk = (((e - s) + WPR - 1) / WPR + 31) & ~31ll;  // whole 32-entry groups per warp
+      s = s + sub * chunk;
+      e = min(e, s + chunk);
     }
+    for (long long base = s; base < e; base += 32) {
+      const int cnt = (int)min((long long)32, e - base);
+      int c = 0;
+      float v = 0.f;
+      if (lane < cnt) {
+        c = idx[base + lane];
+        v = val[base + lane];
+      }
 #pragma unroll 8
-    for (int k = 0; k < cnt; ++k) {
-      const int ck = __shfl_sync(0xffffffffu, c, k);
-      const float vk = __shfl_sync(0xffffffffu, v, k);
-      const float4* wrow = W1T + (size_t)ck * H0v + lane;
+      for (int k = 0; k < cnt; ++k) {
+        const int ck = __shfl_sync(0xffffffffu, c, k);
+        const float vk = __shfl_sync(0xffffffffu, v, k);
+        const float4* wrow = W1T + (size_t)ck * H0v + lane;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const float4 w = __ldg(wrow + i * 32);
-        acc[i].x = fmaf(vk, w.x, acc[i].x);
-        acc[i].y = fmaf(vk, w.y, acc[i].y);
-        acc[i].z = fmaf(vk, w.z, acc[i].z);
-        acc[i].w = fmaf(vk, w.w, acc[i].w);
+        for (int i = 0; i < NV; ++i) {
+          const float4 w = __ldg(wrow + i * 32);
+          acc[i].x = fmaf(vk, w.x, acc[i].x);
+          acc[i].y = fmaf(vk, w.y, acc[i].y);
+          acc[i].z = fmaf(vk, w.z, acc[i].z);
+          acc[i].w = fmaf(vk, w.w, acc[i].w);
+        }
       }
     }
+  }
+  if (WPR > 1) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) part[warp][i * 32 + lane] = acc[i];
+    __syncthreads();
+    if (sub != 0 || row >= n) return;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float4 t = acc[i];
+#pragma unroll
+      for (int w = 1; w < WPR; ++w) {
+        const float4 o = part[warp + w][i * 32 + lane];
+        t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+      }
+      acc[i] = t;
+    }
+  } else if (row >= n) {
+    return;
   }
   float4* zrow = Z + (size_t)row * H0v + lane;
 #pragma unroll
@@ -213,23 +249,41 @@ __global__ void __launch_bounds__(256) k_csr_linear_fwd_generic(const IdxT* __re
   }
 }
 
+template <int NV, typename IdxT>
+static void launch_csr_fwd_nv(int wpr, const IdxT* indptr, const int32_t* idx, const float* val, int n, const float* W1T,
+                              const float* b1, int H0, float* Z, cudaStream_t st) {
+  const float4* W = (const float4*)W1T;
+  const float4* B = (const float4*)b1;
+  float4* Zv = (float4*)Z;
+  if (wpr == 8)
+    k_csr_linear_fwd<NV, 8, IdxT><<<n, 256, 0, st>>>(indptr, idx, val, n, W, B, H0 / 4, Zv);
+  else if (wpr == 4)
+    k_csr_linear_fwd<NV, 4, IdxT><<<scnb_cdiv(n, 2), 256, 0, st>>>(indptr, idx, val, n, W, B, H0 / 4, Zv);
+  else if (wpr == 2)
+    k_csr_linear_fwd<NV, 2, IdxT><<<scnb_cdiv(n, 4), 256, 0, st>>>(indptr, idx, val, n, W, B, H0 / 4, Zv);
+  else
+    k_csr_linear_fwd<NV, 1, IdxT><<<scnb_cdiv(n, 8), 256, 0, st>>>(indptr, idx, val, n, W, B, H0 / 4, Zv);
+}
+
 template <typename IdxT>
 static int launch_csr_linear_fwd(const IdxT* indptr, const int32_t* idx, const float* val, int n, const float* W1T,
                                  const float* b1, int H0, float* Z, cudaStream_t st) {
   if (n == 0) return SCNB_OK;
-  dim3 grid(scnb_cdiv(n, 8)), block(256);
   const bool vec = (H0 % 128 == 0) && (((uintptr_t)W1T | (uintptr_t)Z | (uintptr_t)b1) % 16 == 0);
   const int nv = H0 / 128;
+  // warps per row: enough CTAs (8 warps each) to put >= 2 on every one of the 148 SMs
+  int wpr = 1;
+  while (wpr < 8 && (long long)n * wpr < 8ll * 2 * 148) wpr *= 2;
   if (vec && nv == 1)
-    k_csr_linear_fwd<1, IdxT><<<grid, block, 0, st>>>(indptr, idx, val, n, (const float4*)W1T, (const float4*)b1, H0 / 4, (float4*)Z);
+    launch_csr_fwd_nv<1, IdxT>(wpr, indptr, idx, val, n, W1T, b1, H0, Z, st);
   else if (vec && nv == 2)
-    k_csr_linear_fwd<2, IdxT><<<grid, block, 0, st>>>(indptr, idx, val, n, (const float4*)W1T, (const float4*)b1, H0 / 4, (float4*)Z);
+    launch_csr_fwd_nv<2, IdxT>(wpr, indptr, idx, val, n, W1T, b1, H0, Z, st);
   else if (vec && nv == 4)
-    k_csr_linear_fwd<4, IdxT><<<grid, block, 0, st>>>(indptr, idx, val, n, (const float4*)W1T, (const float4*)b1, H0 / 4, (float4*)Z);
+    launch_csr_fwd_nv<4, IdxT>(wpr, indptr, idx, val, n, W1T, b1, H0, Z, st);
   else if (vec && nv == 8)
-    k_csr_linear_fwd<8, IdxT><<<grid, block, 0, st>>>(indptr, idx, val, n, (const float4*)W1T, (const float4*)b1, H0 / 4, (float4*)Z);
+    launch_csr_fwd_nv<8, IdxT>(wpr, indptr, idx, val, n, W1T, b1, H0, Z, st);
   else
-    k_csr_linear_fwd_generic<IdxT><<<grid, block, 0, st>>>(indptr, idx, val, n, W1T, b1, H0, Z);
+    k_csr_linear_fwd_generic<IdxT><<<scnb_cdiv(n, 8), 256, 0, st>>>(indptr, idx, val, n, W1T, b1, H0, Z);
   SCNB_CHECK_LAUNCH("csr_linear_fwd");
   return SCNB_OK;
 }
@@ -307,6 +361,239 @@ extern "C" int scnb_csr_linear_bwd_dw(const int32_t* b_indptr, const int32_t* b_
     k_csr_linear_bwd_dw_scalar<<<scnb_cdiv(n, 8), 256, 0, st>>>(b_indptr, b_idx, b_val, n, dZ, H0, dW1T);
   SCNB_CHECK_LAUNCH("csr_linear_bwd_dw");
   return SCNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Batch CSR -> gene-major copy ("batch CSC").  gene_cnt[G] holds the per-gene number of non-zero
+// stored entries (accumulated by scnb_csr_gather_rows).  scan: c_ptr = exclusive scan, cursor =
+// c_ptr, gene_cnt <- 0 (ready for the next step).  fill: entry (row, value) of every stored
+// non-zero goes to c_ent[cursor[gene]++].  The order of a gene's entries is the arrival order of the
+// atomics (fp32 summation order of dW1 may differ between runs, as with the atomics of v1).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_csc_scan(int32_t* __restrict__ gene_cnt, int G, int32_t* __restrict__ c_ptr,
+                                                   int32_t* __restrict__ cursor) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  // each thread owns 4 consecutive genes per sweep (int4 loads)
+  for (int base = 0; base < G; base += 4096) {
+    const int g0 = base + tid * 4;
+    int v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (g0 + k < G) ? gene_cnt[g0 + k] : 0;
+    const int tsum = v[0] + v[1] + v[2] + v[3];
+    int x = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      int t = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      warp_tot[lane] = t;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    int excl = carry + (wid ? warp_tot[wid - 1] : 0) + x - tsum;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (g0 + k < G) {
+        c_ptr[g0 + k] = excl;
+        cursor[g0 + k] = excl;
+        gene_cnt[g0 + k] = 0;
+      }
+      excl += v[k];
+    }
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + warp_tot[31];
+    __syncthreads();
+  }
+  if (tid == 0) c_ptr[G] = carry_s;
+}
+
+__global__ void __launch_bounds__(256) k_csc_fill(const int32_t* __restrict__ b_indptr, const int32_t* __restrict__ b_idx,
+                                                  const float* __restrict__ b_val, int n, int32_t* __restrict__ cursor,
+                                                  int2* __restrict__ c_ent) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const int s = b_indptr[row], e = b_indptr[row + 1];
+  for (int j = s + lane; j < e; j += 32) {
+    const float v = b_val[j];
+    if (v != 0.f) {
+      const int pos = atomicAdd(cursor + b_idx[j], 1);
+      c_ent[pos] = make_int2(row, __float_as_int(v));
+    }
+  }
+}
+
+extern "C" int scnb_csr_to_csc(const int32_t* b_indptr, const int32_t* b_idx, const float* b_val, int n, int G,
+                               int32_t* gene_cnt, int32_t* c_ptr, int32_t* cursor, void* c_ent, void* stream) {
+  SCNB_CHECK_ARG(b_indptr && b_idx && b_val && gene_cnt && c_ptr && cursor && c_ent && n >= 0 && G > 0,
+                 "csr_to_csc: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  k_csc_scan<<<1, 1024, 0, st>>>(gene_cnt, G, c_ptr, cursor);
+  SCNB_CHECK_LAUNCH("csr_to_csc/scan");
+  if (n > 0) {
+    const int wpb = 8;
+    k_csc_fill<<<scnb_cdiv(n, wpb), 32 * wpb, 0, st>>>(b_indptr, b_idx, b_val, n, cursor, (int2*)c_ent);
+    SCNB_CHECK_LAUNCH("csr_to_csc/fill");
+  }
+  return SCNB_OK;
+}
+
+// per-gene histogram of the non-zero stored entries of a batch CSR (when the batch was not
+// assembled by scnb_csr_gather_rows, which counts on the fly)
+__global__ void k_csc_count(const int32_t* __restrict__ b_idx, const float* __restrict__ b_val, int nnz,
+                            int32_t* __restrict__ gene_cnt) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nnz; j += gridDim.x * blockDim.x)
+    if (b_val[j] != 0.f) atomicAdd(gene_cnt + b_idx[j], 1);
+}
+
+extern "C" int scnb_csc_count(const int32_t* b_idx, const float* b_val, int nnz, int32_t* gene_cnt, void* stream) {
+  SCNB_CHECK_ARG(b_idx && b_val && gene_cnt && nnz >= 0, "csc_count: bad arguments");
+  if (nnz == 0) return SCNB_OK;
+  const int blocks = scnb_cdiv(nnz, 256) < 148 * 8 ? scnb_cdiv(nnz, 256) : 148 * 8;
+  k_csc_count<<<blocks, 256, 0, (cudaStream_t)stream>>>(b_idx, b_val, nnz, gene_cnt);
+  SCNB_CHECK_LAUNCH("csc_count");
+  return SCNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K8+K9 fused:  for every gene g  grad[g,:] = sum_{(r,v) in column g} v * dZ[r,:]  and, in the same
+// pass, the optimizer update of W1T[g,:] and its two state rows (scnym/model.py:211 backward +
+// optimizer.step(), scnym/trainer.py:671).  The first layer holds ~96 % of all parameters: this
+// kernel reads p, s1, s2 once and writes them once (24 B per parameter), and the gradient never
+// goes to HBM unless `grad_out` is given (parity tests, data-parallel all-reduce).
+// Grid = (H0/64 column slices, gene blocks).  A CTA stages its 64-column slice of dZ in shared
+// memory ([nb][64] fp32, 128 KB at nb=512) once, then its 32 half-warps walk genes g = gb*32+hw,
+// += 32*gridDim.y; 16 lanes x float4 cover the slice.  Entries are loaded 16 at a time (one 128-B
+// line per half-warp) and broadcast by shuffle; the next gene's p/s1/s2 are prefetched before the
+// current gene's entries are consumed.  When nb*256 B exceeds shared memory (large batches) dZ is
+// read through L1/L2 instead (STAGED=false).
+// ---------------------------------------------------------------------------------------------
+template <int OPT, bool STAGED>
+__global__ void __launch_bounds__(512) k_w1_bwd_optim(const int32_t* __restrict__ c_ptr, const int2* __restrict__ c_ent,
+                                                      const float4* __restrict__ dZ, int nb, int H0v, int G,
+                                                      float4* __restrict__ W, float4* __restrict__ grad_out,
+                                                      float4* __restrict__ S1, float4* __restrict__ S2,
+                                                      const float* __restrict__ hp, const int64_t* __restrict__ st) {
+  extern __shared__ float4 dzs[];  // [nb][16]
+  __shared__ OptimConsts cs;
+  const int tid = threadIdx.x;
+  const int slice = blockIdx.x;
+  if (OPT != OPT_NONE && tid == 0) cs = optim_consts(hp, st);
+  if (STAGED) {
+    for (int i = tid; i < nb * 16; i += 512) dzs[i] = dZ[(size_t)(i >> 4) * H0v + slice * 16 + (i & 15)];
+  }
+  __syncthreads();
+  OptimConsts c;
+  if (OPT != OPT_NONE) c = cs;
+  const int hw = tid >> 4, q = tid & 15;
+  const unsigned hmask = 0xffffu << (tid & 16);  // the 16 lanes of this half-warp
+  const int col = slice * 16 + q;
+  const int gstride = gridDim.y * 32;
+  int g = blockIdx.y * 32 + hw;
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f), a = p, b = p;
+  if (OPT != OPT_NONE && g < G) {
+    const size_t o = (size_t)g * H0v + col;
+    p = W[o];
+    a = S1[o];
+    if (OPT != OPT_SGD) b = S2[o];
+  }
+  for (; g < G; g += gstride) {
+    const int gn = g + gstride;
+    float4 pn = make_float4(0.f, 0.f, 0.f, 0.f), an = pn, bn = pn;
+    if (OPT != OPT_NONE && gn < G) {  // prefetch the next gene's parameter/state rows
+      const size_t o = (size_t)gn * H0v + col;
+      pn = W[o];
+      an = S1[o];
+      if (OPT != OPT_SGD) bn = S2[o];
+    }
+    const int js = c_ptr[g], je = c_ptr[g + 1];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int base = js; base < je; base += 16) {
+      const int cnt = min(16, je - base);
+      int2 ent = make_int2(0, 0);
+      if (q < cnt) ent = c_ent[base + q];
+      for (int k = 0; k < cnt; ++k) {
+        const int r = __shfl_sync(hmask, ent.x, k, 16);
+        const float v = __int_as_float(__shfl_sync(hmask, ent.y, k, 16));
+        const float4 d = STAGED ? dzs[r * 16 + q] : __ldg(dZ + (size_t)r * H0v + col);
+        acc.x = fmaf(v, d.x, acc.x);
+        acc.y = fmaf(v, d.y, acc.y);
+        acc.z = fmaf(v, d.z, acc.z);
+        acc.w = fmaf(v, d.w, acc.w);
+      }
+    }
+    const size_t o = (size_t)g * H0v + col;
+    if (grad_out) grad_out[o] = acc;
+    if (OPT != OPT_NONE) {
+      optim_update<OPT>(p.x, acc.x, a.x, b.x, c);
+      optim_update<OPT>(p.y, acc.y, a.y, b.y, c);
+      optim_update<OPT>(p.z, acc.z, a.z, b.z, c);
+      optim_update<OPT>(p.w, acc.w, a.w, b.w, c);
+      W[o] = p;
+      S1[o] = a;
+      if (OPT != OPT_SGD) S2[o] = b;
+      p = pn; a = an; b = bn;
+    }
+  }
+}
+
+template <int OPT>
+static int launch_w1_bwd_optim(const int32_t* c_ptr, const void* c_ent, const float* dZ, int nb, int H0, int G, float* W1T,
+                               float* grad_out, float* s1, float* s2, const float* hp, const int64_t* st4, cudaStream_t st) {
+  const int slices = H0 / 64;
+  const size_t smem = (size_t)nb * 256;
+  const bool staged = smem <= 200 * 1024;
+  // one CTA per SM when the dZ slice is staged (its shared memory fills the SM); more, smaller shares otherwise
+  int gblocks = staged ? (148 / slices > 0 ? 148 / slices : 1) : (148 * 2 / slices > 0 ? 148 * 2 / slices : 1);
+  if (gblocks > scnb_cdiv(G, 32)) gblocks = scnb_cdiv(G, 32);
+  dim3 grid(slices, gblocks);
+  if (staged) {
+    cudaError_t e = cudaFuncSetAttribute(k_w1_bwd_optim<OPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      scnb_set_error("csr_w1_bwd_optim: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+      return SCNB_ERR_CUDA;
+    }
+    k_w1_bwd_optim<OPT, true><<<grid, 512, smem, st>>>(c_ptr, (const int2*)c_ent, (const float4*)dZ, nb, H0 / 4, G, (float4*)W1T,
+                                                       (float4*)grad_out, (float4*)s1, (float4*)s2, hp, st4);
+  } else {
+    k_w1_bwd_optim<OPT, false><<<grid, 512, 0, st>>>(c_ptr, (const int2*)c_ent, (const float4*)dZ, nb, H0 / 4, G, (float4*)W1T,
+                                                     (float4*)grad_out, (float4*)s1, (float4*)s2, hp, st4);
+  }
+  SCNB_CHECK_LAUNCH("csr_w1_bwd_optim");
+  return SCNB_OK;
+}
+
+extern "C" int scnb_csr_w1_bwd_optim(int opt, const int32_t* c_ptr, const void* c_ent, const float* dZ, int nb, int H0, int G,
+                                     float* W1T, float* grad_out, float* state1, float* state2, const float* hp8,
+                                     const int64_t* state4, void* stream) {
+  SCNB_CHECK_ARG(c_ptr && c_ent && dZ && nb >= 0 && H0 > 0 && G > 0, "csr_w1_bwd_optim: bad arguments");
+  SCNB_CHECK_ARG(H0 % 64 == 0 && ((uintptr_t)dZ % 16 == 0), "csr_w1_bwd_optim: H0 must be a multiple of 64 and dZ 16-byte aligned");
+  SCNB_CHECK_ARG(opt == OPT_NONE ? (grad_out != nullptr) : (W1T && state1 && hp8 && state4 && (opt == OPT_SGD || state2)),
+                 "csr_w1_bwd_optim: missing buffers for the requested mode");
+  SCNB_CHECK_ARG((((uintptr_t)W1T | (uintptr_t)grad_out | (uintptr_t)state1 | (uintptr_t)state2) % 16) == 0,
+                 "csr_w1_bwd_optim: parameter/state rows must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (opt) {
+    case OPT_NONE: return launch_w1_bwd_optim<OPT_NONE>(c_ptr, c_ent, dZ, nb, H0, G, W1T, grad_out, state1, state2, hp8, state4, st);
+    case OPT_ADADELTA: return launch_w1_bwd_optim<OPT_ADADELTA>(c_ptr, c_ent, dZ, nb, H0, G, W1T, grad_out, state1, state2, hp8, state4, st);
+    case OPT_ADAM: return launch_w1_bwd_optim<OPT_ADAM>(c_ptr, c_ent, dZ, nb, H0, G, W1T, grad_out, state1, state2, hp8, state4, st);
+    case OPT_ADAMW: return launch_w1_bwd_optim<OPT_ADAMW>(c_ptr, c_ent, dZ, nb, H0, G, W1T, grad_out, state1, state2, hp8, state4, st);
+    case OPT_SGD: return launch_w1_bwd_optim<OPT_SGD>(c_ptr, c_ent, dZ, nb, H0, G, W1T, grad_out, state1, state2, hp8, state4, st);
+    default: scnb_set_error("csr_w1_bwd_optim: unknown optimizer %d", opt); return SCNB_ERR_ARG;
+  }
 }
 
 // out[i] = table ? table[rows ? rows[i] : i] : fill   (labels / domain ids of the sampled rows)

@@ -12,83 +12,92 @@
 #define BN_EPS 1e-5f
 
 // ---------------------------------------------------------------------------------------------
-// SGEMM: 64x64x16 tiles, 256 threads, 4x4 register micro-tile, register-prefetched double buffer.
-// Row-major.  op(A)[m,k] = TA ? A[k*lda+m] : A[m*lda+k];  op(B)[k,n] = TB ? B[n*ldb+k] : B[k*ldb+n].
+// SGEMM (fp32 SIMT): BMxBNx16 tiles, 256 threads, (BM/16)x(BN/16) register micro-tile,
+// register-prefetched double buffer.  Row-major.
+//   op(A)[m,k] = TA ? A[k*lda+m] : A[m*lda+k];  op(B)[k,n] = TB ? B[n*ldb+k] : B[k*ldb+n].
+// The hidden GEMMs of this path are tiny (<= 1024 x 256 x 256): the launcher picks 32-wide tiles
+// when 64x64 tiles would leave most of the 148 SMs idle, and splits K over gridDim.z (atomic
+// accumulation into C, which then must hold the beta*C term already) for the weight-gradient
+// shape M=N=256, K=rows.
 // ---------------------------------------------------------------------------------------------
-#define GBM 64
-#define GBN 64
 #define GBK 16
 #define GPAD 4
 
-template <bool TA, bool VEC>
-__device__ __forceinline__ void load_a_frag(const float* __restrict__ A, int lda, int M, int K, int m0, int k0, int tid,
+template <int BM, bool TA, bool VEC>
+__device__ __forceinline__ void load_a_frag(const float* __restrict__ A, int lda, int M, int K, int m0, int k0, int k1, int tid,
                                             float (&r)[4]) {
+  r[0] = r[1] = r[2] = r[3] = 0.f;
+  if (tid >= BM * 4) return;
   if (!TA) {  // contiguous along k: thread -> (m = tid/4, k = (tid%4)*4 .. +3)
     const int m = m0 + (tid >> 2), k = k0 + ((tid & 3) << 2);
     if (VEC) {
-      if (m < M && k < K) {
+      if (m < M && k < k1) {
         const float4 v = *reinterpret_cast<const float4*>(A + (size_t)m * lda + k);
         r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
-      } else { r[0] = r[1] = r[2] = r[3] = 0.f; }
+      }
     } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) r[i] = (m < M && k + i < K) ? A[(size_t)m * lda + k + i] : 0.f;
+      for (int i = 0; i < 4; ++i) r[i] = (m < M && k + i < k1) ? A[(size_t)m * lda + k + i] : 0.f;
     }
-  } else {  // contiguous along m: thread -> (k = tid/16, m = (tid%16)*4 .. +3)
-    const int k = k0 + (tid >> 4), m = m0 + ((tid & 15) << 2);
+  } else {  // contiguous along m: thread -> (k = tid/(BM/4), m = (tid%(BM/4))*4 .. +3)
+    const int k = k0 + tid / (BM / 4), m = m0 + ((tid % (BM / 4)) << 2);
     if (VEC) {
-      if (k < K && m < M) {
+      if (k < k1 && m < M) {
         const float4 v = *reinterpret_cast<const float4*>(A + (size_t)k * lda + m);
         r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
-      } else { r[0] = r[1] = r[2] = r[3] = 0.f; }
+      }
     } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) r[i] = (k < K && m + i < M) ? A[(size_t)k * lda + m + i] : 0.f;
+      for (int i = 0; i < 4; ++i) r[i] = (k < k1 && m + i < M) ? A[(size_t)k * lda + m + i] : 0.f;
     }
   }
 }
-template <bool TA>
-__device__ __forceinline__ void store_a_frag(float (*As)[GBM + GPAD], int tid, const float (&r)[4]) {
+template <int BM, bool TA>
+__device__ __forceinline__ void store_a_frag(float (*As)[BM + GPAD], int tid, const float (&r)[4]) {
+  if (tid >= BM * 4) return;
   if (!TA) {
     const int m = tid >> 2, k = (tid & 3) << 2;
 #pragma unroll
     for (int i = 0; i < 4; ++i) As[k + i][m] = r[i];
   } else {
-    const int k = tid >> 4, m = (tid & 15) << 2;
+    const int k = tid / (BM / 4), m = (tid % (BM / 4)) << 2;
     *reinterpret_cast<float4*>(&As[k][m]) = make_float4(r[0], r[1], r[2], r[3]);
   }
 }
-template <bool TB, bool VEC>
-__device__ __forceinline__ void load_b_frag(const float* __restrict__ B, int ldb, int N, int K, int n0, int k0, int tid,
+template <int BN, bool TB, bool VEC>
+__device__ __forceinline__ void load_b_frag(const float* __restrict__ B, int ldb, int N, int K, int n0, int k0, int k1, int tid,
                                             float (&r)[4]) {
-  if (!TB) {  // B stored [K,N], contiguous along n: thread -> (k = tid/16, n = (tid%16)*4)
-    const int k = k0 + (tid >> 4), n = n0 + ((tid & 15) << 2);
+  r[0] = r[1] = r[2] = r[3] = 0.f;
+  if (tid >= BN * 4) return;
+  if (!TB) {  // B stored [K,N], contiguous along n: thread -> (k = tid/(BN/4), n = (tid%(BN/4))*4)
+    const int k = k0 + tid / (BN / 4), n = n0 + ((tid % (BN / 4)) << 2);
     if (VEC) {
-      if (k < K && n < N) {
+      if (k < k1 && n < N) {
         const float4 v = *reinterpret_cast<const float4*>(B + (size_t)k * ldb + n);
         r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
-      } else { r[0] = r[1] = r[2] = r[3] = 0.f; }
+      }
     } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) r[i] = (k < K && n + i < N) ? B[(size_t)k * ldb + n + i] : 0.f;
+      for (int i = 0; i < 4; ++i) r[i] = (k < k1 && n + i < N) ? B[(size_t)k * ldb + n + i] : 0.f;
     }
   } else {  // B stored [N,K], contiguous along k: thread -> (n = tid/4, k = (tid%4)*4)
     const int n = n0 + (tid >> 2), k = k0 + ((tid & 3) << 2);
     if (VEC) {
-      if (n < N && k < K) {
+      if (n < N && k < k1) {
         const float4 v = *reinterpret_cast<const float4*>(B + (size_t)n * ldb + k);
         r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
-      } else { r[0] = r[1] = r[2] = r[3] = 0.f; }
+      }
     } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) r[i] = (n < N && k + i < K) ? B[(size_t)n * ldb + k + i] : 0.f;
+      for (int i = 0; i < 4; ++i) r[i] = (n < N && k + i < k1) ? B[(size_t)n * ldb + k + i] : 0.f;
     }
   }
 }
-template <bool TB>
-__device__ __forceinline__ void store_b_frag(float (*Bs)[GBN + GPAD], int tid, const float (&r)[4]) {
+template <int BN, bool TB>
+__device__ __forceinline__ void store_b_frag(float (*Bs)[BN + GPAD], int tid, const float (&r)[4]) {
+  if (tid >= BN * 4) return;
   if (!TB) {
-    const int k = tid >> 4, n = (tid & 15) << 2;
+    const int k = tid / (BN / 4), n = (tid % (BN / 4)) << 2;
     *reinterpret_cast<float4*>(&Bs[k][n]) = make_float4(r[0], r[1], r[2], r[3]);
   } else {
     const int n = tid >> 2, k = (tid & 3) << 2;
@@ -97,58 +106,67 @@ __device__ __forceinline__ void store_b_frag(float (*Bs)[GBN + GPAD], int tid, c
   }
 }
 
-template <bool TA, bool TB, bool VEC>
+template <int BM, int BN, bool TA, bool TB, bool VEC>
 __global__ void __launch_bounds__(256) k_sgemm(int M, int N, int K, const float* __restrict__ A, int lda,
                                                const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
                                                float alpha, float beta, const float* __restrict__ bias, int relu,
-                                               const float* __restrict__ gate) {
-  __shared__ __align__(16) float As[2][GBK][GBM + GPAD];
-  __shared__ __align__(16) float Bs[2][GBK][GBN + GPAD];
+                                               const float* __restrict__ gate, int k_chunk) {
+  constexpr int TM = BM / 16, TN = BN / 16;
+  __shared__ __align__(16) float As[2][GBK][BM + GPAD];
+  __shared__ __align__(16) float Bs[2][GBK][BN + GPAD];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
-  float acc[4][4];
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kb = blockIdx.z * k_chunk, ke = min(K, kb + k_chunk);  // this CTA's K range (split-K)
+  float acc[TM][TN];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
   float ra[4], rb[4];
-  load_a_frag<TA, VEC>(A, lda, M, K, m0, 0, tid, ra);
-  load_b_frag<TB, VEC>(B, ldb, N, K, n0, 0, tid, rb);
-  store_a_frag<TA>(As[0], tid, ra);
-  store_b_frag<TB>(Bs[0], tid, rb);
+  load_a_frag<BM, TA, VEC>(A, lda, M, K, m0, kb, ke, tid, ra);
+  load_b_frag<BN, TB, VEC>(B, ldb, N, K, n0, kb, ke, tid, rb);
+  store_a_frag<BM, TA>(As[0], tid, ra);
+  store_b_frag<BN, TB>(Bs[0], tid, rb);
   __syncthreads();
-  const int nk = (K + GBK - 1) / GBK;
+  const int nk = (ke - kb + GBK - 1) / GBK;
   for (int kt = 0; kt < nk; ++kt) {
     const int cur = kt & 1;
     if (kt + 1 < nk) {
-      load_a_frag<TA, VEC>(A, lda, M, K, m0, (kt + 1) * GBK, tid, ra);
-      load_b_frag<TB, VEC>(B, ldb, N, K, n0, (kt + 1) * GBK, tid, rb);
+      load_a_frag<BM, TA, VEC>(A, lda, M, K, m0, kb + (kt + 1) * GBK, ke, tid, ra);
+      load_b_frag<BN, TB, VEC>(B, ldb, N, K, n0, kb + (kt + 1) * GBK, ke, tid, rb);
     }
 #pragma unroll
     for (int k = 0; k < GBK; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[cur][k][ty << 2]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[cur][k][tx << 2]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      float av[TM], bv[TN];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < TM; ++i) av[i] = As[cur][k][ty * TM + i];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      for (int j = 0; j < TN; ++j) bv[j] = Bs[cur][k][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     if (kt + 1 < nk) {
-      store_a_frag<TA>(As[cur ^ 1], tid, ra);
-      store_b_frag<TB>(Bs[cur ^ 1], tid, rb);
+      store_a_frag<BM, TA>(As[cur ^ 1], tid, ra);
+      store_b_frag<BN, TB>(Bs[cur ^ 1], tid, rb);
     }
     __syncthreads();
   }
+  const bool split = gridDim.z > 1;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + (ty << 2) + i;
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
     if (m >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + (tx << 2) + j;
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tx * TN + j;
       if (n >= N) continue;
       float v = alpha * acc[i][j];
+      if (split) {  // C already holds beta*C (+bias); partial products are accumulated atomically
+        atomicAdd(C + (size_t)m * ldc + n, v);
+        continue;
+      }
       if (beta != 0.f) v += beta * C[(size_t)m * ldc + n];
       if (bias) v += bias[n];
       if (relu) v = fmaxf(v, 0.f);
@@ -158,22 +176,51 @@ __global__ void __launch_bounds__(256) k_sgemm(int M, int N, int K, const float*
   }
 }
 
+template <int BM, int BN>
+static void launch_sgemm_tile(bool tA, bool tB, bool vec, dim3 grid, cudaStream_t st, int M, int N, int K, const float* A, int lda,
+                              const float* B, int ldb, float* C, int ldc, float alpha, float beta, const float* bias, int relu,
+                              const float* gate, int k_chunk) {
+#define SCNB_LAUNCH_SGEMM(TA, TB, V) \
+  k_sgemm<BM, BN, TA, TB, V><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, k_chunk)
+  if (!tA && !tB) { if (vec) SCNB_LAUNCH_SGEMM(false, false, true); else SCNB_LAUNCH_SGEMM(false, false, false); }
+  else if (!tA && tB) { if (vec) SCNB_LAUNCH_SGEMM(false, true, true); else SCNB_LAUNCH_SGEMM(false, true, false); }
+  else if (tA && !tB) { if (vec) SCNB_LAUNCH_SGEMM(true, false, true); else SCNB_LAUNCH_SGEMM(true, false, false); }
+  else { if (vec) SCNB_LAUNCH_SGEMM(true, true, true); else SCNB_LAUNCH_SGEMM(true, true, false); }
+#undef SCNB_LAUNCH_SGEMM
+}
+
 extern "C" int scnb_sgemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                           float* C, int ldc, float alpha, float beta, const float* bias, int relu, const float* gate,
                           void* stream) {
   SCNB_CHECK_ARG(M >= 0 && N >= 0 && K >= 0 && A && B && C, "sgemm: bad arguments");
   if (M == 0 || N == 0) return SCNB_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid(scnb_cdiv(N, GBN), scnb_cdiv(M, GBM)), block(256);
   const bool vec = (lda % 4 == 0) && (ldb % 4 == 0) && (((uintptr_t)A | (uintptr_t)B) % 16 == 0) &&
                    (transA ? (M % 4 == 0) : (K % 4 == 0)) && (transB ? (K % 4 == 0) : (N % 4 == 0));
-#define SCNB_LAUNCH_SGEMM(TA, TB, V) \
-  k_sgemm<TA, TB, V><<<grid, block, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate)
-  if (!transA && !transB) { if (vec) SCNB_LAUNCH_SGEMM(false, false, true); else SCNB_LAUNCH_SGEMM(false, false, false); }
-  else if (!transA && transB) { if (vec) SCNB_LAUNCH_SGEMM(false, true, true); else SCNB_LAUNCH_SGEMM(false, true, false); }
-  else if (transA && !transB) { if (vec) SCNB_LAUNCH_SGEMM(true, false, true); else SCNB_LAUNCH_SGEMM(true, false, false); }
-  else { if (vec) SCNB_LAUNCH_SGEMM(true, true, true); else SCNB_LAUNCH_SGEMM(true, true, false); }
-#undef SCNB_LAUNCH_SGEMM
+  // split-K first (keeps the efficient 64x64 tile): only for plain accumulating products (the dW
+  // shape M,N <= 256, K = rows): no bias / relu / gate, beta == 1
+  int bm = 64, bn = 64;
+  auto ctas = [&](int a, int b) { return (long long)scnb_cdiv(M, a) * scnb_cdiv(N, b); };
+  int splits = 1;
+  const bool splittable = !bias && !relu && !gate && (beta == 1.f) && K >= 128;
+  if (splittable) {
+    const long long c = ctas(bm, bn);
+    while (splits < 32 && c * splits < 2 * 148 && K / (splits * 2) >= 32) splits *= 2;
+  } else {
+    // otherwise fall to 32-wide tiles while the grid would leave most of the 148 SMs idle
+    if (ctas(bm, bn) < 148 && N > 32) bn = 32;
+    if (ctas(bm, bn) < 74 && M > 32) bm = 32;
+  }
+  int k_chunk = scnb_cdiv(scnb_cdiv(K, splits), GBK) * GBK;
+  splits = scnb_cdiv(K, k_chunk);
+  dim3 grid(scnb_cdiv(N, bn), scnb_cdiv(M, bm), splits);
+#define SCNB_TILE(BM_, BN_) \
+  launch_sgemm_tile<BM_, BN_>(transA, transB, vec, grid, st, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, k_chunk)
+  if (bm == 64 && bn == 64) SCNB_TILE(64, 64);
+  else if (bm == 64 && bn == 32) SCNB_TILE(64, 32);
+  else if (bm == 32 && bn == 64) SCNB_TILE(32, 64);
+  else SCNB_TILE(32, 32);
+#undef SCNB_TILE
   SCNB_CHECK_LAUNCH("sgemm");
   return SCNB_OK;
 }
@@ -215,19 +262,28 @@ extern "C" int scnb_colsum(const float* A, int M, int N, int lda, float* out, in
 #define BN_CW 8
 #define BN_RL 128
 
-__device__ __forceinline__ float bn_block_colsum(float v, float (*red)[BN_CW], int cx, int ry) {
-  // reduce over the 128 row lanes of each of the 8 columns; result broadcast to every thread of the column
-  red[ry][cx] = v;
+// Column sums over the 128 row lanes of each of the 8 columns of a 1024-thread block
+// (tid = ry*8 + cx).  A warp holds 4 row lanes x 8 columns: two xor-shuffles fold the row lanes,
+// 32 per-warp partials per column meet in shared memory and every thread adds them in the same
+// order (deterministic).  `red` is [BN_CW][32]; use a different array for each call between
+// two __syncthreads-separated phases.
+__device__ __forceinline__ float bn_block_colsum(float v, float (*red)[32], int cx) {
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane < BN_CW) red[lane][wid] = v;
   __syncthreads();
-  for (int s = BN_RL / 2; s > 0; s >>= 1) {
-    if (ry < s) red[ry][cx] += red[ry + s][cx];
-    __syncthreads();
+  const float4* r4 = reinterpret_cast<const float4*>(red[cx]);
+  float out = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 t = r4[i];
+    out += (t.x + t.y) + (t.z + t.w);
   }
-  float out = red[0][cx];
-  __syncthreads();
   return out;
 }
 
+// Grid = (ceil(H/8), n_seg): one CTA per (8-column group, segment).
 __global__ void __launch_bounds__(1024) k_bn_act_fwd(const float* __restrict__ Z, float* __restrict__ Aout,
                                                      float* __restrict__ pre_out, int H, int n_seg,
                                                      const int32_t* __restrict__ seg_off, int max_rows, int train,
@@ -241,9 +297,11 @@ __global__ void __launch_bounds__(1024) k_bn_act_fwd(const float* __restrict__ Z
   //   pass 1  partial_out != NULL : write local [seg][0]=sum z, [seg][1]=sum z^2, [n_seg*2*H + seg]=row count; no apply
   //   (all-reduce SUM of that buffer over ranks)
   //   pass 2  ext_sums != NULL    : statistics from the reduced sums / counts (ext_cnt), then apply
-  __shared__ float red[BN_RL][BN_CW];
+  __shared__ __align__(16) float red1[BN_CW][32];
+  __shared__ __align__(16) float red2[BN_CW][32];
   const int cx = threadIdx.x & (BN_CW - 1), ry = threadIdx.x / BN_CW;
   const int c = blockIdx.x * BN_CW + cx;
+  const int s = blockIdx.y;
   const bool cok = c < H;
   const float g = cok ? gamma[c] : 1.f, b = cok ? beta[c] : 0.f;
   uint64_t seed = 0, strm = 0;
@@ -252,71 +310,111 @@ __global__ void __launch_bounds__(1024) k_bn_act_fwd(const float* __restrict__ Z
     strm = rng[1] * 64ull + stream_id;
   }
   const float drop_scale = 1.0f / (1.0f - p_drop);
-  for (int s = 0; s < n_seg; ++s) {
-    const int r0 = seg_off[s], r1 = min(seg_off[s + 1], max_rows);
-    const int n = r1 - r0;
-    float mean, invstd;
-    if (train && partial_out) {
-      float a1 = 0.f, a2 = 0.f;
-      if (cok)
-        for (int r = r0 + ry; r < r1; r += BN_RL) {
-          const float z = Z[(size_t)r * H + c];
-          a1 += z;
-          a2 = fmaf(z, z, a2);
-        }
-      a1 = bn_block_colsum(a1, red, cx, ry);
-      a2 = bn_block_colsum(a2, red, cx, ry);
-      if (cok && ry == 0) {
-        partial_out[((size_t)s * 2 + 0) * H + c] = a1;
-        partial_out[((size_t)s * 2 + 1) * H + c] = a2;
-      }
-      if (blockIdx.x == 0 && threadIdx.x == 0) partial_out[(size_t)n_seg * 2 * H + s] = (float)n;
-      continue;
-    }
-    if (train) {
-      float var;
-      if (ext_sums) {
-        const float ng = fmaxf(ext_cnt[s], 1.f);
-        mean = cok ? ext_sums[((size_t)s * 2 + 0) * H + c] / ng : 0.f;
-        var = cok ? fmaxf(ext_sums[((size_t)s * 2 + 1) * H + c] / ng - mean * mean, 0.f) : 1.f;
-      } else {
-        float acc = 0.f;
-        if (cok)
-          for (int r = r0 + ry; r < r1; r += BN_RL) acc += Z[(size_t)r * H + c];
-        mean = bn_block_colsum(acc, red, cx, ry) / (float)max(n, 1);
-        acc = 0.f;
-        if (cok)
-          for (int r = r0 + ry; r < r1; r += BN_RL) {
-            const float d = Z[(size_t)r * H + c] - mean;
-            acc = fmaf(d, d, acc);
-          }
-        var = bn_block_colsum(acc, red, cx, ry) / (float)max(n, 1);
-      }
-      invstd = 1.0f / sqrtf(var + BN_EPS);
-      if (cok && ry == 0 && stats) {
-        stats[((size_t)s * 3 + 0) * H + c] = mean;
-        stats[((size_t)s * 3 + 1) * H + c] = var;
-        stats[((size_t)s * 3 + 2) * H + c] = invstd;
-      }
-    } else {
-      mean = cok ? rmean[c] : 0.f;
-      invstd = cok ? 1.0f / sqrtf(rvar[c] + BN_EPS) : 1.f;
-    }
+  const int r0 = min(seg_off[s], max_rows), r1 = min(seg_off[s + 1], max_rows);
+  const int n = r1 - r0;
+  float mean, invstd;
+  if (train && partial_out) {
+    float a1 = 0.f, a2 = 0.f;
     if (cok)
       for (int r = r0 + ry; r < r1; r += BN_RL) {
-        const size_t o = (size_t)r * H + c;
-        float y = (Z[o] - mean) * invstd * g + b;
-        if (train && p_drop > 0.f) y = dropout_keep(keep_mask, o, seed, strm, p_drop) ? y * drop_scale : 0.f;
-        if (pre_out) pre_out[o] = y;
-        Aout[o] = relu ? fmaxf(y, 0.f) : y;
+        const float z = Z[(size_t)r * H + c];
+        a1 += z;
+        a2 = fmaf(z, z, a2);
       }
+    a1 = bn_block_colsum(a1, red1, cx);
+    a2 = bn_block_colsum(a2, red2, cx);
+    if (cok && ry == 0) {
+      partial_out[((size_t)s * 2 + 0) * H + c] = a1;
+      partial_out[((size_t)s * 2 + 1) * H + c] = a2;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) partial_out[(size_t)n_seg * 2 * H + s] = (float)n;
+    return;
   }
-  // inactive tail rows
-  if (cok && !(train && partial_out))
-    for (int r = min(seg_off[n_seg], max_rows) + ry; r < max_rows; r += BN_RL) {
+  if (train) {
+    float var;
+    if (ext_sums) {
+      const float ng = fmaxf(ext_cnt[s], 1.f);
+      mean = cok ? ext_sums[((size_t)s * 2 + 0) * H + c] / ng : 0.f;
+      var = cok ? fmaxf(ext_sums[((size_t)s * 2 + 1) * H + c] / ng - mean * mean, 0.f) : 1.f;
+    } else {
+      float acc = 0.f;
+      if (cok)
+        for (int r = r0 + ry; r < r1; r += BN_RL) acc += Z[(size_t)r * H + c];
+      mean = bn_block_colsum(acc, red1, cx) / (float)max(n, 1);
+      acc = 0.f;
+      if (cok)
+        for (int r = r0 + ry; r < r1; r += BN_RL) {
+          const float d = Z[(size_t)r * H + c] - mean;
+          acc = fmaf(d, d, acc);
+        }
+      var = bn_block_colsum(acc, red2, cx) / (float)max(n, 1);
+    }
+    invstd = 1.0f / sqrtf(var + BN_EPS);
+    if (cok && ry == 0 && stats) {
+      stats[((size_t)s * 3 + 0) * H + c] = mean;
+      stats[((size_t)s * 3 + 1) * H + c] = var;
+      stats[((size_t)s * 3 + 2) * H + c] = invstd;
+    }
+  } else {
+    mean = cok ? rmean[c] : 0.f;
+    invstd = cok ? 1.0f / sqrtf(rvar[c] + BN_EPS) : 1.f;
+  }
+  if (!cok) return;
+  for (int r = r0 + ry; r < r1; r += BN_RL) {
+    const size_t o = (size_t)r * H + c;
+    float y = (Z[o] - mean) * invstd * g + b;
+    if (train && p_drop > 0.f) y = dropout_keep(keep_mask, o, seed, strm, p_drop) ? y * drop_scale : 0.f;
+    if (pre_out) pre_out[o] = y;
+    Aout[o] = relu ? fmaxf(y, 0.f) : y;
+  }
+  // inactive tail rows (data-dependent DAN segment length): the last segment's CTAs clear them
+  if (s == n_seg - 1)
+    for (int r = r1 + ry; r < max_rows; r += BN_RL) {
       Aout[(size_t)r * H + c] = 0.f;
       if (pre_out) pre_out[(size_t)r * H + c] = 0.f;
     }
+}
+
+// Eval mode (running statistics, no dropout) is purely elementwise: a flat grid-stride kernel over
+// rows [0, seg_off[n_seg]) so that predict-sized inputs (65 536 rows) use the whole chip.
+template <bool VEC4>
+__global__ void __launch_bounds__(256) k_bn_eval_fwd(const float* __restrict__ Z, float* __restrict__ Aout,
+                                                     float* __restrict__ pre_out, int H, const int32_t* __restrict__ seg_off,
+                                                     int n_seg, int max_rows, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, const float* __restrict__ rmean,
+                                                     const float* __restrict__ rvar, int relu) {
+  const int rows = min(seg_off[n_seg], max_rows);
+  if (VEC4) {
+    const int Hv = H >> 2;
+    const size_t total = (size_t)max_rows * Hv, active = (size_t)rows * Hv;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+      float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < active) {
+        const int cv = (int)(i % Hv);
+        const float4 z = reinterpret_cast<const float4*>(Z)[i];
+        const float4 m = reinterpret_cast<const float4*>(rmean)[cv], v = reinterpret_cast<const float4*>(rvar)[cv];
+        const float4 g = reinterpret_cast<const float4*>(gamma)[cv], b = reinterpret_cast<const float4*>(beta)[cv];
+        y.x = (z.x - m.x) * (1.0f / sqrtf(v.x + BN_EPS)) * g.x + b.x;
+        y.y = (z.y - m.y) * (1.0f / sqrtf(v.y + BN_EPS)) * g.y + b.y;
+        y.z = (z.z - m.z) * (1.0f / sqrtf(v.z + BN_EPS)) * g.z + b.z;
+        y.w = (z.w - m.w) * (1.0f / sqrtf(v.w + BN_EPS)) * g.w + b.w;
+      }
+      if (pre_out) reinterpret_cast<float4*>(pre_out)[i] = y;
+      if (relu) y = make_float4(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f), fmaxf(y.z, 0.f), fmaxf(y.w, 0.f));
+      reinterpret_cast<float4*>(Aout)[i] = y;
+    }
+  } else {
+    const size_t total = (size_t)max_rows * H, active = (size_t)rows * H;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+      float y = 0.f;
+      if (i < active) {
+        const int c = (int)(i % H);
+        y = (Z[i] - rmean[c]) * (1.0f / sqrtf(rvar[c] + BN_EPS)) * gamma[c] + beta[c];
+      }
+      if (pre_out) pre_out[i] = y;
+      Aout[i] = relu ? fmaxf(y, 0.f) : y;
+    }
+  }
 }
 
 extern "C" int scnb_bn_act_fwd(const float* Z, float* A, float* pre_out, int H, int n_seg, const int32_t* seg_off_dev,
@@ -330,10 +428,25 @@ extern "C" int scnb_bn_act_fwd(const float* Z, float* A, float* pre_out, int H, 
   SCNB_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "bn_act_fwd: p_drop out of range");
   SCNB_CHECK_ARG(!(dp_partial_out && dp_sums), "bn_act_fwd: partial and reduced statistics are exclusive");
   const float* ext_cnt = dp_sums ? dp_sums + (size_t)n_seg * 2 * H : nullptr;
-  k_bn_act_fwd<<<scnb_cdiv(H, BN_CW), 1024, 0, (cudaStream_t)stream>>>(Z, A, pre_out, H, n_seg, seg_off_dev, max_rows, train,
-                                                                        gamma, beta, running_mean, running_var, stats,
-                                                                        keep_mask, rng, stream_id, p_drop, relu,
-                                                                        dp_partial_out, dp_sums, ext_cnt);
+  if (!train) {
+    if (max_rows == 0) return SCNB_OK;
+    const bool v4 = (H % 4 == 0) && ((((uintptr_t)Z | (uintptr_t)A | (uintptr_t)pre_out | (uintptr_t)gamma | (uintptr_t)beta |
+                                       (uintptr_t)running_mean | (uintptr_t)running_var) % 16) == 0);
+    const size_t work = (size_t)max_rows * (v4 ? H / 4 : H);
+    const int blocks = (int)((work + 255) / 256 < 148 * 16 ? (work + 255) / 256 : 148 * 16);
+    if (v4)
+      k_bn_eval_fwd<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(Z, A, pre_out, H, seg_off_dev, n_seg, max_rows, gamma, beta,
+                                                                    running_mean, running_var, relu);
+    else
+      k_bn_eval_fwd<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(Z, A, pre_out, H, seg_off_dev, n_seg, max_rows, gamma, beta,
+                                                                     running_mean, running_var, relu);
+    SCNB_CHECK_LAUNCH("bn_act_fwd/eval");
+    return SCNB_OK;
+  }
+  dim3 grid(scnb_cdiv(H, BN_CW), n_seg);
+  k_bn_act_fwd<<<grid, 1024, 0, (cudaStream_t)stream>>>(Z, A, pre_out, H, n_seg, seg_off_dev, max_rows, train, gamma, beta,
+                                                         running_mean, running_var, stats, keep_mask, rng, stream_id, p_drop,
+                                                         relu, dp_partial_out, dp_sums, ext_cnt);
   SCNB_CHECK_LAUNCH("bn_act_fwd");
   return SCNB_OK;
 }
@@ -341,6 +454,7 @@ extern "C" int scnb_bn_act_fwd(const float* Z, float* A, float* pre_out, int H, 
 // Backward (train mode).  dA is the gradient w.r.t. the post-ReLU activation A.
 //   dd = dA*[A>0]; dy = dd*keep/(1-p); dbeta += sum dy; dgamma += sum dy*zhat;
 //   dz = gamma*invstd*(dy - mean(dy) - zhat*mean(dy*zhat))
+// Grid = (ceil(H/8), n_seg); dgamma/dbeta receive one atomic add per segment.
 __global__ void __launch_bounds__(1024) k_bn_act_bwd(const float* __restrict__ dA, const float* __restrict__ Z,
                                                      const float* __restrict__ Aact, int H, int n_seg,
                                                      const int32_t* __restrict__ seg_off, int max_rows,
@@ -353,9 +467,11 @@ __global__ void __launch_bounds__(1024) k_bn_act_bwd(const float* __restrict__ d
   // Data-parallel protocol as in the forward: pass 1 (partial_out) writes the local column sums
   // [seg][0]=sum dy, [seg][1]=sum dy*zhat and accumulates the local dgamma/dbeta; after the
   // all-reduce, pass 2 (ext_sums) forms dZ from the global sums and global row counts.
-  __shared__ float red[BN_RL][BN_CW];
+  __shared__ __align__(16) float red1[BN_CW][32];
+  __shared__ __align__(16) float red2[BN_CW][32];
   const int cx = threadIdx.x & (BN_CW - 1), ry = threadIdx.x / BN_CW;
   const int c = blockIdx.x * BN_CW + cx;
+  const int s = blockIdx.y;
   const bool cok = c < H;
   const float g = cok ? gamma[c] : 1.f;
   uint64_t seed = 0, strm = 0;
@@ -364,60 +480,53 @@ __global__ void __launch_bounds__(1024) k_bn_act_bwd(const float* __restrict__ d
     strm = rng[1] * 64ull + stream_id;
   }
   const float drop_scale = 1.0f / (1.0f - p_drop);
-  float dg_tot = 0.f, db_tot = 0.f;
-  for (int s = 0; s < n_seg; ++s) {
-    const int r0 = seg_off[s], r1 = min(seg_off[s + 1], max_rows);
-    const int n = r1 - r0;
-    const float mean = cok ? stats[((size_t)s * 3 + 0) * H + c] : 0.f;
-    const float invstd = cok ? stats[((size_t)s * 3 + 2) * H + c] : 1.f;
-    float s1 = 0.f, s2 = 0.f;
-    float inv_n = 1.0f / (float)max(n, 1);
-    if (ext_sums) {
-      s1 = cok ? ext_sums[((size_t)s * 2 + 0) * H + c] : 0.f;
-      s2 = cok ? ext_sums[((size_t)s * 2 + 1) * H + c] : 0.f;
-      inv_n = 1.0f / fmaxf(ext_cnt[s], 1.f);
-    } else {
-      if (cok)
-        for (int r = r0 + ry; r < r1; r += BN_RL) {
-          const size_t o = (size_t)r * H + c;
-          float dy = dA[o];
-          if (relu && !(Aact[o] > 0.f)) dy = 0.f;
-          if (p_drop > 0.f) dy = dropout_keep(keep_mask, o, seed, strm, p_drop) ? dy * drop_scale : 0.f;
-          s1 += dy;
-          s2 = fmaf(dy, (Z[o] - mean) * invstd, s2);
-        }
-      s1 = bn_block_colsum(s1, red, cx, ry);
-      s2 = bn_block_colsum(s2, red, cx, ry);
-      dg_tot += s2;
-      db_tot += s1;
-      if (partial_out) {
-        if (cok && ry == 0) {
-          partial_out[((size_t)s * 2 + 0) * H + c] = s1;
-          partial_out[((size_t)s * 2 + 1) * H + c] = s2;
-        }
-        if (blockIdx.x == 0 && threadIdx.x == 0) partial_out[(size_t)n_seg * 2 * H + s] = (float)n;
-        continue;
-      }
-    }
-    const float m1 = s1 * inv_n, m2 = s2 * inv_n, k = g * invstd;
+  const int r0 = min(seg_off[s], max_rows), r1 = min(seg_off[s + 1], max_rows);
+  const int n = r1 - r0;
+  const float mean = cok ? stats[((size_t)s * 3 + 0) * H + c] : 0.f;
+  const float invstd = cok ? stats[((size_t)s * 3 + 2) * H + c] : 1.f;
+  float s1 = 0.f, s2 = 0.f;
+  float inv_n = 1.0f / (float)max(n, 1);
+  if (ext_sums) {
+    s1 = cok ? ext_sums[((size_t)s * 2 + 0) * H + c] : 0.f;
+    s2 = cok ? ext_sums[((size_t)s * 2 + 1) * H + c] : 0.f;
+    inv_n = 1.0f / fmaxf(ext_cnt[s], 1.f);
+  } else {
     if (cok)
       for (int r = r0 + ry; r < r1; r += BN_RL) {
         const size_t o = (size_t)r * H + c;
         float dy = dA[o];
         if (relu && !(Aact[o] > 0.f)) dy = 0.f;
         if (p_drop > 0.f) dy = dropout_keep(keep_mask, o, seed, strm, p_drop) ? dy * drop_scale : 0.f;
-        const float zh = (Z[o] - mean) * invstd;
-        dZ[o] = k * (dy - m1 - zh * m2);
+        s1 += dy;
+        s2 = fmaf(dy, (Z[o] - mean) * invstd, s2);
       }
-  }
-  if (cok) {
-    if (!partial_out)
-      for (int r = min(seg_off[n_seg], max_rows) + ry; r < max_rows; r += BN_RL) dZ[(size_t)r * H + c] = 0.f;
-    if (ry == 0 && !ext_sums) {
-      dgamma[c] += dg_tot;
-      dbeta[c] += db_tot;
+    s1 = bn_block_colsum(s1, red1, cx);
+    s2 = bn_block_colsum(s2, red2, cx);
+    if (cok && ry == 0 && n > 0) {
+      atomicAdd(dgamma + c, s2);
+      atomicAdd(dbeta + c, s1);
+    }
+    if (partial_out) {
+      if (cok && ry == 0) {
+        partial_out[((size_t)s * 2 + 0) * H + c] = s1;
+        partial_out[((size_t)s * 2 + 1) * H + c] = s2;
+      }
+      if (blockIdx.x == 0 && threadIdx.x == 0) partial_out[(size_t)n_seg * 2 * H + s] = (float)n;
+      return;
     }
   }
+  if (!cok) return;
+  const float m1 = s1 * inv_n, m2 = s2 * inv_n, k = g * invstd;
+  for (int r = r0 + ry; r < r1; r += BN_RL) {
+    const size_t o = (size_t)r * H + c;
+    float dy = dA[o];
+    if (relu && !(Aact[o] > 0.f)) dy = 0.f;
+    if (p_drop > 0.f) dy = dropout_keep(keep_mask, o, seed, strm, p_drop) ? dy * drop_scale : 0.f;
+    const float zh = (Z[o] - mean) * invstd;
+    dZ[o] = k * (dy - m1 - zh * m2);
+  }
+  if (s == n_seg - 1)
+    for (int r = r1 + ry; r < max_rows; r += BN_RL) dZ[(size_t)r * H + c] = 0.f;
 }
 
 extern "C" int scnb_bn_act_bwd(const float* dA, const float* Z, const float* A, int H, int n_seg, const int32_t* seg_off_dev,
@@ -429,9 +538,10 @@ extern "C" int scnb_bn_act_bwd(const float* dA, const float* Z, const float* A, 
   SCNB_CHECK_ARG(!(p_drop > 0.f) || keep_mask || rng, "bn_act_bwd: dropout needs keep_mask or rng state");
   SCNB_CHECK_ARG(!(dp_partial_out && dp_sums), "bn_act_bwd: partial and reduced sums are exclusive");
   const float* ext_cnt = dp_sums ? dp_sums + (size_t)n_seg * 2 * H : nullptr;
-  k_bn_act_bwd<<<scnb_cdiv(H, BN_CW), 1024, 0, (cudaStream_t)stream>>>(dA, Z, A, H, n_seg, seg_off_dev, max_rows, gamma, stats,
-                                                                        keep_mask, rng, stream_id, p_drop, relu, dZ, dgamma,
-                                                                        dbeta, dp_partial_out, dp_sums, ext_cnt);
+  dim3 grid(scnb_cdiv(H, BN_CW), n_seg);
+  k_bn_act_bwd<<<grid, 1024, 0, (cudaStream_t)stream>>>(dA, Z, A, H, n_seg, seg_off_dev, max_rows, gamma, stats, keep_mask, rng,
+                                                         stream_id, p_drop, relu, dZ, dgamma, dbeta, dp_partial_out, dp_sums,
+                                                         ext_cnt);
   SCNB_CHECK_LAUNCH("bn_act_bwd");
   return SCNB_OK;
 }

@@ -6,9 +6,7 @@
 // Hyper-parameters live in a small device buffer so that a captured CUDA graph can be replayed
 // while lr / weights change:  hp = [lr, weight_decay, beta1, beta2, eps, rho, momentum, 0]
 // state (int64): st = [t (optimizer steps taken), rng_seed, rng_counter, mm_step]
-#include "common.cuh"
-
-enum { OPT_ADADELTA = 0, OPT_ADAM = 1, OPT_ADAMW = 2, OPT_SGD = 3 };
+#include "optim.cuh"
 
 __global__ void k_step_begin(int64_t* st) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -32,45 +30,16 @@ template <int OPT>
 __global__ void __launch_bounds__(256) k_optim(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ s1,
                                                float* __restrict__ s2, size_t n, const float* __restrict__ hp,
                                                const int64_t* __restrict__ st) {
-  __shared__ float sh[4];
-  const float lr = hp[0], wd = hp[1], b1 = hp[2], b2 = hp[3], eps = hp[4], rho = hp[5], mom = hp[6];
-  if (threadIdx.x == 0) {
-    const double t = (double)st[0];
-    const double bc1 = 1.0 - pow((double)b1, t), bc2 = 1.0 - pow((double)b2, t);
-    sh[0] = (float)((double)lr / bc1);  // step_size
-    sh[1] = (float)sqrt(bc2);
-    sh[2] = (st[0] <= 1) ? 1.f : 0.f;   // first step (SGD momentum buffer init)
-  }
+  __shared__ OptimConsts cs;
+  if (threadIdx.x == 0) cs = optim_consts(hp, st);
   __syncthreads();
-  const float step_size = sh[0], bc2_sqrt = sh[1];
-  const bool first = sh[2] != 0.f;
+  const OptimConsts c = cs;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    float pi = p[i], gi = g[i];
-    if (OPT == OPT_ADADELTA) {
-      gi = fmaf(wd, pi, gi);
-      float sq = rho * s1[i] + (1.f - rho) * gi * gi;
-      float acc = s2[i];
-      const float delta = sqrtf(acc + eps) / sqrtf(sq + eps) * gi;
-      acc = rho * acc + (1.f - rho) * delta * delta;
-      s1[i] = sq;
-      s2[i] = acc;
-      p[i] = pi - lr * delta;
-    } else if (OPT == OPT_ADAM || OPT == OPT_ADAMW) {
-      if (OPT == OPT_ADAMW) pi = pi * (1.f - lr * wd);
-      else gi = fmaf(wd, pi, gi);
-      float m = s1[i], v = s2[i];
-      m = m + (1.f - b1) * (gi - m);
-      v = b2 * v + (1.f - b2) * gi * gi;
-      const float denom = sqrtf(v) / bc2_sqrt + eps;
-      s1[i] = m;
-      s2[i] = v;
-      p[i] = pi - step_size * (m / denom);
-    } else {  // SGD with momentum (dampening 0, no nesterov)
-      gi = fmaf(wd, pi, gi);
-      float buf = first ? gi : mom * s1[i] + gi;
-      s1[i] = buf;
-      p[i] = pi - lr * buf;
-    }
+    float pi = p[i], a = s1[i], b = (OPT == OPT_SGD) ? 0.f : s2[i];
+    optim_update<OPT>(pi, g[i], a, b, c);
+    s1[i] = a;
+    if (OPT != OPT_SGD) s2[i] = b;
+    p[i] = pi;
   }
 }
 

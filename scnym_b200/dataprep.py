@@ -126,7 +126,7 @@ def gather_rows(ds: DeviceCSR, rows: Optional[torch.Tensor] = None, row0: int = 
     st = _stream()
     call("scnb_csr_row_offsets", ptr(ds.indptr), ptr(rows), row0, n, ptr(out.indptr), None, st)
     call("scnb_csr_gather_rows", ptr(ds.indptr), ptr(ds.indices), ptr(ds.data), ptr(rows), row0, n, ptr(out.indptr),
-         ptr(out.indices), ptr(out.data), int(augment), 0, n, ptr(keep_mask), ptr(rng), stream_id, float(p_drop), st)
+         ptr(out.indices), ptr(out.data), int(augment), 0, n, ptr(keep_mask), ptr(rng), stream_id, float(p_drop), None, st)
     return out
 
 
@@ -356,7 +356,7 @@ class Log1pDrop(object):
         st = _stream()
         call("scnb_csr_row_offsets", ptr(ds.indptr), None, 0, n, ptr(out.indptr), None, st)
         call("scnb_csr_gather_rows", ptr(ds.indptr), ptr(ds.indices), ptr(ds.data), None, 0, n, ptr(out.indptr), ptr(out.indices),
-             ptr(out.data), 1, 0, n, ptr(keep), None, 0, float(self.p_drop), st)
+             ptr(out.data), 1, 0, n, ptr(keep), None, 0, float(self.p_drop), None, st)
         sample["input"] = out.data[: n * ds.n_cols].view(n, ds.n_cols) if dense else out
         return sample
 

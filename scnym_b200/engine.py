@@ -59,6 +59,7 @@ class EngineConfig:
     class_weight: Optional[List[float]] = None
     seed: int = 0
     use_cuda_graph: bool = True
+    keep_w1_grad: bool = False   # also write the first-layer gradient to HBM (parity tests; implied by data parallelism)
 
 
 class ParamArena(object):
@@ -216,6 +217,12 @@ class TrainEngine(object):
         self.b_indptr, self.b_idx, self.b_val = i32(self.nb + 1), i32(cap), f32(cap)
         H0 = self.widths[0]
         self.Z1 = f32(self.nb, H0)
+        # gene-major copy of the batch for the fused dW1 + optimizer kernel (needs W1T first in the arena)
+        self.P1 = self.G * H0
+        self.fused_w1 = (H0 % 64 == 0) and self.arena.names[0] == self._blk[0]["W"] and self.arena.offsets[self._blk[0]["W"]] == 0
+        if self.fused_w1:
+            self.gene_cnt, self.c_ptr, self.c_cursor = i32(self.G), i32(self.G + 1), i32(self.G)
+            self.c_ent = i32(cap, 2)
         # injected randomness (tests); None -> Philox in-kernel
         self.inj_in_keep_L = None     # uint8 [cap] aligned with batch nnz positions
         self.inj_in_keep_U = None     # list of K uint8 [U*maxnnz]
@@ -318,7 +325,7 @@ class TrainEngine(object):
         blk = self._blk
         self._fetch(st)
         call("scnb_step_begin", ptr(self.state), st)
-        self.arena.grad.zero_()
+        self._zero_grads()
         self.loss_buf.zero_()
         # -- ids of the sampled rows
         call("scnb_gather_i32", ptr(self.lab_y), ptr(self.l_rows), L, 0, ptr(self.lab_ids), st)
@@ -329,10 +336,11 @@ class TrainEngine(object):
         call("scnb_csr_row_offsets", ptr(self.unl.indptr), ptr(self.u_rows), 0, U, ptr(self.b_indptr), None, st)
         call("scnb_csr_row_offsets", ptr(self.lab.indptr), ptr(self.l_rows), 0, L, ptr(self.b_indptr[U:]), ptr(self.b_indptr[U:]), st)
         call("scnb_csr_gather_rows", ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data), ptr(self.u_rows), 0, U,
-             ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), 0, 0, 0, None, None, 0, 0.0, st)
+             ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), 0, 0, 0, None, None, 0, 0.0, self._gene_cnt_ptr(), st)
         call("scnb_csr_gather_rows", ptr(self.lab.indptr), ptr(self.lab.indices), ptr(self.lab.data), ptr(self.l_rows), 0, L,
              ptr(self.b_indptr[U:]), ptr(self.b_idx), ptr(self.b_val), 1, 0, L, ptr(self.inj_in_keep_L), rng, SID_IN_L,
-             c.p_in_drop, st)
+             c.p_in_drop, self._gene_cnt_ptr(), st)
+        self._build_csc(nb, st)
         # -- first layer, once
         call("scnb_csr_linear_fwd", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), nb, self.P(blk[0]["W"]),
              self.P(blk[0]["b"]), H0, ptr(self.Z1), st)
@@ -349,7 +357,7 @@ class TrainEngine(object):
                     km = self.inj_in_keep_U[k] if self.inj_in_keep_U is not None else None
                     call("scnb_csr_gather_rows", ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data),
                          ptr(self.u_rows), 0, U, ptr(self.tb_indptr), ptr(self.tb_idx), ptr(self.tb_val), 1, 0, U, ptr(km), rng,
-                         SID_IN_U + k, c.p_in_drop, st)
+                         SID_IN_U + k, c.p_in_drop, None, st)
                     ip, ix, vv = self.tb_indptr, self.tb_idx, self.tb_val
                 else:
                     ip, ix, vv = self.b_indptr, self.b_idx, self.b_val
@@ -427,9 +435,7 @@ class TrainEngine(object):
         dZ_first = self._student_backward(st, rng, dA_last)
         call("scnb_unmix_rows", ptr(dZ_first), H0, ptr(self.inv3), ptr(self.coef3), nb, ptr(self.dZ1), st)
         call("scnb_colsum", ptr(self.dZ1), nb, H0, H0, self.Gp(blk[0]["b"]), 1, st)
-        call("scnb_csr_linear_bwd_dw", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), nb, ptr(self.dZ1), H0,
-             self.Gp(blk[0]["W"]), st)
-        self._finish_step(st)
+        self._finish_step(st, self.dZ1, nb)
         call("scnb_mm_step_inc", ptr(self.state), st)
 
     def _view(self, buf, rows, width):
@@ -498,13 +504,48 @@ class TrainEngine(object):
             call("scnb_sgemm", 0, 0, R, wp, w, ptr(dZ), w, self.P(blk[a]["W"]), wp, ptr(dA), wp, 1.0, 0.0, None, 0, None, st)
         return None
 
-    def _finish_step(self, st):
-        """optimizer.step() + BatchNorm running statistics in the reference's update order."""
+    def _gene_cnt_ptr(self):
+        return ptr(self.gene_cnt) if self.fused_w1 else None
+
+    def _build_csc(self, n_rows, st):
+        if self.fused_w1:
+            call("scnb_csr_to_csc", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), n_rows, self.G, ptr(self.gene_cnt),
+                 ptr(self.c_ptr), ptr(self.c_cursor), ptr(self.c_ent), st)
+
+    def _zero_grads(self):
+        # the first-layer gradient is either never materialised (fused update) or fully overwritten
+        if self.fused_w1:
+            self.arena.grad[self.P1:].zero_()
+        else:
+            self.arena.grad.zero_()
+
+    def _finish_step(self, st, dZ1, n_rows):
+        """First-layer weight gradient, optimizer.step() and BatchNorm running statistics in the
+        reference's update order.  dZ1: gradient w.r.t. the first Linear's output, rows aligned with the batch CSR."""
         c = self.cfg
-        if self.comm is not None:
-            self.comm.all_reduce_avg(self.arena.grad)  # data-parallel gradient exchange (NCCL over NVLink)
-        call("scnb_optim_step", OPTIMIZER_CODES[c.optimizer], ptr(self.arena.flat), ptr(self.arena.grad),
-             ptr(self.arena.state1), ptr(self.arena.state2), self.arena.total, ptr(self.hp), ptr(self.state), st)
+        H0 = self.widths[0]
+        W1 = self._blk[0]["W"]
+        opt = OPTIMIZER_CODES[c.optimizer]
+        hp, s4 = ptr(self.hp), ptr(self.state)
+        ar = self.arena
+        if not self.fused_w1:
+            call("scnb_csr_linear_bwd_dw", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), n_rows, ptr(dZ1), H0, self.Gp(W1), st)
+            if self.comm is not None:
+                self.comm.all_reduce_avg(ar.grad)
+            call("scnb_optim_step", opt, ptr(ar.flat), ptr(ar.grad), ptr(ar.state1), ptr(ar.state2), ar.total, hp, s4, st)
+        elif self.comm is not None:
+            # data parallel: gradient only (no atomics, every gene row written), exchange, then one update pass
+            call("scnb_csr_w1_bwd_optim", -1, ptr(self.c_ptr), ptr(self.c_ent), ptr(dZ1), n_rows, H0, self.G, None, self.Gp(W1),
+                 None, None, None, None, st)
+            self.comm.all_reduce_avg(ar.grad)  # NCCL over NVLink
+            call("scnb_optim_step", opt, ptr(ar.flat), ptr(ar.grad), ptr(ar.state1), ptr(ar.state2), ar.total, hp, s4, st)
+        else:
+            keep = self.Gp(W1) if c.keep_w1_grad else None
+            call("scnb_csr_w1_bwd_optim", opt, ptr(self.c_ptr), ptr(self.c_ent), ptr(dZ1), n_rows, H0, self.G, ptr(ar.flat), keep,
+                 ptr(ar.state1), ptr(ar.state2), hp, s4, st)
+            rest = ar.total - self.P1
+            call("scnb_optim_step", opt, ptr(ar.flat[self.P1:]), ptr(ar.grad[self.P1:]), ptr(ar.state1[self.P1:]),
+                 ptr(ar.state2[self.P1:]), rest, hp, s4, st)
         done = set()
         for a in range(self.n_app):
             bn = self._blk[a]["bn"]
@@ -557,12 +598,13 @@ class TrainEngine(object):
         blk = self._blk
         self._fetch(st)
         call("scnb_step_begin", ptr(self.state), st)
-        self.arena.grad.zero_()
+        self._zero_grads()
         self.loss_buf.zero_()
         call("scnb_gather_i32", ptr(self.lab_y), ptr(self.l_rows), L, 0, ptr(self.lab_ids), st)
         call("scnb_csr_row_offsets", ptr(self.lab.indptr), ptr(self.l_rows), 0, L, ptr(self.b_indptr), None, st)
         call("scnb_csr_gather_rows", ptr(self.lab.indptr), ptr(self.lab.indices), ptr(self.lab.data), ptr(self.l_rows), 0, L,
-             ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), 0, 0, 0, None, None, 0, 0.0, st)
+             ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), 0, 0, 0, None, None, 0, 0.0, self._gene_cnt_ptr(), st)
+        self._build_csc(L, st)
         call("scnb_csr_linear_fwd", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), L, self.P(blk[0]["W"]),
              self.P(blk[0]["b"]), H0, ptr(self.Zs[0]), st)
         self._student_forward(st, rng)
@@ -580,9 +622,7 @@ class TrainEngine(object):
         call("scnb_colsum", ptr(self.dlogits), L, C, C, self.Gp("model.classif.0.bias"), 1, st)
         dZ1 = self._student_backward(st, rng, dA_last)
         call("scnb_colsum", ptr(dZ1), L, H0, H0, self.Gp(blk[0]["b"]), 1, st)
-        call("scnb_csr_linear_bwd_dw", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), L, ptr(dZ1), H0,
-             self.Gp(blk[0]["W"]), st)
-        self._finish_step(st)
+        self._finish_step(st, dZ1, L)
 
     # ------------------------------------------------------------------------------------
     def _launch(self):

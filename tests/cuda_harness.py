@@ -44,7 +44,7 @@ def build_engine(d, device="cuda"):
                        mean_teacher=bool(d["meta_mean_teacher"]), decay_coef=0.997, use_dan=bool(d["meta_use_dan"]),
                        dan_use_conf_pseudolabels=bool(d["meta_dan_conf"]), dan_scale_loss_pseudoconf=bool(d["meta_dan_scale"]),
                        optimizer=str(d["meta_opt"]), lr=float(d["meta_lr"]), weight_decay=float(d["meta_wd"]), class_weight=cw,
-                       use_cuda_graph=False)
+                       use_cuda_graph=False, keep_w1_grad=True)
     given = bool(int(d["meta_D_given"]))
     eng = TrainEngine(model, cfg, lab, d["lab_y"], int(d["meta_L"]), unlabeled=unl, unlabeled_batch_size=int(d["meta_U"]),
                       dann=dann, labeled_domain=d["lab_dom"] if given else None,

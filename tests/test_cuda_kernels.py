@@ -379,3 +379,112 @@ def test_bad_arguments_raise():
     from scnym_b200._lib import call, ScnbError
     with pytest.raises(ScnbError):
         call("scnb_sgemm", 0, 0, 4, 4, 4, None, 4, None, 4, None, 4, 1.0, 0.0, None, 0, None, _st())
+
+
+@pytest.mark.parametrize("n,H0", [(512, 256), (37, 128), (300, 256), (2500, 128)])
+def test_csr_linear_fwd_split_rows(n, H0):
+    """Warps-per-row split (small batches) and the one-warp-per-row form agree with the dense product."""
+    from oracle import scnym_oracle as O
+    from scnym_b200._lib import call, ptr
+    from scnym_b200.dataprep import DeviceCSR, gather_rows
+    G = 3000
+    ip, ii, dd, _ = O.synth_csr(n, G, 0.05, 3, seed=n)
+    X = O.csr_to_dense(ip, ii, dd, G, np.arange(n))
+    ds = DeviceCSR.from_arrays(ip, ii, dd, G)
+    b = gather_rows(ds, torch.arange(n).cuda())
+    torch.manual_seed(n)
+    WT, b1 = torch.randn(G, H0) * 0.1, torch.randn(H0)
+    Z = torch.empty(n, H0).cuda()
+    call("scnb_csr_linear_fwd", ptr(b.indptr), ptr(b.indices), ptr(b.data), n, ptr(D(WT)), ptr(D(b1)), H0, ptr(Z), _st())
+    _chk("csr fwd split", Z.cpu(), X.double() @ WT.double() + b1.double())
+
+
+@pytest.mark.parametrize("opt", ["none", "adadelta", "adam", "adamw", "sgd"])
+@pytest.mark.parametrize("n,H0", [(96, 128), (1100, 64)])   # dZ slice staged in shared memory / read through L2
+def test_csr_w1_bwd_optim_matches_dense_and_torch_optim(opt, n, H0):
+    from oracle import scnym_oracle as O
+    from scnym_b200._lib import call, ptr, OPTIMIZER_CODES
+    from scnym_b200.dataprep import DeviceCSR, gather_rows
+    G = 700
+    ip, ii, dd, _ = O.synth_csr(n, G, 0.06, 3, seed=5)
+    dd = dd.copy()
+    dd[::7] = 0.0                                   # stored zeros (dropped entries) must be skipped
+    X = O.csr_to_dense(ip, ii, dd, G, np.arange(n))
+    ds = DeviceCSR.from_arrays(ip, ii, dd, G)
+    b = gather_rows(ds, torch.arange(n).cuda())
+    nnz = int(ip[n])
+    cnt = torch.zeros(G, dtype=torch.int32).cuda()
+    c_ptr, cur = torch.zeros(G + 1, dtype=torch.int32).cuda(), torch.zeros(G, dtype=torch.int32).cuda()
+    ent = torch.zeros(nnz, 2, dtype=torch.int32).cuda()
+    torch.manual_seed(3)
+    W0 = torch.randn(G, H0) * 0.1
+    W, s1, s2 = W0.cuda(), torch.zeros(G, H0).cuda(), torch.zeros(G, H0).cuda()
+    rp = W0.clone().requires_grad_(True)
+    kw = dict(lr=1.0 if opt == "adadelta" else 0.01, weight_decay=1e-2)
+    cls = {"adadelta": torch.optim.Adadelta, "adam": torch.optim.Adam, "adamw": torch.optim.AdamW, "sgd": torch.optim.SGD}.get(opt)
+    ropt = None if cls is None else (cls([rp], momentum=0.9, **kw) if opt == "sgd" else cls([rp], **kw))
+    eps = 1e-6 if opt == "adadelta" else 1e-8
+    hp = torch.tensor([kw["lr"], kw["weight_decay"], 0.9, 0.999, eps, 0.9, 0.9, 0.0]).cuda()
+    state = torch.zeros(4, dtype=torch.int64).cuda()
+    for t in range(3):
+        dZ = torch.randn(n, H0)
+        want_g = (X.double().t() @ dZ.double()).float()
+        call("scnb_csc_count", ptr(b.indices), ptr(b.data), nnz, ptr(cnt), _st())
+        call("scnb_csr_to_csc", ptr(b.indptr), ptr(b.indices), ptr(b.data), n, G, ptr(cnt), ptr(c_ptr), ptr(cur), ptr(ent), _st())
+        assert int(cnt.abs().sum()) == 0                      # histogram reset for the next step
+        assert int(c_ptr[G]) == int((dd[:nnz] != 0).sum())
+        grad = torch.full((G, H0), 7.0).cuda()                # every gene row must be overwritten
+        call("scnb_step_begin", ptr(state), _st())
+        if opt == "none":
+            call("scnb_csr_w1_bwd_optim", -1, ptr(c_ptr), ptr(ent), ptr(D(dZ)), n, H0, G, None, ptr(grad), None, None, None, None, _st())
+        else:
+            call("scnb_csr_w1_bwd_optim", OPTIMIZER_CODES[opt], ptr(c_ptr), ptr(ent), ptr(D(dZ)), n, H0, G, ptr(W), ptr(grad),
+                 ptr(s1), ptr(s2), ptr(hp), ptr(state), _st())
+            rp.grad = want_g.clone()
+            ropt.step()
+            _chk(f"{opt} W t={t}", W.cpu(), rp.detach(), tol=5e-6)
+        _chk("dW1", grad.cpu(), want_g, tol=1e-5)
+    if opt == "adam":   # gradient not materialised: same update with grad_out = NULL
+        W2, a2, b2 = W0.cuda(), torch.zeros(G, H0).cuda(), torch.zeros(G, H0).cuda()
+        st2 = torch.zeros(4, dtype=torch.int64).cuda()
+        call("scnb_step_begin", ptr(st2), _st())
+        call("scnb_csc_count", ptr(b.indices), ptr(b.data), nnz, ptr(cnt), _st())
+        call("scnb_csr_to_csc", ptr(b.indptr), ptr(b.indices), ptr(b.data), n, G, ptr(cnt), ptr(c_ptr), ptr(cur), ptr(ent), _st())
+        call("scnb_csr_w1_bwd_optim", 1, ptr(c_ptr), ptr(ent), ptr(D(dZ)), n, H0, G, ptr(W2), None, ptr(a2), ptr(b2), ptr(hp),
+             ptr(st2), _st())
+        r2 = W0.clone().requires_grad_(True)
+        o2 = torch.optim.Adam([r2], **kw)
+        r2.grad = want_g.clone()
+        o2.step()
+        _chk("adam no-grad-out", W2.cpu(), r2.detach(), tol=5e-6)
+
+
+@pytest.mark.parametrize("M,N,K,tA,tB,beta", [(1024, 256, 256, 0, 1, 0.0), (512, 256, 256, 0, 0, 0.0), (256, 256, 1024, 1, 0, 1.0),
+                                               (16, 256, 512, 1, 0, 1.0), (1024, 2, 256, 0, 1, 0.0), (100, 40, 300, 1, 0, 1.0)])
+def test_sgemm_small_tiles_and_split_k(M, N, K, tA, tB, beta):
+    from scnym_b200._lib import call, ptr
+    torch.manual_seed(M + N + K)
+    A = torch.randn((K, M) if tA else (M, K))
+    B = torch.randn((N, K) if tB else (K, N))
+    C0 = torch.randn(M, N)
+    want = (A.t() if tA else A).double() @ (B.t() if tB else B).double() + beta * C0.double()
+    Cd = C0.cuda().clone()
+    Ad, Bd = A.cuda(), B.cuda()
+    call("scnb_sgemm", tA, tB, M, N, K, ptr(Ad), Ad.shape[1], ptr(Bd), Bd.shape[1], ptr(Cd), N, 1.0, beta, None, 0, None, _st())
+    _chk(f"sgemm {M}x{N}x{K}", Cd.cpu(), want.float(), tol=2e-5)
+
+
+def test_bn_eval_fwd_large_rows():
+    from scnym_b200._lib import call, ptr
+    n, H = 5000, 96
+    Z = torch.randn(n, H)
+    g, b, rm, rv = torch.rand(H) + 0.5, torch.randn(H), torch.randn(H), torch.rand(H) + 0.5
+    A, pre = torch.empty(n + 8, H).cuda(), torch.empty(n + 8, H).cuda()
+    Zd = torch.cat([Z, torch.ones(8, H)]).cuda()
+    seg = torch.tensor([0, n], dtype=torch.int32).cuda()
+    call("scnb_bn_act_fwd", ptr(Zd), ptr(A), ptr(pre), H, 1, ptr(seg), n + 8, 0, ptr(D(g)), ptr(D(b)), ptr(D(rm)), ptr(D(rv)),
+         None, None, None, 0, 0.0, 1, None, None, _st())
+    y = (Z.double() - rm.double()) / torch.sqrt(rv.double() + 1e-5) * g.double() + b.double()
+    _chk("bn eval pre", pre[:n].cpu(), y, tol=2e-6)
+    _chk("bn eval relu", A[:n].cpu(), y.clamp_min(0), tol=2e-6)
+    assert float(A[n:].abs().max()) == 0.0 and float(pre[n:].abs().max()) == 0.0

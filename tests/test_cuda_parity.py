@@ -92,7 +92,7 @@ def test_supervised_engine_matches_reference_golden():
     model.load_state_dict(GU.state_from(d, "init/"))
     model = model.cuda()
     lab = DeviceCSR.from_arrays(d["lab_indptr"], d["lab_indices"], d["lab_data"], G)
-    cfg = EngineConfig(optimizer="adadelta", lr=float(d["meta_lr"]), weight_decay=float(d["meta_wd"]), use_cuda_graph=False)
+    cfg = EngineConfig(optimizer="adadelta", lr=float(d["meta_lr"]), weight_decay=float(d["meta_wd"]), use_cuda_graph=False, keep_w1_grad=True)
     eng = TrainEngine(model, cfg, lab, d["lab_y"], B, mode="supervised")
     for s in range(int(d["meta_n_steps"])):
         pre = f"step{s}/"

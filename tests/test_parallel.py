@@ -165,7 +165,7 @@ def test_data_parallel_step_equals_global_batch_oracle(opt_name, lr):
             lab = DeviceCSR.from_arrays(d["lab_indptr"], d["lab_indices"], d["lab_data"], G)
             unl = DeviceCSR.from_arrays(d["unl_indptr"], d["unl_indices"], d["unl_data"], G)
             from scnym_b200.engine import EngineConfig
-            cfg = EngineConfig(optimizer=opt_name, lr=lr, weight_decay=float(d["meta_wd"]), use_cuda_graph=False)
+            cfg = EngineConfig(optimizer=opt_name, lr=lr, weight_decay=float(d["meta_wd"]), use_cuda_graph=False, keep_w1_grad=True)
             eng = TrainEngine(model, cfg, lab, d["lab_y"], l, unlabeled=unl, unlabeled_batch_size=u, dann=dann, mode="mixmatch",
                               comm=ThreadComm(2, shared, rk))
             eng.set_weights(float(d["meta_unsup_w"]), float(d["meta_dan_w"]))
