@@ -150,8 +150,9 @@ def time_kernels(eng, n_steps=12):
         return r
 
     import scnym_b200.engine as E
-    graph_flag = eng.cfg.use_cuda_graph
+    graph_flag, ms_flag = eng.cfg.use_cuda_graph, eng.cfg.multi_stream
     eng.cfg.use_cuda_graph = False
+    eng.cfg.multi_stream = False     # one stream, so that the events bracket each kernel
     E.call = timed
     try:
         for i in range(n_steps + 2):
@@ -161,7 +162,7 @@ def time_kernels(eng, n_steps=12):
         torch.cuda.synchronize()
     finally:
         E.call = orig
-        eng.cfg.use_cuda_graph = graph_flag
+        eng.cfg.use_cuda_graph, eng.cfg.multi_stream = graph_flag, ms_flag
     agg = {}
     for name, s, e in records:
         t = s.elapsed_time(e)

@@ -48,6 +48,23 @@ int scnb_csr_gather_rows(const int64_t* indptr, const int32_t* indices, const fl
                          int32_t* gene_cnt /*NULL or [G]: += per-gene count of non-zero entries (for scnb_csr_to_csc)*/,
                          void* stream);
 
+/* Two sources in one launch (the MixMatch batch [U_raw ; L_aug]): rows [0,nA) from A, [nA,nA+nB) from B. */
+int scnb_csr_gather_rows2(const int64_t* indptr_A, const int32_t* indices_A, const float* data_A, const int64_t* rows_A, int nA,
+                          int augment_A, uint32_t stream_id_A, const int64_t* indptr_B, const int32_t* indices_B,
+                          const float* data_B, const int64_t* rows_B, int nB, int augment_B, uint32_t stream_id_B,
+                          const int32_t* b_indptr, int32_t* b_idx, float* b_val, const uint8_t* keep_mask,
+                          const uint64_t* rng, float p_drop, int32_t* gene_cnt, void* stream);
+
+/* Step prologue in one launch: sampler hand-off (as scnb_fetch_step; tables may be NULL, then
+ * l_rows/u_rows are read as staged), labels/domain ids of the sampled rows
+ * (scnym/dataprep.py:157-162), batch row offsets [U rows ; L rows], zeroing of `zero_buf`
+ * (loss scalars) and the step counters of scnb_step_begin. */
+int scnb_step_prep(const int64_t* l_tab, const int64_t* u_tab, const float* key_tab, const float* gam_tab, int n_tab,
+                   int64_t* state4, int L, int U, int64_t* l_rows, int64_t* u_rows, float* keys, float* gam,
+                   const int32_t* lab_y, const int32_t* lab_dom, const int32_t* unl_dom, int want_dom, int32_t* lab_ids,
+                   int32_t* base_dom, const int64_t* lab_indptr, const int64_t* unl_indptr, int32_t* b_indptr,
+                   float* zero_buf, int n_zero, void* stream);
+
 /* Device-resident sampler hand-off (replaces DataLoader iteration, scnym/trainer.py:574-582):
  * copies the row ids / MixUp randomness of step (state4[0] % n_tab) from per-epoch tables. */
 int scnb_fetch_step(const int64_t* l_tab, const int64_t* u_tab, const float* key_tab, const float* gam_tab, int L, int U,
@@ -127,7 +144,8 @@ int scnb_unmix_rows(const float* dOut, int H, const int32_t* inv3 /*[3][n_base]*
  *      (scnym/losses.py:811-875, 1195-1213).  perm_keys stand in for torch.randperm
  *      (ridx = stable argsort(keys[:n_conf+L])), gamma_raw for Beta(alpha,alpha).sample(). ---- */
 int scnb_pseudolabel(const float* teacher_logits /*[K][U][C]*/, int K, int U, int C, float T, int sharpen,
-                     float min_confidence, float* q, float* conf, uint8_t* confident, float* scratch_UC, void* stream);
+                     float min_confidence, float* q, float* conf, uint8_t* confident, float* scratch_UC,
+                     const int32_t* lab_ids /*NULL or [L]: also write one-hot label rows q[U..U+L)*/, int L, void* stream);
 int scnb_mixmatch_plan(const uint8_t* confident, const float* perm_keys, const float* gamma_raw, int U, int L, int use_dan,
                        int dan_conf_only, int mixup_on, int32_t* counts8, int32_t* seg_off4,
                        int32_t* work_i /*[U + 3(U+L)]*/, int32_t* srcA, int32_t* srcB, float* gam, int Rmax, int32_t* inv3,

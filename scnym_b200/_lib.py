@@ -17,6 +17,8 @@ SIGNATURES = {
     "scnb_csr_row_offsets": [P, P, L, I, P, P, P],
     "scnb_gather_i32": [P, P, I, I, P, P],
     "scnb_csr_gather_rows": [P, P, P, P, L, I, P, P, P, I, I, I, P, P, U32, F, P, P],
+    "scnb_csr_gather_rows2": [P, P, P, P, I, I, U32, P, P, P, P, I, I, U32, P, P, P, P, P, F, P, P],
+    "scnb_step_prep": [P, P, P, P, I, P, I, I, P, P, P, P, P, P, P, I, P, P, P, P, P, P, I, P],
     "scnb_fetch_step": [P, P, P, P, I, I, I, P, P, P, P, P, P],
     "scnb_host_gather_rows": [P, P, P, P, I, P, P, P, L, I],
     "scnb_csr_linear_fwd": [P, P, P, I, P, P, I, P, P],
@@ -34,7 +36,7 @@ SIGNATURES = {
     "scnb_bn_running_update": [P, P, P, P, P, P, P, P, I, I, F, P, P],
     "scnb_mix_rows": [P, I, P, P, P, P, I, P, P],
     "scnb_unmix_rows": [P, I, P, P, I, P, P],
-    "scnb_pseudolabel": [P, I, I, I, F, I, F, P, P, P, P, P],
+    "scnb_pseudolabel": [P, I, I, I, F, I, F, P, P, P, P, P, I, P],
     "scnb_mixmatch_plan": [P, P, P, I, I, I, I, I, P, P, P, P, P, P, I, P, P, P, P],
     "scnb_soft_ce_fwd_bwd": [P, I, I, P, P, P, P, P, I, P, P, I, F, P, P, P, I, P, P],
     "scnb_softmax_mse_fwd_bwd": [P, I, I, P, P, P, P, P, I, I, P, F, P, P, P],

@@ -63,27 +63,63 @@ extern "C" int scnb_csr_row_offsets(const int64_t* indptr, const int64_t* rows, 
 // ---------------------------------------------------------------------------------------------
 // Gather rows into a compact batch CSR; optional log1p_drop on the stored entries only
 // (expm1(0)=0, dropout(0)=0, log1p(0)=0 => support is preserved).
-// One warp per row.  keep_mask (if given) is aligned with the batch nnz order.
+// One 128-thread CTA per row (a 256+256-row training batch then covers the chip); rows [0,nA) come
+// from source A, rows [nA, nA+nB) from source B, so the whole [U_raw ; L_aug] batch is one launch.
+// keep_mask (if given) is aligned with the batch nnz order.  gene_cnt (if given) accumulates the
+// per-gene number of non-zero entries written (histogram for scnb_csr_to_csc).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_gather_rows(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                                                     const float* __restrict__ data, const int64_t* __restrict__ rows,
-                                                     int64_t row0, int n, const int32_t* __restrict__ b_indptr,
-                                                     int32_t* __restrict__ b_idx, float* __restrict__ b_val, int augment,
-                                                     int aug_row_begin, int aug_row_end, const uint8_t* __restrict__ keep_mask,
-                                                     const uint64_t* __restrict__ rng, uint32_t stream_id, float p_drop,
-                                                     float target_sum, int32_t* __restrict__ gene_cnt) {
-  const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= n) return;
-  const int64_t r = rows ? rows[i] : (row0 + i);
-  const int64_t s = indptr[r];
-  const int len = (int)(indptr[r + 1] - s);
+struct GatherSrc {
+  const int64_t* indptr;
+  const int32_t* indices;
+  const float* data;
+  const int64_t* rows;  // NULL: row0 + i
+  int64_t row0;
+  int n;
+  int augment;          // 1: log1p_drop on rows [aug_begin, aug_end) (row index local to this source)
+  int aug_begin, aug_end;
+  uint32_t stream_id;
+};
+
+__device__ __forceinline__ float block128_sum(float v, float* red4) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red4[threadIdx.x >> 5] = v;
+  __syncthreads();
+  const float t = (red4[0] + red4[1]) + (red4[2] + red4[3]);
+  __syncthreads();
+  return t;
+}
+
+#define GR_CACHE 2048  // entries of a row kept in shared memory between the two augmentation passes
+
+// keep decision of the input dropout: injected mask by batch position, else one Philox call per
+// four entries of a thread (entries tid + 128k, k = 4q..4q+3 share counter `pos0 + tid + 512q`).
+__device__ __forceinline__ bool gather_keep(const uint8_t* mask, int pos, const uint4& rnd, int k, float p) {
+  if (mask) return mask[pos] != 0;
+  const uint32_t w = (k & 3) == 0 ? rnd.x : (k & 3) == 1 ? rnd.y : (k & 3) == 2 ? rnd.z : rnd.w;
+  return (float)(w >> 8) * (1.0f / 16777216.0f) >= p;
+}
+
+__global__ void __launch_bounds__(128) k_gather_rows(GatherSrc A, GatherSrc B, const int32_t* __restrict__ b_indptr,
+                                                     int32_t* __restrict__ b_idx, float* __restrict__ b_val,
+                                                     const uint8_t* __restrict__ keep_mask, const uint64_t* __restrict__ rng,
+                                                     float p_drop, float target_sum, int32_t* __restrict__ gene_cnt) {
+  __shared__ float red4[4];
+  __shared__ float e_s[GR_CACHE];
+  __shared__ int32_t c_s[GR_CACHE];
+  const int tid = threadIdx.x;
+  const int i = blockIdx.x;
+  const bool inA = i < A.n;
+  const GatherSrc& S = inA ? A : B;
+  const int li = inA ? i : i - A.n;
+  const int64_t r = S.rows ? S.rows[li] : (S.row0 + li);
+  const int64_t s = S.indptr[r];
+  const int len = (int)(S.indptr[r + 1] - s);
   const int d = b_indptr[i];
-  const bool aug = augment && i >= aug_row_begin && i < aug_row_end;
+  const bool aug = S.augment && li >= S.aug_begin && li < S.aug_end;
   if (!aug) {
-    for (int j = lane; j < len; j += 32) {
-      const int c = indices[s + j];
-      const float v = data[s + j];
+    for (int j = tid; j < len; j += 128) {
+      const int c = S.indices[s + j];
+      const float v = S.data[s + j];
       b_idx[d + j] = c;
       b_val[d + j] = v;
       if (gene_cnt && v != 0.f) atomicAdd(gene_cnt + c, 1);
@@ -94,22 +130,42 @@ __global__ void __launch_bounds__(256) k_gather_rows(const int64_t* __restrict__
   uint64_t seed = 0, strm = 0;
   if (!keep_mask) {
     seed = rng[0];
-    strm = rng[1] * 64ull + stream_id;
+    strm = rng[1] * 64ull + S.stream_id;
   }
+  // pass 1: one trip to DRAM for values and indices; e = expm1(x) * keep / (1-p), cached in shared memory
   float sum = 0.f;
-  for (int j = lane; j < len; j += 32) {
-    float e = expm1f(data[s + j]);
-    bool keep = dropout_keep(keep_mask, (uint64_t)(d + j), seed, strm, p_drop);
-    e = e * (keep ? inv_keep : 0.f);
+  uint4 rnd = make_uint4(0, 0, 0, 0);
+  for (int j = tid, k = 0; j < len; j += 128, ++k) {
+    if (!keep_mask && (k & 3) == 0) {
+      const uint64_t ctr = (uint64_t)(d + tid) + 512ull * (uint64_t)(k >> 2);
+      rnd = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)strm, (uint32_t)(strm >> 32)),
+                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    }
+    float e = expm1f(S.data[s + j]);
+    e = e * (gather_keep(keep_mask, d + j, rnd, k, p_drop) ? inv_keep : 0.f);
     sum += e;
+    if (j < GR_CACHE) {
+      e_s[j] = e;
+      c_s[j] = S.indices[s + j];
+    }
   }
-  sum = warp_sum(sum);
-  for (int j = lane; j < len; j += 32) {
-    float e = expm1f(data[s + j]);
-    bool keep = dropout_keep(keep_mask, (uint64_t)(d + j), seed, strm, p_drop);
-    e = e * (keep ? inv_keep : 0.f);
-    float v = log1pf((e / sum) * target_sum);  // NaN if every entry of the row was dropped, as in the reference
-    const int c = indices[s + j];
+  sum = block128_sum(sum, red4);   // (also orders the shared-memory cache writes before the reads below)
+  for (int j = tid, k = 0; j < len; j += 128, ++k) {
+    float e;
+    int c;
+    if (j < GR_CACHE) {
+      e = e_s[j];
+      c = c_s[j];
+    } else {  // rows longer than the cache: recompute
+      if (!keep_mask && ((k & 3) == 0 || j - 128 < GR_CACHE)) {
+        const uint64_t ctr = (uint64_t)(d + tid) + 512ull * (uint64_t)(k >> 2);
+        rnd = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)strm, (uint32_t)(strm >> 32)),
+                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+      }
+      e = expm1f(S.data[s + j]) * (gather_keep(keep_mask, d + j, rnd, k, p_drop) ? inv_keep : 0.f);
+      c = S.indices[s + j];
+    }
+    const float v = log1pf((e / sum) * target_sum);  // NaN if every entry of the row was dropped, as in the reference
     b_idx[d + j] = c;
     b_val[d + j] = v;
     if (gene_cnt && v != 0.f) atomicAdd(gene_cnt + c, 1);
@@ -123,10 +179,30 @@ extern "C" int scnb_csr_gather_rows(const int64_t* indptr, const int32_t* indice
   SCNB_CHECK_ARG(indptr && indices && data && b_indptr && b_idx && b_val && n >= 0, "csr_gather_rows: bad arguments");
   SCNB_CHECK_ARG(!augment || keep_mask || rng, "csr_gather_rows: augmentation needs keep_mask or rng state");
   if (n == 0) return SCNB_OK;
-  k_gather_rows<<<scnb_cdiv(n, 8), 256, 0, (cudaStream_t)stream>>>(indptr, indices, data, rows, row0, n, b_indptr, b_idx,
-                                                                     b_val, augment, aug_row_begin, aug_row_end, keep_mask,
-                                                                     rng, stream_id, p_drop, 1e6f, gene_cnt);
+  GatherSrc A = {indptr, indices, data, rows, row0, n, augment, aug_row_begin, aug_row_end, stream_id};
+  GatherSrc B = {nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, 0, 0};
+  k_gather_rows<<<n, 128, 0, (cudaStream_t)stream>>>(A, B, b_indptr, b_idx, b_val, keep_mask, rng, p_drop, 1e6f, gene_cnt);
   SCNB_CHECK_LAUNCH("csr_gather_rows");
+  return SCNB_OK;
+}
+
+// Two sources in one launch: rows [0,nA) raw or augmented from A, rows [nA,nA+nB) from B
+// (the MixMatch batch [U_raw ; L_aug]: A = unlabeled, B = labeled with augment_B = 1).
+extern "C" int scnb_csr_gather_rows2(const int64_t* indptr_A, const int32_t* indices_A, const float* data_A,
+                                     const int64_t* rows_A, int nA, int augment_A, uint32_t stream_id_A,
+                                     const int64_t* indptr_B, const int32_t* indices_B, const float* data_B,
+                                     const int64_t* rows_B, int nB, int augment_B, uint32_t stream_id_B,
+                                     const int32_t* b_indptr, int32_t* b_idx, float* b_val, const uint8_t* keep_mask,
+                                     const uint64_t* rng, float p_drop, int32_t* gene_cnt, void* stream) {
+  SCNB_CHECK_ARG(b_indptr && b_idx && b_val && nA >= 0 && nB >= 0, "csr_gather_rows2: bad arguments");
+  SCNB_CHECK_ARG(nA == 0 || (indptr_A && indices_A && data_A), "csr_gather_rows2: source A missing");
+  SCNB_CHECK_ARG(nB == 0 || (indptr_B && indices_B && data_B), "csr_gather_rows2: source B missing");
+  SCNB_CHECK_ARG(!(augment_A || augment_B) || keep_mask || rng, "csr_gather_rows2: augmentation needs keep_mask or rng state");
+  if (nA + nB == 0) return SCNB_OK;
+  GatherSrc A = {indptr_A, indices_A, data_A, rows_A, 0, nA, augment_A, 0, nA, stream_id_A};
+  GatherSrc B = {indptr_B, indices_B, data_B, rows_B, 0, nB, augment_B, 0, nB, stream_id_B};
+  k_gather_rows<<<nA + nB, 128, 0, (cudaStream_t)stream>>>(A, B, b_indptr, b_idx, b_val, keep_mask, rng, p_drop, 1e6f, gene_cnt);
+  SCNB_CHECK_LAUNCH("csr_gather_rows2");
   return SCNB_OK;
 }
 
@@ -371,63 +447,72 @@ extern "C" int scnb_csr_linear_bwd_dw(const int32_t* b_indptr, const int32_t* b_
 // atomics (fp32 summation order of dW1 may differ between runs, as with the atomics of v1).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_csc_scan(int32_t* __restrict__ gene_cnt, int G, int32_t* __restrict__ c_ptr,
-                                                   int32_t* __restrict__ cursor) {
+                                                   int32_t* __restrict__ cursor, int use_smem) {
+  // one sweep: the counts are staged in shared memory with coalesced loads (when they fit), thread t
+  // scans its contiguous genes [t*per, (t+1)*per) there, and the three outputs are written coalesced
+  extern __shared__ int32_t cnt_s[];
   __shared__ int warp_tot[32];
-  __shared__ int carry_s;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) carry_s = 0;
-  __syncthreads();
-  // each thread owns 4 consecutive genes per sweep (int4 loads)
-  for (int base = 0; base < G; base += 4096) {
-    const int g0 = base + tid * 4;
-    int v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = (g0 + k < G) ? gene_cnt[g0 + k] : 0;
-    const int tsum = v[0] + v[1] + v[2] + v[3];
-    int x = tsum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
-    }
-    if (lane == 31) warp_tot[wid] = x;
-    __syncthreads();
-    if (wid == 0) {
-      int t = warp_tot[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int y = __shfl_up_sync(0xffffffffu, t, o);
-        if (lane >= o) t += y;
-      }
-      warp_tot[lane] = t;
-    }
-    __syncthreads();
-    const int carry = carry_s;
-    int excl = carry + (wid ? warp_tot[wid - 1] : 0) + x - tsum;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (g0 + k < G) {
-        c_ptr[g0 + k] = excl;
-        cursor[g0 + k] = excl;
-        gene_cnt[g0 + k] = 0;
-      }
-      excl += v[k];
-    }
-    __syncthreads();
-    if (tid == 1023) carry_s = carry + warp_tot[31];
+  const int per = (G + 1023) / 1024;
+  const int g0 = min(G, tid * per), g1 = min(G, g0 + per);
+  int32_t* cnt = use_smem ? cnt_s : gene_cnt;
+  if (use_smem) {
+    for (int g = tid; g < G; g += 1024) cnt_s[g] = gene_cnt[g];
     __syncthreads();
   }
-  if (tid == 0) c_ptr[G] = carry_s;
+  int tsum = 0;
+  for (int g = g0; g < g1; ++g) tsum += cnt[g];
+  int x = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_tot[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    int t = warp_tot[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, t, o);
+      if (lane >= o) t += y;
+    }
+    warp_tot[lane] = t;
+  }
+  __syncthreads();
+  int excl = (wid ? warp_tot[wid - 1] : 0) + x - tsum;
+  if (use_smem) {
+    for (int g = g0; g < g1; ++g) {
+      const int v = cnt_s[g];
+      cnt_s[g] = excl;
+      excl += v;
+    }
+    __syncthreads();
+    for (int g = tid; g < G; g += 1024) {
+      const int e = cnt_s[g];
+      c_ptr[g] = e;
+      cursor[g] = e;
+      gene_cnt[g] = 0;
+    }
+  } else {
+    for (int g = g0; g < g1; ++g) {
+      const int v = gene_cnt[g];
+      c_ptr[g] = excl;
+      cursor[g] = excl;
+      gene_cnt[g] = 0;
+      excl += v;
+    }
+  }
+  if (tid == 1023) c_ptr[G] = warp_tot[31];
 }
 
-__global__ void __launch_bounds__(256) k_csc_fill(const int32_t* __restrict__ b_indptr, const int32_t* __restrict__ b_idx,
+// one CTA per batch row (coalesced reads of the row, one atomic per non-zero entry)
+__global__ void __launch_bounds__(128) k_csc_fill(const int32_t* __restrict__ b_indptr, const int32_t* __restrict__ b_idx,
                                                   const float* __restrict__ b_val, int n, int32_t* __restrict__ cursor,
                                                   int2* __restrict__ c_ent) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= n) return;
+  const int row = blockIdx.x;
   const int s = b_indptr[row], e = b_indptr[row + 1];
-  for (int j = s + lane; j < e; j += 32) {
+  for (int j = s + threadIdx.x; j < e; j += 128) {
     const float v = b_val[j];
     if (v != 0.f) {
       const int pos = atomicAdd(cursor + b_idx[j], 1);
@@ -441,11 +526,19 @@ extern "C" int scnb_csr_to_csc(const int32_t* b_indptr, const int32_t* b_idx, co
   SCNB_CHECK_ARG(b_indptr && b_idx && b_val && gene_cnt && c_ptr && cursor && c_ent && n >= 0 && G > 0,
                  "csr_to_csc: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  k_csc_scan<<<1, 1024, 0, st>>>(gene_cnt, G, c_ptr, cursor);
+  const size_t scan_smem = (size_t)G * sizeof(int32_t);
+  const int use_smem = scan_smem <= 200 * 1024;
+  if (use_smem && scan_smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_csc_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
+    if (e != cudaSuccess) {
+      scnb_set_error("csr_to_csc: cannot reserve %zu bytes of shared memory: %s", scan_smem, cudaGetErrorString(e));
+      return SCNB_ERR_CUDA;
+    }
+  }
+  k_csc_scan<<<1, 1024, use_smem ? scan_smem : 0, st>>>(gene_cnt, G, c_ptr, cursor, use_smem);
   SCNB_CHECK_LAUNCH("csr_to_csc/scan");
   if (n > 0) {
-    const int wpb = 8;
-    k_csc_fill<<<scnb_cdiv(n, wpb), 32 * wpb, 0, st>>>(b_indptr, b_idx, b_val, n, cursor, (int2*)c_ent);
+    k_csc_fill<<<n, 128, 0, st>>>(b_indptr, b_idx, b_val, n, cursor, (int2*)c_ent);
     SCNB_CHECK_LAUNCH("csr_to_csc/fill");
   }
   return SCNB_OK;
@@ -481,8 +574,10 @@ extern "C" int scnb_csc_count(const int32_t* b_idx, const float* b_val, int nnz,
 // current gene's entries are consumed.  When nb*256 B exceeds shared memory (large batches) dZ is
 // read through L1/L2 instead (STAGED=false).
 // ---------------------------------------------------------------------------------------------
+#define W1_NT 1024          // threads per CTA of the fused dW1+optimizer kernel
+#define W1_HW (W1_NT / 16)  // half-warps (genes in flight) per CTA
 template <int OPT, bool STAGED>
-__global__ void __launch_bounds__(512) k_w1_bwd_optim(const int32_t* __restrict__ c_ptr, const int2* __restrict__ c_ent,
+__global__ void __launch_bounds__(W1_NT) k_w1_bwd_optim(const int32_t* __restrict__ c_ptr, const int2* __restrict__ c_ent,
                                                       const float4* __restrict__ dZ, int nb, int H0v, int G,
                                                       float4* __restrict__ W, float4* __restrict__ grad_out,
                                                       float4* __restrict__ S1, float4* __restrict__ S2,
@@ -493,41 +588,71 @@ __global__ void __launch_bounds__(512) k_w1_bwd_optim(const int32_t* __restrict_
   const int slice = blockIdx.x;
   if (OPT != OPT_NONE && tid == 0) cs = optim_consts(hp, st);
   if (STAGED) {
-    for (int i = tid; i < nb * 16; i += 512) dzs[i] = dZ[(size_t)(i >> 4) * H0v + slice * 16 + (i & 15)];
+    for (int i = tid; i < nb * 16; i += W1_NT) dzs[i] = dZ[(size_t)(i >> 4) * H0v + slice * 16 + (i & 15)];
   }
   __syncthreads();
   OptimConsts c;
   if (OPT != OPT_NONE) c = cs;
-  const int hw = tid >> 4, q = tid & 15;
-  const unsigned hmask = 0xffffu << (tid & 16);  // the 16 lanes of this half-warp
+  // A warp walks two genes at a time (one per half-warp); every loop below has a warp-uniform trip
+  // count (the longer of the two genes; a finished half multiplies by v = 0), so the shuffles use the
+  // full mask and the warp never diverges.
+  const int lane = tid & 31, q = tid & 15, half16 = lane & 16;
+  const int hw = tid >> 4;
   const int col = slice * 16 + q;
-  const int gstride = gridDim.y * 32;
-  int g = blockIdx.y * 32 + hw;
+  const int gstride = gridDim.y * W1_HW;
+  const int g_first = blockIdx.y * W1_HW + hw;
+  const int n_iter = (G - (blockIdx.y * W1_HW + (hw & ~1)) + gstride - 1) / gstride;  // uniform across the warp
+  // software pipeline: column ranges are fetched two genes ahead, entries and parameter/state rows one ahead
   float4 p = make_float4(0.f, 0.f, 0.f, 0.f), a = p, b = p;
-  if (OPT != OPT_NONE && g < G) {
-    const size_t o = (size_t)g * H0v + col;
-    p = W[o];
-    a = S1[o];
-    if (OPT != OPT_SGD) b = S2[o];
-  }
-  for (; g < G; g += gstride) {
-    const int gn = g + gstride;
-    float4 pn = make_float4(0.f, 0.f, 0.f, 0.f), an = pn, bn = pn;
-    if (OPT != OPT_NONE && gn < G) {  // prefetch the next gene's parameter/state rows
-      const size_t o = (size_t)gn * H0v + col;
-      pn = W[o];
-      an = S1[o];
-      if (OPT != OPT_SGD) bn = S2[o];
+  int js = 0, je = 0, jsn = 0, jen = 0;
+  int2 ent = make_int2(0, 0);
+  if (g_first < G) {
+    js = c_ptr[g_first];
+    je = c_ptr[g_first + 1];
+    if (OPT != OPT_NONE) {
+      const size_t o = (size_t)g_first * H0v + col;
+      p = W[o];
+      a = S1[o];
+      if (OPT != OPT_SGD) b = S2[o];
     }
-    const int js = c_ptr[g], je = c_ptr[g + 1];
+    if (js + q < je) ent = c_ent[js + q];
+  }
+  if (g_first + gstride < G) {
+    jsn = c_ptr[g_first + gstride];
+    jen = c_ptr[g_first + gstride + 1];
+  }
+  for (int it = 0; it < n_iter; ++it) {
+    const int g = g_first + it * gstride;
+    const int gn = g + gstride, gnn = gn + gstride;
+    float4 pn = make_float4(0.f, 0.f, 0.f, 0.f), an = pn, bn = pn;
+    int2 entn = make_int2(0, 0);
+    int jsnn = 0, jenn = 0;
+    if (gn < G) {
+      if (jsn + q < jen) entn = c_ent[jsn + q];
+      if (OPT != OPT_NONE) {
+        const size_t o = (size_t)gn * H0v + col;
+        pn = W[o];
+        an = S1[o];
+        if (OPT != OPT_SGD) bn = S2[o];
+      }
+    }
+    if (gnn < G) {
+      jsnn = c_ptr[gnn];
+      jenn = c_ptr[gnn + 1];
+    }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int base = js; base < je; base += 16) {
-      const int cnt = min(16, je - base);
-      int2 ent = make_int2(0, 0);
-      if (q < cnt) ent = c_ent[base + q];
+    const int len = je - js;
+    const int len_max = max(len, __shfl_xor_sync(0xffffffffu, len, 16));
+    for (int base = 0; base < len_max; base += 16) {
+      const int2 e_cur = ent;
+      // next batch of 16 entries of this gene (if any), issued before the current batch is consumed
+      ent = make_int2(0, 0);
+      if (base + 16 + q < len) ent = c_ent[js + base + 16 + q];
+      const int cnt = min(16, len_max - base);
+#pragma unroll 4
       for (int k = 0; k < cnt; ++k) {
-        const int r = __shfl_sync(hmask, ent.x, k, 16);
-        const float v = __int_as_float(__shfl_sync(hmask, ent.y, k, 16));
+        const int r = __shfl_sync(0xffffffffu, e_cur.x, half16 + k);
+        const float v = __int_as_float(__shfl_sync(0xffffffffu, e_cur.y, half16 + k));
         const float4 d = STAGED ? dzs[r * 16 + q] : __ldg(dZ + (size_t)r * H0v + col);
         acc.x = fmaf(v, d.x, acc.x);
         acc.y = fmaf(v, d.y, acc.y);
@@ -535,18 +660,22 @@ __global__ void __launch_bounds__(512) k_w1_bwd_optim(const int32_t* __restrict_
         acc.w = fmaf(v, d.w, acc.w);
       }
     }
-    const size_t o = (size_t)g * H0v + col;
-    if (grad_out) grad_out[o] = acc;
-    if (OPT != OPT_NONE) {
-      optim_update<OPT>(p.x, acc.x, a.x, b.x, c);
-      optim_update<OPT>(p.y, acc.y, a.y, b.y, c);
-      optim_update<OPT>(p.z, acc.z, a.z, b.z, c);
-      optim_update<OPT>(p.w, acc.w, a.w, b.w, c);
-      W[o] = p;
-      S1[o] = a;
-      if (OPT != OPT_SGD) S2[o] = b;
-      p = pn; a = an; b = bn;
+    if (g < G) {
+      const size_t o = (size_t)g * H0v + col;
+      if (grad_out) grad_out[o] = acc;
+      if (OPT != OPT_NONE) {
+        optim_update<OPT>(p.x, acc.x, a.x, b.x, c);
+        optim_update<OPT>(p.y, acc.y, a.y, b.y, c);
+        optim_update<OPT>(p.z, acc.z, a.z, b.z, c);
+        optim_update<OPT>(p.w, acc.w, a.w, b.w, c);
+        W[o] = p;
+        S1[o] = a;
+        if (OPT != OPT_SGD) S2[o] = b;
+      }
     }
+    p = pn; a = an; b = bn;
+    js = jsn; je = jen; ent = entn;
+    jsn = jsnn; jen = jenn;
   }
 }
 
@@ -558,7 +687,7 @@ static int launch_w1_bwd_optim(const int32_t* c_ptr, const void* c_ent, const fl
   const bool staged = smem <= 200 * 1024;
   // one CTA per SM when the dZ slice is staged (its shared memory fills the SM); more, smaller shares otherwise
   int gblocks = staged ? (148 / slices > 0 ? 148 / slices : 1) : (148 * 2 / slices > 0 ? 148 * 2 / slices : 1);
-  if (gblocks > scnb_cdiv(G, 32)) gblocks = scnb_cdiv(G, 32);
+  if (gblocks > scnb_cdiv(G, W1_HW)) gblocks = scnb_cdiv(G, W1_HW);
   dim3 grid(slices, gblocks);
   if (staged) {
     cudaError_t e = cudaFuncSetAttribute(k_w1_bwd_optim<OPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -566,10 +695,10 @@ static int launch_w1_bwd_optim(const int32_t* c_ptr, const void* c_ent, const fl
       scnb_set_error("csr_w1_bwd_optim: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
       return SCNB_ERR_CUDA;
     }
-    k_w1_bwd_optim<OPT, true><<<grid, 512, smem, st>>>(c_ptr, (const int2*)c_ent, (const float4*)dZ, nb, H0 / 4, G, (float4*)W1T,
+    k_w1_bwd_optim<OPT, true><<<grid, W1_NT, smem, st>>>(c_ptr, (const int2*)c_ent, (const float4*)dZ, nb, H0 / 4, G, (float4*)W1T,
                                                        (float4*)grad_out, (float4*)s1, (float4*)s2, hp, st4);
   } else {
-    k_w1_bwd_optim<OPT, false><<<grid, 512, 0, st>>>(c_ptr, (const int2*)c_ent, (const float4*)dZ, nb, H0 / 4, G, (float4*)W1T,
+    k_w1_bwd_optim<OPT, false><<<grid, W1_NT, 0, st>>>(c_ptr, (const int2*)c_ent, (const float4*)dZ, nb, H0 / 4, G, (float4*)W1T,
                                                      (float4*)grad_out, (float4*)s1, (float4*)s2, hp, st4);
   }
   SCNB_CHECK_LAUNCH("csr_w1_bwd_optim");
@@ -594,6 +723,104 @@ extern "C" int scnb_csr_w1_bwd_optim(int opt, const int32_t* c_ptr, const void* 
     case OPT_SGD: return launch_w1_bwd_optim<OPT_SGD>(c_ptr, c_ent, dZ, nb, H0, G, W1T, grad_out, state1, state2, hp8, state4, st);
     default: scnb_set_error("csr_w1_bwd_optim: unknown optimizer %d", opt); return SCNB_ERR_ARG;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Step prologue, one single-CTA launch: (1) sampler hand-off -- row ids / MixUp randomness of step
+// (t % n_tab) from the per-epoch tables (DataLoader iteration, scnym/trainer.py:574-582);
+// (2) labels / domain ids of the sampled rows (SingleCellDS.__getitem__, scnym/dataprep.py:157-162);
+// (3) row offsets of the batch CSR [U rows ; L rows]; (4) zero the loss scalars; (5) advance the
+// device-side step counters (optimizer t, RNG counter).
+// ---------------------------------------------------------------------------------------------
+struct PrepArgs {
+  const int64_t* l_tab; const int64_t* u_tab; const float* key_tab; const float* gam_tab; int n_tab;
+  int64_t* state4; int L, U;
+  int64_t* l_rows; int64_t* u_rows; float* keys; float* gam;
+  const int32_t* lab_y; const int32_t* lab_dom; const int32_t* unl_dom; int want_dom;
+  int32_t* lab_ids; int32_t* base_dom;
+  const int64_t* lab_indptr; const int64_t* unl_indptr;
+  int32_t* b_indptr; float* zero_buf; int n_zero;
+};
+
+__global__ void __launch_bounds__(1024) k_step_prep(PrepArgs a) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int L = a.L, U = a.U, nb = L + U;
+  const int64_t srow = a.l_tab ? (a.state4[0] % (int64_t)a.n_tab) : 0;
+  if (tid == 0) carry_s = 0;
+  for (int i = tid; i < a.n_zero; i += 1024) a.zero_buf[i] = 0.f;
+  __syncthreads();
+  for (int base = 0; base < nb; base += 1024) {
+    const int i = base + tid;
+    int len = 0;
+    if (i < nb) {
+      if (a.key_tab) {
+        a.keys[i] = a.key_tab[srow * nb + i];
+        a.gam[i] = a.gam_tab[srow * nb + i];
+      }
+      if (i < U) {
+        const int64_t r = a.u_tab ? a.u_tab[srow * U + i] : a.u_rows[i];
+        if (a.u_tab) a.u_rows[i] = r;
+        if (a.want_dom) a.base_dom[i] = a.unl_dom ? a.unl_dom[r] : 1;
+        len = (int)(a.unl_indptr[r + 1] - a.unl_indptr[r]);
+      } else {
+        const int li = i - U;
+        const int64_t r = a.l_tab ? a.l_tab[srow * L + li] : a.l_rows[li];
+        if (a.l_tab) a.l_rows[li] = r;
+        a.lab_ids[li] = a.lab_y ? a.lab_y[r] : 0;
+        if (a.want_dom) a.base_dom[i] = a.lab_dom ? a.lab_dom[r] : 0;
+        len = (int)(a.lab_indptr[r + 1] - a.lab_indptr[r]);
+      }
+    }
+    int x = len;  // inclusive warp scan
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      int t = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      warp_tot[lane] = t;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    if (i < nb) a.b_indptr[i] = carry + (wid ? warp_tot[wid - 1] : 0) + x - len;
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + warp_tot[31];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    a.b_indptr[nb] = carry_s;
+    a.state4[0] += 1;  // optimizer step index t (1-based when read by the optimizer kernels)
+    a.state4[2] += 1;  // RNG counter
+  }
+}
+
+extern "C" int scnb_step_prep(const int64_t* l_tab, const int64_t* u_tab, const float* key_tab, const float* gam_tab, int n_tab,
+                              int64_t* state4, int L, int U, int64_t* l_rows, int64_t* u_rows, float* keys, float* gam,
+                              const int32_t* lab_y, const int32_t* lab_dom, const int32_t* unl_dom, int want_dom,
+                              int32_t* lab_ids, int32_t* base_dom, const int64_t* lab_indptr, const int64_t* unl_indptr,
+                              int32_t* b_indptr, float* zero_buf, int n_zero, void* stream) {
+  SCNB_CHECK_ARG(state4 && L > 0 && U >= 0 && l_rows && lab_ids && lab_indptr && b_indptr, "step_prep: bad arguments");
+  SCNB_CHECK_ARG(U == 0 || (u_rows && unl_indptr), "step_prep: unlabeled buffers missing");
+  SCNB_CHECK_ARG(!l_tab || n_tab > 0, "step_prep: empty sampler table");
+  SCNB_CHECK_ARG(!l_tab || U == 0 || u_tab, "step_prep: unlabeled sampler table missing");
+  SCNB_CHECK_ARG(!key_tab || (gam_tab && keys && gam), "step_prep: key/gamma buffers missing");
+  SCNB_CHECK_ARG(!want_dom || base_dom, "step_prep: base_dom missing");
+  SCNB_CHECK_ARG(n_zero == 0 || zero_buf, "step_prep: zero_buf missing");
+  PrepArgs a = {l_tab, u_tab, key_tab, gam_tab, n_tab, state4, L, U, l_rows, u_rows, keys, gam, lab_y, lab_dom, unl_dom,
+                want_dom, lab_ids, base_dom, lab_indptr, unl_indptr, b_indptr, zero_buf, n_zero};
+  k_step_prep<<<1, 1024, 0, (cudaStream_t)stream>>>(a);
+  SCNB_CHECK_LAUNCH("step_prep");
+  return SCNB_OK;
 }
 
 // out[i] = table ? table[rows ? rows[i] : i] : fill   (labels / domain ids of the sampled rows)

@@ -189,12 +189,23 @@ static void launch_sgemm_tile(bool tA, bool tB, bool vec, dim3 grid, cudaStream_
 #undef SCNB_LAUNCH_SGEMM
 }
 
+int scnb_sgemm_panel_try(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+                         int ldc, float alpha, float beta, const float* bias, int relu, const float* gate, cudaStream_t st);
+
 extern "C" int scnb_sgemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                           float* C, int ldc, float alpha, float beta, const float* bias, int relu, const float* gate,
                           void* stream) {
   SCNB_CHECK_ARG(M >= 0 && N >= 0 && K >= 0 && A && B && C, "sgemm: bad arguments");
   if (M == 0 || N == 0) return SCNB_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (K > 0) {  // cp.async panel kernel (gemm_ops.cu) whenever the operands allow 16-byte chunks
+    const int rc = scnb_sgemm_panel_try(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, st);
+    if (rc < 0) return rc;
+    if (rc == 1) {
+      SCNB_CHECK_LAUNCH("sgemm/panel");
+      return SCNB_OK;
+    }
+  }
   const bool vec = (lda % 4 == 0) && (ldb % 4 == 0) && (((uintptr_t)A | (uintptr_t)B) % 16 == 0) &&
                    (transA ? (M % 4 == 0) : (K % 4 == 0)) && (transB ? (K % 4 == 0) : (N % 4 == 0));
   // split-K first (keeps the efficient 64x64 tile): only for plain accumulating products (the dW
@@ -261,6 +272,20 @@ extern "C" int scnb_colsum(const float* A, int M, int N, int lda, float* out, in
 // ---------------------------------------------------------------------------------------------
 #define BN_CW 8
 #define BN_RL 128
+
+// Hidden-layer dropout stream: one Philox call per (row, 8-column group) gives eight 16-bit uniforms;
+// element (r, c) keeps iff uniform[(c & 7)] >= p * 65536.  The scalar and the vector kernels share this
+// definition, so forward and backward always see the same mask whichever variant runs.
+__device__ __forceinline__ bool dropout_keep_h(const uint8_t* mask, int r, int c, int H, uint64_t seed, uint64_t strm, float p) {
+  if (mask) return mask[(size_t)r * H + c] != 0;
+  const uint64_t grp = (uint64_t)r * (uint64_t)((H + 7) >> 3) + (uint64_t)(c >> 3);
+  const uint4 q = philox4x32_10(make_uint4((uint32_t)grp, (uint32_t)(grp >> 32), (uint32_t)strm, (uint32_t)(strm >> 32)),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const int j = c & 7;
+  const uint32_t w = (j >> 1) == 0 ? q.x : (j >> 1) == 1 ? q.y : (j >> 1) == 2 ? q.z : q.w;
+  const uint32_t u = (j & 1) ? (w >> 16) : (w & 0xffffu);
+  return u >= (uint32_t)(p * 65536.0f + 0.5f);
+}
 
 // Column sums over the 128 row lanes of each of the 8 columns of a 1024-thread block
 // (tid = ry*8 + cx).  A warp holds 4 row lanes x 8 columns: two xor-shuffles fold the row lanes,
@@ -363,7 +388,7 @@ __global__ void __launch_bounds__(1024) k_bn_act_fwd(const float* __restrict__ Z
   for (int r = r0 + ry; r < r1; r += BN_RL) {
     const size_t o = (size_t)r * H + c;
     float y = (Z[o] - mean) * invstd * g + b;
-    if (train && p_drop > 0.f) y = dropout_keep(keep_mask, o, seed, strm, p_drop) ? y * drop_scale : 0.f;
+    if (train && p_drop > 0.f) y = dropout_keep_h(keep_mask, r, c, H, seed, strm, p_drop) ? y * drop_scale : 0.f;
     if (pre_out) pre_out[o] = y;
     Aout[o] = relu ? fmaxf(y, 0.f) : y;
   }
@@ -373,6 +398,291 @@ __global__ void __launch_bounds__(1024) k_bn_act_fwd(const float* __restrict__ Z
       Aout[(size_t)r * H + c] = 0.f;
       if (pre_out) pre_out[(size_t)r * H + c] = 0.f;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Vector form of the segmented BatchNorm -> Dropout -> ReLU kernels (H % 8 == 0, 16-byte aligned rows).
+// Grid = (H/8, n_seg), 256 threads: thread t owns rows r0+t, r0+t+256, ... of its segment and, per row,
+// the CTA's 8 columns (two float4 = one 32-byte sector).  One Philox call per (row, 8-column group)
+// yields eight 16-bit uniforms (`keep = u16 >= p*65536`); an injected byte mask is read 8 bytes at a
+// time.  Column sums: butterfly over the 32 lanes, then 8 per-warp partials per column in shared
+// memory that every thread adds in the same order (broadcast reads, deterministic).
+// ---------------------------------------------------------------------------------------------
+#define BNV_T 256
+#define BNV_W (BNV_T / 32)
+
+struct F8 { float v[8]; };
+
+__device__ __forceinline__ F8 ld8(const float* __restrict__ p) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  F8 r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void st8(float* __restrict__ p, const F8& r) {
+  *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+// 8-bit keep pattern (bit j = keep column j) of element group `grp` = row*(H/8) + column group
+__device__ __forceinline__ uint32_t keep8(const uint8_t* __restrict__ mask, size_t elem0, uint64_t grp, uint64_t seed, uint64_t strm,
+                                          uint32_t thr16) {
+  uint32_t bits = 0;
+  if (mask) {
+    const uint2 m = *reinterpret_cast<const uint2*>(mask + elem0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      bits |= (((m.x >> (8 * j)) & 0xffu) != 0u ? 1u : 0u) << j;
+      bits |= (((m.y >> (8 * j)) & 0xffu) != 0u ? 1u : 0u) << (4 + j);
+    }
+    return bits;
+  }
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)grp, (uint32_t)(grp >> 32), (uint32_t)strm, (uint32_t)(strm >> 32)),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    bits |= ((w[j] & 0xffffu) >= thr16 ? 1u : 0u) << (2 * j);
+    bits |= ((w[j] >> 16) >= thr16 ? 1u : 0u) << (2 * j + 1);
+  }
+  return bits;
+}
+// sums over all rows of the CTA for each of the 8 columns; result in every thread
+__device__ __forceinline__ void bnv_colsum8(F8& x, float (*red)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) x.v[j] = warp_sum(x.v[j]);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[wid][j] = x.v[j];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < BNV_W; ++w) t += red[w][j];
+    x.v[j] = t;
+  }
+}
+
+__global__ void __launch_bounds__(BNV_T) k_bn_act_fwd_v8(const float* __restrict__ Z, float* __restrict__ Aout,
+                                                         float* __restrict__ pre_out, int H, int n_seg,
+                                                         const int32_t* __restrict__ seg_off, int max_rows,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         float* __restrict__ stats, const uint8_t* __restrict__ keep_mask,
+                                                         const uint64_t* __restrict__ rng, uint32_t stream_id, float p_drop,
+                                                         int relu, float* __restrict__ partial_out,
+                                                         const float* __restrict__ ext_sums, const float* __restrict__ ext_cnt) {
+  __shared__ __align__(16) float red1[BNV_W][8];
+  __shared__ __align__(16) float red2[BNV_W][8];
+  const int t = threadIdx.x;
+  const int c0 = blockIdx.x * 8, s = blockIdx.y;
+  const int Hg = H >> 3;
+  const int r0 = min(seg_off[s], max_rows), r1 = min(seg_off[s + 1], max_rows);
+  const int n = r1 - r0;
+  const F8 g = ld8(gamma + c0), b = ld8(beta + c0);
+  uint64_t seed = 0, strm = 0;
+  if (p_drop > 0.f && !keep_mask) {
+    seed = rng[0];
+    strm = rng[1] * 64ull + stream_id;
+  }
+  const uint32_t thr16 = (uint32_t)(p_drop * 65536.0f + 0.5f);
+  const float drop_scale = 1.0f / (1.0f - p_drop);
+  F8 mean, invstd;
+  if (partial_out) {  // data-parallel pass 1: local sums only
+    F8 a1, a2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a1.v[j] = a2.v[j] = 0.f;
+    for (int r = r0 + t; r < r1; r += BNV_T) {
+      const F8 z = ld8(Z + (size_t)r * H + c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a1.v[j] += z.v[j]; a2.v[j] = fmaf(z.v[j], z.v[j], a2.v[j]); }
+    }
+    bnv_colsum8(a1, red1);
+    bnv_colsum8(a2, red2);
+    if (t < 8) {
+      partial_out[((size_t)s * 2 + 0) * H + c0 + t] = a1.v[t];
+      partial_out[((size_t)s * 2 + 1) * H + c0 + t] = a2.v[t];
+    }
+    if (blockIdx.x == 0 && t == 0) partial_out[(size_t)n_seg * 2 * H + s] = (float)n;
+    return;
+  }
+  F8 var;
+  if (ext_sums) {
+    const float ng = fmaxf(ext_cnt[s], 1.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mean.v[j] = ext_sums[((size_t)s * 2 + 0) * H + c0 + j] / ng;
+      var.v[j] = fmaxf(ext_sums[((size_t)s * 2 + 1) * H + c0 + j] / ng - mean.v[j] * mean.v[j], 0.f);
+    }
+  } else {
+    const float inv_n = 1.0f / (float)max(n, 1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mean.v[j] = 0.f;
+    for (int r = r0 + t; r < r1; r += BNV_T) {
+      const F8 z = ld8(Z + (size_t)r * H + c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mean.v[j] += z.v[j];
+    }
+    bnv_colsum8(mean, red1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { mean.v[j] *= inv_n; var.v[j] = 0.f; }
+    for (int r = r0 + t; r < r1; r += BNV_T) {
+      const F8 z = ld8(Z + (size_t)r * H + c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = z.v[j] - mean.v[j]; var.v[j] = fmaf(d, d, var.v[j]); }
+    }
+    bnv_colsum8(var, red2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) var.v[j] *= inv_n;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) invstd.v[j] = 1.0f / sqrtf(var.v[j] + BN_EPS);
+  if (stats && t < 8) {
+    // dynamic register indexing would spill: select with a compile-time unrolled loop
+    float m = 0.f, v = 0.f, is = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (j == t) { m = mean.v[j]; v = var.v[j]; is = invstd.v[j]; }
+    stats[((size_t)s * 3 + 0) * H + c0 + t] = m;
+    stats[((size_t)s * 3 + 1) * H + c0 + t] = v;
+    stats[((size_t)s * 3 + 2) * H + c0 + t] = is;
+  }
+  for (int r = r0 + t; r < r1; r += BNV_T) {
+    const size_t o = (size_t)r * H + c0;
+    const F8 z = ld8(Z + o);
+    uint32_t kb = 0xffu;
+    if (p_drop > 0.f) kb = keep8(keep_mask, o, (uint64_t)r * Hg + blockIdx.x, seed, strm, thr16);
+    F8 y;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float yy = (z.v[j] - mean.v[j]) * invstd.v[j] * g.v[j] + b.v[j];
+      if (p_drop > 0.f) yy = ((kb >> j) & 1u) ? yy * drop_scale : 0.f;
+      y.v[j] = yy;
+    }
+    if (pre_out) st8(pre_out + o, y);
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y.v[j] = fmaxf(y.v[j], 0.f);
+    }
+    st8(Aout + o, y);
+  }
+  if (s == n_seg - 1) {  // inactive tail rows (data-dependent DAN segment length)
+    F8 zero;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) zero.v[j] = 0.f;
+    for (int r = r1 + t; r < max_rows; r += BNV_T) {
+      st8(Aout + (size_t)r * H + c0, zero);
+      if (pre_out) st8(pre_out + (size_t)r * H + c0, zero);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(BNV_T) k_bn_act_bwd_v8(const float* __restrict__ dA, const float* __restrict__ Z,
+                                                         const float* __restrict__ Aact, int H, int n_seg,
+                                                         const int32_t* __restrict__ seg_off, int max_rows,
+                                                         const float* __restrict__ gamma, const float* __restrict__ stats,
+                                                         const uint8_t* __restrict__ keep_mask, const uint64_t* __restrict__ rng,
+                                                         uint32_t stream_id, float p_drop, int relu, float* __restrict__ dZ,
+                                                         float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                         float* __restrict__ partial_out, const float* __restrict__ ext_sums,
+                                                         const float* __restrict__ ext_cnt) {
+  __shared__ __align__(16) float red1[BNV_W][8];
+  __shared__ __align__(16) float red2[BNV_W][8];
+  const int t = threadIdx.x;
+  const int c0 = blockIdx.x * 8, s = blockIdx.y;
+  const int Hg = H >> 3;
+  const int r0 = min(seg_off[s], max_rows), r1 = min(seg_off[s + 1], max_rows);
+  const int n = r1 - r0;
+  const F8 g = ld8(gamma + c0);
+  const F8 mean = ld8(stats + ((size_t)s * 3 + 0) * H + c0), invstd = ld8(stats + ((size_t)s * 3 + 2) * H + c0);
+  uint64_t seed = 0, strm = 0;
+  if (p_drop > 0.f && !keep_mask) {
+    seed = rng[0];
+    strm = rng[1] * 64ull + stream_id;
+  }
+  const uint32_t thr16 = (uint32_t)(p_drop * 65536.0f + 0.5f);
+  const float drop_scale = 1.0f / (1.0f - p_drop);
+  F8 s1, s2;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1.v[j] = s2.v[j] = 0.f;
+  float inv_n = 1.0f / (float)max(n, 1);
+  if (ext_sums) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s1.v[j] = ext_sums[((size_t)s * 2 + 0) * H + c0 + j];
+      s2.v[j] = ext_sums[((size_t)s * 2 + 1) * H + c0 + j];
+    }
+    inv_n = 1.0f / fmaxf(ext_cnt[s], 1.f);
+  } else {
+    for (int r = r0 + t; r < r1; r += BNV_T) {
+      const size_t o = (size_t)r * H + c0;
+      const F8 da = ld8(dA + o), z = ld8(Z + o);
+      F8 av;
+      if (relu) av = ld8(Aact + o);
+      uint32_t kb = 0xffu;
+      if (p_drop > 0.f) kb = keep8(keep_mask, o, (uint64_t)r * Hg + blockIdx.x, seed, strm, thr16);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float dy = da.v[j];
+        if (relu && !(av.v[j] > 0.f)) dy = 0.f;
+        if (p_drop > 0.f) dy = ((kb >> j) & 1u) ? dy * drop_scale : 0.f;
+        s1.v[j] += dy;
+        s2.v[j] = fmaf(dy, (z.v[j] - mean.v[j]) * invstd.v[j], s2.v[j]);
+      }
+    }
+    bnv_colsum8(s1, red1);
+    bnv_colsum8(s2, red2);
+    if (t < 8) {
+      float a = 0.f, b2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (j == t) { a = s1.v[j]; b2 = s2.v[j]; }
+      if (n > 0) {
+        atomicAdd(dgamma + c0 + t, b2);
+        atomicAdd(dbeta + c0 + t, a);
+      }
+      if (partial_out) {
+        partial_out[((size_t)s * 2 + 0) * H + c0 + t] = a;
+        partial_out[((size_t)s * 2 + 1) * H + c0 + t] = b2;
+      }
+    }
+    if (partial_out) {
+      if (blockIdx.x == 0 && t == 0) partial_out[(size_t)n_seg * 2 * H + s] = (float)n;
+      return;
+    }
+  }
+  for (int r = r0 + t; r < r1; r += BNV_T) {
+    const size_t o = (size_t)r * H + c0;
+    const F8 da = ld8(dA + o), z = ld8(Z + o);
+    F8 av;
+    if (relu) av = ld8(Aact + o);
+    uint32_t kb = 0xffu;
+    if (p_drop > 0.f) kb = keep8(keep_mask, o, (uint64_t)r * Hg + blockIdx.x, seed, strm, thr16);
+    F8 out;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float dy = da.v[j];
+      if (relu && !(av.v[j] > 0.f)) dy = 0.f;
+      if (p_drop > 0.f) dy = ((kb >> j) & 1u) ? dy * drop_scale : 0.f;
+      const float zh = (z.v[j] - mean.v[j]) * invstd.v[j];
+      out.v[j] = g.v[j] * invstd.v[j] * (dy - s1.v[j] * inv_n - zh * (s2.v[j] * inv_n));
+    }
+    st8(dZ + o, out);
+  }
+  if (s == n_seg - 1) {
+    F8 zero;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) zero.v[j] = 0.f;
+    for (int r = r1 + t; r < max_rows; r += BNV_T) st8(dZ + (size_t)r * H + c0, zero);
+  }
+}
+
+// The vector kernels need whole 32-byte column groups and 16-byte aligned rows (the dropout stream is
+// defined per 8-column group there, so forward and backward must take the same decision: it depends
+// only on H and on pointer alignment, which the caller keeps identical between the two calls).
+static bool bn_vec8_ok(int H, const void* a, const void* b, const void* c, const void* d, const void* e, const void* f,
+                       const void* mask) {
+  const uintptr_t bits = (uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d | (uintptr_t)e | (uintptr_t)f;
+  return (H % 8 == 0) && (bits % 16 == 0) && ((uintptr_t)mask % 8 == 0);
 }
 
 // Eval mode (running statistics, no dropout) is purely elementwise: a flat grid-stride kernel over
@@ -443,6 +753,14 @@ extern "C" int scnb_bn_act_fwd(const float* Z, float* A, float* pre_out, int H, 
     SCNB_CHECK_LAUNCH("bn_act_fwd/eval");
     return SCNB_OK;
   }
+  if (bn_vec8_ok(H, Z, A, pre_out, gamma, beta, stats, keep_mask)) {
+    dim3 gridv(H / 8, n_seg);
+    k_bn_act_fwd_v8<<<gridv, BNV_T, 0, (cudaStream_t)stream>>>(Z, A, pre_out, H, n_seg, seg_off_dev, max_rows, gamma, beta, stats,
+                                                               keep_mask, rng, stream_id, p_drop, relu, dp_partial_out, dp_sums,
+                                                               ext_cnt);
+    SCNB_CHECK_LAUNCH("bn_act_fwd/v8");
+    return SCNB_OK;
+  }
   dim3 grid(scnb_cdiv(H, BN_CW), n_seg);
   k_bn_act_fwd<<<grid, 1024, 0, (cudaStream_t)stream>>>(Z, A, pre_out, H, n_seg, seg_off_dev, max_rows, train, gamma, beta,
                                                          running_mean, running_var, stats, keep_mask, rng, stream_id, p_drop,
@@ -496,7 +814,7 @@ __global__ void __launch_bounds__(1024) k_bn_act_bwd(const float* __restrict__ d
         const size_t o = (size_t)r * H + c;
         float dy = dA[o];
         if (relu && !(Aact[o] > 0.f)) dy = 0.f;
-        if (p_drop > 0.f) dy = dropout_keep(keep_mask, o, seed, strm, p_drop) ? dy * drop_scale : 0.f;
+        if (p_drop > 0.f) dy = dropout_keep_h(keep_mask, r, c, H, seed, strm, p_drop) ? dy * drop_scale : 0.f;
         s1 += dy;
         s2 = fmaf(dy, (Z[o] - mean) * invstd, s2);
       }
@@ -521,7 +839,7 @@ __global__ void __launch_bounds__(1024) k_bn_act_bwd(const float* __restrict__ d
     const size_t o = (size_t)r * H + c;
     float dy = dA[o];
     if (relu && !(Aact[o] > 0.f)) dy = 0.f;
-    if (p_drop > 0.f) dy = dropout_keep(keep_mask, o, seed, strm, p_drop) ? dy * drop_scale : 0.f;
+    if (p_drop > 0.f) dy = dropout_keep_h(keep_mask, r, c, H, seed, strm, p_drop) ? dy * drop_scale : 0.f;
     const float zh = (Z[o] - mean) * invstd;
     dZ[o] = k * (dy - m1 - zh * m2);
   }
@@ -538,6 +856,14 @@ extern "C" int scnb_bn_act_bwd(const float* dA, const float* Z, const float* A, 
   SCNB_CHECK_ARG(!(p_drop > 0.f) || keep_mask || rng, "bn_act_bwd: dropout needs keep_mask or rng state");
   SCNB_CHECK_ARG(!(dp_partial_out && dp_sums), "bn_act_bwd: partial and reduced sums are exclusive");
   const float* ext_cnt = dp_sums ? dp_sums + (size_t)n_seg * 2 * H : nullptr;
+  if (bn_vec8_ok(H, dA, Z, A, gamma, dZ, stats, keep_mask)) {
+    dim3 gridv(H / 8, n_seg);
+    k_bn_act_bwd_v8<<<gridv, BNV_T, 0, (cudaStream_t)stream>>>(dA, Z, A, H, n_seg, seg_off_dev, max_rows, gamma, stats, keep_mask,
+                                                               rng, stream_id, p_drop, relu, dZ, dgamma, dbeta, dp_partial_out,
+                                                               dp_sums, ext_cnt);
+    SCNB_CHECK_LAUNCH("bn_act_bwd/v8");
+    return SCNB_OK;
+  }
   dim3 grid(scnb_cdiv(H, BN_CW), n_seg);
   k_bn_act_bwd<<<grid, 1024, 0, (cudaStream_t)stream>>>(dA, Z, A, H, n_seg, seg_off_dev, max_rows, gamma, stats, keep_mask, rng,
                                                          stream_id, p_drop, relu, dZ, dgamma, dbeta, dp_partial_out, dp_sums,

@@ -14,10 +14,17 @@
 __global__ void __launch_bounds__(256) k_pseudolabel(const float* __restrict__ logits, int K, int U, int C, float T,
                                                      int sharpen, float min_conf, float* __restrict__ q,
                                                      float* __restrict__ conf, uint8_t* __restrict__ confident,
-                                                     float* __restrict__ scratch) {
+                                                     float* __restrict__ scratch, const int32_t* __restrict__ lab_ids,
+                                                     int L) {
   const int lane = threadIdx.x & 31;
   const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (u >= U) return;
+  if (u >= U) {  // rows [U, U+L) of q: one-hot labels of the labeled rows (SingleCellDS, dataprep.py:157-160)
+    if (lab_ids && u < U + L) {
+      const int id = lab_ids[u - U];
+      for (int c = lane; c < C; c += 32) q[(size_t)u * C + c] = (c == id) ? 1.f : 0.f;
+    }
+    return;
+  }
   float* qb = scratch + (size_t)u * C;  // mean probabilities
   for (int c = lane; c < C; c += 32) qb[c] = 0.f;
   __syncwarp();
@@ -67,11 +74,13 @@ __global__ void __launch_bounds__(256) k_pseudolabel(const float* __restrict__ l
 }
 
 extern "C" int scnb_pseudolabel(const float* teacher_logits, int K, int U, int C, float T, int sharpen, float min_confidence,
-                                float* q, float* conf, uint8_t* confident, float* scratch_UC, void* stream) {
+                                float* q, float* conf, uint8_t* confident, float* scratch_UC, const int32_t* lab_ids, int L,
+                                void* stream) {
   SCNB_CHECK_ARG(teacher_logits && q && conf && confident && scratch_UC && K > 0 && U >= 0 && C > 0, "pseudolabel: bad arguments");
-  if (U == 0) return SCNB_OK;
-  k_pseudolabel<<<scnb_cdiv(U, 8), 256, 0, (cudaStream_t)stream>>>(teacher_logits, K, U, C, T, sharpen, min_confidence, q, conf,
-                                                                     confident, scratch_UC);
+  const int rows = U + (lab_ids ? L : 0);
+  if (rows == 0) return SCNB_OK;
+  k_pseudolabel<<<scnb_cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(teacher_logits, K, U, C, T, sharpen, min_confidence, q, conf,
+                                                                        confident, scratch_UC, lab_ids, L);
   SCNB_CHECK_LAUNCH("pseudolabel");
   return SCNB_OK;
 }
@@ -97,13 +106,10 @@ struct PlanPtrs {
   float* coef3;       // [3][U+L]
 };
 
-__global__ void __launch_bounds__(1024) k_plan_compact(const uint8_t* __restrict__ confident, int U, int L, int use_dan,
-                                                       int dan_conf_only, PlanPtrs P) {
-  __shared__ int wtot[32];
-  __shared__ int carry_s;
-  __shared__ int n_conf_s;
+__device__ void plan_compact_body(const uint8_t* __restrict__ confident, int U, int L, int use_dan, int dan_conf_only,
+                                  const PlanPtrs& P, int* wtot, int* carry_s, int* n_conf_s) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) carry_s = 0;
+  if (tid == 0) (*carry_s) = 0;
   __syncthreads();
   // exclusive scan of the confident flags
   for (int base = 0; base < U; base += 1024) {
@@ -127,16 +133,16 @@ __global__ void __launch_bounds__(1024) k_plan_compact(const uint8_t* __restrict
       wtot[lane] = t;
     }
     __syncthreads();
-    const int carry = carry_s;
+    const int carry = (*carry_s);
     const int excl = carry + (wid ? wtot[wid - 1] : 0) + x - f;
     if (i < U) P.cpos[i] = f ? excl : (i - excl);  // rank among confident, or among unconfident
     __syncthreads();
-    if (tid == 1023) carry_s = carry + wtot[31];
+    if (tid == 1023) (*carry_s) = carry + wtot[31];
     __syncthreads();
   }
   if (tid == 0) {
-    const int n_conf = carry_s;
-    n_conf_s = n_conf;
+    const int n_conf = (*carry_s);
+    (*n_conf_s) = n_conf;
     const int n_dan_unl = use_dan ? (dan_conf_only ? n_conf : U) : 0;
     const int n_dan = use_dan ? L + n_dan_unl : 0;
     P.counts[0] = n_conf;
@@ -154,10 +160,18 @@ __global__ void __launch_bounds__(1024) k_plan_compact(const uint8_t* __restrict
     P.seg_off[3] = U + L + n_dan;
   }
   __syncthreads();
-  const int n_conf = n_conf_s;
+  const int n_conf = (*n_conf_s);
   for (int i = tid; i < U; i += 1024)
     if (confident[i]) P.cat2base[P.cpos[i]] = i;
   for (int i = tid; i < L; i += 1024) P.cat2base[n_conf + i] = U + i;
+}
+
+__global__ void __launch_bounds__(1024) k_plan_compact(const uint8_t* __restrict__ confident, int U, int L, int use_dan,
+                                                       int dan_conf_only, PlanPtrs P) {
+  __shared__ int wtot[32];
+  __shared__ int carry_s;
+  __shared__ int n_conf_s;
+  plan_compact_body(confident, U, L, use_dan, dan_conf_only, P, wtot, &carry_s, &n_conf_s);
 }
 
 // rank[j] = #{k < n_mm : key[k] < key[j] or (key[k]==key[j] and k<j)};  ridx[rank[j]] = j
@@ -186,10 +200,9 @@ __global__ void __launch_bounds__(256) k_plan_rank(const float* __restrict__ key
   }
 }
 
-__global__ void __launch_bounds__(256) k_plan_maps(const uint8_t* __restrict__ confident, const float* __restrict__ gamma_raw,
-                                                   int U, int L, int use_dan, int dan_conf_only, int mixup_on, int Rmax,
-                                                   PlanPtrs P) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
+__device__ __forceinline__ void plan_maps_item(int i, const uint8_t* __restrict__ confident, const float* __restrict__ gamma_raw,
+                                               int U, int L, int use_dan, int dan_conf_only, int mixup_on, int Rmax,
+                                               const PlanPtrs& P) {
   const int n_conf = P.counts[0], n_dan_unl = P.counts[6];
   const int nb = U + L;
   // ---- forward maps over super-batch rows ----
@@ -276,6 +289,62 @@ __global__ void __launch_bounds__(256) k_plan_maps(const uint8_t* __restrict__ c
   }
 }
 
+__global__ void __launch_bounds__(256) k_plan_maps(const uint8_t* __restrict__ confident, const float* __restrict__ gamma_raw,
+                                                   int U, int L, int use_dan, int dan_conf_only, int mixup_on, int Rmax,
+                                                   PlanPtrs P) {
+  plan_maps_item(blockIdx.x * 256 + threadIdx.x, confident, gamma_raw, U, L, use_dan, dan_conf_only, mixup_on, Rmax, P);
+}
+
+// Whole plan in ONE single-CTA launch for training-sized batches (U+L <= PLAN_SMEM_KEYS): compaction,
+// O(n^2) ranking of the permutation keys out of shared memory, forward and inverse row maps.
+#define PLAN_SMEM_KEYS 4096
+__global__ void __launch_bounds__(1024) k_plan_all(const uint8_t* __restrict__ confident, const float* __restrict__ keys,
+                                                   const float* __restrict__ gamma_raw, int U, int L, int use_dan,
+                                                   int dan_conf_only, int mixup_on, int Rmax, PlanPtrs P) {
+  __shared__ int wtot[32];
+  __shared__ int carry_s, n_conf_s;
+  __shared__ float skeys[PLAN_SMEM_KEYS];
+  __shared__ int srank[PLAN_SMEM_KEYS];
+  plan_compact_body(confident, U, L, use_dan, dan_conf_only, P, wtot, &carry_s, &n_conf_s);
+  __syncthreads();
+  const int tid = threadIdx.x, nb = U + L;
+  if (mixup_on) {
+    // O(n^2) ranking out of shared memory; `parts` threads share one key (each counts a slice of the
+    // other keys) so that all 1024 threads work when n is small
+    const int n = n_conf_s + L;
+    for (int k = tid; k < n; k += 1024) {
+      skeys[k] = keys[k];
+      srank[k] = 0;
+    }
+    __syncthreads();
+    int parts = 1;
+    while (parts < 32 && n * parts * 2 <= 1024) parts *= 2;
+    const int slice = (n + parts - 1) / parts;
+    for (int w = tid; w < n * parts; w += 1024) {
+      const int j = w / parts, part = w % parts;
+      const int t0 = part * slice, t1 = min(n, t0 + slice);
+      const float kj = skeys[j];
+      int r = 0;
+      for (int t = t0; t < t1; ++t) {
+        const float kv = skeys[t];
+        r += (kv < kj || (kv == kj && t < j)) ? 1 : 0;
+      }
+      if (parts == 1) srank[j] = r;
+      else atomicAdd(&srank[j], r);
+    }
+    __syncthreads();
+    for (int j = tid; j < n; j += 1024) {
+      const int r = srank[j];
+      P.rank[j] = r;
+      P.ridx[r] = j;
+    }
+  }
+  __syncthreads();
+  const int lim = Rmax > nb ? Rmax : nb;
+  for (int i = tid; i < lim; i += 1024)
+    plan_maps_item(i, confident, gamma_raw, U, L, use_dan, dan_conf_only, mixup_on, Rmax, P);
+}
+
 extern "C" int scnb_mixmatch_plan(const uint8_t* confident, const float* perm_keys, const float* gamma_raw, int U, int L,
                                   int use_dan, int dan_conf_only, int mixup_on, int32_t* counts8, int32_t* seg_off4,
                                   int32_t* work_i /* [U + 3*(U+L)] */, int32_t* srcA, int32_t* srcB, float* gam, int Rmax,
@@ -298,6 +367,11 @@ extern "C" int scnb_mixmatch_plan(const uint8_t* confident, const float* perm_ke
   P.gam = gam;
   P.inv3 = inv3;
   P.coef3 = coef3;
+  if (nb <= PLAN_SMEM_KEYS) {
+    k_plan_all<<<1, 1024, 0, st>>>(confident, perm_keys, gamma_raw, U, L, use_dan, dan_conf_only, mixup_on, Rmax, P);
+    SCNB_CHECK_LAUNCH("mixmatch_plan/all");
+    return SCNB_OK;
+  }
   k_plan_compact<<<1, 1024, 0, st>>>(confident, U, L, use_dan, dan_conf_only, P);
   SCNB_CHECK_LAUNCH("mixmatch_plan/compact");
   if (mixup_on) {

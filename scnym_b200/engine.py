@@ -59,6 +59,7 @@ class EngineConfig:
     class_weight: Optional[List[float]] = None
     seed: int = 0
     use_cuda_graph: bool = True
+    multi_stream: bool = True    # run independent kernels of the step on side streams (parallel graph branches)
     keep_w1_grad: bool = False   # also write the first-layer gradient to HBM (parity tests; implied by data parallelism)
 
 
@@ -271,7 +272,10 @@ class TrainEngine(object):
         self.logits = f32(self.nb if mode == "mixmatch" else L, self.C)
         self.dlogits = torch.zeros_like(self.logits)
         wmax = max(self.widths)
-        self.dA, self.dZ = f32(R, wmax), f32(R, wmax)
+        self.dA = f32(R, wmax)
+        self.dZs = [f32(R, w) for w in self.widths]   # one per application: weight-gradient GEMMs overlap the dA chain
+        self._side = None
+        self._ev_grl, self._ev_csc, self._ev_zero = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         self.dZ1 = f32(self.nb, H0) if mode == "mixmatch" else None
         if self.use_dan:
             self.Hd, self.dHd = f32(self.Rd, self.H), f32(self.Rd, self.H)
@@ -318,29 +322,56 @@ class TrainEngine(object):
             return tw, (lambda a: (bn[a][0], bn[a][1]))
         return (lambda name: self.arena.w(name)), (lambda a: (self._blk[a]["bn"].running_mean, self._blk[a]["bn"].running_var))
 
+    # ---- stream plumbing: the step is a DAG; independent kernels go to side streams so that a captured
+    #      graph keeps only ~22 launches on its critical path (data parallelism keeps one stream: the
+    #      collectives must be issued in the same order on every rank) ----
+    def _streams(self):
+        main = torch.cuda.current_stream()
+        if self.comm is not None or not self.cfg.multi_stream:
+            return main, main, main
+        if self._side is None:
+            self._side = (torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev))
+        return main, self._side[0], self._side[1]
+
+    @staticmethod
+    def _after(waiter, other):
+        """`waiter` continues only after everything issued so far on `other`."""
+        if waiter is not other:
+            waiter.wait_stream(other)
+
+    def _prep(self, st):
+        t = self._tabs or {}
+        mm = self.mode == "mixmatch"
+        call("scnb_step_prep", ptr(t.get("l")), ptr(t.get("u")), ptr(t.get("k")), ptr(t.get("g")), int(t.get("n", 0)),
+             ptr(self.state), self.L, self.U, ptr(self.l_rows), ptr(self.u_rows) if mm else None, ptr(self.perm_keys),
+             ptr(self.gamma_raw), ptr(self.lab_y), ptr(self.lab_dom), ptr(self.unl_dom), int(self.use_dan), ptr(self.lab_ids),
+             ptr(self.base_dom) if self.use_dan else None, ptr(self.lab.indptr), ptr(self.unl.indptr) if mm else None,
+             ptr(self.b_indptr), ptr(self.loss_buf), 8, st)
+
     def _launch_mixmatch(self):
-        c, st = self.cfg, torch.cuda.current_stream().cuda_stream
+        c = self.cfg
+        main, sW, sD = self._streams()   # main chain / weight-gradient + bookkeeping branch / domain-adversary branch
+        if not self.use_dan:
+            sD = main                    # never forked: a join would reference a stream outside the capture
+        st = main.cuda_stream
         L, U, nb, R, C, H0 = self.L, self.U, self.nb, self.Rmax, self.C, self.widths[0]
         rng = ptr(self.state[1:3])
         blk = self._blk
-        self._fetch(st)
-        call("scnb_step_begin", ptr(self.state), st)
-        self._zero_grads()
-        self.loss_buf.zero_()
-        # -- ids of the sampled rows
-        call("scnb_gather_i32", ptr(self.lab_y), ptr(self.l_rows), L, 0, ptr(self.lab_ids), st)
-        if self.use_dan:
-            call("scnb_gather_i32", ptr(self.unl_dom), ptr(self.u_rows), U, 1, ptr(self.base_dom), st)
-            call("scnb_gather_i32", ptr(self.lab_dom), ptr(self.l_rows), L, 0, ptr(self.base_dom[U:]), st)
-        # -- batch CSR [U_raw ; L_aug]
-        call("scnb_csr_row_offsets", ptr(self.unl.indptr), ptr(self.u_rows), 0, U, ptr(self.b_indptr), None, st)
-        call("scnb_csr_row_offsets", ptr(self.lab.indptr), ptr(self.l_rows), 0, L, ptr(self.b_indptr[U:]), ptr(self.b_indptr[U:]), st)
-        call("scnb_csr_gather_rows", ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data), ptr(self.u_rows), 0, U,
-             ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), 0, 0, 0, None, None, 0, 0.0, self._gene_cnt_ptr(), st)
-        call("scnb_csr_gather_rows", ptr(self.lab.indptr), ptr(self.lab.indices), ptr(self.lab.data), ptr(self.l_rows), 0, L,
-             ptr(self.b_indptr[U:]), ptr(self.b_idx), ptr(self.b_val), 1, 0, L, ptr(self.inj_in_keep_L), rng, SID_IN_L,
-             c.p_in_drop, self._gene_cnt_ptr(), st)
-        self._build_csc(nb, st)
+        self._prep(st)
+        # -- batch CSR [U_raw ; L_aug] (+ per-gene histogram), one launch
+        call("scnb_csr_gather_rows2", ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data), ptr(self.u_rows), U, 0, 0,
+             ptr(self.lab.indptr), ptr(self.lab.indices), ptr(self.lab.data), ptr(self.l_rows), L, 1, SID_IN_L,
+             ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), ptr(self.inj_in_keep_L), rng, c.p_in_drop,
+             self._gene_cnt_ptr(), st)
+        # branch W: gene-major copy of the batch (needed only by the last kernel of the step), gradient zeroing
+        self._after(sW, main)
+        with torch.cuda.stream(sW):
+            self._zero_grads()
+            if sW is not main:
+                self._ev_zero.record(sW)
+            self._build_csc(nb, sW.cuda_stream)
+            if sW is not main:
+                self._ev_csc.record(sW)
         # -- first layer, once
         call("scnb_csr_linear_fwd", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), nb, self.P(blk[0]["W"]),
              self.P(blk[0]["b"]), H0, ptr(self.Z1), st)
@@ -379,9 +410,10 @@ class TrainEngine(object):
                 tz = self.TZ[a + 1]
         call("scnb_sgemm", 0, 1, KU, C, self.H, ptr(self.TA[-1]), self.H, ptr(tw("model.classif.0.weight")), self.H,
              ptr(self.t_logits), C, 1.0, 0.0, ptr(tw("model.classif.0.bias")), 0, None, st)
+        # pseudolabels q[0,U) and the one-hot labels of the labeled rows q[U,U+L)
         call("scnb_pseudolabel", ptr(self.t_logits), K, U, C, float(c.T if c.T is not None else 1.0), int(c.T is not None),
-             float(c.pseudolabel_min_confidence), ptr(self.Ycat), ptr(self.conf), ptr(self.confident), ptr(self.pl_scratch), st)
-        call("scnb_onehot_rows", ptr(self.lab_ids), None, 0, L, C, ptr(self.Ycat[U:]), st)
+             float(c.pseudolabel_min_confidence), ptr(self.Ycat), ptr(self.conf), ptr(self.confident), ptr(self.pl_scratch),
+             ptr(self.lab_ids), L, st)
         # -- MixUp plan + hidden-space MixUp (losses.py:811-875)
         call("scnb_mixmatch_plan", ptr(self.confident), ptr(self.perm_keys), ptr(self.gamma_raw), U, L, int(self.use_dan),
              int(c.dan_use_conf_pseudolabels), int(c.mixup_alpha > 0.0), ptr(self.counts), ptr(self.seg_off),
@@ -391,52 +423,58 @@ class TrainEngine(object):
              ptr(self.Zs[0]), st)
         # -- student super-batch forward
         self._student_forward(st, rng)
-        call("scnb_sgemm", 0, 1, nb, C, self.H, ptr(self.As[-1]), self.H, self.P("model.classif.0.weight"), self.H,
-             ptr(self.logits), C, 1.0, 0.0, self.P("model.classif.0.bias"), 0, None, st)
+        Hh = self.H
+        dA_last = self._view(self.dA, R, Hh)
+        # branch D: domain adversary head, its loss and the reversed gradient into the embedding
         if self.use_dan:
             d0, d1 = self._dan_names()
             Ae = self.As[-1][nb:]
-            call("scnb_sgemm", 0, 1, self.Rd, self.H, self.H, ptr(Ae), self.H, self.P(d0 + ".weight"), self.H, ptr(self.Hd),
-                 self.H, 1.0, 0.0, self.P(d0 + ".bias"), 1, None, st)
-            call("scnb_sgemm", 0, 1, self.Rd, self.D, self.H, ptr(self.Hd), self.H, self.P(d1 + ".weight"), self.H,
-                 ptr(self.dlog), self.D, 1.0, 0.0, self.P(d1 + ".bias"), 0, None, st)
-            call("scnb_onehot_rows", ptr(self.base_dom), ptr(self.srcA), nb, self.Rd, self.D, ptr(self.dlabel), st)
-        # -- losses + dLogits (losses.py:896-923, 1224-1243; trainer.py:651-656)
+            self._after(sD, main)
+            sd = sD.cuda_stream
+            call("scnb_sgemm", 0, 1, self.Rd, Hh, Hh, ptr(Ae), Hh, self.P(d0 + ".weight"), Hh, ptr(self.Hd), Hh, 1.0, 0.0,
+                 self.P(d0 + ".bias"), 1, None, sd)
+            call("scnb_sgemm", 0, 1, self.Rd, self.D, Hh, ptr(self.Hd), Hh, self.P(d1 + ".weight"), Hh, ptr(self.dlog), self.D,
+                 1.0, 0.0, self.P(d1 + ".bias"), 0, None, sd)
+            call("scnb_onehot_rows", ptr(self.base_dom), ptr(self.srcA), nb, self.Rd, self.D, ptr(self.dlabel), sd)
+            call("scnb_soft_ce_fwd_bwd", ptr(self.dlog), self.Rd, self.D, ptr(self.counts[2:]), ptr(self.dlabel), None, None,
+                 None, 0, None, ptr(self.counts[2:]), 0, 1.0, ptr(self.pconf) if c.dan_scale_loss_pseudoconf else None,
+                 ptr(self.ddlog), ptr(self.loss_buf[4:]), 1, None, sd)
+            call("scnb_sgemm", 0, 0, self.Rd, Hh, self.D, ptr(self.ddlog), self.D, self.P(d1 + ".weight"), Hh, ptr(self.dHd), Hh,
+                 1.0, 0.0, None, 0, ptr(self.Hd), sd)
+            # gradient reversal: dEmbed = -w * dHd W  (model.py:338)
+            call("scnb_sgemm", 0, 0, self.Rd, Hh, Hh, ptr(self.dHd), Hh, self.P(d0 + ".weight"), Hh, ptr(dA_last[nb:]), Hh,
+                 -self.dan_weight, 0.0, None, 0, None, sd)
+            if sD is not main:
+                self._ev_grl.record(sD)
+            # the head's own weight gradients (needed only by the optimizer)
+            if sD is not main:
+                sD.wait_event(self._ev_zero)   # after the gradient zeroing
+            call("scnb_sgemm", 1, 0, self.D, Hh, self.Rd, ptr(self.ddlog), self.D, ptr(self.Hd), Hh, self.Gp(d1 + ".weight"), Hh,
+                 1.0, 1.0, None, 0, None, sd)
+            call("scnb_colsum", ptr(self.ddlog), self.Rd, self.D, self.D, self.Gp(d1 + ".bias"), 1, sd)
+            call("scnb_sgemm", 1, 0, Hh, Hh, self.Rd, ptr(self.dHd), Hh, ptr(Ae), Hh, self.Gp(d0 + ".weight"), Hh, 1.0, 1.0, None,
+                 0, None, sd)
+            call("scnb_colsum", ptr(self.dHd), self.Rd, Hh, Hh, self.Gp(d0 + ".bias"), 1, sd)
+        # -- classifier, losses + dLogits (losses.py:896-923, 1224-1243; trainer.py:651-656)
+        call("scnb_sgemm", 0, 1, nb, C, Hh, ptr(self.As[-1]), Hh, self.P("model.classif.0.weight"), Hh,
+             ptr(self.logits), C, 1.0, 0.0, self.P("model.classif.0.bias"), 0, None, st)
         call("scnb_softmax_mse_fwd_bwd", ptr(self.logits), U, C, ptr(self.counts), ptr(self.Ycat), ptr(self.srcA),
              ptr(self.srcB), ptr(self.gam), 0, U, None, self.unsup_weight, ptr(self.dlogits), ptr(self.loss_buf[2:]), st)
         call("scnb_soft_ce_fwd_bwd", ptr(self.logits[U:]), L, C, None, ptr(self.Ycat), ptr(self.srcA), ptr(self.srcB),
              ptr(self.gam), U, ptr(self.class_weight), None, L, 1.0, None, ptr(self.dlogits[U:]), ptr(self.loss_buf), 1, None, st)
-        if self.use_dan:
-            call("scnb_soft_ce_fwd_bwd", ptr(self.dlog), self.Rd, self.D, ptr(self.counts[2:]), ptr(self.dlabel), None, None,
-                 None, 0, None, ptr(self.counts[2:]), 0, 1.0, ptr(self.pconf) if c.dan_scale_loss_pseudoconf else None,
-                 ptr(self.ddlog), ptr(self.loss_buf[4:]), 1, None, st)
-        # -- backward
-        Hh = self.H
-        dA_last = self._view(self.dA, R, Hh)
+        # -- backward: the dA chain stays on the main stream, weight gradients go to branch W
         call("scnb_sgemm", 0, 0, nb, Hh, C, ptr(self.dlogits), C, self.P("model.classif.0.weight"), Hh, ptr(dA_last), Hh, 1.0,
              0.0, None, 0, None, st)
+        self._after(sW, main)
+        sw = sW.cuda_stream
         call("scnb_sgemm", 1, 0, C, Hh, nb, ptr(self.dlogits), C, ptr(self.As[-1]), Hh, self.Gp("model.classif.0.weight"), Hh,
-             1.0, 1.0, None, 0, None, st)
-        call("scnb_colsum", ptr(self.dlogits), nb, C, C, self.Gp("model.classif.0.bias"), 1, st)
-        if self.use_dan:
-            d0, d1 = self._dan_names()
-            Ae = self.As[-1][nb:]
-            call("scnb_sgemm", 1, 0, self.D, Hh, self.Rd, ptr(self.ddlog), self.D, ptr(self.Hd), Hh, self.Gp(d1 + ".weight"), Hh,
-                 1.0, 1.0, None, 0, None, st)
-            call("scnb_colsum", ptr(self.ddlog), self.Rd, self.D, self.D, self.Gp(d1 + ".bias"), 1, st)
-            call("scnb_sgemm", 0, 0, self.Rd, Hh, self.D, ptr(self.ddlog), self.D, self.P(d1 + ".weight"), Hh, ptr(self.dHd), Hh,
-                 1.0, 0.0, None, 0, ptr(self.Hd), st)
-            call("scnb_sgemm", 1, 0, Hh, Hh, self.Rd, ptr(self.dHd), Hh, ptr(Ae), Hh, self.Gp(d0 + ".weight"), Hh, 1.0, 1.0, None,
-                 0, None, st)
-            call("scnb_colsum", ptr(self.dHd), self.Rd, Hh, Hh, self.Gp(d0 + ".bias"), 1, st)
-            # gradient reversal: dEmbed = -w * dHd W  (model.py:338)
-            call("scnb_sgemm", 0, 0, self.Rd, Hh, Hh, ptr(self.dHd), Hh, self.P(d0 + ".weight"), Hh, ptr(dA_last[nb:]), Hh,
-                 -self.dan_weight, 0.0, None, 0, None, st)
-        dZ_first = self._student_backward(st, rng, dA_last)
+             1.0, 1.0, None, 0, None, sw)
+        call("scnb_colsum", ptr(self.dlogits), nb, C, C, self.Gp("model.classif.0.bias"), 1, sw)
+        if self.use_dan and sD is not main:
+            main.wait_event(self._ev_grl)
+        dZ_first = self._student_backward(main, sW, rng, dA_last)
         call("scnb_unmix_rows", ptr(dZ_first), H0, ptr(self.inv3), ptr(self.coef3), nb, ptr(self.dZ1), st)
-        call("scnb_colsum", ptr(self.dZ1), nb, H0, H0, self.Gp(blk[0]["b"]), 1, st)
-        self._finish_step(st, self.dZ1, nb)
-        call("scnb_mm_step_inc", ptr(self.state), st)
+        self._finish_step(main, sW, sD, self.dZ1, nb)
 
     def _view(self, buf, rows, width):
         """[rows, width] contiguous view at the start of a scratch buffer."""
@@ -477,17 +515,21 @@ class TrainEngine(object):
                 call("scnb_sgemm", 0, 1, R, w2, w, ptr(self.As[a]), w, self.P(blk[a + 1]["W"]), w, ptr(self.Zs[a + 1]), w2, 1.0,
                      0.0, self.P(blk[a + 1]["b"]), 0, None, st)
 
-    def _student_backward(self, st, rng, dA):
-        """dA: gradient w.r.t. As[-1].  Returns dZ of the first application ([R, H0])."""
+    def _student_backward(self, main, sW, rng, dA):
+        """dA: gradient w.r.t. As[-1].  Returns dZ of the first application ([R, H0]).
+        The dA chain runs on `main`; weight/bias gradients of the hidden Linear layers on `sW`."""
         blk, R = self._blk, self.Rmax
+        st, sw = main.cuda_stream, sW.cuda_stream
         for a in range(self.n_app - 1, -1, -1):
             w = self.widths[a]
             p = float(blk[a]["drop"].p)
-            dZ = self._view(self.dZ, R, w)
+            dZ = self.dZs[a]
             bwd = lambda part, sums: call(
                 "scnb_bn_act_bwd", ptr(dA), ptr(self.Zs[a]), ptr(self.As[a]), w, self.n_seg, ptr(self.seg_off), R,
                 self.P(blk[a]["g"]), ptr(self.stats[a]), self._hidden_keep(a), rng, SID_HID + a, p, 1, ptr(dZ),
                 self.Gp(blk[a]["g"]), self.Gp(blk[a]["beta"]), part, sums, st)
+            if a == self.n_app - 1 and sW is not main:
+                main.wait_event(self._ev_zero)   # BatchNorm gamma/beta gradients accumulate into zeroed buffers
             if self.comm is None:
                 bwd(None, None)
             else:
@@ -497,11 +539,12 @@ class TrainEngine(object):
             if a == 0:
                 return dZ
             wp = self.widths[a - 1]
-            call("scnb_sgemm", 1, 0, w, wp, R, ptr(dZ), w, ptr(self.As[a - 1]), wp, self.Gp(blk[a]["W"]), wp, 1.0, 1.0, None, 0,
-                 None, st)
-            call("scnb_colsum", ptr(dZ), R, w, w, self.Gp(blk[a]["b"]), 1, st)
             dA = self._view(self.dA, R, wp)
             call("scnb_sgemm", 0, 0, R, wp, w, ptr(dZ), w, self.P(blk[a]["W"]), wp, ptr(dA), wp, 1.0, 0.0, None, 0, None, st)
+            self._after(sW, main)
+            call("scnb_sgemm", 1, 0, w, wp, R, ptr(dZ), w, ptr(self.As[a - 1]), wp, self.Gp(blk[a]["W"]), wp, 1.0, 1.0, None, 0,
+                 None, sw)
+            call("scnb_colsum", ptr(dZ), R, w, w, self.Gp(blk[a]["b"]), 1, sw)
         return None
 
     def _gene_cnt_ptr(self):
@@ -519,16 +562,25 @@ class TrainEngine(object):
         else:
             self.arena.grad.zero_()
 
-    def _finish_step(self, st, dZ1, n_rows):
+    def _finish_step(self, main, sW, sD, dZ1, n_rows):
         """First-layer weight gradient, optimizer.step() and BatchNorm running statistics in the
-        reference's update order.  dZ1: gradient w.r.t. the first Linear's output, rows aligned with the batch CSR."""
+        reference's update order.  dZ1: gradient w.r.t. the first Linear's output, rows aligned with
+        the batch CSR.  main: fused dW1 + update of W1T; branch W: everything else."""
         c = self.cfg
         H0 = self.widths[0]
-        W1 = self._blk[0]["W"]
+        blk0 = self._blk[0]
+        W1 = blk0["W"]
         opt = OPTIMIZER_CODES[c.optimizer]
         hp, s4 = ptr(self.hp), ptr(self.state)
         ar = self.arena
+        st, sw = main.cuda_stream, sW.cuda_stream
+        self._after(sW, main)     # dZ1 ready
+        self._after(sW, sD)       # domain-head gradients ready
+        call("scnb_colsum", ptr(dZ1), n_rows, H0, H0, self.Gp(blk0["b"]), 1, sw)
+        if sW is not main:
+            main.wait_event(self._ev_csc)   # batch CSC (built at the start of the step on branch W)
         if not self.fused_w1:
+            self._after(main, sW)   # every other gradient is complete before the one optimizer pass
             call("scnb_csr_linear_bwd_dw", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), n_rows, ptr(dZ1), H0, self.Gp(W1), st)
             if self.comm is not None:
                 self.comm.all_reduce_avg(ar.grad)
@@ -545,7 +597,7 @@ class TrainEngine(object):
                  ptr(ar.state1), ptr(ar.state2), hp, s4, st)
             rest = ar.total - self.P1
             call("scnb_optim_step", opt, ptr(ar.flat[self.P1:]), ptr(ar.grad[self.P1:]), ptr(ar.state1[self.P1:]),
-                 ptr(ar.state2[self.P1:]), rest, hp, s4, st)
+                 ptr(ar.state2[self.P1:]), rest, hp, s4, sw)
         done = set()
         for a in range(self.n_app):
             bn = self._blk[a]["bn"]
@@ -558,12 +610,16 @@ class TrainEngine(object):
             sp = [ptr(self.stats[b]) for b in apps] + [None] * (4 - len(apps))
             call("scnb_bn_running_update", ptr(bn.running_mean), ptr(bn.running_var), ptr(bn.num_batches_tracked), sp[0], sp[1],
                  sp[2], sp[3], ptr(self.seg_off), self.n_seg, self.widths[a], float(bn.momentum),
-                 ptr(self.dp_fwd[a][self.n_seg * 2 * self.widths[a]:]) if self.comm is not None else None, st)
+                 ptr(self.dp_fwd[a][self.n_seg * 2 * self.widths[a]:]) if self.comm is not None else None, sw)
         if self.loss_hist is not None:
             mm = self.mode == "mixmatch"
             call("scnb_record_step", ptr(self.loss_buf), ptr(self.loss_hist), int(self.loss_hist.shape[0]),
                  ptr(self.conf) if mm else None, self.U if mm else 0, ptr(self.conf_ring) if mm else None,
-                 int(self.conf_ring.shape[0]) if mm else 0, ptr(self.state), st)
+                 int(self.conf_ring.shape[0]) if mm else 0, ptr(self.state), sw)
+        if self.mode == "mixmatch":
+            call("scnb_mm_step_inc", ptr(self.state), sw)
+        self._after(main, sW)
+        self._after(main, sD)
 
     def enable_history(self, capacity: int, ring: int = 64):
         """Keep per-step loss scalars (and the last `ring` steps' pseudolabel confidences) on the
@@ -592,19 +648,23 @@ class TrainEngine(object):
     # ------------------------------------------------------------------------------------
     def _launch_supervised(self):
         """Trainer.train_epoch body (trainer.py:189-256): raw batch -> model -> CE -> backward -> step."""
-        st = torch.cuda.current_stream().cuda_stream
+        main, sW, _ = self._streams()
+        sD = main
+        st = main.cuda_stream
         L, C, H0 = self.L, self.C, self.widths[0]
         rng = ptr(self.state[1:3])
         blk = self._blk
-        self._fetch(st)
-        call("scnb_step_begin", ptr(self.state), st)
-        self._zero_grads()
-        self.loss_buf.zero_()
-        call("scnb_gather_i32", ptr(self.lab_y), ptr(self.l_rows), L, 0, ptr(self.lab_ids), st)
-        call("scnb_csr_row_offsets", ptr(self.lab.indptr), ptr(self.l_rows), 0, L, ptr(self.b_indptr), None, st)
+        self._prep(st)
         call("scnb_csr_gather_rows", ptr(self.lab.indptr), ptr(self.lab.indices), ptr(self.lab.data), ptr(self.l_rows), 0, L,
              ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), 0, 0, 0, None, None, 0, 0.0, self._gene_cnt_ptr(), st)
-        self._build_csc(L, st)
+        self._after(sW, main)
+        with torch.cuda.stream(sW):
+            self._zero_grads()
+            if sW is not main:
+                self._ev_zero.record(sW)
+            self._build_csc(L, sW.cuda_stream)
+            if sW is not main:
+                self._ev_csc.record(sW)
         call("scnb_csr_linear_fwd", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), L, self.P(blk[0]["W"]),
              self.P(blk[0]["b"]), H0, ptr(self.Zs[0]), st)
         self._student_forward(st, rng)
@@ -617,12 +677,13 @@ class TrainEngine(object):
         dA_last = self._view(self.dA, L, Hh)
         call("scnb_sgemm", 0, 0, L, Hh, C, ptr(self.dlogits), C, self.P("model.classif.0.weight"), Hh, ptr(dA_last), Hh, 1.0, 0.0,
              None, 0, None, st)
+        self._after(sW, main)
+        sw = sW.cuda_stream
         call("scnb_sgemm", 1, 0, C, Hh, L, ptr(self.dlogits), C, ptr(self.As[-1]), Hh, self.Gp("model.classif.0.weight"), Hh, 1.0,
-             1.0, None, 0, None, st)
-        call("scnb_colsum", ptr(self.dlogits), L, C, C, self.Gp("model.classif.0.bias"), 1, st)
-        dZ1 = self._student_backward(st, rng, dA_last)
-        call("scnb_colsum", ptr(dZ1), L, H0, H0, self.Gp(blk[0]["b"]), 1, st)
-        self._finish_step(st, dZ1, L)
+             1.0, None, 0, None, sw)
+        call("scnb_colsum", ptr(self.dlogits), L, C, C, self.Gp("model.classif.0.bias"), 1, sw)
+        dZ1 = self._student_backward(main, sW, rng, dA_last)
+        self._finish_step(main, sW, sD, dZ1, L)
 
     # ------------------------------------------------------------------------------------
     def _launch(self):

@@ -226,7 +226,7 @@ class MixMatchLoss(InterpolationConsistencyLoss):
         scratch = torch.empty((U, C), device=tl.device)
         T = self.T
         call("scnb_pseudolabel", ptr(tl), K, U, C, float(T if T is not None else 1.0), int(T is not None),
-             float(self.pseudolabel_min_confidence), ptr(q), ptr(conf), ptr(flag), ptr(scratch), Fn._stream())
+             float(self.pseudolabel_min_confidence), ptr(q), ptr(conf), ptr(flag), ptr(scratch), None, 0, Fn._stream())
         confident = flag.bool()
         self._store_confidence(confident, conf)
         return q, confident

@@ -232,7 +232,7 @@ def test_pseudolabel(K, T, C):
     want_q = O.sharpen_labels(qbar.clone(), T).float()
     q, cf = torch.empty(U, C).cuda(), torch.empty(U).cuda()
     flag = torch.empty(U, dtype=torch.uint8).cuda()
-    call("scnb_pseudolabel", ptr(D(logits)), K, U, C, T, 1, tau, ptr(q), ptr(cf), ptr(flag), ptr(D(torch.empty(U, C))), _st())
+    call("scnb_pseudolabel", ptr(D(logits)), K, U, C, T, 1, tau, ptr(q), ptr(cf), ptr(flag), ptr(D(torch.empty(U, C))), None, 0, _st())
     _chk("q", q.cpu(), want_q)
     _chk("conf", cf.cpu(), conf)
     exact = (conf - tau).abs() > 1e-6
