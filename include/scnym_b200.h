@@ -164,6 +164,28 @@ int scnb_softmax_mse_fwd_bwd(const float* logits, int n_max, int C, const int32_
                              const float* weight_dev, float weight, float* dlogits, float* loss_out, void* stream);
 int scnb_onehot_rows(const int32_t* ids, const int32_t* src, int src_off, int n, int C, float* out, void* stream);
 
+/* ---- Fused heads (one warp per row; weights staged in shared memory).  Each replaces a
+ *      Linear -> loss -> Linear-backward chain of four launches on the step's critical path:
+ *      classifier + MixMatch losses + dA (scnym/model.py:229, scnym/losses.py:880-923);
+ *      classifier + supervised CE + dA (scnym/trainer.py:215-233);
+ *      DAN output layer + domain CE + ReLU-gated dHd (scnym/model.py:377-383, scnym/losses.py:1209-1243);
+ *      teacher classifier + pseudolabels (scnym/losses.py:676-735).
+ *      Need H % 128 == 0, H <= 1024, C*H*4 <= 96 KB; return -3 (unsupported) otherwise. ---- */
+int scnb_classif_mixmatch_fused(const float* A /*[U+L,H]*/, const float* Wc, const float* bc, int H, int C, int U, int L,
+                                const int32_t* n_conf_dev, const float* Y, const int32_t* mapA, const int32_t* mapB,
+                                const float* gam, const float* class_weight, float unsup_weight, float* logits, float* dlogits,
+                                float* dA /*[U+L,H]*/, float* loss8, void* stream);
+int scnb_classif_supervised_fused(const float* A, const float* Wc, const float* bc, int H, int C, int n, const float* Y,
+                                  const float* class_weight, float* logits, float* dlogits, float* dA, float* loss8,
+                                  void* stream);
+int scnb_dan_tail_fused(const float* Hd /*[Rd,H] post-ReLU*/, const float* W2, const float* b2, int H, int D, int Rd,
+                        const int32_t* n_rows_dev, const int32_t* dom_ids, const int32_t* src, int src_off,
+                        const float* loss_scale_dev, float* dlog, float* dlabel, float* ddlog, float* dHd, float* loss2,
+                        void* stream);
+int scnb_teacher_head_fused(const float* TA /*[K*U,H]*/, const float* Wc, const float* bc, int H, int C, int K, int U, float T,
+                            int sharpen, float min_confidence, float* t_logits, float* q, float* conf, uint8_t* confident,
+                            float* scratch_UC, const int32_t* lab_ids, int L, void* stream);
+
 /* ---- K9/K10: optimizer.step() (scnym/trainer.py:234,671,1089; torch.optim.{Adadelta,Adam,AdamW,SGD}
  *      selected at scnym/main.py:36-41,374-396) over the flat parameter arena, and the mean-teacher
  *      EMA (scnym/losses.py:382-406).  opt: 0 adadelta, 1 adam, 2 adamw, 3 sgd(momentum).

@@ -40,6 +40,10 @@ SIGNATURES = {
     "scnb_mixmatch_plan": [P, P, P, I, I, I, I, I, P, P, P, P, P, P, I, P, P, P, P],
     "scnb_soft_ce_fwd_bwd": [P, I, I, P, P, P, P, P, I, P, P, I, F, P, P, P, I, P, P],
     "scnb_softmax_mse_fwd_bwd": [P, I, I, P, P, P, P, P, I, I, P, F, P, P, P],
+    "scnb_classif_mixmatch_fused": [P, P, P, I, I, I, I, P, P, P, P, P, P, F, P, P, P, P, P],
+    "scnb_classif_supervised_fused": [P, P, P, I, I, I, P, P, P, P, P, P, P],
+    "scnb_dan_tail_fused": [P, P, P, I, I, I, P, P, P, I, P, P, P, P, P, P, P],
+    "scnb_teacher_head_fused": [P, P, P, I, I, I, I, F, I, F, P, P, P, P, P, P, I, P],
     "scnb_onehot_rows": [P, P, I, I, I, P, P],
     "scnb_step_begin": [P, P],
     "scnb_mm_step_inc": [P, P],

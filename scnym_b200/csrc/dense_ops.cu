@@ -8,6 +8,7 @@
 // separate batch statistics; seg_off lives in device memory because the DAN segment length is
 // data dependent when pseudolabel thresholding is on.  Rows >= seg_off[n_seg] are written as 0.
 #include "common.cuh"
+#include <stdlib.h>
 
 #define BN_EPS 1e-5f
 
@@ -189,6 +190,17 @@ static void launch_sgemm_tile(bool tA, bool tB, bool vec, dim3 grid, cudaStream_
 #undef SCNB_LAUNCH_SGEMM
 }
 
+int scnb_tgemm_try(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                   float alpha, float beta, const float* bias, int relu, const float* gate, cudaStream_t st);
+// 1 (default): 3xTF32 mma.sync kernel for the hidden GEMMs; 0: fp32 SIMT panel kernel.  SCNB_GEMM=simt selects 0.
+static int scnb_gemm_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("SCNB_GEMM");
+    mode = (e && e[0] == 's') ? 0 : 1;
+  }
+  return mode;
+}
 int scnb_sgemm_panel_try(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
                          int ldc, float alpha, float beta, const float* bias, int relu, const float* gate, cudaStream_t st);
 
@@ -198,8 +210,10 @@ extern "C" int scnb_sgemm(int transA, int transB, int M, int N, int K, const flo
   SCNB_CHECK_ARG(M >= 0 && N >= 0 && K >= 0 && A && B && C, "sgemm: bad arguments");
   if (M == 0 || N == 0) return SCNB_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (K > 0) {  // cp.async panel kernel (gemm_ops.cu) whenever the operands allow 16-byte chunks
-    const int rc = scnb_sgemm_panel_try(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, st);
+  if (K > 0) {  // 3xTF32 tensor-core kernel, else the fp32 cp.async panel kernel (gemm_ops.cu), when operands allow 16-byte chunks
+    int rc = 0;
+    if (scnb_gemm_mode() == 1) rc = scnb_tgemm_try(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, st);
+    if (rc == 0) rc = scnb_sgemm_panel_try(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, st);
     if (rc < 0) return rc;
     if (rc == 1) {
       SCNB_CHECK_LAUNCH("sgemm/panel");

@@ -245,3 +245,205 @@ int scnb_sgemm_panel_try(int transA, int transB, int M, int N, int K, const floa
 #undef PK_GO
   return rc < 0 ? rc : 1;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Tensor-core variant for the same three product shapes: 3xTF32 (error-compensated) mma.sync.
+//   x = hi + lo with hi = tf32(x), lo = tf32(x - hi);  A*B ~= Ahi*Bhi + Ahi*Blo + Alo*Bhi
+// keeps ~21 mantissa bits per product, which the 1e-4 parity budget needs (a single TF32 pass does
+// not: SURVEY.md §7).  One CTA = one 32x32 output tile; its 4 warps split the K chunk held in shared
+// memory four ways (each runs m16n8k8 over a 32x32 warp tile) and meet in shared memory, so the
+// serial MMA chain per warp is K/32 steps and a 1024x256 output still spreads over 256 CTAs.
+// Operand panels are fetched whole (K chunk <= 256) with cp.async: one L2 round trip per chunk.
+// Fragment reads are bank-conflict free: row strides are = 4 (k-contiguous panels) or 8
+// (k-row panels) modulo 32 words.
+// ---------------------------------------------------------------------------------------------
+#define TG_KC 256
+#define TG_SR (TG_KC + 4)   // stride of a [32][KC] panel (k contiguous)
+#define TG_SC 40            // stride of a [KC][32] panel (k rows)
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// [32][kc] panel from a matrix whose rows are k-contiguous
+__device__ __forceinline__ void tg_load_rows(float* __restrict__ sm, const float* __restrict__ X, int ld, int row0, int nrows,
+                                             int k0, int kend, int kc, int tid) {
+  const int cpr = kc >> 2;
+  for (int ch = tid; ch < 32 * cpr; ch += 128) {
+    const int r = ch / cpr, kq = ch % cpr;
+    const int gr = row0 + r, gk = k0 + kq * 4;
+    const bool ok = gr < nrows && gk < kend;
+    cp_async16(sm + r * TG_SR + kq * 4, ok ? X + (size_t)gr * ld + gk : X, ok);
+  }
+}
+// [kc][32] panel from a matrix stored [k][cols]
+__device__ __forceinline__ void tg_load_cols(float* __restrict__ sm, const float* __restrict__ X, int ld, int col0, int ncols,
+                                             int k0, int kend, int kc, int tid) {
+  for (int ch = tid; ch < kc * 8; ch += 128) {
+    const int k = ch >> 3, cq = ch & 7;
+    const int gk = k0 + k, gc = col0 + cq * 4;
+    const bool ok = gk < kend && gc < ncols;
+    cp_async16(sm + k * TG_SC + cq * 4, ok ? X + (size_t)gk * ld + gc : X, ok);
+  }
+}
+
+template <int LAY>
+__global__ void __launch_bounds__(128) k_tgemm(int M, int N, int K, const float* __restrict__ A, int lda,
+                                               const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc, float alpha,
+                                               float beta, const float* __restrict__ bias, int relu,
+                                               const float* __restrict__ gate, int k_chunk) {
+  constexpr int A_FLOATS = (LAY == 2) ? TG_KC * TG_SC : 32 * TG_SR;
+  constexpr int B_FLOATS = (LAY == 0) ? 32 * TG_SR : TG_KC * TG_SC;
+  extern __shared__ __align__(16) float tg_smem[];
+  float* As = tg_smem;
+  float* Bs = tg_smem + A_FLOATS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int kb = blockIdx.z * k_chunk, ke = min(K, kb + k_chunk);
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
+  for (int k0 = kb; k0 < ke; k0 += TG_KC) {
+    const int kc = min(TG_KC, ((ke - k0) + 31) & ~31);  // chunk width, padded to 32 (zero-filled beyond ke)
+    if (k0 > kb) __syncthreads();                        // previous chunk fully consumed
+    if (LAY == 2) tg_load_cols(As, A, lda, m0, M, k0, ke, kc, tid);
+    else tg_load_rows(As, A, lda, m0, M, k0, ke, kc, tid);
+    if (LAY == 0) tg_load_rows(Bs, B, ldb, n0, N, k0, ke, kc, tid);
+    else tg_load_cols(Bs, B, ldb, n0, N, k0, ke, kc, tid);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    // this warp's quarter of the chunk
+    const int kw = kc >> 2;
+    for (int kk = warp * kw; kk < (warp + 1) * kw; kk += 8) {
+      uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float x0, x1, x2, x3;
+        if (LAY == 2) {  // A stored [k][m]
+          x0 = As[(kk + t) * TG_SC + 16 * i + g];
+          x1 = As[(kk + t) * TG_SC + 16 * i + g + 8];
+          x2 = As[(kk + t + 4) * TG_SC + 16 * i + g];
+          x3 = As[(kk + t + 4) * TG_SC + 16 * i + g + 8];
+        } else {         // A stored [m][k]
+          x0 = As[(16 * i + g) * TG_SR + kk + t];
+          x1 = As[(16 * i + g + 8) * TG_SR + kk + t];
+          x2 = As[(16 * i + g) * TG_SR + kk + t + 4];
+          x3 = As[(16 * i + g + 8) * TG_SR + kk + t + 4];
+        }
+        split_tf32(x0, ah[i][0], al[i][0]);
+        split_tf32(x1, ah[i][1], al[i][1]);
+        split_tf32(x2, ah[i][2], al[i][2]);
+        split_tf32(x3, ah[i][3], al[i][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float y0, y1;
+        if (LAY == 0) {  // B stored [n][k]
+          y0 = Bs[(8 * j + g) * TG_SR + kk + t];
+          y1 = Bs[(8 * j + g) * TG_SR + kk + t + 4];
+        } else {         // B stored [k][n]
+          y0 = Bs[(kk + t) * TG_SC + 8 * j + g];
+          y1 = Bs[(kk + t + 4) * TG_SC + 8 * j + g];
+        }
+        split_tf32(y0, bh[j][0], bl[j][0]);
+        split_tf32(y1, bh[j][1], bl[j][1]);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          mma_tf32(acc[i][j], al[i], bh[j]);
+          mma_tf32(acc[i][j], ah[i], bl[j]);
+          mma_tf32(acc[i][j], ah[i], bh[j]);
+        }
+    }
+  }
+  // cross-warp reduction of the four K quarters (the operand panels are dead: reuse their memory)
+  __syncthreads();
+  float* red = tg_smem;  // [4][32][33]
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = 16 * i + g, c = 8 * j + 2 * t;
+      red[(warp * 32 + r) * 33 + c] = acc[i][j][0];
+      red[(warp * 32 + r) * 33 + c + 1] = acc[i][j][1];
+      red[(warp * 32 + r + 8) * 33 + c] = acc[i][j][2];
+      red[(warp * 32 + r + 8) * 33 + c + 1] = acc[i][j][3];
+    }
+  __syncthreads();
+  const bool split = gridDim.z > 1;
+  for (int e = tid; e < 1024; e += 128) {
+    const int r = e >> 5, c = e & 31;
+    const int m = m0 + r, n = n0 + c;
+    if (m >= M || n >= N) continue;
+    float v = (red[r * 33 + c] + red[(32 + r) * 33 + c]) + (red[(64 + r) * 33 + c] + red[(96 + r) * 33 + c]);
+    v *= alpha;
+    if (split) {
+      atomicAdd(C + (size_t)m * ldc + n, v);
+      continue;
+    }
+    if (beta != 0.f) v += beta * C[(size_t)m * ldc + n];
+    if (bias) v += bias[n];
+    if (relu) v = fmaxf(v, 0.f);
+    if (gate && !(gate[(size_t)m * ldc + n] > 0.f)) v = 0.f;
+    C[(size_t)m * ldc + n] = v;
+  }
+}
+
+template <int LAY>
+static int launch_tgemm(dim3 grid, cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+                        int ldc, float alpha, float beta, const float* bias, int relu, const float* gate, int k_chunk) {
+  constexpr int A_FLOATS = (LAY == 2) ? TG_KC * TG_SC : 32 * TG_SR;
+  constexpr int B_FLOATS = (LAY == 0) ? 32 * TG_SR : TG_KC * TG_SC;
+  constexpr int smem = (A_FLOATS + B_FLOATS) * (int)sizeof(float);
+  static_assert(smem >= 4 * 32 * 33 * (int)sizeof(float), "reduction buffer must fit in the operand panels");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_tgemm<LAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      scnb_set_error("sgemm: cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
+      return SCNB_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  k_tgemm<LAY><<<grid, 128, smem, st>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, k_chunk);
+  return SCNB_OK;
+}
+
+// Returns 1 if launched, 0 if not applicable, <0 on error.
+int scnb_tgemm_try(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                   float alpha, float beta, const float* bias, int relu, const float* gate, cudaStream_t st) {
+  if (transA && transB) return 0;
+  const int lay = transA ? 2 : (transB ? 0 : 1);
+  if ((lda % 4) || (ldb % 4) || (((uintptr_t)A | (uintptr_t)B) % 16)) return 0;
+  if (lay == 0 && (K % 4)) return 0;
+  if (lay == 1 && ((K % 4) || (N % 4))) return 0;
+  if (lay == 2 && ((M % 4) || (N % 4))) return 0;
+  const long long tiles = (long long)scnb_cdiv(M, 32) * scnb_cdiv(N, 32);
+  int splits = 1;
+  const bool splittable = !bias && !relu && !gate && (beta == 1.f) && K >= 128;
+  if (splittable)
+    while (splits < 32 && tiles * splits < 2 * 148 && K / (splits * 2) >= 64) splits *= 2;
+  int k_chunk = scnb_cdiv(scnb_cdiv(K, splits), 32) * 32;
+  splits = scnb_cdiv(K, k_chunk);
+  dim3 grid(scnb_cdiv(N, 32), scnb_cdiv(M, 32), splits);
+  int rc;
+  if (lay == 0) rc = launch_tgemm<0>(grid, st, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, k_chunk);
+  else if (lay == 1) rc = launch_tgemm<1>(grid, st, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, k_chunk);
+  else rc = launch_tgemm<2>(grid, st, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, k_chunk);
+  return rc < 0 ? rc : 1;
+}

@@ -11,13 +11,13 @@
 // ---------------------------------------------------------------------------------------------
 // Pseudolabels.  One warp per unlabeled row.  logits: [K][U][C].
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_pseudolabel(const float* __restrict__ logits, int K, int U, int C, float T,
+// One warp, one row `u` of q: pseudolabel of unlabeled cell u (u < U) or one-hot label of labeled row u-U.
+__device__ __forceinline__ void pseudolabel_row(int u, const float* __restrict__ logits, int K, int U, int C, float T,
                                                      int sharpen, float min_conf, float* __restrict__ q,
                                                      float* __restrict__ conf, uint8_t* __restrict__ confident,
                                                      float* __restrict__ scratch, const int32_t* __restrict__ lab_ids,
                                                      int L) {
   const int lane = threadIdx.x & 31;
-  const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (u >= U) {  // rows [U, U+L) of q: one-hot labels of the labeled rows (SingleCellDS, dataprep.py:157-160)
     if (lab_ids && u < U + L) {
       const int id = lab_ids[u - U];
@@ -71,6 +71,15 @@ __global__ void __launch_bounds__(256) k_pseudolabel(const float* __restrict__ l
     s = warp_sum(s);
     for (int c = lane; c < C; c += 32) qo[c] = powf(qb[c], e) / s;
   }
+}
+
+__global__ void __launch_bounds__(256) k_pseudolabel(const float* __restrict__ logits, int K, int U, int C, float T,
+                                                     int sharpen, float min_conf, float* __restrict__ q,
+                                                     float* __restrict__ conf, uint8_t* __restrict__ confident,
+                                                     float* __restrict__ scratch, const int32_t* __restrict__ lab_ids,
+                                                     int L) {
+  const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  pseudolabel_row(u, logits, K, U, C, T, sharpen, min_conf, q, conf, confident, scratch, lab_ids, L);
 }
 
 extern "C" int scnb_pseudolabel(const float* teacher_logits, int K, int U, int C, float T, int sharpen, float min_confidence,
@@ -391,7 +400,8 @@ extern "C" int scnb_mixmatch_plan(const uint8_t* confident, const float* perm_ke
 //   dz = grad_scale * (w_i/n_norm) * (softmax(z)*sum_c y_c - y)
 // Rows >= *n_rows_dev are inactive: dz = 0.  loss_out[0] += loss (atomic); loss_out[1] += #argmax hits.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_soft_ce(const float* __restrict__ Zl, int n_max, int C,
+// One warp, one row `i` of the soft-target cross entropy (see k_soft_ce).
+__device__ __forceinline__ void ce_row(int i, const float* __restrict__ Zl, int n_max, int C,
                                                  const int32_t* __restrict__ n_rows_dev, const float* __restrict__ Y,
                                                  const int32_t* __restrict__ mapA, const int32_t* __restrict__ mapB,
                                                  const float* __restrict__ gam, int map_off,
@@ -400,8 +410,6 @@ __global__ void __launch_bounds__(256) k_soft_ce(const float* __restrict__ Zl, i
                                                  float* __restrict__ dZ, float* __restrict__ loss_out, int count_acc,
                                                  float* __restrict__ row_loss) {
   const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= n_max) return;
   const int n_rows = n_rows_dev ? min(*n_rows_dev, n_max) : n_max;
   float* dz = dZ ? dZ + (size_t)i * C : nullptr;
   if (i >= n_rows) {
@@ -476,6 +484,20 @@ __global__ void __launch_bounds__(256) k_soft_ce(const float* __restrict__ Zl, i
   }
 }
 
+__global__ void __launch_bounds__(256) k_soft_ce(const float* __restrict__ Zl, int n_max, int C,
+                                                 const int32_t* __restrict__ n_rows_dev, const float* __restrict__ Y,
+                                                 const int32_t* __restrict__ mapA, const int32_t* __restrict__ mapB,
+                                                 const float* __restrict__ gam, int map_off,
+                                                 const float* __restrict__ class_weight, const int32_t* __restrict__ n_norm_dev,
+                                                 int n_norm, float grad_scale, const float* __restrict__ loss_scale_dev,
+                                                 float* __restrict__ dZ, float* __restrict__ loss_out, int count_acc,
+                                                 float* __restrict__ row_loss) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n_max) return;
+  ce_row(i, Zl, n_max, C, n_rows_dev, Y, mapA, mapB, gam, map_off, class_weight, n_norm_dev, n_norm, grad_scale, loss_scale_dev, dZ,
+         loss_out, count_acc, row_loss);
+}
+
 extern "C" int scnb_soft_ce_fwd_bwd(const float* logits, int n_max, int C, const int32_t* n_rows_dev, const float* Y,
                                     const int32_t* mapA, const int32_t* mapB, const float* gam, int map_off,
                                     const float* class_weight, const int32_t* n_norm_dev, int n_norm, float grad_scale,
@@ -495,15 +517,14 @@ extern "C" int scnb_soft_ce_fwd_bwd(const float* logits, int n_max, int C, const
 //   L_u = (1/n_norm) sum_{i < n_conf} sum_c (softmax(z_i)_c - y'_ic)^2 ;  rows >= n_conf get zero loss/grad.
 //   dz = p * (g - sum_c g_c p_c),  g = 2 (p - y') * weight / n_norm
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_softmax_mse(const float* __restrict__ Zl, int n_max, int C,
+// One warp, one row `i` of the masked MSE on probabilities (see k_softmax_mse).
+__device__ __forceinline__ void mse_row(int i, const float* __restrict__ Zl, int n_max, int C,
                                                      const int32_t* __restrict__ n_conf_dev, const float* __restrict__ Y,
                                                      const int32_t* __restrict__ mapA, const int32_t* __restrict__ mapB,
                                                      const float* __restrict__ gam, int map_off, int n_norm,
                                                      const float* __restrict__ weight_dev, float weight,
                                                      float* __restrict__ dZ, float* __restrict__ loss_out) {
   const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= n_max) return;
   const int n_conf = n_conf_dev ? min(*n_conf_dev, n_max) : n_max;
   float* dz = dZ ? dZ + (size_t)i * C : nullptr;
   if (i >= n_conf) {
@@ -549,6 +570,17 @@ __global__ void __launch_bounds__(256) k_softmax_mse(const float* __restrict__ Z
     }
   }
   if (lane == 0) atomicAdd(loss_out, sq * inv_n);
+}
+
+__global__ void __launch_bounds__(256) k_softmax_mse(const float* __restrict__ Zl, int n_max, int C,
+                                                     const int32_t* __restrict__ n_conf_dev, const float* __restrict__ Y,
+                                                     const int32_t* __restrict__ mapA, const int32_t* __restrict__ mapB,
+                                                     const float* __restrict__ gam, int map_off, int n_norm,
+                                                     const float* __restrict__ weight_dev, float weight,
+                                                     float* __restrict__ dZ, float* __restrict__ loss_out) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n_max) return;
+  mse_row(i, Zl, n_max, C, n_conf_dev, Y, mapA, mapB, gam, map_off, n_norm, weight_dev, weight, dZ, loss_out);
 }
 
 extern "C" int scnb_softmax_mse_fwd_bwd(const float* logits, int n_max, int C, const int32_t* n_conf_dev, const float* Y,
@@ -622,5 +654,245 @@ extern "C" int scnb_predict_head(const float* logits_sum, int n_models, int n, i
   if (n == 0) return SCNB_OK;
   k_predict_head<<<scnb_cdiv(n, 8), 256, 0, (cudaStream_t)stream>>>(logits_sum, 1.0f / (float)n_models, n, C, pred, prob, score);
   SCNB_CHECK_LAUNCH("predict_head");
+  return SCNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused heads.  The classifier (H -> C), the last layer of the domain adversary (H -> D) and their
+// losses are a few kFLOP per row: as separate GEMM / loss / GEMM launches they cost four dependent
+// kernels each on the step's critical path.  Here one warp owns one row: it forms the C (or D)
+// logits against the weight matrix staged in shared memory, runs the loss row function on them and
+// immediately back-propagates dLogits through the same weights.  H must be a multiple of 128
+// (lane owns float4 groups h = (i*32 + lane)*4) and C*H floats must fit in shared memory;
+// otherwise the engine keeps the unfused sequence.
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void head_logits(const float* __restrict__ a_row, const float* __restrict__ Ws,
+                                            const float* __restrict__ bias, int C, int H, float* __restrict__ z_row,
+                                            float4 (&a)[NV], int lane) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) a[i] = *reinterpret_cast<const float4*>(a_row + (i * 32 + lane) * 4);
+  for (int c = 0; c < C; ++c) {
+    float p = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 w = *reinterpret_cast<const float4*>(Ws + (size_t)c * H + (i * 32 + lane) * 4);
+      p = fmaf(a[i].x, w.x, p);
+      p = fmaf(a[i].y, w.y, p);
+      p = fmaf(a[i].z, w.z, p);
+      p = fmaf(a[i].w, w.w, p);
+    }
+    p = warp_sum(p);
+    if (lane == (c & 31)) z_row[c] = p + (bias ? bias[c] : 0.f);
+  }
+  __syncwarp();
+}
+// out_row[h] = scale * sum_c dz[c] * W[c][h]   (optionally gated by act[h] > 0: ReLU backward)
+template <int NV>
+__device__ __forceinline__ void head_backprop(const float* __restrict__ dz_row, const float* __restrict__ Ws, int C, int H,
+                                              float scale, const float4* gate_act, float* __restrict__ out_row, int lane) {
+  float4 acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = 0; c < C; ++c) {
+    const float d = dz_row[c];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 w = *reinterpret_cast<const float4*>(Ws + (size_t)c * H + (i * 32 + lane) * 4);
+      acc[i].x = fmaf(d, w.x, acc[i].x);
+      acc[i].y = fmaf(d, w.y, acc[i].y);
+      acc[i].z = fmaf(d, w.z, acc[i].z);
+      acc[i].w = fmaf(d, w.w, acc[i].w);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float4 v = make_float4(scale * acc[i].x, scale * acc[i].y, scale * acc[i].z, scale * acc[i].w);
+    if (gate_act) {
+      const float4 gt = gate_act[i];
+      if (!(gt.x > 0.f)) v.x = 0.f;
+      if (!(gt.y > 0.f)) v.y = 0.f;
+      if (!(gt.z > 0.f)) v.z = 0.f;
+      if (!(gt.w > 0.f)) v.w = 0.f;
+    }
+    *reinterpret_cast<float4*>(out_row + (i * 32 + lane) * 4) = v;
+  }
+}
+__device__ __forceinline__ void stage_weights(float* Ws, const float* __restrict__ W, int n) {
+  for (int i = threadIdx.x * 4; i < n; i += blockDim.x * 4) *reinterpret_cast<float4*>(Ws + i) = *reinterpret_cast<const float4*>(W + i);
+  __syncthreads();
+}
+
+// MixMatch student head: rows [0,U) interpolation-consistency MSE, rows [U,U+L) soft-target CE
+// (scnym/model.py:229 classifier; scnym/losses.py:880-923), dA = dLogits Wc.
+template <int NV>
+__global__ void __launch_bounds__(256) k_classif_mixmatch(const float* __restrict__ A, const float* __restrict__ Wc,
+                                                          const float* __restrict__ bc, int H, int C, int U, int L,
+                                                          const int32_t* __restrict__ n_conf_dev, const float* __restrict__ Y,
+                                                          const int32_t* __restrict__ mapA, const int32_t* __restrict__ mapB,
+                                                          const float* __restrict__ gam, const float* __restrict__ class_weight,
+                                                          float unsup_weight, float* __restrict__ logits,
+                                                          float* __restrict__ dlogits, float* __restrict__ dA,
+                                                          float* __restrict__ loss8) {
+  extern __shared__ __align__(16) float Ws[];
+  stage_weights(Ws, Wc, C * H);
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= U + L) return;
+  float4 a[NV];
+  head_logits<NV>(A + (size_t)r * H, Ws, bc, C, H, logits + (size_t)r * C, a, lane);
+  if (r < U)
+    mse_row(r, logits, U, C, n_conf_dev, Y, mapA, mapB, gam, 0, U, nullptr, unsup_weight, dlogits, loss8 + 2);
+  else
+    ce_row(r - U, logits + (size_t)U * C, L, C, nullptr, Y, mapA, mapB, gam, U, class_weight, nullptr, L, 1.0f, nullptr,
+           dlogits + (size_t)U * C, loss8, 1, nullptr);
+  __syncwarp();
+  head_backprop<NV>(dlogits + (size_t)r * C, Ws, C, H, 1.0f, nullptr, dA + (size_t)r * H, lane);
+}
+
+// Supervised head: CE against one-hot integer labels (Trainer step, scnym/trainer.py:189-256).
+template <int NV>
+__global__ void __launch_bounds__(256) k_classif_supervised(const float* __restrict__ A, const float* __restrict__ Wc,
+                                                            const float* __restrict__ bc, int H, int C, int n,
+                                                            const float* __restrict__ Y, const float* __restrict__ class_weight,
+                                                            float* __restrict__ logits, float* __restrict__ dlogits,
+                                                            float* __restrict__ dA, float* __restrict__ loss8) {
+  extern __shared__ __align__(16) float Ws[];
+  stage_weights(Ws, Wc, C * H);
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n) return;
+  float4 a[NV];
+  head_logits<NV>(A + (size_t)r * H, Ws, bc, C, H, logits + (size_t)r * C, a, lane);
+  ce_row(r, logits, n, C, nullptr, Y, nullptr, nullptr, nullptr, 0, class_weight, nullptr, n, 1.0f, nullptr, dlogits, loss8, 1,
+         nullptr);
+  __syncwarp();
+  head_backprop<NV>(dlogits + (size_t)r * C, Ws, C, H, 1.0f, nullptr, dA + (size_t)r * H, lane);
+}
+
+// Domain adversary tail: Hd = relu(Linear(H,H)(embed)) -> Linear(H,D) -> CE against the domain label
+// (scnym/model.py:377-383, scnym/losses.py:1209-1243) -> dHd = (ddlog W2) * [Hd > 0].
+template <int NV>
+__global__ void __launch_bounds__(256) k_dan_tail(const float* __restrict__ Hd, const float* __restrict__ W2,
+                                                  const float* __restrict__ b2, int H, int D, int Rd,
+                                                  const int32_t* __restrict__ n_rows_dev, const int32_t* __restrict__ dom_ids,
+                                                  const int32_t* __restrict__ src, int src_off,
+                                                  const float* __restrict__ loss_scale_dev, float* __restrict__ dlog,
+                                                  float* __restrict__ dlabel, float* __restrict__ ddlog,
+                                                  float* __restrict__ dHd, float* __restrict__ loss2) {
+  extern __shared__ __align__(16) float Ws[];
+  stage_weights(Ws, W2, D * H);
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= Rd) return;
+  float4 a[NV];
+  head_logits<NV>(Hd + (size_t)r * H, Ws, b2, D, H, dlog + (size_t)r * D, a, lane);
+  const int id = dom_ids[src ? src[src_off + r] : r];
+  for (int c = lane; c < D; c += 32) dlabel[(size_t)r * D + c] = (c == id) ? 1.f : 0.f;
+  __syncwarp();
+  ce_row(r, dlog, Rd, D, n_rows_dev, dlabel, nullptr, nullptr, nullptr, 0, nullptr, n_rows_dev, 0, 1.0f, loss_scale_dev, ddlog,
+         loss2, 1, nullptr);
+  __syncwarp();
+  head_backprop<NV>(ddlog + (size_t)r * D, Ws, D, H, 1.0f, a, dHd + (size_t)r * H, lane);
+}
+
+// Teacher head: classifier on the K eval-mode views of cell u, then pseudolabel (+ label one-hots).
+template <int NV>
+__global__ void __launch_bounds__(256) k_teacher_head(const float* __restrict__ TA, const float* __restrict__ Wc,
+                                                      const float* __restrict__ bc, int H, int C, int K, int U, float T,
+                                                      int sharpen, float min_conf, float* __restrict__ t_logits,
+                                                      float* __restrict__ q, float* __restrict__ conf,
+                                                      uint8_t* __restrict__ confident, float* __restrict__ scratch,
+                                                      const int32_t* __restrict__ lab_ids, int L) {
+  extern __shared__ __align__(16) float Ws[];
+  stage_weights(Ws, Wc, C * H);
+  const int lane = threadIdx.x & 31;
+  const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (u < U) {
+    float4 a[NV];
+    for (int k = 0; k < K; ++k) {
+      const size_t row = (size_t)k * U + u;
+      head_logits<NV>(TA + row * H, Ws, bc, C, H, t_logits + row * C, a, lane);
+    }
+  }
+  pseudolabel_row(u, t_logits, K, U, C, T, sharpen, min_conf, q, conf, confident, scratch, lab_ids, L);
+}
+
+static bool head_fusable(int H, int C, const void* p0, const void* p1, const void* p2) {
+  const uintptr_t bits = (uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2;
+  return (H % 128 == 0) && H <= 1024 && (size_t)C * H * sizeof(float) <= 96 * 1024 && (bits % 16 == 0);
+}
+#define HEAD_DISPATCH(KERNEL, rows, smem, st, ...)                                                   \
+  do {                                                                                               \
+    const int nv__ = H / 128;                                                                        \
+    dim3 grid__(scnb_cdiv(rows, 8));                                                                 \
+    if ((smem) > 48 * 1024) {                                                                        \
+      cudaFuncSetAttribute(KERNEL<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem));     \
+      cudaFuncSetAttribute(KERNEL<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem));     \
+      cudaFuncSetAttribute(KERNEL<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem));     \
+      cudaFuncSetAttribute(KERNEL<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem));     \
+    }                                                                                                \
+    if (nv__ == 1) KERNEL<1><<<grid__, 256, smem, st>>>(__VA_ARGS__);                                \
+    else if (nv__ == 2) KERNEL<2><<<grid__, 256, smem, st>>>(__VA_ARGS__);                           \
+    else if (nv__ <= 4) { if (nv__ == 4) KERNEL<4><<<grid__, 256, smem, st>>>(__VA_ARGS__); else return SCNB_ERR_UNSUPPORTED; } \
+    else if (nv__ == 8) KERNEL<8><<<grid__, 256, smem, st>>>(__VA_ARGS__);                           \
+    else return SCNB_ERR_UNSUPPORTED;                                                                \
+  } while (0)
+
+// Returns SCNB_ERR_UNSUPPORTED (-3) when the shape cannot be fused (caller falls back to the unfused sequence).
+extern "C" int scnb_classif_mixmatch_fused(const float* A, const float* Wc, const float* bc, int H, int C, int U, int L,
+                                           const int32_t* n_conf_dev, const float* Y, const int32_t* mapA, const int32_t* mapB,
+                                           const float* gam, const float* class_weight, float unsup_weight, float* logits,
+                                           float* dlogits, float* dA, float* loss8, void* stream) {
+  SCNB_CHECK_ARG(A && Wc && Y && mapA && logits && dlogits && dA && loss8 && H > 0 && C > 0 && U >= 0 && L >= 0,
+                 "classif_mixmatch_fused: bad arguments");
+  if (!head_fusable(H, C, A, Wc, dA) || (H / 128 != 1 && H / 128 != 2 && H / 128 != 4 && H / 128 != 8)) return SCNB_ERR_UNSUPPORTED;
+  if (U + L == 0) return SCNB_OK;
+  const size_t smem = (size_t)C * H * sizeof(float);
+  HEAD_DISPATCH(k_classif_mixmatch, U + L, smem, (cudaStream_t)stream, A, Wc, bc, H, C, U, L, n_conf_dev, Y, mapA, mapB, gam,
+                class_weight, unsup_weight, logits, dlogits, dA, loss8);
+  SCNB_CHECK_LAUNCH("classif_mixmatch_fused");
+  return SCNB_OK;
+}
+
+extern "C" int scnb_classif_supervised_fused(const float* A, const float* Wc, const float* bc, int H, int C, int n, const float* Y,
+                                             const float* class_weight, float* logits, float* dlogits, float* dA, float* loss8,
+                                             void* stream) {
+  SCNB_CHECK_ARG(A && Wc && Y && logits && dlogits && dA && loss8 && H > 0 && C > 0 && n >= 0, "classif_supervised_fused: bad arguments");
+  if (!head_fusable(H, C, A, Wc, dA) || (H / 128 != 1 && H / 128 != 2 && H / 128 != 4 && H / 128 != 8)) return SCNB_ERR_UNSUPPORTED;
+  if (n == 0) return SCNB_OK;
+  const size_t smem = (size_t)C * H * sizeof(float);
+  HEAD_DISPATCH(k_classif_supervised, n, smem, (cudaStream_t)stream, A, Wc, bc, H, C, n, Y, class_weight, logits, dlogits, dA, loss8);
+  SCNB_CHECK_LAUNCH("classif_supervised_fused");
+  return SCNB_OK;
+}
+
+extern "C" int scnb_dan_tail_fused(const float* Hd, const float* W2, const float* b2, int H, int D, int Rd,
+                                   const int32_t* n_rows_dev, const int32_t* dom_ids, const int32_t* src, int src_off,
+                                   const float* loss_scale_dev, float* dlog, float* dlabel, float* ddlog, float* dHd, float* loss2,
+                                   void* stream) {
+  SCNB_CHECK_ARG(Hd && W2 && dom_ids && dlog && dlabel && ddlog && dHd && loss2 && H > 0 && D > 0 && Rd >= 0,
+                 "dan_tail_fused: bad arguments");
+  if (!head_fusable(H, D, Hd, W2, dHd) || (H / 128 != 1 && H / 128 != 2 && H / 128 != 4 && H / 128 != 8)) return SCNB_ERR_UNSUPPORTED;
+  if (Rd == 0) return SCNB_OK;
+  const size_t smem = (size_t)D * H * sizeof(float);
+  HEAD_DISPATCH(k_dan_tail, Rd, smem, (cudaStream_t)stream, Hd, W2, b2, H, D, Rd, n_rows_dev, dom_ids, src, src_off, loss_scale_dev,
+                dlog, dlabel, ddlog, dHd, loss2);
+  SCNB_CHECK_LAUNCH("dan_tail_fused");
+  return SCNB_OK;
+}
+
+extern "C" int scnb_teacher_head_fused(const float* TA, const float* Wc, const float* bc, int H, int C, int K, int U, float T,
+                                       int sharpen, float min_confidence, float* t_logits, float* q, float* conf,
+                                       uint8_t* confident, float* scratch_UC, const int32_t* lab_ids, int L, void* stream) {
+  SCNB_CHECK_ARG(TA && Wc && t_logits && q && conf && confident && scratch_UC && H > 0 && C > 0 && K > 0 && U >= 0,
+                 "teacher_head_fused: bad arguments");
+  if (!head_fusable(H, C, TA, Wc, Wc) || (H / 128 != 1 && H / 128 != 2 && H / 128 != 4 && H / 128 != 8)) return SCNB_ERR_UNSUPPORTED;
+  const int rows = U + (lab_ids ? L : 0);
+  if (rows == 0) return SCNB_OK;
+  const size_t smem = (size_t)C * H * sizeof(float);
+  HEAD_DISPATCH(k_teacher_head, rows, smem, (cudaStream_t)stream, TA, Wc, bc, H, C, K, U, T, sharpen, min_confidence, t_logits, q,
+                conf, confident, scratch_UC, lab_ids, L);
+  SCNB_CHECK_LAUNCH("teacher_head_fused");
   return SCNB_OK;
 }

@@ -59,6 +59,7 @@ class EngineConfig:
     class_weight: Optional[List[float]] = None
     seed: int = 0
     use_cuda_graph: bool = True
+    fuse_heads: bool = True      # one-warp-per-row classifier/DAN-tail/teacher-head kernels (Linear + loss + backward)
     multi_stream: bool = True    # run independent kernels of the step on side streams (parallel graph branches)
     keep_w1_grad: bool = False   # also write the first-layer gradient to HBM (parity tests; implied by data parallelism)
 
@@ -275,6 +276,9 @@ class TrainEngine(object):
         self.dA = f32(R, wmax)
         self.dZs = [f32(R, w) for w in self.widths]   # one per application: weight-gradient GEMMs overlap the dA chain
         self._side = None
+        fus = lambda c: (self.H % 128 == 0 and self.H // 128 in (1, 2, 4, 8) and c * self.H * 4 <= 96 * 1024)
+        self.fuse_classif = bool(cfg.fuse_heads and fus(self.C))
+        self.fuse_dan = bool(cfg.fuse_heads and self.use_dan and fus(self.D))
         self._ev_grl, self._ev_csc, self._ev_zero = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         self.dZ1 = f32(self.nb, H0) if mode == "mixmatch" else None
         if self.use_dan:
@@ -408,12 +412,17 @@ class TrainEngine(object):
                      ptr(tw(blk[a + 1]["W"])), self.widths[a], ptr(self.TZ[a + 1]), self.widths[a + 1], 1.0, 0.0,
                      ptr(tw(blk[a + 1]["b"])), 0, None, st)
                 tz = self.TZ[a + 1]
-        call("scnb_sgemm", 0, 1, KU, C, self.H, ptr(self.TA[-1]), self.H, ptr(tw("model.classif.0.weight")), self.H,
-             ptr(self.t_logits), C, 1.0, 0.0, ptr(tw("model.classif.0.bias")), 0, None, st)
-        # pseudolabels q[0,U) and the one-hot labels of the labeled rows q[U,U+L)
-        call("scnb_pseudolabel", ptr(self.t_logits), K, U, C, float(c.T if c.T is not None else 1.0), int(c.T is not None),
-             float(c.pseudolabel_min_confidence), ptr(self.Ycat), ptr(self.conf), ptr(self.confident), ptr(self.pl_scratch),
-             ptr(self.lab_ids), L, st)
+        pl_args = (float(c.T if c.T is not None else 1.0), int(c.T is not None), float(c.pseudolabel_min_confidence))
+        if self.fuse_classif:
+            # teacher classifier + pseudolabels q[0,U) + one-hot labels q[U,U+L) in one launch
+            call("scnb_teacher_head_fused", ptr(self.TA[-1]), ptr(tw("model.classif.0.weight")), ptr(tw("model.classif.0.bias")),
+                 self.H, C, K, U, pl_args[0], pl_args[1], pl_args[2], ptr(self.t_logits), ptr(self.Ycat), ptr(self.conf),
+                 ptr(self.confident), ptr(self.pl_scratch), ptr(self.lab_ids), L, st)
+        else:
+            call("scnb_sgemm", 0, 1, KU, C, self.H, ptr(self.TA[-1]), self.H, ptr(tw("model.classif.0.weight")), self.H,
+                 ptr(self.t_logits), C, 1.0, 0.0, ptr(tw("model.classif.0.bias")), 0, None, st)
+            call("scnb_pseudolabel", ptr(self.t_logits), K, U, C, pl_args[0], pl_args[1], pl_args[2], ptr(self.Ycat),
+                 ptr(self.conf), ptr(self.confident), ptr(self.pl_scratch), ptr(self.lab_ids), L, st)
         # -- MixUp plan + hidden-space MixUp (losses.py:811-875)
         call("scnb_mixmatch_plan", ptr(self.confident), ptr(self.perm_keys), ptr(self.gamma_raw), U, L, int(self.use_dan),
              int(c.dan_use_conf_pseudolabels), int(c.mixup_alpha > 0.0), ptr(self.counts), ptr(self.seg_off),
@@ -433,14 +442,19 @@ class TrainEngine(object):
             sd = sD.cuda_stream
             call("scnb_sgemm", 0, 1, self.Rd, Hh, Hh, ptr(Ae), Hh, self.P(d0 + ".weight"), Hh, ptr(self.Hd), Hh, 1.0, 0.0,
                  self.P(d0 + ".bias"), 1, None, sd)
-            call("scnb_sgemm", 0, 1, self.Rd, self.D, Hh, ptr(self.Hd), Hh, self.P(d1 + ".weight"), Hh, ptr(self.dlog), self.D,
-                 1.0, 0.0, self.P(d1 + ".bias"), 0, None, sd)
-            call("scnb_onehot_rows", ptr(self.base_dom), ptr(self.srcA), nb, self.Rd, self.D, ptr(self.dlabel), sd)
-            call("scnb_soft_ce_fwd_bwd", ptr(self.dlog), self.Rd, self.D, ptr(self.counts[2:]), ptr(self.dlabel), None, None,
-                 None, 0, None, ptr(self.counts[2:]), 0, 1.0, ptr(self.pconf) if c.dan_scale_loss_pseudoconf else None,
-                 ptr(self.ddlog), ptr(self.loss_buf[4:]), 1, None, sd)
-            call("scnb_sgemm", 0, 0, self.Rd, Hh, self.D, ptr(self.ddlog), self.D, self.P(d1 + ".weight"), Hh, ptr(self.dHd), Hh,
-                 1.0, 0.0, None, 0, ptr(self.Hd), sd)
+            scale = ptr(self.pconf) if c.dan_scale_loss_pseudoconf else None
+            if self.fuse_dan:
+                call("scnb_dan_tail_fused", ptr(self.Hd), self.P(d1 + ".weight"), self.P(d1 + ".bias"), Hh, self.D, self.Rd,
+                     ptr(self.counts[2:]), ptr(self.base_dom), ptr(self.srcA), nb, scale, ptr(self.dlog), ptr(self.dlabel),
+                     ptr(self.ddlog), ptr(self.dHd), ptr(self.loss_buf[4:]), sd)
+            else:
+                call("scnb_sgemm", 0, 1, self.Rd, self.D, Hh, ptr(self.Hd), Hh, self.P(d1 + ".weight"), Hh, ptr(self.dlog), self.D,
+                     1.0, 0.0, self.P(d1 + ".bias"), 0, None, sd)
+                call("scnb_onehot_rows", ptr(self.base_dom), ptr(self.srcA), nb, self.Rd, self.D, ptr(self.dlabel), sd)
+                call("scnb_soft_ce_fwd_bwd", ptr(self.dlog), self.Rd, self.D, ptr(self.counts[2:]), ptr(self.dlabel), None, None,
+                     None, 0, None, ptr(self.counts[2:]), 0, 1.0, scale, ptr(self.ddlog), ptr(self.loss_buf[4:]), 1, None, sd)
+                call("scnb_sgemm", 0, 0, self.Rd, Hh, self.D, ptr(self.ddlog), self.D, self.P(d1 + ".weight"), Hh, ptr(self.dHd),
+                     Hh, 1.0, 0.0, None, 0, ptr(self.Hd), sd)
             # gradient reversal: dEmbed = -w * dHd W  (model.py:338)
             call("scnb_sgemm", 0, 0, self.Rd, Hh, Hh, ptr(self.dHd), Hh, self.P(d0 + ".weight"), Hh, ptr(dA_last[nb:]), Hh,
                  -self.dan_weight, 0.0, None, 0, None, sd)
@@ -455,16 +469,21 @@ class TrainEngine(object):
             call("scnb_sgemm", 1, 0, Hh, Hh, self.Rd, ptr(self.dHd), Hh, ptr(Ae), Hh, self.Gp(d0 + ".weight"), Hh, 1.0, 1.0, None,
                  0, None, sd)
             call("scnb_colsum", ptr(self.dHd), self.Rd, Hh, Hh, self.Gp(d0 + ".bias"), 1, sd)
-        # -- classifier, losses + dLogits (losses.py:896-923, 1224-1243; trainer.py:651-656)
-        call("scnb_sgemm", 0, 1, nb, C, Hh, ptr(self.As[-1]), Hh, self.P("model.classif.0.weight"), Hh,
-             ptr(self.logits), C, 1.0, 0.0, self.P("model.classif.0.bias"), 0, None, st)
-        call("scnb_softmax_mse_fwd_bwd", ptr(self.logits), U, C, ptr(self.counts), ptr(self.Ycat), ptr(self.srcA),
-             ptr(self.srcB), ptr(self.gam), 0, U, None, self.unsup_weight, ptr(self.dlogits), ptr(self.loss_buf[2:]), st)
-        call("scnb_soft_ce_fwd_bwd", ptr(self.logits[U:]), L, C, None, ptr(self.Ycat), ptr(self.srcA), ptr(self.srcB),
-             ptr(self.gam), U, ptr(self.class_weight), None, L, 1.0, None, ptr(self.dlogits[U:]), ptr(self.loss_buf), 1, None, st)
-        # -- backward: the dA chain stays on the main stream, weight gradients go to branch W
-        call("scnb_sgemm", 0, 0, nb, Hh, C, ptr(self.dlogits), C, self.P("model.classif.0.weight"), Hh, ptr(dA_last), Hh, 1.0,
-             0.0, None, 0, None, st)
+        # -- classifier, losses + dLogits (losses.py:896-923, 1224-1243; trainer.py:651-656) and dA of the classifier
+        if self.fuse_classif:
+            call("scnb_classif_mixmatch_fused", ptr(self.As[-1]), self.P("model.classif.0.weight"), self.P("model.classif.0.bias"),
+                 Hh, C, U, L, ptr(self.counts), ptr(self.Ycat), ptr(self.srcA), ptr(self.srcB), ptr(self.gam),
+                 ptr(self.class_weight), self.unsup_weight, ptr(self.logits), ptr(self.dlogits), ptr(dA_last), ptr(self.loss_buf), st)
+        else:
+            call("scnb_sgemm", 0, 1, nb, C, Hh, ptr(self.As[-1]), Hh, self.P("model.classif.0.weight"), Hh,
+                 ptr(self.logits), C, 1.0, 0.0, self.P("model.classif.0.bias"), 0, None, st)
+            call("scnb_softmax_mse_fwd_bwd", ptr(self.logits), U, C, ptr(self.counts), ptr(self.Ycat), ptr(self.srcA),
+                 ptr(self.srcB), ptr(self.gam), 0, U, None, self.unsup_weight, ptr(self.dlogits), ptr(self.loss_buf[2:]), st)
+            call("scnb_soft_ce_fwd_bwd", ptr(self.logits[U:]), L, C, None, ptr(self.Ycat), ptr(self.srcA), ptr(self.srcB),
+                 ptr(self.gam), U, ptr(self.class_weight), None, L, 1.0, None, ptr(self.dlogits[U:]), ptr(self.loss_buf), 1, None, st)
+            # -- backward: the dA chain stays on the main stream, weight gradients go to branch W
+            call("scnb_sgemm", 0, 0, nb, Hh, C, ptr(self.dlogits), C, self.P("model.classif.0.weight"), Hh, ptr(dA_last), Hh, 1.0,
+                 0.0, None, 0, None, st)
         self._after(sW, main)
         sw = sW.cuda_stream
         call("scnb_sgemm", 1, 0, C, Hh, nb, ptr(self.dlogits), C, ptr(self.As[-1]), Hh, self.Gp("model.classif.0.weight"), Hh,
@@ -668,15 +687,20 @@ class TrainEngine(object):
         call("scnb_csr_linear_fwd", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), L, self.P(blk[0]["W"]),
              self.P(blk[0]["b"]), H0, ptr(self.Zs[0]), st)
         self._student_forward(st, rng)
-        call("scnb_sgemm", 0, 1, L, C, self.H, ptr(self.As[-1]), self.H, self.P("model.classif.0.weight"), self.H,
-             ptr(self.logits), C, 1.0, 0.0, self.P("model.classif.0.bias"), 0, None, st)
-        call("scnb_onehot_rows", ptr(self.lab_ids), None, 0, L, C, ptr(self.Ycat), st)
-        call("scnb_soft_ce_fwd_bwd", ptr(self.logits), L, C, None, ptr(self.Ycat), None, None, None, 0, ptr(self.class_weight),
-             None, L, 1.0, None, ptr(self.dlogits), ptr(self.loss_buf), 1, None, st)
         Hh = self.H
         dA_last = self._view(self.dA, L, Hh)
-        call("scnb_sgemm", 0, 0, L, Hh, C, ptr(self.dlogits), C, self.P("model.classif.0.weight"), Hh, ptr(dA_last), Hh, 1.0, 0.0,
-             None, 0, None, st)
+        call("scnb_onehot_rows", ptr(self.lab_ids), None, 0, L, C, ptr(self.Ycat), st)
+        if self.fuse_classif:
+            call("scnb_classif_supervised_fused", ptr(self.As[-1]), self.P("model.classif.0.weight"), self.P("model.classif.0.bias"),
+                 Hh, C, L, ptr(self.Ycat), ptr(self.class_weight), ptr(self.logits), ptr(self.dlogits), ptr(dA_last),
+                 ptr(self.loss_buf), st)
+        else:
+            call("scnb_sgemm", 0, 1, L, C, self.H, ptr(self.As[-1]), self.H, self.P("model.classif.0.weight"), self.H,
+                 ptr(self.logits), C, 1.0, 0.0, self.P("model.classif.0.bias"), 0, None, st)
+            call("scnb_soft_ce_fwd_bwd", ptr(self.logits), L, C, None, ptr(self.Ycat), None, None, None, 0, ptr(self.class_weight),
+                 None, L, 1.0, None, ptr(self.dlogits), ptr(self.loss_buf), 1, None, st)
+            call("scnb_sgemm", 0, 0, L, Hh, C, ptr(self.dlogits), C, self.P("model.classif.0.weight"), Hh, ptr(dA_last), Hh, 1.0, 0.0,
+                 None, 0, None, st)
         self._after(sW, main)
         sw = sW.cuda_stream
         call("scnb_sgemm", 1, 0, C, Hh, L, ptr(self.dlogits), C, ptr(self.As[-1]), Hh, self.Gp("model.classif.0.weight"), Hh, 1.0,

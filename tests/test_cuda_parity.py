@@ -76,6 +76,10 @@ def test_engine_step_matches_reference_golden(case):
     dict(G=1000, L=40, U=56, C=5, H0=96, H=72, n_layers=2, tau=0.22, dan_conf=True, dan_scale=True, opt_name="sgd", lr=0.05,
          mean_teacher=True, n_steps=2, seed=13),
     dict(G=777, L=33, U=17, C=3, H0=40, H=24, n_layers=1, opt_name="adamw", lr=1e-3, wd=1e-2, seed=14),
+    # fused heads (H % 128 == 0) with thresholded pseudolabels, confident-only DAN rows and given domains
+    dict(G=1200, L=40, U=48, C=7, H0=128, H=256, n_layers=2, tau=0.2, dan_conf=True, dan_scale=True, D_given=4, opt_name="adam",
+         n_steps=2, seed=15),
+    dict(G=900, L=24, U=40, C=4, H0=64, H=128, n_layers=3, K=2, aug_pl=True, opt_name="adadelta", lr=1.0, seed=16),
 ])
 def test_engine_step_matches_oracle(kw):
     from tests import cuda_harness as CH
