@@ -189,54 +189,32 @@ def algorithmic_bytes(eng, name):
 
 
 def time_e2e(args, device, rank, world):
-    """`e2e`: same step through the host-buffer entry (pinned staging -> H2D -> step -> loss D2H)."""
-    from scnym_b200.dataprep import HostBatchFeeder
-    from scnym_b200.engine import TrainEngine
+    """`e2e`: the same step through the public host-buffer entry `scnym_b200.hostfeed.HostTrainPipeline`:
+    the expression matrices live in HOST memory; every step's batch is gathered on the host into pinned
+    memory, copied host->device, trained on, and the step's loss scalars are copied back and read on the
+    host -- all inside the timed region (the three stages are pipelined across steps)."""
+    from scnym_b200.hostfeed import HostTrainPipeline
     c = CFG
     n_host = 20_000  # host-resident sample of the same synthetic matrices (throughput is per step)
     model, dann, cfg, lab, y, unl = build_train(device, rank, seed_off=7, n_lab=n_host, n_unl=n_host)
-    fl = HostBatchFeeder(lab.indptr.cpu().numpy(), lab.indices.cpu().numpy(), lab.data.cpu().numpy(), c["G"], c["L"], device,
-                         labels=y.cpu().numpy())
-    fu = HostBatchFeeder(unl.indptr.cpu().numpy(), unl.indices.cpu().numpy(), unl.data.cpu().numpy(), c["G"], c["U"], device)
+    host = lambda t: t.cpu().numpy()
+    pipe = HostTrainPipeline(model, cfg, lab=(host(lab.indptr), host(lab.indices), host(lab.data), host(y)),
+                             unl=(host(unl.indptr), host(unl.indices), host(unl.data)), n_genes=c["G"], batch_size=c["L"],
+                             unlabeled_batch_size=c["U"], dann=dann, device=device, n_threads=4, seed=5 + rank, comm=make_comm(world))
     del lab, unl
-    eng = TrainEngine(model.to(device), cfg, fl.csr, fl.d_y, c["L"], unlabeled=fu.csr, unlabeled_batch_size=c["U"], dann=dann,
-                      mode="mixmatch", comm=make_comm(world))
-    eng.set_weights(1.0, 0.1)
-    eng.l_rows.copy_(torch.arange(c["L"]))
-    eng.u_rows.copy_(torch.arange(c["U"]))
-    rng = np.random.default_rng(5 + rank)
-    n = c["L"] + c["U"]
-    keys_p = torch.empty(n).pin_memory()
-    gam_p = torch.empty(n).pin_memory()
-    loss_p = torch.empty(8).pin_memory()
-    steps, warm = max(args.steps // 2, 20), max(args.warmup // 2, 3)
-    h2d = d2h = 0
-
-    def one():
-        nonlocal h2d, d2h
-        b = fl.feed(rng.integers(0, n_host, c["L"]))
-        b += fu.feed(rng.integers(0, n_host, c["U"]))
-        keys_p.copy_(torch.from_numpy(rng.random(n).astype(np.float32)))
-        gam_p.copy_(torch.from_numpy(rng.beta(0.3, 0.3, n).astype(np.float32)))
-        eng.perm_keys.copy_(keys_p, non_blocking=True)
-        eng.gamma_raw.copy_(gam_p, non_blocking=True)
-        eng.step()
-        loss_p.copy_(eng.loss_buf, non_blocking=True)
-        torch.cuda.synchronize()
-        h2d, d2h = b + 2 * n * 4, 8 * 4
-        return float(loss_p[0])
-
-    for _ in range(warm):
-        one()
+    pipe.engine.set_weights(1.0, 0.1)
+    steps, warm = max(args.steps, 50), max(args.warmup, 5)
+    for l in pipe.run(warm):
+        pass
     barrier(world)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        l = one()
+    for l in pipe.run(steps):
+        pass
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    assert np.isfinite(l)
-    return dt / steps * 1e3, h2d, d2h
+    assert np.isfinite(l["loss"]), l
+    return dt / steps * 1e3, pipe.h2d_bytes_last, pipe.d2h_bytes_last
 
 
 def time_predict(device, rank):

@@ -1,5 +1,6 @@
 // C-ABI glue: error reporting, version, device query.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -24,4 +25,15 @@ extern "C" int scnb_device_arch(void) {
   cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
   cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
   return major * 10 + minor;
+}
+
+// Programmatic dependent launch switch (common.cuh): SCNB_PDL=1 enables it.  Measured on B200 inside a captured
+// graph it changes the step time by < 1 % (graph launches already hide the launch latency), so it is off by default.
+int scnb_pdl_enabled(void) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SCNB_PDL");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on;
 }

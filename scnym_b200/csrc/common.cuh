@@ -31,7 +31,35 @@ void scnb_set_error(const char* fmt, ...);
 
 static inline int scnb_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Programmatic dependent launch (PDL): a kernel launched with scnb_launch_pdl may be scheduled while
+// its predecessor in the stream is still draining, which hides its launch latency -- the step is a
+// chain of ~25 short dependent kernels.  Such a kernel starts with PDL_ENTRY(): wait until the
+// predecessor grid has completed and its writes are visible, then allow its own successor to be
+// scheduled.  Both instructions are no-ops for a kernel launched the ordinary way.
+int scnb_pdl_enabled(void);   // SCNB_PDL=1 enables (api.cu; off by default: no measurable gain inside CUDA graphs)
+
 #ifdef __CUDACC__
+#define PDL_ENTRY()                                             \
+  do {                                                          \
+    asm volatile("griddepcontrol.wait;" ::: "memory");          \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+  } while (0)
+
+template <typename... P, typename... A>
+static inline cudaError_t scnb_launch_pdl(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = scnb_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

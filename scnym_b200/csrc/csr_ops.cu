@@ -80,11 +80,13 @@ struct GatherSrc {
   uint32_t stream_id;
 };
 
-__device__ __forceinline__ float block128_sum(float v, float* red4) {
+#define GR_T 256  // threads per gathered row
+
+__device__ __forceinline__ float gather_block_sum(float v, float* red8) {
   v = warp_sum(v);
-  if ((threadIdx.x & 31) == 0) red4[threadIdx.x >> 5] = v;
+  if ((threadIdx.x & 31) == 0) red8[threadIdx.x >> 5] = v;
   __syncthreads();
-  const float t = (red4[0] + red4[1]) + (red4[2] + red4[3]);
+  const float t = ((red8[0] + red8[1]) + (red8[2] + red8[3])) + ((red8[4] + red8[5]) + (red8[6] + red8[7]));
   __syncthreads();
   return t;
 }
@@ -92,18 +94,19 @@ __device__ __forceinline__ float block128_sum(float v, float* red4) {
 #define GR_CACHE 2048  // entries of a row kept in shared memory between the two augmentation passes
 
 // keep decision of the input dropout: injected mask by batch position, else one Philox call per
-// four entries of a thread (entries tid + 128k, k = 4q..4q+3 share counter `pos0 + tid + 512q`).
+// four entries of a thread (entries tid + GR_T*k, k = 4q..4q+3 share counter `pos0 + tid + 4*GR_T*q`).
 __device__ __forceinline__ bool gather_keep(const uint8_t* mask, int pos, const uint4& rnd, int k, float p) {
   if (mask) return mask[pos] != 0;
   const uint32_t w = (k & 3) == 0 ? rnd.x : (k & 3) == 1 ? rnd.y : (k & 3) == 2 ? rnd.z : rnd.w;
   return (float)(w >> 8) * (1.0f / 16777216.0f) >= p;
 }
 
-__global__ void __launch_bounds__(128) k_gather_rows(GatherSrc A, GatherSrc B, const int32_t* __restrict__ b_indptr,
+__global__ void __launch_bounds__(GR_T) k_gather_rows(GatherSrc A, GatherSrc B, const int32_t* __restrict__ b_indptr,
                                                      int32_t* __restrict__ b_idx, float* __restrict__ b_val,
                                                      const uint8_t* __restrict__ keep_mask, const uint64_t* __restrict__ rng,
                                                      float p_drop, float target_sum, int32_t* __restrict__ gene_cnt) {
-  __shared__ float red4[4];
+  PDL_ENTRY();
+  __shared__ float red8[8];
   __shared__ float e_s[GR_CACHE];
   __shared__ int32_t c_s[GR_CACHE];
   const int tid = threadIdx.x;
@@ -117,7 +120,7 @@ __global__ void __launch_bounds__(128) k_gather_rows(GatherSrc A, GatherSrc B, c
   const int d = b_indptr[i];
   const bool aug = S.augment && li >= S.aug_begin && li < S.aug_end;
   if (!aug) {
-    for (int j = tid; j < len; j += 128) {
+    for (int j = tid; j < len; j += GR_T) {
       const int c = S.indices[s + j];
       const float v = S.data[s + j];
       b_idx[d + j] = c;
@@ -135,9 +138,9 @@ __global__ void __launch_bounds__(128) k_gather_rows(GatherSrc A, GatherSrc B, c
   // pass 1: one trip to DRAM for values and indices; e = expm1(x) * keep / (1-p), cached in shared memory
   float sum = 0.f;
   uint4 rnd = make_uint4(0, 0, 0, 0);
-  for (int j = tid, k = 0; j < len; j += 128, ++k) {
+  for (int j = tid, k = 0; j < len; j += GR_T, ++k) {
     if (!keep_mask && (k & 3) == 0) {
-      const uint64_t ctr = (uint64_t)(d + tid) + 512ull * (uint64_t)(k >> 2);
+      const uint64_t ctr = (uint64_t)(d + tid) + (uint64_t)(4 * GR_T) * (uint64_t)(k >> 2);
       rnd = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)strm, (uint32_t)(strm >> 32)),
                           make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
     }
@@ -149,16 +152,16 @@ __global__ void __launch_bounds__(128) k_gather_rows(GatherSrc A, GatherSrc B, c
       c_s[j] = S.indices[s + j];
     }
   }
-  sum = block128_sum(sum, red4);   // (also orders the shared-memory cache writes before the reads below)
-  for (int j = tid, k = 0; j < len; j += 128, ++k) {
+  sum = gather_block_sum(sum, red8);   // (also orders the shared-memory cache writes before the reads below)
+  for (int j = tid, k = 0; j < len; j += GR_T, ++k) {
     float e;
     int c;
     if (j < GR_CACHE) {
       e = e_s[j];
       c = c_s[j];
     } else {  // rows longer than the cache: recompute
-      if (!keep_mask && ((k & 3) == 0 || j - 128 < GR_CACHE)) {
-        const uint64_t ctr = (uint64_t)(d + tid) + 512ull * (uint64_t)(k >> 2);
+      if (!keep_mask && ((k & 3) == 0 || j - GR_T < GR_CACHE)) {
+        const uint64_t ctr = (uint64_t)(d + tid) + (uint64_t)(4 * GR_T) * (uint64_t)(k >> 2);
         rnd = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)strm, (uint32_t)(strm >> 32)),
                             make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
       }
@@ -181,7 +184,7 @@ extern "C" int scnb_csr_gather_rows(const int64_t* indptr, const int32_t* indice
   if (n == 0) return SCNB_OK;
   GatherSrc A = {indptr, indices, data, rows, row0, n, augment, aug_row_begin, aug_row_end, stream_id};
   GatherSrc B = {nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, 0, 0};
-  k_gather_rows<<<n, 128, 0, (cudaStream_t)stream>>>(A, B, b_indptr, b_idx, b_val, keep_mask, rng, p_drop, 1e6f, gene_cnt);
+  k_gather_rows<<<n, GR_T, 0, (cudaStream_t)stream>>>(A, B, b_indptr, b_idx, b_val, keep_mask, rng, p_drop, 1e6f, gene_cnt);
   SCNB_CHECK_LAUNCH("csr_gather_rows");
   return SCNB_OK;
 }
@@ -201,7 +204,8 @@ extern "C" int scnb_csr_gather_rows2(const int64_t* indptr_A, const int32_t* ind
   if (nA + nB == 0) return SCNB_OK;
   GatherSrc A = {indptr_A, indices_A, data_A, rows_A, 0, nA, augment_A, 0, nA, stream_id_A};
   GatherSrc B = {indptr_B, indices_B, data_B, rows_B, 0, nB, augment_B, 0, nB, stream_id_B};
-  k_gather_rows<<<nA + nB, 128, 0, (cudaStream_t)stream>>>(A, B, b_indptr, b_idx, b_val, keep_mask, rng, p_drop, 1e6f, gene_cnt);
+  scnb_launch_pdl(k_gather_rows, dim3(nA + nB), dim3(GR_T), 0, (cudaStream_t)stream, A, B, b_indptr, b_idx, b_val, keep_mask, rng, p_drop, 1e6f,
+                  gene_cnt);
   SCNB_CHECK_LAUNCH("csr_gather_rows2");
   return SCNB_OK;
 }
@@ -219,6 +223,7 @@ template <int NV, int WPR, typename IdxT>
 __global__ void __launch_bounds__(256) k_csr_linear_fwd(const IdxT* __restrict__ indptr, const int32_t* __restrict__ idx,
                                                         const float* __restrict__ val, int n, const float4* __restrict__ W1T,
                                                         const float4* __restrict__ b1, int H0v, float4* __restrict__ Z) {
+  PDL_ENTRY();
   constexpr int RPC = 8 / WPR;  // rows per CTA
   __shared__ float4 part[WPR > 1 ? 8 : 1][NV * 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -332,13 +337,13 @@ static void launch_csr_fwd_nv(int wpr, const IdxT* indptr, const int32_t* idx, c
   const float4* B = (const float4*)b1;
   float4* Zv = (float4*)Z;
   if (wpr == 8)
-    k_csr_linear_fwd<NV, 8, IdxT><<<n, 256, 0, st>>>(indptr, idx, val, n, W, B, H0 / 4, Zv);
+    scnb_launch_pdl(k_csr_linear_fwd<NV, 8, IdxT>, dim3(n), dim3(256), 0, st, indptr, idx, val, n, W, B, H0 / 4, Zv);
   else if (wpr == 4)
-    k_csr_linear_fwd<NV, 4, IdxT><<<scnb_cdiv(n, 2), 256, 0, st>>>(indptr, idx, val, n, W, B, H0 / 4, Zv);
+    scnb_launch_pdl(k_csr_linear_fwd<NV, 4, IdxT>, dim3(scnb_cdiv(n, 2)), dim3(256), 0, st, indptr, idx, val, n, W, B, H0 / 4, Zv);
   else if (wpr == 2)
-    k_csr_linear_fwd<NV, 2, IdxT><<<scnb_cdiv(n, 4), 256, 0, st>>>(indptr, idx, val, n, W, B, H0 / 4, Zv);
+    scnb_launch_pdl(k_csr_linear_fwd<NV, 2, IdxT>, dim3(scnb_cdiv(n, 4)), dim3(256), 0, st, indptr, idx, val, n, W, B, H0 / 4, Zv);
   else
-    k_csr_linear_fwd<NV, 1, IdxT><<<scnb_cdiv(n, 8), 256, 0, st>>>(indptr, idx, val, n, W, B, H0 / 4, Zv);
+    scnb_launch_pdl(k_csr_linear_fwd<NV, 1, IdxT>, dim3(scnb_cdiv(n, 8)), dim3(256), 0, st, indptr, idx, val, n, W, B, H0 / 4, Zv);
 }
 
 template <typename IdxT>
@@ -448,6 +453,7 @@ extern "C" int scnb_csr_linear_bwd_dw(const int32_t* b_indptr, const int32_t* b_
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_csc_scan(int32_t* __restrict__ gene_cnt, int G, int32_t* __restrict__ c_ptr,
                                                    int32_t* __restrict__ cursor, int use_smem) {
+  PDL_ENTRY();
   // one sweep: the counts are staged in shared memory with coalesced loads (when they fit), thread t
   // scans its contiguous genes [t*per, (t+1)*per) there, and the three outputs are written coalesced
   extern __shared__ int32_t cnt_s[];
@@ -510,6 +516,7 @@ __global__ void __launch_bounds__(1024) k_csc_scan(int32_t* __restrict__ gene_cn
 __global__ void __launch_bounds__(128) k_csc_fill(const int32_t* __restrict__ b_indptr, const int32_t* __restrict__ b_idx,
                                                   const float* __restrict__ b_val, int n, int32_t* __restrict__ cursor,
                                                   int2* __restrict__ c_ent) {
+  PDL_ENTRY();
   const int row = blockIdx.x;
   const int s = b_indptr[row], e = b_indptr[row + 1];
   for (int j = s + threadIdx.x; j < e; j += 128) {
@@ -535,10 +542,10 @@ extern "C" int scnb_csr_to_csc(const int32_t* b_indptr, const int32_t* b_idx, co
       return SCNB_ERR_CUDA;
     }
   }
-  k_csc_scan<<<1, 1024, use_smem ? scan_smem : 0, st>>>(gene_cnt, G, c_ptr, cursor, use_smem);
+  scnb_launch_pdl(k_csc_scan, dim3(1), dim3(1024), use_smem ? scan_smem : 0, st, gene_cnt, G, c_ptr, cursor, use_smem);
   SCNB_CHECK_LAUNCH("csr_to_csc/scan");
   if (n > 0) {
-    k_csc_fill<<<n, 128, 0, st>>>(b_indptr, b_idx, b_val, n, cursor, (int2*)c_ent);
+    scnb_launch_pdl(k_csc_fill, dim3(n), dim3(128), 0, st, b_indptr, b_idx, b_val, n, cursor, (int2*)c_ent);
     SCNB_CHECK_LAUNCH("csr_to_csc/fill");
   }
   return SCNB_OK;
@@ -582,6 +589,7 @@ __global__ void __launch_bounds__(W1_NT) k_w1_bwd_optim(const int32_t* __restric
                                                       float4* __restrict__ W, float4* __restrict__ grad_out,
                                                       float4* __restrict__ S1, float4* __restrict__ S2,
                                                       const float* __restrict__ hp, const int64_t* __restrict__ st) {
+  PDL_ENTRY();
   extern __shared__ float4 dzs[];  // [nb][16]
   __shared__ OptimConsts cs;
   const int tid = threadIdx.x;
@@ -695,7 +703,7 @@ static int launch_w1_bwd_optim(const int32_t* c_ptr, const void* c_ent, const fl
       scnb_set_error("csr_w1_bwd_optim: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
       return SCNB_ERR_CUDA;
     }
-    k_w1_bwd_optim<OPT, true><<<grid, W1_NT, smem, st>>>(c_ptr, (const int2*)c_ent, (const float4*)dZ, nb, H0 / 4, G, (float4*)W1T,
+    scnb_launch_pdl(k_w1_bwd_optim<OPT, true>, grid, dim3(W1_NT), smem, st, c_ptr, (const int2*)c_ent, (const float4*)dZ, nb, H0 / 4, G, (float4*)W1T,
                                                        (float4*)grad_out, (float4*)s1, (float4*)s2, hp, st4);
   } else {
     k_w1_bwd_optim<OPT, false><<<grid, W1_NT, 0, st>>>(c_ptr, (const int2*)c_ent, (const float4*)dZ, nb, H0 / 4, G, (float4*)W1T,
@@ -743,6 +751,7 @@ struct PrepArgs {
 };
 
 __global__ void __launch_bounds__(1024) k_step_prep(PrepArgs a) {
+  PDL_ENTRY();
   __shared__ int warp_tot[32];
   __shared__ int carry_s;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -818,7 +827,7 @@ extern "C" int scnb_step_prep(const int64_t* l_tab, const int64_t* u_tab, const 
   SCNB_CHECK_ARG(n_zero == 0 || zero_buf, "step_prep: zero_buf missing");
   PrepArgs a = {l_tab, u_tab, key_tab, gam_tab, n_tab, state4, L, U, l_rows, u_rows, keys, gam, lab_y, lab_dom, unl_dom,
                 want_dom, lab_ids, base_dom, lab_indptr, unl_indptr, b_indptr, zero_buf, n_zero};
-  k_step_prep<<<1, 1024, 0, (cudaStream_t)stream>>>(a);
+  scnb_launch_pdl(k_step_prep, dim3(1), dim3(1024), 0, (cudaStream_t)stream, a);
   SCNB_CHECK_LAUNCH("step_prep");
   return SCNB_OK;
 }

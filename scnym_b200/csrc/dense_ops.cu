@@ -255,6 +255,7 @@ extern "C" int scnb_sgemm(int transA, int transB, int M, int N, int K, const flo
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_colsum(const float* __restrict__ A, int M, int N, int lda, float* __restrict__ out,
                                                  int accumulate) {
+  PDL_ENTRY();
   __shared__ float red[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(1024) k_colsum(const float* __restrict__ A, in
 
 extern "C" int scnb_colsum(const float* A, int M, int N, int lda, float* out, int accumulate, void* stream) {
   SCNB_CHECK_ARG(A && out && M >= 0 && N > 0, "colsum: bad arguments");
-  k_colsum<<<scnb_cdiv(N, 32), 1024, 0, (cudaStream_t)stream>>>(A, M, N, lda, out, accumulate);
+  scnb_launch_pdl(k_colsum, dim3(scnb_cdiv(N, 32)), dim3(1024), 0, (cudaStream_t)stream, A, M, N, lda, out, accumulate);
   SCNB_CHECK_LAUNCH("colsum");
   return SCNB_OK;
 }
@@ -487,6 +488,7 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_fwd_v8(const float* __restrict
                                                          const uint64_t* __restrict__ rng, uint32_t stream_id, float p_drop,
                                                          int relu, float* __restrict__ partial_out,
                                                          const float* __restrict__ ext_sums, const float* __restrict__ ext_cnt) {
+  PDL_ENTRY();
   __shared__ __align__(16) float red1[BNV_W][8];
   __shared__ __align__(16) float red2[BNV_W][8];
   const int t = threadIdx.x;
@@ -600,6 +602,7 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_bwd_v8(const float* __restrict
                                                          float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                          float* __restrict__ partial_out, const float* __restrict__ ext_sums,
                                                          const float* __restrict__ ext_cnt) {
+  PDL_ENTRY();
   __shared__ __align__(16) float red1[BNV_W][8];
   __shared__ __align__(16) float red2[BNV_W][8];
   const int t = threadIdx.x;
@@ -707,6 +710,7 @@ __global__ void __launch_bounds__(256) k_bn_eval_fwd(const float* __restrict__ Z
                                                      int n_seg, int max_rows, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, const float* __restrict__ rmean,
                                                      const float* __restrict__ rvar, int relu) {
+  PDL_ENTRY();
   const int rows = min(seg_off[n_seg], max_rows);
   if (VEC4) {
     const int Hv = H >> 2;
@@ -759,7 +763,7 @@ extern "C" int scnb_bn_act_fwd(const float* Z, float* A, float* pre_out, int H, 
     const size_t work = (size_t)max_rows * (v4 ? H / 4 : H);
     const int blocks = (int)((work + 255) / 256 < 148 * 16 ? (work + 255) / 256 : 148 * 16);
     if (v4)
-      k_bn_eval_fwd<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(Z, A, pre_out, H, seg_off_dev, n_seg, max_rows, gamma, beta,
+      scnb_launch_pdl(k_bn_eval_fwd<true>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, Z, A, pre_out, H, seg_off_dev, n_seg, max_rows, gamma, beta,
                                                                     running_mean, running_var, relu);
     else
       k_bn_eval_fwd<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(Z, A, pre_out, H, seg_off_dev, n_seg, max_rows, gamma, beta,
@@ -769,7 +773,7 @@ extern "C" int scnb_bn_act_fwd(const float* Z, float* A, float* pre_out, int H, 
   }
   if (bn_vec8_ok(H, Z, A, pre_out, gamma, beta, stats, keep_mask)) {
     dim3 gridv(H / 8, n_seg);
-    k_bn_act_fwd_v8<<<gridv, BNV_T, 0, (cudaStream_t)stream>>>(Z, A, pre_out, H, n_seg, seg_off_dev, max_rows, gamma, beta, stats,
+    scnb_launch_pdl(k_bn_act_fwd_v8, gridv, dim3(BNV_T), 0, (cudaStream_t)stream, Z, A, pre_out, H, n_seg, seg_off_dev, max_rows, gamma, beta, stats,
                                                                keep_mask, rng, stream_id, p_drop, relu, dp_partial_out, dp_sums,
                                                                ext_cnt);
     SCNB_CHECK_LAUNCH("bn_act_fwd/v8");
@@ -872,7 +876,7 @@ extern "C" int scnb_bn_act_bwd(const float* dA, const float* Z, const float* A, 
   const float* ext_cnt = dp_sums ? dp_sums + (size_t)n_seg * 2 * H : nullptr;
   if (bn_vec8_ok(H, dA, Z, A, gamma, dZ, stats, keep_mask)) {
     dim3 gridv(H / 8, n_seg);
-    k_bn_act_bwd_v8<<<gridv, BNV_T, 0, (cudaStream_t)stream>>>(dA, Z, A, H, n_seg, seg_off_dev, max_rows, gamma, stats, keep_mask,
+    scnb_launch_pdl(k_bn_act_bwd_v8, gridv, dim3(BNV_T), 0, (cudaStream_t)stream, dA, Z, A, H, n_seg, seg_off_dev, max_rows, gamma, stats, keep_mask,
                                                                rng, stream_id, p_drop, relu, dZ, dgamma, dbeta, dp_partial_out,
                                                                dp_sums, ext_cnt);
     SCNB_CHECK_LAUNCH("bn_act_bwd/v8");
@@ -944,6 +948,7 @@ extern "C" int scnb_bn_running_update(float* running_mean, float* running_var, i
 __global__ void __launch_bounds__(256) k_mix_rows(const float* __restrict__ Z, int H, const int32_t* __restrict__ srcA,
                                                   const int32_t* __restrict__ srcB, const float* __restrict__ gam,
                                                   const int32_t* __restrict__ n_active, int max_rows, float* __restrict__ out) {
+  PDL_ENTRY();
   const int i = blockIdx.x;
   const int na = n_active ? min(*n_active, max_rows) : max_rows;
   float* o = out + (size_t)i * H;
@@ -967,13 +972,14 @@ extern "C" int scnb_mix_rows(const float* Z, int H, const int32_t* srcA, const i
                              const int32_t* n_active_dev, int max_rows, float* out, void* stream) {
   SCNB_CHECK_ARG(Z && srcA && out && H > 0 && max_rows >= 0, "mix_rows: bad arguments");
   if (max_rows == 0) return SCNB_OK;
-  k_mix_rows<<<max_rows, 256, 0, (cudaStream_t)stream>>>(Z, H, srcA, srcB, gam, n_active_dev, max_rows, out);
+  scnb_launch_pdl(k_mix_rows, dim3(max_rows), dim3(256), 0, (cudaStream_t)stream, Z, H, srcA, srcB, gam, n_active_dev, max_rows, out);
   SCNB_CHECK_LAUNCH("mix_rows");
   return SCNB_OK;
 }
 
 __global__ void __launch_bounds__(256) k_unmix_rows(const float* __restrict__ dOut, int H, const int32_t* __restrict__ inv,
                                                     const float* __restrict__ coef, int n_base, float* __restrict__ dZ) {
+  PDL_ENTRY();
   const int r = blockIdx.x;
   int i0 = inv[r], i1 = inv[n_base + r], i2 = inv[2 * n_base + r];
   float c0 = coef[r], c1 = coef[n_base + r], c2 = coef[2 * n_base + r];
@@ -990,7 +996,7 @@ extern "C" int scnb_unmix_rows(const float* dOut, int H, const int32_t* inv3, co
                                void* stream) {
   SCNB_CHECK_ARG(dOut && inv3 && coef3 && dZ && H > 0 && n_base >= 0, "unmix_rows: bad arguments");
   if (n_base == 0) return SCNB_OK;
-  k_unmix_rows<<<n_base, 256, 0, (cudaStream_t)stream>>>(dOut, H, inv3, coef3, n_base, dZ);
+  scnb_launch_pdl(k_unmix_rows, dim3(n_base), dim3(256), 0, (cudaStream_t)stream, dOut, H, inv3, coef3, n_base, dZ);
   SCNB_CHECK_LAUNCH("unmix_rows");
   return SCNB_OK;
 }

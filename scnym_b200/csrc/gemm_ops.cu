@@ -8,6 +8,7 @@
 // shape is picked so that the grid covers the 148 SMs (down to 16x32).  fp32 FMA throughout: the
 // parity budget (1e-4) rules out single-pass TF32/BF16.
 #include "common.cuh"
+#include <stdlib.h>
 
 #define PK_THREADS 256
 #define PK_STAGES 3
@@ -272,33 +273,40 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// [32][kc] panel from a matrix whose rows are k-contiguous
+// [32][kc] panel from a matrix whose rows are k-contiguous (fixed 64-chunk rows: shifts, no divisions)
 __device__ __forceinline__ void tg_load_rows(float* __restrict__ sm, const float* __restrict__ X, int ld, int row0, int nrows,
-                                             int k0, int kend, int kc, int tid) {
-  const int cpr = kc >> 2;
-  for (int ch = tid; ch < 32 * cpr; ch += 128) {
-    const int r = ch / cpr, kq = ch % cpr;
-    const int gr = row0 + r, gk = k0 + kq * 4;
-    const bool ok = gr < nrows && gk < kend;
-    cp_async16(sm + r * TG_SR + kq * 4, ok ? X + (size_t)gr * ld + gk : X, ok);
+                                             int k0, int kend, int kc, int tid, int nthr) {
+  const int kq = tid & 63;               // 16-byte chunk within the row, fixed per thread (nthr is a multiple of 64)
+  const int gk = k0 + kq * 4;
+  if (kq * 4 >= kc) return;
+  const bool kok = gk < kend;
+  const float* src = X + (size_t)row0 * ld + gk;
+  float* dst = sm + kq * 4;
+  for (int r = tid >> 6; r < 32; r += nthr >> 6) {
+    const bool ok = kok && (row0 + r) < nrows;
+    cp_async16(dst + r * TG_SR, ok ? src + (size_t)r * ld : X, ok);
   }
 }
 // [kc][32] panel from a matrix stored [k][cols]
 __device__ __forceinline__ void tg_load_cols(float* __restrict__ sm, const float* __restrict__ X, int ld, int col0, int ncols,
-                                             int k0, int kend, int kc, int tid) {
-  for (int ch = tid; ch < kc * 8; ch += 128) {
-    const int k = ch >> 3, cq = ch & 7;
-    const int gk = k0 + k, gc = col0 + cq * 4;
-    const bool ok = gk < kend && gc < ncols;
-    cp_async16(sm + k * TG_SC + cq * 4, ok ? X + (size_t)gk * ld + gc : X, ok);
+                                             int k0, int kend, int kc, int tid, int nthr) {
+  const int cq = tid & 7;
+  const int gc = col0 + cq * 4;
+  const bool cok = gc < ncols;
+  const float* src = X + (size_t)k0 * ld + gc;
+  float* dst = sm + cq * 4;
+  for (int k = tid >> 3; k < kc; k += nthr >> 3) {
+    const bool ok = cok && (k0 + k) < kend;
+    cp_async16(dst + k * TG_SC, ok ? src + (size_t)k * ld : X, ok);
   }
 }
 
-template <int LAY>
-__global__ void __launch_bounds__(128) k_tgemm(int M, int N, int K, const float* __restrict__ A, int lda,
+template <int LAY, int NW>
+__global__ void __launch_bounds__(32 * NW) k_tgemm(int M, int N, int K, const float* __restrict__ A, int lda,
                                                const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc, float alpha,
                                                float beta, const float* __restrict__ bias, int relu,
                                                const float* __restrict__ gate, int k_chunk) {
+  PDL_ENTRY();
   constexpr int A_FLOATS = (LAY == 2) ? TG_KC * TG_SC : 32 * TG_SR;
   constexpr int B_FLOATS = (LAY == 0) ? 32 * TG_SR : TG_KC * TG_SC;
   extern __shared__ __align__(16) float tg_smem[];
@@ -316,17 +324,17 @@ __global__ void __launch_bounds__(128) k_tgemm(int M, int N, int K, const float*
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
   for (int k0 = kb; k0 < ke; k0 += TG_KC) {
-    const int kc = min(TG_KC, ((ke - k0) + 31) & ~31);  // chunk width, padded to 32 (zero-filled beyond ke)
+    const int kc = min(TG_KC, ((ke - k0) + 8 * NW - 1) / (8 * NW) * (8 * NW));  // chunk width, padded (zero-filled beyond ke)
     if (k0 > kb) __syncthreads();                        // previous chunk fully consumed
-    if (LAY == 2) tg_load_cols(As, A, lda, m0, M, k0, ke, kc, tid);
-    else tg_load_rows(As, A, lda, m0, M, k0, ke, kc, tid);
-    if (LAY == 0) tg_load_rows(Bs, B, ldb, n0, N, k0, ke, kc, tid);
-    else tg_load_cols(Bs, B, ldb, n0, N, k0, ke, kc, tid);
+    if (LAY == 2) tg_load_cols(As, A, lda, m0, M, k0, ke, kc, tid, 32 * NW);
+    else tg_load_rows(As, A, lda, m0, M, k0, ke, kc, tid, 32 * NW);
+    if (LAY == 0) tg_load_rows(Bs, B, ldb, n0, N, k0, ke, kc, tid, 32 * NW);
+    else tg_load_cols(Bs, B, ldb, n0, N, k0, ke, kc, tid, 32 * NW);
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    // this warp's quarter of the chunk
-    const int kw = kc >> 2;
+    // this warp's share of the chunk
+    const int kw = kc / NW;
     for (int kk = warp * kw; kk < (warp + 1) * kw; kk += 8) {
       uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
 #pragma unroll
@@ -373,7 +381,7 @@ __global__ void __launch_bounds__(128) k_tgemm(int M, int N, int K, const float*
   }
   // cross-warp reduction of the four K quarters (the operand panels are dead: reuse their memory)
   __syncthreads();
-  float* red = tg_smem;  // [4][32][33]
+  float* red = tg_smem;  // [NW][32][33]
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -386,11 +394,13 @@ __global__ void __launch_bounds__(128) k_tgemm(int M, int N, int K, const float*
     }
   __syncthreads();
   const bool split = gridDim.z > 1;
-  for (int e = tid; e < 1024; e += 128) {
+  for (int e = tid; e < 1024; e += 32 * NW) {
     const int r = e >> 5, c = e & 31;
     const int m = m0 + r, n = n0 + c;
     if (m >= M || n >= N) continue;
-    float v = (red[r * 33 + c] + red[(32 + r) * 33 + c]) + (red[(64 + r) * 33 + c] + red[(96 + r) * 33 + c]);
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) v += red[(w * 32 + r) * 33 + c];
     v *= alpha;
     if (split) {
       atomicAdd(C + (size_t)m * ldc + n, v);
@@ -404,23 +414,23 @@ __global__ void __launch_bounds__(128) k_tgemm(int M, int N, int K, const float*
   }
 }
 
-template <int LAY>
+template <int LAY, int NW>
 static int launch_tgemm(dim3 grid, cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
                         int ldc, float alpha, float beta, const float* bias, int relu, const float* gate, int k_chunk) {
   constexpr int A_FLOATS = (LAY == 2) ? TG_KC * TG_SC : 32 * TG_SR;
   constexpr int B_FLOATS = (LAY == 0) ? 32 * TG_SR : TG_KC * TG_SC;
-  constexpr int smem = (A_FLOATS + B_FLOATS) * (int)sizeof(float);
-  static_assert(smem >= 4 * 32 * 33 * (int)sizeof(float), "reduction buffer must fit in the operand panels");
+  constexpr int panels = (A_FLOATS + B_FLOATS) * (int)sizeof(float), redbuf = NW * 32 * 33 * (int)sizeof(float);
+  constexpr int smem = panels > redbuf ? panels : redbuf;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_tgemm<LAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(k_tgemm<LAY, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       scnb_set_error("sgemm: cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
       return SCNB_ERR_CUDA;
     }
     attr_set = true;
   }
-  k_tgemm<LAY><<<grid, 128, smem, st>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, k_chunk);
+  scnb_launch_pdl(k_tgemm<LAY, NW>, grid, dim3(32 * NW), smem, st, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, k_chunk);
   return SCNB_OK;
 }
 
@@ -441,9 +451,20 @@ int scnb_tgemm_try(int transA, int transB, int M, int N, int K, const float* A, 
   int k_chunk = scnb_cdiv(scnb_cdiv(K, splits), 32) * 32;
   splits = scnb_cdiv(K, k_chunk);
   dim3 grid(scnb_cdiv(N, 32), scnb_cdiv(M, 32), splits);
+  static int nw = 0;  // warps per CTA = ways the K chunk is split inside the CTA (SCNB_TG_WARPS = 4 | 8 | 16)
+  if (nw == 0) {
+    const char* e = getenv("SCNB_TG_WARPS");
+    nw = e ? atoi(e) : 8;
+    if (nw != 4 && nw != 8 && nw != 16) nw = 8;
+  }
   int rc;
-  if (lay == 0) rc = launch_tgemm<0>(grid, st, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, k_chunk);
-  else if (lay == 1) rc = launch_tgemm<1>(grid, st, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, k_chunk);
-  else rc = launch_tgemm<2>(grid, st, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, k_chunk);
+#define TG_GO(NW_)                                                                                                              \
+  rc = (lay == 0)   ? launch_tgemm<0, NW_>(grid, st, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, k_chunk)   \
+       : (lay == 1) ? launch_tgemm<1, NW_>(grid, st, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, k_chunk)   \
+                    : launch_tgemm<2, NW_>(grid, st, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, k_chunk)
+  if (nw == 4) TG_GO(4);
+  else if (nw == 8) TG_GO(8);
+  else TG_GO(16);
+#undef TG_GO
   return rc < 0 ? rc : 1;
 }

@@ -310,6 +310,7 @@ __global__ void __launch_bounds__(256) k_plan_maps(const uint8_t* __restrict__ c
 __global__ void __launch_bounds__(1024) k_plan_all(const uint8_t* __restrict__ confident, const float* __restrict__ keys,
                                                    const float* __restrict__ gamma_raw, int U, int L, int use_dan,
                                                    int dan_conf_only, int mixup_on, int Rmax, PlanPtrs P) {
+  PDL_ENTRY();
   __shared__ int wtot[32];
   __shared__ int carry_s, n_conf_s;
   __shared__ float skeys[PLAN_SMEM_KEYS];
@@ -318,34 +319,38 @@ __global__ void __launch_bounds__(1024) k_plan_all(const uint8_t* __restrict__ c
   __syncthreads();
   const int tid = threadIdx.x, nb = U + L;
   if (mixup_on) {
-    // O(n^2) ranking out of shared memory; `parts` threads share one key (each counts a slice of the
-    // other keys) so that all 1024 threads work when n is small
+    // stable argsort of the n permutation keys: bitonic sort of (key, index) pairs in shared memory
+    // (lexicographic order on the pair == torch.argsort(keys, stable=True)); padded to a power of two
     const int n = n_conf_s + L;
-    for (int k = tid; k < n; k += 1024) {
-      skeys[k] = keys[k];
-      srank[k] = 0;
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (int k = tid; k < np2; k += 1024) {
+      skeys[k] = k < n ? keys[k] : INFINITY;
+      srank[k] = k;
     }
     __syncthreads();
-    int parts = 1;
-    while (parts < 32 && n * parts * 2 <= 1024) parts *= 2;
-    const int slice = (n + parts - 1) / parts;
-    for (int w = tid; w < n * parts; w += 1024) {
-      const int j = w / parts, part = w % parts;
-      const int t0 = part * slice, t1 = min(n, t0 + slice);
-      const float kj = skeys[j];
-      int r = 0;
-      for (int t = t0; t < t1; ++t) {
-        const float kv = skeys[t];
-        r += (kv < kj || (kv == kj && t < j)) ? 1 : 0;
+    for (int kk = 2; kk <= np2; kk <<= 1) {
+      for (int j = kk >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < np2; i += 1024) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const float ka = skeys[i], kb = skeys[ixj];
+            const int ia = srank[i], ib = srank[ixj];
+            const bool a_gt_b = (ka > kb) || (ka == kb && ia > ib);
+            const bool up = (i & kk) == 0;
+            if (a_gt_b == up) {
+              skeys[i] = kb; skeys[ixj] = ka;
+              srank[i] = ib; srank[ixj] = ia;
+            }
+          }
+        }
+        __syncthreads();
       }
-      if (parts == 1) srank[j] = r;
-      else atomicAdd(&srank[j], r);
     }
-    __syncthreads();
-    for (int j = tid; j < n; j += 1024) {
-      const int r = srank[j];
-      P.rank[j] = r;
+    for (int r = tid; r < n; r += 1024) {
+      const int j = srank[r];   // padding (key = +inf, index >= n) sorts after every real key
       P.ridx[r] = j;
+      P.rank[j] = r;
     }
   }
   __syncthreads();
@@ -377,7 +382,7 @@ extern "C" int scnb_mixmatch_plan(const uint8_t* confident, const float* perm_ke
   P.inv3 = inv3;
   P.coef3 = coef3;
   if (nb <= PLAN_SMEM_KEYS) {
-    k_plan_all<<<1, 1024, 0, st>>>(confident, perm_keys, gamma_raw, U, L, use_dan, dan_conf_only, mixup_on, Rmax, P);
+    scnb_launch_pdl(k_plan_all, dim3(1), dim3(1024), 0, st, confident, perm_keys, gamma_raw, U, L, use_dan, dan_conf_only, mixup_on, Rmax, P);
     SCNB_CHECK_LAUNCH("mixmatch_plan/all");
     return SCNB_OK;
   }
@@ -734,6 +739,7 @@ __global__ void __launch_bounds__(256) k_classif_mixmatch(const float* __restric
                                                           float unsup_weight, float* __restrict__ logits,
                                                           float* __restrict__ dlogits, float* __restrict__ dA,
                                                           float* __restrict__ loss8) {
+  PDL_ENTRY();
   extern __shared__ __align__(16) float Ws[];
   stage_weights(Ws, Wc, C * H);
   const int lane = threadIdx.x & 31;
@@ -757,6 +763,7 @@ __global__ void __launch_bounds__(256) k_classif_supervised(const float* __restr
                                                             const float* __restrict__ Y, const float* __restrict__ class_weight,
                                                             float* __restrict__ logits, float* __restrict__ dlogits,
                                                             float* __restrict__ dA, float* __restrict__ loss8) {
+  PDL_ENTRY();
   extern __shared__ __align__(16) float Ws[];
   stage_weights(Ws, Wc, C * H);
   const int lane = threadIdx.x & 31;
@@ -780,6 +787,7 @@ __global__ void __launch_bounds__(256) k_dan_tail(const float* __restrict__ Hd, 
                                                   const float* __restrict__ loss_scale_dev, float* __restrict__ dlog,
                                                   float* __restrict__ dlabel, float* __restrict__ ddlog,
                                                   float* __restrict__ dHd, float* __restrict__ loss2) {
+  PDL_ENTRY();
   extern __shared__ __align__(16) float Ws[];
   stage_weights(Ws, W2, D * H);
   const int lane = threadIdx.x & 31;
@@ -804,6 +812,7 @@ __global__ void __launch_bounds__(256) k_teacher_head(const float* __restrict__ 
                                                       float* __restrict__ q, float* __restrict__ conf,
                                                       uint8_t* __restrict__ confident, float* __restrict__ scratch,
                                                       const int32_t* __restrict__ lab_ids, int L) {
+  PDL_ENTRY();
   extern __shared__ __align__(16) float Ws[];
   stage_weights(Ws, Wc, C * H);
   const int lane = threadIdx.x & 31;
@@ -832,10 +841,10 @@ static bool head_fusable(int H, int C, const void* p0, const void* p1, const voi
       cudaFuncSetAttribute(KERNEL<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem));     \
       cudaFuncSetAttribute(KERNEL<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem));     \
     }                                                                                                \
-    if (nv__ == 1) KERNEL<1><<<grid__, 256, smem, st>>>(__VA_ARGS__);                                \
-    else if (nv__ == 2) KERNEL<2><<<grid__, 256, smem, st>>>(__VA_ARGS__);                           \
-    else if (nv__ <= 4) { if (nv__ == 4) KERNEL<4><<<grid__, 256, smem, st>>>(__VA_ARGS__); else return SCNB_ERR_UNSUPPORTED; } \
-    else if (nv__ == 8) KERNEL<8><<<grid__, 256, smem, st>>>(__VA_ARGS__);                           \
+    if (nv__ == 1) scnb_launch_pdl(KERNEL<1>, grid__, dim3(256), smem, st, __VA_ARGS__);                                \
+    else if (nv__ == 2) scnb_launch_pdl(KERNEL<2>, grid__, dim3(256), smem, st, __VA_ARGS__);                           \
+    else if (nv__ <= 4) { if (nv__ == 4) scnb_launch_pdl(KERNEL<4>, grid__, dim3(256), smem, st, __VA_ARGS__); else return SCNB_ERR_UNSUPPORTED; } \
+    else if (nv__ == 8) scnb_launch_pdl(KERNEL<8>, grid__, dim3(256), smem, st, __VA_ARGS__);                           \
     else return SCNB_ERR_UNSUPPORTED;                                                                \
   } while (0)
 

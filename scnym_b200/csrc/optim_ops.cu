@@ -30,6 +30,7 @@ template <int OPT>
 __global__ void __launch_bounds__(256) k_optim(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ s1,
                                                float* __restrict__ s2, size_t n, const float* __restrict__ hp,
                                                const int64_t* __restrict__ st) {
+  PDL_ENTRY();
   __shared__ OptimConsts cs;
   if (threadIdx.x == 0) cs = optim_consts(hp, st);
   __syncthreads();
@@ -51,10 +52,10 @@ extern "C" int scnb_optim_step(int opt, float* params, const float* grads, float
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
   switch (opt) {
-    case OPT_ADADELTA: k_optim<OPT_ADADELTA><<<blocks, 256, 0, st>>>(params, grads, state1, state2, (size_t)n, hp8, state4); break;
-    case OPT_ADAM: k_optim<OPT_ADAM><<<blocks, 256, 0, st>>>(params, grads, state1, state2, (size_t)n, hp8, state4); break;
-    case OPT_ADAMW: k_optim<OPT_ADAMW><<<blocks, 256, 0, st>>>(params, grads, state1, state2, (size_t)n, hp8, state4); break;
-    case OPT_SGD: k_optim<OPT_SGD><<<blocks, 256, 0, st>>>(params, grads, state1, state2, (size_t)n, hp8, state4); break;
+    case OPT_ADADELTA: scnb_launch_pdl(k_optim<OPT_ADADELTA>, dim3(blocks), dim3(256), 0, st, params, grads, state1, state2, (size_t)n, hp8, state4); break;
+    case OPT_ADAM: scnb_launch_pdl(k_optim<OPT_ADAM>, dim3(blocks), dim3(256), 0, st, params, grads, state1, state2, (size_t)n, hp8, state4); break;
+    case OPT_ADAMW: scnb_launch_pdl(k_optim<OPT_ADAMW>, dim3(blocks), dim3(256), 0, st, params, grads, state1, state2, (size_t)n, hp8, state4); break;
+    case OPT_SGD: scnb_launch_pdl(k_optim<OPT_SGD>, dim3(blocks), dim3(256), 0, st, params, grads, state1, state2, (size_t)n, hp8, state4); break;
     default: scnb_set_error("optim_step: unknown optimizer %d", opt); return SCNB_ERR_ARG;
   }
   SCNB_CHECK_LAUNCH("optim_step");

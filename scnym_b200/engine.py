@@ -802,6 +802,14 @@ class TrainEngine(object):
             self.kernels_per_step = _lib.launch_count - before
         self.steps_done += 1
 
+    def prepare(self):
+        """Capture the step graph for the current loss weights without running a step (so that the first
+        `step()` of a pipelined caller does not capture while copies are in flight on other streams)."""
+        if self.cfg.use_cuda_graph and (self._graph is None or self._graph_key != (self.unsup_weight, self.dan_weight)):
+            if self.mode == "mixmatch" and self.cfg.mean_teacher and self.teacher_bn is None:
+                self.teacher_bn = [(b["bn"].running_mean.clone(), b["bn"].running_var.clone()) for b in self._blk]
+            self._capture((self.unsup_weight, self.dan_weight))
+
     def _capture(self, key):
         # warm-up on a side stream is not needed: the library allocates nothing; but the first
         # eager pass must not double-apply a step, so capture directly.

@@ -1,0 +1,241 @@
+"""Training fed from HOST-resident expression matrices (the end-to-end / out-of-HBM entry).
+
+The reference assembles every minibatch on the host (`SingleCellDS.__getitem__` + collate,
+scnym/dataprep.py:114-168; `DataLoader` iteration scnym/trainer.py:574-582) and copies a dense
+[B, G] tensor to the device each step (scnym/trainer.py:589-599).  `HostTrainPipeline` keeps that
+contract -- inputs start in host memory every step, the loss comes back to the host every step --
+but overlaps the three stages:
+
+  producer thread   batch i+1: sample rows, gather their CSR rows into a pinned blob (C threads,
+                    `scnb_host_gather_rows`), draw the MixUp keys / Beta draws
+  copy stream       H2D of blob i+1 into one of two device landing buffers
+  compute stream    device-to-device stash of landing buffer i into the engine's staging CSR,
+                    replay of the captured step graph, D2H of the 8 loss scalars
+
+so a step costs max(host gather, PCIe copy, device step) instead of their sum.  The loss of step i
+is read on the host after step i+1 has been enqueued.
+"""
+import queue
+import threading
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .dataprep import DeviceCSR
+
+
+class _HostCSR(object):
+    def __init__(self, indptr, indices, data, labels=None, domains=None):
+        self.indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        self.indices = np.ascontiguousarray(indices, dtype=np.int32)
+        self.data = np.ascontiguousarray(data, dtype=np.float32)
+        self.labels = None if labels is None else np.ascontiguousarray(labels, dtype=np.int32)
+        self.domains = None if domains is None else np.ascontiguousarray(domains, dtype=np.int32)
+        self.n_rows = self.indptr.shape[0] - 1
+        self.max_row_nnz = int(np.diff(self.indptr).max()) if self.n_rows > 0 else 1
+
+
+class _BlobLayout(object):
+    """Byte layout of one batch blob: fixed-size header regions, then the four variable CSR regions."""
+
+    def __init__(self, L, U, cap_l, cap_u):
+        self.L, self.U, self.cap_l, self.cap_u = L, U, cap_l, cap_u
+        off = 0
+        self.regions = {}
+
+        def add(name, count, dtype):
+            nonlocal off
+            nbytes = count * np.dtype(dtype).itemsize
+            self.regions[name] = (off, count, dtype)
+            off += (nbytes + 15) // 16 * 16
+
+        add("indptr_l", L + 1, np.int64)
+        add("indptr_u", U + 1, np.int64)
+        add("y_l", L, np.int32)
+        add("dom_l", L, np.int32)
+        add("dom_u", max(U, 1), np.int32)
+        add("keys", L + U, np.float32)
+        add("gam", L + U, np.float32)
+        self.header_bytes = off
+        add("idx_l", cap_l, np.int32)
+        add("val_l", cap_l, np.float32)
+        add("idx_u", max(cap_u, 1), np.int32)
+        add("val_u", max(cap_u, 1), np.float32)
+        self.total_bytes = off
+
+    def views(self, blob: torch.Tensor):
+        """name -> typed 1-D torch view into a uint8 blob (host or device)."""
+        tdt = {np.int64: torch.int64, np.int32: torch.int32, np.float32: torch.float32}
+        out = {}
+        for name, (o, count, dt) in self.regions.items():
+            nbytes = count * np.dtype(dt).itemsize
+            out[name] = blob[o:o + nbytes].view(tdt[dt])
+        return out
+
+
+class HostTrainPipeline(object):
+    """Drive a `TrainEngine` (mode "mixmatch") from host-resident labeled / unlabeled CSR matrices.
+
+    pipe = HostTrainPipeline(model, cfg, lab=(indptr, indices, data, y[, domain]), unl=(indptr, indices, data[, domain]),
+                             n_genes=G, batch_size=256, dann=dann)
+    for losses in pipe.run(n_steps): ...        # dict of the step's loss scalars, one per step
+    """
+
+    def __init__(self, model, cfg, lab, unl, n_genes: int, batch_size: int, unlabeled_batch_size: Optional[int] = None, dann=None,
+                 device="cuda", n_threads: int = 4, seed: int = 0, prefetch: int = 3, comm=None) -> None:
+        from .engine import TrainEngine
+        if not torch.cuda.is_available():
+            raise _lib.ScnbError("HostTrainPipeline needs a CUDA device (no CPU fallback)")
+        self.dev = torch.device(device)
+        self.L = int(batch_size)
+        self.U = int(unlabeled_batch_size if unlabeled_batch_size is not None else batch_size)
+        self.lab = _HostCSR(*lab[:3], labels=lab[3], domains=lab[4] if len(lab) > 4 else None)
+        self.unl = _HostCSR(*unl[:3], domains=unl[3] if len(unl) > 3 else None)
+        self.n_threads = int(n_threads)
+        self.alpha = max(float(cfg.mixup_alpha), 1e-3)
+        cap_l, cap_u = self.L * self.lab.max_row_nnz, self.U * self.unl.max_row_nnz
+        self.layout = _BlobLayout(self.L, self.U, cap_l, cap_u)
+        lay = self.layout
+        # pinned blobs (producer <-> copy stream) and two device landing buffers
+        self.n_blobs = max(int(prefetch), 2) + 1
+        self.blobs = [torch.empty(lay.total_bytes, dtype=torch.uint8).pin_memory() for _ in range(self.n_blobs)]
+        self.blob_np = [{k: v.numpy() for k, v in lay.views(b).items()} for b in self.blobs]
+        self.blob_t = [lay.views(b) for b in self.blobs]
+        self.land = [torch.zeros(lay.total_bytes, dtype=torch.uint8, device=self.dev) for _ in range(2)]
+        self.land_t = [lay.views(b) for b in self.land]
+        # the engine's staging batch: one device blob with the same layout (rows 0..B-1 of its CSRs are the batch)
+        self.stage = torch.zeros(lay.total_bytes, dtype=torch.uint8, device=self.dev)
+        self.s = lay.views(self.stage)
+        csr_l = DeviceCSR(self.s["indptr_l"], self.s["idx_l"], self.s["val_l"], int(n_genes), self.lab.max_row_nnz)
+        csr_l.n_rows = self.L
+        csr_u = DeviceCSR(self.s["indptr_u"], self.s["idx_u"], self.s["val_u"], int(n_genes), self.unl.max_row_nnz)
+        csr_u.n_rows = self.U
+        given = self.lab.domains is not None and self.unl.domains is not None
+        self.engine = TrainEngine(model.to(self.dev), cfg, csr_l, self.s["y_l"], self.L, unlabeled=csr_u, unlabeled_batch_size=self.U,
+                                  dann=dann, labeled_domain=self.s["dom_l"] if given else None,
+                                  unlabeled_domain=self.s["dom_u"] if given else None, mode="mixmatch", comm=comm)
+        self.engine.l_rows.copy_(torch.arange(self.L))
+        self.engine.u_rows.copy_(torch.arange(self.U))
+        # MixUp randomness is read straight from the staging blob (set before the step graph is captured)
+        self.engine.perm_keys, self.engine.gamma_raw = self.s["keys"], self.s["gam"]
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.ev_h2d = [torch.cuda.Event() for _ in range(2)]
+        self.ev_stash = [torch.cuda.Event() for _ in range(2)]
+        self.loss_pin = [torch.zeros(8).pin_memory() for _ in range(2)]
+        self.ev_done = [torch.cuda.Event() for _ in range(2)]
+        self.rng = np.random.default_rng(seed)
+        self.h2d_bytes_last = 0
+        self.d2h_bytes_last = 8 * 4
+
+    # ---- producer (runs in a thread; the C gather releases the GIL) ----------------------------
+    def _produce(self, k: int):
+        h = _lib.lib()
+        v, L, U = self.blob_np[k], self.L, self.U
+        lrows = self.rng.integers(0, self.lab.n_rows, L).astype(np.int64)
+        urows = self.rng.integers(0, self.unl.n_rows, U).astype(np.int64)
+        for src, rows, ip, ix, vv, cap in ((self.lab, lrows, "indptr_l", "idx_l", "val_l", self.layout.cap_l),
+                                            (self.unl, urows, "indptr_u", "idx_u", "val_u", self.layout.cap_u)):
+            rc = h.scnb_host_gather_rows(src.indptr.ctypes.data, src.indices.ctypes.data, src.data.ctypes.data, rows.ctypes.data,
+                                         rows.shape[0], v[ip].ctypes.data, v[ix].ctypes.data, v[vv].ctypes.data, cap, self.n_threads)
+            if rc != 0:
+                raise _lib.ScnbError(h.scnb_last_error().decode())
+        v["y_l"][:] = self.lab.labels[lrows]
+        if self.lab.domains is not None:
+            v["dom_l"][:] = self.lab.domains[lrows]
+        if self.unl.domains is not None:
+            v["dom_u"][:U] = self.unl.domains[urows]
+        v["keys"][:] = self.rng.random(L + U, dtype=np.float32)
+        v["gam"][:] = self.rng.beta(self.alpha, self.alpha, L + U).astype(np.float32)
+        return int(v["indptr_l"][L]), int(v["indptr_u"][U])
+
+    def _producer_loop(self, n_steps, free_q, ready_q):
+        try:
+            for _ in range(n_steps):
+                k = free_q.get()
+                if k is None:
+                    return
+                nnz = self._produce(k)
+                ready_q.put((k, nnz))
+        except BaseException as e:  # surface producer failures in the consumer
+            ready_q.put(e)
+
+    # ---- consumer ------------------------------------------------------------------------------
+    def _enqueue_h2d(self, k, nnz, slot):
+        """Copy blob k -> landing buffer `slot` on the copy stream (exact bytes: header + used CSR prefixes)."""
+        src, dst, hb = self.blobs[k], self.land[slot], self.layout.header_bytes
+        nl, nu = nnz
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.ev_stash[slot])     # landing buffer no longer read by an earlier stash
+            dst[:hb].copy_(src[:hb], non_blocking=True)
+            for name, n in (("idx_l", nl), ("val_l", nl), ("idx_u", nu), ("val_u", nu)):
+                if n > 0:
+                    self.land_t[slot][name][:n].copy_(self.blob_t[k][name][:n], non_blocking=True)
+            self.ev_h2d[slot].record(self.copy_stream)
+        return hb + 8 * (nl + nu)
+
+    def _enqueue_step(self, nnz, slot):
+        eng, lt, s = self.engine, self.land_t[slot], self.s
+        nl, nu = nnz
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.ev_h2d[slot])
+        hb = self.layout.header_bytes
+        self.stage[:hb].copy_(self.land[slot][:hb], non_blocking=True)   # indptrs, labels, domains, keys, gammas
+        for name, n in (("idx_l", nl), ("val_l", nl), ("idx_u", nu), ("val_u", nu)):
+            if n > 0:
+                s[name][:n].copy_(lt[name][:n], non_blocking=True)
+        self.ev_stash[slot].record(cur)
+        eng.step()
+        self.loss_pin[slot].copy_(eng.loss_buf, non_blocking=True)
+        self.ev_done[slot].record(cur)
+
+    def _read_loss(self, slot):
+        self.ev_done[slot].synchronize()
+        v = self.loss_pin[slot].tolist()
+        eng = self.engine
+        out = {"sup_loss": v[0], "sup_acc": v[1] / max(self.L, 1), "unsup_loss": v[2]}
+        if eng.use_dan:
+            out["dan_loss"] = v[4]
+        out["loss"] = v[0] + eng.unsup_weight * v[2] + (v[4] if eng.use_dan else 0.0)
+        return out
+
+    def run(self, n_steps: int):
+        """Generator over `n_steps` training steps; yields the loss dict of each step (in order)."""
+        self.engine.prepare()
+        torch.cuda.synchronize()
+        free_q, ready_q = queue.Queue(), queue.Queue()
+        for k in range(self.n_blobs):
+            free_q.put(k)
+        th = threading.Thread(target=self._producer_loop, args=(n_steps, free_q, ready_q), daemon=True)
+        th.start()
+
+        def next_ready():
+            item = ready_q.get()
+            if isinstance(item, BaseException):
+                raise item
+            return item
+
+        try:
+            pending = None           # (slot, blob) of the step whose loss has not been read yet
+            nxt = next_ready() if n_steps > 0 else None
+            if nxt is not None:
+                self.h2d_bytes_last = self._enqueue_h2d(nxt[0], nxt[1], 0)
+            for i in range(n_steps):
+                slot = i % 2
+                k, nnz = nxt
+                # upload of batch i+1 is enqueued before step i so that it overlaps step i on the device
+                nxt = next_ready() if i + 1 < n_steps else None
+                if nxt is not None:
+                    self._enqueue_h2d(nxt[0], nxt[1], 1 - slot)
+                self._enqueue_step(nnz, slot)
+                if pending is not None:
+                    yield self._read_loss(pending[0])
+                    free_q.put(pending[1])     # its H2D finished long ago: the pinned blob can be refilled
+                pending = (slot, k)
+            if pending is not None:
+                yield self._read_loss(pending[0])
+                free_q.put(pending[1])
+        finally:
+            free_q.put(None)
+            th.join(timeout=5.0)

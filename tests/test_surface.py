@@ -287,3 +287,42 @@ def test_mixmatch_loss_module_level_matches_reference_golden():
     unl = {"input": inp["Ux"].cuda(), "output": torch.zeros(24).cuda()}
     _, unsup0, _ = mm(model=model, labeled_sample=data, unlabeled_sample=unl)
     assert float(unsup0) == 0.0
+
+
+@pytest.mark.gpu
+def test_host_train_pipeline_feeds_the_engine_from_host_memory():
+    """HostTrainPipeline: host CSR -> pinned blob -> H2D -> staged batch -> step; losses come back per step."""
+    from oracle import scnym_oracle as O
+    from scnym_b200.engine import EngineConfig
+    from scnym_b200.hostfeed import HostTrainPipeline
+    from scnym_b200.model import CellTypeCLF, DANN
+    G, C, L, U, n = 600, 4, 32, 48, 300
+    lp, li, ld, ly = O.synth_csr(n, G, 0.06, C, seed=21)
+    up, ui, ud, _ = O.synth_csr(n, G, 0.06, C, seed=22)
+    torch.manual_seed(0)
+    model = CellTypeCLF(n_genes=G, n_cell_types=C, n_hidden=128, n_hidden_init=128, n_layers=2)
+    dann = DANN(model, n_domains=2)
+    cfg = EngineConfig(optimizer="adam", lr=1e-3, weight_decay=1e-4, seed=3)
+    pipe = HostTrainPipeline(model, cfg, lab=(lp, li, ld, ly), unl=(up, ui, ud), n_genes=G, batch_size=L, unlabeled_batch_size=U,
+                             dann=dann, seed=9)
+    pipe.engine.set_weights(1.0, 0.1)
+    w0 = model.classif[0].weight.detach().clone()
+    losses = list(pipe.run(7))
+    assert len(losses) == 7 and all(np.isfinite(l["loss"]) for l in losses)
+    assert pipe.h2d_bytes_last > 8 * (L + U) and pipe.d2h_bytes_last == 32
+    assert not torch.equal(w0, model.classif[0].weight.detach())
+    # the staged unlabeled rows of the LAST step are exactly the host rows the producer sampled
+    rng = np.random.default_rng(9)
+    for _ in range(7):
+        lrows = rng.integers(0, n, L)
+        urows = rng.integers(0, n, U)
+        rng.random(L + U, dtype=np.float32)
+        rng.beta(0.3, 0.3, L + U)
+    want_idx = np.concatenate([ui[up[r]:up[r + 1]] for r in urows])
+    want_val = np.concatenate([ud[up[r]:up[r + 1]] for r in urows])
+    eng = pipe.engine
+    nnz_u = int(eng.b_indptr[U])
+    assert nnz_u == want_idx.size
+    assert np.array_equal(eng.b_idx[:nnz_u].cpu().numpy(), want_idx)
+    assert np.array_equal(eng.b_val[:nnz_u].cpu().numpy(), want_val)
+    assert np.array_equal(eng.lab_ids.cpu().numpy(), ly[lrows].astype(np.int32))
