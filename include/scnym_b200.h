@@ -87,6 +87,18 @@ int scnb_csr_linear_fwd_i64(const int64_t* indptr /*first row of the range*/, co
 int scnb_csr_linear_bwd_dw(const int32_t* b_indptr, const int32_t* b_idx, const float* b_val, int n, const float* dZ,
                            int H0, float* dW1T, void* stream);
 
+/* ---- K2b: dense tensor-core form of the first layer (densify-then-tcgen05 GEMM, bf16x3 split with fp32
+ *      accumulation in TMEM).  scnb_w1_planes splits W1T into two bf16 planes laid out as 128-byte-swizzled
+ *      shared-memory tile images (ceil(G/64) tiles of H0*64 elements per plane); scnb_csr_linear_fwd_tc{,_i64}
+ *      computes Z = X W1T + b1 from a batch CSR (int32 indptr) or a row range of a dataset CSR (int64 indptr).
+ *      ksplits <= 0: choose the number of gene-axis splits automatically.  H0 in {32,...,256}, multiple of 32. ---- */
+int scnb_w1_planes(const float* W1T, int G, int H0, void* planes_hi, void* planes_lo, void* stream);
+int scnb_csr_linear_fwd_tc(const int32_t* b_indptr, const int32_t* b_idx, const float* b_val, int n, int G, int H0,
+                           const void* planes_hi, const void* planes_lo, const float* b1, float* Z, int ksplits, void* stream);
+int scnb_csr_linear_fwd_tc_i64(const int64_t* indptr, const int32_t* indices, const float* data, int n, int G, int H0,
+                               const void* planes_hi, const void* planes_lo, const float* b1, float* Z, int ksplits,
+                               void* stream);
+
 /* ---- K8+K9 fused: first-layer weight gradient AND optimizer.step() for W1T in one pass
  *      (scnym/model.py:211 backward + scnym/trainer.py:671 / torch.optim rules, scnym/main.py:36-41,374-396).
  *      The batch is first transposed to gene-major order ("batch CSC"): gene_cnt[G] is the histogram

@@ -24,6 +24,9 @@ SIGNATURES = {
     "scnb_csr_linear_fwd": [P, P, P, I, P, P, I, P, P],
     "scnb_csr_linear_fwd_i64": [P, P, P, I, P, P, I, P, P],
     "scnb_csr_linear_bwd_dw": [P, P, P, I, P, I, P, P],
+    "scnb_w1_planes": [P, I, I, P, P, P],
+    "scnb_csr_linear_fwd_tc": [P, P, P, I, I, I, P, P, P, P, I, P],
+    "scnb_csr_linear_fwd_tc_i64": [P, P, P, I, I, I, P, P, P, P, I, P],
     "scnb_csc_count": [P, P, I, P, P],
     "scnb_csr_to_csc": [P, P, P, I, I, P, P, P, P, P],
     "scnb_csr_w1_bwd_optim": [I, P, P, P, I, I, I, P, P, P, P, P, P, P],

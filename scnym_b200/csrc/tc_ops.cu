@@ -1,0 +1,373 @@
+// Dense (tensor-core) form of the first layer for sm_100a: densify-then-tcgen05 GEMM.
+//   Z[n, H0] = X_csr[n, G] * W1T[G, H0] + b1        (scnym/model.py:211 on CSR input)
+// The warp-per-row SpMM (csr_ops.cu) gathers 1 KB of W1T per stored entry through L2 (1 MB per cell at
+// G=20 000, 5 %), which caps it at the L2->SM bandwidth.  Here a CTA owns a 128-row tile of X and walks
+// the gene axis in tiles of 64 genes:
+//   * W1T is pre-split into two bf16 planes (hi = bf16(w), lo = bf16(w - hi)) stored as ready-made
+//     128-byte-swizzled K-major shared-memory images, one per gene tile, so one elected thread brings
+//     a tile in with a single 1-D bulk copy (cp.async.bulk + mbarrier complete_tx), no tensor map;
+//   * 128 threads (one per row) densify the row's entries of that gene tile into two swizzled bf16
+//     A tiles (hi, lo) -- everything else in the tile is zero;
+//   * one thread issues tcgen05.mma (kind::f16, M=128, N=H0, K=16) x 4 K-slices x 3 products
+//       acc += A_lo B_hi + A_hi B_lo + A_hi B_hi        (fp32 accumulate in TMEM)
+//     which keeps ~16 mantissa bits per product (relative error ~2^-16 per term, well inside the 1e-4
+//     parity budget; a single bf16 or tf32 pass is not: SURVEY.md §7);
+//   * tcgen05.commit frees the stage; after the last tile the four densify warps read the accumulator
+//     back with tcgen05.ld and write (or, when the gene axis is split over CTAs, atomically add) Z.
+// Pipeline: `stages` shared-memory stages (A_hi, A_lo, B_hi, B_lo), mbarriers full_b / full_a / empty.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+#define TC_M 128
+#define TC_KT 64                    // genes per tile = one 128-byte swizzle row of bf16
+#define TC_A_BYTES (TC_M * 128)     // one A plane of a stage
+#define TC_THREADS 192              // warp 0: B loader, warp 1: TMEM + MMA issuer, warps 2-5: densify + epilogue
+#define TC_SPIN_LIMIT (1u << 28)    // watchdog: trap instead of hanging the GPU if a barrier never completes
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > TC_SPIN_LIMIT) __trap();
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, 128-byte swizzle, dense 128-byte rows: LBO = 16 B (unused), SBO = 1024 B (8-row group), version 1
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  const uint32_t lo = ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);
+  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+__device__ __forceinline__ void st_shared_zero16(uint32_t addr) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// W1T fp32 [G, H0]  ->  two bf16 planes, tile kt = genes [64 kt, 64 kt + 64): image[n][k] at byte
+// n*128 + ((k>>3) ^ (n&7))*16 + (k&7)*2   (K-major rows of 128 B, 16-byte chunks XOR-swizzled by row).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_w1_planes(const float* __restrict__ W1T, int G, int H0, uint16_t* __restrict__ hi,
+                                                   uint16_t* __restrict__ lo) {
+  extern __shared__ float wt[];  // [64][H0 + 1]
+  const int kt = blockIdx.x, tid = threadIdx.x;
+  const int S = H0 + 1;
+  for (int e = tid; e < TC_KT * H0; e += 256) {
+    const int k = e / H0, n = e - k * H0;
+    const int g = kt * TC_KT + k;
+    wt[k * S + n] = g < G ? W1T[(size_t)g * H0 + n] : 0.f;
+  }
+  __syncthreads();
+  const size_t tile = (size_t)kt * H0 * TC_KT;  // elements per plane tile
+  for (int e = tid; e < H0 * 8; e += 256) {
+    const int n = e >> 3, c = e & 7;
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float x0 = wt[(8 * c + 2 * j) * S + n], x1 = wt[(8 * c + 2 * j + 1) * S + n];
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+      h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      l[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    const size_t off = tile + (size_t)n * 64 + (size_t)((c ^ (n & 7)) * 8);  // in bf16 elements
+    *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+extern "C" int scnb_w1_planes(const float* W1T, int G, int H0, void* planes_hi, void* planes_lo, void* stream) {
+  SCNB_CHECK_ARG(W1T && planes_hi && planes_lo && G > 0 && H0 > 0 && H0 % 8 == 0, "w1_planes: bad arguments");
+  SCNB_CHECK_ARG((((uintptr_t)planes_hi | (uintptr_t)planes_lo) % 16) == 0, "w1_planes: planes must be 16-byte aligned");
+  const int n_kt = scnb_cdiv(G, TC_KT);
+  const size_t smem = (size_t)TC_KT * (H0 + 1) * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_w1_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      scnb_set_error("w1_planes: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+      return SCNB_ERR_CUDA;
+    }
+  }
+  k_w1_planes<<<n_kt, 256, smem, (cudaStream_t)stream>>>(W1T, G, H0, (uint16_t*)planes_hi, (uint16_t*)planes_lo);
+  SCNB_CHECK_LAUNCH("w1_planes");
+  return SCNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename IdxT>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ idx,
+                                                                    const float* __restrict__ val, int n_rows,
+                                                                    const uint8_t* __restrict__ planes_hi,
+                                                                    const uint8_t* __restrict__ planes_lo, int N, int n_ktiles,
+                                                                    const float* __restrict__ bias, float* __restrict__ Z,
+                                                                    int stages, int tmem_cols) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  const uint32_t raw = smem_u32(tc_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;              // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* sm = tc_smem_raw + (base - raw);
+  const uint32_t B_BYTES = (uint32_t)N * 128u;
+  const uint32_t STAGE_BYTES = 2u * TC_A_BYTES + 2u * B_BYTES;
+  const uint32_t bars = base + (uint32_t)stages * STAGE_BYTES;  // full_b[S] | full_a[S] | empty[S] | acc | tmem slot
+  const uint32_t bar_full_b = bars, bar_full_a = bars + 8u * stages, bar_empty = bars + 16u * stages,
+                 bar_acc = bars + 24u * stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (size_t)stages * STAGE_BYTES + 24 * stages + 8);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // this CTA's share of the gene tiles
+  const int per = (n_ktiles + gridDim.y - 1) / gridDim.y;
+  const int kt0 = blockIdx.y * per, kt1 = min(n_ktiles, kt0 + per);
+  const int n_it = max(kt1 - kt0, 0);
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(bar_full_b + 8u * s, 1);
+      mbar_init(bar_full_a + 8u * s, 128);
+      mbar_init(bar_empty + 8u * s, 1);
+    }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== B loader: one bulk copy per plane per gene tile =====
+    if (lane == 0) {
+      for (int i = 0; i < n_it; ++i) {
+        const int s = i % stages;
+        const uint32_t ph = (uint32_t)(i / stages) & 1u;
+        mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+        const uint32_t stage = base + (uint32_t)s * STAGE_BYTES;
+        mbar_arrive_expect_tx(bar_full_b + 8u * s, 2u * B_BYTES);
+        const size_t off = (size_t)(kt0 + i) * B_BYTES;
+        bulk_g2s(stage + 2u * TC_A_BYTES, planes_hi + off, B_BYTES, bar_full_b + 8u * s);
+        bulk_g2s(stage + 2u * TC_A_BYTES + B_BYTES, planes_lo + off, B_BYTES, bar_full_b + 8u * s);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+      for (int i = 0; i < n_it; ++i) {
+        const int s = i % stages;
+        const uint32_t ph = (uint32_t)(i / stages) & 1u;
+        mbar_wait(bar_full_b + 8u * s, ph);
+        mbar_wait(bar_full_a + 8u * s, ph);
+        tc_fence_after();
+        const uint32_t stage = base + (uint32_t)s * STAGE_BYTES;
+        const uint64_t a_hi = umma_desc_sw128(stage), a_lo = umma_desc_sw128(stage + TC_A_BYTES);
+        const uint64_t b_hi = umma_desc_sw128(stage + 2u * TC_A_BYTES), b_lo = umma_desc_sw128(stage + 2u * TC_A_BYTES + B_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_KT / 16; ++k) {
+          const uint64_t ko = (uint64_t)(k * 2);  // 32 bytes per K=16 slice, in 16-byte units
+          tc_mma_bf16(tmem_base, a_lo + ko, b_hi + ko, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          tc_mma_bf16(tmem_base, a_hi + ko, b_lo + ko, idesc, 1u);
+          tc_mma_bf16(tmem_base, a_hi + ko, b_hi + ko, idesc, 1u);
+        }
+        tc_commit(bar_empty + 8u * s);   // stage reusable once these MMAs have read it
+      }
+      if (n_it > 0) tc_commit(bar_acc);  // accumulator complete
+    }
+  } else {
+    // ===== densify (one thread per row of the tile), then epilogue =====
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;                  // row within the tile == TMEM lane
+    const long long grow = (long long)blockIdx.x * TC_M + r;
+    long long p = 0, pend = 0;
+    if (grow < n_rows) {
+      p = (long long)indptr[grow];
+      pend = (long long)indptr[grow + 1];
+    }
+    if (kt0 > 0 && p < pend) {  // first stored gene >= kt0*64 (rows are sorted by gene)
+      const int target = kt0 * TC_KT;
+      long long lo_p = p, hi_p = pend;
+      while (lo_p < hi_p) {
+        const long long mid = (lo_p + hi_p) >> 1;
+        if (idx[mid] < target) lo_p = mid + 1; else hi_p = mid;
+      }
+      p = lo_p;
+    }
+    const int NONE = 0x7fffffff;
+    int c0 = p < pend ? idx[p] : NONE, c1 = p + 1 < pend ? idx[p + 1] : NONE;
+    float v0 = p < pend ? val[p] : 0.f, v1 = p + 1 < pend ? val[p + 1] : 0.f;
+    const uint32_t rsw = (uint32_t)(r & 7);
+    for (int i = 0; i < n_it; ++i) {
+      const int s = i % stages;
+      const uint32_t ph = (uint32_t)(i / stages) & 1u;
+      mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+      const uint32_t row_hi = base + (uint32_t)s * STAGE_BYTES + (uint32_t)r * 128u, row_lo = row_hi + TC_A_BYTES;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {                // clear the row (lanes stagger the chunk: no bank conflicts)
+        const uint32_t ch = (uint32_t)((j + lane) & 7) << 4;
+        st_shared_zero16(row_hi + ch);
+        st_shared_zero16(row_lo + ch);
+      }
+      const int k0 = (kt0 + i) * TC_KT, kend = k0 + TC_KT;
+      while (c0 < kend) {
+        const uint32_t g = (uint32_t)(c0 - k0);
+        const __nv_bfloat16 h = __float2bfloat16_rn(v0);
+        const __nv_bfloat16 l = __float2bfloat16_rn(v0 - __bfloat162float(h));
+        const uint32_t off = (((g >> 3) ^ rsw) << 4) + ((g & 7u) << 1);
+        st_shared_u16(row_hi + off, __bfloat16_as_ushort(h));
+        st_shared_u16(row_lo + off, __bfloat16_as_ushort(l));
+        ++p;
+        c0 = c1;
+        v0 = v1;
+        c1 = p + 1 < pend ? idx[p + 1] : NONE;
+        v1 = p + 1 < pend ? val[p + 1] : 0.f;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+      mbar_arrive(bar_full_a + 8u * s);
+    }
+    if (n_it > 0) {
+      mbar_wait(bar_acc, 0);
+      tc_fence_after();
+      const bool split = gridDim.y > 1;
+      const bool add_bias = bias && blockIdx.y == 0;
+      for (int cb = 0; cb < N; cb += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (grow < n_rows) {
+          float* out = Z + (size_t)grow * N + cb;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                   __uint_as_float(v[j + 3]));
+            if (add_bias) {
+              o.x += bias[cb + j]; o.y += bias[cb + j + 1]; o.z += bias[cb + j + 2]; o.w += bias[cb + j + 3];
+            }
+            if (split) atomicAdd(reinterpret_cast<float4*>(out + j), o);
+            else *reinterpret_cast<float4*>(out + j) = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+template <typename IdxT>
+static int launch_dense_fwd_tc(const IdxT* indptr, const int32_t* idx, const float* val, int n, int G, int H0, const void* hi,
+                               const void* lo, const float* b1, float* Z, int ksplits, cudaStream_t st) {
+  const int n_kt = scnb_cdiv(G, TC_KT);
+  const int row_tiles = scnb_cdiv(n, TC_M);
+  if (ksplits <= 0) {  // auto: cover the 148 SMs when there are few row tiles
+    ksplits = 1;
+    while (row_tiles * ksplits * 2 <= 148 && ksplits * 2 <= n_kt) ksplits *= 2;
+    if (row_tiles * ksplits < 148 && row_tiles < 148) ksplits = 148 / row_tiles > n_kt ? n_kt : 148 / row_tiles;
+    if (ksplits < 1) ksplits = 1;
+  }
+  if (ksplits > n_kt) ksplits = n_kt;
+  const size_t stage_bytes = 2 * (size_t)TC_A_BYTES + 2 * (size_t)H0 * 128;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > 4) stages = 4;
+  if (stages < 2) {
+    scnb_set_error("csr_linear_fwd_tc: H0=%d needs more shared memory than one SM has", H0);
+    return SCNB_ERR_UNSUPPORTED;
+  }
+  const size_t smem = 1024 + stages * stage_bytes + 24 * stages + 16 + 16;
+  int tmem_cols = 32;
+  while (tmem_cols < H0) tmem_cols *= 2;
+  cudaError_t e = cudaFuncSetAttribute(k_csr_dense_fwd_tc<IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    scnb_set_error("csr_linear_fwd_tc: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+    return SCNB_ERR_CUDA;
+  }
+  if (ksplits > 1) {  // partial products of the gene-axis splits are added atomically
+    e = cudaMemsetAsync(Z, 0, (size_t)n * H0 * sizeof(float), st);
+    if (e != cudaSuccess) {
+      scnb_set_error("csr_linear_fwd_tc: memset failed: %s", cudaGetErrorString(e));
+      return SCNB_ERR_CUDA;
+    }
+  }
+  dim3 grid(row_tiles, ksplits);
+  k_csr_dense_fwd_tc<IdxT><<<grid, TC_THREADS, smem, st>>>(indptr, idx, val, n, (const uint8_t*)hi, (const uint8_t*)lo, H0, n_kt, b1, Z,
+                                                          stages, tmem_cols);
+  SCNB_CHECK_LAUNCH("csr_linear_fwd_tc");
+  return SCNB_OK;
+}
+
+static int tc_check(int n, int G, int H0, const void* hi, const void* lo, const float* Z) {
+  SCNB_CHECK_ARG(n >= 0 && G > 0 && hi && lo && Z, "csr_linear_fwd_tc: bad arguments");
+  SCNB_CHECK_ARG(H0 >= 16 && H0 <= 256 && H0 % 32 == 0, "csr_linear_fwd_tc: H0 must be a multiple of 32 in [32, 256] (got %d)", H0);
+  SCNB_CHECK_ARG((((uintptr_t)hi | (uintptr_t)lo | (uintptr_t)Z) % 16) == 0, "csr_linear_fwd_tc: buffers must be 16-byte aligned");
+  return SCNB_OK;
+}
+
+extern "C" int scnb_csr_linear_fwd_tc(const int32_t* b_indptr, const int32_t* b_idx, const float* b_val, int n, int G, int H0,
+                                      const void* planes_hi, const void* planes_lo, const float* b1, float* Z, int ksplits,
+                                      void* stream) {
+  SCNB_CHECK_ARG(b_indptr && b_idx && b_val, "csr_linear_fwd_tc: null CSR");
+  int rc = tc_check(n, G, H0, planes_hi, planes_lo, Z);
+  if (rc != SCNB_OK) return rc;
+  if (n == 0) return SCNB_OK;
+  return launch_dense_fwd_tc<int32_t>(b_indptr, b_idx, b_val, n, G, H0, planes_hi, planes_lo, b1, Z, ksplits, (cudaStream_t)stream);
+}
+
+extern "C" int scnb_csr_linear_fwd_tc_i64(const int64_t* indptr, const int32_t* indices, const float* data, int n, int G, int H0,
+                                          const void* planes_hi, const void* planes_lo, const float* b1, float* Z, int ksplits,
+                                          void* stream) {
+  SCNB_CHECK_ARG(indptr && indices && data, "csr_linear_fwd_tc_i64: null CSR");
+  int rc = tc_check(n, G, H0, planes_hi, planes_lo, Z);
+  if (rc != SCNB_OK) return rc;
+  if (n == 0) return SCNB_OK;
+  return launch_dense_fwd_tc<int64_t>(indptr, indices, data, n, G, H0, planes_hi, planes_lo, b1, Z, ksplits, (cudaStream_t)stream);
+}

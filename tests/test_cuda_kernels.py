@@ -488,3 +488,36 @@ def test_bn_eval_fwd_large_rows():
     _chk("bn eval pre", pre[:n].cpu(), y, tol=2e-6)
     _chk("bn eval relu", A[:n].cpu(), y.clamp_min(0), tol=2e-6)
     assert float(A[n:].abs().max()) == 0.0 and float(pre[n:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("n,G,H0,ksplits", [(300, 1000, 128, 1), (300, 1000, 256, 0), (130, 777, 64, 3), (512, 2048, 256, 0),
+                                            (1, 64, 32, 1)])
+def test_csr_linear_fwd_tensor_core_matches_dense(n, G, H0, ksplits):
+    """densify-then-tcgen05 first layer (bf16x3 split, fp32 TMEM accumulation) against the fp64 dense product."""
+    from oracle import scnym_oracle as O
+    from scnym_b200._lib import call, ptr
+    from scnym_b200.dataprep import DeviceCSR, gather_rows
+    ip, ii, dd, _ = O.synth_csr(n, G, 0.07, 3, seed=n + H0)
+    X = O.csr_to_dense(ip, ii, dd, G, np.arange(n))
+    ds = DeviceCSR.from_arrays(ip, ii, dd, G)
+    torch.manual_seed(G)
+    WT, b1 = torch.randn(G, H0) * 0.1, torch.randn(H0)
+    n_kt = (G + 63) // 64
+    hi = torch.zeros(n_kt * H0 * 64, dtype=torch.int16).cuda()
+    lo = torch.zeros(n_kt * H0 * 64, dtype=torch.int16).cuda()
+    WTd = D(WT)
+    call("scnb_w1_planes", ptr(WTd), G, H0, ptr(hi), ptr(lo), _st())
+    want = X.double() @ WT.double() + b1.double()
+    # dataset CSR (int64 indptr), rows [0, n)
+    Z = torch.full((n, H0), 7.0).cuda()
+    call("scnb_csr_linear_fwd_tc_i64", ptr(ds.indptr), ptr(ds.indices), ptr(ds.data), n, G, H0, ptr(hi), ptr(lo), ptr(D(b1)), ptr(Z),
+         ksplits, _st())
+    torch.cuda.synchronize()
+    _chk("tc fwd i64", Z.cpu(), want, tol=3e-5)
+    # batch CSR (int32 indptr), permuted rows, no bias
+    rows = torch.randperm(n)
+    b = gather_rows(ds, rows.cuda())
+    Z2 = torch.full((n, H0), -3.0).cuda()
+    call("scnb_csr_linear_fwd_tc", ptr(b.indptr), ptr(b.indices), ptr(b.data), n, G, H0, ptr(hi), ptr(lo), None, ptr(Z2), ksplits, _st())
+    torch.cuda.synchronize()
+    _chk("tc fwd batch", Z2.cpu(), X[rows].double() @ WT.double(), tol=3e-5)
