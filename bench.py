@@ -232,6 +232,8 @@ def time_predict(device, rank):
     prob = torch.empty((N, c["C"]), device=device)
     emb = torch.empty((N, c["H"]), device=device)
 
+    run.refresh_planes()
+
     def one_pass():
         for s in range(0, N, run.chunk):
             n = min(run.chunk, N - s)

@@ -19,10 +19,13 @@
 
 #include "common.cuh"
 
-#define TC_M 128
-#define TC_KT 64                    // genes per tile = one 128-byte swizzle row of bf16
-#define TC_A_BYTES (TC_M * 128)     // one A plane of a stage
-#define TC_THREADS 192              // warp 0: B loader, warp 1: TMEM + MMA issuer, warps 2-5: densify + epilogue
+#define TC_M 128                    // rows per MMA (TMEM lanes)
+// Two tile geometries (template parameters HALVES, KT of the kernel):
+//   <1, 64>: 128 rows per CTA, 64 genes per tile (128-byte rows, SWIZZLE_128B)
+//   <2, 32>: 256 rows per CTA (two accumulators in TMEM), 32 genes per tile (64-byte rows, SWIZZLE_64B).
+//            Every W1T tile feeds two MMA row blocks, which halves the W1T bytes each SM pulls through L2
+//            per MMA cycle -- at <1,64> the 148 SMs together ask for ~12 TB/s, the L2 limit.
+#define TC_W 8                      // entries per prefetch window of a densify thread
 #define TC_SPIN_LIMIT (1u << 28)    // watchdog: trap instead of hanging the GPU if a barrier never completes
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -67,11 +70,20 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// K-major, 128-byte swizzle, dense 128-byte rows: LBO = 16 B (unused), SBO = 1024 B (8-row group), version 1
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+// K-major operand tile with dense rows of ROWB = 2*KT bytes (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B):
+// LBO = 16 B (unused for swizzled K-major), SBO = 8 rows, descriptor version 1 (Blackwell)
+template <int KT>
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
+  constexpr uint32_t ROWB = 2 * KT;
+  constexpr uint32_t LAYOUT = (ROWB == 128) ? 2u : 4u;
   const uint32_t lo = ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);
-  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  const uint32_t hi = ((8u * ROWB) >> 4) | (1u << 14) | (LAYOUT << 29);
   return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+// byte offset of 16-byte chunk `c` of row `r` inside a swizzled tile (relative to the row start)
+template <int KT>
+__device__ __forceinline__ uint32_t swz_chunk(uint32_t c, uint32_t r) {
+  return (KT == 64) ? ((c ^ (r & 7u)) << 4) : ((c ^ ((r >> 1) & 3u)) << 4);
 }
 __device__ __forceinline__ void st_shared_zero16(uint32_t addr) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
@@ -81,23 +93,25 @@ __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// W1T fp32 [G, H0]  ->  two bf16 planes, tile kt = genes [64 kt, 64 kt + 64): image[n][k] at byte
-// n*128 + ((k>>3) ^ (n&7))*16 + (k&7)*2   (K-major rows of 128 B, 16-byte chunks XOR-swizzled by row).
+// W1T fp32 [G, H0]  ->  two bf16 planes, tile kt = genes [KT kt, KT kt + KT): image[n][k] at byte
+// n*2KT + swizzle(chunk k>>3, row n) + (k&7)*2   (K-major rows of 2KT bytes, 16-byte chunks XOR-swizzled by row).
 // ---------------------------------------------------------------------------------------------
+template <int KT>
 __global__ void __launch_bounds__(256) k_w1_planes(const float* __restrict__ W1T, int G, int H0, uint16_t* __restrict__ hi,
                                                    uint16_t* __restrict__ lo) {
-  extern __shared__ float wt[];  // [64][H0 + 1]
+  extern __shared__ float wt[];  // [KT][H0 + 1]
+  constexpr int CPR = KT / 8;    // 16-byte chunks per row
   const int kt = blockIdx.x, tid = threadIdx.x;
   const int S = H0 + 1;
-  for (int e = tid; e < TC_KT * H0; e += 256) {
+  for (int e = tid; e < KT * H0; e += 256) {
     const int k = e / H0, n = e - k * H0;
-    const int g = kt * TC_KT + k;
+    const int g = kt * KT + k;
     wt[k * S + n] = g < G ? W1T[(size_t)g * H0 + n] : 0.f;
   }
   __syncthreads();
-  const size_t tile = (size_t)kt * H0 * TC_KT;  // elements per plane tile
-  for (int e = tid; e < H0 * 8; e += 256) {
-    const int n = e >> 3, c = e & 7;
+  const size_t tile = (size_t)kt * H0 * KT;  // elements per plane tile
+  for (int e = tid; e < H0 * CPR; e += 256) {
+    const int n = e / CPR, c = e % CPR;
     uint32_t h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -107,43 +121,52 @@ __global__ void __launch_bounds__(256) k_w1_planes(const float* __restrict__ W1T
       h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
       l[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
     }
-    const size_t off = tile + (size_t)n * 64 + (size_t)((c ^ (n & 7)) * 8);  // in bf16 elements
+    const size_t off = tile + (size_t)n * KT + (size_t)(swz_chunk<KT>((uint32_t)c, (uint32_t)n) >> 1);  // in bf16 elements
     *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
 
+// Tile geometry used for a given first-layer width (shared by the plane builder and the GEMM launcher).
+static inline int tc_tile_genes(int H0) { return 32; }
+
 extern "C" int scnb_w1_planes(const float* W1T, int G, int H0, void* planes_hi, void* planes_lo, void* stream) {
   SCNB_CHECK_ARG(W1T && planes_hi && planes_lo && G > 0 && H0 > 0 && H0 % 8 == 0, "w1_planes: bad arguments");
   SCNB_CHECK_ARG((((uintptr_t)planes_hi | (uintptr_t)planes_lo) % 16) == 0, "w1_planes: planes must be 16-byte aligned");
-  const int n_kt = scnb_cdiv(G, TC_KT);
-  const size_t smem = (size_t)TC_KT * (H0 + 1) * sizeof(float);
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k_w1_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      scnb_set_error("w1_planes: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
-      return SCNB_ERR_CUDA;
-    }
+  const int KT = tc_tile_genes(H0);
+  const int n_kt = scnb_cdiv(G, KT);
+  const size_t smem = (size_t)KT * (H0 + 1) * sizeof(float);
+  if (KT == 64) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_w1_planes<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_w1_planes<64><<<n_kt, 256, smem, (cudaStream_t)stream>>>(W1T, G, H0, (uint16_t*)planes_hi, (uint16_t*)planes_lo);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_w1_planes<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_w1_planes<32><<<n_kt, 256, smem, (cudaStream_t)stream>>>(W1T, G, H0, (uint16_t*)planes_hi, (uint16_t*)planes_lo);
   }
-  k_w1_planes<<<n_kt, 256, smem, (cudaStream_t)stream>>>(W1T, G, H0, (uint16_t*)planes_hi, (uint16_t*)planes_lo);
   SCNB_CHECK_LAUNCH("w1_planes");
   return SCNB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
-template <typename IdxT>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ idx,
-                                                                    const float* __restrict__ val, int n_rows,
-                                                                    const uint8_t* __restrict__ planes_hi,
-                                                                    const uint8_t* __restrict__ planes_lo, int N, int n_ktiles,
-                                                                    const float* __restrict__ bias, float* __restrict__ Z,
-                                                                    int stages, int tmem_cols) {
+// Roles: warp 0 = W1T tile loader, warp 1 = TMEM allocation + MMA issuer, warps 2..2+4*HALVES-1 = densify
+// (one thread per row of the CTA's tile) and, afterwards, epilogue (TMEM -> registers -> Z).
+// ---------------------------------------------------------------------------------------------
+template <typename IdxT, int HALVES, int KT>
+__global__ void __launch_bounds__(64 + 128 * HALVES, 1)
+k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ idx, const float* __restrict__ val, int n_rows,
+                   const uint8_t* __restrict__ planes_hi, const uint8_t* __restrict__ planes_lo, int N, int n_ktiles,
+                   const float* __restrict__ bias, float* __restrict__ Z, int stages, int tmem_cols) {
+  constexpr uint32_t ROWB = 2 * KT;                       // bytes per operand row (bf16)
+  constexpr uint32_t A_HALF = TC_M * ROWB;                // one 128-row A block of one plane
+  constexpr uint32_t A_PLANE = HALVES * A_HALF;
+  constexpr int CPR = KT / 8;                             // 16-byte chunks per row
+  constexpr int ROWS = TC_M * HALVES;
   extern __shared__ uint8_t tc_smem_raw[];
   const uint32_t raw = smem_u32(tc_smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;              // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t base = (raw + 1023u) & ~1023u;           // swizzled tiles need (at most) 1024-byte alignment
   uint8_t* sm = tc_smem_raw + (base - raw);
-  const uint32_t B_BYTES = (uint32_t)N * 128u;
-  const uint32_t STAGE_BYTES = 2u * TC_A_BYTES + 2u * B_BYTES;
+  const uint32_t B_BYTES = (uint32_t)N * ROWB;
+  const uint32_t STAGE_BYTES = 2u * A_PLANE + 2u * B_BYTES;   // A_hi | A_lo | B_hi | B_lo
   const uint32_t bars = base + (uint32_t)stages * STAGE_BYTES;  // full_b[S] | full_a[S] | empty[S] | acc | tmem slot
   const uint32_t bar_full_b = bars, bar_full_a = bars + 8u * stages, bar_empty = bars + 16u * stages,
                  bar_acc = bars + 24u * stages;
@@ -157,7 +180,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_csr_dense_fwd_tc(const IdxT* 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(bar_full_b + 8u * s, 1);
-      mbar_init(bar_full_a + 8u * s, 128);
+      mbar_init(bar_full_a + 8u * s, ROWS);
       mbar_init(bar_empty + 8u * s, 1);
     }
     mbar_init(bar_acc, 1);
@@ -174,7 +197,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_csr_dense_fwd_tc(const IdxT* 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== B loader: one bulk copy per plane per gene tile =====
+    // ===== W1T loader: one bulk copy per plane per gene tile =====
     if (lane == 0) {
       for (int i = 0; i < n_it; ++i) {
         const int s = i % stages;
@@ -183,8 +206,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_csr_dense_fwd_tc(const IdxT* 
         const uint32_t stage = base + (uint32_t)s * STAGE_BYTES;
         mbar_arrive_expect_tx(bar_full_b + 8u * s, 2u * B_BYTES);
         const size_t off = (size_t)(kt0 + i) * B_BYTES;
-        bulk_g2s(stage + 2u * TC_A_BYTES, planes_hi + off, B_BYTES, bar_full_b + 8u * s);
-        bulk_g2s(stage + 2u * TC_A_BYTES + B_BYTES, planes_lo + off, B_BYTES, bar_full_b + 8u * s);
+        bulk_g2s(stage + 2u * A_PLANE, planes_hi + off, B_BYTES, bar_full_b + 8u * s);
+        bulk_g2s(stage + 2u * A_PLANE + B_BYTES, planes_lo + off, B_BYTES, bar_full_b + 8u * s);
       }
     }
   } else if (warp == 1) {
@@ -198,31 +221,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_csr_dense_fwd_tc(const IdxT* 
         mbar_wait(bar_full_a + 8u * s, ph);
         tc_fence_after();
         const uint32_t stage = base + (uint32_t)s * STAGE_BYTES;
-        const uint64_t a_hi = umma_desc_sw128(stage), a_lo = umma_desc_sw128(stage + TC_A_BYTES);
-        const uint64_t b_hi = umma_desc_sw128(stage + 2u * TC_A_BYTES), b_lo = umma_desc_sw128(stage + 2u * TC_A_BYTES + B_BYTES);
+        const uint64_t b_hi = umma_desc_kmajor<KT>(stage + 2u * A_PLANE), b_lo = umma_desc_kmajor<KT>(stage + 2u * A_PLANE + B_BYTES);
 #pragma unroll
-        for (int k = 0; k < TC_KT / 16; ++k) {
-          const uint64_t ko = (uint64_t)(k * 2);  // 32 bytes per K=16 slice, in 16-byte units
-          tc_mma_bf16(tmem_base, a_lo + ko, b_hi + ko, idesc, (i > 0 || k > 0) ? 1u : 0u);
-          tc_mma_bf16(tmem_base, a_hi + ko, b_lo + ko, idesc, 1u);
-          tc_mma_bf16(tmem_base, a_hi + ko, b_hi + ko, idesc, 1u);
+        for (int h = 0; h < HALVES; ++h) {
+          const uint64_t a_hi = umma_desc_kmajor<KT>(stage + (uint32_t)h * A_HALF);
+          const uint64_t a_lo = umma_desc_kmajor<KT>(stage + A_PLANE + (uint32_t)h * A_HALF);
+          const uint32_t d = tmem_base + (uint32_t)(h * N);   // accumulator of this row block: columns [h*N, h*N + N)
+#pragma unroll
+          for (int k = 0; k < KT / 16; ++k) {
+            const uint64_t ko = (uint64_t)(k * 2);  // 32 bytes per K=16 slice, in 16-byte units
+            tc_mma_bf16(d, a_lo + ko, b_hi + ko, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            tc_mma_bf16(d, a_hi + ko, b_lo + ko, idesc, 1u);
+            tc_mma_bf16(d, a_hi + ko, b_hi + ko, idesc, 1u);
+          }
         }
         tc_commit(bar_empty + 8u * s);   // stage reusable once these MMAs have read it
       }
-      if (n_it > 0) tc_commit(bar_acc);  // accumulator complete
+      if (n_it > 0) tc_commit(bar_acc);  // accumulators complete
     }
   } else {
     // ===== densify (one thread per row of the tile), then epilogue =====
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;                  // row within the tile == TMEM lane
-    const long long grow = (long long)blockIdx.x * TC_M + r;
+    const int half = (warp - 2) >> 2;             // which 128-row block
+    const int rl = q * 32 + lane;                 // row within the block == TMEM lane
+    const int r = half * TC_M + rl;               // row within the CTA tile
+    const long long grow = (long long)blockIdx.x * ROWS + r;
     long long p = 0, pend = 0;
     if (grow < n_rows) {
       p = (long long)indptr[grow];
       pend = (long long)indptr[grow + 1];
     }
-    if (kt0 > 0 && p < pend) {  // first stored gene >= kt0*64 (rows are sorted by gene)
-      const int target = kt0 * TC_KT;
+    if (kt0 > 0 && p < pend) {  // first stored gene >= kt0*KT (rows are sorted by gene)
+      const int target = kt0 * KT;
       long long lo_p = p, hi_p = pend;
       while (lo_p < hi_p) {
         const long long mid = (lo_p + hi_p) >> 1;
@@ -230,34 +260,65 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_csr_dense_fwd_tc(const IdxT* 
       }
       p = lo_p;
     }
+    // Entries are consumed from a register window of TC_W (gene, value) pairs; the next window is already
+    // in flight while the current one is consumed, so the per-lane memory latency of this divergent walk
+    // is paid once per window and off the critical path (a warp otherwise stalls on its slowest lane at
+    // every entry).
     const int NONE = 0x7fffffff;
-    int c0 = p < pend ? idx[p] : NONE, c1 = p + 1 < pend ? idx[p + 1] : NONE;
-    float v0 = p < pend ? val[p] : 0.f, v1 = p + 1 < pend ? val[p + 1] : 0.f;
-    const uint32_t rsw = (uint32_t)(r & 7);
+    int cw[TC_W], cn[TC_W];
+    float vw[TC_W], vn[TC_W];
+#pragma unroll
+    for (int w = 0; w < TC_W; ++w) {
+      cw[w] = p + w < pend ? idx[p + w] : NONE;
+      vw[w] = p + w < pend ? val[p + w] : 0.f;
+    }
+#pragma unroll
+    for (int w = 0; w < TC_W; ++w) {
+      cn[w] = p + TC_W + w < pend ? idx[p + TC_W + w] : NONE;
+      vn[w] = p + TC_W + w < pend ? val[p + TC_W + w] : 0.f;
+    }
+    int wpos = 0;
     for (int i = 0; i < n_it; ++i) {
       const int s = i % stages;
       const uint32_t ph = (uint32_t)(i / stages) & 1u;
       mbar_wait(bar_empty + 8u * s, ph ^ 1u);
-      const uint32_t row_hi = base + (uint32_t)s * STAGE_BYTES + (uint32_t)r * 128u, row_lo = row_hi + TC_A_BYTES;
+      const uint32_t row_hi = base + (uint32_t)s * STAGE_BYTES + (uint32_t)half * A_HALF + (uint32_t)rl * ROWB;
+      const uint32_t row_lo = row_hi + A_PLANE;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {                // clear the row (lanes stagger the chunk: no bank conflicts)
-        const uint32_t ch = (uint32_t)((j + lane) & 7) << 4;
+      for (int j = 0; j < CPR; ++j) {              // clear the row (lanes stagger the chunk: no bank conflicts)
+        const uint32_t ch = (uint32_t)((j + lane) & (CPR - 1)) << 4;
         st_shared_zero16(row_hi + ch);
         st_shared_zero16(row_lo + ch);
       }
-      const int k0 = (kt0 + i) * TC_KT, kend = k0 + TC_KT;
-      while (c0 < kend) {
-        const uint32_t g = (uint32_t)(c0 - k0);
-        const __nv_bfloat16 h = __float2bfloat16_rn(v0);
-        const __nv_bfloat16 l = __float2bfloat16_rn(v0 - __bfloat162float(h));
-        const uint32_t off = (((g >> 3) ^ rsw) << 4) + ((g & 7u) << 1);
-        st_shared_u16(row_hi + off, __bfloat16_as_ushort(h));
-        st_shared_u16(row_lo + off, __bfloat16_as_ushort(l));
-        ++p;
-        c0 = c1;
-        v0 = v1;
-        c1 = p + 1 < pend ? idx[p + 1] : NONE;
-        v1 = p + 1 < pend ? val[p + 1] : 0.f;
+      const int k0 = (kt0 + i) * KT, kend = k0 + KT;
+      while (true) {
+#pragma unroll
+        for (int w = 0; w < TC_W; ++w) {
+          if (w >= wpos && cw[w] < kend) {
+            const uint32_t g = (uint32_t)(cw[w] - k0);
+            const __nv_bfloat16 h = __float2bfloat16_rn(vw[w]);
+            const __nv_bfloat16 l = __float2bfloat16_rn(vw[w] - __bfloat162float(h));
+            const uint32_t off = swz_chunk<KT>(g >> 3, (uint32_t)rl) + ((g & 7u) << 1);
+            st_shared_u16(row_hi + off, __bfloat16_as_ushort(h));
+            st_shared_u16(row_lo + off, __bfloat16_as_ushort(l));
+            wpos = w + 1;
+          }
+        }
+        if (wpos < TC_W) break;                    // the window still holds entries of later tiles
+        // window exhausted: the prefetched one becomes current, the one after it is requested now
+        p += TC_W;
+#pragma unroll
+        for (int w = 0; w < TC_W; ++w) {
+          cw[w] = cn[w];
+          vw[w] = vn[w];
+        }
+#pragma unroll
+        for (int w = 0; w < TC_W; ++w) {
+          cn[w] = p + TC_W + w < pend ? idx[p + TC_W + w] : NONE;
+          vn[w] = p + TC_W + w < pend ? val[p + TC_W + w] : 0.f;
+        }
+        wpos = 0;
+        if (cw[0] >= kend) break;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
       mbar_arrive(bar_full_a + 8u * s);
@@ -269,7 +330,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_csr_dense_fwd_tc(const IdxT* 
       const bool add_bias = bias && blockIdx.y == 0;
       for (int cb = 0; cb < N; cb += 32) {
         uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * N + cb);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -304,29 +365,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_csr_dense_fwd_tc(const IdxT* 
   }
 }
 
-template <typename IdxT>
+template <typename IdxT, int HALVES, int KT>
 static int launch_dense_fwd_tc(const IdxT* indptr, const int32_t* idx, const float* val, int n, int G, int H0, const void* hi,
                                const void* lo, const float* b1, float* Z, int ksplits, cudaStream_t st) {
-  const int n_kt = scnb_cdiv(G, TC_KT);
-  const int row_tiles = scnb_cdiv(n, TC_M);
-  if (ksplits <= 0) {  // auto: cover the 148 SMs when there are few row tiles
-    ksplits = 1;
-    while (row_tiles * ksplits * 2 <= 148 && ksplits * 2 <= n_kt) ksplits *= 2;
-    if (row_tiles * ksplits < 148 && row_tiles < 148) ksplits = 148 / row_tiles > n_kt ? n_kt : 148 / row_tiles;
+  constexpr int ROWS = TC_M * HALVES;
+  const int n_kt = scnb_cdiv(G, KT);
+  const int row_tiles = scnb_cdiv(n, ROWS);
+  if (ksplits <= 0) {  // auto: split the gene axis until the grid covers the 148 SMs
+    ksplits = 148 / row_tiles;
     if (ksplits < 1) ksplits = 1;
   }
   if (ksplits > n_kt) ksplits = n_kt;
-  const size_t stage_bytes = 2 * (size_t)TC_A_BYTES + 2 * (size_t)H0 * 128;
+  const size_t stage_bytes = 2 * (size_t)ROWS * 2 * KT + 2 * (size_t)H0 * 2 * KT;
   int stages = (int)((200 * 1024) / stage_bytes);
-  if (stages > 4) stages = 4;
+  if (stages > 6) stages = 6;
   if (stages < 2) {
     scnb_set_error("csr_linear_fwd_tc: H0=%d needs more shared memory than one SM has", H0);
     return SCNB_ERR_UNSUPPORTED;
   }
   const size_t smem = 1024 + stages * stage_bytes + 24 * stages + 16 + 16;
   int tmem_cols = 32;
-  while (tmem_cols < H0) tmem_cols *= 2;
-  cudaError_t e = cudaFuncSetAttribute(k_csr_dense_fwd_tc<IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  while (tmem_cols < HALVES * H0) tmem_cols *= 2;
+  cudaError_t e = cudaFuncSetAttribute(k_csr_dense_fwd_tc<IdxT, HALVES, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     scnb_set_error("csr_linear_fwd_tc: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
     return SCNB_ERR_CUDA;
@@ -339,15 +399,15 @@ static int launch_dense_fwd_tc(const IdxT* indptr, const int32_t* idx, const flo
     }
   }
   dim3 grid(row_tiles, ksplits);
-  k_csr_dense_fwd_tc<IdxT><<<grid, TC_THREADS, smem, st>>>(indptr, idx, val, n, (const uint8_t*)hi, (const uint8_t*)lo, H0, n_kt, b1, Z,
-                                                          stages, tmem_cols);
+  k_csr_dense_fwd_tc<IdxT, HALVES, KT><<<grid, 64 + 128 * HALVES, smem, st>>>(indptr, idx, val, n, (const uint8_t*)hi, (const uint8_t*)lo,
+                                                                            H0, n_kt, b1, Z, stages, tmem_cols);
   SCNB_CHECK_LAUNCH("csr_linear_fwd_tc");
   return SCNB_OK;
 }
 
 static int tc_check(int n, int G, int H0, const void* hi, const void* lo, const float* Z) {
   SCNB_CHECK_ARG(n >= 0 && G > 0 && hi && lo && Z, "csr_linear_fwd_tc: bad arguments");
-  SCNB_CHECK_ARG(H0 >= 16 && H0 <= 256 && H0 % 32 == 0, "csr_linear_fwd_tc: H0 must be a multiple of 32 in [32, 256] (got %d)", H0);
+  SCNB_CHECK_ARG(H0 >= 32 && H0 <= 256 && H0 % 32 == 0, "csr_linear_fwd_tc: H0 must be a multiple of 32 in [32, 256] (got %d)", H0);
   SCNB_CHECK_ARG((((uintptr_t)hi | (uintptr_t)lo | (uintptr_t)Z) % 16) == 0, "csr_linear_fwd_tc: buffers must be 16-byte aligned");
   return SCNB_OK;
 }
@@ -359,7 +419,8 @@ extern "C" int scnb_csr_linear_fwd_tc(const int32_t* b_indptr, const int32_t* b_
   int rc = tc_check(n, G, H0, planes_hi, planes_lo, Z);
   if (rc != SCNB_OK) return rc;
   if (n == 0) return SCNB_OK;
-  return launch_dense_fwd_tc<int32_t>(b_indptr, b_idx, b_val, n, G, H0, planes_hi, planes_lo, b1, Z, ksplits, (cudaStream_t)stream);
+  return launch_dense_fwd_tc<int32_t, 2, 32>(b_indptr, b_idx, b_val, n, G, H0, planes_hi, planes_lo, b1, Z, ksplits,
+                                             (cudaStream_t)stream);
 }
 
 extern "C" int scnb_csr_linear_fwd_tc_i64(const int64_t* indptr, const int32_t* indices, const float* data, int n, int G, int H0,
@@ -369,5 +430,6 @@ extern "C" int scnb_csr_linear_fwd_tc_i64(const int64_t* indptr, const int32_t* 
   int rc = tc_check(n, G, H0, planes_hi, planes_lo, Z);
   if (rc != SCNB_OK) return rc;
   if (n == 0) return SCNB_OK;
-  return launch_dense_fwd_tc<int64_t>(indptr, indices, data, n, G, H0, planes_hi, planes_lo, b1, Z, ksplits, (cudaStream_t)stream);
+  return launch_dense_fwd_tc<int64_t, 2, 32>(indptr, indices, data, n, G, H0, planes_hi, planes_lo, b1, Z, ksplits,
+                                             (cudaStream_t)stream);
 }

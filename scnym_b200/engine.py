@@ -18,6 +18,8 @@ Algebra exploited:
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -59,6 +61,7 @@ class EngineConfig:
     class_weight: Optional[List[float]] = None
     seed: int = 0
     use_cuda_graph: bool = True
+    first_layer: str = "auto"   # "spmm": warp-per-row CSR SpMM; "tc": densify-then-tcgen05 GEMM; "auto": env SCNB_FIRST_LAYER or spmm
     fuse_heads: bool = True      # one-warp-per-row classifier/DAN-tail/teacher-head kernels (Linear + loss + backward)
     multi_stream: bool = True    # run independent kernels of the step on side streams (parallel graph branches)
     keep_w1_grad: bool = False   # also write the first-layer gradient to HBM (parity tests; implied by data parallelism)
@@ -275,6 +278,13 @@ class TrainEngine(object):
         wmax = max(self.widths)
         self.dA = f32(R, wmax)
         self.dZs = [f32(R, w) for w in self.widths]   # one per application: weight-gradient GEMMs overlap the dA chain
+        fl = cfg.first_layer if cfg.first_layer != "auto" else os.environ.get("SCNB_FIRST_LAYER", "spmm")
+        self.tc_first = (fl == "tc") and (H0 % 32 == 0) and (32 <= H0 <= 256)
+        if self.tc_first:
+            n_kt = (self.G + 63) // 64
+            self.w1_hi = torch.zeros(n_kt * H0 * 64, dtype=torch.int16, device=dev)
+            self.w1_lo = torch.zeros(n_kt * H0 * 64, dtype=torch.int16, device=dev)
+            self._ev_planes = torch.cuda.Event()
         self._side = None
         fus = lambda c: (self.H % 128 == 0 and self.H // 128 in (1, 2, 4, 8) and c * self.H * 4 <= 96 * 1024)
         self.fuse_classif = bool(cfg.fuse_heads and fus(self.C))
@@ -343,6 +353,28 @@ class TrainEngine(object):
         if waiter is not other:
             waiter.wait_stream(other)
 
+    def _refresh_planes(self, main, sW):
+        """bf16 hi/lo planes of the current W1T for the tensor-core first layer (on the side branch, overlapping
+        the step prologue); recomputed every step because the optimizer has just changed W1T."""
+        if not self.tc_first:
+            return
+        self._after(sW, main)
+        call("scnb_w1_planes", self.P(self._blk[0]["W"]), self.G, self.widths[0], ptr(self.w1_hi), ptr(self.w1_lo), sW.cuda_stream)
+        if sW is not main:
+            self._ev_planes.record(sW)
+
+    def _first_layer(self, main, sW, n_rows, Z):
+        st = main.cuda_stream
+        blk0 = self._blk[0]
+        if self.tc_first:
+            if sW is not main:
+                main.wait_event(self._ev_planes)
+            call("scnb_csr_linear_fwd_tc", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), n_rows, self.G, self.widths[0],
+                 ptr(self.w1_hi), ptr(self.w1_lo), self.P(blk0["b"]), ptr(Z), 0, st)
+        else:
+            call("scnb_csr_linear_fwd", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), n_rows, self.P(blk0["W"]),
+                 self.P(blk0["b"]), self.widths[0], ptr(Z), st)
+
     def _prep(self, st):
         t = self._tabs or {}
         mm = self.mode == "mixmatch"
@@ -361,6 +393,7 @@ class TrainEngine(object):
         L, U, nb, R, C, H0 = self.L, self.U, self.nb, self.Rmax, self.C, self.widths[0]
         rng = ptr(self.state[1:3])
         blk = self._blk
+        self._refresh_planes(main, sW)
         self._prep(st)
         # -- batch CSR [U_raw ; L_aug] (+ per-gene histogram), one launch
         call("scnb_csr_gather_rows2", ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data), ptr(self.u_rows), U, 0, 0,
@@ -377,8 +410,7 @@ class TrainEngine(object):
             if sW is not main:
                 self._ev_csc.record(sW)
         # -- first layer, once
-        call("scnb_csr_linear_fwd", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), nb, self.P(blk[0]["W"]),
-             self.P(blk[0]["b"]), H0, ptr(self.Z1), st)
+        self._first_layer(main, sW, nb, self.Z1)
         # -- teacher (eval mode, losses.py:660-737)
         tw, tbn = self._teacher_ptrs()
         if c.mean_teacher:
@@ -673,6 +705,7 @@ class TrainEngine(object):
         L, C, H0 = self.L, self.C, self.widths[0]
         rng = ptr(self.state[1:3])
         blk = self._blk
+        self._refresh_planes(main, sW)
         self._prep(st)
         call("scnb_csr_gather_rows", ptr(self.lab.indptr), ptr(self.lab.indices), ptr(self.lab.data), ptr(self.l_rows), 0, L,
              ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), 0, 0, 0, None, None, 0, 0.0, self._gene_cnt_ptr(), st)
@@ -684,8 +717,7 @@ class TrainEngine(object):
             self._build_csc(L, sW.cuda_stream)
             if sW is not main:
                 self._ev_csc.record(sW)
-        call("scnb_csr_linear_fwd", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), L, self.P(blk[0]["W"]),
-             self.P(blk[0]["b"]), H0, ptr(self.Zs[0]), st)
+        self._first_layer(main, sW, L, self.Zs[0])
         self._student_forward(st, rng)
         Hh = self.H
         dA_last = self._view(self.dA, L, Hh)

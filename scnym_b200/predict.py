@@ -8,6 +8,9 @@ as CSR and one pass of kernels per row chunk emits argmax, probabilities/scores 
 import os
 from typing import Optional, Union
 
+# first layer of batched inference: "tc" = densify-then-tcgen05 GEMM (bf16x3), "spmm" = warp-per-row CSR SpMM
+FIRST_LAYER = os.environ.get("SCNB_PREDICT_FIRST_LAYER", "tc")
+
 import numpy as np
 import torch
 
@@ -16,7 +19,7 @@ from ._lib import call, ptr
 from .dataprep import DeviceCSR
 from .model import CellTypeCLF
 
-CHUNK_ROWS = 65536  # rows per kernel launch; eval-mode results do not depend on it
+CHUNK_ROWS = 148 * 2 * 256  # rows per kernel launch (two full waves of 256-row tensor-core tiles on 148 SMs); results do not depend on it
 
 
 class EvalRunner(object):
@@ -37,6 +40,22 @@ class EvalRunner(object):
         self.logits = f32(self.chunk, self.C)
         self.seg = torch.zeros(2, dtype=torch.int32, device=self.dev)
         self._seg_n = -1
+        H0, G = self.widths[0], m0.n_genes
+        self.use_tc = FIRST_LAYER == "tc" and H0 % 32 == 0 and 32 <= H0 <= 256
+        self.G = G
+        if self.use_tc:
+            n_kt = (G + 63) // 64
+            self.planes = [(torch.zeros(n_kt * H0 * 64, dtype=torch.int16, device=self.dev),
+                            torch.zeros(n_kt * H0 * 64, dtype=torch.int16, device=self.dev)) for _ in self.models]
+
+    def refresh_planes(self):
+        """bf16 hi/lo planes of every model's first-layer weight (call after the weights change)."""
+        if not self.use_tc:
+            return
+        st = torch.cuda.current_stream().cuda_stream
+        for model, (hi, lo) in zip(self.models, self.planes):
+            lin = model.block_modules()[0][0]
+            call("scnb_w1_planes", ptr(lin.weight_t()), self.G, self.widths[0], ptr(hi), ptr(lo), st)
 
     def _set_seg(self, n):
         if n != self._seg_n:
@@ -51,7 +70,11 @@ class EvalRunner(object):
             blocks = model.block_modules()
             for a, (lin, bn, _) in enumerate(blocks):
                 w = self.widths[a]
-                if a == 0:
+                if a == 0 and self.use_tc:
+                    hi, lo = self.planes[mi]
+                    call("scnb_csr_linear_fwd_tc_i64", ptr(ds.indptr[row0:]), ptr(ds.indices), ptr(ds.data), n, self.G, w,
+                         ptr(hi), ptr(lo), ptr(lin.bias), ptr(self.Z[0]), 0, st)
+                elif a == 0:
                     wt = lin.weight_t()
                     call("scnb_csr_linear_fwd_i64", ptr(ds.indptr[row0:]), ptr(ds.indices), ptr(ds.data), n, ptr(wt),
                          ptr(lin.bias), w, ptr(self.Z[0]), st)
@@ -76,6 +99,7 @@ class EvalRunner(object):
         prob = torch.empty((N, self.C), dtype=torch.float32, device=dev) if want_prob else None
         score = torch.empty((N, self.C), dtype=torch.float32, device=dev) if want_score else None
         embed = torch.empty((N, self.widths[-1]), dtype=torch.float32, device=dev) if want_embed else None
+        self.refresh_planes()
         for s in range(0, N, self.chunk):
             n = min(self.chunk, N - s)
             self.run_chunk(ds, row0 + s, n, pred[s:], prob[s:] if prob is not None else None,

@@ -213,6 +213,7 @@ class Trainer(object):
             pred = torch.empty(N, dtype=torch.int64, device=dev)
             scratch = torch.zeros(2, device=dev)
             cwd = None if cw is None else torch.as_tensor(cw, dtype=torch.float32, device=dev)
+            run.refresh_planes()
             for s in range(0, N, run.chunk):
                 n = min(run.chunk, N - s)
                 run.run_chunk(csr, s, n, pred[s:], None, None, None)
