@@ -33,6 +33,16 @@ WORKLOAD = ("config2: MixMatch+DAN semi-supervised train, G=20000 genes, 100k la
             "~5% CSR density, L=U=256, n_hidden_init=n_hidden=256, n_layers=2, C=16, D=2 (inferred domains), K=1, "
             "T=0.5, alpha=0.3, Adam(lr=1e-3, wd=1e-4)")
 CFG = dict(G=20000, n_lab=100_000, n_unl=100_000, density=0.05, L=256, U=256, H0=256, H=256, n_layers=2, C=16, D=2)
+# The other BASELINE.json configs (parity-test shapes; `--config N` times them, the default bench line is config 2)
+CONFIGS = {
+    2: (CFG, WORKLOAD),
+    3: (dict(G=30000, n_lab=125_000, n_unl=125_000, density=0.05, L=256, U=256, H0=256, H=256, n_layers=2, C=16, D=8, given_domains=True),
+        "config3: MixMatch+DAN with 8 given domains, G=30000 genes, 5% CSR density, per-rank L=U=256 (cells sharded over ranks; "
+        "125k labeled + 125k unlabeled per rank), n_hidden_init=n_hidden=256, n_layers=2, C=16, K=1, Adam"),
+    5: (dict(G=20000, n_lab=40_000, n_unl=40_000, density=0.20, L=4096, U=4096, H0=256, H=1024, n_layers=3, C=16, D=8, given_domains=True),
+        "config5: large-batch MixMatch+DAN, G=20000 genes, ~20% CSR density, L=U=4096, n_hidden_init=256, n_hidden=1024, n_layers=3, "
+        "C=16, D=8 given domains, K=1, Adam"),
+}
 
 
 def peaks():
@@ -102,12 +112,24 @@ def build_train(device, rank, seed_off=0, n_lab=None, n_unl=None, host_copy=Fals
     return model, dann, cfg, lab, y, unl
 
 
+def given_domains(device, n_lab, n_unl, rank):
+    """Domain ids when the config supplies them (labeled rows use domains [0, D/2), unlabeled [D/2, D))."""
+    if not CFG.get("given_domains"):
+        return None, None
+    g = torch.Generator().manual_seed(77 + rank)
+    D = CFG["D"]
+    ld = torch.randint(0, max(D // 2, 1), (n_lab,), generator=g, dtype=torch.int32).to(device)
+    ud = torch.randint(max(D // 2, 1), D, (n_unl,), generator=g, dtype=torch.int32).to(device)
+    return ld, ud
+
+
 def time_device_resident(args, device, rank, world):
     """`value`: graph-replayed steps, datasets + sampler tables resident in HBM."""
     from scnym_b200.engine import TrainEngine
     model, dann, cfg, lab, y, unl = build_train(device, rank)
+    ld, ud = given_domains(device, lab.n_rows, unl.n_rows, rank)
     eng = TrainEngine(model.to(device), cfg, lab, y.to(torch.int32), CFG["L"], unlabeled=unl, unlabeled_batch_size=CFG["U"],
-                      dann=dann, mode="mixmatch", comm=make_comm(world))
+                      dann=dann, labeled_domain=ld, unlabeled_domain=ud, mode="mixmatch", comm=make_comm(world))
     eng.set_weights(unsup_weight=1.0, dan_weight=0.1)
     n_tab = args.steps + args.warmup
     gen = torch.Generator(device=device)
@@ -322,7 +344,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-predict", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config to time (default 2)")
     args = ap.parse_args()
+    global CFG, WORKLOAD
+    CFG, WORKLOAD = CONFIGS[args.config]
+    if args.config != 2:
+        args.no_predict = args.no_cpu_baseline = True
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

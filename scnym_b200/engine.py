@@ -61,7 +61,7 @@ class EngineConfig:
     class_weight: Optional[List[float]] = None
     seed: int = 0
     use_cuda_graph: bool = True
-    first_layer: str = "auto"   # "spmm": warp-per-row CSR SpMM; "tc": densify-then-tcgen05 GEMM; "auto": env SCNB_FIRST_LAYER or spmm
+    first_layer: str = "auto"   # "spmm": warp-per-row CSR SpMM; "tc": densify-then-tcgen05 GEMM (bf16x3); "auto": tc from 512 rows per step
     fuse_heads: bool = True      # one-warp-per-row classifier/DAN-tail/teacher-head kernels (Linear + loss + backward)
     multi_stream: bool = True    # run independent kernels of the step on side streams (parallel graph branches)
     keep_w1_grad: bool = False   # also write the first-layer gradient to HBM (parity tests; implied by data parallelism)
@@ -243,6 +243,7 @@ class TrainEngine(object):
             self.Ycat = f32(self.nb, self.C)
             self.conf = f32(U)
             self.confident = torch.zeros(U, dtype=torch.uint8, device=dev)
+            self._all_confident = torch.ones(max(U, 1), dtype=torch.uint8, device=dev)
             self.pl_scratch = f32(U, self.C)
             self.lab_ids = i32(L)
             self.base_dom = i32(self.nb)
@@ -278,7 +279,11 @@ class TrainEngine(object):
         wmax = max(self.widths)
         self.dA = f32(R, wmax)
         self.dZs = [f32(R, w) for w in self.widths]   # one per application: weight-gradient GEMMs overlap the dA chain
-        fl = cfg.first_layer if cfg.first_layer != "auto" else os.environ.get("SCNB_FIRST_LAYER", "spmm")
+        # "auto": the tensor-core form pays off once the batch fills at least two 256-row tiles (measured: 512 rows,
+        # 5 % density: 22 us vs 40 us for the SpMM; 8192 rows, 20 %: ~10x); tiny batches keep the exact-fp32 SpMM
+        fl = cfg.first_layer
+        if fl == "auto":
+            fl = os.environ.get("SCNB_FIRST_LAYER", "tc" if self.nb >= 512 else "spmm")
         self.tc_first = (fl == "tc") and (H0 % 32 == 0) and (32 <= H0 <= 256)
         if self.tc_first:
             n_kt = (self.G + 63) // 64
@@ -290,6 +295,7 @@ class TrainEngine(object):
         self.fuse_classif = bool(cfg.fuse_heads and fus(self.C))
         self.fuse_dan = bool(cfg.fuse_heads and self.use_dan and fus(self.D))
         self._ev_grl, self._ev_csc, self._ev_zero = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        self._ev_teacher = torch.cuda.Event()
         self.dZ1 = f32(self.nb, H0) if mode == "mixmatch" else None
         if self.use_dan:
             self.Hd, self.dHd = f32(self.Rd, self.H), f32(self.Rd, self.H)
@@ -337,14 +343,14 @@ class TrainEngine(object):
         return (lambda name: self.arena.w(name)), (lambda a: (self._blk[a]["bn"].running_mean, self._blk[a]["bn"].running_var))
 
     # ---- stream plumbing: the step is a DAG; independent kernels go to side streams so that a captured
-    #      graph keeps only ~22 launches on its critical path (data parallelism keeps one stream: the
-    #      collectives must be issued in the same order on every rank) ----
+    #      graph keeps only ~22 launches on its critical path.  Under data parallelism every collective is
+    #      issued from the main stream, in the same order on every rank; the side branches carry compute only. ----
     def _streams(self):
         main = torch.cuda.current_stream()
-        if self.comm is not None or not self.cfg.multi_stream:
+        if not self.cfg.multi_stream:
             return main, main, main
         if self._side is None:
-            self._side = (torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev))
+            self._side = tuple(torch.cuda.Stream(device=self.dev) for _ in range(3))
         return main, self._side[0], self._side[1]
 
     @staticmethod
@@ -411,52 +417,20 @@ class TrainEngine(object):
                 self._ev_csc.record(sW)
         # -- first layer, once
         self._first_layer(main, sW, nb, self.Z1)
-        # -- teacher (eval mode, losses.py:660-737)
-        tw, tbn = self._teacher_ptrs()
-        if c.mean_teacher:
-            call("scnb_ema_update", ptr(self.teacher_flat), ptr(self.arena.flat), self.n_model_params, c.decay_coef,
-                 ptr(self.state), st)
-        K = self.K_eff
-        if self.teacher_own_spmm:
-            for k in range(K):
-                if c.augment_pseudolabels:
-                    call("scnb_csr_row_offsets", ptr(self.unl.indptr), ptr(self.u_rows), 0, U, ptr(self.tb_indptr), None, st)
-                    km = self.inj_in_keep_U[k] if self.inj_in_keep_U is not None else None
-                    call("scnb_csr_gather_rows", ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data),
-                         ptr(self.u_rows), 0, U, ptr(self.tb_indptr), ptr(self.tb_idx), ptr(self.tb_val), 1, 0, U, ptr(km), rng,
-                         SID_IN_U + k, c.p_in_drop, None, st)
-                    ip, ix, vv = self.tb_indptr, self.tb_idx, self.tb_val
-                else:
-                    ip, ix, vv = self.b_indptr, self.b_idx, self.b_val
-                call("scnb_csr_linear_fwd", ptr(ip), ptr(ix), ptr(vv), U, ptr(tw(blk[0]["W"])), ptr(tw(blk[0]["b"])), H0,
-                     ptr(self.TZ1[k * U:]), st)
-            tz = self.TZ1
+        # -- teacher (eval mode, losses.py:660-737).  With pseudolabel_min_confidence <= 0 every unlabeled row is
+        #    "confident", so the MixUp plan and the student forward do not depend on the teacher: it runs on its own
+        #    branch and is joined in front of the losses.
+        teacher_async = (c.pseudolabel_min_confidence <= 0.0) and sW is not main
+        if teacher_async:
+            sT = self._side[2]
+            self._after(sT, main)
+            self._teacher_forward(sT.cuda_stream, rng)
+            self._ev_teacher.record(sT)
         else:
-            tz = self.Z1  # rows [0, U)
-        KU = K * U
-        seg_t = self._const_seg(KU)
-        for a in range(self.n_app):
-            rm, rv = tbn(a)
-            call("scnb_bn_act_fwd", ptr(tz), ptr(self.TA[a]), None, self.widths[a], 1, ptr(seg_t), KU, 0, ptr(tw(blk[a]["g"])),
-                 ptr(tw(blk[a]["beta"])), ptr(rm), ptr(rv), None, None, None, 0, 0.0, 1, None, None, st)
-            if a + 1 < self.n_app:
-                call("scnb_sgemm", 0, 1, KU, self.widths[a + 1], self.widths[a], ptr(self.TA[a]), self.widths[a],
-                     ptr(tw(blk[a + 1]["W"])), self.widths[a], ptr(self.TZ[a + 1]), self.widths[a + 1], 1.0, 0.0,
-                     ptr(tw(blk[a + 1]["b"])), 0, None, st)
-                tz = self.TZ[a + 1]
-        pl_args = (float(c.T if c.T is not None else 1.0), int(c.T is not None), float(c.pseudolabel_min_confidence))
-        if self.fuse_classif:
-            # teacher classifier + pseudolabels q[0,U) + one-hot labels q[U,U+L) in one launch
-            call("scnb_teacher_head_fused", ptr(self.TA[-1]), ptr(tw("model.classif.0.weight")), ptr(tw("model.classif.0.bias")),
-                 self.H, C, K, U, pl_args[0], pl_args[1], pl_args[2], ptr(self.t_logits), ptr(self.Ycat), ptr(self.conf),
-                 ptr(self.confident), ptr(self.pl_scratch), ptr(self.lab_ids), L, st)
-        else:
-            call("scnb_sgemm", 0, 1, KU, C, self.H, ptr(self.TA[-1]), self.H, ptr(tw("model.classif.0.weight")), self.H,
-                 ptr(self.t_logits), C, 1.0, 0.0, ptr(tw("model.classif.0.bias")), 0, None, st)
-            call("scnb_pseudolabel", ptr(self.t_logits), K, U, C, pl_args[0], pl_args[1], pl_args[2], ptr(self.Ycat),
-                 ptr(self.conf), ptr(self.confident), ptr(self.pl_scratch), ptr(self.lab_ids), L, st)
+            self._teacher_forward(st, rng)
+        conf_flags = self._all_confident if teacher_async else self.confident
         # -- MixUp plan + hidden-space MixUp (losses.py:811-875)
-        call("scnb_mixmatch_plan", ptr(self.confident), ptr(self.perm_keys), ptr(self.gamma_raw), U, L, int(self.use_dan),
+        call("scnb_mixmatch_plan", ptr(conf_flags), ptr(self.perm_keys), ptr(self.gamma_raw), U, L, int(self.use_dan),
              int(c.dan_use_conf_pseudolabels), int(c.mixup_alpha > 0.0), ptr(self.counts), ptr(self.seg_off),
              ptr(self.plan_work), ptr(self.srcA), ptr(self.srcB), ptr(self.gam), R, ptr(self.inv3), ptr(self.coef3),
              ptr(self.pconf), st)
@@ -502,6 +476,8 @@ class TrainEngine(object):
                  0, None, sd)
             call("scnb_colsum", ptr(self.dHd), self.Rd, Hh, Hh, self.Gp(d0 + ".bias"), 1, sd)
         # -- classifier, losses + dLogits (losses.py:896-923, 1224-1243; trainer.py:651-656) and dA of the classifier
+        if teacher_async:
+            main.wait_event(self._ev_teacher)
         if self.fuse_classif:
             call("scnb_classif_mixmatch_fused", ptr(self.As[-1]), self.P("model.classif.0.weight"), self.P("model.classif.0.bias"),
                  Hh, C, U, L, ptr(self.counts), ptr(self.Ycat), ptr(self.srcA), ptr(self.srcB), ptr(self.gam),
@@ -526,6 +502,55 @@ class TrainEngine(object):
         dZ_first = self._student_backward(main, sW, rng, dA_last)
         call("scnb_unmix_rows", ptr(dZ_first), H0, ptr(self.inv3), ptr(self.coef3), nb, ptr(self.dZ1), st)
         self._finish_step(main, sW, sD, self.dZ1, nb)
+
+    def _teacher_forward(self, st, rng):
+        """Eval-mode teacher pass on stream `st`: pseudolabels q[0,U) (+ one-hot labels q[U,U+L)), confidences."""
+        c = self.cfg
+        L, U, C, H0 = self.L, self.U, self.C, self.widths[0]
+        blk = self._blk
+        tw, tbn = self._teacher_ptrs()
+        if c.mean_teacher:
+            call("scnb_ema_update", ptr(self.teacher_flat), ptr(self.arena.flat), self.n_model_params, c.decay_coef,
+                 ptr(self.state), st)
+        K = self.K_eff
+        if self.teacher_own_spmm:
+            for k in range(K):
+                if c.augment_pseudolabels:
+                    call("scnb_csr_row_offsets", ptr(self.unl.indptr), ptr(self.u_rows), 0, U, ptr(self.tb_indptr), None, st)
+                    km = self.inj_in_keep_U[k] if self.inj_in_keep_U is not None else None
+                    call("scnb_csr_gather_rows", ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data),
+                         ptr(self.u_rows), 0, U, ptr(self.tb_indptr), ptr(self.tb_idx), ptr(self.tb_val), 1, 0, U, ptr(km), rng,
+                         SID_IN_U + k, c.p_in_drop, None, st)
+                    ip, ix, vv = self.tb_indptr, self.tb_idx, self.tb_val
+                else:
+                    ip, ix, vv = self.b_indptr, self.b_idx, self.b_val
+                call("scnb_csr_linear_fwd", ptr(ip), ptr(ix), ptr(vv), U, ptr(tw(blk[0]["W"])), ptr(tw(blk[0]["b"])), H0,
+                     ptr(self.TZ1[k * U:]), st)
+            tz = self.TZ1
+        else:
+            tz = self.Z1  # rows [0, U)
+        KU = K * U
+        seg_t = self._const_seg(KU)
+        for a in range(self.n_app):
+            rm, rv = tbn(a)
+            call("scnb_bn_act_fwd", ptr(tz), ptr(self.TA[a]), None, self.widths[a], 1, ptr(seg_t), KU, 0, ptr(tw(blk[a]["g"])),
+                 ptr(tw(blk[a]["beta"])), ptr(rm), ptr(rv), None, None, None, 0, 0.0, 1, None, None, st)
+            if a + 1 < self.n_app:
+                call("scnb_sgemm", 0, 1, KU, self.widths[a + 1], self.widths[a], ptr(self.TA[a]), self.widths[a],
+                     ptr(tw(blk[a + 1]["W"])), self.widths[a], ptr(self.TZ[a + 1]), self.widths[a + 1], 1.0, 0.0,
+                     ptr(tw(blk[a + 1]["b"])), 0, None, st)
+                tz = self.TZ[a + 1]
+        pl_args = (float(c.T if c.T is not None else 1.0), int(c.T is not None), float(c.pseudolabel_min_confidence))
+        if self.fuse_classif:
+            # teacher classifier + pseudolabels q[0,U) + one-hot labels q[U,U+L) in one launch
+            call("scnb_teacher_head_fused", ptr(self.TA[-1]), ptr(tw("model.classif.0.weight")), ptr(tw("model.classif.0.bias")),
+                 self.H, C, K, U, pl_args[0], pl_args[1], pl_args[2], ptr(self.t_logits), ptr(self.Ycat), ptr(self.conf),
+                 ptr(self.confident), ptr(self.pl_scratch), ptr(self.lab_ids), L, st)
+        else:
+            call("scnb_sgemm", 0, 1, KU, C, self.H, ptr(self.TA[-1]), self.H, ptr(tw("model.classif.0.weight")), self.H,
+                 ptr(self.t_logits), C, 1.0, 0.0, ptr(tw("model.classif.0.bias")), 0, None, st)
+            call("scnb_pseudolabel", ptr(self.t_logits), K, U, C, pl_args[0], pl_args[1], pl_args[2], ptr(self.Ycat),
+                 ptr(self.conf), ptr(self.confident), ptr(self.pl_scratch), ptr(self.lab_ids), L, st)
 
     def _view(self, buf, rows, width):
         """[rows, width] contiguous view at the start of a scratch buffer."""
@@ -640,6 +665,7 @@ class TrainEngine(object):
             # data parallel: gradient only (no atomics, every gene row written), exchange, then one update pass
             call("scnb_csr_w1_bwd_optim", -1, ptr(self.c_ptr), ptr(self.c_ent), ptr(dZ1), n_rows, H0, self.G, None, self.Gp(W1),
                  None, None, None, None, st)
+            self._after(main, sW)              # every other gradient (branch W, and branch D through it) is complete
             self.comm.all_reduce_avg(ar.grad)  # NCCL over NVLink
             call("scnb_optim_step", opt, ptr(ar.flat), ptr(ar.grad), ptr(ar.state1), ptr(ar.state2), ar.total, hp, s4, st)
         else:
