@@ -99,6 +99,20 @@ int scnb_csr_linear_fwd_tc_i64(const int64_t* indptr, const int32_t* indices, co
                                const void* planes_hi, const void* planes_lo, const float* b1, float* Z, int ksplits,
                                void* stream);
 
+/* Tensor-core hidden layers for batched predict: nn.Linear weights as B planes (scnb_linear_planes), eval-mode
+ * BatchNorm->ReLU that also emits its output as tiled bf16 A planes (scnb_bn_eval_planes; A_out / pre_out / planes
+ * may each be NULL), and Y = A W^T + b from planes only (scnb_linear_fwd_tc_planes).  Plane sizes in bf16 elements:
+ * A: ceil(n/256)*256 * K;  W: N * ceil(K/32)*32. */
+int scnb_linear_planes(const float* W /*[N,K]*/, int N, int K, void* planes_hi, void* planes_lo, void* stream);
+int scnb_bn_eval_planes(const float* Z, int n_rows, int H, const float* gamma, const float* beta, const float* running_mean,
+                        const float* running_var, int relu, float* A_out, float* pre_out, void* planes_hi, void* planes_lo,
+                        void* stream);
+int scnb_linear_fwd_tc_planes(const void* a_hi, const void* a_lo, int n, int K, int N, const void* w_hi, const void* w_lo,
+                              const float* bias, float* Y, void* stream);
+/* out[n,C] (+)= A[n,H] W[C,H]^T + b for a small C (classifier logits of predict; one warp per row). */
+int scnb_head_logits(const float* A, const float* W, const float* b, int H, int C, int n, float* out, int accumulate,
+                     void* stream);
+
 /* ---- K8+K9 fused: first-layer weight gradient AND optimizer.step() for W1T in one pass
  *      (scnym/model.py:211 backward + scnym/trainer.py:671 / torch.optim rules, scnym/main.py:36-41,374-396).
  *      The batch is first transposed to gene-major order ("batch CSC"): gene_cnt[G] is the histogram

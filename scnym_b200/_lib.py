@@ -27,6 +27,10 @@ SIGNATURES = {
     "scnb_w1_planes": [P, I, I, P, P, P],
     "scnb_csr_linear_fwd_tc": [P, P, P, I, I, I, P, P, P, P, I, P],
     "scnb_csr_linear_fwd_tc_i64": [P, P, P, I, I, I, P, P, P, P, I, P],
+    "scnb_linear_planes": [P, I, I, P, P, P],
+    "scnb_bn_eval_planes": [P, I, I, P, P, P, P, I, P, P, P, P, P],
+    "scnb_linear_fwd_tc_planes": [P, P, I, I, I, P, P, P, P, P],
+    "scnb_head_logits": [P, P, P, I, I, I, P, I, P],
     "scnb_csc_count": [P, P, I, P, P],
     "scnb_csr_to_csc": [P, P, P, I, I, P, P, P, P, P],
     "scnb_csr_w1_bwd_optim": [I, P, P, P, I, I, I, P, P, P, P, P, P, P],

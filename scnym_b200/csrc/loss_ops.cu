@@ -905,3 +905,61 @@ extern "C" int scnb_teacher_head_fused(const float* TA, const float* Wc, const f
   SCNB_CHECK_LAUNCH("teacher_head_fused");
   return SCNB_OK;
 }
+
+// Small-output Linear for inference: out[r, :] (+)= A[r, :] W^T + b with C <= a few dozen outputs (the classifier,
+// scnym/model.py:229, in Predicter.predict scnym/predict.py:178-192).  One warp per row, weights in shared memory.
+template <int NV>
+__global__ void __launch_bounds__(256) k_head_logits(const float* __restrict__ A, const float* __restrict__ W,
+                                                     const float* __restrict__ b, int H, int C, int n, float* __restrict__ out,
+                                                     int accumulate) {
+  PDL_ENTRY();
+  extern __shared__ __align__(16) float Ws[];
+  stage_weights(Ws, W, C * H);
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n; r += gridDim.x * wpb) {
+    float4 a[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) a[i] = *reinterpret_cast<const float4*>(A + (size_t)r * H + (i * 32 + lane) * 4);
+    for (int c = 0; c < C; ++c) {
+      float p = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float4 w = *reinterpret_cast<const float4*>(Ws + (size_t)c * H + (i * 32 + lane) * 4);
+        p = fmaf(a[i].x, w.x, p);
+        p = fmaf(a[i].y, w.y, p);
+        p = fmaf(a[i].z, w.z, p);
+        p = fmaf(a[i].w, w.w, p);
+      }
+      p = warp_sum(p);
+      if (lane == (c & 31)) {
+        float v = p + (b ? b[c] : 0.f);
+        if (accumulate) v += out[(size_t)r * C + c];
+        out[(size_t)r * C + c] = v;
+      }
+    }
+  }
+}
+
+extern "C" int scnb_head_logits(const float* A, const float* W, const float* b, int H, int C, int n, float* out, int accumulate,
+                                void* stream) {
+  SCNB_CHECK_ARG(A && W && out && H > 0 && C > 0 && n >= 0, "head_logits: bad arguments");
+  if (!head_fusable(H, C, A, W, W) || (H / 128 != 1 && H / 128 != 2 && H / 128 != 4 && H / 128 != 8)) return SCNB_ERR_UNSUPPORTED;
+  if (n == 0) return SCNB_OK;
+  const size_t smem = (size_t)C * H * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nv = H / 128;
+  const int blocks = scnb_cdiv(n, 8) < 148 * 8 ? scnb_cdiv(n, 8) : 148 * 8;
+#define HL_GO(NV_)                                                                                                  \
+  do {                                                                                                              \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_head_logits<NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    k_head_logits<NV_><<<blocks, 256, smem, st>>>(A, W, b, H, C, n, out, accumulate);                               \
+  } while (0)
+  if (nv == 1) HL_GO(1);
+  else if (nv == 2) HL_GO(2);
+  else if (nv == 4) HL_GO(4);
+  else HL_GO(8);
+#undef HL_GO
+  SCNB_CHECK_LAUNCH("head_logits");
+  return SCNB_OK;
+}

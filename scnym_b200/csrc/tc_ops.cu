@@ -97,16 +97,24 @@ __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
 // n*2KT + swizzle(chunk k>>3, row n) + (k&7)*2   (K-major rows of 2KT bytes, 16-byte chunks XOR-swizzled by row).
 // ---------------------------------------------------------------------------------------------
 template <int KT>
-__global__ void __launch_bounds__(256) k_w1_planes(const float* __restrict__ W1T, int G, int H0, uint16_t* __restrict__ hi,
-                                                   uint16_t* __restrict__ lo) {
+__global__ void __launch_bounds__(256) k_w1_planes(const float* __restrict__ W1T, int G, int H0, long long ld_k, long long ld_n,
+                                                   uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
   extern __shared__ float wt[];  // [KT][H0 + 1]
   constexpr int CPR = KT / 8;    // 16-byte chunks per row
   const int kt = blockIdx.x, tid = threadIdx.x;
   const int S = H0 + 1;
-  for (int e = tid; e < KT * H0; e += 256) {
-    const int k = e / H0, n = e - k * H0;
-    const int g = kt * KT + k;
-    wt[k * S + n] = g < G ? W1T[(size_t)g * H0 + n] : 0.f;
+  if (ld_n == 1) {            // [K, N] storage (first-layer W1T): consecutive threads walk n
+    for (int e = tid; e < KT * H0; e += 256) {
+      const int k = e / H0, n = e - k * H0;
+      const int g = kt * KT + k;
+      wt[k * S + n] = g < G ? W1T[(size_t)g * ld_k + n] : 0.f;
+    }
+  } else {                    // [N, K] storage (nn.Linear weight): consecutive threads walk k
+    for (int e = tid; e < KT * H0; e += 256) {
+      const int n = e / KT, k = e - n * KT;
+      const int g = kt * KT + k;
+      wt[k * S + n] = g < G ? W1T[(size_t)g * ld_k + (size_t)n * ld_n] : 0.f;
+    }
   }
   __syncthreads();
   const size_t tile = (size_t)kt * H0 * KT;  // elements per plane tile
@@ -138,12 +146,106 @@ extern "C" int scnb_w1_planes(const float* W1T, int G, int H0, void* planes_hi, 
   const size_t smem = (size_t)KT * (H0 + 1) * sizeof(float);
   if (KT == 64) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_w1_planes<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_w1_planes<64><<<n_kt, 256, smem, (cudaStream_t)stream>>>(W1T, G, H0, (uint16_t*)planes_hi, (uint16_t*)planes_lo);
+    k_w1_planes<64><<<n_kt, 256, smem, (cudaStream_t)stream>>>(W1T, G, H0, (long long)H0, 1ll, (uint16_t*)planes_hi, (uint16_t*)planes_lo);
   } else {
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_w1_planes<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_w1_planes<32><<<n_kt, 256, smem, (cudaStream_t)stream>>>(W1T, G, H0, (uint16_t*)planes_hi, (uint16_t*)planes_lo);
+    k_w1_planes<32><<<n_kt, 256, smem, (cudaStream_t)stream>>>(W1T, G, H0, (long long)H0, 1ll, (uint16_t*)planes_hi, (uint16_t*)planes_lo);
   }
   SCNB_CHECK_LAUNCH("w1_planes");
+  return SCNB_OK;
+}
+
+// Same planes for an nn.Linear weight W [N = out_features, K = in_features] (row-major): the B operand of
+// Y = A W^T on the tensor-core path (scnym/model.py:218 hidden layers).
+extern "C" int scnb_linear_planes(const float* W, int N, int K, void* planes_hi, void* planes_lo, void* stream) {
+  SCNB_CHECK_ARG(W && planes_hi && planes_lo && N > 0 && K > 0 && N % 8 == 0, "linear_planes: bad arguments");
+  SCNB_CHECK_ARG((((uintptr_t)planes_hi | (uintptr_t)planes_lo) % 16) == 0, "linear_planes: planes must be 16-byte aligned");
+  const int n_kt = scnb_cdiv(K, 32);
+  const size_t smem = (size_t)32 * (N + 1) * sizeof(float);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k_w1_planes<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_w1_planes<32><<<n_kt, 256, smem, (cudaStream_t)stream>>>(W, K, N, 1ll, (long long)K, (uint16_t*)planes_hi, (uint16_t*)planes_lo);
+  SCNB_CHECK_LAUNCH("linear_planes");
+  return SCNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Eval-mode BatchNorm -> ReLU that ALSO emits its output as the A operand of the next tensor-core GEMM:
+// two bf16 planes tiled [row tile of 256][k tile of 32] in the SWIZZLE_64B shared-memory image layout
+// (so the GEMM brings a tile in with one bulk copy).  Rows >= n_rows of the last tile are written as zeros.
+// One thread per (row, 8-column group).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bn_eval_planes(const float* __restrict__ Z, int n_rows, int H,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        const float* __restrict__ rmean, const float* __restrict__ rvar,
+                                                        int relu, float* __restrict__ A_out, float* __restrict__ pre_out,
+                                                        uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+  const int Hg = H >> 3;
+  const long long rows_pad = ((long long)n_rows + 255) / 256 * 256;
+  const long long total = rows_pad * Hg;
+  const int n_kt = H >> 5;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / Hg;
+    const int cg = (int)(e - r * Hg), c0 = cg * 8;
+    float y[8];
+    if (r < n_rows) {
+      const float4 z0 = *reinterpret_cast<const float4*>(Z + r * H + c0), z1 = *reinterpret_cast<const float4*>(Z + r * H + c0 + 4);
+      const float z[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        y[j] = (z[j] - rmean[c]) * (1.0f / sqrtf(rvar[c] + 1e-5f)) * gamma[c] + beta[c];
+      }
+      if (pre_out) {
+        *reinterpret_cast<float4*>(pre_out + r * H + c0) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(pre_out + r * H + c0 + 4) = make_float4(y[4], y[5], y[6], y[7]);
+      }
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
+      }
+      if (A_out) {
+        *reinterpret_cast<float4*>(A_out + r * H + c0) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(A_out + r * H + c0 + 4) = make_float4(y[4], y[5], y[6], y[7]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = 0.f;
+    }
+    if (hi) {
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(y[2 * j]), h1 = __float2bfloat16_rn(y[2 * j + 1]);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(y[2 * j] - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(y[2 * j + 1] - __bfloat162float(h1));
+        h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        l[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      }
+      const long long rt = r >> 8;
+      const uint32_t rr = (uint32_t)(r & 255), rl = rr & 127u;
+      const int kt = cg >> 2;
+      const size_t tile = ((size_t)rt * n_kt + kt) * (256 * 32);             // bf16 elements per (row tile, k tile)
+      const size_t off = tile + (size_t)rr * 32 + (size_t)(swz_chunk<32>((uint32_t)(cg & 3), rl) >> 1);
+      *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+  }
+}
+
+extern "C" int scnb_bn_eval_planes(const float* Z, int n_rows, int H, const float* gamma, const float* beta,
+                                   const float* running_mean, const float* running_var, int relu, float* A_out, float* pre_out,
+                                   void* planes_hi, void* planes_lo, void* stream) {
+  SCNB_CHECK_ARG(Z && gamma && beta && running_mean && running_var && n_rows >= 0 && H > 0 && H % 32 == 0,
+                 "bn_eval_planes: bad arguments (H must be a multiple of 32)");
+  SCNB_CHECK_ARG((planes_hi == nullptr) == (planes_lo == nullptr), "bn_eval_planes: give both planes or neither");
+  SCNB_CHECK_ARG((((uintptr_t)Z | (uintptr_t)A_out | (uintptr_t)pre_out | (uintptr_t)planes_hi | (uintptr_t)planes_lo) % 16) == 0,
+                 "bn_eval_planes: buffers must be 16-byte aligned");
+  if (n_rows == 0) return SCNB_OK;
+  const long long total = ((long long)n_rows + 255) / 256 * 256 * (H / 8);
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  k_bn_eval_planes<<<blocks, 256, 0, (cudaStream_t)stream>>>(Z, n_rows, H, gamma, beta, running_mean, running_var, relu, A_out,
+                                                            pre_out, (uint16_t*)planes_hi, (uint16_t*)planes_lo);
+  SCNB_CHECK_LAUNCH("bn_eval_planes");
   return SCNB_OK;
 }
 
@@ -151,11 +253,14 @@ extern "C" int scnb_w1_planes(const float* W1T, int G, int H0, void* planes_hi, 
 // Roles: warp 0 = W1T tile loader, warp 1 = TMEM allocation + MMA issuer, warps 2..2+4*HALVES-1 = densify
 // (one thread per row of the CTA's tile) and, afterwards, epilogue (TMEM -> registers -> Z).
 // ---------------------------------------------------------------------------------------------
-template <typename IdxT, int HALVES, int KT>
+// DENSE_A: the A operand is not densified from a CSR but arrives as pre-tiled bf16 planes (a_hi / a_lo, written by
+// scnb_bn_eval_planes) that the loader thread bulk-copies next to the W tiles; warps 2.. then only run the epilogue.
+template <typename IdxT, int HALVES, int KT, bool DENSE_A>
 __global__ void __launch_bounds__(64 + 128 * HALVES, 1)
 k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ idx, const float* __restrict__ val, int n_rows,
                    const uint8_t* __restrict__ planes_hi, const uint8_t* __restrict__ planes_lo, int N, int n_ktiles,
-                   const float* __restrict__ bias, float* __restrict__ Z, int stages, int tmem_cols) {
+                   const float* __restrict__ bias, float* __restrict__ Z, int stages, int tmem_cols,
+                   const uint8_t* __restrict__ a_hi_planes, const uint8_t* __restrict__ a_lo_planes) {
   constexpr uint32_t ROWB = 2 * KT;                       // bytes per operand row (bf16)
   constexpr uint32_t A_HALF = TC_M * ROWB;                // one 128-row A block of one plane
   constexpr uint32_t A_PLANE = HALVES * A_HALF;
@@ -204,10 +309,15 @@ k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ 
         const uint32_t ph = (uint32_t)(i / stages) & 1u;
         mbar_wait(bar_empty + 8u * s, ph ^ 1u);
         const uint32_t stage = base + (uint32_t)s * STAGE_BYTES;
-        mbar_arrive_expect_tx(bar_full_b + 8u * s, 2u * B_BYTES);
+        mbar_arrive_expect_tx(bar_full_b + 8u * s, 2u * B_BYTES + (DENSE_A ? 2u * A_PLANE : 0u));
         const size_t off = (size_t)(kt0 + i) * B_BYTES;
         bulk_g2s(stage + 2u * A_PLANE, planes_hi + off, B_BYTES, bar_full_b + 8u * s);
         bulk_g2s(stage + 2u * A_PLANE + B_BYTES, planes_lo + off, B_BYTES, bar_full_b + 8u * s);
+        if (DENSE_A) {
+          const size_t aoff = ((size_t)blockIdx.x * n_ktiles + (size_t)(kt0 + i)) * A_PLANE;
+          bulk_g2s(stage, a_hi_planes + aoff, A_PLANE, bar_full_b + 8u * s);
+          bulk_g2s(stage + A_PLANE, a_lo_planes + aoff, A_PLANE, bar_full_b + 8u * s);
+        }
       }
     }
   } else if (warp == 1) {
@@ -218,7 +328,7 @@ k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ 
         const int s = i % stages;
         const uint32_t ph = (uint32_t)(i / stages) & 1u;
         mbar_wait(bar_full_b + 8u * s, ph);
-        mbar_wait(bar_full_a + 8u * s, ph);
+        if (!DENSE_A) mbar_wait(bar_full_a + 8u * s, ph);
         tc_fence_after();
         const uint32_t stage = base + (uint32_t)s * STAGE_BYTES;
         const uint64_t b_hi = umma_desc_kmajor<KT>(stage + 2u * A_PLANE), b_lo = umma_desc_kmajor<KT>(stage + 2u * A_PLANE + B_BYTES);
@@ -247,7 +357,7 @@ k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ 
     const int r = half * TC_M + rl;               // row within the CTA tile
     const long long grow = (long long)blockIdx.x * ROWS + r;
     long long p = 0, pend = 0;
-    if (grow < n_rows) {
+    if (!DENSE_A && grow < n_rows) {
       p = (long long)indptr[grow];
       pend = (long long)indptr[grow + 1];
     }
@@ -277,8 +387,12 @@ k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ 
       cn[w] = p + TC_W + w < pend ? idx[p + TC_W + w] : NONE;
       vn[w] = p + TC_W + w < pend ? val[p + TC_W + w] : 0.f;
     }
-    int wpos = 0;
-    for (int i = 0; i < n_it; ++i) {
+    // The head of the window is always cw[0] (consumed entries are shifted out), so every lane that still has an
+    // entry for this tile executes the SAME store instruction: one shared-memory wavefront group per step of the
+    // loop instead of one per lane (the MMA reads its operands from the same shared memory; stores that
+    // serialise per lane take the bandwidth it needs).
+    int cnt = TC_W;                                // entries of the current window not yet consumed (incl. NONE padding)
+    for (int i = 0; i < (DENSE_A ? 0 : n_it); ++i) {
       const int s = i % stages;
       const uint32_t ph = (uint32_t)(i / stages) & 1u;
       mbar_wait(bar_empty + 8u * s, ph ^ 1u);
@@ -292,19 +406,22 @@ k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ 
       }
       const int k0 = (kt0 + i) * KT, kend = k0 + KT;
       while (true) {
+        while (cw[0] < kend) {
+          const uint32_t g = (uint32_t)(cw[0] - k0);
+          const __nv_bfloat16 h = __float2bfloat16_rn(vw[0]);
+          const __nv_bfloat16 l = __float2bfloat16_rn(vw[0] - __bfloat162float(h));
+          const uint32_t off = swz_chunk<KT>(g >> 3, (uint32_t)rl) + ((g & 7u) << 1);
+          st_shared_u16(row_hi + off, __bfloat16_as_ushort(h));
+          st_shared_u16(row_lo + off, __bfloat16_as_ushort(l));
 #pragma unroll
-        for (int w = 0; w < TC_W; ++w) {
-          if (w >= wpos && cw[w] < kend) {
-            const uint32_t g = (uint32_t)(cw[w] - k0);
-            const __nv_bfloat16 h = __float2bfloat16_rn(vw[w]);
-            const __nv_bfloat16 l = __float2bfloat16_rn(vw[w] - __bfloat162float(h));
-            const uint32_t off = swz_chunk<KT>(g >> 3, (uint32_t)rl) + ((g & 7u) << 1);
-            st_shared_u16(row_hi + off, __bfloat16_as_ushort(h));
-            st_shared_u16(row_lo + off, __bfloat16_as_ushort(l));
-            wpos = w + 1;
+          for (int w = 0; w + 1 < TC_W; ++w) {     // shift the window: the next entry becomes the head
+            cw[w] = cw[w + 1];
+            vw[w] = vw[w + 1];
           }
+          cw[TC_W - 1] = NONE;
+          --cnt;
         }
-        if (wpos < TC_W) break;                    // the window still holds entries of later tiles
+        if (cnt > 0) break;                        // the head belongs to a later tile (or the row is finished)
         // window exhausted: the prefetched one becomes current, the one after it is requested now
         p += TC_W;
 #pragma unroll
@@ -317,7 +434,7 @@ k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ 
           cn[w] = p + TC_W + w < pend ? idx[p + TC_W + w] : NONE;
           vn[w] = p + TC_W + w < pend ? val[p + TC_W + w] : 0.f;
         }
-        wpos = 0;
+        cnt = TC_W;
         if (cw[0] >= kend) break;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
@@ -365,9 +482,10 @@ k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ 
   }
 }
 
-template <typename IdxT, int HALVES, int KT>
+template <typename IdxT, int HALVES, int KT, bool DENSE_A>
 static int launch_dense_fwd_tc(const IdxT* indptr, const int32_t* idx, const float* val, int n, int G, int H0, const void* hi,
-                               const void* lo, const float* b1, float* Z, int ksplits, cudaStream_t st) {
+                               const void* lo, const float* b1, float* Z, int ksplits, cudaStream_t st, const void* a_hi = nullptr,
+                               const void* a_lo = nullptr) {
   constexpr int ROWS = TC_M * HALVES;
   const int n_kt = scnb_cdiv(G, KT);
   const int row_tiles = scnb_cdiv(n, ROWS);
@@ -386,7 +504,7 @@ static int launch_dense_fwd_tc(const IdxT* indptr, const int32_t* idx, const flo
   const size_t smem = 1024 + stages * stage_bytes + 24 * stages + 16 + 16;
   int tmem_cols = 32;
   while (tmem_cols < HALVES * H0) tmem_cols *= 2;
-  cudaError_t e = cudaFuncSetAttribute(k_csr_dense_fwd_tc<IdxT, HALVES, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_csr_dense_fwd_tc<IdxT, HALVES, KT, DENSE_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     scnb_set_error("csr_linear_fwd_tc: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
     return SCNB_ERR_CUDA;
@@ -399,8 +517,9 @@ static int launch_dense_fwd_tc(const IdxT* indptr, const int32_t* idx, const flo
     }
   }
   dim3 grid(row_tiles, ksplits);
-  k_csr_dense_fwd_tc<IdxT, HALVES, KT><<<grid, 64 + 128 * HALVES, smem, st>>>(indptr, idx, val, n, (const uint8_t*)hi, (const uint8_t*)lo,
-                                                                            H0, n_kt, b1, Z, stages, tmem_cols);
+  k_csr_dense_fwd_tc<IdxT, HALVES, KT, DENSE_A><<<grid, 64 + 128 * HALVES, smem, st>>>(
+      indptr, idx, val, n, (const uint8_t*)hi, (const uint8_t*)lo, H0, n_kt, b1, Z, stages, tmem_cols, (const uint8_t*)a_hi,
+      (const uint8_t*)a_lo);
   SCNB_CHECK_LAUNCH("csr_linear_fwd_tc");
   return SCNB_OK;
 }
@@ -419,7 +538,7 @@ extern "C" int scnb_csr_linear_fwd_tc(const int32_t* b_indptr, const int32_t* b_
   int rc = tc_check(n, G, H0, planes_hi, planes_lo, Z);
   if (rc != SCNB_OK) return rc;
   if (n == 0) return SCNB_OK;
-  return launch_dense_fwd_tc<int32_t, 2, 32>(b_indptr, b_idx, b_val, n, G, H0, planes_hi, planes_lo, b1, Z, ksplits,
+  return launch_dense_fwd_tc<int32_t, 2, 32, false>(b_indptr, b_idx, b_val, n, G, H0, planes_hi, planes_lo, b1, Z, ksplits,
                                              (cudaStream_t)stream);
 }
 
@@ -430,6 +549,20 @@ extern "C" int scnb_csr_linear_fwd_tc_i64(const int64_t* indptr, const int32_t* 
   int rc = tc_check(n, G, H0, planes_hi, planes_lo, Z);
   if (rc != SCNB_OK) return rc;
   if (n == 0) return SCNB_OK;
-  return launch_dense_fwd_tc<int64_t, 2, 32>(indptr, indices, data, n, G, H0, planes_hi, planes_lo, b1, Z, ksplits,
+  return launch_dense_fwd_tc<int64_t, 2, 32, false>(indptr, indices, data, n, G, H0, planes_hi, planes_lo, b1, Z, ksplits,
                                              (cudaStream_t)stream);
+}
+
+// Y[n, N] = A[n, K] W[N, K]^T + b with both operands given as pre-tiled bf16 hi/lo planes
+// (A: scnb_bn_eval_planes, W: scnb_linear_planes): the hidden nn.Linear layers of batched predict
+// (scnym/model.py:218; scnym/predict.py:178-192) on tcgen05.
+extern "C" int scnb_linear_fwd_tc_planes(const void* a_hi, const void* a_lo, int n, int K, int N, const void* w_hi, const void* w_lo,
+                                         const float* bias, float* Y, void* stream) {
+  SCNB_CHECK_ARG(a_hi && a_lo && w_hi && w_lo && Y && n >= 0 && K > 0 && K % 32 == 0, "linear_fwd_tc_planes: bad arguments");
+  SCNB_CHECK_ARG(N >= 32 && N <= 256 && N % 32 == 0, "linear_fwd_tc_planes: N must be a multiple of 32 in [32, 256] (got %d)", N);
+  SCNB_CHECK_ARG((((uintptr_t)a_hi | (uintptr_t)a_lo | (uintptr_t)w_hi | (uintptr_t)w_lo | (uintptr_t)Y) % 16) == 0,
+                 "linear_fwd_tc_planes: buffers must be 16-byte aligned");
+  if (n == 0) return SCNB_OK;
+  return launch_dense_fwd_tc<int32_t, 2, 32, true>(nullptr, nullptr, nullptr, n, K, N, w_hi, w_lo, bias, Y, 1, (cudaStream_t)stream,
+                                                   a_hi, a_lo);
 }

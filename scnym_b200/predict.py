@@ -43,19 +43,33 @@ class EvalRunner(object):
         H0, G = self.widths[0], m0.n_genes
         self.use_tc = FIRST_LAYER == "tc" and H0 % 32 == 0 and 32 <= H0 <= 256
         self.G = G
+        i16 = lambda n: torch.zeros(n, dtype=torch.int16, device=self.dev)
         if self.use_tc:
             n_kt = (G + 63) // 64
-            self.planes = [(torch.zeros(n_kt * H0 * 64, dtype=torch.int16, device=self.dev),
-                            torch.zeros(n_kt * H0 * 64, dtype=torch.int16, device=self.dev)) for _ in self.models]
+            self.planes = [(i16(n_kt * H0 * 64), i16(n_kt * H0 * 64)) for _ in self.models]
+        # hidden layers a >= 1 on tcgen05 when their widths allow it: A planes come from the previous BN kernel
+        ok = lambda a: (self.widths[a] % 32 == 0 and 32 <= self.widths[a] <= 256 and self.widths[a - 1] % 32 == 0)
+        self.tc_hidden = [FIRST_LAYER == "tc" and a >= 1 and ok(a) for a in range(len(self.widths))]
+        rows_pad = (self.chunk + 255) // 256 * 256
+        self.a_planes = [((i16(rows_pad * self.widths[a - 1]), i16(rows_pad * self.widths[a - 1])) if self.tc_hidden[a] else None)
+                         for a in range(len(self.widths))]
+        self.w_planes = [[((i16(self.widths[a] * self.widths[a - 1]), i16(self.widths[a] * self.widths[a - 1]))
+                           if self.tc_hidden[a] else None) for a in range(len(self.widths))] for _ in self.models]
+        H = self.widths[-1]
+        self.fuse_head = (H % 128 == 0 and H // 128 in (1, 2, 4, 8) and self.C * H * 4 <= 96 * 1024)
 
     def refresh_planes(self):
-        """bf16 hi/lo planes of every model's first-layer weight (call after the weights change)."""
-        if not self.use_tc:
-            return
+        """bf16 hi/lo planes of every model's Linear weights (call after the weights change)."""
         st = torch.cuda.current_stream().cuda_stream
-        for model, (hi, lo) in zip(self.models, self.planes):
-            lin = model.block_modules()[0][0]
-            call("scnb_w1_planes", ptr(lin.weight_t()), self.G, self.widths[0], ptr(hi), ptr(lo), st)
+        for mi, model in enumerate(self.models):
+            blocks = model.block_modules()
+            if self.use_tc:
+                hi, lo = self.planes[mi]
+                call("scnb_w1_planes", ptr(blocks[0][0].weight_t()), self.G, self.widths[0], ptr(hi), ptr(lo), st)
+            for a in range(1, len(blocks)):
+                if self.tc_hidden[a]:
+                    hi, lo = self.w_planes[mi][a]
+                    call("scnb_linear_planes", ptr(blocks[a][0].weight), self.widths[a], self.widths[a - 1], ptr(hi), ptr(lo), st)
 
     def _set_seg(self, n):
         if n != self._seg_n:
@@ -68,6 +82,7 @@ class EvalRunner(object):
         self._set_seg(n)
         for mi, model in enumerate(self.models):
             blocks = model.block_modules()
+            n_blk = len(blocks)
             for a, (lin, bn, _) in enumerate(blocks):
                 w = self.widths[a]
                 if a == 0 and self.use_tc:
@@ -78,18 +93,33 @@ class EvalRunner(object):
                     wt = lin.weight_t()
                     call("scnb_csr_linear_fwd_i64", ptr(ds.indptr[row0:]), ptr(ds.indices), ptr(ds.data), n, ptr(wt),
                          ptr(lin.bias), w, ptr(self.Z[0]), st)
+                elif self.tc_hidden[a]:
+                    (ahi, alo), (whi, wlo) = self.a_planes[a], self.w_planes[mi][a]
+                    call("scnb_linear_fwd_tc_planes", ptr(ahi), ptr(alo), n, self.widths[a - 1], w, ptr(whi), ptr(wlo),
+                         ptr(lin.bias), ptr(self.Z[a]), st)
                 else:
                     wp = self.widths[a - 1]
                     call("scnb_sgemm", 0, 1, n, w, wp, ptr(self.A[a - 1]), wp, ptr(lin.weight), wp, ptr(self.Z[a]), w, 1.0, 0.0,
                          ptr(lin.bias), 0, None, st)
-                last = a == len(blocks) - 1
+                last = a == n_blk - 1
                 pre = embed if (last and mi == 0 and embed is not None) else None
-                call("scnb_bn_act_fwd", ptr(self.Z[a]), ptr(self.A[a]), ptr(pre), w, 1, ptr(self.seg), n, 0, ptr(bn.weight),
-                     ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var), None, None, None, 0, 0.0, 1, None, None, st)
+                nxt_tc = (not last) and self.tc_hidden[a + 1]
+                if nxt_tc and w % 32 == 0:
+                    # BatchNorm -> ReLU whose output goes straight into the next layer's tensor-core operand planes
+                    ahi, alo = self.a_planes[a + 1]
+                    call("scnb_bn_eval_planes", ptr(self.Z[a]), n, w, ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean),
+                         ptr(bn.running_var), 1, None, ptr(pre), ptr(ahi), ptr(alo), st)
+                else:
+                    call("scnb_bn_act_fwd", ptr(self.Z[a]), ptr(self.A[a]), ptr(pre), w, 1, ptr(self.seg), n, 0, ptr(bn.weight),
+                         ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var), None, None, None, 0, 0.0, 1, None, None, st)
             clf = model.classif[0]
             H = self.widths[-1]
-            call("scnb_sgemm", 0, 1, n, self.C, H, ptr(self.A[-1]), H, ptr(clf.weight), H, ptr(self.logits), self.C, 1.0,
-                 0.0 if mi == 0 else 1.0, ptr(clf.bias), 0, None, st)
+            if self.fuse_head:
+                call("scnb_head_logits", ptr(self.A[-1]), ptr(clf.weight), ptr(clf.bias), H, self.C, n, ptr(self.logits),
+                     0 if mi == 0 else 1, st)
+            else:
+                call("scnb_sgemm", 0, 1, n, self.C, H, ptr(self.A[-1]), H, ptr(clf.weight), H, ptr(self.logits), self.C, 1.0,
+                     0.0 if mi == 0 else 1.0, ptr(clf.bias), 0, None, st)
         call("scnb_predict_head", ptr(self.logits), len(self.models), n, self.C, ptr(pred), ptr(prob), ptr(score), st)
 
     def run(self, ds: DeviceCSR, want_prob=True, want_score=False, want_embed=False, row0: int = 0, n_rows: Optional[int] = None):

@@ -521,3 +521,38 @@ def test_csr_linear_fwd_tensor_core_matches_dense(n, G, H0, ksplits):
     call("scnb_csr_linear_fwd_tc", ptr(b.indptr), ptr(b.indices), ptr(b.data), n, G, H0, ptr(hi), ptr(lo), None, ptr(Z2), ksplits, _st())
     torch.cuda.synchronize()
     _chk("tc fwd batch", Z2.cpu(), X[rows].double() @ WT.double(), tol=3e-5)
+
+
+@pytest.mark.parametrize("n,K,N", [(300, 256, 256), (1000, 64, 128), (5, 32, 32)])
+def test_tensor_core_hidden_layer_from_planes(n, K, N):
+    """BatchNorm(eval)->ReLU emitting bf16 operand planes, nn.Linear weight planes, Y = A W^T + b on tcgen05."""
+    from scnym_b200._lib import call, ptr
+    torch.manual_seed(n + K)
+    Z = torch.randn(n, K)
+    g, b, rm, rv = torch.rand(K) + 0.5, torch.randn(K) * 0.3, torch.randn(K) * 0.2, torch.rand(K) + 0.5
+    W, bias = torch.randn(N, K) * 0.1, torch.randn(N)
+    rows_pad = (n + 255) // 256 * 256
+    ahi, alo = torch.zeros(rows_pad * K, dtype=torch.int16).cuda(), torch.zeros(rows_pad * K, dtype=torch.int16).cuda()
+    whi, wlo = torch.zeros(N * K, dtype=torch.int16).cuda(), torch.zeros(N * K, dtype=torch.int16).cuda()
+    A, pre = torch.empty(n, K).cuda(), torch.empty(n, K).cuda()
+    call("scnb_bn_eval_planes", ptr(D(Z)), n, K, ptr(D(g)), ptr(D(b)), ptr(D(rm)), ptr(D(rv)), 1, ptr(A), ptr(pre), ptr(ahi), ptr(alo), _st())
+    y = (Z.double() - rm.double()) / torch.sqrt(rv.double() + 1e-5) * g.double() + b.double()
+    _chk("bn planes pre", pre.cpu(), y, tol=2e-6)
+    _chk("bn planes act", A.cpu(), y.clamp_min(0), tol=2e-6)
+    call("scnb_linear_planes", ptr(D(W)), N, K, ptr(whi), ptr(wlo), _st())
+    Y = torch.full((n, N), 9.0).cuda()
+    call("scnb_linear_fwd_tc_planes", ptr(ahi), ptr(alo), n, K, N, ptr(whi), ptr(wlo), ptr(D(bias)), ptr(Y), _st())
+    torch.cuda.synchronize()
+    _chk("tc linear", Y.cpu(), y.clamp_min(0) @ W.double().t() + bias.double(), tol=3e-5)
+
+
+def test_head_logits_small_output_linear():
+    from scnym_b200._lib import call, ptr
+    n, H, C = 777, 256, 11
+    A, W, b = torch.randn(n, H), torch.randn(C, H) * 0.1, torch.randn(C)
+    out = torch.ones(n, C).cuda()
+    call("scnb_head_logits", ptr(D(A)), ptr(D(W)), ptr(D(b)), H, C, n, ptr(out), 0, _st())
+    want = A.double() @ W.double().t() + b.double()
+    _chk("head logits", out.cpu(), want)
+    call("scnb_head_logits", ptr(D(A)), ptr(D(W)), ptr(D(b)), H, C, n, ptr(out), 1, _st())
+    _chk("head logits acc", out.cpu(), 2 * want)
