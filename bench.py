@@ -53,6 +53,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(entry):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/r01_traffic.json: measured under ncu, never during a timed run)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(entry, {}).get("dram_bytes_per_launch")
+
+
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -204,6 +213,7 @@ def algorithmic_bytes(eng, name):
     table = {
         "scnb_csr_linear_fwd": 8 * nnz + 4 * G * H0 + 4 * nb * H0,          # CSR stream + W1T once + Z
         "scnb_csr_linear_bwd_dw": 8 * nnz + 4 * nb * H0 + 4 * G * H0,       # CSR stream + dZ + dW1T written once
+        "scnb_csr_linear_fwd_tc": 8 * nnz + 4 * G * H0 + 4 * nb * H0,       # CSR stream + the two bf16 planes of W1T once + Z
         "scnb_csr_w1_bwd_optim": 8 * nnz + 4 * nb * H0 + 24 * G * H0,       # batch entries + dZ + read p,m,v / write p,m,v of W1T
         "scnb_optim_step": 28 * (P - G * H0 if getattr(eng, "fused_w1", False) else P),   # read p,g,m,v / write p,m,v
     }
@@ -274,7 +284,44 @@ def time_predict(device, rank):
     cells = passes * N
     nnz = tile.nnz
     bytes_per_cell = 8.0 * nnz / N + 4 * (c["C"] + c["H"] + 2)
-    return cells / (ms * 1e-3), ms, cells, bytes_per_cell
+    # per-kernel time of one full chunk (CUDA events around every C-ABI call, eager)
+    import scnym_b200.predict as Pm
+    from scnym_b200 import _lib
+    stream, recs, orig = torch.cuda.current_stream(), [], _lib.call
+
+    def timed(name, *a):
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record(stream)
+        r = orig(name, *a)
+        e_.record(stream)
+        recs.append((name, s_, e_))
+        return r
+
+    Pm.call = timed
+    try:
+        n = min(run.chunk, N)
+        for i in range(3):
+            if i == 1:
+                recs.clear()
+            run.run_chunk(tile, 0, n, pred, prob, None, emb)
+        torch.cuda.synchronize()
+    finally:
+        Pm.call = orig
+    per = {}
+    for name, s_, e_ in recs:
+        per[name] = per.get(name, 0.0) + s_.elapsed_time(e_) / 2
+    extra = {"chunk_rows": n, "kernel_ms_per_chunk": {k: round(v, 4) for k, v in sorted(per.items(), key=lambda kv: -kv[1])}}
+    t_first = per.get("scnb_csr_linear_fwd_tc_i64")
+    if t_first:
+        # issued tensor work of the first layer: rows x G x H0 MACs x 3 bf16 products, against the measured bf16 peak
+        flops = 2.0 * 3.0 * n * c["G"] * c["H0"]
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        peak_tf = float(pk.get("bf16_tflops", 1590.0))
+        extra["first_layer"] = {"kernel": "scnb_csr_linear_fwd_tc_i64 (densify-then-tcgen05, bf16x3)", "ms": t_first,
+                                "issued_tflops": flops / (t_first * 1e-3) / 1e12, "peak_tflops": peak_tf,
+                                "frac_of_bf16_peak": flops / (t_first * 1e-3) / 1e12 / peak_tf,
+                                "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if pk else "fallback 1.59 PFLOP/s"}
+    return cells / (ms * 1e-3), ms, cells, bytes_per_cell, extra
 
 
 def cpu_reference_step_time(n_steps, warmup, budget_s=25.0, seed=0):
@@ -402,7 +449,7 @@ def main():
         ab = algorithmic_bytes(eng, dom)
         achieved = ab / (per_launch[dom] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": how, "algorithmic_bytes_per_launch": ab, "ms_per_launch": per_launch[dom],
+                "traffic": ncu_traffic(dom), "peak_source": how, "algorithmic_bytes_per_launch": ab, "ms_per_launch": per_launch[dom],
                 "step_share": per_step[dom] / sum(per_step.values()),
                 "kernel_ms_per_step": {k: round(v, 5) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])}}
         step_bytes = 8 * int(eng.b_indptr[eng.nb].item()) + 36 * eng.arena.total
@@ -417,10 +464,11 @@ def main():
 
     predict = None
     if rank == 0 and not args.no_predict:
-        pv, pms, pcells, bpc = time_predict(device, rank)
+        pv, pms, pcells, bpc, pextra = time_predict(device, rank)
         peak, _ = peaks()
         predict = {"value": pv, "unit": "cells/s", "cells": pcells, "ms": pms, "workload": "config4 shape: 2^18-row tile x16 passes, "
                    "G=20000, 5% CSR, outputs argmax+prob+embed", "bytes_per_cell": bpc, "frac_of_hbm": pv * bpc / 1e9 / peak}
+        predict.update(pextra)
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
