@@ -215,6 +215,7 @@ def algorithmic_bytes(eng, name):
         "scnb_csr_linear_bwd_dw": 8 * nnz + 4 * nb * H0 + 4 * G * H0,       # CSR stream + dZ + dW1T written once
         "scnb_csr_linear_fwd_tc": 8 * nnz + 4 * G * H0 + 4 * nb * H0,       # CSR stream + the two bf16 planes of W1T once + Z
         "scnb_csr_w1_bwd_optim": 8 * nnz + 4 * nb * H0 + 24 * G * H0,       # batch entries + dZ + read p,m,v / write p,m,v of W1T
+        "scnb_csr_w1_bwd_optim_tc": 8 * nnz + 4 * nb * H0 + 24 * G * H0,    # same bytes, tcgen05 form
         "scnb_optim_step": 28 * (P - G * H0 if getattr(eng, "fused_w1", False) else P),   # read p,g,m,v / write p,m,v
     }
     return table.get(name)

@@ -99,6 +99,16 @@ int scnb_csr_linear_fwd_tc_i64(const int64_t* indptr, const int32_t* indices, co
                                const void* planes_hi, const void* planes_lo, const float* b1, float* Z, int ksplits,
                                void* stream);
 
+/* Tensor-core form of the fused dW1 + optimizer kernel: D[genes, H0] = X^T dZ1 as a tcgen05 GEMM (bf16x3, fp32 in
+ * TMEM) with the optimizer in the epilogue.  scnb_row_gene_splits finds, for every batch row, where each block of
+ * scnb_w1tc_gene_block(G) consecutive genes starts (splits: [(ceil(G/block)+1) * nb] int32); the dZ1 operand is given as
+ * bf16 planes built by scnb_w1_planes(dZ1, nb, H0, ...).  opt / grad_out as in scnb_csr_w1_bwd_optim. */
+int scnb_w1tc_gene_block(int G);
+int scnb_row_gene_splits(const int32_t* b_indptr, const int32_t* b_idx, int nb, int G, int32_t* splits, void* stream);
+int scnb_csr_w1_bwd_optim_tc(int opt, const int32_t* splits, const int32_t* b_idx, const float* b_val, int nb, int H0, int G,
+                             const void* dz_planes_hi, const void* dz_planes_lo, float* W1T, float* grad_out, float* state1,
+                             float* state2, const float* hp8, const int64_t* state4, void* stream);
+
 /* Tensor-core hidden layers for batched predict: nn.Linear weights as B planes (scnb_linear_planes), eval-mode
  * BatchNorm->ReLU that also emits its output as tiled bf16 A planes (scnb_bn_eval_planes; A_out / pre_out / planes
  * may each be NULL), and Y = A W^T + b from planes only (scnb_linear_fwd_tc_planes).  Plane sizes in bf16 elements:

@@ -62,6 +62,7 @@ class EngineConfig:
     seed: int = 0
     use_cuda_graph: bool = True
     first_layer: str = "auto"   # "spmm": warp-per-row CSR SpMM; "tc": densify-then-tcgen05 GEMM (bf16x3); "auto": tc from 512 rows per step
+    w1_update: str = "auto"     # first-layer gradient+optimizer kernel: "simt" (batch CSC), "tc" (tcgen05 GEMM), "auto": tc from 512 rows
     fuse_heads: bool = True      # one-warp-per-row classifier/DAN-tail/teacher-head kernels (Linear + loss + backward)
     multi_stream: bool = True    # run independent kernels of the step on side streams (parallel graph branches)
     keep_w1_grad: bool = False   # also write the first-layer gradient to HBM (parity tests; implied by data parallelism)
@@ -225,7 +226,19 @@ class TrainEngine(object):
         # gene-major copy of the batch for the fused dW1 + optimizer kernel (needs W1T first in the arena)
         self.P1 = self.G * H0
         self.fused_w1 = (H0 % 64 == 0) and self.arena.names[0] == self._blk[0]["W"] and self.arena.offsets[self._blk[0]["W"]] == 0
-        if self.fused_w1:
+        wu = cfg.w1_update
+        if wu == "auto":
+            wu = os.environ.get("SCNB_W1_UPDATE", "tc" if self.nb >= 512 else "simt")
+        self.w1_tc = bool(self.fused_w1 and wu == "tc" and H0 % 32 == 0 and 32 <= H0 <= 256)
+        if self.w1_tc:
+            # tensor-core dW1 + optimizer: per-row split points of the gene blocks, bf16 planes of dZ1
+            gt = _lib.lib().scnb_w1tc_gene_block(self.G)
+            n_blk = (self.G + gt - 1) // gt
+            self.w1_splits = i32((n_blk + 1) * self.nb)
+            n_pad = (self.nb + 31) // 32 * 32
+            self.dz_hi = torch.zeros(n_pad * H0, dtype=torch.int16, device=dev)
+            self.dz_lo = torch.zeros(n_pad * H0, dtype=torch.int16, device=dev)
+        elif self.fused_w1:
             self.gene_cnt, self.c_ptr, self.c_cursor = i32(self.G), i32(self.G + 1), i32(self.G)
             self.c_ent = i32(cap, 2)
         # injected randomness (tests); None -> Philox in-kernel
@@ -624,10 +637,14 @@ class TrainEngine(object):
         return None
 
     def _gene_cnt_ptr(self):
-        return ptr(self.gene_cnt) if self.fused_w1 else None
+        return ptr(self.gene_cnt) if (self.fused_w1 and not self.w1_tc) else None
 
     def _build_csc(self, n_rows, st):
-        if self.fused_w1:
+        """Inputs of the first-layer backward that depend only on the batch: per-row gene-block split points
+        (tensor-core kernel) or the gene-major copy of the batch (SIMT kernel)."""
+        if self.w1_tc:
+            call("scnb_row_gene_splits", ptr(self.b_indptr), ptr(self.b_idx), n_rows, self.G, ptr(self.w1_splits), st)
+        elif self.fused_w1:
             call("scnb_csr_to_csc", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), n_rows, self.G, ptr(self.gene_cnt),
                  ptr(self.c_ptr), ptr(self.c_cursor), ptr(self.c_ent), st)
 
@@ -663,15 +680,25 @@ class TrainEngine(object):
             call("scnb_optim_step", opt, ptr(ar.flat), ptr(ar.grad), ptr(ar.state1), ptr(ar.state2), ar.total, hp, s4, st)
         elif self.comm is not None:
             # data parallel: gradient only (no atomics, every gene row written), exchange, then one update pass
-            call("scnb_csr_w1_bwd_optim", -1, ptr(self.c_ptr), ptr(self.c_ent), ptr(dZ1), n_rows, H0, self.G, None, self.Gp(W1),
-                 None, None, None, None, st)
+            if self.w1_tc:
+                call("scnb_w1_planes", ptr(dZ1), n_rows, H0, ptr(self.dz_hi), ptr(self.dz_lo), st)
+                call("scnb_csr_w1_bwd_optim_tc", -1, ptr(self.w1_splits), ptr(self.b_idx), ptr(self.b_val), n_rows, H0, self.G,
+                     ptr(self.dz_hi), ptr(self.dz_lo), None, self.Gp(W1), None, None, None, None, st)
+            else:
+                call("scnb_csr_w1_bwd_optim", -1, ptr(self.c_ptr), ptr(self.c_ent), ptr(dZ1), n_rows, H0, self.G, None, self.Gp(W1),
+                     None, None, None, None, st)
             self._after(main, sW)              # every other gradient (branch W, and branch D through it) is complete
             self.comm.all_reduce_avg(ar.grad)  # NCCL over NVLink
             call("scnb_optim_step", opt, ptr(ar.flat), ptr(ar.grad), ptr(ar.state1), ptr(ar.state2), ar.total, hp, s4, st)
         else:
             keep = self.Gp(W1) if c.keep_w1_grad else None
-            call("scnb_csr_w1_bwd_optim", opt, ptr(self.c_ptr), ptr(self.c_ent), ptr(dZ1), n_rows, H0, self.G, ptr(ar.flat), keep,
-                 ptr(ar.state1), ptr(ar.state2), hp, s4, st)
+            if self.w1_tc:
+                call("scnb_w1_planes", ptr(dZ1), n_rows, H0, ptr(self.dz_hi), ptr(self.dz_lo), st)
+                call("scnb_csr_w1_bwd_optim_tc", opt, ptr(self.w1_splits), ptr(self.b_idx), ptr(self.b_val), n_rows, H0, self.G,
+                     ptr(self.dz_hi), ptr(self.dz_lo), ptr(ar.flat), keep, ptr(ar.state1), ptr(ar.state2), hp, s4, st)
+            else:
+                call("scnb_csr_w1_bwd_optim", opt, ptr(self.c_ptr), ptr(self.c_ent), ptr(dZ1), n_rows, H0, self.G, ptr(ar.flat), keep,
+                     ptr(ar.state1), ptr(ar.state2), hp, s4, st)
             rest = ar.total - self.P1
             call("scnb_optim_step", opt, ptr(ar.flat[self.P1:]), ptr(ar.grad[self.P1:]), ptr(ar.state1[self.P1:]),
                  ptr(ar.state2[self.P1:]), rest, hp, s4, sw)

@@ -237,6 +237,7 @@ def test_engine_step_with_tensor_core_first_layer_matches_reference_golden():
     import scnym_b200.engine as E
     eng2_cfg = eng.cfg
     eng2_cfg.first_layer = "tc"
+    eng2_cfg.w1_update = "tc"      # tcgen05 dW1 + optimizer kernel as well
     model, dann = CH.build_models(d)
     from scnym_b200.dataprep import DeviceCSR
     G = int(d["meta_G"])
@@ -246,7 +247,7 @@ def test_engine_step_with_tensor_core_first_layer_matches_reference_golden():
     eng = E.TrainEngine(model, eng2_cfg, lab, d["lab_y"], int(d["meta_L"]), unlabeled=unl, unlabeled_batch_size=int(d["meta_U"]),
                         dann=dann, labeled_domain=d["lab_dom"] if given else None, unlabeled_domain=d["unl_dom"] if given else None,
                         mode="mixmatch")
-    assert eng.tc_first
+    assert eng.tc_first and eng.w1_tc
     eng.set_weights(float(d["meta_unsup_w"]), float(d["meta_dan_w"]))
     CH.inject_step(eng, d, 0)
     eng.step()
