@@ -91,7 +91,8 @@ int scnb_csr_linear_bwd_dw(const int32_t* b_indptr, const int32_t* b_idx, const 
  *      accumulation in TMEM).  scnb_w1_planes splits W1T into two bf16 planes laid out as 128-byte-swizzled
  *      shared-memory tile images (ceil(G/64) tiles of H0*64 elements per plane); scnb_csr_linear_fwd_tc{,_i64}
  *      computes Z = X W1T + b1 from a batch CSR (int32 indptr) or a row range of a dataset CSR (int64 indptr).
- *      ksplits <= 0: choose the number of gene-axis splits automatically.  H0 in {32,...,256}, multiple of 32. ---- */
+ *      ksplits == 0: choose the number of gene-axis splits automatically; ksplits < 0: the same, and the caller has
+ *      already zeroed Z (the partial products of the splits are added atomically).  H0 in {32,...,256}, multiple of 32. ---- */
 int scnb_w1_planes(const float* W1T, int G, int H0, void* planes_hi, void* planes_lo, void* stream);
 int scnb_csr_linear_fwd_tc(const int32_t* b_indptr, const int32_t* b_idx, const float* b_val, int n, int G, int H0,
                            const void* planes_hi, const void* planes_lo, const float* b1, float* Z, int ksplits, void* stream);
@@ -99,15 +100,19 @@ int scnb_csr_linear_fwd_tc_i64(const int64_t* indptr, const int32_t* indices, co
                                const void* planes_hi, const void* planes_lo, const float* b1, float* Z, int ksplits,
                                void* stream);
 
-/* Tensor-core form of the fused dW1 + optimizer kernel: D[genes, H0] = X^T dZ1 as a tcgen05 GEMM (bf16x3, fp32 in
- * TMEM) with the optimizer in the epilogue.  scnb_row_gene_splits finds, for every batch row, where each block of
- * scnb_w1tc_gene_block(G) consecutive genes starts (splits: [(ceil(G/block)+1) * nb] int32); the dZ1 operand is given as
- * bf16 planes built by scnb_w1_planes(dZ1, nb, H0, ...).  opt / grad_out as in scnb_csr_w1_bwd_optim. */
+/* Tensor-core form of the fused dW1 + optimizer kernel (replaces the backward of nn.Linear in scnym/model.py:211 plus
+ * torch.optim's step on that weight, scnym/main.py:374-396): D^T[H0, genes] = dZ1^T X as a tcgen05 GEMM (bf16x3, fp32 in
+ * TMEM, one CTA per SM owning scnb_w1tc_gene_block(G) consecutive genes) with the optimizer in the epilogue.
+ * scnb_row_gene_splits finds, for every batch row, where each gene block starts (splits: [(ceil(G/block)+1) * nb] int32);
+ * the dZ1 operand is given as bf16 planes built by scnb_w1_planes(dZ1, nb, H0, ...).  opt / grad_out as in
+ * scnb_csr_w1_bwd_optim.  planes_hi_out / planes_lo_out (both or neither; opt >= 0 only): the updated W1T is also
+ * written as the bf16 operand planes scnb_csr_linear_fwd_tc reads, so the next step needs no scnb_w1_planes pass. */
 int scnb_w1tc_gene_block(int G);
 int scnb_row_gene_splits(const int32_t* b_indptr, const int32_t* b_idx, int nb, int G, int32_t* splits, void* stream);
 int scnb_csr_w1_bwd_optim_tc(int opt, const int32_t* splits, const int32_t* b_idx, const float* b_val, int nb, int H0, int G,
                              const void* dz_planes_hi, const void* dz_planes_lo, float* W1T, float* grad_out, float* state1,
-                             float* state2, const float* hp8, const int64_t* state4, void* stream);
+                             float* state2, const float* hp8, const int64_t* state4, void* planes_hi_out, void* planes_lo_out,
+                             void* stream);
 
 /* Tensor-core hidden layers for batched predict: nn.Linear weights as B planes (scnb_linear_planes), eval-mode
  * BatchNorm->ReLU that also emits its output as tiled bf16 A planes (scnb_bn_eval_planes; A_out / pre_out / planes

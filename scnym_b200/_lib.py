@@ -29,7 +29,7 @@ SIGNATURES = {
     "scnb_csr_linear_fwd_tc_i64": [P, P, P, I, I, I, P, P, P, P, I, P],
     "scnb_w1tc_gene_block": [I],
     "scnb_row_gene_splits": [P, P, I, I, P, P],
-    "scnb_csr_w1_bwd_optim_tc": [I, P, P, P, I, I, I, P, P, P, P, P, P, P, P, P],
+    "scnb_csr_w1_bwd_optim_tc": [I, P, P, P, I, I, I, P, P, P, P, P, P, P, P, P, P, P],
     "scnb_linear_planes": [P, I, I, P, P, P],
     "scnb_bn_eval_planes": [P, I, I, P, P, P, P, I, P, P, P, P, P],
     "scnb_linear_fwd_tc_planes": [P, P, I, I, I, P, P, P, P, P],

@@ -490,6 +490,7 @@ static int launch_dense_fwd_tc(const IdxT* indptr, const int32_t* idx, const flo
   constexpr int ROWS = TC_M * HALVES;
   const int n_kt = scnb_cdiv(G, KT);
   const int row_tiles = scnb_cdiv(n, ROWS);
+  const bool prezeroed = ksplits < 0;   // the caller has already cleared Z (off its critical path)
   if (ksplits <= 0) {  // auto: split the gene axis until the grid covers the 148 SMs
     ksplits = 148 / row_tiles;
     if (ksplits < 1) ksplits = 1;
@@ -510,7 +511,7 @@ static int launch_dense_fwd_tc(const IdxT* indptr, const int32_t* idx, const flo
     scnb_set_error("csr_linear_fwd_tc: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
     return SCNB_ERR_CUDA;
   }
-  if (ksplits > 1) {  // partial products of the gene-axis splits are added atomically
+  if (ksplits > 1 && !prezeroed) {  // partial products of the gene-axis splits are added atomically
     e = cudaMemsetAsync(Z, 0, (size_t)n * H0 * sizeof(float), st);
     if (e != cudaSuccess) {
       scnb_set_error("csr_linear_fwd_tc: memset failed: %s", cudaGetErrorString(e));
@@ -599,60 +600,50 @@ __global__ void __launch_bounds__(128) k_row_gene_splits(const int32_t* __restri
   }
 }
 
-#define W1TC_THREADS 192
+#define W1TC_THREADS 320   // warp 0: dZ1 tile loader + L2 prefetch, warp 1: MMA issuer, warps 2-9: densify, then epilogue
+#define W1TC_DENSE 256     // densify / epilogue threads
 
-// cluster helpers (the dZ1 tiles are multicast to the W1TC_CL CTAs of a cluster)
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar), "h"(mask)
-               : "memory");
-}
-__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
-               : "memory");
-}
-
-template <int OPT, int CL>
-__global__ void __launch_bounds__(W1TC_THREADS, 2)
+// D^T[c, g] = sum_r dZ1[r, c] * X[r, g]: the MMA's M axis is the H0 axis (two 128-lane accumulators for H0 = 256), its
+// N axis the CTA's genes (any multiple of 16 up to 256, so a gene block of ceil(G / 148) genes is not padded to 128),
+// K the batch rows.  One CTA per SM.
+//   A operand: bf16 hi/lo planes of dZ1 (scnb_w1_planes: tile i = batch rows [32 i, 32 i + 32), image [c][r]) by bulk copy;
+//   B operand: X^T tile [gene][r], densified from the batch CSR by 256 threads (8 per batch row of the tile);
+//   acc += dz_lo x_hi + dz_hi x_lo + dz_hi x_hi  (fp32 in TMEM).
+// Epilogue: TMEM lane = column c of W1T, TMEM column = gene.  tcgen05.ld hands a warp 32 consecutive c of 16 genes, so
+// for every gene the warp reads and writes 128 contiguous bytes of the parameter / state rows -- coalesced without a
+// transposition through shared memory; the 48 loads of a 16-gene chunk are in flight before the first update.
+template <int OPT>
+__global__ void __launch_bounds__(W1TC_THREADS, 1)
 k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict__ b_idx, const float* __restrict__ b_val, int nb,
-                  int GT, int G, int N, const uint8_t* __restrict__ dz_hi, const uint8_t* __restrict__ dz_lo, float* __restrict__ W,
-                  float* __restrict__ grad_out, float* __restrict__ S1, float* __restrict__ S2, const float* __restrict__ hp,
-                  const int64_t* __restrict__ st, int stages, int tmem_cols, int pass_cols, long long* __restrict__ dbg, int dbg_mode) {
+                  int GT, int NT, int G, int H0, const uint8_t* __restrict__ dz_hi, const uint8_t* __restrict__ dz_lo,
+                  float* __restrict__ W, float* __restrict__ grad_out, float* __restrict__ S1, float* __restrict__ S2,
+                  const float* __restrict__ hp, const int64_t* __restrict__ st, uint8_t* __restrict__ pl_hi,
+                  uint8_t* __restrict__ pl_lo, int stages, int tmem_cols, long long* __restrict__ dbg) {
   constexpr int KT = 32;
-  constexpr uint32_t ROWB = 2 * KT, A_PLANE = TC_M * ROWB;   // 8 KB per plane
-  constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1u);
-  // optional phase timestamps (SCNB_W1TC_DBG=1): dbg[0..] by the first densify thread of CTA 0, dbg[64..] by its MMA thread,
-  // dbg[128 + 4 b ..] wall-clock stamps of CTA b
-#define W1TC_STAMP(slot) do { if (dbg && blockIdx.x == 0) dbg[slot] = clock64(); } while (0)
-#define W1TC_GSTAMP(k) do { if (dbg) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[128 + 4 * blockIdx.x + (k)] = (long long)t_; } } while (0)
+  constexpr uint32_t ROWB = 2 * KT;
+#define W1TC_GSTAMP(k) do { if (dbg) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[4 * blockIdx.x + (k)] = (long long)t_; } } while (0)
   extern __shared__ uint8_t tc_smem_raw[];
   __shared__ OptimConsts cs;
   const uint32_t raw = smem_u32(tc_smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;   // the dynamic window starts at the same CTA-relative offset in every CTA
+  const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = tc_smem_raw + (base - raw);
-  const uint32_t B_BYTES = (uint32_t)N * ROWB;
-  const uint32_t STAGE_BYTES = 2u * A_PLANE + 2u * B_BYTES;
+  const uint32_t A_PLANE = (uint32_t)H0 * ROWB, B_PLANE = (uint32_t)NT * ROWB;
+  const uint32_t STAGE_BYTES = 2u * A_PLANE + 2u * B_PLANE;        // [dz_hi][dz_lo][x_hi][x_lo]
   const uint32_t bars = base + (uint32_t)stages * STAGE_BYTES;
-  const uint32_t bar_full_b = bars, bar_full_a = bars + 8u * stages, bar_empty = bars + 16u * stages, bar_acc = bars + 24u * stages;
+  const uint32_t bar_full_dz = bars, bar_full_x = bars + 8u * stages, bar_empty = bars + 16u * stages, bar_acc = bars + 24u * stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (size_t)stages * STAGE_BYTES + 24 * stages + 8);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c = blockIdx.x;
   const int g0 = c * GT, g1 = min(G, g0 + GT);
-  const bool has_genes = g1 > g0;                  // false only for CTAs padding the grid to a multiple of the cluster size
   const int n_it = (nb + KT - 1) / KT;
+  const int halves = (H0 + 127) >> 7;
+  if (tid == 32) W1TC_GSTAMP(3);
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(bar_full_b + 8u * s, 1);
-      mbar_init(bar_full_a + 8u * s, 128);
-      mbar_init(bar_empty + 8u * s, CL);            // every CTA of the cluster releases a stage (it receives multicast data)
+      mbar_init(bar_full_dz + 8u * s, 1);
+      mbar_init(bar_full_x + 8u * s, W1TC_DENSE / 2);
+      mbar_init(bar_empty + 8u * s, 1);
     }
     mbar_init(bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -665,117 +656,113 @@ k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict_
   }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) {   // peers' barriers are initialised before anything is multicast to them
-    cluster_arrive();
-    cluster_wait();
-  }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 1 && OPT != OPT_NONE && has_genes) {
-      // The main loop only uses L2->SM bandwidth (dZ1 tiles); HBM is idle.  Ask L2 for this CTA's parameter and
-      // optimizer-state rows now (contiguous: W1T is gene-major), so the epilogue's reads hit L2 and the kernel's
-      // HBM reads overlap its tensor-core phase.
-      const size_t off = (size_t)g0 * N;
-      const uint32_t bytes = (uint32_t)(g1 - g0) * (uint32_t)N * 4u;
+    if (lane == 1 && OPT != OPT_NONE) {
+      // The main loop only uses L2->SM bandwidth (dZ1 tiles) and the tensor pipe; HBM is idle.  Ask L2 for this CTA's
+      // parameter and optimizer-state rows now (contiguous: W1T is gene-major), so that the kernel's HBM reads overlap
+      // its tensor-core phase and the epilogue's loads hit L2.
+      const size_t off = (size_t)g0 * H0;
+      const uint32_t bytes = (uint32_t)(g1 - g0) * (uint32_t)H0 * 4u;
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(W + off), "r"(bytes) : "memory");
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(S1 + off), "r"(bytes) : "memory");
       if (OPT != OPT_SGD) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(S2 + off), "r"(bytes) : "memory");
     }
-    if (lane == 0) {  // ===== dZ1 tile loader: this CTA brings 1/CL of every tile and multicasts it to the cluster =====
-      const uint32_t rk = CL > 1 ? cluster_ctarank() : 0u;
-      const uint32_t SL = B_BYTES / CL;
+    if (lane == 0) {  // ===== dZ1 tile loader =====
       for (int i = 0; i < n_it; ++i) {
         const int s = i % stages;
         const uint32_t ph = (uint32_t)(i / stages) & 1u;
         mbar_wait(bar_empty + 8u * s, ph ^ 1u);
         const uint32_t stage = base + (uint32_t)s * STAGE_BYTES;
-        mbar_arrive_expect_tx(bar_full_b + 8u * s, 2u * B_BYTES);
-        const size_t off = (size_t)i * B_BYTES + (size_t)rk * SL;
-        if (CL > 1) {
-          bulk_g2s_mc(stage + 2u * A_PLANE + rk * SL, dz_hi + off, SL, bar_full_b + 8u * s, CL_MASK);
-          bulk_g2s_mc(stage + 2u * A_PLANE + B_BYTES + rk * SL, dz_lo + off, SL, bar_full_b + 8u * s, CL_MASK);
-        } else {
-          bulk_g2s(stage + 2u * A_PLANE, dz_hi + off, B_BYTES, bar_full_b + 8u * s);
-          bulk_g2s(stage + 2u * A_PLANE + B_BYTES, dz_lo + off, B_BYTES, bar_full_b + 8u * s);
-        }
+        mbar_arrive_expect_tx(bar_full_dz + 8u * s, 2u * A_PLANE);
+        const size_t off = (size_t)i * A_PLANE;
+        bulk_g2s(stage, dz_hi + off, A_PLANE, bar_full_dz + 8u * s);
+        bulk_g2s(stage + A_PLANE, dz_lo + off, A_PLANE, bar_full_dz + 8u * s);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ===== MMA issuer =====
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
       for (int i = 0; i < n_it; ++i) {
         const int s = i % stages;
         const uint32_t ph = (uint32_t)(i / stages) & 1u;
-        mbar_wait(bar_full_b + 8u * s, ph);
-        if (i < 16) W1TC_STAMP(64 + 2 * i);
-        mbar_wait(bar_full_a + 8u * s, ph);
-        if (i < 16) W1TC_STAMP(65 + 2 * i);
+        mbar_wait(bar_full_dz + 8u * s, ph);
+        mbar_wait(bar_full_x + 8u * s, ph);
         tc_fence_after();
         const uint32_t stage = base + (uint32_t)s * STAGE_BYTES;
-        const uint64_t a_hi = umma_desc_kmajor<KT>(stage), a_lo = umma_desc_kmajor<KT>(stage + A_PLANE);
-        const uint64_t b_hi = umma_desc_kmajor<KT>(stage + 2u * A_PLANE), b_lo = umma_desc_kmajor<KT>(stage + 2u * A_PLANE + B_BYTES);
+        const uint64_t x_hi = umma_desc_kmajor<KT>(stage + 2u * A_PLANE), x_lo = umma_desc_kmajor<KT>(stage + 2u * A_PLANE + B_PLANE);
+        for (int h = 0; h < halves; ++h) {
+          const uint64_t d_hi = umma_desc_kmajor<KT>(stage + (uint32_t)h * TC_M * ROWB);
+          const uint64_t d_lo = umma_desc_kmajor<KT>(stage + A_PLANE + (uint32_t)h * TC_M * ROWB);
+          const uint32_t acc = tmem_base + (uint32_t)(h * NT);
 #pragma unroll
-        for (int k = 0; k < KT / 16; ++k) {
-          const uint64_t ko = (uint64_t)(k * 2);
-          tc_mma_bf16(tmem_base, a_lo + ko, b_hi + ko, idesc, (i > 0 || k > 0) ? 1u : 0u);
-          tc_mma_bf16(tmem_base, a_hi + ko, b_lo + ko, idesc, 1u);
-          tc_mma_bf16(tmem_base, a_hi + ko, b_hi + ko, idesc, 1u);
+          for (int k = 0; k < KT / 16; ++k) {
+            const uint64_t ko = (uint64_t)(k * 2);
+            tc_mma_bf16(acc, d_lo + ko, x_hi + ko, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            tc_mma_bf16(acc, d_hi + ko, x_lo + ko, idesc, 1u);
+            tc_mma_bf16(acc, d_hi + ko, x_hi + ko, idesc, 1u);
+          }
         }
-        // release the stage to every CTA of the cluster; nobody waits for the last `stages` releases, so they are not
-        // sent (no remote arrival can then target a CTA that has left its main loop)
-        if (i + stages < n_it) {
-          if (CL > 1) tc_commit_mc(bar_empty + 8u * s, CL_MASK); else tc_commit(bar_empty + 8u * s);
-        }
+        tc_commit(bar_empty + 8u * s);
       }
       tc_commit(bar_acc);
     }
   } else {
-    // ===== densify X^T tiles from the batch CSR (4 threads per batch row of the tile) =====
-    const int t = tid - 64;                 // 0..127
-    const int rl = t >> 2, sub = t & 3;     // batch row within the k-tile, entry phase
+    // ===== densify X^T tiles from the batch CSR.  The refill of a stage is a chain of latencies (entry loads, clear,
+    // barrier, scatter, proxy fence, arrive), so the eight warps work as two groups of four on alternate k-tiles: two
+    // refills are in flight.  Within a group 4 threads share a batch row of the tile. =====
+    const int t = tid - 64;                 // 0..255
+    const int grp = t >> 7, tg = t & 127;   // densify group, thread within the group
+    const int rl = tg >> 2, sub = tg & 3;   // batch row within the k-tile, entry phase
     const int32_t* sp0 = splits + (size_t)c * nb;
     const int32_t* sp1 = splits + (size_t)(c + 1) * nb;
-    // this thread's entry range of the first tile is requested early
-    int lo = 0, hi = 0;
-    if (has_genes && rl < nb) { lo = sp0[rl]; hi = sp1[rl]; }
-    if (t == 0) W1TC_STAMP(0);
+    // software pipeline over this group's k-tiles: split points are fetched two tiles ahead and the tile's first entries
+    // one tile ahead, so no global-memory latency sits between the release of a stage and its refill
+    int lo = 0, hi = 0, lo_n = 0, hi_n = 0;
+    if (grp < n_it && grp * KT + rl < nb) { lo = sp0[grp * KT + rl]; hi = sp1[grp * KT + rl]; }
+    if (grp + 2 < n_it && (grp + 2) * KT + rl < nb) { lo_n = sp0[(grp + 2) * KT + rl]; hi_n = sp1[(grp + 2) * KT + rl]; }
+    int gj[4];
+    float vj[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int pj = lo + sub + 4 * j;
+      gj[j] = pj < hi ? b_idx[pj] : -1;
+      vj[j] = pj < hi ? b_val[pj] : 0.f;
+    }
     if (t == 0) W1TC_GSTAMP(0);
-    for (int i = 0; i < n_it; ++i) {
+    const uint32_t n_chunks = 2u * B_PLANE / 16u;
+    for (int i = grp; i < n_it; i += 2) {
       const int s = i % stages;
       const uint32_t ph = (uint32_t)(i / stages) & 1u;
-      // next tile's range (hidden behind this tile's work)
-      const int rn = (i + 1) * KT + rl;
-      int lo_n = 0, hi_n = 0;
-      if (has_genes && i + 1 < n_it && rn < nb) { lo_n = sp0[rn]; hi_n = sp1[rn]; }
-      // this tile's entries (<= a few per thread): issue the loads before waiting for the stage
-      int gj[4];
-      float vj[4];
+      const int rn2 = (i + 4) * KT + rl;
+      int lo_n2 = 0, hi_n2 = 0;
+      if (i + 4 < n_it && rn2 < nb) { lo_n2 = sp0[rn2]; hi_n2 = sp1[rn2]; }
+      int gn[4];
+      float vn[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int pj = lo + sub + 4 * j;
-        gj[j] = pj < hi ? b_idx[pj] : -1;
-        vj[j] = pj < hi ? b_val[pj] : 0.f;
+      for (int j = 0; j < 4; ++j) {         // first entries of this group's next tile
+        const int pj = lo_n + sub + 4 * j;
+        gn[j] = pj < hi_n ? b_idx[pj] : -1;
+        vn[j] = pj < hi_n ? b_val[pj] : 0.f;
       }
       mbar_wait(bar_empty + 8u * s, ph ^ 1u);
-      if (t == 0 && i < 16) W1TC_STAMP(1 + 2 * i);
-      const uint32_t a_hi_base = base + (uint32_t)s * STAGE_BYTES, a_lo_base = a_hi_base + A_PLANE;
-      {  // clear the two A planes of the stage: 16 KB = 128 threads x 8 x 16 B, consecutive threads consecutive chunks
-#pragma unroll
-        for (int j = 0; j < 8; ++j) st_shared_zero16(a_hi_base + (uint32_t)(j * 128 + t) * 16u);
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // all clears before any scatter (only the 4 densify warps)
-      const uint32_t kcol = (uint32_t)rl;             // k position of this batch row within the tile
+      const uint32_t x_hi_base = base + (uint32_t)s * STAGE_BYTES + 2u * A_PLANE, x_lo_base = x_hi_base + B_PLANE;
+      for (uint32_t ch = (uint32_t)tg; ch < n_chunks; ch += 128u) st_shared_zero16(x_hi_base + ch * 16u);
+      // all clears before any scatter: named barrier of this group's four warps
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+      const uint32_t kcol = (uint32_t)rl;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (gj[j] >= 0 && vj[j] != 0.f) {
-          const uint32_t g = (uint32_t)(gj[j] - g0);  // gene row of the A tile
+          const uint32_t g = (uint32_t)(gj[j] - g0);
           const __nv_bfloat16 h = __float2bfloat16_rn(vj[j]);
           const __nv_bfloat16 l = __float2bfloat16_rn(vj[j] - __bfloat162float(h));
           const uint32_t off = g * ROWB + swz_chunk<KT>(kcol >> 3, g) + ((kcol & 7u) << 1);
-          st_shared_u16(a_hi_base + off, __bfloat16_as_ushort(h));
-          st_shared_u16(a_lo_base + off, __bfloat16_as_ushort(l));
+          st_shared_u16(x_hi_base + off, __bfloat16_as_ushort(h));
+          st_shared_u16(x_lo_base + off, __bfloat16_as_ushort(l));
         }
       }
       for (int pj = lo + sub + 16; pj < hi; pj += 4) {   // rows with more than 16 entries in this gene block
@@ -785,129 +772,115 @@ k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict_
           const __nv_bfloat16 h = __float2bfloat16_rn(v);
           const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
           const uint32_t off = g * ROWB + swz_chunk<KT>(kcol >> 3, g) + ((kcol & 7u) << 1);
-          st_shared_u16(a_hi_base + off, __bfloat16_as_ushort(h));
-          st_shared_u16(a_lo_base + off, __bfloat16_as_ushort(l));
+          st_shared_u16(x_hi_base + off, __bfloat16_as_ushort(h));
+          st_shared_u16(x_lo_base + off, __bfloat16_as_ushort(l));
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(bar_full_a + 8u * s);
-      if (t == 0 && i < 16) W1TC_STAMP(2 + 2 * i);
-      lo = lo_n;
-      hi = hi_n;
+      mbar_arrive(bar_full_x + 8u * s);
+      lo = lo_n; hi = hi_n;
+      lo_n = lo_n2; hi_n = hi_n2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { gj[j] = gn[j]; vj[j] = vn[j]; }
     }
-  }
-  __syncwarp();
-  if (CL > 1) cluster_arrive();   // matched by the wait in front of the exit
-  // ----- epilogue (all six warps).  TMEM gives each thread one gene's accumulator row; touching p / m / v that way
-  // would be 32 different 1 KB rows per load instruction.  So warps 2-5 transpose `pass_cols` accumulator columns at a
-  // time through shared memory (the operand stages are free now) and then one WARP owns a (gene row, 128-column block)
-  // item: its lanes read and write consecutive 16-byte pieces of the parameter and state rows.  The loads of the next
-  // group of four items are in flight while the current group is updated and stored. -----
-  {
-    OptimConsts oc;
-    if (OPT != OPT_NONE) oc = cs;
-    const int NP = pass_cols + 4;                   // row pitch of the staging tile in floats
-    float* gsm = reinterpret_cast<float*>(sm);      // [genes][NP]
-    const int n_valid = g1 - g0;
-    const int q = warp & 3;
-    const int ncb = (pass_cols + 127) / 128;        // 128-column blocks per pass
-    const bool lane_on = lane * 4 < pass_cols;
-    for (int pass = 0; pass * pass_cols < N; ++pass) {
-      if (warp >= 2) {
-        if (pass == 0) {
-          mbar_wait(bar_acc, 0);
-          tc_fence_after();
-          if (tid == 64) W1TC_STAMP(40);
-          if (tid == 64) W1TC_GSTAMP(1);
-        }
-        for (int cb = 0; cb < pass_cols; cb += 32) {
-          uint32_t v[32];
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(pass * pass_cols + cb);
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-              : "r"(taddr)
-              : "memory");
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (q * 32 + lane < n_valid) {
-            float* dst = gsm + (size_t)(q * 32 + lane) * NP + cb;
+    // ===== epilogue: warp (h, q) owns columns c = 128 h + 32 q + lane of W1T for all genes of the CTA =====
+    const int q = warp & 3;                  // TMEM lane quarter this warp may read
+    const int h = (warp - 2) >> 2;
+    const int col = h * 128 + q * 32 + lane;
+    if (h * 128 + q * 32 < H0) {
+      OptimConsts oc;
+      if (OPT != OPT_NONE) oc = cs;
+      const int n_g = g1 - g0;
+      float p[16], a[16], b[16];
+      auto load_chunk = [&](int gb, float(&pp)[16], float(&aa)[16], float(&bb)[16]) {
+        if (OPT == OPT_NONE) return;
+        const int n_here = n_g - gb;
+        const size_t o0 = (size_t)(g0 + gb) * H0 + col;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                               __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        for (int j = 0; j < 16; ++j) {
+          if (j < n_here) {
+            pp[j] = W[o0 + (size_t)j * H0];
+            aa[j] = S1[o0 + (size_t)j * H0];
+            bb[j] = (OPT != OPT_SGD) ? S2[o0 + (size_t)j * H0] : 0.f;
           }
         }
-      }
-      __syncthreads();
-      const int items = n_valid * ncb;
-      if (tid == 64 && pass == 0) W1TC_GSTAMP(3);
-      for (int it0 = warp; it0 < items; it0 += 24) {
-        float4 gr[4], p4[4], a4[4], b4[4];
-        size_t o4[4];
+      };
+      load_chunk(0, p, a, b);          // in flight while the last MMAs drain
+      mbar_wait(bar_acc, 0);
+      tc_fence_after();
+      if (t == 0) W1TC_GSTAMP(1);
+      for (int gb = 0; gb < n_g; gb += 16) {
+        uint32_t v[16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * NT + gb);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr)
+            : "memory");
+        float pn[16], an[16], bn[16];
+        if (gb + 16 < n_g) load_chunk(gb + 16, pn, an, bn);   // next chunk's rows, in flight during this chunk's update
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int n_here = n_g - gb;
+        const size_t o0 = (size_t)(g0 + gb) * H0 + col;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int it = it0 + 6 * u;
-          if (it < items && lane_on) {
-            const int r = it / ncb, cbk = it - r * ncb;
-            const size_t o = (size_t)(g0 + r) * N + pass * pass_cols + cbk * 128 + lane * 4;
-            o4[u] = o;
-            gr[u] = *reinterpret_cast<const float4*>(gsm + (size_t)r * NP + cbk * 128 + lane * 4);
-            if (OPT != OPT_NONE && !(dbg_mode & 1)) {
-              p4[u] = *reinterpret_cast<const float4*>(W + o);
-              a4[u] = *reinterpret_cast<const float4*>(S1 + o);
-              b4[u] = (OPT != OPT_SGD) ? *reinterpret_cast<const float4*>(S2 + o) : make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
-              p4[u] = a4[u] = b4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int it = it0 + 6 * u;
-          if (it < items && lane_on) {
-            const size_t o = o4[u];
-            if (grad_out) *reinterpret_cast<float4*>(grad_out + o) = gr[u];
+        for (int j = 0; j < 16; ++j) {
+          if (j < n_here) {
+            const float gr = __uint_as_float(v[j]);
+            if (grad_out) grad_out[o0 + (size_t)j * H0] = gr;
             if (OPT != OPT_NONE) {
-              optim_update<OPT>(p4[u].x, gr[u].x, a4[u].x, b4[u].x, oc);
-              optim_update<OPT>(p4[u].y, gr[u].y, a4[u].y, b4[u].y, oc);
-              optim_update<OPT>(p4[u].z, gr[u].z, a4[u].z, b4[u].z, oc);
-              optim_update<OPT>(p4[u].w, gr[u].w, a4[u].w, b4[u].w, oc);
-              if (!(dbg_mode & 2) || p4[u].x == 123.456f) {
-                *reinterpret_cast<float4*>(W + o) = p4[u];
-                *reinterpret_cast<float4*>(S1 + o) = a4[u];
-                if (OPT != OPT_SGD) *reinterpret_cast<float4*>(S2 + o) = b4[u];
-              }
+              optim_update<OPT>(p[j], gr, a[j], b[j], oc);
+              W[o0 + (size_t)j * H0] = p[j];
+              S1[o0 + (size_t)j * H0] = a[j];
+              if (OPT != OPT_SGD) S2[o0 + (size_t)j * H0] = b[j];
             }
           }
         }
+        if (OPT != OPT_NONE && pl_hi) {
+          // bf16 hi/lo operand planes of the UPDATED rows for the next step's tensor-core forward (same image as
+          // k_w1_planes<32>: tile = 32 genes, row = column of W1T, 16-byte chunk = 8 consecutive genes, XOR-swizzled)
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (8 * u < n_here) {
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float x0 = (8 * u + 2 * j) < n_here ? p[8 * u + 2 * j] : 0.f;
+                const float x1 = (8 * u + 2 * j + 1) < n_here ? p[8 * u + 2 * j + 1] : 0.f;
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              }
+              const uint32_t gg = (uint32_t)(g0 + gb + 8 * u);
+              const size_t off = ((size_t)(gg >> 5) * H0 * KT) * 2 + (size_t)col * ROWB + swz_chunk<KT>((gg & 31u) >> 3, (uint32_t)col);
+              *reinterpret_cast<uint4*>(pl_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              *reinterpret_cast<uint4*>(pl_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { p[j] = pn[j]; a[j] = an[j]; b[j] = bn[j]; }
       }
-      __syncthreads();
-      if (tid == 64) W1TC_STAMP(41 + (pass < 2 ? pass : 1));
-      if (tid == 64) W1TC_GSTAMP(2);
+    } else {
+      mbar_wait(bar_acc, 0);
+      tc_fence_after();
     }
+    if (t == 0) W1TC_GSTAMP(2);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
-  if (CL > 1) cluster_wait();
-#undef W1TC_STAMP
 #undef W1TC_GSTAMP
 }
 
-
-// gene block width used by the tensor-core dW1 kernel for G genes: enough blocks for two CTAs on each of the 148 SMs
+// gene block of a CTA of the tensor-core dW1 kernel: one CTA per SM when the block fits one MMA (N <= 256)
 static inline int w1tc_gene_block(int G) {
-  int n_cta = 2 * 148;
-  int gt = (G + n_cta - 1) / n_cta;
-  if (gt > TC_M) gt = TC_M;
-  if (gt < 8) gt = 8;
+  int gt = ((G + 147) / 148 + 7) / 8 * 8;   // multiple of 8: a 16-byte chunk of the operand planes never straddles two CTAs
+  if (gt > 256) gt = 256;
+  if (gt < 16) gt = 16;
   return gt;
 }
 
@@ -923,109 +896,52 @@ extern "C" int scnb_row_gene_splits(const int32_t* b_indptr, const int32_t* b_id
   return SCNB_OK;
 }
 
-template <int OPT, int CL>
-static int launch_w1_bwd_optim_tc(const int32_t* splits, const int32_t* b_idx, const float* b_val, int nb, int H0, int G, const void* dz_hi,
-                                  const void* dz_lo, float* W1T, float* grad_out, float* s1, float* s2, const float* hp,
-                                  const int64_t* st4, cudaStream_t st, long long* dbg) {
+template <int OPT>
+static int launch_w1_bwd_optim_tc_any(const int32_t* splits, const int32_t* b_idx, const float* b_val, int nb, int H0, int G,
+                                      const void* dz_hi, const void* dz_lo, float* W1T, float* grad_out, float* s1, float* s2,
+                                      const float* hp, const int64_t* st4, void* pl_hi, void* pl_lo, cudaStream_t st) {
   const int GT = w1tc_gene_block(G);
+  const int NT = (GT + 15) / 16 * 16;
   const int n_blk = scnb_cdiv(G, GT);
-  const int grid = scnb_cdiv(n_blk, CL) * CL;          // whole clusters; CTAs past the last gene block only feed the multicast
-  const size_t stage_bytes = 2 * (size_t)TC_M * 64 + 2 * (size_t)H0 * 64;
-  int stages = (int)((104 * 1024) / stage_bytes);   // two CTAs per SM
-  if (stages > 4) stages = 4;
+  const int halves = (H0 + 127) / 128;
+  const size_t stage_bytes = 2 * (size_t)H0 * 64 + 2 * (size_t)NT * 64;
+  // the last half-tile of the dZ1 planes may be read past H0 rows by the M = 128 MMA (the lanes it feeds are never
+  // read back): keep that read inside the dynamic window
+  const size_t slack = (size_t)(halves * 128 - H0) * 64;
+  int stages = (int)((200 * 1024 - slack) / stage_bytes);
+  if (stages > 6) stages = 6;
   if (stages < 2) stages = 2;
-  const size_t smem = 1024 + stages * stage_bytes + 24 * stages + 16 + 16;
+  const size_t smem = 1024 + stages * stage_bytes + slack + 24 * stages + 16 + 16;
   int tmem_cols = 32;
-  while (tmem_cols < H0) tmem_cols *= 2;
-  // accumulator columns transposed through shared memory per epilogue pass: all of them when GT rows fit the freed stages
-  int pass_cols = H0;
-  static int dbg_mode = -1, dbg_pass = 0;
-  if (dbg_mode < 0) {
-    const char* ev = getenv("SCNB_W1TC_MODE");
-    dbg_mode = ev ? atoi(ev) : 0;
-    ev = getenv("SCNB_W1TC_PASS");
-    dbg_pass = ev ? atoi(ev) : 0;
-  }
-  if (dbg_pass) pass_cols = dbg_pass;
-  if ((size_t)GT * (pass_cols + 4) * 4 > stages * stage_bytes) pass_cols = H0 > 128 ? 128 : H0;
-  if ((size_t)GT * (pass_cols + 4) * 4 > stages * stage_bytes) pass_cols = 32;
-  cudaError_t e = cudaFuncSetAttribute(k_w1_bwd_optim_tc<OPT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  while (tmem_cols < halves * NT) tmem_cols *= 2;
+  cudaError_t e = cudaFuncSetAttribute(k_w1_bwd_optim_tc<OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     scnb_set_error("csr_w1_bwd_optim_tc: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
     return SCNB_ERR_CUDA;
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(W1TC_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = CL;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = CL > 1 ? 1 : 0;
-  e = cudaLaunchKernelEx(&cfg, k_w1_bwd_optim_tc<OPT, CL>, splits, b_idx, b_val, nb, GT, G, H0, (const uint8_t*)dz_hi,
-                         (const uint8_t*)dz_lo, W1T, grad_out, s1, s2, hp, st4, stages, tmem_cols, pass_cols, dbg, dbg_mode);
-  if (e != cudaSuccess) {
-    scnb_set_error("csr_w1_bwd_optim_tc: launch failed: %s", cudaGetErrorString(e));
-    return SCNB_ERR_CUDA;
-  }
-  return SCNB_OK;
-}
-
-// cluster size for the dZ1 multicast (SCNB_W1TC_CL = 1 | 2 | 4 overrides; default 1)
-static int w1tc_cluster() {
-  static int cl = 0;
-  if (!cl) {
-    const char* ev = getenv("SCNB_W1TC_CL");
-    cl = ev ? atoi(ev) : 1;   // measured on B200: the main loop is tensor-bound, not L2-bound; multicast gains nothing
-    if (cl != 1 && cl != 2 && cl != 4) cl = 1;
-  }
-  return cl;
-}
-
-template <int OPT>
-static int launch_w1_bwd_optim_tc_any(const int32_t* splits, const int32_t* b_idx, const float* b_val, int nb, int H0, int G,
-                                      const void* dz_hi, const void* dz_lo, float* W1T, float* grad_out, float* s1, float* s2,
-                                      const float* hp, const int64_t* st4, cudaStream_t st) {
-  const int GT = w1tc_gene_block(G);
-  const int n_blk = scnb_cdiv(G, GT);
   static long long* dbg = nullptr;
   static int dbg_on = -1;
   if (dbg_on < 0) {
     const char* ev = getenv("SCNB_W1TC_DBG");
     dbg_on = (ev && ev[0] == '1') ? 1 : 0;
-    if (dbg_on) cudaMalloc(&dbg, (128 + 4 * 4096) * sizeof(long long));
+    if (dbg_on) cudaMalloc(&dbg, 4 * 4096 * sizeof(long long));
   }
-  long long* d = dbg_on ? dbg : nullptr;
-  int rc;
-  switch (w1tc_cluster()) {
-    case 1: rc = launch_w1_bwd_optim_tc<OPT, 1>(splits, b_idx, b_val, nb, H0, G, dz_hi, dz_lo, W1T, grad_out, s1, s2, hp, st4, st, d); break;
-    case 2: rc = launch_w1_bwd_optim_tc<OPT, 2>(splits, b_idx, b_val, nb, H0, G, dz_hi, dz_lo, W1T, grad_out, s1, s2, hp, st4, st, d); break;
-    default: rc = launch_w1_bwd_optim_tc<OPT, 4>(splits, b_idx, b_val, nb, H0, G, dz_hi, dz_lo, W1T, grad_out, s1, s2, hp, st4, st, d); break;
-  }
-  if (rc != SCNB_OK) return rc;
-  if (dbg_on) {  // debugging aid only (synchronises): phase timestamps of CTA 0 in SM clock cycles
-    long long h[128];
+  k_w1_bwd_optim_tc<OPT><<<n_blk, W1TC_THREADS, smem, st>>>(splits, b_idx, b_val, nb, GT, NT, G, H0, (const uint8_t*)dz_hi,
+                                                          (const uint8_t*)dz_lo, W1T, grad_out, s1, s2, hp, st4, (uint8_t*)pl_hi, (uint8_t*)pl_lo,
+                                                          stages, tmem_cols, dbg_on ? dbg : nullptr);
+  SCNB_CHECK_LAUNCH("csr_w1_bwd_optim_tc");
+  if (dbg_on && n_blk <= 4096) {  // debugging aid only (synchronises): per-CTA wall-clock stamps (ns)
+    static long long hc[4 * 4096];
     cudaStreamSynchronize(st);
-    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[w1tc] densify: start 0");
-    for (int i = 0; i < 16; ++i) fprintf(stderr, " | t%d wait+%lld fill+%lld", i, h[1 + 2 * i] - h[0], h[2 + 2 * i] - h[0]);
-    fprintf(stderr, "\n[w1tc] acc ready +%lld, epilogue half0 +%lld half1 +%lld\n[w1tc] mma:", h[40] - h[0], h[41] - h[0], h[42] - h[0]);
-    for (int i = 0; i < 16; ++i) fprintf(stderr, " | t%d B+%lld A+%lld", i, h[64 + 2 * i] - h[0], h[65 + 2 * i] - h[0]);
-    fprintf(stderr, "\n");
-    if (n_blk <= 4096) {  // per-CTA wall-clock stamps (ns): start, accumulator ready, end of each epilogue half
-      static long long hc[4 * 4096];
-      cudaMemcpy(hc, dbg + 128, sizeof(long long) * 4 * n_blk, cudaMemcpyDeviceToHost);
-      long long t0 = hc[0];
-      for (int b = 0; b < n_blk; ++b) if (hc[4 * b] < t0) t0 = hc[4 * b];
-      for (int k = 0; k < 4; ++k) {
-        long long mn = 1LL << 62, mx = 0, sum = 0;
-        for (int b = 0; b < n_blk; ++b) { long long v = hc[4 * b + k] - t0; if (v < mn) mn = v; if (v > mx) mx = v; sum += v; }
-        fprintf(stderr, "[w1tc] cta stamp %d: min %lld mean %lld max %lld ns\n", k, mn, sum / n_blk, mx);
-      }
+    cudaMemcpy(hc, dbg, sizeof(long long) * 4 * n_blk, cudaMemcpyDeviceToHost);
+    long long t0 = hc[3];
+    for (int b = 0; b < n_blk; ++b) if (hc[4 * b + 3] < t0) t0 = hc[4 * b + 3];
+    const char* nm[4] = {"start", "accumulator ready", "end", "kernel entry"};
+    for (int k = 0; k < 4; ++k) {
+      long long mn = 1LL << 62, mx = 0, sum = 0;
+      for (int b = 0; b < n_blk; ++b) { long long v = hc[4 * b + k] - t0; if (v < mn) mn = v; if (v > mx) mx = v; sum += v; }
+      fprintf(stderr, "[w1tc] %s: min %lld mean %lld max %lld ns (%d CTAs, %d stages, GT %d NT %d)\n", nm[k], mn, sum / n_blk, mx, n_blk,
+              stages, GT, NT);
     }
   }
   return SCNB_OK;
@@ -1033,15 +949,18 @@ static int launch_w1_bwd_optim_tc_any(const int32_t* splits, const int32_t* b_id
 
 extern "C" int scnb_csr_w1_bwd_optim_tc(int opt, const int32_t* splits, const int32_t* b_idx, const float* b_val, int nb, int H0, int G,
                                         const void* dz_planes_hi, const void* dz_planes_lo, float* W1T, float* grad_out,
-                                        float* state1, float* state2, const float* hp8, const int64_t* state4, void* stream) {
+                                        float* state1, float* state2, const float* hp8, const int64_t* state4, void* planes_hi_out,
+                                        void* planes_lo_out, void* stream) {
   SCNB_CHECK_ARG(splits && b_idx && b_val && dz_planes_hi && dz_planes_lo && nb > 0 && G > 0, "csr_w1_bwd_optim_tc: bad arguments");
   SCNB_CHECK_ARG(H0 >= 32 && H0 <= 256 && H0 % 32 == 0, "csr_w1_bwd_optim_tc: H0 must be a multiple of 32 in [32, 256] (got %d)", H0);
   SCNB_CHECK_ARG(opt == OPT_NONE ? (grad_out != nullptr) : (W1T && state1 && hp8 && state4 && (opt == OPT_SGD || state2)),
                  "csr_w1_bwd_optim_tc: missing buffers for the requested mode");
   SCNB_CHECK_ARG((((uintptr_t)W1T | (uintptr_t)grad_out | (uintptr_t)state1 | (uintptr_t)state2 | (uintptr_t)dz_planes_hi |
                    (uintptr_t)dz_planes_lo) % 16) == 0, "csr_w1_bwd_optim_tc: buffers must be 16-byte aligned");
+  SCNB_CHECK_ARG((planes_hi_out == nullptr) == (planes_lo_out == nullptr) && ((uintptr_t)planes_hi_out | (uintptr_t)planes_lo_out) % 16 == 0,
+                 "csr_w1_bwd_optim_tc: operand planes must be given together, 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-#define W1TC_GO(O) return launch_w1_bwd_optim_tc_any<O>(splits, b_idx, b_val, nb, H0, G, dz_planes_hi, dz_planes_lo, W1T, grad_out, state1, state2, hp8, state4, st)
+#define W1TC_GO(O) return launch_w1_bwd_optim_tc_any<O>(splits, b_idx, b_val, nb, H0, G, dz_planes_hi, dz_planes_lo, W1T, grad_out, state1, state2, hp8, state4, planes_hi_out, planes_lo_out, st)
   switch (opt) {
     case OPT_NONE: W1TC_GO(OPT_NONE);
     case OPT_ADADELTA: W1TC_GO(OPT_ADADELTA);

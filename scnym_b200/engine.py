@@ -303,12 +303,17 @@ class TrainEngine(object):
             self.w1_hi = torch.zeros(n_kt * H0 * 64, dtype=torch.int16, device=dev)
             self.w1_lo = torch.zeros(n_kt * H0 * 64, dtype=torch.int16, device=dev)
             self._ev_planes = torch.cuda.Event()
+        # the tensor-core dW1 + optimizer kernel writes the operand planes of the updated W1T itself (single process
+        # only: under data parallelism the update happens in the arena-wide optimizer pass)
+        self.w1_emits_planes = bool(self.tc_first and self.w1_tc and comm is None)
+        self._planes_version = None
+        self._bn_running_done = False
         self._side = None
         fus = lambda c: (self.H % 128 == 0 and self.H // 128 in (1, 2, 4, 8) and c * self.H * 4 <= 96 * 1024)
         self.fuse_classif = bool(cfg.fuse_heads and fus(self.C))
         self.fuse_dan = bool(cfg.fuse_heads and self.use_dan and fus(self.D))
         self._ev_grl, self._ev_csc, self._ev_zero = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
-        self._ev_teacher = torch.cuda.Event()
+        self._ev_teacher, self._ev_plan, self._ev_bnrun, self._ev_z1 = (torch.cuda.Event() for _ in range(4))
         self.dZ1 = f32(self.nb, H0) if mode == "mixmatch" else None
         if self.use_dan:
             self.Hd, self.dHd = f32(self.Rd, self.H), f32(self.Rd, self.H)
@@ -363,7 +368,7 @@ class TrainEngine(object):
         if not self.cfg.multi_stream:
             return main, main, main
         if self._side is None:
-            self._side = tuple(torch.cuda.Stream(device=self.dev) for _ in range(3))
+            self._side = tuple(torch.cuda.Stream(device=self.dev) for _ in range(4))
         return main, self._side[0], self._side[1]
 
     @staticmethod
@@ -375,21 +380,35 @@ class TrainEngine(object):
     def _refresh_planes(self, main, sW):
         """bf16 hi/lo planes of the current W1T for the tensor-core first layer (on the side branch, overlapping
         the step prologue); recomputed every step because the optimizer has just changed W1T."""
-        if not self.tc_first:
+        if not self.tc_first or self.w1_emits_planes:
             return
         self._after(sW, main)
         call("scnb_w1_planes", self.P(self._blk[0]["W"]), self.G, self.widths[0], ptr(self.w1_hi), ptr(self.w1_lo), sW.cuda_stream)
         if sW is not main:
             self._ev_planes.record(sW)
 
-    def _first_layer(self, main, sW, n_rows, Z):
+    def _sync_planes(self):
+        """With `w1_emits_planes` the step itself keeps the operand planes current.  They are rebuilt here, eagerly,
+        only when something outside the engine's kernels has written the parameter arena since (load_state_dict, a
+        torch optimizer, manual edits): torch bumps the arena's version counter on every in-place op, our kernels do not."""
+        if not self.w1_emits_planes:
+            return
+        v = self.arena.flat._version
+        if v != self._planes_version:
+            call("scnb_w1_planes", self.P(self._blk[0]["W"]), self.G, self.widths[0], ptr(self.w1_hi), ptr(self.w1_lo),
+                 torch.cuda.current_stream().cuda_stream)
+            self._planes_version = v
+
+    def _first_layer(self, main, sW, n_rows, Z, prezeroed=False):
         st = main.cuda_stream
         blk0 = self._blk[0]
         if self.tc_first:
-            if sW is not main:
+            if sW is not main and not self.w1_emits_planes:
                 main.wait_event(self._ev_planes)
+            if prezeroed:
+                main.wait_event(self._ev_z1)
             call("scnb_csr_linear_fwd_tc", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), n_rows, self.G, self.widths[0],
-                 ptr(self.w1_hi), ptr(self.w1_lo), self.P(blk0["b"]), ptr(Z), 0, st)
+                 ptr(self.w1_hi), ptr(self.w1_lo), self.P(blk0["b"]), ptr(Z), -1 if prezeroed else 0, st)
         else:
             call("scnb_csr_linear_fwd", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), n_rows, self.P(blk0["W"]),
                  self.P(blk0["b"]), self.widths[0], ptr(Z), st)
@@ -413,7 +432,21 @@ class TrainEngine(object):
         rng = ptr(self.state[1:3])
         blk = self._blk
         self._refresh_planes(main, sW)
+        z1_pre = self.tc_first and sW is not main
+        if z1_pre:   # the split-K first layer accumulates into Z1: clear it on the side branch, off the critical path
+            self._after(sW, main)
+            with torch.cuda.stream(sW):
+                self.Z1.zero_()
+            self._ev_z1.record(sW)
         self._prep(st)
+        # With pseudolabel_min_confidence <= 0 every unlabeled row is "confident": the MixUp plan depends only on the
+        # step's random draws, so it runs on its own branch next to the gather and the first layer.
+        teacher_async = (c.pseudolabel_min_confidence <= 0.0) and sW is not main
+        if teacher_async:
+            sP = self._side[3]
+            self._after(sP, main)
+            self._plan(self._all_confident, sP.cuda_stream)
+            self._ev_plan.record(sP)
         # -- batch CSR [U_raw ; L_aug] (+ per-gene histogram), one launch
         call("scnb_csr_gather_rows2", ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data), ptr(self.u_rows), U, 0, 0,
              ptr(self.lab.indptr), ptr(self.lab.indices), ptr(self.lab.data), ptr(self.l_rows), L, 1, SID_IN_L,
@@ -429,11 +462,10 @@ class TrainEngine(object):
             if sW is not main:
                 self._ev_csc.record(sW)
         # -- first layer, once
-        self._first_layer(main, sW, nb, self.Z1)
+        self._first_layer(main, sW, nb, self.Z1, prezeroed=z1_pre)
         # -- teacher (eval mode, losses.py:660-737).  With pseudolabel_min_confidence <= 0 every unlabeled row is
         #    "confident", so the MixUp plan and the student forward do not depend on the teacher: it runs on its own
         #    branch and is joined in front of the losses.
-        teacher_async = (c.pseudolabel_min_confidence <= 0.0) and sW is not main
         if teacher_async:
             sT = self._side[2]
             self._after(sT, main)
@@ -441,16 +473,26 @@ class TrainEngine(object):
             self._ev_teacher.record(sT)
         else:
             self._teacher_forward(st, rng)
-        conf_flags = self._all_confident if teacher_async else self.confident
         # -- MixUp plan + hidden-space MixUp (losses.py:811-875)
-        call("scnb_mixmatch_plan", ptr(conf_flags), ptr(self.perm_keys), ptr(self.gamma_raw), U, L, int(self.use_dan),
-             int(c.dan_use_conf_pseudolabels), int(c.mixup_alpha > 0.0), ptr(self.counts), ptr(self.seg_off),
-             ptr(self.plan_work), ptr(self.srcA), ptr(self.srcB), ptr(self.gam), R, ptr(self.inv3), ptr(self.coef3),
-             ptr(self.pconf), st)
+        if teacher_async:
+            main.wait_event(self._ev_plan)
+        else:
+            self._plan(self.confident, st)
         call("scnb_mix_rows", ptr(self.Z1), H0, ptr(self.srcA), ptr(self.srcB), ptr(self.gam), ptr(self.counts[3:]), R,
              ptr(self.Zs[0]), st)
         # -- student super-batch forward
         self._student_forward(st, rng)
+        # BatchNorm running statistics as soon as the forward statistics exist, off the critical path (the
+        # stream of the MixUp plan is idle by now); the eval-mode teacher must have read the OLD running statistics first
+        self._bn_running_done = False
+        if sW is not main:
+            sB = self._side[3]          # the plan's branch, long idle by now
+            self._after(sB, main)
+            if teacher_async:
+                sB.wait_event(self._ev_teacher)
+            self._bn_running_update(sB.cuda_stream)
+            self._ev_bnrun.record(sB)
+            self._bn_running_done = True
         Hh = self.H
         dA_last = self._view(self.dA, R, Hh)
         # branch D: domain adversary head, its loss and the reversed gradient into the embedding
@@ -515,6 +557,13 @@ class TrainEngine(object):
         dZ_first = self._student_backward(main, sW, rng, dA_last)
         call("scnb_unmix_rows", ptr(dZ_first), H0, ptr(self.inv3), ptr(self.coef3), nb, ptr(self.dZ1), st)
         self._finish_step(main, sW, sD, self.dZ1, nb)
+
+    def _plan(self, conf_flags, st):
+        c = self.cfg
+        call("scnb_mixmatch_plan", ptr(conf_flags), ptr(self.perm_keys), ptr(self.gamma_raw), self.U, self.L, int(self.use_dan),
+             int(c.dan_use_conf_pseudolabels), int(c.mixup_alpha > 0.0), ptr(self.counts), ptr(self.seg_off),
+             ptr(self.plan_work), ptr(self.srcA), ptr(self.srcB), ptr(self.gam), self.Rmax, ptr(self.inv3), ptr(self.coef3),
+             ptr(self.pconf), st)
 
     def _teacher_forward(self, st, rng):
         """Eval-mode teacher pass on stream `st`: pseudolabels q[0,U) (+ one-hot labels q[U,U+L)), confidences."""
@@ -683,7 +732,7 @@ class TrainEngine(object):
             if self.w1_tc:
                 call("scnb_w1_planes", ptr(dZ1), n_rows, H0, ptr(self.dz_hi), ptr(self.dz_lo), st)
                 call("scnb_csr_w1_bwd_optim_tc", -1, ptr(self.w1_splits), ptr(self.b_idx), ptr(self.b_val), n_rows, H0, self.G,
-                     ptr(self.dz_hi), ptr(self.dz_lo), None, self.Gp(W1), None, None, None, None, st)
+                     ptr(self.dz_hi), ptr(self.dz_lo), None, self.Gp(W1), None, None, None, None, None, None, st)
             else:
                 call("scnb_csr_w1_bwd_optim", -1, ptr(self.c_ptr), ptr(self.c_ent), ptr(dZ1), n_rows, H0, self.G, None, self.Gp(W1),
                      None, None, None, None, st)
@@ -695,13 +744,30 @@ class TrainEngine(object):
             if self.w1_tc:
                 call("scnb_w1_planes", ptr(dZ1), n_rows, H0, ptr(self.dz_hi), ptr(self.dz_lo), st)
                 call("scnb_csr_w1_bwd_optim_tc", opt, ptr(self.w1_splits), ptr(self.b_idx), ptr(self.b_val), n_rows, H0, self.G,
-                     ptr(self.dz_hi), ptr(self.dz_lo), ptr(ar.flat), keep, ptr(ar.state1), ptr(ar.state2), hp, s4, st)
+                     ptr(self.dz_hi), ptr(self.dz_lo), ptr(ar.flat), keep, ptr(ar.state1), ptr(ar.state2), hp, s4,
+                     ptr(self.w1_hi) if self.w1_emits_planes else None, ptr(self.w1_lo) if self.w1_emits_planes else None, st)
             else:
                 call("scnb_csr_w1_bwd_optim", opt, ptr(self.c_ptr), ptr(self.c_ent), ptr(dZ1), n_rows, H0, self.G, ptr(ar.flat), keep,
                      ptr(ar.state1), ptr(ar.state2), hp, s4, st)
             rest = ar.total - self.P1
             call("scnb_optim_step", opt, ptr(ar.flat[self.P1:]), ptr(ar.grad[self.P1:]), ptr(ar.state1[self.P1:]),
                  ptr(ar.state2[self.P1:]), rest, hp, s4, sw)
+        if not self._bn_running_done:
+            self._bn_running_update(sw)
+        if self.loss_hist is not None:
+            mm = self.mode == "mixmatch"
+            call("scnb_record_step", ptr(self.loss_buf), ptr(self.loss_hist), int(self.loss_hist.shape[0]),
+                 ptr(self.conf) if mm else None, self.U if mm else 0, ptr(self.conf_ring) if mm else None,
+                 int(self.conf_ring.shape[0]) if mm else 0, ptr(self.state), sw)
+        if self.mode == "mixmatch":
+            call("scnb_mm_step_inc", ptr(self.state), sw)
+        self._after(main, sW)
+        self._after(main, sD)
+        if self._bn_running_done:
+            main.wait_event(self._ev_bnrun)
+
+    def _bn_running_update(self, sw):
+        """BatchNorm running statistics (momentum update over the step's forward passes, in the reference's order)."""
         done = set()
         for a in range(self.n_app):
             bn = self._blk[a]["bn"]
@@ -715,15 +781,6 @@ class TrainEngine(object):
             call("scnb_bn_running_update", ptr(bn.running_mean), ptr(bn.running_var), ptr(bn.num_batches_tracked), sp[0], sp[1],
                  sp[2], sp[3], ptr(self.seg_off), self.n_seg, self.widths[a], float(bn.momentum),
                  ptr(self.dp_fwd[a][self.n_seg * 2 * self.widths[a]:]) if self.comm is not None else None, sw)
-        if self.loss_hist is not None:
-            mm = self.mode == "mixmatch"
-            call("scnb_record_step", ptr(self.loss_buf), ptr(self.loss_hist), int(self.loss_hist.shape[0]),
-                 ptr(self.conf) if mm else None, self.U if mm else 0, ptr(self.conf_ring) if mm else None,
-                 int(self.conf_ring.shape[0]) if mm else 0, ptr(self.state), sw)
-        if self.mode == "mixmatch":
-            call("scnb_mm_step_inc", ptr(self.state), sw)
-        self._after(main, sW)
-        self._after(main, sD)
 
     def enable_history(self, capacity: int, ring: int = 64):
         """Keep per-step loss scalars (and the last `ring` steps' pseudolabel confidences) on the
@@ -876,6 +933,7 @@ class TrainEngine(object):
         if self.mode == "mixmatch" and self.cfg.mean_teacher and self.teacher_bn is None:
             self.teacher_bn = [(b["bn"].running_mean.clone(), b["bn"].running_var.clone()) for b in self._blk]
         injected = any(x is not None for x in (self.inj_in_keep_L, self.inj_in_keep_U, self.inj_hidden_keep))
+        self._sync_planes()
         if self.cfg.use_cuda_graph and not injected:
             key = (self.unsup_weight, self.dan_weight)
             if self._graph is None or self._graph_key != key:

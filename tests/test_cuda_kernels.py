@@ -586,6 +586,9 @@ def test_csr_w1_bwd_optim_tensor_core(opt, n, G, H0):
     eps = 1e-6 if opt == "adadelta" else 1e-8
     hp = torch.tensor([kw["lr"], kw["weight_decay"], 0.9, 0.999, eps, 0.9, 0.9, 0.0]).cuda()
     state = torch.zeros(4, dtype=torch.int64).cuda()
+    n_kt = (G + 63) // 64
+    pl_hi, pl_lo = (torch.zeros(n_kt * H0 * 64, dtype=torch.int16).cuda() for _ in range(2))
+    want_hi, want_lo = (torch.zeros(n_kt * H0 * 64, dtype=torch.int16).cuda() for _ in range(2))
     call("scnb_row_gene_splits", ptr(b.indptr), ptr(b.indices), n, G, ptr(splits), _st())
     for t in range(2):
         dZ = torch.randn(n, H0)
@@ -596,10 +599,14 @@ def test_csr_w1_bwd_optim_tensor_core(opt, n, G, H0):
         call("scnb_step_begin", ptr(state), _st())
         if opt == "none":
             call("scnb_csr_w1_bwd_optim_tc", -1, ptr(splits), ptr(b.indices), ptr(b.data), n, H0, G, ptr(dz_hi), ptr(dz_lo), None,
-                 ptr(grad), None, None, None, None, _st())
+                 ptr(grad), None, None, None, None, None, None, _st())
         else:
             call("scnb_csr_w1_bwd_optim_tc", OPTIMIZER_CODES[opt], ptr(splits), ptr(b.indices), ptr(b.data), n, H0, G, ptr(dz_hi),
-                 ptr(dz_lo), ptr(W), ptr(grad), ptr(s1), ptr(s2), ptr(hp), ptr(state), _st())
+                 ptr(dz_lo), ptr(W), ptr(grad), ptr(s1), ptr(s2), ptr(hp), ptr(state), ptr(pl_hi), ptr(pl_lo), _st())
+            # the operand planes emitted by the epilogue are those scnb_w1_planes builds from the updated W1T
+            call("scnb_w1_planes", ptr(W), G, H0, ptr(want_hi), ptr(want_lo), _st())
+            torch.cuda.synchronize()
+            assert torch.equal(pl_hi, want_hi) and torch.equal(pl_lo, want_lo), "operand planes of the updated W1T"
         torch.cuda.synchronize()
         _chk("tc dW1", grad.cpu(), want_g, tol=3e-5)
         if opt != "none":

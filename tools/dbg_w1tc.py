@@ -16,13 +16,14 @@ dZ = torch.randn(n, H0).cuda()
 st = torch.cuda.current_stream().cuda_stream
 call("scnb_row_gene_splits", ptr(b.indptr), ptr(b.indices), n, G, ptr(splits), st)
 call("scnb_w1_planes", ptr(dZ), n, H0, ptr(dz_hi), ptr(dz_lo), st)
+pl_hi = torch.zeros(((G + 63) // 64) * H0 * 64, dtype=torch.int16).cuda(); pl_lo = torch.zeros_like(pl_hi)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 for it in range(4):
     if os.environ.get("W1TC_FLUSH", "0") == "1":
         flush.fill_(it)
     ev[0].record()
-    call("scnb_csr_w1_bwd_optim_tc", 1, ptr(splits), ptr(b.indices), ptr(b.data), n, H0, G, ptr(dz_hi), ptr(dz_lo), ptr(W), None, ptr(s1), ptr(s2), ptr(hp), ptr(state), st)
+    call("scnb_csr_w1_bwd_optim_tc", 1, ptr(splits), ptr(b.indices), ptr(b.data), n, H0, G, ptr(dz_hi), ptr(dz_lo), ptr(W), None, ptr(s1), ptr(s2), ptr(hp), ptr(state), ptr(pl_hi), ptr(pl_lo), st)
     ev[1].record()
     torch.cuda.synchronize()
     print("launch", it, "ms", ev[0].elapsed_time(ev[1]), file=sys.stderr)
