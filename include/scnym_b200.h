@@ -166,6 +166,31 @@ int scnb_bn_act_bwd(const float* dA, const float* Z, const float* A, int H, int 
                     int max_rows, const float* gamma, const float* stats, const uint8_t* keep_mask, const uint64_t* rng,
                     uint32_t stream_id, float p_drop, int relu, float* dZ, float* dgamma /*+=*/, float* dbeta /*+=*/,
                     float* dp_partial_out /*local sum dy, sum dy*zhat, counts*/, const float* dp_sums, void* stream);
+
+/* ---- data-parallel BatchNorm in ONE launch: the per-segment column sums are all-reduced inside the kernel through
+ *      peer-addressable exchange buffers (CUDA IPC over NVLink / NVSwitch), replacing the partial -> NCCL all-reduce ->
+ *      apply protocol of scnb_bn_act_fwd/bwd.  Equivalence target: nn.BatchNorm1d of scnym/model.py:217 on the
+ *      concatenated global batch.  peer_bufs: device array [world] of the ranks' exchange buffers as
+ *      addressable from this process (own buffer at [rank]); each buffer holds scnb_bn_peer_bytes(H, n_seg, n_slots,
+ *      world) bytes, zeroed before the first step.  slot: index of this BatchNorm call within the step (< n_slots);
+ *      epoch: device scalar > 0 that changes every step (the optimizer step count).  global_sums_out (may be NULL):
+ *      [n_seg][2][H] global sums + [n_seg] global row counts, as scnb_bn_running_update's dp_counts expects.
+ *      scnb_peer_alloc/open/close/free: exchange buffers as cudaMalloc memory + 64-byte CUDA IPC handles. ---- */
+int scnb_bn_peer_bytes(int H, int n_seg, int n_slots, int world);   /* returns the byte count (> 0), not a status */
+int scnb_bn_act_fwd_peer(const float* Z, float* A, float* pre_out, int H, int n_seg, const int32_t* seg_off_dev, int max_rows,
+                         const float* gamma, const float* beta, float* stats, const uint8_t* keep_mask, const uint64_t* rng,
+                         uint32_t stream_id, float p_drop, int relu, const uint64_t* peer_bufs, int rank, int world, int slot,
+                         int n_slots, const int64_t* epoch, long long buf_bytes, float* global_sums_out, void* stream);
+int scnb_bn_act_bwd_peer(const float* dA, const float* Z, const float* A, int H, int n_seg, const int32_t* seg_off_dev,
+                         int max_rows, const float* gamma, const float* stats, const uint8_t* keep_mask, const uint64_t* rng,
+                         uint32_t stream_id, float p_drop, int relu, float* dZ, float* dgamma, float* dbeta,
+                         const uint64_t* peer_bufs, int rank, int world, int slot, int n_slots, const int64_t* epoch,
+                         long long buf_bytes, void* stream);
+int scnb_peer_alloc(long long bytes, void** ptr_out, void* handle64_out);
+int scnb_peer_open(const void* handle64, void** ptr_out);
+int scnb_peer_close(void* ptr);
+int scnb_peer_free(void* ptr);
+
 int scnb_bn_eval_bwd(const float* dA, const float* A, int relu, int rows, int H, const float* gamma,
                      const float* running_var, float* dZ, void* stream);
 int scnb_bn_running_update(float* running_mean, float* running_var, int64_t* num_batches_tracked, const float* stats0,

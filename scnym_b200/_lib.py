@@ -43,6 +43,13 @@ SIGNATURES = {
     "scnb_bn_eval_bwd": [P, P, I, I, I, P, P, P, P],
     "scnb_bn_act_fwd": [P, P, P, I, I, P, I, I, P, P, P, P, P, P, P, U32, F, I, P, P, P],
     "scnb_bn_act_bwd": [P, P, P, I, I, P, I, P, P, P, P, U32, F, I, P, P, P, P, P, P],
+    "scnb_bn_act_fwd_peer": [P, P, P, I, I, P, I, P, P, P, P, P, U32, F, I, P, I, I, I, I, P, L, P, P],
+    "scnb_bn_act_bwd_peer": [P, P, P, I, I, P, I, P, P, P, P, U32, F, I, P, P, P, P, I, I, I, I, P, L, P],
+    "scnb_bn_peer_bytes": [I, I, I, I],
+    "scnb_peer_alloc": [L, P, P],
+    "scnb_peer_open": [P, P],
+    "scnb_peer_close": [P],
+    "scnb_peer_free": [P],
     "scnb_bn_running_update": [P, P, P, P, P, P, P, P, I, I, F, P, P],
     "scnb_mix_rows": [P, I, P, P, P, P, I, P, P],
     "scnb_unmix_rows": [P, I, P, P, I, P, P],

@@ -480,6 +480,78 @@ __device__ __forceinline__ void bnv_colsum8(F8& x, float (*red)[8]) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cross-rank BatchNorm statistics through peer memory (data-parallel training, one process per GPU).
+// Every rank owns an exchange buffer that all ranks can address (CUDA IPC over NVLink / NVSwitch; bufs[r] is rank
+// r's buffer as seen from this process).  A BatchNorm CTA owns 8 columns of one segment on every rank, so the
+// all-reduce decomposes per CTA: it stores its 16 local column sums + its row count as one 128-byte packet into
+// EVERY rank's buffer, publishes it with a release flag (the step number), waits for the packets of all ranks in its
+// own buffer and adds them in rank order -- bit-identical statistics on all ranks, no collective launch, one kernel.
+// Packets are double-buffered by step parity; the gradient all-reduce that ends a step separates reuses.
+//   packet(slot, parity, src, cta) : 32 words = [sum_a[8] | sum_b[8] | rows | ... | flag]
+// ---------------------------------------------------------------------------------------------
+struct PeerX {
+  const unsigned long long* bufs;   // device array [world] of exchange-buffer base addresses (NULL: no exchange)
+  const long long* epoch;           // device scalar: step number (> 0, changes every step)
+  int rank, world, slot, spin_limit;
+  int cta_stride;                   // packets reserved per (slot, parity, source rank): >= CTAs of any launch using the buffer
+};
+
+#define PEER_PKT_WORDS 32
+
+__device__ __forceinline__ void peer_allreduce17(const PeerX& px, F8& a, F8& b, float& rows, float* xs /* shared [32] */) {
+  const int t = threadIdx.x;
+  const unsigned e = (unsigned)px.epoch[0];
+  const size_t n_cta = (size_t)px.cta_stride, cta = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+  const size_t pkt0 = ((size_t)(px.slot * 2 + (int)(e & 1u)) * px.world) * n_cta + cta;   // + src * n_cta
+  if (t < 32) {
+    float mine = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (t == j) mine = a.v[j];
+      if (t == 8 + j) mine = b.v[j];
+    }
+    if (t == 16) mine = rows;
+    const size_t my_pkt = (pkt0 + (size_t)px.rank * n_cta) * PEER_PKT_WORDS;
+    if (t < 17) {
+      for (int p = 0; p < px.world; ++p) {
+        float* dst = reinterpret_cast<float*>(px.bufs[p]) + my_pkt;
+        asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(dst + t), "f"(mine) : "memory");
+      }
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (t < px.world) {   // publish to rank t, then wait for rank t's packet in the local buffer
+      unsigned* flag = reinterpret_cast<unsigned*>(px.bufs[t]) + my_pkt + (PEER_PKT_WORDS - 1);
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(e) : "memory");
+      const unsigned* mine_f = reinterpret_cast<const unsigned*>(px.bufs[px.rank]) + (pkt0 + (size_t)t * n_cta) * PEER_PKT_WORDS +
+                               (PEER_PKT_WORDS - 1);
+      unsigned got = 0;
+      int spins = 0;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(mine_f) : "memory");
+        if (got != e && ++spins > px.spin_limit) __trap();   // a peer never arrived: fail loudly instead of hanging the GPU
+      } while (got != e);
+    }
+    __syncwarp();
+    if (t < 17) {
+      float acc = 0.f;
+      for (int p = 0; p < px.world; ++p) {
+        const float* src = reinterpret_cast<const float*>(px.bufs[px.rank]) + (pkt0 + (size_t)p * n_cta) * PEER_PKT_WORDS;
+        float v;
+        asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(src + t) : "memory");
+        acc += v;
+      }
+      xs[t] = acc;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a.v[j] = xs[j]; b.v[j] = xs[8 + j]; }
+  rows = xs[16];
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(BNV_T) k_bn_act_fwd_v8(const float* __restrict__ Z, float* __restrict__ Aout,
                                                          float* __restrict__ pre_out, int H, int n_seg,
                                                          const int32_t* __restrict__ seg_off, int max_rows,
@@ -487,10 +559,12 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_fwd_v8(const float* __restrict
                                                          float* __restrict__ stats, const uint8_t* __restrict__ keep_mask,
                                                          const uint64_t* __restrict__ rng, uint32_t stream_id, float p_drop,
                                                          int relu, float* __restrict__ partial_out,
-                                                         const float* __restrict__ ext_sums, const float* __restrict__ ext_cnt) {
+                                                         const float* __restrict__ ext_sums, const float* __restrict__ ext_cnt,
+                                                         PeerX px, float* __restrict__ glob_out) {
   PDL_ENTRY();
   __shared__ __align__(16) float red1[BNV_W][8];
   __shared__ __align__(16) float red2[BNV_W][8];
+  __shared__ float xs[32];
   const int t = threadIdx.x;
   const int c0 = blockIdx.x * 8, s = blockIdx.y;
   const int Hg = H >> 3;
@@ -524,7 +598,36 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_fwd_v8(const float* __restrict
     return;
   }
   F8 var;
-  if (ext_sums) {
+  if (px.bufs) {  // data parallel, one launch: local sums -> peer-memory all-reduce -> global statistics
+    F8 a1, a2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a1.v[j] = a2.v[j] = 0.f;
+    for (int r = r0 + t; r < r1; r += BNV_T) {
+      const F8 z = ld8(Z + (size_t)r * H + c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a1.v[j] += z.v[j]; a2.v[j] = fmaf(z.v[j], z.v[j], a2.v[j]); }
+    }
+    bnv_colsum8(a1, red1);
+    bnv_colsum8(a2, red2);
+    float rows = (float)n;
+    peer_allreduce17(px, a1, a2, rows, xs);
+    if (glob_out) {   // [seg][2][H] global sums + [seg] global rows: what the running-statistics update reads
+      if (t < 8) {
+        float u = 0.f, w = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j == t) { u = a1.v[j]; w = a2.v[j]; }
+        glob_out[((size_t)s * 2 + 0) * H + c0 + t] = u;
+        glob_out[((size_t)s * 2 + 1) * H + c0 + t] = w;
+      }
+      if (blockIdx.x == 0 && t == 0) glob_out[(size_t)n_seg * 2 * H + s] = rows;
+    }
+    const float ng = fmaxf(rows, 1.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mean.v[j] = a1.v[j] / ng;
+      var.v[j] = fmaxf(a2.v[j] / ng - mean.v[j] * mean.v[j], 0.f);
+    }
+  } else if (ext_sums) {
     const float ng = fmaxf(ext_cnt[s], 1.f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -601,10 +704,11 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_bwd_v8(const float* __restrict
                                                          uint32_t stream_id, float p_drop, int relu, float* __restrict__ dZ,
                                                          float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                          float* __restrict__ partial_out, const float* __restrict__ ext_sums,
-                                                         const float* __restrict__ ext_cnt) {
+                                                         const float* __restrict__ ext_cnt, PeerX px) {
   PDL_ENTRY();
   __shared__ __align__(16) float red1[BNV_W][8];
   __shared__ __align__(16) float red2[BNV_W][8];
+  __shared__ float xs[32];
   const int t = threadIdx.x;
   const int c0 = blockIdx.x * 8, s = blockIdx.y;
   const int Hg = H >> 3;
@@ -665,6 +769,11 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_bwd_v8(const float* __restrict
     if (partial_out) {
       if (blockIdx.x == 0 && t == 0) partial_out[(size_t)n_seg * 2 * H + s] = (float)n;
       return;
+    }
+    if (px.bufs) {   // data parallel, one launch: the two column sums and the row count become global here
+      float rows = (float)n;
+      peer_allreduce17(px, s1, s2, rows, xs);
+      inv_n = 1.0f / fmaxf(rows, 1.f);
     }
   }
   for (int r = r0 + t; r < r1; r += BNV_T) {
@@ -775,7 +884,7 @@ extern "C" int scnb_bn_act_fwd(const float* Z, float* A, float* pre_out, int H, 
     dim3 gridv(H / 8, n_seg);
     scnb_launch_pdl(k_bn_act_fwd_v8, gridv, dim3(BNV_T), 0, (cudaStream_t)stream, Z, A, pre_out, H, n_seg, seg_off_dev, max_rows, gamma, beta, stats,
                                                                keep_mask, rng, stream_id, p_drop, relu, dp_partial_out, dp_sums,
-                                                               ext_cnt);
+                                                               ext_cnt, PeerX{nullptr, nullptr, 0, 1, 0, 0, 0}, (float*)nullptr);
     SCNB_CHECK_LAUNCH("bn_act_fwd/v8");
     return SCNB_OK;
   }
@@ -878,7 +987,7 @@ extern "C" int scnb_bn_act_bwd(const float* dA, const float* Z, const float* A, 
     dim3 gridv(H / 8, n_seg);
     scnb_launch_pdl(k_bn_act_bwd_v8, gridv, dim3(BNV_T), 0, (cudaStream_t)stream, dA, Z, A, H, n_seg, seg_off_dev, max_rows, gamma, stats, keep_mask,
                                                                rng, stream_id, p_drop, relu, dZ, dgamma, dbeta, dp_partial_out,
-                                                               dp_sums, ext_cnt);
+                                                               dp_sums, ext_cnt, PeerX{nullptr, nullptr, 0, 1, 0, 0, 0});
     SCNB_CHECK_LAUNCH("bn_act_bwd/v8");
     return SCNB_OK;
   }
@@ -887,6 +996,75 @@ extern "C" int scnb_bn_act_bwd(const float* dA, const float* Z, const float* A, 
                                                          stream_id, p_drop, relu, dZ, dgamma, dbeta, dp_partial_out, dp_sums,
                                                          ext_cnt);
   SCNB_CHECK_LAUNCH("bn_act_bwd");
+  return SCNB_OK;
+}
+
+// ---- data-parallel one-launch forms: statistics all-reduced through peer memory inside the kernel ----
+static int peer_check(const char* who, const unsigned long long* peer_bufs, int rank, int world, int slot, int n_slots,
+                      const long long* epoch, long long buf_bytes, int H, int n_seg, int* cta_stride) {
+  SCNB_CHECK_ARG(peer_bufs && epoch && world >= 1 && world <= 32 && rank >= 0 && rank < world && slot >= 0 && slot < n_slots,
+                 "%s: bad peer arguments", who);
+  // the buffer is cut into n_slots * 2 (step parity) * world (source rank) equal runs of packets
+  *cta_stride = (int)(buf_bytes / ((long long)n_slots * 2 * world * PEER_PKT_WORDS * 4));
+  SCNB_CHECK_ARG(*cta_stride >= (H / 8) * n_seg, "%s: exchange buffer too small (%lld bytes: %d packets per run, %d needed)", who,
+                 buf_bytes, *cta_stride, (H / 8) * n_seg);
+  return SCNB_OK;
+}
+
+static int peer_spin_limit() {
+  static int v = 0;
+  if (!v) {
+    const char* ev = getenv("SCNB_PEER_SPIN_LIMIT");
+    v = ev ? atoi(ev) : (1 << 24);   // ~10 s of polling before the kernel traps
+    if (v <= 0) v = 1 << 24;
+  }
+  return v;
+}
+
+extern "C" int scnb_bn_peer_bytes(int H, int n_seg, int n_slots, int world) {
+  return (int)((size_t)n_slots * 2 * world * (size_t)((H + 7) / 8) * n_seg * PEER_PKT_WORDS * 4);
+}
+
+extern "C" int scnb_bn_act_fwd_peer(const float* Z, float* A, float* pre_out, int H, int n_seg, const int32_t* seg_off_dev,
+                                    int max_rows, const float* gamma, const float* beta, float* stats, const uint8_t* keep_mask,
+                                    const uint64_t* rng, uint32_t stream_id, float p_drop, int relu, const uint64_t* peer_bufs,
+                                    int rank, int world, int slot, int n_slots, const int64_t* epoch, long long buf_bytes,
+                                    float* global_sums_out, void* stream) {
+  SCNB_CHECK_ARG(Z && A && gamma && beta && seg_off_dev && stats && H > 0 && n_seg > 0 && max_rows >= 0, "bn_act_fwd_peer: bad arguments");
+  SCNB_CHECK_ARG(!(p_drop > 0.f) || keep_mask || rng, "bn_act_fwd_peer: dropout needs keep_mask or rng state");
+  SCNB_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "bn_act_fwd_peer: p_drop out of range");
+  SCNB_CHECK_ARG(bn_vec8_ok(H, Z, A, pre_out, gamma, beta, stats, keep_mask),
+                 "bn_act_fwd_peer: needs H %% 8 == 0 and 16-byte aligned buffers");
+  int stride = 0;
+  int rc = peer_check("bn_act_fwd_peer", (const unsigned long long*)peer_bufs, rank, world, slot, n_slots, (const long long*)epoch,
+                      buf_bytes, H, n_seg, &stride);
+  if (rc != SCNB_OK) return rc;
+  PeerX px{(const unsigned long long*)peer_bufs, (const long long*)epoch, rank, world, slot, peer_spin_limit(), stride};
+  k_bn_act_fwd_v8<<<dim3(H / 8, n_seg), BNV_T, 0, (cudaStream_t)stream>>>(Z, A, pre_out, H, n_seg, seg_off_dev, max_rows, gamma, beta, stats,
+                                                                         keep_mask, rng, stream_id, p_drop, relu, nullptr, nullptr,
+                                                                         nullptr, px, global_sums_out);
+  SCNB_CHECK_LAUNCH("bn_act_fwd_peer");
+  return SCNB_OK;
+}
+
+extern "C" int scnb_bn_act_bwd_peer(const float* dA, const float* Z, const float* A, int H, int n_seg, const int32_t* seg_off_dev,
+                                    int max_rows, const float* gamma, const float* stats, const uint8_t* keep_mask,
+                                    const uint64_t* rng, uint32_t stream_id, float p_drop, int relu, float* dZ, float* dgamma,
+                                    float* dbeta, const uint64_t* peer_bufs, int rank, int world, int slot, int n_slots,
+                                    const int64_t* epoch, long long buf_bytes, void* stream) {
+  SCNB_CHECK_ARG(dA && Z && A && gamma && stats && dZ && dgamma && dbeta && seg_off_dev && H > 0 && n_seg > 0,
+                 "bn_act_bwd_peer: bad arguments");
+  SCNB_CHECK_ARG(!(p_drop > 0.f) || keep_mask || rng, "bn_act_bwd_peer: dropout needs keep_mask or rng state");
+  SCNB_CHECK_ARG(bn_vec8_ok(H, dA, Z, A, gamma, dZ, stats, keep_mask), "bn_act_bwd_peer: needs H %% 8 == 0 and 16-byte aligned buffers");
+  int stride = 0;
+  int rc = peer_check("bn_act_bwd_peer", (const unsigned long long*)peer_bufs, rank, world, slot, n_slots, (const long long*)epoch,
+                      buf_bytes, H, n_seg, &stride);
+  if (rc != SCNB_OK) return rc;
+  PeerX px{(const unsigned long long*)peer_bufs, (const long long*)epoch, rank, world, slot, peer_spin_limit(), stride};
+  k_bn_act_bwd_v8<<<dim3(H / 8, n_seg), BNV_T, 0, (cudaStream_t)stream>>>(dA, Z, A, H, n_seg, seg_off_dev, max_rows, gamma, stats, keep_mask, rng,
+                                                                         stream_id, p_drop, relu, dZ, dgamma, dbeta, nullptr, nullptr,
+                                                                         nullptr, px);
+  SCNB_CHECK_LAUNCH("bn_act_bwd_peer");
   return SCNB_OK;
 }
 

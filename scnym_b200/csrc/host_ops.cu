@@ -36,3 +36,60 @@ extern "C" int scnb_host_gather_rows(const int64_t* indptr, const int32_t* indic
   }
   return SCNB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Peer-addressable exchange buffers for the data-parallel BatchNorm kernels (one process per GPU): plain cudaMalloc
+// memory exported / opened through CUDA IPC, so that a kernel on one GPU can store into every other GPU's buffer over
+// NVLink / NVSwitch.  handle: 64 opaque bytes (cudaIpcMemHandle_t) that the host side ships to the other ranks.
+// ---------------------------------------------------------------------------------------------
+extern "C" int scnb_peer_alloc(long long bytes, void** ptr_out, void* handle64_out) {
+  SCNB_CHECK_ARG(bytes > 0 && ptr_out && handle64_out, "peer_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e == cudaSuccess) e = cudaMemset(p, 0, bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    if (p) cudaFree(p);
+    scnb_set_error("peer_alloc: %s", cudaGetErrorString(e));
+    return SCNB_ERR_CUDA;
+  }
+  memcpy(handle64_out, &h, sizeof(h));
+  *ptr_out = p;
+  return SCNB_OK;
+}
+
+extern "C" int scnb_peer_open(const void* handle64, void** ptr_out) {
+  SCNB_CHECK_ARG(handle64 && ptr_out, "peer_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    scnb_set_error("peer_open: %s", cudaGetErrorString(e));
+    return SCNB_ERR_CUDA;
+  }
+  *ptr_out = p;
+  return SCNB_OK;
+}
+
+extern "C" int scnb_peer_close(void* ptr) {
+  if (!ptr) return SCNB_OK;
+  cudaError_t e = cudaIpcCloseMemHandle(ptr);
+  if (e != cudaSuccess) {
+    scnb_set_error("peer_close: %s", cudaGetErrorString(e));
+    return SCNB_ERR_CUDA;
+  }
+  return SCNB_OK;
+}
+
+extern "C" int scnb_peer_free(void* ptr) {
+  if (!ptr) return SCNB_OK;
+  cudaError_t e = cudaFree(ptr);
+  if (e != cudaSuccess) {
+    scnb_set_error("peer_free: %s", cudaGetErrorString(e));
+    return SCNB_ERR_CUDA;
+  }
+  return SCNB_OK;
+}

@@ -283,6 +283,13 @@ class TrainEngine(object):
             # cross-rank exchange buffers per application: [n_seg][2][w] sums + [n_seg] row counts
             self.dp_fwd = [f32(self.n_seg * 2 * w + self.n_seg) for w in self.widths]
             self.dp_bwd = [f32(self.n_seg * 2 * w + self.n_seg) for w in self.widths]
+            # in-kernel all-reduce of the BatchNorm statistics through peer memory when the communicator offers it
+            self.peer = None
+            mk = getattr(comm, "make_peer_exchange", None)
+            if mk is not None and all(w % 8 == 0 for w in self.widths):
+                self.peer_slots = 2 * len(self.widths)
+                nbytes = max(_lib.lib().scnb_bn_peer_bytes(w, self.n_seg, self.peer_slots, comm.world) for w in self.widths)
+                self.peer = mk(int(nbytes), dev)
             self.comm.broadcast(self.arena.flat)  # identical replicas to start from
             for b in self._blk:
                 self.comm.broadcast(b["bn"].running_mean)
@@ -644,6 +651,11 @@ class TrainEngine(object):
                 SID_HID + a, p, 1, part, sums, st)
             if self.comm is None:
                 fwd(None, None)
+            elif self.peer is not None:   # one launch: statistics all-reduced inside the kernel over peer memory
+                px = self.peer
+                call("scnb_bn_act_fwd_peer", ptr(self.Zs[a]), ptr(self.As[a]), None, w, self.n_seg, ptr(self.seg_off), R,
+                     self.P(blk[a]["g"]), self.P(blk[a]["beta"]), ptr(self.stats[a]), self._hidden_keep(a), rng, SID_HID + a, p, 1,
+                     ptr(px.ptrs), px.rank, px.world, a, self.peer_slots, ptr(self.state), px.nbytes, ptr(self.dp_fwd[a]), st)
             else:  # cross-rank BatchNorm statistics: local sums -> all-reduce -> apply
                 fwd(ptr(self.dp_fwd[a]), None)
                 self.comm.all_reduce_sum(self.dp_fwd[a])
@@ -670,6 +682,12 @@ class TrainEngine(object):
                 main.wait_event(self._ev_zero)   # BatchNorm gamma/beta gradients accumulate into zeroed buffers
             if self.comm is None:
                 bwd(None, None)
+            elif self.peer is not None:
+                px = self.peer
+                call("scnb_bn_act_bwd_peer", ptr(dA), ptr(self.Zs[a]), ptr(self.As[a]), w, self.n_seg, ptr(self.seg_off), R,
+                     self.P(blk[a]["g"]), ptr(self.stats[a]), self._hidden_keep(a), rng, SID_HID + a, p, 1, ptr(dZ),
+                     self.Gp(blk[a]["g"]), self.Gp(blk[a]["beta"]), ptr(px.ptrs), px.rank, px.world, self.n_app + a, self.peer_slots,
+                     ptr(self.state), px.nbytes, st)
             else:
                 bwd(ptr(self.dp_bwd[a]), None)
                 self.comm.all_reduce_sum(self.dp_bwd[a])

@@ -56,6 +56,64 @@ class TorchDistComm(object):
     def barrier(self) -> None:
         dist.barrier(group=self.group)
 
+    def make_peer_exchange(self, nbytes: int, device) -> Optional["PeerExchange"]:
+        """Peer-memory exchange buffers for the in-kernel BatchNorm all-reduce (NCCL process groups on one node only;
+        SCNB_DP_PEER=0 keeps the partial -> NCCL all-reduce -> apply protocol)."""
+        import os
+        if not self._avg or os.environ.get("SCNB_DP_PEER", "1") == "0":
+            return None
+        return PeerExchange.from_dist(nbytes, device, self.group)
+
+
+class PeerExchange(object):
+    """Exchange buffers of all ranks as addressable from this process: `ptrs` is a device int64 array [world] (own
+    buffer at [rank]) that the data-parallel BatchNorm kernels (`scnb_bn_act_fwd_peer` / `_bwd_peer`) store into and
+    poll -- the cross-rank statistics all-reduce happens inside those kernels, over NVLink / NVSwitch peer memory."""
+
+    def __init__(self, addrs, rank: int, world: int, nbytes: int, device, owned=None, opened=(), keep=None) -> None:
+        self.rank, self.world, self.nbytes = int(rank), int(world), int(nbytes)
+        self.ptrs = torch.tensor([int(a) for a in addrs], dtype=torch.int64, device=device)
+        self._owned, self._opened, self._keep = owned, list(opened), keep
+
+    @classmethod
+    def from_dist(cls, nbytes: int, device, group=None) -> "PeerExchange":
+        """One cudaMalloc buffer per rank, shared through CUDA IPC handles (one process per GPU, one node)."""
+        import ctypes
+        from . import _lib
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        with torch.cuda.device(device):
+            own = ctypes.c_void_p()
+            handle = ctypes.create_string_buffer(64)
+            _lib.call("scnb_peer_alloc", int(nbytes), ctypes.byref(own), handle)
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            addrs, opened = [], []
+            for r in range(world):
+                if r == rank:
+                    addrs.append(own.value)
+                else:
+                    q = ctypes.c_void_p()
+                    _lib.call("scnb_peer_open", ctypes.create_string_buffer(handles[r], 64), ctypes.byref(q))
+                    addrs.append(q.value)
+                    opened.append(q.value)
+            torch.cuda.synchronize()
+        dist.barrier(group=group)          # every buffer is zeroed and mapped everywhere before the first kernel polls it
+        return cls(addrs, rank, world, nbytes, device, owned=own.value, opened=opened)
+
+    @classmethod
+    def local(cls, buffers, rank: int) -> "PeerExchange":
+        """Emulated ranks inside one process (tests): `buffers` are the ranks' zeroed uint8 CUDA tensors."""
+        return cls([b.data_ptr() for b in buffers], rank, len(buffers), buffers[0].numel(), buffers[0].device, keep=buffers)
+
+    def close(self) -> None:
+        from . import _lib
+        for q in self._opened:
+            _lib.call("scnb_peer_close", q)
+        self._opened = []
+        if self._owned:
+            _lib.call("scnb_peer_free", self._owned)
+            self._owned = None
+
 
 def merge_bn_sums(sums: torch.Tensor, n_seg: int, width: int, eps: float = 1e-5):
     """Host restatement of what the kernels do with an all-reduced exchange buffer

@@ -110,9 +110,24 @@ class ThreadComm(object):
         self.sh["bar"].wait()
 
 
+class PeerThreadComm(ThreadComm):
+    """Same, plus peer-addressable exchange buffers: the BatchNorm kernels of the two emulated ranks then wait for each
+    other ON THE DEVICE (they run concurrently on different streams of the one GPU), as they do across GPUs."""
+
+    def make_peer_exchange(self, nbytes, device):
+        from scnym_b200.parallel import PeerExchange
+        self.sh["peer"][self.rank] = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        torch.cuda.synchronize()
+        self.sh["bar"].wait()
+        px = PeerExchange.local(list(self.sh["peer"]), self.rank)
+        self.sh["bar"].wait()
+        return px
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("opt_name,lr", [("sgd", 0.05), ("adadelta", 1.0)])
-def test_data_parallel_step_equals_global_batch_oracle(opt_name, lr):
+@pytest.mark.parametrize("opt_name,lr,peer", [("sgd", 0.05, False), ("adadelta", 1.0, False), ("sgd", 0.05, True), ("adadelta", 1.0, True)])
+def test_data_parallel_step_equals_global_batch_oracle(opt_name, lr, peer, monkeypatch):
+    monkeypatch.setenv("SCNB_PEER_SPIN_LIMIT", str(1 << 21))   # a missing peer traps after ~1 s instead of ~10 s
     from oracle import scnym_oracle as O
     from tests import cuda_harness as CH
     kw = dict(G=600, L=24, U=32, C=5, H0=64, H=48, n_layers=2, opt_name=opt_name, lr=lr, n_steps=1, D_given=0)
@@ -151,7 +166,7 @@ def test_data_parallel_step_equals_global_batch_oracle(opt_name, lr):
     oopt = O.OracleOptimizer(om.parameters(), GU.optim_config(cases[0]))
     out, grads, _ = O.train_step(om, oopt, GU.step_config(cases[0]), Lx, Ly, Ux, rnd_g)
     # ---- two emulated ranks ----
-    shared = {"slots": [None, None], "bar": threading.Barrier(2)}
+    shared = {"slots": [None, None], "peer": [None, None], "bar": threading.Barrier(2)}
     engines, errors = [None, None], []
 
     def worker(rk):
@@ -166,12 +181,14 @@ def test_data_parallel_step_equals_global_batch_oracle(opt_name, lr):
             unl = DeviceCSR.from_arrays(d["unl_indptr"], d["unl_indices"], d["unl_data"], G)
             from scnym_b200.engine import EngineConfig
             cfg = EngineConfig(optimizer=opt_name, lr=lr, weight_decay=float(d["meta_wd"]), use_cuda_graph=False, keep_w1_grad=True)
-            eng = TrainEngine(model, cfg, lab, d["lab_y"], l, unlabeled=unl, unlabeled_batch_size=u, dann=dann, mode="mixmatch",
-                              comm=ThreadComm(2, shared, rk))
-            eng.set_weights(float(d["meta_unsup_w"]), float(d["meta_dan_w"]))
-            CH.inject_step(eng, d, 0)
-            eng.step()
-            torch.cuda.synchronize()
+            with torch.cuda.stream(torch.cuda.Stream()):       # one stream per emulated rank: their kernels overlap
+                eng = TrainEngine(model, cfg, lab, d["lab_y"], l, unlabeled=unl, unlabeled_batch_size=u, dann=dann, mode="mixmatch",
+                                  comm=(PeerThreadComm if peer else ThreadComm)(2, shared, rk))
+                assert (eng.peer is not None) == peer
+                eng.set_weights(float(d["meta_unsup_w"]), float(d["meta_dan_w"]))
+                CH.inject_step(eng, d, 0)
+                eng.step()
+                torch.cuda.synchronize()
             engines[rk] = eng
         except Exception as e:  # pragma: no cover
             errors.append(e)
