@@ -484,11 +484,13 @@ __device__ __forceinline__ void bnv_colsum8(F8& x, float (*red)[8]) {
 // Cross-rank BatchNorm statistics through peer memory (data-parallel training, one process per GPU).
 // Every rank owns an exchange buffer that all ranks can address (CUDA IPC over NVLink / NVSwitch; bufs[r] is rank
 // r's buffer as seen from this process).  A BatchNorm CTA owns 8 columns of one segment on every rank, so the
-// all-reduce decomposes per CTA: it stores its 16 local column sums + its row count as one 128-byte packet into
-// EVERY rank's buffer, publishes it with a release flag (the step number), waits for the packets of all ranks in its
-// own buffer and adds them in rank order -- bit-identical statistics on all ranks, no collective launch, one kernel.
-// Packets are double-buffered by step parity; the gradient all-reduce that ends a step separates reuses.
-//   packet(slot, parity, src, cta) : 32 words = [sum_a[8] | sum_b[8] | rows | ... | flag]
+// all-reduce decomposes per CTA: it stores its 16 local column sums + its row count into EVERY rank's buffer and adds
+// what the other ranks stored into its own, in rank order -- bit-identical statistics on all ranks, no collective
+// launch, one kernel.  Each value travels as one 8-byte word {value, step number}: the word is written atomically, so
+// the step number doubles as its ready flag and no fence or separate flag round-trip is needed (the "LL" protocol);
+// the cost of the exchange is one NVLink store latency.  Packets are double-buffered by step parity; the gradient
+// exchange that ends a step separates reuses.
+//   packet(slot, parity, src, cta) : 32 words of 8 bytes = [sum_a[8] | sum_b[8] | rows | unused]
 // ---------------------------------------------------------------------------------------------
 struct PeerX {
   const unsigned long long* bufs;   // device array [world] of exchange-buffer base addresses (NULL: no exchange)
@@ -497,53 +499,37 @@ struct PeerX {
   int cta_stride;                   // packets reserved per (slot, parity, source rank): >= CTAs of any launch using the buffer
 };
 
-#define PEER_PKT_WORDS 32
+#define PEER_PKT_WORDS 32           // 8-byte words per packet
 
 __device__ __forceinline__ void peer_allreduce17(const PeerX& px, F8& a, F8& b, float& rows, float* xs /* shared [32] */) {
   const int t = threadIdx.x;
   const unsigned e = (unsigned)px.epoch[0];
   const size_t n_cta = (size_t)px.cta_stride, cta = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
   const size_t pkt0 = ((size_t)(px.slot * 2 + (int)(e & 1u)) * px.world) * n_cta + cta;   // + src * n_cta
-  if (t < 32) {
-    float mine = 0.f;
+  if (t < 17) {
+    float mine = rows;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       if (t == j) mine = a.v[j];
       if (t == 8 + j) mine = b.v[j];
     }
-    if (t == 16) mine = rows;
-    const size_t my_pkt = (pkt0 + (size_t)px.rank * n_cta) * PEER_PKT_WORDS;
-    if (t < 17) {
-      for (int p = 0; p < px.world; ++p) {
-        float* dst = reinterpret_cast<float*>(px.bufs[p]) + my_pkt;
-        asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(dst + t), "f"(mine) : "memory");
-      }
+    const size_t my_word = (pkt0 + (size_t)px.rank * n_cta) * PEER_PKT_WORDS + t;
+    for (int p = 0; p < px.world; ++p) {
+      uint2* dst = reinterpret_cast<uint2*>(px.bufs[p]) + my_word;
+      asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(__float_as_uint(mine)), "r"(e) : "memory");
     }
-    __threadfence_system();
-    __syncwarp();
-    if (t < px.world) {   // publish to rank t, then wait for rank t's packet in the local buffer
-      unsigned* flag = reinterpret_cast<unsigned*>(px.bufs[t]) + my_pkt + (PEER_PKT_WORDS - 1);
-      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(e) : "memory");
-      const unsigned* mine_f = reinterpret_cast<const unsigned*>(px.bufs[px.rank]) + (pkt0 + (size_t)t * n_cta) * PEER_PKT_WORDS +
-                               (PEER_PKT_WORDS - 1);
-      unsigned got = 0;
+    float acc = 0.f;
+    for (int p = 0; p < px.world; ++p) {   // rank order: the same sum on every rank
+      const uint2* src = reinterpret_cast<const uint2*>(px.bufs[px.rank]) + (pkt0 + (size_t)p * n_cta) * PEER_PKT_WORDS + t;
+      uint32_t v, f;
       int spins = 0;
       do {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(mine_f) : "memory");
-        if (got != e && ++spins > px.spin_limit) __trap();   // a peer never arrived: fail loudly instead of hanging the GPU
-      } while (got != e);
+        asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(f) : "l"(src) : "memory");
+        if (f != e && ++spins > px.spin_limit) __trap();   // a peer never arrived: fail loudly instead of hanging the GPU
+      } while (f != e);
+      acc += __uint_as_float(v);
     }
-    __syncwarp();
-    if (t < 17) {
-      float acc = 0.f;
-      for (int p = 0; p < px.world; ++p) {
-        const float* src = reinterpret_cast<const float*>(px.bufs[px.rank]) + (pkt0 + (size_t)p * n_cta) * PEER_PKT_WORDS;
-        float v;
-        asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(src + t) : "memory");
-        acc += v;
-      }
-      xs[t] = acc;
-    }
+    xs[t] = acc;
   }
   __syncthreads();
 #pragma unroll
@@ -1005,7 +991,7 @@ static int peer_check(const char* who, const unsigned long long* peer_bufs, int 
   SCNB_CHECK_ARG(peer_bufs && epoch && world >= 1 && world <= 32 && rank >= 0 && rank < world && slot >= 0 && slot < n_slots,
                  "%s: bad peer arguments", who);
   // the buffer is cut into n_slots * 2 (step parity) * world (source rank) equal runs of packets
-  *cta_stride = (int)(buf_bytes / ((long long)n_slots * 2 * world * PEER_PKT_WORDS * 4));
+  *cta_stride = (int)(buf_bytes / ((long long)n_slots * 2 * world * PEER_PKT_WORDS * 8));
   SCNB_CHECK_ARG(*cta_stride >= (H / 8) * n_seg, "%s: exchange buffer too small (%lld bytes: %d packets per run, %d needed)", who,
                  buf_bytes, *cta_stride, (H / 8) * n_seg);
   return SCNB_OK;
@@ -1022,7 +1008,7 @@ static int peer_spin_limit() {
 }
 
 extern "C" int scnb_bn_peer_bytes(int H, int n_seg, int n_slots, int world) {
-  return (int)((size_t)n_slots * 2 * world * (size_t)((H + 7) / 8) * n_seg * PEER_PKT_WORDS * 4);
+  return (int)((size_t)n_slots * 2 * world * (size_t)((H + 7) / 8) * n_seg * PEER_PKT_WORDS * 8);
 }
 
 extern "C" int scnb_bn_act_fwd_peer(const float* Z, float* A, float* pre_out, int H, int n_seg, const int32_t* seg_off_dev,

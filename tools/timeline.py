@@ -21,11 +21,19 @@ def main():
     ap.add_argument("--config", type=int, default=2)
     a = ap.parse_args()
     bench.CFG, _ = bench.CONFIGS[a.config]
-    dev = torch.device("cuda", 0)
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    comm = None
+    if world > 1:   # under torchrun: data-parallel step, rank 0 prints its timeline
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        from scnym_b200.parallel import TorchDistComm
+        comm = TorchDistComm()
     from scnym_b200.engine import TrainEngine
-    model, dann, cfg, lab, y, unl = bench.build_train(dev, 0, n_lab=a.cells, n_unl=a.cells)
+    model, dann, cfg, lab, y, unl = bench.build_train(dev, rank, n_lab=a.cells, n_unl=a.cells)
     eng = TrainEngine(model.to(dev), cfg, lab, y.to(torch.int32), bench.CFG["L"], unlabeled=unl, unlabeled_batch_size=bench.CFG["U"],
-                      dann=dann, mode="mixmatch")
+                      dann=dann, mode="mixmatch", comm=comm)
     eng.set_weights(1.0, 0.1)
     eng.sample_epoch_tables(a.steps + 12)
     for _ in range(10):
@@ -36,6 +44,8 @@ def main():
         for _ in range(a.steps):
             eng.step()
         torch.cuda.synchronize()
+    if rank != 0:
+        os._exit(0)
     path = os.path.join(tempfile.mkdtemp(), "trace.json")
     prof.export_chrome_trace(path)
     ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") == "kernel"]
@@ -51,6 +61,9 @@ def main():
     for e in seg:
         s = streams.index(e["args"].get("stream"))
         print(f"{e['ts'] - t0:8.1f} +{e['dur']:6.1f} = {e['ts'] - t0 + e['dur']:8.1f}  s{s}  {'    ' * s}{e['name'][:60]}")
+    sys.stdout.flush()
+    if world > 1:
+        os._exit(0)
 
 
 if __name__ == "__main__":
