@@ -162,6 +162,17 @@ def time_device_resident(args, device, rank, world):
     ms = e0.elapsed_time(e1)
     losses = eng.losses()
     assert np.isfinite(losses["loss"]), losses
+    if world > 1:
+        # data-parallel invariant, checked outside the timed region on every run: after the same number of steps every
+        # rank holds bit-identical parameters, optimizer step count and BatchNorm running statistics
+        bufs = [eng.arena.flat] + [b["bn"].running_mean for b in eng._blk] + [b["bn"].running_var for b in eng._blk]
+        sig = torch.stack([torch.cat([x.double().sum().view(1), x.double().abs().max().view(1)]) for x in bufs]).view(-1)
+        sig = torch.cat([sig, eng.state[:1].double()])
+        hi, lo = sig.clone(), sig.clone()
+        torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN)
+        assert torch.equal(hi, lo) and bool(torch.isfinite(hi).all()), "data-parallel replicas diverged"
+        losses["replicas_identical"] = True
     return eng, ms, clocks, losses
 
 

@@ -263,6 +263,17 @@ int scnb_optim_step(int opt, float* params, const float* grads, float* state1, f
                     const float* hp8, const int64_t* state4, void* stream);
 int scnb_record_step(const float* loss8, float* hist, int hist_cap, const float* conf, int U, float* conf_ring, int ring_cap,
                      const int64_t* state4, void* stream);
+/* Data-parallel gradient exchange fused with the optimizer over peer memory (replaces ncclAllReduce(AVG) of the gradient
+ * arena followed by scnb_optim_step; equivalence target: torch.optim.step() of scnym/main.py:374-396 on the gradient of
+ * the global batch).  Every rank's exchange buffer (scnb_peer_alloc) holds a 1 KB flag block at off_flags, its gradient
+ * arena at off_grad and its parameter arena at off_flat (`total` floats each, total % 4 == 0).  Rank r reduces slice r of
+ * all ranks' gradients with peer loads, updates that slice (state1/state2: local arrays of `total` floats, only the
+ * owned slice is touched) and stores the new parameters into every rank's parameter arena; the call returns (in stream
+ * order) when all ranks have done so.  epoch: device scalar > 0 that changes every step. */
+int scnb_dp_reduce_optim_bcast(int opt, const uint64_t* peer_bufs, int rank, int world, long long off_flags, long long off_grad,
+                               long long off_flat, long long total, float* state1, float* state2, const float* hp8,
+                               const int64_t* state4, const int64_t* epoch, void* stream);
+
 int scnb_ema_update(float* teacher, const float* params, long long n, float decay, const int64_t* state4, void* stream);
 
 /* ---- Predict head: Predicter.predict (scnym/predict.py:178-192): ensemble-mean logits,

@@ -65,6 +65,7 @@ SIGNATURES = {
     "scnb_step_begin": [P, P],
     "scnb_mm_step_inc": [P, P],
     "scnb_optim_step": [I, P, P, P, P, L, P, P, P],
+    "scnb_dp_reduce_optim_bcast": [I, P, I, I, L, L, L, L, P, P, P, P, P, P],
     "scnb_ema_update": [P, P, L, F, P, P],
     "scnb_record_step": [P, P, I, P, I, P, I, P, P],
     "scnb_predict_head": [P, I, I, I, P, P, P, P],

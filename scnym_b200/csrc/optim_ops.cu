@@ -6,6 +6,8 @@
 // Hyper-parameters live in a small device buffer so that a captured CUDA graph can be replayed
 // while lr / weights change:  hp = [lr, weight_decay, beta1, beta2, eps, rho, momentum, 0]
 // state (int64): st = [t (optimizer steps taken), rng_seed, rng_counter, mm_step]
+#include <stdlib.h>
+
 #include "optim.cuh"
 
 __global__ void k_step_begin(int64_t* st) {
@@ -105,5 +107,133 @@ extern "C" int scnb_record_step(const float* loss8, float* hist, int hist_cap, c
   const int n = U > 8 ? U : 8;
   k_record_step<<<scnb_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(loss8, hist, hist_cap, conf, U, conf_ring, ring_cap, state4);
   SCNB_CHECK_LAUNCH("record_step");
+  return SCNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Data-parallel gradient exchange fused with the optimizer, over peer memory (one process per GPU, one node):
+//   reduce-scatter  : rank r owns the r-th slice of the flat arena; it LOADS that slice of every rank's gradient arena
+//                     over NVLink (fixed rank order -> the same sum wherever it is computed) and averages;
+//   optimizer       : Adadelta / Adam / AdamW / SGD on the owned slice only (optimizer state is touched by its owner
+//                     alone: 1/world of the single-GPU HBM traffic);
+//   all-gather      : the updated parameters are STORED straight into every rank's parameter arena.
+// Replaces ncclAllReduce(grad arena) + scnb_optim_step(whole arena): no intermediate averaged gradient, no second pass.
+// Each rank's exchange buffer holds [... | flags | gradient arena | parameter arena]; bufs[p] + off_* address rank p's.
+// Protocol (flags carry the step number, so nothing is ever reset):
+//   ready[r] : rank r's gradients of this step are complete (written by r into every rank's flag block at kernel start)
+//   done[r]  : rank r has read all gradients it needs and its parameter stores are visible (written by its last CTA)
+// A rank's kernel returns only when every done[] flag has arrived: its parameter arena is then complete and its
+// gradient arena may be overwritten by the next step.
+// ---------------------------------------------------------------------------------------------
+struct DpX {
+  const unsigned long long* bufs;
+  const long long* epoch;
+  long long off_flags, off_grad, off_flat;   // byte offsets inside every rank's exchange buffer
+  int rank, world, spin_limit;
+};
+
+__device__ __forceinline__ void dp_wait_flag(const unsigned* f, unsigned e, int spin_limit) {
+  unsigned got;
+  int spins = 0;
+  do {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(f) : "memory");
+    if (got != e && ++spins > spin_limit) __trap();
+  } while (got != e);
+}
+
+template <int OPT>
+__global__ void __launch_bounds__(256) k_dp_reduce_optim_bcast(DpX dx, float* __restrict__ s1, float* __restrict__ s2,
+                                                               long long total, const float* __restrict__ hp,
+                                                               const int64_t* __restrict__ st) {
+  __shared__ OptimConsts cs;
+  __shared__ int is_last;
+  const int t = threadIdx.x;
+  const unsigned e = (unsigned)dx.epoch[0];
+  // flag block layout (u32 words): ready[r] at 2r, done[r] at 64 + 2r, CTA counter at 128
+  unsigned* my_flags = reinterpret_cast<unsigned*>(dx.bufs[dx.rank] + dx.off_flags);
+  if (blockIdx.x == 0 && t < dx.world) {
+    __threadfence_system();
+    unsigned* f = reinterpret_cast<unsigned*>(dx.bufs[t] + dx.off_flags) + 2 * dx.rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(e) : "memory");
+  }
+  if (t == 0) cs = optim_consts(hp, st);
+  if (t < dx.world) dp_wait_flag(my_flags + 2 * t, e, dx.spin_limit);
+  __syncthreads();
+  const OptimConsts c = cs;
+  const float inv_w = 1.0f / (float)dx.world;
+  const long long n4 = total >> 2;                                   // arena length is a multiple of 4 floats
+  const long long per = (n4 + dx.world - 1) / dx.world;              // float4 elements per rank
+  const long long lo = per * dx.rank, hi = min(n4, lo + per);
+  float4* s1v = reinterpret_cast<float4*>(s1);
+  float4* s2v = reinterpret_cast<float4*>(s2);
+  const float4* my_flat = reinterpret_cast<const float4*>(dx.bufs[dx.rank] + dx.off_flat);
+  for (long long i = lo + (long long)blockIdx.x * blockDim.x + t; i < hi; i += (long long)gridDim.x * blockDim.x) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < dx.world; ++p) {
+      const float4* gp = reinterpret_cast<const float4*>(dx.bufs[p] + dx.off_grad) + i;
+      float4 v;
+      asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(gp) : "memory");
+      g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+    }
+    g.x *= inv_w; g.y *= inv_w; g.z *= inv_w; g.w *= inv_w;
+    float4 pi = my_flat[i], a = s1v[i], b = (OPT == OPT_SGD) ? make_float4(0.f, 0.f, 0.f, 0.f) : s2v[i];
+    optim_update<OPT>(pi.x, g.x, a.x, b.x, c);
+    optim_update<OPT>(pi.y, g.y, a.y, b.y, c);
+    optim_update<OPT>(pi.z, g.z, a.z, b.z, c);
+    optim_update<OPT>(pi.w, g.w, a.w, b.w, c);
+    s1v[i] = a;
+    if (OPT != OPT_SGD) s2v[i] = b;
+    for (int p = 0; p < dx.world; ++p) {
+      float4* dst = reinterpret_cast<float4*>(dx.bufs[p] + dx.off_flat) + i;
+      asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(pi.x), "f"(pi.y), "f"(pi.z), "f"(pi.w) : "memory");
+    }
+  }
+  // completion: every CTA's stores are fenced, the last CTA to finish publishes done[rank] and waits for all ranks
+  __syncthreads();
+  if (t == 0) {
+    __threadfence_system();
+    const unsigned ticket = atomicAdd(my_flags + 128, 1u);
+    is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    if (t == 0) my_flags[128] = 0u;
+    if (t < dx.world) {
+      __threadfence_system();
+      unsigned* f = reinterpret_cast<unsigned*>(dx.bufs[t] + dx.off_flags) + 64 + 2 * dx.rank;
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(e) : "memory");
+      dp_wait_flag(my_flags + 64 + 2 * t, e, dx.spin_limit);
+    }
+  }
+}
+
+extern "C" int scnb_dp_reduce_optim_bcast(int opt, const uint64_t* peer_bufs, int rank, int world, long long off_flags,
+                                          long long off_grad, long long off_flat, long long total, float* state1, float* state2,
+                                          const float* hp8, const int64_t* state4, const int64_t* epoch, void* stream) {
+  SCNB_CHECK_ARG(peer_bufs && state1 && hp8 && state4 && epoch && total >= 0 && total % 4 == 0, "dp_reduce_optim_bcast: bad arguments");
+  SCNB_CHECK_ARG(world >= 1 && world <= 32 && rank >= 0 && rank < world, "dp_reduce_optim_bcast: bad rank/world");
+  SCNB_CHECK_ARG(opt == OPT_SGD || state2, "dp_reduce_optim_bcast: second state buffer required");
+  SCNB_CHECK_ARG(off_flags % 16 == 0 && off_grad % 16 == 0 && off_flat % 16 == 0, "dp_reduce_optim_bcast: offsets must be 16-byte aligned");
+  if (total == 0) return SCNB_OK;
+  static int spin = 0;
+  if (!spin) {
+    const char* ev = getenv("SCNB_PEER_SPIN_LIMIT");
+    spin = ev ? atoi(ev) : (1 << 24);
+    if (spin <= 0) spin = 1 << 24;
+  }
+  DpX dx{(const unsigned long long*)peer_bufs, (const long long*)epoch, off_flags, off_grad, off_flat, rank, world, spin};
+  // every CTA of every rank is resident at once (they wait for each other): 2 CTAs per SM
+  const long long per = ((total >> 2) + world - 1) / world;
+  int blocks = (int)((per + 255) / 256 < 148 * 2 ? (per + 255) / 256 : 148 * 2);
+  if (blocks < 1) blocks = 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (opt) {
+    case OPT_ADADELTA: k_dp_reduce_optim_bcast<OPT_ADADELTA><<<blocks, 256, 0, st>>>(dx, state1, state2, total, hp8, state4); break;
+    case OPT_ADAM: k_dp_reduce_optim_bcast<OPT_ADAM><<<blocks, 256, 0, st>>>(dx, state1, state2, total, hp8, state4); break;
+    case OPT_ADAMW: k_dp_reduce_optim_bcast<OPT_ADAMW><<<blocks, 256, 0, st>>>(dx, state1, state2, total, hp8, state4); break;
+    case OPT_SGD: k_dp_reduce_optim_bcast<OPT_SGD><<<blocks, 256, 0, st>>>(dx, state1, state2, total, hp8, state4); break;
+    default: scnb_set_error("dp_reduce_optim_bcast: unknown optimizer %d", opt); return SCNB_ERR_ARG;
+  }
+  SCNB_CHECK_LAUNCH("dp_reduce_optim_bcast");
   return SCNB_OK;
 }

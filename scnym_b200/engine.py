@@ -76,7 +76,18 @@ class ParamArena(object):
     `torch.save` behave as before while the optimizer is one elementwise kernel.
     """
 
-    def __init__(self, named_params: List, device) -> None:
+    @staticmethod
+    def padded_total(named_params: List) -> int:
+        seen, total = set(), 0
+        for _, p in named_params:
+            if id(p) not in seen:
+                seen.add(id(p))
+                total += (p.numel() + 3) // 4 * 4
+        return total
+
+    def __init__(self, named_params: List, device, flat=None, grad=None) -> None:
+        """flat / grad: optional externally allocated fp32 buffers of `padded_total` elements (data parallelism keeps
+        the parameter and gradient arenas in peer-addressable memory)."""
         self.names, self.params, self.offsets, self.sizes = [], [], {}, {}
         total = 0
         seen = set()
@@ -91,8 +102,10 @@ class ParamArena(object):
             self.sizes[name] = n
             total += (n + 3) // 4 * 4  # keep every tensor 16-byte aligned
         self.total = total
-        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
-        self.grad = torch.zeros(total, dtype=torch.float32, device=device)
+        if flat is not None and (flat.numel() != total or grad is None or grad.numel() != total):
+            raise ValueError("external arena buffers must hold padded_total() floats")
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device) if flat is None else flat.zero_()
+        self.grad = torch.zeros(total, dtype=torch.float32, device=device) if grad is None else grad.zero_()
         self.state1 = torch.zeros(total, dtype=torch.float32, device=device)
         self.state2 = torch.zeros(total, dtype=torch.float32, device=device)
         self._views, self._gviews = {}, {}
@@ -175,7 +188,27 @@ class TrainEngine(object):
             named += [("dan." + n, p) for n, p in self.dann.domain_clf.named_parameters()]
         if extra_named_params:
             named += list(extra_named_params)
-        self.arena = ParamArena(named, dev)
+        # Data parallelism over peer memory: one exchange buffer per rank holds
+        #   [BatchNorm packets | flag block | gradient arena | parameter arena]
+        # so that the BatchNorm kernels and the fused gradient-reduce + optimizer kernel of every rank can address them.
+        self.peer = None
+        flat = grad = None
+        mk = getattr(self.comm, "make_peer_exchange", None) if self.comm is not None else None
+        if mk is not None and all(w % 8 == 0 for w in self.widths):
+            n_seg = (3 if self.use_dan else 2) if mode == "mixmatch" else 1
+            self.peer_slots = 2 * len(self.widths)
+            bn_bytes = max(_lib.lib().scnb_bn_peer_bytes(w, n_seg, self.peer_slots, self.comm.world) for w in self.widths)
+            total = ParamArena.padded_total(named)
+            rnd = lambda b: (b + 255) // 256 * 256
+            self.peer_bn_bytes = rnd(bn_bytes)
+            self.peer_off_flags = self.peer_bn_bytes
+            self.peer_off_grad = self.peer_off_flags + 1024
+            self.peer_off_flat = self.peer_off_grad + rnd(4 * total)
+            self.peer = mk(self.peer_off_flat + rnd(4 * total), dev)
+            if self.peer is not None:
+                grad = self.peer.tensor(self.peer_off_grad, total)
+                flat = self.peer.tensor(self.peer_off_flat, total)
+        self.arena = ParamArena(named, dev, flat=flat, grad=grad)
         self.n_model_params = sum(((p.numel() + 3) // 4 * 4) for n, p in zip(self.arena.names, self.arena.params)
                                   if n.startswith("model."))
         # block application -> parameter names
@@ -283,13 +316,6 @@ class TrainEngine(object):
             # cross-rank exchange buffers per application: [n_seg][2][w] sums + [n_seg] row counts
             self.dp_fwd = [f32(self.n_seg * 2 * w + self.n_seg) for w in self.widths]
             self.dp_bwd = [f32(self.n_seg * 2 * w + self.n_seg) for w in self.widths]
-            # in-kernel all-reduce of the BatchNorm statistics through peer memory when the communicator offers it
-            self.peer = None
-            mk = getattr(comm, "make_peer_exchange", None)
-            if mk is not None and all(w % 8 == 0 for w in self.widths):
-                self.peer_slots = 2 * len(self.widths)
-                nbytes = max(_lib.lib().scnb_bn_peer_bytes(w, self.n_seg, self.peer_slots, comm.world) for w in self.widths)
-                self.peer = mk(int(nbytes), dev)
             self.comm.broadcast(self.arena.flat)  # identical replicas to start from
             for b in self._blk:
                 self.comm.broadcast(b["bn"].running_mean)
@@ -655,7 +681,7 @@ class TrainEngine(object):
                 px = self.peer
                 call("scnb_bn_act_fwd_peer", ptr(self.Zs[a]), ptr(self.As[a]), None, w, self.n_seg, ptr(self.seg_off), R,
                      self.P(blk[a]["g"]), self.P(blk[a]["beta"]), ptr(self.stats[a]), self._hidden_keep(a), rng, SID_HID + a, p, 1,
-                     ptr(px.ptrs), px.rank, px.world, a, self.peer_slots, ptr(self.state), px.nbytes, ptr(self.dp_fwd[a]), st)
+                     ptr(px.ptrs), px.rank, px.world, a, self.peer_slots, ptr(self.state), self.peer_bn_bytes, ptr(self.dp_fwd[a]), st)
             else:  # cross-rank BatchNorm statistics: local sums -> all-reduce -> apply
                 fwd(ptr(self.dp_fwd[a]), None)
                 self.comm.all_reduce_sum(self.dp_fwd[a])
@@ -687,7 +713,7 @@ class TrainEngine(object):
                 call("scnb_bn_act_bwd_peer", ptr(dA), ptr(self.Zs[a]), ptr(self.As[a]), w, self.n_seg, ptr(self.seg_off), R,
                      self.P(blk[a]["g"]), ptr(self.stats[a]), self._hidden_keep(a), rng, SID_HID + a, p, 1, ptr(dZ),
                      self.Gp(blk[a]["g"]), self.Gp(blk[a]["beta"]), ptr(px.ptrs), px.rank, px.world, self.n_app + a, self.peer_slots,
-                     ptr(self.state), px.nbytes, st)
+                     ptr(self.state), self.peer_bn_bytes, st)
             else:
                 bwd(ptr(self.dp_bwd[a]), None)
                 self.comm.all_reduce_sum(self.dp_bwd[a])
@@ -755,8 +781,14 @@ class TrainEngine(object):
                 call("scnb_csr_w1_bwd_optim", -1, ptr(self.c_ptr), ptr(self.c_ent), ptr(dZ1), n_rows, H0, self.G, None, self.Gp(W1),
                      None, None, None, None, st)
             self._after(main, sW)              # every other gradient (branch W, and branch D through it) is complete
-            self.comm.all_reduce_avg(ar.grad)  # NCCL over NVLink
-            call("scnb_optim_step", opt, ptr(ar.flat), ptr(ar.grad), ptr(ar.state1), ptr(ar.state2), ar.total, hp, s4, st)
+            if self.peer is not None:
+                # reduce-scatter (peer loads) + optimizer on the owned slice + all-gather (peer stores), one kernel
+                px = self.peer
+                call("scnb_dp_reduce_optim_bcast", opt, ptr(px.ptrs), px.rank, px.world, self.peer_off_flags, self.peer_off_grad,
+                     self.peer_off_flat, ar.total, ptr(ar.state1), ptr(ar.state2), hp, s4, s4, st)
+            else:
+                self.comm.all_reduce_avg(ar.grad)  # NCCL over NVLink
+                call("scnb_optim_step", opt, ptr(ar.flat), ptr(ar.grad), ptr(ar.state1), ptr(ar.state2), ar.total, hp, s4, st)
         else:
             keep = self.Gp(W1) if c.keep_w1_grad else None
             if self.w1_tc:

@@ -105,6 +105,21 @@ class PeerExchange(object):
         """Emulated ranks inside one process (tests): `buffers` are the ranks' zeroed uint8 CUDA tensors."""
         return cls([b.data_ptr() for b in buffers], rank, len(buffers), buffers[0].numel(), buffers[0].device, keep=buffers)
 
+    def tensor(self, offset_bytes: int, n_floats: int) -> torch.Tensor:
+        """fp32 view of [offset_bytes, offset_bytes + 4 n_floats) of this rank's own buffer."""
+        if offset_bytes % 16 or offset_bytes + 4 * n_floats > self.nbytes:
+            raise ValueError("bad exchange-buffer region")
+        if self._keep is not None:      # emulated ranks: the buffer is a torch tensor
+            return self._keep[self.rank][offset_bytes: offset_bytes + 4 * n_floats].view(torch.float32)
+
+        class _Raw(object):             # cudaMalloc memory owned by this object, exposed through the CUDA array interface
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (int(self._owned) + int(offset_bytes), False),
+                                        "version": 2, "strides": None}
+        raw._owner = self
+        return torch.as_tensor(raw, device=self.ptrs.device)
+
     def close(self) -> None:
         from . import _lib
         for q in self._opened:

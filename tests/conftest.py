@@ -3,6 +3,11 @@ import sys
 
 import pytest
 
+# The data-parallel tests emulate two ranks on ONE GPU whose kernels wait for each other on the device.  With the default
+# 8 hardware work queues, two engines' streams can alias onto one queue and serialise behind a waiting kernel (a deadlock
+# that cannot happen across real GPUs); must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -614,3 +614,47 @@ def test_csr_w1_bwd_optim_tensor_core(opt, n, G, H0):
             rp.grad = grad.cpu().clone()
             ropt.step()
             _chk(f"tc {opt} W t={t}", W.cpu(), rp.detach(), tol=5e-6)
+
+
+@pytest.mark.parametrize("opt", ["sgd", "adam", "adadelta"])
+@pytest.mark.parametrize("world,total", [(2, 4096 + 8), (3, 40), (4, 1 << 18)])
+def test_dp_reduce_optim_bcast_emulated_ranks(opt, world, total):
+    """Fused gradient reduce-scatter + optimizer + parameter all-gather over peer memory: `world` emulated ranks on one
+    GPU (one stream each, their kernels wait for each other on the device) against torch.optim on the averaged gradient."""
+    from scnym_b200._lib import call, ptr, OPTIMIZER_CODES
+    rnd = lambda b: (b + 255) // 256 * 256
+    off_flags, off_grad = 256, 256 + 1024
+    off_flat = off_grad + rnd(4 * total)
+    nbytes = off_flat + rnd(4 * total)
+    bufs = [torch.zeros(nbytes, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device="cuda")
+    view = lambda b, off: b[off: off + 4 * total].view(torch.float32)
+    torch.manual_seed(5)
+    p0 = torch.randn(total)
+    kw = dict(lr=1.0 if opt == "adadelta" else 0.01, weight_decay=1e-2)
+    cls = {"adadelta": torch.optim.Adadelta, "adam": torch.optim.Adam, "sgd": torch.optim.SGD}[opt]
+    rp = p0.clone().requires_grad_(True)
+    ropt = cls([rp], momentum=0.9, **kw) if opt == "sgd" else cls([rp], **kw)
+    eps = 1e-6 if opt == "adadelta" else 1e-8
+    hp = torch.tensor([kw["lr"], kw["weight_decay"], 0.9, 0.999, eps, 0.9, 0.9, 0.0]).cuda()
+    state = torch.zeros(4, dtype=torch.int64).cuda()
+    s1 = [torch.zeros(total).cuda() for _ in range(world)]
+    s2 = [torch.zeros(total).cuda() for _ in range(world)]
+    for r in range(world):
+        view(bufs[r], off_flat).copy_(p0)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    for step in range(3):
+        grads = [torch.randn(total) for _ in range(world)]
+        for r in range(world):
+            view(bufs[r], off_grad).copy_(grads[r])
+        call("scnb_step_begin", ptr(state), _st())
+        torch.cuda.synchronize()
+        for r in range(world):
+            call("scnb_dp_reduce_optim_bcast", OPTIMIZER_CODES[opt], ptr(ptrs), r, world, off_flags, off_grad, off_flat, total,
+                 ptr(s1[r]), ptr(s2[r]), ptr(hp), ptr(state), ptr(state), streams[r].cuda_stream)
+        torch.cuda.synchronize()
+        rp.grad = torch.stack(grads).sum(0) / world
+        ropt.step()
+        for r in range(world):
+            _chk(f"{opt} rank {r} step {step}", view(bufs[r], off_flat).cpu(), rp.detach(), tol=2e-5)
+        assert all(torch.equal(view(bufs[0], off_flat), view(bufs[r], off_flat)) for r in range(world)), "replicas differ"
