@@ -141,7 +141,7 @@ __device__ __forceinline__ void dp_wait_flag(const unsigned* f, unsigned e, int 
   } while (got != e);
 }
 
-template <int OPT>
+template <int OPT, int UNR>
 __global__ void __launch_bounds__(256) k_dp_reduce_optim_bcast(DpX dx, float* __restrict__ s1, float* __restrict__ s2,
                                                                long long total, const float* __restrict__ hp,
                                                                const int64_t* __restrict__ st) {
@@ -167,25 +167,52 @@ __global__ void __launch_bounds__(256) k_dp_reduce_optim_bcast(DpX dx, float* __
   float4* s1v = reinterpret_cast<float4*>(s1);
   float4* s2v = reinterpret_cast<float4*>(s2);
   const float4* my_flat = reinterpret_cast<const float4*>(dx.bufs[dx.rank] + dx.off_flat);
-  for (long long i = lo + (long long)blockIdx.x * blockDim.x + t; i < hi; i += (long long)gridDim.x * blockDim.x) {
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  // UNR float4 elements per thread and trip: all of their peer loads (UNR x world, ~2-3 us NVLink latency each) are in
+  // flight together
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = lo + (long long)blockIdx.x * blockDim.x + t; i0 < hi; i0 += stride * UNR) {
+    float4 g[UNR], pi[UNR], a[UNR], b[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int p = 0; p < dx.world; ++p) {
-      const float4* gp = reinterpret_cast<const float4*>(dx.bufs[p] + dx.off_grad) + i;
-      float4 v;
-      asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(gp) : "memory");
-      g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+      const float4* gp = reinterpret_cast<const float4*>(dx.bufs[p] + dx.off_grad);
+      float4 v[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {      // issue every load before the first dependent add (a warp issues in order)
+        const long long i = i0 + u * stride;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // weak (coalesced, L2-only) loads: the ready flags were acquired at system scope above, and this kernel reads
+        // every gradient address once, so nothing stale can be hit; strong .sys accesses would travel as 16-byte requests
+        if (i < hi) v[u] = __ldcg(gp + i);
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) { g[u].x += v[u].x; g[u].y += v[u].y; g[u].z += v[u].z; g[u].w += v[u].w; }
     }
-    g.x *= inv_w; g.y *= inv_w; g.z *= inv_w; g.w *= inv_w;
-    float4 pi = my_flat[i], a = s1v[i], b = (OPT == OPT_SGD) ? make_float4(0.f, 0.f, 0.f, 0.f) : s2v[i];
-    optim_update<OPT>(pi.x, g.x, a.x, b.x, c);
-    optim_update<OPT>(pi.y, g.y, a.y, b.y, c);
-    optim_update<OPT>(pi.z, g.z, a.z, b.z, c);
-    optim_update<OPT>(pi.w, g.w, a.w, b.w, c);
-    s1v[i] = a;
-    if (OPT != OPT_SGD) s2v[i] = b;
-    for (int p = 0; p < dx.world; ++p) {
-      float4* dst = reinterpret_cast<float4*>(dx.bufs[p] + dx.off_flat) + i;
-      asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(pi.x), "f"(pi.y), "f"(pi.z), "f"(pi.w) : "memory");
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < hi) {
+        pi[u] = my_flat[i];
+        a[u] = s1v[i];
+        b[u] = (OPT == OPT_SGD) ? make_float4(0.f, 0.f, 0.f, 0.f) : s2v[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < hi) {
+        g[u].x *= inv_w; g[u].y *= inv_w; g[u].z *= inv_w; g[u].w *= inv_w;
+        optim_update<OPT>(pi[u].x, g[u].x, a[u].x, b[u].x, c);
+        optim_update<OPT>(pi[u].y, g[u].y, a[u].y, b[u].y, c);
+        optim_update<OPT>(pi[u].z, g[u].z, a[u].z, b[u].z, c);
+        optim_update<OPT>(pi[u].w, g[u].w, a[u].w, b[u].w, c);
+        s1v[i] = a[u];
+        if (OPT != OPT_SGD) s2v[i] = b[u];
+        for (int p = 0; p < dx.world; ++p) {
+          float4* dst = reinterpret_cast<float4*>(dx.bufs[p] + dx.off_flat) + i;
+          __stcg(dst, pi[u]);   // weak store; made visible by the system-scope fence in front of the done flag
+        }
+      }
     }
   }
   // completion: every CTA's stores are fenced, the last CTA to finish publishes done[rank] and waits for all ranks
@@ -222,18 +249,36 @@ extern "C" int scnb_dp_reduce_optim_bcast(int opt, const uint64_t* peer_bufs, in
     if (spin <= 0) spin = 1 << 24;
   }
   DpX dx{(const unsigned long long*)peer_bufs, (const long long*)epoch, off_flags, off_grad, off_flat, rank, world, spin};
-  // every CTA of every rank is resident at once (they wait for each other): 2 CTAs per SM
+  // CTAs only wait for flags that are already on their way (no CTA waits for another CTA of its own grid except the last
+  // one to finish), so the grid need not be co-resident: 4 float4 per thread, at most 4 CTAs per SM
   const long long per = ((total >> 2) + world - 1) / world;
-  int blocks = (int)((per + 255) / 256 < 148 * 2 ? (per + 255) / 256 : 148 * 2);
+  static int unr = 0, cta_per_sm = 0;
+  if (!unr) {
+    const char* ev = getenv("SCNB_DP_UNR");
+    unr = ev ? atoi(ev) : 4;
+    if (unr != 1 && unr != 2 && unr != 4) unr = 4;
+    ev = getenv("SCNB_DP_CTAS");
+    cta_per_sm = ev ? atoi(ev) : 2;
+    if (cta_per_sm < 1 || cta_per_sm > 8) cta_per_sm = 2;
+  }
+  const long long want = (per + unr * 256 - 1) / (unr * 256);
+  int blocks = (int)(want < 148 * cta_per_sm ? want : 148 * cta_per_sm);
   if (blocks < 1) blocks = 1;
   cudaStream_t st = (cudaStream_t)stream;
+#define DP_GO(O)                                                                                                    \
+  do {                                                                                                              \
+    if (unr == 4) k_dp_reduce_optim_bcast<O, 4><<<blocks, 256, 0, st>>>(dx, state1, state2, total, hp8, state4);      \
+    else if (unr == 2) k_dp_reduce_optim_bcast<O, 2><<<blocks, 256, 0, st>>>(dx, state1, state2, total, hp8, state4); \
+    else k_dp_reduce_optim_bcast<O, 1><<<blocks, 256, 0, st>>>(dx, state1, state2, total, hp8, state4);              \
+  } while (0)
   switch (opt) {
-    case OPT_ADADELTA: k_dp_reduce_optim_bcast<OPT_ADADELTA><<<blocks, 256, 0, st>>>(dx, state1, state2, total, hp8, state4); break;
-    case OPT_ADAM: k_dp_reduce_optim_bcast<OPT_ADAM><<<blocks, 256, 0, st>>>(dx, state1, state2, total, hp8, state4); break;
-    case OPT_ADAMW: k_dp_reduce_optim_bcast<OPT_ADAMW><<<blocks, 256, 0, st>>>(dx, state1, state2, total, hp8, state4); break;
-    case OPT_SGD: k_dp_reduce_optim_bcast<OPT_SGD><<<blocks, 256, 0, st>>>(dx, state1, state2, total, hp8, state4); break;
+    case OPT_ADADELTA: DP_GO(OPT_ADADELTA); break;
+    case OPT_ADAM: DP_GO(OPT_ADAM); break;
+    case OPT_ADAMW: DP_GO(OPT_ADAMW); break;
+    case OPT_SGD: DP_GO(OPT_SGD); break;
     default: scnb_set_error("dp_reduce_optim_bcast: unknown optimizer %d", opt); return SCNB_ERR_ARG;
   }
+#undef DP_GO
   SCNB_CHECK_LAUNCH("dp_reduce_optim_bcast");
   return SCNB_OK;
 }

@@ -256,7 +256,12 @@ extern "C" int scnb_bn_eval_planes(const float* Z, int n_rows, int H, const floa
 // ---------------------------------------------------------------------------------------------
 // DENSE_A: the A operand is not densified from a CSR but arrives as pre-tiled bf16 planes (a_hi / a_lo, written by
 // scnb_bn_eval_planes) that the loader thread bulk-copies next to the W tiles; warps 2.. then only run the epilogue.
-template <typename IdxT, int HALVES, int KT, bool DENSE_A>
+// TRN (split-K training form, H0 a multiple of 128): the accumulator is kept TRANSPOSED, D^T[H0, rows] = W1T^T X^T -- the
+// W1T plane tile is the MMA's A operand (M = 128 columns of Z per accumulator), the densified X tile its B operand
+// (N = 256 rows).  TMEM lanes are then columns of Z, so a warp of the epilogue adds 32 CONSECUTIVE floats of one row of Z
+// per instruction (one 128-byte line per atomic request) instead of 32 rows x 16 bytes: the 148 partial products of the
+// gene-axis split meet in L2 with a quarter of the atomic transactions.
+template <typename IdxT, int HALVES, int KT, bool DENSE_A, bool TRN>
 __global__ void __launch_bounds__(64 + 128 * HALVES, 1)
 k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ idx, const float* __restrict__ val, int n_rows,
                    const uint8_t* __restrict__ planes_hi, const uint8_t* __restrict__ planes_lo, int N, int n_ktiles,
@@ -324,7 +329,7 @@ k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ 
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((TRN ? ROWS : N) >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
       for (int i = 0; i < n_it; ++i) {
         const int s = i % stages;
         const uint32_t ph = (uint32_t)(i / stages) & 1u;
@@ -333,6 +338,23 @@ k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ 
         tc_fence_after();
         const uint32_t stage = base + (uint32_t)s * STAGE_BYTES;
         const uint64_t b_hi = umma_desc_kmajor<KT>(stage + 2u * A_PLANE), b_lo = umma_desc_kmajor<KT>(stage + 2u * A_PLANE + B_BYTES);
+        if (TRN) {
+          const uint64_t x_hi = umma_desc_kmajor<KT>(stage), x_lo = umma_desc_kmajor<KT>(stage + A_PLANE);
+          for (int h = 0; h < (N >> 7); ++h) {       // 128 columns of Z per accumulator: TMEM columns [h*ROWS, h*ROWS + ROWS)
+            const uint64_t w_hi = umma_desc_kmajor<KT>(stage + 2u * A_PLANE + (uint32_t)h * A_HALF);
+            const uint64_t w_lo = umma_desc_kmajor<KT>(stage + 2u * A_PLANE + B_BYTES + (uint32_t)h * A_HALF);
+            const uint32_t d = tmem_base + (uint32_t)(h * ROWS);
+#pragma unroll
+            for (int k = 0; k < KT / 16; ++k) {
+              const uint64_t ko = (uint64_t)(k * 2);
+              tc_mma_bf16(d, w_lo + ko, x_hi + ko, idesc, (i > 0 || k > 0) ? 1u : 0u);
+              tc_mma_bf16(d, w_hi + ko, x_lo + ko, idesc, 1u);
+              tc_mma_bf16(d, w_hi + ko, x_hi + ko, idesc, 1u);
+            }
+          }
+          tc_commit(bar_empty + 8u * s);
+          continue;
+        }
 #pragma unroll
         for (int h = 0; h < HALVES; ++h) {
           const uint64_t a_hi = umma_desc_kmajor<KT>(stage + (uint32_t)h * A_HALF);
@@ -441,7 +463,35 @@ k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ 
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
       mbar_arrive(bar_full_a + 8u * s);
     }
-    if (n_it > 0) {
+    if (TRN && n_it > 0) {
+      mbar_wait(bar_acc, 0);
+      tc_fence_after();
+      const int col = half * TC_M + rl;                 // column of Z held by this TMEM lane
+      if (half * TC_M < N) {
+        const float bc = (bias && blockIdx.y == 0) ? bias[col] : 0.f;
+        for (int r0 = 0; r0 < ROWS; r0 += 32) {
+          if ((long long)blockIdx.x * ROWS + r0 >= n_rows) break;
+          uint32_t v[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * ROWS + r0);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+              : "r"(taddr)
+              : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float* out = Z + ((size_t)blockIdx.x * ROWS + r0) * N + col;
+          const int n_here = (int)min((long long)32, (long long)n_rows - ((long long)blockIdx.x * ROWS + r0));
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < n_here) atomicAdd(out + (size_t)j * N, __uint_as_float(v[j]) + bc);
+        }
+      }
+    } else if (n_it > 0) {
       mbar_wait(bar_acc, 0);
       tc_fence_after();
       const bool split = gridDim.y > 1;
@@ -483,7 +533,7 @@ k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ 
   }
 }
 
-template <typename IdxT, int HALVES, int KT, bool DENSE_A>
+template <typename IdxT, int HALVES, int KT, bool DENSE_A, bool TRN = false>
 static int launch_dense_fwd_tc(const IdxT* indptr, const int32_t* idx, const float* val, int n, int G, int H0, const void* hi,
                                const void* lo, const float* b1, float* Z, int ksplits, cudaStream_t st, const void* a_hi = nullptr,
                                const void* a_lo = nullptr) {
@@ -504,9 +554,12 @@ static int launch_dense_fwd_tc(const IdxT* indptr, const int32_t* idx, const flo
     return SCNB_ERR_UNSUPPORTED;
   }
   const size_t smem = 1024 + stages * stage_bytes + 24 * stages + 16 + 16;
+  if (TRN && (ksplits <= 1 || H0 % 128 != 0))   // the transposed accumulator only pays for (and is only built for) split-K sums
+    return launch_dense_fwd_tc<IdxT, HALVES, KT, DENSE_A, false>(indptr, idx, val, n, G, H0, hi, lo, b1, Z, prezeroed ? -1 : ksplits, st,
+                                                                 a_hi, a_lo);
   int tmem_cols = 32;
-  while (tmem_cols < HALVES * H0) tmem_cols *= 2;
-  cudaError_t e = cudaFuncSetAttribute(k_csr_dense_fwd_tc<IdxT, HALVES, KT, DENSE_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  while (tmem_cols < (TRN ? (H0 / 128) * ROWS : HALVES * H0)) tmem_cols *= 2;
+  cudaError_t e = cudaFuncSetAttribute(k_csr_dense_fwd_tc<IdxT, HALVES, KT, DENSE_A, TRN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     scnb_set_error("csr_linear_fwd_tc: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
     return SCNB_ERR_CUDA;
@@ -519,7 +572,7 @@ static int launch_dense_fwd_tc(const IdxT* indptr, const int32_t* idx, const flo
     }
   }
   dim3 grid(row_tiles, ksplits);
-  k_csr_dense_fwd_tc<IdxT, HALVES, KT, DENSE_A><<<grid, 64 + 128 * HALVES, smem, st>>>(
+  k_csr_dense_fwd_tc<IdxT, HALVES, KT, DENSE_A, TRN><<<grid, 64 + 128 * HALVES, smem, st>>>(
       indptr, idx, val, n, (const uint8_t*)hi, (const uint8_t*)lo, H0, n_kt, b1, Z, stages, tmem_cols, (const uint8_t*)a_hi,
       (const uint8_t*)a_lo);
   SCNB_CHECK_LAUNCH("csr_linear_fwd_tc");
@@ -540,7 +593,7 @@ extern "C" int scnb_csr_linear_fwd_tc(const int32_t* b_indptr, const int32_t* b_
   int rc = tc_check(n, G, H0, planes_hi, planes_lo, Z);
   if (rc != SCNB_OK) return rc;
   if (n == 0) return SCNB_OK;
-  return launch_dense_fwd_tc<int32_t, 2, 32, false>(b_indptr, b_idx, b_val, n, G, H0, planes_hi, planes_lo, b1, Z, ksplits,
+  return launch_dense_fwd_tc<int32_t, 2, 32, false, true>(b_indptr, b_idx, b_val, n, G, H0, planes_hi, planes_lo, b1, Z, ksplits,
                                              (cudaStream_t)stream);
 }
 
