@@ -204,6 +204,10 @@ int scnb_mix_rows(const float* Z, int H, const int32_t* srcA, const int32_t* src
                   const int32_t* n_active_dev, int max_rows, float* out, void* stream);
 int scnb_unmix_rows(const float* dOut, int H, const int32_t* inv3 /*[3][n_base]*/, const float* coef3, int n_base,
                     float* dZ, void* stream);
+/* scnb_unmix_rows that also writes dZ as the bf16 hi/lo operand planes scnb_csr_w1_bwd_optim_tc reads (the layout
+ * scnb_w1_planes(dZ, n_base, H, ...) produces; planes hold ceil(n_base/32)*32*H bf16 each, zeroed once by the caller). */
+int scnb_unmix_rows_planes(const float* dOut, int H, const int32_t* inv3, const float* coef3, int n_base, float* dZ,
+                           void* planes_hi, void* planes_lo, void* stream);
 
 /* ---- K6: MixMatchLoss._generate_labels + sharpen_labels (scnym/losses.py:660-737, 529-573) and
  *      the confident/unconfident split, MixUp permutation and DAN row selection

@@ -53,6 +53,7 @@ SIGNATURES = {
     "scnb_bn_running_update": [P, P, P, P, P, P, P, P, I, I, F, P, P],
     "scnb_mix_rows": [P, I, P, P, P, P, I, P, P],
     "scnb_unmix_rows": [P, I, P, P, I, P, P],
+    "scnb_unmix_rows_planes": [P, I, P, P, I, P, P, P, P],
     "scnb_pseudolabel": [P, I, I, I, F, I, F, P, P, P, P, P, I, P],
     "scnb_mixmatch_plan": [P, P, P, I, I, I, I, I, P, P, P, P, P, P, I, P, P, P, P],
     "scnb_soft_ce_fwd_bwd": [P, I, I, P, P, P, P, P, I, P, P, I, F, P, P, P, I, P, P],

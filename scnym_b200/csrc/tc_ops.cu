@@ -929,6 +929,60 @@ k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict_
 #undef W1TC_GSTAMP
 }
 
+// MixUp adjoint (scnb_unmix_rows: dZ1[r] = sum_k coef[k][r] * dOut[inv[k][r]]) that also emits dZ1 as the bf16 hi/lo
+// operand planes of the tensor-core dW1 kernel (tile = 32 batch rows, plane row = column of dZ1, 16-byte chunk = 8
+// consecutive batch rows): a CTA owns 8 batch rows -- one chunk of every plane row -- and thread t column t, so the
+// separate scnb_w1_planes pass over dZ1 (and its launch on the critical chain) disappears.
+__global__ void __launch_bounds__(256) k_unmix_rows_planes(const float* __restrict__ dOut, int H, const int32_t* __restrict__ inv,
+                                                           const float* __restrict__ coef, int n_base, float* __restrict__ dZ,
+                                                           uint8_t* __restrict__ pl_hi, uint8_t* __restrict__ pl_lo) {
+  __shared__ int s_inv[8][3];
+  __shared__ float s_coef[8][3];
+  const int r0 = blockIdx.x * 8;
+  if (threadIdx.x < 24) {
+    const int j = threadIdx.x / 3, k = threadIdx.x % 3, r = r0 + j;
+    s_inv[j][k] = r < n_base ? inv[k * n_base + r] : -1;
+    s_coef[j][k] = r < n_base ? coef[k * n_base + r] : 0.f;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float x = 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int i = s_inv[j][k];
+        if (i >= 0) x = fmaf(s_coef[j][k], dOut[(size_t)i * H + c], x);
+      }
+      v[j] = x;
+      if (r0 + j < n_base) dZ[(size_t)(r0 + j) * H + c] = x;
+    }
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
+      hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    const size_t off = ((size_t)(r0 >> 5) * H * 32) * 2 + (size_t)c * 64 + swz_chunk<32>((uint32_t)(r0 & 31) >> 3, (uint32_t)c);
+    *reinterpret_cast<uint4*>(pl_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(pl_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+}
+
+extern "C" int scnb_unmix_rows_planes(const float* dOut, int H, const int32_t* inv3, const float* coef3, int n_base, float* dZ,
+                                      void* planes_hi, void* planes_lo, void* stream) {
+  SCNB_CHECK_ARG(dOut && inv3 && coef3 && dZ && planes_hi && planes_lo && H > 0 && n_base >= 0, "unmix_rows_planes: bad arguments");
+  SCNB_CHECK_ARG(H % 32 == 0 && (((uintptr_t)planes_hi | (uintptr_t)planes_lo) % 16) == 0, "unmix_rows_planes: H %% 32 and 16-byte aligned planes");
+  if (n_base == 0) return SCNB_OK;
+  k_unmix_rows_planes<<<scnb_cdiv(n_base, 8), H < 256 ? H : 256, 0, (cudaStream_t)stream>>>(dOut, H, inv3, coef3, n_base, dZ, (uint8_t*)planes_hi,
+                                                                                         (uint8_t*)planes_lo);
+  SCNB_CHECK_LAUNCH("unmix_rows_planes");
+  return SCNB_OK;
+}
+
 // gene block of a CTA of the tensor-core dW1 kernel: one CTA per SM when the block fits one MMA (N <= 256)
 static inline int w1tc_gene_block(int G) {
   int gt = ((G + 147) / 148 + 7) / 8 * 8;   // multiple of 8: a 16-byte chunk of the operand planes never straddles two CTAs

@@ -341,12 +341,15 @@ class TrainEngine(object):
         self.w1_emits_planes = bool(self.tc_first and self.w1_tc and comm is None)
         self._planes_version = None
         self._bn_running_done = False
+        self._dz_planes_ready = False
         self._side = None
         fus = lambda c: (self.H % 128 == 0 and self.H // 128 in (1, 2, 4, 8) and c * self.H * 4 <= 96 * 1024)
         self.fuse_classif = bool(cfg.fuse_heads and fus(self.C))
         self.fuse_dan = bool(cfg.fuse_heads and self.use_dan and fus(self.D))
         self._ev_grl, self._ev_csc, self._ev_zero = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         self._ev_teacher, self._ev_plan, self._ev_bnrun, self._ev_z1 = (torch.cuda.Event() for _ in range(4))
+        self._ev_dz = [torch.cuda.Event() for _ in self.widths]
+        self._ev_prep = torch.cuda.Event()
         self.dZ1 = f32(self.nb, H0) if mode == "mixmatch" else None
         if self.use_dan:
             self.Hd, self.dHd = f32(self.Rd, self.H), f32(self.Rd, self.H)
@@ -476,15 +479,18 @@ class TrainEngine(object):
         # step's random draws, so it runs on its own branch next to the gather and the first layer.
         teacher_async = (c.pseudolabel_min_confidence <= 0.0) and sW is not main
         if teacher_async:
-            sP = self._side[3]
-            self._after(sP, main)
-            self._plan(self._all_confident, sP.cuda_stream)
-            self._ev_plan.record(sP)
-        # -- batch CSR [U_raw ; L_aug] (+ per-gene histogram), one launch
+            self._ev_prep.record(main)
+        # -- batch CSR [U_raw ; L_aug] (+ per-gene histogram), one launch (issued before the plan: the graph releases
+        #    the children of a node one after the other, and the gather is the one on the critical chain)
         call("scnb_csr_gather_rows2", ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data), ptr(self.u_rows), U, 0, 0,
              ptr(self.lab.indptr), ptr(self.lab.indices), ptr(self.lab.data), ptr(self.l_rows), L, 1, SID_IN_L,
              ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), ptr(self.inj_in_keep_L), rng, c.p_in_drop,
              self._gene_cnt_ptr(), st)
+        if teacher_async:
+            sP = self._side[3]
+            sP.wait_event(self._ev_prep)
+            self._plan(self._all_confident, sP.cuda_stream)
+            self._ev_plan.record(sP)
         # branch W: gene-major copy of the batch (needed only by the last kernel of the step), gradient zeroing
         self._after(sW, main)
         with torch.cuda.stream(sW):
@@ -588,7 +594,12 @@ class TrainEngine(object):
         if self.use_dan and sD is not main:
             main.wait_event(self._ev_grl)
         dZ_first = self._student_backward(main, sW, rng, dA_last)
-        call("scnb_unmix_rows", ptr(dZ_first), H0, ptr(self.inv3), ptr(self.coef3), nb, ptr(self.dZ1), st)
+        self._dz_planes_ready = bool(self.w1_tc)
+        if self.w1_tc:   # MixUp adjoint + bf16 operand planes of dZ1 for the tensor-core dW1 kernel, one launch
+            call("scnb_unmix_rows_planes", ptr(dZ_first), H0, ptr(self.inv3), ptr(self.coef3), nb, ptr(self.dZ1), ptr(self.dz_hi),
+                 ptr(self.dz_lo), st)
+        else:
+            call("scnb_unmix_rows", ptr(dZ_first), H0, ptr(self.inv3), ptr(self.coef3), nb, ptr(self.dZ1), st)
         self._finish_step(main, sW, sD, self.dZ1, nb)
 
     def _plan(self, conf_flags, st):
@@ -722,8 +733,16 @@ class TrainEngine(object):
                 return dZ
             wp = self.widths[a - 1]
             dA = self._view(self.dA, R, wp)
+            # the weight / bias gradients need dZ only: fork branch W here, BEFORE the dA product joins the main chain, so
+            # that the next BatchNorm backward (which waits for dA) is the only kernel released when that product ends
+            # (the graph releases the children of a node one after the other, ~5 us apart: the dA product is issued first
+            # and is the only child of its parent on the critical chain)
+            ev = self._ev_dz[a]
+            if sW is not main:
+                ev.record(main)
             call("scnb_sgemm", 0, 0, R, wp, w, ptr(dZ), w, self.P(blk[a]["W"]), wp, ptr(dA), wp, 1.0, 0.0, None, 0, None, st)
-            self._after(sW, main)
+            if sW is not main:
+                sW.wait_event(ev)
             call("scnb_sgemm", 1, 0, w, wp, R, ptr(dZ), w, ptr(self.As[a - 1]), wp, self.Gp(blk[a]["W"]), wp, 1.0, 1.0, None, 0,
                  None, sw)
             call("scnb_colsum", ptr(dZ), R, w, w, self.Gp(blk[a]["b"]), 1, sw)
@@ -774,7 +793,8 @@ class TrainEngine(object):
         elif self.comm is not None:
             # data parallel: gradient only (no atomics, every gene row written), exchange, then one update pass
             if self.w1_tc:
-                call("scnb_w1_planes", ptr(dZ1), n_rows, H0, ptr(self.dz_hi), ptr(self.dz_lo), st)
+                if not self._dz_planes_ready:
+                    call("scnb_w1_planes", ptr(dZ1), n_rows, H0, ptr(self.dz_hi), ptr(self.dz_lo), st)
                 call("scnb_csr_w1_bwd_optim_tc", -1, ptr(self.w1_splits), ptr(self.b_idx), ptr(self.b_val), n_rows, H0, self.G,
                      ptr(self.dz_hi), ptr(self.dz_lo), None, self.Gp(W1), None, None, None, None, None, None, st)
             else:
@@ -792,7 +812,8 @@ class TrainEngine(object):
         else:
             keep = self.Gp(W1) if c.keep_w1_grad else None
             if self.w1_tc:
-                call("scnb_w1_planes", ptr(dZ1), n_rows, H0, ptr(self.dz_hi), ptr(self.dz_lo), st)
+                if not self._dz_planes_ready:
+                    call("scnb_w1_planes", ptr(dZ1), n_rows, H0, ptr(self.dz_hi), ptr(self.dz_lo), st)
                 call("scnb_csr_w1_bwd_optim_tc", opt, ptr(self.w1_splits), ptr(self.b_idx), ptr(self.b_val), n_rows, H0, self.G,
                      ptr(self.dz_hi), ptr(self.dz_lo), ptr(ar.flat), keep, ptr(ar.state1), ptr(ar.state2), hp, s4,
                      ptr(self.w1_hi) if self.w1_emits_planes else None, ptr(self.w1_lo) if self.w1_emits_planes else None, st)

@@ -658,3 +658,23 @@ def test_dp_reduce_optim_bcast_emulated_ranks(opt, world, total):
         for r in range(world):
             _chk(f"{opt} rank {r} step {step}", view(bufs[r], off_flat).cpu(), rp.detach(), tol=2e-5)
         assert all(torch.equal(view(bufs[0], off_flat), view(bufs[r], off_flat)) for r in range(world)), "replicas differ"
+
+
+@pytest.mark.parametrize("n,H", [(512, 256), (70, 64), (33, 128)])
+def test_unmix_rows_planes_equals_unmix_then_planes(n, H):
+    """Fused MixUp adjoint + bf16 operand planes == scnb_unmix_rows followed by scnb_w1_planes, bit for bit."""
+    from scnym_b200._lib import call, ptr
+    torch.manual_seed(n)
+    R = 2 * n
+    dOut = torch.randn(R, H).cuda()
+    inv = torch.randint(-1, R, (3, n), dtype=torch.int32).cuda()
+    coef = torch.rand(3, n).cuda()
+    n_pad = (n + 31) // 32 * 32
+    dz_a, dz_b = torch.zeros(n, H).cuda(), torch.zeros(n, H).cuda()
+    hi_a, lo_a, hi_b, lo_b = (torch.zeros(n_pad * H, dtype=torch.int16).cuda() for _ in range(4))
+    call("scnb_unmix_rows", ptr(dOut), H, ptr(inv), ptr(coef), n, ptr(dz_a), _st())
+    call("scnb_w1_planes", ptr(dz_a), n, H, ptr(hi_a), ptr(lo_a), _st())
+    call("scnb_unmix_rows_planes", ptr(dOut), H, ptr(inv), ptr(coef), n, ptr(dz_b), ptr(hi_b), ptr(lo_b), _st())
+    torch.cuda.synchronize()
+    assert torch.equal(dz_a, dz_b)
+    assert torch.equal(hi_a, hi_b) and torch.equal(lo_a, lo_b)
