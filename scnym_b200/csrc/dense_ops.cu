@@ -565,6 +565,9 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_fwd_v8(const float* __restrict
   const uint32_t thr16 = (uint32_t)(p_drop * 65536.0f + 0.5f);
   const float drop_scale = 1.0f / (1.0f - p_drop);
   F8 mean, invstd;
+  const bool cached = (n <= 2 * BNV_T) && !partial_out && !ext_sums && !px.bufs;
+  const bool has0 = t < n, has1 = t + BNV_T < n;
+  F8 zc0, zc1;
   if (partial_out) {  // data-parallel pass 1: local sums only
     F8 a1, a2;
 #pragma unroll
@@ -624,18 +627,33 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_fwd_v8(const float* __restrict
     const float inv_n = 1.0f / (float)max(n, 1);
 #pragma unroll
     for (int j = 0; j < 8; ++j) mean.v[j] = 0.f;
-    for (int r = r0 + t; r < r1; r += BNV_T) {
-      const F8 z = ld8(Z + (size_t)r * H + c0);
+    if (cached) {   // <= 2 rows per thread: Z is read from global memory once and stays in registers for all passes
+      if (has0) zc0 = ld8(Z + (size_t)(r0 + t) * H + c0);
+      if (has1) zc1 = ld8(Z + (size_t)(r0 + t + BNV_T) * H + c0);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) mean.v[j] += z.v[j];
+      for (int j = 0; j < 8; ++j) mean.v[j] = (has0 ? zc0.v[j] : 0.f) + (has1 ? zc1.v[j] : 0.f);
+    } else {
+      for (int r = r0 + t; r < r1; r += BNV_T) {
+        const F8 z = ld8(Z + (size_t)r * H + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mean.v[j] += z.v[j];
+      }
     }
     bnv_colsum8(mean, red1);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { mean.v[j] *= inv_n; var.v[j] = 0.f; }
-    for (int r = r0 + t; r < r1; r += BNV_T) {
-      const F8 z = ld8(Z + (size_t)r * H + c0);
+    if (cached) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { const float d = z.v[j] - mean.v[j]; var.v[j] = fmaf(d, d, var.v[j]); }
+      for (int j = 0; j < 8; ++j) {
+        const float d0 = has0 ? zc0.v[j] - mean.v[j] : 0.f, d1 = has1 ? zc1.v[j] - mean.v[j] : 0.f;
+        var.v[j] = fmaf(d0, d0, d1 * d1);
+      }
+    } else {
+      for (int r = r0 + t; r < r1; r += BNV_T) {
+        const F8 z = ld8(Z + (size_t)r * H + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = z.v[j] - mean.v[j]; var.v[j] = fmaf(d, d, var.v[j]); }
+      }
     }
     bnv_colsum8(var, red2);
 #pragma unroll
@@ -654,7 +672,7 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_fwd_v8(const float* __restrict
   }
   for (int r = r0 + t; r < r1; r += BNV_T) {
     const size_t o = (size_t)r * H + c0;
-    const F8 z = ld8(Z + o);
+    const F8 z = cached ? (r == r0 + t ? zc0 : zc1) : ld8(Z + o);
     uint32_t kb = 0xffu;
     if (p_drop > 0.f) kb = keep8(keep_mask, o, (uint64_t)r * Hg + blockIdx.x, seed, strm, thr16);
     F8 y;
@@ -713,6 +731,8 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_bwd_v8(const float* __restrict
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1.v[j] = s2.v[j] = 0.f;
   float inv_n = 1.0f / (float)max(n, 1);
+  const bool cached = (n <= 2 * BNV_T) && !ext_sums && !partial_out;
+  F8 dyc0, zhc0, dyc1, zhc1;
   if (ext_sums) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -721,7 +741,8 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_bwd_v8(const float* __restrict
     }
     inv_n = 1.0f / fmaxf(ext_cnt[s], 1.f);
   } else {
-    for (int r = r0 + t; r < r1; r += BNV_T) {
+    int slot = 0;
+    for (int r = r0 + t; r < r1; r += BNV_T, ++slot) {
       const size_t o = (size_t)r * H + c0;
       const F8 da = ld8(dA + o), z = ld8(Z + o);
       F8 av;
@@ -733,8 +754,12 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_bwd_v8(const float* __restrict
         float dy = da.v[j];
         if (relu && !(av.v[j] > 0.f)) dy = 0.f;
         if (p_drop > 0.f) dy = ((kb >> j) & 1u) ? dy * drop_scale : 0.f;
+        const float zh = (z.v[j] - mean.v[j]) * invstd.v[j];
         s1.v[j] += dy;
-        s2.v[j] = fmaf(dy, (z.v[j] - mean.v[j]) * invstd.v[j], s2.v[j]);
+        s2.v[j] = fmaf(dy, zh, s2.v[j]);
+        if (cached) {   // <= 2 rows per thread: dy and zhat stay in registers for the second pass
+          if (slot == 0) { dyc0.v[j] = dy; zhc0.v[j] = zh; } else { dyc1.v[j] = dy; zhc1.v[j] = zh; }
+        }
       }
     }
     bnv_colsum8(s1, red1);
@@ -762,23 +787,36 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_bwd_v8(const float* __restrict
       inv_n = 1.0f / fmaxf(rows, 1.f);
     }
   }
-  for (int r = r0 + t; r < r1; r += BNV_T) {
-    const size_t o = (size_t)r * H + c0;
-    const F8 da = ld8(dA + o), z = ld8(Z + o);
-    F8 av;
-    if (relu) av = ld8(Aact + o);
-    uint32_t kb = 0xffu;
-    if (p_drop > 0.f) kb = keep8(keep_mask, o, (uint64_t)r * Hg + blockIdx.x, seed, strm, thr16);
-    F8 out;
+  if (cached) {
+    int slot = 0;
+    for (int r = r0 + t; r < r1; r += BNV_T, ++slot) {
+      F8 out;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float dy = da.v[j];
-      if (relu && !(av.v[j] > 0.f)) dy = 0.f;
-      if (p_drop > 0.f) dy = ((kb >> j) & 1u) ? dy * drop_scale : 0.f;
-      const float zh = (z.v[j] - mean.v[j]) * invstd.v[j];
-      out.v[j] = g.v[j] * invstd.v[j] * (dy - s1.v[j] * inv_n - zh * (s2.v[j] * inv_n));
+      for (int j = 0; j < 8; ++j) {
+        const float dy = slot == 0 ? dyc0.v[j] : dyc1.v[j], zh = slot == 0 ? zhc0.v[j] : zhc1.v[j];
+        out.v[j] = g.v[j] * invstd.v[j] * (dy - s1.v[j] * inv_n - zh * (s2.v[j] * inv_n));
+      }
+      st8(dZ + (size_t)r * H + c0, out);
     }
-    st8(dZ + o, out);
+  } else {
+    for (int r = r0 + t; r < r1; r += BNV_T) {
+      const size_t o = (size_t)r * H + c0;
+      const F8 da = ld8(dA + o), z = ld8(Z + o);
+      F8 av;
+      if (relu) av = ld8(Aact + o);
+      uint32_t kb = 0xffu;
+      if (p_drop > 0.f) kb = keep8(keep_mask, o, (uint64_t)r * Hg + blockIdx.x, seed, strm, thr16);
+      F8 out;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float dy = da.v[j];
+        if (relu && !(av.v[j] > 0.f)) dy = 0.f;
+        if (p_drop > 0.f) dy = ((kb >> j) & 1u) ? dy * drop_scale : 0.f;
+        const float zh = (z.v[j] - mean.v[j]) * invstd.v[j];
+        out.v[j] = g.v[j] * invstd.v[j] * (dy - s1.v[j] * inv_n - zh * (s2.v[j] * inv_n));
+      }
+      st8(dZ + o, out);
+    }
   }
   if (s == n_seg - 1) {
     F8 zero;
