@@ -142,7 +142,7 @@ __device__ __forceinline__ void dp_wait_flag(const unsigned* f, unsigned e, int 
 }
 
 template <int OPT, int UNR>
-__global__ void __launch_bounds__(256) k_dp_reduce_optim_bcast(DpX dx, float* __restrict__ s1, float* __restrict__ s2,
+__global__ void __launch_bounds__(256, 2) k_dp_reduce_optim_bcast(DpX dx, float* __restrict__ s1, float* __restrict__ s2,
                                                                long long total, const float* __restrict__ hp,
                                                                const int64_t* __restrict__ st) {
   __shared__ OptimConsts cs;
@@ -167,52 +167,45 @@ __global__ void __launch_bounds__(256) k_dp_reduce_optim_bcast(DpX dx, float* __
   float4* s1v = reinterpret_cast<float4*>(s1);
   float4* s2v = reinterpret_cast<float4*>(s2);
   const float4* my_flat = reinterpret_cast<const float4*>(dx.bufs[dx.rank] + dx.off_flat);
-  // UNR float4 elements per thread and trip: all of their peer loads (UNR x world, ~2-3 us NVLink latency each) are in
-  // flight together
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i0 = lo + (long long)blockIdx.x * blockDim.x + t; i0 < hi; i0 += stride * UNR) {
-    float4 g[UNR], pi[UNR], a[UNR], b[UNR];
+  // One float4 element per thread and trip, software-pipelined: the peer loads of the NEXT trip (up to 8 ranks, all in
+  // flight together -- a warp issues in order, so a load -> add -> load chain would pay one NVLink round trip per rank)
+  // are issued before this trip's update and peer stores, so NVLink carries gradient reads and parameter writes at the
+  // same time instead of in alternating phases.
+  const long long stride = (long long)gridDim.x * blockDim.x * UNR;
+  auto load_grads = [&](long long i, float4(&v)[8]) {
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = 0; p < dx.world; ++p) {
-      const float4* gp = reinterpret_cast<const float4*>(dx.bufs[p] + dx.off_grad);
-      float4 v[UNR];
-#pragma unroll
-      for (int u = 0; u < UNR; ++u) {      // issue every load before the first dependent add (a warp issues in order)
-        const long long i = i0 + u * stride;
-        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        // weak (coalesced, L2-only) loads: the ready flags were acquired at system scope above, and this kernel reads
-        // every gradient address once, so nothing stale can be hit; strong .sys accesses would travel as 16-byte requests
-        if (i < hi) v[u] = __ldcg(gp + i);
+    for (int q = 0; q < 8; ++q)
+      if (q < dx.world) {
+        // weak (coalesced, L2-only) loads: the ready flags were acquired at system scope above and every gradient
+        // address is read once per launch, so nothing stale can be hit; strong .sys accesses travel as 16-byte requests
+        v[q] = __ldcg(reinterpret_cast<const float4*>(dx.bufs[q] + dx.off_grad) + i);
       }
+  };
+  for (int u0 = 0; u0 < UNR; ++u0) {   // UNR interleaved passes keep the per-thread state small
+    long long i = lo + ((long long)blockIdx.x * UNR + u0) * blockDim.x + t;
+    float4 vc[8], vn[8];
+    if (i < hi) load_grads(i, vc);
+    for (; i < hi; i += stride) {
+      const long long nx = i + stride;
+      if (nx < hi) load_grads(nx, vn);
+      float4 pi = my_flat[i], a = s1v[i], b = (OPT == OPT_SGD) ? make_float4(0.f, 0.f, 0.f, 0.f) : s2v[i];
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) { g[u].x += v[u].x; g[u].y += v[u].y; g[u].z += v[u].z; g[u].w += v[u].w; }
-    }
+      for (int q = 0; q < 8; ++q)        // rank order: the same sum wherever it is computed
+        if (q < dx.world) { g.x += vc[q].x; g.y += vc[q].y; g.z += vc[q].z; g.w += vc[q].w; }
+      g.x *= inv_w; g.y *= inv_w; g.z *= inv_w; g.w *= inv_w;
+      optim_update<OPT>(pi.x, g.x, a.x, b.x, c);
+      optim_update<OPT>(pi.y, g.y, a.y, b.y, c);
+      optim_update<OPT>(pi.z, g.z, a.z, b.z, c);
+      optim_update<OPT>(pi.w, g.w, a.w, b.w, c);
+      s1v[i] = a;
+      if (OPT != OPT_SGD) s2v[i] = b;
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const long long i = i0 + u * stride;
-      if (i < hi) {
-        pi[u] = my_flat[i];
-        a[u] = s1v[i];
-        b[u] = (OPT == OPT_SGD) ? make_float4(0.f, 0.f, 0.f, 0.f) : s2v[i];
-      }
-    }
+      for (int q = 0; q < 8; ++q)
+        if (q < dx.world)   // weak store; made visible by the system-scope fence in front of the done flag
+          __stcg(reinterpret_cast<float4*>(dx.bufs[q] + dx.off_flat) + i, pi);
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const long long i = i0 + u * stride;
-      if (i < hi) {
-        g[u].x *= inv_w; g[u].y *= inv_w; g[u].z *= inv_w; g[u].w *= inv_w;
-        optim_update<OPT>(pi[u].x, g[u].x, a[u].x, b[u].x, c);
-        optim_update<OPT>(pi[u].y, g[u].y, a[u].y, b[u].y, c);
-        optim_update<OPT>(pi[u].z, g[u].z, a[u].z, b[u].z, c);
-        optim_update<OPT>(pi[u].w, g[u].w, a[u].w, b[u].w, c);
-        s1v[i] = a[u];
-        if (OPT != OPT_SGD) s2v[i] = b[u];
-        for (int p = 0; p < dx.world; ++p) {
-          float4* dst = reinterpret_cast<float4*>(dx.bufs[p] + dx.off_flat) + i;
-          __stcg(dst, pi[u]);   // weak store; made visible by the system-scope fence in front of the done flag
-        }
-      }
+      for (int q = 0; q < 8; ++q) vc[q] = vn[q];
     }
   }
   // completion: every CTA's stores are fenced, the last CTA to finish publishes done[rank] and waits for all ranks
@@ -238,7 +231,7 @@ extern "C" int scnb_dp_reduce_optim_bcast(int opt, const uint64_t* peer_bufs, in
                                           long long off_grad, long long off_flat, long long total, float* state1, float* state2,
                                           const float* hp8, const int64_t* state4, const int64_t* epoch, void* stream) {
   SCNB_CHECK_ARG(peer_bufs && state1 && hp8 && state4 && epoch && total >= 0 && total % 4 == 0, "dp_reduce_optim_bcast: bad arguments");
-  SCNB_CHECK_ARG(world >= 1 && world <= 32 && rank >= 0 && rank < world, "dp_reduce_optim_bcast: bad rank/world");
+  SCNB_CHECK_ARG(world >= 1 && world <= 8 && rank >= 0 && rank < world, "dp_reduce_optim_bcast: bad rank/world (one NVSwitch node: world <= 8)");
   SCNB_CHECK_ARG(opt == OPT_SGD || state2, "dp_reduce_optim_bcast: second state buffer required");
   SCNB_CHECK_ARG(off_flags % 16 == 0 && off_grad % 16 == 0 && off_flat % 16 == 0, "dp_reduce_optim_bcast: offsets must be 16-byte aligned");
   if (total == 0) return SCNB_OK;
@@ -255,8 +248,8 @@ extern "C" int scnb_dp_reduce_optim_bcast(int opt, const uint64_t* peer_bufs, in
   static int unr = 0, cta_per_sm = 0;
   if (!unr) {
     const char* ev = getenv("SCNB_DP_UNR");
-    unr = ev ? atoi(ev) : 4;
-    if (unr != 1 && unr != 2 && unr != 4) unr = 4;
+    unr = ev ? atoi(ev) : 1;
+    if (unr != 1 && unr != 2) unr = 1;
     ev = getenv("SCNB_DP_CTAS");
     cta_per_sm = ev ? atoi(ev) : 2;
     if (cta_per_sm < 1 || cta_per_sm > 8) cta_per_sm = 2;
@@ -267,8 +260,7 @@ extern "C" int scnb_dp_reduce_optim_bcast(int opt, const uint64_t* peer_bufs, in
   cudaStream_t st = (cudaStream_t)stream;
 #define DP_GO(O)                                                                                                    \
   do {                                                                                                              \
-    if (unr == 4) k_dp_reduce_optim_bcast<O, 4><<<blocks, 256, 0, st>>>(dx, state1, state2, total, hp8, state4);      \
-    else if (unr == 2) k_dp_reduce_optim_bcast<O, 2><<<blocks, 256, 0, st>>>(dx, state1, state2, total, hp8, state4); \
+    if (unr == 2) k_dp_reduce_optim_bcast<O, 2><<<blocks, 256, 0, st>>>(dx, state1, state2, total, hp8, state4); \
     else k_dp_reduce_optim_bcast<O, 1><<<blocks, 256, 0, st>>>(dx, state1, state2, total, hp8, state4);              \
   } while (0)
   switch (opt) {
