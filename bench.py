@@ -272,9 +272,14 @@ def time_e2e(args, device, rank, world):
     n_host = 20_000  # host-resident sample of the same synthetic matrices (throughput is per step)
     model, dann, cfg, lab, y, unl = build_train(device, rank, seed_off=7, n_lab=n_host, n_unl=n_host)
     host = lambda t: t.cpu().numpy()
+    # host threads for batch assembly: the box's cores are shared by the ranks
+    cores = max((os.cpu_count() or 8) // world, 1)
+    n_thr = max(min(4, cores), 1)
+    n_prod = max(min(3, cores // n_thr), 1)
     pipe = HostTrainPipeline(model, cfg, lab=(host(lab.indptr), host(lab.indices), host(lab.data), host(y)),
                              unl=(host(unl.indptr), host(unl.indices), host(unl.data)), n_genes=c["G"], batch_size=c["L"],
-                             unlabeled_batch_size=c["U"], dann=dann, device=device, n_threads=4, seed=5 + rank, comm=make_comm(world))
+                             unlabeled_batch_size=c["U"], dann=dann, device=device, n_threads=n_thr, seed=5 + rank, comm=make_comm(world),
+                             n_producers=n_prod)
     del lab, unl
     pipe.engine.set_weights(1.0, 0.1)
     steps, warm = max(args.steps, 50), max(args.warmup, 5)

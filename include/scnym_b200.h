@@ -75,6 +75,12 @@ int scnb_fetch_step(const int64_t* l_tab, const int64_t* u_tab, const float* key
 int scnb_host_gather_rows(const int64_t* indptr, const int32_t* indices, const float* data, const int64_t* rows, int n,
                           int64_t* out_indptr, int32_t* out_indices, float* out_data, long long out_capacity,
                           int n_threads);
+/* Labeled and unlabeled rows of one MixMatch batch in one call (worker threads started once, next rows prefetched);
+ * n_b == 0 gathers the first matrix only. */
+int scnb_host_gather_rows2(const int64_t* indptr_a, const int32_t* indices_a, const float* data_a, const int64_t* rows_a, int n_a,
+                           int64_t* out_indptr_a, int32_t* out_indices_a, float* out_data_a, long long cap_a,
+                           const int64_t* indptr_b, const int32_t* indices_b, const float* data_b, const int64_t* rows_b, int n_b,
+                           int64_t* out_indptr_b, int32_t* out_indices_b, float* out_data_b, long long cap_b, int n_threads);
 
 /* ---- K2a/K8: first layer nn.Linear(n_genes, n_hidden_init) (scnym/model.py:211) on CSR input.
  *      fwd: Z = X W1T + b1.   bwd: dW1T += X^T dZ (caller zeroes dW1T).  dX is never formed: the

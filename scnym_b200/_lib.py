@@ -21,6 +21,7 @@ SIGNATURES = {
     "scnb_step_prep": [P, P, P, P, I, P, I, I, P, P, P, P, P, P, P, I, P, P, P, P, P, P, I, P],
     "scnb_fetch_step": [P, P, P, P, I, I, I, P, P, P, P, P, P],
     "scnb_host_gather_rows": [P, P, P, P, I, P, P, P, L, I],
+    "scnb_host_gather_rows2": [P, P, P, P, I, P, P, P, L, P, P, P, P, I, P, P, P, L, I],
     "scnb_csr_linear_fwd": [P, P, P, I, P, P, I, P, P],
     "scnb_csr_linear_fwd_i64": [P, P, P, I, P, P, I, P, P],
     "scnb_csr_linear_bwd_dw": [P, P, P, I, P, I, P, P],

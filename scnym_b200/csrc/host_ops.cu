@@ -93,3 +93,78 @@ extern "C" int scnb_peer_free(void* ptr) {
   }
   return SCNB_OK;
 }
+
+// Both matrices of a MixMatch batch (labeled and unlabeled rows) in ONE call: the worker threads are started once and
+// share the n_a + n_b rows, and the source rows of the next few copies are prefetched (the gather is a latency-bound
+// random read of host memory).  Same outputs as two scnb_host_gather_rows calls.
+extern "C" int scnb_host_gather_rows2(const int64_t* indptr_a, const int32_t* indices_a, const float* data_a, const int64_t* rows_a,
+                                      int n_a, int64_t* out_indptr_a, int32_t* out_indices_a, float* out_data_a,
+                                      long long cap_a, const int64_t* indptr_b, const int32_t* indices_b, const float* data_b,
+                                      const int64_t* rows_b, int n_b, int64_t* out_indptr_b, int32_t* out_indices_b,
+                                      float* out_data_b, long long cap_b, int n_threads) {
+  SCNB_CHECK_ARG(indptr_a && indices_a && data_a && rows_a && out_indptr_a && out_indices_a && out_data_a && n_a >= 0,
+                 "host_gather_rows2: bad arguments (first matrix)");
+  SCNB_CHECK_ARG(n_b == 0 || (indptr_b && indices_b && data_b && rows_b && out_indptr_b && out_indices_b && out_data_b && n_b > 0),
+                 "host_gather_rows2: bad arguments (second matrix)");
+  out_indptr_a[0] = 0;
+  for (int i = 0; i < n_a; ++i) out_indptr_a[i + 1] = out_indptr_a[i] + (indptr_a[rows_a[i] + 1] - indptr_a[rows_a[i]]);
+  SCNB_CHECK_ARG(out_indptr_a[n_a] <= cap_a, "host_gather_rows2: staging capacity %lld < batch nnz %lld", cap_a,
+                 (long long)out_indptr_a[n_a]);
+  if (n_b > 0) {
+    out_indptr_b[0] = 0;
+    for (int i = 0; i < n_b; ++i) out_indptr_b[i + 1] = out_indptr_b[i] + (indptr_b[rows_b[i] + 1] - indptr_b[rows_b[i]]);
+    SCNB_CHECK_ARG(out_indptr_b[n_b] <= cap_b, "host_gather_rows2: staging capacity %lld < batch nnz %lld", cap_b,
+                   (long long)out_indptr_b[n_b]);
+  }
+  const int n = n_a + n_b;
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > n) n_threads = n > 0 ? n : 1;
+  auto src_of = [&](int i, const int32_t*& ix, const float*& vv, int64_t& len) {
+    if (i < n_a) {
+      const int64_t s = indptr_a[rows_a[i]];
+      len = indptr_a[rows_a[i] + 1] - s;
+      ix = indices_a + s;
+      vv = data_a + s;
+    } else {
+      const int64_t s = indptr_b[rows_b[i - n_a]];
+      len = indptr_b[rows_b[i - n_a] + 1] - s;
+      ix = indices_b + s;
+      vv = data_b + s;
+    }
+  };
+  auto work = [&](int t) {
+    for (int i = t; i < n; i += n_threads) {
+      const int nx = i + n_threads;
+      if (nx < n) {   // touch the head of the next row this thread will copy
+        const int32_t* pix;
+        const float* pvv;
+        int64_t plen;
+        src_of(nx, pix, pvv, plen);
+        for (int64_t o = 0; o < plen; o += 16) {
+          __builtin_prefetch(pix + o);
+          __builtin_prefetch(pvv + o);
+        }
+      }
+      const int32_t* ix;
+      const float* vv;
+      int64_t len;
+      src_of(i, ix, vv, len);
+      if (i < n_a) {
+        memcpy(out_indices_a + out_indptr_a[i], ix, (size_t)len * sizeof(int32_t));
+        memcpy(out_data_a + out_indptr_a[i], vv, (size_t)len * sizeof(float));
+      } else {
+        memcpy(out_indices_b + out_indptr_b[i - n_a], ix, (size_t)len * sizeof(int32_t));
+        memcpy(out_data_b + out_indptr_b[i - n_a], vv, (size_t)len * sizeof(float));
+      }
+    }
+  };
+  if (n_threads == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+  }
+  return SCNB_OK;
+}

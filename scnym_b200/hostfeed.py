@@ -6,8 +6,10 @@ scnym/dataprep.py:114-168; `DataLoader` iteration scnym/trainer.py:574-582) and 
 contract -- inputs start in host memory every step, the loss comes back to the host every step --
 but overlaps the three stages:
 
-  producer thread   batch i+1: sample rows, gather their CSR rows into a pinned blob (C threads,
-                    `scnb_host_gather_rows`), draw the MixUp keys / Beta draws
+  producer threads  batches i+1, i+2, ...: sample rows, gather their CSR rows into a pinned blob (C threads,
+                    `scnb_host_gather_rows`), draw the MixUp keys / Beta draws; `n_producers` of them work on
+                    consecutive steps in parallel (the gather is a latency-bound random read of host memory and
+                    releases the GIL), the consumer takes their batches in step order
   copy stream       H2D of blob i+1 into one of two device landing buffers
   compute stream    device-to-device stash of landing buffer i into the engine's staging CSR,
                     replay of the captured step graph, D2H of the 8 loss scalars
@@ -84,7 +86,7 @@ class HostTrainPipeline(object):
     """
 
     def __init__(self, model, cfg, lab, unl, n_genes: int, batch_size: int, unlabeled_batch_size: Optional[int] = None, dann=None,
-                 device="cuda", n_threads: int = 4, seed: int = 0, prefetch: int = 3, comm=None) -> None:
+                 device="cuda", n_threads: int = 4, seed: int = 0, prefetch: int = 3, comm=None, n_producers: int = 1) -> None:
         from .engine import TrainEngine
         if not torch.cuda.is_available():
             raise _lib.ScnbError("HostTrainPipeline needs a CUDA device (no CPU fallback)")
@@ -99,7 +101,8 @@ class HostTrainPipeline(object):
         self.layout = _BlobLayout(self.L, self.U, cap_l, cap_u)
         lay = self.layout
         # pinned blobs (producer <-> copy stream) and two device landing buffers
-        self.n_blobs = max(int(prefetch), 2) + 1
+        self.n_producers = max(int(n_producers), 1)
+        self.n_blobs = max(int(prefetch) + 1, 3 * self.n_producers)
         self.blobs = [torch.empty(lay.total_bytes, dtype=torch.uint8).pin_memory() for _ in range(self.n_blobs)]
         self.blob_np = [{k: v.numpy() for k, v in lay.views(b).items()} for b in self.blobs]
         self.blob_t = [lay.views(b) for b in self.blobs]
@@ -125,38 +128,57 @@ class HostTrainPipeline(object):
         self.ev_stash = [torch.cuda.Event() for _ in range(2)]
         self.loss_pin = [torch.zeros(8).pin_memory() for _ in range(2)]
         self.ev_done = [torch.cuda.Event() for _ in range(2)]
-        self.rng = np.random.default_rng(seed)
+        self.rngs = [np.random.default_rng([seed, j]) for j in range(self.n_producers)]
+        self._tabs = [None] * self.n_producers
         self.h2d_bytes_last = 0
         self.d2h_bytes_last = 8 * 4
 
     # ---- producer (runs in a thread; the C gather releases the GIL) ----------------------------
-    def _produce(self, k: int):
+    _TAB = 128   # steps of random draws made at once per producer (amortises numpy call overhead held under the GIL)
+
+    def _draws(self, j):
+        """Next step's sampled rows / MixUp keys / Beta draws of producer j, from tables refilled every _TAB steps."""
+        tab = self._tabs[j]
+        if tab is None or tab["pos"] >= self._TAB:
+            rng, L, U, T = self.rngs[j], self.L, self.U, self._TAB
+            tab = {"pos": 0, "l": rng.integers(0, self.lab.n_rows, (T, L)).astype(np.int64),
+                   "u": rng.integers(0, self.unl.n_rows, (T, U)).astype(np.int64),
+                   "k": rng.random((T, L + U), dtype=np.float32),
+                   "g": rng.beta(self.alpha, self.alpha, (T, L + U)).astype(np.float32)}
+            self._tabs[j] = tab
+        i = tab["pos"]
+        tab["pos"] = i + 1
+        return tab["l"][i], tab["u"][i], tab["k"][i], tab["g"][i]
+
+    def _produce(self, k: int, j: int):
         h = _lib.lib()
         v, L, U = self.blob_np[k], self.L, self.U
-        lrows = self.rng.integers(0, self.lab.n_rows, L).astype(np.int64)
-        urows = self.rng.integers(0, self.unl.n_rows, U).astype(np.int64)
-        for src, rows, ip, ix, vv, cap in ((self.lab, lrows, "indptr_l", "idx_l", "val_l", self.layout.cap_l),
-                                            (self.unl, urows, "indptr_u", "idx_u", "val_u", self.layout.cap_u)):
-            rc = h.scnb_host_gather_rows(src.indptr.ctypes.data, src.indices.ctypes.data, src.data.ctypes.data, rows.ctypes.data,
-                                         rows.shape[0], v[ip].ctypes.data, v[ix].ctypes.data, v[vv].ctypes.data, cap, self.n_threads)
-            if rc != 0:
-                raise _lib.ScnbError(h.scnb_last_error().decode())
+        lrows, urows, keys, gam = self._draws(j)
+        a, b = self.lab, self.unl
+        rc = h.scnb_host_gather_rows2(a.indptr.ctypes.data, a.indices.ctypes.data, a.data.ctypes.data, lrows.ctypes.data, L,
+                                      v["indptr_l"].ctypes.data, v["idx_l"].ctypes.data, v["val_l"].ctypes.data, self.layout.cap_l,
+                                      b.indptr.ctypes.data, b.indices.ctypes.data, b.data.ctypes.data, urows.ctypes.data, U,
+                                      v["indptr_u"].ctypes.data, v["idx_u"].ctypes.data, v["val_u"].ctypes.data, self.layout.cap_u,
+                                      self.n_threads)
+        if rc != 0:
+            raise _lib.ScnbError(h.scnb_last_error().decode())
         v["y_l"][:] = self.lab.labels[lrows]
         if self.lab.domains is not None:
             v["dom_l"][:] = self.lab.domains[lrows]
         if self.unl.domains is not None:
             v["dom_u"][:U] = self.unl.domains[urows]
-        v["keys"][:] = self.rng.random(L + U, dtype=np.float32)
-        v["gam"][:] = self.rng.beta(self.alpha, self.alpha, L + U).astype(np.float32)
+        v["keys"][:] = keys
+        v["gam"][:] = gam
         return int(v["indptr_l"][L]), int(v["indptr_u"][U])
 
-    def _producer_loop(self, n_steps, free_q, ready_q):
+    def _producer_loop(self, j, n_steps, free_q, ready_q):
+        """Producer j assembles steps j, j + P, j + 2P, ... and hands them over through its own queue."""
         try:
-            for _ in range(n_steps):
+            for _ in range(j, n_steps, self.n_producers):
                 k = free_q.get()
                 if k is None:
                     return
-                nnz = self._produce(k)
+                nnz = self._produce(k, j)
                 ready_q.put((k, nnz))
         except BaseException as e:  # surface producer failures in the consumer
             ready_q.put(e)
@@ -166,14 +188,24 @@ class HostTrainPipeline(object):
         """Copy blob k -> landing buffer `slot` on the copy stream (exact bytes: header + used CSR prefixes)."""
         src, dst, hb = self.blobs[k], self.land[slot], self.layout.header_bytes
         nl, nu = nnz
+        exact = hb + 8 * (nl + nu)
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.ev_stash[slot])     # landing buffer no longer read by an earlier stash
-            dst[:hb].copy_(src[:hb], non_blocking=True)
-            for name, n in (("idx_l", nl), ("val_l", nl), ("idx_u", nu), ("val_u", nu)):
-                if n > 0:
-                    self.land_t[slot][name][:n].copy_(self.blob_t[k][name][:n], non_blocking=True)
+            if self._whole_blob(exact):
+                dst.copy_(src, non_blocking=True)                # one transfer: the unused capacity is small
+                exact = self.layout.total_bytes
+            else:
+                dst[:hb].copy_(src[:hb], non_blocking=True)
+                for name, n in (("idx_l", nl), ("val_l", nl), ("idx_u", nu), ("val_u", nu)):
+                    if n > 0:
+                        self.land_t[slot][name][:n].copy_(self.blob_t[k][name][:n], non_blocking=True)
             self.ev_h2d[slot].record(self.copy_stream)
-        return hb + 8 * (nl + nu)
+        return exact
+
+    def _whole_blob(self, exact_bytes):
+        """Move the whole blob in one copy when its unused capacity (rows shorter than the longest row) is below 25 %:
+        five enqueues and their launch gaps cost more than the extra bytes."""
+        return self.layout.total_bytes <= 1.25 * exact_bytes
 
     def _enqueue_step(self, nnz, slot):
         eng, lt, s = self.engine, self.land_t[slot], self.s
@@ -181,10 +213,13 @@ class HostTrainPipeline(object):
         cur = torch.cuda.current_stream()
         cur.wait_event(self.ev_h2d[slot])
         hb = self.layout.header_bytes
-        self.stage[:hb].copy_(self.land[slot][:hb], non_blocking=True)   # indptrs, labels, domains, keys, gammas
-        for name, n in (("idx_l", nl), ("val_l", nl), ("idx_u", nu), ("val_u", nu)):
-            if n > 0:
-                s[name][:n].copy_(lt[name][:n], non_blocking=True)
+        if self._whole_blob(hb + 8 * (nl + nu)):
+            self.stage.copy_(self.land[slot], non_blocking=True)
+        else:
+            self.stage[:hb].copy_(self.land[slot][:hb], non_blocking=True)   # indptrs, labels, domains, keys, gammas
+            for name, n in (("idx_l", nl), ("val_l", nl), ("idx_u", nu), ("val_u", nu)):
+                if n > 0:
+                    s[name][:n].copy_(lt[name][:n], non_blocking=True)
         self.ev_stash[slot].record(cur)
         eng.step()
         self.loss_pin[slot].copy_(eng.loss_buf, non_blocking=True)
@@ -204,14 +239,20 @@ class HostTrainPipeline(object):
         """Generator over `n_steps` training steps; yields the loss dict of each step (in order)."""
         self.engine.prepare()
         torch.cuda.synchronize()
-        free_q, ready_q = queue.Queue(), queue.Queue()
+        P = self.n_producers
+        # every producer owns its own pinned blobs (blob k belongs to producer k mod P): a producer that runs ahead can
+        # then never starve the one whose batch the consumer is waiting for
+        free_qs, ready_qs = [queue.Queue() for _ in range(P)], [queue.Queue() for _ in range(P)]
         for k in range(self.n_blobs):
-            free_q.put(k)
-        th = threading.Thread(target=self._producer_loop, args=(n_steps, free_q, ready_q), daemon=True)
-        th.start()
+            free_qs[k % P].put(k)
+        ths = [threading.Thread(target=self._producer_loop, args=(j, n_steps, free_qs[j], ready_qs[j]), daemon=True) for j in range(P)]
+        for th in ths:
+            th.start()
+        taken = [0]
 
         def next_ready():
-            item = ready_q.get()
+            item = ready_qs[taken[0] % P].get()      # step order: producer (step mod P) made it
+            taken[0] += 1
             if isinstance(item, BaseException):
                 raise item
             return item
@@ -231,11 +272,13 @@ class HostTrainPipeline(object):
                 self._enqueue_step(nnz, slot)
                 if pending is not None:
                     yield self._read_loss(pending[0])
-                    free_q.put(pending[1])     # its H2D finished long ago: the pinned blob can be refilled
+                    free_qs[pending[1] % P].put(pending[1])     # its H2D finished long ago: the pinned blob can be refilled
                 pending = (slot, k)
             if pending is not None:
                 yield self._read_loss(pending[0])
-                free_q.put(pending[1])
+                free_qs[pending[1] % P].put(pending[1])
         finally:
-            free_q.put(None)
-            th.join(timeout=5.0)
+            for q in free_qs:
+                q.put(None)
+            for th in ths:
+                th.join(timeout=5.0)

@@ -92,3 +92,43 @@ def test_param_arena_aliases_module_parameters():
     m.classif[0].weight.data = torch.zeros(3, 8)
     with pytest.raises(RuntimeError):
         arena.check_aliasing()
+
+
+def test_host_gather_rows_matches_numpy():
+    """CPU entry points of the library (no GPU needed): row gather of host CSR matrices into staging buffers, one matrix
+    (`scnb_host_gather_rows`) and the labeled+unlabeled pair in one call (`scnb_host_gather_rows2`); ragged and empty rows."""
+    import numpy as np
+    from scnym_b200 import _lib
+    h = _lib.lib()
+    rng = np.random.default_rng(0)
+
+    def make(n, g):
+        nnz = rng.integers(0, 40, n)
+        nnz[::7] = 0
+        indptr = np.concatenate([[0], np.cumsum(nnz)]).astype(np.int64)
+        return indptr, rng.integers(0, g, indptr[-1]).astype(np.int32), rng.random(indptr[-1], dtype=np.float32)
+
+    def want(m, rows):
+        ip, ix, vv = m
+        seg = [np.arange(ip[r], ip[r + 1]) for r in rows]
+        cat = np.concatenate(seg) if seg else np.zeros(0, np.int64)
+        return np.concatenate([[0], np.cumsum([len(s) for s in seg])]).astype(np.int64), ix[cat], vv[cat]
+
+    A, B = make(300, 1000), make(200, 1000)
+    ra, rb = rng.integers(0, 300, 64).astype(np.int64), rng.integers(0, 200, 48).astype(np.int64)
+    P = lambda x: x.ctypes.data
+    for threads in (1, 3, 8):
+        oa = (np.zeros(65, np.int64), np.zeros(64 * 40, np.int32), np.zeros(64 * 40, np.float32))
+        ob = (np.zeros(49, np.int64), np.zeros(48 * 40, np.int32), np.zeros(48 * 40, np.float32))
+        assert h.scnb_host_gather_rows2(P(A[0]), P(A[1]), P(A[2]), P(ra), 64, P(oa[0]), P(oa[1]), P(oa[2]), 64 * 40,
+                                        P(B[0]), P(B[1]), P(B[2]), P(rb), 48, P(ob[0]), P(ob[1]), P(ob[2]), 48 * 40, threads) == 0
+        o1 = (np.zeros(65, np.int64), np.zeros(64 * 40, np.int32), np.zeros(64 * 40, np.float32))
+        assert h.scnb_host_gather_rows(P(A[0]), P(A[1]), P(A[2]), P(ra), 64, P(o1[0]), P(o1[1]), P(o1[2]), 64 * 40, threads) == 0
+        for got, m, rows in ((oa, A, ra), (ob, B, rb), (o1, A, ra)):
+            wip, wix, wv = want(m, rows)
+            assert np.array_equal(got[0], wip)
+            assert np.array_equal(got[1][: wip[-1]], wix) and np.array_equal(got[2][: wip[-1]], wv)
+    # capacity check
+    assert h.scnb_host_gather_rows2(P(A[0]), P(A[1]), P(A[2]), P(ra), 64, P(oa[0]), P(oa[1]), P(oa[2]), 3,
+                                    P(B[0]), P(B[1]), P(B[2]), P(rb), 48, P(ob[0]), P(ob[1]), P(ob[2]), 48 * 40, 2) != 0
+    assert b"capacity" in h.scnb_last_error()

@@ -312,12 +312,10 @@ def test_host_train_pipeline_feeds_the_engine_from_host_memory():
     assert pipe.h2d_bytes_last > 8 * (L + U) and pipe.d2h_bytes_last == 32
     assert not torch.equal(w0, model.classif[0].weight.detach())
     # the staged unlabeled rows of the LAST step are exactly the host rows the producer sampled
-    rng = np.random.default_rng(9)
-    for _ in range(7):
-        lrows = rng.integers(0, n, L)
-        urows = rng.integers(0, n, U)
-        rng.random(L + U, dtype=np.float32)
-        rng.beta(0.3, 0.3, L + U)
+    # (one producer: step i used row i of its table of pre-drawn samples)
+    tab = pipe._tabs[0]
+    assert tab["pos"] == 7
+    lrows, urows = tab["l"][6], tab["u"][6]
     want_idx = np.concatenate([ui[up[r]:up[r + 1]] for r in urows])
     want_val = np.concatenate([ud[up[r]:up[r + 1]] for r in urows])
     eng = pipe.engine
