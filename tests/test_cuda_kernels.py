@@ -559,7 +559,7 @@ def test_head_logits_small_output_linear():
 
 
 @pytest.mark.parametrize("opt", ["none", "adam", "adadelta", "sgd"])
-@pytest.mark.parametrize("n,G,H0", [(96, 700, 128), (512, 3000, 256), (70, 300, 64)])
+@pytest.mark.parametrize("n,G,H0", [(96, 700, 128), (512, 3000, 256), (70, 300, 64), (512, 20000, 256)])
 def test_csr_w1_bwd_optim_tensor_core(opt, n, G, H0):
     """tcgen05 dW1 + optimizer kernel (X^T dZ1 with the update in the epilogue) against the dense product / torch.optim."""
     from oracle import scnym_oracle as O

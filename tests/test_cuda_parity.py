@@ -259,3 +259,60 @@ def test_engine_step_with_tensor_core_first_layer_matches_reference_golden():
     _chk("pseudolabels", got["pseudolabels"], d[pre + "pseudolabels"])
     for n, g in got["grads"].items():
         _chk("grad/" + n, g, d[pre + "grad/" + n])
+
+
+@pytest.mark.parametrize("opt_name,lr,n_steps", [("sgd", 0.05, 2), ("adadelta", 1.0, 1)])
+def test_full_size_tensor_core_step_agrees_with_fp32_step(opt_name, lr, n_steps):
+    """BASELINE config-2 shape (G = 20 000 genes, L = U = 256, H0 = H = 256, 5 % CSR, MixMatch + DAN), too large for the CPU
+    oracle to finish in seconds: the production path (tcgen05 first layer, tcgen05 dW1 + optimizer with fused operand
+    planes, graph replay) against the exact-fp32 path of the same engine (warp-per-row SpMM, SIMT dW1 + optimizer, eager)
+    on identical batches and Philox streams.  Two steps, so that the second forward runs on the operand planes the first
+    step's optimizer epilogue emitted: losses, logits, first-layer outputs and gradients, every parameter and BatchNorm
+    buffer agree within the 1e-4 budget (measured: <= 1e-5) and the predicted classes of the labeled rows are identical.
+    (Longer runs are not comparable element-wise: a ~1e-5 difference in a pre-activation that lies within 1e-5 of zero
+    eventually flips a ReLU gate in one of the two runs -- observed at the third SGD step and, with Adadelta's large
+    first update, at the second -- and the trajectories part; Adadelta is therefore compared after one step.)"""
+    import bench
+    from scnym_b200.engine import EngineConfig, TrainEngine
+    from scnym_b200.model import CellTypeCLF, DANN
+    from scnym_b200.synth import synth_device_csr
+    c = bench.CONFIGS[2][0]
+    dev = torch.device("cuda", 0)
+    lab, y = synth_device_csr(4096, c["G"], c["density"], c["C"], seed=0, device=dev)
+    unl, _ = synth_device_csr(4096, c["G"], c["density"], c["C"], seed=1, device=dev)
+    runs = []
+    for fl, wu, graph in (("spmm", "simt", False), ("tc", "tc", True)):
+        torch.manual_seed(0)
+        model = CellTypeCLF(n_genes=c["G"], n_cell_types=c["C"], n_hidden=c["H"], n_hidden_init=c["H0"], n_layers=c["n_layers"])
+        dann = DANN(model, n_domains=c["D"])
+        cfg = EngineConfig(n_augmentations=1, T=0.5, augment_pseudolabels=False, pseudolabel_min_confidence=0.0, mixup_alpha=0.3,
+                           use_dan=True, optimizer=opt_name, lr=lr, weight_decay=1e-4, seed=77, first_layer=fl, w1_update=wu,
+                           use_cuda_graph=graph)
+        eng = TrainEngine(model.to(dev), cfg, lab, y.to(torch.int32), c["L"], unlabeled=unl, unlabeled_batch_size=c["U"], dann=dann,
+                          mode="mixmatch")
+        assert eng.tc_first == (fl == "tc") and eng.w1_tc == (wu == "tc") and eng.w1_emits_planes == (wu == "tc")
+        eng.set_weights(1.0, 0.1)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(5)
+        eng.sample_epoch_tables(n_steps, generator=gen)
+        losses = []
+        for _ in range(n_steps):
+            eng.step()
+            losses.append(eng.losses())
+        torch.cuda.synchronize()
+        runs.append(dict(losses=losses, Z1=eng.Z1.detach().cpu().clone(), dZ1=eng.dZ1.detach().cpu().clone(),
+                         logits=eng.logits.detach().cpu().clone(),
+                         params={n: p.detach().cpu().clone() for n, p in model.named_parameters()},
+                         bn={n: b.detach().cpu().clone() for n, b in model.named_buffers() if "running" in n}))
+    a, b = runs
+    for s in range(n_steps):
+        for k in ("sup_loss", "unsup_loss", "dan_loss"):
+            _chk(f"step{s}/{k}", torch.tensor(b["losses"][s][k]), torch.tensor(a["losses"][s][k]))
+    _chk("Z1", b["Z1"], a["Z1"])
+    _chk("dZ1", b["dZ1"], a["dZ1"])
+    _chk("logits", b["logits"], a["logits"])
+    assert torch.equal(b["logits"][c["U"]:].argmax(1), a["logits"][c["U"]:].argmax(1))
+    for n in a["params"]:
+        _chk("param/" + n, b["params"][n], a["params"][n])
+    for n in a["bn"]:
+        _chk("bn/" + n, b["bn"][n], a["bn"][n])
