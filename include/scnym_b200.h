@@ -155,6 +155,9 @@ int scnb_csr_w1_bwd_optim(int opt, const int32_t* c_ptr, const void* c_ent, cons
 int scnb_sgemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
                int ldc, float alpha, float beta, const float* bias, int relu, const float* gate /*ReLU-bwd mask, C layout*/,
                void* stream);
+/* scnb_sgemm sends products of at least `flops` = 2 M N K (default 2e9, 0 = never) to the tcgen05 kernel (bf16x3 split,
+ * fp32 accumulation in TMEM, operands converted from fp32 inside the kernel); smaller ones keep the 3xTF32 mma.sync kernel. */
+int scnb_gemm_tc_min_flops(long long flops);
 int scnb_colsum(const float* A, int M, int N, int lda, float* out, int accumulate, void* stream);
 int scnb_relu_bwd(const float* g, const float* y, float* out, long long n, void* stream);
 

@@ -39,6 +39,7 @@ SIGNATURES = {
     "scnb_csr_to_csc": [P, P, P, I, I, P, P, P, P, P],
     "scnb_csr_w1_bwd_optim": [I, P, P, P, I, I, I, P, P, P, P, P, P, P],
     "scnb_sgemm": [I, I, I, I, I, P, I, P, I, P, I, F, F, P, I, P, P],
+    "scnb_gemm_tc_min_flops": [L],
     "scnb_colsum": [P, I, I, I, P, I, P],
     "scnb_relu_bwd": [P, P, P, L, P],
     "scnb_bn_eval_bwd": [P, P, I, I, I, P, P, P, P],

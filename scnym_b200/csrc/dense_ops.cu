@@ -203,6 +203,8 @@ static int scnb_gemm_mode() {
 }
 int scnb_sgemm_panel_try(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
                          int ldc, float alpha, float beta, const float* bias, int relu, const float* gate, cudaStream_t st);
+int scnb_gemm_tc_try(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                     float alpha, float beta, const float* bias, int relu, const float* gate, cudaStream_t st);
 
 extern "C" int scnb_sgemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                           float* C, int ldc, float alpha, float beta, const float* bias, int relu, const float* gate,
@@ -211,8 +213,9 @@ extern "C" int scnb_sgemm(int transA, int transB, int M, int N, int K, const flo
   if (M == 0 || N == 0) return SCNB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (K > 0) {  // 3xTF32 tensor-core kernel, else the fp32 cp.async panel kernel (gemm_ops.cu), when operands allow 16-byte chunks
-    int rc = 0;
-    if (scnb_gemm_mode() == 1) rc = scnb_tgemm_try(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, st);
+    // large products: tcgen05 bf16x3 kernel (tc_gemm.cu); small ones: the latency-oriented 3xTF32 mma.sync kernel
+    int rc = scnb_gemm_tc_try(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, st);
+    if (rc == 0 && scnb_gemm_mode() == 1) rc = scnb_tgemm_try(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, st);
     if (rc == 0) rc = scnb_sgemm_panel_try(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, st);
     if (rc < 0) return rc;
     if (rc == 1) {

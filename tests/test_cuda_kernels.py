@@ -678,3 +678,41 @@ def test_unmix_rows_planes_equals_unmix_then_planes(n, H):
     torch.cuda.synchronize()
     assert torch.equal(dz_a, dz_b)
     assert torch.equal(hi_a, hi_b) and torch.equal(lo_a, lo_b)
+
+
+@pytest.mark.parametrize("lay,M,N,K,extras", [
+    (0, 1024, 320, 1000, "bias_relu"), (0, 300, 256, 64, "plain"), (0, 2048, 1024, 1024, "bias"),
+    (1, 1024, 320, 1000, "gate"), (1, 384, 64, 200, "alpha"),
+    (2, 256, 512, 8192, "beta1"), (2, 1024, 1024, 4096, "beta1"), (2, 128, 72, 260, "plain")])
+def test_sgemm_tcgen05_path_matches_fp64(lay, M, N, K, extras):
+    """scnb_sgemm's tcgen05 kernel (bf16x3, operands split from fp32 in the kernel) for the three nn.Linear layouts
+    (forward, input gradient, weight gradient incl. the K split), ragged M / N / K and every epilogue option."""
+    from scnym_b200._lib import call, ptr
+    call("scnb_gemm_tc_min_flops", 1)
+    try:
+        torch.manual_seed(lay * 100 + M)
+        tA, tB = (lay == 2), (lay == 0)
+        A = torch.randn((K, M) if tA else (M, K)).cuda()
+        B = torch.randn((N, K) if tB else (K, N)).cuda()
+        C0 = torch.randn(M, N).cuda()
+        C = C0.clone()
+        bias = torch.randn(N).cuda() if "bias" in extras else None
+        gate = (torch.rand(M, N) > 0.3).float().cuda() if extras == "gate" else None
+        alpha = -0.37 if extras == "alpha" else 1.0
+        beta = 1.0 if extras == "beta1" else 0.0
+        relu = 1 if "relu" in extras else 0
+        call("scnb_sgemm", int(tA), int(tB), M, N, K, ptr(A), A.shape[1], ptr(B), B.shape[1], ptr(C), N, alpha, beta, ptr(bias), relu,
+             ptr(gate), _st())
+        torch.cuda.synchronize()
+        opA = A.double().t() if tA else A.double()
+        opB = B.double().t() if tB else B.double()
+        want = alpha * (opA @ opB) + beta * C0.double()
+        if bias is not None:
+            want = want + bias.double()
+        if relu:
+            want = want.clamp_min(0)
+        if gate is not None:
+            want = want * (gate.double() > 0)
+        _chk(f"tc gemm lay {lay} {extras}", C.cpu(), want.float().cpu(), tol=3e-5)
+    finally:
+        call("scnb_gemm_tc_min_flops", 2_000_000_000)
