@@ -77,3 +77,14 @@ __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
 
+
+// hi = bf16(x), lo = bf16(x - hi) for two values at once, packed as {x0 in the low half, x1 in the high half}.  The packed
+// conversion (F2FP.BF16.F32.PACK_AB) issues at ALU rate; the scalar F2F.BF16.F32 runs on the quarter-rate conversion pipe
+// and made the operand staging of the tcgen05 GEMM conversion-bound.
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - h0, x1 - h1);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}

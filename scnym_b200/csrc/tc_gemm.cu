@@ -26,12 +26,7 @@
 __device__ __forceinline__ void tg5_split8(const float (&x)[8], uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * j]), h1 = __float2bfloat16_rn(x[2 * j + 1]);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * j] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x[2 * j + 1] - __bfloat162float(h1));
-    h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-  }
+  for (int j = 0; j < 4; ++j) split_bf16x2(x[2 * j], x[2 * j + 1], h[j], l[j]);
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
@@ -61,23 +56,41 @@ __device__ __forceinline__ float ld_shared_f(uint32_t addr) {
 //       hi / lo planes are written over the fp32 image (a tile of `rows` x 32 fp32 and its two planes are both rows*128 B).
 // fp32 image: KMAJOR (X[row][k]): [rows][32] floats;  else (X[k][row]): [32][rows] floats.
 // A thread's task = (row r, 8-k chunk c): rows of 64 bytes per plane, chunk c of row r at r*64 + swizzle(c, r).
-template <bool KMAJOR>
-__device__ __forceinline__ void tg5_fetch(const float* __restrict__ X, int ld, int row0, int n_rows, int tile_rows, int k0, int k_end,
-                                          uint32_t smem, int t) {
-  if (KMAJOR) {
-    for (int q = t; q < tile_rows * 8; q += TG5_LOAD) {          // 16-byte pieces: 8 per row, consecutive threads along k
-      const int r = q >> 3, c4 = q & 7;
-      const int gr = row0 + r, gk = k0 + 4 * c4;
-      const bool ok = gr < n_rows && gk < k_end;                 // K % 4 == 0: a piece is entirely inside or outside
-      cp_async16_zfill(smem + (uint32_t)q * 16u, ok ? X + (size_t)gr * ld + gk : X, ok);
-    }
-  } else {
-    const int pr = tile_rows >> 2;                               // 16-byte pieces per k row, consecutive threads along rows
-    for (int q = t; q < 32 * pr; q += TG5_LOAD) {
-      const int k = q / pr, r4 = q - k * pr;
-      const int gr = row0 + 4 * r4, gk = k0 + k;
-      const bool ok = gr < n_rows && gk < k_end;                 // n_rows % 4 == 0
-      cp_async16_zfill(smem + (uint32_t)q * 16u, ok ? X + (size_t)gk * ld + gr : X, ok);
+// A thread's NP 16-byte pieces of an operand tile: global address of the piece in the FIRST k-tile, its k offset inside a
+// k-tile and its validity are fixed for the whole K walk, so they are computed once; per k-tile a piece costs one cp.async
+// and one pointer increment (the address arithmetic per piece had made the staging warps issue-bound: ncu, 5 900
+// warp instructions per k-tile).
+template <int NP>
+struct Tg5Pieces {
+  const float* p[NP];
+  int kk[NP];        // k offset of the piece inside a k-tile; -1: the piece does not exist (outside the tile / matrix rows)
+  size_t step;       // elements to advance per k-tile
+};
+template <bool KMAJOR, int NP>
+__device__ __forceinline__ void tg5_pieces(Tg5Pieces<NP>& pc, const float* __restrict__ X, int ld, int row0, int n_rows, int tile_rows,
+                                           int kb, int t) {
+  pc.step = KMAJOR ? (size_t)TG5_KT : (size_t)TG5_KT * ld;
+  const int pr = tile_rows >> 2;
+#pragma unroll
+  for (int u = 0; u < NP; ++u) {
+    const int q = t + u * TG5_LOAD;
+    int r, kk;
+    if (KMAJOR) { r = q >> 3; kk = 4 * (q & 7); } else { kk = q / pr; r = 4 * (q - kk * pr); }
+    const bool ok = (KMAJOR ? q < tile_rows * 8 : q < 32 * pr) && (row0 + r < n_rows);
+    pc.kk[u] = ok ? kk : -1;
+    pc.p[u] = ok ? (KMAJOR ? X + (size_t)(row0 + r) * ld + kb + kk : X + (size_t)(kb + kk) * ld + row0 + r) : X;
+  }
+}
+template <int NP>
+__device__ __forceinline__ void tg5_fetch(Tg5Pieces<NP>& pc, int k_left /* K elements left from this k-tile's start */, uint32_t smem,
+                                          int t, int n_pieces) {
+#pragma unroll
+  for (int u = 0; u < NP; ++u) {
+    const int q = t + u * TG5_LOAD;
+    if (q < n_pieces) {                                            // pieces of the tile image (zero-filled when invalid)
+      const bool ok = pc.kk[u] >= 0 && pc.kk[u] < k_left;
+      cp_async16_zfill(smem + (uint32_t)q * 16u, pc.p[u], ok);
+      pc.p[u] += pc.step;
     }
   }
 }
@@ -178,23 +191,26 @@ k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int lda, const float
   } else if (warp >= 2) {
     // ===== operand staging: fp32 tiles -> bf16 hi / lo planes in shared memory =====
     const int t = tid - 64;
-    constexpr int PF = 2;                       // k-tiles fetched ahead (stages >= PF + 1)
-    auto fetch = [&](int i) {
+    constexpr int PF = 3;                       // k-tiles fetched ahead (stages >= PF + 1)
+    Tg5Pieces<4> pa;
+    Tg5Pieces<8> pb;
+    tg5_pieces<LAY != 2, 4>(pa, A, lda, m0, M, TG5_BM, kb, t);
+    tg5_pieces<LAY == 0, 8>(pb, B, ldb, n0, N, n_tile, kb, t);
+    const int np_a = TG5_BM * 8, np_b = n_tile * 8;                // 16-byte pieces of the two fp32 tile images
+    auto fetch = [&](int i) {   // k-tiles are fetched in order: the piece pointers advance by one k-tile per call
       const int s = i % stages;
       mbar_wait(bar_empty + 8u * s, ((uint32_t)(i / stages) & 1u) ^ 1u);      // the MMAs that read this stage are done
       const uint32_t stage = base + (uint32_t)s * STAGE_BYTES;
-      const int k0 = kb + i * TG5_KT;
-      tg5_fetch<LAY != 2>(A, lda, m0, M, TG5_BM, k0, ke, stage, t);
-      tg5_fetch<LAY == 0>(B, ldb, n0, N, n_tile, k0, ke, stage + 2u * A_PLANE, t);
+      const int k_left = ke - (kb + i * TG5_KT);
+      tg5_fetch<4>(pa, k_left, stage, t, np_a);
+      tg5_fetch<8>(pb, k_left, stage + 2u * A_PLANE, t, np_b);
     };
     for (int j = 0; j < PF; ++j) {
       if (j < n_it) fetch(j);
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
     for (int i = 0; i < n_it; ++i) {
-      if (i + PF < n_it) fetch(i + PF);
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_group %0;" ::"n"(PF) : "memory");           // this thread's pieces of tile i have landed
+      asm volatile("cp.async.wait_group %0;" ::"n"(PF - 1) : "memory");       // this thread's pieces of tile i have landed
       asm volatile("bar.sync 1, 256;" ::: "memory");                           // ... and everybody else's
       const uint32_t stage = base + (uint32_t)(i % stages) * STAGE_BYTES;
       float xa[2][8], xb[4][8];
@@ -205,6 +221,8 @@ k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int lda, const float
       tg5_write<LAY == 0, 4>(stage + 2u * A_PLANE, stage + 2u * A_PLANE + B_PLANE, n_tile, t, xb);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(bar_full + 8u * (i % stages));
+      if (i + PF < n_it) fetch(i + PF);         // refill the stage the tensor core released longest ago
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
     // ===== epilogue: TMEM lane = row of C; warps 2-5 take columns [0, 128), warps 6-9 columns [128, 256) =====
     if (n_it > 0) {

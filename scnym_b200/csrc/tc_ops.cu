@@ -54,10 +54,7 @@ __global__ void __launch_bounds__(256) k_w1_planes(const float* __restrict__ W1T
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float x0 = wt[(8 * c + 2 * j) * S + n], x1 = wt[(8 * c + 2 * j + 1) * S + n];
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-      const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-      h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-      l[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      split_bf16x2(x0, x1, h[j], l[j]);
     }
     const size_t off = tile + (size_t)n * KT + (size_t)(swz_chunk<KT>((uint32_t)c, (uint32_t)n) >> 1);  // in bf16 elements
     *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
@@ -144,13 +141,7 @@ __global__ void __launch_bounds__(256) k_bn_eval_planes(const float* __restrict_
     if (hi) {
       uint32_t h[4], l[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(y[2 * j]), h1 = __float2bfloat16_rn(y[2 * j + 1]);
-        const __nv_bfloat16 l0 = __float2bfloat16_rn(y[2 * j] - __bfloat162float(h0));
-        const __nv_bfloat16 l1 = __float2bfloat16_rn(y[2 * j + 1] - __bfloat162float(h1));
-        h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        l[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-      }
+      for (int j = 0; j < 4; ++j) split_bf16x2(y[2 * j], y[2 * j + 1], h[j], l[j]);
       const long long rt = r >> 8;
       const uint32_t rr = (uint32_t)(r & 255), rl = rr & 127u;
       const int kt = cg >> 2;
@@ -829,10 +820,7 @@ k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict_
               for (int j = 0; j < 4; ++j) {
                 const float x0 = (8 * u + 2 * j) < n_here ? p[8 * u + 2 * j] : 0.f;
                 const float x1 = (8 * u + 2 * j + 1) < n_here ? p[8 * u + 2 * j + 1] : 0.f;
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-                const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-                hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                split_bf16x2(x0, x1, hw[j], lw[j]);
               }
               const uint32_t gg = (uint32_t)(g0 + gb + 8 * u);
               const size_t off = ((size_t)(gg >> 5) * H0 * KT) * 2 + (size_t)col * ROWB + swz_chunk<KT>((gg & 31u) >> 3, (uint32_t)col);
@@ -890,10 +878,7 @@ __global__ void __launch_bounds__(256) k_unmix_rows_planes(const float* __restri
     uint32_t hw[4], lw[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
-      const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
-      hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-      lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      split_bf16x2(v[2 * j], v[2 * j + 1], hw[j], lw[j]);
     }
     const size_t off = ((size_t)(r0 >> 5) * H * 32) * 2 + (size_t)c * 64 + swz_chunk<32>((uint32_t)(r0 & 31) >> 3, (uint32_t)c);
     *reinterpret_cast<uint4*>(pl_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
