@@ -294,6 +294,20 @@ int scnb_ema_update(float* teacher, const float* params, long long n, float deca
 int scnb_predict_head(const float* logits_sum, int n_models, int n, int C, int64_t* pred, float* prob, float* score,
                       void* stream);
 
+/* ---- Gene re-indexing in front of predict: utils.build_classification_matrix (scnym/utils.py:155-233, called at
+ *      scnym/api.py:670-675) on a CSR matrix resident in HBM.  col_map[sample column] = model column or -1 (built on the
+ *      host by one hash join; must be injective on its non-negative entries).  Two calls, both asynchronous:
+ *      scnb_csr_remap_count writes the indptr of the re-indexed matrix (out_indptr[n_rows+1], starting at 0) using
+ *      `workspace` (scnb_csr_remap_workspace_len(n_rows) int64 words); scnb_csr_remap_fill writes every row's surviving
+ *      entries sorted by model column (bitmap + prefix popcount per row, no sort).  indptr addresses `indices`/`data`
+ *      absolutely, so a row range of a larger matrix is passed as indptr + first_row. ---- */
+int scnb_csr_remap_workspace_len(long long n_rows);
+int scnb_csr_remap_count(const int64_t* indptr, const int32_t* indices, const int32_t* col_map, int n_src_cols,
+                         long long n_rows, int64_t* out_indptr, void* workspace, void* stream);
+int scnb_csr_remap_fill(const int64_t* indptr, const int32_t* indices, const float* data, const int32_t* col_map,
+                        int n_src_cols, int n_dst_cols, long long n_rows, const int64_t* out_indptr, int32_t* out_indices,
+                        float* out_data, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -521,6 +521,36 @@ def predict(models: Sequence[OracleModel], X: torch.Tensor, batch_size: int = 10
 
 
 # ----------------------------------------------------------------------------
+# Gene re-indexing in front of predict  (reference: scnym/utils.py:155-233)
+# ----------------------------------------------------------------------------
+def build_classification_matrix(X, model_genes, sample_genes, gene_batch_size: int = 512):
+    """Dense numpy restatement of `build_classification_matrix`: returns the [cells, len(model_genes)] matrix
+    as a dense float64 array (the reference returns a CSR for CSR input; compare `.toarray()`).
+      utils.py:188-192  identical gene lists -> the input itself
+      utils.py:209-217  for every sample gene i found in the model: (model index, i), in sample order
+      utils.py:222-227  N[:, model batch] = X[:, sample batch], batches of `gene_batch_size` pairs
+    A sample gene that occurs twice is assigned twice, so its LAST column wins; a model gene that occurs twice
+    makes `.item()` raise ValueError."""
+    import numpy as np
+    model_genes, sample_genes = np.asarray(model_genes), np.asarray(sample_genes)
+    Xd = X.toarray() if hasattr(X, "toarray") else np.asarray(X)
+    if len(model_genes) == len(sample_genes) and np.all(model_genes == sample_genes):
+        return Xd
+    N = np.zeros((Xd.shape[0], len(model_genes)))
+    pairs = []
+    for i, g in enumerate(sample_genes):
+        hits = np.where(g == model_genes)[0]
+        if len(hits) > 1:
+            raise ValueError("ambiguous model gene %r" % (g,))
+        if len(hits) == 1:
+            pairs.append((int(hits[0]), i))
+    for b in range(0, len(pairs), gene_batch_size):
+        for m, i in pairs[b:b + gene_batch_size]:   # in order: a later pair overwrites an earlier one
+            N[:, m] = Xd[:, i]
+    return N
+
+
+# ----------------------------------------------------------------------------
 # Helpers shared by tests / golden generation
 # ----------------------------------------------------------------------------
 def synth_csr(n_cells: int, n_genes: int, density: float, n_classes: int, seed: int,

@@ -72,6 +72,9 @@ SIGNATURES = {
     "scnb_ema_update": [P, P, L, F, P, P],
     "scnb_record_step": [P, P, I, P, I, P, I, P, P],
     "scnb_predict_head": [P, I, I, I, P, P, P, P],
+    "scnb_csr_remap_workspace_len": [L],
+    "scnb_csr_remap_count": [P, P, P, I, L, P, P, P],
+    "scnb_csr_remap_fill": [P, P, P, P, I, I, L, P, P, P, P],
 }
 
 OPTIMIZER_CODES = {"none": -1, "adadelta": 0, "adam": 1, "adamw": 2, "sgd": 3}

@@ -215,10 +215,18 @@ def scnym_predict(adata, config: dict) -> None:
     print(f"Loaded model predicting {results['n_cell_types']} classes from {results['n_genes']} features")
     print(results["class_names"])
     print("Building a classification matrix...")
-    X = utils.build_classification_matrix(X=utils.get_adata_asarray(adata), model_genes=np.array(results["gene_names"]),
-                                          sample_genes=np.array(adata.var_names))
+    # scnym/api.py:670-675 builds a re-indexed copy of the matrix on the host; here only the column map is built on
+    # the host and every row chunk is re-indexed in HBM in front of its first layer (predict.EvalRunner.run)
+    X = utils.get_adata_asarray(adata)
+    model_genes, sample_genes = np.array(results["gene_names"]), np.array(adata.var_names)
+    col_map = None
+    if len(model_genes) == len(sample_genes) and np.all(model_genes == sample_genes):
+        print("Gene names match exactly, returning input.")
+    else:
+        col_map = utils.gene_column_map(model_genes, sample_genes)
+        print("Found %d common genes." % int((col_map >= 0).sum()))
     print("Predicting cell types...")
-    pred, prob, _, emb = P.predict_device(X, want_prob=True, want_embed=True)
+    pred, prob, _, emb = P.predict_device(X, want_prob=True, want_embed=True, col_map=col_map)
     pred = pred.cpu().numpy()
     names = [results["class_names"][p] for p in pred]
     prob = pd.DataFrame(prob.cpu().numpy(), columns=results["class_names"], index=adata.obs_names)

@@ -77,6 +77,38 @@ class DeviceCSR(object):
         return DeviceCSR(ip, self.indices, self.data, self.n_cols, self.max_row_nnz)
 
 
+def remap_columns(ds: DeviceCSR, col_map: torch.Tensor, n_cols_out: int, row0: int = 0, n_rows: Optional[int] = None,
+                  out: Optional[tuple] = None) -> DeviceCSR:
+    """Rows [row0, row0+n_rows) of `ds` with column c moved to col_map[c] (dropped where col_map[c] < 0), every row
+    sorted by its new column: the device form of `utils.build_classification_matrix` (scnym/utils.py:155-233).
+    `col_map` (int32 [ds.n_cols], on the device) must be injective on its non-negative entries.
+    `out = (indptr int64 [>= n_rows+1], indices int32 [cap], data fp32 [cap], workspace int64)` reuses caller buffers
+    whose capacity covers the range's stored entries (no host synchronisation at all); otherwise exact-size outputs are
+    allocated, which reads the new entry count back once."""
+    n = ds.n_rows - row0 if n_rows is None else int(n_rows)
+    if col_map.dtype != torch.int32 or col_map.numel() != ds.n_cols:
+        raise TypeError("remap_columns: col_map must be int32 with one entry per input column")
+    _lib.require_cuda(ds.data, col_map)
+    st = _stream()
+    dev = ds.device
+    ip_in = ds.indptr[row0:]
+    if out is None:
+        ws = torch.empty(_lib.lib().scnb_csr_remap_workspace_len(n), dtype=torch.int64, device=dev)
+        ip = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    else:
+        ip, idx, val, ws = out
+    call("scnb_csr_remap_count", ptr(ip_in), ptr(ds.indices), ptr(col_map), ds.n_cols, n, ptr(ip), ptr(ws), st)
+    if out is None:
+        total = int(ip[n].item()) if n > 0 else 0
+        idx = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        val = torch.empty(max(total, 1), dtype=torch.float32, device=dev)
+    call("scnb_csr_remap_fill", ptr(ip_in), ptr(ds.indices), ptr(ds.data), ptr(col_map), ds.n_cols, int(n_cols_out), n, ptr(ip),
+         ptr(idx), ptr(val), st)
+    if out is None:
+        idx, val = idx[:total], val[:total]
+    return DeviceCSR(ip[:n + 1], idx, val, int(n_cols_out), max_row_nnz=min(ds.max_row_nnz, int(n_cols_out)))
+
+
 class CSRBatch(object):
     """Compact CSR minibatch on device (int32 indptr)."""
 

@@ -16,7 +16,7 @@ import torch
 
 from . import _lib
 from ._lib import call, ptr
-from .dataprep import DeviceCSR
+from .dataprep import DeviceCSR, remap_columns
 from .model import CellTypeCLF
 
 CHUNK_ROWS = 148 * 2 * 256  # rows per kernel launch (two full waves of 256-row tensor-core tiles on 148 SMs); results do not depend on it
@@ -122,7 +122,11 @@ class EvalRunner(object):
                      0.0 if mi == 0 else 1.0, ptr(clf.bias), 0, None, st)
         call("scnb_predict_head", ptr(self.logits), len(self.models), n, self.C, ptr(pred), ptr(prob), ptr(score), st)
 
-    def run(self, ds: DeviceCSR, want_prob=True, want_score=False, want_embed=False, row0: int = 0, n_rows: Optional[int] = None):
+    def run(self, ds: DeviceCSR, want_prob=True, want_score=False, want_embed=False, row0: int = 0, n_rows: Optional[int] = None,
+            col_map: Optional[torch.Tensor] = None):
+        """`col_map` (int32 [ds.n_cols] on the device, model column of every column of `ds` or -1): the atlas is in its
+        own gene order and every row chunk is re-indexed to the model's genes in HBM right before its first layer
+        (scnym/utils.py:155-233 folded into the predict loop: the re-indexed atlas is never materialised)."""
         N = ds.n_rows - row0 if n_rows is None else n_rows
         dev = self.dev
         pred = torch.empty(N, dtype=torch.int64, device=dev)
@@ -130,9 +134,25 @@ class EvalRunner(object):
         score = torch.empty((N, self.C), dtype=torch.float32, device=dev) if want_score else None
         embed = torch.empty((N, self.widths[-1]), dtype=torch.float32, device=dev) if want_embed else None
         self.refresh_planes()
+        scratch = None
+        if col_map is not None:
+            if N > 0:
+                starts = torch.arange(row0, row0 + N + self.chunk, self.chunk, device=ds.indptr.device).clamp_(max=row0 + N)
+                bounds = ds.indptr[starts]
+                cap = max(int((bounds[1:] - bounds[:-1]).max().item()), 1)   # stored entries of the fullest chunk (one read-back)
+            else:
+                cap = 1
+            n_ws = _lib.lib().scnb_csr_remap_workspace_len(self.chunk)
+            scratch = (torch.empty(self.chunk + 1, dtype=torch.int64, device=dev), torch.empty(cap, dtype=torch.int32, device=dev),
+                       torch.empty(cap, dtype=torch.float32, device=dev), torch.empty(n_ws, dtype=torch.int64, device=dev))
+        elif ds.n_cols != self.G:
+            raise ValueError("%d genes in X, %d genes in model." % (ds.n_cols, self.G))
         for s in range(0, N, self.chunk):
             n = min(self.chunk, N - s)
-            self.run_chunk(ds, row0 + s, n, pred[s:], prob[s:] if prob is not None else None,
+            part, r0 = ds, row0 + s
+            if col_map is not None:
+                part, r0 = remap_columns(ds, col_map, self.G, row0 + s, n, out=scratch), 0
+            self.run_chunk(part, r0, n, pred[s:], prob[s:] if prob is not None else None,
                            score[s:] if score is not None else None, embed[s:] if embed is not None else None)
         return pred, prob, score, embed
 
@@ -189,13 +209,18 @@ class Predicter(object):
             return predictions, names, score.cpu().numpy()
         return predictions, names
 
-    def predict_device(self, X, want_prob=True, want_score=False, want_embed=False):
-        """Device-resident results (torch CUDA tensors); X may be ndarray, scipy CSR, dense torch or DeviceCSR."""
+    def predict_device(self, X, want_prob=True, want_score=False, want_embed=False, col_map=None):
+        """Device-resident results (torch CUDA tensors); X may be ndarray, scipy CSR, dense torch or DeviceCSR.
+        `col_map` (see `utils.gene_column_map`): X is in its own gene order and is re-indexed chunk by chunk on the device."""
         if isinstance(X, torch.Tensor):
             X = X.detach().cpu().numpy()
-        ds = DeviceCSR.from_any(X, device=next(self.models[0].parameters()).device)
+        dev = next(self.models[0].parameters()).device
+        ds = DeviceCSR.from_any(X, device=dev)
+        if col_map is not None:
+            col_map = torch.as_tensor(np.asarray(col_map, dtype=np.int32) if not isinstance(col_map, torch.Tensor) else col_map)
+            col_map = col_map.to(device=dev, dtype=torch.int32)
         if self._runner is None:
             self._runner = EvalRunner(self.models, chunk_rows=min(CHUNK_ROWS, max(ds.n_rows, 1)))
         elif self._runner.chunk < min(CHUNK_ROWS, ds.n_rows):
             self._runner = EvalRunner(self.models, chunk_rows=min(CHUNK_ROWS, ds.n_rows))
-        return self._runner.run(ds, want_prob, want_score, want_embed)
+        return self._runner.run(ds, want_prob, want_score, want_embed, col_map=col_map)

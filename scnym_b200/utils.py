@@ -14,23 +14,48 @@ def get_adata_asarray(adata) -> Union[np.ndarray, sparse.csr_matrix]:
     return np.array(adata.X)
 
 
+def gene_column_map(model_genes: np.ndarray, sample_genes: np.ndarray) -> np.ndarray:
+    """int32 [len(sample_genes)]: the model column of every sample column, -1 where the model lacks the gene
+    (the mapping loop of scnym/utils.py:209-217 as one hash join).  A gene repeated in the sample keeps its LAST
+    column, as the reference's column-batch assignment does; a gene repeated in the model is ambiguous and raises
+    ValueError like the reference's `.item()`."""
+    model_genes, sample_genes = np.asarray(model_genes), np.asarray(sample_genes)
+    midx = pd.Index(model_genes)
+    if midx.has_duplicates:
+        dup = set(midx[midx.duplicated()])
+        if dup & set(sample_genes.tolist()):
+            raise ValueError("can only convert an array of size 1 to a Python scalar")
+    pos = pd.Series(np.arange(len(model_genes)), index=midx)
+    pos = pos[~pos.index.duplicated(keep="first")]
+    dest = pos.reindex(pd.Index(sample_genes)).to_numpy()
+    dest = np.where(np.isnan(dest), -1, dest).astype(np.int32)
+    sidx = pd.Index(sample_genes)
+    if sidx.has_duplicates:
+        dest[sidx.duplicated(keep="last")] = -1
+    return dest
+
+
 def build_classification_matrix(X, model_genes: np.ndarray, sample_genes: np.ndarray, gene_batch_size: int = 512):
     """[Cells, len(model_genes)] matrix in the model's gene order; genes the sample lacks stay zero
     (scnym/utils.py:155-233).  The reference maps genes with an O(genes^2) Python loop and copies
-    through a LIL matrix; this is one hash join plus a CSR column re-index."""
-    if type(X) not in (np.ndarray, sparse.csr_matrix):
+    through a LIL matrix; here the map is one hash join (`gene_column_map`).  A `DeviceCSR` is re-indexed in HBM by
+    `dataprep.remap_columns` (scnb_csr_remap_count / scnb_csr_remap_fill) and comes back as a `DeviceCSR`; the two host
+    types the reference accepts come back as the same host type (`type(N)` matches `type(X)`, utils.py:181-182)."""
+    from .dataprep import DeviceCSR
+    if type(X) not in (np.ndarray, sparse.csr_matrix, DeviceCSR):
         raise TypeError(f"X is type {type(X)}, must `np.ndarray` or `sparse.csr_matrix`")
     model_genes, sample_genes = np.asarray(model_genes), np.asarray(sample_genes)
     if len(model_genes) == len(sample_genes) and np.all(model_genes == sample_genes):
         print("Gene names match exactly, returning input.")
         return X
-    pos = pd.Series(np.arange(len(model_genes)), index=pd.Index(model_genes))
-    pos = pos[~pos.index.duplicated(keep="first")]
-    dest = pos.reindex(pd.Index(sample_genes)).to_numpy()          # model column of each sample column, NaN if absent
-    present = ~np.isnan(dest)
-    dest_i = np.where(present, dest, -1).astype(np.int64)
+    dest_i = gene_column_map(model_genes, sample_genes)
+    present = dest_i >= 0
     n_cells = X.shape[0]
-    if type(X) == np.ndarray:
+    if type(X) == DeviceCSR:
+        import torch
+        from .dataprep import remap_columns
+        N = remap_columns(X, torch.as_tensor(dest_i).to(X.device), len(model_genes))
+    elif type(X) == np.ndarray:
         N = np.zeros((n_cells, len(model_genes)))
         N[:, dest_i[present]] = X[:, np.where(present)[0]]
     else:
