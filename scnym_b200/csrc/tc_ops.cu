@@ -585,7 +585,27 @@ __global__ void __launch_bounds__(128) k_row_gene_splits(const int32_t* __restri
 // Epilogue: TMEM lane = column c of W1T, TMEM column = gene.  tcgen05.ld hands a warp 32 consecutive c of 16 genes, so
 // for every gene the warp reads and writes 128 contiguous bytes of the parameter / state rows -- coalesced without a
 // transposition through shared memory; the 48 loads of a 16-gene chunk are in flight before the first update.
-template <int OPT>
+// EXP: experiment switch of tools/exp_w1tc.py (0 = production).  1: epilogue without parameter/state loads, 2: without
+// stores, 3: without the L2 prefetch, 4: parameter/state/plane traffic with an L2 evict_last policy.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float ldg_l2hint(const float* a, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void stg_l2hint(float* a, float v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(a), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stg_l2hint_v4(void* a, uint4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol)
+               : "memory");
+}
+
+template <int OPT, int EXP = 0>
 __global__ void __launch_bounds__(W1TC_THREADS, 1)
 k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict__ b_idx, const float* __restrict__ b_val, int nb,
                   int GT, int NT, int G, int H0, const uint8_t* __restrict__ dz_hi, const uint8_t* __restrict__ dz_lo,
@@ -633,15 +653,23 @@ k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 1 && OPT != OPT_NONE) {
+    if (lane == 1 && OPT != OPT_NONE && EXP != 3) {
       // The main loop only uses L2->SM bandwidth (dZ1 tiles) and the tensor pipe; HBM is idle.  Ask L2 for this CTA's
       // parameter and optimizer-state rows now (contiguous: W1T is gene-major), so that the kernel's HBM reads overlap
       // its tensor-core phase and the epilogue's loads hit L2.
       const size_t off = (size_t)g0 * H0;
       const uint32_t bytes = (uint32_t)(g1 - g0) * (uint32_t)H0 * 4u;
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(W + off), "r"(bytes) : "memory");
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(S1 + off), "r"(bytes) : "memory");
-      if (OPT != OPT_SGD) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(S2 + off), "r"(bytes) : "memory");
+      if (EXP == 4) {
+        const uint64_t pol = l2_policy_evict_last();
+        asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(W + off), "r"(bytes), "l"(pol) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(S1 + off), "r"(bytes), "l"(pol) : "memory");
+        if (OPT != OPT_SGD)
+          asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(S2 + off), "r"(bytes), "l"(pol) : "memory");
+      } else {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(W + off), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(S1 + off), "r"(bytes) : "memory");
+        if (OPT != OPT_SGD) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(S2 + off), "r"(bytes) : "memory");
+      }
     }
     if (lane == 0) {  // ===== dZ1 tile loader =====
       for (int i = 0; i < n_it; ++i) {
@@ -765,6 +793,8 @@ k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict_
       if (OPT != OPT_NONE) oc = cs;
       const int n_g = g1 - g0;
       float p[16], a[16], b[16];
+      uint64_t pol = 0;
+      if (EXP == 4) pol = l2_policy_evict_last();
       auto load_chunk = [&](int gb, float(&pp)[16], float(&aa)[16], float(&bb)[16]) {
         if (OPT == OPT_NONE) return;
         const int n_here = n_g - gb;
@@ -772,9 +802,17 @@ k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict_
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           if (j < n_here) {
-            pp[j] = W[o0 + (size_t)j * H0];
-            aa[j] = S1[o0 + (size_t)j * H0];
-            bb[j] = (OPT != OPT_SGD) ? S2[o0 + (size_t)j * H0] : 0.f;
+            if (EXP == 1) {
+              pp[j] = 0.01f; aa[j] = 0.f; bb[j] = 0.f;
+            } else if (EXP == 4) {
+              pp[j] = ldg_l2hint(W + o0 + (size_t)j * H0, pol);
+              aa[j] = ldg_l2hint(S1 + o0 + (size_t)j * H0, pol);
+              bb[j] = (OPT != OPT_SGD) ? ldg_l2hint(S2 + o0 + (size_t)j * H0, pol) : 0.f;
+            } else {
+              pp[j] = W[o0 + (size_t)j * H0];
+              aa[j] = S1[o0 + (size_t)j * H0];
+              bb[j] = (OPT != OPT_SGD) ? S2[o0 + (size_t)j * H0] : 0.f;
+            }
           }
         }
       };
@@ -803,13 +841,20 @@ k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict_
             if (grad_out) grad_out[o0 + (size_t)j * H0] = gr;
             if (OPT != OPT_NONE) {
               optim_update<OPT>(p[j], gr, a[j], b[j], oc);
-              W[o0 + (size_t)j * H0] = p[j];
-              S1[o0 + (size_t)j * H0] = a[j];
-              if (OPT != OPT_SGD) S2[o0 + (size_t)j * H0] = b[j];
+              if (EXP == 2 && gr != 1234.5678f) continue;   // experiment: nothing is stored (the loads stay live)
+              if (EXP == 4) {
+                stg_l2hint(W + o0 + (size_t)j * H0, p[j], pol);
+                stg_l2hint(S1 + o0 + (size_t)j * H0, a[j], pol);
+                if (OPT != OPT_SGD) stg_l2hint(S2 + o0 + (size_t)j * H0, b[j], pol);
+              } else {
+                W[o0 + (size_t)j * H0] = p[j];
+                S1[o0 + (size_t)j * H0] = a[j];
+                if (OPT != OPT_SGD) S2[o0 + (size_t)j * H0] = b[j];
+              }
             }
           }
         }
-        if (OPT != OPT_NONE && pl_hi) {
+        if (OPT != OPT_NONE && pl_hi && EXP != 2) {
           // bf16 hi/lo operand planes of the UPDATED rows for the next step's tensor-core forward (same image as
           // k_w1_planes<32>: tile = 32 genes, row = column of W1T, 16-byte chunk = 8 consecutive genes, XOR-swizzled)
 #pragma unroll
@@ -824,8 +869,13 @@ k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict_
               }
               const uint32_t gg = (uint32_t)(g0 + gb + 8 * u);
               const size_t off = ((size_t)(gg >> 5) * H0 * KT) * 2 + (size_t)col * ROWB + swz_chunk<KT>((gg & 31u) >> 3, (uint32_t)col);
-              *reinterpret_cast<uint4*>(pl_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-              *reinterpret_cast<uint4*>(pl_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              if (EXP == 4) {
+                stg_l2hint_v4(pl_hi + off, make_uint4(hw[0], hw[1], hw[2], hw[3]), pol);
+                stg_l2hint_v4(pl_lo + off, make_uint4(lw[0], lw[1], lw[2], lw[3]), pol);
+              } else {
+                *reinterpret_cast<uint4*>(pl_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                *reinterpret_cast<uint4*>(pl_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              }
             }
           }
         }
@@ -917,7 +967,7 @@ extern "C" int scnb_row_gene_splits(const int32_t* b_indptr, const int32_t* b_id
   return SCNB_OK;
 }
 
-template <int OPT>
+template <int OPT, int EXP = 0>
 static int launch_w1_bwd_optim_tc_any(const int32_t* splits, const int32_t* b_idx, const float* b_val, int nb, int H0, int G,
                                       const void* dz_hi, const void* dz_lo, float* W1T, float* grad_out, float* s1, float* s2,
                                       const float* hp, const int64_t* st4, void* pl_hi, void* pl_lo, cudaStream_t st) {
@@ -935,7 +985,7 @@ static int launch_w1_bwd_optim_tc_any(const int32_t* splits, const int32_t* b_id
   const size_t smem = 1024 + stages * stage_bytes + slack + 24 * stages + 16 + 16;
   int tmem_cols = 32;
   while (tmem_cols < halves * NT) tmem_cols *= 2;
-  cudaError_t e = cudaFuncSetAttribute(k_w1_bwd_optim_tc<OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_w1_bwd_optim_tc<OPT, EXP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     scnb_set_error("csr_w1_bwd_optim_tc: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
     return SCNB_ERR_CUDA;
@@ -947,7 +997,7 @@ static int launch_w1_bwd_optim_tc_any(const int32_t* splits, const int32_t* b_id
     dbg_on = (ev && ev[0] == '1') ? 1 : 0;
     if (dbg_on) cudaMalloc(&dbg, 4 * 4096 * sizeof(long long));
   }
-  k_w1_bwd_optim_tc<OPT><<<n_blk, W1TC_THREADS, smem, st>>>(splits, b_idx, b_val, nb, GT, NT, G, H0, (const uint8_t*)dz_hi,
+  k_w1_bwd_optim_tc<OPT, EXP><<<n_blk, W1TC_THREADS, smem, st>>>(splits, b_idx, b_val, nb, GT, NT, G, H0, (const uint8_t*)dz_hi,
                                                           (const uint8_t*)dz_lo, W1T, grad_out, s1, s2, hp, st4, (uint8_t*)pl_hi, (uint8_t*)pl_lo,
                                                           stages, tmem_cols, dbg_on ? dbg : nullptr);
   SCNB_CHECK_LAUNCH("csr_w1_bwd_optim_tc");
@@ -982,6 +1032,16 @@ extern "C" int scnb_csr_w1_bwd_optim_tc(int opt, const int32_t* splits, const in
                  "csr_w1_bwd_optim_tc: operand planes must be given together, 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
 #define W1TC_GO(O) return launch_w1_bwd_optim_tc_any<O>(splits, b_idx, b_val, nb, H0, G, dz_planes_hi, dz_planes_lo, W1T, grad_out, state1, state2, hp8, state4, planes_hi_out, planes_lo_out, st)
+  if (opt == OPT_ADAM) {   // experiment switch (tools/exp_w1tc.py): read per launch so one process can time every mode
+    const char* ev = getenv("SCNB_W1TC_EXP");
+    const int exp_mode = ev ? atoi(ev) : 0;
+#define W1TC_EXP_GO(E) return launch_w1_bwd_optim_tc_any<OPT_ADAM, E>(splits, b_idx, b_val, nb, H0, G, dz_planes_hi, dz_planes_lo, W1T, grad_out, state1, state2, hp8, state4, planes_hi_out, planes_lo_out, st)
+    if (exp_mode == 1) W1TC_EXP_GO(1);
+    if (exp_mode == 2) W1TC_EXP_GO(2);
+    if (exp_mode == 3) W1TC_EXP_GO(3);
+    if (exp_mode == 4) W1TC_EXP_GO(4);
+#undef W1TC_EXP_GO
+  }
   switch (opt) {
     case OPT_NONE: W1TC_GO(OPT_NONE);
     case OPT_ADADELTA: W1TC_GO(OPT_ADADELTA);

@@ -167,8 +167,10 @@ def test_device_remap_row_range_and_caller_buffers():
 
 @pytest.mark.gpu
 def test_predict_with_col_map_equals_predict_on_reindexed_matrix():
-    """`Predicter.predict_device(X, col_map=...)` (chunk-wise device re-indexing inside the predict loop) gives the very same
-    bits as predict on the matrix re-indexed beforehand by the host form, across several chunks."""
+    """`Predicter.predict_device(X, col_map=...)` (chunk-wise device re-indexing inside the predict loop) against predict on
+    the matrix re-indexed beforehand by the host form, across several chunks.  The re-indexed rows are bit-identical (tests
+    above); the first layer adds its gene-axis partial products with atomics, so logits agree to rounding (1e-5), the
+    predicted classes exactly."""
     import tempfile
     from scnym_b200.model import CellTypeCLF
     from scnym_b200.predict import EvalRunner, Predicter
@@ -193,12 +195,15 @@ def test_predict_with_col_map_equals_predict_on_reindexed_matrix():
     runner = EvalRunner(P.models, chunk_rows=256)     # 4 chunks, the last one ragged
     a = runner.run(DeviceCSR.from_scipy(X), True, True, True, col_map=torch.as_tensor(cm).cuda())
     b = runner.run(DeviceCSR.from_scipy(Xm), True, True, True)
-    for x, y in zip(a, b):
-        assert torch.equal(x, y)
+    def same(u, v):
+        assert torch.equal(u[0], v[0])                                        # argmax exact
+        for x, y in zip(u[1:], v[1:]):
+            assert float((x - y).abs().max()) <= 1e-5 * float(y.abs().max())
+
+    same(a, b)
     c = P.predict_device(X, want_prob=True, want_score=True, want_embed=True, col_map=cm)     # the public entry, one chunk
     d = P.predict_device(Xm, want_prob=True, want_score=True, want_embed=True)
-    for x, y in zip(c, d):
-        assert torch.equal(x, y)
-    assert torch.equal(a[0], c[0])
+    same(c, d)
+    same(a, c)
     with pytest.raises(ValueError):
         P.predict_device(X)            # sample gene count without a column map
