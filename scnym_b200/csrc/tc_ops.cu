@@ -555,6 +555,8 @@ extern "C" int scnb_linear_fwd_tc_planes(const void* a_hi, const void* a_lo, int
 //   * acc += A_lo B_hi + A_hi B_lo + A_hi B_hi in fp32 (TMEM); the epilogue reads it back 32 columns at a time and
 //     applies Adadelta / Adam / AdamW / SGD to 128-byte segments of the gene's parameter and state rows.
 // =============================================================================================
+#include <type_traits>
+
 #include "optim.cuh"
 
 // splits[b * nb + r] = first position p of row r (absolute index into b_idx) with b_idx[p] >= b * GT, b = 0..n_blk
@@ -575,6 +577,7 @@ __global__ void __launch_bounds__(128) k_row_gene_splits(const int32_t* __restri
 
 #define W1TC_THREADS 320   // warp 0: dZ1 tile loader + L2 prefetch, warp 1: MMA issuer, warps 2-9: densify, then epilogue
 #define W1TC_DENSE 256     // densify / epilogue threads
+#define W1TC_SINK_BYTES 16384u
 
 // D^T[c, g] = sum_r dZ1[r, c] * X[r, g]: the MMA's M axis is the H0 axis (two 128-lane accumulators for H0 = 256), its
 // N axis the CTA's genes (any multiple of 16 up to 256, so a gene block of ceil(G / 148) genes is not padded to 128),
@@ -585,27 +588,19 @@ __global__ void __launch_bounds__(128) k_row_gene_splits(const int32_t* __restri
 // Epilogue: TMEM lane = column c of W1T, TMEM column = gene.  tcgen05.ld hands a warp 32 consecutive c of 16 genes, so
 // for every gene the warp reads and writes 128 contiguous bytes of the parameter / state rows -- coalesced without a
 // transposition through shared memory; the 48 loads of a 16-gene chunk are in flight before the first update.
-// EXP: experiment switch of tools/exp_w1tc.py (0 = production).  1: epilogue without parameter/state loads, 2: without
-// stores, 3: without the L2 prefetch, 4: parameter/state/plane traffic with an L2 evict_last policy.
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ float ldg_l2hint(const float* a, uint64_t pol) {
-  float v;
-  asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ void stg_l2hint(float* a, float v, uint64_t pol) {
-  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(a), "f"(v), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void stg_l2hint_v4(void* a, uint4 v, uint64_t pol) {
-  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol)
-               : "memory");
-}
-
-template <int OPT, int EXP = 0>
+// EXP selects how the epilogue gets the parameter / optimizer-state rows (tools/exp_w1tc.py times the forms side by side):
+//   0  register form: every epilogue thread loads the rows of the next 16-gene chunk while it updates the current one;
+//   6  as 0, and the rows are READ once during the tensor phase (bulk copies into a 16 KB shared-memory sink, a few per
+//      k-tile) so that they sit in L2 when the epilogue asks for them.  (cp.async.bulk.prefetch.L2 and prefetch.global.L2
+//      were measured to have no effect here; real reads do.)
+//   8  ring form: after the last MMA the freed operand stages become a ring of 16-gene chunks [p rows | m rows | v rows]
+//      filled by bulk copies (up to the whole ring, ~190 KB, in flight per SM instead of 48 KB of register loads that
+//      queue behind the epilogue's own stores); the epilogue warps read their columns from shared memory;
+//   9  8 + the sink reads of 6.
+// HC: first-layer width known at compile time (256) or 0 = use the run-time H0.  The epilogue addresses 64 rows of four
+// arrays per 16-gene chunk; with a run-time row pitch that is ~390 of its 900 warp instructions per chunk (ncu source
+// view, profiles/r01_ncu_full_v12_w1tc_ring.txt), with HC every row is an immediate offset from one pointer per array.
+template <int OPT, int EXP = 0, int HC = 0>
 __global__ void __launch_bounds__(W1TC_THREADS, 1)
 k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict__ b_idx, const float* __restrict__ b_val, int nb,
                   int GT, int NT, int G, int H0, const uint8_t* __restrict__ dz_hi, const uint8_t* __restrict__ dz_lo,
@@ -614,6 +609,7 @@ k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict_
                   uint8_t* __restrict__ pl_lo, int stages, int tmem_cols, long long* __restrict__ dbg) {
   constexpr int KT = 32;
   constexpr uint32_t ROWB = 2 * KT;
+  if (HC) H0 = HC;                                   // lets the compiler fold the row pitch
 #define W1TC_GSTAMP(k) do { if (dbg) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[4 * blockIdx.x + (k)] = (long long)t_; } } while (0)
   extern __shared__ uint8_t tc_smem_raw[];
   __shared__ OptimConsts cs;
@@ -625,6 +621,15 @@ k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict_
   const uint32_t bars = base + (uint32_t)stages * STAGE_BYTES;
   const uint32_t bar_full_dz = bars, bar_full_x = bars + 8u * stages, bar_empty = bars + 16u * stages, bar_acc = bars + 24u * stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (size_t)stages * STAGE_BYTES + 24 * stages + 8);
+  constexpr bool SINK = (EXP == 6 || EXP == 9), RING = (EXP == 8 || EXP == 9);
+  // behind everything else: [16 KB sink (SINK only)][sink mbarrier][ring full x 8][ring empty x 8]
+  const uint32_t sink = (bars + 24u * (uint32_t)stages + 16u + 127u) & ~127u;
+  const uint32_t bar_sink = sink + (SINK ? W1TC_SINK_BYTES : 0u);
+  const uint32_t ring_full = bar_sink + 16u, ring_empty = ring_full + 64u;
+  const int n_arr = (OPT == OPT_SGD) ? 2 : 3;                       // parameter, state1[, state2]
+  const uint32_t arr_stride = 16u * (uint32_t)H0 * 4u;              // 16 gene rows of one array
+  const uint32_t slot_bytes = (uint32_t)n_arr * arr_stride;
+  const int n_slots = min(8, (int)(((uint32_t)stages * STAGE_BYTES) / slot_bytes));   // >= 2 (stages >= 3)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c = blockIdx.x;
   const int g0 = c * GT, g1 = min(G, g0 + GT);
@@ -639,6 +644,13 @@ k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict_
       mbar_init(bar_empty + 8u * s, 1);
     }
     mbar_init(bar_acc, 1);
+    if (SINK) mbar_init(bar_sink, 1);
+    if (RING) {
+      for (int k = 0; k < 8; ++k) {
+        mbar_init(ring_full + 8u * k, 1);
+        mbar_init(ring_empty + 8u * k, (uint32_t)(H0 >> 5));       // one arrival per epilogue warp that owns columns
+      }
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (OPT != OPT_NONE) cs = optim_consts(hp, st);
   }
@@ -653,25 +665,24 @@ k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 1 && OPT != OPT_NONE && EXP != 3) {
-      // The main loop only uses L2->SM bandwidth (dZ1 tiles) and the tensor pipe; HBM is idle.  Ask L2 for this CTA's
-      // parameter and optimizer-state rows now (contiguous: W1T is gene-major), so that the kernel's HBM reads overlap
-      // its tensor-core phase and the epilogue's loads hit L2.
+    if (lane == 1 && OPT != OPT_NONE && EXP == 0) {
+      // Ask L2 for this CTA's parameter and optimizer-state rows (contiguous: W1T is gene-major) while HBM is idle.
+      // Measured: no effect on B200 (tools/exp_w1tc.py); kept in the register form only.
       const size_t off = (size_t)g0 * H0;
       const uint32_t bytes = (uint32_t)(g1 - g0) * (uint32_t)H0 * 4u;
-      if (EXP == 4) {
-        const uint64_t pol = l2_policy_evict_last();
-        asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(W + off), "r"(bytes), "l"(pol) : "memory");
-        asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(S1 + off), "r"(bytes), "l"(pol) : "memory");
-        if (OPT != OPT_SGD)
-          asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(S2 + off), "r"(bytes), "l"(pol) : "memory");
-      } else {
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(W + off), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(S1 + off), "r"(bytes) : "memory");
-        if (OPT != OPT_SGD) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(S2 + off), "r"(bytes) : "memory");
-      }
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(W + off), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(S1 + off), "r"(bytes) : "memory");
+      if (OPT != OPT_SGD) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(S2 + off), "r"(bytes) : "memory");
     }
     if (lane == 0) {  // ===== dZ1 tile loader =====
+      // SINK: this CTA's parameter / state rows, 16 KB at a time behind each dZ1 tile
+      const uint32_t row_bytes = (uint32_t)(g1 - g0) * (uint32_t)H0 * 4u;
+      const int n_rd = (OPT == OPT_NONE || !SINK) ? 0 : n_arr;
+      const int per_arr = (int)((row_bytes + W1TC_SINK_BYTES - 1u) / W1TC_SINK_BYTES);
+      const int n_sink = n_rd * per_arr;
+      const int per_it = (n_sink + n_it - 1) / n_it;
+      int k_sink = 0;
+      if (n_sink > 0) mbar_arrive_expect_tx(bar_sink, (uint32_t)n_rd * row_bytes);
       for (int i = 0; i < n_it; ++i) {
         const int s = i % stages;
         const uint32_t ph = (uint32_t)(i / stages) & 1u;
@@ -681,6 +692,31 @@ k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict_
         const size_t off = (size_t)i * A_PLANE;
         bulk_g2s(stage, dz_hi + off, A_PLANE, bar_full_dz + 8u * s);
         bulk_g2s(stage + A_PLANE, dz_lo + off, A_PLANE, bar_full_dz + 8u * s);
+        for (int u = 0; u < per_it && k_sink < n_sink; ++u, ++k_sink) {
+          const int a = k_sink / per_arr, j = k_sink % per_arr;
+          const float* arr = a == 0 ? W : (a == 1 ? S1 : S2);
+          const uint32_t o = (uint32_t)j * W1TC_SINK_BYTES;
+          const uint32_t len = min(W1TC_SINK_BYTES, row_bytes - o);
+          bulk_g2s(sink, reinterpret_cast<const uint8_t*>(arr + (size_t)g0 * H0) + o, len, bar_sink);
+        }
+      }
+      if (n_sink > 0) mbar_wait(bar_sink, 0);   // no bulk copy may be in flight when the CTA exits
+      if (RING && OPT != OPT_NONE) {
+        // ===== ring producer: the stages are free once every MMA has read them =====
+        mbar_wait(bar_acc, 0);
+        const int n_g = g1 - g0;
+        for (int gb = 0, k = 0; gb < n_g; gb += 16, ++k) {
+          const int slot = k % n_slots;
+          const uint32_t use = (uint32_t)(k / n_slots);
+          if (use > 0) mbar_wait(ring_empty + 8u * slot, (use - 1u) & 1u);
+          const uint32_t bytes = (uint32_t)min(16, n_g - gb) * (uint32_t)H0 * 4u;
+          const uint32_t dst = base + (uint32_t)slot * slot_bytes;
+          const size_t off = (size_t)(g0 + gb) * H0;
+          mbar_arrive_expect_tx(ring_full + 8u * slot, (uint32_t)n_arr * bytes);
+          bulk_g2s(dst, W + off, bytes, ring_full + 8u * slot);
+          bulk_g2s(dst + arr_stride, S1 + off, bytes, ring_full + 8u * slot);
+          if (OPT != OPT_SGD) bulk_g2s(dst + 2u * arr_stride, S2 + off, bytes, ring_full + 8u * slot);
+        }
       }
     }
   } else if (warp == 1) {
@@ -793,8 +829,6 @@ k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict_
       if (OPT != OPT_NONE) oc = cs;
       const int n_g = g1 - g0;
       float p[16], a[16], b[16];
-      uint64_t pol = 0;
-      if (EXP == 4) pol = l2_policy_evict_last();
       auto load_chunk = [&](int gb, float(&pp)[16], float(&aa)[16], float(&bb)[16]) {
         if (OPT == OPT_NONE) return;
         const int n_here = n_g - gb;
@@ -802,26 +836,14 @@ k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict_
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           if (j < n_here) {
-            if (EXP == 1) {
-              pp[j] = 0.01f; aa[j] = 0.f; bb[j] = 0.f;
-            } else if (EXP == 4) {
-              pp[j] = ldg_l2hint(W + o0 + (size_t)j * H0, pol);
-              aa[j] = ldg_l2hint(S1 + o0 + (size_t)j * H0, pol);
-              bb[j] = (OPT != OPT_SGD) ? ldg_l2hint(S2 + o0 + (size_t)j * H0, pol) : 0.f;
-            } else {
-              pp[j] = W[o0 + (size_t)j * H0];
-              aa[j] = S1[o0 + (size_t)j * H0];
-              bb[j] = (OPT != OPT_SGD) ? S2[o0 + (size_t)j * H0] : 0.f;
-            }
+            pp[j] = W[o0 + (size_t)j * H0];
+            aa[j] = S1[o0 + (size_t)j * H0];
+            bb[j] = (OPT != OPT_SGD) ? S2[o0 + (size_t)j * H0] : 0.f;
           }
         }
       };
-      load_chunk(0, p, a, b);          // in flight while the last MMAs drain
-      mbar_wait(bar_acc, 0);
-      tc_fence_after();
-      if (t == 0) W1TC_GSTAMP(1);
-      for (int gb = 0; gb < n_g; gb += 16) {
-        uint32_t v[16];
+      // gradient of 16 genes from TMEM (asynchronous; completed by tmem_wait)
+      auto tmem_load16 = [&](int gb, uint32_t(&v)[16]) {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * NT + gb);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -829,58 +851,106 @@ k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict_
               "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
             : "r"(taddr)
             : "memory");
-        float pn[16], an[16], bn[16];
-        if (gb + 16 < n_g) load_chunk(gb + 16, pn, an, bn);   // next chunk's rows, in flight during this chunk's update
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const int n_here = n_g - gb;
+      };
+      // optimizer update of the chunk's rows (this thread's column), stores, operand planes of the updated rows.
+      // `full` (a std::integral_constant): all 16 rows exist -- no per-row predicates.
+      auto finish_chunk = [&](int gb, const uint32_t(&v)[16], float(&pp)[16], float(&aa)[16], float(&bb)[16], auto full) {
+        constexpr bool FULL = decltype(full)::value;
+        const int n_here = FULL ? 16 : n_g - gb;
         const size_t o0 = (size_t)(g0 + gb) * H0 + col;
+        float* const pw = W + o0;
+        float* const p1 = S1 + o0;
+        float* const p2 = S2 + o0;
+        float* const pg = grad_out ? grad_out + o0 : nullptr;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          if (j < n_here) {
+          if (FULL || j < n_here) {
             const float gr = __uint_as_float(v[j]);
-            if (grad_out) grad_out[o0 + (size_t)j * H0] = gr;
+            if (pg) pg[j * H0] = gr;
             if (OPT != OPT_NONE) {
-              optim_update<OPT>(p[j], gr, a[j], b[j], oc);
-              if (EXP == 2 && gr != 1234.5678f) continue;   // experiment: nothing is stored (the loads stay live)
-              if (EXP == 4) {
-                stg_l2hint(W + o0 + (size_t)j * H0, p[j], pol);
-                stg_l2hint(S1 + o0 + (size_t)j * H0, a[j], pol);
-                if (OPT != OPT_SGD) stg_l2hint(S2 + o0 + (size_t)j * H0, b[j], pol);
-              } else {
-                W[o0 + (size_t)j * H0] = p[j];
-                S1[o0 + (size_t)j * H0] = a[j];
-                if (OPT != OPT_SGD) S2[o0 + (size_t)j * H0] = b[j];
-              }
+              optim_update<OPT>(pp[j], gr, aa[j], bb[j], oc);
+              pw[j * H0] = pp[j];
+              p1[j * H0] = aa[j];
+              if (OPT != OPT_SGD) p2[j * H0] = bb[j];
             }
           }
         }
-        if (OPT != OPT_NONE && pl_hi && EXP != 2) {
+        if (OPT != OPT_NONE && pl_hi) {
           // bf16 hi/lo operand planes of the UPDATED rows for the next step's tensor-core forward (same image as
           // k_w1_planes<32>: tile = 32 genes, row = column of W1T, 16-byte chunk = 8 consecutive genes, XOR-swizzled)
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            if (8 * u < n_here) {
+            if (FULL || 8 * u < n_here) {
               uint32_t hw[4], lw[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float x0 = (8 * u + 2 * j) < n_here ? p[8 * u + 2 * j] : 0.f;
-                const float x1 = (8 * u + 2 * j + 1) < n_here ? p[8 * u + 2 * j + 1] : 0.f;
+                const float x0 = (FULL || (8 * u + 2 * j) < n_here) ? pp[8 * u + 2 * j] : 0.f;
+                const float x1 = (FULL || (8 * u + 2 * j + 1) < n_here) ? pp[8 * u + 2 * j + 1] : 0.f;
                 split_bf16x2(x0, x1, hw[j], lw[j]);
               }
               const uint32_t gg = (uint32_t)(g0 + gb + 8 * u);
               const size_t off = ((size_t)(gg >> 5) * H0 * KT) * 2 + (size_t)col * ROWB + swz_chunk<KT>((gg & 31u) >> 3, (uint32_t)col);
-              if (EXP == 4) {
-                stg_l2hint_v4(pl_hi + off, make_uint4(hw[0], hw[1], hw[2], hw[3]), pol);
-                stg_l2hint_v4(pl_lo + off, make_uint4(lw[0], lw[1], lw[2], lw[3]), pol);
-              } else {
-                *reinterpret_cast<uint4*>(pl_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                *reinterpret_cast<uint4*>(pl_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-              }
+              *reinterpret_cast<uint4*>(pl_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              *reinterpret_cast<uint4*>(pl_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
             }
           }
         }
+      };
+      auto finish = [&](int gb, const uint32_t(&v)[16], float(&pp)[16], float(&aa)[16], float(&bb)[16]) {
+        if (n_g - gb >= 16) finish_chunk(gb, v, pp, aa, bb, std::true_type{});
+        else finish_chunk(gb, v, pp, aa, bb, std::false_type{});
+      };
+      if (RING) {
+        mbar_wait(bar_acc, 0);
+        tc_fence_after();
+        if (t == 0) W1TC_GSTAMP(1);
+        for (int gb = 0, k = 0; gb < n_g; gb += 16, ++k) {
+          uint32_t v[16];
+          tmem_load16(gb, v);
+          if (OPT != OPT_NONE) {
+            const int slot = k % n_slots;
+            const uint32_t use = (uint32_t)(k / n_slots);
+            mbar_wait(ring_full + 8u * slot, use & 1u);
+            const float* sp = reinterpret_cast<const float*>(sm + (size_t)slot * slot_bytes) + col;
+            const int n_here = n_g - gb;
+            if (n_here >= 16) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { p[j] = pn[j]; a[j] = an[j]; b[j] = bn[j]; }
+              for (int j = 0; j < 16; ++j) {
+                p[j] = sp[j * H0];
+                a[j] = sp[16 * H0 + j * H0];
+                b[j] = (OPT != OPT_SGD) ? sp[32 * H0 + j * H0] : 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (j < n_here) {
+                  p[j] = sp[j * H0];
+                  a[j] = sp[16 * H0 + j * H0];
+                  b[j] = (OPT != OPT_SGD) ? sp[32 * H0 + j * H0] : 0.f;
+                }
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ring_empty + 8u * slot);      // this warp has its columns of the slot in registers
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          finish(gb, v, p, a, b);
+        }
+      } else {
+        load_chunk(0, p, a, b);          // in flight while the last MMAs drain
+        mbar_wait(bar_acc, 0);
+        tc_fence_after();
+        if (t == 0) W1TC_GSTAMP(1);
+        for (int gb = 0; gb < n_g; gb += 16) {
+          uint32_t v[16];
+          tmem_load16(gb, v);
+          float pn[16], an[16], bn[16];
+          if (gb + 16 < n_g) load_chunk(gb + 16, pn, an, bn);   // next chunk's rows, in flight during this chunk's update
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          finish(gb, v, p, a, b);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { p[j] = pn[j]; a[j] = an[j]; b[j] = bn[j]; }
+        }
       }
     } else {
       mbar_wait(bar_acc, 0);
@@ -967,7 +1037,7 @@ extern "C" int scnb_row_gene_splits(const int32_t* b_indptr, const int32_t* b_id
   return SCNB_OK;
 }
 
-template <int OPT, int EXP = 0>
+template <int OPT, int EXP = 0, int HC = 0>
 static int launch_w1_bwd_optim_tc_any(const int32_t* splits, const int32_t* b_idx, const float* b_val, int nb, int H0, int G,
                                       const void* dz_hi, const void* dz_lo, float* W1T, float* grad_out, float* s1, float* s2,
                                       const float* hp, const int64_t* st4, void* pl_hi, void* pl_lo, cudaStream_t st) {
@@ -982,10 +1052,10 @@ static int launch_w1_bwd_optim_tc_any(const int32_t* splits, const int32_t* b_id
   int stages = (int)((200 * 1024 - slack) / stage_bytes);
   if (stages > 6) stages = 6;
   if (stages < 2) stages = 2;
-  const size_t smem = 1024 + stages * stage_bytes + slack + 24 * stages + 16 + 16;
+  const size_t smem = 1024 + stages * stage_bytes + slack + 24 * stages + 16 + 16 + ((EXP == 6 || EXP == 9) ? W1TC_SINK_BYTES : 0) + 128 + 16 + 128;
   int tmem_cols = 32;
   while (tmem_cols < halves * NT) tmem_cols *= 2;
-  cudaError_t e = cudaFuncSetAttribute(k_w1_bwd_optim_tc<OPT, EXP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_w1_bwd_optim_tc<OPT, EXP, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     scnb_set_error("csr_w1_bwd_optim_tc: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
     return SCNB_ERR_CUDA;
@@ -997,7 +1067,7 @@ static int launch_w1_bwd_optim_tc_any(const int32_t* splits, const int32_t* b_id
     dbg_on = (ev && ev[0] == '1') ? 1 : 0;
     if (dbg_on) cudaMalloc(&dbg, 4 * 4096 * sizeof(long long));
   }
-  k_w1_bwd_optim_tc<OPT, EXP><<<n_blk, W1TC_THREADS, smem, st>>>(splits, b_idx, b_val, nb, GT, NT, G, H0, (const uint8_t*)dz_hi,
+  k_w1_bwd_optim_tc<OPT, EXP, HC><<<n_blk, W1TC_THREADS, smem, st>>>(splits, b_idx, b_val, nb, GT, NT, G, H0, (const uint8_t*)dz_hi,
                                                           (const uint8_t*)dz_lo, W1T, grad_out, s1, s2, hp, st4, (uint8_t*)pl_hi, (uint8_t*)pl_lo,
                                                           stages, tmem_cols, dbg_on ? dbg : nullptr);
   SCNB_CHECK_LAUNCH("csr_w1_bwd_optim_tc");
@@ -1031,23 +1101,40 @@ extern "C" int scnb_csr_w1_bwd_optim_tc(int opt, const int32_t* splits, const in
   SCNB_CHECK_ARG((planes_hi_out == nullptr) == (planes_lo_out == nullptr) && ((uintptr_t)planes_hi_out | (uintptr_t)planes_lo_out) % 16 == 0,
                  "csr_w1_bwd_optim_tc: operand planes must be given together, 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-#define W1TC_GO(O) return launch_w1_bwd_optim_tc_any<O>(splits, b_idx, b_val, nb, H0, G, dz_planes_hi, dz_planes_lo, W1T, grad_out, state1, state2, hp8, state4, planes_hi_out, planes_lo_out, st)
-  if (opt == OPT_ADAM) {   // experiment switch (tools/exp_w1tc.py): read per launch so one process can time every mode
-    const char* ev = getenv("SCNB_W1TC_EXP");
-    const int exp_mode = ev ? atoi(ev) : 0;
-#define W1TC_EXP_GO(E) return launch_w1_bwd_optim_tc_any<OPT_ADAM, E>(splits, b_idx, b_val, nb, H0, G, dz_planes_hi, dz_planes_lo, W1T, grad_out, state1, state2, hp8, state4, planes_hi_out, planes_lo_out, st)
-    if (exp_mode == 1) W1TC_EXP_GO(1);
-    if (exp_mode == 2) W1TC_EXP_GO(2);
-    if (exp_mode == 3) W1TC_EXP_GO(3);
-    if (exp_mode == 4) W1TC_EXP_GO(4);
-#undef W1TC_EXP_GO
+#define W1TC_GO(O, E, HCV) return launch_w1_bwd_optim_tc_any<O, E, HCV>(splits, b_idx, b_val, nb, H0, G, dz_planes_hi, dz_planes_lo, W1T, grad_out, state1, state2, hp8, state4, planes_hi_out, planes_lo_out, st)
+  // Form of the epilogue (see the kernel): 9 = ring + sink reads is the production form, specialised for the default width
+  // H0 = 256.  SCNB_W1TC_EXP=0 selects the register form, 6 / 8 (Adam only) the two halves of 9 on their own, 10 the
+  // production form without the H0 specialisation.  Read per launch so that tools/exp_w1tc.py can time every form in one
+  // process.
+  const char* ev = getenv("SCNB_W1TC_EXP");
+  const int form = ev ? atoi(ev) : 9;
+  if (opt == OPT_ADAM && form == 6) W1TC_GO(OPT_ADAM, 6, 0);
+  if (opt == OPT_ADAM && form == 8) W1TC_GO(OPT_ADAM, 8, 0);
+  if (form == 0) {
+    switch (opt) {
+      case OPT_ADADELTA: W1TC_GO(OPT_ADADELTA, 0, 0);
+      case OPT_ADAM: W1TC_GO(OPT_ADAM, 0, 0);
+      case OPT_ADAMW: W1TC_GO(OPT_ADAMW, 0, 0);
+      case OPT_SGD: W1TC_GO(OPT_SGD, 0, 0);
+      default: break;
+    }
+  }
+  if (H0 == 256 && form != 10) {
+    switch (opt) {
+      case OPT_NONE: W1TC_GO(OPT_NONE, 0, 256);
+      case OPT_ADADELTA: W1TC_GO(OPT_ADADELTA, 9, 256);
+      case OPT_ADAM: W1TC_GO(OPT_ADAM, 9, 256);
+      case OPT_ADAMW: W1TC_GO(OPT_ADAMW, 9, 256);
+      case OPT_SGD: W1TC_GO(OPT_SGD, 9, 256);
+      default: break;
+    }
   }
   switch (opt) {
-    case OPT_NONE: W1TC_GO(OPT_NONE);
-    case OPT_ADADELTA: W1TC_GO(OPT_ADADELTA);
-    case OPT_ADAM: W1TC_GO(OPT_ADAM);
-    case OPT_ADAMW: W1TC_GO(OPT_ADAMW);
-    case OPT_SGD: W1TC_GO(OPT_SGD);
+    case OPT_NONE: W1TC_GO(OPT_NONE, 0, 0);
+    case OPT_ADADELTA: W1TC_GO(OPT_ADADELTA, 9, 0);
+    case OPT_ADAM: W1TC_GO(OPT_ADAM, 9, 0);
+    case OPT_ADAMW: W1TC_GO(OPT_ADAMW, 9, 0);
+    case OPT_SGD: W1TC_GO(OPT_SGD, 9, 0);
     default: scnb_set_error("csr_w1_bwd_optim_tc: unknown optimizer %d", opt); return SCNB_ERR_ARG;
   }
 #undef W1TC_GO

@@ -36,7 +36,24 @@ def ev():
     return torch.cuda.Event(enable_timing=True)
 
 
-modes = [int(x) for x in sys.argv[1:]] or [0, 1, 2, 3, 4]
+modes = [int(x) for x in sys.argv[1:]] or [0, 6, 8, 9]
+
+# every form must produce the same bits as the register form (same MMA order, same optimizer arithmetic)
+W0, s10, s20 = W.clone(), s1.clone(), s2.clone()
+ref = None
+for m in [0] + [x for x in modes if x != 0]:
+    os.environ["SCNB_W1TC_EXP"] = str(m)
+    W.copy_(W0); s1.copy_(s10); s2.copy_(s20); pl_hi.zero_(); pl_lo.zero_()
+    for _ in range(2):
+        launch()
+    torch.cuda.synchronize()
+    got = [x.clone() for x in (W, s1, s2, pl_hi, pl_lo)]
+    if ref is None:
+        ref = got
+        assert not torch.equal(W, W0)
+    else:
+        ok = [bool(torch.equal(x, y)) for x, y in zip(got, ref)]
+        print(f"mode {m}: identical to the register form (W, m, v, planes hi, lo): {ok}", flush=True)
 for m in modes:
     os.environ["SCNB_W1TC_EXP"] = str(m)
     os.environ.pop("SCNB_W1TC_DBG", None)
