@@ -132,7 +132,8 @@ __device__ __forceinline__ void tg5_write(uint32_t smem_hi, uint32_t smem_lo, in
 template <int LAY>
 __global__ void __launch_bounds__(TG5_THREADS, 1)
 k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
-          float alpha, float beta, const float* __restrict__ bias, int relu, const float* __restrict__ gate, int k_chunk, int stages) {
+          float alpha, float beta, const float* __restrict__ bias, int relu, const float* __restrict__ gate, int k_chunk, int stages,
+          int bn /* columns of C per CTA: a multiple of 16, <= TG5_BN (small products use narrow tiles to cover more SMs) */) {
   constexpr uint32_t A_PLANE = TG5_BM * 64, B_PLANE = TG5_BN * 64;
   constexpr uint32_t STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;   // A_hi | A_lo | B_hi | B_lo = 48 KB
   extern __shared__ uint8_t tc_smem_raw[];
@@ -143,11 +144,11 @@ k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int lda, const float
   const uint32_t bar_full = bars, bar_empty = bars + 8u * stages, bar_acc = bars + 16u * stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (size_t)stages * STAGE_BYTES + 16 * stages + 8);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.y * TG5_BM, n0 = blockIdx.x * TG5_BN;
+  const int m0 = blockIdx.y * TG5_BM, n0 = blockIdx.x * bn;
   const int kb = blockIdx.z * k_chunk, ke = min(K, kb + k_chunk);
   const int n_it = (ke - kb + TG5_KT - 1) / TG5_KT;
   // rows of the B tile that exist, rounded up to the MMA's N granularity (16)
-  const int n_tile = min(TG5_BN, (N - n0 + 15) / 16 * 16);
+  const int n_tile = min(bn, (N - n0 + 15) / 16 * 16);
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -300,12 +301,19 @@ int scnb_gemm_tc_try(int transA, int transB, int M, int N, int K, const float* A
   const double flops = 2.0 * M * (double)N * K;
   if (tg5_min_flops() <= 0.0 || flops < tg5_min_flops()) return 0;
   if (M < TG5_BM || N < 64 || K < 64) return 0;
+  // tile width: 256 columns; SCNB_GEMM_TC_BN = 32 / 64 / 128 narrows the tiles (tools/bench_gemm_small.py).  Measured on the
+  // 1024 x 256 x 256 products of config 2 the narrow-tile form needs 16.7 us against 10.4 us of the mma.sync kernel (TMEM
+  // allocation, a 4-stage pipeline and the fp32 -> bf16 staging are fixed costs per CTA), so those stay where they are.
+  static int bn_env = -1;
+  if (bn_env < 0) { const char* e = getenv("SCNB_GEMM_TC_BN"); bn_env = e ? atoi(e) : 0; }
+  int bn = TG5_BN;
+  if (bn_env >= 32 && bn_env <= TG5_BN && bn_env % 32 == 0) bn = bn_env;
   // 16-byte cp.async pieces: leading dimensions and bases aligned; pieces never straddle a matrix edge
   if ((lda % 4) || (ldb % 4) || (((uintptr_t)A | (uintptr_t)B) % 16)) return 0;
   if (lay == 0 && (K % 4)) return 0;                 // A[m][k], B[n][k]
   if (lay == 1 && ((K % 4) || (N % 4))) return 0;    // A[m][k], B[k][n]
   if (lay == 2 && ((M % 4) || (N % 4))) return 0;    // A[k][m], B[k][n]
-  const long long tiles = (long long)scnb_cdiv(M, TG5_BM) * scnb_cdiv(N, TG5_BN);
+  const long long tiles = (long long)scnb_cdiv(M, TG5_BM) * scnb_cdiv(N, bn);
   int splits = 1;
   const bool splittable = !bias && !relu && !gate && (beta == 1.f);
   if (splittable)
@@ -314,12 +322,12 @@ int scnb_gemm_tc_try(int transA, int transB, int M, int N, int K, const float* A
   splits = scnb_cdiv(K, k_chunk);
   const int stages = 4;
   const size_t smem = 1024 + (size_t)stages * (2 * TG5_BM * 64 + 2 * TG5_BN * 64) + 16 * stages + 16 + 16;
-  dim3 grid(scnb_cdiv(N, TG5_BN), scnb_cdiv(M, TG5_BM), splits);
+  dim3 grid(scnb_cdiv(N, bn), scnb_cdiv(M, TG5_BM), splits);
   cudaError_t e;
 #define TG5_GO(L)                                                                                                          \
   e = cudaFuncSetAttribute(k_gemm_tc<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
   if (e == cudaSuccess)                                                                                                    \
-    k_gemm_tc<L><<<grid, TG5_THREADS, smem, st>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, k_chunk, stages)
+    k_gemm_tc<L><<<grid, TG5_THREADS, smem, st>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, k_chunk, stages, bn)
   if (lay == 0) { TG5_GO(0); } else if (lay == 1) { TG5_GO(1); } else { TG5_GO(2); }
 #undef TG5_GO
   if (e != cudaSuccess) {
