@@ -406,9 +406,16 @@ k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ 
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           float* out = Z + ((size_t)blockIdx.x * ROWS + r0) * N + col;
           const int n_here = (int)min((long long)32, (long long)n_rows - ((long long)blockIdx.x * ROWS + r0));
+          // full 32-row groups at the default width: immediate row offsets, no predicates (a third of the epilogue's
+          // instructions were 64-bit address arithmetic, as in the dW1 kernel)
+          if (n_here == 32 && N == 256) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < n_here) atomicAdd(out + (size_t)j * N, __uint_as_float(v[j]) + bc);
+            for (int j = 0; j < 32; ++j) atomicAdd(out + j * 256, __uint_as_float(v[j]) + bc);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < n_here) atomicAdd(out + (size_t)j * N, __uint_as_float(v[j]) + bc);
+          }
         }
       }
     } else if (n_it > 0) {
