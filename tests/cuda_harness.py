@@ -31,7 +31,7 @@ def build_models(d, device="cuda"):
     return model, dann
 
 
-def build_engine(d, device="cuda"):
+def build_engine(d, device="cuda", first_layer=None, w1_update=None, multi_stream=None):
     from scnym_b200.dataprep import DeviceCSR
     from scnym_b200.engine import TrainEngine, EngineConfig
     model, dann = build_models(d, device)
@@ -45,6 +45,12 @@ def build_engine(d, device="cuda"):
                        dan_use_conf_pseudolabels=bool(d["meta_dan_conf"]), dan_scale_loss_pseudoconf=bool(d["meta_dan_scale"]),
                        optimizer=str(d["meta_opt"]), lr=float(d["meta_lr"]), weight_decay=float(d["meta_wd"]), class_weight=cw,
                        use_cuda_graph=False, keep_w1_grad=True)
+    if first_layer is not None:
+        cfg.first_layer = first_layer
+    if w1_update is not None:
+        cfg.w1_update = w1_update
+    if multi_stream is not None:
+        cfg.multi_stream = multi_stream
     given = bool(int(d["meta_D_given"]))
     eng = TrainEngine(model, cfg, lab, d["lab_y"], int(d["meta_L"]), unlabeled=unl, unlabeled_batch_size=int(d["meta_U"]),
                       dann=dann, labeled_domain=d["lab_dom"] if given else None,
