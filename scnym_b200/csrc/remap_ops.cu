@@ -9,6 +9,8 @@
 // model's genes; the position of an entry in the output row is then the number of marked bits below its own
 // (per-word prefix popcount + popcount of the low bits of its word): O(nnz + G/32) per row, no sort.
 // HBM traffic: 4 B per stored entry in pass 1, 8 B read + 8 B written per entry in pass 2 (col_map stays in L1/L2).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #define REMAP_ROWS_PER_CTA 64   // rows whose counts one CTA of the counting pass scans locally
@@ -98,7 +100,9 @@ __global__ void __launch_bounds__(256) k_remap_add_offsets(int64_t* __restrict__
 // Measured (profiles/r01_ncu_full_v12_remap.txt): 65 536 rows of ~1 000 entries in 556 us, L2 throughput 70 %, DRAM 21 %:
 // the col_map gathers (one 32-byte sector per 4-byte entry, the shared-memory carve-out leaves little L1) and the placing
 // stores keep L2 busy.  Staging the placed row in shared memory to write full lines was tried and was slower (+12 %).
-// Next: persistent CTAs that keep col_map in shared memory.
+// A persistent form (one CTA per SM, col_map in shared memory, a warp per row with its own bitmap / prefix / 1024-entry
+// staging area so that rows leave as full lines) was also tried: correct, but 1.54 ms against 0.73 ms per 75 776-row
+// chunk -- eight warps per SM walking rows one after the other hide far less latency than sixteen CTAs per SM.
 // A thread owns REMAP_E entries of a 128 x REMAP_E tile of the row; their loads (index, then col_map and value) are issued
 // together so that a row costs three memory latencies, not three per entry.  Rows that fit one tile (<= 1024 stored entries:
 // every row at 5 % of 20 000 genes) keep new column and value in registers between the marking and the placing phase;
@@ -227,6 +231,7 @@ extern "C" int scnb_csr_remap_fill(const int64_t* indptr, const int32_t* indices
   if (n_rows == 0) return SCNB_OK;
   SCNB_CHECK_ARG(out_indices && out_data, "csr_remap_fill: missing output buffers");
   const int nw = (n_dst_cols + 31) / 32;
+  cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = 2 * sizeof(uint32_t) * (size_t)nw;
   SCNB_CHECK_ARG(smem <= 200 * 1024, "csr_remap_fill: %d destination genes need %zu bytes of shared memory (limit 200 KB)",
                  n_dst_cols, smem);
@@ -237,8 +242,8 @@ extern "C" int scnb_csr_remap_fill(const int64_t* indptr, const int32_t* indices
       return SCNB_ERR_CUDA;
     }
   }
-  k_remap_fill<<<(unsigned)n_rows, 128, smem, (cudaStream_t)stream>>>(indptr, indices, data, col_map, n_src_cols, nw, out_indptr,
-                                                                    out_indices, out_data);
+  k_remap_fill<<<(unsigned)n_rows, 128, smem, st>>>(indptr, indices, data, col_map, n_src_cols, nw, out_indptr,
+                                                  out_indices, out_data);
   SCNB_CHECK_LAUNCH("csr_remap_fill");
   return SCNB_OK;
 }
