@@ -275,7 +275,7 @@ def time_e2e(args, device, rank, world):
     # host threads for batch assembly: the box's cores are shared by the ranks
     cores = max((os.cpu_count() or 8) // world, 1)
     n_thr = max(min(4, cores), 1)
-    n_prod = max(min(3, cores // n_thr), 1)
+    n_prod = max(min(int(os.environ.get("SCNB_E2E_PRODUCERS", "3")), cores // n_thr), 1)
     pipe = HostTrainPipeline(model, cfg, lab=(host(lab.indptr), host(lab.indices), host(lab.data), host(y)),
                              unl=(host(unl.indptr), host(unl.indices), host(unl.data)), n_genes=c["G"], batch_size=c["L"],
                              unlabeled_batch_size=c["U"], dann=dann, device=device, n_threads=n_thr, seed=5 + rank, comm=make_comm(world),
