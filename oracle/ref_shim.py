@@ -16,7 +16,44 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("SCNYM_REFERENCE_ROOT", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+INSTALLED_ROOT = os.path.join(HERE, "_ref")      # `pip install --target oracle/_ref` of the unmodified reference (git-ignored)
+
+
+def _pick_root():
+    env = os.environ.get("SCNYM_REFERENCE_ROOT")
+    if env:
+        return env
+    # the source tree exists in the build container only; the installed copy travels to the GPU box
+    if os.path.isdir("/root/reference/scnym"):
+        return "/root/reference"
+    return INSTALLED_ROOT
+
+
+REFERENCE_ROOT = _pick_root()
+
+
+def install_reference(src="/root/reference", force=False):
+    """`pip install --no-deps --target oracle/_ref` of the UNMODIFIED reference (run by `__graft_entry__.build()` in the build
+    container).  /root/reference is read-only and the build writes an egg-info into the source tree, so the install runs from
+    a scratch copy.  Returns True when oracle/_ref holds the package."""
+    import shutil
+    import subprocess
+    import tempfile
+    if os.path.isdir(os.path.join(INSTALLED_ROOT, "scnym")) and not force:
+        return True
+    if not os.path.isdir(os.path.join(src, "scnym")):
+        return False
+    tmp = tempfile.mkdtemp(prefix="scnym_ref_src_")
+    try:
+        work = os.path.join(tmp, "reference")
+        shutil.copytree(src, work, ignore=shutil.ignore_patterns(".git", "notebooks", "assets"))
+        cmd = [sys.executable, "-m", "pip", "install", "--quiet", "--no-index", "--no-build-isolation", "--no-deps", "--find-links",
+               "/opt/wheelhouse", "--target", INSTALLED_ROOT, "--upgrade", work]
+        rc = subprocess.call(cmd)
+        return rc == 0 and os.path.isdir(os.path.join(INSTALLED_ROOT, "scnym"))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 def reference_available() -> bool:

@@ -172,9 +172,19 @@ class OracleModel:
         return (z - blk.rm) / torch.sqrt(blk.rv + BN_EPS) * blk.g + blk.beta
 
     def embed(self, x, train: bool, drop_keep: Optional[Sequence[torch.Tensor]] = None,
-              pre_relu_last: bool = False):
+              pre_relu_last: bool = False, gates: Optional[Sequence[torch.Tensor]] = None,
+              trace: Optional[list] = None):
         """`model.embed(x)` (model.py:210-226,273).  `drop_keep[i]` is the 0/1 keep
-        mask of the i-th Dropout application (train mode only)."""
+        mask of the i-th Dropout application (train mode only).
+
+        Test instrumentation (never changes the arithmetic when left at None):
+          trace  list that receives the detached pre-ReLU tensor of every block, so that a parity
+                 test can measure how close each pre-activation is to the ReLU threshold;
+          gates  per-block boolean [rows, width] tensors that REPLACE the ReLU decision
+                 (`a = y * gate`): the parity tests re-run a step with the gates the device
+                 took, so that a pre-activation within rounding noise of zero -- whose side of
+                 the threshold is decided by summation order, on any hardware -- is counted
+                 explicitly instead of widening the tolerance for every entry."""
         a = x
         for i, blk in enumerate(self.blocks):
             z = a @ blk.W.t() + blk.b
@@ -183,21 +193,27 @@ class OracleModel:
                 y = y * (drop_keep[i][: y.shape[0]].to(y.dtype) / (1.0 - blk.p_drop))
             else:
                 y = self._bn_eval(z, blk)
+            if trace is not None:
+                trace.append(y.detach().clone())
             if pre_relu_last and i == len(self.blocks) - 1:
                 return y
-            a = torch.relu(y)
+            a = torch.relu(y) if gates is None else y * gates[i][: y.shape[0]].to(y.dtype)
         return a
 
-    def forward(self, x, train: bool, drop_keep=None, return_embed: bool = False):
-        e = self.embed(x, train, drop_keep)
+    def forward(self, x, train: bool, drop_keep=None, return_embed: bool = False, gates=None, trace=None):
+        e = self.embed(x, train, drop_keep, gates=gates, trace=trace)
         logits = e @ self.Wc.t() + self.bc
         return (logits, e) if return_embed else logits
 
-    def dann_forward(self, x, train: bool, drop_keep, grl_weight: float):
+    def dann_forward(self, x, train: bool, drop_keep, grl_weight: float, gates=None, trace=None,
+                     head_gate=None, head_trace=None):
         """DANN.forward (model.py:395-424)."""
-        e = self.embed(x, train, drop_keep)
+        e = self.embed(x, train, drop_keep, gates=gates, trace=trace)
         r = _GradReverse.apply(e, grl_weight)
-        h = torch.relu(r @ self.dan[0].t() + self.dan[1])
+        hp = r @ self.dan[0].t() + self.dan[1]
+        if head_trace is not None:
+            head_trace.append(hp.detach().clone())
+        h = torch.relu(hp) if head_gate is None else hp * head_gate[: hp.shape[0]].to(hp.dtype)
         return h @ self.dan[2].t() + self.dan[3], e
 
 
@@ -371,7 +387,8 @@ class StepRandomness:
 
 
 def mixmatch_dan_losses(model: OracleModel, teacher: OracleModel, cfg: StepConfig,
-                        Lx, Ly, Ux, rnd: StepRandomness, Ldom=None, Udom=None):
+                        Lx, Ly, Ux, rnd: StepRandomness, Ldom=None, Udom=None,
+                        gates: Optional[Dict[str, list]] = None, trace: Optional[Dict[str, list]] = None):
     """Forward part of one SemiSupervisedTrainer minibatch (trainer.py:602-656).
 
     Returns dict with sup/unsup/dan losses, total loss (autograd-attached), the
@@ -379,8 +396,13 @@ def mixmatch_dan_losses(model: OracleModel, teacher: OracleModel, cfg: StepConfi
     student forwards (and hence of BN running-stat updates) follows the
     reference: unlabeled-mixed, labeled-mixed (losses.py:880-886), DAN concat
     (losses.py:1209-1213).
+
+    `gates` / `trace` (test instrumentation, see OracleModel.embed): dicts keyed "U", "L", "D"
+    (the three student passes; per-block lists) and "Dh" (the ReLU of the domain classifier).
     """
     out = {}
+    gt = (lambda k: None) if gates is None else (lambda k: gates.get(k))
+    tr = (lambda k: None) if trace is None else (lambda k: trace.setdefault(k, []))
     U, L = Ux.shape[0], Lx.shape[0]
     # (1) pseudolabels -- losses.py:660-737 (no_grad, teacher in eval mode)
     with torch.no_grad():
@@ -412,8 +434,8 @@ def mixmatch_dan_losses(model: OracleModel, teacher: OracleModel, cfg: StepConfi
     u_m = torch.cat([mix_x[:n_conf], Ux[uidx]], 0)
     u_y = torch.cat([mix_y[:n_conf], q[uidx]], 0)
     l_m, l_y = mix_x[n_conf:], mix_y[n_conf:]
-    u_logits = model.forward(u_m, train=True, drop_keep=rnd.drop_keep_U)
-    l_logits = model.forward(l_m, train=True, drop_keep=rnd.drop_keep_L)
+    u_logits = model.forward(u_m, train=True, drop_keep=rnd.drop_keep_U, gates=gt("U"), trace=tr("U"))
+    l_logits = model.forward(l_m, train=True, drop_keep=rnd.drop_keep_L, gates=gt("L"), trace=tr("L"))
     # (5) losses -- losses.py:896-923
     if cfg.unsup_criterion == "mse":
         per = ((softmax(u_logits) - u_y) ** 2).sum(dim=1)
@@ -442,7 +464,9 @@ def mixmatch_dan_losses(model: OracleModel, teacher: OracleModel, cfg: StepConfi
         p_conf = ux.shape[0] / max(U, 1)
         x = torch.cat([Lx_aug, ux], 0)
         dlabel = torch.cat([src, tgt], 0).to(Lx.dtype)
-        dlogits, emb = model.dann_forward(x, True, rnd.drop_keep_D, cfg.dan_weight)
+        hg = gt("Dh")
+        dlogits, emb = model.dann_forward(x, True, rnd.drop_keep_D, cfg.dan_weight, gates=gt("D"), trace=tr("D"),
+                                          head_gate=None if hg is None else hg[0], head_trace=tr("Dh"))
         dan = cross_entropy(dlogits, dlabel)
         if cfg.dan_scale_loss_pseudoconf:
             dan = dan * p_conf
@@ -455,7 +479,7 @@ def mixmatch_dan_losses(model: OracleModel, teacher: OracleModel, cfg: StepConfi
 
 def train_step(model: OracleModel, opt: OracleOptimizer, cfg: StepConfig, Lx, Ly, Ux,
                rnd: StepRandomness, Ldom=None, Udom=None, teacher: Optional[OracleModel] = None,
-               mm_step: int = 0):
+               mm_step: int = 0, gates=None, trace=None):
     """zero_grad -> criteria -> backward -> optimizer.step (trainer.py:602-671).
     Returns (outputs dict, grads by name, teacher)."""
     params = model.parameters()
@@ -472,7 +496,7 @@ def train_step(model: OracleModel, opt: OracleOptimizer, cfg: StepConfig, Lx, Ly
                 t.mul_(alpha).add_(m.detach(), alpha=1 - alpha)
     else:
         teacher = model.snapshot_eval()
-    out = mixmatch_dan_losses(model, teacher, cfg, Lx, Ly, Ux, rnd, Ldom, Udom)
+    out = mixmatch_dan_losses(model, teacher, cfg, Lx, Ly, Ux, rnd, Ldom, Udom, gates=gates, trace=trace)
     out["loss"].backward()
     names = [n for n, _ in model.named_parameters()]
     grads = {n: (p.grad.detach().clone() if p.grad is not None else None)

@@ -157,6 +157,113 @@ class EvalRunner(object):
         return pred, prob, score, embed
 
 
+def _pin(a: np.ndarray):
+    """Page-lock a host array IN PLACE for asynchronous copies (cudaHostRegister; nothing is copied).  Returns
+    (torch view, unpin callable).  When registration is refused the data go through one pinned copy instead."""
+    t = torch.from_numpy(a)
+    if t.numel() == 0 or t.is_pinned():
+        return t, (lambda: None)
+    rt = torch.cuda.cudart()
+    try:
+        rc = rt.cudaHostRegister(t.data_ptr(), t.numel() * t.element_size(), 0)
+        if int(rc) == 0:
+            return t, (lambda: rt.cudaHostUnregister(t.data_ptr()))
+    except Exception:
+        pass
+    return t.pin_memory(), (lambda: None)
+
+
+class HostAtlasStream(object):
+    """Predict over an expression matrix that lives in HOST memory (scipy CSR), end to end:
+    host CSR -> device -> predictions / probabilities / embedding back in host arrays.
+
+    The reference's path (scnym/api.py:656-714, scnym/predict.py:160-205) densifies every cell on the host, copies a
+    dense [1024, G] batch per step and runs a second full pass for the embedding.  Here the CSR arrays are page-locked
+    in place and streamed in row chunks through two device staging slots: the H2D copy of chunk i+1, the kernels of
+    chunk i and the D2H copy of chunk i-1's results run concurrently on three streams (both DMA directions busy), so
+    the wall time is max(PCIe in, compute, PCIe out) instead of their sum."""
+
+    def __init__(self, runner: EvalRunner, cap_nnz: int, want_prob=True, want_score=False, want_embed=True) -> None:
+        self.r = runner
+        dev, ch = runner.dev, runner.chunk
+        self.cap = int(max(cap_nnz, 1))
+        mk = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=dev)
+        self.slots = []
+        for _ in range(2):
+            self.slots.append(dict(
+                ip=mk(ch + 1, dt=torch.int64), ix=mk(self.cap, dt=torch.int32), dv=mk(self.cap),
+                pred=mk(ch, dt=torch.int64), prob=mk(ch, runner.C) if want_prob else None,
+                score=mk(ch, runner.C) if want_score else None, emb=mk(ch, runner.widths[-1]) if want_embed else None,
+                ev_in=torch.cuda.Event(), ev_comp=torch.cuda.Event(), ev_out=torch.cuda.Event()))
+        self.ip_pin = [torch.empty(ch + 1, dtype=torch.int64).pin_memory() for _ in range(2)]
+        self.s_in, self.s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    def run(self, indptr: np.ndarray, indices: np.ndarray, data: np.ndarray, out: Optional[dict] = None):
+        """indptr int64 [N+1], indices int32 [nnz], data fp32 [nnz] (host, C-contiguous).  Returns a dict of pinned host
+        tensors: pred int64 [N], prob / score fp32 [N, C], embed fp32 [N, H] (those requested)."""
+        r, ch = self.r, self.r.chunk
+        N = int(indptr.shape[0] - 1)
+        ix_t, un1 = _pin(indices)
+        dv_t, un2 = _pin(data)
+        want = self.slots[0]
+        if out is None:
+            out = dict(pred=torch.empty(N, dtype=torch.int64).pin_memory())
+            for k, w in (("prob", r.C), ("score", r.C), ("emb", r.widths[-1])):
+                if want[k] is not None:
+                    out[k] = torch.empty((N, w), dtype=torch.float32).pin_memory()
+        main = torch.cuda.current_stream()
+        self.h2d_bytes = self.d2h_bytes = 0
+        r.refresh_planes()
+        try:
+            starts = list(range(0, N, ch))
+
+            def upload(i):
+                s = starts[i]
+                n = min(ch, N - s)
+                a, b = int(indptr[s]), int(indptr[s + n])
+                if b - a > self.cap:
+                    raise ValueError("HostAtlasStream: a row chunk holds more stored entries than the staging capacity")
+                sl, pin = self.slots[i % 2], self.ip_pin[i % 2]
+                with torch.cuda.stream(self.s_in):
+                    self.s_in.wait_event(sl["ev_comp"])          # the slot's previous chunk has been consumed
+                    sl["ev_in"].synchronize() if i >= 2 else None  # its pinned indptr copy has left the host buffer
+                    np.subtract(indptr[s:s + n + 1], a, out=pin.numpy()[:n + 1])
+                    sl["ip"][:n + 1].copy_(pin[:n + 1], non_blocking=True)
+                    sl["ix"][:b - a].copy_(ix_t[a:b], non_blocking=True)
+                    sl["dv"][:b - a].copy_(dv_t[a:b], non_blocking=True)
+                    sl["ev_in"].record(self.s_in)
+                self.h2d_bytes += 8 * (n + 1) + 8 * (b - a)
+                return n
+
+            n_next = upload(0) if starts else 0
+            for i, s in enumerate(starts):
+                n = n_next
+                if i + 1 < len(starts):
+                    n_next = upload(i + 1)
+                sl = self.slots[i % 2]
+                main.wait_event(sl["ev_in"])
+                main.wait_event(sl["ev_out"])                    # the slot's previous results have left the device
+                ds = DeviceCSR(sl["ip"][:n + 1], sl["ix"], sl["dv"], r.G, max_row_nnz=r.G)
+                r.run_chunk(ds, 0, n, sl["pred"], sl["prob"], sl["score"], sl["emb"])
+                sl["ev_comp"].record(main)
+                with torch.cuda.stream(self.s_out):
+                    self.s_out.wait_event(sl["ev_comp"])
+                    out["pred"][s:s + n].copy_(sl["pred"][:n], non_blocking=True)
+                    self.d2h_bytes += 8 * n
+                    for k in ("prob", "score", "emb"):
+                        if sl[k] is not None:
+                            out[k][s:s + n].copy_(sl[k][:n], non_blocking=True)
+                            self.d2h_bytes += 4 * n * sl[k].shape[1]
+                    sl["ev_out"].record(self.s_out)
+            self.s_out.synchronize()
+            main.synchronize()
+        finally:
+            torch.cuda.synchronize()
+            un1(), un2()
+        return out
+
+
 class Predicter(object):
     """Predict cell types from expression data using `CellTypeCLF` (scnym/predict.py:12-216)."""
 
@@ -198,16 +305,50 @@ class Predicter(object):
         return_prob = kwargs.get("return_prob", None)
         if output not in ["prob", "score"] and output is not None:
             raise ValueError(f"{output} is not a valid additional output.")
-        pred, prob, score, _ = self.predict_device(X, want_prob=True, want_score=(output == "score"), want_embed=False)
-        predictions = pred.cpu().numpy()
+        from scipy import sparse
+        if sparse.isspmatrix_csr(X) and X.shape[0] > 0:
+            # host-resident CSR: streamed through the device in row chunks, results land in host arrays
+            res = self.predict_host(X, want_prob=True, want_score=(output == "score"), want_embed=False)
+            predictions = res["pred"].numpy()
+            prob_h = res["prob"].numpy()
+            score_h = res["score"].numpy() if "score" in res else None
+        else:
+            pred, prob, score, _ = self.predict_device(X, want_prob=True, want_score=(output == "score"), want_embed=False)
+            predictions = pred.cpu().numpy()
+            prob_h = prob.cpu().numpy()
+            score_h = score.cpu().numpy() if score is not None else None
         names = [self.labels[p] for p in predictions] if self.labels is not None else None
         if return_prob is True:
-            return predictions, names, prob.cpu().numpy()
+            return predictions, names, prob_h
         elif output is not None:
             if output == "prob":
-                return predictions, names, prob.cpu().numpy()
-            return predictions, names, score.cpu().numpy()
+                return predictions, names, prob_h
+            return predictions, names, score_h
         return predictions, names
+
+    def predict_host(self, X, want_prob=True, want_score=False, want_embed=True, chunk_rows: Optional[int] = None):
+        """scipy CSR in host memory -> dict of host (pinned) tensors `pred`, `prob`, `score`, `emb` (see HostAtlasStream)."""
+        from scipy import sparse
+        if not sparse.isspmatrix_csr(X):
+            X = sparse.csr_matrix(X)
+        if not X.has_sorted_indices:
+            X = X.sorted_indices()
+        if X.shape[1] != self.n_genes:
+            raise ValueError("%d genes in X, %d genes in model." % (X.shape[1], self.n_genes))
+        ip = np.ascontiguousarray(X.indptr, dtype=np.int64)
+        ix = np.ascontiguousarray(X.indices, dtype=np.int32)
+        dv = np.ascontiguousarray(X.data, dtype=np.float32)
+        N = X.shape[0]
+        ch = int(chunk_rows or min(CHUNK_ROWS, max(N, 1)))
+        if self._runner is None or self._runner.chunk != ch:
+            self._runner = EvalRunner(self.models, chunk_rows=ch)
+            self._stream = None
+        cap = int(max(ip[min(s + ch, N)] - ip[s] for s in range(0, N, ch)))
+        key = (want_prob, want_score, want_embed)
+        if getattr(self, "_stream", None) is None or self._stream.cap < cap or self._stream_key != key:
+            self._stream = HostAtlasStream(self._runner, cap, want_prob, want_score, want_embed)
+            self._stream_key = key
+        return self._stream.run(ip, ix, dv)
 
     def predict_device(self, X, want_prob=True, want_score=False, want_embed=False, col_map=None):
         """Device-resident results (torch CUDA tensors); X may be ndarray, scipy CSR, dense torch or DeviceCSR.

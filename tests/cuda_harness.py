@@ -31,7 +31,7 @@ def build_models(d, device="cuda"):
     return model, dann
 
 
-def build_engine(d, device="cuda", first_layer=None, w1_update=None, multi_stream=None):
+def build_engine(d, device="cuda", first_layer=None, w1_update=None, multi_stream=None, comm=None):
     from scnym_b200.dataprep import DeviceCSR
     from scnym_b200.engine import TrainEngine, EngineConfig
     model, dann = build_models(d, device)
@@ -54,7 +54,7 @@ def build_engine(d, device="cuda", first_layer=None, w1_update=None, multi_strea
     given = bool(int(d["meta_D_given"]))
     eng = TrainEngine(model, cfg, lab, d["lab_y"], int(d["meta_L"]), unlabeled=unl, unlabeled_batch_size=int(d["meta_U"]),
                       dann=dann, labeled_domain=d["lab_dom"] if given else None,
-                      unlabeled_domain=d["unl_dom"] if given else None, mode="mixmatch")
+                      unlabeled_domain=d["unl_dom"] if given else None, mode="mixmatch", comm=comm)
     eng.set_weights(float(d["meta_unsup_w"]), float(d["meta_dan_w"]))
     return eng
 
@@ -198,3 +198,271 @@ def oracle_case(*, G, L, U, C, H0, H, n_layers, K=1, T=0.5, aug_pl=False, tau=0.
         for n, b in om.buffers().items():
             d[pre + "post/" + n] = b.numpy().copy()
     return d
+
+
+# ---------------------------------------------------------------------------------------------
+# Gate-aware comparison (full-shape parity tests, smoke(), bench.py's data-parallel check)
+# ---------------------------------------------------------------------------------------------
+def oracle_step0(d, gates=None, trace=None):
+    """Re-run step 0 of a case on the ORACLE from the case's initial weights (optionally with the ReLU
+    decisions replaced by `gates`, optionally recording every pre-ReLU tensor into `trace`)."""
+    model_st, dan_st = GU.split_state(GU.state_from(d, "init/"))
+    om = O.OracleModel(model_st, n_layers=int(d["meta_n_layers"]), dan_state=dan_st)
+    opt = O.OracleOptimizer(om.parameters(), GU.optim_config(d))
+    inp = GU.step_inputs(d, 0)
+    out, grads, _ = O.train_step(om, opt, GU.step_config(d), inp["Lx"], inp["Ly"], inp["Ux"], inp["rnd"], inp["Ldom"],
+                                 inp["Udom"], teacher=None, mm_step=0, gates=gates, trace=trace)
+    post = {n: p.detach().clone() for n, p in om.named_parameters()}
+    post.update({n: b.clone() for n, b in om.buffers().items()})
+    return out, grads, post
+
+
+def engine_gates(eng):
+    """The ReLU decisions the device took in the last step, in the oracle's pass layout
+    ("U" / "L" / "D": per block application; "Dh": the domain classifier's hidden ReLU)."""
+    torch.cuda.synchronize()
+    U, nb = eng.U, eng.nb
+    g = {"U": [(A[:U] > 0).cpu() for A in eng.As], "L": [(A[U:nb] > 0).cpu() for A in eng.As]}
+    if eng.use_dan:
+        g["D"] = [(A[nb:] > 0).cpu() for A in eng.As]
+        g["Dh"] = [(eng.Hd > 0).cpu()]
+    return g
+
+
+def gate_flips(gates, trace, margin=1e-4):
+    """Compare the device's ReLU decisions with the oracle's.  Returns (n_flipped, n_total, worst), where `worst` is the
+    largest |pre-activation| (oracle value, relative to the tensor's max) among the entries decided differently.  A flip
+    is legitimate only where the pre-activation is rounding noise: callers assert `worst <= margin`."""
+    flipped = total = 0
+    worst = 0.0
+    for key, ys in trace.items():
+        for i, y in enumerate(ys):
+            ge = gates[key][i][: y.shape[0]]
+            go = y > 0
+            diff = ge != go
+            total += y.numel()
+            n = int(diff.sum())
+            if n:
+                flipped += n
+                worst = max(worst, float(y[diff].abs().max()) / max(float(y.abs().max()), 1e-30))
+    return flipped, total, worst
+
+
+def compare_step0(eng, d, tol=1e-4, margin=1e-4, max_flip_frac=2e-5, adam_mask=1e-3):
+    """Engine (already stepped once on the case's injected step 0) against the oracle, gate-aware:
+      * losses, logits, pseudolabels, confident flags against the plain oracle run;
+      * every ReLU decision compared; entries decided differently must be rounding noise (|pre-activation| <= margin
+        relative) and rare (<= max_flip_frac of all decisions); they are COUNTED and returned;
+      * gradients at `tol` against the oracle re-run with the device's decisions (identical to the plain run when
+        nothing flipped);
+      * the optimizer rule: post-step parameters == the oracle optimizer applied to the DEVICE gradients (all entries,
+        1e-5), and post-step parameters against the oracle's own on entries whose gradient is above `adam_mask` of
+        the tensor's largest (below that, Adam's lr*g/(|g|+eps) turns summation noise into O(lr) changes, in the
+        reference on other hardware just the same);
+      * BatchNorm buffers at `tol`.
+    Returns a dict of the measured errors (asserts on failure)."""
+    got = collect(eng)
+    trace = {}
+    out0, grads0, post0 = oracle_step0(d, trace=trace)
+    rep = {}
+    def chk(name, a, b, t=tol):
+        e = GU.rel_err(a, b)
+        rep[name] = e
+        assert e <= t, f"{name}: rel err {e:.3e} > {t}"
+    chk("sup_loss", got["sup_loss"], out0["sup_loss"].detach())
+    chk("unsup_loss", got["unsup_loss"], out0["unsup_loss"].detach())
+    if eng.use_dan:
+        chk("dan_loss", got["dan_loss"], out0["dan_loss"].detach())
+    chk("labeled_logits", got["labeled_logits"], out0["labeled_logits"].detach())
+    chk("pseudolabels", got["pseudolabels"], out0["pseudolabels"].float())
+    assert np.array_equal(got["confident"], out0["confident"].numpy())
+    assert np.array_equal(got["labeled_logits"].argmax(1).numpy(), out0["labeled_logits"].detach().argmax(1).numpy())
+    gates = engine_gates(eng)
+    if not eng.use_dan:
+        trace.pop("D", None), trace.pop("Dh", None)
+    flipped, total, worst = gate_flips(gates, trace, margin)
+    rep["relu_decisions"], rep["relu_flipped"], rep["relu_flip_worst_preact"] = total, flipped, worst
+    assert worst <= margin, f"a ReLU decision differs where the pre-activation is not noise: {worst:.3e}"
+    assert flipped <= max(max_flip_frac * total, 2), f"{flipped} of {total} ReLU decisions differ"
+    grads, post = grads0, post0
+    if flipped:
+        _, grads, post = oracle_step0(d, gates=gates)
+    worst_g = 0.0
+    for n, g in got["grads"].items():
+        e = GU.rel_err(g, grads[n])
+        worst_g = max(worst_g, e)
+        assert e <= tol, f"grad/{n}: rel err {e:.3e} > {tol}"
+    rep["grad_worst"] = worst_g
+    # optimizer rule pinned on the device's own gradients (every entry)
+    model_st, dan_st = GU.split_state(GU.state_from(d, "init/"))
+    rm = O.OracleModel(model_st, n_layers=int(d["meta_n_layers"]), dan_state=dan_st)
+    ro = O.OracleOptimizer(rm.parameters(), GU.optim_config(d))
+    ro.step([got["grads"][n].clone() for n, _ in rm.named_parameters()])
+    worst_r = worst_p = 0.0
+    for n, p in rm.named_parameters():
+        e = GU.rel_err(got["post"][n], p.detach())
+        worst_r = max(worst_r, e)
+        assert e <= 1e-5, f"optimizer replay post/{n}: rel err {e:.3e}"
+        gref = grads[n].double().abs()
+        m = gref > adam_mask * float(gref.max()) if float(gref.max()) > 1e-7 else torch.zeros_like(gref, dtype=torch.bool)
+        if bool(m.any()):
+            a, b = got["post"][n].double()[m], post[n].double()[m]
+            e = float((a - b).abs().max()) / max(float(post[n].double().abs().max()), 1e-30)
+            worst_p = max(worst_p, e)
+            assert e <= tol, f"post/{n} (|g| > {adam_mask} max|g|): rel err {e:.3e} > {tol}"
+    rep["post_replay_worst"], rep["post_masked_worst"] = worst_r, worst_p
+    for n, b in post.items():
+        if n.endswith("num_batches_tracked"):
+            assert int(got["post"][n]) == int(b), n
+        elif "running" in n:
+            chk("post/" + n, got["post"][n], b)
+    return rep
+
+
+# ---------------------------------------------------------------------------------------------
+# Data-parallel job against the oracle on the CONCATENATED global batch (real ranks: bench.py --gpus N)
+# ---------------------------------------------------------------------------------------------
+def global_batch_inputs(cases):
+    """Oracle inputs of the global batch that `len(cases)` ranks jointly process (rank r steps on cases[r]'s injected
+    step 0): batches concatenated rank by rank, MixUp permutation block-diagonal (rank-local), dropout masks stacked
+    in the oracle's row order ([U of all ranks ; L of all ranks] for MixUp, [L_aug of all ; U of all] for the DAN pass)."""
+    W = len(cases)
+    inp = [GU.step_inputs(c, 0) for c in cases]
+    cat = lambda f: torch.cat([f(i) for i in inp], 0)
+    Lx, Ly, Ux = cat(lambda i: i["Lx"]), cat(lambda i: i["Ly"]), cat(lambda i: i["Ux"])
+    Ldom = cat(lambda i: i["Ldom"]) if inp[0]["Ldom"] is not None else None
+    Udom = cat(lambda i: i["Udom"]) if inp[0]["Udom"] is not None else None
+    r = [i["rnd"] for i in inp]
+    l, u = inp[0]["Lx"].shape[0], inp[0]["Ux"].shape[0]
+    n_loc, n_g = u + l, W * (u + l)
+
+    def gidx(rank, i):  # local MixUp-concat index -> global concat index
+        return rank * u + i if i < u else W * u + rank * l + (i - u)
+
+    ridx_g, gam_g = np.zeros(n_g, dtype=np.int64), np.zeros(n_g, dtype=np.float32)
+    for rk in range(W):
+        ridx_l, _ = O.mixup_indices(r[rk].perm_keys, r[rk].gamma_raw, n_loc)
+        for i in range(n_loc):
+            ridx_g[gidx(rk, i)] = gidx(rk, int(ridx_l[i]))
+            gam_g[gidx(rk, i)] = float(r[rk].gamma_raw[i])
+    keys_g = np.zeros(n_g, dtype=np.float32)
+    # argsort(keys_g)[j] must equal ridx_g[j]: rank the global rows so that sorted position j holds row ridx_g[j]
+    keys_g[ridx_g] = (np.arange(n_g, dtype=np.float64) / n_g).astype(np.float32)
+    na = len(r[0].drop_keep_U)
+    rnd_g = O.StepRandomness(
+        in_keep_L=torch.cat([x.in_keep_L for x in r]), perm_keys=torch.from_numpy(keys_g), gamma_raw=torch.from_numpy(gam_g),
+        drop_keep_U=[torch.cat([x.drop_keep_U[a] for x in r]) for a in range(na)],
+        drop_keep_L=[torch.cat([x.drop_keep_L[a] for x in r]) for a in range(na)],
+        drop_keep_D=[torch.cat([x.drop_keep_D[a][:l] for x in r] + [x.drop_keep_D[a][l:] for x in r]) for a in range(na)])
+    return dict(Lx=Lx, Ly=Ly, Ux=Ux, rnd=rnd_g, Ldom=Ldom, Udom=Udom)
+
+
+def oracle_global_step(cases, gates=None, trace=None):
+    g = global_batch_inputs(cases)
+    model_st, dan_st = GU.split_state(GU.state_from(cases[0], "init/"))
+    om = O.OracleModel(model_st, n_layers=int(cases[0]["meta_n_layers"]), dan_state=dan_st)
+    opt = O.OracleOptimizer(om.parameters(), GU.optim_config(cases[0]))
+    out, grads, _ = O.train_step(om, opt, GU.step_config(cases[0]), g["Lx"], g["Ly"], g["Ux"], g["rnd"], g["Ldom"], g["Udom"],
+                                 gates=gates, trace=trace)
+    post = {n: p.detach().clone() for n, p in om.named_parameters()}
+    post.update({n: b.clone() for n, b in om.buffers().items()})
+    return out, grads, post
+
+
+DP_CASE = dict(G=2048, L=256, U=256, C=16, H0=256, H=256, n_layers=2, D_given=8, opt_name="adam", lr=1e-3, wd=1e-4, n_steps=1,
+               density=0.05, n_cells=512)
+
+
+def dp_compare(device, rank, world, comm, tol=1e-4, margin=1e-4):
+    """One injected step of the production data-parallel path on `world` REAL ranks (torch.distributed initialised, one GPU
+    each); rank 0 compares the job with the oracle on the concatenated global batch: losses (mean over ranks), averaged
+    gradients, post-step parameters (identical on every rank), BatchNorm buffers at `tol`; ReLU decisions one by one
+    (see compare_step0).  Returns a report dict on rank 0 (None elsewhere); raises AssertionError on a mismatch."""
+    import torch.distributed as dist
+    cases = [oracle_case(seed=500 + r, **DP_CASE) for r in (range(world) if rank == 0 else [0, rank])]
+    d = cases[rank] if rank == 0 else cases[1]
+    for k in list(d.keys()):
+        if k.startswith("init/"):
+            d[k] = cases[0][k]                          # identical replicas
+    if rank == 0:
+        for c in cases[1:]:
+            for k in list(c.keys()):
+                if k.startswith("init/"):
+                    c[k] = cases[0][k]
+    eng = build_engine(d, device=device, comm=comm)
+    assert eng.comm is not None and eng.tc_first and eng.w1_tc, "the production data-parallel kernels were not selected"
+    inject_step(eng, d, 0)
+    eng.step()
+    torch.cuda.synchronize()
+    got = collect(eng)
+    U, nb, l = eng.U, eng.nb, eng.L
+    # ---- gather what rank 0 needs ----
+    loss_t = torch.tensor([got["sup_loss"], got["unsup_loss"], got["dan_loss"]], device=device, dtype=torch.float64)
+    dist.all_reduce(loss_t, op=dist.ReduceOp.SUM)
+    loss_t /= world
+    names = list(got["grads"].keys())
+    avg = {}
+    for n in names:
+        g = got["grads"][n].to(device).contiguous()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        avg[n] = (g / world).cpu()
+    parts = [(A > 0).to(torch.uint8).reshape(-1) for A in eng.As] + [(eng.Hd > 0).to(torch.uint8).reshape(-1)]
+    flat = torch.cat(parts)
+    allg = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(allg, flat)
+    flat_p = torch.cat([got["post"][n].reshape(-1).float() for n in sorted(got["post"]) if "num_batches" not in n]).to(device)
+    hi, lo = flat_p.clone(), flat_p.clone()
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    identical = bool(torch.equal(hi, lo))
+    if rank != 0:
+        return None
+    assert identical, "post-step parameters / BatchNorm buffers differ between ranks"
+    # ---- global gates in the oracle's row order ----
+    sizes = [A.numel() for A in eng.As] + [eng.Hd.numel()]
+    gates = {"U": [], "L": [], "D": [], "Dh": []}
+    off = 0
+    for a, A in enumerate(eng.As):
+        w = A.shape[1]
+        per = [allg[r][off:off + sizes[a]].view(-1, w).bool().cpu() for r in range(world)]
+        gates["U"].append(torch.cat([x[:U] for x in per]))
+        gates["L"].append(torch.cat([x[U:nb] for x in per]))
+        gates["D"].append(torch.cat([x[nb:nb + l] for x in per] + [x[nb + l:] for x in per]))
+        off += sizes[a]
+    per = [allg[r][off:off + sizes[-1]].view(-1, eng.Hd.shape[1]).bool().cpu() for r in range(world)]
+    gates["Dh"].append(torch.cat([x[:l] for x in per] + [x[l:] for x in per]))
+    trace = {}
+    out0, grads, post = oracle_global_step(cases, trace=trace)
+    flipped, total, worst = gate_flips(gates, trace, margin)
+    assert worst <= margin, f"a ReLU decision differs where the pre-activation is not noise: {worst:.3e}"
+    assert flipped <= max(2e-5 * total, 2), f"{flipped} of {total} ReLU decisions differ"
+    if flipped:
+        _, grads, post = oracle_global_step(cases, gates=gates)
+    rep = {"world": world, "relu_decisions": total, "relu_flipped": flipped, "shape": {k: DP_CASE[k] for k in ("G", "L", "U", "H0", "H", "D_given")}}
+    for i, k in enumerate(("sup_loss", "unsup_loss", "dan_loss")):
+        e = GU.rel_err(loss_t[i].cpu(), out0[k].detach())
+        rep[k + "_err"] = e
+        assert e <= tol, f"{k}: {e:.3e}"
+    worst_g = 0.0
+    for n in names:
+        e = GU.rel_err(avg[n], grads[n])
+        worst_g = max(worst_g, e)
+        assert e <= tol, f"grad/{n}: rel err {e:.3e}"
+    worst_p = 0.0
+    for n, p in post.items():
+        if n.endswith("num_batches_tracked"):
+            assert int(got["post"][n]) == int(p), n
+            continue
+        if "running" in n:
+            e = GU.rel_err(got["post"][n], p)
+            assert e <= tol, f"post/{n}: {e:.3e}"
+            continue
+        gref = grads[n].double().abs()
+        if float(gref.max()) < 1e-7:
+            continue
+        m = gref > 1e-3 * float(gref.max())
+        e = float((got["post"][n].double()[m] - p.double()[m]).abs().max()) / max(float(p.double().abs().max()), 1e-30)
+        worst_p = max(worst_p, e)
+        assert e <= tol, f"post/{n}: {e:.3e}"
+    rep.update({"grad_worst": worst_g, "post_masked_worst": worst_p, "replicas_identical": identical, "parity": "green"})
+    return rep

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import scnym_oracle as O
 from tests import golden_util as GU
 
 pytestmark = pytest.mark.gpu
@@ -42,8 +43,12 @@ def _run_and_compare(d):
         assert np.array_equal(got["confident"], d[pre + "confident"])
         for n, g in got["grads"].items():
             _chk("grad/" + n, g, d[pre + "grad/" + n])
-        # Adam amplifies summation-order noise on zero-gradient entries (see tests/test_oracle.py)
-        post_tol = 2e-3 if _is_adam(d) else TOL
+        # Post-step parameters.  Adadelta / SGD: every entry at 1e-4.  Adam / AdamW: the first update is
+        # lr*g/(|g|+eps), so an entry whose gradient is summation noise moves by O(lr) in either direction (in the
+        # reference on other hardware just the same).  Instead of widening the tolerance for every entry, (i) the
+        # update RULE is pinned on all entries by replaying the oracle optimizer on the device's own gradients, and
+        # (ii) the parameters are compared at 1e-4 wherever the reference gradient is above 1e-3 of the tensor's
+        # largest (tests/cuda_harness.py::compare_step0 derives the threshold).
         for n, v in got["post"].items():
             key = pre + "post/" + n
             if key not in d.files:
@@ -51,10 +56,23 @@ def _run_and_compare(d):
             if n.endswith("num_batches_tracked"):
                 assert int(v) == int(d[key]), n
                 continue
-            if _is_adam(d) and GU.is_pre_bn_bias(n):
+            if "running" in n or not _is_adam(d):
+                _chk("post/" + n, v, d[key])
                 continue
-            tol = TOL if ("running" in n) else post_tol
-            _chk("post/" + n, v, d[key], tol=tol)
+            gref = torch.from_numpy(np.array(d[pre + "grad/" + n])).double().abs()
+            if float(gref.max()) < 1e-7:
+                continue
+            m = gref > 1e-3 * float(gref.max())
+            want = torch.from_numpy(np.array(d[key])).double()
+            e = float((v.double()[m] - want[m]).abs().max()) / float(want.abs().max())
+            assert e <= TOL, f"post/{n} on |g| > 1e-3 max|g|: rel err {e:.3e}"
+        if _is_adam(d) and s == 0:
+            model_st, dan_st = GU.split_state(GU.state_from(d, "init/"))
+            rm = O.OracleModel(model_st, n_layers=int(d["meta_n_layers"]), dan_state=dan_st)
+            ro = O.OracleOptimizer(rm.parameters(), GU.optim_config(d))
+            ro.step([got["grads"][n].clone() for n, _ in rm.named_parameters()])
+            for n, p in rm.named_parameters():
+                _chk("optimizer replay post/" + n, got["post"][n], p.detach(), tol=1e-5)
         if _is_adam(d):
             sd = {k: torch.from_numpy(np.array(d[pre + "post/" + k])) for k in eng.model.state_dict().keys()
                   if "running" not in k and "num_batches" not in k}
