@@ -272,6 +272,9 @@ int scnb_teacher_head_fused(const float* TA /*[K*U,H]*/, const float* Wc, const 
  *      state4 = [t, rng_seed, rng_counter, mixmatch_step] (device int64). ---- */
 int scnb_step_begin(int64_t* state4, void* stream);
 int scnb_mm_step_inc(int64_t* state4, void* stream);
+/* optimizer.zero_grad() (scnym/trainer.py:608) for the accumulation targets of the step: zero up to two 16-byte aligned fp32
+ * buffers of na / nb floats (multiples of 4) in one launch. */
+int scnb_zero2(float* a, long long na, float* b, long long nb, void* stream);
 int scnb_optim_step(int opt, float* params, const float* grads, float* state1, float* state2, long long n,
                     const float* hp8, const int64_t* state4, void* stream);
 int scnb_record_step(const float* loss8, float* hist, int hist_cap, const float* conf, int U, float* conf_ring, int ring_cap,

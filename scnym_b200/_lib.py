@@ -67,6 +67,7 @@ SIGNATURES = {
     "scnb_onehot_rows": [P, P, I, I, I, P, P],
     "scnb_step_begin": [P, P],
     "scnb_mm_step_inc": [P, P],
+    "scnb_zero2": [P, L, P, L, P],
     "scnb_optim_step": [I, P, P, P, P, L, P, P, P],
     "scnb_dp_reduce_optim_bcast": [I, P, I, I, L, L, L, L, P, P, P, P, P, P],
     "scnb_ema_update": [P, P, L, F, P, P],

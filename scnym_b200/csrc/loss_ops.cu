@@ -54,6 +54,7 @@ __device__ __forceinline__ void pseudolabel_row(int u, const float* __restrict__
     const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
     if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
   }
+  if (besti >= C) besti = 0;   // a row of NaN / -inf compares false everywhere: torch.max returns index 0 there
   if (lane == 0) {
     conf[u] = best;
     confident[u] = best >= min_conf ? 1 : 0;
@@ -448,6 +449,7 @@ __device__ __forceinline__ void ce_row(int i, const float* __restrict__ Zl, int 
     const int oi = __shfl_xor_sync(0xffffffffu, am, o);
     if (om > m || (om == m && oi < am)) { m = om; am = oi; }
   }
+  if (am >= C) am = 0;         // all-NaN / all -inf row (see pseudolabel_row)
   float s = 0.f;
   for (int c = lane; c < C; c += 32) s += expf(z[c] - m);
   s = warp_sum(s);
@@ -469,6 +471,7 @@ __device__ __forceinline__ void ce_row(int i, const float* __restrict__ Zl, int 
       const int oi = __shfl_xor_sync(0xffffffffu, yam, o);
       if (om > ym || (om == ym && oi < yam)) { ym = om; yam = oi; }
     }
+    if (yam >= C) yam = 0;
   }
   dot = warp_sum(dot);
   ysum = warp_sum(ysum);
@@ -642,6 +645,7 @@ __global__ void __launch_bounds__(256) k_predict_head(const float* __restrict__ 
     const int oi = __shfl_xor_sync(0xffffffffu, am, o);
     if (om > m || (om == m && oi < am)) { m = om; am = oi; }
   }
+  if (am >= C) am = 0;         // all-NaN / all -inf row: a valid class index, as torch.max gives
   float s = 0.f;
   for (int c = lane; c < C; c += 32) s += expf(z[c] * inv_models - m);
   s = warp_sum(s);

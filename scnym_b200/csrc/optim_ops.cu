@@ -89,6 +89,26 @@ extern "C" int scnb_mm_step_inc(int64_t* state4, void* stream) {
   return SCNB_OK;
 }
 
+// Zero-fill of up to two fp32 buffers in one launch (16-byte aligned; the step's accumulation targets: the split-K first
+// layer output and the gradient arena behind the first layer) -- keeps every launch of the captured step inside this library.
+__global__ void __launch_bounds__(256) k_zero2(float4* __restrict__ a, long long na4, float4* __restrict__ b, long long nb4) {
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = i0; i < na4; i += stride) a[i] = z;
+  for (long long i = i0; i < nb4; i += stride) b[i] = z;
+}
+
+extern "C" int scnb_zero2(float* a, long long na, float* b, long long nb, void* stream) {
+  SCNB_CHECK_ARG(na >= 0 && nb >= 0 && (na == 0 || a) && (nb == 0 || b), "zero2: bad arguments");
+  SCNB_CHECK_ARG(na % 4 == 0 && nb % 4 == 0 && ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0), "zero2: buffers must be 16-byte aligned multiples of 4 floats");
+  if (na + nb == 0) return SCNB_OK;
+  const long long n4 = (na > nb ? na : nb) / 4;
+  const int grid = (int)(n4 / 256 + 1 < 148 * 4 ? n4 / 256 + 1 : 148 * 4);
+  k_zero2<<<grid, 256, 0, (cudaStream_t)stream>>>((float4*)a, na / 4, (float4*)b, nb / 4);
+  SCNB_CHECK_LAUNCH("zero2");
+  return SCNB_OK;
+}
+
 // Per-step bookkeeping without host syncs: loss scalars of step t go to hist[(t-1) % hist_cap],
 // pseudolabel confidences to conf_ring[(t-1) % ring_cap] (replaces the per-step .item()/.cpu()
 // reads of scnym/trainer.py:666-681 and losses.py:714-725; read back once per epoch).

@@ -167,6 +167,8 @@ class TrainEngine(object):
         self.dann = dann if self.use_dan else None
         self.G, self.C = model.n_genes, model.n_cell_types
         blocks = model.block_modules()
+        if any(b[1].running_mean is None for b in blocks):
+            raise NotImplementedError("TrainEngine needs BatchNorm running statistics (track_running_stats=True, the shipped default)")
         self.n_app = len(blocks)
         self.widths = [blk[0].out_features for blk in blocks]
         self.H = self.widths[-1]
@@ -340,6 +342,15 @@ class TrainEngine(object):
         # only: under data parallelism the update happens in the arena-wide optimizer pass)
         self.w1_emits_planes = bool(self.tc_first and self.w1_tc and comm is None)
         self._planes_version = None
+        if hasattr(model, "register_load_state_dict_post_hook"):
+            import weakref
+            me = weakref.ref(self)
+
+            def _on_load(module, incompatible_keys):   # must return None
+                eng = me()
+                if eng is not None:
+                    eng.invalidate_planes()
+            model.register_load_state_dict_post_hook(_on_load)
         self._bn_running_done = False
         self._dz_planes_ready = False
         self._side = None
@@ -423,13 +434,21 @@ class TrainEngine(object):
         if sW is not main:
             self._ev_planes.record(sW)
 
+    def invalidate_planes(self):
+        """Call after writing the first-layer weight from outside the engine's kernels through a path torch cannot see
+        (raw `.data` edits, another library): the next step rebuilds the bf16 operand planes of W1T before it runs."""
+        self._planes_version = None
+
     def _sync_planes(self):
-        """With `w1_emits_planes` the step itself keeps the operand planes current.  They are rebuilt here, eagerly,
-        only when something outside the engine's kernels has written the parameter arena since (load_state_dict, a
-        torch optimizer, manual edits): torch bumps the arena's version counter on every in-place op, our kernels do not."""
+        """With `w1_emits_planes` the step itself keeps the operand planes current.  They are rebuilt here, eagerly, when
+        something outside the engine's kernels may have written the first-layer weight since: `load_state_dict` (a
+        post-hook on the model calls `invalidate_planes`), in-place torch ops on the Parameter or on the arena (a torch
+        optimizer, `p.copy_()`: both version counters are tracked -- a Parameter re-pointed at an arena view keeps its
+        OWN counter, the arena's does not move), every new epoch of sampler tables, and an explicit `invalidate_planes()`."""
         if not self.w1_emits_planes:
             return
-        v = self.arena.flat._version
+        w1 = self.arena.params[0]
+        v = (self.arena.flat._version, w1._version)
         if v != self._planes_version:
             call("scnb_w1_planes", self.P(self._blk[0]["W"]), self.G, self.widths[0], ptr(self.w1_hi), ptr(self.w1_lo),
                  torch.cuda.current_stream().cuda_stream)
@@ -471,9 +490,9 @@ class TrainEngine(object):
         z1_pre = self.tc_first and sW is not main
         if z1_pre:   # the split-K first layer accumulates into Z1: clear it on the side branch, off the critical path
             self._after(sW, main)
-            with torch.cuda.stream(sW):
-                self.Z1.zero_()
+            self._zero_grads(sW.cuda_stream, also=self.Z1)     # one launch: Z1 and the gradient arena behind the first layer
             self._ev_z1.record(sW)
+            self._ev_zero.record(sW)
         self._prep(st)
         # With pseudolabel_min_confidence <= 0 every unlabeled row is "confident": the MixUp plan depends only on the
         # step's random draws, so it runs on its own branch next to the gather and the first layer.
@@ -493,13 +512,13 @@ class TrainEngine(object):
             self._ev_plan.record(sP)
         # branch W: gene-major copy of the batch (needed only by the last kernel of the step), gradient zeroing
         self._after(sW, main)
-        with torch.cuda.stream(sW):
-            self._zero_grads()
+        if not z1_pre:
+            self._zero_grads(sW.cuda_stream)
             if sW is not main:
                 self._ev_zero.record(sW)
-            self._build_csc(nb, sW.cuda_stream)
-            if sW is not main:
-                self._ev_csc.record(sW)
+        self._build_csc(nb, sW.cuda_stream)
+        if sW is not main:
+            self._ev_csc.record(sW)
         # -- first layer, once
         self._first_layer(main, sW, nb, self.Z1, prezeroed=z1_pre)
         # -- teacher (eval mode, losses.py:660-737).  With pseudolabel_min_confidence <= 0 every unlabeled row is
@@ -760,12 +779,12 @@ class TrainEngine(object):
             call("scnb_csr_to_csc", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), n_rows, self.G, ptr(self.gene_cnt),
                  ptr(self.c_ptr), ptr(self.c_cursor), ptr(self.c_ent), st)
 
-    def _zero_grads(self):
-        # the first-layer gradient is either never materialised (fused update) or fully overwritten
-        if self.fused_w1:
-            self.arena.grad[self.P1:].zero_()
-        else:
-            self.arena.grad.zero_()
+    def _zero_grads(self, st, also=None):
+        """optimizer.zero_grad() (trainer.py:608) for what the step accumulates into: the gradient arena (behind the first
+        layer when the fused update never materialises dW1, or overwrites it) and, optionally, one more buffer."""
+        g = self.arena.grad[self.P1:] if self.fused_w1 else self.arena.grad
+        n2 = 0 if also is None else also.numel()
+        call("scnb_zero2", ptr(g), g.numel(), ptr(also), n2, st)
 
     def _finish_step(self, main, sW, sD, dZ1, n_rows):
         """First-layer weight gradient, optimizer.step() and BatchNorm running statistics in the
@@ -891,13 +910,12 @@ class TrainEngine(object):
         call("scnb_csr_gather_rows", ptr(self.lab.indptr), ptr(self.lab.indices), ptr(self.lab.data), ptr(self.l_rows), 0, L,
              ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), 0, 0, 0, None, None, 0, 0.0, self._gene_cnt_ptr(), st)
         self._after(sW, main)
-        with torch.cuda.stream(sW):
-            self._zero_grads()
-            if sW is not main:
-                self._ev_zero.record(sW)
-            self._build_csc(L, sW.cuda_stream)
-            if sW is not main:
-                self._ev_csc.record(sW)
+        self._zero_grads(sW.cuda_stream)
+        if sW is not main:
+            self._ev_zero.record(sW)
+        self._build_csc(L, sW.cuda_stream)
+        if sW is not main:
+            self._ev_csc.record(sW)
         self._first_layer(main, sW, L, self.Zs[0])
         self._student_forward(st, rng)
         Hh = self.H
@@ -955,6 +973,7 @@ class TrainEngine(object):
         else:
             self._tabs = new
             self._graph = None  # pointers changed: re-capture
+        self.invalidate_planes()   # once per epoch: one cheap plane rebuild guards against unseen writes to W1
 
     def sample_epoch_tables(self, n_steps: int, generator: Optional[torch.Generator] = None):
         """Draw one epoch of batches on the device: shuffled labeled rows without replacement

@@ -176,16 +176,18 @@ class _BnActFn(torch.autograd.Function):
         n, H = z.shape
         a = torch.empty_like(z)
         seg = _seg_off(n, z.device)
-        stats = torch.empty((1, 3, H), device=z.device, dtype=torch.float32) if training else None
-        call("scnb_bn_act_fwd", ptr(z), ptr(a), None, H, 1, ptr(seg), n, int(training), ptr(gamma), ptr(beta),
+        tracked = bn.running_mean is not None
+        batch_stats = training or not tracked      # BatchNorm1d(track_running_stats=False) normalises with batch statistics always
+        stats = torch.empty((1, 3, H), device=z.device, dtype=torch.float32) if batch_stats else None
+        if batch_stats and n < 2:
+            raise ValueError("Expected more than 1 value per channel when training")
+        call("scnb_bn_act_fwd", ptr(z), ptr(a), None, H, 1, ptr(seg), n, int(batch_stats), ptr(gamma), ptr(beta),
              ptr(bn.running_mean), ptr(bn.running_var), ptr(stats), ptr(keep), None, 0,
              float(p_drop if training else 0.0), int(relu), None, None, _stream())
-        if training:
-            if n < 2:
-                raise ValueError("Expected more than 1 value per channel when training")
+        if training and tracked:
             call("scnb_bn_running_update", ptr(bn.running_mean), ptr(bn.running_var), ptr(bn.num_batches_tracked), ptr(stats),
                  None, None, None, ptr(seg), 1, H, float(bn.momentum), None, _stream())
-        ctx.training, ctx.p_drop, ctx.relu, ctx.bn = training, float(p_drop if training else 0.0), relu, bn
+        ctx.training, ctx.p_drop, ctx.relu, ctx.bn = batch_stats, float(p_drop if training else 0.0), relu, bn
         ctx.save_for_backward(z, a, gamma, stats, keep, seg)
         return a
 

@@ -128,32 +128,54 @@ class HostTrainPipeline(object):
         self.ev_stash = [torch.cuda.Event() for _ in range(2)]
         self.loss_pin = [torch.zeros(8).pin_memory() for _ in range(2)]
         self.ev_done = [torch.cuda.Event() for _ in range(2)]
-        self.rngs = [np.random.default_rng([seed, j]) for j in range(self.n_producers)]
-        self._tabs = [None] * self.n_producers
+        self._tab_rng = np.random.default_rng(seed)
+        self._tab_lock = threading.Lock()
+        self._blocks, self._perm_state, self._step0 = {}, {}, 0
         self.h2d_bytes_last = 0
         self.d2h_bytes_last = 8 * 4
 
     # ---- producer (runs in a thread; the C gather releases the GIL) ----------------------------
-    _TAB = 128   # steps of random draws made at once per producer (amortises numpy call overhead held under the GIL)
+    _TAB = 128   # steps of random draws made at once (amortises numpy call overhead held under the GIL)
 
-    def _draws(self, j):
-        """Next step's sampled rows / MixUp keys / Beta draws of producer j, from tables refilled every _TAB steps."""
-        tab = self._tabs[j]
-        if tab is None or tab["pos"] >= self._TAB:
-            rng, L, U, T = self.rngs[j], self.L, self.U, self._TAB
-            tab = {"pos": 0, "l": rng.integers(0, self.lab.n_rows, (T, L)).astype(np.int64),
-                   "u": rng.integers(0, self.unl.n_rows, (T, U)).astype(np.int64),
-                   "k": rng.random((T, L + U), dtype=np.float32),
-                   "g": rng.beta(self.alpha, self.alpha, (T, L + U)).astype(np.float32)}
-            self._tabs[j] = tab
-        i = tab["pos"]
-        tab["pos"] = i + 1
+    def _perm_rows(self, which, n_rows, per, n_steps):
+        """`n_steps` consecutive minibatches of `per` rows from a running shuffled pass over [0, n_rows): every pass is a
+        fresh permutation, batches never straddle passes (`DataLoader(shuffle=True, drop_last=True)`, scnym/main.py:317-323;
+        the unlabeled loader wraps around through `repeater`, main.py:48-68).  Same semantics as
+        `TrainEngine.sample_epoch_tables`."""
+        st = self._perm_state.setdefault(which, {"perm": None, "pos": 0})
+        out = np.empty((n_steps, per), dtype=np.int64)
+        for i in range(n_steps):
+            if st["perm"] is None or st["pos"] + per > n_rows:
+                st["perm"], st["pos"] = self._tab_rng.permutation(n_rows), 0
+                if per > n_rows:      # fewer rows than one batch: sample with replacement (degenerate, tests only)
+                    st["perm"] = self._tab_rng.integers(0, n_rows, per)
+            out[i] = st["perm"][st["pos"]:st["pos"] + per]
+            st["pos"] += per
+        return out
+
+    def _block(self, b):
+        """Random draws of steps [b*_TAB, (b+1)*_TAB), generated once (by whichever producer needs them first)."""
+        with self._tab_lock:
+            while b not in self._blocks:
+                nb = (max(self._blocks) + 1) if self._blocks else 0
+                T, L, U, rng = self._TAB, self.L, self.U, self._tab_rng
+                self._blocks[nb] = {"l": self._perm_rows("l", self.lab.n_rows, L, T), "u": self._perm_rows("u", self.unl.n_rows, U, T),
+                                    "k": rng.random((T, L + U), dtype=np.float32),
+                                    "g": rng.beta(self.alpha, self.alpha, (T, L + U)).astype(np.float32)}
+                for old in [k for k in self._blocks if k < nb - 2]:
+                    del self._blocks[old]
+            return self._blocks[b]
+
+    def _draws(self, step):
+        """Sampled rows / MixUp keys / Beta draws of global step `step`."""
+        tab = self._block(step // self._TAB)
+        i = step % self._TAB
         return tab["l"][i], tab["u"][i], tab["k"][i], tab["g"][i]
 
-    def _produce(self, k: int, j: int):
+    def _produce(self, k: int, step: int):
         h = _lib.lib()
         v, L, U = self.blob_np[k], self.L, self.U
-        lrows, urows, keys, gam = self._draws(j)
+        lrows, urows, keys, gam = self._draws(step)
         a, b = self.lab, self.unl
         rc = h.scnb_host_gather_rows2(a.indptr.ctypes.data, a.indices.ctypes.data, a.data.ctypes.data, lrows.ctypes.data, L,
                                       v["indptr_l"].ctypes.data, v["idx_l"].ctypes.data, v["val_l"].ctypes.data, self.layout.cap_l,
@@ -174,11 +196,11 @@ class HostTrainPipeline(object):
     def _producer_loop(self, j, n_steps, free_q, ready_q):
         """Producer j assembles steps j, j + P, j + 2P, ... and hands them over through its own queue."""
         try:
-            for _ in range(j, n_steps, self.n_producers):
+            for i in range(j, n_steps, self.n_producers):
                 k = free_q.get()
                 if k is None:
                     return
-                nnz = self._produce(k, j)
+                nnz = self._produce(k, self._step0 + i)
                 ready_q.put((k, nnz))
         except BaseException as e:  # surface producer failures in the consumer
             ready_q.put(e)
@@ -282,3 +304,4 @@ class HostTrainPipeline(object):
                 q.put(None)
             for th in ths:
                 th.join(timeout=5.0)
+            self._step0 += n_steps

@@ -62,13 +62,12 @@ class CellTypeCLF(nn.Module):
         use_raw_counts: bool = False,
     ) -> None:
         super().__init__()
-        if residual or not batch_norm or n_decoder_layers > 1 or use_raw_counts or not track_running_stats:
+        if residual or not batch_norm or n_decoder_layers > 1 or use_raw_counts:
             # non-default variants are outside the hot path; no shipped
             # CONFIGS entry reaches them (scnym/api.py:98-103).
             raise NotImplementedError(
                 "scnym_b200.CellTypeCLF implements the configuration scnym_api ships "
-                "(residual=False, batch_norm=True, track_running_stats=True, n_decoder_layers<=1, "
-                "use_raw_counts=False)")
+                "(residual=False, batch_norm=True, n_decoder_layers<=1, use_raw_counts=False)")
         self.n_genes = n_genes
         self.n_cell_types = n_cell_types
         self.n_hidden = n_hidden
@@ -84,17 +83,20 @@ class CellTypeCLF(nn.Module):
         # RNG-order parity with the reference constructor (model.py:169-233): the shared hidden
         # Linear is created first, then the (unused here) ResBlock's two Linears, then the
         # first two embed Linears, then the classifier.
-        vanilla_layer = [nn.Linear(n_hidden, n_hidden), nn.BatchNorm1d(n_hidden), nn.Dropout(), nn.ReLU(inplace=True)]
+        # track_running_stats=False (model.py:150-153): batch statistics in training AND evaluation, no running buffers;
+        # served by the module-level path (functional.bn_act); the fused engine / batched predict need the running buffers
+        BN = lambda w: nn.BatchNorm1d(w, track_running_stats=track_running_stats)
+        vanilla_layer = [nn.Linear(n_hidden, n_hidden), BN(n_hidden), nn.Dropout(), nn.ReLU(inplace=True)]
         nn.Linear(n_hidden, n_hidden)  # ResBlock.linear00 draw
         nn.Linear(n_hidden, n_hidden)  # ResBlock.linear01 draw
         hidden_layers = vanilla_layer * (n_layers - 1)  # the SAME module objects repeated (model.py:207)
         self.embed = nn.Sequential(
             GeneLinear(n_genes, n_hidden_init),
-            nn.BatchNorm1d(n_hidden_init),
+            BN(n_hidden_init),
             nn.Dropout(),
             nn.ReLU(inplace=True),
             nn.Linear(n_hidden_init, n_hidden),
-            nn.BatchNorm1d(n_hidden),
+            BN(n_hidden),
             nn.Dropout(),
             nn.ReLU(inplace=True),
             *hidden_layers,

@@ -26,8 +26,53 @@ class FusedOptimizer(torch.optim.Optimizer):
         super().__init__(params, defaults)
         self.engine = None  # set by a TrainEngine that took ownership of the update
 
+    # ---- state owned by a TrainEngine: moments and step count live in the engine's arena ----
+    def state_dict(self):
+        """torch's layout, plus -- when a TrainEngine owns the update -- the engine's moment arenas and step counters under
+        "engine" (otherwise saving / resuming would silently reset Adam / Adadelta state)."""
+        sd = super().state_dict()
+        eng = self.engine
+        if eng is not None:
+            sd["engine"] = {"state1": eng.arena.state1.detach().cpu().clone(), "state2": eng.arena.state2.detach().cpu().clone(),
+                            "state4": eng.state.detach().cpu().clone(), "names": list(eng.arena.names),
+                            "offsets": dict(eng.arena.offsets)}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        es = state_dict.pop("engine", None)
+        super().load_state_dict(state_dict)
+        if es is not None:
+            eng = self.engine
+            if eng is None:
+                self._pending_engine_state = es      # adopted by the next TrainEngine that takes ownership
+            else:
+                self._apply_engine_state(eng, es)
+
+    @staticmethod
+    def _apply_engine_state(eng, es):
+        if list(es["names"]) != list(eng.arena.names) or es["state1"].numel() != eng.arena.state1.numel():
+            raise ValueError("optimizer state was saved for a different parameter arena")
+        eng.arena.state1.copy_(es["state1"])
+        eng.arena.state2.copy_(es["state2"])
+        seed = eng.state[1].clone()
+        eng.state.copy_(es["state4"])
+        eng.state[1] = seed                          # the Philox seed stays the engine's own
+
+    def attach_engine(self, eng):
+        """Called by the trainer when a TrainEngine takes over `optimizer.step()` for these parameters."""
+        self.engine = eng
+        es = getattr(self, "_pending_engine_state", None)
+        if es is not None:
+            self._apply_engine_state(eng, es)
+            self._pending_engine_state = None
+
     @torch.no_grad()
     def step(self, closure=None):
+        if self.engine is not None:
+            raise RuntimeError("FusedOptimizer.step(): a TrainEngine owns the update of these parameters (its step() applies the "
+                               "optimizer with the moments kept in its arena); a separate step() here would start a second, "
+                               "independent optimizer state -- detach the engine (optimizer.engine = None) first")
         loss = None
         if closure is not None:
             with torch.enable_grad():

@@ -1,15 +1,19 @@
-"""Data-parallel plumbing: one process per GPU, `torch.distributed` (NCCL over NVLink / NVSwitch).
+"""Data-parallel plumbing: one process per GPU; `torch.distributed` (NCCL) is the RENDEZVOUS, peer memory the data plane.
 
 The reference is single-process (no distributed code); the equivalence target of
 data-parallel training is the reference step on the CONCATENATED global batch:
   * every rank draws its own labeled / unlabeled minibatch from its own shard of the cells;
-  * BatchNorm batch statistics are global: per layer and per pass the ranks all-reduce
-    (sum z, sum z^2, rows) in the forward and (sum dy, sum dy*zhat) in the backward
-    (`scnb_bn_act_fwd/bwd` two-pass protocol);
-  * parameter gradients are averaged with one all-reduce over the flat gradient arena, after
-    which every rank applies the identical fused optimizer update;
+  * BatchNorm batch statistics are global.  Product path (one node, NCCL process group): every rank owns a
+    CUDA-IPC exchange buffer mapped by all ranks (`PeerExchange`); the BatchNorm kernels store their partial
+    sums into every peer's buffer over NVLink / NVSwitch and add what the peers stored, inside the kernel
+    (`scnb_bn_act_fwd_peer` / `_bwd_peer`) -- no collective launch.  Fallback (`SCNB_DP_PEER=0`, gloo tests):
+    partial sums -> `all_reduce_sum` -> apply (`scnb_bn_act_fwd/bwd` two-pass protocol);
+  * parameter gradients: `scnb_dp_reduce_optim_bcast` reduce-scatters them with peer loads, applies the
+    optimizer to the owned slice and stores the new parameters into every rank's arena (fallback: one NCCL
+    all-reduce over the flat gradient arena + the elementwise optimizer kernel);
   * MixUp permutations stay rank-local (block-diagonal in the global batch);
   * inference shards rows contiguously and needs no communication.
+NCCL itself is used to exchange the IPC handles, to broadcast the initial replica and for barriers.
 """
 from typing import Optional, Tuple
 

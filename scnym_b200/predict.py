@@ -32,6 +32,8 @@ class EvalRunner(object):
         if self.dev.type != "cuda":
             raise _lib.ScnbError("scnym_b200 inference needs the models on a CUDA device (no CPU fallback)")
         self.widths = [b[0].out_features for b in m0.block_modules()]
+        if any(b[1].running_mean is None for m in self.models for b in m.block_modules()):
+            raise NotImplementedError("batched predict needs BatchNorm running statistics (track_running_stats=True)")
         self.C = m0.n_cell_types
         self.chunk = int(chunk_rows)
         f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.dev)

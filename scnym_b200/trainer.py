@@ -122,7 +122,7 @@ class Trainer(object):
         dev = self._device if self._device.type == "cuda" else torch.device("cuda")
         self.model.to(dev)
         eng = TrainEngine(self.model, cfg, ds.device_csr(dev), ds.y_labels.numpy(), dl.batch_size, mode="supervised")
-        self.optimizer.engine = eng
+        self.optimizer.attach_engine(eng)
         return eng
 
     # ---- epochs --------------------------------------------------------------------------
@@ -348,7 +348,7 @@ class SemiSupervisedTrainer(Trainer):
                           unlabeled_batch_size=ul.batch_size, dann=dan.dann if dan is not None else None,
                           labeled_domain=np.asarray(ds.dom_labels) if given else None,
                           unlabeled_domain=np.asarray(uds.dom_labels) if given else None, mode="mixmatch")
-        self.optimizer.engine = eng
+        self.optimizer.attach_engine(eng)
         return eng
 
     def _train_epoch_fused(self):

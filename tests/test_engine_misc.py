@@ -1,0 +1,102 @@
+"""Engine behaviours around the step: operand planes after external weight writes, optimizer state
+ownership, NaN rows in the argmax kernels."""
+import numpy as np
+import pytest
+import torch
+
+from tests import golden_util as GU
+
+pytestmark = pytest.mark.gpu
+
+
+def _case():
+    from tests import cuda_harness as CH
+    return CH.oracle_case(G=1024, L=256, U=256, C=6, H0=256, H=128, n_layers=2, opt_name="sgd", lr=0.05, n_steps=1, seed=41)
+
+
+def test_operand_planes_follow_load_state_dict_and_inplace_writes():
+    """Tensor-core path (bf16 operand planes of W1T emitted by the optimizer epilogue): after `load_state_dict`, after an
+    in-place torch write to the Parameter, and after `invalidate_planes()` following a raw `.data` write, the next step's
+    first layer must see the NEW weights -- compared with the exact-fp32 path that reads W1T directly."""
+    from tests import cuda_harness as CH
+    d = _case()
+    eng_tc = CH.build_engine(d, first_layer="tc", w1_update="tc")
+    eng_fp = CH.build_engine(d, first_layer="spmm", w1_update="simt")
+    assert eng_tc.w1_emits_planes and not eng_fp.tc_first
+    for eng in (eng_tc, eng_fp):
+        CH.inject_step(eng, d, 0)
+        eng.step()
+    torch.cuda.synchronize()
+    g = torch.Generator().manual_seed(3)
+
+    def new_state(model):
+        sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        sd["embed.0.weight"] = sd["embed.0.weight"] + 0.05 * torch.randn(sd["embed.0.weight"].shape, generator=g)
+        return sd
+
+    def check(tag):
+        for eng in (eng_tc, eng_fp):
+            CH.inject_step(eng, d, 0)
+            eng.step()
+        torch.cuda.synchronize()
+        e = GU.rel_err(eng_tc.Z1.cpu(), eng_fp.Z1.cpu())
+        assert e < 1e-4, f"{tag}: first-layer output of the tensor-core path is stale ({e:.3e})"
+        # bring both engines back to identical parameters for the next scenario
+        eng_tc.model.load_state_dict({k: v.detach().cpu() for k, v in eng_fp.model.state_dict().items()})
+
+    sd = new_state(eng_fp.model)
+    eng_tc.model.load_state_dict(sd); eng_fp.model.load_state_dict(sd)
+    check("load_state_dict")
+    delta = 0.03 * torch.randn(eng_fp.model.embed[0].weight.shape, generator=g).cuda()
+    with torch.no_grad():
+        eng_tc.model.embed[0].weight.add_(delta); eng_fp.model.embed[0].weight.add_(delta)
+    check("in-place write to the Parameter")
+    eng_tc.model.embed[0].weight.data.mul_(1.01); eng_fp.model.embed[0].weight.data.mul_(1.01)
+    eng_tc.invalidate_planes()
+    check("raw .data write + invalidate_planes()")
+    eng_tc.arena.check_aliasing()
+
+
+def test_optimizer_state_is_owned_by_the_engine_and_round_trips(tmp_path):
+    from scnym_b200 import optim as OPT
+    from tests import cuda_harness as CH
+    d = _case()
+    eng = CH.build_engine(d)
+    opt = OPT.Adam(eng.model.parameters(), lr=1e-3)
+    opt.attach_engine(eng)
+    with pytest.raises(RuntimeError):
+        opt.step()
+    CH.inject_step(eng, d, 0)
+    eng.step()
+    sd = opt.state_dict()
+    assert "engine" in sd and float(sd["engine"]["state1"].abs().max()) > 0 and int(sd["engine"]["state4"][0]) == 1
+    eng2 = CH.build_engine(d)
+    opt2 = OPT.Adam(eng2.model.parameters(), lr=1e-3)
+    opt2.load_state_dict(sd)            # before the engine exists: adopted on attach
+    opt2.attach_engine(eng2)
+    assert torch.equal(eng2.arena.state1.cpu(), sd["engine"]["state1"]) and int(eng2.state[0]) == 1
+
+
+def test_argmax_kernels_return_a_valid_class_for_nan_rows():
+    from scnym_b200._lib import call, ptr
+    C, n = 5, 4
+    z = torch.randn(n, C, device="cuda")
+    z[1] = float("nan")
+    z[2] = float("-inf")
+    pred = torch.full((n,), -7, dtype=torch.int64, device="cuda")
+    prob = torch.empty(n, C, device="cuda")
+    call("scnb_predict_head", ptr(z), 1, n, C, ptr(pred), ptr(prob), None, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    p = pred.cpu().numpy()
+    assert np.all((p >= 0) & (p < C)), p
+    assert p[0] == int(z[0].argmax()) and p[1] == 0 and p[2] == 0
+    # pseudolabels with T = 0 (one-hot of the argmax): a NaN row still gets a one-hot, not an all-zero row
+    U = n
+    q = torch.zeros(U, C, device="cuda")
+    conf = torch.zeros(U, device="cuda")
+    flag = torch.zeros(U, dtype=torch.uint8, device="cuda")
+    scratch = torch.zeros(U, C, device="cuda")
+    call("scnb_pseudolabel", ptr(z), 1, U, C, 0.0, 1, 0.0, ptr(q), ptr(conf), ptr(flag), ptr(scratch), None, 0,
+         torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert float(q[1].sum()) == 1.0 and float(q[1, 0]) == 1.0

@@ -311,11 +311,13 @@ def test_host_train_pipeline_feeds_the_engine_from_host_memory():
     assert len(losses) == 7 and all(np.isfinite(l["loss"]) for l in losses)
     assert pipe.h2d_bytes_last > 8 * (L + U) and pipe.d2h_bytes_last == 32
     assert not torch.equal(w0, model.classif[0].weight.detach())
-    # the staged unlabeled rows of the LAST step are exactly the host rows the producer sampled
-    # (one producer: step i used row i of its table of pre-drawn samples)
-    tab = pipe._tabs[0]
-    assert tab["pos"] == 7
-    lrows, urows = tab["l"][6], tab["u"][6]
+    # the staged unlabeled rows of the LAST step are exactly the host rows sampled for step 6 (tables of pre-drawn samples)
+    assert pipe._step0 == 7
+    lrows, urows, _, _ = pipe._draws(6)
+    # shuffled passes without replacement, batches never straddle a pass (DataLoader(shuffle, drop_last) semantics)
+    per_pass = n // L
+    first_pass = np.concatenate([pipe._draws(s)[0] for s in range(per_pass)])
+    assert len(set(first_pass.tolist())) == per_pass * L
     want_idx = np.concatenate([ui[up[r]:up[r + 1]] for r in urows])
     want_val = np.concatenate([ud[up[r]:up[r + 1]] for r in urows])
     eng = pipe.engine
