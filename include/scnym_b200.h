@@ -218,6 +218,38 @@ int scnb_unmix_rows(const float* dOut, int H, const int32_t* inv3 /*[3][n_base]*
 int scnb_unmix_rows_planes(const float* dOut, int H, const int32_t* inv3, const float* coef3, int n_base, float* dZ,
                            void* planes_hi, void* planes_lo, void* stream);
 
+/* ---- Fused hidden stack (hidden_ops.cu): `[Linear -> BatchNorm1d(train) -> Dropout -> ReLU] x n` of CellTypeCLF.embed
+ *      (scnym/model.py:210-233) on the student super-batch and its adjoint, with BatchNorm -> Dropout -> ReLU applied while
+ *      the GEMM's A operand is staged in shared memory.  Unit of work: a 32-row x 64-column tile; BatchNorm statistics
+ *      travel between launches as per-tile partials `part[rows/32][2][H]` ((mean, M2) forward, (sum dY, sum dY*zhat)
+ *      backward) that every consumer combines per segment in a fixed order.  seg_off_host: HOST int32 [n_seg + 1] row
+ *      offsets (multiples of 32, n_seg <= 3); stats: [n_seg][3][H] = mean, biased var, invstd (as scnb_bn_act_fwd);
+ *      dropout stream ids / injected masks as scnb_bn_act_fwd.  All buffers 16-byte aligned, H % 64 == 0. ---- */
+/* out = MixUp(Z) rows (dataprep.py:665-689; srcA == NULL: out = Z) + tile statistics of out */
+int scnb_hs_mix(const float* Z, int H, const int32_t* srcA, const int32_t* srcB, const float* gam, int R, float* out,
+                float* part, void* stream);
+/* A = relu(drop(bn(Z))) of the last application (input of the heads); writes stats */
+int scnb_hs_act(const float* Z, float* A, int H, int R, int n_seg, const int32_t* seg_off_host, const float* part,
+                const float* gamma, const float* beta, float* stats, const uint8_t* keep_mask, const uint64_t* rng,
+                uint32_t stream_id, float p_drop, void* stream);
+/* Aout = relu(drop(bn(Zin))) (materialised), Zout = Aout W^T + bias (W [N, K]; 3xTF32), tile statistics of Zout; writes stats_in */
+int scnb_hs_fwd(const float* Zin, float* Aout, const float* part_in, float* stats_in, const float* gamma, const float* beta,
+                const uint8_t* keep_mask, const uint64_t* rng, uint32_t stream_id, float p_drop, const float* W,
+                const float* bias, float* Zout, float* part_out, int K, int N, int R, int n_seg,
+                const int32_t* seg_off_host, void* stream);
+/* dY = dA * [A > 0] / (1-p) of the last application + tile sums */
+int scnb_hs_bwd_act(const float* dA, const float* Z, const float* A, int H, int R, int n_seg, const int32_t* seg_off_host,
+                    const float* stats, float p_drop, float* dY, float* part, void* stream);
+/* dZout = BatchNorm backward of dYin (materialised; dgamma / dbeta += segment totals), dA = dZout W (W [K, N]),
+ * dYout = dA * [Aprev > 0] / (1-p_prev) + tile sums against (Zprev, stats_prev) */
+int scnb_hs_bwd(const float* dYin, const float* Zin, const float* stats_in, const float* part_in, const float* gamma,
+                float* dgamma, float* dbeta, float* dZout, const float* W, const float* Zprev, const float* Aprev,
+                const float* stats_prev, float p_drop_prev, float* dYout, float* part_out, int K, int N, int R, int n_seg,
+                const int32_t* seg_off_host, void* stream);
+/* dZ of application 0 from dY (feeds the MixUp adjoint and the first-layer weight gradient) */
+int scnb_hs_bwd_in(const float* dY, const float* Z, int H, int R, int n_seg, const int32_t* seg_off_host, const float* stats,
+                   const float* part, const float* gamma, float* dgamma, float* dbeta, float* dZ, void* stream);
+
 /* ---- K6: MixMatchLoss._generate_labels + sharpen_labels (scnym/losses.py:660-737, 529-573) and
  *      the confident/unconfident split, MixUp permutation and DAN row selection
  *      (scnym/losses.py:811-875, 1195-1213).  perm_keys stand in for torch.randperm

@@ -75,7 +75,11 @@ def load_reference(modules=("model", "dataprep", "losses", "utils", "trainer", "
     if not reference_available():
         raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
     if "scnym" in sys.modules and getattr(sys.modules["scnym"], "__scnym_ref__", False):
-        return sys.modules["scnym"]
+        pkg = sys.modules["scnym"]
+        for n in modules:                       # an earlier call may have loaded a subset only
+            if not hasattr(pkg, n):
+                setattr(pkg, n, importlib.import_module("scnym." + n))
+        return pkg
     try:
         import anndata  # noqa: F401
     except Exception:

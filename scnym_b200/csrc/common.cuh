@@ -93,6 +93,32 @@ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t stream, 
   uint32_t v = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
   return (float)(v >> 8) * (1.0f / 16777216.0f);
 }
+// Hidden-layer dropout stream (shared by every BatchNorm -> Dropout -> ReLU kernel, forward and backward, so that all of
+// them see the same mask): one Philox call per (row, 8-column group) gives eight 16-bit uniforms, element j keeps iff
+// uniform[j] >= thr16 = round(p * 65536); an injected byte mask is read 8 bytes at a time (elem0 = row*H + first column).
+// 8-bit keep pattern (bit j = keep column j) of element group `grp` = row*(H/8) + column group
+__device__ __forceinline__ uint32_t keep8(const uint8_t* __restrict__ mask, size_t elem0, uint64_t grp, uint64_t seed, uint64_t strm,
+                                          uint32_t thr16) {
+  uint32_t bits = 0;
+  if (mask) {
+    const uint2 m = *reinterpret_cast<const uint2*>(mask + elem0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      bits |= (((m.x >> (8 * j)) & 0xffu) != 0u ? 1u : 0u) << j;
+      bits |= (((m.y >> (8 * j)) & 0xffu) != 0u ? 1u : 0u) << (4 + j);
+    }
+    return bits;
+  }
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)grp, (uint32_t)(grp >> 32), (uint32_t)strm, (uint32_t)(strm >> 32)),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    bits |= ((w[j] & 0xffffu) >= thr16 ? 1u : 0u) << (2 * j);
+    bits |= ((w[j] >> 16) >= thr16 ? 1u : 0u) << (2 * j + 1);
+  }
+  return bits;
+}
 // keep decision for dropout: injected mask wins; else Philox(seed, stream, idx) >= p.
 __device__ __forceinline__ bool dropout_keep(const uint8_t* mask, uint64_t idx, uint64_t seed, uint64_t stream, float p) {
   if (mask) return mask[idx] != 0;

@@ -441,29 +441,6 @@ __device__ __forceinline__ void st8(float* __restrict__ p, const F8& r) {
   *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
   *reinterpret_cast<float4*>(p + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
 }
-// 8-bit keep pattern (bit j = keep column j) of element group `grp` = row*(H/8) + column group
-__device__ __forceinline__ uint32_t keep8(const uint8_t* __restrict__ mask, size_t elem0, uint64_t grp, uint64_t seed, uint64_t strm,
-                                          uint32_t thr16) {
-  uint32_t bits = 0;
-  if (mask) {
-    const uint2 m = *reinterpret_cast<const uint2*>(mask + elem0);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      bits |= (((m.x >> (8 * j)) & 0xffu) != 0u ? 1u : 0u) << j;
-      bits |= (((m.y >> (8 * j)) & 0xffu) != 0u ? 1u : 0u) << (4 + j);
-    }
-    return bits;
-  }
-  const uint4 r = philox4x32_10(make_uint4((uint32_t)grp, (uint32_t)(grp >> 32), (uint32_t)strm, (uint32_t)(strm >> 32)),
-                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    bits |= ((w[j] & 0xffffu) >= thr16 ? 1u : 0u) << (2 * j);
-    bits |= ((w[j] >> 16) >= thr16 ? 1u : 0u) << (2 * j + 1);
-  }
-  return bits;
-}
 // sums over all rows of the CTA for each of the 8 columns; result in every thread
 __device__ __forceinline__ void bnv_colsum8(F8& x, float (*red)[8]) {
 #pragma unroll

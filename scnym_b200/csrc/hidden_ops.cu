@@ -1,0 +1,747 @@
+// Fused hidden stack of the scNym training step (sm_100a): BatchNorm -> Dropout -> ReLU folded into the GEMMs around it.
+//
+// Reference arithmetic: `[Linear -> BatchNorm1d(train) -> Dropout(0.5) -> ReLU] x n` (scnym/model.py:210-233, SURVEY
+// Appendix A2) on the student super-batch [U-mixed | L-mixed | DAN] with per-segment batch statistics, and its adjoint.
+//
+// The unfused path runs every BatchNorm and every Linear as its own launch (12 launches on the step's critical chain,
+// each 5-12 us for <= 1 MB of data).  Here a 32-row x 64-column output tile is the unit of work and the data-dependent
+// parts of BatchNorm travel between launches as per-tile partial statistics:
+//
+//   forward  hs_mix      Z0 = MixUp(Z1) (hidden-space MixUp, dataprep.py:665-689)            + tile statistics of Z0
+//            hs_fwd(a)   A[a-1] = relu(drop(bn(Z[a-1]))) applied WHILE the A operand is staged in shared memory,
+//                        Z[a] = A[a-1] W_a^T + b_a (3xTF32 mma.sync, fp32 accumulate)          + tile statistics of Z[a]
+//            hs_act      A[last] = relu(drop(bn(Z[last])))                                    (input of the heads)
+//   backward hs_bwd_act  dY[last] = dA[last] * [A > 0] / (1-p)                                + tile sums (dy, dy*zhat)
+//            hs_bwd(a)   dZ[a] = gamma*invstd*(dY - mean(dY) - zhat*mean(dY*zhat)) applied while staging the A operand,
+//                        dA[a-1] = dZ[a] W_a;  dY[a-1] = dA[a-1] * [A[a-1] > 0] / (1-p) in the epilogue + tile sums
+//            hs_bwd_in   dZ[0] (input of the MixUp adjoint)
+//
+// Tile statistics are (mean, M2 = sum (z - mean)^2) over the tile's 32 rows, combined per segment with Chan's parallel
+// formula in a FIXED order by every consumer: the result is as accurate as the two-pass form of the unfused kernels and
+// bit-reproducible run to run (no atomics in the statistics).  Backward tile sums are plain sums combined in tile order.
+// Segment boundaries must be multiples of 32 rows and known on the host (pseudolabel thresholding off): the engine
+// falls back to the unfused kernels otherwise.
+#include "common.cuh"
+#include <stdlib.h>
+
+#define BN_EPS 1e-5f
+#define HS_BM 32
+#define HS_BN 64
+#define HS_T 256
+#define HS_MAXSEG 3
+
+struct HsSeg {
+  int n_seg;
+  int off[HS_MAXSEG + 1];   // row offsets, multiples of HS_BM
+};
+
+__device__ __forceinline__ int hs_seg_of(const HsSeg& sg, int row) {
+  int s = 0;
+#pragma unroll
+  for (int i = 1; i < HS_MAXSEG; ++i)
+    if (i < sg.n_seg && row >= sg.off[i]) s = i;
+  return s;
+}
+
+// ---- small PTX helpers (same forms as gemm_ops.cu) ----
+__device__ __forceinline__ void hs_cp16(float* smem_dst, const float* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void hs_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void hs_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void hs_split(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void hs_mma(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// Per-segment batch statistics of column c from the tile partials part[tile][2][H] (tiles t0 .. t1-1 of 32 rows each),
+// combined in tile order (Chan et al.; equal tile sizes).
+__device__ __forceinline__ void hs_combine_stats(const float* __restrict__ part, int H, int c, int t0, int t1, float& mean, float& var) {
+  float m = 0.f;
+  for (int t = t0; t < t1; ++t) m += part[((size_t)t * 2 + 0) * H + c];
+  m /= (float)(t1 - t0);
+  float M2 = 0.f;
+  for (int t = t0; t < t1; ++t) {
+    const float d = part[((size_t)t * 2 + 0) * H + c] - m;
+    M2 += part[((size_t)t * 2 + 1) * H + c] + (float)HS_BM * d * d;
+  }
+  mean = m;
+  var = M2 / (float)((t1 - t0) * HS_BM);
+}
+// plain sums of the backward partials (sum dy, sum dy*zhat) over a segment's tiles, in tile order
+__device__ __forceinline__ void hs_combine_sums(const float* __restrict__ part, int H, int c, int t0, int t1, float& s1, float& s2) {
+  float a = 0.f, b = 0.f;
+  for (int t = t0; t < t1; ++t) {
+    a += part[((size_t)t * 2 + 0) * H + c];
+    b += part[((size_t)t * 2 + 1) * H + c];
+  }
+  s1 = a;
+  s2 = b;
+}
+
+// Column statistics of a 32 x 64 tile held as v[8] per thread (thread -> row = tid/8, columns (tid%8)*8 .. +7):
+// mean and M2 over the 32 rows, written to part[tile][0/1][c0 + ..].  red: shared [32][64 + 1].
+__device__ __forceinline__ void hs_tile_stats_rowmajor(const float (&v)[8], float (*red)[HS_BN + 1], float* __restrict__ part, int H,
+                                                       int tile, int c0) {
+  const int tid = threadIdx.x, r = tid >> 3, cg = (tid & 7) << 3;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[r][cg + j] = v[j];
+  __syncthreads();
+  float mean = 0.f;
+  if (tid < HS_BN) {
+#pragma unroll 8
+    for (int i = 0; i < HS_BM; ++i) mean += red[i][tid];
+    mean *= (1.0f / HS_BM);
+    float m2 = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < HS_BM; ++i) {
+      const float d = red[i][tid] - mean;
+      m2 = fmaf(d, d, m2);
+    }
+    part[((size_t)tile * 2 + 0) * H + c0 + tid] = mean;
+    part[((size_t)tile * 2 + 1) * H + c0 + tid] = m2;
+  }
+  __syncthreads();
+}
+// same for two plain sums (backward): a[8], b[8] per thread
+__device__ __forceinline__ void hs_tile_sums_rowmajor(const float (&a)[8], const float (&b)[8], float (*red)[HS_BN + 1],
+                                                      float* __restrict__ part, int H, int tile, int c0) {
+  const int tid = threadIdx.x, r = tid >> 3, cg = (tid & 7) << 3;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[r][cg + j] = a[j];
+  __syncthreads();
+  if (tid < HS_BN) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < HS_BM; ++i) s += red[i][tid];
+    part[((size_t)tile * 2 + 0) * H + c0 + tid] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[r][cg + j] = b[j];
+  __syncthreads();
+  if (tid < HS_BN) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < HS_BM; ++i) s += red[i][tid];
+    part[((size_t)tile * 2 + 1) * H + c0 + tid] = s;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void hs_ld8(const float* __restrict__ p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void hs_st8(float* __restrict__ p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// hs_mix: out[i,:] = gam[i]*Z[srcA[i],:] + (1-gam[i])*Z[srcB[i],:] (srcA == NULL: out = Z, statistics only) + tile
+// statistics of `out`.  grid = (H/64, R/32), 256 threads: thread -> (row tid/8, 8 columns).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(HS_T) k_hs_mix(const float* __restrict__ Z, int H, const int32_t* __restrict__ srcA,
+                                                 const int32_t* __restrict__ srcB, const float* __restrict__ gam, int R,
+                                                 float* __restrict__ out, float* __restrict__ part) {
+  PDL_ENTRY();
+  __shared__ float red[HS_BM][HS_BN + 1];
+  const int tid = threadIdx.x, c0 = blockIdx.x * HS_BN, tile = blockIdx.y;
+  const int i = tile * HS_BM + (tid >> 3), c = c0 + ((tid & 7) << 3);
+  float v[8];
+  if (!srcA) {
+    hs_ld8(Z + (size_t)i * H + c, v);
+  } else {
+    const int a = srcA[i], b = srcB ? srcB[i] : a;
+    const float g = gam ? gam[i] : 1.f;
+    hs_ld8(Z + (size_t)a * H + c, v);
+    if (!(a == b || g == 1.f)) {
+      float w[8];
+      hs_ld8(Z + (size_t)b * H + c, w);
+      const float g1 = 1.f - g;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = g * v[j] + g1 * w[j];
+    }
+  }
+  if (out != Z) hs_st8(out + (size_t)i * H + c, v);
+  hs_tile_stats_rowmajor(v, red, part, H, tile, c0);
+}
+
+extern "C" int scnb_hs_mix(const float* Z, int H, const int32_t* srcA, const int32_t* srcB, const float* gam, int R, float* out,
+                           float* part, void* stream) {
+  SCNB_CHECK_ARG(Z && out && part && H > 0 && H % HS_BN == 0 && R > 0 && R % HS_BM == 0, "hs_mix: needs H %% 64 == 0, rows %% 32 == 0");
+  scnb_launch_pdl(k_hs_mix, dim3(H / HS_BN, R / HS_BM), dim3(HS_T), 0, (cudaStream_t)stream, Z, H, srcA, srcB, gam, R, out, part);
+  SCNB_CHECK_LAUNCH("hs_mix");
+  return SCNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// hs_act: A = relu(drop(bn(Z))) for the LAST application (the heads read A); writes the segment statistics.
+// grid = (H/64, R/32).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(HS_T) k_hs_act(const float* __restrict__ Z, float* __restrict__ A, int H, HsSeg sg,
+                                                 const float* __restrict__ part, const float* __restrict__ gamma,
+                                                 const float* __restrict__ beta, float* __restrict__ stats,
+                                                 const uint8_t* __restrict__ keep_mask, const uint64_t* __restrict__ rng,
+                                                 uint32_t stream_id, float p_drop) {
+  PDL_ENTRY();
+  __shared__ float sMean[HS_BN], sInv[HS_BN];
+  const int tid = threadIdx.x, c0 = blockIdx.x * HS_BN, tile = blockIdx.y;
+  const int row0 = tile * HS_BM, s = hs_seg_of(sg, row0);
+  const int t0 = sg.off[s] / HS_BM, t1 = sg.off[s + 1] / HS_BM;
+  if (tid < HS_BN) {
+    float mean, var;
+    hs_combine_stats(part, H, c0 + tid, t0, t1, mean, var);
+    const float inv = 1.0f / sqrtf(var + BN_EPS);
+    sMean[tid] = mean;
+    sInv[tid] = inv;
+    if (tile == t0) {
+      stats[((size_t)s * 3 + 0) * H + c0 + tid] = mean;
+      stats[((size_t)s * 3 + 1) * H + c0 + tid] = var;
+      stats[((size_t)s * 3 + 2) * H + c0 + tid] = inv;
+    }
+  }
+  __syncthreads();
+  uint64_t seed = 0, strm = 0;
+  if (p_drop > 0.f && !keep_mask) {
+    seed = rng[0];
+    strm = rng[1] * 64ull + stream_id;
+  }
+  const uint32_t thr16 = (uint32_t)(p_drop * 65536.0f + 0.5f);
+  const float drop_scale = 1.0f / (1.0f - p_drop);
+  const int r = row0 + (tid >> 3), cl = (tid & 7) << 3, c = c0 + cl;
+  const size_t o = (size_t)r * H + c;
+  float z[8], g[8], b[8];
+  hs_ld8(Z + o, z);
+  hs_ld8(gamma + c, g);
+  hs_ld8(beta + c, b);
+  uint32_t kb = 0xffu;
+  if (p_drop > 0.f) kb = keep8(keep_mask, o, (uint64_t)r * (H >> 3) + (c >> 3), seed, strm, thr16);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float y = (z[j] - sMean[cl + j]) * sInv[cl + j] * g[j] + b[j];
+    if (p_drop > 0.f) y = ((kb >> j) & 1u) ? y * drop_scale : 0.f;
+    z[j] = fmaxf(y, 0.f);
+  }
+  hs_st8(A + o, z);
+}
+
+extern "C" int scnb_hs_act(const float* Z, float* A, int H, int R, int n_seg, const int32_t* seg_off_host, const float* part,
+                           const float* gamma, const float* beta, float* stats, const uint8_t* keep_mask, const uint64_t* rng,
+                           uint32_t stream_id, float p_drop, void* stream) {
+  SCNB_CHECK_ARG(Z && A && part && gamma && beta && stats && seg_off_host, "hs_act: null argument");
+  SCNB_CHECK_ARG(H % HS_BN == 0 && R % HS_BM == 0 && n_seg >= 1 && n_seg <= HS_MAXSEG, "hs_act: bad shape");
+  SCNB_CHECK_ARG(!(p_drop > 0.f) || keep_mask || rng, "hs_act: dropout needs keep_mask or rng state");
+  HsSeg sg;
+  sg.n_seg = n_seg;
+  for (int i = 0; i <= HS_MAXSEG; ++i) sg.off[i] = seg_off_host[i <= n_seg ? i : n_seg];
+  for (int i = 0; i <= n_seg; ++i) SCNB_CHECK_ARG(sg.off[i] % HS_BM == 0, "hs_act: segment boundaries must be multiples of 32 rows");
+  SCNB_CHECK_ARG(sg.off[n_seg] == R, "hs_act: segments must cover all rows");
+  scnb_launch_pdl(k_hs_act, dim3(H / HS_BN, R / HS_BM), dim3(HS_T), 0, (cudaStream_t)stream, Z, A, H, sg, part, gamma, beta, stats,
+                  keep_mask, rng, stream_id, p_drop);
+  SCNB_CHECK_LAUNCH("hs_act");
+  return SCNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Tile GEMM core: 32 x 64 output tile, K (multiple of 16, <= 512) staged whole in shared memory.
+//   sA : [32][K + 4]  (row-major, k contiguous)
+//   sB : LAY 0 (NT: weight stored [n][k])  [64][K + 4];  LAY 1 (NN: weight stored [k][n])  [K][64 + 8]
+// 8 warps = 4 (16-column slices) x 2 (K halves); a warp runs m16n8k8 3xTF32 over a 32 x 16 tile of its K half; the two
+// halves meet in shared memory.  Result: acc[2 m-tiles][2 n-tiles][4] valid in the warps with kh == 0.
+// Fragment reads are bank-conflict free: row strides are 4 (k-contiguous) or 8 (k-row panels) modulo 32 words.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int LAY>
+__device__ __forceinline__ void hs_tile_mma(const float* __restrict__ sA, const float* __restrict__ sB, int K, float* __restrict__ sRed,
+                                            float (&acc)[2][2][4]) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wn = warp & 3, kh = warp >> 2;
+  const int SA = K + 4, SBr = K + 4, SBc = HS_BN + 8;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
+  const int kb = kh * (K >> 1), ke = kb + (K >> 1);
+#pragma unroll 2
+  for (int kk = kb; kk < ke; kk += 8) {
+    uint32_t ah[2][4], al[2][4], bh[2][2], bl[2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float x0 = sA[(16 * i + g) * SA + kk + t];
+      const float x1 = sA[(16 * i + g + 8) * SA + kk + t];
+      const float x2 = sA[(16 * i + g) * SA + kk + t + 4];
+      const float x3 = sA[(16 * i + g + 8) * SA + kk + t + 4];
+      hs_split(x0, ah[i][0], al[i][0]);
+      hs_split(x1, ah[i][1], al[i][1]);
+      hs_split(x2, ah[i][2], al[i][2]);
+      hs_split(x3, ah[i][3], al[i][3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int n = wn * 16 + 8 * j + g;
+      float y0, y1;
+      if (LAY == 0) {
+        y0 = sB[n * SBr + kk + t];
+        y1 = sB[n * SBr + kk + t + 4];
+      } else {
+        y0 = sB[(kk + t) * SBc + n];
+        y1 = sB[(kk + t + 4) * SBc + n];
+      }
+      hs_split(y0, bh[j][0], bl[j][0]);
+      hs_split(y1, bh[j][1], bl[j][1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        hs_mma(acc[i][j], al[i], bh[j]);
+        hs_mma(acc[i][j], ah[i], bl[j]);
+        hs_mma(acc[i][j], ah[i], bh[j]);
+      }
+  }
+  // the upper K half hands its accumulators over through shared memory (sRed: [4 warps][32 lanes][16])
+  if (kh == 1) {
+    float* dst = sRed + ((size_t)wn * 32 + lane) * 16;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dst[(i * 2 + j) * 4 + c] = acc[i][j][c];
+  }
+  __syncthreads();
+  if (kh == 0) {
+    const float* src = sRed + ((size_t)wn * 32 + lane) * 16;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[i][j][c] += src[(i * 2 + j) * 4 + c];
+  }
+}
+
+// Column reduction over the 32 rows of the tile for the accumulator layout of hs_tile_mma (warps with kh == 0):
+// lane (g, t) holds rows {g, g+8, 16+g, 24+g} of columns wn*16 + 8j + 2t + e.  Returns the 32-row sum in every lane.
+__device__ __forceinline__ float hs_col_sum32(float x) {
+  x += __shfl_xor_sync(0xffffffffu, x, 4);
+  x += __shfl_xor_sync(0xffffffffu, x, 8);
+  x += __shfl_xor_sync(0xffffffffu, x, 16);
+  return x;
+}
+
+struct HsFwdArgs {
+  const float* Zin;      // [R, K] pre-BatchNorm input of application a-1
+  float* Aout;           // [R, K] activation of application a-1 (materialised by the column-tile-0 CTAs)
+  const float* part_in;  // [R/32][2][K] tile statistics of Zin
+  float* stats_in;       // [n_seg][3][K] segment statistics of Zin (written here)
+  const float* gamma;    // BatchNorm of application a-1
+  const float* beta;
+  const uint8_t* keep;   // injected dropout mask of application a-1 ([R, K] bytes) or NULL
+  const uint64_t* rng;
+  uint32_t stream_id;
+  float p_drop;
+  const float* W;        // [N, K] Linear of application a
+  const float* bias;     // [N]
+  float* Zout;           // [R, N]
+  float* part_out;       // [R/32][2][N]
+  int K, N, R;
+  HsSeg sg;
+};
+
+// grid = (N/64, R/32); dynamic shared memory: sA 32*(K+4) + sB 64*(K+4) + 4*K + 2048 floats.
+__global__ void __launch_bounds__(HS_T) k_hs_fwd(const __grid_constant__ HsFwdArgs p) {
+  PDL_ENTRY();
+  extern __shared__ __align__(16) float hs_smem[];
+  const int K = p.K, N = p.N;
+  float* sA = hs_smem;
+  float* sB = sA + HS_BM * (K + 4);
+  float* sMean = sB + HS_BN * (K + 4);
+  float* sInv = sMean + K;
+  float* sGam = sInv + K;
+  float* sBet = sGam + K;
+  float* sRed = sBet + K;        // 2048 floats
+  const int tid = threadIdx.x, n0 = blockIdx.x * HS_BN, tile = blockIdx.y, row0 = tile * HS_BM;
+  const int s = hs_seg_of(p.sg, row0);
+  const int t0 = p.sg.off[s] / HS_BM, t1 = p.sg.off[s + 1] / HS_BM;
+  // stage the raw operands
+  const int cpr = K >> 2;   // 16-byte chunks per row
+  for (int ch = tid; ch < HS_BM * cpr; ch += HS_T) {
+    const int r = ch / cpr, q = ch - r * cpr;
+    hs_cp16(sA + r * (K + 4) + q * 4, p.Zin + (size_t)(row0 + r) * K + q * 4);
+  }
+  for (int ch = tid; ch < HS_BN * cpr; ch += HS_T) {
+    const int r = ch / cpr, q = ch - r * cpr;
+    hs_cp16(sB + r * (K + 4) + q * 4, p.W + (size_t)(n0 + r) * K + q * 4);
+  }
+  hs_commit();
+  // segment statistics of the input while the copies fly
+  for (int c = tid; c < K; c += HS_T) {
+    float mean, var;
+    hs_combine_stats(p.part_in, K, c, t0, t1, mean, var);
+    const float inv = 1.0f / sqrtf(var + BN_EPS);
+    sMean[c] = mean;
+    sInv[c] = inv;
+    sGam[c] = p.gamma[c];
+    sBet[c] = p.beta[c];
+    if (blockIdx.x == 0 && tile == t0) {
+      p.stats_in[((size_t)s * 3 + 0) * K + c] = mean;
+      p.stats_in[((size_t)s * 3 + 1) * K + c] = var;
+      p.stats_in[((size_t)s * 3 + 2) * K + c] = inv;
+    }
+  }
+  hs_wait_all();
+  __syncthreads();
+  // BatchNorm -> Dropout -> ReLU in place on the A operand
+  uint64_t seed = 0, strm = 0;
+  if (p.p_drop > 0.f && !p.keep) {
+    seed = p.rng[0];
+    strm = p.rng[1] * 64ull + p.stream_id;
+  }
+  const uint32_t thr16 = (uint32_t)(p.p_drop * 65536.0f + 0.5f);
+  const float drop_scale = 1.0f / (1.0f - p.p_drop);
+  const int gpr = K >> 3;   // 8-column groups per row
+  for (int e = tid; e < HS_BM * gpr; e += HS_T) {
+    const int r = e / gpr, gi = e - r * gpr, c = gi << 3;
+    float* a = sA + r * (K + 4) + c;
+    const int rg = row0 + r;
+    const size_t o = (size_t)rg * K + c;
+    uint32_t kb = 0xffu;
+    if (p.p_drop > 0.f) kb = keep8(p.keep, o, (uint64_t)rg * gpr + gi, seed, strm, thr16);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float y = (a[j] - sMean[c + j]) * sInv[c + j] * sGam[c + j] + sBet[c + j];
+      if (p.p_drop > 0.f) y = ((kb >> j) & 1u) ? y * drop_scale : 0.f;
+      v[j] = fmaxf(y, 0.f);
+      a[j] = v[j];
+    }
+    if (blockIdx.x == 0) hs_st8(p.Aout + o, v);
+  }
+  __syncthreads();
+  float acc[2][2][4];
+  hs_tile_mma<0>(sA, sB, K, sRed, acc);
+  // epilogue (warps of the lower K half): bias, Z[a] tile, tile statistics
+  const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3, wn = warp & 3;
+  if (warp < 4) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = n0 + wn * 16 + 8 * j + 2 * t;
+      const float b0 = p.bias ? p.bias[c] : 0.f, b1 = p.bias ? p.bias[c + 1] : 0.f;
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        acc[i][j][0] += b0; acc[i][j][1] += b1; acc[i][j][2] += b0; acc[i][j][3] += b1;
+        const int r = row0 + 16 * i + g;
+        *reinterpret_cast<float2*>(p.Zout + (size_t)r * N + c) = make_float2(acc[i][j][0], acc[i][j][1]);
+        *reinterpret_cast<float2*>(p.Zout + (size_t)(r + 8) * N + c) = make_float2(acc[i][j][2], acc[i][j][3]);
+        s0 += acc[i][j][0] + acc[i][j][2];
+        s1 += acc[i][j][1] + acc[i][j][3];
+      }
+      const float m0 = hs_col_sum32(s0) * (1.0f / HS_BM), m1 = hs_col_sum32(s1) * (1.0f / HS_BM);
+      float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float d;
+        d = acc[i][j][0] - m0; q0 = fmaf(d, d, q0);
+        d = acc[i][j][2] - m0; q0 = fmaf(d, d, q0);
+        d = acc[i][j][1] - m1; q1 = fmaf(d, d, q1);
+        d = acc[i][j][3] - m1; q1 = fmaf(d, d, q1);
+      }
+      q0 = hs_col_sum32(q0);
+      q1 = hs_col_sum32(q1);
+      if (g == 0) {
+        *reinterpret_cast<float2*>(p.part_out + ((size_t)tile * 2 + 0) * N + c) = make_float2(m0, m1);
+        *reinterpret_cast<float2*>(p.part_out + ((size_t)tile * 2 + 1) * N + c) = make_float2(q0, q1);
+      }
+    }
+  }
+}
+
+static int hs_fill_seg(HsSeg& sg, int n_seg, const int32_t* seg_off_host, int R, const char* who) {
+  SCNB_CHECK_ARG(seg_off_host && n_seg >= 1 && n_seg <= HS_MAXSEG, "%s: bad segments", who);
+  sg.n_seg = n_seg;
+  for (int i = 0; i <= HS_MAXSEG; ++i) sg.off[i] = seg_off_host[i <= n_seg ? i : n_seg];
+  for (int i = 0; i <= n_seg; ++i) SCNB_CHECK_ARG(sg.off[i] % HS_BM == 0, "%s: segment boundaries must be multiples of 32 rows", who);
+  SCNB_CHECK_ARG(sg.off[0] == 0 && sg.off[n_seg] == R, "%s: segments must cover all rows", who);
+  return SCNB_OK;
+}
+
+template <typename KernelT>
+static int hs_set_smem(KernelT kern, size_t bytes, const char* who) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+      scnb_set_error("%s: cannot reserve %zu bytes of shared memory: %s", who, bytes, cudaGetErrorString(e));
+      return SCNB_ERR_CUDA;
+    }
+  }
+  return SCNB_OK;
+}
+
+extern "C" int scnb_hs_fwd(const float* Zin, float* Aout, const float* part_in, float* stats_in, const float* gamma,
+                           const float* beta, const uint8_t* keep_mask, const uint64_t* rng, uint32_t stream_id, float p_drop,
+                           const float* W, const float* bias, float* Zout, float* part_out, int K, int N, int R, int n_seg,
+                           const int32_t* seg_off_host, void* stream) {
+  SCNB_CHECK_ARG(Zin && Aout && part_in && stats_in && gamma && beta && W && Zout && part_out, "hs_fwd: null argument");
+  SCNB_CHECK_ARG(K % 16 == 0 && K >= 16 && K <= 512 && N % HS_BN == 0 && R % HS_BM == 0, "hs_fwd: needs K %% 16 == 0 (<= 512), N %% 64 == 0, rows %% 32 == 0");
+  SCNB_CHECK_ARG(!(p_drop > 0.f) || keep_mask || rng, "hs_fwd: dropout needs keep_mask or rng state");
+  SCNB_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "hs_fwd: p_drop out of range");
+  HsFwdArgs a;
+  a.Zin = Zin; a.Aout = Aout; a.part_in = part_in; a.stats_in = stats_in; a.gamma = gamma; a.beta = beta; a.keep = keep_mask;
+  a.rng = rng; a.stream_id = stream_id; a.p_drop = p_drop; a.W = W; a.bias = bias; a.Zout = Zout; a.part_out = part_out;
+  a.K = K; a.N = N; a.R = R;
+  int rc = hs_fill_seg(a.sg, n_seg, seg_off_host, R, "hs_fwd");
+  if (rc != SCNB_OK) return rc;
+  const size_t smem = ((size_t)(HS_BM + HS_BN) * (K + 4) + 4 * (size_t)K + 2048) * sizeof(float);
+  rc = hs_set_smem(k_hs_fwd, smem, "hs_fwd");
+  if (rc != SCNB_OK) return rc;
+  scnb_launch_pdl(k_hs_fwd, dim3(N / HS_BN, R / HS_BM), dim3(HS_T), smem, (cudaStream_t)stream, a);
+  SCNB_CHECK_LAUNCH("hs_fwd");
+  return SCNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// hs_bwd_act: dY = dA * [A > 0] / (1-p) for the LAST application + tile sums (sum dY, sum dY*zhat).  grid = (H/64, R/32).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(HS_T) k_hs_bwd_act(const float* __restrict__ dA, const float* __restrict__ Z,
+                                                     const float* __restrict__ A, int H, HsSeg sg, const float* __restrict__ stats,
+                                                     float p_drop, float* __restrict__ dY, float* __restrict__ part) {
+  PDL_ENTRY();
+  __shared__ float red[HS_BM][HS_BN + 1];
+  const int tid = threadIdx.x, c0 = blockIdx.x * HS_BN, tile = blockIdx.y;
+  const int r = tile * HS_BM + (tid >> 3), c = c0 + ((tid & 7) << 3);
+  const int s = hs_seg_of(sg, tile * HS_BM);
+  const size_t o = (size_t)r * H + c;
+  const float drop_scale = 1.0f / (1.0f - p_drop);
+  float da[8], z[8], a[8], mean[8], inv[8], dy[8], dyz[8];
+  hs_ld8(dA + o, da);
+  hs_ld8(Z + o, z);
+  hs_ld8(A + o, a);
+  hs_ld8(stats + ((size_t)s * 3 + 0) * H + c, mean);
+  hs_ld8(stats + ((size_t)s * 3 + 2) * H + c, inv);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    dy[j] = a[j] > 0.f ? da[j] * drop_scale : 0.f;      // A > 0 implies the element was kept by the dropout
+    dyz[j] = dy[j] * ((z[j] - mean[j]) * inv[j]);
+  }
+  hs_st8(dY + o, dy);
+  hs_tile_sums_rowmajor(dy, dyz, red, part, H, tile, c0);
+}
+
+extern "C" int scnb_hs_bwd_act(const float* dA, const float* Z, const float* A, int H, int R, int n_seg, const int32_t* seg_off_host,
+                               const float* stats, float p_drop, float* dY, float* part, void* stream) {
+  SCNB_CHECK_ARG(dA && Z && A && stats && dY && part, "hs_bwd_act: null argument");
+  SCNB_CHECK_ARG(H % HS_BN == 0 && R % HS_BM == 0 && p_drop >= 0.f && p_drop < 1.f, "hs_bwd_act: bad shape");
+  HsSeg sg;
+  int rc = hs_fill_seg(sg, n_seg, seg_off_host, R, "hs_bwd_act");
+  if (rc != SCNB_OK) return rc;
+  scnb_launch_pdl(k_hs_bwd_act, dim3(H / HS_BN, R / HS_BM), dim3(HS_T), 0, (cudaStream_t)stream, dA, Z, A, H, sg, stats, p_drop, dY, part);
+  SCNB_CHECK_LAUNCH("hs_bwd_act");
+  return SCNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// hs_bwd: dZ[a] = gamma*invstd*(dY - mean(dY) - zhat*mean(dY*zhat)) formed while the A operand is staged (and written
+// out by the column-tile-0 CTAs, for the weight gradients), dA[a-1] = dZ[a] W_a, dY[a-1] = dA[a-1]*[A[a-1] > 0]/(1-p)
+// in the epilogue + tile sums.  The segment totals of (dY, dY*zhat) are the BatchNorm beta / gamma gradients.
+// ---------------------------------------------------------------------------------------------------------------------
+struct HsBwdArgs {
+  const float* dYin;     // [R, K] gradient w.r.t. the BatchNorm output of application a (before the dropout scale: already applied)
+  const float* Zin;      // [R, K] pre-BatchNorm input of application a
+  const float* stats_in; // [n_seg][3][K]
+  const float* part_in;  // [R/32][2][K] tile sums of (dY, dY*zhat)
+  const float* gamma;    // [K]
+  float* dgamma;         // [K] += over segments
+  float* dbeta;
+  float* dZout;          // [R, K] materialised dZ[a]
+  const float* W;        // [K, N] Linear of application a (out = K, in = N)
+  const float* Zprev;    // [R, N] pre-BatchNorm input of application a-1
+  const float* Aprev;    // [R, N] activation of application a-1
+  const float* stats_prev;  // [n_seg][3][N]
+  float p_drop_prev;
+  float* dYout;          // [R, N]
+  float* part_out;       // [R/32][2][N]
+  int K, N, R;
+  HsSeg sg;
+};
+
+// grid = (N/64, R/32); dynamic shared memory: sA 32*(K+4) + sB K*(64+8) + 2*K + 2048 floats.
+__global__ void __launch_bounds__(HS_T) k_hs_bwd(const __grid_constant__ HsBwdArgs p) {
+  PDL_ENTRY();
+  extern __shared__ __align__(16) float hs_smem[];
+  const int K = p.K, N = p.N;
+  float* sA = hs_smem;                       // dY tile, transformed into dZ in place
+  float* sB = sA + HS_BM * (K + 4);          // W_a panel [K][64 + 8]
+  float* sZ = sB + K * (HS_BN + 8);          // Z[a] tile [32][K + 4]
+  float* sM1 = sZ + HS_BM * (K + 4);         // mean(dY) per column
+  float* sM2 = sM1 + K;                      // mean(dY*zhat)
+  float* sRed = sM2 + K;                     // 2048 floats
+  const int tid = threadIdx.x, n0 = blockIdx.x * HS_BN, tile = blockIdx.y, row0 = tile * HS_BM;
+  const int s = hs_seg_of(p.sg, row0);
+  const int t0 = p.sg.off[s] / HS_BM, t1 = p.sg.off[s + 1] / HS_BM;
+  const int cpr = K >> 2;
+  for (int ch = tid; ch < HS_BM * cpr; ch += HS_T) {
+    const int r = ch / cpr, q = ch - r * cpr;
+    hs_cp16(sA + r * (K + 4) + q * 4, p.dYin + (size_t)(row0 + r) * K + q * 4);
+    hs_cp16(sZ + r * (K + 4) + q * 4, p.Zin + (size_t)(row0 + r) * K + q * 4);
+  }
+  for (int ch = tid; ch < K * (HS_BN / 4); ch += HS_T) {
+    const int k = ch >> 4, q = ch & 15;
+    hs_cp16(sB + k * (HS_BN + 8) + q * 4, p.W + (size_t)k * N + n0 + q * 4);
+  }
+  hs_commit();
+  const float inv_n = 1.0f / (float)((t1 - t0) * HS_BM);
+  for (int c = tid; c < K; c += HS_T) {
+    float s1, s2;
+    hs_combine_sums(p.part_in, K, c, t0, t1, s1, s2);
+    sM1[c] = s1 * inv_n;
+    sM2[c] = s2 * inv_n;
+    if (blockIdx.x == 0 && tile == t0) {   // one CTA per segment: BatchNorm parameter gradients
+      atomicAdd(p.dbeta + c, s1);
+      atomicAdd(p.dgamma + c, s2);
+    }
+  }
+  hs_wait_all();
+  __syncthreads();
+  const float* mean = p.stats_in + ((size_t)s * 3 + 0) * K;
+  const float* invs = p.stats_in + ((size_t)s * 3 + 2) * K;
+  const int gpr = K >> 3;
+  for (int e = tid; e < HS_BM * gpr; e += HS_T) {
+    const int r = e / gpr, gi = e - r * gpr, c = gi << 3;
+    float* a = sA + r * (K + 4) + c;
+    const float* z = sZ + r * (K + 4) + c;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float is = invs[c + j];
+      const float zh = (z[j] - mean[c + j]) * is;
+      v[j] = p.gamma[c + j] * is * (a[j] - sM1[c + j] - zh * sM2[c + j]);
+      a[j] = v[j];
+    }
+    if (blockIdx.x == 0) hs_st8(p.dZout + (size_t)(row0 + r) * K + c, v);
+  }
+  __syncthreads();
+  float acc[2][2][4];
+  hs_tile_mma<1>(sA, sB, K, sRed, acc);
+  const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3, wn = warp & 3;
+  if (warp < 4) {
+    const float drop_scale = 1.0f / (1.0f - p.p_drop_prev);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = n0 + wn * 16 + 8 * j + 2 * t;
+      const float2 mu = *reinterpret_cast<const float2*>(p.stats_prev + ((size_t)s * 3 + 0) * N + c);
+      const float2 is = *reinterpret_cast<const float2*>(p.stats_prev + ((size_t)s * 3 + 2) * N + c);
+      float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = row0 + 16 * i + g + 8 * h;
+          const float2 av = *reinterpret_cast<const float2*>(p.Aprev + (size_t)r * N + c);
+          const float2 zv = *reinterpret_cast<const float2*>(p.Zprev + (size_t)r * N + c);
+          const float d0 = av.x > 0.f ? acc[i][j][2 * h] * drop_scale : 0.f;
+          const float d1 = av.y > 0.f ? acc[i][j][2 * h + 1] * drop_scale : 0.f;
+          *reinterpret_cast<float2*>(p.dYout + (size_t)r * N + c) = make_float2(d0, d1);
+          s1a += d0;
+          s1b += d1;
+          s2a = fmaf(d0, (zv.x - mu.x) * is.x, s2a);
+          s2b = fmaf(d1, (zv.y - mu.y) * is.y, s2b);
+        }
+      }
+      s1a = hs_col_sum32(s1a); s1b = hs_col_sum32(s1b);
+      s2a = hs_col_sum32(s2a); s2b = hs_col_sum32(s2b);
+      if (g == 0) {
+        *reinterpret_cast<float2*>(p.part_out + ((size_t)tile * 2 + 0) * N + c) = make_float2(s1a, s1b);
+        *reinterpret_cast<float2*>(p.part_out + ((size_t)tile * 2 + 1) * N + c) = make_float2(s2a, s2b);
+      }
+    }
+  }
+}
+
+extern "C" int scnb_hs_bwd(const float* dYin, const float* Zin, const float* stats_in, const float* part_in, const float* gamma,
+                           float* dgamma, float* dbeta, float* dZout, const float* W, const float* Zprev, const float* Aprev,
+                           const float* stats_prev, float p_drop_prev, float* dYout, float* part_out, int K, int N, int R, int n_seg,
+                           const int32_t* seg_off_host, void* stream) {
+  SCNB_CHECK_ARG(dYin && Zin && stats_in && part_in && gamma && dgamma && dbeta && dZout && W && Zprev && Aprev && stats_prev &&
+                     dYout && part_out, "hs_bwd: null argument");
+  SCNB_CHECK_ARG(K % 16 == 0 && K >= 16 && K <= 256 && N % HS_BN == 0 && R % HS_BM == 0, "hs_bwd: needs K %% 16 == 0 (<= 256), N %% 64 == 0, rows %% 32 == 0");
+  SCNB_CHECK_ARG(p_drop_prev >= 0.f && p_drop_prev < 1.f, "hs_bwd: p_drop out of range");
+  HsBwdArgs a;
+  a.dYin = dYin; a.Zin = Zin; a.stats_in = stats_in; a.part_in = part_in; a.gamma = gamma; a.dgamma = dgamma; a.dbeta = dbeta;
+  a.dZout = dZout; a.W = W; a.Zprev = Zprev; a.Aprev = Aprev; a.stats_prev = stats_prev; a.p_drop_prev = p_drop_prev; a.dYout = dYout;
+  a.part_out = part_out; a.K = K; a.N = N; a.R = R;
+  int rc = hs_fill_seg(a.sg, n_seg, seg_off_host, R, "hs_bwd");
+  if (rc != SCNB_OK) return rc;
+  const size_t smem = ((size_t)2 * HS_BM * (K + 4) + (size_t)K * (HS_BN + 8) + 2 * (size_t)K + 2048) * sizeof(float);
+  rc = hs_set_smem(k_hs_bwd, smem, "hs_bwd");
+  if (rc != SCNB_OK) return rc;
+  scnb_launch_pdl(k_hs_bwd, dim3(N / HS_BN, R / HS_BM), dim3(HS_T), smem, (cudaStream_t)stream, a);
+  SCNB_CHECK_LAUNCH("hs_bwd");
+  return SCNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// hs_bwd_in: dZ[0] from dY[0] (application 0 has no Linear inside the stack: its input gradient feeds the MixUp adjoint
+// and the first-layer weight gradient).  grid = (H/64, R/32).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(HS_T) k_hs_bwd_in(const float* __restrict__ dY, const float* __restrict__ Z, int H, HsSeg sg,
+                                                    const float* __restrict__ stats, const float* __restrict__ part,
+                                                    const float* __restrict__ gamma, float* __restrict__ dgamma,
+                                                    float* __restrict__ dbeta, float* __restrict__ dZ) {
+  PDL_ENTRY();
+  __shared__ float sM1[HS_BN], sM2[HS_BN];
+  const int tid = threadIdx.x, c0 = blockIdx.x * HS_BN, tile = blockIdx.y, row0 = tile * HS_BM;
+  const int s = hs_seg_of(sg, row0);
+  const int t0 = sg.off[s] / HS_BM, t1 = sg.off[s + 1] / HS_BM;
+  if (tid < HS_BN) {
+    float s1, s2;
+    hs_combine_sums(part, H, c0 + tid, t0, t1, s1, s2);
+    const float inv_n = 1.0f / (float)((t1 - t0) * HS_BM);
+    sM1[tid] = s1 * inv_n;
+    sM2[tid] = s2 * inv_n;
+    if (tile == t0) {
+      atomicAdd(dbeta + c0 + tid, s1);
+      atomicAdd(dgamma + c0 + tid, s2);
+    }
+  }
+  __syncthreads();
+  const int r = row0 + (tid >> 3), cl = (tid & 7) << 3, c = c0 + cl;
+  const size_t o = (size_t)r * H + c;
+  float dy[8], z[8], mean[8], inv[8], g[8];
+  hs_ld8(dY + o, dy);
+  hs_ld8(Z + o, z);
+  hs_ld8(stats + ((size_t)s * 3 + 0) * H + c, mean);
+  hs_ld8(stats + ((size_t)s * 3 + 2) * H + c, inv);
+  hs_ld8(gamma + c, g);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float zh = (z[j] - mean[j]) * inv[j];
+    dy[j] = g[j] * inv[j] * (dy[j] - sM1[cl + j] - zh * sM2[cl + j]);
+  }
+  hs_st8(dZ + o, dy);
+}
+
+extern "C" int scnb_hs_bwd_in(const float* dY, const float* Z, int H, int R, int n_seg, const int32_t* seg_off_host, const float* stats,
+                              const float* part, const float* gamma, float* dgamma, float* dbeta, float* dZ, void* stream) {
+  SCNB_CHECK_ARG(dY && Z && stats && part && gamma && dgamma && dbeta && dZ, "hs_bwd_in: null argument");
+  SCNB_CHECK_ARG(H % HS_BN == 0 && R % HS_BM == 0, "hs_bwd_in: bad shape");
+  HsSeg sg;
+  int rc = hs_fill_seg(sg, n_seg, seg_off_host, R, "hs_bwd_in");
+  if (rc != SCNB_OK) return rc;
+  scnb_launch_pdl(k_hs_bwd_in, dim3(H / HS_BN, R / HS_BM), dim3(HS_T), 0, (cudaStream_t)stream, dY, Z, H, sg, stats, part, gamma, dgamma,
+                  dbeta, dZ);
+  SCNB_CHECK_LAUNCH("hs_bwd_in");
+  return SCNB_OK;
+}

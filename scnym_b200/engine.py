@@ -63,6 +63,7 @@ class EngineConfig:
     use_cuda_graph: bool = True
     first_layer: str = "auto"   # "spmm": warp-per-row CSR SpMM; "tc": densify-then-tcgen05 GEMM (bf16x3); "auto": tc from 512 rows per step
     w1_update: str = "auto"     # first-layer gradient+optimizer kernel: "simt" (batch CSC), "tc" (tcgen05 GEMM), "auto": tc from 512 rows
+    hidden: str = "auto"        # hidden stack: "fused" (BatchNorm folded into the tile GEMMs, hidden_ops.cu), "unfused", "auto"
     fuse_heads: bool = True      # one-warp-per-row classifier/DAN-tail/teacher-head kernels (Linear + loss + backward)
     multi_stream: bool = True    # run independent kernels of the step on side streams (parallel graph branches)
     keep_w1_grad: bool = False   # also write the first-layer gradient to HBM (parity tests; implied by data parallelism)
@@ -327,6 +328,23 @@ class TrainEngine(object):
         wmax = max(self.widths)
         self.dA = f32(R, wmax)
         self.dZs = [f32(R, w) for w in self.widths]   # one per application: weight-gradient GEMMs overlap the dA chain
+        # fused hidden stack (hidden_ops.cu): BatchNorm -> Dropout -> ReLU folded into 32 x 64 tile GEMMs, statistics carried
+        # between launches as per-tile partials.  Needs static segment boundaries on 32-row tiles (no pseudolabel
+        # thresholding), 64-column tiles and operand panels that fit shared memory; single process for now.
+        seg_host = [0, U, U + L, U + L + self.Rd][: self.n_seg + 1] if mode == "mixmatch" else [0, L]
+        hs_ok = (self.comm is None and all(w % 64 == 0 for w in self.widths) and all(w <= 256 for w in self.widths[1:])
+                 and self.widths[0] <= 512 and all(o % 32 == 0 for o in seg_host) and R <= 4096
+                 and (mode != "mixmatch" or cfg.pseudolabel_min_confidence <= 0.0))
+        hm = cfg.hidden if cfg.hidden != "auto" else os.environ.get("SCNB_HIDDEN", "fused")
+        if hm == "fused" and not hs_ok and cfg.hidden == "fused":
+            raise ValueError("hidden='fused' needs widths % 64 == 0 (<= 256 after the first), segment sizes % 32 == 0, "
+                             "no pseudolabel thresholding and a single process")
+        self.hs_fused = bool(hm == "fused" and hs_ok)
+        if self.hs_fused:
+            self._seg_host = np.asarray(seg_host + [seg_host[-1]] * (4 - len(seg_host)), dtype=np.int32)
+            self.dYs = [f32(R, w) for w in self.widths]
+            self.pf = [f32(R // 32, 2, w) for w in self.widths]
+            self.pb = [f32(R // 32, 2, w) for w in self.widths]
         # "auto": the tensor-core form pays off once the batch fills at least two 256-row tiles (measured: 512 rows,
         # 5 % density: 22 us vs 40 us for the SpMM; 8192 rows, 20 %: ~10x); tiny batches keep the exact-fp32 SpMM
         fl = cfg.first_layer
@@ -536,8 +554,11 @@ class TrainEngine(object):
             main.wait_event(self._ev_plan)
         else:
             self._plan(self.confident, st)
-        call("scnb_mix_rows", ptr(self.Z1), H0, ptr(self.srcA), ptr(self.srcB), ptr(self.gam), ptr(self.counts[3:]), R,
-             ptr(self.Zs[0]), st)
+        if self.hs_fused:    # hidden-space MixUp + tile statistics of its output, one launch
+            call("scnb_hs_mix", ptr(self.Z1), H0, ptr(self.srcA), ptr(self.srcB), ptr(self.gam), R, ptr(self.Zs[0]), ptr(self.pf[0]), st)
+        else:
+            call("scnb_mix_rows", ptr(self.Z1), H0, ptr(self.srcA), ptr(self.srcB), ptr(self.gam), ptr(self.counts[3:]), R,
+                 ptr(self.Zs[0]), st)
         # -- student super-batch forward
         self._student_forward(st, rng)
         # BatchNorm running statistics as soon as the forward statistics exist, off the critical path (the
@@ -698,6 +719,20 @@ class TrainEngine(object):
 
     def _student_forward(self, st, rng):
         blk, R = self._blk, self.Rmax
+        if self.hs_fused:
+            seg = self._seg_host.ctypes.data
+            if self.mode != "mixmatch":   # no MixUp in front: tile statistics of the first layer's output
+                call("scnb_hs_mix", ptr(self.Zs[0]), self.widths[0], None, None, None, R, ptr(self.Zs[0]), ptr(self.pf[0]), st)
+            for a in range(1, self.n_app):
+                k, n = self.widths[a - 1], self.widths[a]
+                call("scnb_hs_fwd", ptr(self.Zs[a - 1]), ptr(self.As[a - 1]), ptr(self.pf[a - 1]), ptr(self.stats[a - 1]),
+                     self.P(blk[a - 1]["g"]), self.P(blk[a - 1]["beta"]), self._hidden_keep(a - 1), rng, SID_HID + a - 1,
+                     float(blk[a - 1]["drop"].p), self.P(blk[a]["W"]), self.P(blk[a]["b"]), ptr(self.Zs[a]), ptr(self.pf[a]), k, n, R,
+                     self.n_seg, seg, st)
+            a = self.n_app - 1
+            call("scnb_hs_act", ptr(self.Zs[a]), ptr(self.As[a]), self.widths[a], R, self.n_seg, seg, ptr(self.pf[a]), self.P(blk[a]["g"]),
+                 self.P(blk[a]["beta"]), ptr(self.stats[a]), self._hidden_keep(a), rng, SID_HID + a, float(blk[a]["drop"].p), st)
+            return
         for a in range(self.n_app):
             w = self.widths[a]
             p = float(blk[a]["drop"].p)
@@ -726,6 +761,8 @@ class TrainEngine(object):
         The dA chain runs on `main`; weight/bias gradients of the hidden Linear layers on `sW`."""
         blk, R = self._blk, self.Rmax
         st, sw = main.cuda_stream, sW.cuda_stream
+        if self.hs_fused:
+            return self._student_backward_fused(main, sW, dA)
         for a in range(self.n_app - 1, -1, -1):
             w = self.widths[a]
             p = float(blk[a]["drop"].p)
@@ -766,6 +803,34 @@ class TrainEngine(object):
                  None, sw)
             call("scnb_colsum", ptr(dZ), R, w, w, self.Gp(blk[a]["b"]), 1, sw)
         return None
+
+    def _student_backward_fused(self, main, sW, dA):
+        """Backward of the fused hidden stack (hidden_ops.cu).  The dA chain stays on `main`; the Linear weight / bias
+        gradients (from the materialised dZ[a] and A[a-1]) go to branch W."""
+        blk, R = self._blk, self.Rmax
+        st, sw = main.cuda_stream, sW.cuda_stream
+        seg = self._seg_host.ctypes.data
+        last = self.n_app - 1
+        if sW is not main:
+            main.wait_event(self._ev_zero)   # BatchNorm gamma / beta gradients accumulate into zeroed buffers
+        call("scnb_hs_bwd_act", ptr(dA), ptr(self.Zs[last]), ptr(self.As[last]), self.widths[last], R, self.n_seg, seg,
+             ptr(self.stats[last]), float(blk[last]["drop"].p), ptr(self.dYs[last]), ptr(self.pb[last]), st)
+        for a in range(last, 0, -1):
+            k, n = self.widths[a], self.widths[a - 1]
+            call("scnb_hs_bwd", ptr(self.dYs[a]), ptr(self.Zs[a]), ptr(self.stats[a]), ptr(self.pb[a]), self.P(blk[a]["g"]),
+                 self.Gp(blk[a]["g"]), self.Gp(blk[a]["beta"]), ptr(self.dZs[a]), self.P(blk[a]["W"]), ptr(self.Zs[a - 1]),
+                 ptr(self.As[a - 1]), ptr(self.stats[a - 1]), float(blk[a - 1]["drop"].p), ptr(self.dYs[a - 1]), ptr(self.pb[a - 1]),
+                 k, n, R, self.n_seg, seg, st)
+            ev = self._ev_dz[a]
+            if sW is not main:
+                ev.record(main)
+                sW.wait_event(ev)
+            call("scnb_sgemm", 1, 0, k, n, R, ptr(self.dZs[a]), k, ptr(self.As[a - 1]), n, self.Gp(blk[a]["W"]), n, 1.0, 1.0, None, 0,
+                 None, sw)
+            call("scnb_colsum", ptr(self.dZs[a]), R, k, k, self.Gp(blk[a]["b"]), 1, sw)
+        call("scnb_hs_bwd_in", ptr(self.dYs[0]), ptr(self.Zs[0]), self.widths[0], R, self.n_seg, seg, ptr(self.stats[0]), ptr(self.pb[0]),
+             self.P(blk[0]["g"]), self.Gp(blk[0]["g"]), self.Gp(blk[0]["beta"]), ptr(self.dZs[0]), st)
+        return self.dZs[0]
 
     def _gene_cnt_ptr(self):
         return ptr(self.gene_cnt) if (self.fused_w1 and not self.w1_tc) else None

@@ -425,8 +425,9 @@ class SemiSupervisedTrainer(Trainer):
         i = 0
         run = dict(loss=0.0, sup=0.0, uns=0.0, dom=0.0, corrects=0.0, total=0.0)
         btrans = self.batch_transformers.get("train", None)
-        if self._unsup_iter is None:
-            self._unsup_iter = iter(self.unsup_dataloader)
+        # `iter_unsup_dl = iter(self.unsup_dataloader)` per epoch (scnym/trainer.py:574): a plain DataLoader starts over, the
+        # `repeater` generator fit_model passes carries on
+        self._unsup_iter = iter(self.unsup_dataloader)
         for data in self.dataloaders["train"]:
             try:
                 unsup_data = next(self._unsup_iter)
@@ -514,11 +515,17 @@ class MultiTaskTrainer(Trainer):
             running[idx] += crit_loss.item() if train else float(w_loss.item())
         return loss
 
+    def _restart_unsup(self):
+        """`iter_unsup_dl = iter(self.unsup_dataloader)` at the start of every training and validation pass
+        (scnym/trainer.py:1000, 1132): a plain DataLoader starts over, a `repeater` generator carries on."""
+        self._unsup_iter = iter(self.unsup_dataloader) if self.unsup_dataloader is not None else None
+
     def train_epoch(self) -> float:
         self.model.train(True)
         dev = self._device
         running = np.zeros(len(self.criteria))
         btrans = self.batch_transformers.get("train", None)
+        self._restart_unsup()
         for data in self.dataloaders["train"]:
             if btrans is not None:
                 data = btrans(data)
@@ -543,6 +550,7 @@ class MultiTaskTrainer(Trainer):
         running = np.zeros(len(self.criteria))
         corrects, total = 0.0, 0
         btrans = self.batch_transformers.get("val", None)
+        self._restart_unsup()
         for data in self.dataloaders["val"]:
             if btrans is not None:
                 data = btrans(data)
