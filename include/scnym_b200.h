@@ -232,11 +232,13 @@ int scnb_hs_mix(const float* Z, int H, const int32_t* srcA, const int32_t* srcB,
 int scnb_hs_act(const float* Z, float* A, int H, int R, int n_seg, const int32_t* seg_off_host, const float* part,
                 const float* gamma, const float* beta, float* stats, const uint8_t* keep_mask, const uint64_t* rng,
                 uint32_t stream_id, float p_drop, void* stream);
-/* Aout = relu(drop(bn(Zin))) (materialised), Zout = Aout W^T + bias (W [N, K]; 3xTF32), tile statistics of Zout; writes stats_in */
+/* Aout = relu(drop(bn(Zin))) (materialised), Zout = Aout W^T + bias (W [N, K]; 3xTF32), tile statistics of Zout; writes stats_in.
+ * running_mean / running_var non-NULL: eval mode (the MixMatch teacher, scnym/losses.py:660-737): running statistics,
+ * no dropout; part_in / stats_in / Aout / part_out may then be NULL. */
 int scnb_hs_fwd(const float* Zin, float* Aout, const float* part_in, float* stats_in, const float* gamma, const float* beta,
                 const uint8_t* keep_mask, const uint64_t* rng, uint32_t stream_id, float p_drop, const float* W,
                 const float* bias, float* Zout, float* part_out, int K, int N, int R, int n_seg,
-                const int32_t* seg_off_host, void* stream);
+                const int32_t* seg_off_host, const float* running_mean, const float* running_var, void* stream);
 /* dY = dA * [A > 0] / (1-p) of the last application + tile sums */
 int scnb_hs_bwd_act(const float* dA, const float* Z, const float* A, int H, int R, int n_seg, const int32_t* seg_off_host,
                     const float* stats, float p_drop, float* dY, float* part, void* stream);

@@ -62,25 +62,72 @@ __device__ __forceinline__ void hs_mma(float (&d)[4], const uint32_t (&a)[4], co
 }
 
 // Per-segment batch statistics of column c from the tile partials part[tile][2][H] (tiles t0 .. t1-1 of 32 rows each),
-// combined in tile order (Chan et al.; equal tile sizes).
+// combined in tile order (Chan et al.; equal tile sizes).  Up to 16 tiles per segment (the usual case: <= 512 rows) all
+// partials are fetched in ONE round trip (independent loads); longer segments go in chunks of 8.
+#define HS_CT 16
 __device__ __forceinline__ void hs_combine_stats(const float* __restrict__ part, int H, int c, int t0, int t1, float& mean, float& var) {
-  float m = 0.f;
-  for (int t = t0; t < t1; ++t) m += part[((size_t)t * 2 + 0) * H + c];
-  m /= (float)(t1 - t0);
-  float M2 = 0.f;
-  for (int t = t0; t < t1; ++t) {
-    const float d = part[((size_t)t * 2 + 0) * H + c] - m;
-    M2 += part[((size_t)t * 2 + 1) * H + c] + (float)HS_BM * d * d;
+  const int n = t1 - t0;
+  float m = 0.f, M2 = 0.f;
+  if (n <= HS_CT) {
+    float mt[HS_CT], qt[HS_CT];
+#pragma unroll
+    for (int i = 0; i < HS_CT; ++i) {
+      const bool ok = i < n;
+      mt[i] = ok ? part[((size_t)(t0 + i) * 2 + 0) * H + c] : 0.f;
+      qt[i] = ok ? part[((size_t)(t0 + i) * 2 + 1) * H + c] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < HS_CT; ++i) m += mt[i];
+    m /= (float)n;
+#pragma unroll
+    for (int i = 0; i < HS_CT; ++i)
+      if (i < n) {
+        const float d = mt[i] - m;
+        M2 += qt[i] + (float)HS_BM * d * d;
+      }
+  } else {
+    for (int t = t0; t < t1; t += 8) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (t + i < t1) ? part[((size_t)(t + i) * 2 + 0) * H + c] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m += v[i];
+    }
+    m /= (float)n;
+    for (int t = t0; t < t1; t += 8) {
+      float v[8], q[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const bool ok = t + i < t1;
+        v[i] = ok ? part[((size_t)(t + i) * 2 + 0) * H + c] : m;
+        q[i] = ok ? part[((size_t)(t + i) * 2 + 1) * H + c] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = v[i] - m;
+        M2 += q[i] + (float)HS_BM * d * d;
+      }
+    }
   }
   mean = m;
-  var = M2 / (float)((t1 - t0) * HS_BM);
+  var = M2 / (float)(n * HS_BM);
 }
 // plain sums of the backward partials (sum dy, sum dy*zhat) over a segment's tiles, in tile order
 __device__ __forceinline__ void hs_combine_sums(const float* __restrict__ part, int H, int c, int t0, int t1, float& s1, float& s2) {
   float a = 0.f, b = 0.f;
-  for (int t = t0; t < t1; ++t) {
-    a += part[((size_t)t * 2 + 0) * H + c];
-    b += part[((size_t)t * 2 + 1) * H + c];
+  for (int t = t0; t < t1; t += HS_CT) {
+    float u[HS_CT], w[HS_CT];
+#pragma unroll
+    for (int i = 0; i < HS_CT; ++i) {
+      const bool ok = t + i < t1;
+      u[i] = ok ? part[((size_t)(t + i) * 2 + 0) * H + c] : 0.f;
+      w[i] = ok ? part[((size_t)(t + i) * 2 + 1) * H + c] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < HS_CT; ++i) {
+      a += u[i];
+      b += w[i];
+    }
   }
   s1 = a;
   s2 = b;
@@ -343,9 +390,11 @@ __device__ __forceinline__ float hs_col_sum32(float x) {
 
 struct HsFwdArgs {
   const float* Zin;      // [R, K] pre-BatchNorm input of application a-1
-  float* Aout;           // [R, K] activation of application a-1 (materialised by the column-tile-0 CTAs)
-  const float* part_in;  // [R/32][2][K] tile statistics of Zin
-  float* stats_in;       // [n_seg][3][K] segment statistics of Zin (written here)
+  float* Aout;           // [R, K] activation of application a-1 (materialised by the column-tile-0 CTAs; NULL: not kept)
+  const float* part_in;  // [R/32][2][K] tile statistics of Zin (train mode)
+  float* stats_in;       // [n_seg][3][K] segment statistics of Zin (written here; train mode)
+  const float* rmean;    // eval mode (the MixMatch teacher, losses.py:660-737): running statistics instead of batch
+  const float* rvar;     //   statistics, no dropout, no statistics of the output
   const float* gamma;    // BatchNorm of application a-1
   const float* beta;
   const uint8_t* keep;   // injected dropout mask of application a-1 ([R, K] bytes) or NULL
@@ -387,15 +436,21 @@ __global__ void __launch_bounds__(HS_T) k_hs_fwd(const __grid_constant__ HsFwdAr
   }
   hs_commit();
   // segment statistics of the input while the copies fly
+  const bool eval = p.rmean != nullptr;
   for (int c = tid; c < K; c += HS_T) {
     float mean, var;
-    hs_combine_stats(p.part_in, K, c, t0, t1, mean, var);
+    if (eval) {
+      mean = p.rmean[c];
+      var = p.rvar[c];
+    } else {
+      hs_combine_stats(p.part_in, K, c, t0, t1, mean, var);
+    }
     const float inv = 1.0f / sqrtf(var + BN_EPS);
     sMean[c] = mean;
     sInv[c] = inv;
     sGam[c] = p.gamma[c];
     sBet[c] = p.beta[c];
-    if (blockIdx.x == 0 && tile == t0) {
+    if (!eval && blockIdx.x == 0 && tile == t0) {
       p.stats_in[((size_t)s * 3 + 0) * K + c] = mean;
       p.stats_in[((size_t)s * 3 + 1) * K + c] = var;
       p.stats_in[((size_t)s * 3 + 2) * K + c] = inv;
@@ -411,23 +466,32 @@ __global__ void __launch_bounds__(HS_T) k_hs_fwd(const __grid_constant__ HsFwdAr
   }
   const uint32_t thr16 = (uint32_t)(p.p_drop * 65536.0f + 0.5f);
   const float drop_scale = 1.0f / (1.0f - p.p_drop);
-  const int gpr = K >> 3;   // 8-column groups per row
-  for (int e = tid; e < HS_BM * gpr; e += HS_T) {
-    const int r = e / gpr, gi = e - r * gpr, c = gi << 3;
+  const int gpr = K >> 3;   // 8-column groups per row (the dropout stream is defined per group)
+  const int fpr = K >> 2;   // float4 per row: consecutive lanes take consecutive float4 (no shared-memory bank conflicts)
+  for (int f = tid; f < HS_BM * fpr; f += HS_T) {
+    const int r = f / fpr, q = f - r * fpr, c = q << 2;
     float* a = sA + r * (K + 4) + c;
     const int rg = row0 + r;
-    const size_t o = (size_t)rg * K + c;
-    uint32_t kb = 0xffu;
-    if (p.p_drop > 0.f) kb = keep8(p.keep, o, (uint64_t)rg * gpr + gi, seed, strm, thr16);
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float y = (a[j] - sMean[c + j]) * sInv[c + j] * sGam[c + j] + sBet[c + j];
-      if (p.p_drop > 0.f) y = ((kb >> j) & 1u) ? y * drop_scale : 0.f;
-      v[j] = fmaxf(y, 0.f);
-      a[j] = v[j];
+    uint32_t kb = 0xfu;
+    if (p.p_drop > 0.f)
+      kb = keep8(p.keep, (size_t)rg * K + (c & ~7), (uint64_t)rg * gpr + (c >> 3), seed, strm, thr16) >> (c & 4);
+    const float4 z = *reinterpret_cast<const float4*>(a);
+    const float4 mu = *reinterpret_cast<const float4*>(sMean + c), is = *reinterpret_cast<const float4*>(sInv + c);
+    const float4 gm = *reinterpret_cast<const float4*>(sGam + c), bt = *reinterpret_cast<const float4*>(sBet + c);
+    float4 y;
+    y.x = (z.x - mu.x) * is.x * gm.x + bt.x;
+    y.y = (z.y - mu.y) * is.y * gm.y + bt.y;
+    y.z = (z.z - mu.z) * is.z * gm.z + bt.z;
+    y.w = (z.w - mu.w) * is.w * gm.w + bt.w;
+    if (p.p_drop > 0.f) {
+      y.x = (kb & 1u) ? y.x * drop_scale : 0.f;
+      y.y = (kb & 2u) ? y.y * drop_scale : 0.f;
+      y.z = (kb & 4u) ? y.z * drop_scale : 0.f;
+      y.w = (kb & 8u) ? y.w * drop_scale : 0.f;
     }
-    if (blockIdx.x == 0) hs_st8(p.Aout + o, v);
+    y = make_float4(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f), fmaxf(y.z, 0.f), fmaxf(y.w, 0.f));
+    *reinterpret_cast<float4*>(a) = y;
+    if (blockIdx.x == 0 && p.Aout) *reinterpret_cast<float4*>(p.Aout + (size_t)rg * K + c) = y;
   }
   __syncthreads();
   float acc[2][2][4];
@@ -461,7 +525,7 @@ __global__ void __launch_bounds__(HS_T) k_hs_fwd(const __grid_constant__ HsFwdAr
       }
       q0 = hs_col_sum32(q0);
       q1 = hs_col_sum32(q1);
-      if (g == 0) {
+      if (g == 0 && p.part_out) {
         *reinterpret_cast<float2*>(p.part_out + ((size_t)tile * 2 + 0) * N + c) = make_float2(m0, m1);
         *reinterpret_cast<float2*>(p.part_out + ((size_t)tile * 2 + 1) * N + c) = make_float2(q0, q1);
       }
@@ -493,15 +557,17 @@ static int hs_set_smem(KernelT kern, size_t bytes, const char* who) {
 extern "C" int scnb_hs_fwd(const float* Zin, float* Aout, const float* part_in, float* stats_in, const float* gamma,
                            const float* beta, const uint8_t* keep_mask, const uint64_t* rng, uint32_t stream_id, float p_drop,
                            const float* W, const float* bias, float* Zout, float* part_out, int K, int N, int R, int n_seg,
-                           const int32_t* seg_off_host, void* stream) {
-  SCNB_CHECK_ARG(Zin && Aout && part_in && stats_in && gamma && beta && W && Zout && part_out, "hs_fwd: null argument");
+                           const int32_t* seg_off_host, const float* running_mean, const float* running_var, void* stream) {
+  SCNB_CHECK_ARG(Zin && gamma && beta && W && Zout, "hs_fwd: null argument");
+  SCNB_CHECK_ARG((running_mean && running_var && p_drop == 0.f) || (!running_mean && part_in && stats_in && Aout && part_out),
+                 "hs_fwd: train mode needs part_in / stats_in / Aout / part_out, eval mode running statistics and no dropout");
   SCNB_CHECK_ARG(K % 16 == 0 && K >= 16 && K <= 512 && N % HS_BN == 0 && R % HS_BM == 0, "hs_fwd: needs K %% 16 == 0 (<= 512), N %% 64 == 0, rows %% 32 == 0");
   SCNB_CHECK_ARG(!(p_drop > 0.f) || keep_mask || rng, "hs_fwd: dropout needs keep_mask or rng state");
   SCNB_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "hs_fwd: p_drop out of range");
   HsFwdArgs a;
   a.Zin = Zin; a.Aout = Aout; a.part_in = part_in; a.stats_in = stats_in; a.gamma = gamma; a.beta = beta; a.keep = keep_mask;
   a.rng = rng; a.stream_id = stream_id; a.p_drop = p_drop; a.W = W; a.bias = bias; a.Zout = Zout; a.part_out = part_out;
-  a.K = K; a.N = N; a.R = R;
+  a.K = K; a.N = N; a.R = R; a.rmean = running_mean; a.rvar = running_var;
   int rc = hs_fill_seg(a.sg, n_seg, seg_off_host, R, "hs_fwd");
   if (rc != SCNB_OK) return rc;
   const size_t smem = ((size_t)(HS_BM + HS_BN) * (K + 4) + 4 * (size_t)K + 2048) * sizeof(float);
@@ -577,7 +643,7 @@ struct HsBwdArgs {
   HsSeg sg;
 };
 
-// grid = (N/64, R/32); dynamic shared memory: sA 32*(K+4) + sB K*(64+8) + 2*K + 2048 floats.
+// grid = (N/64, R/32); dynamic shared memory: sA, sZ 32*(K+4) each + sB K*(64+8) + 5*K + 2048 floats.
 __global__ void __launch_bounds__(HS_T) k_hs_bwd(const __grid_constant__ HsBwdArgs p) {
   PDL_ENTRY();
   extern __shared__ __align__(16) float hs_smem[];
@@ -587,7 +653,10 @@ __global__ void __launch_bounds__(HS_T) k_hs_bwd(const __grid_constant__ HsBwdAr
   float* sZ = sB + K * (HS_BN + 8);          // Z[a] tile [32][K + 4]
   float* sM1 = sZ + HS_BM * (K + 4);         // mean(dY) per column
   float* sM2 = sM1 + K;                      // mean(dY*zhat)
-  float* sRed = sM2 + K;                     // 2048 floats
+  float* sMu = sM2 + K;                      // BatchNorm mean / invstd / gamma of application a
+  float* sIs = sMu + K;
+  float* sGm = sIs + K;
+  float* sRed = sGm + K;                     // 2048 floats
   const int tid = threadIdx.x, n0 = blockIdx.x * HS_BN, tile = blockIdx.y, row0 = tile * HS_BM;
   const int s = hs_seg_of(p.sg, row0);
   const int t0 = p.sg.off[s] / HS_BM, t1 = p.sg.off[s + 1] / HS_BM;
@@ -608,6 +677,9 @@ __global__ void __launch_bounds__(HS_T) k_hs_bwd(const __grid_constant__ HsBwdAr
     hs_combine_sums(p.part_in, K, c, t0, t1, s1, s2);
     sM1[c] = s1 * inv_n;
     sM2[c] = s2 * inv_n;
+    sMu[c] = p.stats_in[((size_t)s * 3 + 0) * K + c];
+    sIs[c] = p.stats_in[((size_t)s * 3 + 2) * K + c];
+    sGm[c] = p.gamma[c];
     if (blockIdx.x == 0 && tile == t0) {   // one CTA per segment: BatchNorm parameter gradients
       atomicAdd(p.dbeta + c, s1);
       atomicAdd(p.dgamma + c, s2);
@@ -615,22 +687,21 @@ __global__ void __launch_bounds__(HS_T) k_hs_bwd(const __grid_constant__ HsBwdAr
   }
   hs_wait_all();
   __syncthreads();
-  const float* mean = p.stats_in + ((size_t)s * 3 + 0) * K;
-  const float* invs = p.stats_in + ((size_t)s * 3 + 2) * K;
-  const int gpr = K >> 3;
-  for (int e = tid; e < HS_BM * gpr; e += HS_T) {
-    const int r = e / gpr, gi = e - r * gpr, c = gi << 3;
+  const int fpr = K >> 2;
+  for (int f = tid; f < HS_BM * fpr; f += HS_T) {
+    const int r = f / fpr, q = f - r * fpr, c = q << 2;
     float* a = sA + r * (K + 4) + c;
-    const float* z = sZ + r * (K + 4) + c;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float is = invs[c + j];
-      const float zh = (z[j] - mean[c + j]) * is;
-      v[j] = p.gamma[c + j] * is * (a[j] - sM1[c + j] - zh * sM2[c + j]);
-      a[j] = v[j];
-    }
-    if (blockIdx.x == 0) hs_st8(p.dZout + (size_t)(row0 + r) * K + c, v);
+    const float4 dy = *reinterpret_cast<const float4*>(a), z = *reinterpret_cast<const float4*>(sZ + r * (K + 4) + c);
+    const float4 mu = *reinterpret_cast<const float4*>(sMu + c), is = *reinterpret_cast<const float4*>(sIs + c);
+    const float4 gm = *reinterpret_cast<const float4*>(sGm + c);
+    const float4 m1 = *reinterpret_cast<const float4*>(sM1 + c), m2 = *reinterpret_cast<const float4*>(sM2 + c);
+    float4 v;
+    v.x = gm.x * is.x * (dy.x - m1.x - (z.x - mu.x) * is.x * m2.x);
+    v.y = gm.y * is.y * (dy.y - m1.y - (z.y - mu.y) * is.y * m2.y);
+    v.z = gm.z * is.z * (dy.z - m1.z - (z.z - mu.z) * is.z * m2.z);
+    v.w = gm.w * is.w * (dy.w - m1.w - (z.w - mu.w) * is.w * m2.w);
+    *reinterpret_cast<float4*>(a) = v;
+    if (blockIdx.x == 0) *reinterpret_cast<float4*>(p.dZout + (size_t)(row0 + r) * K + c) = v;
   }
   __syncthreads();
   float acc[2][2][4];
@@ -684,7 +755,7 @@ extern "C" int scnb_hs_bwd(const float* dYin, const float* Zin, const float* sta
   a.part_out = part_out; a.K = K; a.N = N; a.R = R;
   int rc = hs_fill_seg(a.sg, n_seg, seg_off_host, R, "hs_bwd");
   if (rc != SCNB_OK) return rc;
-  const size_t smem = ((size_t)2 * HS_BM * (K + 4) + (size_t)K * (HS_BN + 8) + 2 * (size_t)K + 2048) * sizeof(float);
+  const size_t smem = ((size_t)2 * HS_BM * (K + 4) + (size_t)K * (HS_BN + 8) + 5 * (size_t)K + 2048) * sizeof(float);
   rc = hs_set_smem(k_hs_bwd, smem, "hs_bwd");
   if (rc != SCNB_OK) return rc;
   scnb_launch_pdl(k_hs_bwd, dim3(N / HS_BN, R / HS_BM), dim3(HS_T), smem, (cudaStream_t)stream, a);

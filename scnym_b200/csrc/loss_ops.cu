@@ -745,19 +745,26 @@ __global__ void __launch_bounds__(256) k_classif_mixmatch(const float* __restric
                                                           float* __restrict__ loss8) {
   PDL_ENTRY();
   extern __shared__ __align__(16) float Ws[];
+  // The rows' loss terms meet in shared memory first: one global atomic per CTA and scalar instead of one per row
+  // (hundreds of same-address atomics serialise in L2 and were most of this kernel's duration).
+  __shared__ float sl[8];
+  if (threadIdx.x < 8) sl[threadIdx.x] = 0.f;
   stage_weights(Ws, Wc, C * H);
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= U + L) return;
-  float4 a[NV];
-  head_logits<NV>(A + (size_t)r * H, Ws, bc, C, H, logits + (size_t)r * C, a, lane);
-  if (r < U)
-    mse_row(r, logits, U, C, n_conf_dev, Y, mapA, mapB, gam, 0, U, nullptr, unsup_weight, dlogits, loss8 + 2);
-  else
-    ce_row(r - U, logits + (size_t)U * C, L, C, nullptr, Y, mapA, mapB, gam, U, class_weight, nullptr, L, 1.0f, nullptr,
-           dlogits + (size_t)U * C, loss8, 1, nullptr);
-  __syncwarp();
-  head_backprop<NV>(dlogits + (size_t)r * C, Ws, C, H, 1.0f, nullptr, dA + (size_t)r * H, lane);
+  if (r < U + L) {
+    float4 a[NV];
+    head_logits<NV>(A + (size_t)r * H, Ws, bc, C, H, logits + (size_t)r * C, a, lane);
+    if (r < U)
+      mse_row(r, logits, U, C, n_conf_dev, Y, mapA, mapB, gam, 0, U, nullptr, unsup_weight, dlogits, sl + 2);
+    else
+      ce_row(r - U, logits + (size_t)U * C, L, C, nullptr, Y, mapA, mapB, gam, U, class_weight, nullptr, L, 1.0f, nullptr,
+             dlogits + (size_t)U * C, sl, 1, nullptr);
+    __syncwarp();
+    head_backprop<NV>(dlogits + (size_t)r * C, Ws, C, H, 1.0f, nullptr, dA + (size_t)r * H, lane);
+  }
+  __syncthreads();
+  if (threadIdx.x < 4 && sl[threadIdx.x] != 0.f) atomicAdd(loss8 + threadIdx.x, sl[threadIdx.x]);
 }
 
 // Supervised head: CE against one-hot integer labels (Trainer step, scnym/trainer.py:189-256).
@@ -769,16 +776,21 @@ __global__ void __launch_bounds__(256) k_classif_supervised(const float* __restr
                                                             float* __restrict__ dA, float* __restrict__ loss8) {
   PDL_ENTRY();
   extern __shared__ __align__(16) float Ws[];
+  __shared__ float sl[8];
+  if (threadIdx.x < 8) sl[threadIdx.x] = 0.f;
   stage_weights(Ws, Wc, C * H);
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= n) return;
-  float4 a[NV];
-  head_logits<NV>(A + (size_t)r * H, Ws, bc, C, H, logits + (size_t)r * C, a, lane);
-  ce_row(r, logits, n, C, nullptr, Y, nullptr, nullptr, nullptr, 0, class_weight, nullptr, n, 1.0f, nullptr, dlogits, loss8, 1,
-         nullptr);
-  __syncwarp();
-  head_backprop<NV>(dlogits + (size_t)r * C, Ws, C, H, 1.0f, nullptr, dA + (size_t)r * H, lane);
+  if (r < n) {
+    float4 a[NV];
+    head_logits<NV>(A + (size_t)r * H, Ws, bc, C, H, logits + (size_t)r * C, a, lane);
+    ce_row(r, logits, n, C, nullptr, Y, nullptr, nullptr, nullptr, 0, class_weight, nullptr, n, 1.0f, nullptr, dlogits, sl, 1,
+           nullptr);
+    __syncwarp();
+    head_backprop<NV>(dlogits + (size_t)r * C, Ws, C, H, 1.0f, nullptr, dA + (size_t)r * H, lane);
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 && sl[threadIdx.x] != 0.f) atomicAdd(loss8 + threadIdx.x, sl[threadIdx.x]);
 }
 
 // Domain adversary tail: Hd = relu(Linear(H,H)(embed)) -> Linear(H,D) -> CE against the domain label
@@ -793,19 +805,24 @@ __global__ void __launch_bounds__(256) k_dan_tail(const float* __restrict__ Hd, 
                                                   float* __restrict__ dHd, float* __restrict__ loss2) {
   PDL_ENTRY();
   extern __shared__ __align__(16) float Ws[];
+  __shared__ float sl[8];
+  if (threadIdx.x < 8) sl[threadIdx.x] = 0.f;
   stage_weights(Ws, W2, D * H);
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= Rd) return;
-  float4 a[NV];
-  head_logits<NV>(Hd + (size_t)r * H, Ws, b2, D, H, dlog + (size_t)r * D, a, lane);
-  const int id = dom_ids[src ? src[src_off + r] : r];
-  for (int c = lane; c < D; c += 32) dlabel[(size_t)r * D + c] = (c == id) ? 1.f : 0.f;
-  __syncwarp();
-  ce_row(r, dlog, Rd, D, n_rows_dev, dlabel, nullptr, nullptr, nullptr, 0, nullptr, n_rows_dev, 0, 1.0f, loss_scale_dev, ddlog,
-         loss2, 1, nullptr);
-  __syncwarp();
-  head_backprop<NV>(ddlog + (size_t)r * D, Ws, D, H, 1.0f, a, dHd + (size_t)r * H, lane);
+  if (r < Rd) {
+    float4 a[NV];
+    head_logits<NV>(Hd + (size_t)r * H, Ws, b2, D, H, dlog + (size_t)r * D, a, lane);
+    const int id = dom_ids[src ? src[src_off + r] : r];
+    for (int c = lane; c < D; c += 32) dlabel[(size_t)r * D + c] = (c == id) ? 1.f : 0.f;
+    __syncwarp();
+    ce_row(r, dlog, Rd, D, n_rows_dev, dlabel, nullptr, nullptr, nullptr, 0, nullptr, n_rows_dev, 0, 1.0f, loss_scale_dev, ddlog,
+           sl, 1, nullptr);
+    __syncwarp();
+    head_backprop<NV>(ddlog + (size_t)r * D, Ws, D, H, 1.0f, a, dHd + (size_t)r * H, lane);
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 && sl[threadIdx.x] != 0.f) atomicAdd(loss2 + threadIdx.x, sl[threadIdx.x]);
 }
 
 // Teacher head: classifier on the K eval-mode views of cell u, then pseudolabel (+ label one-hots).

@@ -342,6 +342,8 @@ class TrainEngine(object):
         self.hs_fused = bool(hm == "fused" and hs_ok)
         if self.hs_fused:
             self._seg_host = np.asarray(seg_host + [seg_host[-1]] * (4 - len(seg_host)), dtype=np.int32)
+            ku = self.K_eff * U if mode == "mixmatch" else 0
+            self._seg_teacher = np.asarray([0, ku, ku, ku], dtype=np.int32)
             self.dYs = [f32(R, w) for w in self.widths]
             self.pf = [f32(R // 32, 2, w) for w in self.widths]
             self.pb = [f32(R // 32, 2, w) for w in self.widths]
@@ -677,7 +679,19 @@ class TrainEngine(object):
             tz = self.Z1  # rows [0, U)
         KU = K * U
         seg_t = self._const_seg(KU)
-        for a in range(self.n_app):
+        if self.hs_fused and KU % 32 == 0:
+            # eval-mode BatchNorm -> ReLU folded into the next Linear's operand staging (hidden_ops.cu), one launch per layer
+            seg1 = self._seg_teacher.ctypes.data
+            for a in range(1, self.n_app):
+                rm, rv = tbn(a - 1)
+                k, n = self.widths[a - 1], self.widths[a]
+                call("scnb_hs_fwd", ptr(tz), None, None, None, ptr(tw(blk[a - 1]["g"])), ptr(tw(blk[a - 1]["beta"])), None, None, 0, 0.0,
+                     ptr(tw(blk[a]["W"])), ptr(tw(blk[a]["b"])), ptr(self.TZ[a]), None, k, n, KU, 1, seg1, ptr(rm), ptr(rv), st)
+                tz = self.TZ[a]
+            a0 = self.n_app - 1
+        else:
+            a0 = 0
+        for a in range(a0, self.n_app):
             rm, rv = tbn(a)
             call("scnb_bn_act_fwd", ptr(tz), ptr(self.TA[a]), None, self.widths[a], 1, ptr(seg_t), KU, 0, ptr(tw(blk[a]["g"])),
                  ptr(tw(blk[a]["beta"])), ptr(rm), ptr(rv), None, None, None, 0, 0.0, 1, None, None, st)
@@ -728,7 +742,7 @@ class TrainEngine(object):
                 call("scnb_hs_fwd", ptr(self.Zs[a - 1]), ptr(self.As[a - 1]), ptr(self.pf[a - 1]), ptr(self.stats[a - 1]),
                      self.P(blk[a - 1]["g"]), self.P(blk[a - 1]["beta"]), self._hidden_keep(a - 1), rng, SID_HID + a - 1,
                      float(blk[a - 1]["drop"].p), self.P(blk[a]["W"]), self.P(blk[a]["b"]), ptr(self.Zs[a]), ptr(self.pf[a]), k, n, R,
-                     self.n_seg, seg, st)
+                     self.n_seg, seg, None, None, st)
             a = self.n_app - 1
             call("scnb_hs_act", ptr(self.Zs[a]), ptr(self.As[a]), self.widths[a], R, self.n_seg, seg, ptr(self.pf[a]), self.P(blk[a]["g"]),
                  self.P(blk[a]["beta"]), ptr(self.stats[a]), self._hidden_keep(a), rng, SID_HID + a, float(blk[a]["drop"].p), st)
