@@ -260,13 +260,11 @@ def time_kernels(eng, n_steps=12):
         eng.cfg.use_cuda_graph, eng.cfg.multi_stream = graph_flag, ms_flag
     agg = {}
     for name, s, e in records:
-        t = s.elapsed_time(e)
-        a = agg.setdefault(name, [0.0, 0])
-        a[0] += t
-        a[1] += 1
-    per_step = {k: v[0] / n_steps for k, v in agg.items()}
-    per_launch = {k: v[0] / v[1] for k, v in agg.items()}
-    counts = {k: v[1] // n_steps for k, v in agg.items()}
+        agg.setdefault(name, []).append(s.elapsed_time(e))
+    # median per launch (a single host hiccup inside one event pair must not make a 10 us kernel look dominant)
+    per_launch = {k: float(np.median(v)) for k, v in agg.items()}
+    counts = {k: len(v) // n_steps for k, v in agg.items()}
+    per_step = {k: per_launch[k] * len(agg[k]) / n_steps for k in agg}
     return per_step, per_launch, counts
 
 

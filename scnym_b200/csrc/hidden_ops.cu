@@ -27,7 +27,10 @@
 #define BN_EPS 1e-5f
 #define HS_BM 32
 #define HS_BN 64
-#define HS_T 256
+#define HS_T 512          // threads of the tile-GEMM kernels: 16 warps = 4 column slices x 4 K quarters
+#define HS_TE 256         // threads of the elementwise tile kernels (thread -> row tid/8, 8 columns)
+#define HS_KQ 4           // K splits inside a CTA
+#define HS_RED (3 * 4 * 16 * 32)   // floats of the cross-warp accumulator hand-over
 #define HS_MAXSEG 3
 
 struct HsSeg {
@@ -196,7 +199,7 @@ __device__ __forceinline__ void hs_st8(float* __restrict__ p, const float (&v)[8
 // hs_mix: out[i,:] = gam[i]*Z[srcA[i],:] + (1-gam[i])*Z[srcB[i],:] (srcA == NULL: out = Z, statistics only) + tile
 // statistics of `out`.  grid = (H/64, R/32), 256 threads: thread -> (row tid/8, 8 columns).
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(HS_T) k_hs_mix(const float* __restrict__ Z, int H, const int32_t* __restrict__ srcA,
+__global__ void __launch_bounds__(HS_TE) k_hs_mix(const float* __restrict__ Z, int H, const int32_t* __restrict__ srcA,
                                                  const int32_t* __restrict__ srcB, const float* __restrict__ gam, int R,
                                                  float* __restrict__ out, float* __restrict__ part) {
   PDL_ENTRY();
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(HS_T) k_hs_mix(const float* __restrict__ Z, in
 extern "C" int scnb_hs_mix(const float* Z, int H, const int32_t* srcA, const int32_t* srcB, const float* gam, int R, float* out,
                            float* part, void* stream) {
   SCNB_CHECK_ARG(Z && out && part && H > 0 && H % HS_BN == 0 && R > 0 && R % HS_BM == 0, "hs_mix: needs H %% 64 == 0, rows %% 32 == 0");
-  scnb_launch_pdl(k_hs_mix, dim3(H / HS_BN, R / HS_BM), dim3(HS_T), 0, (cudaStream_t)stream, Z, H, srcA, srcB, gam, R, out, part);
+  scnb_launch_pdl(k_hs_mix, dim3(H / HS_BN, R / HS_BM), dim3(HS_TE), 0, (cudaStream_t)stream, Z, H, srcA, srcB, gam, R, out, part);
   SCNB_CHECK_LAUNCH("hs_mix");
   return SCNB_OK;
 }
@@ -234,7 +237,7 @@ extern "C" int scnb_hs_mix(const float* Z, int H, const int32_t* srcA, const int
 // hs_act: A = relu(drop(bn(Z))) for the LAST application (the heads read A); writes the segment statistics.
 // grid = (H/64, R/32).
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(HS_T) k_hs_act(const float* __restrict__ Z, float* __restrict__ A, int H, HsSeg sg,
+__global__ void __launch_bounds__(HS_TE) k_hs_act(const float* __restrict__ Z, float* __restrict__ A, int H, HsSeg sg,
                                                  const float* __restrict__ part, const float* __restrict__ gamma,
                                                  const float* __restrict__ beta, float* __restrict__ stats,
                                                  const uint8_t* __restrict__ keep_mask, const uint64_t* __restrict__ rng,
@@ -292,7 +295,7 @@ extern "C" int scnb_hs_act(const float* Z, float* A, int H, int R, int n_seg, co
   for (int i = 0; i <= HS_MAXSEG; ++i) sg.off[i] = seg_off_host[i <= n_seg ? i : n_seg];
   for (int i = 0; i <= n_seg; ++i) SCNB_CHECK_ARG(sg.off[i] % HS_BM == 0, "hs_act: segment boundaries must be multiples of 32 rows");
   SCNB_CHECK_ARG(sg.off[n_seg] == R, "hs_act: segments must cover all rows");
-  scnb_launch_pdl(k_hs_act, dim3(H / HS_BN, R / HS_BM), dim3(HS_T), 0, (cudaStream_t)stream, Z, A, H, sg, part, gamma, beta, stats,
+  scnb_launch_pdl(k_hs_act, dim3(H / HS_BN, R / HS_BM), dim3(HS_TE), 0, (cudaStream_t)stream, Z, A, H, sg, part, gamma, beta, stats,
                   keep_mask, rng, stream_id, p_drop);
   SCNB_CHECK_LAUNCH("hs_act");
   return SCNB_OK;
@@ -302,8 +305,8 @@ extern "C" int scnb_hs_act(const float* Z, float* A, int H, int R, int n_seg, co
 // Tile GEMM core: 32 x 64 output tile, K (multiple of 16, <= 512) staged whole in shared memory.
 //   sA : [32][K + 4]  (row-major, k contiguous)
 //   sB : LAY 0 (NT: weight stored [n][k])  [64][K + 4];  LAY 1 (NN: weight stored [k][n])  [K][64 + 8]
-// 8 warps = 4 (16-column slices) x 2 (K halves); a warp runs m16n8k8 3xTF32 over a 32 x 16 tile of its K half; the two
-// halves meet in shared memory.  Result: acc[2 m-tiles][2 n-tiles][4] valid in the warps with kh == 0.
+// 16 warps = 4 (16-column slices) x 4 (K quarters); a warp runs m16n8k8 3xTF32 over a 32 x 16 tile of its K quarter; the
+// quarters meet in shared memory.  Result: acc[2 m-tiles][2 n-tiles][4] valid in the warps of quarter 0 (warp < 4).
 // Fragment reads are bank-conflict free: row strides are 4 (k-contiguous) or 8 (k-row panels) modulo 32 words.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int LAY>
@@ -311,7 +314,7 @@ __device__ __forceinline__ void hs_tile_mma(const float* __restrict__ sA, const 
                                             float (&acc)[2][2][4]) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int wn = warp & 3, kh = warp >> 2;
+  const int wn = warp & 3, kq = warp >> 2;
   const int SA = K + 4, SBr = K + 4, SBc = HS_BN + 8;
 #pragma unroll
   for (int i = 0; i < 2; ++i)
@@ -319,7 +322,7 @@ __device__ __forceinline__ void hs_tile_mma(const float* __restrict__ sA, const 
     for (int j = 0; j < 2; ++j)
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
-  const int kb = kh * (K >> 1), ke = kb + (K >> 1);
+  const int kb = kq * (K / HS_KQ), ke = kb + K / HS_KQ;
 #pragma unroll 2
   for (int kk = kb; kk < ke; kk += 8) {
     uint32_t ah[2][4], al[2][4], bh[2][2], bl[2][2];
@@ -357,25 +360,29 @@ __device__ __forceinline__ void hs_tile_mma(const float* __restrict__ sA, const 
         hs_mma(acc[i][j], ah[i], bh[j]);
       }
   }
-  // the upper K half hands its accumulators over through shared memory (sRed: [4 warps][32 lanes][16])
-  if (kh == 1) {
-    float* dst = sRed + ((size_t)wn * 32 + lane) * 16;
+  // K quarters 1..3 hand their accumulators over through shared memory (sRed: [3][4 slices][16 values][32 lanes]: a
+  // warp's store of one value is one conflict-free 128-byte line); quarter 0 adds them in a fixed order
+  if (kq > 0) {
+    float* dst = sRed + ((size_t)((kq - 1) * 4 + wn) * 16) * 32 + lane;
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
       for (int j = 0; j < 2; ++j)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) dst[(i * 2 + j) * 4 + c] = acc[i][j][c];
+        for (int c = 0; c < 4; ++c) dst[((i * 2 + j) * 4 + c) * 32] = acc[i][j][c];
   }
   __syncthreads();
-  if (kh == 0) {
-    const float* src = sRed + ((size_t)wn * 32 + lane) * 16;
+  if (kq == 0) {
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int q = 0; q < HS_KQ - 1; ++q) {
+      const float* src = sRed + ((size_t)(q * 4 + wn) * 16) * 32 + lane;
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[i][j][c] += src[(i * 2 + j) * 4 + c];
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[i][j][c] += src[((i * 2 + j) * 4 + c) * 32];
+    }
   }
 }
 
@@ -409,7 +416,7 @@ struct HsFwdArgs {
   HsSeg sg;
 };
 
-// grid = (N/64, R/32); dynamic shared memory: sA 32*(K+4) + sB 64*(K+4) + 4*K + 2048 floats.
+// grid = (N/64, R/32), 512 threads; dynamic shared memory: sA 32*(K+4) + sB 64*(K+4) + 4*K + HS_RED floats.
 __global__ void __launch_bounds__(HS_T) k_hs_fwd(const __grid_constant__ HsFwdArgs p) {
   PDL_ENTRY();
   extern __shared__ __align__(16) float hs_smem[];
@@ -420,7 +427,7 @@ __global__ void __launch_bounds__(HS_T) k_hs_fwd(const __grid_constant__ HsFwdAr
   float* sInv = sMean + K;
   float* sGam = sInv + K;
   float* sBet = sGam + K;
-  float* sRed = sBet + K;        // 2048 floats
+  float* sRed = sBet + K;        // HS_RED floats
   const int tid = threadIdx.x, n0 = blockIdx.x * HS_BN, tile = blockIdx.y, row0 = tile * HS_BM;
   const int s = hs_seg_of(p.sg, row0);
   const int t0 = p.sg.off[s] / HS_BM, t1 = p.sg.off[s + 1] / HS_BM;
@@ -473,8 +480,14 @@ __global__ void __launch_bounds__(HS_T) k_hs_fwd(const __grid_constant__ HsFwdAr
     float* a = sA + r * (K + 4) + c;
     const int rg = row0 + r;
     uint32_t kb = 0xfu;
-    if (p.p_drop > 0.f)
-      kb = keep8(p.keep, (size_t)rg * K + (c & ~7), (uint64_t)rg * gpr + (c >> 3), seed, strm, thr16) >> (c & 4);
+    if (p.p_drop > 0.f) {
+      // lanes 2j and 2j+1 hold the two float4 of one 8-column dropout group: one Philox call per pair (whole warps run
+      // every iteration of this loop: 8K elements in steps of 512 threads)
+      uint32_t k8 = 0;
+      if (!(tid & 1)) k8 = keep8(p.keep, (size_t)rg * K + (c & ~7), (uint64_t)rg * gpr + (c >> 3), seed, strm, thr16);
+      k8 = __shfl_sync(0xffffffffu, k8, (tid & 31) & ~1);
+      kb = k8 >> (c & 4);
+    }
     const float4 z = *reinterpret_cast<const float4*>(a);
     const float4 mu = *reinterpret_cast<const float4*>(sMean + c), is = *reinterpret_cast<const float4*>(sInv + c);
     const float4 gm = *reinterpret_cast<const float4*>(sGam + c), bt = *reinterpret_cast<const float4*>(sBet + c);
@@ -561,7 +574,7 @@ extern "C" int scnb_hs_fwd(const float* Zin, float* Aout, const float* part_in, 
   SCNB_CHECK_ARG(Zin && gamma && beta && W && Zout, "hs_fwd: null argument");
   SCNB_CHECK_ARG((running_mean && running_var && p_drop == 0.f) || (!running_mean && part_in && stats_in && Aout && part_out),
                  "hs_fwd: train mode needs part_in / stats_in / Aout / part_out, eval mode running statistics and no dropout");
-  SCNB_CHECK_ARG(K % 16 == 0 && K >= 16 && K <= 512 && N % HS_BN == 0 && R % HS_BM == 0, "hs_fwd: needs K %% 16 == 0 (<= 512), N %% 64 == 0, rows %% 32 == 0");
+  SCNB_CHECK_ARG(K % 32 == 0 && K >= 32 && K <= 512 && N % HS_BN == 0 && R % HS_BM == 0, "hs_fwd: needs K %% 32 == 0 (<= 512), N %% 64 == 0, rows %% 32 == 0");
   SCNB_CHECK_ARG(!(p_drop > 0.f) || keep_mask || rng, "hs_fwd: dropout needs keep_mask or rng state");
   SCNB_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "hs_fwd: p_drop out of range");
   HsFwdArgs a;
@@ -570,7 +583,7 @@ extern "C" int scnb_hs_fwd(const float* Zin, float* Aout, const float* part_in, 
   a.K = K; a.N = N; a.R = R; a.rmean = running_mean; a.rvar = running_var;
   int rc = hs_fill_seg(a.sg, n_seg, seg_off_host, R, "hs_fwd");
   if (rc != SCNB_OK) return rc;
-  const size_t smem = ((size_t)(HS_BM + HS_BN) * (K + 4) + 4 * (size_t)K + 2048) * sizeof(float);
+  const size_t smem = ((size_t)(HS_BM + HS_BN) * (K + 4) + 4 * (size_t)K + HS_RED) * sizeof(float);
   rc = hs_set_smem(k_hs_fwd, smem, "hs_fwd");
   if (rc != SCNB_OK) return rc;
   scnb_launch_pdl(k_hs_fwd, dim3(N / HS_BN, R / HS_BM), dim3(HS_T), smem, (cudaStream_t)stream, a);
@@ -581,7 +594,7 @@ extern "C" int scnb_hs_fwd(const float* Zin, float* Aout, const float* part_in, 
 // ---------------------------------------------------------------------------------------------------------------------
 // hs_bwd_act: dY = dA * [A > 0] / (1-p) for the LAST application + tile sums (sum dY, sum dY*zhat).  grid = (H/64, R/32).
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(HS_T) k_hs_bwd_act(const float* __restrict__ dA, const float* __restrict__ Z,
+__global__ void __launch_bounds__(HS_TE) k_hs_bwd_act(const float* __restrict__ dA, const float* __restrict__ Z,
                                                      const float* __restrict__ A, int H, HsSeg sg, const float* __restrict__ stats,
                                                      float p_drop, float* __restrict__ dY, float* __restrict__ part) {
   PDL_ENTRY();
@@ -613,7 +626,7 @@ extern "C" int scnb_hs_bwd_act(const float* dA, const float* Z, const float* A, 
   HsSeg sg;
   int rc = hs_fill_seg(sg, n_seg, seg_off_host, R, "hs_bwd_act");
   if (rc != SCNB_OK) return rc;
-  scnb_launch_pdl(k_hs_bwd_act, dim3(H / HS_BN, R / HS_BM), dim3(HS_T), 0, (cudaStream_t)stream, dA, Z, A, H, sg, stats, p_drop, dY, part);
+  scnb_launch_pdl(k_hs_bwd_act, dim3(H / HS_BN, R / HS_BM), dim3(HS_TE), 0, (cudaStream_t)stream, dA, Z, A, H, sg, stats, p_drop, dY, part);
   SCNB_CHECK_LAUNCH("hs_bwd_act");
   return SCNB_OK;
 }
@@ -656,7 +669,7 @@ __global__ void __launch_bounds__(HS_T) k_hs_bwd(const __grid_constant__ HsBwdAr
   float* sMu = sM2 + K;                      // BatchNorm mean / invstd / gamma of application a
   float* sIs = sMu + K;
   float* sGm = sIs + K;
-  float* sRed = sGm + K;                     // 2048 floats
+  float* sRed = sGm + K;                     // HS_RED floats
   const int tid = threadIdx.x, n0 = blockIdx.x * HS_BN, tile = blockIdx.y, row0 = tile * HS_BM;
   const int s = hs_seg_of(p.sg, row0);
   const int t0 = p.sg.off[s] / HS_BM, t1 = p.sg.off[s + 1] / HS_BM;
@@ -747,7 +760,7 @@ extern "C" int scnb_hs_bwd(const float* dYin, const float* Zin, const float* sta
                            const int32_t* seg_off_host, void* stream) {
   SCNB_CHECK_ARG(dYin && Zin && stats_in && part_in && gamma && dgamma && dbeta && dZout && W && Zprev && Aprev && stats_prev &&
                      dYout && part_out, "hs_bwd: null argument");
-  SCNB_CHECK_ARG(K % 16 == 0 && K >= 16 && K <= 256 && N % HS_BN == 0 && R % HS_BM == 0, "hs_bwd: needs K %% 16 == 0 (<= 256), N %% 64 == 0, rows %% 32 == 0");
+  SCNB_CHECK_ARG(K % 32 == 0 && K >= 32 && K <= 256 && N % HS_BN == 0 && R % HS_BM == 0, "hs_bwd: needs K %% 32 == 0 (<= 256), N %% 64 == 0, rows %% 32 == 0");
   SCNB_CHECK_ARG(p_drop_prev >= 0.f && p_drop_prev < 1.f, "hs_bwd: p_drop out of range");
   HsBwdArgs a;
   a.dYin = dYin; a.Zin = Zin; a.stats_in = stats_in; a.part_in = part_in; a.gamma = gamma; a.dgamma = dgamma; a.dbeta = dbeta;
@@ -755,7 +768,7 @@ extern "C" int scnb_hs_bwd(const float* dYin, const float* Zin, const float* sta
   a.part_out = part_out; a.K = K; a.N = N; a.R = R;
   int rc = hs_fill_seg(a.sg, n_seg, seg_off_host, R, "hs_bwd");
   if (rc != SCNB_OK) return rc;
-  const size_t smem = ((size_t)2 * HS_BM * (K + 4) + (size_t)K * (HS_BN + 8) + 5 * (size_t)K + 2048) * sizeof(float);
+  const size_t smem = ((size_t)2 * HS_BM * (K + 4) + (size_t)K * (HS_BN + 8) + 5 * (size_t)K + HS_RED) * sizeof(float);
   rc = hs_set_smem(k_hs_bwd, smem, "hs_bwd");
   if (rc != SCNB_OK) return rc;
   scnb_launch_pdl(k_hs_bwd, dim3(N / HS_BN, R / HS_BM), dim3(HS_T), smem, (cudaStream_t)stream, a);
@@ -767,7 +780,7 @@ extern "C" int scnb_hs_bwd(const float* dYin, const float* Zin, const float* sta
 // hs_bwd_in: dZ[0] from dY[0] (application 0 has no Linear inside the stack: its input gradient feeds the MixUp adjoint
 // and the first-layer weight gradient).  grid = (H/64, R/32).
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(HS_T) k_hs_bwd_in(const float* __restrict__ dY, const float* __restrict__ Z, int H, HsSeg sg,
+__global__ void __launch_bounds__(HS_TE) k_hs_bwd_in(const float* __restrict__ dY, const float* __restrict__ Z, int H, HsSeg sg,
                                                     const float* __restrict__ stats, const float* __restrict__ part,
                                                     const float* __restrict__ gamma, float* __restrict__ dgamma,
                                                     float* __restrict__ dbeta, float* __restrict__ dZ) {
@@ -811,7 +824,7 @@ extern "C" int scnb_hs_bwd_in(const float* dY, const float* Z, int H, int R, int
   HsSeg sg;
   int rc = hs_fill_seg(sg, n_seg, seg_off_host, R, "hs_bwd_in");
   if (rc != SCNB_OK) return rc;
-  scnb_launch_pdl(k_hs_bwd_in, dim3(H / HS_BN, R / HS_BM), dim3(HS_T), 0, (cudaStream_t)stream, dY, Z, H, sg, stats, part, gamma, dgamma,
+  scnb_launch_pdl(k_hs_bwd_in, dim3(H / HS_BN, R / HS_BM), dim3(HS_TE), 0, (cudaStream_t)stream, dY, Z, H, sg, stats, part, gamma, dgamma,
                   dbeta, dZ);
   SCNB_CHECK_LAUNCH("hs_bwd_in");
   return SCNB_OK;

@@ -732,6 +732,46 @@ __device__ __forceinline__ void stage_weights(float* Ws, const float* __restrict
   __syncthreads();
 }
 
+// Short-chain variant for C <= 32 outputs (the usual number of cell types / domains): the per-class partial dot products of
+// all lanes meet in a per-warp shared-memory tile [C][33] and lane c adds its class's 32 partials -- one transposed pass
+// instead of C dependent butterfly reductions -- and the logits stay in shared memory (`zs[C]`) for the loss row function
+// and the back-propagation, instead of a store -> load round trip through global memory.  Per-warp scratch: HEAD_WS floats.
+#define HEAD_WS (32 * 33 + 64)
+template <int NV>
+__device__ __forceinline__ void head_logits_s(const float* __restrict__ a_row, const float* __restrict__ Ws,
+                                              const float* __restrict__ bias, int C, int H, float* __restrict__ wsm,
+                                              float4 (&a)[NV], int lane) {
+  float* sp = wsm;               // [C][33]
+  float* zs = wsm + 32 * 33;     // [32] logits
+#pragma unroll
+  for (int i = 0; i < NV; ++i) a[i] = *reinterpret_cast<const float4*>(a_row + (i * 32 + lane) * 4);
+  for (int c = 0; c < C; ++c) {
+    float p = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 w = *reinterpret_cast<const float4*>(Ws + (size_t)c * H + (i * 32 + lane) * 4);
+      p = fmaf(a[i].x, w.x, p);
+      p = fmaf(a[i].y, w.y, p);
+      p = fmaf(a[i].z, w.z, p);
+      p = fmaf(a[i].w, w.w, p);
+    }
+    sp[c * 33 + lane] = p;
+  }
+  __syncwarp();
+  if (lane < C) {
+    float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      z0 += sp[lane * 33 + i];
+      z1 += sp[lane * 33 + i + 1];
+      z2 += sp[lane * 33 + i + 2];
+      z3 += sp[lane * 33 + i + 3];
+    }
+    zs[lane] = ((z0 + z1) + (z2 + z3)) + (bias ? bias[lane] : 0.f);
+  }
+  __syncwarp();
+}
+
 // MixMatch student head: rows [0,U) interpolation-consistency MSE, rows [U,U+L) soft-target CE
 // (scnym/model.py:229 classifier; scnym/losses.py:880-923), dA = dLogits Wc.
 template <int NV>
@@ -754,14 +794,31 @@ __global__ void __launch_bounds__(256) k_classif_mixmatch(const float* __restric
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r < U + L) {
     float4 a[NV];
-    head_logits<NV>(A + (size_t)r * H, Ws, bc, C, H, logits + (size_t)r * C, a, lane);
-    if (r < U)
-      mse_row(r, logits, U, C, n_conf_dev, Y, mapA, mapB, gam, 0, U, nullptr, unsup_weight, dlogits, sl + 2);
-    else
-      ce_row(r - U, logits + (size_t)U * C, L, C, nullptr, Y, mapA, mapB, gam, U, class_weight, nullptr, L, 1.0f, nullptr,
-             dlogits + (size_t)U * C, sl, 1, nullptr);
-    __syncwarp();
-    head_backprop<NV>(dlogits + (size_t)r * C, Ws, C, H, 1.0f, nullptr, dA + (size_t)r * H, lane);
+    if (C <= 32) {
+      float* wsm = Ws + (size_t)C * H + (threadIdx.x >> 5) * HEAD_WS;
+      float* zs = wsm + 32 * 33;
+      float* dzs = zs + 32;
+      head_logits_s<NV>(A + (size_t)r * H, Ws, bc, C, H, wsm, a, lane);
+      if (lane < C) logits[(size_t)r * C + lane] = zs[lane];
+      // the row functions address row i of a [rows, C] array: hand them the shared-memory row through a shifted base
+      if (r < U)
+        mse_row(r, zs - (size_t)r * C, U, C, n_conf_dev, Y, mapA, mapB, gam, 0, U, nullptr, unsup_weight, dzs - (size_t)r * C, sl + 2);
+      else
+        ce_row(r - U, zs - (size_t)(r - U) * C, L, C, nullptr, Y, mapA, mapB, gam, U, class_weight, nullptr, L, 1.0f, nullptr,
+               dzs - (size_t)(r - U) * C, sl, 1, nullptr);
+      __syncwarp();
+      if (lane < C) dlogits[(size_t)r * C + lane] = dzs[lane];
+      head_backprop<NV>(dzs, Ws, C, H, 1.0f, nullptr, dA + (size_t)r * H, lane);
+    } else {
+      head_logits<NV>(A + (size_t)r * H, Ws, bc, C, H, logits + (size_t)r * C, a, lane);
+      if (r < U)
+        mse_row(r, logits, U, C, n_conf_dev, Y, mapA, mapB, gam, 0, U, nullptr, unsup_weight, dlogits, sl + 2);
+      else
+        ce_row(r - U, logits + (size_t)U * C, L, C, nullptr, Y, mapA, mapB, gam, U, class_weight, nullptr, L, 1.0f, nullptr,
+               dlogits + (size_t)U * C, sl, 1, nullptr);
+      __syncwarp();
+      head_backprop<NV>(dlogits + (size_t)r * C, Ws, C, H, 1.0f, nullptr, dA + (size_t)r * H, lane);
+    }
   }
   __syncthreads();
   if (threadIdx.x < 4 && sl[threadIdx.x] != 0.f) atomicAdd(loss8 + threadIdx.x, sl[threadIdx.x]);
@@ -783,11 +840,24 @@ __global__ void __launch_bounds__(256) k_classif_supervised(const float* __restr
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r < n) {
     float4 a[NV];
-    head_logits<NV>(A + (size_t)r * H, Ws, bc, C, H, logits + (size_t)r * C, a, lane);
-    ce_row(r, logits, n, C, nullptr, Y, nullptr, nullptr, nullptr, 0, class_weight, nullptr, n, 1.0f, nullptr, dlogits, sl, 1,
-           nullptr);
-    __syncwarp();
-    head_backprop<NV>(dlogits + (size_t)r * C, Ws, C, H, 1.0f, nullptr, dA + (size_t)r * H, lane);
+    if (C <= 32) {
+      float* wsm = Ws + (size_t)C * H + (threadIdx.x >> 5) * HEAD_WS;
+      float* zs = wsm + 32 * 33;
+      float* dzs = zs + 32;
+      head_logits_s<NV>(A + (size_t)r * H, Ws, bc, C, H, wsm, a, lane);
+      if (lane < C) logits[(size_t)r * C + lane] = zs[lane];
+      ce_row(r, zs - (size_t)r * C, n, C, nullptr, Y, nullptr, nullptr, nullptr, 0, class_weight, nullptr, n, 1.0f, nullptr,
+             dzs - (size_t)r * C, sl, 1, nullptr);
+      __syncwarp();
+      if (lane < C) dlogits[(size_t)r * C + lane] = dzs[lane];
+      head_backprop<NV>(dzs, Ws, C, H, 1.0f, nullptr, dA + (size_t)r * H, lane);
+    } else {
+      head_logits<NV>(A + (size_t)r * H, Ws, bc, C, H, logits + (size_t)r * C, a, lane);
+      ce_row(r, logits, n, C, nullptr, Y, nullptr, nullptr, nullptr, 0, class_weight, nullptr, n, 1.0f, nullptr, dlogits, sl, 1,
+             nullptr);
+      __syncwarp();
+      head_backprop<NV>(dlogits + (size_t)r * C, Ws, C, H, 1.0f, nullptr, dA + (size_t)r * H, lane);
+    }
   }
   __syncthreads();
   if (threadIdx.x < 2 && sl[threadIdx.x] != 0.f) atomicAdd(loss8 + threadIdx.x, sl[threadIdx.x]);
@@ -812,14 +882,34 @@ __global__ void __launch_bounds__(256) k_dan_tail(const float* __restrict__ Hd, 
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r < Rd) {
     float4 a[NV];
-    head_logits<NV>(Hd + (size_t)r * H, Ws, b2, D, H, dlog + (size_t)r * D, a, lane);
     const int id = dom_ids[src ? src[src_off + r] : r];
-    for (int c = lane; c < D; c += 32) dlabel[(size_t)r * D + c] = (c == id) ? 1.f : 0.f;
-    __syncwarp();
-    ce_row(r, dlog, Rd, D, n_rows_dev, dlabel, nullptr, nullptr, nullptr, 0, nullptr, n_rows_dev, 0, 1.0f, loss_scale_dev, ddlog,
-           sl, 1, nullptr);
-    __syncwarp();
-    head_backprop<NV>(ddlog + (size_t)r * D, Ws, D, H, 1.0f, a, dHd + (size_t)r * H, lane);
+    if (D <= 32) {
+      float* wsm = Ws + (size_t)D * H + (threadIdx.x >> 5) * HEAD_WS;
+      float* zs = wsm + 32 * 33;
+      float* dzs = zs + 32;
+      float* ys = wsm;               // the [C][33] tile is free once the logits are formed: one-hot label row
+      head_logits_s<NV>(Hd + (size_t)r * H, Ws, b2, D, H, wsm, a, lane);
+      if (lane < D) {
+        dlog[(size_t)r * D + lane] = zs[lane];
+        const float y = (lane == id) ? 1.f : 0.f;
+        dlabel[(size_t)r * D + lane] = y;
+        ys[lane] = y;
+      }
+      __syncwarp();
+      ce_row(r, zs - (size_t)r * D, Rd, D, n_rows_dev, ys - (size_t)r * D, nullptr, nullptr, nullptr, 0, nullptr, n_rows_dev, 0, 1.0f,
+             loss_scale_dev, dzs - (size_t)r * D, sl, 1, nullptr);
+      __syncwarp();
+      if (lane < D) ddlog[(size_t)r * D + lane] = dzs[lane];
+      head_backprop<NV>(dzs, Ws, D, H, 1.0f, a, dHd + (size_t)r * H, lane);
+    } else {
+      head_logits<NV>(Hd + (size_t)r * H, Ws, b2, D, H, dlog + (size_t)r * D, a, lane);
+      for (int c = lane; c < D; c += 32) dlabel[(size_t)r * D + c] = (c == id) ? 1.f : 0.f;
+      __syncwarp();
+      ce_row(r, dlog, Rd, D, n_rows_dev, dlabel, nullptr, nullptr, nullptr, 0, nullptr, n_rows_dev, 0, 1.0f, loss_scale_dev, ddlog,
+             sl, 1, nullptr);
+      __syncwarp();
+      head_backprop<NV>(ddlog + (size_t)r * D, Ws, D, H, 1.0f, a, dHd + (size_t)r * H, lane);
+    }
   }
   __syncthreads();
   if (threadIdx.x < 2 && sl[threadIdx.x] != 0.f) atomicAdd(loss2 + threadIdx.x, sl[threadIdx.x]);
@@ -838,6 +928,16 @@ __global__ void __launch_bounds__(256) k_teacher_head(const float* __restrict__ 
   stage_weights(Ws, Wc, C * H);
   const int lane = threadIdx.x & 31;
   const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (u < U && K == 1 && C <= 32) {   // one view: logits and the mean-probability scratch stay in shared memory
+    float4 a[NV];
+    float* wsm = Ws + (size_t)C * H + (threadIdx.x >> 5) * HEAD_WS;
+    float* zs = wsm + 32 * 33;
+    float* qs = zs + 32;
+    head_logits_s<NV>(TA + (size_t)u * H, Ws, bc, C, H, wsm, a, lane);
+    if (lane < C) t_logits[(size_t)u * C + lane] = zs[lane];
+    pseudolabel_row(u, zs - (size_t)u * C, 1, U, C, T, sharpen, min_conf, q, conf, confident, qs - (size_t)u * C, lab_ids, L);
+    return;
+  }
   if (u < U) {
     float4 a[NV];
     for (int k = 0; k < K; ++k) {
@@ -878,7 +978,7 @@ extern "C" int scnb_classif_mixmatch_fused(const float* A, const float* Wc, cons
                  "classif_mixmatch_fused: bad arguments");
   if (!head_fusable(H, C, A, Wc, dA) || (H / 128 != 1 && H / 128 != 2 && H / 128 != 4 && H / 128 != 8)) return SCNB_ERR_UNSUPPORTED;
   if (U + L == 0) return SCNB_OK;
-  const size_t smem = (size_t)C * H * sizeof(float);
+  const size_t smem = ((size_t)C * H + (C <= 32 ? 8 * HEAD_WS : 0)) * sizeof(float);
   HEAD_DISPATCH(k_classif_mixmatch, U + L, smem, (cudaStream_t)stream, A, Wc, bc, H, C, U, L, n_conf_dev, Y, mapA, mapB, gam,
                 class_weight, unsup_weight, logits, dlogits, dA, loss8);
   SCNB_CHECK_LAUNCH("classif_mixmatch_fused");
@@ -891,7 +991,7 @@ extern "C" int scnb_classif_supervised_fused(const float* A, const float* Wc, co
   SCNB_CHECK_ARG(A && Wc && Y && logits && dlogits && dA && loss8 && H > 0 && C > 0 && n >= 0, "classif_supervised_fused: bad arguments");
   if (!head_fusable(H, C, A, Wc, dA) || (H / 128 != 1 && H / 128 != 2 && H / 128 != 4 && H / 128 != 8)) return SCNB_ERR_UNSUPPORTED;
   if (n == 0) return SCNB_OK;
-  const size_t smem = (size_t)C * H * sizeof(float);
+  const size_t smem = ((size_t)C * H + (C <= 32 ? 8 * HEAD_WS : 0)) * sizeof(float);
   HEAD_DISPATCH(k_classif_supervised, n, smem, (cudaStream_t)stream, A, Wc, bc, H, C, n, Y, class_weight, logits, dlogits, dA, loss8);
   SCNB_CHECK_LAUNCH("classif_supervised_fused");
   return SCNB_OK;
@@ -905,7 +1005,7 @@ extern "C" int scnb_dan_tail_fused(const float* Hd, const float* W2, const float
                  "dan_tail_fused: bad arguments");
   if (!head_fusable(H, D, Hd, W2, dHd) || (H / 128 != 1 && H / 128 != 2 && H / 128 != 4 && H / 128 != 8)) return SCNB_ERR_UNSUPPORTED;
   if (Rd == 0) return SCNB_OK;
-  const size_t smem = (size_t)D * H * sizeof(float);
+  const size_t smem = ((size_t)D * H + (D <= 32 ? 8 * HEAD_WS : 0)) * sizeof(float);
   HEAD_DISPATCH(k_dan_tail, Rd, smem, (cudaStream_t)stream, Hd, W2, b2, H, D, Rd, n_rows_dev, dom_ids, src, src_off, loss_scale_dev,
                 dlog, dlabel, ddlog, dHd, loss2);
   SCNB_CHECK_LAUNCH("dan_tail_fused");
@@ -920,7 +1020,7 @@ extern "C" int scnb_teacher_head_fused(const float* TA, const float* Wc, const f
   if (!head_fusable(H, C, TA, Wc, Wc) || (H / 128 != 1 && H / 128 != 2 && H / 128 != 4 && H / 128 != 8)) return SCNB_ERR_UNSUPPORTED;
   const int rows = U + (lab_ids ? L : 0);
   if (rows == 0) return SCNB_OK;
-  const size_t smem = (size_t)C * H * sizeof(float);
+  const size_t smem = ((size_t)C * H + (C <= 32 ? 8 * HEAD_WS : 0)) * sizeof(float);
   HEAD_DISPATCH(k_teacher_head, rows, smem, (cudaStream_t)stream, TA, Wc, bc, H, C, K, U, T, sharpen, min_confidence, t_logits, q,
                 conf, confident, scratch_UC, lab_ids, L);
   SCNB_CHECK_LAUNCH("teacher_head_fused");
