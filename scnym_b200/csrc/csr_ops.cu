@@ -75,12 +75,73 @@ struct GatherSrc {
   const int64_t* rows;  // NULL: row0 + i
   int64_t row0;
   int n;
-  int augment;          // 1: log1p_drop on rows [aug_begin, aug_end) (row index local to this source)
+  int augment;          // augmentation scheme of rows [aug_begin, aug_end) (row index local to this source), AUG_* below
   int aug_begin, aug_end;
   uint32_t stream_id;
 };
 
 #define GR_T 256  // threads per gathered row
+
+// Augmentation schemes of scnym/dataprep.py:730-754 (AUGMENTATION_SCHEMES), all on the STORED entries only: every stage maps 0
+// to 0 (expm1, Poisson sampling with its rate-0 guard, dropout, masking, log1p), so the support of a row is preserved.
+//   1 log1p_drop          ExpMinusOne -> InputDropout(p) -> LibrarySizeNormalize(log1p)                 (dataprep.py:721-729)
+//   2 log1p_mask          ExpMinusOne -> GeneMasking(p, p_apply) -> LibrarySizeNormalize(log1p)         (:405-465)
+//   3 log1p_poisson       ExpMinusOne -> PoissonSample(depth 1) -> LibrarySizeNormalize(log1p)          (:277-341)
+//   4 log1p_poisson_drop  ExpMinusOne -> PoissonSample(depth U(0.1, 2)) -> InputDropout(p) -> LibrarySizeNormalize(log1p)
+//   5 count_poisson       PoissonSample(depth 1) on raw counts, no normalisation
+#define AUG_NONE 0
+#define AUG_DROP 1
+#define AUG_MASK 2
+#define AUG_POIS 3
+#define AUG_POIS_DROP 4
+#define AUG_COUNT_POIS 5
+
+struct AugExtra {
+  int n_genes;             // G (gene masking draws floor(G * p) genes per row, from ALL genes)
+  float p_apply;           // GeneMasking: probability that the batch is masked at all
+  const float* inj_pois;   // injected Poisson samples by batch nnz position (tests), or NULL
+  const float* inj_row_r;  // injected per-row depth factors (tests), or NULL
+};
+
+__device__ __forceinline__ float u01(uint32_t w) { return ((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f); }   // (0, 1)
+
+// Poisson(lam) from a counter-based stream: entry `pos` of logical stream `strm` (re-evaluating it gives the same draw).
+// lam < 10: inversion by sequential search; else PTRS, Hormann's transformed rejection with squeeze (the algorithm numpy
+// and torch use for large rates); the rare exact acceptance test runs in double precision.
+__device__ float poisson_draw(float lam, uint64_t pos, uint64_t seed, uint64_t strm) {
+  if (!(lam > 0.f)) return 0.f;
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  if (lam < 10.f) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)pos, (uint32_t)(pos >> 32), (uint32_t)strm, (uint32_t)(strm >> 32)), key);
+    const float u = u01(r.x);
+    float p = expf(-lam), F = p;
+    int k = 0;
+    while (u > F && k < 256) {
+      ++k;
+      p *= lam / (float)k;
+      F += p;
+    }
+    return (float)k;
+  }
+  const float slam = sqrtf(lam), b = 0.931f + 2.53f * slam, a = -0.059f + 0.02483f * b;
+  const float invalpha = 1.1239f + 1.1328f / (b - 3.4f), vr = 0.9277f - 3.6224f / (b - 2.f);
+  uint4 r = make_uint4(0, 0, 0, 0);
+  for (int trial = 0; trial < 64; ++trial) {
+    if ((trial & 1) == 0) {
+      const uint64_t sub = strm + ((uint64_t)(1 + (trial >> 1)) << 40);   // a fresh counter block every two trials
+      r = philox4x32_10(make_uint4((uint32_t)pos, (uint32_t)(pos >> 32), (uint32_t)sub, (uint32_t)(sub >> 32)), key);
+    }
+    const float U = u01((trial & 1) ? r.z : r.x) - 0.5f, V = u01((trial & 1) ? r.w : r.y);
+    const float us = 0.5f - fabsf(U);
+    const float k = floorf((2.f * a / us + b) * U + lam + 0.43f);
+    if (us >= 0.07f && V <= vr) return k;
+    if (k < 0.f || (us < 0.013f && V > us)) continue;
+    const double lhs = (double)logf(V) + (double)logf(invalpha) - (double)logf(a / (us * us) + b);
+    const double rhs = -(double)lam + (double)k * log((double)lam) - lgamma((double)k + 1.0);
+    if (lhs <= rhs) return k;
+  }
+  return floorf(lam + 0.5f);
+}
 
 __device__ __forceinline__ float gather_block_sum(float v, float* red8) {
   v = warp_sum(v);
@@ -101,14 +162,19 @@ __device__ __forceinline__ bool gather_keep(const uint8_t* mask, int pos, const 
   return (float)(w >> 8) * (1.0f / 16777216.0f) >= p;
 }
 
+#define GR_MASKBITS 32768   // entries of a row whose gene-masking decisions are held in shared memory (exact sampling)
+
+// EXT = false: schemes 0 / 1 only (the step's hot path: the Poisson sampler and the masking scan are compiled out)
+template <bool EXT>
 __global__ void __launch_bounds__(GR_T) k_gather_rows(GatherSrc A, GatherSrc B, const int32_t* __restrict__ b_indptr,
                                                      int32_t* __restrict__ b_idx, float* __restrict__ b_val,
                                                      const uint8_t* __restrict__ keep_mask, const uint64_t* __restrict__ rng,
-                                                     float p_drop, float target_sum, int32_t* __restrict__ gene_cnt) {
+                                                     float p_drop, float target_sum, int32_t* __restrict__ gene_cnt, AugExtra X) {
   PDL_ENTRY();
   __shared__ float red8[8];
   __shared__ float e_s[GR_CACHE];
   __shared__ int32_t c_s[GR_CACHE];
+  __shared__ uint32_t mbits[EXT ? GR_MASKBITS / 32 : 1];   // gene masking: bit j = entry j of the row is masked
   const int tid = threadIdx.x;
   const int i = blockIdx.x;
   const bool inA = i < A.n;
@@ -118,8 +184,9 @@ __global__ void __launch_bounds__(GR_T) k_gather_rows(GatherSrc A, GatherSrc B, 
   const int64_t s = S.indptr[r];
   const int len = (int)(S.indptr[r + 1] - s);
   const int d = b_indptr[i];
-  const bool aug = S.augment && li >= S.aug_begin && li < S.aug_end;
-  if (!aug) {
+  int mode = (S.augment && li >= S.aug_begin && li < S.aug_end) ? S.augment : AUG_NONE;
+  if (!EXT && mode != AUG_NONE) mode = AUG_DROP;
+  if (mode == AUG_NONE) {
     for (int j = tid; j < len; j += GR_T) {
       const int c = S.indices[s + j];
       const float v = S.data[s + j];
@@ -129,23 +196,69 @@ __global__ void __launch_bounds__(GR_T) k_gather_rows(GatherSrc A, GatherSrc B, 
     }
     return;
   }
-  const float inv_keep = 1.0f / (1.0f - p_drop);
+  const bool drop = !EXT || mode == AUG_DROP || mode == AUG_POIS_DROP;   // Bernoulli input dropout, scaled by 1/(1-p)
+  const bool pois = EXT && (mode == AUG_POIS || mode == AUG_POIS_DROP || mode == AUG_COUNT_POIS);
+  const float inv_keep = drop ? 1.0f / (1.0f - p_drop) : 1.0f;
   uint64_t seed = 0, strm = 0;
-  if (!keep_mask) {
+  if (rng) {
     seed = rng[0];
     strm = rng[1] * 64ull + S.stream_id;
   }
-  // pass 1: one trip to DRAM for values and indices; e = expm1(x) * keep / (1-p), cached in shared memory
+  // per-row Poisson depth factor: U(0.1, 2.0) as `rand * (0.1 - 2.0) + 2.0` (dataprep.py:318-321); 1 otherwise
+  float row_r = 1.0f;
+  if (EXT && mode == AUG_POIS_DROP) {
+    const float u = X.inj_row_r ? X.inj_row_r[i] : philox_uniform(seed, strm + 33, (uint64_t)i);
+    row_r = u * (0.1f - 2.0f) + 2.0f;
+  }
+  // gene masking: with probability p_apply (one decision per batch, dataprep.py:439-442) every row loses floor(G*p) genes
+  // drawn without replacement from ALL G genes; restricted to the row's stored entries that is Knuth's selection sampling
+  // over the entries (entry t is taken with probability (m - taken) / (G - t)): exact, one pass of thread 0.
+  bool mask_on = false;
+  if (EXT && mode == AUG_MASK && !keep_mask) {
+    mask_on = philox_uniform(seed, strm + 35, 0) <= X.p_apply;
+    if (mask_on) {
+      for (int w = tid; w < GR_MASKBITS / 32; w += GR_T) mbits[w] = 0u;
+      __syncthreads();
+      if (tid == 0) {
+        const int G = X.n_genes;
+        int left = (int)floorf((float)G * p_drop);
+        const int n_scan = min(len, GR_MASKBITS);
+        for (int t = 0; t < n_scan && left > 0; ++t) {
+          const float u = philox_uniform(seed, strm + 34, (uint64_t)d + (uint64_t)t);
+          if (u * (float)(G - t) < (float)left) {
+            mbits[t >> 5] |= 1u << (t & 31);
+            --left;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // value of entry j after every random stage and before the library-size normalisation
+  auto entry = [&](int j, int k, uint4& rnd) -> float {
+    const float x = S.data[s + j];
+    float e = (EXT && mode == AUG_COUNT_POIS) ? x : expm1f(x);
+    if (pois) e = X.inj_pois ? (x == 0.f ? 0.f : X.inj_pois[d + j]) : (e > 0.f ? poisson_draw(e * row_r, (uint64_t)(d + j), seed, strm + 32) : 0.f);
+    if (drop) e = e * (gather_keep(keep_mask, d + j, rnd, k, p_drop) ? inv_keep : 0.f);
+    if (EXT && mode == AUG_MASK) {
+      if (keep_mask) e = keep_mask[d + j] ? e : 0.f;
+      else if (mask_on) {
+        const bool m = j < GR_MASKBITS ? ((mbits[j >> 5] >> (j & 31)) & 1u) : (philox_uniform(seed, strm + 34, (uint64_t)d + (uint64_t)j) < p_drop);
+        if (m) e = 0.f;
+      }
+    }
+    return e;
+  };
+  // pass 1: one trip to DRAM for values and indices; the transformed value is cached in shared memory
   float sum = 0.f;
   uint4 rnd = make_uint4(0, 0, 0, 0);
   for (int j = tid, k = 0; j < len; j += GR_T, ++k) {
-    if (!keep_mask && (k & 3) == 0) {
+    if (drop && !keep_mask && (k & 3) == 0) {
       const uint64_t ctr = (uint64_t)(d + tid) + (uint64_t)(4 * GR_T) * (uint64_t)(k >> 2);
       rnd = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)strm, (uint32_t)(strm >> 32)),
                           make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
     }
-    float e = expm1f(S.data[s + j]);
-    e = e * (gather_keep(keep_mask, d + j, rnd, k, p_drop) ? inv_keep : 0.f);
+    const float e = entry(j, k, rnd);
     sum += e;
     if (j < GR_CACHE) {
       e_s[j] = e;
@@ -159,16 +272,18 @@ __global__ void __launch_bounds__(GR_T) k_gather_rows(GatherSrc A, GatherSrc B, 
     if (j < GR_CACHE) {
       e = e_s[j];
       c = c_s[j];
-    } else {  // rows longer than the cache: recompute
-      if (!keep_mask && ((k & 3) == 0 || j - GR_T < GR_CACHE)) {
+    } else {  // rows longer than the cache: recompute (every random stage is counter-based: the same draw again)
+      if (drop && !keep_mask && ((k & 3) == 0 || j - GR_T < GR_CACHE)) {
         const uint64_t ctr = (uint64_t)(d + tid) + (uint64_t)(4 * GR_T) * (uint64_t)(k >> 2);
         rnd = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)strm, (uint32_t)(strm >> 32)),
                             make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
       }
-      e = expm1f(S.data[s + j]) * (gather_keep(keep_mask, d + j, rnd, k, p_drop) ? inv_keep : 0.f);
+      e = entry(j, k, rnd);
       c = S.indices[s + j];
     }
-    const float v = log1pf((e / sum) * target_sum);  // NaN if every entry of the row was dropped, as in the reference
+    // count_poisson returns the sampled counts; every other scheme ends in LibrarySizeNormalize(log1p)
+    // (NaN if every entry of the row was dropped, as in the reference)
+    const float v = (EXT && mode == AUG_COUNT_POIS) ? e : log1pf((e / sum) * target_sum);
     b_idx[d + j] = c;
     b_val[d + j] = v;
     if (gene_cnt && v != 0.f) atomicAdd(gene_cnt + c, 1);
@@ -184,7 +299,7 @@ extern "C" int scnb_csr_gather_rows(const int64_t* indptr, const int32_t* indice
   if (n == 0) return SCNB_OK;
   GatherSrc A = {indptr, indices, data, rows, row0, n, augment, aug_row_begin, aug_row_end, stream_id};
   GatherSrc B = {nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, 0, 0};
-  k_gather_rows<<<n, GR_T, 0, (cudaStream_t)stream>>>(A, B, b_indptr, b_idx, b_val, keep_mask, rng, p_drop, 1e6f, gene_cnt);
+  k_gather_rows<false><<<n, GR_T, 0, (cudaStream_t)stream>>>(A, B, b_indptr, b_idx, b_val, keep_mask, rng, p_drop, 1e6f, gene_cnt, AugExtra{0, 0.f, nullptr, nullptr});
   SCNB_CHECK_LAUNCH("csr_gather_rows");
   return SCNB_OK;
 }
@@ -204,9 +319,35 @@ extern "C" int scnb_csr_gather_rows2(const int64_t* indptr_A, const int32_t* ind
   if (nA + nB == 0) return SCNB_OK;
   GatherSrc A = {indptr_A, indices_A, data_A, rows_A, 0, nA, augment_A, 0, nA, stream_id_A};
   GatherSrc B = {indptr_B, indices_B, data_B, rows_B, 0, nB, augment_B, 0, nB, stream_id_B};
-  scnb_launch_pdl(k_gather_rows, dim3(nA + nB), dim3(GR_T), 0, (cudaStream_t)stream, A, B, b_indptr, b_idx, b_val, keep_mask, rng, p_drop, 1e6f,
-                  gene_cnt);
+  scnb_launch_pdl(k_gather_rows<false>, dim3(nA + nB), dim3(GR_T), 0, (cudaStream_t)stream, A, B, b_indptr, b_idx, b_val, keep_mask, rng, p_drop, 1e6f,
+                  gene_cnt, AugExtra{0, 0.f, nullptr, nullptr});
   SCNB_CHECK_LAUNCH("csr_gather_rows2");
+  return SCNB_OK;
+}
+
+// The other augmentation schemes of scnym/dataprep.py:730-754 (`scheme`: 2 log1p_mask, 3 log1p_poisson, 4 log1p_poisson_drop,
+// 5 count_poisson; 1 = log1p_drop is also accepted) on rows [0, n) of one source.  Randomness: `keep_mask` (Bernoulli dropout
+// keeps of scheme 1 / 4, or the per-entry gene-masking keeps of scheme 2 with the batch-level apply decision folded in),
+// `inj_poisson` (sampled values by batch nnz position) and `inj_row_depth` (per-row uniforms of the depth factor) inject the
+// reference's draws in tests; NULL: counter-based Philox streams of (rng[0], rng[1], stream_id).
+extern "C" int scnb_csr_gather_rows_aug(const int64_t* indptr, const int32_t* indices, const float* data, const int64_t* rows,
+                                        int64_t row0, int n, const int32_t* b_indptr, int32_t* b_idx, float* b_val, int scheme,
+                                        int n_genes, float p_drop, float p_apply, const uint8_t* keep_mask, const float* inj_poisson,
+                                        const float* inj_row_depth, const uint64_t* rng, uint32_t stream_id, int32_t* gene_cnt,
+                                        void* stream) {
+  SCNB_CHECK_ARG(indptr && indices && data && b_indptr && b_idx && b_val && n >= 0, "csr_gather_rows_aug: bad arguments");
+  SCNB_CHECK_ARG(scheme >= AUG_DROP && scheme <= AUG_COUNT_POIS, "csr_gather_rows_aug: unknown augmentation scheme %d", scheme);
+  SCNB_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f && p_apply >= 0.f && p_apply <= 1.f && n_genes > 0, "csr_gather_rows_aug: bad parameters");
+  const bool need_keep = scheme == AUG_DROP || scheme == AUG_POIS_DROP || scheme == AUG_MASK;
+  const bool need_pois = scheme == AUG_POIS || scheme == AUG_POIS_DROP || scheme == AUG_COUNT_POIS;
+  SCNB_CHECK_ARG(rng || ((!need_keep || keep_mask) && (!need_pois || inj_poisson) && (scheme != AUG_POIS_DROP || inj_row_depth)),
+                 "csr_gather_rows_aug: needs rng state or every injected draw of the scheme");
+  if (n == 0) return SCNB_OK;
+  GatherSrc A = {indptr, indices, data, rows, row0, n, scheme, 0, n, stream_id};
+  GatherSrc B = {nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, 0, 0};
+  k_gather_rows<true><<<n, GR_T, 0, (cudaStream_t)stream>>>(A, B, b_indptr, b_idx, b_val, keep_mask, rng, p_drop, 1e6f, gene_cnt,
+                                                            AugExtra{n_genes, p_apply, inj_poisson, inj_row_depth});
+  SCNB_CHECK_LAUNCH("csr_gather_rows_aug");
   return SCNB_OK;
 }
 

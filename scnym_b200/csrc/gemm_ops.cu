@@ -249,8 +249,8 @@ int scnb_sgemm_panel_try(int transA, int transB, int M, int N, int K, const floa
 
 // ---------------------------------------------------------------------------------------------
 // Tensor-core variant for the same three product shapes: 3xTF32 (error-compensated) mma.sync.
-//   x = hi + lo with hi = tf32(x), lo = tf32(x - hi);  A*B ~= Ahi*Bhi + Ahi*Blo + Alo*Bhi
-// keeps ~21 mantissa bits per product, which the 1e-4 parity budget needs (a single TF32 pass does
+//   x = hi + lo with hi = trunc_tf32(x), lo = x - hi;  A*B ~= Ahi*Bhi + Ahi*Blo + Alo*Bhi
+// keeps ~20 mantissa bits per product, which the 1e-4 parity budget needs (a single TF32 pass does
 // not: SURVEY.md §7).  One CTA = one 32x32 output tile; its 4 warps split the K chunk held in shared
 // memory four ways (each runs m16n8k8 over a 32x32 warp tile) and meet in shared memory, so the
 // serial MMA chain per warp is K/32 steps and a 1024x256 output still spreads over 256 CTAs.
@@ -262,10 +262,12 @@ int scnb_sgemm_panel_try(int transA, int transB, int M, int N, int K, const floa
 #define TG_SR (TG_KC + 4)   // stride of a [32][KC] panel (k contiguous)
 #define TG_SC 40            // stride of a [KC][32] panel (k rows)
 
+// The tensor core ignores the low 13 mantissa bits of a tf32 operand register: hi = x as it is (read as trunc(x)),
+// lo = x - trunc(x) (exact in fp32).  Two full-rate instructions per element; `cvt.rna.tf32.f32` is emulated on sm_100a
+// with ~4 instructions per conversion, which made these loops issue-bound (profiles/r02_ncu_hidden_stack.txt).
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  hi = __float_as_uint(x);
+  lo = __float_as_uint(x - __uint_as_float(hi & 0xffffe000u));
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"

@@ -53,15 +53,38 @@ __device__ __forceinline__ void hs_cp16(float* smem_dst, const float* gsrc) {
 }
 __device__ __forceinline__ void hs_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void hs_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+// 3xTF32 operand split.  The tensor core reads a tf32 operand from a 32-bit register and ignores the low 13 mantissa bits,
+// so `hi` is x itself (used as trunc(x)) and `lo = x - trunc(x)` is exact in fp32 (then truncated the same way): two
+// full-rate instructions per element.  (`cvt.rna.tf32.f32` is emulated on sm_100a -- add / compare / select / mask, and
+// again for the residual: nine instructions per element, which made the MMA loop issue-bound.)  |lo| < 2^-10 |x|, so the
+// dropped terms (lo*lo and the truncation of lo) are below 2^-20 relative per product.
 __device__ __forceinline__ void hs_split(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  hi = __float_as_uint(x);
+  lo = __float_as_uint(x - __uint_as_float(hi & 0xffffe000u));
 }
 __device__ __forceinline__ void hs_mma(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// Stage `rows` rows of `cpr` 16-byte chunks each (row pitches: `gld` floats in global memory, `sld` in shared memory).
+// When the chunk count per row divides the thread count every thread keeps its chunk column and walks rows with plain
+// additions (the generic index arithmetic was a third of the tile kernels' instructions).
+__device__ __forceinline__ void hs_stage_rows(float* __restrict__ sdst, int sld, const float* __restrict__ gsrc, size_t gld, int rows,
+                                              int cpr) {
+  const int tid = threadIdx.x;
+  if (HS_T % cpr == 0) {
+    const int rpp = HS_T / cpr, r0 = tid / cpr, q = tid - r0 * cpr;
+    float* d = sdst + r0 * sld + q * 4;
+    const float* g = gsrc + (size_t)r0 * gld + q * 4;
+    for (int r = r0; r < rows; r += rpp, d += rpp * sld, g += (size_t)rpp * gld) hs_cp16(d, g);
+  } else {
+    for (int ch = tid; ch < rows * cpr; ch += HS_T) {
+      const int r = ch / cpr, q = ch - r * cpr;
+      hs_cp16(sdst + r * sld + q * 4, gsrc + (size_t)r * gld + q * 4);
+    }
+  }
 }
 
 // Per-segment batch statistics of column c from the tile partials part[tile][2][H] (tiles t0 .. t1-1 of 32 rows each),
@@ -432,15 +455,8 @@ __global__ void __launch_bounds__(HS_T) k_hs_fwd(const __grid_constant__ HsFwdAr
   const int s = hs_seg_of(p.sg, row0);
   const int t0 = p.sg.off[s] / HS_BM, t1 = p.sg.off[s + 1] / HS_BM;
   // stage the raw operands
-  const int cpr = K >> 2;   // 16-byte chunks per row
-  for (int ch = tid; ch < HS_BM * cpr; ch += HS_T) {
-    const int r = ch / cpr, q = ch - r * cpr;
-    hs_cp16(sA + r * (K + 4) + q * 4, p.Zin + (size_t)(row0 + r) * K + q * 4);
-  }
-  for (int ch = tid; ch < HS_BN * cpr; ch += HS_T) {
-    const int r = ch / cpr, q = ch - r * cpr;
-    hs_cp16(sB + r * (K + 4) + q * 4, p.W + (size_t)(n0 + r) * K + q * 4);
-  }
+  hs_stage_rows(sA, K + 4, p.Zin + (size_t)row0 * K, K, HS_BM, K >> 2);
+  hs_stage_rows(sB, K + 4, p.W + (size_t)n0 * K, K, HS_BN, K >> 2);
   hs_commit();
   // segment statistics of the input while the copies fly
   const bool eval = p.rmean != nullptr;
@@ -673,16 +689,9 @@ __global__ void __launch_bounds__(HS_T) k_hs_bwd(const __grid_constant__ HsBwdAr
   const int tid = threadIdx.x, n0 = blockIdx.x * HS_BN, tile = blockIdx.y, row0 = tile * HS_BM;
   const int s = hs_seg_of(p.sg, row0);
   const int t0 = p.sg.off[s] / HS_BM, t1 = p.sg.off[s + 1] / HS_BM;
-  const int cpr = K >> 2;
-  for (int ch = tid; ch < HS_BM * cpr; ch += HS_T) {
-    const int r = ch / cpr, q = ch - r * cpr;
-    hs_cp16(sA + r * (K + 4) + q * 4, p.dYin + (size_t)(row0 + r) * K + q * 4);
-    hs_cp16(sZ + r * (K + 4) + q * 4, p.Zin + (size_t)(row0 + r) * K + q * 4);
-  }
-  for (int ch = tid; ch < K * (HS_BN / 4); ch += HS_T) {
-    const int k = ch >> 4, q = ch & 15;
-    hs_cp16(sB + k * (HS_BN + 8) + q * 4, p.W + (size_t)k * N + n0 + q * 4);
-  }
+  hs_stage_rows(sA, K + 4, p.dYin + (size_t)row0 * K, K, HS_BM, K >> 2);
+  hs_stage_rows(sZ, K + 4, p.Zin + (size_t)row0 * K, K, HS_BM, K >> 2);
+  hs_stage_rows(sB, HS_BN + 8, p.W + n0, N, K, HS_BN / 4);
   hs_commit();
   const float inv_n = 1.0f / (float)((t1 - t0) * HS_BM);
   for (int c = tid; c < K; c += HS_T) {
