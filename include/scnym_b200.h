@@ -54,6 +54,17 @@ int scnb_csr_gather_rows2(const int64_t* indptr_A, const int32_t* indices_A, con
                           const float* data_B, const int64_t* rows_B, int nB, int augment_B, uint32_t stream_id_B,
                           const int32_t* b_indptr, int32_t* b_idx, float* b_val, const uint8_t* keep_mask,
                           const uint64_t* rng, float p_drop, int32_t* gene_cnt, void* stream);
+/* The other augmentation schemes of scnym/dataprep.py:730-754 (AUGMENTATION_SCHEMES) on rows [0, n) of one source, on the
+ * STORED entries only (every stage maps 0 to 0).  scheme: 1 log1p_drop (:721-729), 2 log1p_mask (GeneMasking :405-465),
+ * 3 log1p_poisson (PoissonSample :277-341), 4 log1p_poisson_drop (depth ~ U(0.1, 2), then InputDropout), 5 count_poisson
+ * (Poisson on raw counts, no normalisation).  Randomness: counter-based Philox streams of (rng[0], rng[1], stream_id), or
+ * injected draws (tests): keep_mask (dropout keeps / gene-masking keeps by batch nnz position), inj_poisson (sampled values by
+ * batch nnz position), inj_row_depth (per-row uniforms of the depth factor). */
+int scnb_csr_gather_rows_aug(const int64_t* indptr, const int32_t* indices, const float* data, const int64_t* rows,
+                             int64_t row0, int n, const int32_t* b_indptr, int32_t* b_idx, float* b_val, int scheme,
+                             int n_genes, float p_drop, float p_apply, const uint8_t* keep_mask, const float* inj_poisson,
+                             const float* inj_row_depth, const uint64_t* rng, uint32_t stream_id, int32_t* gene_cnt,
+                             void* stream);
 
 /* Step prologue in one launch: sampler hand-off (as scnb_fetch_step; tables may be NULL, then
  * l_rows/u_rows are read as staged), labels/domain ids of the sampled rows

@@ -59,6 +59,37 @@ def log1p_drop(x: torch.Tensor, keep: torch.Tensor, p_drop: float = 0.1,
     return torch.log1p(prop * counts_per_cell_after)
 
 
+def _lib_norm_log1p(e: torch.Tensor, counts_per_cell_after: float = 1e6) -> torch.Tensor:
+    """LibrarySizeNormalize(log1p=True) (dataprep.py:245-253)."""
+    size = torch.sum(e, dim=1).reshape(-1, 1)
+    return torch.log1p(e / size * counts_per_cell_after)
+
+
+def augment_rows(x: torch.Tensor, scheme: str, keep: Optional[torch.Tensor] = None, pois: Optional[torch.Tensor] = None,
+                 p_drop: float = 0.1) -> torch.Tensor:
+    """`AUGMENTATION_SCHEMES[scheme]` (dataprep.py:730-754) on dense rows with every random draw INJECTED.
+      log1p_drop          keep = Bernoulli keeps of InputDropout (:491: x * keep / (1-p))
+      log1p_mask          keep = 0 on the genes GeneMasking zeroes (:405-465: floor(G*p) genes per row without replacement, the
+                          whole batch untouched with probability 1 - p_apply => keep all ones); no rescaling
+      log1p_poisson       pois = the Poisson samples of PoissonSample (:277-341: rate = expm1(x) * depth, zero rates stay 0)
+      log1p_poisson_drop  pois (depth ~ U(0.1, 2) already inside the samples), then InputDropout keeps
+      count_poisson       pois on raw counts, no normalisation"""
+    if scheme == "log1p_drop":
+        return log1p_drop(x, keep, p_drop)
+    if scheme == "count_poisson":
+        return torch.where(x == 0.0, torch.zeros_like(x), pois.to(x.dtype))
+    e = torch.expm1(x)
+    if scheme == "log1p_mask":
+        e = e * keep.to(x.dtype)
+    elif scheme in ("log1p_poisson", "log1p_poisson_drop"):
+        e = torch.where(e == 0.0, torch.zeros_like(e), pois.to(x.dtype))     # PoissonSample casts back to float32 (:340)
+        if scheme == "log1p_poisson_drop":
+            e = e * (keep.to(x.dtype) / (1.0 - p_drop))
+    else:
+        raise ValueError(scheme)
+    return _lib_norm_log1p(e)
+
+
 # ----------------------------------------------------------------------------
 # Model  (reference: scnym/model.py:85-283 CellTypeCLF, :286-424 GradReverse/DANN)
 # ----------------------------------------------------------------------------
@@ -373,6 +404,7 @@ class StepConfig:
     decay_coef: float = 0.997
     p_in_drop: float = 0.1
     class_weight: Optional[torch.Tensor] = None
+    augment: str = "log1p_drop"          # AUGMENTATION_SCHEMES key (main.py:176)
 
 
 @dataclass
@@ -384,6 +416,8 @@ class StepRandomness:
     drop_keep_L: List[torch.Tensor]               # [L,H*]
     drop_keep_D: List[torch.Tensor] = field(default_factory=list)  # [L+U',H*]
     in_keep_U: Optional[torch.Tensor] = None      # [K,U,G] when augment_pseudolabels
+    pois_L: Optional[torch.Tensor] = None         # [L,G] injected Poisson samples (log1p_poisson* schemes)
+    pois_U: Optional[torch.Tensor] = None         # [K,U,G]
 
 
 def mixmatch_dan_losses(model: OracleModel, teacher: OracleModel, cfg: StepConfig,
@@ -410,7 +444,8 @@ def mixmatch_dan_losses(model: OracleModel, teacher: OracleModel, cfg: StepConfi
         for k in range(cfg.n_augmentations):
             xk = Ux.clone()
             if cfg.augment_pseudolabels:
-                xk = log1p_drop(xk, rnd.in_keep_U[k], cfg.p_in_drop)
+                xk = augment_rows(xk, cfg.augment, rnd.in_keep_U[k] if rnd.in_keep_U is not None else None,
+                                  rnd.pois_U[k] if rnd.pois_U is not None else None, cfg.p_in_drop)
             guesses.append(softmax(teacher.forward(xk, train=False)))
         qbar = torch.stack(guesses, 0).mean(0)
         conf, _ = qbar.max(dim=1)
@@ -419,7 +454,7 @@ def mixmatch_dan_losses(model: OracleModel, teacher: OracleModel, cfg: StepConfi
         q = q.to(Ly.dtype)
     out["pseudolabels"], out["confident"], out["confidence"] = q, confident, conf
     # (2) augment labelled -- losses.py:801 (replaces the caller's "input")
-    Lx_aug = log1p_drop(Lx, rnd.in_keep_L, cfg.p_in_drop)
+    Lx_aug = augment_rows(Lx, cfg.augment, rnd.in_keep_L, rnd.pois_L, cfg.p_in_drop)
     # (3) MixUp over [confident unlabelled ; labelled] -- losses.py:811-846
     cidx = torch.where(confident)[0]
     uidx = torch.where(~confident)[0]

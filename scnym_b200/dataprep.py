@@ -465,24 +465,63 @@ class SampleMixUp(object):
         return sample
 
 
+AUG_CODES = {"log1p_drop": 1, "log1p_mask": 2, "log1p_poisson": 3, "log1p_poisson_drop": 4, "count_poisson": 5}
+
+
+class SparseAugment(object):
+    """The other `AUGMENTATION_SCHEMES` of the reference (scnym/dataprep.py:730-754) as ONE device kernel over the stored
+    entries (`scnb_csr_gather_rows_aug`): every stage maps 0 to 0, so the support of a row is preserved.
+      log1p_mask          ExpMinusOne -> GeneMasking(p_drop=0.1, p_apply=0.5) -> LibrarySizeNormalize(log1p)   (:405-465)
+      log1p_poisson       ExpMinusOne -> PoissonSample() -> LibrarySizeNormalize(log1p)                        (:277-341)
+      log1p_poisson_drop  ExpMinusOne -> PoissonSample(depth=(0.1, 2.0)) -> InputDropout(0.1) -> LibrarySizeNormalize(log1p)
+      count_poisson       PoissonSample() on raw counts
+    Accepts a sample dict whose "input" is a CSRBatch or a dense CUDA tensor and replaces it, like the reference Compose.
+    Test hooks (class-level queues, popped per call): KEEP_INJECT (0/1 keeps, dense [B, G] or per nnz), POIS_INJECT
+    (sampled values, same layout), ROWU_INJECT (per-row uniforms of the depth factor)."""
+    KEEP_INJECT, POIS_INJECT, ROWU_INJECT = [], [], []
+    _seed = [0x5c9b200, 0]
+
+    def __init__(self, scheme: str, p_drop: float = 0.1, p_apply: float = 0.5) -> None:
+        if scheme not in AUG_CODES:
+            raise ValueError(f"unknown augmentation scheme {scheme!r}")
+        self.scheme, self.code, self.p_drop, self.p_apply = scheme, AUG_CODES[scheme], float(p_drop), float(p_apply)
+
+    def __call__(self, sample: dict) -> dict:
+        x = sample["input"]
+        dense = isinstance(x, torch.Tensor)
+        if dense:
+            _lib.require_cuda(x)
+            ds = _dense_as_csr(x.detach())
+        else:
+            ds = DeviceCSR(x.indptr.to(torch.int64), x.indices, x.data, x.n_cols, max(int(x.indices.numel() // max(x.n_rows, 1)), 1))
+        dev = ds.device
+        pop = lambda q, dt: (q.pop(0).to(device=dev, dtype=dt).contiguous().view(-1) if q else None)
+        keep = pop(SparseAugment.KEEP_INJECT, torch.uint8) if self.code in (1, 2, 4) else None
+        pois = pop(SparseAugment.POIS_INJECT, torch.float32) if self.code in (3, 4, 5) else None
+        rowu = pop(SparseAugment.ROWU_INJECT, torch.float32) if self.code == 4 else None
+        n, cap = ds.n_rows, max(int(ds.data.numel()), 1)
+        out = CSRBatch(torch.empty(n + 1, dtype=torch.int32, device=dev), torch.empty(cap, dtype=torch.int32, device=dev),
+                       torch.empty(cap, dtype=torch.float32, device=dev), n, ds.n_cols)
+        SparseAugment._seed[1] += 1
+        rng = torch.tensor(SparseAugment._seed, dtype=torch.int64, device=dev)
+        st = _stream()
+        call("scnb_csr_row_offsets", ptr(ds.indptr), None, 0, n, ptr(out.indptr), None, st)
+        call("scnb_csr_gather_rows_aug", ptr(ds.indptr), ptr(ds.indices), ptr(ds.data), None, 0, n, ptr(out.indptr), ptr(out.indices),
+             ptr(out.data), self.code, ds.n_cols, self.p_drop, self.p_apply, ptr(keep), ptr(pois), ptr(rowu), ptr(rng), 0, None, st)
+        sample["input"] = out.data[: n * ds.n_cols].view(n, ds.n_cols) if dense else out
+        return sample
+
+
 def identity(x):
     return x
 
 
-def _unsupported_scheme(name):
-    def f(sample):
-        raise NotImplementedError(
-            f"augmentation scheme {name!r} is outside the scnym_api configurations (api.py:87 fixes 'log1p_drop'); "
-            "SURVEY.md §2 row 16")
-    return f
-
-
 AUGMENTATION_SCHEMES = {
     "log1p_drop": Log1pDrop(p_drop=0.1),
-    "log1p_mask": _unsupported_scheme("log1p_mask"),
-    "log1p_poisson": _unsupported_scheme("log1p_poisson"),
-    "log1p_poisson_drop": _unsupported_scheme("log1p_poisson_drop"),
-    "count_poisson": _unsupported_scheme("count_poisson"),
+    "log1p_mask": SparseAugment("log1p_mask", p_drop=0.1, p_apply=0.5),
+    "log1p_poisson": SparseAugment("log1p_poisson"),
+    "log1p_poisson_drop": SparseAugment("log1p_poisson_drop", p_drop=0.1),
+    "count_poisson": SparseAugment("count_poisson"),
     "None": identity,
     "none": identity,
     None: identity,

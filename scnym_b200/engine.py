@@ -46,6 +46,8 @@ class EngineConfig:
     mean_teacher: bool = False
     decay_coef: float = 0.997
     p_in_drop: float = 0.1
+    augment: str = "log1p_drop"      # AUGMENTATION_SCHEMES key (dataprep.py:730-754): log1p_drop | log1p_mask | log1p_poisson | log1p_poisson_drop
+    p_mask_apply: float = 0.5        # GeneMasking p_apply (log1p_mask)
     # DANLoss (losses.py:1043-1105)
     use_dan: bool = True
     dan_use_conf_pseudolabels: bool = False
@@ -278,6 +280,14 @@ class TrainEngine(object):
             self.gene_cnt, self.c_ptr, self.c_cursor = i32(self.G), i32(self.G + 1), i32(self.G)
             self.c_ent = i32(cap, 2)
         # injected randomness (tests); None -> Philox in-kernel
+        from .dataprep import AUG_CODES
+        if cfg.augment not in AUG_CODES or cfg.augment == "count_poisson":
+            raise ValueError(f"augmentation scheme {cfg.augment!r} is not a log1p(CPM) scheme the MixMatch step can use")
+        self.aug_code = AUG_CODES[cfg.augment]
+        self.inj_pois_L = None        # fp32 [cap] injected Poisson samples at batch nnz positions (tests)
+        self.inj_rowu_L = None        # fp32 [L] injected per-row depth uniforms (tests)
+        self.inj_pois_U = None        # list of K fp32 [U*maxnnz] (augmented teacher views)
+        self.inj_rowu_U = None
         self.inj_in_keep_L = None     # uint8 [cap] aligned with batch nnz positions
         self.inj_in_keep_U = None     # list of K uint8 [U*maxnnz]
         self.inj_hidden_keep = None   # list over applications of uint8 [Rmax, H_a]
@@ -521,10 +531,17 @@ class TrainEngine(object):
             self._ev_prep.record(main)
         # -- batch CSR [U_raw ; L_aug] (+ per-gene histogram), one launch (issued before the plan: the graph releases
         #    the children of a node one after the other, and the gather is the one on the critical chain)
-        call("scnb_csr_gather_rows2", ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data), ptr(self.u_rows), U, 0, 0,
-             ptr(self.lab.indptr), ptr(self.lab.indices), ptr(self.lab.data), ptr(self.l_rows), L, 1, SID_IN_L,
-             ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), ptr(self.inj_in_keep_L), rng, c.p_in_drop,
-             self._gene_cnt_ptr(), st)
+        if self.aug_code == 1:
+            call("scnb_csr_gather_rows2", ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data), ptr(self.u_rows), U, 0, 0,
+                 ptr(self.lab.indptr), ptr(self.lab.indices), ptr(self.lab.data), ptr(self.l_rows), L, 1, SID_IN_L,
+                 ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), ptr(self.inj_in_keep_L), rng, c.p_in_drop,
+                 self._gene_cnt_ptr(), st)
+        else:   # the other schemes of dataprep.py:730-754: raw unlabeled rows, then the labeled rows through the scheme
+            call("scnb_csr_gather_rows", ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data), ptr(self.u_rows), 0, U,
+                 ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), 0, 0, 0, None, None, 0, 0.0, self._gene_cnt_ptr(), st)
+            call("scnb_csr_gather_rows_aug", ptr(self.lab.indptr), ptr(self.lab.indices), ptr(self.lab.data), ptr(self.l_rows), 0, L,
+                 ptr(self.b_indptr[U:]), ptr(self.b_idx), ptr(self.b_val), self.aug_code, self.G, c.p_in_drop, c.p_mask_apply,
+                 ptr(self.inj_in_keep_L), ptr(self.inj_pois_L), ptr(self.inj_rowu_L), rng, SID_IN_L, self._gene_cnt_ptr(), st)
         if teacher_async:
             sP = self._side[3]
             sP.wait_event(self._ev_prep)
@@ -666,9 +683,16 @@ class TrainEngine(object):
                 if c.augment_pseudolabels:
                     call("scnb_csr_row_offsets", ptr(self.unl.indptr), ptr(self.u_rows), 0, U, ptr(self.tb_indptr), None, st)
                     km = self.inj_in_keep_U[k] if self.inj_in_keep_U is not None else None
-                    call("scnb_csr_gather_rows", ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data),
-                         ptr(self.u_rows), 0, U, ptr(self.tb_indptr), ptr(self.tb_idx), ptr(self.tb_val), 1, 0, U, ptr(km), rng,
-                         SID_IN_U + k, c.p_in_drop, None, st)
+                    if self.aug_code == 1:
+                        call("scnb_csr_gather_rows", ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data),
+                             ptr(self.u_rows), 0, U, ptr(self.tb_indptr), ptr(self.tb_idx), ptr(self.tb_val), 1, 0, U, ptr(km), rng,
+                             SID_IN_U + k, c.p_in_drop, None, st)
+                    else:
+                        pk = self.inj_pois_U[k] if self.inj_pois_U is not None else None
+                        ru = self.inj_rowu_U[k] if self.inj_rowu_U is not None else None
+                        call("scnb_csr_gather_rows_aug", ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data),
+                             ptr(self.u_rows), 0, U, ptr(self.tb_indptr), ptr(self.tb_idx), ptr(self.tb_val), self.aug_code, self.G,
+                             c.p_in_drop, c.p_mask_apply, ptr(km), ptr(pk), ptr(ru), rng, SID_IN_U + k, None, st)
                     ip, ix, vv = self.tb_indptr, self.tb_idx, self.tb_val
                 else:
                     ip, ix, vv = self.b_indptr, self.b_idx, self.b_val
@@ -1101,7 +1125,8 @@ class TrainEngine(object):
         """Run one training step on whatever is staged in the input buffers."""
         if self.mode == "mixmatch" and self.cfg.mean_teacher and self.teacher_bn is None:
             self.teacher_bn = [(b["bn"].running_mean.clone(), b["bn"].running_var.clone()) for b in self._blk]
-        injected = any(x is not None for x in (self.inj_in_keep_L, self.inj_in_keep_U, self.inj_hidden_keep))
+        injected = any(x is not None for x in (self.inj_in_keep_L, self.inj_in_keep_U, self.inj_hidden_keep, self.inj_pois_L,
+                                               self.inj_rowu_L, self.inj_pois_U, self.inj_rowu_U))
         self._sync_planes()
         if self.cfg.use_cuda_graph and not injected:
             key = (self.unsup_weight, self.dan_weight)

@@ -330,13 +330,15 @@ class SemiSupervisedTrainer(Trainer):
         if not (self._fusable_base() and isinstance(mm, MixMatchLoss) and isinstance(ul, DeviceLoader)
                 and isinstance(mm.unsup_criterion, nn.MSELoss) and ok_sup and (dan is None or isinstance(dan, DANLoss))
                 and (dan is None or _criterion_class_weight(dan.dan_criterion) == (True, None))
-                and getattr(mm.augment, "p_drop", None) is not None and mm.teacher_eval and mm.teacher_bn_running_stats is None):
+                and getattr(mm.augment, "p_drop", None) is not None and getattr(mm.augment, "scheme", "log1p_drop") != "count_poisson"
+                and mm.teacher_eval and mm.teacher_bn_running_stats is None):
             return None
         dl = self.dataloaders["train"]
         ds, uds = dl.dataset, ul.dataset
         cfg = self._engine_cfg(n_augmentations=mm.n_augmentations, T=mm.T, augment_pseudolabels=mm.augment_pseudolabels,
                                pseudolabel_min_confidence=mm.pseudolabel_min_confidence, mixup_alpha=mm.mixup_op.alpha,
                                mean_teacher=mm.mean_teacher, decay_coef=mm.decay_coef, p_in_drop=mm.augment.p_drop,
+                               augment=getattr(mm.augment, "scheme", "log1p_drop"), p_mask_apply=getattr(mm.augment, "p_apply", 0.5),
                                use_dan=dan is not None,
                                dan_use_conf_pseudolabels=bool(dan.use_conf_pseudolabels) if dan is not None else False,
                                dan_scale_loss_pseudoconf=bool(dan.scale_loss_pseudoconf) if dan is not None else False,

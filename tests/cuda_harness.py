@@ -44,7 +44,8 @@ def build_engine(d, device="cuda", first_layer=None, w1_update=None, multi_strea
                        mean_teacher=bool(d["meta_mean_teacher"]), decay_coef=0.997, use_dan=bool(d["meta_use_dan"]),
                        dan_use_conf_pseudolabels=bool(d["meta_dan_conf"]), dan_scale_loss_pseudoconf=bool(d["meta_dan_scale"]),
                        optimizer=str(d["meta_opt"]), lr=float(d["meta_lr"]), weight_decay=float(d["meta_wd"]), class_weight=cw,
-                       use_cuda_graph=False, keep_w1_grad=True)
+                       use_cuda_graph=False, keep_w1_grad=True,
+                       augment=str(d["meta_augment"]) if "meta_augment" in d.files else "log1p_drop")
     if first_layer is not None:
         cfg.first_layer = first_layer
     if w1_update is not None:
@@ -60,12 +61,15 @@ def build_engine(d, device="cuda", first_layer=None, w1_update=None, multi_strea
 
 
 def _row_keep(indptr, indices, rows, dense_keep):
-    """Per-nnz keep bytes (batch order) from a dense [rows, G] keep mask."""
+    """Per-nnz values (batch order) from a dense [rows, G] array (keep masks come back as uint8, anything else as is)."""
     out = []
     for i, r in enumerate(rows):
         s, e = indptr[r], indptr[r + 1]
         out.append(dense_keep[i, indices[s:e]])
-    return np.concatenate(out).astype(np.uint8) if out else np.zeros(0, np.uint8)
+    if not out:
+        return np.zeros(0, np.uint8)
+    v = np.concatenate(out)
+    return v.astype(np.uint8) if dense_keep.dtype == np.uint8 or dense_keep.dtype == bool else v
 
 
 def inject_step(eng, d, s):
@@ -80,6 +84,12 @@ def inject_step(eng, d, s):
     full = np.ones(eng.cap, dtype=np.uint8)
     full[u_len:u_len + keepL.size] = keepL
     eng.inj_in_keep_L = torch.from_numpy(full).to(dev)
+    if (pre + "pois_L") in d.files:    # injected Poisson samples of the labelled rows, at absolute batch-nnz positions
+        pl = _row_keep(d["lab_indptr"], d["lab_indices"], lrow, d[pre + "pois_L"]).astype(np.float32)
+        fullp = np.zeros(eng.cap, dtype=np.float32)
+        fullp[u_len:u_len + pl.size] = pl
+        eng.inj_pois_L = torch.from_numpy(fullp).to(dev)
+        eng.inj_rowu_L = torch.zeros(eng.L, dtype=torch.float32, device=dev)   # unused once the samples are injected
     if (pre + "in_keep_U") in d.files:
         ku = d[pre + "in_keep_U"]
         eng.inj_in_keep_U = []
@@ -125,7 +135,7 @@ def collect(eng):
 
 def oracle_case(*, G, L, U, C, H0, H, n_layers, K=1, T=0.5, aug_pl=False, tau=0.0, D_given=0, opt_name="adam", lr=1e-3,
                 wd=1e-4, unsup_w=1.0, dan_w=0.1, n_steps=1, mean_teacher=False, dan_conf=False, dan_scale=False,
-                density=0.05, seed=0, use_dan=True, n_cells=None):
+                density=0.05, seed=0, use_dan=True, n_cells=None, augment="log1p_drop"):
     """Build a case in the golden format whose expected values come from the ORACLE (for sizes
     the golden fixtures do not cover)."""
     torch.manual_seed(seed)
@@ -138,7 +148,7 @@ def oracle_case(*, G, L, U, C, H0, H, n_layers, K=1, T=0.5, aug_pl=False, tau=0.
              meta_aug_pl=int(aug_pl), meta_tau=tau, meta_D=n_domains, meta_D_given=int(bool(D_given)), meta_opt=opt_name,
              meta_lr=lr, meta_wd=wd, meta_unsup_w=unsup_w, meta_dan_w=dan_w, meta_n_steps=n_steps,
              meta_mean_teacher=int(mean_teacher), meta_dan_conf=int(dan_conf), meta_dan_scale=int(dan_scale),
-             meta_use_dan=int(use_dan), meta_unsup_criterion="mse", lab_indptr=lp, lab_indices=li, lab_data=ld, lab_y=ly,
+             meta_use_dan=int(use_dan), meta_unsup_criterion="mse", meta_augment=augment, lab_indptr=lp, lab_indices=li, lab_data=ld, lab_y=ly,
              unl_indptr=up, unl_indices=ui, unl_data=ud)
     if D_given:
         d["lab_dom"] = rng.integers(0, max(D_given // 2, 1), size=n_cells).astype(np.int64)
@@ -171,6 +181,15 @@ def oracle_case(*, G, L, U, C, H0, H, n_layers, K=1, T=0.5, aug_pl=False, tau=0.
         d[pre + "lrow"] = rng.choice(n_cells, size=L, replace=False)
         d[pre + "urow"] = rng.choice(n_cells, size=U, replace=False)
         d[pre + "in_keep_L"] = (rng.random((L, G)) < 0.9).astype(np.uint8)
+        if augment == "log1p_mask":      # GeneMasking: floor(G * 0.1) genes per row, without replacement (applied batch)
+            km = np.ones((L, G), dtype=np.uint8)
+            for r in range(L):
+                km[r, rng.choice(G, size=int(np.floor(G * 0.1)), replace=False)] = 0
+            d[pre + "in_keep_L"] = km
+        if augment in ("log1p_poisson", "log1p_poisson_drop"):
+            Lx0 = O.csr_to_dense(lp, li, ld, G, d[pre + "lrow"]).numpy().astype(np.float64)
+            depth = rng.random(L) * (0.1 - 2.0) + 2.0 if augment == "log1p_poisson_drop" else np.ones(L)
+            d[pre + "pois_L"] = rng.poisson(np.expm1(Lx0) * depth[:, None]).astype(np.float32)
         if aug_pl:
             d[pre + "in_keep_U"] = (rng.random((K, U, G)) < 0.9).astype(np.uint8)
         d[pre + "perm_keys"] = rng.random(U + L).astype(np.float32)

@@ -59,7 +59,8 @@ def step_config(d):
                         dan_weight=float(d["meta_dan_w"]),
                         dan_use_conf_pseudolabels=bool(d["meta_dan_conf"]),
                         dan_scale_loss_pseudoconf=bool(d["meta_dan_scale"]),
-                        mean_teacher=bool(d["meta_mean_teacher"]), class_weight=cw)
+                        mean_teacher=bool(d["meta_mean_teacher"]), class_weight=cw,
+                        augment=str(d["meta_augment"]) if "meta_augment" in d.files else "log1p_drop")
 
 
 def optim_config(d):
@@ -89,7 +90,8 @@ def step_inputs(d, s):
                            drop_keep_U=[t(f"keep_U{i}") for i in range(na)],
                            drop_keep_L=[t(f"keep_L{i}") for i in range(na)],
                            drop_keep_D=[t(f"keep_D{i}") for i in range(na)],
-                           in_keep_U=t("in_keep_U") if (pre + "in_keep_U") in d.files else None)
+                           in_keep_U=t("in_keep_U") if (pre + "in_keep_U") in d.files else None,
+                           pois_L=t("pois_L") if (pre + "pois_L") in d.files else None)
     return dict(Lx=Lx, Ly=Ly, Ux=Ux, Ldom=Ldom, Udom=Udom, rnd=rnd, lrow=lrow, urow=urow)
 
 
