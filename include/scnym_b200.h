@@ -259,6 +259,9 @@ int scnb_hs_bwd(const float* dYin, const float* Zin, const float* stats_in, cons
                 float* dgamma, float* dbeta, float* dZout, const float* W, const float* Zprev, const float* Aprev,
                 const float* stats_prev, float p_drop_prev, float* dYout, float* part_out, int K, int N, int R, int n_seg,
                 const int32_t* seg_off_host, void* stream);
+/* dW[M, N] += dZ[R, M]^T A[R, N], db[M] += column sums of dZ (db may be NULL): weight / bias gradient of a hidden Linear
+ *  in one launch; accumulates with atomics into the zeroed gradient arena; M, N % 64 == 0 */
+int scnb_hs_dw(const float* dZ, int M, const float* A, int N, int R, float* dW, float* db, void* stream);
 /* dZ of application 0 from dY (feeds the MixUp adjoint and the first-layer weight gradient) */
 int scnb_hs_bwd_in(const float* dY, const float* Z, int H, int R, int n_seg, const int32_t* seg_off_host, const float* stats,
                    const float* part, const float* gamma, float* dgamma, float* dbeta, float* dZ, void* stream);

@@ -838,3 +838,89 @@ extern "C" int scnb_hs_bwd_in(const float* dY, const float* Z, int H, int R, int
   SCNB_CHECK_LAUNCH("hs_bwd_in");
   return SCNB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// hs_dw: weight and bias gradient of a hidden Linear from the materialised dZ [R, M] (M = out features) and its input
+// activation A [R, N]:  dW[M, N] += dZ^T A,  db[M] += column sums of dZ   (dW = dz^T a, db = sum_n dz).
+// One CTA = a 64 x 64 tile of dW over a chunk of 128 rows (grid = (N/64, M/64, ceil(R/128))); partial products are added
+// to dW with atomics (the gradient arena is zeroed at the start of the step).  16 warps as 4 x 4 sub-tiles of 16 x 16,
+// 3xTF32.  Replaces a split-K GEMM launch plus a column-sum launch per layer on the step's weight-gradient branch.
+// ---------------------------------------------------------------------------------------------------------------------
+#define HS_DW_ROWS 128
+__global__ void __launch_bounds__(HS_T) k_hs_dw(const float* __restrict__ dZ, int M, const float* __restrict__ A, int N, int R,
+                                                float* __restrict__ dW, float* __restrict__ db) {
+  PDL_ENTRY();
+  extern __shared__ __align__(16) float hs_smem[];
+  constexpr int SP = HS_BN + 8;
+  float* sD = hs_smem;                      // [128][72]  dZ[rows][m0 .. m0+63]
+  float* sA = sD + HS_DW_ROWS * SP;         // [128][72]  A[rows][n0 .. n0+63]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3, wm = warp >> 2, wn = warp & 3;
+  const int n0 = blockIdx.x * HS_BN, m0 = blockIdx.y * HS_BN, r0 = blockIdx.z * HS_DW_ROWS;
+  const int rows = min(HS_DW_ROWS, R - r0);
+  // 128 rows x 16 chunks per panel = 2048 chunks each, 4 per thread; rows beyond R are zero-filled
+  for (int ch = tid; ch < HS_DW_ROWS * 16; ch += HS_T) {
+    const int r = ch >> 4, q = ch & 15;
+    if (r < rows) {
+      hs_cp16(sD + r * SP + q * 4, dZ + (size_t)(r0 + r) * M + m0 + q * 4);
+      hs_cp16(sA + r * SP + q * 4, A + (size_t)(r0 + r) * N + n0 + q * 4);
+    } else {
+      *reinterpret_cast<float4*>(sD + r * SP + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(sA + r * SP + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  hs_commit();
+  hs_wait_all();
+  __syncthreads();
+  float acc[2][4];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
+#pragma unroll 4
+  for (int kk = 0; kk < HS_DW_ROWS; kk += 8) {
+    uint32_t ah[4], al[4], bh[2][2], bl[2][2];
+    const float* pa = sD + (kk + t) * SP + wm * 16 + g;
+    hs_split(pa[0], ah[0], al[0]);
+    hs_split(pa[8], ah[1], al[1]);
+    hs_split(pa[4 * SP], ah[2], al[2]);
+    hs_split(pa[4 * SP + 8], ah[3], al[3]);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float* pb = sA + (kk + t) * SP + wn * 16 + 8 * j + g;
+      hs_split(pb[0], bh[j][0], bl[j][0]);
+      hs_split(pb[4 * SP], bh[j][1], bl[j][1]);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      hs_mma(acc[j], al, bh[j]);
+      hs_mma(acc[j], ah, bl[j]);
+      hs_mma(acc[j], ah, bh[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int m = m0 + wm * 16 + g, n = n0 + wn * 16 + 8 * j + 2 * t;
+    atomicAdd(dW + (size_t)m * N + n, acc[j][0]);
+    atomicAdd(dW + (size_t)m * N + n + 1, acc[j][1]);
+    atomicAdd(dW + (size_t)(m + 8) * N + n, acc[j][2]);
+    atomicAdd(dW + (size_t)(m + 8) * N + n + 1, acc[j][3]);
+  }
+  if (db && blockIdx.x == 0 && tid < HS_BN) {   // bias gradient: one column-tile row of CTAs adds its rows' column sums
+    float s = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < HS_DW_ROWS; ++r) s += sD[r * SP + tid];
+    atomicAdd(db + m0 + tid, s);
+  }
+}
+
+extern "C" int scnb_hs_dw(const float* dZ, int M, const float* A, int N, int R, float* dW, float* db, void* stream) {
+  SCNB_CHECK_ARG(dZ && A && dW && M > 0 && N > 0 && R > 0, "hs_dw: bad arguments");
+  SCNB_CHECK_ARG(M % HS_BN == 0 && N % HS_BN == 0 && (((uintptr_t)dZ | (uintptr_t)A) % 16 == 0), "hs_dw: needs M, N %% 64 == 0 and 16-byte aligned operands");
+  const size_t smem = (size_t)2 * HS_DW_ROWS * (HS_BN + 8) * sizeof(float);
+  int rc = hs_set_smem(k_hs_dw, smem, "hs_dw");
+  if (rc != SCNB_OK) return rc;
+  scnb_launch_pdl(k_hs_dw, dim3(N / HS_BN, M / HS_BN, scnb_cdiv(R, HS_DW_ROWS)), dim3(HS_T), smem, (cudaStream_t)stream, dZ, M, A, N, R, dW, db);
+  SCNB_CHECK_LAUNCH("hs_dw");
+  return SCNB_OK;
+}

@@ -625,9 +625,12 @@ class TrainEngine(object):
             call("scnb_sgemm", 1, 0, self.D, Hh, self.Rd, ptr(self.ddlog), self.D, ptr(self.Hd), Hh, self.Gp(d1 + ".weight"), Hh,
                  1.0, 1.0, None, 0, None, sd)
             call("scnb_colsum", ptr(self.ddlog), self.Rd, self.D, self.D, self.Gp(d1 + ".bias"), 1, sd)
-            call("scnb_sgemm", 1, 0, Hh, Hh, self.Rd, ptr(self.dHd), Hh, ptr(Ae), Hh, self.Gp(d0 + ".weight"), Hh, 1.0, 1.0, None,
-                 0, None, sd)
-            call("scnb_colsum", ptr(self.dHd), self.Rd, Hh, Hh, self.Gp(d0 + ".bias"), 1, sd)
+            if self.hs_fused:
+                call("scnb_hs_dw", ptr(self.dHd), Hh, ptr(Ae), Hh, self.Rd, self.Gp(d0 + ".weight"), self.Gp(d0 + ".bias"), sd)
+            else:
+                call("scnb_sgemm", 1, 0, Hh, Hh, self.Rd, ptr(self.dHd), Hh, ptr(Ae), Hh, self.Gp(d0 + ".weight"), Hh, 1.0, 1.0, None,
+                     0, None, sd)
+                call("scnb_colsum", ptr(self.dHd), self.Rd, Hh, Hh, self.Gp(d0 + ".bias"), 1, sd)
         # -- classifier, losses + dLogits (losses.py:896-923, 1224-1243; trainer.py:651-656) and dA of the classifier
         if teacher_async:
             main.wait_event(self._ev_teacher)
@@ -863,9 +866,7 @@ class TrainEngine(object):
             if sW is not main:
                 ev.record(main)
                 sW.wait_event(ev)
-            call("scnb_sgemm", 1, 0, k, n, R, ptr(self.dZs[a]), k, ptr(self.As[a - 1]), n, self.Gp(blk[a]["W"]), n, 1.0, 1.0, None, 0,
-                 None, sw)
-            call("scnb_colsum", ptr(self.dZs[a]), R, k, k, self.Gp(blk[a]["b"]), 1, sw)
+            call("scnb_hs_dw", ptr(self.dZs[a]), k, ptr(self.As[a - 1]), n, R, self.Gp(blk[a]["W"]), self.Gp(blk[a]["b"]), sw)
         call("scnb_hs_bwd_in", ptr(self.dYs[0]), ptr(self.Zs[0]), self.widths[0], R, self.n_seg, seg, ptr(self.stats[0]), ptr(self.pb[0]),
              self.P(blk[0]["g"]), self.Gp(blk[0]["g"]), self.Gp(blk[0]["beta"]), ptr(self.dZs[0]), st)
         return self.dZs[0]
@@ -1045,6 +1046,21 @@ class TrainEngine(object):
 
     # ------------------------------------------------------------------------------------
     def _launch(self):
+        if self.cfg.multi_stream and os.environ.get("SCNB_MAIN_PRIORITY", "1") != "0":
+            # the critical chain runs on a high-priority stream: when its next kernel and a side branch's (weight gradients,
+            # running statistics, teacher) both have CTAs pending, the chain's are placed first (the side streams keep the
+            # default, lowest priority); captured graphs keep the priority as a kernel-node attribute
+            if getattr(self, "_hi", None) is None:
+                self._hi = torch.cuda.Stream(device=self.dev, priority=-1)
+            cur = torch.cuda.current_stream()
+            self._hi.wait_stream(cur)
+            with torch.cuda.stream(self._hi):
+                self._launch_inner()
+            cur.wait_stream(self._hi)
+        else:
+            self._launch_inner()
+
+    def _launch_inner(self):
         if self.mode == "mixmatch":
             self._launch_mixmatch()
         else:
