@@ -258,13 +258,23 @@ int scnb_hs_bwd_act(const float* dA, const float* Z, const float* A, int H, int 
 int scnb_hs_bwd(const float* dYin, const float* Zin, const float* stats_in, const float* part_in, const float* gamma,
                 float* dgamma, float* dbeta, float* dZout, const float* W, const float* Zprev, const float* Aprev,
                 const float* stats_prev, float p_drop_prev, float* dYout, float* part_out, int K, int N, int R, int n_seg,
-                const int32_t* seg_off_host, void* stream);
+                const int32_t* seg_off_host, const float* bmean_in /* data parallel: global means instead of part_in */, void* stream);
 /* dW[M, N] += dZ[R, M]^T A[R, N], db[M] += column sums of dZ (db may be NULL): weight / bias gradient of a hidden Linear
  *  in one launch; accumulates with atomics into the zeroed gradient arena; M, N % 64 == 0 */
 int scnb_hs_dw(const float* dZ, int M, const float* A, int N, int R, float* dW, float* db, void* stream);
 /* dZ of application 0 from dY (feeds the MixUp adjoint and the first-layer weight gradient) */
 int scnb_hs_bwd_in(const float* dY, const float* Z, int H, int R, int n_seg, const int32_t* seg_off_host, const float* stats,
-                   const float* part, const float* gamma, float* dgamma, float* dbeta, float* dZ, void* stream);
+                   const float* part, const float* gamma, float* dgamma, float* dbeta, float* dZ, const float* bmean_in,
+                   float* db /* NULL or [H]: += column sums of dZ (bias gradient of the Linear in front) */, void* stream);
+/* Data parallel (one process per GPU; equivalence target: the reference step on the CONCATENATED global batch): exchange of
+ * the per-segment statistics between a producer of tile partials and their consumer, through peer memory (CUDA IPC buffers
+ * over NVLink / NVSwitch, `peer_bufs[world]` as scnb_bn_act_fwd_peer).  kind 0 (forward): out = stats[n_seg][3][H] (global
+ * mean, biased var, invstd), cnt_out[n_seg] = global rows; kind 1 (backward): out = bmean[n_seg][2][H] (global means of dY and
+ * dY*zhat), and this rank's LOCAL sums are added to dgamma / dbeta.  Consumers then take part_in = NULL. */
+int scnb_hs_peer_bytes(int H_max, int n_seg, int n_slots, int world);   /* bytes of the exchange region */
+int scnb_hs_xchg(int kind, const float* part, int H, int R, int n_seg, const int32_t* seg_off_host, const uint64_t* peer_bufs,
+                 int rank, int world, int slot, int n_slots, int H_max, const int64_t* epoch, long long buf_bytes, float* out,
+                 float* cnt_out, float* dgamma, float* dbeta, void* stream);
 
 /* ---- K6: MixMatchLoss._generate_labels + sharpen_labels (scnym/losses.py:660-737, 529-573) and
  *      the confident/unconfident split, MixUp permutation and DAN row selection

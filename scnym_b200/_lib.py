@@ -59,9 +59,11 @@ SIGNATURES = {
     "scnb_hs_act": [P, P, I, I, I, P, P, P, P, P, P, P, U32, F, P],
     "scnb_hs_fwd": [P, P, P, P, P, P, P, P, U32, F, P, P, P, P, I, I, I, I, P, P, P, P],
     "scnb_hs_bwd_act": [P, P, P, I, I, I, P, P, F, P, P, P],
-    "scnb_hs_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, F, P, P, I, I, I, I, P, P],
+    "scnb_hs_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, F, P, P, I, I, I, I, P, P, P],
     "scnb_hs_dw": [P, I, P, I, I, P, P, P],
-    "scnb_hs_bwd_in": [P, P, I, I, I, P, P, P, P, P, P, P, P],
+    "scnb_hs_bwd_in": [P, P, I, I, I, P, P, P, P, P, P, P, P, P, P],
+    "scnb_hs_peer_bytes": [I, I, I, I],
+    "scnb_hs_xchg": [I, P, I, I, I, P, P, I, I, I, I, I, P, L, P, P, P, P, P],
     "scnb_unmix_rows": [P, I, P, P, I, P, P],
     "scnb_unmix_rows_planes": [P, I, P, P, I, P, P, P, P],
     "scnb_pseudolabel": [P, I, I, I, F, I, F, P, P, P, P, P, I, P],

@@ -271,15 +271,20 @@ __global__ void __launch_bounds__(HS_TE) k_hs_act(const float* __restrict__ Z, f
   const int row0 = tile * HS_BM, s = hs_seg_of(sg, row0);
   const int t0 = sg.off[s] / HS_BM, t1 = sg.off[s + 1] / HS_BM;
   if (tid < HS_BN) {
-    float mean, var;
-    hs_combine_stats(part, H, c0 + tid, t0, t1, mean, var);
-    const float inv = 1.0f / sqrtf(var + BN_EPS);
-    sMean[tid] = mean;
-    sInv[tid] = inv;
-    if (tile == t0) {
-      stats[((size_t)s * 3 + 0) * H + c0 + tid] = mean;
-      stats[((size_t)s * 3 + 1) * H + c0 + tid] = var;
-      stats[((size_t)s * 3 + 2) * H + c0 + tid] = inv;
+    if (!part) {   // data parallel: the exchange kernel has written the GLOBAL segment statistics
+      sMean[tid] = stats[((size_t)s * 3 + 0) * H + c0 + tid];
+      sInv[tid] = stats[((size_t)s * 3 + 2) * H + c0 + tid];
+    } else {
+      float mean, var;
+      hs_combine_stats(part, H, c0 + tid, t0, t1, mean, var);
+      const float inv = 1.0f / sqrtf(var + BN_EPS);
+      sMean[tid] = mean;
+      sInv[tid] = inv;
+      if (tile == t0) {
+        stats[((size_t)s * 3 + 0) * H + c0 + tid] = mean;
+        stats[((size_t)s * 3 + 1) * H + c0 + tid] = var;
+        stats[((size_t)s * 3 + 2) * H + c0 + tid] = inv;
+      }
     }
   }
   __syncthreads();
@@ -310,7 +315,7 @@ __global__ void __launch_bounds__(HS_TE) k_hs_act(const float* __restrict__ Z, f
 extern "C" int scnb_hs_act(const float* Z, float* A, int H, int R, int n_seg, const int32_t* seg_off_host, const float* part,
                            const float* gamma, const float* beta, float* stats, const uint8_t* keep_mask, const uint64_t* rng,
                            uint32_t stream_id, float p_drop, void* stream) {
-  SCNB_CHECK_ARG(Z && A && part && gamma && beta && stats && seg_off_host, "hs_act: null argument");
+  SCNB_CHECK_ARG(Z && A && gamma && beta && stats && seg_off_host, "hs_act: null argument");
   SCNB_CHECK_ARG(H % HS_BN == 0 && R % HS_BM == 0 && n_seg >= 1 && n_seg <= HS_MAXSEG, "hs_act: bad shape");
   SCNB_CHECK_ARG(!(p_drop > 0.f) || keep_mask || rng, "hs_act: dropout needs keep_mask or rng state");
   HsSeg sg;
@@ -461,19 +466,25 @@ __global__ void __launch_bounds__(HS_T) k_hs_fwd(const __grid_constant__ HsFwdAr
   // segment statistics of the input while the copies fly
   const bool eval = p.rmean != nullptr;
   for (int c = tid; c < K; c += HS_T) {
-    float mean, var;
+    float mean, var, inv;
+    const bool given = !eval && !p.part_in;   // data parallel: GLOBAL statistics already in stats_in
     if (eval) {
       mean = p.rmean[c];
       var = p.rvar[c];
+      inv = 1.0f / sqrtf(var + BN_EPS);
+    } else if (given) {
+      mean = p.stats_in[((size_t)s * 3 + 0) * K + c];
+      var = 0.f;
+      inv = p.stats_in[((size_t)s * 3 + 2) * K + c];
     } else {
       hs_combine_stats(p.part_in, K, c, t0, t1, mean, var);
+      inv = 1.0f / sqrtf(var + BN_EPS);
     }
-    const float inv = 1.0f / sqrtf(var + BN_EPS);
     sMean[c] = mean;
     sInv[c] = inv;
     sGam[c] = p.gamma[c];
     sBet[c] = p.beta[c];
-    if (!eval && blockIdx.x == 0 && tile == t0) {
+    if (!eval && !given && blockIdx.x == 0 && tile == t0) {
       p.stats_in[((size_t)s * 3 + 0) * K + c] = mean;
       p.stats_in[((size_t)s * 3 + 1) * K + c] = var;
       p.stats_in[((size_t)s * 3 + 2) * K + c] = inv;
@@ -588,8 +599,9 @@ extern "C" int scnb_hs_fwd(const float* Zin, float* Aout, const float* part_in, 
                            const float* W, const float* bias, float* Zout, float* part_out, int K, int N, int R, int n_seg,
                            const int32_t* seg_off_host, const float* running_mean, const float* running_var, void* stream) {
   SCNB_CHECK_ARG(Zin && gamma && beta && W && Zout, "hs_fwd: null argument");
-  SCNB_CHECK_ARG((running_mean && running_var && p_drop == 0.f) || (!running_mean && part_in && stats_in && Aout && part_out),
-                 "hs_fwd: train mode needs part_in / stats_in / Aout / part_out, eval mode running statistics and no dropout");
+  SCNB_CHECK_ARG((running_mean && running_var && p_drop == 0.f) || (!running_mean && stats_in && Aout && part_out),
+                 "hs_fwd: train mode needs stats_in / Aout / part_out (+ part_in unless the statistics are given), eval mode running "
+                 "statistics and no dropout");
   SCNB_CHECK_ARG(K % 32 == 0 && K >= 32 && K <= 512 && N % HS_BN == 0 && R % HS_BM == 0, "hs_fwd: needs K %% 32 == 0 (<= 512), N %% 64 == 0, rows %% 32 == 0");
   SCNB_CHECK_ARG(!(p_drop > 0.f) || keep_mask || rng, "hs_fwd: dropout needs keep_mask or rng state");
   SCNB_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "hs_fwd: p_drop out of range");
@@ -656,7 +668,8 @@ struct HsBwdArgs {
   const float* dYin;     // [R, K] gradient w.r.t. the BatchNorm output of application a (before the dropout scale: already applied)
   const float* Zin;      // [R, K] pre-BatchNorm input of application a
   const float* stats_in; // [n_seg][3][K]
-  const float* part_in;  // [R/32][2][K] tile sums of (dY, dY*zhat)
+  const float* part_in;  // [R/32][2][K] tile sums of (dY, dY*zhat); NULL: bmean_in holds the GLOBAL segment means
+  const float* bmean_in; // [n_seg][2][K] mean(dY), mean(dY*zhat) (data parallel)
   const float* gamma;    // [K]
   float* dgamma;         // [K] += over segments
   float* dbeta;
@@ -695,17 +708,22 @@ __global__ void __launch_bounds__(HS_T) k_hs_bwd(const __grid_constant__ HsBwdAr
   hs_commit();
   const float inv_n = 1.0f / (float)((t1 - t0) * HS_BM);
   for (int c = tid; c < K; c += HS_T) {
-    float s1, s2;
-    hs_combine_sums(p.part_in, K, c, t0, t1, s1, s2);
-    sM1[c] = s1 * inv_n;
-    sM2[c] = s2 * inv_n;
+    if (!p.part_in) {
+      sM1[c] = p.bmean_in[((size_t)s * 2 + 0) * K + c];
+      sM2[c] = p.bmean_in[((size_t)s * 2 + 1) * K + c];
+    } else {
+      float s1, s2;
+      hs_combine_sums(p.part_in, K, c, t0, t1, s1, s2);
+      sM1[c] = s1 * inv_n;
+      sM2[c] = s2 * inv_n;
+      if (blockIdx.x == 0 && tile == t0) {   // one CTA per segment: BatchNorm parameter gradients
+        atomicAdd(p.dbeta + c, s1);
+        atomicAdd(p.dgamma + c, s2);
+      }
+    }
     sMu[c] = p.stats_in[((size_t)s * 3 + 0) * K + c];
     sIs[c] = p.stats_in[((size_t)s * 3 + 2) * K + c];
     sGm[c] = p.gamma[c];
-    if (blockIdx.x == 0 && tile == t0) {   // one CTA per segment: BatchNorm parameter gradients
-      atomicAdd(p.dbeta + c, s1);
-      atomicAdd(p.dgamma + c, s2);
-    }
   }
   hs_wait_all();
   __syncthreads();
@@ -766,15 +784,15 @@ __global__ void __launch_bounds__(HS_T) k_hs_bwd(const __grid_constant__ HsBwdAr
 extern "C" int scnb_hs_bwd(const float* dYin, const float* Zin, const float* stats_in, const float* part_in, const float* gamma,
                            float* dgamma, float* dbeta, float* dZout, const float* W, const float* Zprev, const float* Aprev,
                            const float* stats_prev, float p_drop_prev, float* dYout, float* part_out, int K, int N, int R, int n_seg,
-                           const int32_t* seg_off_host, void* stream) {
-  SCNB_CHECK_ARG(dYin && Zin && stats_in && part_in && gamma && dgamma && dbeta && dZout && W && Zprev && Aprev && stats_prev &&
-                     dYout && part_out, "hs_bwd: null argument");
+                           const int32_t* seg_off_host, const float* bmean_in, void* stream) {
+  SCNB_CHECK_ARG(dYin && Zin && stats_in && (part_in || bmean_in) && gamma && dZout && W && Zprev && Aprev && stats_prev &&
+                     dYout && part_out && (!part_in || (dgamma && dbeta)), "hs_bwd: null argument");
   SCNB_CHECK_ARG(K % 32 == 0 && K >= 32 && K <= 256 && N % HS_BN == 0 && R % HS_BM == 0, "hs_bwd: needs K %% 32 == 0 (<= 256), N %% 64 == 0, rows %% 32 == 0");
   SCNB_CHECK_ARG(p_drop_prev >= 0.f && p_drop_prev < 1.f, "hs_bwd: p_drop out of range");
   HsBwdArgs a;
   a.dYin = dYin; a.Zin = Zin; a.stats_in = stats_in; a.part_in = part_in; a.gamma = gamma; a.dgamma = dgamma; a.dbeta = dbeta;
   a.dZout = dZout; a.W = W; a.Zprev = Zprev; a.Aprev = Aprev; a.stats_prev = stats_prev; a.p_drop_prev = p_drop_prev; a.dYout = dYout;
-  a.part_out = part_out; a.K = K; a.N = N; a.R = R;
+  a.part_out = part_out; a.K = K; a.N = N; a.R = R; a.bmean_in = bmean_in;
   int rc = hs_fill_seg(a.sg, n_seg, seg_off_host, R, "hs_bwd");
   if (rc != SCNB_OK) return rc;
   const size_t smem = ((size_t)2 * HS_BM * (K + 4) + (size_t)K * (HS_BN + 8) + 5 * (size_t)K + HS_RED) * sizeof(float);
@@ -792,21 +810,27 @@ extern "C" int scnb_hs_bwd(const float* dYin, const float* Zin, const float* sta
 __global__ void __launch_bounds__(HS_TE) k_hs_bwd_in(const float* __restrict__ dY, const float* __restrict__ Z, int H, HsSeg sg,
                                                     const float* __restrict__ stats, const float* __restrict__ part,
                                                     const float* __restrict__ gamma, float* __restrict__ dgamma,
-                                                    float* __restrict__ dbeta, float* __restrict__ dZ) {
+                                                    float* __restrict__ dbeta, float* __restrict__ dZ,
+                                                    const float* __restrict__ bmean, float* __restrict__ db) {
   PDL_ENTRY();
   __shared__ float sM1[HS_BN], sM2[HS_BN];
   const int tid = threadIdx.x, c0 = blockIdx.x * HS_BN, tile = blockIdx.y, row0 = tile * HS_BM;
   const int s = hs_seg_of(sg, row0);
   const int t0 = sg.off[s] / HS_BM, t1 = sg.off[s + 1] / HS_BM;
   if (tid < HS_BN) {
-    float s1, s2;
-    hs_combine_sums(part, H, c0 + tid, t0, t1, s1, s2);
-    const float inv_n = 1.0f / (float)((t1 - t0) * HS_BM);
-    sM1[tid] = s1 * inv_n;
-    sM2[tid] = s2 * inv_n;
-    if (tile == t0) {
-      atomicAdd(dbeta + c0 + tid, s1);
-      atomicAdd(dgamma + c0 + tid, s2);
+    if (!part) {
+      sM1[tid] = bmean[((size_t)s * 2 + 0) * H + c0 + tid];
+      sM2[tid] = bmean[((size_t)s * 2 + 1) * H + c0 + tid];
+    } else {
+      float s1, s2;
+      hs_combine_sums(part, H, c0 + tid, t0, t1, s1, s2);
+      const float inv_n = 1.0f / (float)((t1 - t0) * HS_BM);
+      sM1[tid] = s1 * inv_n;
+      sM2[tid] = s2 * inv_n;
+      if (tile == t0) {
+        atomicAdd(dbeta + c0 + tid, s1);
+        atomicAdd(dgamma + c0 + tid, s2);
+      }
     }
   }
   __syncthreads();
@@ -824,17 +848,31 @@ __global__ void __launch_bounds__(HS_TE) k_hs_bwd_in(const float* __restrict__ d
     dy[j] = g[j] * inv[j] * (dy[j] - sM1[cl + j] - zh * sM2[cl + j]);
   }
   hs_st8(dZ + o, dy);
+  if (db) {   // bias gradient of the Linear in front of application 0: column sums of dZ[0] over all rows
+    __shared__ float red[HS_BM][HS_BN + 1];
+    const int rr = tid >> 3;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[rr][cl + j] = dy[j];
+    __syncthreads();
+    if (tid < HS_BN) {
+      float sacc = 0.f;
+#pragma unroll 8
+      for (int i = 0; i < HS_BM; ++i) sacc += red[i][tid];
+      atomicAdd(db + c0 + tid, sacc);
+    }
+  }
 }
 
 extern "C" int scnb_hs_bwd_in(const float* dY, const float* Z, int H, int R, int n_seg, const int32_t* seg_off_host, const float* stats,
-                              const float* part, const float* gamma, float* dgamma, float* dbeta, float* dZ, void* stream) {
-  SCNB_CHECK_ARG(dY && Z && stats && part && gamma && dgamma && dbeta && dZ, "hs_bwd_in: null argument");
+                              const float* part, const float* gamma, float* dgamma, float* dbeta, float* dZ, const float* bmean_in,
+                              float* db, void* stream) {
+  SCNB_CHECK_ARG(dY && Z && stats && (part || bmean_in) && gamma && dZ && (!part || (dgamma && dbeta)), "hs_bwd_in: null argument");
   SCNB_CHECK_ARG(H % HS_BN == 0 && R % HS_BM == 0, "hs_bwd_in: bad shape");
   HsSeg sg;
   int rc = hs_fill_seg(sg, n_seg, seg_off_host, R, "hs_bwd_in");
   if (rc != SCNB_OK) return rc;
   scnb_launch_pdl(k_hs_bwd_in, dim3(H / HS_BN, R / HS_BM), dim3(HS_TE), 0, (cudaStream_t)stream, dY, Z, H, sg, stats, part, gamma, dgamma,
-                  dbeta, dZ);
+                  dbeta, dZ, bmean_in, db);
   SCNB_CHECK_LAUNCH("hs_bwd_in");
   return SCNB_OK;
 }
@@ -842,23 +880,23 @@ extern "C" int scnb_hs_bwd_in(const float* dY, const float* Z, int H, int R, int
 // ---------------------------------------------------------------------------------------------------------------------
 // hs_dw: weight and bias gradient of a hidden Linear from the materialised dZ [R, M] (M = out features) and its input
 // activation A [R, N]:  dW[M, N] += dZ^T A,  db[M] += column sums of dZ   (dW = dz^T a, db = sum_n dz).
-// One CTA = a 64 x 64 tile of dW over a chunk of 128 rows (grid = (N/64, M/64, ceil(R/128))); partial products are added
+// One CTA = a 64 x 64 tile of dW over a chunk of 64 rows (grid = (N/64, M/64, ceil(R/64))); partial products are added
 // to dW with atomics (the gradient arena is zeroed at the start of the step).  16 warps as 4 x 4 sub-tiles of 16 x 16,
 // 3xTF32.  Replaces a split-K GEMM launch plus a column-sum launch per layer on the step's weight-gradient branch.
 // ---------------------------------------------------------------------------------------------------------------------
-#define HS_DW_ROWS 128
+#define HS_DW_ROWS 64    // 37 KB of shared memory per CTA: co-resides with a tile-GEMM CTA of the critical chain on the same SM
 __global__ void __launch_bounds__(HS_T) k_hs_dw(const float* __restrict__ dZ, int M, const float* __restrict__ A, int N, int R,
                                                 float* __restrict__ dW, float* __restrict__ db) {
   PDL_ENTRY();
   extern __shared__ __align__(16) float hs_smem[];
   constexpr int SP = HS_BN + 8;
-  float* sD = hs_smem;                      // [128][72]  dZ[rows][m0 .. m0+63]
-  float* sA = sD + HS_DW_ROWS * SP;         // [128][72]  A[rows][n0 .. n0+63]
+  float* sD = hs_smem;                      // [64][72]  dZ[rows][m0 .. m0+63]
+  float* sA = sD + HS_DW_ROWS * SP;         // [64][72]  A[rows][n0 .. n0+63]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3, wm = warp >> 2, wn = warp & 3;
   const int n0 = blockIdx.x * HS_BN, m0 = blockIdx.y * HS_BN, r0 = blockIdx.z * HS_DW_ROWS;
   const int rows = min(HS_DW_ROWS, R - r0);
-  // 128 rows x 16 chunks per panel = 2048 chunks each, 4 per thread; rows beyond R are zero-filled
+  // 64 rows x 16 chunks per panel; rows beyond R are zero-filled
   for (int ch = tid; ch < HS_DW_ROWS * 16; ch += HS_T) {
     const int r = ch >> 4, q = ch & 15;
     if (r < rows) {
@@ -922,5 +960,130 @@ extern "C" int scnb_hs_dw(const float* dZ, int M, const float* A, int N, int R, 
   if (rc != SCNB_OK) return rc;
   scnb_launch_pdl(k_hs_dw, dim3(N / HS_BN, M / HS_BN, scnb_cdiv(R, HS_DW_ROWS)), dim3(HS_T), smem, (cudaStream_t)stream, dZ, M, A, N, R, dW, db);
   SCNB_CHECK_LAUNCH("hs_dw");
+  return SCNB_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// hs_xchg: cross-rank exchange of the per-segment BatchNorm statistics (data-parallel training, one process per GPU,
+// statistics over the CONCATENATED global batch).  One launch between the kernel that wrote the tile partials and the one
+// that consumes them: grid = (H/64, n_seg), 128 threads.  A CTA combines the LOCAL tiles of its (64 columns, segment),
+// stores the result into every rank's exchange buffer over NVLink / NVSwitch peer memory and merges what the peers stored,
+// in rank order (bit-identical statistics on every rank).  Every value travels as one 8-byte word {value, step number}: the
+// step number is its ready flag ("LL" protocol), buffers are double-buffered by step parity.
+//   forward  (kind 0): (mean, M2, rows) merged with Chan's formula -> stats[seg][3][H] = mean, biased var, invstd; cnt[seg] = rows
+//   backward (kind 1): (sum dY, sum dY*zhat, rows) -> bmean[seg][2][H] = global means; the LOCAL sums are also this rank's
+//                      BatchNorm beta / gamma gradients (averaged with all other gradients by the gradient exchange)
+// packet (slot, parity, src rank, seg, column block) = 136 words: [v0[64] | v1[64] | rows | pad]
+// ---------------------------------------------------------------------------------------------------------------------
+#define HS_PKT 136
+struct HsPeer {
+  const unsigned long long* bufs;   // [world] exchange-buffer base addresses as seen from this process
+  const long long* epoch;           // device scalar: step number
+  int rank, world, slot, ncb_max, spin_limit;
+};
+
+__device__ __forceinline__ void hs_ll_store(unsigned long long base, size_t word, float v, unsigned e) {
+  uint2* dst = reinterpret_cast<uint2*>(base) + word;
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(__float_as_uint(v)), "r"(e) : "memory");
+}
+__device__ __forceinline__ float hs_ll_load(unsigned long long base, size_t word, unsigned e, int spin_limit) {
+  const uint2* src = reinterpret_cast<const uint2*>(base) + word;
+  uint32_t v, f;
+  int spins = 0;
+  do {
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(f) : "l"(src) : "memory");
+    if (f != e && ++spins > spin_limit) __trap();   // a peer never arrived: fail loudly instead of hanging the GPU
+  } while (f != e);
+  return __uint_as_float(v);
+}
+
+__global__ void __launch_bounds__(128) k_hs_xchg(int kind, const float* __restrict__ part, int H, HsSeg sg, HsPeer px,
+                                                 float* __restrict__ out, float* __restrict__ cnt_out, float* __restrict__ dgamma,
+                                                 float* __restrict__ dbeta) {
+  PDL_ENTRY();
+  const int tid = threadIdx.x, cb = blockIdx.x, s = blockIdx.y, c = cb * HS_BN + tid;
+  const int t0 = sg.off[s] / HS_BM, t1 = sg.off[s + 1] / HS_BM;
+  const unsigned e = (unsigned)px.epoch[0];
+  const float n_loc = (float)((t1 - t0) * HS_BM);
+  const size_t pkt0 = ((((size_t)(px.slot * 2 + (int)(e & 1u)) * px.world) * sg.n_seg + 0) * px.ncb_max) * HS_PKT;   // + src, seg, cb below
+  auto pkt = [&](int src) { return pkt0 + (((size_t)src * sg.n_seg + s) * px.ncb_max + cb) * HS_PKT; };
+  if (tid < HS_BN) {
+    float v0, v1;
+    if (kind == 0) {
+      float var;
+      hs_combine_stats(part, H, c, t0, t1, v0, var);
+      v1 = var * n_loc;                         // M2
+    } else {
+      hs_combine_sums(part, H, c, t0, t1, v0, v1);
+      if (t1 > t0) {
+        atomicAdd(dbeta + c, v0);
+        atomicAdd(dgamma + c, v1);
+      }
+    }
+    const size_t mine = pkt(px.rank);
+    for (int p = 0; p < px.world; ++p) {
+      hs_ll_store(px.bufs[p], mine + tid, v0, e);
+      hs_ll_store(px.bufs[p], mine + 64 + tid, v1, e);
+      if (tid == 0) hs_ll_store(px.bufs[p], mine + 128, n_loc, e);
+    }
+    const unsigned long long own = px.bufs[px.rank];
+    float n = 0.f, a = 0.f, b = 0.f;    // forward: running (rows, mean, M2); backward: (rows, sum, sum)
+    for (int p = 0; p < px.world; ++p) {   // rank order: the same result on every rank
+      const size_t w = pkt(p);
+      const float u0 = hs_ll_load(own, w + tid, e, px.spin_limit);
+      const float u1 = hs_ll_load(own, w + 64 + tid, e, px.spin_limit);
+      const float np_ = hs_ll_load(own, w + 128, e, px.spin_limit);
+      if (kind == 0) {
+        if (np_ > 0.f) {
+          const float nn = n + np_, d = u0 - a;
+          a += d * (np_ / nn);
+          b += u1 + d * d * (n * np_ / nn);
+          n = nn;
+        }
+      } else {
+        a += u0;
+        b += u1;
+        n += np_;
+      }
+    }
+    const float ng = fmaxf(n, 1.f);
+    if (kind == 0) {
+      const float var = b / ng;
+      out[((size_t)s * 3 + 0) * H + c] = a;
+      out[((size_t)s * 3 + 1) * H + c] = var;
+      out[((size_t)s * 3 + 2) * H + c] = 1.0f / sqrtf(var + BN_EPS);
+    } else {
+      out[((size_t)s * 2 + 0) * H + c] = a / ng;
+      out[((size_t)s * 2 + 1) * H + c] = b / ng;
+    }
+    if (cnt_out && cb == 0 && tid == 0) cnt_out[s] = n;
+  }
+}
+
+extern "C" int scnb_hs_peer_bytes(int H_max, int n_seg, int n_slots, int world) {
+  return (int)((long long)n_slots * 2 * world * n_seg * (long long)((H_max + HS_BN - 1) / HS_BN) * HS_PKT * 8);
+}
+
+extern "C" int scnb_hs_xchg(int kind, const float* part, int H, int R, int n_seg, const int32_t* seg_off_host, const uint64_t* peer_bufs,
+                            int rank, int world, int slot, int n_slots, int H_max, const int64_t* epoch, long long buf_bytes,
+                            float* out, float* cnt_out, float* dgamma, float* dbeta, void* stream) {
+  SCNB_CHECK_ARG(part && out && peer_bufs && epoch && (kind == 0 || kind == 1), "hs_xchg: bad arguments");
+  SCNB_CHECK_ARG(kind == 0 || (dgamma && dbeta), "hs_xchg: backward exchange needs dgamma / dbeta");
+  SCNB_CHECK_ARG(H % HS_BN == 0 && H <= H_max && world >= 1 && world <= 32 && rank >= 0 && rank < world && slot >= 0 && slot < n_slots,
+                 "hs_xchg: bad shape / rank / slot");
+  SCNB_CHECK_ARG(buf_bytes >= scnb_hs_peer_bytes(H_max, n_seg, n_slots, world), "hs_xchg: exchange buffer too small");
+  HsSeg sg;
+  int rc = hs_fill_seg(sg, n_seg, seg_off_host, R, "hs_xchg");
+  if (rc != SCNB_OK) return rc;
+  static int spin = 0;
+  if (!spin) {
+    const char* ev = getenv("SCNB_PEER_SPIN_LIMIT");
+    spin = ev ? atoi(ev) : (1 << 24);
+    if (spin <= 0) spin = 1 << 24;
+  }
+  HsPeer px{(const unsigned long long*)peer_bufs, (const long long*)epoch, rank, world, slot, (H_max + HS_BN - 1) / HS_BN, spin};
+  k_hs_xchg<<<dim3(H / HS_BN, n_seg), 128, 0, (cudaStream_t)stream>>>(kind, part, H, sg, px, out, cnt_out, dgamma, dbeta);
+  SCNB_CHECK_LAUNCH("hs_xchg");
   return SCNB_OK;
 }

@@ -203,6 +203,7 @@ class TrainEngine(object):
             n_seg = (3 if self.use_dan else 2) if mode == "mixmatch" else 1
             self.peer_slots = 2 * len(self.widths)
             bn_bytes = max(_lib.lib().scnb_bn_peer_bytes(w, n_seg, self.peer_slots, self.comm.world) for w in self.widths)
+            bn_bytes = max(bn_bytes, _lib.lib().scnb_hs_peer_bytes(max(self.widths), n_seg, self.peer_slots, self.comm.world))
             total = ParamArena.padded_total(named)
             rnd = lambda b: (b + 255) // 256 * 256
             self.peer_bn_bytes = rnd(bn_bytes)
@@ -342,7 +343,7 @@ class TrainEngine(object):
         # between launches as per-tile partials.  Needs static segment boundaries on 32-row tiles (no pseudolabel
         # thresholding), 64-column tiles and operand panels that fit shared memory; single process for now.
         seg_host = [0, U, U + L, U + L + self.Rd][: self.n_seg + 1] if mode == "mixmatch" else [0, L]
-        hs_ok = (self.comm is None and all(w % 64 == 0 for w in self.widths) and all(w <= 256 for w in self.widths[1:])
+        hs_ok = ((self.comm is None or self.peer is not None) and all(w % 64 == 0 for w in self.widths) and all(w <= 256 for w in self.widths[1:])
                  and self.widths[0] <= 512 and all(o % 32 == 0 for o in seg_host) and R <= 4096
                  and (mode != "mixmatch" or cfg.pseudolabel_min_confidence <= 0.0))
         hm = cfg.hidden if cfg.hidden != "auto" else os.environ.get("SCNB_HIDDEN", "fused")
@@ -357,6 +358,8 @@ class TrainEngine(object):
             self.dYs = [f32(R, w) for w in self.widths]
             self.pf = [f32(R // 32, 2, w) for w in self.widths]
             self.pb = [f32(R // 32, 2, w) for w in self.widths]
+            if self.comm is not None:   # data parallel: global backward means per application, written by scnb_hs_xchg
+                self.bmean = [f32(self.n_seg, 2, w) for w in self.widths]
         # "auto": the tensor-core form pays off once the batch fills at least two 256-row tiles (measured: 512 rows,
         # 5 % density: 22 us vs 40 us for the SpMM; 8192 rows, 20 %: ~10x); tiny batches keep the exact-fp32 SpMM
         fl = cfg.first_layer
@@ -758,20 +761,40 @@ class TrainEngine(object):
     def _hidden_keep(self, a):
         return ptr(self.inj_hidden_keep[a]) if self.inj_hidden_keep is not None else None
 
+    def _xchg(self, kind, a, st):
+        """Data parallel: make the statistics of application `a` global (scnb_hs_xchg over peer memory).  kind 0: forward tile
+        statistics pf[a] -> stats[a] (+ global row counts for the running-statistics update); kind 1: backward tile sums pb[a]
+        -> bmean[a], this rank's local sums into the BatchNorm parameter gradients."""
+        px, blk = self.peer, self._blk
+        w = self.widths[a]
+        if kind == 0:
+            call("scnb_hs_xchg", 0, ptr(self.pf[a]), w, self.Rmax, self.n_seg, self._seg_host.ctypes.data, ptr(px.ptrs), px.rank, px.world,
+                 a, self.peer_slots, max(self.widths), ptr(self.state), self.peer_bn_bytes, ptr(self.stats[a]),
+                 ptr(self.dp_fwd[a][self.n_seg * 2 * w:]), None, None, st)
+        else:
+            call("scnb_hs_xchg", 1, ptr(self.pb[a]), w, self.Rmax, self.n_seg, self._seg_host.ctypes.data, ptr(px.ptrs), px.rank, px.world,
+                 self.n_app + a, self.peer_slots, max(self.widths), ptr(self.state), self.peer_bn_bytes, ptr(self.bmean[a]), None,
+                 self.Gp(blk[a]["g"]), self.Gp(blk[a]["beta"]), st)
+
     def _student_forward(self, st, rng):
         blk, R = self._blk, self.Rmax
         if self.hs_fused:
             seg = self._seg_host.ctypes.data
+            dp = self.comm is not None
             if self.mode != "mixmatch":   # no MixUp in front: tile statistics of the first layer's output
                 call("scnb_hs_mix", ptr(self.Zs[0]), self.widths[0], None, None, None, R, ptr(self.Zs[0]), ptr(self.pf[0]), st)
             for a in range(1, self.n_app):
                 k, n = self.widths[a - 1], self.widths[a]
-                call("scnb_hs_fwd", ptr(self.Zs[a - 1]), ptr(self.As[a - 1]), ptr(self.pf[a - 1]), ptr(self.stats[a - 1]),
+                if dp:
+                    self._xchg(0, a - 1, st)
+                call("scnb_hs_fwd", ptr(self.Zs[a - 1]), ptr(self.As[a - 1]), None if dp else ptr(self.pf[a - 1]), ptr(self.stats[a - 1]),
                      self.P(blk[a - 1]["g"]), self.P(blk[a - 1]["beta"]), self._hidden_keep(a - 1), rng, SID_HID + a - 1,
                      float(blk[a - 1]["drop"].p), self.P(blk[a]["W"]), self.P(blk[a]["b"]), ptr(self.Zs[a]), ptr(self.pf[a]), k, n, R,
                      self.n_seg, seg, None, None, st)
             a = self.n_app - 1
-            call("scnb_hs_act", ptr(self.Zs[a]), ptr(self.As[a]), self.widths[a], R, self.n_seg, seg, ptr(self.pf[a]), self.P(blk[a]["g"]),
+            if dp:
+                self._xchg(0, a, st)
+            call("scnb_hs_act", ptr(self.Zs[a]), ptr(self.As[a]), self.widths[a], R, self.n_seg, seg, None if dp else ptr(self.pf[a]), self.P(blk[a]["g"]),
                  self.P(blk[a]["beta"]), ptr(self.stats[a]), self._hidden_keep(a), rng, SID_HID + a, float(blk[a]["drop"].p), st)
             return
         for a in range(self.n_app):
@@ -854,21 +877,27 @@ class TrainEngine(object):
         last = self.n_app - 1
         if sW is not main:
             main.wait_event(self._ev_zero)   # BatchNorm gamma / beta gradients accumulate into zeroed buffers
+        dp = self.comm is not None
         call("scnb_hs_bwd_act", ptr(dA), ptr(self.Zs[last]), ptr(self.As[last]), self.widths[last], R, self.n_seg, seg,
              ptr(self.stats[last]), float(blk[last]["drop"].p), ptr(self.dYs[last]), ptr(self.pb[last]), st)
         for a in range(last, 0, -1):
             k, n = self.widths[a], self.widths[a - 1]
-            call("scnb_hs_bwd", ptr(self.dYs[a]), ptr(self.Zs[a]), ptr(self.stats[a]), ptr(self.pb[a]), self.P(blk[a]["g"]),
+            if dp:
+                self._xchg(1, a, st)
+            call("scnb_hs_bwd", ptr(self.dYs[a]), ptr(self.Zs[a]), ptr(self.stats[a]), None if dp else ptr(self.pb[a]), self.P(blk[a]["g"]),
                  self.Gp(blk[a]["g"]), self.Gp(blk[a]["beta"]), ptr(self.dZs[a]), self.P(blk[a]["W"]), ptr(self.Zs[a - 1]),
                  ptr(self.As[a - 1]), ptr(self.stats[a - 1]), float(blk[a - 1]["drop"].p), ptr(self.dYs[a - 1]), ptr(self.pb[a - 1]),
-                 k, n, R, self.n_seg, seg, st)
+                 k, n, R, self.n_seg, seg, ptr(self.bmean[a]) if dp else None, st)
             ev = self._ev_dz[a]
             if sW is not main:
                 ev.record(main)
                 sW.wait_event(ev)
             call("scnb_hs_dw", ptr(self.dZs[a]), k, ptr(self.As[a - 1]), n, R, self.Gp(blk[a]["W"]), self.Gp(blk[a]["b"]), sw)
-        call("scnb_hs_bwd_in", ptr(self.dYs[0]), ptr(self.Zs[0]), self.widths[0], R, self.n_seg, seg, ptr(self.stats[0]), ptr(self.pb[0]),
-             self.P(blk[0]["g"]), self.Gp(blk[0]["g"]), self.Gp(blk[0]["beta"]), ptr(self.dZs[0]), st)
+        if dp:
+            self._xchg(1, 0, st)
+        call("scnb_hs_bwd_in", ptr(self.dYs[0]), ptr(self.Zs[0]), self.widths[0], R, self.n_seg, seg, ptr(self.stats[0]),
+             None if dp else ptr(self.pb[0]), self.P(blk[0]["g"]), self.Gp(blk[0]["g"]), self.Gp(blk[0]["beta"]), ptr(self.dZs[0]),
+             ptr(self.bmean[0]) if dp else None, self.Gp(blk[0]["b"]), st)
         return self.dZs[0]
 
     def _gene_cnt_ptr(self):
@@ -904,7 +933,8 @@ class TrainEngine(object):
         st, sw = main.cuda_stream, sW.cuda_stream
         self._after(sW, main)     # dZ1 ready
         self._after(sW, sD)       # domain-head gradients ready
-        call("scnb_colsum", ptr(dZ1), n_rows, H0, H0, self.Gp(blk0["b"]), 1, sw)
+        if not self.hs_fused:   # (fused hidden stack: db1 = column sums of dZ[0] over all passes, added by scnb_hs_bwd_in)
+            call("scnb_colsum", ptr(dZ1), n_rows, H0, H0, self.Gp(blk0["b"]), 1, sw)
         if sW is not main:
             main.wait_event(self._ev_csc)   # batch CSC (built at the start of the step on branch W)
         if not self.fused_w1:

@@ -125,8 +125,9 @@ class PeerThreadComm(ThreadComm):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("opt_name,lr,peer", [("sgd", 0.05, False), ("adadelta", 1.0, False), ("sgd", 0.05, True), ("adadelta", 1.0, True)])
-def test_data_parallel_step_equals_global_batch_oracle(opt_name, lr, peer, monkeypatch):
+@pytest.mark.parametrize("opt_name,lr,peer,fused", [("sgd", 0.05, False, False), ("adadelta", 1.0, False, False), ("sgd", 0.05, True, False),
+                                                     ("adadelta", 1.0, True, False), ("sgd", 0.05, True, True), ("adadelta", 1.0, True, True)])
+def test_data_parallel_step_equals_global_batch_oracle(opt_name, lr, peer, fused, monkeypatch):
     """peer=False: host-side rendezvous for every exchange.  peer=True: the product path of a one-node NCCL job -- the
     BatchNorm statistics and the gradient reduce-scatter + optimizer + parameter all-gather run inside kernels that wait
     for the other rank ON THE DEVICE.  Two such ranks share one GPU here, so each emulated rank drains its stream after
@@ -146,6 +147,8 @@ def test_data_parallel_step_equals_global_batch_oracle(opt_name, lr, peer, monke
     from oracle import scnym_oracle as O
     from tests import cuda_harness as CH
     kw = dict(G=600, L=24, U=32, C=5, H0=64, H=48, n_layers=2, opt_name=opt_name, lr=lr, n_steps=1, D_given=0)
+    if fused:   # shapes the fused hidden stack takes (hidden_ops.cu): statistics exchanged by scnb_hs_xchg between its launches
+        kw.update(L=32, U=64, H0=128, H=64)
     cases = [CH.oracle_case(seed=31, **kw), CH.oracle_case(seed=32, **kw)]
     for k in list(cases[1].keys()):
         if k.startswith("init/"):
@@ -199,7 +202,7 @@ def test_data_parallel_step_equals_global_batch_oracle(opt_name, lr, peer, monke
             with torch.cuda.stream(torch.cuda.Stream()):       # one stream per emulated rank: their kernels overlap
                 eng = TrainEngine(model, cfg, lab, d["lab_y"], l, unlabeled=unl, unlabeled_batch_size=u, dann=dann, mode="mixmatch",
                                   comm=(PeerThreadComm if peer else ThreadComm)(2, shared, rk))
-                assert (eng.peer is not None) == peer
+                assert (eng.peer is not None) == peer and eng.hs_fused == fused
                 eng.set_weights(float(d["meta_unsup_w"]), float(d["meta_dan_w"]))
                 CH.inject_step(eng, d, 0)
                 eng.step()
