@@ -728,6 +728,16 @@ def main():
             __graft_entry__.build()
     barrier(world)
 
+    single_same = None
+    if world > 1:
+        # the SAME workload on one GPU without any exchange (every rank runs its own copy; rank 0 reports), so that the scaling
+        # of this configuration can be read off one run: the driver's N = 1 line is config 2, a different workload
+        _e, ms1, _c, _l, _s = time_device_resident(args, device, rank, 1)
+        single_same = {"value": cells_per_step / (ms1 / args.steps * 1e-3), "unit": "cells/s", "ms_per_step": ms1 / args.steps,
+                       "note": "this config on ONE GPU (no data parallelism), measured on rank 0 in the same run"}
+        del _e
+        torch.cuda.empty_cache()
+        barrier(world)
     eng, ms, clocks, losses, sampler = time_device_resident(args, device, rank, world)
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     if world > 1:
@@ -826,6 +836,7 @@ def main():
                 "data": "synthetic", "config": config_dict(world), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": launches * args.steps, "launches_per_step": launches, "roofline": roof, "cpu_baseline": cpu,
                 "gpu_eager_baseline": gpu_eager, "predict": predict, "sampler_draw": sampler, "dp_parity": dp,
+                "single_gpu_same_config": single_same,
                 "losses_last_step": {k: (round(float(v), 6) if not isinstance(v, bool) else v) for k, v in losses.items()}}
         print(json.dumps(line))
     if world > 1:
