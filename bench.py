@@ -674,7 +674,18 @@ def dp_parity(device, rank, world):
         return {"parity": "FAILED", "error": str(e)[:300]}
 
 
+def _claim_stdout():
+    """Keep the real stdout for the ONE JSON line: everything else that writes to file descriptor 1 (NCCL's version banner,
+    the reference's prints, tqdm) goes to stderr.  Returns a file object on the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(os.dup(2), "w")
+    return real
+
+
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -713,7 +724,7 @@ def main():
                                  "sample": f"{done} steps of {what} on {cores} host threads, one process "
                                            f"(the reference has no data-parallel mode: the same figure at every N)"},
                 "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
         return
 
     if not torch.cuda.is_available():
@@ -838,7 +849,7 @@ def main():
                 "gpu_eager_baseline": gpu_eager, "predict": predict, "sampler_draw": sampler, "dp_parity": dp,
                 "single_gpu_same_config": single_same,
                 "losses_last_step": {k: (round(float(v), 6) if not isinstance(v, bool) else v) for k, v in losses.items()}}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         # Kernels of the step wait for peers on the device; tearing the process group down underneath a replayed graph can
         # block forever, so synchronise, flush and leave without destroy_process_group().

@@ -271,6 +271,7 @@ int scnb_hs_bwd_in(const float* dY, const float* Z, int H, int R, int n_seg, con
  * over NVLink / NVSwitch, `peer_bufs[world]` as scnb_bn_act_fwd_peer).  kind 0 (forward): out = stats[n_seg][3][H] (global
  * mean, biased var, invstd), cnt_out[n_seg] = global rows; kind 1 (backward): out = bmean[n_seg][2][H] (global means of dY and
  * dY*zhat), and this rank's LOCAL sums are added to dgamma / dbeta.  Consumers then take part_in = NULL. */
+int scnb_hs_debug_read(unsigned long long* out32_host);   /* SCNB_HS_DBG=1: %globaltimer phase stamps of CTA (0,0) (tools/hs_phases.py) */
 int scnb_hs_peer_bytes(int H_max, int n_seg, int n_slots, int world);   /* bytes of the exchange region */
 int scnb_hs_xchg(int kind, const float* part, int H, int R, int n_seg, const int32_t* seg_off_host, const uint64_t* peer_bufs,
                  int rank, int world, int slot, int n_slots, int H_max, const int64_t* epoch, long long buf_bytes, float* out,

@@ -63,6 +63,7 @@ SIGNATURES = {
     "scnb_hs_dw": [P, I, P, I, I, P, P, P],
     "scnb_hs_bwd_in": [P, P, I, I, I, P, P, P, P, P, P, P, P, P, P],
     "scnb_hs_peer_bytes": [I, I, I, I],
+    "scnb_hs_debug_read": [P],
     "scnb_hs_xchg": [I, P, I, I, I, P, P, I, I, I, I, I, P, L, P, P, P, P, P],
     "scnb_unmix_rows": [P, I, P, P, I, P, P],
     "scnb_unmix_rows_planes": [P, I, P, P, I, P, P, P, P],

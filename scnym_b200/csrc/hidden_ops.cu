@@ -33,6 +33,32 @@
 #define HS_RED (3 * 4 * 16 * 32)   // floats of the cross-warp accumulator hand-over
 #define HS_MAXSEG 3
 
+// Phase stamps of CTA (0, 0) of the tile-GEMM kernels (SCNB_HS_DBG=1; tools/hs_phases.py reads them): %globaltimer in ns.
+__device__ unsigned long long g_hs_dbg[2][16];
+__device__ __forceinline__ void hs_stamp(int on, int kern, int slot) {
+  if (on && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_hs_dbg[kern][slot] = t;
+  }
+}
+static int hs_dbg_on() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SCNB_HS_DBG");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}
+extern "C" int scnb_hs_debug_read(unsigned long long* out32_host) {
+  cudaError_t e = cudaMemcpyFromSymbol(out32_host, g_hs_dbg, sizeof(unsigned long long) * 32);
+  if (e != cudaSuccess) {
+    scnb_set_error("hs_debug_read: %s", cudaGetErrorString(e));
+    return SCNB_ERR_CUDA;
+  }
+  return SCNB_OK;
+}
+
 struct HsSeg {
   int n_seg;
   int off[HS_MAXSEG + 1];   // row offsets, multiples of HS_BM
@@ -441,6 +467,7 @@ struct HsFwdArgs {
   float* Zout;           // [R, N]
   float* part_out;       // [R/32][2][N]
   int K, N, R;
+  int dbg;
   HsSeg sg;
 };
 
@@ -459,10 +486,12 @@ __global__ void __launch_bounds__(HS_T) k_hs_fwd(const __grid_constant__ HsFwdAr
   const int tid = threadIdx.x, n0 = blockIdx.x * HS_BN, tile = blockIdx.y, row0 = tile * HS_BM;
   const int s = hs_seg_of(p.sg, row0);
   const int t0 = p.sg.off[s] / HS_BM, t1 = p.sg.off[s + 1] / HS_BM;
+  hs_stamp(p.dbg, 0, 0);
   // stage the raw operands
   hs_stage_rows(sA, K + 4, p.Zin + (size_t)row0 * K, K, HS_BM, K >> 2);
   hs_stage_rows(sB, K + 4, p.W + (size_t)n0 * K, K, HS_BN, K >> 2);
   hs_commit();
+  hs_stamp(p.dbg, 0, 1);
   // segment statistics of the input while the copies fly
   const bool eval = p.rmean != nullptr;
   for (int c = tid; c < K; c += HS_T) {
@@ -490,8 +519,10 @@ __global__ void __launch_bounds__(HS_T) k_hs_fwd(const __grid_constant__ HsFwdAr
       p.stats_in[((size_t)s * 3 + 2) * K + c] = inv;
     }
   }
+  hs_stamp(p.dbg, 0, 2);
   hs_wait_all();
   __syncthreads();
+  hs_stamp(p.dbg, 0, 3);
   // BatchNorm -> Dropout -> ReLU in place on the A operand
   uint64_t seed = 0, strm = 0;
   if (p.p_drop > 0.f && !p.keep) {
@@ -534,8 +565,10 @@ __global__ void __launch_bounds__(HS_T) k_hs_fwd(const __grid_constant__ HsFwdAr
     if (blockIdx.x == 0 && p.Aout) *reinterpret_cast<float4*>(p.Aout + (size_t)rg * K + c) = y;
   }
   __syncthreads();
+  hs_stamp(p.dbg, 0, 4);
   float acc[2][2][4];
   hs_tile_mma<0>(sA, sB, K, sRed, acc);
+  hs_stamp(p.dbg, 0, 5);
   // epilogue (warps of the lower K half): bias, Z[a] tile, tile statistics
   const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3, wn = warp & 3;
   if (warp < 4) {
@@ -571,6 +604,7 @@ __global__ void __launch_bounds__(HS_T) k_hs_fwd(const __grid_constant__ HsFwdAr
       }
     }
   }
+  hs_stamp(p.dbg, 0, 6);
 }
 
 static int hs_fill_seg(HsSeg& sg, int n_seg, const int32_t* seg_off_host, int R, const char* who) {
@@ -608,7 +642,7 @@ extern "C" int scnb_hs_fwd(const float* Zin, float* Aout, const float* part_in, 
   HsFwdArgs a;
   a.Zin = Zin; a.Aout = Aout; a.part_in = part_in; a.stats_in = stats_in; a.gamma = gamma; a.beta = beta; a.keep = keep_mask;
   a.rng = rng; a.stream_id = stream_id; a.p_drop = p_drop; a.W = W; a.bias = bias; a.Zout = Zout; a.part_out = part_out;
-  a.K = K; a.N = N; a.R = R; a.rmean = running_mean; a.rvar = running_var;
+  a.K = K; a.N = N; a.R = R; a.rmean = running_mean; a.rvar = running_var; a.dbg = hs_dbg_on();
   int rc = hs_fill_seg(a.sg, n_seg, seg_off_host, R, "hs_fwd");
   if (rc != SCNB_OK) return rc;
   const size_t smem = ((size_t)(HS_BM + HS_BN) * (K + 4) + 4 * (size_t)K + HS_RED) * sizeof(float);
