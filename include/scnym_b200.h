@@ -236,19 +236,23 @@ int scnb_unmix_rows_planes(const float* dOut, int H, const int32_t* inv3, const 
  *      backward) that every consumer combines per segment in a fixed order.  seg_off_host: HOST int32 [n_seg + 1] row
  *      offsets (multiples of 32, n_seg <= 3); stats: [n_seg][3][H] = mean, biased var, invstd (as scnb_bn_act_fwd);
  *      dropout stream ids / injected masks as scnb_bn_act_fwd.  All buffers 16-byte aligned, H % 64 == 0. ---- */
-/* out = MixUp(Z) rows (dataprep.py:665-689; srcA == NULL: out = Z) + tile statistics of out */
+/* out = MixUp(Z) rows (dataprep.py:665-689; srcA == NULL: out = Z) + tile statistics of out.  keep_out (NULL or uint8 [R, H]):
+ * also draws the dropout keep bytes of application 0 (Philox stream `stream_id` of (rng[0], rng[1]), keep probability 1-p_drop):
+ * the kernel that PRODUCES a pre-BatchNorm tensor emits its dropout mask once, every consumer of those rows reads bytes. */
 int scnb_hs_mix(const float* Z, int H, const int32_t* srcA, const int32_t* srcB, const float* gam, int R, float* out,
-                float* part, void* stream);
+                float* part, uint8_t* keep_out, const uint64_t* rng, uint32_t stream_id, float p_drop, void* stream);
 /* A = relu(drop(bn(Z))) of the last application (input of the heads); writes stats */
 int scnb_hs_act(const float* Z, float* A, int H, int R, int n_seg, const int32_t* seg_off_host, const float* part,
                 const float* gamma, const float* beta, float* stats, const uint8_t* keep_mask, const uint64_t* rng,
                 uint32_t stream_id, float p_drop, void* stream);
-/* Aout = relu(drop(bn(Zin))) (materialised), Zout = Aout W^T + bias (W [N, K]; 3xTF32), tile statistics of Zout; writes stats_in.
- * running_mean / running_var non-NULL: eval mode (the MixMatch teacher, scnym/losses.py:660-737): running statistics,
- * no dropout; part_in / stats_in / Aout / part_out may then be NULL. */
+/* Aout = relu(drop(bn(Zin))) (materialised; keep_mask = keep bytes [R, K] of that dropout, generated by the producer of Zin or
+ * injected), Zout = Aout W^T + bias (W [N, K]; 3xTF32), tile statistics of Zout; writes stats_in; keep_out as scnb_hs_mix (the
+ * mask of the application whose input Zout is).  running_mean / running_var non-NULL: eval mode (the MixMatch teacher,
+ * scnym/losses.py:660-737): running statistics, no dropout; part_in / stats_in / Aout / part_out may then be NULL.
+ * part_in == NULL in train mode: the (global, data-parallel) statistics are already in stats_in. */
 int scnb_hs_fwd(const float* Zin, float* Aout, const float* part_in, float* stats_in, const float* gamma, const float* beta,
-                const uint8_t* keep_mask, const uint64_t* rng, uint32_t stream_id, float p_drop, const float* W,
-                const float* bias, float* Zout, float* part_out, int K, int N, int R, int n_seg,
+                const uint8_t* keep_mask, float p_drop, const float* W, const float* bias, float* Zout, float* part_out,
+                uint8_t* keep_out, const uint64_t* rng, uint32_t out_stream_id, float out_p_drop, int K, int N, int R, int n_seg,
                 const int32_t* seg_off_host, const float* running_mean, const float* running_var, void* stream);
 /* dY = dA * [A > 0] / (1-p) of the last application + tile sums */
 int scnb_hs_bwd_act(const float* dA, const float* Z, const float* A, int H, int R, int n_seg, const int32_t* seg_off_host,

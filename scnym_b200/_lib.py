@@ -55,9 +55,9 @@ SIGNATURES = {
     "scnb_peer_free": [P],
     "scnb_bn_running_update": [P, P, P, P, P, P, P, P, I, I, F, P, P],
     "scnb_mix_rows": [P, I, P, P, P, P, I, P, P],
-    "scnb_hs_mix": [P, I, P, P, P, I, P, P, P],
+    "scnb_hs_mix": [P, I, P, P, P, I, P, P, P, P, U32, F, P],
     "scnb_hs_act": [P, P, I, I, I, P, P, P, P, P, P, P, U32, F, P],
-    "scnb_hs_fwd": [P, P, P, P, P, P, P, P, U32, F, P, P, P, P, I, I, I, I, P, P, P, P],
+    "scnb_hs_fwd": [P, P, P, P, P, P, P, F, P, P, P, P, P, P, U32, F, I, I, I, I, P, P, P, P],
     "scnb_hs_bwd_act": [P, P, P, I, I, I, P, P, F, P, P, P],
     "scnb_hs_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, F, P, P, I, I, I, I, P, P, P],
     "scnb_hs_dw": [P, I, P, I, I, P, P, P],

@@ -22,6 +22,7 @@
 // Segment boundaries must be multiples of 32 rows and known on the host (pseudolabel thresholding off): the engine
 // falls back to the unfused kernels otherwise.
 #include "common.cuh"
+#include "tc_common.cuh"
 #include <stdlib.h>
 
 #define BN_EPS 1e-5f
@@ -30,7 +31,6 @@
 #define HS_T 512          // threads of the tile-GEMM kernels: 16 warps = 4 column slices x 4 K quarters
 #define HS_TE 256         // threads of the elementwise tile kernels (thread -> row tid/8, 8 columns)
 #define HS_KQ 4           // K splits inside a CTA
-#define HS_RED (3 * 4 * 16 * 32)   // floats of the cross-warp accumulator hand-over
 #define HS_MAXSEG 3
 
 // Phase stamps of CTA (0, 0) of the tile-GEMM kernels (SCNB_HS_DBG=1; tools/hs_phases.py reads them): %globaltimer in ns.
@@ -235,6 +235,8 @@ __device__ __forceinline__ void hs_tile_sums_rowmajor(const float (&a)[8], const
   __syncthreads();
 }
 
+__device__ __forceinline__ void hs_emit_keep(uint8_t* __restrict__ keep_out, int H, int row0, int c0, const uint64_t* __restrict__ rng,
+                                             uint32_t stream_id, float p_drop);
 __device__ __forceinline__ void hs_ld8(const float* __restrict__ p, float (&v)[8]) {
   const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -250,7 +252,8 @@ __device__ __forceinline__ void hs_st8(float* __restrict__ p, const float (&v)[8
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(HS_TE) k_hs_mix(const float* __restrict__ Z, int H, const int32_t* __restrict__ srcA,
                                                  const int32_t* __restrict__ srcB, const float* __restrict__ gam, int R,
-                                                 float* __restrict__ out, float* __restrict__ part) {
+                                                 float* __restrict__ out, float* __restrict__ part, uint8_t* __restrict__ keep_out,
+                                                 const uint64_t* __restrict__ rng, uint32_t stream_id, float p_drop) {
   PDL_ENTRY();
   __shared__ float red[HS_BM][HS_BN + 1];
   const int tid = threadIdx.x, c0 = blockIdx.x * HS_BN, tile = blockIdx.y;
@@ -272,12 +275,15 @@ __global__ void __launch_bounds__(HS_TE) k_hs_mix(const float* __restrict__ Z, i
   }
   if (out != Z) hs_st8(out + (size_t)i * H + c, v);
   hs_tile_stats_rowmajor(v, red, part, H, tile, c0);
+  if (keep_out) hs_emit_keep(keep_out, H, tile * HS_BM, c0, rng, stream_id, p_drop);   // dropout keep bytes of application 0
 }
 
 extern "C" int scnb_hs_mix(const float* Z, int H, const int32_t* srcA, const int32_t* srcB, const float* gam, int R, float* out,
-                           float* part, void* stream) {
+                           float* part, uint8_t* keep_out, const uint64_t* rng, uint32_t stream_id, float p_drop, void* stream) {
   SCNB_CHECK_ARG(Z && out && part && H > 0 && H % HS_BN == 0 && R > 0 && R % HS_BM == 0, "hs_mix: needs H %% 64 == 0, rows %% 32 == 0");
-  scnb_launch_pdl(k_hs_mix, dim3(H / HS_BN, R / HS_BM), dim3(HS_TE), 0, (cudaStream_t)stream, Z, H, srcA, srcB, gam, R, out, part);
+  SCNB_CHECK_ARG(!keep_out || (rng && p_drop > 0.f && p_drop < 1.f), "hs_mix: keep_out needs rng state and 0 < p_drop < 1");
+  scnb_launch_pdl(k_hs_mix, dim3(H / HS_BN, R / HS_BM), dim3(HS_TE), 0, (cudaStream_t)stream, Z, H, srcA, srcB, gam, R, out, part, keep_out,
+                  rng, stream_id, p_drop);
   SCNB_CHECK_LAUNCH("hs_mix");
   return SCNB_OK;
 }
@@ -356,16 +362,19 @@ extern "C" int scnb_hs_act(const float* Z, float* A, int H, int R, int n_seg, co
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Tile GEMM core: 32 x 64 output tile, K (multiple of 16, <= 512) staged whole in shared memory.
+// Tile GEMM core: 32 x 64 output tile, K (multiple of 32, <= 512) staged whole in shared memory.
 //   sA : [32][K + 4]  (row-major, k contiguous)
 //   sB : LAY 0 (NT: weight stored [n][k])  [64][K + 4];  LAY 1 (NN: weight stored [k][n])  [K][64 + 8]
-// 16 warps = 4 (16-column slices) x 4 (K quarters); a warp runs m16n8k8 3xTF32 over a 32 x 16 tile of its K quarter; the
-// quarters meet in shared memory.  Result: acc[2 m-tiles][2 n-tiles][4] valid in the warps of quarter 0 (warp < 4).
+// 16 warps = 4 (16-column slices) x 4 (K quarters); a warp runs m16n8k8 3xTF32 over a 32 x 16 tile of its K quarter.  The
+// four partial tiles then meet in shared memory as plain [4][32][72] row-major tiles (sT, which may alias the operand
+// panels: callers synchronise before and after), so that the epilogue runs on ALL 512 threads with float4 rows.
 // Fragment reads are bank-conflict free: row strides are 4 (k-contiguous) or 8 (k-row panels) modulo 32 words.
 // ---------------------------------------------------------------------------------------------------------------------
+#define HS_TP (HS_BN + 8)                       // row pitch of a partial tile
+#define HS_TILE_FLOATS (HS_KQ * HS_BM * HS_TP)  // floats of the four partial tiles
+
 template <int LAY>
-__device__ __forceinline__ void hs_tile_mma(const float* __restrict__ sA, const float* __restrict__ sB, int K, float* __restrict__ sRed,
-                                            float (&acc)[2][2][4]) {
+__device__ __forceinline__ void hs_tile_mma(const float* __restrict__ sA, const float* __restrict__ sB, int K, float (&acc)[2][2][4]) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int wn = warp & 3, kq = warp >> 2;
@@ -414,39 +423,55 @@ __device__ __forceinline__ void hs_tile_mma(const float* __restrict__ sA, const 
         hs_mma(acc[i][j], ah[i], bh[j]);
       }
   }
-  // K quarters 1..3 hand their accumulators over through shared memory (sRed: [3][4 slices][16 values][32 lanes]: a
-  // warp's store of one value is one conflict-free 128-byte line); quarter 0 adds them in a fixed order
-  if (kq > 0) {
-    float* dst = sRed + ((size_t)((kq - 1) * 4 + wn) * 16) * 32 + lane;
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) dst[((i * 2 + j) * 4 + c) * 32] = acc[i][j][c];
-  }
-  __syncthreads();
-  if (kq == 0) {
-#pragma unroll
-    for (int q = 0; q < HS_KQ - 1; ++q) {
-      const float* src = sRed + ((size_t)(q * 4 + wn) * 16) * 32 + lane;
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) acc[i][j][c] += src[((i * 2 + j) * 4 + c) * 32];
-    }
-  }
 }
-
-// Column reduction over the 32 rows of the tile for the accumulator layout of hs_tile_mma (warps with kh == 0):
-// lane (g, t) holds rows {g, g+8, 16+g, 24+g} of columns wn*16 + 8j + 2t + e.  Returns the 32-row sum in every lane.
-__device__ __forceinline__ float hs_col_sum32(float x) {
-  x += __shfl_xor_sync(0xffffffffu, x, 4);
-  x += __shfl_xor_sync(0xffffffffu, x, 8);
-  x += __shfl_xor_sync(0xffffffffu, x, 16);
-  return x;
+// this warp's partial accumulators -> sT[kq][row][col] (lane (g, t): rows 16i + g (+8), columns wn*16 + 8j + 2t, +1)
+__device__ __forceinline__ void hs_tile_store_partials(float* __restrict__ sT, const float (&acc)[2][2][4]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3, wn = warp & 3, kq = warp >> 2;
+  float* base = sT + (size_t)kq * HS_BM * HS_TP;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = wn * 16 + 8 * j + 2 * t;
+      *reinterpret_cast<float2*>(base + (16 * i + g) * HS_TP + c) = make_float2(acc[i][j][0], acc[i][j][1]);
+      *reinterpret_cast<float2*>(base + (16 * i + g + 8) * HS_TP + c) = make_float2(acc[i][j][2], acc[i][j][3]);
+    }
+}
+// element group of thread `tid` in the epilogue: row tid/16, columns 4 (tid%16) .. +3; sum of the four partial tiles
+__device__ __forceinline__ float4 hs_tile_sum4(const float* __restrict__ sT, int row, int c4) {
+  float4 v = *reinterpret_cast<const float4*>(sT + row * HS_TP + c4);
+#pragma unroll
+  for (int q = 1; q < HS_KQ; ++q) {
+    const float4 u = *reinterpret_cast<const float4*>(sT + (size_t)q * HS_BM * HS_TP + row * HS_TP + c4);
+    v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+  }
+  return v;
+}
+// one bulk copy per row: `rows` rows of `bytes` bytes, global pitch gld floats -> shared pitch sld floats (thread r issues row r)
+__device__ __forceinline__ void hs_bulk_rows(float* sdst, int sld, const float* gsrc, size_t gld, int rows, uint32_t bytes, uint32_t bar,
+                                             int tid0) {
+  for (int r = (int)threadIdx.x - tid0; r >= 0 && r < rows; r += HS_T) bulk_g2s(smem_u32(sdst + (size_t)r * sld), gsrc + (size_t)r * gld, bytes, bar);
+}
+// 0/1 keep bytes of the four columns c .. c+3 of row rg (mask: [R, H] bytes) as a 4-bit pattern
+__device__ __forceinline__ uint32_t hs_keep4(const uint8_t* __restrict__ mask, size_t elem) {
+  const uint32_t m = *reinterpret_cast<const uint32_t*>(mask + elem);
+  return ((m & 0xffu) ? 1u : 0u) | ((m & 0xff00u) ? 2u : 0u) | ((m & 0xff0000u) ? 4u : 0u) | ((m & 0xff000000u) ? 8u : 0u);
+}
+// Dropout keep bytes of a 32 x 64 tile of application `a`'s BatchNorm output (rows row0.., columns c0..), written by the
+// kernel that PRODUCES Z[a] (one Philox call per (row, 8-column group), the stream every BatchNorm -> Dropout kernel of this
+// library uses): the consumers, which all stage the same rows, then read bytes instead of each re-running Philox.
+__device__ __forceinline__ void hs_emit_keep(uint8_t* __restrict__ keep_out, int H, int row0, int c0, const uint64_t* __restrict__ rng,
+                                             uint32_t stream_id, float p_drop) {
+  const int tid = threadIdx.x;
+  if (tid >= HS_BM * (HS_BN / 8)) return;
+  const int r = row0 + (tid >> 3), c = c0 + ((tid & 7) << 3);
+  const uint64_t seed = rng[0], strm = rng[1] * 64ull + stream_id;
+  const uint32_t thr16 = (uint32_t)(p_drop * 65536.0f + 0.5f);
+  const uint32_t kb = keep8(nullptr, 0, (uint64_t)r * (uint64_t)(H >> 3) + (uint64_t)(c >> 3), seed, strm, thr16);
+  uint2 o;
+  o.x = (kb & 1u) | ((kb & 2u) << 7) | ((kb & 4u) << 14) | ((kb & 8u) << 21);
+  o.y = ((kb >> 4) & 1u) | ((kb & 32u) << 3) | ((kb & 64u) << 10) | ((kb & 128u) << 17);
+  *reinterpret_cast<uint2*>(keep_out + (size_t)r * H + c) = o;
 }
 
 struct HsFwdArgs {
@@ -458,39 +483,49 @@ struct HsFwdArgs {
   const float* rvar;     //   statistics, no dropout, no statistics of the output
   const float* gamma;    // BatchNorm of application a-1
   const float* beta;
-  const uint8_t* keep;   // injected dropout mask of application a-1 ([R, K] bytes) or NULL
-  const uint64_t* rng;
-  uint32_t stream_id;
+  const uint8_t* keep;   // dropout keep bytes of application a-1 ([R, K]; written by the producer of Zin, or injected)
   float p_drop;
   const float* W;        // [N, K] Linear of application a
   const float* bias;     // [N]
   float* Zout;           // [R, N]
   float* part_out;       // [R/32][2][N]
+  uint8_t* keep_out;     // [R, N] dropout keep bytes of application a (NULL: not generated here)
+  const uint64_t* rng;
+  uint32_t out_stream_id;
+  float out_p_drop;
   int K, N, R;
   int dbg;
   HsSeg sg;
 };
 
-// grid = (N/64, R/32), 512 threads; dynamic shared memory: sA 32*(K+4) + sB 64*(K+4) + 4*K + HS_RED floats.
+// grid = (N/64, R/32), 512 threads; dynamic shared memory: sA 32*(K+4) + max(sB 64*(K+4), partial tiles) + 4*K floats.
 __global__ void __launch_bounds__(HS_T) k_hs_fwd(const __grid_constant__ HsFwdArgs p) {
   PDL_ENTRY();
   extern __shared__ __align__(16) float hs_smem[];
+  __shared__ __align__(8) unsigned long long bar_mem;
   const int K = p.K, N = p.N;
+  const int b_floats = max(HS_BN * (K + 4), HS_TILE_FLOATS);
   float* sA = hs_smem;
   float* sB = sA + HS_BM * (K + 4);
-  float* sMean = sB + HS_BN * (K + 4);
+  float* sT = sB;                       // partial tiles alias the weight panel once the MMAs are done
+  float* sMean = sB + b_floats;
   float* sInv = sMean + K;
   float* sGam = sInv + K;
   float* sBet = sGam + K;
-  float* sRed = sBet + K;        // HS_RED floats
   const int tid = threadIdx.x, n0 = blockIdx.x * HS_BN, tile = blockIdx.y, row0 = tile * HS_BM;
   const int s = hs_seg_of(p.sg, row0);
   const int t0 = p.sg.off[s] / HS_BM, t1 = p.sg.off[s + 1] / HS_BM;
+  const uint32_t bar = smem_u32(&bar_mem);
   hs_stamp(p.dbg, 0, 0);
-  // stage the raw operands
-  hs_stage_rows(sA, K + 4, p.Zin + (size_t)row0 * K, K, HS_BM, K >> 2);
-  hs_stage_rows(sB, K + 4, p.W + (size_t)n0 * K, K, HS_BN, K >> 2);
-  hs_commit();
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // stage the raw operands: one bulk copy per row (96 copies per CTA instead of 6144 16-byte cp.async)
+  if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)((HS_BM + HS_BN) * K * sizeof(float)));
+  hs_bulk_rows(sA, K + 4, p.Zin + (size_t)row0 * K, K, HS_BM, (uint32_t)(K * sizeof(float)), bar, 0);
+  hs_bulk_rows(sB, K + 4, p.W + (size_t)n0 * K, K, HS_BN, (uint32_t)(K * sizeof(float)), bar, HS_BM);
   hs_stamp(p.dbg, 0, 1);
   // segment statistics of the input while the copies fly
   const bool eval = p.rmean != nullptr;
@@ -520,32 +555,16 @@ __global__ void __launch_bounds__(HS_T) k_hs_fwd(const __grid_constant__ HsFwdAr
     }
   }
   hs_stamp(p.dbg, 0, 2);
-  hs_wait_all();
+  mbar_wait(bar, 0);
   __syncthreads();
   hs_stamp(p.dbg, 0, 3);
-  // BatchNorm -> Dropout -> ReLU in place on the A operand
-  uint64_t seed = 0, strm = 0;
-  if (p.p_drop > 0.f && !p.keep) {
-    seed = p.rng[0];
-    strm = p.rng[1] * 64ull + p.stream_id;
-  }
-  const uint32_t thr16 = (uint32_t)(p.p_drop * 65536.0f + 0.5f);
+  // BatchNorm -> Dropout -> ReLU in place on the A operand (consecutive lanes take consecutive float4: no bank conflicts)
   const float drop_scale = 1.0f / (1.0f - p.p_drop);
-  const int gpr = K >> 3;   // 8-column groups per row (the dropout stream is defined per group)
-  const int fpr = K >> 2;   // float4 per row: consecutive lanes take consecutive float4 (no shared-memory bank conflicts)
-  for (int f = tid; f < HS_BM * fpr; f += HS_T) {
-    const int r = f / fpr, q = f - r * fpr, c = q << 2;
+  const bool drop = p.p_drop > 0.f;
+  const int fpr = K >> 2;
+  auto transform = [&](int r, int c) {
     float* a = sA + r * (K + 4) + c;
     const int rg = row0 + r;
-    uint32_t kb = 0xfu;
-    if (p.p_drop > 0.f) {
-      // lanes 2j and 2j+1 hold the two float4 of one 8-column dropout group: one Philox call per pair (whole warps run
-      // every iteration of this loop: 8K elements in steps of 512 threads)
-      uint32_t k8 = 0;
-      if (!(tid & 1)) k8 = keep8(p.keep, (size_t)rg * K + (c & ~7), (uint64_t)rg * gpr + (c >> 3), seed, strm, thr16);
-      k8 = __shfl_sync(0xffffffffu, k8, (tid & 31) & ~1);
-      kb = k8 >> (c & 4);
-    }
     const float4 z = *reinterpret_cast<const float4*>(a);
     const float4 mu = *reinterpret_cast<const float4*>(sMean + c), is = *reinterpret_cast<const float4*>(sInv + c);
     const float4 gm = *reinterpret_cast<const float4*>(sGam + c), bt = *reinterpret_cast<const float4*>(sBet + c);
@@ -554,7 +573,8 @@ __global__ void __launch_bounds__(HS_T) k_hs_fwd(const __grid_constant__ HsFwdAr
     y.y = (z.y - mu.y) * is.y * gm.y + bt.y;
     y.z = (z.z - mu.z) * is.z * gm.z + bt.z;
     y.w = (z.w - mu.w) * is.w * gm.w + bt.w;
-    if (p.p_drop > 0.f) {
+    if (drop) {
+      const uint32_t kb = hs_keep4(p.keep, (size_t)rg * K + c);
       y.x = (kb & 1u) ? y.x * drop_scale : 0.f;
       y.y = (kb & 2u) ? y.y * drop_scale : 0.f;
       y.z = (kb & 4u) ? y.z * drop_scale : 0.f;
@@ -563,47 +583,54 @@ __global__ void __launch_bounds__(HS_T) k_hs_fwd(const __grid_constant__ HsFwdAr
     y = make_float4(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f), fmaxf(y.z, 0.f), fmaxf(y.w, 0.f));
     *reinterpret_cast<float4*>(a) = y;
     if (blockIdx.x == 0 && p.Aout) *reinterpret_cast<float4*>(p.Aout + (size_t)rg * K + c) = y;
+  };
+  if (HS_T % fpr == 0) {   // every thread keeps its float4 column and walks rows (no divisions in the loop)
+    const int rpp = HS_T / fpr, r0 = tid / fpr, c = (tid - r0 * fpr) << 2;
+#pragma unroll 4
+    for (int r = r0; r < HS_BM; r += rpp) transform(r, c);
+  } else {
+    for (int f = tid; f < HS_BM * fpr; f += HS_T) {
+      const int r = f / fpr;
+      transform(r, (f - r * fpr) << 2);
+    }
   }
   __syncthreads();
   hs_stamp(p.dbg, 0, 4);
   float acc[2][2][4];
-  hs_tile_mma<0>(sA, sB, K, sRed, acc);
+  hs_tile_mma<0>(sA, sB, K, acc);
+  __syncthreads();                       // every warp is done with the weight panel: the partial tiles may overwrite it
+  hs_tile_store_partials(sT, acc);
+  __syncthreads();
   hs_stamp(p.dbg, 0, 5);
-  // epilogue (warps of the lower K half): bias, Z[a] tile, tile statistics
-  const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3, wn = warp & 3;
-  if (warp < 4) {
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int c = n0 + wn * 16 + 8 * j + 2 * t;
-      const float b0 = p.bias ? p.bias[c] : 0.f, b1 = p.bias ? p.bias[c + 1] : 0.f;
-      float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        acc[i][j][0] += b0; acc[i][j][1] += b1; acc[i][j][2] += b0; acc[i][j][3] += b1;
-        const int r = row0 + 16 * i + g;
-        *reinterpret_cast<float2*>(p.Zout + (size_t)r * N + c) = make_float2(acc[i][j][0], acc[i][j][1]);
-        *reinterpret_cast<float2*>(p.Zout + (size_t)(r + 8) * N + c) = make_float2(acc[i][j][2], acc[i][j][3]);
-        s0 += acc[i][j][0] + acc[i][j][2];
-        s1 += acc[i][j][1] + acc[i][j][3];
+  // epilogue on all threads: thread -> (row tid/16, 4 columns): bias, Z[a] tile, tile statistics
+  {
+    const int row = tid >> 4, c4 = (tid & 15) << 2;
+    float4 v = hs_tile_sum4(sT, row, c4);
+    if (p.bias) {
+      const float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + c4);
+      v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+    }
+    *reinterpret_cast<float4*>(p.Zout + (size_t)(row0 + row) * N + n0 + c4) = v;
+    *reinterpret_cast<float4*>(sT + row * HS_TP + c4) = v;      // own elements only: no hazard with other threads' reads
+  }
+  if (p.part_out) {
+    __syncthreads();
+    if (tid < HS_BN) {
+      float mean = 0.f;
+#pragma unroll 8
+      for (int i = 0; i < HS_BM; ++i) mean += sT[i * HS_TP + tid];
+      mean *= (1.0f / HS_BM);
+      float m2 = 0.f;
+#pragma unroll 8
+      for (int i = 0; i < HS_BM; ++i) {
+        const float d = sT[i * HS_TP + tid] - mean;
+        m2 = fmaf(d, d, m2);
       }
-      const float m0 = hs_col_sum32(s0) * (1.0f / HS_BM), m1 = hs_col_sum32(s1) * (1.0f / HS_BM);
-      float q0 = 0.f, q1 = 0.f;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        float d;
-        d = acc[i][j][0] - m0; q0 = fmaf(d, d, q0);
-        d = acc[i][j][2] - m0; q0 = fmaf(d, d, q0);
-        d = acc[i][j][1] - m1; q1 = fmaf(d, d, q1);
-        d = acc[i][j][3] - m1; q1 = fmaf(d, d, q1);
-      }
-      q0 = hs_col_sum32(q0);
-      q1 = hs_col_sum32(q1);
-      if (g == 0 && p.part_out) {
-        *reinterpret_cast<float2*>(p.part_out + ((size_t)tile * 2 + 0) * N + c) = make_float2(m0, m1);
-        *reinterpret_cast<float2*>(p.part_out + ((size_t)tile * 2 + 1) * N + c) = make_float2(q0, q1);
-      }
+      p.part_out[((size_t)tile * 2 + 0) * N + n0 + tid] = mean;
+      p.part_out[((size_t)tile * 2 + 1) * N + n0 + tid] = m2;
     }
   }
+  if (p.keep_out) hs_emit_keep(p.keep_out, N, row0, n0, p.rng, p.out_stream_id, p.out_p_drop);
   hs_stamp(p.dbg, 0, 6);
 }
 
@@ -629,23 +656,29 @@ static int hs_set_smem(KernelT kern, size_t bytes, const char* who) {
 }
 
 extern "C" int scnb_hs_fwd(const float* Zin, float* Aout, const float* part_in, float* stats_in, const float* gamma,
-                           const float* beta, const uint8_t* keep_mask, const uint64_t* rng, uint32_t stream_id, float p_drop,
-                           const float* W, const float* bias, float* Zout, float* part_out, int K, int N, int R, int n_seg,
-                           const int32_t* seg_off_host, const float* running_mean, const float* running_var, void* stream) {
+                           const float* beta, const uint8_t* keep_mask, float p_drop, const float* W, const float* bias, float* Zout,
+                           float* part_out, uint8_t* keep_out, const uint64_t* rng, uint32_t out_stream_id, float out_p_drop, int K,
+                           int N, int R, int n_seg, const int32_t* seg_off_host, const float* running_mean,
+                           const float* running_var, void* stream) {
   SCNB_CHECK_ARG(Zin && gamma && beta && W && Zout, "hs_fwd: null argument");
   SCNB_CHECK_ARG((running_mean && running_var && p_drop == 0.f) || (!running_mean && stats_in && Aout && part_out),
                  "hs_fwd: train mode needs stats_in / Aout / part_out (+ part_in unless the statistics are given), eval mode running "
                  "statistics and no dropout");
   SCNB_CHECK_ARG(K % 32 == 0 && K >= 32 && K <= 512 && N % HS_BN == 0 && R % HS_BM == 0, "hs_fwd: needs K %% 32 == 0 (<= 512), N %% 64 == 0, rows %% 32 == 0");
-  SCNB_CHECK_ARG(!(p_drop > 0.f) || keep_mask || rng, "hs_fwd: dropout needs keep_mask or rng state");
+  SCNB_CHECK_ARG(!(p_drop > 0.f) || keep_mask, "hs_fwd: dropout needs the keep bytes of the input application");
+  SCNB_CHECK_ARG(!keep_out || (rng && out_p_drop > 0.f && out_p_drop < 1.f), "hs_fwd: keep_out needs rng state and 0 < out_p_drop < 1");
   SCNB_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "hs_fwd: p_drop out of range");
+  SCNB_CHECK_ARG((((uintptr_t)Zin | (uintptr_t)W | (uintptr_t)Zout | (uintptr_t)bias | (uintptr_t)keep_mask | (uintptr_t)keep_out) % 16) == 0,
+                 "hs_fwd: operands must be 16-byte aligned");
   HsFwdArgs a;
   a.Zin = Zin; a.Aout = Aout; a.part_in = part_in; a.stats_in = stats_in; a.gamma = gamma; a.beta = beta; a.keep = keep_mask;
-  a.rng = rng; a.stream_id = stream_id; a.p_drop = p_drop; a.W = W; a.bias = bias; a.Zout = Zout; a.part_out = part_out;
+  a.p_drop = p_drop; a.W = W; a.bias = bias; a.Zout = Zout; a.part_out = part_out; a.keep_out = keep_out; a.rng = rng;
+  a.out_stream_id = out_stream_id; a.out_p_drop = out_p_drop;
   a.K = K; a.N = N; a.R = R; a.rmean = running_mean; a.rvar = running_var; a.dbg = hs_dbg_on();
   int rc = hs_fill_seg(a.sg, n_seg, seg_off_host, R, "hs_fwd");
   if (rc != SCNB_OK) return rc;
-  const size_t smem = ((size_t)(HS_BM + HS_BN) * (K + 4) + 4 * (size_t)K + HS_RED) * sizeof(float);
+  const size_t b_floats = (size_t)HS_BN * (K + 4) > (size_t)HS_TILE_FLOATS ? (size_t)HS_BN * (K + 4) : (size_t)HS_TILE_FLOATS;
+  const size_t smem = ((size_t)HS_BM * (K + 4) + b_floats + 4 * (size_t)K) * sizeof(float);
   rc = hs_set_smem(k_hs_fwd, smem, "hs_fwd");
   if (rc != SCNB_OK) return rc;
   scnb_launch_pdl(k_hs_fwd, dim3(N / HS_BN, R / HS_BM), dim3(HS_T), smem, (cudaStream_t)stream, a);
@@ -719,27 +752,35 @@ struct HsBwdArgs {
   HsSeg sg;
 };
 
-// grid = (N/64, R/32); dynamic shared memory: sA, sZ 32*(K+4) each + sB K*(64+8) + 5*K + 2048 floats.
+// grid = (N/64, R/32), 512 threads; dynamic shared memory: sA, sZ 32*(K+4) each + max(sB K*(64+8), partial tiles) + 5*K floats.
 __global__ void __launch_bounds__(HS_T) k_hs_bwd(const __grid_constant__ HsBwdArgs p) {
   PDL_ENTRY();
   extern __shared__ __align__(16) float hs_smem[];
+  __shared__ __align__(8) unsigned long long bar_mem;
   const int K = p.K, N = p.N;
+  const int b_floats = max(K * (HS_BN + 8), HS_TILE_FLOATS);
   float* sA = hs_smem;                       // dY tile, transformed into dZ in place
-  float* sB = sA + HS_BM * (K + 4);          // W_a panel [K][64 + 8]
-  float* sZ = sB + K * (HS_BN + 8);          // Z[a] tile [32][K + 4]
-  float* sM1 = sZ + HS_BM * (K + 4);         // mean(dY) per column
+  float* sZ = sA + HS_BM * (K + 4);          // Z[a] tile [32][K + 4]
+  float* sB = sZ + HS_BM * (K + 4);          // W_a panel [K][64 + 8]
+  float* sT = sB;                            // partial tiles alias the weight panel after the MMAs
+  float* sM1 = sB + b_floats;                // mean(dY) per column
   float* sM2 = sM1 + K;                      // mean(dY*zhat)
   float* sMu = sM2 + K;                      // BatchNorm mean / invstd / gamma of application a
   float* sIs = sMu + K;
   float* sGm = sIs + K;
-  float* sRed = sGm + K;                     // HS_RED floats
   const int tid = threadIdx.x, n0 = blockIdx.x * HS_BN, tile = blockIdx.y, row0 = tile * HS_BM;
   const int s = hs_seg_of(p.sg, row0);
   const int t0 = p.sg.off[s] / HS_BM, t1 = p.sg.off[s + 1] / HS_BM;
-  hs_stage_rows(sA, K + 4, p.dYin + (size_t)row0 * K, K, HS_BM, K >> 2);
-  hs_stage_rows(sZ, K + 4, p.Zin + (size_t)row0 * K, K, HS_BM, K >> 2);
-  hs_stage_rows(sB, HS_BN + 8, p.W + n0, N, K, HS_BN / 4);
-  hs_commit();
+  const uint32_t bar = smem_u32(&bar_mem);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)((2 * HS_BM * K + K * HS_BN) * sizeof(float)));
+  hs_bulk_rows(sA, K + 4, p.dYin + (size_t)row0 * K, K, HS_BM, (uint32_t)(K * sizeof(float)), bar, 0);
+  hs_bulk_rows(sZ, K + 4, p.Zin + (size_t)row0 * K, K, HS_BM, (uint32_t)(K * sizeof(float)), bar, HS_BM);
+  hs_bulk_rows(sB, HS_BN + 8, p.W + n0, N, K, (uint32_t)(HS_BN * sizeof(float)), bar, 2 * HS_BM);
   const float inv_n = 1.0f / (float)((t1 - t0) * HS_BM);
   for (int c = tid; c < K; c += HS_T) {
     if (!p.part_in) {
@@ -759,11 +800,17 @@ __global__ void __launch_bounds__(HS_T) k_hs_bwd(const __grid_constant__ HsBwdAr
     sIs[c] = p.stats_in[((size_t)s * 3 + 2) * K + c];
     sGm[c] = p.gamma[c];
   }
-  hs_wait_all();
+  // operands of the epilogue, fetched while the copies fly: thread -> (row tid/16, 4 columns) of the previous application
+  const int erow = tid >> 4, ec4 = (tid & 15) << 2;
+  const size_t eo = (size_t)(row0 + erow) * N + n0 + ec4;
+  const float4 av = *reinterpret_cast<const float4*>(p.Aprev + eo);
+  const float4 zv = *reinterpret_cast<const float4*>(p.Zprev + eo);
+  const float4 pmu = *reinterpret_cast<const float4*>(p.stats_prev + ((size_t)s * 3 + 0) * N + n0 + ec4);
+  const float4 pis = *reinterpret_cast<const float4*>(p.stats_prev + ((size_t)s * 3 + 2) * N + n0 + ec4);
+  mbar_wait(bar, 0);
   __syncthreads();
   const int fpr = K >> 2;
-  for (int f = tid; f < HS_BM * fpr; f += HS_T) {
-    const int r = f / fpr, q = f - r * fpr, c = q << 2;
+  auto transform = [&](int r, int c) {
     float* a = sA + r * (K + 4) + c;
     const float4 dy = *reinterpret_cast<const float4*>(a), z = *reinterpret_cast<const float4*>(sZ + r * (K + 4) + c);
     const float4 mu = *reinterpret_cast<const float4*>(sMu + c), is = *reinterpret_cast<const float4*>(sIs + c);
@@ -776,42 +823,48 @@ __global__ void __launch_bounds__(HS_T) k_hs_bwd(const __grid_constant__ HsBwdAr
     v.w = gm.w * is.w * (dy.w - m1.w - (z.w - mu.w) * is.w * m2.w);
     *reinterpret_cast<float4*>(a) = v;
     if (blockIdx.x == 0) *reinterpret_cast<float4*>(p.dZout + (size_t)(row0 + r) * K + c) = v;
+  };
+  if (HS_T % fpr == 0) {
+    const int rpp = HS_T / fpr, r0 = tid / fpr, c = (tid - r0 * fpr) << 2;
+#pragma unroll 4
+    for (int r = r0; r < HS_BM; r += rpp) transform(r, c);
+  } else {
+    for (int f = tid; f < HS_BM * fpr; f += HS_T) {
+      const int r = f / fpr;
+      transform(r, (f - r * fpr) << 2);
+    }
   }
   __syncthreads();
   float acc[2][2][4];
-  hs_tile_mma<1>(sA, sB, K, sRed, acc);
-  const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3, wn = warp & 3;
-  if (warp < 4) {
+  hs_tile_mma<1>(sA, sB, K, acc);
+  __syncthreads();
+  hs_tile_store_partials(sT, acc);
+  __syncthreads();
+  // epilogue on all threads: dY[a-1] = dA[a-1] * [A[a-1] > 0] / (1-p), tile sums of (dY, dY*zhat)
+  {
     const float drop_scale = 1.0f / (1.0f - p.p_drop_prev);
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int c = n0 + wn * 16 + 8 * j + 2 * t;
-      const float2 mu = *reinterpret_cast<const float2*>(p.stats_prev + ((size_t)s * 3 + 0) * N + c);
-      const float2 is = *reinterpret_cast<const float2*>(p.stats_prev + ((size_t)s * 3 + 2) * N + c);
-      float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int r = row0 + 16 * i + g + 8 * h;
-          const float2 av = *reinterpret_cast<const float2*>(p.Aprev + (size_t)r * N + c);
-          const float2 zv = *reinterpret_cast<const float2*>(p.Zprev + (size_t)r * N + c);
-          const float d0 = av.x > 0.f ? acc[i][j][2 * h] * drop_scale : 0.f;
-          const float d1 = av.y > 0.f ? acc[i][j][2 * h + 1] * drop_scale : 0.f;
-          *reinterpret_cast<float2*>(p.dYout + (size_t)r * N + c) = make_float2(d0, d1);
-          s1a += d0;
-          s1b += d1;
-          s2a = fmaf(d0, (zv.x - mu.x) * is.x, s2a);
-          s2b = fmaf(d1, (zv.y - mu.y) * is.y, s2b);
-        }
-      }
-      s1a = hs_col_sum32(s1a); s1b = hs_col_sum32(s1b);
-      s2a = hs_col_sum32(s2a); s2b = hs_col_sum32(s2b);
-      if (g == 0) {
-        *reinterpret_cast<float2*>(p.part_out + ((size_t)tile * 2 + 0) * N + c) = make_float2(s1a, s1b);
-        *reinterpret_cast<float2*>(p.part_out + ((size_t)tile * 2 + 1) * N + c) = make_float2(s2a, s2b);
-      }
-    }
+    const float4 da = hs_tile_sum4(sT, erow, ec4);
+    float4 d, dz;
+    d.x = av.x > 0.f ? da.x * drop_scale : 0.f;       // A > 0 implies the element was kept by the dropout
+    d.y = av.y > 0.f ? da.y * drop_scale : 0.f;
+    d.z = av.z > 0.f ? da.z * drop_scale : 0.f;
+    d.w = av.w > 0.f ? da.w * drop_scale : 0.f;
+    dz.x = d.x * ((zv.x - pmu.x) * pis.x);
+    dz.y = d.y * ((zv.y - pmu.y) * pis.y);
+    dz.z = d.z * ((zv.z - pmu.z) * pis.z);
+    dz.w = d.w * ((zv.w - pmu.w) * pis.w);
+    *reinterpret_cast<float4*>(p.dYout + eo) = d;
+    *reinterpret_cast<float4*>(sT + erow * HS_TP + ec4) = d;                                  // partial tile 0: own elements
+    *reinterpret_cast<float4*>(sT + (size_t)HS_BM * HS_TP + erow * HS_TP + ec4) = dz;         // partial tile 1: own elements
+  }
+  __syncthreads();
+  if (tid < 2 * HS_BN) {
+    const int which = tid >> 6, c = tid & (HS_BN - 1);
+    const float* src = sT + (size_t)which * HS_BM * HS_TP + c;
+    float acc1 = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < HS_BM; ++i) acc1 += src[i * HS_TP];
+    p.part_out[((size_t)tile * 2 + which) * N + n0 + c] = acc1;
   }
 }
 
@@ -829,7 +882,8 @@ extern "C" int scnb_hs_bwd(const float* dYin, const float* Zin, const float* sta
   a.part_out = part_out; a.K = K; a.N = N; a.R = R; a.bmean_in = bmean_in;
   int rc = hs_fill_seg(a.sg, n_seg, seg_off_host, R, "hs_bwd");
   if (rc != SCNB_OK) return rc;
-  const size_t smem = ((size_t)2 * HS_BM * (K + 4) + (size_t)K * (HS_BN + 8) + 5 * (size_t)K + HS_RED) * sizeof(float);
+  const size_t b_floats = (size_t)K * (HS_BN + 8) > (size_t)HS_TILE_FLOATS ? (size_t)K * (HS_BN + 8) : (size_t)HS_TILE_FLOATS;
+  const size_t smem = ((size_t)2 * HS_BM * (K + 4) + b_floats + 5 * (size_t)K) * sizeof(float);
   rc = hs_set_smem(k_hs_bwd, smem, "hs_bwd");
   if (rc != SCNB_OK) return rc;
   scnb_launch_pdl(k_hs_bwd, dim3(N / HS_BN, R / HS_BM), dim3(HS_T), smem, (cudaStream_t)stream, a);

@@ -358,6 +358,8 @@ class TrainEngine(object):
             self.dYs = [f32(R, w) for w in self.widths]
             self.pf = [f32(R // 32, 2, w) for w in self.widths]
             self.pb = [f32(R // 32, 2, w) for w in self.widths]
+            # dropout keep bytes of the applications consumed by a tile GEMM: drawn once by the kernel that produces Z[a]
+            self.keepbuf = [torch.ones((R, w), dtype=torch.uint8, device=dev) for w in self.widths[:-1]]
             if self.comm is not None:   # data parallel: global backward means per application, written by scnb_hs_xchg
                 self.bmean = [f32(self.n_seg, 2, w) for w in self.widths]
         # "auto": the tensor-core form pays off once the batch fills at least two 256-row tiles (measured: 512 rows,
@@ -577,7 +579,9 @@ class TrainEngine(object):
         else:
             self._plan(self.confident, st)
         if self.hs_fused:    # hidden-space MixUp + tile statistics of its output, one launch
-            call("scnb_hs_mix", ptr(self.Z1), H0, ptr(self.srcA), ptr(self.srcB), ptr(self.gam), R, ptr(self.Zs[0]), ptr(self.pf[0]), st)
+            ko = None if (self.inj_hidden_keep is not None or float(blk[0]["drop"].p) <= 0.0) else ptr(self.keepbuf[0])
+            call("scnb_hs_mix", ptr(self.Z1), H0, ptr(self.srcA), ptr(self.srcB), ptr(self.gam), R, ptr(self.Zs[0]), ptr(self.pf[0]), ko, rng,
+                 SID_HID, float(blk[0]["drop"].p), st)
         else:
             call("scnb_mix_rows", ptr(self.Z1), H0, ptr(self.srcA), ptr(self.srcB), ptr(self.gam), ptr(self.counts[3:]), R,
                  ptr(self.Zs[0]), st)
@@ -715,8 +719,9 @@ class TrainEngine(object):
             for a in range(1, self.n_app):
                 rm, rv = tbn(a - 1)
                 k, n = self.widths[a - 1], self.widths[a]
-                call("scnb_hs_fwd", ptr(tz), None, None, None, ptr(tw(blk[a - 1]["g"])), ptr(tw(blk[a - 1]["beta"])), None, None, 0, 0.0,
-                     ptr(tw(blk[a]["W"])), ptr(tw(blk[a]["b"])), ptr(self.TZ[a]), None, k, n, KU, 1, seg1, ptr(rm), ptr(rv), st)
+                call("scnb_hs_fwd", ptr(tz), None, None, None, ptr(tw(blk[a - 1]["g"])), ptr(tw(blk[a - 1]["beta"])), None, 0.0,
+                     ptr(tw(blk[a]["W"])), ptr(tw(blk[a]["b"])), ptr(self.TZ[a]), None, None, None, 0, 0.0, k, n, KU, 1, seg1, ptr(rm),
+                     ptr(rv), st)
                 tz = self.TZ[a]
             a0 = self.n_app - 1
         else:
@@ -781,16 +786,20 @@ class TrainEngine(object):
         if self.hs_fused:
             seg = self._seg_host.ctypes.data
             dp = self.comm is not None
-            if self.mode != "mixmatch":   # no MixUp in front: tile statistics of the first layer's output
-                call("scnb_hs_mix", ptr(self.Zs[0]), self.widths[0], None, None, None, R, ptr(self.Zs[0]), ptr(self.pf[0]), st)
+            inj = self.inj_hidden_keep is not None
+            pd = [float(b["drop"].p) for b in blk]
+            keep_out = lambda a: (ptr(self.keepbuf[a]) if (a < self.n_app - 1 and not inj and pd[a] > 0.0) else None)
+            keep_in = lambda a: (self._hidden_keep(a) if inj else (ptr(self.keepbuf[a]) if pd[a] > 0.0 else None))
+            if self.mode != "mixmatch":   # no MixUp in front: tile statistics (and the dropout keep bytes) of the first layer's output
+                call("scnb_hs_mix", ptr(self.Zs[0]), self.widths[0], None, None, None, R, ptr(self.Zs[0]), ptr(self.pf[0]), keep_out(0), rng,
+                     SID_HID, pd[0], st)
             for a in range(1, self.n_app):
                 k, n = self.widths[a - 1], self.widths[a]
                 if dp:
                     self._xchg(0, a - 1, st)
                 call("scnb_hs_fwd", ptr(self.Zs[a - 1]), ptr(self.As[a - 1]), None if dp else ptr(self.pf[a - 1]), ptr(self.stats[a - 1]),
-                     self.P(blk[a - 1]["g"]), self.P(blk[a - 1]["beta"]), self._hidden_keep(a - 1), rng, SID_HID + a - 1,
-                     float(blk[a - 1]["drop"].p), self.P(blk[a]["W"]), self.P(blk[a]["b"]), ptr(self.Zs[a]), ptr(self.pf[a]), k, n, R,
-                     self.n_seg, seg, None, None, st)
+                     self.P(blk[a - 1]["g"]), self.P(blk[a - 1]["beta"]), keep_in(a - 1), pd[a - 1], self.P(blk[a]["W"]), self.P(blk[a]["b"]),
+                     ptr(self.Zs[a]), ptr(self.pf[a]), keep_out(a), rng, SID_HID + a, pd[a], k, n, R, self.n_seg, seg, None, None, st)
             a = self.n_app - 1
             if dp:
                 self._xchg(0, a, st)

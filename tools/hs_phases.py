@@ -24,15 +24,17 @@ stats = torch.zeros(3, 3, K, device=dev)
 A = torch.zeros(R, K, device=dev)
 Zo = torch.zeros(R, N, device=dev)
 rng = torch.tensor([123, 1], dtype=torch.int64, device=dev)
+keep2 = torch.ones(R, N, dtype=torch.uint8, device=dev)
 seg = np.asarray([0, 256, 512, 1024], dtype=np.int32)
 st = torch.cuda.current_stream().cuda_stream
-call("scnb_hs_mix", ptr(Z), K, None, None, None, R, ptr(Z), ptr(part), st)
+keep = torch.ones(R, K, dtype=torch.uint8, device=dev)
+call("scnb_hs_mix", ptr(Z), K, None, None, None, R, ptr(Z), ptr(part), ptr(keep), ptr(rng), 16, 0.5, st)
 names = ["start", "cp.async issued", "stats combined", "operands landed", "A transformed", "mma + reduce", "epilogue"]
 for it in range(4):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    call("scnb_hs_fwd", ptr(Z), ptr(A), ptr(part), ptr(stats), ptr(gam), ptr(bet), None, ptr(rng), 16, 0.5, ptr(W), ptr(b), ptr(Zo), ptr(part2),
-         K, N, R, 3, seg.ctypes.data, None, None, st)
+    call("scnb_hs_fwd", ptr(Z), ptr(A), ptr(part), ptr(stats), ptr(gam), ptr(bet), ptr(keep), 0.5, ptr(W), ptr(b), ptr(Zo), ptr(part2),
+         ptr(keep2), ptr(rng), 17, 0.5, K, N, R, 3, seg.ctypes.data, None, None, st)
     e1.record()
     torch.cuda.synchronize()
     buf = (ctypes.c_ulonglong * 32)()
