@@ -53,7 +53,8 @@ int scnb_csr_gather_rows2(const int64_t* indptr_A, const int32_t* indices_A, con
                           int augment_A, uint32_t stream_id_A, const int64_t* indptr_B, const int32_t* indices_B,
                           const float* data_B, const int64_t* rows_B, int nB, int augment_B, uint32_t stream_id_B,
                           const int32_t* b_indptr, int32_t* b_idx, float* b_val, const uint8_t* keep_mask,
-                          const uint64_t* rng, float p_drop, int32_t* gene_cnt, void* stream);
+                          const uint64_t* rng, float p_drop, int32_t* gene_cnt, int ctr_off /* as scnb_csr_gather_rows_aug */,
+                          void* stream);
 /* The other augmentation schemes of scnym/dataprep.py:730-754 (AUGMENTATION_SCHEMES) on rows [0, n) of one source, on the
  * STORED entries only (every stage maps 0 to 0).  scheme: 1 log1p_drop (:721-729), 2 log1p_mask (GeneMasking :405-465),
  * 3 log1p_poisson (PoissonSample :277-341), 4 log1p_poisson_drop (depth ~ U(0.1, 2), then InputDropout), 5 count_poisson
@@ -64,6 +65,7 @@ int scnb_csr_gather_rows_aug(const int64_t* indptr, const int32_t* indices, cons
                              int64_t row0, int n, const int32_t* b_indptr, int32_t* b_idx, float* b_val, int scheme,
                              int n_genes, float p_drop, float p_apply, const uint8_t* keep_mask, const float* inj_poisson,
                              const float* inj_row_depth, const uint64_t* rng, uint32_t stream_id, int32_t* gene_cnt,
+                             int ctr_off /* added to the RNG step counter rng[1]: 1 when the next step's batch is assembled early */,
                              void* stream);
 
 /* Step prologue in one launch: sampler hand-off (as scnb_fetch_step; tables may be NULL, then
@@ -74,7 +76,9 @@ int scnb_step_prep(const int64_t* l_tab, const int64_t* u_tab, const float* key_
                    int64_t* state4, int L, int U, int64_t* l_rows, int64_t* u_rows, float* keys, float* gam,
                    const int32_t* lab_y, const int32_t* lab_dom, const int32_t* unl_dom, int want_dom, int32_t* lab_ids,
                    int32_t* base_dom, const int64_t* lab_indptr, const int64_t* unl_indptr, int32_t* b_indptr,
-                   float* zero_buf, int n_zero, void* stream);
+                   float* zero_buf, int n_zero,
+                   int phases /* 1: assemble the batch of table row state4[0] % n_tab; 2: advance counters + zero; 3: both */,
+                   void* stream);
 
 /* Device-resident sampler hand-off (replaces DataLoader iteration, scnym/trainer.py:574-582):
  * copies the row ids / MixUp randomness of step (state4[0] % n_tab) from per-epoch tables. */

@@ -17,9 +17,9 @@ SIGNATURES = {
     "scnb_csr_row_offsets": [P, P, L, I, P, P, P],
     "scnb_gather_i32": [P, P, I, I, P, P],
     "scnb_csr_gather_rows": [P, P, P, P, L, I, P, P, P, I, I, I, P, P, U32, F, P, P],
-    "scnb_csr_gather_rows2": [P, P, P, P, I, I, U32, P, P, P, P, I, I, U32, P, P, P, P, P, F, P, P],
-    "scnb_csr_gather_rows_aug": [P, P, P, P, L, I, P, P, P, I, I, F, F, P, P, P, P, U32, P, P],
-    "scnb_step_prep": [P, P, P, P, I, P, I, I, P, P, P, P, P, P, P, I, P, P, P, P, P, P, I, P],
+    "scnb_csr_gather_rows2": [P, P, P, P, I, I, U32, P, P, P, P, I, I, U32, P, P, P, P, P, F, P, I, P],
+    "scnb_csr_gather_rows_aug": [P, P, P, P, L, I, P, P, P, I, I, F, F, P, P, P, P, U32, P, I, P],
+    "scnb_step_prep": [P, P, P, P, I, P, I, I, P, P, P, P, P, P, P, I, P, P, P, P, P, P, I, I, P],
     "scnb_fetch_step": [P, P, P, P, I, I, I, P, P, P, P, P, P],
     "scnb_host_gather_rows": [P, P, P, P, I, P, P, P, L, I],
     "scnb_host_gather_rows2": [P, P, P, P, I, P, P, P, L, P, P, P, P, I, P, P, P, L, I],

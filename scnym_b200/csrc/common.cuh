@@ -39,6 +39,11 @@ static inline int scnb_cdiv(long long a, long long b) { return (int)((a + b - 1)
 int scnb_pdl_enabled(void);   // SCNB_PDL=1 enables (api.cu; off by default: no measurable gain inside CUDA graphs)
 
 #ifdef __CUDACC__
+// Split form: PDL_LAUNCH() first thing (lets the successor start its own prologue as soon as this grid's CTAs are placed),
+// then everything that does not read the predecessor's output (barrier setup, weight panels, BatchNorm parameters), then
+// PDL_WAIT() in front of the first access to the predecessor's output.
+#define PDL_LAUNCH() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
 #define PDL_ENTRY()                                             \
   do {                                                          \
     asm volatile("griddepcontrol.wait;" ::: "memory");          \

@@ -101,6 +101,7 @@ struct AugExtra {
   float p_apply;           // GeneMasking: probability that the batch is masked at all
   const float* inj_pois;   // injected Poisson samples by batch nnz position (tests), or NULL
   const float* inj_row_r;  // injected per-row depth factors (tests), or NULL
+  int ctr_off;             // added to the RNG step counter rng[1] (1 when the batch of the next step is assembled early)
 };
 
 __device__ __forceinline__ float u01(uint32_t w) { return ((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f); }   // (0, 1)
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(GR_T) k_gather_rows(GatherSrc A, GatherSrc B, 
   uint64_t seed = 0, strm = 0;
   if (rng) {
     seed = rng[0];
-    strm = rng[1] * 64ull + S.stream_id;
+    strm = (rng[1] + (uint64_t)X.ctr_off) * 64ull + S.stream_id;   // ctr_off = 1: the batch of the NEXT step, assembled early
   }
   // per-row Poisson depth factor: U(0.1, 2.0) as `rand * (0.1 - 2.0) + 2.0` (dataprep.py:318-321); 1 otherwise
   float row_r = 1.0f;
@@ -299,7 +300,7 @@ extern "C" int scnb_csr_gather_rows(const int64_t* indptr, const int32_t* indice
   if (n == 0) return SCNB_OK;
   GatherSrc A = {indptr, indices, data, rows, row0, n, augment, aug_row_begin, aug_row_end, stream_id};
   GatherSrc B = {nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, 0, 0};
-  k_gather_rows<false><<<n, GR_T, 0, (cudaStream_t)stream>>>(A, B, b_indptr, b_idx, b_val, keep_mask, rng, p_drop, 1e6f, gene_cnt, AugExtra{0, 0.f, nullptr, nullptr});
+  k_gather_rows<false><<<n, GR_T, 0, (cudaStream_t)stream>>>(A, B, b_indptr, b_idx, b_val, keep_mask, rng, p_drop, 1e6f, gene_cnt, AugExtra{0, 0.f, nullptr, nullptr, 0});
   SCNB_CHECK_LAUNCH("csr_gather_rows");
   return SCNB_OK;
 }
@@ -311,7 +312,7 @@ extern "C" int scnb_csr_gather_rows2(const int64_t* indptr_A, const int32_t* ind
                                      const int64_t* indptr_B, const int32_t* indices_B, const float* data_B,
                                      const int64_t* rows_B, int nB, int augment_B, uint32_t stream_id_B,
                                      const int32_t* b_indptr, int32_t* b_idx, float* b_val, const uint8_t* keep_mask,
-                                     const uint64_t* rng, float p_drop, int32_t* gene_cnt, void* stream) {
+                                     const uint64_t* rng, float p_drop, int32_t* gene_cnt, int ctr_off, void* stream) {
   SCNB_CHECK_ARG(b_indptr && b_idx && b_val && nA >= 0 && nB >= 0, "csr_gather_rows2: bad arguments");
   SCNB_CHECK_ARG(nA == 0 || (indptr_A && indices_A && data_A), "csr_gather_rows2: source A missing");
   SCNB_CHECK_ARG(nB == 0 || (indptr_B && indices_B && data_B), "csr_gather_rows2: source B missing");
@@ -320,7 +321,7 @@ extern "C" int scnb_csr_gather_rows2(const int64_t* indptr_A, const int32_t* ind
   GatherSrc A = {indptr_A, indices_A, data_A, rows_A, 0, nA, augment_A, 0, nA, stream_id_A};
   GatherSrc B = {indptr_B, indices_B, data_B, rows_B, 0, nB, augment_B, 0, nB, stream_id_B};
   scnb_launch_pdl(k_gather_rows<false>, dim3(nA + nB), dim3(GR_T), 0, (cudaStream_t)stream, A, B, b_indptr, b_idx, b_val, keep_mask, rng, p_drop, 1e6f,
-                  gene_cnt, AugExtra{0, 0.f, nullptr, nullptr});
+                  gene_cnt, AugExtra{0, 0.f, nullptr, nullptr, ctr_off});
   SCNB_CHECK_LAUNCH("csr_gather_rows2");
   return SCNB_OK;
 }
@@ -334,7 +335,7 @@ extern "C" int scnb_csr_gather_rows_aug(const int64_t* indptr, const int32_t* in
                                         int64_t row0, int n, const int32_t* b_indptr, int32_t* b_idx, float* b_val, int scheme,
                                         int n_genes, float p_drop, float p_apply, const uint8_t* keep_mask, const float* inj_poisson,
                                         const float* inj_row_depth, const uint64_t* rng, uint32_t stream_id, int32_t* gene_cnt,
-                                        void* stream) {
+                                        int ctr_off, void* stream) {
   SCNB_CHECK_ARG(indptr && indices && data && b_indptr && b_idx && b_val && n >= 0, "csr_gather_rows_aug: bad arguments");
   SCNB_CHECK_ARG(scheme >= AUG_DROP && scheme <= AUG_COUNT_POIS, "csr_gather_rows_aug: unknown augmentation scheme %d", scheme);
   SCNB_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f && p_apply >= 0.f && p_apply <= 1.f && n_genes > 0, "csr_gather_rows_aug: bad parameters");
@@ -346,7 +347,7 @@ extern "C" int scnb_csr_gather_rows_aug(const int64_t* indptr, const int32_t* in
   GatherSrc A = {indptr, indices, data, rows, row0, n, scheme, 0, n, stream_id};
   GatherSrc B = {nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, 0, 0};
   k_gather_rows<true><<<n, GR_T, 0, (cudaStream_t)stream>>>(A, B, b_indptr, b_idx, b_val, keep_mask, rng, p_drop, 1e6f, gene_cnt,
-                                                            AugExtra{n_genes, p_apply, inj_poisson, inj_row_depth});
+                                                            AugExtra{n_genes, p_apply, inj_poisson, inj_row_depth, ctr_off});
   SCNB_CHECK_LAUNCH("csr_gather_rows_aug");
   return SCNB_OK;
 }
@@ -889,6 +890,9 @@ struct PrepArgs {
   int32_t* lab_ids; int32_t* base_dom;
   const int64_t* lab_indptr; const int64_t* unl_indptr;
   int32_t* b_indptr; float* zero_buf; int n_zero;
+  int phases;   // bit 0: sampler hand-off, labels, row offsets of the batch whose table row is state4[0] % n_tab;
+                // bit 1: advance the step counters and zero the loss scalars.  3 = the whole prologue (one launch at the start
+                // of a step); 1 / 2 split it so that the batch of step t+1 can be assembled while step t is still running.
 };
 
 __global__ void __launch_bounds__(1024) k_step_prep(PrepArgs a) {
@@ -899,9 +903,10 @@ __global__ void __launch_bounds__(1024) k_step_prep(PrepArgs a) {
   const int L = a.L, U = a.U, nb = L + U;
   const int64_t srow = a.l_tab ? (a.state4[0] % (int64_t)a.n_tab) : 0;
   if (tid == 0) carry_s = 0;
-  for (int i = tid; i < a.n_zero; i += 1024) a.zero_buf[i] = 0.f;
+  if (a.phases & 2)
+    for (int i = tid; i < a.n_zero; i += 1024) a.zero_buf[i] = 0.f;
   __syncthreads();
-  for (int base = 0; base < nb; base += 1024) {
+  for (int base = 0; (a.phases & 1) && base < nb; base += 1024) {
     const int i = base + tid;
     int len = 0;
     if (i < nb) {
@@ -948,9 +953,11 @@ __global__ void __launch_bounds__(1024) k_step_prep(PrepArgs a) {
     __syncthreads();
   }
   if (tid == 0) {
-    a.b_indptr[nb] = carry_s;
-    a.state4[0] += 1;  // optimizer step index t (1-based when read by the optimizer kernels)
-    a.state4[2] += 1;  // RNG counter
+    if (a.phases & 1) a.b_indptr[nb] = carry_s;
+    if (a.phases & 2) {
+      a.state4[0] += 1;  // optimizer step index t (1-based when read by the optimizer kernels)
+      a.state4[2] += 1;  // RNG counter
+    }
   }
 }
 
@@ -958,8 +965,9 @@ extern "C" int scnb_step_prep(const int64_t* l_tab, const int64_t* u_tab, const 
                               int64_t* state4, int L, int U, int64_t* l_rows, int64_t* u_rows, float* keys, float* gam,
                               const int32_t* lab_y, const int32_t* lab_dom, const int32_t* unl_dom, int want_dom,
                               int32_t* lab_ids, int32_t* base_dom, const int64_t* lab_indptr, const int64_t* unl_indptr,
-                              int32_t* b_indptr, float* zero_buf, int n_zero, void* stream) {
+                              int32_t* b_indptr, float* zero_buf, int n_zero, int phases, void* stream) {
   SCNB_CHECK_ARG(state4 && L > 0 && U >= 0 && l_rows && lab_ids && lab_indptr && b_indptr, "step_prep: bad arguments");
+  SCNB_CHECK_ARG(phases >= 1 && phases <= 3, "step_prep: phases must be 1 (batch), 2 (counters) or 3 (both)");
   SCNB_CHECK_ARG(U == 0 || (u_rows && unl_indptr), "step_prep: unlabeled buffers missing");
   SCNB_CHECK_ARG(!l_tab || n_tab > 0, "step_prep: empty sampler table");
   SCNB_CHECK_ARG(!l_tab || U == 0 || u_tab, "step_prep: unlabeled sampler table missing");
@@ -967,7 +975,7 @@ extern "C" int scnb_step_prep(const int64_t* l_tab, const int64_t* u_tab, const 
   SCNB_CHECK_ARG(!want_dom || base_dom, "step_prep: base_dom missing");
   SCNB_CHECK_ARG(n_zero == 0 || zero_buf, "step_prep: zero_buf missing");
   PrepArgs a = {l_tab, u_tab, key_tab, gam_tab, n_tab, state4, L, U, l_rows, u_rows, keys, gam, lab_y, lab_dom, unl_dom,
-                want_dom, lab_ids, base_dom, lab_indptr, unl_indptr, b_indptr, zero_buf, n_zero};
+                want_dom, lab_ids, base_dom, lab_indptr, unl_indptr, b_indptr, zero_buf, n_zero, phases};
   scnb_launch_pdl(k_step_prep, dim3(1), dim3(1024), 0, (cudaStream_t)stream, a);
   SCNB_CHECK_LAUNCH("step_prep");
   return SCNB_OK;

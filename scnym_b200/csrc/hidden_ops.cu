@@ -500,7 +500,7 @@ struct HsFwdArgs {
 
 // grid = (N/64, R/32), 512 threads; dynamic shared memory: sA 32*(K+4) + max(sB 64*(K+4), partial tiles) + 4*K floats.
 __global__ void __launch_bounds__(HS_T) k_hs_fwd(const __grid_constant__ HsFwdArgs p) {
-  PDL_ENTRY();
+  PDL_LAUNCH();
   extern __shared__ __align__(16) float hs_smem[];
   __shared__ __align__(8) unsigned long long bar_mem;
   const int K = p.K, N = p.N;
@@ -524,8 +524,14 @@ __global__ void __launch_bounds__(HS_T) k_hs_fwd(const __grid_constant__ HsFwdAr
   __syncthreads();
   // stage the raw operands: one bulk copy per row (96 copies per CTA instead of 6144 16-byte cp.async)
   if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)((HS_BM + HS_BN) * K * sizeof(float)));
-  hs_bulk_rows(sA, K + 4, p.Zin + (size_t)row0 * K, K, HS_BM, (uint32_t)(K * sizeof(float)), bar, 0);
+  // the weight panel and the BatchNorm parameters do not depend on the kernel in front: fetched before the dependency wait
   hs_bulk_rows(sB, K + 4, p.W + (size_t)n0 * K, K, HS_BN, (uint32_t)(K * sizeof(float)), bar, HS_BM);
+  for (int c = tid; c < K; c += HS_T) {
+    sGam[c] = p.gamma[c];
+    sBet[c] = p.beta[c];
+  }
+  PDL_WAIT();
+  hs_bulk_rows(sA, K + 4, p.Zin + (size_t)row0 * K, K, HS_BM, (uint32_t)(K * sizeof(float)), bar, 0);
   hs_stamp(p.dbg, 0, 1);
   // segment statistics of the input while the copies fly
   const bool eval = p.rmean != nullptr;
@@ -546,8 +552,6 @@ __global__ void __launch_bounds__(HS_T) k_hs_fwd(const __grid_constant__ HsFwdAr
     }
     sMean[c] = mean;
     sInv[c] = inv;
-    sGam[c] = p.gamma[c];
-    sBet[c] = p.beta[c];
     if (!eval && !given && blockIdx.x == 0 && tile == t0) {
       p.stats_in[((size_t)s * 3 + 0) * K + c] = mean;
       p.stats_in[((size_t)s * 3 + 1) * K + c] = var;
@@ -754,7 +758,7 @@ struct HsBwdArgs {
 
 // grid = (N/64, R/32), 512 threads; dynamic shared memory: sA, sZ 32*(K+4) each + max(sB K*(64+8), partial tiles) + 5*K floats.
 __global__ void __launch_bounds__(HS_T) k_hs_bwd(const __grid_constant__ HsBwdArgs p) {
-  PDL_ENTRY();
+  PDL_LAUNCH();
   extern __shared__ __align__(16) float hs_smem[];
   __shared__ __align__(8) unsigned long long bar_mem;
   const int K = p.K, N = p.N;
@@ -778,9 +782,22 @@ __global__ void __launch_bounds__(HS_T) k_hs_bwd(const __grid_constant__ HsBwdAr
   }
   __syncthreads();
   if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)((2 * HS_BM * K + K * HS_BN) * sizeof(float)));
-  hs_bulk_rows(sA, K + 4, p.dYin + (size_t)row0 * K, K, HS_BM, (uint32_t)(K * sizeof(float)), bar, 0);
-  hs_bulk_rows(sZ, K + 4, p.Zin + (size_t)row0 * K, K, HS_BM, (uint32_t)(K * sizeof(float)), bar, HS_BM);
+  // the weight panel, this application's pre-BatchNorm tile and statistics come from the forward pass: before the wait
   hs_bulk_rows(sB, HS_BN + 8, p.W + n0, N, K, (uint32_t)(HS_BN * sizeof(float)), bar, 2 * HS_BM);
+  hs_bulk_rows(sZ, K + 4, p.Zin + (size_t)row0 * K, K, HS_BM, (uint32_t)(K * sizeof(float)), bar, HS_BM);
+  for (int c = tid; c < K; c += HS_T) {
+    sMu[c] = p.stats_in[((size_t)s * 3 + 0) * K + c];
+    sIs[c] = p.stats_in[((size_t)s * 3 + 2) * K + c];
+    sGm[c] = p.gamma[c];
+  }
+  const int erow = tid >> 4, ec4 = (tid & 15) << 2;
+  const size_t eo = (size_t)(row0 + erow) * N + n0 + ec4;
+  const float4 av = *reinterpret_cast<const float4*>(p.Aprev + eo);
+  const float4 zv = *reinterpret_cast<const float4*>(p.Zprev + eo);
+  const float4 pmu = *reinterpret_cast<const float4*>(p.stats_prev + ((size_t)s * 3 + 0) * N + n0 + ec4);
+  const float4 pis = *reinterpret_cast<const float4*>(p.stats_prev + ((size_t)s * 3 + 2) * N + n0 + ec4);
+  PDL_WAIT();
+  hs_bulk_rows(sA, K + 4, p.dYin + (size_t)row0 * K, K, HS_BM, (uint32_t)(K * sizeof(float)), bar, 0);
   const float inv_n = 1.0f / (float)((t1 - t0) * HS_BM);
   for (int c = tid; c < K; c += HS_T) {
     if (!p.part_in) {
@@ -796,17 +813,7 @@ __global__ void __launch_bounds__(HS_T) k_hs_bwd(const __grid_constant__ HsBwdAr
         atomicAdd(p.dgamma + c, s2);
       }
     }
-    sMu[c] = p.stats_in[((size_t)s * 3 + 0) * K + c];
-    sIs[c] = p.stats_in[((size_t)s * 3 + 2) * K + c];
-    sGm[c] = p.gamma[c];
   }
-  // operands of the epilogue, fetched while the copies fly: thread -> (row tid/16, 4 columns) of the previous application
-  const int erow = tid >> 4, ec4 = (tid & 15) << 2;
-  const size_t eo = (size_t)(row0 + erow) * N + n0 + ec4;
-  const float4 av = *reinterpret_cast<const float4*>(p.Aprev + eo);
-  const float4 zv = *reinterpret_cast<const float4*>(p.Zprev + eo);
-  const float4 pmu = *reinterpret_cast<const float4*>(p.stats_prev + ((size_t)s * 3 + 0) * N + n0 + ec4);
-  const float4 pis = *reinterpret_cast<const float4*>(p.stats_prev + ((size_t)s * 3 + 2) * N + n0 + ec4);
   mbar_wait(bar, 0);
   __syncthreads();
   const int fpr = K >> 2;

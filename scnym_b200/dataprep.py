@@ -507,7 +507,7 @@ class SparseAugment(object):
         st = _stream()
         call("scnb_csr_row_offsets", ptr(ds.indptr), None, 0, n, ptr(out.indptr), None, st)
         call("scnb_csr_gather_rows_aug", ptr(ds.indptr), ptr(ds.indices), ptr(ds.data), None, 0, n, ptr(out.indptr), ptr(out.indices),
-             ptr(out.data), self.code, ds.n_cols, self.p_drop, self.p_apply, ptr(keep), ptr(pois), ptr(rowu), ptr(rng), 0, None, st)
+             ptr(out.data), self.code, ds.n_cols, self.p_drop, self.p_apply, ptr(keep), ptr(pois), ptr(rowu), ptr(rng), 0, None, 0, st)
         sample["input"] = out.data[: n * ds.n_cols].view(n, ds.n_cols) if dense else out
         return sample
 

@@ -143,6 +143,21 @@ class ParamArena(object):
                 raise RuntimeError(f"parameter {name} no longer aliases the engine arena; rebuild the engine")
 
 
+# Everything the step's prologue (sampler hand-off, row gather, MixUp plan, gene-block splits) writes and the rest of the step
+# only reads.  Held twice: while step t runs on one set, the prologue of step t+1 fills the other (see TrainEngine.step).
+_BATCH_FIELDS = ("b_indptr", "b_idx", "b_val", "l_rows", "u_rows", "perm_keys", "gamma_raw", "lab_ids", "base_dom", "counts",
+                 "seg_off", "plan_work", "srcA", "srcB", "gam", "inv3", "coef3", "pconf", "w1_splits")
+
+
+def _batch_field(name):
+    def fget(self):
+        return self.__dict__["_sets"][self.__dict__["_cur"]][name]
+
+    def fset(self, v):
+        self.__dict__["_sets"][self.__dict__["_cur"]][name] = v
+    return property(fget, fset)
+
+
 class TrainEngine(object):
     """Device-resident training step for `CellTypeCLF` (+ `DANN` head).
 
@@ -157,6 +172,7 @@ class TrainEngine(object):
         if not torch.cuda.is_available():
             raise _lib.ScnbError("TrainEngine needs a CUDA device (no CPU fallback)")
         _lib.lib()
+        self.__dict__["_sets"], self.__dict__["_cur"] = [{}, {}], 0
         self.model, self.cfg, self.mode = model, cfg, mode
         self.comm = comm if (comm is not None and comm.world > 1) else None
         self.dev = labeled.device
@@ -410,6 +426,17 @@ class TrainEngine(object):
         self._graph_key = None
         self.steps_done = 0
         self.kernels_per_step = None
+        # Prologue of step t+1 (sampler hand-off, row gather + augmentation, MixUp plan, gene-block splits: ~18 us at the
+        # front of the critical chain, none of it depends on the weights) assembled WHILE step t runs, into the second set of
+        # batch buffers.  Needs everything the prologue produces to be independent of the teacher (no thresholding) and of
+        # host-staged rows (sampler tables on the device), and the step to be a replayed graph.
+        self.prefetch_ok = bool(mode == "mixmatch" and cfg.pseudolabel_min_confidence <= 0.0 and not self.teacher_own_spmm
+                                and self.aug_code == 1 and self.w1_tc and self.tc_first and cfg.multi_stream
+                                and os.environ.get("SCNB_PREFETCH", "1") != "0")
+        if self.prefetch_ok:
+            self._sets[1] = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in self._sets[0].items()}
+        self._pf_graphs, self._next_p, self._prefetch_valid = {}, 0, False
+        self._ev_adv, self._ev_fl, self._ev_pf = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
 
     # ------------------------------------------------------------------------------------
     def set_hyper(self, lr=None, weight_decay=None):
@@ -450,7 +477,7 @@ class TrainEngine(object):
         if not self.cfg.multi_stream:
             return main, main, main
         if self._side is None:
-            self._side = tuple(torch.cuda.Stream(device=self.dev) for _ in range(4))
+            self._side = tuple(torch.cuda.Stream(device=self.dev) for _ in range(5))
         return main, self._side[0], self._side[1]
 
     @staticmethod
@@ -503,14 +530,39 @@ class TrainEngine(object):
             call("scnb_csr_linear_fwd", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), n_rows, self.P(blk0["W"]),
                  self.P(blk0["b"]), self.widths[0], ptr(Z), st)
 
-    def _prep(self, st):
+    def _prep(self, st, phases=3):
         t = self._tabs or {}
         mm = self.mode == "mixmatch"
         call("scnb_step_prep", ptr(t.get("l")), ptr(t.get("u")), ptr(t.get("k")), ptr(t.get("g")), int(t.get("n", 0)),
              ptr(self.state), self.L, self.U, ptr(self.l_rows), ptr(self.u_rows) if mm else None, ptr(self.perm_keys),
              ptr(self.gamma_raw), ptr(self.lab_y), ptr(self.lab_dom), ptr(self.unl_dom), int(self.use_dan), ptr(self.lab_ids),
              ptr(self.base_dom) if self.use_dan else None, ptr(self.lab.indptr), ptr(self.unl.indptr) if mm else None,
-             ptr(self.b_indptr), ptr(self.loss_buf), 8, st)
+             ptr(self.b_indptr), ptr(self.loss_buf), 8, int(phases), st)
+
+    def _gather_batch(self, st, rng, ctr_off=0):
+        """Batch CSR [U_raw ; L_aug] (+ per-gene histogram for the SIMT dW1 path).  ctr_off = 1: the batch of the NEXT step."""
+        c, L, U = self.cfg, self.L, self.U
+        if self.aug_code == 1:
+            call("scnb_csr_gather_rows2", ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data), ptr(self.u_rows), U, 0, 0,
+                 ptr(self.lab.indptr), ptr(self.lab.indices), ptr(self.lab.data), ptr(self.l_rows), L, 1, SID_IN_L,
+                 ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), ptr(self.inj_in_keep_L), rng, c.p_in_drop,
+                 self._gene_cnt_ptr(), int(ctr_off), st)
+        else:   # the other schemes of dataprep.py:730-754: raw unlabeled rows, then the labeled rows through the scheme
+            call("scnb_csr_gather_rows", ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data), ptr(self.u_rows), 0, U,
+                 ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), 0, 0, 0, None, None, 0, 0.0, self._gene_cnt_ptr(), st)
+            call("scnb_csr_gather_rows_aug", ptr(self.lab.indptr), ptr(self.lab.indices), ptr(self.lab.data), ptr(self.l_rows), 0, L,
+                 ptr(self.b_indptr[U:]), ptr(self.b_idx), ptr(self.b_val), self.aug_code, self.G, c.p_in_drop, c.p_mask_apply,
+                 ptr(self.inj_in_keep_L), ptr(self.inj_pois_L), ptr(self.inj_rowu_L), rng, SID_IN_L, self._gene_cnt_ptr(),
+                 int(ctr_off), st)
+
+    def _prologue_next(self, stream, rng):
+        """The whole prologue of the step that comes AFTER the counters' current value, into the current set of batch
+        buffers, on one stream: sampler hand-off (table row state[0] % n), gather (RNG counter + 1), MixUp plan, splits."""
+        st = stream.cuda_stream
+        self._prep(st, phases=1)
+        self._gather_batch(st, rng, ctr_off=1)
+        self._plan(self._all_confident, st)
+        self._build_csc(self.nb, st)
 
     def _launch_mixmatch(self):
         c = self.cfg
@@ -528,41 +580,54 @@ class TrainEngine(object):
             self._zero_grads(sW.cuda_stream, also=self.Z1)     # one launch: Z1 and the gradient arena behind the first layer
             self._ev_z1.record(sW)
             self._ev_zero.record(sW)
-        self._prep(st)
-        # With pseudolabel_min_confidence <= 0 every unlabeled row is "confident": the MixUp plan depends only on the
-        # step's random draws, so it runs on its own branch next to the gather and the first layer.
+        pre = bool(getattr(self, "_prefetched", False))   # this step's batch was assembled during the previous step
         teacher_async = (c.pseudolabel_min_confidence <= 0.0) and sW is not main
-        if teacher_async:
-            self._ev_prep.record(main)
-        # -- batch CSR [U_raw ; L_aug] (+ per-gene histogram), one launch (issued before the plan: the graph releases
-        #    the children of a node one after the other, and the gather is the one on the critical chain)
-        if self.aug_code == 1:
-            call("scnb_csr_gather_rows2", ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data), ptr(self.u_rows), U, 0, 0,
-                 ptr(self.lab.indptr), ptr(self.lab.indices), ptr(self.lab.data), ptr(self.l_rows), L, 1, SID_IN_L,
-                 ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), ptr(self.inj_in_keep_L), rng, c.p_in_drop,
-                 self._gene_cnt_ptr(), st)
-        else:   # the other schemes of dataprep.py:730-754: raw unlabeled rows, then the labeled rows through the scheme
-            call("scnb_csr_gather_rows", ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data), ptr(self.u_rows), 0, U,
-                 ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), 0, 0, 0, None, None, 0, 0.0, self._gene_cnt_ptr(), st)
-            call("scnb_csr_gather_rows_aug", ptr(self.lab.indptr), ptr(self.lab.indices), ptr(self.lab.data), ptr(self.l_rows), 0, L,
-                 ptr(self.b_indptr[U:]), ptr(self.b_idx), ptr(self.b_val), self.aug_code, self.G, c.p_in_drop, c.p_mask_apply,
-                 ptr(self.inj_in_keep_L), ptr(self.inj_pois_L), ptr(self.inj_rowu_L), rng, SID_IN_L, self._gene_cnt_ptr(), st)
-        if teacher_async:
-            sP = self._side[3]
-            sP.wait_event(self._ev_prep)
-            self._plan(self._all_confident, sP.cuda_stream)
-            self._ev_plan.record(sP)
-        # branch W: gene-major copy of the batch (needed only by the last kernel of the step), gradient zeroing
-        self._after(sW, main)
-        if not z1_pre:
-            self._zero_grads(sW.cuda_stream)
-            if sW is not main:
-                self._ev_zero.record(sW)
-        self._build_csc(nb, sW.cuda_stream)
-        if sW is not main:
+        if pre:
+            # only the counters are left of the prologue: advanced on branch W, needed from the hidden stack on
+            call("scnb_step_prep", None, None, None, None, 0, ptr(self.state), L, U, ptr(self.l_rows), ptr(self.u_rows), None, None,
+                 None, None, None, 0, ptr(self.lab_ids), None, ptr(self.lab.indptr), ptr(self.unl.indptr), ptr(self.b_indptr),
+                 ptr(self.loss_buf), 8, 2, sW.cuda_stream)
+            self._ev_adv.record(sW)
             self._ev_csc.record(sW)
+        else:
+            self._prep(st)
+            # With pseudolabel_min_confidence <= 0 every unlabeled row is "confident": the MixUp plan depends only on the
+            # step's random draws, so it runs on its own branch next to the gather and the first layer.
+            if teacher_async:
+                self._ev_prep.record(main)
+            # -- batch CSR [U_raw ; L_aug] (+ per-gene histogram), one launch (issued before the plan: the graph releases
+            #    the children of a node one after the other, and the gather is the one on the critical chain)
+            self._gather_batch(st, rng)
+            if teacher_async:
+                sP = self._side[3]
+                sP.wait_event(self._ev_prep)
+                self._plan(self._all_confident, sP.cuda_stream)
+                self._ev_plan.record(sP)
+            # branch W: gene-major copy of the batch (needed only by the last kernel of the step), gradient zeroing
+            self._after(sW, main)
+            if not z1_pre:
+                self._zero_grads(sW.cuda_stream)
+                if sW is not main:
+                    self._ev_zero.record(sW)
+            self._build_csc(nb, sW.cuda_stream)
+            if sW is not main:
+                self._ev_csc.record(sW)
         # -- first layer, once
         self._first_layer(main, sW, nb, self.Z1, prezeroed=z1_pre)
+        if pre:
+            # the prologue of the NEXT step, into the other set of batch buffers, on an idle low-priority branch (it reads
+            # the sampler tables and the datasets only; it must see this step's counters: after the advance)
+            main.wait_event(self._ev_adv)
+            self._ev_fl.record(main)
+            sF = self._side[4]
+            sF.wait_event(self._ev_fl)
+            cur = self.__dict__["_cur"]
+            self.__dict__["_cur"] = 1 - cur
+            try:
+                self._prologue_next(sF, rng)
+            finally:
+                self.__dict__["_cur"] = cur
+            self._ev_pf.record(sF)
         # -- teacher (eval mode, losses.py:660-737).  With pseudolabel_min_confidence <= 0 every unlabeled row is
         #    "confident", so the MixUp plan and the student forward do not depend on the teacher: it runs on its own
         #    branch and is joined in front of the losses.
@@ -574,7 +639,9 @@ class TrainEngine(object):
         else:
             self._teacher_forward(st, rng)
         # -- MixUp plan + hidden-space MixUp (losses.py:811-875)
-        if teacher_async:
+        if pre:
+            pass                              # the MixUp plan of this step was part of the prefetched prologue
+        elif teacher_async:
             main.wait_event(self._ev_plan)
         else:
             self._plan(self.confident, st)
@@ -670,6 +737,8 @@ class TrainEngine(object):
         else:
             call("scnb_unmix_rows", ptr(dZ_first), H0, ptr(self.inv3), ptr(self.coef3), nb, ptr(self.dZ1), st)
         self._finish_step(main, sW, sD, self.dZ1, nb)
+        if pre:
+            main.wait_event(self._ev_pf)   # the next step's batch is complete when this step is
 
     def _plan(self, conf_flags, st):
         c = self.cfg
@@ -1023,6 +1092,7 @@ class TrainEngine(object):
             self.loss_hist = torch.zeros((capacity, 8), dtype=torch.float32, device=self.dev)
             self.conf_ring = torch.zeros((ring, max(self.U, 1)), dtype=torch.float32, device=self.dev)
             self._graph = None
+            self._pf_graphs = {}
         self._hist_t0 = int(self.steps_done)
 
     def history(self):
@@ -1131,6 +1201,8 @@ class TrainEngine(object):
         else:
             self._tabs = new
             self._graph = None  # pointers changed: re-capture
+            self._pf_graphs = {}
+        self._prefetch_valid = False   # a batch assembled ahead of time came from the old tables
         self.invalidate_planes()   # once per epoch: one cheap plane rebuild guards against unseen writes to W1
 
     def sample_epoch_tables(self, n_steps: int, generator: Optional[torch.Generator] = None):
@@ -1183,12 +1255,30 @@ class TrainEngine(object):
         injected = any(x is not None for x in (self.inj_in_keep_L, self.inj_in_keep_U, self.inj_hidden_keep, self.inj_pois_L,
                                                self.inj_rowu_L, self.inj_pois_U, self.inj_rowu_U))
         self._sync_planes()
-        if self.cfg.use_cuda_graph and not injected:
+        graph = self.cfg.use_cuda_graph and not injected
+        if graph and self.prefetch_ok and self._tabs is not None and self.cfg.multi_stream:
+            # replayed steps on device-resident sampler tables: the batch of step t+1 is assembled while step t runs
+            p = self._next_p
+            self.__dict__["_cur"] = p
+            if not self._prefetch_valid:   # first step, or the tables changed: assemble this step's batch now
+                self._prologue_next(torch.cuda.current_stream(), ptr(self.state[1:3]))
+            key = (self.unsup_weight, self.dan_weight, p)
+            if key not in self._pf_graphs:
+                self._prefetched = True
+                try:
+                    self._pf_graphs[key] = self._capture_graph()
+                finally:
+                    self._prefetched = False
+            self._pf_graphs[key].replay()
+            self._next_p, self._prefetch_valid = 1 - p, True
+        elif graph:
+            self._prefetch_valid = False
             key = (self.unsup_weight, self.dan_weight)
             if self._graph is None or self._graph_key != key:
                 self._capture(key)
             self._graph.replay()
         else:
+            self._prefetch_valid = False
             before = _lib.launch_count
             self._launch()
             self.kernels_per_step = _lib.launch_count - before
@@ -1202,7 +1292,7 @@ class TrainEngine(object):
                 self.teacher_bn = [(b["bn"].running_mean.clone(), b["bn"].running_var.clone()) for b in self._blk]
             self._capture((self.unsup_weight, self.dan_weight))
 
-    def _capture(self, key):
+    def _capture_graph(self):
         # warm-up on a side stream is not needed: the library allocates nothing; but the first
         # eager pass must not double-apply a step, so capture directly.
         self.arena.check_aliasing()
@@ -1212,7 +1302,10 @@ class TrainEngine(object):
         with torch.cuda.graph(g):
             self._launch()
         self.kernels_per_step = _lib.launch_count - before
-        self._graph, self._graph_key = g, key
+        return g
+
+    def _capture(self, key):
+        self._graph, self._graph_key = self._capture_graph(), key
 
     def losses(self) -> Dict[str, float]:
         """Read the last step's scalars (one D2H copy; the only host sync the engine exposes)."""
@@ -1228,3 +1321,7 @@ class TrainEngine(object):
         else:
             out["loss"] = v[0]
         return out
+
+
+for _n in _BATCH_FIELDS:
+    setattr(TrainEngine, _n, _batch_field(_n))

@@ -100,3 +100,56 @@ def test_argmax_kernels_return_a_valid_class_for_nan_rows():
          torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert float(q[1].sum()) == 1.0 and float(q[1, 0]) == 1.0
+
+
+def test_prefetched_prologue_assembles_the_same_batches(monkeypatch):
+    """Replayed steps on device-resident sampler tables assemble the batch of step t+1 while step t runs (second set of
+    batch buffers, one graph per parity).  Against the same engine with SCNB_PREFETCH=0 (prologue at the head of the
+    step): the sampled rows, batch CSR (input dropout included), MixUp plan and gene splits of EVERY step are bit-identical
+    -- across a change of tables in the middle (a new epoch invalidates the batch assembled ahead of time) -- and the
+    losses of the first steps agree within the fp32 budget."""
+    import bench
+    from scnym_b200.engine import EngineConfig, TrainEngine
+    from scnym_b200.model import CellTypeCLF, DANN
+    from scnym_b200.synth import synth_device_csr
+    c = dict(bench.CONFIGS[2][0])
+    dev = torch.device("cuda", 0)
+    lab, y = synth_device_csr(2048, c["G"], c["density"], c["C"], seed=0, device=dev)
+    unl, _ = synth_device_csr(2048, c["G"], c["density"], c["C"], seed=1, device=dev)
+    fields = ("l_rows", "u_rows", "lab_ids", "base_dom", "b_indptr", "srcA", "srcB", "gam", "w1_splits")
+    runs = []
+    for pf in ("1", "0"):
+        monkeypatch.setenv("SCNB_PREFETCH", pf)
+        torch.manual_seed(0)
+        model = CellTypeCLF(n_genes=c["G"], n_cell_types=c["C"], n_hidden=c["H"], n_hidden_init=c["H0"], n_layers=c["n_layers"])
+        dann = DANN(model, n_domains=c["D"])
+        cfg = EngineConfig(n_augmentations=1, T=0.5, augment_pseudolabels=False, pseudolabel_min_confidence=0.0, mixup_alpha=0.3,
+                           use_dan=True, optimizer="sgd", lr=0.01, seed=9, use_cuda_graph=True)
+        eng = TrainEngine(model.to(dev), cfg, lab, y.to(torch.int32), c["L"], unlabeled=unl, unlabeled_batch_size=c["U"], dann=dann,
+                          mode="mixmatch")
+        assert eng.prefetch_ok == (pf == "1")
+        eng.set_weights(1.0, 0.1)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(5)
+        rec = []
+        for epoch in range(2):
+            eng.sample_epoch_tables(3, generator=gen)
+            for _ in range(3 if epoch == 0 else 4):     # the second epoch wraps around its table once
+                eng.step()
+                torch.cuda.synchronize()
+                nnz = int(eng.b_indptr[-1])
+                snap = {k: getattr(eng, k).detach().cpu().clone() for k in fields}
+                snap["b_idx"] = eng.b_idx[:nnz].cpu().clone()
+                snap["b_val"] = eng.b_val[:nnz].cpu().clone()
+                snap["losses"] = eng.losses()
+                rec.append(snap)
+        assert bool(eng._pf_graphs) == (pf == "1")
+        runs.append(rec)
+    a, b = runs
+    assert len(a) == len(b) == 7
+    for s, (x, z) in enumerate(zip(a, b)):
+        for k in fields + ("b_idx", "b_val"):
+            assert torch.equal(x[k], z[k]), f"step {s}: {k} differs between the prefetched and the in-step prologue"
+    for s in range(2):
+        for k in ("sup_loss", "unsup_loss", "dan_loss"):
+            assert abs(a[s]["losses"][k] - b[s]["losses"][k]) <= 1e-4 * max(1.0, abs(b[s]["losses"][k])), (s, k)
