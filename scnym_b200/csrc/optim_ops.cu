@@ -9,6 +9,7 @@
 #include <stdlib.h>
 
 #include "optim.cuh"
+#include "tc_common.cuh"
 
 __global__ void k_step_begin(int64_t* st) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -150,6 +151,7 @@ struct DpX {
   const long long* epoch;
   long long off_flags, off_grad, off_flat;   // byte offsets inside every rank's exchange buffer
   int rank, world, spin_limit;
+  int probe;   // timing experiments only (SCNB_DP_PROBE): bit 0 = no stores to peers, bit 1 = no loads from peers (results are wrong)
 };
 
 __device__ __forceinline__ void dp_wait_flag(const unsigned* f, unsigned e, int spin_limit) {
@@ -161,71 +163,121 @@ __device__ __forceinline__ void dp_wait_flag(const unsigned* f, unsigned e, int 
   } while (got != e);
 }
 
-template <int OPT, int UNR>
-__global__ void __launch_bounds__(256, 2) k_dp_reduce_optim_bcast(DpX dx, float* __restrict__ s1, float* __restrict__ s2,
-                                                               long long total, const float* __restrict__ hp,
-                                                               const int64_t* __restrict__ st) {
+// Bulk-copy form.  A peer load over NVLink has ~2-3 us of latency: with one 16-byte load per thread and peer in flight
+// (the first version of this kernel: 75 us for the 31 MB arena of config 3 at two ranks, ~200 GB/s per direction) the link
+// idles most of the time.  Here one thread per CTA keeps `stages` chunks of DPB_F4 float4 elements in flight with
+// cp.async.bulk -- the slice of every rank's gradient arena (peer memory) and the CTA's own p / state rows land in shared
+// memory -- so a persistent grid of one CTA per SM has several MB outstanding; the 256 threads then sum in rank order,
+// apply the optimizer and store the new parameters to every rank (posted stores, nothing waits for them until the
+// fence in front of the done flag).
+#define DPB_T 256
+#define DPB_F4 512    // float4 elements per chunk and source: 8 KB
+
+template <int OPT>
+__global__ void __launch_bounds__(DPB_T, 1) k_dp_reduce_optim_bcast(DpX dx, float* __restrict__ s1, float* __restrict__ s2,
+                                                                   long long total, const float* __restrict__ hp,
+                                                                   const int64_t* __restrict__ st, int stages) {
+  extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ OptimConsts cs;
   __shared__ int is_last;
-  const int t = threadIdx.x;
+  __shared__ __align__(8) unsigned long long bars[8];
+  const int t = threadIdx.x, W = dx.world;
+  constexpr bool TWO = (OPT != OPT_SGD);
+  const int nsrc = W + 2 + (TWO ? 1 : 0);                       // gradient of every rank, p, state1 (, state2)
+  const uint32_t stage_bytes = (uint32_t)nsrc * DPB_F4 * 16u;
   const unsigned e = (unsigned)dx.epoch[0];
   // flag block layout (u32 words): ready[r] at 2r, done[r] at 64 + 2r, CTA counter at 128
   unsigned* my_flags = reinterpret_cast<unsigned*>(dx.bufs[dx.rank] + dx.off_flags);
-  if (blockIdx.x == 0 && t < dx.world) {
-    __threadfence_system();
-    unsigned* f = reinterpret_cast<unsigned*>(dx.bufs[t] + dx.off_flags) + 2 * dx.rank;
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(e) : "memory");
-  }
-  if (t == 0) cs = optim_consts(hp, st);
-  if (t < dx.world) dp_wait_flag(my_flags + 2 * t, e, dx.spin_limit);
-  __syncthreads();
-  const OptimConsts c = cs;
-  const float inv_w = 1.0f / (float)dx.world;
   const long long n4 = total >> 2;                                   // arena length is a multiple of 4 floats
-  const long long per = (n4 + dx.world - 1) / dx.world;              // float4 elements per rank
+  const long long per = (n4 + W - 1) / W;                            // float4 elements per rank
   const long long lo = per * dx.rank, hi = min(n4, lo + per);
+  const long long nchunk = hi > lo ? (hi - lo + DPB_F4 - 1) / DPB_F4 : 0;
+  const long long mine = nchunk > blockIdx.x ? (nchunk - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // chunks of this CTA
   float4* s1v = reinterpret_cast<float4*>(s1);
   float4* s2v = reinterpret_cast<float4*>(s2);
   const float4* my_flat = reinterpret_cast<const float4*>(dx.bufs[dx.rank] + dx.off_flat);
-  // One float4 element per thread and trip, software-pipelined: the peer loads of the NEXT trip (up to 8 ranks, all in
-  // flight together -- a warp issues in order, so a load -> add -> load chain would pay one NVLink round trip per rank)
-  // are issued before this trip's update and peer stores, so NVLink carries gradient reads and parameter writes at the
-  // same time instead of in alternating phases.
-  const long long stride = (long long)gridDim.x * blockDim.x * UNR;
-  auto load_grads = [&](long long i, float4(&v)[8]) {
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-      if (q < dx.world) {
-        // weak (coalesced, L2-only) loads: the ready flags were acquired at system scope above and every gradient
-        // address is read once per launch, so nothing stale can be hit; strong .sys accesses travel as 16-byte requests
-        v[q] = __ldcg(reinterpret_cast<const float4*>(dx.bufs[q] + dx.off_grad) + i);
-      }
+  // thread 0: every source of the CTA's j-th chunk into stage j % stages.  which: 1 = this rank's own rows (p, state,
+  // gradient: nothing to wait for), 2 = the peers' gradients (after their ready flags), 3 = both
+  auto issue = [&](long long j, int which) {
+    const int s = (int)(j % stages);
+    const long long base = lo + (blockIdx.x + j * gridDim.x) * DPB_F4;
+    const uint32_t bytes = (uint32_t)min((long long)DPB_F4, hi - base) * 16u;
+    const uint32_t bar = smem_u32(&bars[s]);
+    const uint32_t dst = smem_u32(dsm) + (uint32_t)s * stage_bytes;
+    if (which & 1) {
+      mbar_arrive_expect_tx(bar, bytes * (uint32_t)nsrc);
+      bulk_g2s(dst + (uint32_t)W * DPB_F4 * 16u, my_flat + base, bytes, bar);
+      bulk_g2s(dst + (uint32_t)(W + 1) * DPB_F4 * 16u, s1v + base, bytes, bar);
+      if (TWO) bulk_g2s(dst + (uint32_t)(W + 2) * DPB_F4 * 16u, s2v + base, bytes, bar);
+    }
+    for (int q = 0; q < W; ++q)
+      if (which & (q == dx.rank ? 1 : 2))
+        bulk_g2s(dst + (uint32_t)q * DPB_F4 * 16u,
+                 reinterpret_cast<const float4*>(dx.bufs[(dx.probe & 2) ? dx.rank : q] + dx.off_grad) + base, bytes, bar);
   };
-  for (int u0 = 0; u0 < UNR; ++u0) {   // UNR interleaved passes keep the per-thread state small
-    long long i = lo + ((long long)blockIdx.x * UNR + u0) * blockDim.x + t;
-    float4 vc[8], vn[8];
-    if (i < hi) load_grads(i, vc);
-    for (; i < hi; i += stride) {
-      const long long nx = i + stride;
-      if (nx < hi) load_grads(nx, vn);
-      float4 pi = my_flat[i], a = s1v[i], b = (OPT == OPT_SGD) ? make_float4(0.f, 0.f, 0.f, 0.f) : s2v[i];
-      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t == 0) {
+    for (int s = 0; s < stages; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // this rank's gradients were written through the generic proxy by the kernels in front: order the bulk (async-proxy)
+    // reads behind them, and start on the local rows before anything is known about the peers
+    asm volatile("fence.proxy.async;" ::: "memory");
+    for (long long j = 0; j < mine && j < stages; ++j) issue(j, 1);
+  }
+  if (t == 32) cs = optim_consts(hp, st);     // double-precision pow / sqrt: off the loader's path
+  if (blockIdx.x == 0 && t >= 64 && t < 64 + W) {
+    __threadfence_system();
+    unsigned* f = reinterpret_cast<unsigned*>(dx.bufs[t - 64] + dx.off_flags) + 2 * dx.rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(e) : "memory");
+  }
+  if (t >= 96 && t < 96 + W) dp_wait_flag(my_flags + 2 * (t - 96), e, dx.spin_limit);
+  __syncthreads();
+  if (t == 0) {
+    asm volatile("fence.proxy.async;" ::: "memory");   // the peers' gradients, seen through the flags acquired above
+    for (long long j = 0; j < mine && j < stages; ++j) issue(j, 2);
+  }
+  const OptimConsts c = cs;
+  const float inv_w = 1.0f / (float)W;
+  for (long long j = 0; j < mine; ++j) {
+    const int s = (int)(j % stages);
+    const long long base = lo + (blockIdx.x + j * gridDim.x) * DPB_F4;
+    const int n = (int)min((long long)DPB_F4, hi - base);
+    mbar_wait(smem_u32(&bars[s]), (uint32_t)((j / stages) & 1));
+    const float4* sv = reinterpret_cast<const float4*>(dsm + (size_t)s * stage_bytes);
+    float4 g[2], pi[2], a[2], b[2];
 #pragma unroll
-      for (int q = 0; q < 8; ++q)        // rank order: the same sum wherever it is computed
-        if (q < dx.world) { g.x += vc[q].x; g.y += vc[q].y; g.z += vc[q].z; g.w += vc[q].w; }
-      g.x *= inv_w; g.y *= inv_w; g.z *= inv_w; g.w *= inv_w;
-      optim_update<OPT>(pi.x, g.x, a.x, b.x, c);
-      optim_update<OPT>(pi.y, g.y, a.y, b.y, c);
-      optim_update<OPT>(pi.z, g.z, a.z, b.z, c);
-      optim_update<OPT>(pi.w, g.w, a.w, b.w, c);
-      s1v[i] = a;
-      if (OPT != OPT_SGD) s2v[i] = b;
+    for (int h = 0; h < 2; ++h) {
+      const int i = t + h * DPB_T;
+      g[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < n) {
+        for (int q = 0; q < W; ++q) {        // rank order: the same sum wherever it is computed
+          const float4 v = sv[q * DPB_F4 + i];
+          g[h].x += v.x; g[h].y += v.y; g[h].z += v.z; g[h].w += v.w;
+        }
+        pi[h] = sv[W * DPB_F4 + i];
+        a[h] = sv[(W + 1) * DPB_F4 + i];
+        b[h] = TWO ? sv[(W + 2) * DPB_F4 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    __syncthreads();                          // the stage has been read: refill it
+    if (t == 0 && j + stages < mine) issue(j + stages, 3);
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (q < dx.world)   // weak store; made visible by the system-scope fence in front of the done flag
-          __stcg(reinterpret_cast<float4*>(dx.bufs[q] + dx.off_flat) + i, pi);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) vc[q] = vn[q];
+    for (int h = 0; h < 2; ++h) {
+      const int i = t + h * DPB_T;
+      if (i < n) {
+        float4 gg = g[h];
+        gg.x *= inv_w; gg.y *= inv_w; gg.z *= inv_w; gg.w *= inv_w;
+        if (!(dx.probe & 8)) {
+        optim_update<OPT>(pi[h].x, gg.x, a[h].x, b[h].x, c);
+        optim_update<OPT>(pi[h].y, gg.y, a[h].y, b[h].y, c);
+        optim_update<OPT>(pi[h].z, gg.z, a[h].z, b[h].z, c);
+        optim_update<OPT>(pi[h].w, gg.w, a[h].w, b[h].w, c);
+        } else { pi[h].x += gg.x; }
+        if ((dx.probe & 4) && pi[h].x != 123.456f) continue;
+        s1v[base + i] = a[h];
+        if (TWO) s2v[base + i] = b[h];
+        for (int q = 0; q < W; ++q)   // weak store; made visible by the system-scope fence in front of the done flag
+          if (!(dx.probe & 1) || q == dx.rank) __stcg(reinterpret_cast<float4*>(dx.bufs[q] + dx.off_flat) + base + i, pi[h]);
+      }
     }
   }
   // completion: every CTA's stores are fenced, the last CTA to finish publishes done[rank] and waits for all ranks
@@ -238,7 +290,7 @@ __global__ void __launch_bounds__(256, 2) k_dp_reduce_optim_bcast(DpX dx, float*
   __syncthreads();
   if (is_last) {
     if (t == 0) my_flags[128] = 0u;
-    if (t < dx.world) {
+    if (t < W) {
       __threadfence_system();
       unsigned* f = reinterpret_cast<unsigned*>(dx.bufs[t] + dx.off_flags) + 64 + 2 * dx.rank;
       asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(e) : "memory");
@@ -261,27 +313,49 @@ extern "C" int scnb_dp_reduce_optim_bcast(int opt, const uint64_t* peer_bufs, in
     spin = ev ? atoi(ev) : (1 << 24);
     if (spin <= 0) spin = 1 << 24;
   }
-  DpX dx{(const unsigned long long*)peer_bufs, (const long long*)epoch, off_flags, off_grad, off_flat, rank, world, spin};
-  // CTAs only wait for flags that are already on their way (no CTA waits for another CTA of its own grid except the last
-  // one to finish), so the grid need not be co-resident: 4 float4 per thread, at most 4 CTAs per SM
-  const long long per = ((total >> 2) + world - 1) / world;
-  static int unr = 0, cta_per_sm = 0;
-  if (!unr) {
-    const char* ev = getenv("SCNB_DP_UNR");
-    unr = ev ? atoi(ev) : 1;
-    if (unr != 1 && unr != 2) unr = 1;
-    ev = getenv("SCNB_DP_CTAS");
-    cta_per_sm = ev ? atoi(ev) : 2;
-    if (cta_per_sm < 1 || cta_per_sm > 8) cta_per_sm = 2;
+  static int probe = -1;
+  if (probe < 0) {
+    const char* ev = getenv("SCNB_DP_PROBE");
+    probe = ev ? atoi(ev) : 0;
   }
-  const long long want = (per + unr * 256 - 1) / (unr * 256);
-  int blocks = (int)(want < 148 * cta_per_sm ? want : 148 * cta_per_sm);
+  DpX dx{(const unsigned long long*)peer_bufs, (const long long*)epoch, off_flags, off_grad, off_flat, rank, world, spin, probe};
+  // One CTA per SM, every CTA co-resident with its peers' (a CTA waits only for flags that are already on their way and
+  // for the last CTA of the OTHER grids).  Ranks emulated on one GPU (tests) share its SMs: SCNB_DP_GRID caps the grid.
+  const long long per = ((total >> 2) + world - 1) / world;
+  static int grid_cap = 0;
+  if (!grid_cap) {
+    const char* ev = getenv("SCNB_DP_GRID");
+    grid_cap = ev ? atoi(ev) : 148;
+    if (grid_cap < 1 || grid_cap > 148) grid_cap = 148;
+  }
+  const long long want = (per + DPB_F4 - 1) / DPB_F4;
+  int blocks = (int)(want < grid_cap ? want : grid_cap);
   if (blocks < 1) blocks = 1;
+  const int nsrc = world + 2 + (opt != OPT_SGD ? 1 : 0);
+  int stages = (200 * 1024) / (nsrc * DPB_F4 * 16);
+  if (stages > 6) stages = 6;
+  static int stage_cap = -1;
+  if (stage_cap < 0) {
+    const char* ev = getenv("SCNB_DP_STAGES");
+    stage_cap = ev ? atoi(ev) : 0;
+  }
+  if (stage_cap > 0 && stages > stage_cap) stages = stage_cap;
+  if ((long long)stages > (want + blocks - 1) / blocks) stages = (int)((want + blocks - 1) / blocks);
+  if (stages < 1) stages = 1;
+  const size_t smem = (size_t)stages * nsrc * DPB_F4 * 16;
   cudaStream_t st = (cudaStream_t)stream;
-#define DP_GO(O)                                                                                                    \
-  do {                                                                                                              \
-    if (unr == 2) k_dp_reduce_optim_bcast<O, 2><<<blocks, 256, 0, st>>>(dx, state1, state2, total, hp8, state4); \
-    else k_dp_reduce_optim_bcast<O, 1><<<blocks, 256, 0, st>>>(dx, state1, state2, total, hp8, state4);              \
+#define DP_GO(O)                                                                                                         \
+  do {                                                                                                                   \
+    static bool attr = false;                                                                                            \
+    if (!attr) {                                                                                                         \
+      cudaError_t ce = cudaFuncSetAttribute(k_dp_reduce_optim_bcast<O>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+      if (ce != cudaSuccess) {                                                                                           \
+        scnb_set_error("dp_reduce_optim_bcast: cannot reserve shared memory: %s", cudaGetErrorString(ce));               \
+        return SCNB_ERR_CUDA;                                                                                            \
+      }                                                                                                                  \
+      attr = true;                                                                                                       \
+    }                                                                                                                    \
+    k_dp_reduce_optim_bcast<O><<<blocks, DPB_T, smem, st>>>(dx, state1, state2, total, hp8, state4, stages);          \
   } while (0)
   switch (opt) {
     case OPT_ADADELTA: DP_GO(OPT_ADADELTA); break;

@@ -7,6 +7,9 @@ import pytest
 # 8 hardware work queues, two engines' streams can alias onto one queue and serialise behind a waiting kernel (a deadlock
 # that cannot happen across real GPUs); must be set before the CUDA context exists.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# Same emulation: the gradient exchange kernel runs one persistent CTA per SM and waits for its peers' kernels; up to four
+# emulated ranks must fit on the one GPU together.
+os.environ.setdefault("SCNB_DP_GRID", "32")
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:

@@ -51,7 +51,8 @@ def main():
     ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") == "kernel"]
     ev.sort(key=lambda e: e["ts"])
     # split into steps at the first kernel of the step
-    starts = [i for i, e in enumerate(ev) if e["name"].startswith("k_step_prep")]
+    first = "k_zero2" if any(e["name"].startswith("k_zero2") for e in ev) else "k_step_prep"
+    starts = [i for i, e in enumerate(ev) if e["name"].startswith(first)]
     k = len(starts) // 2
     seg = ev[starts[k]: starts[k + 1]] if k + 1 < len(starts) else ev[starts[k]:]
     t0 = seg[0]["ts"]
