@@ -385,27 +385,34 @@ def roofline_block(eng, per_step, per_launch, world, ms_per_step):
     return roof
 
 
-def time_e2e(args, device, rank, world):
-    """`e2e`: the same step through the public host-buffer entry `scnym_b200.hostfeed.HostTrainPipeline`:
-    the FULL expression matrices of the workload live in HOST memory; every step's batch is gathered on the host into
-    pinned memory, copied host->device, trained on, and the step's loss scalars are copied back and read on the
-    host -- all inside the timed region (the three stages are pipelined across steps)."""
-    from scnym_b200.hostfeed import HostTrainPipeline
+def time_e2e(args, device, rank, world, feed="mapped"):
+    """`e2e`: the same step through the public host-buffer entries of `scnym_b200.hostfeed`: the FULL expression matrices
+    of the workload live in HOST memory, every step's batch is brought to the device inside the timed region and the
+    step's loss scalars are read on the host after every step.
+      feed = "mapped" (`HostMappedTrainPipeline`): the matrices are page-locked in place and mapped; the step's own row
+             gather reads the sampled rows over PCIe while the previous step runs; the loss lands in mapped host memory.
+      feed = "staged" (`HostTrainPipeline`): producer threads gather each batch into pinned blobs, one H2D copy per step,
+             device-side stash, same read-back; the three stages are pipelined across steps."""
+    from scnym_b200.hostfeed import HostMappedTrainPipeline, HostTrainPipeline
     c = CFG
     model, dann, cfg, lab, y, unl = build_train(device, rank, seed_off=7)
     ld, ud = given_domains(device, lab.n_rows, unl.n_rows, rank)
     host = lambda t: t.cpu().numpy()
-    # host threads for batch assembly: the box's cores are shared by the ranks
-    cores = max((os.cpu_count() or 8) // world, 1)
-    n_thr = max(min(4, cores), 1)
-    n_prod = max(min(int(os.environ.get("SCNB_E2E_PRODUCERS", "3")), cores // n_thr), 1)
     lab_t = (host(lab.indptr), host(lab.indices), host(lab.data), host(y)) + ((host(ld),) if ld is not None else ())
     unl_t = (host(unl.indptr), host(unl.indices), host(unl.data)) + ((host(ud),) if ud is not None else ())
     n_host = lab.n_rows + unl.n_rows
     del lab, unl
     torch.cuda.empty_cache()
-    pipe = HostTrainPipeline(model, cfg, lab=lab_t, unl=unl_t, n_genes=c["G"], batch_size=c["L"], unlabeled_batch_size=c["U"],
-                             dann=dann, device=device, n_threads=n_thr, seed=5 + rank, comm=make_comm(world), n_producers=n_prod)
+    if feed == "mapped":
+        pipe = HostMappedTrainPipeline(model, cfg, lab=lab_t, unl=unl_t, n_genes=c["G"], batch_size=c["L"], unlabeled_batch_size=c["U"],
+                                       dann=dann, device=device, seed=5 + rank, comm=make_comm(world))
+    else:
+        # host threads for batch assembly: the box's cores are shared by the ranks
+        cores = max((os.cpu_count() or 8) // world, 1)
+        n_thr = max(min(4, cores), 1)
+        n_prod = max(min(int(os.environ.get("SCNB_E2E_PRODUCERS", "3")), cores // n_thr), 1)
+        pipe = HostTrainPipeline(model, cfg, lab=lab_t, unl=unl_t, n_genes=c["G"], batch_size=c["L"], unlabeled_batch_size=c["U"],
+                                 dann=dann, device=device, n_threads=n_thr, seed=5 + rank, comm=make_comm(world), n_producers=n_prod)
     pipe.engine.set_weights(1.0, 0.1)
     steps, warm = max(args.steps, 50), max(args.warmup, 5)
     for l in pipe.run(warm):
@@ -418,7 +425,9 @@ def time_e2e(args, device, rank, world):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     assert np.isfinite(l["loss"]), l
-    return dt / steps * 1e3, pipe.h2d_bytes_last, pipe.d2h_bytes_last, n_host
+    out = (dt / steps * 1e3, pipe.h2d_bytes_last, pipe.d2h_bytes_last, n_host)
+    pipe.close()
+    return out
 
 
 def time_predict(device, rank, passes=16):
@@ -766,13 +775,21 @@ def main():
 
     e2e = None
     if not args.no_e2e:
-        e2e_ms, h2d, d2h, n_host = time_e2e(args, device, rank, world)
-        t = torch.tensor([e2e_ms], device=device, dtype=torch.float64)
-        if world > 1:
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        e2e = {"value": cells_per_step * world / (float(t.item()) * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "host_cells_per_rank": n_host}
-        torch.cuda.empty_cache()
+        feeds = {}
+        for feed in ("mapped", "staged"):
+            e2e_ms, h2d, d2h, n_host = time_e2e(args, device, rank, world, feed=feed)
+            t = torch.tensor([e2e_ms], device=device, dtype=torch.float64)
+            if world > 1:
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            feeds[feed] = {"value": cells_per_step * world / (float(t.item()) * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": h2d,
+                           "d2h_bytes_per_step": d2h, "host_cells_per_rank": n_host}
+            torch.cuda.empty_cache()
+        # both public host-buffer entries are timed; the headline is the one a user would pick (the faster)
+        best = max(feeds, key=lambda k: feeds[k]["value"])
+        e2e = dict(feeds[best], feed=("hostfeed.HostMappedTrainPipeline" if best == "mapped" else "hostfeed.HostTrainPipeline"),
+                   feeds={k: v["value"] for k, v in feeds.items()},
+                   note="mapped: the step's row gather reads the sampled rows of the page-locked host matrices over PCIe and the "
+                        "loss is stored into mapped host memory; staged: producer threads -> pinned blob -> one H2D copy per step")
 
     dp = None
     if world > 1:

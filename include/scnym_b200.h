@@ -55,6 +55,21 @@ int scnb_csr_gather_rows2(const int64_t* indptr_A, const int32_t* indices_A, con
                           const int32_t* b_indptr, int32_t* b_idx, float* b_val, const uint8_t* keep_mask,
                           const uint64_t* rng, float p_drop, int32_t* gene_cnt, int ctr_off /* as scnb_csr_gather_rows_aug */,
                           void* stream);
+/* scnb_csr_gather_rows2 without its shared-memory row cache (the second pass re-reads the row): 32 bytes of shared memory
+ * per CTA, so it runs next to a kernel that holds nearly all of an SM's shared memory.  Same arguments and results. */
+int scnb_csr_gather_rows2_nocache(const int64_t* indptr_A, const int32_t* indices_A, const float* data_A, const int64_t* rows_A,
+                                  int nA, int augment_A, uint32_t stream_id_A, const int64_t* indptr_B, const int32_t* indices_B,
+                                  const float* data_B, const int64_t* rows_B, int nB, int augment_B, uint32_t stream_id_B,
+                                  const int32_t* b_indptr, int32_t* b_idx, float* b_val, const uint8_t* keep_mask,
+                                  const uint64_t* rng, float p_drop, int32_t* gene_cnt, int ctr_off, void* stream);
+/* Sampled rows of two HOST-resident matrices (page-locked + mapped: scnb_host_register_mapped) -> a device staging CSR with
+ * the batch's row order [A ; B] and offsets (b_indptr from scnb_step_prep; st_indptr: the same offsets as int64, nA+nB+1),
+ * copied verbatim over PCIe by a persistent grid of <= max_ctas (0: 148) light CTAs.  The staged rows are then the source
+ * of scnb_csr_gather_rows2.  Replaces host-side minibatch assembly + the per-step `.to(device)` of
+ * scnym/dataprep.py:114-168, scnym/trainer.py:589-599. */
+int scnb_csr_fetch_rows2(const int64_t* indptr_A, const int32_t* indices_A, const float* data_A, const int64_t* rows_A, int nA,
+                         const int64_t* indptr_B, const int32_t* indices_B, const float* data_B, const int64_t* rows_B, int nB,
+                         const int32_t* b_indptr, int64_t* st_indptr, int32_t* st_idx, float* st_val, int max_ctas, void* stream);
 /* The other augmentation schemes of scnym/dataprep.py:730-754 (AUGMENTATION_SCHEMES) on rows [0, n) of one source, on the
  * STORED entries only (every stage maps 0 to 0).  scheme: 1 log1p_drop (:721-729), 2 log1p_mask (GeneMasking :405-465),
  * 3 log1p_poisson (PoissonSample :277-341), 4 log1p_poisson_drop (depth ~ U(0.1, 2), then InputDropout), 5 count_poisson
@@ -214,6 +229,17 @@ int scnb_peer_alloc(long long bytes, void** ptr_out, void* handle64_out);
 int scnb_peer_open(const void* handle64, void** ptr_out);
 int scnb_peer_close(void* ptr);
 int scnb_peer_free(void* ptr);
+/* Host memory that kernels can store into (cudaHostAllocMapped) and a <= 256-float publish kernel: the per-step loss
+ * read-back of the host-buffer pipeline (replaces the `loss.item()` of scnym/trainer.py:666-681) without a copy-engine
+ * transfer. */
+int scnb_host_alloc_mapped(long long bytes, void** host_ptr_out, void** dev_ptr_out);
+int scnb_host_free_mapped(void* host_ptr);
+int scnb_publish_f32(const float* src, int n, float* dst_mapped, void* stream);
+/* Page-lock + map an existing host array (cudaHostRegisterMapped): dev_ptr_out is what kernels dereference.  Feeds the row
+ * gather (scnb_step_prep / scnb_csr_gather_rows2) straight from host-resident CSR matrices -- the host-side minibatch
+ * assembly of scnym/dataprep.py:114-168 + the per-step copy of scnym/trainer.py:589-599 without host threads. */
+int scnb_host_register_mapped(void* host_ptr, long long bytes, void** dev_ptr_out);
+int scnb_host_unregister(void* host_ptr);
 
 int scnb_bn_eval_bwd(const float* dA, const float* A, int relu, int rows, int H, const float* gamma,
                      const float* running_var, float* dZ, void* stream);

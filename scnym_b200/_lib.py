@@ -18,6 +18,8 @@ SIGNATURES = {
     "scnb_gather_i32": [P, P, I, I, P, P],
     "scnb_csr_gather_rows": [P, P, P, P, L, I, P, P, P, I, I, I, P, P, U32, F, P, P],
     "scnb_csr_gather_rows2": [P, P, P, P, I, I, U32, P, P, P, P, I, I, U32, P, P, P, P, P, F, P, I, P],
+    "scnb_csr_gather_rows2_nocache": [P, P, P, P, I, I, U32, P, P, P, P, I, I, U32, P, P, P, P, P, F, P, I, P],
+    "scnb_csr_fetch_rows2": [P, P, P, P, I, P, P, P, P, I, P, P, P, P, I, P],
     "scnb_csr_gather_rows_aug": [P, P, P, P, L, I, P, P, P, I, I, F, F, P, P, P, P, U32, P, I, P],
     "scnb_step_prep": [P, P, P, P, I, P, I, I, P, P, P, P, P, P, P, I, P, P, P, P, P, P, I, I, P],
     "scnb_fetch_step": [P, P, P, P, I, I, I, P, P, P, P, P, P],
@@ -50,6 +52,11 @@ SIGNATURES = {
     "scnb_bn_act_bwd_peer": [P, P, P, I, I, P, I, P, P, P, P, U32, F, I, P, P, P, P, I, I, I, I, P, L, P],
     "scnb_bn_peer_bytes": [I, I, I, I],
     "scnb_peer_alloc": [L, P, P],
+    "scnb_host_alloc_mapped": [L, P, P],
+    "scnb_host_free_mapped": [P],
+    "scnb_publish_f32": [P, I, P, P],
+    "scnb_host_register_mapped": [P, L, P],
+    "scnb_host_unregister": [P],
     "scnb_peer_open": [P, P],
     "scnb_peer_close": [P],
     "scnb_peer_free": [P],

@@ -166,15 +166,20 @@ __device__ __forceinline__ bool gather_keep(const uint8_t* mask, int pos, const 
 #define GR_MASKBITS 32768   // entries of a row whose gene-masking decisions are held in shared memory (exact sampling)
 
 // EXT = false: schemes 0 / 1 only (the step's hot path: the Poisson sampler and the masking scan are compiled out)
-template <bool EXT>
+// CACHE = false: no shared-memory row cache -- the second pass re-reads the row and recomputes its (counter-based) random
+// stages.  32 bytes of shared memory per CTA: this form fits on an SM next to a kernel that holds nearly all of it (the
+// dW1 + optimizer kernel), which is where the batch of the NEXT step is assembled when its rows arrive late (host-mapped
+// matrices, scnb_csr_fetch_rows2).
+template <bool EXT, bool CACHE = true>
 __global__ void __launch_bounds__(GR_T) k_gather_rows(GatherSrc A, GatherSrc B, const int32_t* __restrict__ b_indptr,
                                                      int32_t* __restrict__ b_idx, float* __restrict__ b_val,
                                                      const uint8_t* __restrict__ keep_mask, const uint64_t* __restrict__ rng,
                                                      float p_drop, float target_sum, int32_t* __restrict__ gene_cnt, AugExtra X) {
   PDL_ENTRY();
   __shared__ float red8[8];
-  __shared__ float e_s[GR_CACHE];
-  __shared__ int32_t c_s[GR_CACHE];
+  constexpr int NCACHE = CACHE ? GR_CACHE : 0;
+  __shared__ float e_s[CACHE ? GR_CACHE : 1];
+  __shared__ int32_t c_s[CACHE ? GR_CACHE : 1];
   __shared__ uint32_t mbits[EXT ? GR_MASKBITS / 32 : 1];   // gene masking: bit j = entry j of the row is masked
   const int tid = threadIdx.x;
   const int i = blockIdx.x;
@@ -261,7 +266,7 @@ __global__ void __launch_bounds__(GR_T) k_gather_rows(GatherSrc A, GatherSrc B, 
     }
     const float e = entry(j, k, rnd);
     sum += e;
-    if (j < GR_CACHE) {
+    if (j < NCACHE) {
       e_s[j] = e;
       c_s[j] = S.indices[s + j];
     }
@@ -270,11 +275,11 @@ __global__ void __launch_bounds__(GR_T) k_gather_rows(GatherSrc A, GatherSrc B, 
   for (int j = tid, k = 0; j < len; j += GR_T, ++k) {
     float e;
     int c;
-    if (j < GR_CACHE) {
+    if (j < NCACHE) {
       e = e_s[j];
       c = c_s[j];
     } else {  // rows longer than the cache: recompute (every random stage is counter-based: the same draw again)
-      if (drop && !keep_mask && ((k & 3) == 0 || j - GR_T < GR_CACHE)) {
+      if (drop && !keep_mask && ((k & 3) == 0 || j - GR_T < NCACHE)) {
         const uint64_t ctr = (uint64_t)(d + tid) + (uint64_t)(4 * GR_T) * (uint64_t)(k >> 2);
         rnd = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)strm, (uint32_t)(strm >> 32)),
                             make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
@@ -323,6 +328,96 @@ extern "C" int scnb_csr_gather_rows2(const int64_t* indptr_A, const int32_t* ind
   scnb_launch_pdl(k_gather_rows<false>, dim3(nA + nB), dim3(GR_T), 0, (cudaStream_t)stream, A, B, b_indptr, b_idx, b_val, keep_mask, rng, p_drop, 1e6f,
                   gene_cnt, AugExtra{0, 0.f, nullptr, nullptr, ctr_off});
   SCNB_CHECK_LAUNCH("csr_gather_rows2");
+  return SCNB_OK;
+}
+
+// Sampled rows of two HOST-resident matrices (page-locked + mapped, scnb_host_register_mapped) -> a device staging CSR laid
+// out like the batch (rows [A ; B], offsets = b_indptr, also written as the int64 `st_indptr` the gather expects), verbatim.
+// The reads travel over PCIe (~2 us latency, ~45 GB/s): a persistent grid of at most one light CTA per SM -- no shared
+// memory, 8 loads in flight per thread, ~1 MB outstanding in total -- so that the step's own kernels keep their SM
+// resources while the upload of the NEXT step's rows is in flight (the augmenting gather itself, with its shared-memory
+// row cache, then runs on the staged rows in HBM).  Replaces the host-side minibatch assembly + `.to(device)` of
+// scnym/dataprep.py:114-168 / trainer.py:589-599.
+__global__ void __launch_bounds__(256) k_fetch_rows(GatherSrc A, GatherSrc B, const int32_t* __restrict__ b_indptr,
+                                                    int64_t* __restrict__ st_indptr, int32_t* __restrict__ st_idx,
+                                                    float* __restrict__ st_val) {
+  const int tid = threadIdx.x, n = A.n + B.n;
+  if (blockIdx.x == 0)
+    for (int i = tid; i <= n; i += 256) st_indptr[i] = (int64_t)b_indptr[i];
+  auto start_of = [&](int i) -> int64_t {
+    const bool inA = i < A.n;
+    const GatherSrc& S = inA ? A : B;
+    const int li = inA ? i : i - A.n;
+    return S.indptr[S.rows ? S.rows[li] : (S.row0 + li)];
+  };
+  int i = blockIdx.x;
+  int64_t s = i < n ? start_of(i) : 0;
+  for (; i < n; i += gridDim.x) {
+    const int nx = i + gridDim.x;
+    const int64_t s_next = nx < n ? start_of(nx) : 0;     // the next row's offset (a host read) is in flight during this row
+    const bool inA = i < A.n;
+    const int32_t* __restrict__ ix = (inA ? A.indices : B.indices) + s;
+    const float* __restrict__ vv = (inA ? A.data : B.data) + s;
+    const int d = b_indptr[i], len = b_indptr[i + 1] - d;
+    for (int j0 = 0; j0 < len; j0 += 4 * 256) {
+      int c[4];
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * 256 + tid;
+        if (j < len) {
+          c[u] = ix[j];
+          v[u] = vv[j];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * 256 + tid;
+        if (j < len) {
+          st_idx[d + j] = c[u];
+          st_val[d + j] = v[u];
+        }
+      }
+    }
+    s = s_next;
+  }
+}
+
+extern "C" int scnb_csr_fetch_rows2(const int64_t* indptr_A, const int32_t* indices_A, const float* data_A, const int64_t* rows_A,
+                                    int nA, const int64_t* indptr_B, const int32_t* indices_B, const float* data_B,
+                                    const int64_t* rows_B, int nB, const int32_t* b_indptr, int64_t* st_indptr, int32_t* st_idx,
+                                    float* st_val, int max_ctas, void* stream) {
+  SCNB_CHECK_ARG(b_indptr && st_indptr && st_idx && st_val && nA >= 0 && nB >= 0, "csr_fetch_rows2: bad arguments");
+  SCNB_CHECK_ARG(nA == 0 || (indptr_A && indices_A && data_A), "csr_fetch_rows2: source A missing");
+  SCNB_CHECK_ARG(nB == 0 || (indptr_B && indices_B && data_B), "csr_fetch_rows2: source B missing");
+  if (nA + nB == 0) return SCNB_OK;
+  GatherSrc A = {indptr_A, indices_A, data_A, rows_A, 0, nA, 0, 0, 0, 0};
+  GatherSrc B = {indptr_B, indices_B, data_B, rows_B, 0, nB, 0, 0, 0, 0};
+  int grid = max_ctas > 0 ? max_ctas : 148;
+  if (grid > nA + nB) grid = nA + nB;
+  k_fetch_rows<<<grid, 256, 0, (cudaStream_t)stream>>>(A, B, b_indptr, st_indptr, st_idx, st_val);
+  SCNB_CHECK_LAUNCH("csr_fetch_rows2");
+  return SCNB_OK;
+}
+
+// scnb_csr_gather_rows2 without the shared-memory row cache (see k_gather_rows<.., CACHE = false>): same arguments, same
+// results bit for bit.
+extern "C" int scnb_csr_gather_rows2_nocache(const int64_t* indptr_A, const int32_t* indices_A, const float* data_A,
+                                             const int64_t* rows_A, int nA, int augment_A, uint32_t stream_id_A,
+                                             const int64_t* indptr_B, const int32_t* indices_B, const float* data_B,
+                                             const int64_t* rows_B, int nB, int augment_B, uint32_t stream_id_B,
+                                             const int32_t* b_indptr, int32_t* b_idx, float* b_val, const uint8_t* keep_mask,
+                                             const uint64_t* rng, float p_drop, int32_t* gene_cnt, int ctr_off, void* stream) {
+  SCNB_CHECK_ARG(b_indptr && b_idx && b_val && nA >= 0 && nB >= 0, "csr_gather_rows2_nocache: bad arguments");
+  SCNB_CHECK_ARG(nA == 0 || (indptr_A && indices_A && data_A), "csr_gather_rows2_nocache: source A missing");
+  SCNB_CHECK_ARG(nB == 0 || (indptr_B && indices_B && data_B), "csr_gather_rows2_nocache: source B missing");
+  SCNB_CHECK_ARG(!(augment_A || augment_B) || keep_mask || rng, "csr_gather_rows2_nocache: augmentation needs keep_mask or rng state");
+  if (nA + nB == 0) return SCNB_OK;
+  GatherSrc A = {indptr_A, indices_A, data_A, rows_A, 0, nA, augment_A, 0, nA, stream_id_A};
+  GatherSrc B = {indptr_B, indices_B, data_B, rows_B, 0, nB, augment_B, 0, nB, stream_id_B};
+  k_gather_rows<false, false><<<nA + nB, GR_T, 0, (cudaStream_t)stream>>>(A, B, b_indptr, b_idx, b_val, keep_mask, rng, p_drop, 1e6f,
+                                                                          gene_cnt, AugExtra{0, 0.f, nullptr, nullptr, ctr_off});
+  SCNB_CHECK_LAUNCH("csr_gather_rows2_nocache");
   return SCNB_OK;
 }
 

@@ -94,6 +94,83 @@ extern "C" int scnb_peer_free(void* ptr) {
   return SCNB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Host memory a kernel can store into (cudaHostAllocMapped): the per-step loss scalars of the host-buffer pipeline
+// (hostfeed.py; the reference reads `loss.item()` every step, scnym/trainer.py:666-681) are published by a one-CTA kernel
+// instead of a device-to-host memcpy, which the copy engine queues behind the 4.6 MB upload of a later batch.
+// ---------------------------------------------------------------------------------------------
+extern "C" int scnb_host_alloc_mapped(long long bytes, void** host_ptr_out, void** dev_ptr_out) {
+  SCNB_CHECK_ARG(bytes > 0 && host_ptr_out && dev_ptr_out, "host_alloc_mapped: bad arguments");
+  void *h = nullptr, *d = nullptr;
+  cudaError_t e = cudaHostAlloc(&h, (size_t)bytes, cudaHostAllocMapped | cudaHostAllocPortable);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer(&d, h, 0);
+  if (e != cudaSuccess) {
+    if (h) cudaFreeHost(h);
+    scnb_set_error("host_alloc_mapped: %s", cudaGetErrorString(e));
+    return SCNB_ERR_CUDA;
+  }
+  memset(h, 0, (size_t)bytes);
+  *host_ptr_out = h;
+  *dev_ptr_out = d;
+  return SCNB_OK;
+}
+
+extern "C" int scnb_host_free_mapped(void* host_ptr) {
+  if (!host_ptr) return SCNB_OK;
+  cudaError_t e = cudaFreeHost(host_ptr);
+  if (e != cudaSuccess) {
+    scnb_set_error("host_free_mapped: %s", cudaGetErrorString(e));
+    return SCNB_ERR_CUDA;
+  }
+  return SCNB_OK;
+}
+
+// Page-lock an existing host array in place and map it into the device's address space (cudaHostRegisterMapped): the row
+// gather of the training step then reads the sampled rows straight out of host memory over PCIe -- no host threads, no
+// staging blob, no copy-engine transfer (the reference assembles every minibatch on the host, scnym/dataprep.py:114-168).
+extern "C" int scnb_host_register_mapped(void* host_ptr, long long bytes, void** dev_ptr_out) {
+  SCNB_CHECK_ARG(host_ptr && bytes > 0 && dev_ptr_out, "host_register_mapped: bad arguments");
+  void* d = nullptr;
+  cudaError_t e = cudaHostRegister(host_ptr, (size_t)bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
+  if (e == cudaSuccess) {
+    e = cudaHostGetDevicePointer(&d, host_ptr, 0);
+    if (e != cudaSuccess) cudaHostUnregister(host_ptr);
+  }
+  if (e != cudaSuccess) {
+    scnb_set_error("host_register_mapped: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return SCNB_ERR_CUDA;
+  }
+  *dev_ptr_out = d;
+  return SCNB_OK;
+}
+
+extern "C" int scnb_host_unregister(void* host_ptr) {
+  if (!host_ptr) return SCNB_OK;
+  cudaError_t e = cudaHostUnregister(host_ptr);
+  if (e != cudaSuccess) {
+    scnb_set_error("host_unregister: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return SCNB_ERR_CUDA;
+  }
+  return SCNB_OK;
+}
+
+__global__ void k_publish_f32(const float* __restrict__ src, int n, float* __restrict__ dst) {
+  const int i = threadIdx.x;
+  if (i < n) dst[i] = src[i];
+  __threadfence_system();
+}
+
+// dst_mapped[i] = src[i], i < n <= 256 (dst_mapped: device pointer of scnb_host_alloc_mapped memory); visible to the host
+// once the stream has passed this launch
+extern "C" int scnb_publish_f32(const float* src, int n, float* dst_mapped, void* stream) {
+  SCNB_CHECK_ARG(src && dst_mapped && n > 0 && n <= 256, "publish_f32: bad arguments");
+  k_publish_f32<<<1, 256, 0, (cudaStream_t)stream>>>(src, n, dst_mapped);
+  SCNB_CHECK_LAUNCH("publish_f32");
+  return SCNB_OK;
+}
+
 // Both matrices of a MixMatch batch (labeled and unlabeled rows) in ONE call: the worker threads are started once and
 // share the n_a + n_b rows, and the source rows of the next few copies are prefetched (the gather is a latency-bound
 // random read of host memory).  Same outputs as two scnb_host_gather_rows calls.

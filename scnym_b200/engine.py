@@ -173,6 +173,7 @@ class TrainEngine(object):
             raise _lib.ScnbError("TrainEngine needs a CUDA device (no CPU fallback)")
         _lib.lib()
         self.__dict__["_sets"], self.__dict__["_cur"] = [{}, {}], 0
+        self.post_launch = None
         self.model, self.cfg, self.mode = model, cfg, mode
         self.comm = comm if (comm is not None and comm.world > 1) else None
         self.dev = labeled.device
@@ -251,6 +252,8 @@ class TrainEngine(object):
             # device int32 tensors are borrowed as they are (host-batch staging buffers are rewritten every step)
             if x is None:
                 return None
+            if getattr(x, "is_mapped_host", False):      # page-locked host array mapped into the device (hostfeed.MappedArray)
+                return x
             if isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.int32:
                 return x
             if isinstance(x, torch.Tensor):
@@ -276,6 +279,12 @@ class TrainEngine(object):
         cap = self.nb * maxnnz
         self.cap = cap
         self.b_indptr, self.b_idx, self.b_val = i32(self.nb + 1), i32(cap), f32(cap)
+        # matrices that stay in (page-locked, mapped) HOST memory: the sampled rows are first fetched verbatim over PCIe into
+        # a device staging CSR by a light persistent kernel, and the augmenting gather then reads the staged rows
+        self.host_mapped = bool(getattr(labeled.indices, "is_mapped_host", False))
+        if self.host_mapped:
+            self.st_indptr = torch.zeros(self.nb + 1, dtype=torch.int64, device=dev)
+            self.st_idx, self.st_val = i32(cap), f32(cap)
         H0 = self.widths[0]
         self.Z1 = f32(self.nb, H0)
         # gene-major copy of the batch for the fused dW1 + optimizer kernel (needs W1T first in the arena)
@@ -437,6 +446,7 @@ class TrainEngine(object):
             self._sets[1] = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in self._sets[0].items()}
         self._pf_graphs, self._next_p, self._prefetch_valid = {}, 0, False
         self._ev_adv, self._ev_fl, self._ev_pf = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        self._ev_loss, self._ev_pub, self._ev_pplan, self._ev_pplan_done, self._ev_fetched = (torch.cuda.Event() for _ in range(5))
 
     # ------------------------------------------------------------------------------------
     def set_hyper(self, lr=None, weight_decay=None):
@@ -477,7 +487,7 @@ class TrainEngine(object):
         if not self.cfg.multi_stream:
             return main, main, main
         if self._side is None:
-            self._side = tuple(torch.cuda.Stream(device=self.dev) for _ in range(5))
+            self._side = tuple(torch.cuda.Stream(device=self.dev) for _ in range(6))
         return main, self._side[0], self._side[1]
 
     @staticmethod
@@ -539,10 +549,23 @@ class TrainEngine(object):
              ptr(self.base_dom) if self.use_dan else None, ptr(self.lab.indptr), ptr(self.unl.indptr) if mm else None,
              ptr(self.b_indptr), ptr(self.loss_buf), 8, int(phases), st)
 
-    def _gather_batch(self, st, rng, ctr_off=0):
+    def _gather_batch(self, st, rng, ctr_off=0, fetched=None):
         """Batch CSR [U_raw ; L_aug] (+ per-gene histogram for the SIMT dW1 path).  ctr_off = 1: the batch of the NEXT step."""
         c, L, U = self.cfg, self.L, self.U
-        if self.aug_code == 1:
+        if self.host_mapped and self.aug_code == 1:
+            call("scnb_csr_fetch_rows2", ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data), ptr(self.u_rows), U,
+                 ptr(self.lab.indptr), ptr(self.lab.indices), ptr(self.lab.data), ptr(self.l_rows), L, ptr(self.b_indptr),
+                 ptr(self.st_indptr), ptr(self.st_idx), ptr(self.st_val), int(os.environ.get("SCNB_FETCH_CTAS", "24")), st)
+            if fetched is not None:     # (recorded on the stream that `st` belongs to: the prefetch branch)
+                fetched.record(self._side[4])
+            sp = self.st_indptr
+            call("scnb_csr_gather_rows2_nocache", ptr(sp), ptr(self.st_idx), ptr(self.st_val), None, U, 0, 0,
+                 ptr(sp[U:]), ptr(self.st_idx), ptr(self.st_val), None, L, 1, SID_IN_L,
+                 ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), ptr(self.inj_in_keep_L), rng, c.p_in_drop,
+                 self._gene_cnt_ptr(), int(ctr_off), st)
+        elif self.host_mapped:
+            raise NotImplementedError("host-mapped matrices are fed through the log1p_drop gather only")
+        elif self.aug_code == 1:
             call("scnb_csr_gather_rows2", ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data), ptr(self.u_rows), U, 0, 0,
                  ptr(self.lab.indptr), ptr(self.lab.indices), ptr(self.lab.data), ptr(self.l_rows), L, 1, SID_IN_L,
                  ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), ptr(self.inj_in_keep_L), rng, c.p_in_drop,
@@ -560,9 +583,23 @@ class TrainEngine(object):
         buffers, on one stream: sampler hand-off (table row state[0] % n), gather (RNG counter + 1), MixUp plan, splits."""
         st = stream.cuda_stream
         self._prep(st, phases=1)
-        self._gather_batch(st, rng, ctr_off=1)
-        self._plan(self._all_confident, st)
-        self._build_csc(self.nb, st)
+        side = self._side[5] if (self.host_mapped and self._side is not None and stream is self._side[4]) else None
+        if side is None:
+            self._gather_batch(st, rng, ctr_off=1)
+            self._plan(self._all_confident, st)
+            self._build_csc(self.nb, st)
+            return
+        # Rows fetched from host memory take ~100 us.  What does not need them runs next to the fetch on a branch of its
+        # own (the MixUp plan: only the hand-off), and what needs only their gene indices (the gene-block split points)
+        # runs next to the augmenting gather that follows it -- not behind either.
+        self._ev_pplan.record(stream)
+        side.wait_event(self._ev_pplan)
+        self._plan(self._all_confident, side.cuda_stream)
+        self._gather_batch(st, rng, ctr_off=1, fetched=self._ev_fetched)
+        side.wait_event(self._ev_fetched)
+        self._build_csc(self.nb, side.cuda_stream, idx=self.st_idx)
+        self._ev_pplan_done.record(side)
+        stream.wait_event(self._ev_pplan_done)
 
     def _launch_mixmatch(self):
         c = self.cfg
@@ -620,7 +657,7 @@ class TrainEngine(object):
             main.wait_event(self._ev_adv)
             self._ev_fl.record(main)
             sF = self._side[4]
-            sF.wait_event(self._ev_fl)
+            sF.wait_event(self._ev_adv if os.environ.get("SCNB_PREFETCH_AT", "start") == "start" else self._ev_fl)
             cur = self.__dict__["_cur"]
             self.__dict__["_cur"] = 1 - cur
             try:
@@ -729,6 +766,18 @@ class TrainEngine(object):
         call("scnb_colsum", ptr(self.dlogits), nb, C, C, self.Gp("model.classif.0.bias"), 1, sw)
         if self.use_dan and sD is not main:
             main.wait_event(self._ev_grl)
+        published = False
+        if self.post_launch is not None and sW is not main:
+            # the step's loss scalars are final once both heads have run: a feeding pipeline's read-back goes out now, on
+            # the (idle) branch of the running statistics, instead of behind the dW1 kernel at the end of the step
+            sQ = self._side[3]
+            self._ev_loss.record(main)
+            sQ.wait_event(self._ev_loss)
+            with torch.cuda.stream(sQ):
+                self.post_launch(self)
+            self._ev_pub.record(sQ)
+            published = True
+        self._published = published
         dZ_first = self._student_backward(main, sW, rng, dA_last)
         self._dz_planes_ready = bool(self.w1_tc)
         if self.w1_tc:   # MixUp adjoint + bf16 operand planes of dZ1 for the tensor-core dW1 kernel, one launch
@@ -737,6 +786,8 @@ class TrainEngine(object):
         else:
             call("scnb_unmix_rows", ptr(dZ_first), H0, ptr(self.inv3), ptr(self.coef3), nb, ptr(self.dZ1), st)
         self._finish_step(main, sW, sD, self.dZ1, nb)
+        if published:
+            main.wait_event(self._ev_pub)
         if pre:
             main.wait_event(self._ev_pf)   # the next step's batch is complete when this step is
 
@@ -981,11 +1032,13 @@ class TrainEngine(object):
     def _gene_cnt_ptr(self):
         return ptr(self.gene_cnt) if (self.fused_w1 and not self.w1_tc) else None
 
-    def _build_csc(self, n_rows, st):
+    def _build_csc(self, n_rows, st, idx=None):
         """Inputs of the first-layer backward that depend only on the batch: per-row gene-block split points
         (tensor-core kernel) or the gene-major copy of the batch (SIMT kernel)."""
         if self.w1_tc:
-            call("scnb_row_gene_splits", ptr(self.b_indptr), ptr(self.b_idx), n_rows, self.G, ptr(self.w1_splits), st)
+            # (idx: the staged rows of a host-mapped batch -- same entries, same positions as b_idx)
+            call("scnb_row_gene_splits", ptr(self.b_indptr), ptr(self.b_idx if idx is None else idx), n_rows, self.G,
+                 ptr(self.w1_splits), st)
         elif self.fused_w1:
             call("scnb_csr_to_csc", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), n_rows, self.G, ptr(self.gene_cnt),
                  ptr(self.c_ptr), ptr(self.c_cursor), ptr(self.c_ent), st)
@@ -1174,6 +1227,9 @@ class TrainEngine(object):
             self._launch_mixmatch()
         else:
             self._launch_supervised()
+        if self.post_launch is not None and not getattr(self, "_published", False):
+            self.post_launch(self)           # a feeding pipeline's read-back, inside the same graph (set before any capture)
+        self._published = False
 
     def _fetch(self, st):
         if self._tabs is None:
@@ -1291,6 +1347,34 @@ class TrainEngine(object):
             if self.mode == "mixmatch" and self.cfg.mean_teacher and self.teacher_bn is None:
                 self.teacher_bn = [(b["bn"].running_mean.clone(), b["bn"].running_var.clone()) for b in self._blk]
             self._capture((self.unsup_weight, self.dan_weight))
+
+    def begin_step(self):
+        """What `step()` does on the host before the step's launches (for callers that replay a graph of their own made
+        by `capture_step`)."""
+        if self.mode == "mixmatch" and self.cfg.mean_teacher and self.teacher_bn is None:
+            self.teacher_bn = [(b["bn"].running_mean.clone(), b["bn"].running_var.clone()) for b in self._blk]
+        self._sync_planes()
+
+    def end_step(self):
+        self._prefetch_valid = False
+        self.steps_done += 1
+
+    def capture_step(self, pre=None, post=None):
+        """One CUDA graph of [pre()] + the step + [post()]: lets a feeding pipeline put its staging copy and its loss
+        read-back into the same launch as the step.  Replay it between `begin_step()` and `end_step()`."""
+        self.begin_step()
+        self.arena.check_aliasing()
+        g = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        before = _lib.launch_count
+        with torch.cuda.graph(g):
+            if pre is not None:
+                pre()
+            self._launch()
+            if post is not None:
+                post()
+        self.kernels_per_step = _lib.launch_count - before
+        return g
 
     def _capture_graph(self):
         # warm-up on a side stream is not needed: the library allocates nothing; but the first

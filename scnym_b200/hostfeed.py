@@ -102,11 +102,12 @@ class HostTrainPipeline(object):
         lay = self.layout
         # pinned blobs (producer <-> copy stream) and two device landing buffers
         self.n_producers = max(int(n_producers), 1)
-        self.n_blobs = max(int(prefetch) + 1, 3 * self.n_producers)
+        self.n_blobs = max(int(prefetch) + 2, 3 * self.n_producers + 1)
         self.blobs = [torch.empty(lay.total_bytes, dtype=torch.uint8).pin_memory() for _ in range(self.n_blobs)]
         self.blob_np = [{k: v.numpy() for k, v in lay.views(b).items()} for b in self.blobs]
         self.blob_t = [lay.views(b) for b in self.blobs]
-        self.land = [torch.zeros(lay.total_bytes, dtype=torch.uint8, device=self.dev) for _ in range(2)]
+        self.n_land = 3     # uploads run two steps ahead of the step that consumes them
+        self.land = [torch.zeros(lay.total_bytes, dtype=torch.uint8, device=self.dev) for _ in range(self.n_land)]
         self.land_t = [lay.views(b) for b in self.land]
         # the engine's staging batch: one device blob with the same layout (rows 0..B-1 of its CSRs are the batch)
         self.stage = torch.zeros(lay.total_bytes, dtype=torch.uint8, device=self.dev)
@@ -124,15 +125,22 @@ class HostTrainPipeline(object):
         # MixUp randomness is read straight from the staging blob (set before the step graph is captured)
         self.engine.perm_keys, self.engine.gamma_raw = self.s["keys"], self.s["gam"]
         self.copy_stream = torch.cuda.Stream(device=self.dev)
-        self.ev_h2d = [torch.cuda.Event() for _ in range(2)]
-        self.ev_stash = [torch.cuda.Event() for _ in range(2)]
-        self.loss_pin = [torch.zeros(8).pin_memory() for _ in range(2)]
-        self.ev_done = [torch.cuda.Event() for _ in range(2)]
+        self.ev_h2d = [torch.cuda.Event() for _ in range(self.n_land)]
+        self.ev_stash = [torch.cuda.Event() for _ in range(self.n_land)]
+        self.ev_done = [torch.cuda.Event() for _ in range(self.n_land)]
+        # loss scalars come back through host memory the device can store into: a device-to-host memcpy is queued by the
+        # copy engine behind the upload of a later batch (150 us), a 32-byte store is not
+        import ctypes
+        hp, dp = ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.call("scnb_host_alloc_mapped", 64 * self.n_land, ctypes.byref(hp), ctypes.byref(dp))
+        self._loss_host_ptr, self._loss_dev_ptr = hp.value, dp.value
+        self.loss_host = np.ctypeslib.as_array(ctypes.cast(hp.value, ctypes.POINTER(ctypes.c_float)), shape=(16 * self.n_land,))
+        self._graphs = {}
         self._tab_rng = np.random.default_rng(seed)
         self._tab_lock = threading.Lock()
         self._blocks, self._perm_state, self._step0 = {}, {}, 0
         self.h2d_bytes_last = 0
-        self.d2h_bytes_last = 8 * 4
+        self.d2h_bytes_last = 8 * 4       # stored by the publish kernel into mapped host memory
 
     # ---- producer (runs in a thread; the C gather releases the GIL) ----------------------------
     _TAB = 128   # steps of random draws made at once (amortises numpy call overhead held under the GIL)
@@ -229,27 +237,42 @@ class HostTrainPipeline(object):
         five enqueues and their launch gaps cost more than the extra bytes."""
         return self.layout.total_bytes <= 1.25 * exact_bytes
 
+    def _step_graph(self, slot):
+        """[landing buffer `slot` -> staging batch] + the step + [loss scalars -> mapped host memory] as ONE graph launch
+        (the whole blob is stashed: a device-to-device copy of its unused capacity costs less than separate launches)."""
+        eng = self.engine
+        key = (slot, eng.unsup_weight, eng.dan_weight)
+        g = self._graphs.get(key)
+        if g is None:
+            dst = self._loss_dev_ptr + 64 * slot
+            # the read-back is launched by the engine as soon as the losses are final (mid-step, on an idle branch)
+            eng.post_launch = lambda e: _lib.call("scnb_publish_f32", _lib.ptr(e.loss_buf), 8, dst, torch.cuda.current_stream().cuda_stream)
+            try:
+                g = eng.capture_step(pre=lambda: self.stage.copy_(self.land[slot], non_blocking=True))
+            finally:
+                eng.post_launch = None
+            self._graphs[key] = g
+        return g
+
     def _enqueue_step(self, nnz, slot):
-        eng, lt, s = self.engine, self.land_t[slot], self.s
-        nl, nu = nnz
+        eng = self.engine
         cur = torch.cuda.current_stream()
         cur.wait_event(self.ev_h2d[slot])
-        hb = self.layout.header_bytes
-        if self._whole_blob(hb + 8 * (nl + nu)):
-            self.stage.copy_(self.land[slot], non_blocking=True)
+        if eng.cfg.use_cuda_graph:
+            g = self._step_graph(slot)
+            eng.begin_step()
+            g.replay()
+            eng.end_step()
         else:
-            self.stage[:hb].copy_(self.land[slot][:hb], non_blocking=True)   # indptrs, labels, domains, keys, gammas
-            for name, n in (("idx_l", nl), ("val_l", nl), ("idx_u", nu), ("val_u", nu)):
-                if n > 0:
-                    s[name][:n].copy_(lt[name][:n], non_blocking=True)
+            self.stage.copy_(self.land[slot], non_blocking=True)
+            eng.step()
+            _lib.call("scnb_publish_f32", _lib.ptr(eng.loss_buf), 8, self._loss_dev_ptr + 64 * slot, cur.cuda_stream)
         self.ev_stash[slot].record(cur)
-        eng.step()
-        self.loss_pin[slot].copy_(eng.loss_buf, non_blocking=True)
         self.ev_done[slot].record(cur)
 
     def _read_loss(self, slot):
         self.ev_done[slot].synchronize()
-        v = self.loss_pin[slot].tolist()
+        v = self.loss_host[16 * slot: 16 * slot + 8].tolist()
         eng = self.engine
         out = {"sup_loss": v[0], "sup_acc": v[1] / max(self.L, 1), "unsup_loss": v[2]}
         if eng.use_dan:
@@ -257,9 +280,24 @@ class HostTrainPipeline(object):
         out["loss"] = v[0] + eng.unsup_weight * v[2] + (v[4] if eng.use_dan else 0.0)
         return out
 
+    def close(self):
+        if getattr(self, "_loss_host_ptr", None):
+            torch.cuda.synchronize()
+            self.loss_host = None
+            _lib.call("scnb_host_free_mapped", self._loss_host_ptr)
+            self._loss_host_ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def run(self, n_steps: int):
         """Generator over `n_steps` training steps; yields the loss dict of each step (in order)."""
-        self.engine.prepare()
+        if self.engine.cfg.use_cuda_graph:
+            for slot in range(self.n_land):      # capture before copies are in flight on other streams
+                self._step_graph(slot)
         torch.cuda.synchronize()
         P = self.n_producers
         # every producer owns its own pinned blobs (blob k belongs to producer k mod P): a producer that runs ahead can
@@ -280,17 +318,25 @@ class HostTrainPipeline(object):
             return item
 
         try:
+            NL = self.n_land
             pending = None           # (slot, blob) of the step whose loss has not been read yet
-            nxt = next_ready() if n_steps > 0 else None
-            if nxt is not None:
-                self.h2d_bytes_last = self._enqueue_h2d(nxt[0], nxt[1], 0)
+            ahead = []               # uploaded (or uploading) batches not yet stepped: (blob, nnz), in step order
+            fetched = 0
+            while fetched < min(2, n_steps):     # uploads run two steps ahead of the compute stream
+                item = next_ready()
+                b = self._enqueue_h2d(item[0], item[1], fetched % NL)
+                if fetched == 0:
+                    self.h2d_bytes_last = b
+                ahead.append(item)
+                fetched += 1
             for i in range(n_steps):
-                slot = i % 2
-                k, nnz = nxt
-                # upload of batch i+1 is enqueued before step i so that it overlaps step i on the device
-                nxt = next_ready() if i + 1 < n_steps else None
-                if nxt is not None:
-                    self._enqueue_h2d(nxt[0], nxt[1], 1 - slot)
+                slot = i % NL
+                k, nnz = ahead.pop(0)
+                if fetched < n_steps:
+                    item = next_ready()
+                    self._enqueue_h2d(item[0], item[1], fetched % NL)
+                    ahead.append(item)
+                    fetched += 1
                 self._enqueue_step(nnz, slot)
                 if pending is not None:
                     yield self._read_loss(pending[0])
@@ -305,3 +351,173 @@ class HostTrainPipeline(object):
             for th in ths:
                 th.join(timeout=5.0)
             self._step0 += n_steps
+
+
+class MappedArray(object):
+    """A host numpy array, page-locked in place and mapped into the device's address space: `data_ptr()` is what a kernel
+    dereferences (reads travel over PCIe when the kernel runs).  Quacks like the tensors the engine borrows pointers from."""
+    is_mapped_host = True
+    is_cuda = True
+
+    def __init__(self, arr: np.ndarray) -> None:
+        import ctypes
+        self.arr = np.ascontiguousarray(arr)
+        self._host_ptr = None
+        if self.arr.size == 0:
+            self._dev_ptr = 0
+            return
+        dp = ctypes.c_void_p()
+        _lib.call("scnb_host_register_mapped", self.arr.ctypes.data, int(self.arr.nbytes), ctypes.byref(dp))
+        self._host_ptr, self._dev_ptr = self.arr.ctypes.data, dp.value
+
+    def data_ptr(self):
+        return self._dev_ptr
+
+    def numel(self):
+        return int(self.arr.size)
+
+    def close(self):
+        if self._host_ptr is not None:
+            _lib.call("scnb_host_unregister", self._host_ptr)
+            self._host_ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MappedHostCSR(object):
+    """Host-resident expression matrix whose arrays the device reads in place (same attributes as `DeviceCSR`)."""
+
+    def __init__(self, indptr, indices, data, n_cols: int, device) -> None:
+        ip = np.ascontiguousarray(indptr, dtype=np.int64)
+        self.n_rows = int(ip.shape[0] - 1)
+        self.n_cols = int(n_cols)
+        self.max_row_nnz = int(np.diff(ip).max()) if self.n_rows > 0 else 0
+        self.indptr = MappedArray(ip)
+        self.indices = MappedArray(np.ascontiguousarray(indices, dtype=np.int32))
+        self.data = MappedArray(np.ascontiguousarray(data, dtype=np.float32))
+        self.device = torch.device(device)
+
+    @property
+    def shape(self):
+        return (self.n_rows, self.n_cols)
+
+    @property
+    def nnz(self):
+        return self.data.numel()
+
+    def close(self):
+        for a in (self.indptr, self.indices, self.data):
+            a.close()
+
+
+class HostMappedTrainPipeline(object):
+    """Training straight out of HOST-resident matrices with no host work per step: the labeled / unlabeled CSR arrays (and
+    labels, domains) are page-locked in place and mapped into the device; the step's own prologue -- sampler hand-off and
+    row gather, `scnb_step_prep` + `scnb_csr_gather_rows2` -- reads the sampled rows over PCIe while the previous step is
+    still running (the engine assembles the batch of step t+1 during step t), and the loss scalars are stored into mapped
+    host memory by the last launch of the step's graph.  Same contract as `HostTrainPipeline` (inputs in host memory at
+    every step, loss on the host after every step; replaces the DataLoader + per-step `.to(device)` of
+    scnym/trainer.py:574-599), without producer threads, staging blobs or copy-engine transfers.
+
+    pipe = HostMappedTrainPipeline(model, cfg, lab=(indptr, indices, data, y[, domain]), unl=(indptr, indices, data[, domain]),
+                                   n_genes=G, batch_size=256, dann=dann)
+    for losses in pipe.run(n_steps): ...
+    """
+
+    def __init__(self, model, cfg, lab, unl, n_genes: int, batch_size: int, unlabeled_batch_size: Optional[int] = None, dann=None,
+                 device="cuda", seed: int = 0, comm=None) -> None:
+        import ctypes
+        from .engine import TrainEngine
+        if not torch.cuda.is_available():
+            raise _lib.ScnbError("HostMappedTrainPipeline needs a CUDA device (no CPU fallback)")
+        self.dev = torch.device(device)
+        self.L = int(batch_size)
+        self.U = int(unlabeled_batch_size if unlabeled_batch_size is not None else batch_size)
+        self.lab = MappedHostCSR(lab[0], lab[1], lab[2], n_genes, self.dev)
+        self.unl = MappedHostCSR(unl[0], unl[1], unl[2], n_genes, self.dev)
+        i32 = lambda x: MappedArray(np.ascontiguousarray(x, dtype=np.int32))
+        self.y = i32(lab[3])
+        given = len(lab) > 4 and lab[4] is not None and len(unl) > 3 and unl[3] is not None
+        self.dom_l = i32(lab[4]) if given else None
+        self.dom_u = i32(unl[3]) if given else None
+        self.engine = TrainEngine(model.to(self.dev), cfg, self.lab, self.y, self.L, unlabeled=self.unl, unlabeled_batch_size=self.U,
+                                  dann=dann, labeled_domain=self.dom_l, unlabeled_domain=self.dom_u, mode="mixmatch", comm=comm)
+        hp, dp = ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.call("scnb_host_alloc_mapped", 128, ctypes.byref(hp), ctypes.byref(dp))
+        self._loss_host_ptr, self._loss_dev_ptr = hp.value, dp.value
+        self.loss_host = np.ctypeslib.as_array(ctypes.cast(hp.value, ctypes.POINTER(ctypes.c_float)), shape=(32,))
+        # one read-back slot per set of batch buffers (the engine replays one graph per set when it assembles batches ahead)
+        self.engine.post_launch = lambda eng: _lib.call(
+            "scnb_publish_f32", _lib.ptr(eng.loss_buf), 8, self._loss_dev_ptr + 64 * eng.__dict__["_cur"],
+            torch.cuda.current_stream().cuda_stream)
+        self.ev_done = [torch.cuda.Event() for _ in range(2)]
+        self.gen = torch.Generator(device=self.dev)
+        self.gen.manual_seed(int(seed))
+        self.epoch_steps = 256
+        self.h2d_bytes_last = 0
+        self.d2h_bytes_last = 8 * 4
+
+    def _loss(self, slot):
+        self.ev_done[slot].synchronize()
+        v = self.loss_host[16 * slot: 16 * slot + 8].tolist()
+        eng = self.engine
+        out = {"sup_loss": v[0], "sup_acc": v[1] / max(self.L, 1), "unsup_loss": v[2]}
+        if eng.use_dan:
+            out["dan_loss"] = v[4]
+        out["loss"] = v[0] + eng.unsup_weight * v[2] + (v[4] if eng.use_dan else 0.0)
+        return out
+
+    def batch_bytes(self):
+        """Host bytes the step that just ran pulled over PCIe: its rows' index / value entries, their row offsets, labels."""
+        eng = self.engine
+        nnz = int(eng.b_indptr[-1].item())
+        per_row = 16 + 4 + (8 if self.dom_l is not None else 0)
+        return 8 * nnz + per_row * (self.L + self.U)
+
+    def run(self, n_steps: int):
+        """Generator over `n_steps` training steps; yields the loss dict of each step (in order).  The loss of step i is
+        read after step i+1 has been enqueued when the engine alternates between two sets of batch buffers (two read-back
+        slots); otherwise after every step."""
+        eng = self.engine
+        cur = torch.cuda.current_stream()
+        pending = None
+        done = 0
+        while done < n_steps:
+            n = min(self.epoch_steps, n_steps - done)
+            if eng._tabs is None or eng._tabs["n"] != self.epoch_steps or self._left == 0:
+                eng.sample_epoch_tables(self.epoch_steps, generator=self.gen)
+                self._left = self.epoch_steps
+            n = min(n, self._left)
+            for _ in range(n):
+                eng.step()
+                slot = eng.__dict__["_cur"]
+                lag = bool(eng._pf_graphs)
+                self.ev_done[slot].record(cur)
+                if pending is not None:
+                    yield self._loss(pending)
+                    pending = None
+                if lag:
+                    pending = slot
+                else:
+                    yield self._loss(slot)
+            self._left -= n
+            done += n
+        self.h2d_bytes_last = self.batch_bytes()
+        if pending is not None:
+            yield self._loss(pending)
+
+    _left = 0
+
+    def close(self):
+        torch.cuda.synchronize()
+        for a in (self.lab, self.unl, self.y, self.dom_l, self.dom_u):
+            if a is not None:
+                a.close()
+        if self._loss_host_ptr:
+            self.loss_host = None
+            _lib.call("scnb_host_free_mapped", self._loss_host_ptr)
+            self._loss_host_ptr = None

@@ -326,3 +326,89 @@ def test_host_train_pipeline_feeds_the_engine_from_host_memory():
     assert np.array_equal(eng.b_idx[:nnz_u].cpu().numpy(), want_idx)
     assert np.array_equal(eng.b_val[:nnz_u].cpu().numpy(), want_val)
     assert np.array_equal(eng.lab_ids.cpu().numpy(), ly[lrows].astype(np.int32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", ["small", "config2"])
+def test_host_mapped_pipeline_reads_the_same_batches_as_device_resident_training(shape):
+    """HostMappedTrainPipeline: the matrices stay in (page-locked, mapped) HOST memory and the step's own row gather reads
+    the sampled rows over PCIe; the loss is stored into mapped host memory.  Against a TrainEngine on device-resident
+    copies of the same matrices with the same sampler seed: identical sampled rows, bit-identical batch CSR (input
+    dropout included), labels and domains at every step, losses of the first steps within the fp32 budget -- on the
+    small shape (batch assembled at the head of the step) and at the config-2 batch shape (tensor-core path: the batch of
+    step t+1 is assembled while step t runs, one read-back slot per set of batch buffers)."""
+    from oracle import scnym_oracle as O
+    from scnym_b200.dataprep import DeviceCSR
+    from scnym_b200.engine import EngineConfig, TrainEngine
+    from scnym_b200.hostfeed import HostMappedTrainPipeline
+    from scnym_b200.model import CellTypeCLF, DANN
+    if shape == "small":
+        G, C, L, U, n, H, dens = 600, 4, 32, 64, 300, 128, 0.06
+    else:
+        G, C, L, U, n, H, dens = 4096, 8, 256, 256, 2048, 256, 0.05
+    lp, li, ld, ly = O.synth_csr(n, G, dens, C, seed=21)
+    up, ui, ud, _ = O.synth_csr(n, G, dens, C, seed=22)
+    dl = (np.arange(n) % 3).astype(np.int32)
+    du = (np.arange(n) % 3 + 1).astype(np.int32) % 3
+    dev = torch.device("cuda", 0)
+
+    def build():
+        torch.manual_seed(0)
+        model = CellTypeCLF(n_genes=G, n_cell_types=C, n_hidden=H, n_hidden_init=H, n_layers=2)
+        return model, DANN(model, n_domains=3), EngineConfig(optimizer="sgd", lr=0.01, seed=3, pseudolabel_min_confidence=0.0)
+
+    model, dann, cfg = build()
+    pipe = HostMappedTrainPipeline(model, cfg, lab=(lp, li, ld, ly, dl), unl=(up, ui, ud, du), n_genes=G, batch_size=L,
+                                   unlabeled_batch_size=U, dann=dann, seed=9)
+    pipe.epoch_steps = 4
+    pipe.engine.set_weights(1.0, 0.1)
+    assert bool(pipe.engine.prefetch_ok) == (shape == "config2")
+    model2, dann2, cfg2 = build()
+    t = lambda a, dt: torch.as_tensor(np.asarray(a), dtype=dt).to(dev)
+    lab = DeviceCSR(t(lp, torch.int64), t(li, torch.int32), t(ld, torch.float32), G)
+    unl = DeviceCSR(t(up, torch.int64), t(ui, torch.int32), t(ud, torch.float32), G)
+    eng = TrainEngine(model2.to(dev), cfg2, lab, t(ly, torch.int32), L, unlabeled=unl, unlabeled_batch_size=U, dann=dann2,
+                      labeled_domain=t(dl, torch.int32), unlabeled_domain=t(du, torch.int32), mode="mixmatch")
+    eng.set_weights(1.0, 0.1)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(9)
+    it = pipe.run(6)
+    fields = ("l_rows", "u_rows", "lab_ids", "base_dom", "b_indptr")
+    pe = pipe.engine
+
+    def snapshot(e):
+        nnz = int(e.b_indptr[-1])
+        d = {k: getattr(e, k).clone() for k in fields}
+        d["b_idx"], d["b_val"] = e.b_idx[:nnz].clone(), e.b_val[:nnz].clone()
+        return d
+
+    ahead = None     # the pipeline's batch of the step the reference engine runs next (it yields losses one step late)
+    compared = 0
+    for s in range(6):
+        if s % 4 == 0:
+            eng.sample_epoch_tables(4, generator=gen)
+        eng.step()
+        torch.cuda.synchronize()
+        mine = snapshot(eng)
+        if ahead is not None:
+            for k in mine:
+                assert torch.equal(ahead[k], mine[k]), (s, k)
+            compared += 1
+        got = next(it)
+        torch.cuda.synchronize()
+        if pe._pf_graphs:
+            ahead = snapshot(pe) if s + 1 < 6 else None
+        else:
+            theirs = snapshot(pe)
+            for k in mine:
+                assert torch.equal(theirs[k], mine[k]), (s, k)
+            compared += 1
+        want = eng.losses()
+        if s < 2:
+            for k in ("sup_loss", "unsup_loss", "dan_loss"):
+                assert abs(got[k] - want[k]) <= 1e-4 * max(1.0, abs(want[k])), (s, k, got[k], want[k])
+        assert np.isfinite(got["loss"])
+    assert compared >= 5
+    assert list(it) == []
+    assert pipe.d2h_bytes_last == 32 and pipe.h2d_bytes_last > 8 * (L + U)
+    pipe.close()

@@ -22,8 +22,13 @@ def wrap(name, key):
 wrap("_enqueue_h2d", "h2d"); wrap("_enqueue_step", "step"); wrap("_read_loss", "read")
 orig_prod = pipe._produce
 tp = [0.0, 0]
+seen = {}
 def prod(k, j):
-    t0 = time.perf_counter(); r = orig_prod(k, j); tp[0] += time.perf_counter() - t0; tp[1] += 1; return r
+    if os.environ.get("NOPROD") and k in seen:      # experiment: re-upload the blob as it is (no host gather, no CPU writes)
+        return seen[k]
+    t0 = time.perf_counter(); r = orig_prod(k, j); tp[0] += time.perf_counter() - t0; tp[1] += 1
+    seen[k] = r
+    return r
 pipe._produce = prod
 for _ in pipe.run(20): pass
 for k in T: T[k] = 0.0
