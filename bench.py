@@ -91,9 +91,11 @@ def ncu_traffic(entry):
     for name in ("r02_traffic.json", "r01_traffic.json"):
         p = os.path.join(ROOT, "profiles", name)
         if os.path.exists(p):
-            v = json.load(open(p)).get(entry, {}).get("dram_bytes_per_launch")
-            if v is not None:
-                return v
+            tab = json.load(open(p))
+            for key in (entry, entry.split(" ")[0] + "]" if "[" in entry else entry, entry.split("[")[0]):
+                v = tab.get(key, {}).get("dram_bytes_per_launch") if isinstance(tab.get(key), dict) else None
+                if v is not None:
+                    return v
     return None
 
 
@@ -195,11 +197,13 @@ def time_device_resident(args, device, rank, world):
     if rank == 0:
         cs.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.cudart().cudaProfilerStart()     # `ncu --profile-from-start off` lists exactly the timed steps' launches
     e0.record()
     for _ in range(args.steps):
         eng.step()
     e1.record()
     torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
     barrier(world)
     clocks = cs.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
@@ -224,6 +228,13 @@ def launch_key(name, a):
     """Aggregation key of a C-ABI call in the per-kernel timing: GEMM launches are told apart by layout and shape."""
     if name == "scnb_sgemm":
         return f"scnb_sgemm[{'T' if a[0] else 'N'}{'T' if a[1] else 'N'} {a[2]}x{a[3]}x{a[4]}]"
+    if name == "scnb_hs_fwd":     # (Zin .. K, N, R at 16..18, running_mean at 21): the student's train-mode launches and the
+        mode = "eval" if a[21] else "train"   # teacher's eval-mode ones are different kernels' worth of work
+        return f"scnb_hs_fwd[{mode} {a[18]}x{a[17]}x{a[16]}]"
+    if name == "scnb_hs_bwd":
+        return f"scnb_hs_bwd[{a[17]}x{a[16]}x{a[15]}]"
+    if name == "scnb_hs_dw":
+        return f"scnb_hs_dw[{a[1]}x{a[3]}x{a[4]}]"
     return name
 
 
@@ -304,6 +315,20 @@ def kernel_cost(eng, key):
         _, a = LAST_ARGS[key]
         M, N, K = a[2], a[3], a[4]
         return {"bound": "tensor", "flops": 2.0 * M * N * K, "issued_flops": 6.0 * M * N * K, "bytes": 4.0 * (M * K + K * N + M * N)}
+    if name in ("scnb_hs_fwd", "scnb_hs_bwd", "scnb_hs_dw"):
+        # tile GEMMs of the fused hidden stack (3xTF32 mma.sync): 2MNK of the fp32 product, three products issued; bytes:
+        # operand / result tensors once (forward: Z in, A + Z out, W; backward: dY, Z in, dZ + dY out, W; dW: dZ, A in, dW out)
+        _, a = LAST_ARGS[key]
+        if name == "scnb_hs_fwd":
+            K_, N_, R_ = a[16], a[17], a[18]
+            by = 4.0 * (R_ * K_ * 2 + R_ * N_ + K_ * N_)
+        elif name == "scnb_hs_bwd":
+            K_, N_, R_ = a[15], a[16], a[17]
+            by = 4.0 * (R_ * K_ * 3 + R_ * N_ * 2 + K_ * N_)
+        else:
+            K_, N_, R_ = a[1], a[3], a[4]
+            by = 4.0 * (R_ * K_ + R_ * N_ + K_ * N_)
+        return {"bound": "tensor", "flops": 2.0 * R_ * K_ * N_, "issued_flops": 6.0 * R_ * K_ * N_, "bytes": by}
     if name == "scnb_csr_linear_fwd_tc":
         # bytes: CSR stream + the two bf16 planes of W1T once + Z; tensor work: densified bf16x3 product
         return {"bound": "tensor", "flops": 2.0 * nnz * H0, "issued_flops": 6.0 * nb * G * H0, "bytes": 8.0 * nnz + 4.0 * G * H0 + 4.0 * nb * H0}
