@@ -88,6 +88,8 @@ def tensor_peak():
 def ncu_traffic(entry):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, from the committed `ncu --set full` captures
     (profiles/r0N_traffic.json: measured under ncu, never during a timed run)."""
+    if CFG is not CONFIGS[2][0]:      # the captures are of the config-2 step
+        return None
     for name in ("r02_traffic.json", "r01_traffic.json"):
         p = os.path.join(ROOT, "profiles", name)
         if os.path.exists(p):
