@@ -382,6 +382,22 @@ int scnb_record_step(const float* loss8, float* hist, int hist_cap, const float*
 int scnb_dp_reduce_optim_bcast(int opt, const uint64_t* peer_bufs, int rank, int world, long long off_flags, long long off_grad,
                                long long off_flat, long long total, float* state1, float* state2, const float* hp8,
                                const int64_t* state4, const int64_t* epoch, void* stream);
+/* Push form of the same exchange.  Ownership: rank r owns floats [r*S, (r+1)*S) of the arena, S = scnb_dp_slice_floats
+ * (the even share rounded up to 256 floats).  scnb_csr_w1_bwd_push_tc is the data-parallel form of
+ * scnb_csr_w1_bwd_optim_tc(opt = -1): every gradient row of W1T (arena floats [0, G*H0)) is stored, while the kernel runs,
+ * into region `rank` of the OWNER's inbox (off_inbox of its exchange buffer, `world` regions of S floats) instead of a local
+ * gradient arena.  scnb_dp_reduce_optim_bcast2 then takes the gradients of arena floats [0, pushed_floats) of its slice
+ * from its own inbox (local memory) and pulls only the rest from the peers; off_inbox < 0: identical to
+ * scnb_dp_reduce_optim_bcast.  The link then carries gradient stores during the dW1 kernel and parameter stores during
+ * the exchange, instead of both (plus load round trips) inside the exchange. */
+int scnb_dp_slice_floats(long long total, int world, long long* slice_floats_out);
+int scnb_csr_w1_bwd_push_tc(const int32_t* splits, const int32_t* b_idx, const float* b_val, int nb, int H0, int G,
+                            const void* dz_planes_hi, const void* dz_planes_lo, const uint64_t* peer_bufs, int rank, int world,
+                            long long off_inbox, long long total, float* grad_out /* NULL, or also keep the local gradient */,
+                            void* stream);
+int scnb_dp_reduce_optim_bcast2(int opt, const uint64_t* peer_bufs, int rank, int world, long long off_flags, long long off_grad,
+                                long long off_flat, long long off_inbox, long long pushed_floats, long long total, float* state1,
+                                float* state2, const float* hp8, const int64_t* state4, const int64_t* epoch, void* stream);
 
 int scnb_ema_update(float* teacher, const float* params, long long n, float decay, const int64_t* state4, void* stream);
 

@@ -88,6 +88,9 @@ SIGNATURES = {
     "scnb_zero2": [P, L, P, L, P],
     "scnb_optim_step": [I, P, P, P, P, L, P, P, P],
     "scnb_dp_reduce_optim_bcast": [I, P, I, I, L, L, L, L, P, P, P, P, P, P],
+    "scnb_dp_reduce_optim_bcast2": [I, P, I, I, L, L, L, L, L, L, P, P, P, P, P, P],
+    "scnb_dp_slice_floats": [L, I, P],
+    "scnb_csr_w1_bwd_push_tc": [P, P, P, I, I, I, P, P, P, I, I, L, L, P, P],
     "scnb_ema_update": [P, P, L, F, P, P],
     "scnb_record_step": [P, P, I, P, I, P, I, P, P],
     "scnb_predict_head": [P, I, I, I, P, P, P, P],

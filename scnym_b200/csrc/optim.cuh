@@ -74,3 +74,12 @@ __device__ __forceinline__ void optim_update(float& p, float g, float& a, float&
     p = p - c.lr * buf;
   }
 }
+
+// Data-parallel ownership of the flat arena: rank r owns float4 elements [r * S, min(n4, (r + 1) * S)), S = this many
+// float4 -- the even share rounded up to 64 float4 (256 floats), so that a row of W1T (H0 floats, H0 | 256) never
+// straddles two owners (the dW1 kernel then sends each gradient row to exactly one rank).
+__host__ __device__ __forceinline__ long long dp_slice_f4(long long total_floats, int world) {
+  const long long n4 = total_floats >> 2;
+  const long long per = (n4 + world - 1) / world;
+  return (per + 63) / 64 * 64;
+}

@@ -151,6 +151,8 @@ struct DpX {
   const long long* epoch;
   long long off_flags, off_grad, off_flat;   // byte offsets inside every rank's exchange buffer
   int rank, world, spin_limit;
+  long long off_inbox;   // >= 0: gradients of arena elements [0, pushed_f4) were PUSHED by their producers into the owners' inboxes
+  long long pushed_f4;   //        (scnb_csr_w1_bwd_push_tc): region q of this rank's inbox = rank q's gradient of this rank's slice
   int probe;   // timing experiments only (SCNB_DP_PROBE): bit 0 = no stores to peers, bit 1 = no loads from peers (results are wrong)
 };
 
@@ -189,10 +191,17 @@ __global__ void __launch_bounds__(DPB_T, 1) k_dp_reduce_optim_bcast(DpX dx, floa
   // flag block layout (u32 words): ready[r] at 2r, done[r] at 64 + 2r, CTA counter at 128
   unsigned* my_flags = reinterpret_cast<unsigned*>(dx.bufs[dx.rank] + dx.off_flags);
   const long long n4 = total >> 2;                                   // arena length is a multiple of 4 floats
-  const long long per = (n4 + W - 1) / W;                            // float4 elements per rank
+  const long long per = dp_slice_f4(total, W);                       // float4 elements per rank
   const long long lo = per * dx.rank, hi = min(n4, lo + per);
-  const long long nchunk = hi > lo ? (hi - lo + DPB_F4 - 1) / DPB_F4 : 0;
+  // two runs of chunks: [lo, mid) whose gradients sit in this rank's inbox, [mid, hi) pulled from the peers' arenas
+  const long long mid = (dx.off_inbox >= 0) ? max(lo, min(hi, dx.pushed_f4)) : lo;
+  const long long nchunk_a = mid > lo ? (mid - lo + DPB_F4 - 1) / DPB_F4 : 0;
+  const long long nchunk = nchunk_a + (hi > mid ? (hi - mid + DPB_F4 - 1) / DPB_F4 : 0);
   const long long mine = nchunk > blockIdx.x ? (nchunk - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // chunks of this CTA
+  auto chunk_range = [&](long long k, long long& base, long long& lim) -> bool {   // true: inbox run
+    if (k < nchunk_a) { base = lo + k * DPB_F4; lim = mid; return true; }
+    base = mid + (k - nchunk_a) * DPB_F4; lim = hi; return false;
+  };
   float4* s1v = reinterpret_cast<float4*>(s1);
   float4* s2v = reinterpret_cast<float4*>(s2);
   const float4* my_flat = reinterpret_cast<const float4*>(dx.bufs[dx.rank] + dx.off_flat);
@@ -200,8 +209,9 @@ __global__ void __launch_bounds__(DPB_T, 1) k_dp_reduce_optim_bcast(DpX dx, floa
   // gradient: nothing to wait for), 2 = the peers' gradients (after their ready flags), 3 = both
   auto issue = [&](long long j, int which) {
     const int s = (int)(j % stages);
-    const long long base = lo + (blockIdx.x + j * gridDim.x) * DPB_F4;
-    const uint32_t bytes = (uint32_t)min((long long)DPB_F4, hi - base) * 16u;
+    long long base, lim;
+    const bool inbox = chunk_range(blockIdx.x + j * gridDim.x, base, lim);
+    const uint32_t bytes = (uint32_t)min((long long)DPB_F4, lim - base) * 16u;
     const uint32_t bar = smem_u32(&bars[s]);
     const uint32_t dst = smem_u32(dsm) + (uint32_t)s * stage_bytes;
     if (which & 1) {
@@ -210,10 +220,18 @@ __global__ void __launch_bounds__(DPB_T, 1) k_dp_reduce_optim_bcast(DpX dx, floa
       bulk_g2s(dst + (uint32_t)(W + 1) * DPB_F4 * 16u, s1v + base, bytes, bar);
       if (TWO) bulk_g2s(dst + (uint32_t)(W + 2) * DPB_F4 * 16u, s2v + base, bytes, bar);
     }
-    for (int q = 0; q < W; ++q)
-      if (which & (q == dx.rank ? 1 : 2))
+    for (int q = 0; q < W; ++q) {
+      if (inbox) {
+        // every rank's gradient of this slice is in LOCAL memory (region q of the inbox), but it was written by rank q:
+        // all of them wait for the ready flags (the own region too -- one rule)
+        if (which & 2)
+          bulk_g2s(dst + (uint32_t)q * DPB_F4 * 16u,
+                   reinterpret_cast<const float4*>(dx.bufs[dx.rank] + dx.off_inbox) + (long long)q * per + (base - lo), bytes, bar);
+      } else if (which & (q == dx.rank ? 1 : 2)) {
         bulk_g2s(dst + (uint32_t)q * DPB_F4 * 16u,
                  reinterpret_cast<const float4*>(dx.bufs[(dx.probe & 2) ? dx.rank : q] + dx.off_grad) + base, bytes, bar);
+      }
+    }
   };
   if (t == 0) {
     for (int s = 0; s < stages; ++s) mbar_init(smem_u32(&bars[s]), 1);
@@ -239,8 +257,9 @@ __global__ void __launch_bounds__(DPB_T, 1) k_dp_reduce_optim_bcast(DpX dx, floa
   const float inv_w = 1.0f / (float)W;
   for (long long j = 0; j < mine; ++j) {
     const int s = (int)(j % stages);
-    const long long base = lo + (blockIdx.x + j * gridDim.x) * DPB_F4;
-    const int n = (int)min((long long)DPB_F4, hi - base);
+    long long base, lim;
+    chunk_range(blockIdx.x + j * gridDim.x, base, lim);
+    const int n = (int)min((long long)DPB_F4, lim - base);
     mbar_wait(smem_u32(&bars[s]), (uint32_t)((j / stages) & 1));
     const float4* sv = reinterpret_cast<const float4*>(dsm + (size_t)s * stage_bytes);
     float4 g[2], pi[2], a[2], b[2];
@@ -299,10 +318,31 @@ __global__ void __launch_bounds__(DPB_T, 1) k_dp_reduce_optim_bcast(DpX dx, floa
   }
 }
 
+extern "C" int scnb_dp_slice_floats(long long total, int world, long long* slice_floats_out) {
+  SCNB_CHECK_ARG(total >= 0 && total % 4 == 0 && world >= 1 && slice_floats_out, "dp_slice_floats: bad arguments");
+  *slice_floats_out = 4 * dp_slice_f4(total, world);
+  return SCNB_OK;
+}
+
+extern "C" int scnb_dp_reduce_optim_bcast2(int opt, const uint64_t* peer_bufs, int rank, int world, long long off_flags,
+                                           long long off_grad, long long off_flat, long long off_inbox, long long pushed_floats,
+                                           long long total, float* state1, float* state2, const float* hp8,
+                                           const int64_t* state4, const int64_t* epoch, void* stream);
+
 extern "C" int scnb_dp_reduce_optim_bcast(int opt, const uint64_t* peer_bufs, int rank, int world, long long off_flags,
                                           long long off_grad, long long off_flat, long long total, float* state1, float* state2,
                                           const float* hp8, const int64_t* state4, const int64_t* epoch, void* stream) {
+  return scnb_dp_reduce_optim_bcast2(opt, peer_bufs, rank, world, off_flags, off_grad, off_flat, -1, 0, total, state1, state2, hp8,
+                                     state4, epoch, stream);
+}
+
+extern "C" int scnb_dp_reduce_optim_bcast2(int opt, const uint64_t* peer_bufs, int rank, int world, long long off_flags,
+                                           long long off_grad, long long off_flat, long long off_inbox, long long pushed_floats,
+                                           long long total, float* state1, float* state2, const float* hp8,
+                                           const int64_t* state4, const int64_t* epoch, void* stream) {
   SCNB_CHECK_ARG(peer_bufs && state1 && hp8 && state4 && epoch && total >= 0 && total % 4 == 0, "dp_reduce_optim_bcast: bad arguments");
+  SCNB_CHECK_ARG(off_inbox < 0 || (off_inbox % 16 == 0 && pushed_floats >= 0 && pushed_floats <= total && pushed_floats % 4 == 0),
+                 "dp_reduce_optim_bcast: bad inbox arguments");
   SCNB_CHECK_ARG(world >= 1 && world <= 8 && rank >= 0 && rank < world, "dp_reduce_optim_bcast: bad rank/world (one NVSwitch node: world <= 8)");
   SCNB_CHECK_ARG(opt == OPT_SGD || state2, "dp_reduce_optim_bcast: second state buffer required");
   SCNB_CHECK_ARG(off_flags % 16 == 0 && off_grad % 16 == 0 && off_flat % 16 == 0, "dp_reduce_optim_bcast: offsets must be 16-byte aligned");
@@ -318,10 +358,11 @@ extern "C" int scnb_dp_reduce_optim_bcast(int opt, const uint64_t* peer_bufs, in
     const char* ev = getenv("SCNB_DP_PROBE");
     probe = ev ? atoi(ev) : 0;
   }
-  DpX dx{(const unsigned long long*)peer_bufs, (const long long*)epoch, off_flags, off_grad, off_flat, rank, world, spin, probe};
+  DpX dx{(const unsigned long long*)peer_bufs, (const long long*)epoch, off_flags, off_grad, off_flat, rank, world, spin, off_inbox,
+         pushed_floats >> 2, probe};
   // One CTA per SM, every CTA co-resident with its peers' (a CTA waits only for flags that are already on their way and
   // for the last CTA of the OTHER grids).  Ranks emulated on one GPU (tests) share its SMs: SCNB_DP_GRID caps the grid.
-  const long long per = ((total >> 2) + world - 1) / world;
+  const long long per = dp_slice_f4(total, world);
   static int grid_cap = 0;
   if (!grid_cap) {
     const char* ev = getenv("SCNB_DP_GRID");

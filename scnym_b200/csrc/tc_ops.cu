@@ -386,13 +386,14 @@ k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ 
     if (TRN && n_it > 0) {
       mbar_wait(bar_acc, 0);
       tc_fence_after();
-      const int col = half * TC_M + rl;                 // column of Z held by this TMEM lane
-      if (half * TC_M < N) {
+      // accumulator hh holds columns [128 hh, 128 hh + 128) of Z; a CTA has HALVES warp groups for N / 128 accumulators
+      for (int hh = half; hh * TC_M < N; hh += HALVES) {
+        const int col = hh * TC_M + rl;                 // column of Z held by this TMEM lane
         const float bc = (bias && blockIdx.y == 0) ? bias[col] : 0.f;
         for (int r0 = 0; r0 < ROWS; r0 += 32) {
           if ((long long)blockIdx.x * ROWS + r0 >= n_rows) break;
           uint32_t v[32];
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * ROWS + r0);
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hh * ROWS + r0);
           asm volatile(
               "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -520,6 +521,16 @@ extern "C" int scnb_csr_linear_fwd_tc(const int32_t* b_indptr, const int32_t* b_
   int rc = tc_check(n, G, H0, planes_hi, planes_lo, Z);
   if (rc != SCNB_OK) return rc;
   if (n == 0) return SCNB_OK;
+  // SCNB_FWD_ROWS=128: 128-row CTAs (twice the row tiles, half the gene splits: half the split-K atomics, twice the
+  // operand-plane reads out of L2); default 256
+  static int rows128 = -1;
+  if (rows128 < 0) {
+    const char* ev = getenv("SCNB_FWD_ROWS");
+    rows128 = (ev && atoi(ev) == 128) ? 1 : 0;
+  }
+  if (rows128)
+    return launch_dense_fwd_tc<int32_t, 1, 32, false, true>(b_indptr, b_idx, b_val, n, G, H0, planes_hi, planes_lo, b1, Z, ksplits,
+                                                            (cudaStream_t)stream);
   return launch_dense_fwd_tc<int32_t, 2, 32, false, true>(b_indptr, b_idx, b_val, n, G, H0, planes_hi, planes_lo, b1, Z, ksplits,
                                              (cudaStream_t)stream);
 }
@@ -613,7 +624,8 @@ k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict_
                   int GT, int NT, int G, int H0, const uint8_t* __restrict__ dz_hi, const uint8_t* __restrict__ dz_lo,
                   float* __restrict__ W, float* __restrict__ grad_out, float* __restrict__ S1, float* __restrict__ S2,
                   const float* __restrict__ hp, const int64_t* __restrict__ st, uint8_t* __restrict__ pl_hi,
-                  uint8_t* __restrict__ pl_lo, int stages, int tmem_cols, long long* __restrict__ dbg) {
+                  uint8_t* __restrict__ pl_lo, int stages, int tmem_cols, long long* __restrict__ dbg,
+                  const unsigned long long* __restrict__ push_bufs, long long off_inbox, long long per_f4, int push_rank) {
   constexpr int KT = 32;
   constexpr uint32_t ROWB = 2 * KT;
   if (HC) H0 = HC;                                   // lets the compiler fold the row pitch
@@ -869,10 +881,30 @@ k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict_
         float* const p1 = S1 + o0;
         float* const p2 = S2 + o0;
         float* const pg = grad_out ? grad_out + o0 : nullptr;
+        // data parallel, push form: gradient row g goes straight into the inbox of the rank that owns row g of the arena
+        // (region `push_rank` of that rank's inbox; rows never straddle owners: per_f4 is a multiple of a row) -- posted
+        // NVLink stores that overlap this kernel instead of round-trip loads in the exchange kernel behind it
+        int own = 0;
+        long long own_next = 0, rows_per = 0;
+        float* pushp = nullptr;
+        if (OPT == OPT_NONE && push_bufs) {
+          rows_per = per_f4 / (H0 >> 2);
+          own = (int)((long long)(g0 + gb) / rows_per);
+          own_next = (long long)(own + 1) * rows_per;
+          pushp = reinterpret_cast<float*>(push_bufs[own] + off_inbox) + ((long long)push_rank - own) * per_f4 * 4 + o0;
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           if (FULL || j < n_here) {
             const float gr = __uint_as_float(v[j]);
+            if (OPT == OPT_NONE && push_bufs) {
+              while ((long long)(g0 + gb + j) >= own_next) {
+                ++own;
+                own_next += rows_per;
+                pushp = reinterpret_cast<float*>(push_bufs[own] + off_inbox) + ((long long)push_rank - own) * per_f4 * 4 + o0;
+              }
+              pushp[j * H0] = gr;
+            }
             if (pg) pg[j * H0] = gr;
             if (OPT != OPT_NONE) {
               optim_update<OPT>(pp[j], gr, aa[j], bb[j], oc);
@@ -1047,7 +1079,9 @@ extern "C" int scnb_row_gene_splits(const int32_t* b_indptr, const int32_t* b_id
 template <int OPT, int EXP = 0, int HC = 0>
 static int launch_w1_bwd_optim_tc_any(const int32_t* splits, const int32_t* b_idx, const float* b_val, int nb, int H0, int G,
                                       const void* dz_hi, const void* dz_lo, float* W1T, float* grad_out, float* s1, float* s2,
-                                      const float* hp, const int64_t* st4, void* pl_hi, void* pl_lo, cudaStream_t st) {
+                                      const float* hp, const int64_t* st4, void* pl_hi, void* pl_lo, cudaStream_t st,
+                                      const unsigned long long* push_bufs = nullptr, long long off_inbox = 0, long long per_f4 = 0,
+                                      int push_rank = 0) {
   const int GT = w1tc_gene_block(G);
   const int NT = (GT + 15) / 16 * 16;
   const int n_blk = scnb_cdiv(G, GT);
@@ -1076,7 +1110,7 @@ static int launch_w1_bwd_optim_tc_any(const int32_t* splits, const int32_t* b_id
   }
   k_w1_bwd_optim_tc<OPT, EXP, HC><<<n_blk, W1TC_THREADS, smem, st>>>(splits, b_idx, b_val, nb, GT, NT, G, H0, (const uint8_t*)dz_hi,
                                                           (const uint8_t*)dz_lo, W1T, grad_out, s1, s2, hp, st4, (uint8_t*)pl_hi, (uint8_t*)pl_lo,
-                                                          stages, tmem_cols, dbg_on ? dbg : nullptr);
+                                                          stages, tmem_cols, dbg_on ? dbg : nullptr, push_bufs, off_inbox, per_f4, push_rank);
   SCNB_CHECK_LAUNCH("csr_w1_bwd_optim_tc");
   if (dbg_on && n_blk <= 4096) {  // debugging aid only (synchronises): per-CTA wall-clock stamps (ns)
     static long long hc[4 * 4096];
@@ -1145,4 +1179,27 @@ extern "C" int scnb_csr_w1_bwd_optim_tc(int opt, const int32_t* splits, const in
     default: scnb_set_error("csr_w1_bwd_optim_tc: unknown optimizer %d", opt); return SCNB_ERR_ARG;
   }
 #undef W1TC_GO
+}
+
+// Data-parallel form of the tensor-core dW1 kernel: gradient only, and every gradient row is STORED straight into the
+// inbox of the rank that owns that row of the flat arena (scnb_dp_slice_floats; region `rank` of the owner's inbox at
+// off_inbox of its exchange buffer) while the kernel runs -- scnb_dp_reduce_optim_bcast2 then finds all ranks' gradients of
+// its slice in local memory.  Needs 256 %% H0 == 0 (a row of W1T never straddles two owners).  grad_out (may be NULL): also
+// keep the local gradient [G, H0] (parity tests).
+extern "C" int scnb_csr_w1_bwd_push_tc(const int32_t* splits, const int32_t* b_idx, const float* b_val, int nb, int H0, int G,
+                                       const void* dz_planes_hi, const void* dz_planes_lo, const uint64_t* peer_bufs, int rank,
+                                       int world, long long off_inbox, long long total, float* grad_out, void* stream) {
+  SCNB_CHECK_ARG(splits && b_idx && b_val && dz_planes_hi && dz_planes_lo && peer_bufs, "csr_w1_bwd_push_tc: null argument");
+  SCNB_CHECK_ARG(nb > 0 && G > 0 && H0 >= 32 && H0 <= 256 && 256 % H0 == 0, "csr_w1_bwd_push_tc: H0 must divide 256 (got %d)", H0);
+  SCNB_CHECK_ARG(world >= 1 && world <= 8 && rank >= 0 && rank < world && off_inbox >= 0 && off_inbox % 16 == 0 &&
+                     total >= (long long)G * H0 && total % 4 == 0, "csr_w1_bwd_push_tc: bad exchange arguments");
+  SCNB_CHECK_ARG((((uintptr_t)dz_planes_hi | (uintptr_t)dz_planes_lo) % 16) == 0, "csr_w1_bwd_push_tc: buffers must be 16-byte aligned");
+  const long long per_f4 = dp_slice_f4(total, world);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned long long* pb = (const unsigned long long*)peer_bufs;
+  if (H0 == 256)
+    return launch_w1_bwd_optim_tc_any<OPT_NONE, 0, 256>(splits, b_idx, b_val, nb, H0, G, dz_planes_hi, dz_planes_lo, nullptr, grad_out,
+                                                        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st, pb, off_inbox, per_f4, rank);
+  return launch_w1_bwd_optim_tc_any<OPT_NONE, 0, 0>(splits, b_idx, b_val, nb, H0, G, dz_planes_hi, dz_planes_lo, nullptr, grad_out, nullptr,
+                                                    nullptr, nullptr, nullptr, nullptr, nullptr, st, pb, off_inbox, per_f4, rank);
 }

@@ -227,7 +227,13 @@ class TrainEngine(object):
             self.peer_off_flags = self.peer_bn_bytes
             self.peer_off_grad = self.peer_off_flags + 1024
             self.peer_off_flat = self.peer_off_grad + rnd(4 * total)
-            self.peer = mk(self.peer_off_flat + rnd(4 * total), dev)
+            # inbox: `world` regions of one ownership slice each -- the dW1 kernel of every rank stores its gradient rows
+            # straight into the owner's inbox (scnb_csr_w1_bwd_push_tc)
+            import ctypes as _ct
+            sl = _ct.c_longlong()
+            call("scnb_dp_slice_floats", int(total), int(self.comm.world), _ct.byref(sl))
+            self.peer_off_inbox = self.peer_off_flat + rnd(4 * total)
+            self.peer = mk(self.peer_off_inbox + rnd(4 * sl.value * self.comm.world), dev)
             if self.peer is not None:
                 grad = self.peer.tensor(self.peer_off_grad, total)
                 flat = self.peer.tensor(self.peer_off_flat, total)
@@ -566,7 +572,11 @@ class TrainEngine(object):
         elif self.host_mapped:
             raise NotImplementedError("host-mapped matrices are fed through the log1p_drop gather only")
         elif self.aug_code == 1:
-            call("scnb_csr_gather_rows2", ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data), ptr(self.u_rows), U, 0, 0,
+            # assembled one step ahead, the gather starts while the first layer (one CTA per SM holding nearly all of its
+            # shared memory) runs: the cache-free form fits next to it and is done before the hidden stack starts
+            light = ctr_off == 1 and os.environ.get("SCNB_PREFETCH_GATHER", "nocache") == "nocache"
+            call("scnb_csr_gather_rows2_nocache" if light else "scnb_csr_gather_rows2",
+                 ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data), ptr(self.u_rows), U, 0, 0,
                  ptr(self.lab.indptr), ptr(self.lab.indices), ptr(self.lab.data), ptr(self.l_rows), L, 1, SID_IN_L,
                  ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), ptr(self.inj_in_keep_L), rng, c.p_in_drop,
                  self._gene_cnt_ptr(), int(ctr_off), st)
@@ -1076,11 +1086,18 @@ class TrainEngine(object):
             call("scnb_optim_step", opt, ptr(ar.flat), ptr(ar.grad), ptr(ar.state1), ptr(ar.state2), ar.total, hp, s4, st)
         elif self.comm is not None:
             # data parallel: gradient only (no atomics, every gene row written), exchange, then one update pass
+            push = bool(self.w1_tc and self.peer is not None and 256 % H0 == 0 and os.environ.get("SCNB_DP_PUSH", "1") != "0")
             if self.w1_tc:
                 if not self._dz_planes_ready:
                     call("scnb_w1_planes", ptr(dZ1), n_rows, H0, ptr(self.dz_hi), ptr(self.dz_lo), st)
-                call("scnb_csr_w1_bwd_optim_tc", -1, ptr(self.w1_splits), ptr(self.b_idx), ptr(self.b_val), n_rows, H0, self.G,
-                     ptr(self.dz_hi), ptr(self.dz_lo), None, self.Gp(W1), None, None, None, None, None, None, st)
+                if push:   # gradient rows go straight to their owners' inboxes while the kernel runs
+                    px = self.peer
+                    call("scnb_csr_w1_bwd_push_tc", ptr(self.w1_splits), ptr(self.b_idx), ptr(self.b_val), n_rows, H0, self.G,
+                         ptr(self.dz_hi), ptr(self.dz_lo), ptr(px.ptrs), px.rank, px.world, self.peer_off_inbox, ar.total,
+                         self.Gp(W1) if c.keep_w1_grad else None, st)
+                else:
+                    call("scnb_csr_w1_bwd_optim_tc", -1, ptr(self.w1_splits), ptr(self.b_idx), ptr(self.b_val), n_rows, H0, self.G,
+                         ptr(self.dz_hi), ptr(self.dz_lo), None, self.Gp(W1), None, None, None, None, None, None, st)
             else:
                 call("scnb_csr_w1_bwd_optim", -1, ptr(self.c_ptr), ptr(self.c_ent), ptr(dZ1), n_rows, H0, self.G, None, self.Gp(W1),
                      None, None, None, None, st)
@@ -1088,8 +1105,9 @@ class TrainEngine(object):
             if self.peer is not None:
                 # reduce-scatter (peer loads) + optimizer on the owned slice + all-gather (peer stores), one kernel
                 px = self.peer
-                call("scnb_dp_reduce_optim_bcast", opt, ptr(px.ptrs), px.rank, px.world, self.peer_off_flags, self.peer_off_grad,
-                     self.peer_off_flat, ar.total, ptr(ar.state1), ptr(ar.state2), hp, s4, s4, st)
+                call("scnb_dp_reduce_optim_bcast2", opt, ptr(px.ptrs), px.rank, px.world, self.peer_off_flags, self.peer_off_grad,
+                     self.peer_off_flat, self.peer_off_inbox if push else -1, self.P1 if push else 0, ar.total, ptr(ar.state1),
+                     ptr(ar.state2), hp, s4, s4, st)
             else:
                 self.comm.all_reduce_avg(ar.grad)  # NCCL over NVLink
                 call("scnb_optim_step", opt, ptr(ar.flat), ptr(ar.grad), ptr(ar.state1), ptr(ar.state2), ar.total, hp, s4, st)

@@ -126,7 +126,8 @@ class PeerThreadComm(ThreadComm):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("opt_name,lr,peer,fused", [("sgd", 0.05, False, False), ("adadelta", 1.0, False, False), ("sgd", 0.05, True, False),
-                                                     ("adadelta", 1.0, True, False), ("sgd", 0.05, True, True), ("adadelta", 1.0, True, True)])
+                                                     ("adadelta", 1.0, True, False), ("sgd", 0.05, True, True), ("adadelta", 1.0, True, True),
+                                                     ("sgd", 0.05, True, "tc"), ("adadelta", 1.0, True, "tc")])
 def test_data_parallel_step_equals_global_batch_oracle(opt_name, lr, peer, fused, monkeypatch):
     """peer=False: host-side rendezvous for every exchange.  peer=True: the product path of a one-node NCCL job -- the
     BatchNorm statistics and the gradient reduce-scatter + optimizer + parameter all-gather run inside kernels that wait
@@ -147,6 +148,8 @@ def test_data_parallel_step_equals_global_batch_oracle(opt_name, lr, peer, fused
     from oracle import scnym_oracle as O
     from tests import cuda_harness as CH
     kw = dict(G=600, L=24, U=32, C=5, H0=64, H=48, n_layers=2, opt_name=opt_name, lr=lr, n_steps=1, D_given=0)
+    tc = fused == "tc"   # + tensor-core first layer and dW1: every rank's gradient rows are PUSHED into the owners' inboxes
+    fused = bool(fused)
     if fused:   # shapes the fused hidden stack takes (hidden_ops.cu): statistics exchanged by scnb_hs_xchg between its launches
         kw.update(L=32, U=64, H0=128, H=64)
     cases = [CH.oracle_case(seed=31, **kw), CH.oracle_case(seed=32, **kw)]
@@ -198,11 +201,12 @@ def test_data_parallel_step_equals_global_batch_oracle(opt_name, lr, peer, fused
             lab = DeviceCSR.from_arrays(d["lab_indptr"], d["lab_indices"], d["lab_data"], G)
             unl = DeviceCSR.from_arrays(d["unl_indptr"], d["unl_indices"], d["unl_data"], G)
             from scnym_b200.engine import EngineConfig
-            cfg = EngineConfig(optimizer=opt_name, lr=lr, weight_decay=float(d["meta_wd"]), use_cuda_graph=False, keep_w1_grad=True)
+            cfg = EngineConfig(optimizer=opt_name, lr=lr, weight_decay=float(d["meta_wd"]), use_cuda_graph=False, keep_w1_grad=True,
+                               first_layer="tc" if tc else "auto", w1_update="tc" if tc else "auto")
             with torch.cuda.stream(torch.cuda.Stream()):       # one stream per emulated rank: their kernels overlap
                 eng = TrainEngine(model, cfg, lab, d["lab_y"], l, unlabeled=unl, unlabeled_batch_size=u, dann=dann, mode="mixmatch",
                                   comm=(PeerThreadComm if peer else ThreadComm)(2, shared, rk))
-                assert (eng.peer is not None) == peer and eng.hs_fused == fused
+                assert (eng.peer is not None) == peer and eng.hs_fused == fused and eng.w1_tc == tc
                 eng.set_weights(float(d["meta_unsup_w"]), float(d["meta_dan_w"]))
                 CH.inject_step(eng, d, 0)
                 eng.step()
