@@ -245,7 +245,9 @@ __global__ void __launch_bounds__(GR_T) k_gather_rows(GatherSrc A, GatherSrc B, 
     const float x = S.data[s + j];
     float e = (EXT && mode == AUG_COUNT_POIS) ? x : expm1f(x);
     if (pois) e = X.inj_pois ? (x == 0.f ? 0.f : X.inj_pois[d + j]) : (e > 0.f ? poisson_draw(e * row_r, (uint64_t)(d + j), seed, strm + 32) : 0.f);
-    if (drop) e = e * (gather_keep(keep_mask, d + j, rnd, k, p_drop) ? inv_keep : 0.f);
+    // (explicitly rounded product / sum below: both passes of the cache-free form, and the cached form, must produce the
+    //  same bits whatever the compiler would otherwise contract into an FMA)
+    if (drop) e = __fmul_rn(e, gather_keep(keep_mask, d + j, rnd, k, p_drop) ? inv_keep : 0.f);
     if (EXT && mode == AUG_MASK) {
       if (keep_mask) e = keep_mask[d + j] ? e : 0.f;
       else if (mask_on) {
@@ -265,7 +267,7 @@ __global__ void __launch_bounds__(GR_T) k_gather_rows(GatherSrc A, GatherSrc B, 
                           make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
     }
     const float e = entry(j, k, rnd);
-    sum += e;
+    sum = __fadd_rn(sum, e);
     if (j < NCACHE) {
       e_s[j] = e;
       c_s[j] = S.indices[s + j];

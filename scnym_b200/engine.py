@@ -538,7 +538,7 @@ class TrainEngine(object):
         if self.tc_first:
             if sW is not main and not self.w1_emits_planes:
                 main.wait_event(self._ev_planes)
-            if prezeroed:
+            if prezeroed and not getattr(self, "_zero_at_end", False):
                 main.wait_event(self._ev_z1)
             call("scnb_csr_linear_fwd_tc", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), n_rows, self.G, self.widths[0],
                  ptr(self.w1_hi), ptr(self.w1_lo), self.P(blk0["b"]), ptr(Z), -1 if prezeroed else 0, st)
@@ -572,9 +572,9 @@ class TrainEngine(object):
         elif self.host_mapped:
             raise NotImplementedError("host-mapped matrices are fed through the log1p_drop gather only")
         elif self.aug_code == 1:
-            # assembled one step ahead, the gather starts while the first layer (one CTA per SM holding nearly all of its
-            # shared memory) runs: the cache-free form fits next to it and is done before the hidden stack starts
-            light = ctr_off == 1 and os.environ.get("SCNB_PREFETCH_GATHER", "nocache") == "nocache"
+            # (SCNB_PREFETCH_GATHER=nocache: the cache-free form, which could share an SM with the first layer's CTA; measured:
+            # the block scheduler does not co-schedule it with the tcgen05 kernels either way -- no gain, off)
+            light = ctr_off == 1 and os.environ.get("SCNB_PREFETCH_GATHER", "cache") == "nocache"
             call("scnb_csr_gather_rows2_nocache" if light else "scnb_csr_gather_rows2",
                  ptr(self.unl.indptr), ptr(self.unl.indices), ptr(self.unl.data), ptr(self.u_rows), U, 0, 0,
                  ptr(self.lab.indptr), ptr(self.lab.indices), ptr(self.lab.data), ptr(self.l_rows), L, 1, SID_IN_L,
@@ -622,12 +622,18 @@ class TrainEngine(object):
         blk = self._blk
         self._refresh_planes(main, sW)
         z1_pre = self.tc_first and sW is not main
-        if z1_pre:   # the split-K first layer accumulates into Z1: clear it on the side branch, off the critical path
+        pre = bool(getattr(self, "_prefetched", False))   # this step's batch was assembled during the previous step
+        # SCNB_ZERO_AT_END=1: replayed, prefetched steps clear Z1 and the gradient arena at the END of the previous step
+        # (branch W, behind the optimizer and under the dW1 kernel) so that nothing is in front of the first layer.
+        # Measured: 0.1604 vs 0.1613 ms -- not worth gradients that read as zero after a step; off by default
+        self._zero_at_end = bool(pre and z1_pre and os.environ.get("SCNB_ZERO_AT_END", "0") == "1")
+        if z1_pre and not self._zero_at_end:   # the split-K first layer accumulates into Z1: clear it on the side branch
             self._after(sW, main)
             self._zero_grads(sW.cuda_stream, also=self.Z1)     # one launch: Z1 and the gradient arena behind the first layer
             self._ev_z1.record(sW)
             self._ev_zero.record(sW)
-        pre = bool(getattr(self, "_prefetched", False))   # this step's batch was assembled during the previous step
+        elif self._zero_at_end:
+            self._after(sW, main)
         teacher_async = (c.pseudolabel_min_confidence <= 0.0) and sW is not main
         if pre:
             # only the counters are left of the prologue: advanced on branch W, needed from the hidden stack on
@@ -742,7 +748,8 @@ class TrainEngine(object):
                 self._ev_grl.record(sD)
             # the head's own weight gradients (needed only by the optimizer)
             if sD is not main:
-                sD.wait_event(self._ev_zero)   # after the gradient zeroing
+                if not self._zero_at_end:
+                    sD.wait_event(self._ev_zero)   # after the gradient zeroing
             call("scnb_sgemm", 1, 0, self.D, Hh, self.Rd, ptr(self.ddlog), self.D, ptr(self.Hd), Hh, self.Gp(d1 + ".weight"), Hh,
                  1.0, 1.0, None, 0, None, sd)
             call("scnb_colsum", ptr(self.ddlog), self.Rd, self.D, self.D, self.Gp(d1 + ".bias"), 1, sd)
@@ -975,7 +982,8 @@ class TrainEngine(object):
                 self.P(blk[a]["g"]), ptr(self.stats[a]), self._hidden_keep(a), rng, SID_HID + a, p, 1, ptr(dZ),
                 self.Gp(blk[a]["g"]), self.Gp(blk[a]["beta"]), part, sums, st)
             if a == self.n_app - 1 and sW is not main:
-                main.wait_event(self._ev_zero)   # BatchNorm gamma/beta gradients accumulate into zeroed buffers
+                if not getattr(self, "_zero_at_end", False):
+                    main.wait_event(self._ev_zero)   # BatchNorm gamma/beta gradients accumulate into zeroed buffers
             if self.comm is None:
                 bwd(None, None)
             elif self.peer is not None:
@@ -1015,7 +1023,8 @@ class TrainEngine(object):
         seg = self._seg_host.ctypes.data
         last = self.n_app - 1
         if sW is not main:
-            main.wait_event(self._ev_zero)   # BatchNorm gamma / beta gradients accumulate into zeroed buffers
+            if not getattr(self, "_zero_at_end", False):
+                main.wait_event(self._ev_zero)   # BatchNorm gamma / beta gradients accumulate into zeroed buffers
         dp = self.comm is not None
         call("scnb_hs_bwd_act", ptr(dA), ptr(self.Zs[last]), ptr(self.As[last]), self.widths[last], R, self.n_seg, seg,
              ptr(self.stats[last]), float(blk[last]["drop"].p), ptr(self.dYs[last]), ptr(self.pb[last]), st)
@@ -1134,6 +1143,8 @@ class TrainEngine(object):
                  int(self.conf_ring.shape[0]) if mm else 0, ptr(self.state), sw)
         if self.mode == "mixmatch":
             call("scnb_mm_step_inc", ptr(self.state), sw)
+        if getattr(self, "_zero_at_end", False):    # for the NEXT step (every consumer of this step's gradients is behind us on sW)
+            self._zero_grads(sw, also=self.Z1)
         self._after(main, sW)
         self._after(main, sD)
         if self._bn_running_done:
@@ -1336,7 +1347,11 @@ class TrainEngine(object):
             self.__dict__["_cur"] = p
             if not self._prefetch_valid:   # first step, or the tables changed: assemble this step's batch now
                 self._prologue_next(torch.cuda.current_stream(), ptr(self.state[1:3]))
+                if self.tc_first:          # (a replayed step leaves Z1 / the gradient arena cleared for its successor)
+                    self._zero_grads(torch.cuda.current_stream().cuda_stream, also=self.Z1)
             key = (self.unsup_weight, self.dan_weight, p)
+            if self._pf_graphs and next(iter(self._pf_graphs))[:2] != key[:2]:
+                self._pf_graphs = {}      # the loss weights are launch arguments: a new epoch's weights retire the old graphs
             if key not in self._pf_graphs:
                 self._prefetched = True
                 try:

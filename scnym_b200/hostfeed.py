@@ -242,6 +242,8 @@ class HostTrainPipeline(object):
         (the whole blob is stashed: a device-to-device copy of its unused capacity costs less than separate launches)."""
         eng = self.engine
         key = (slot, eng.unsup_weight, eng.dan_weight)
+        if self._graphs and next(iter(self._graphs))[1:] != key[1:]:
+            self._graphs = {}             # the loss weights are launch arguments: new weights retire the old graphs
         g = self._graphs.get(key)
         if g is None:
             dst = self._loss_dev_ptr + 64 * slot

@@ -118,8 +118,9 @@ def test_prefetched_prologue_assembles_the_same_batches(monkeypatch):
     unl, _ = synth_device_csr(2048, c["G"], c["density"], c["C"], seed=1, device=dev)
     fields = ("l_rows", "u_rows", "lab_ids", "base_dom", "b_indptr", "srcA", "srcB", "gam", "w1_splits")
     runs = []
-    for pf in ("1", "0"):
+    for pf, gather in (("1", "cache"), ("0", "cache"), ("1", "nocache")):   # (+ the cache-free form of the gather: same bits)
         monkeypatch.setenv("SCNB_PREFETCH", pf)
+        monkeypatch.setenv("SCNB_PREFETCH_GATHER", gather)
         torch.manual_seed(0)
         model = CellTypeCLF(n_genes=c["G"], n_cell_types=c["C"], n_hidden=c["H"], n_hidden_init=c["H0"], n_layers=c["n_layers"])
         dann = DANN(model, n_domains=c["D"])
@@ -145,11 +146,13 @@ def test_prefetched_prologue_assembles_the_same_batches(monkeypatch):
                 rec.append(snap)
         assert bool(eng._pf_graphs) == (pf == "1")
         runs.append(rec)
-    a, b = runs
-    assert len(a) == len(b) == 7
-    for s, (x, z) in enumerate(zip(a, b)):
+    a, b, a2 = runs
+    assert len(a) == len(b) == len(a2) == 7
+    same = lambda u, v: torch.equal(u, v) or (u.dtype.is_floating_point and torch.equal(torch.nan_to_num(u, nan=-1.0), torch.nan_to_num(v, nan=-1.0)))
+    for s, (x, z, x2) in enumerate(zip(a, b, a2)):
         for k in fields + ("b_idx", "b_val"):
-            assert torch.equal(x[k], z[k]), f"step {s}: {k} differs between the prefetched and the in-step prologue"
+            assert same(x[k], z[k]), f"step {s}: {k} differs between the prefetched and the in-step prologue"
+            assert same(x2[k], z[k]), f"step {s}: {k} differs between the cache-free and the cached gather"
     for s in range(2):
         for k in ("sup_loss", "unsup_loss", "dan_loss"):
             assert abs(a[s]["losses"][k] - b[s]["losses"][k]) <= 1e-4 * max(1.0, abs(b[s]["losses"][k])), (s, k)

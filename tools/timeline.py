@@ -52,6 +52,8 @@ def main():
     ev.sort(key=lambda e: e["ts"])
     # split into steps at the first kernel of the step
     first = "k_zero2" if any(e["name"].startswith("k_zero2") for e in ev) else "k_step_prep"
+    if os.environ.get("SCNB_ZERO_AT_END") == "1":
+        first = "void k_csr_dense_fwd_tc"
     starts = [i for i, e in enumerate(ev) if e["name"].startswith(first)]
     k = len(starts) // 2
     seg = ev[starts[k]: starts[k + 1]] if k + 1 < len(starts) else ev[starts[k]:]
