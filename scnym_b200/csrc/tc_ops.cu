@@ -106,13 +106,33 @@ __global__ void __launch_bounds__(256) k_bn_eval_planes(const float* __restrict_
                                                         const float* __restrict__ rmean, const float* __restrict__ rvar,
                                                         int relu, float* __restrict__ A_out, float* __restrict__ pre_out,
                                                         uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+  // per-column constants once per CTA: the IEEE sqrt + division per ELEMENT made this pass issue-bound (0.9 TB/s)
+  extern __shared__ float bnp_smem[];
+  float* s_mean = bnp_smem;
+  float* s_inv = s_mean + H;
+  float* s_gam = s_inv + H;
+  float* s_bet = s_gam + H;
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    s_mean[c] = rmean[c];
+    s_inv[c] = 1.0f / sqrtf(rvar[c] + 1e-5f);
+    s_gam[c] = gamma[c];
+    s_bet[c] = beta[c];
+  }
+  __syncthreads();
   const int Hg = H >> 3;
   const long long rows_pad = ((long long)n_rows + 255) / 256 * 256;
   const long long total = rows_pad * Hg;
   const int n_kt = H >> 5;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const long long r = e / Hg;
-    const int cg = (int)(e - r * Hg), c0 = cg * 8;
+  // (256 % Hg == 0: a thread keeps its column group and walks rows -- no 64-bit division per element)
+  const bool fixed_cg = (256 % Hg) == 0;
+  const int rows_per_it = fixed_cg ? 256 / Hg : 0;
+  const long long e0 = fixed_cg ? (long long)blockIdx.x * rows_per_it + threadIdx.x / Hg : (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long e_end = fixed_cg ? rows_pad : total;
+  const long long e_step = fixed_cg ? (long long)gridDim.x * rows_per_it : (long long)gridDim.x * blockDim.x;
+  const int cg_fixed = fixed_cg ? (int)(threadIdx.x % Hg) : 0;
+  for (long long e = e0; e < e_end; e += e_step) {
+    const long long r = fixed_cg ? e : e / Hg;
+    const int cg = fixed_cg ? cg_fixed : (int)(e - r * Hg), c0 = cg * 8;
     float y[8];
     if (r < n_rows) {
       const float4 z0 = *reinterpret_cast<const float4*>(Z + r * H + c0), z1 = *reinterpret_cast<const float4*>(Z + r * H + c0 + 4);
@@ -120,7 +140,7 @@ __global__ void __launch_bounds__(256) k_bn_eval_planes(const float* __restrict_
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int c = c0 + j;
-        y[j] = (z[j] - rmean[c]) * (1.0f / sqrtf(rvar[c] + 1e-5f)) * gamma[c] + beta[c];
+        y[j] = (z[j] - s_mean[c]) * s_inv[c] * s_gam[c] + s_bet[c];
       }
       if (pre_out) {
         *reinterpret_cast<float4*>(pre_out + r * H + c0) = make_float4(y[0], y[1], y[2], y[3]);
@@ -164,7 +184,8 @@ extern "C" int scnb_bn_eval_planes(const float* Z, int n_rows, int H, const floa
   if (n_rows == 0) return SCNB_OK;
   const long long total = ((long long)n_rows + 255) / 256 * 256 * (H / 8);
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  k_bn_eval_planes<<<blocks, 256, 0, (cudaStream_t)stream>>>(Z, n_rows, H, gamma, beta, running_mean, running_var, relu, A_out,
+  SCNB_CHECK_ARG(H <= 2048, "bn_eval_planes: H must be <= 2048 (got %d)", H);
+  k_bn_eval_planes<<<blocks, 256, 4 * (size_t)H * sizeof(float), (cudaStream_t)stream>>>(Z, n_rows, H, gamma, beta, running_mean, running_var, relu, A_out,
                                                             pre_out, (uint16_t*)planes_hi, (uint16_t*)planes_lo);
   SCNB_CHECK_LAUNCH("bn_eval_planes");
   return SCNB_OK;

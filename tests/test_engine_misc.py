@@ -156,3 +156,46 @@ def test_prefetched_prologue_assembles_the_same_batches(monkeypatch):
     for s in range(2):
         for k in ("sup_loss", "unsup_loss", "dan_loss"):
             assert abs(a[s]["losses"][k] - b[s]["losses"][k]) <= 1e-4 * max(1.0, abs(b[s]["losses"][k])), (s, k)
+
+
+def test_device_sampler_tables_follow_dataloader_semantics():
+    """`sample_epoch_tables` (the device-side replacement of DataLoader(shuffle=True, drop_last=True) + `repeater`,
+    scnym/main.py:48-68,317-323): inside one pass over a dataset no row repeats, a batch never straddles two passes, every
+    pass is a fresh permutation, the unlabeled loader wraps around as often as the epoch needs, MixUp keys are uniform in
+    [0, 1) and the Beta(alpha, alpha) draws lie in [0, 1] with the right mean and the U-shape of alpha < 1."""
+    from scnym_b200.engine import EngineConfig, TrainEngine
+    from scnym_b200.model import CellTypeCLF, DANN
+    from scnym_b200.synth import synth_device_csr
+    dev = torch.device("cuda", 0)
+    n_lab, n_unl, L, U, G = 1000, 700, 64, 96, 512
+    lab, y = synth_device_csr(n_lab, G, 0.05, 4, seed=0, device=dev)
+    unl, _ = synth_device_csr(n_unl, G, 0.05, 4, seed=1, device=dev)
+    torch.manual_seed(0)
+    model = CellTypeCLF(n_genes=G, n_cell_types=4, n_hidden=64, n_hidden_init=64, n_layers=1)
+    eng = TrainEngine(model.to(dev), EngineConfig(mixup_alpha=0.3, seed=1), lab, y.to(torch.int32), L, unlabeled=unl,
+                      unlabeled_batch_size=U, dann=DANN(model, n_domains=2), mode="mixmatch")
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(11)
+    n_steps = 40
+    eng.sample_epoch_tables(n_steps, generator=gen)
+    t = eng._tabs
+    assert t["n"] == n_steps and tuple(t["l"].shape) == (n_steps, L) and tuple(t["u"].shape) == (n_steps, U)
+    for tab, n_rows, per in ((t["l"].cpu().numpy(), n_lab, L), (t["u"].cpu().numpy(), n_unl, U)):
+        assert tab.min() >= 0 and tab.max() < n_rows
+        per_pass = n_rows // per                      # drop_last: batches per pass
+        passes = [tab[i:i + per_pass].ravel() for i in range(0, n_steps, per_pass)]
+        for p in passes:
+            assert len(set(p.tolist())) == p.size, "a row repeats inside one pass over the data"
+        full = [p for p in passes if p.size == per_pass * per]
+        assert len(full) >= 2 and not np.array_equal(np.sort(full[0]), full[0]), "passes are not shuffled"
+        assert not np.array_equal(full[0], full[1]), "two passes used the same permutation"
+    keys, gam = t["k"].cpu().numpy(), t["g"].cpu().numpy()
+    assert keys.shape == gam.shape == (n_steps, L + U)
+    assert keys.min() >= 0.0 and keys.max() < 1.0 and abs(keys.mean() - 0.5) < 0.02
+    assert gam.min() >= 0.0 and gam.max() <= 1.0 and abs(gam.mean() - 0.5) < 0.03
+    assert ((gam < 0.1) | (gam > 0.9)).mean() > 0.45, "Beta(0.3, 0.3) puts most of its mass near 0 and 1"
+    # a second epoch draws new tables into the same device buffers (a captured graph stays valid)
+    ptr_before = t["l"].data_ptr()
+    first = t["l"].clone()
+    eng.sample_epoch_tables(n_steps, generator=gen)
+    assert eng._tabs["l"].data_ptr() == ptr_before and not torch.equal(eng._tabs["l"], first)
