@@ -323,7 +323,9 @@ def compare_step0(eng, d, tol=1e-4, margin=1e-4, max_flip_frac=2e-5, adam_mask=1
         worst_r = max(worst_r, e)
         assert e <= 1e-5, f"optimizer replay post/{n}: rel err {e:.3e}"
         gref = grads[n].double().abs()
-        m = gref > adam_mask * float(gref.max()) if float(gref.max()) > 1e-7 else torch.zeros_like(gref, dtype=torch.bool)
+        # (and above 100 eps of Adam: near |g| ~ eps the first update lr g / (|g| + eps) amplifies a 1e-4 gradient
+        #  difference a thousandfold -- the optimizer replay above covers those entries)
+        m = (gref > max(adam_mask * float(gref.max()), 1e-6)) if float(gref.max()) > 1e-7 else torch.zeros_like(gref, dtype=torch.bool)
         if bool(m.any()):
             a, b = got["post"][n].double()[m], post[n].double()[m]
             e = float((a - b).abs().max()) / max(float(post[n].double().abs().max()), 1e-30)
@@ -479,7 +481,12 @@ def dp_compare(device, rank, world, comm, tol=1e-4, margin=1e-4):
         gref = grads[n].double().abs()
         if float(gref.max()) < 1e-7:
             continue
-        m = gref > 1e-3 * float(gref.max())
+        # entries whose gradient is far above Adam's eps (1e-8): near |g| ~ eps the first update lr g / (|g| + eps)
+        # amplifies a 1e-4 gradient difference a thousandfold (seen at 4 ranks on the domain classifier, whose averaged
+        # gradient is ~1e-4)
+        m = gref > max(1e-3 * float(gref.max()), 1e-6)
+        if not bool(m.any()):
+            continue
         e = float((got["post"][n].double()[m] - p.double()[m]).abs().max()) / max(float(p.double().abs().max()), 1e-30)
         worst_p = max(worst_p, e)
         assert e <= tol, f"post/{n}: {e:.3e}"
