@@ -267,6 +267,19 @@ def gate_flips(gates, trace, margin=1e-4):
     return flipped, total, worst
 
 
+def adam_safe_mask(gref, p_init, cfg, frac=1e-3):
+    """Entries on which Adam's first update lr * g' / (|g'| + eps), g' = g + wd * p (coupled weight decay), is well
+    conditioned: |g'| far above eps (1e-8) and above `frac` of the tensor's largest gradient.  Near g' ~ 0 -- which weight
+    decay produces wherever it cancels a small gradient -- a 1e-4 gradient difference is amplified a thousandfold; those
+    entries are covered by the optimizer replay on the device's own gradient instead."""
+    g = gref.double()
+    eff = g + (float(cfg.weight_decay) * p_init.double() if str(cfg.name) == "adam" else 0.0)
+    gmax = float(g.abs().max())
+    if gmax <= 1e-7:
+        return torch.zeros_like(g, dtype=torch.bool)
+    return (g.abs() > max(frac * gmax, 1e-6)) & (eff.abs() > max(frac * gmax, 1e-6))
+
+
 def compare_step0(eng, d, tol=1e-4, margin=1e-4, max_flip_frac=2e-5, adam_mask=1e-3):
     """Engine (already stepped once on the case's injected step 0) against the oracle, gate-aware:
       * losses, logits, pseudolabels, confident flags against the plain oracle run;
@@ -315,17 +328,16 @@ def compare_step0(eng, d, tol=1e-4, margin=1e-4, max_flip_frac=2e-5, adam_mask=1
     # optimizer rule pinned on the device's own gradients (every entry)
     model_st, dan_st = GU.split_state(GU.state_from(d, "init/"))
     rm = O.OracleModel(model_st, n_layers=int(d["meta_n_layers"]), dan_state=dan_st)
-    ro = O.OracleOptimizer(rm.parameters(), GU.optim_config(d))
+    ocfg = GU.optim_config(d)
+    ro = O.OracleOptimizer(rm.parameters(), ocfg)
+    init = {n: p.detach().clone() for n, p in rm.named_parameters()}
     ro.step([got["grads"][n].clone() for n, _ in rm.named_parameters()])
     worst_r = worst_p = 0.0
     for n, p in rm.named_parameters():
         e = GU.rel_err(got["post"][n], p.detach())
         worst_r = max(worst_r, e)
         assert e <= 1e-5, f"optimizer replay post/{n}: rel err {e:.3e}"
-        gref = grads[n].double().abs()
-        # (and above 100 eps of Adam: near |g| ~ eps the first update lr g / (|g| + eps) amplifies a 1e-4 gradient
-        #  difference a thousandfold -- the optimizer replay above covers those entries)
-        m = (gref > max(adam_mask * float(gref.max()), 1e-6)) if float(gref.max()) > 1e-7 else torch.zeros_like(gref, dtype=torch.bool)
+        m = adam_safe_mask(grads[n], init[n], ocfg, adam_mask)
         if bool(m.any()):
             a, b = got["post"][n].double()[m], post[n].double()[m]
             e = float((a - b).abs().max()) / max(float(post[n].double().abs().max()), 1e-30)
@@ -423,10 +435,15 @@ def dp_compare(device, rank, world, comm, tol=1e-4, margin=1e-4):
     loss_t /= world
     names = list(got["grads"].keys())
     avg = {}
-    for n in names:
+    inv_w = torch.tensor(1.0 / world, dtype=torch.float32, device=device)
+    for n in names:   # summed in rank order, then scaled: the exchange kernel's arithmetic, bit for bit
         g = got["grads"][n].to(device).contiguous()
-        dist.all_reduce(g, op=dist.ReduceOp.SUM)
-        avg[n] = (g / world).cpu()
+        parts_g = [torch.empty_like(g) for _ in range(world)]
+        dist.all_gather(parts_g, g)
+        acc = torch.zeros_like(g)
+        for q in range(world):
+            acc += parts_g[q]
+        avg[n] = (acc * inv_w).cpu()
     parts = [(A > 0).to(torch.uint8).reshape(-1) for A in eng.As] + [(eng.Hd > 0).to(torch.uint8).reshape(-1)]
     flat = torch.cat(parts)
     allg = [torch.empty_like(flat) for _ in range(world)]
@@ -469,6 +486,20 @@ def dp_compare(device, rank, world, comm, tol=1e-4, margin=1e-4):
         e = GU.rel_err(avg[n], grads[n])
         worst_g = max(worst_g, e)
         assert e <= tol, f"grad/{n}: rel err {e:.3e}"
+    # the update rule pinned on the job's own averaged gradient, every entry (the exchange kernel's optimizer)
+    d0 = cases[0]
+    model_st, dan_st = GU.split_state(GU.state_from(d0, "init/"))
+    rm = O.OracleModel(model_st, n_layers=int(d0["meta_n_layers"]), dan_state=dan_st)
+    ocfg = GU.optim_config(d0)
+    ro = O.OracleOptimizer(rm.parameters(), ocfg)
+    init = {n: p.detach().clone() for n, p in rm.named_parameters()}
+    ro.step([avg[n].clone() for n, _ in rm.named_parameters()])
+    worst_r = 0.0
+    for n, p in rm.named_parameters():
+        e = GU.rel_err(got["post"][n], p.detach())
+        worst_r = max(worst_r, e)
+        assert e <= 1e-5, f"optimizer replay post/{n}: rel err {e:.3e}"
+    rep["post_replay_worst"] = worst_r
     worst_p = 0.0
     for n, p in post.items():
         if n.endswith("num_batches_tracked"):
@@ -478,13 +509,10 @@ def dp_compare(device, rank, world, comm, tol=1e-4, margin=1e-4):
             e = GU.rel_err(got["post"][n], p)
             assert e <= tol, f"post/{n}: {e:.3e}"
             continue
-        gref = grads[n].double().abs()
-        if float(gref.max()) < 1e-7:
+        if n not in init:
             continue
-        # entries whose gradient is far above Adam's eps (1e-8): near |g| ~ eps the first update lr g / (|g| + eps)
-        # amplifies a 1e-4 gradient difference a thousandfold (seen at 4 ranks on the domain classifier, whose averaged
-        # gradient is ~1e-4)
-        m = gref > max(1e-3 * float(gref.max()), 1e-6)
+        # (seen at 4 ranks on the domain classifier, whose averaged gradient is ~1e-5: weight decay cancels it in places)
+        m = adam_safe_mask(grads[n], init[n], ocfg)
         if not bool(m.any()):
             continue
         e = float((got["post"][n].double()[m] - p.double()[m]).abs().max()) / max(float(p.double().abs().max()), 1e-30)
