@@ -135,6 +135,16 @@ int scnb_csr_linear_fwd_tc(const int32_t* b_indptr, const int32_t* b_idx, const 
 int scnb_csr_linear_fwd_tc_i64(const int64_t* indptr, const int32_t* indices, const float* data, int n, int G, int H0,
                                const void* planes_hi, const void* planes_lo, const float* b1, float* Z, int ksplits,
                                void* stream);
+/* The split forward with its per-row starting points precomputed (scnym/model.py:211 on the batch CSR, same result as
+ * scnb_csr_linear_fwd_tc with automatic splits): scnb_csr_linear_fwd_tc_geometry reports the number of gene-axis splits
+ * and the genes per split for a batch of n rows; scnb_row_fwd_splits fills fwd_splits[(ksplits + 1) * n] (position of
+ * the first entry of row r with gene >= s * genes_per_split); scnb_csr_linear_fwd_tc_splits (ksplits <= 0 as above) then
+ * starts every CTA at its entry without a binary search at the head of the step. */
+int scnb_csr_linear_fwd_tc_geometry(int n, int G, int H0, int* ksplits, int* genes_per_split);
+int scnb_row_fwd_splits(const int32_t* b_indptr, const int32_t* b_idx, int n, int G, int H0, int32_t* fwd_splits, void* stream);
+int scnb_csr_linear_fwd_tc_splits(const int32_t* b_indptr, const int32_t* b_idx, const float* b_val, int n, int G, int H0,
+                                  const void* planes_hi, const void* planes_lo, const float* b1, float* Z, int ksplits,
+                                  const int32_t* fwd_splits, void* stream);
 
 /* Tensor-core form of the fused dW1 + optimizer kernel (replaces the backward of nn.Linear in scnym/model.py:211 plus
  * torch.optim's step on that weight, scnym/main.py:374-396): D^T[H0, genes] = dZ1^T X as a tcgen05 GEMM (bf16x3, fp32 in
@@ -145,6 +155,9 @@ int scnb_csr_linear_fwd_tc_i64(const int64_t* indptr, const int32_t* indices, co
  * written as the bf16 operand planes scnb_csr_linear_fwd_tc reads, so the next step needs no scnb_w1_planes pass. */
 int scnb_w1tc_gene_block(int G);
 int scnb_row_gene_splits(const int32_t* b_indptr, const int32_t* b_idx, int nb, int G, int32_t* splits, void* stream);
+/* scnb_row_gene_splits and scnb_row_fwd_splits in one launch (both tables depend only on the batch). */
+int scnb_row_gene_splits2(const int32_t* b_indptr, const int32_t* b_idx, int nb, int G, int H0, int32_t* splits,
+                          int32_t* fwd_splits, void* stream);
 int scnb_csr_w1_bwd_optim_tc(int opt, const int32_t* splits, const int32_t* b_idx, const float* b_val, int nb, int H0, int G,
                              const void* dz_planes_hi, const void* dz_planes_lo, float* W1T, float* grad_out, float* state1,
                              float* state2, const float* hp8, const int64_t* state4, void* planes_hi_out, void* planes_lo_out,

@@ -31,7 +31,11 @@ SIGNATURES = {
     "scnb_w1_planes": [P, I, I, P, P, P],
     "scnb_csr_linear_fwd_tc": [P, P, P, I, I, I, P, P, P, P, I, P],
     "scnb_csr_linear_fwd_tc_i64": [P, P, P, I, I, I, P, P, P, P, I, P],
+    "scnb_csr_linear_fwd_tc_geometry": [I, I, I, P, P],
+    "scnb_row_fwd_splits": [P, P, I, I, I, P, P],
+    "scnb_csr_linear_fwd_tc_splits": [P, P, P, I, I, I, P, P, P, P, I, P, P],
     "scnb_w1tc_gene_block": [I],
+    "scnb_row_gene_splits2": [P, P, I, I, I, P, P, P],
     "scnb_row_gene_splits": [P, P, I, I, P, P],
     "scnb_csr_w1_bwd_optim_tc": [I, P, P, P, I, I, I, P, P, P, P, P, P, P, P, P, P, P],
     "scnb_linear_planes": [P, I, I, P, P, P],

@@ -207,7 +207,9 @@ __global__ void __launch_bounds__(64 + 128 * HALVES, 1)
 k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ idx, const float* __restrict__ val, int n_rows,
                    const uint8_t* __restrict__ planes_hi, const uint8_t* __restrict__ planes_lo, int N, int n_ktiles,
                    const float* __restrict__ bias, float* __restrict__ Z, int stages, int tmem_cols,
-                   const uint8_t* __restrict__ a_hi_planes, const uint8_t* __restrict__ a_lo_planes) {
+                   const uint8_t* __restrict__ a_hi_planes, const uint8_t* __restrict__ a_lo_planes,
+                   const int32_t* __restrict__ fwd_splits, long long* __restrict__ dbg) {
+#define FWDTC_GSTAMP(k) do { if (dbg) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[4 * (blockIdx.y * gridDim.x + blockIdx.x) + (k)] = (long long)t_; } } while (0)
   constexpr uint32_t ROWB = 2 * KT;                       // bytes per operand row (bf16)
   constexpr uint32_t A_HALF = TC_M * ROWB;                // one 128-row A block of one plane
   constexpr uint32_t A_PLANE = HALVES * A_HALF;
@@ -321,11 +323,17 @@ k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ 
     const int r = half * TC_M + rl;               // row within the CTA tile
     const long long grow = (long long)blockIdx.x * ROWS + r;
     long long p = 0, pend = 0;
-    if (!DENSE_A && grow < n_rows) {
+    if (tid == 64) FWDTC_GSTAMP(0);
+    if (!DENSE_A && fwd_splits && grow < n_rows) {
+      // split points of this CTA's gene range, found off the critical path (scnb_row_fwd_splits): the ten dependent loads
+      // of the binary search below were ~5 us at the head of every step
+      p = (long long)fwd_splits[(size_t)blockIdx.y * n_rows + grow];
+      pend = (long long)fwd_splits[(size_t)(blockIdx.y + 1) * n_rows + grow];
+    } else if (!DENSE_A && grow < n_rows) {
       p = (long long)indptr[grow];
       pend = (long long)indptr[grow + 1];
     }
-    if (kt0 > 0 && p < pend) {  // first stored gene >= kt0*KT (rows are sorted by gene)
+    if (!fwd_splits && kt0 > 0 && p < pend) {  // first stored gene >= kt0*KT (rows are sorted by gene)
       const int target = kt0 * KT;
       long long lo_p = p, hi_p = pend;
       while (lo_p < hi_p) {
@@ -356,6 +364,7 @@ k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ 
     // loop instead of one per lane (the MMA reads its operands from the same shared memory; stores that
     // serialise per lane take the bandwidth it needs).
     int cnt = TC_W;                                // entries of the current window not yet consumed (incl. NONE padding)
+    if (tid == 64) FWDTC_GSTAMP(1);
     for (int i = 0; i < (DENSE_A ? 0 : n_it); ++i) {
       const int s = i % stages;
       const uint32_t ph = (uint32_t)(i / stages) & 1u;
@@ -407,12 +416,16 @@ k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ 
     if (TRN && n_it > 0) {
       mbar_wait(bar_acc, 0);
       tc_fence_after();
+      if (tid == 64) FWDTC_GSTAMP(2);
       // accumulator hh holds columns [128 hh, 128 hh + 128) of Z; a CTA has HALVES warp groups for N / 128 accumulators
       for (int hh = half; hh * TC_M < N; hh += HALVES) {
         const int col = hh * TC_M + rl;                 // column of Z held by this TMEM lane
         const float bc = (bias && blockIdx.y == 0) ? bias[col] : 0.f;
-        for (int r0 = 0; r0 < ROWS; r0 += 32) {
-          if ((long long)blockIdx.x * ROWS + r0 >= n_rows) break;
+        // every gene split adds into the same rows of Z: the splits start at different 32-row groups, so that at any moment
+        // the CTAs of a row tile are spread over different lines (the L2 atomic unit serialises per address)
+        for (int rr = 0; rr < ROWS; rr += 32) {
+          const int r0 = (rr + 32 * (int)blockIdx.y) & (ROWS - 1);
+          if ((long long)blockIdx.x * ROWS + r0 >= n_rows) continue;
           uint32_t v[32];
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hh * ROWS + r0);
           asm volatile(
@@ -475,25 +488,53 @@ k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ 
       }
     }
   }
+  if (tid == 64) FWDTC_GSTAMP(3);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
+#undef FWDTC_GSTAMP
+}
+
+// splits[b * nb + r] = first position p of row r (absolute index into b_idx) with b_idx[p] >= b * GT, b = 0..n_blk;
+// optionally a second table with its own block size in the same launch (the split points of the tensor-core forward).
+__global__ void __launch_bounds__(128) k_row_gene_splits(const int32_t* __restrict__ b_indptr, const int32_t* __restrict__ b_idx,
+                                                         int nb, int GT, int n_blk, int32_t* __restrict__ splits, int GT2 = 0,
+                                                         int n_blk2 = 0, int32_t* __restrict__ splits2 = nullptr) {
+  const int r = blockIdx.x;
+  const int s = b_indptr[r], e = b_indptr[r + 1];
+  const int n1 = splits ? n_blk + 1 : 0, n2 = splits2 ? n_blk2 + 1 : 0;
+  for (int b = threadIdx.x; b < n1 + n2; b += blockDim.x) {
+    const bool second = b >= n1;
+    const int bb = second ? b - n1 : b;
+    const int target = bb * (second ? GT2 : GT);
+    int lo = s, hi = e;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (b_idx[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    (second ? splits2 : splits)[(size_t)bb * nb + r] = lo;
+  }
+}
+
+// gene-axis splits of the training forward: until the grid covers the 148 SMs
+static inline int fwd_tc_auto_splits(int n, int G, int rows_per_cta, int KT) {
+  const int row_tiles = scnb_cdiv(n, rows_per_cta), n_kt = scnb_cdiv(G, KT);
+  int ks = 148 / row_tiles;
+  if (ks < 1) ks = 1;
+  return ks > n_kt ? n_kt : ks;
 }
 
 template <typename IdxT, int HALVES, int KT, bool DENSE_A, bool TRN = false>
 static int launch_dense_fwd_tc(const IdxT* indptr, const int32_t* idx, const float* val, int n, int G, int H0, const void* hi,
                                const void* lo, const float* b1, float* Z, int ksplits, cudaStream_t st, const void* a_hi = nullptr,
-                               const void* a_lo = nullptr) {
+                               const void* a_lo = nullptr, const int32_t* fwd_splits = nullptr) {
   constexpr int ROWS = TC_M * HALVES;
   const int n_kt = scnb_cdiv(G, KT);
   const int row_tiles = scnb_cdiv(n, ROWS);
   const bool prezeroed = ksplits < 0;   // the caller has already cleared Z (off its critical path)
-  if (ksplits <= 0) {  // auto: split the gene axis until the grid covers the 148 SMs
-    ksplits = 148 / row_tiles;
-    if (ksplits < 1) ksplits = 1;
-  }
+  if (ksplits <= 0) ksplits = fwd_tc_auto_splits(n, G, ROWS, KT);
   if (ksplits > n_kt) ksplits = n_kt;
   const size_t stage_bytes = 2 * (size_t)ROWS * 2 * KT + 2 * (size_t)H0 * 2 * KT;
   int stages = (int)((200 * 1024) / stage_bytes);
@@ -505,7 +546,7 @@ static int launch_dense_fwd_tc(const IdxT* indptr, const int32_t* idx, const flo
   const size_t smem = 1024 + stages * stage_bytes + 24 * stages + 16 + 16;
   if (TRN && (ksplits <= 1 || H0 % 128 != 0))   // the transposed accumulator only pays for (and is only built for) split-K sums
     return launch_dense_fwd_tc<IdxT, HALVES, KT, DENSE_A, false>(indptr, idx, val, n, G, H0, hi, lo, b1, Z, prezeroed ? -1 : ksplits, st,
-                                                                 a_hi, a_lo);
+                                                                 a_hi, a_lo, fwd_splits);
   int tmem_cols = 32;
   while (tmem_cols < (TRN ? (H0 / 128) * ROWS : HALVES * H0)) tmem_cols *= 2;
   cudaError_t e = cudaFuncSetAttribute(k_csr_dense_fwd_tc<IdxT, HALVES, KT, DENSE_A, TRN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -521,10 +562,38 @@ static int launch_dense_fwd_tc(const IdxT* indptr, const int32_t* idx, const flo
     }
   }
   dim3 grid(row_tiles, ksplits);
+  static long long* dbg = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) {
+    const char* ev = getenv("SCNB_FWDTC_DBG");
+    dbg_on = (ev && ev[0] == '1') ? 1 : 0;
+    if (dbg_on) cudaMalloc(&dbg, 4 * 4096 * sizeof(long long));
+  }
+  const int n_cta = row_tiles * ksplits;
+  const bool stamp = dbg_on && !DENSE_A && n_cta <= 4096;
   k_csr_dense_fwd_tc<IdxT, HALVES, KT, DENSE_A, TRN><<<grid, 64 + 128 * HALVES, smem, st>>>(
       indptr, idx, val, n, (const uint8_t*)hi, (const uint8_t*)lo, H0, n_kt, b1, Z, stages, tmem_cols, (const uint8_t*)a_hi,
-      (const uint8_t*)a_lo);
+      (const uint8_t*)a_lo, fwd_splits, stamp ? dbg : nullptr);
   SCNB_CHECK_LAUNCH("csr_linear_fwd_tc");
+  if (stamp) {  // debugging aid only (synchronises): per-CTA wall-clock stamps (ns)
+    static long long hc[4 * 4096];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hc, dbg, sizeof(long long) * 4 * n_cta, cudaMemcpyDeviceToHost);
+    long long t0 = 1LL << 62;
+    for (int b = 0; b < n_cta; ++b) if (hc[4 * b] && hc[4 * b] < t0) t0 = hc[4 * b];
+    const char* nm[4] = {"set up", "row windows loaded", "accumulator ready", "end"};
+    for (int k = 0; k < 4; ++k) {
+      long long mn = 1LL << 62, mx = 0, sum = 0;
+      int cnt = 0;
+      for (int b = 0; b < n_cta; ++b) {
+        if (!hc[4 * b + k] || !hc[4 * b + 2]) continue;   // (CTAs without gene tiles never reach stamp 2)
+        long long v = hc[4 * b + k] - t0; if (v < mn) mn = v; if (v > mx) mx = v; sum += v; ++cnt;
+      }
+      fprintf(stderr, "[fwdtc] %s: min %lld mean %lld max %lld ns (%d of %d CTAs, %d stages, splits table %s)\n", nm[k], mn,
+              cnt ? sum / cnt : 0, mx, cnt, n_cta, stages, fwd_splits ? "yes" : "no");
+    }
+    cudaMemset(dbg, 0, sizeof(long long) * 4 * n_cta);
+  }
   return SCNB_OK;
 }
 
@@ -554,6 +623,45 @@ extern "C" int scnb_csr_linear_fwd_tc(const int32_t* b_indptr, const int32_t* b_
                                                             (cudaStream_t)stream);
   return launch_dense_fwd_tc<int32_t, 2, 32, false, true>(b_indptr, b_idx, b_val, n, G, H0, planes_hi, planes_lo, b1, Z, ksplits,
                                              (cudaStream_t)stream);
+}
+
+// Geometry of scnb_csr_linear_fwd_tc with automatic splits: number of gene-axis splits and genes per split.
+extern "C" int scnb_csr_linear_fwd_tc_geometry(int n, int G, int H0, int* ksplits, int* genes_per_split) {
+  SCNB_CHECK_ARG(n > 0 && G > 0 && ksplits && genes_per_split, "csr_linear_fwd_tc_geometry: bad arguments");
+  (void)H0;
+  const int KT = 32, ROWS = 256;
+  const int ks = fwd_tc_auto_splits(n, G, ROWS, KT);
+  *ksplits = ks;
+  *genes_per_split = scnb_cdiv(scnb_cdiv(G, KT), ks) * KT;
+  return SCNB_OK;
+}
+
+// fwd_splits[s * n + r] = first position p of batch row r with b_idx[p] >= s * genes_per_split, s = 0..ksplits: where
+// each CTA of the split forward starts (and ends) in every row.  Depends only on the batch, so the engine computes it
+// on the prologue branch, one step ahead.
+extern "C" int scnb_row_fwd_splits(const int32_t* b_indptr, const int32_t* b_idx, int n, int G, int H0, int32_t* fwd_splits,
+                                   void* stream) {
+  SCNB_CHECK_ARG(b_indptr && b_idx && fwd_splits && n >= 0 && G > 0, "row_fwd_splits: bad arguments");
+  if (n == 0) return SCNB_OK;
+  int ks = 0, gp = 0;
+  scnb_csr_linear_fwd_tc_geometry(n, G, H0, &ks, &gp);
+  k_row_gene_splits<<<n, 128, 0, (cudaStream_t)stream>>>(b_indptr, b_idx, n, gp, ks, fwd_splits);
+  SCNB_CHECK_LAUNCH("row_fwd_splits");
+  return SCNB_OK;
+}
+
+// scnb_csr_linear_fwd_tc with the split points of scnb_row_fwd_splits (automatic splits only: ksplits 0, or < 0 when Z is
+// already zeroed).
+extern "C" int scnb_csr_linear_fwd_tc_splits(const int32_t* b_indptr, const int32_t* b_idx, const float* b_val, int n, int G, int H0,
+                                             const void* planes_hi, const void* planes_lo, const float* b1, float* Z, int ksplits,
+                                             const int32_t* fwd_splits, void* stream) {
+  SCNB_CHECK_ARG(b_indptr && b_idx && b_val && fwd_splits, "csr_linear_fwd_tc_splits: null CSR or split table");
+  SCNB_CHECK_ARG(ksplits <= 0, "csr_linear_fwd_tc_splits: the split table is laid out for the automatic geometry (ksplits <= 0)");
+  int rc = tc_check(n, G, H0, planes_hi, planes_lo, Z);
+  if (rc != SCNB_OK) return rc;
+  if (n == 0) return SCNB_OK;
+  return launch_dense_fwd_tc<int32_t, 2, 32, false, true>(b_indptr, b_idx, b_val, n, G, H0, planes_hi, planes_lo, b1, Z, ksplits,
+                                                          (cudaStream_t)stream, nullptr, nullptr, fwd_splits);
 }
 
 extern "C" int scnb_csr_linear_fwd_tc_i64(const int64_t* indptr, const int32_t* indices, const float* data, int n, int G, int H0,
@@ -598,21 +706,6 @@ extern "C" int scnb_linear_fwd_tc_planes(const void* a_hi, const void* a_lo, int
 
 #include "optim.cuh"
 
-// splits[b * nb + r] = first position p of row r (absolute index into b_idx) with b_idx[p] >= b * GT, b = 0..n_blk
-__global__ void __launch_bounds__(128) k_row_gene_splits(const int32_t* __restrict__ b_indptr, const int32_t* __restrict__ b_idx,
-                                                         int nb, int GT, int n_blk, int32_t* __restrict__ splits) {
-  const int r = blockIdx.x;
-  const int s = b_indptr[r], e = b_indptr[r + 1];
-  for (int b = threadIdx.x; b <= n_blk; b += blockDim.x) {
-    const int target = b * GT;
-    int lo = s, hi = e;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (b_idx[mid] < target) lo = mid + 1; else hi = mid;
-    }
-    splits[(size_t)b * nb + r] = lo;
-  }
-}
 
 #define W1TC_THREADS 320   // warp 0: dZ1 tile loader + L2 prefetch, warp 1: MMA issuer, warps 2-9: densify, then epilogue
 #define W1TC_DENSE 256     // densify / epilogue threads
@@ -1086,6 +1179,20 @@ static inline int w1tc_gene_block(int G) {
 }
 
 extern "C" int scnb_w1tc_gene_block(int G) { return w1tc_gene_block(G); }
+
+// both tables in one launch (the prologue branch of the step): dW1 gene blocks and the forward's gene splits
+extern "C" int scnb_row_gene_splits2(const int32_t* b_indptr, const int32_t* b_idx, int nb, int G, int H0, int32_t* splits,
+                                     int32_t* fwd_splits, void* stream) {
+  SCNB_CHECK_ARG(b_indptr && b_idx && splits && fwd_splits && nb >= 0 && G > 0, "row_gene_splits2: bad arguments");
+  if (nb == 0) return SCNB_OK;
+  const int GT = w1tc_gene_block(G);
+  const int n_blk = scnb_cdiv(G, GT);
+  int ks = 0, gp = 0;
+  scnb_csr_linear_fwd_tc_geometry(nb, G, H0, &ks, &gp);
+  k_row_gene_splits<<<nb, 128, 0, (cudaStream_t)stream>>>(b_indptr, b_idx, nb, GT, n_blk, splits, gp, ks, fwd_splits);
+  SCNB_CHECK_LAUNCH("row_gene_splits2");
+  return SCNB_OK;
+}
 
 extern "C" int scnb_row_gene_splits(const int32_t* b_indptr, const int32_t* b_idx, int nb, int G, int32_t* splits, void* stream) {
   SCNB_CHECK_ARG(b_indptr && b_idx && splits && nb >= 0 && G > 0, "row_gene_splits: bad arguments");

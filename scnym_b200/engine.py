@@ -18,6 +18,7 @@ Algebra exploited:
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
+import ctypes
 import os
 
 import numpy as np
@@ -146,7 +147,7 @@ class ParamArena(object):
 # Everything the step's prologue (sampler hand-off, row gather, MixUp plan, gene-block splits) writes and the rest of the step
 # only reads.  Held twice: while step t runs on one set, the prologue of step t+1 fills the other (see TrainEngine.step).
 _BATCH_FIELDS = ("b_indptr", "b_idx", "b_val", "l_rows", "u_rows", "perm_keys", "gamma_raw", "lab_ids", "base_dom", "counts",
-                 "seg_off", "plan_work", "srcA", "srcB", "gam", "inv3", "coef3", "pconf", "w1_splits")
+                 "seg_off", "plan_work", "srcA", "srcB", "gam", "inv3", "coef3", "pconf", "w1_splits", "fwd_splits")
 
 
 def _batch_field(name):
@@ -300,11 +301,17 @@ class TrainEngine(object):
         if wu == "auto":
             wu = os.environ.get("SCNB_W1_UPDATE", "tc" if self.nb >= 512 else "simt")
         self.w1_tc = bool(self.fused_w1 and wu == "tc" and H0 % 32 == 0 and 32 <= H0 <= 256)
+        self.fwd_splits = None
         if self.w1_tc:
             # tensor-core dW1 + optimizer: per-row split points of the gene blocks, bf16 planes of dZ1
             gt = _lib.lib().scnb_w1tc_gene_block(self.G)
             n_blk = (self.G + gt - 1) // gt
             self.w1_splits = i32((n_blk + 1) * self.nb)
+            # where every gene split of the tensor-core forward starts in every batch row (same launch as w1_splits; used by
+            # steps whose batch was assembled one step ahead, so the forward's CTAs do not search for their first entry)
+            ks, gp = ctypes.c_int(0), ctypes.c_int(0)
+            call("scnb_csr_linear_fwd_tc_geometry", self.nb, self.G, H0, ctypes.addressof(ks), ctypes.addressof(gp))
+            self.fwd_splits = i32((ks.value + 1) * self.nb)
             n_pad = (self.nb + 31) // 32 * 32
             self.dz_hi = torch.zeros(n_pad * H0, dtype=torch.int16, device=dev)
             self.dz_lo = torch.zeros(n_pad * H0, dtype=torch.int16, device=dev)
@@ -532,7 +539,7 @@ class TrainEngine(object):
                  torch.cuda.current_stream().cuda_stream)
             self._planes_version = v
 
-    def _first_layer(self, main, sW, n_rows, Z, prezeroed=False):
+    def _first_layer(self, main, sW, n_rows, Z, prezeroed=False, splits_ready=False):
         st = main.cuda_stream
         blk0 = self._blk[0]
         if self.tc_first:
@@ -540,8 +547,13 @@ class TrainEngine(object):
                 main.wait_event(self._ev_planes)
             if prezeroed and not getattr(self, "_zero_at_end", False):
                 main.wait_event(self._ev_z1)
-            call("scnb_csr_linear_fwd_tc", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), n_rows, self.G, self.widths[0],
-                 ptr(self.w1_hi), ptr(self.w1_lo), self.P(blk0["b"]), ptr(Z), -1 if prezeroed else 0, st)
+            if splits_ready and n_rows == self.nb and self.fwd_splits is not None and os.environ.get("SCNB_FWD_SPLITS", "1") != "0":
+                call("scnb_csr_linear_fwd_tc_splits", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), n_rows, self.G,
+                     self.widths[0], ptr(self.w1_hi), ptr(self.w1_lo), self.P(blk0["b"]), ptr(Z), -1 if prezeroed else 0,
+                     ptr(self.fwd_splits), st)
+            else:
+                call("scnb_csr_linear_fwd_tc", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), n_rows, self.G, self.widths[0],
+                     ptr(self.w1_hi), ptr(self.w1_lo), self.P(blk0["b"]), ptr(Z), -1 if prezeroed else 0, st)
         else:
             call("scnb_csr_linear_fwd", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), n_rows, self.P(blk0["W"]),
                  self.P(blk0["b"]), self.widths[0], ptr(Z), st)
@@ -666,7 +678,7 @@ class TrainEngine(object):
             if sW is not main:
                 self._ev_csc.record(sW)
         # -- first layer, once
-        self._first_layer(main, sW, nb, self.Z1, prezeroed=z1_pre)
+        self._first_layer(main, sW, nb, self.Z1, prezeroed=z1_pre, splits_ready=pre)
         if pre:
             # the prologue of the NEXT step, into the other set of batch buffers, on an idle low-priority branch (it reads
             # the sampler tables and the datasets only; it must see this step's counters: after the advance)
@@ -1056,8 +1068,12 @@ class TrainEngine(object):
         (tensor-core kernel) or the gene-major copy of the batch (SIMT kernel)."""
         if self.w1_tc:
             # (idx: the staged rows of a host-mapped batch -- same entries, same positions as b_idx)
-            call("scnb_row_gene_splits", ptr(self.b_indptr), ptr(self.b_idx if idx is None else idx), n_rows, self.G,
-                 ptr(self.w1_splits), st)
+            if n_rows == self.nb and self.fwd_splits is not None:
+                call("scnb_row_gene_splits2", ptr(self.b_indptr), ptr(self.b_idx if idx is None else idx), n_rows, self.G,
+                     self.widths[0], ptr(self.w1_splits), ptr(self.fwd_splits), st)
+            else:
+                call("scnb_row_gene_splits", ptr(self.b_indptr), ptr(self.b_idx if idx is None else idx), n_rows, self.G,
+                     ptr(self.w1_splits), st)
         elif self.fused_w1:
             call("scnb_csr_to_csc", ptr(self.b_indptr), ptr(self.b_idx), ptr(self.b_val), n_rows, self.G, ptr(self.gene_cnt),
                  ptr(self.c_ptr), ptr(self.c_cursor), ptr(self.c_ent), st)

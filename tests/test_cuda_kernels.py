@@ -495,7 +495,7 @@ def test_bn_eval_fwd_large_rows():
 def test_csr_linear_fwd_tensor_core_matches_dense(n, G, H0, ksplits):
     """densify-then-tcgen05 first layer (bf16x3 split, fp32 TMEM accumulation) against the fp64 dense product."""
     from oracle import scnym_oracle as O
-    from scnym_b200._lib import call, ptr
+    from scnym_b200._lib import call, lib, ptr
     from scnym_b200.dataprep import DeviceCSR, gather_rows
     ip, ii, dd, _ = O.synth_csr(n, G, 0.07, 3, seed=n + H0)
     X = O.csr_to_dense(ip, ii, dd, G, np.arange(n))
@@ -521,6 +521,32 @@ def test_csr_linear_fwd_tensor_core_matches_dense(n, G, H0, ksplits):
     call("scnb_csr_linear_fwd_tc", ptr(b.indptr), ptr(b.indices), ptr(b.data), n, G, H0, ptr(hi), ptr(lo), None, ptr(Z2), ksplits, _st())
     torch.cuda.synchronize()
     _chk("tc fwd batch", Z2.cpu(), X[rows].double() @ WT.double(), tol=3e-5)
+    if ksplits == 0:
+        # the same product with every CTA's starting entry precomputed (scnb_row_fwd_splits; one launch with the dW1 gene
+        # blocks through scnb_row_gene_splits2): the form the engine uses when the batch was assembled one step ahead
+        import ctypes
+        ks, gp = ctypes.c_int(0), ctypes.c_int(0)
+        call("scnb_csr_linear_fwd_tc_geometry", n, G, H0, ctypes.addressof(ks), ctypes.addressof(gp))
+        assert ks.value >= 1 and gp.value % 32 == 0 and ks.value * gp.value >= G
+        sp = torch.full(((ks.value + 1) * n,), -1, dtype=torch.int32).cuda()
+        call("scnb_row_fwd_splits", ptr(b.indptr), ptr(b.indices), n, G, H0, ptr(sp), _st())
+        ipb, idb = b.indptr.cpu().numpy(), b.indices.cpu().numpy()
+        want_sp = np.stack([[ipb[r] + np.searchsorted(idb[ipb[r]:ipb[r + 1]], s * gp.value) for r in range(n)]
+                            for s in range(ks.value + 1)]).reshape(-1)
+        assert np.array_equal(sp.cpu().numpy(), want_sp)
+        gt = lib().scnb_w1tc_gene_block(G)
+        nblk = (G + gt - 1) // gt
+        s1, s1b = torch.zeros((nblk + 1) * n, dtype=torch.int32).cuda(), torch.zeros((nblk + 1) * n, dtype=torch.int32).cuda()
+        sp2 = torch.zeros_like(sp)
+        call("scnb_row_gene_splits", ptr(b.indptr), ptr(b.indices), n, G, ptr(s1), _st())
+        call("scnb_row_gene_splits2", ptr(b.indptr), ptr(b.indices), n, G, H0, ptr(s1b), ptr(sp2), _st())
+        assert torch.equal(s1, s1b) and torch.equal(sp, sp2)
+        for prezeroed in (0, -1):
+            Z3 = torch.zeros(n, H0).cuda() if prezeroed else torch.full((n, H0), 5.0).cuda()
+            call("scnb_csr_linear_fwd_tc_splits", ptr(b.indptr), ptr(b.indices), ptr(b.data), n, G, H0, ptr(hi), ptr(lo), ptr(D(b1)),
+                 ptr(Z3), prezeroed, ptr(sp), _st())
+            torch.cuda.synchronize()
+            _chk("tc fwd batch, split table", Z3.cpu(), X[rows].double() @ WT.double() + b1.double(), tol=3e-5)
 
 
 @pytest.mark.parametrize("n,K,N", [(300, 256, 256), (1000, 64, 128), (5, 32, 32)])
