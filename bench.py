@@ -331,7 +331,12 @@ def kernel_cost(eng, key):
             K_, N_, R_ = a[1], a[3], a[4]
             by = 4.0 * (R_ * K_ + R_ * N_ + K_ * N_)
         return {"bound": "tensor", "flops": 2.0 * R_ * K_ * N_, "issued_flops": 6.0 * R_ * K_ * N_, "bytes": by}
-    if name == "scnb_csr_linear_fwd_tc":
+    if name == "scnb_hs_dan_head":
+        # adversary branch in one launch (head_ops.cu): Hd = A W1^T and dA = dHd W1 as 3xTF32 tile products; bytes: Z in, A, Hd,
+        # dHd, dY out, W1 once
+        Rd_, H_ = eng.Rd, eng.H
+        return {"bound": "tensor", "flops": 4.0 * Rd_ * H_ * H_, "issued_flops": 12.0 * Rd_ * H_ * H_, "bytes": 4.0 * (5 * Rd_ * H_ + H_ * H_)}
+    if name in ("scnb_csr_linear_fwd_tc", "scnb_csr_linear_fwd_tc_splits"):
         # bytes: CSR stream + the two bf16 planes of W1T once + Z; tensor work: densified bf16x3 product
         return {"bound": "tensor", "flops": 2.0 * nnz * H0, "issued_flops": 6.0 * nb * G * H0, "bytes": 8.0 * nnz + 4.0 * G * H0 + 4.0 * nb * H0}
     dp = eng.comm is not None
@@ -345,15 +350,18 @@ def kernel_cost(eng, key):
         "scnb_csr_gather_rows2": hbm(16 * nnz),                                  # dataset rows in, batch CSR out
         "scnb_csr_gather_rows": hbm(16 * nnz),
         "scnb_row_gene_splits": hbm(4 * nnz),
+        "scnb_row_gene_splits2": hbm(4 * nnz),
         "scnb_w1_planes": hbm(8 * G * H0),
         "scnb_mix_rows": hbm(4 * H0 * (nb + R)),
         "scnb_unmix_rows": hbm(4 * H0 * (R + nb)),
         "scnb_unmix_rows_planes": hbm(4 * H0 * (R + nb) + 4 * nb * H0),
+        "scnb_hs_bwd_in_unmix_planes": hbm(4 * H0 * (2 * R + nb) + 4 * nb * H0),   # dY, Z in; dZ1 + planes out
         "scnb_bn_act_fwd": hbm(8 * R * (Hs / len(eng.widths))),                 # Z in, A out
         "scnb_bn_act_bwd": hbm(16 * R * (Hs / len(eng.widths))),                # dA, Z, A in, dZ out
         "scnb_bn_act_fwd_peer": hbm(8 * R * (Hs / len(eng.widths))),
         "scnb_bn_act_bwd_peer": hbm(16 * R * (Hs / len(eng.widths))),
         "scnb_classif_mixmatch_fused": hbm(4 * nb * (2 * eng.H + 3 * eng.C)),
+        "scnb_hs_classif_head": hbm(4 * nb * (3 * eng.H + 3 * eng.C)),           # Z in, A + dY out, logits / dlogits
         "scnb_dan_tail_fused": hbm(4 * eng.Rd * (2 * eng.H + 3 * max(eng.D, 1))) if eng.use_dan else None,
         "scnb_teacher_head_fused": hbm(4 * eng.U * (eng.H + 2 * eng.C)),
         "scnb_colsum": hbm(4 * R * eng.H),

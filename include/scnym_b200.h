@@ -297,6 +297,31 @@ int scnb_hs_fwd(const float* Zin, float* Aout, const float* part_in, float* stat
                 const uint8_t* keep_mask, float p_drop, const float* W, const float* bias, float* Zout, float* part_out,
                 uint8_t* keep_out, const uint64_t* rng, uint32_t out_stream_id, float out_p_drop, int K, int N, int R, int n_seg,
                 const int32_t* seg_off_host, const float* running_mean, const float* running_var, void* stream);
+/* Heads fused with the ends of the hidden stack (head_ops.cu), one launch per branch from the pre-BatchNorm Z of the LAST
+ * application to dY of that application and its tile sums (the input of scnb_hs_bwd) -- replaces scnb_hs_act, the head
+ * kernels and scnb_hs_bwd_act.  Common arguments: Z / A [R, H], part_in (tile statistics of Z; NULL: `stats` already holds the
+ * global segment statistics), stats (written unless given), gamma / beta of the last BatchNorm, keep = dropout keep bytes [R, H]
+ * of that application (scnb_hs_fwd's keep_out), dY [R, H], part_out [R/32][2][H].  Both return -3 (SCNB_ERR_UNSUPPORTED) for
+ * shapes they are not built for (H not 128 / 256, more than 32 classes / domains).
+ *   scnb_hs_classif_head: rows [0, U + L) (whole segments): activation (scnym/model.py:219-227), classifier (model.py:229),
+ *     MSE on rows [0, U) / soft-target CE on rows [U, U + L) with dLogits (scnym/losses.py:880-923; arguments as
+ *     scnb_classif_mixmatch_fused), dA = dLogits Wc, dY = dA [A > 0] / (1-p).
+ *   scnb_hs_dan_head: rows [row_base, R) (whole segments): activation, Hd = relu(A W1^T + b1), domain logits Hd W2^T + b2, CE
+ *     against the domain label (scnym/model.py:377-383, scnym/losses.py:1209-1243; arguments as scnb_dan_tail_fused),
+ *     dHd = (ddlog W2) [Hd > 0], gradient reversal dA = -dan_weight dHd W1 (model.py:338), dY.  Hd / dHd [R - row_base, H] and
+ *     dlog / dlabel / ddlog [R - row_base, D] are kept for the head's weight gradients.  A thread-block cluster of H/64 CTAs
+ *     shares a 32-row tile through distributed shared memory. */
+int scnb_hs_classif_head(const float* Z, float* A, const float* part_in, float* stats, const float* gamma, const float* beta,
+                         const uint8_t* keep, float p_drop, int H, int R, int n_seg, const int32_t* seg_off_host, const float* Wc,
+                         const float* bc, int C, int U, int L, const int32_t* n_conf_dev, const float* Y, const int32_t* mapA,
+                         const int32_t* mapB, const float* gam, const float* class_weight, float unsup_weight, float* logits,
+                         float* dlogits, float* loss8, float* dY, float* part_out, void* stream);
+int scnb_hs_dan_head(const float* Z, float* A, const float* part_in, float* stats, const float* gamma, const float* beta,
+                     const uint8_t* keep, float p_drop, int H, int R, int row_base, int n_seg, const int32_t* seg_off_host,
+                     const float* W1, const float* b1, const float* W2, const float* b2, int D, const int32_t* n_rows_dev,
+                     const int32_t* dom_ids, const int32_t* src, int src_off, const float* loss_scale_dev, float dan_weight,
+                     float* Hd, float* dHd, float* dlog, float* dlabel, float* ddlog, float* loss2, float* dY, float* part_out,
+                     void* stream);
 /* dY = dA * [A > 0] / (1-p) of the last application + tile sums */
 int scnb_hs_bwd_act(const float* dA, const float* Z, const float* A, int H, int R, int n_seg, const int32_t* seg_off_host,
                     const float* stats, float p_drop, float* dY, float* part, void* stream);
@@ -313,12 +338,20 @@ int scnb_hs_dw(const float* dZ, int M, const float* A, int N, int R, float* dW, 
 int scnb_hs_bwd_in(const float* dY, const float* Z, int H, int R, int n_seg, const int32_t* seg_off_host, const float* stats,
                    const float* part, const float* gamma, float* dgamma, float* dbeta, float* dZ, const float* bmean_in,
                    float* db /* NULL or [H]: += column sums of dZ (bias gradient of the Linear in front) */, void* stream);
+/* scnb_hs_bwd_in, scnb_unmix_rows and the operand planes of scnb_unmix_rows_planes in one launch: dZ1[r] = sum_k coef3[k][r] *
+ * dZ0[inv3[k][r]] with dZ0 (the BatchNorm backward of application 0) formed on the fly and never written; dgamma / dbeta / db as
+ * scnb_hs_bwd_in; planes as scnb_unmix_rows_planes (MixMatch steps on the tensor-core dW1 path). */
+int scnb_hs_bwd_in_unmix_planes(const float* dY, const float* Z, int H, int R, int n_seg, const int32_t* seg_off_host,
+                                const float* stats, const float* part, const float* gamma, float* dgamma, float* dbeta,
+                                const float* bmean_in, float* db, const int32_t* inv3, const float* coef3, int n_base, float* dZ1,
+                                void* planes_hi, void* planes_lo, void* stream);
 /* Data parallel (one process per GPU; equivalence target: the reference step on the CONCATENATED global batch): exchange of
  * the per-segment statistics between a producer of tile partials and their consumer, through peer memory (CUDA IPC buffers
  * over NVLink / NVSwitch, `peer_bufs[world]` as scnb_bn_act_fwd_peer).  kind 0 (forward): out = stats[n_seg][3][H] (global
  * mean, biased var, invstd), cnt_out[n_seg] = global rows; kind 1 (backward): out = bmean[n_seg][2][H] (global means of dY and
  * dY*zhat), and this rank's LOCAL sums are added to dgamma / dbeta.  Consumers then take part_in = NULL. */
 int scnb_hs_debug_read(unsigned long long* out32_host);   /* SCNB_HS_DBG=1: %globaltimer phase stamps of CTA (0,0) (tools/hs_phases.py) */
+int scnb_hh_debug_read(unsigned long long* out32_host);   /* the same for the fused head kernels (tools/head_phases.py) */
 int scnb_hs_peer_bytes(int H_max, int n_seg, int n_slots, int world);   /* bytes of the exchange region */
 int scnb_hs_xchg(int kind, const float* part, int H, int R, int n_seg, const int32_t* seg_off_host, const uint64_t* peer_bufs,
                  int rank, int world, int slot, int n_slots, int H_max, const int64_t* epoch, long long buf_bytes, float* out,
@@ -370,6 +403,13 @@ int scnb_dan_tail_fused(const float* Hd /*[Rd,H] post-ReLU*/, const float* W2, c
 int scnb_teacher_head_fused(const float* TA /*[K*U,H]*/, const float* Wc, const float* bc, int H, int C, int K, int U, float T,
                             int sharpen, float min_confidence, float* t_logits, float* q, float* conf, uint8_t* confident,
                             float* scratch_UC, const int32_t* lab_ids, int L, void* stream);
+/* scnb_teacher_head_fused on the PRE-BatchNorm output TZ [U, H] of the last hidden Linear: eval-mode BatchNorm (running
+ * statistics, scnym/model.py:219-227 under model.eval(); scnym/losses.py:660-737) -> ReLU applied while a row is loaded.
+ * One view (K == 1), C <= 32; returns -3 otherwise. */
+int scnb_teacher_head_bn_fused(const float* TZ, const float* gamma, const float* beta, const float* running_mean,
+                               const float* running_var, const float* Wc, const float* bc, int H, int C, int K, int U, float T,
+                               int sharpen, float min_confidence, float* t_logits, float* q, float* conf, uint8_t* confident,
+                               float* scratch_UC, const int32_t* lab_ids, int L, void* stream);
 
 /* ---- K9/K10: optimizer.step() (scnym/trainer.py:234,671,1089; torch.optim.{Adadelta,Adam,AdamW,SGD}
  *      selected at scnym/main.py:36-41,374-396) over the flat parameter arena, and the mean-teacher

@@ -28,6 +28,9 @@ SIGNATURES = {
     "scnb_csr_linear_fwd": [P, P, P, I, P, P, I, P, P],
     "scnb_csr_linear_fwd_i64": [P, P, P, I, P, P, I, P, P],
     "scnb_csr_linear_bwd_dw": [P, P, P, I, P, I, P, P],
+    "scnb_hs_classif_head": [P, P, P, P, P, P, P, F, I, I, I, P, P, P, I, I, I, P, P, P, P, P, P, F, P, P, P, P, P, P],
+    "scnb_hs_dan_head": [P, P, P, P, P, P, P, F, I, I, I, I, P, P, P, P, P, I, P, P, P, I, P, F, P, P, P, P, P, P, P, P, P],
+    "scnb_hs_bwd_in_unmix_planes": [P, P, I, I, I, P, P, P, P, P, P, P, P, P, P, I, P, P, P, P],
     "scnb_w1_planes": [P, I, I, P, P, P],
     "scnb_csr_linear_fwd_tc": [P, P, P, I, I, I, P, P, P, P, I, P],
     "scnb_csr_linear_fwd_tc_i64": [P, P, P, I, I, I, P, P, P, P, I, P],
@@ -75,6 +78,7 @@ SIGNATURES = {
     "scnb_hs_bwd_in": [P, P, I, I, I, P, P, P, P, P, P, P, P, P, P],
     "scnb_hs_peer_bytes": [I, I, I, I],
     "scnb_hs_debug_read": [P],
+    "scnb_hh_debug_read": [P],
     "scnb_hs_xchg": [I, P, I, I, I, P, P, I, I, I, I, I, P, L, P, P, P, P, P],
     "scnb_unmix_rows": [P, I, P, P, I, P, P],
     "scnb_unmix_rows_planes": [P, I, P, P, I, P, P, P, P],
@@ -86,6 +90,7 @@ SIGNATURES = {
     "scnb_classif_supervised_fused": [P, P, P, I, I, I, P, P, P, P, P, P, P],
     "scnb_dan_tail_fused": [P, P, P, I, I, I, P, P, P, I, P, P, P, P, P, P, P],
     "scnb_teacher_head_fused": [P, P, P, I, I, I, I, F, I, F, P, P, P, P, P, P, I, P],
+    "scnb_teacher_head_bn_fused": [P, P, P, P, P, P, P, I, I, I, I, F, I, F, P, P, P, P, P, P, I, P],
     "scnb_onehot_rows": [P, P, I, I, I, P, P],
     "scnb_step_begin": [P, P],
     "scnb_mm_step_inc": [P, P],

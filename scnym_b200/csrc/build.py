@@ -4,7 +4,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["api.cu", "host_ops.cu", "csr_ops.cu", "remap_ops.cu", "dense_ops.cu", "hidden_ops.cu", "gemm_ops.cu", "tc_ops.cu", "tc_gemm.cu", "loss_ops.cu", "optim_ops.cu"]
+SOURCES = ["api.cu", "host_ops.cu", "csr_ops.cu", "remap_ops.cu", "dense_ops.cu", "hidden_ops.cu", "head_ops.cu", "gemm_ops.cu", "tc_ops.cu", "tc_gemm.cu", "loss_ops.cu", "optim_ops.cu"]
 OUT = os.path.join(os.path.dirname(HERE), "libscnym_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

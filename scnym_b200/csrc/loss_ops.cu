@@ -7,6 +7,7 @@
 //   scnb_softmax_mse_fwd_bwd  sum_c (softmax(z)-y)^2 masked mean + dLogits      (losses.py:880-913)
 //   scnb_predict_head       ensemble-mean logits -> argmax / softmax            (predict.py:178-192)
 #include "common.cuh"
+#include "loss_rows.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // Pseudolabels.  One warp per unlabeled row.  logits: [K][U][C].
@@ -399,99 +400,6 @@ extern "C" int scnb_mixmatch_plan(const uint8_t* confident, const float* perm_ke
   return SCNB_OK;
 }
 
-// ---------------------------------------------------------------------------------------------
-// Soft-target cross entropy, mean over `n_norm` rows, with dLogits.  One warp per row.
-//   label row i = gam[i]*Y[mapA[i]] + (1-gam[i])*Y[mapB[i]]   (maps optional -> Y[i])
-//   loss_i = -w_i * sum_c y_c * log_softmax(z)_c ;  w_i = max_c(cw_c*y_c) if class weights
-//   dz = grad_scale * (w_i/n_norm) * (softmax(z)*sum_c y_c - y)
-// Rows >= *n_rows_dev are inactive: dz = 0.  loss_out[0] += loss (atomic); loss_out[1] += #argmax hits.
-// ---------------------------------------------------------------------------------------------
-// One warp, one row `i` of the soft-target cross entropy (see k_soft_ce).
-__device__ __forceinline__ void ce_row(int i, const float* __restrict__ Zl, int n_max, int C,
-                                                 const int32_t* __restrict__ n_rows_dev, const float* __restrict__ Y,
-                                                 const int32_t* __restrict__ mapA, const int32_t* __restrict__ mapB,
-                                                 const float* __restrict__ gam, int map_off,
-                                                 const float* __restrict__ class_weight, const int32_t* __restrict__ n_norm_dev,
-                                                 int n_norm, float grad_scale, const float* __restrict__ loss_scale_dev,
-                                                 float* __restrict__ dZ, float* __restrict__ loss_out, int count_acc,
-                                                 float* __restrict__ row_loss) {
-  const int lane = threadIdx.x & 31;
-  const int n_rows = n_rows_dev ? min(*n_rows_dev, n_max) : n_max;
-  float* dz = dZ ? dZ + (size_t)i * C : nullptr;
-  if (i >= n_rows) {
-    if (dz)
-      for (int c = lane; c < C; c += 32) dz[c] = 0.f;
-    if (row_loss && lane == 0) row_loss[i] = 0.f;
-    return;
-  }
-  const float nn = (float)(n_norm_dev ? max(*n_norm_dev, 1) : max(n_norm, 1));
-  const float ls = loss_scale_dev ? *loss_scale_dev : 1.f;
-  const float* z = Zl + (size_t)i * C;
-  int a = i, b = i;
-  float g = 1.f;
-  if (mapA) {
-    a = mapA[map_off + i];
-    b = mapB ? mapB[map_off + i] : a;
-    g = gam ? gam[map_off + i] : 1.f;
-  }
-  const float* ya = Y + (size_t)a * C;
-  const float* yb = Y + (size_t)b * C;
-  const float g1 = 1.f - g;
-  float m = -INFINITY;
-  int am = 0x7fffffff;
-  for (int c = lane; c < C; c += 32) {
-    const float v = z[c];
-    if (v > m) { m = v; am = c; }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float om = __shfl_xor_sync(0xffffffffu, m, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, am, o);
-    if (om > m || (om == m && oi < am)) { m = om; am = oi; }
-  }
-  if (am >= C) am = 0;         // all-NaN / all -inf row (see pseudolabel_row)
-  float s = 0.f;
-  for (int c = lane; c < C; c += 32) s += expf(z[c] - m);
-  s = warp_sum(s);
-  const float lse = logf(s);
-  float dot = 0.f, ysum = 0.f, w = -INFINITY;
-  float ym = -INFINITY;  // argmax of the dominant label row (the original, un-mixed label)
-  int yam = 0x7fffffff;
-  for (int c = lane; c < C; c += 32) {
-    const float y = (a == b) ? ya[c] : g * ya[c] + g1 * yb[c];
-    dot += y * ((z[c] - m) - lse);
-    ysum += y;
-    if (class_weight) w = fmaxf(w, class_weight[c] * y);
-    if (ya[c] > ym) { ym = ya[c]; yam = c; }
-  }
-  if (count_acc) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float om = __shfl_xor_sync(0xffffffffu, ym, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, yam, o);
-      if (om > ym || (om == ym && oi < yam)) { ym = om; yam = oi; }
-    }
-    if (yam >= C) yam = 0;
-  }
-  dot = warp_sum(dot);
-  ysum = warp_sum(ysum);
-  w = class_weight ? warp_max(w) : 1.f;
-  const float li = -dot * w;
-  if (dz) {
-    const float k = grad_scale * ls * w / nn;
-    for (int c = lane; c < C; c += 32) {
-      const float y = (a == b) ? ya[c] : g * ya[c] + g1 * yb[c];
-      const float p = expf(z[c] - m) / s;
-      dz[c] = k * (p * ysum - y);
-    }
-  }
-  if (lane == 0) {
-    if (row_loss) row_loss[i] = li * ls;
-    atomicAdd(loss_out, li * ls / nn);
-    if (count_acc && yam == am) atomicAdd(loss_out + 1, 1.0f);
-  }
-}
-
 __global__ void __launch_bounds__(256) k_soft_ce(const float* __restrict__ Zl, int n_max, int C,
                                                  const int32_t* __restrict__ n_rows_dev, const float* __restrict__ Y,
                                                  const int32_t* __restrict__ mapA, const int32_t* __restrict__ mapB,
@@ -518,66 +426,6 @@ extern "C" int scnb_soft_ce_fwd_bwd(const float* logits, int n_max, int C, const
                                                                      loss_scale_dev, dlogits, loss_out2, count_acc, row_loss_out);
   SCNB_CHECK_LAUNCH("soft_ce_fwd_bwd");
   return SCNB_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Interpolation-consistency MSE on probabilities (losses.py:880-913):
-//   L_u = (1/n_norm) sum_{i < n_conf} sum_c (softmax(z_i)_c - y'_ic)^2 ;  rows >= n_conf get zero loss/grad.
-//   dz = p * (g - sum_c g_c p_c),  g = 2 (p - y') * weight / n_norm
-// ---------------------------------------------------------------------------------------------
-// One warp, one row `i` of the masked MSE on probabilities (see k_softmax_mse).
-__device__ __forceinline__ void mse_row(int i, const float* __restrict__ Zl, int n_max, int C,
-                                                     const int32_t* __restrict__ n_conf_dev, const float* __restrict__ Y,
-                                                     const int32_t* __restrict__ mapA, const int32_t* __restrict__ mapB,
-                                                     const float* __restrict__ gam, int map_off, int n_norm,
-                                                     const float* __restrict__ weight_dev, float weight,
-                                                     float* __restrict__ dZ, float* __restrict__ loss_out) {
-  const int lane = threadIdx.x & 31;
-  const int n_conf = n_conf_dev ? min(*n_conf_dev, n_max) : n_max;
-  float* dz = dZ ? dZ + (size_t)i * C : nullptr;
-  if (i >= n_conf) {
-    if (dz)
-      for (int c = lane; c < C; c += 32) dz[c] = 0.f;
-    return;
-  }
-  const float wgt = weight_dev ? *weight_dev : weight;
-  const float* z = Zl + (size_t)i * C;
-  int a = i, b = i;
-  float g = 1.f;
-  if (mapA) {
-    a = mapA[map_off + i];
-    b = mapB ? mapB[map_off + i] : a;
-    g = gam ? gam[map_off + i] : 1.f;
-  }
-  const float* ya = Y + (size_t)a * C;
-  const float* yb = Y + (size_t)b * C;
-  const float g1 = 1.f - g;
-  float m = -INFINITY;
-  for (int c = lane; c < C; c += 32) m = fmaxf(m, z[c]);
-  m = warp_max(m);
-  float s = 0.f;
-  for (int c = lane; c < C; c += 32) s += expf(z[c] - m);
-  s = warp_sum(s);
-  float sq = 0.f, gp = 0.f;
-  for (int c = lane; c < C; c += 32) {
-    const float y = (a == b) ? ya[c] : g * ya[c] + g1 * yb[c];
-    const float p = expf(z[c] - m) / s;
-    const float d = p - y;
-    sq = fmaf(d, d, sq);
-    gp = fmaf(d, p, gp);
-  }
-  sq = warp_sum(sq);
-  gp = warp_sum(gp);
-  const float inv_n = 1.0f / (float)max(n_norm, 1);
-  if (dz) {
-    const float k = 2.0f * wgt * inv_n;
-    for (int c = lane; c < C; c += 32) {
-      const float y = (a == b) ? ya[c] : g * ya[c] + g1 * yb[c];
-      const float p = expf(z[c] - m) / s;
-      dz[c] = k * p * ((p - y) - gp);
-    }
-  }
-  if (lane == 0) atomicAdd(loss_out, sq * inv_n);
 }
 
 __global__ void __launch_bounds__(256) k_softmax_mse(const float* __restrict__ Zl, int n_max, int C,
@@ -664,112 +512,6 @@ extern "C" int scnb_predict_head(const float* logits_sum, int n_models, int n, i
   k_predict_head<<<scnb_cdiv(n, 8), 256, 0, (cudaStream_t)stream>>>(logits_sum, 1.0f / (float)n_models, n, C, pred, prob, score);
   SCNB_CHECK_LAUNCH("predict_head");
   return SCNB_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Fused heads.  The classifier (H -> C), the last layer of the domain adversary (H -> D) and their
-// losses are a few kFLOP per row: as separate GEMM / loss / GEMM launches they cost four dependent
-// kernels each on the step's critical path.  Here one warp owns one row: it forms the C (or D)
-// logits against the weight matrix staged in shared memory, runs the loss row function on them and
-// immediately back-propagates dLogits through the same weights.  H must be a multiple of 128
-// (lane owns float4 groups h = (i*32 + lane)*4) and C*H floats must fit in shared memory;
-// otherwise the engine keeps the unfused sequence.
-// ---------------------------------------------------------------------------------------------
-template <int NV>
-__device__ __forceinline__ void head_logits(const float* __restrict__ a_row, const float* __restrict__ Ws,
-                                            const float* __restrict__ bias, int C, int H, float* __restrict__ z_row,
-                                            float4 (&a)[NV], int lane) {
-#pragma unroll
-  for (int i = 0; i < NV; ++i) a[i] = *reinterpret_cast<const float4*>(a_row + (i * 32 + lane) * 4);
-  for (int c = 0; c < C; ++c) {
-    float p = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const float4 w = *reinterpret_cast<const float4*>(Ws + (size_t)c * H + (i * 32 + lane) * 4);
-      p = fmaf(a[i].x, w.x, p);
-      p = fmaf(a[i].y, w.y, p);
-      p = fmaf(a[i].z, w.z, p);
-      p = fmaf(a[i].w, w.w, p);
-    }
-    p = warp_sum(p);
-    if (lane == (c & 31)) z_row[c] = p + (bias ? bias[c] : 0.f);
-  }
-  __syncwarp();
-}
-// out_row[h] = scale * sum_c dz[c] * W[c][h]   (optionally gated by act[h] > 0: ReLU backward)
-template <int NV>
-__device__ __forceinline__ void head_backprop(const float* __restrict__ dz_row, const float* __restrict__ Ws, int C, int H,
-                                              float scale, const float4* gate_act, float* __restrict__ out_row, int lane) {
-  float4 acc[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int c = 0; c < C; ++c) {
-    const float d = dz_row[c];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const float4 w = *reinterpret_cast<const float4*>(Ws + (size_t)c * H + (i * 32 + lane) * 4);
-      acc[i].x = fmaf(d, w.x, acc[i].x);
-      acc[i].y = fmaf(d, w.y, acc[i].y);
-      acc[i].z = fmaf(d, w.z, acc[i].z);
-      acc[i].w = fmaf(d, w.w, acc[i].w);
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    float4 v = make_float4(scale * acc[i].x, scale * acc[i].y, scale * acc[i].z, scale * acc[i].w);
-    if (gate_act) {
-      const float4 gt = gate_act[i];
-      if (!(gt.x > 0.f)) v.x = 0.f;
-      if (!(gt.y > 0.f)) v.y = 0.f;
-      if (!(gt.z > 0.f)) v.z = 0.f;
-      if (!(gt.w > 0.f)) v.w = 0.f;
-    }
-    *reinterpret_cast<float4*>(out_row + (i * 32 + lane) * 4) = v;
-  }
-}
-__device__ __forceinline__ void stage_weights(float* Ws, const float* __restrict__ W, int n) {
-  for (int i = threadIdx.x * 4; i < n; i += blockDim.x * 4) *reinterpret_cast<float4*>(Ws + i) = *reinterpret_cast<const float4*>(W + i);
-  __syncthreads();
-}
-
-// Short-chain variant for C <= 32 outputs (the usual number of cell types / domains): the per-class partial dot products of
-// all lanes meet in a per-warp shared-memory tile [C][33] and lane c adds its class's 32 partials -- one transposed pass
-// instead of C dependent butterfly reductions -- and the logits stay in shared memory (`zs[C]`) for the loss row function
-// and the back-propagation, instead of a store -> load round trip through global memory.  Per-warp scratch: HEAD_WS floats.
-#define HEAD_WS (32 * 33 + 64)
-template <int NV>
-__device__ __forceinline__ void head_logits_s(const float* __restrict__ a_row, const float* __restrict__ Ws,
-                                              const float* __restrict__ bias, int C, int H, float* __restrict__ wsm,
-                                              float4 (&a)[NV], int lane) {
-  float* sp = wsm;               // [C][33]
-  float* zs = wsm + 32 * 33;     // [32] logits
-#pragma unroll
-  for (int i = 0; i < NV; ++i) a[i] = *reinterpret_cast<const float4*>(a_row + (i * 32 + lane) * 4);
-  for (int c = 0; c < C; ++c) {
-    float p = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const float4 w = *reinterpret_cast<const float4*>(Ws + (size_t)c * H + (i * 32 + lane) * 4);
-      p = fmaf(a[i].x, w.x, p);
-      p = fmaf(a[i].y, w.y, p);
-      p = fmaf(a[i].z, w.z, p);
-      p = fmaf(a[i].w, w.w, p);
-    }
-    sp[c * 33 + lane] = p;
-  }
-  __syncwarp();
-  if (lane < C) {
-    float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      z0 += sp[lane * 33 + i];
-      z1 += sp[lane * 33 + i + 1];
-      z2 += sp[lane * 33 + i + 2];
-      z3 += sp[lane * 33 + i + 3];
-    }
-    zs[lane] = ((z0 + z1) + (z2 + z3)) + (bias ? bias[lane] : 0.f);
-  }
-  __syncwarp();
 }
 
 // MixMatch student head: rows [0,U) interpolation-consistency MSE, rows [U,U+L) soft-target CE
@@ -922,12 +664,45 @@ __global__ void __launch_bounds__(256) k_teacher_head(const float* __restrict__ 
                                                       int sharpen, float min_conf, float* __restrict__ t_logits,
                                                       float* __restrict__ q, float* __restrict__ conf,
                                                       uint8_t* __restrict__ confident, float* __restrict__ scratch,
-                                                      const int32_t* __restrict__ lab_ids, int L) {
+                                                      const int32_t* __restrict__ lab_ids, int L, const float* __restrict__ bn_gamma,
+                                                      const float* __restrict__ bn_beta, const float* __restrict__ bn_rmean,
+                                                      const float* __restrict__ bn_rvar) {
   PDL_ENTRY();
   extern __shared__ __align__(16) float Ws[];
-  stage_weights(Ws, Wc, C * H);
   const int lane = threadIdx.x & 31;
   const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (bn_gamma && K == 1 && C <= 32) {
+    // TA holds the PRE-BatchNorm output of the last hidden Linear: eval-mode BatchNorm -> ReLU (running statistics,
+    // scnym/model.py:219-227 under model.eval()) is applied as the row is loaded -- one launch less on the teacher's chain.
+    // The row and the column constants are requested before the weights are staged.
+    float4 a[NV];
+    if (u < U) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c4 = i * 32 + lane;
+        const float4 z = *reinterpret_cast<const float4*>(TA + (size_t)u * H + c4 * 4);
+        const float4 m = reinterpret_cast<const float4*>(bn_rmean)[c4], v = reinterpret_cast<const float4*>(bn_rvar)[c4];
+        const float4 g = reinterpret_cast<const float4*>(bn_gamma)[c4], b = reinterpret_cast<const float4*>(bn_beta)[c4];
+        a[i].x = fmaxf((z.x - m.x) * (1.0f / sqrtf(v.x + 1e-5f)) * g.x + b.x, 0.f);
+        a[i].y = fmaxf((z.y - m.y) * (1.0f / sqrtf(v.y + 1e-5f)) * g.y + b.y, 0.f);
+        a[i].z = fmaxf((z.z - m.z) * (1.0f / sqrtf(v.z + 1e-5f)) * g.z + b.z, 0.f);
+        a[i].w = fmaxf((z.w - m.w) * (1.0f / sqrtf(v.w + 1e-5f)) * g.w + b.w, 0.f);
+      }
+    }
+    stage_weights(Ws, Wc, C * H);
+    if (u < U) {
+      float* wsm = Ws + (size_t)C * H + (threadIdx.x >> 5) * HEAD_WS;
+      float* zs = wsm + 32 * 33;
+      float* qs = zs + 32;
+      head_logits_s_regs<NV>(a, Ws, bc, C, H, wsm, lane);
+      if (lane < C) t_logits[(size_t)u * C + lane] = zs[lane];
+      pseudolabel_row(u, zs - (size_t)u * C, 1, U, C, T, sharpen, min_conf, q, conf, confident, qs - (size_t)u * C, lab_ids, L);
+      return;
+    }
+    pseudolabel_row(u, t_logits, K, U, C, T, sharpen, min_conf, q, conf, confident, scratch, lab_ids, L);
+    return;
+  }
+  stage_weights(Ws, Wc, C * H);
   if (u < U && K == 1 && C <= 32) {   // one view: logits and the mean-probability scratch stay in shared memory
     float4 a[NV];
     float* wsm = Ws + (size_t)C * H + (threadIdx.x >> 5) * HEAD_WS;
@@ -1012,9 +787,10 @@ extern "C" int scnb_dan_tail_fused(const float* Hd, const float* W2, const float
   return SCNB_OK;
 }
 
-extern "C" int scnb_teacher_head_fused(const float* TA, const float* Wc, const float* bc, int H, int C, int K, int U, float T,
-                                       int sharpen, float min_confidence, float* t_logits, float* q, float* conf,
-                                       uint8_t* confident, float* scratch_UC, const int32_t* lab_ids, int L, void* stream) {
+static int teacher_head_launch(const float* TA, const float* Wc, const float* bc, int H, int C, int K, int U, float T, int sharpen,
+                               float min_confidence, float* t_logits, float* q, float* conf, uint8_t* confident, float* scratch_UC,
+                               const int32_t* lab_ids, int L, const float* bn_gamma, const float* bn_beta, const float* bn_rmean,
+                               const float* bn_rvar, void* stream) {
   SCNB_CHECK_ARG(TA && Wc && t_logits && q && conf && confident && scratch_UC && H > 0 && C > 0 && K > 0 && U >= 0,
                  "teacher_head_fused: bad arguments");
   if (!head_fusable(H, C, TA, Wc, Wc) || (H / 128 != 1 && H / 128 != 2 && H / 128 != 4 && H / 128 != 8)) return SCNB_ERR_UNSUPPORTED;
@@ -1022,9 +798,30 @@ extern "C" int scnb_teacher_head_fused(const float* TA, const float* Wc, const f
   if (rows == 0) return SCNB_OK;
   const size_t smem = ((size_t)C * H + (C <= 32 ? 8 * HEAD_WS : 0)) * sizeof(float);
   HEAD_DISPATCH(k_teacher_head, rows, smem, (cudaStream_t)stream, TA, Wc, bc, H, C, K, U, T, sharpen, min_confidence, t_logits, q,
-                conf, confident, scratch_UC, lab_ids, L);
+                conf, confident, scratch_UC, lab_ids, L, bn_gamma, bn_beta, bn_rmean, bn_rvar);
   SCNB_CHECK_LAUNCH("teacher_head_fused");
   return SCNB_OK;
+}
+
+extern "C" int scnb_teacher_head_fused(const float* TA, const float* Wc, const float* bc, int H, int C, int K, int U, float T,
+                                       int sharpen, float min_confidence, float* t_logits, float* q, float* conf,
+                                       uint8_t* confident, float* scratch_UC, const int32_t* lab_ids, int L, void* stream) {
+  return teacher_head_launch(TA, Wc, bc, H, C, K, U, T, sharpen, min_confidence, t_logits, q, conf, confident, scratch_UC, lab_ids, L,
+                             nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+// The same head on the PRE-BatchNorm output TZ of the last hidden Linear: eval-mode BatchNorm (running statistics) -> ReLU is
+// applied while the row is loaded.  One view (K == 1) and at most 32 classes; -3 (SCNB_ERR_UNSUPPORTED) otherwise.
+extern "C" int scnb_teacher_head_bn_fused(const float* TZ, const float* gamma, const float* beta, const float* running_mean,
+                                          const float* running_var, const float* Wc, const float* bc, int H, int C, int K, int U,
+                                          float T, int sharpen, float min_confidence, float* t_logits, float* q, float* conf,
+                                          uint8_t* confident, float* scratch_UC, const int32_t* lab_ids, int L, void* stream) {
+  SCNB_CHECK_ARG(gamma && beta && running_mean && running_var, "teacher_head_bn_fused: null BatchNorm argument");
+  if (K != 1 || C > 32) return SCNB_ERR_UNSUPPORTED;
+  SCNB_CHECK_ARG((((uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)running_mean | (uintptr_t)running_var) % 16) == 0,
+                 "teacher_head_bn_fused: BatchNorm vectors must be 16-byte aligned");
+  return teacher_head_launch(TZ, Wc, bc, H, C, K, U, T, sharpen, min_confidence, t_logits, q, conf, confident, scratch_UC, lab_ids, L,
+                             gamma, beta, running_mean, running_var, stream);
 }
 
 // Small-output Linear for inference: out[r, :] (+)= A[r, :] W^T + b with C <= a few dozen outputs (the classifier,

@@ -397,7 +397,7 @@ class TrainEngine(object):
             self.pf = [f32(R // 32, 2, w) for w in self.widths]
             self.pb = [f32(R // 32, 2, w) for w in self.widths]
             # dropout keep bytes of the applications consumed by a tile GEMM: drawn once by the kernel that produces Z[a]
-            self.keepbuf = [torch.ones((R, w), dtype=torch.uint8, device=dev) for w in self.widths[:-1]]
+            self.keepbuf = [torch.ones((R, w), dtype=torch.uint8, device=dev) for w in self.widths]
             if self.comm is not None:   # data parallel: global backward means per application, written by scnb_hs_xchg
                 self.bmean = [f32(self.n_seg, 2, w) for w in self.widths]
         # "auto": the tensor-core form pays off once the batch fills at least two 256-row tiles (measured: 512 rows,
@@ -430,6 +430,10 @@ class TrainEngine(object):
         fus = lambda c: (self.H % 128 == 0 and self.H // 128 in (1, 2, 4, 8) and c * self.H * 4 <= 96 * 1024)
         self.fuse_classif = bool(cfg.fuse_heads and fus(self.C))
         self.fuse_dan = bool(cfg.fuse_heads and self.use_dan and fus(self.D))
+        # heads fused with the ends of the hidden stack (head_ops.cu): last BatchNorm -> Dropout -> ReLU, head, losses, dA and the
+        # adjoint of the last activation in one launch per branch (SCNB_HEADS=split keeps the five-launch chain)
+        self.heads_fused = bool(self.hs_fused and mode == "mixmatch" and cfg.fuse_heads and self.H in (128, 256) and self.C <= 32
+                                and (not self.use_dan or self.D <= 32) and os.environ.get("SCNB_HEADS", "fused") != "split")
         self._ev_grl, self._ev_csc, self._ev_zero = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         self._ev_teacher, self._ev_plan, self._ev_bnrun, self._ev_z1 = (torch.cuda.Event() for _ in range(4))
         self._ev_dz = [torch.cuda.Event() for _ in self.widths]
@@ -722,7 +726,9 @@ class TrainEngine(object):
         # BatchNorm running statistics as soon as the forward statistics exist, off the critical path (the
         # stream of the MixUp plan is idle by now); the eval-mode teacher must have read the OLD running statistics first
         self._bn_running_done = False
-        if sW is not main:
+        hf = self.heads_fused
+
+        def running_update():
             sB = self._side[3]          # the plan's branch, long idle by now
             self._after(sB, main)
             if teacher_async:
@@ -730,18 +736,35 @@ class TrainEngine(object):
             self._bn_running_update(sB.cuda_stream)
             self._ev_bnrun.record(sB)
             self._bn_running_done = True
+        if sW is not main and not hf:
+            running_update()
         Hh = self.H
         dA_last = self._view(self.dA, R, Hh)
+        if hf:
+            last = self.n_app - 1
+            pl = float(blk[last]["drop"].p)
+            keep_last = self._hidden_keep(last) if self.inj_hidden_keep is not None else (ptr(self.keepbuf[last]) if pl > 0.0 else None)
+            head_in = (ptr(self.Zs[last]), ptr(self.As[last]), None if self.comm is not None else ptr(self.pf[last]), ptr(self.stats[last]),
+                       self.P(blk[last]["g"]), self.P(blk[last]["beta"]), keep_last, pl, Hh, R)
+            seg = self._seg_host.ctypes.data
         # branch D: domain adversary head, its loss and the reversed gradient into the embedding
         if self.use_dan:
             d0, d1 = self._dan_names()
             Ae = self.As[-1][nb:]
             self._after(sD, main)
             sd = sD.cuda_stream
-            call("scnb_sgemm", 0, 1, self.Rd, Hh, Hh, ptr(Ae), Hh, self.P(d0 + ".weight"), Hh, ptr(self.Hd), Hh, 1.0, 0.0,
-                 self.P(d0 + ".bias"), 1, None, sd)
             scale = ptr(self.pconf) if c.dan_scale_loss_pseudoconf else None
-            if self.fuse_dan:
+            if hf:
+                call("scnb_hs_dan_head", *head_in, nb, self.n_seg, seg, self.P(d0 + ".weight"), self.P(d0 + ".bias"),
+                     self.P(d1 + ".weight"), self.P(d1 + ".bias"), self.D, ptr(self.counts[2:]), ptr(self.base_dom), ptr(self.srcA), nb,
+                     scale, float(self.dan_weight), ptr(self.Hd), ptr(self.dHd), ptr(self.dlog), ptr(self.dlabel), ptr(self.ddlog),
+                     ptr(self.loss_buf[4:]), ptr(self.dYs[last]), ptr(self.pb[last]), sd)
+            else:
+                call("scnb_sgemm", 0, 1, self.Rd, Hh, Hh, ptr(Ae), Hh, self.P(d0 + ".weight"), Hh, ptr(self.Hd), Hh, 1.0, 0.0,
+                     self.P(d0 + ".bias"), 1, None, sd)
+            if hf:
+                pass
+            elif self.fuse_dan:
                 call("scnb_dan_tail_fused", ptr(self.Hd), self.P(d1 + ".weight"), self.P(d1 + ".bias"), Hh, self.D, self.Rd,
                      ptr(self.counts[2:]), ptr(self.base_dom), ptr(self.srcA), nb, scale, ptr(self.dlog), ptr(self.dlabel),
                      ptr(self.ddlog), ptr(self.dHd), ptr(self.loss_buf[4:]), sd)
@@ -754,8 +777,9 @@ class TrainEngine(object):
                 call("scnb_sgemm", 0, 0, self.Rd, Hh, self.D, ptr(self.ddlog), self.D, self.P(d1 + ".weight"), Hh, ptr(self.dHd),
                      Hh, 1.0, 0.0, None, 0, ptr(self.Hd), sd)
             # gradient reversal: dEmbed = -w * dHd W  (model.py:338)
-            call("scnb_sgemm", 0, 0, self.Rd, Hh, Hh, ptr(self.dHd), Hh, self.P(d0 + ".weight"), Hh, ptr(dA_last[nb:]), Hh,
-                 -self.dan_weight, 0.0, None, 0, None, sd)
+            if not hf:
+                call("scnb_sgemm", 0, 0, self.Rd, Hh, Hh, ptr(self.dHd), Hh, self.P(d0 + ".weight"), Hh, ptr(dA_last[nb:]), Hh,
+                     -self.dan_weight, 0.0, None, 0, None, sd)
             if sD is not main:
                 self._ev_grl.record(sD)
             # the head's own weight gradients (needed only by the optimizer)
@@ -774,7 +798,11 @@ class TrainEngine(object):
         # -- classifier, losses + dLogits (losses.py:896-923, 1224-1243; trainer.py:651-656) and dA of the classifier
         if teacher_async:
             main.wait_event(self._ev_teacher)
-        if self.fuse_classif:
+        if hf:
+            call("scnb_hs_classif_head", *head_in, self.n_seg, seg, self.P("model.classif.0.weight"), self.P("model.classif.0.bias"), C, U, L,
+                 ptr(self.counts), ptr(self.Ycat), ptr(self.srcA), ptr(self.srcB), ptr(self.gam), ptr(self.class_weight),
+                 self.unsup_weight, ptr(self.logits), ptr(self.dlogits), ptr(self.loss_buf), ptr(self.dYs[last]), ptr(self.pb[last]), st)
+        elif self.fuse_classif:
             call("scnb_classif_mixmatch_fused", ptr(self.As[-1]), self.P("model.classif.0.weight"), self.P("model.classif.0.bias"),
                  Hh, C, U, L, ptr(self.counts), ptr(self.Ycat), ptr(self.srcA), ptr(self.srcB), ptr(self.gam),
                  ptr(self.class_weight), self.unsup_weight, ptr(self.logits), ptr(self.dlogits), ptr(dA_last), ptr(self.loss_buf), st)
@@ -795,6 +823,8 @@ class TrainEngine(object):
         call("scnb_colsum", ptr(self.dlogits), nb, C, C, self.Gp("model.classif.0.bias"), 1, sw)
         if self.use_dan and sD is not main:
             main.wait_event(self._ev_grl)
+        if sW is not main and hf:
+            running_update()      # the statistics of the last application are written by the head kernels
         published = False
         if self.post_launch is not None and sW is not main:
             # the step's loss scalars are final once both heads have run: a feeding pipeline's read-back goes out now, on
@@ -809,7 +839,9 @@ class TrainEngine(object):
         self._published = published
         dZ_first = self._student_backward(main, sW, rng, dA_last)
         self._dz_planes_ready = bool(self.w1_tc)
-        if self.w1_tc:   # MixUp adjoint + bf16 operand planes of dZ1 for the tensor-core dW1 kernel, one launch
+        if dZ_first is None:
+            pass         # (scnb_hs_bwd_in_unmix_planes has written dZ1 and its planes)
+        elif self.w1_tc:   # MixUp adjoint + bf16 operand planes of dZ1 for the tensor-core dW1 kernel, one launch
             call("scnb_unmix_rows_planes", ptr(dZ_first), H0, ptr(self.inv3), ptr(self.coef3), nb, ptr(self.dZ1), ptr(self.dz_hi),
                  ptr(self.dz_lo), st)
         else:
@@ -875,6 +907,17 @@ class TrainEngine(object):
             a0 = self.n_app - 1
         else:
             a0 = 0
+        pl_args = (float(c.T if c.T is not None else 1.0), int(c.T is not None), float(c.pseudolabel_min_confidence))
+        if (self.hs_fused and KU % 32 == 0 and self.fuse_classif and K == 1 and C <= 32 and self.H % 128 == 0
+                and os.environ.get("SCNB_TEACHER_HEAD", "bn") == "bn"):
+            # last eval-mode BatchNorm -> ReLU applied by the head kernel as it loads a row: one launch less on the teacher's
+            # chain, which joins the student in front of the classifier head
+            last = self.n_app - 1
+            rm, rv = tbn(last)
+            call("scnb_teacher_head_bn_fused", ptr(tz), ptr(tw(blk[last]["g"])), ptr(tw(blk[last]["beta"])), ptr(rm), ptr(rv),
+                 ptr(tw("model.classif.0.weight")), ptr(tw("model.classif.0.bias")), self.H, C, K, U, pl_args[0], pl_args[1], pl_args[2],
+                 ptr(self.t_logits), ptr(self.Ycat), ptr(self.conf), ptr(self.confident), ptr(self.pl_scratch), ptr(self.lab_ids), L, st)
+            return
         for a in range(a0, self.n_app):
             rm, rv = tbn(a)
             call("scnb_bn_act_fwd", ptr(tz), ptr(self.TA[a]), None, self.widths[a], 1, ptr(seg_t), KU, 0, ptr(tw(blk[a]["g"])),
@@ -937,7 +980,8 @@ class TrainEngine(object):
             dp = self.comm is not None
             inj = self.inj_hidden_keep is not None
             pd = [float(b["drop"].p) for b in blk]
-            keep_out = lambda a: (ptr(self.keepbuf[a]) if (a < self.n_app - 1 and not inj and pd[a] > 0.0) else None)
+            hf = bool(getattr(self, "heads_fused", False))
+            keep_out = lambda a: (ptr(self.keepbuf[a]) if ((a < self.n_app - 1 or hf) and not inj and pd[a] > 0.0) else None)
             keep_in = lambda a: (self._hidden_keep(a) if inj else (ptr(self.keepbuf[a]) if pd[a] > 0.0 else None))
             if self.mode != "mixmatch":   # no MixUp in front: tile statistics (and the dropout keep bytes) of the first layer's output
                 call("scnb_hs_mix", ptr(self.Zs[0]), self.widths[0], None, None, None, R, ptr(self.Zs[0]), ptr(self.pf[0]), keep_out(0), rng,
@@ -952,6 +996,8 @@ class TrainEngine(object):
             a = self.n_app - 1
             if dp:
                 self._xchg(0, a, st)
+            if hf:
+                return          # the head kernels apply the last BatchNorm -> Dropout -> ReLU themselves
             call("scnb_hs_act", ptr(self.Zs[a]), ptr(self.As[a]), self.widths[a], R, self.n_seg, seg, None if dp else ptr(self.pf[a]), self.P(blk[a]["g"]),
                  self.P(blk[a]["beta"]), ptr(self.stats[a]), self._hidden_keep(a), rng, SID_HID + a, float(blk[a]["drop"].p), st)
             return
@@ -1038,8 +1084,9 @@ class TrainEngine(object):
             if not getattr(self, "_zero_at_end", False):
                 main.wait_event(self._ev_zero)   # BatchNorm gamma / beta gradients accumulate into zeroed buffers
         dp = self.comm is not None
-        call("scnb_hs_bwd_act", ptr(dA), ptr(self.Zs[last]), ptr(self.As[last]), self.widths[last], R, self.n_seg, seg,
-             ptr(self.stats[last]), float(blk[last]["drop"].p), ptr(self.dYs[last]), ptr(self.pb[last]), st)
+        if not getattr(self, "heads_fused", False):
+            call("scnb_hs_bwd_act", ptr(dA), ptr(self.Zs[last]), ptr(self.As[last]), self.widths[last], R, self.n_seg, seg,
+                 ptr(self.stats[last]), float(blk[last]["drop"].p), ptr(self.dYs[last]), ptr(self.pb[last]), st)
         for a in range(last, 0, -1):
             k, n = self.widths[a], self.widths[a - 1]
             if dp:
@@ -1055,6 +1102,15 @@ class TrainEngine(object):
             call("scnb_hs_dw", ptr(self.dZs[a]), k, ptr(self.As[a - 1]), n, R, self.Gp(blk[a]["W"]), self.Gp(blk[a]["b"]), sw)
         if dp:
             self._xchg(1, 0, st)
+        if self.mode == "mixmatch" and self.w1_tc and os.environ.get("SCNB_BWD_IN", "split") == "fused":
+            # BatchNorm backward of application 0 + MixUp adjoint + bf16 operand planes of dZ1 in one launch (head_ops.cu).
+            # Measured slower than the two launches it replaces (16.4 us against 4.2 + 6.7: one column per thread is a chain of
+            # ~8 dependent round trips), so it is an off-by-default switch (SCNB_BWD_IN=fused)
+            call("scnb_hs_bwd_in_unmix_planes", ptr(self.dYs[0]), ptr(self.Zs[0]), self.widths[0], R, self.n_seg, seg, ptr(self.stats[0]),
+                 None if dp else ptr(self.pb[0]), self.P(blk[0]["g"]), self.Gp(blk[0]["g"]), self.Gp(blk[0]["beta"]),
+                 ptr(self.bmean[0]) if dp else None, self.Gp(blk[0]["b"]), ptr(self.inv3), ptr(self.coef3), self.nb, ptr(self.dZ1),
+                 ptr(self.dz_hi), ptr(self.dz_lo), st)
+            return None     # dZ1 and its planes are written
         call("scnb_hs_bwd_in", ptr(self.dYs[0]), ptr(self.Zs[0]), self.widths[0], R, self.n_seg, seg, ptr(self.stats[0]),
              None if dp else ptr(self.pb[0]), self.P(blk[0]["g"]), self.Gp(blk[0]["g"]), self.Gp(blk[0]["beta"]), ptr(self.dZs[0]),
              ptr(self.bmean[0]) if dp else None, self.Gp(blk[0]["b"]), st)

@@ -199,3 +199,54 @@ def test_device_sampler_tables_follow_dataloader_semantics():
     first = t["l"].clone()
     eng.sample_epoch_tables(n_steps, generator=gen)
     assert eng._tabs["l"].data_ptr() == ptr_before and not torch.equal(eng._tabs["l"], first)
+
+
+@pytest.mark.parametrize("H,use_dan", [(256, True), (128, True), (256, False)])
+def test_fused_heads_match_the_split_chain_on_device_randomness(monkeypatch, H, use_dan):
+    """head_ops.cu (last BatchNorm -> Dropout -> ReLU + head + losses + adjoint of the activation in one launch per branch; the
+    adversary branch as a thread-block cluster) against the five-launch chain it replaces (SCNB_HEADS=split), on the
+    device's own randomness: the dropout mask of the last application now arrives as keep bytes written by the producer of
+    Z[last] instead of a Philox call in scnb_hs_act -- same stream, so the two engines must see the same mask.  Losses, every
+    gradient and the BatchNorm statistics of the first step agree within fp32 summation-order noise."""
+    from scnym_b200.engine import EngineConfig, TrainEngine
+    from scnym_b200.model import CellTypeCLF, DANN
+    from scnym_b200.synth import synth_device_csr
+    dev = torch.device("cuda", 0)
+    G, C, L, U = 3000, 11, 96, 64
+    lab, y = synth_device_csr(1024, G, 0.05, C, seed=0, device=dev)
+    unl, _ = synth_device_csr(1024, G, 0.05, C, seed=1, device=dev)
+    out = []
+    for mode in ("fused", "split"):
+        monkeypatch.setenv("SCNB_HEADS", mode)
+        monkeypatch.setenv("SCNB_BWD_IN", mode)     # likewise scnb_hs_bwd_in_unmix_planes against scnb_hs_bwd_in + scnb_unmix_rows_planes
+        monkeypatch.setenv("SCNB_W1_UPDATE", "tc")   # (the tensor-core dW1 path, which reads dZ1 as operand planes, at this small batch)
+        torch.manual_seed(3)
+        model = CellTypeCLF(n_genes=G, n_cell_types=C, n_hidden=H, n_hidden_init=256, n_layers=2)
+        dann = DANN(model, n_domains=2) if use_dan else None
+        cfg = EngineConfig(n_augmentations=1, T=0.5, augment_pseudolabels=False, pseudolabel_min_confidence=0.0, mixup_alpha=0.3,
+                           use_dan=use_dan, optimizer="sgd", lr=0.0, seed=11, use_cuda_graph=False)
+        eng = TrainEngine(model.to(dev), cfg, lab, y.to(torch.int32), L, unlabeled=unl, unlabeled_batch_size=U, dann=dann,
+                          mode="mixmatch")
+        assert eng.hs_fused and eng.w1_tc and eng.heads_fused == (mode == "fused")
+        eng.set_weights(1.0, 0.1)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(5)
+        eng.sample_epoch_tables(2, generator=gen)
+        eng.step()
+        torch.cuda.synchronize()
+        last = eng.n_app - 1
+        out.append(dict(losses=eng.losses(), grad=eng.arena.grad.detach().clone(), stats=eng.stats[last].detach().clone(),
+                        A=eng.As[last].detach().clone(), dY=eng.dYs[last].detach().clone(), logits=eng.logits.detach().clone(),
+                        dZ1=eng.dZ1.detach().clone(), dz_hi=eng.dz_hi.detach().clone(), dz_lo=eng.dz_lo.detach().clone()))
+    a, b = out
+    assert torch.equal(a["A"] > 0, b["A"] > 0), "the two paths applied different dropout masks / ReLU gates"
+    for k in ("dz_hi", "dz_lo"):     # bf16 planes: compare as numbers
+        a[k], b[k] = a[k].view(torch.bfloat16).float(), b[k].view(torch.bfloat16).float()
+    d = (a["dz_hi"] + a["dz_lo"]) - (b["dz_hi"] + b["dz_lo"])
+    assert float(d.abs().max()) <= 2e-5 * float((b["dz_hi"] + b["dz_lo"]).abs().max())
+    for k in ("stats", "A", "logits", "dY", "grad", "dZ1"):
+        den = float(b[k].abs().max()) + 1e-30
+        err = float((a[k] - b[k]).abs().max()) / den
+        assert err < 2e-5, (k, err)
+    for k in ("sup_loss", "unsup_loss") + (("dan_loss",) if use_dan else ()):
+        assert abs(a["losses"][k] - b["losses"][k]) <= 2e-6 * max(1.0, abs(b["losses"][k])), (k, a["losses"][k], b["losses"][k])

@@ -34,7 +34,16 @@ def test_config2_full_shape_step_matches_oracle():
     """BASELINE config 2: G = 20 000, L = U = 256, H0 = H = 256, n_layers = 2, 5 % CSR, MixMatch + DAN (2 inferred domains), Adam."""
     eng, _ = _run(dict(G=20000, L=256, U=256, C=16, H0=256, H=256, n_layers=2, opt_name="adam", lr=1e-3, wd=1e-4, seed=31,
                        density=0.05, n_cells=768))
-    assert eng.w1_emits_planes and eng.hs_fused
+    assert eng.w1_emits_planes and eng.hs_fused and eng.heads_fused
+
+
+def test_config2_full_shape_split_heads_match_oracle(monkeypatch):
+    """The same shape with the heads as separate launches behind scnb_hs_act (SCNB_HEADS=split: the chain head_ops.cu replaces,
+    still taken for widths other than 128 / 256 or more than 32 classes / domains)."""
+    monkeypatch.setenv("SCNB_HEADS", "split")
+    eng, _ = _run(dict(G=20000, L=256, U=256, C=16, H0=256, H=256, n_layers=2, opt_name="adam", lr=1e-3, wd=1e-4, seed=37,
+                       density=0.05, n_cells=768))
+    assert eng.hs_fused and not eng.heads_fused
 
 
 def test_config2_shape_unfused_hidden_stack_matches_oracle():
@@ -60,6 +69,8 @@ def test_config2_shape_unfused_hidden_stack_matches_oracle():
     dict(G=900, L=64, U=32, C=4, H0=64, H=128, n_layers=1, opt_name="sgd", lr=0.05, seed=52),                     # one hidden Linear
     dict(G=1200, L=96, U=96, C=5, H0=192, H=192, n_layers=2, use_dan=False, opt_name="adamw", lr=1e-3, wd=1e-2, seed=53),  # no adversary
     dict(G=800, L=32, U=32, C=3, H0=512, H=256, n_layers=2, opt_name="adam", seed=54),                             # K = 512 operand panel
+    dict(G=1000, L=64, U=96, C=32, H0=128, H=128, n_layers=2, D_given=5, opt_name="adam", seed=55),                # fused heads, cluster of 2, 32 classes
+    dict(G=1100, L=96, U=32, C=7, H0=256, H=256, n_layers=2, use_dan=False, opt_name="adadelta", lr=1.0, seed=56),  # fused classifier head alone
 ])
 def test_fused_hidden_stack_shapes_match_oracle(kw):
     """Other shapes of the fused hidden stack (hidden_ops.cu): shared modules, 2-4 applications, 2 / 3 segments,
@@ -78,7 +89,7 @@ def test_config3_shape_step_matches_oracle():
     """BASELINE config 3 (per-rank shape): G = 30 000, 8 GIVEN domains, L = U = 256."""
     eng, _ = _run(dict(G=30000, L=256, U=256, C=16, H0=256, H=256, n_layers=2, D_given=8, opt_name="adam", lr=1e-3, wd=1e-4,
                        seed=33, density=0.05, n_cells=768))
-    assert eng.D == 8 and eng.hs_fused
+    assert eng.D == 8 and eng.hs_fused and eng.heads_fused
 
 
 def test_config5_shape_step_matches_oracle():
