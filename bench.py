@@ -258,6 +258,9 @@ def time_kernels(eng, n_steps=12):
         return r
 
     import scnym_b200.engine as E
+    ws = getattr(eng, "_gemm_ws", None)
+    if ws:   # the eager single-stream pass issues the large products on THIS stream: lend it the main chain's operand-plane workspace
+        _lib.call("scnb_gemm_tc_workspace", stream.cuda_stream, ws[0].data_ptr() + (-ws[0].data_ptr()) % 1024, ws[0].numel() - 1024)
     graph_flag, ms_flag = eng.cfg.use_cuda_graph, eng.cfg.multi_stream
     eng.cfg.use_cuda_graph = False
     eng.cfg.multi_stream = False     # one stream, so that the events bracket each kernel

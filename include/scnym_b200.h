@@ -199,8 +199,17 @@ int scnb_sgemm(int transA, int transB, int M, int N, int K, const float* A, int 
                int ldc, float alpha, float beta, const float* bias, int relu, const float* gate /*ReLU-bwd mask, C layout*/,
                void* stream);
 /* scnb_sgemm sends products of at least `flops` = 2 M N K (default 2e9, 0 = never) to the tcgen05 kernel (bf16x3 split,
- * fp32 accumulation in TMEM, operands converted from fp32 inside the kernel); smaller ones keep the 3xTF32 mma.sync kernel. */
+ * fp32 accumulation in TMEM, operands converted from fp32 inside the kernel, or beforehand into planes -- below); smaller ones keep the 3xTF32 mma.sync kernel. */
 int scnb_gemm_tc_min_flops(long long flops);
+int scnb_gemm_tc_min_flops_get(long long* flops_out);
+/* Planes form of the tcgen05 product (tc_gemm.cu): when the caller has registered a workspace for the stream a large product
+ * is issued on, both operands are first written once as bf16 hi / lo planes tiled [256 rows][32 k] in the shared-memory image
+ * the MMA wants (scnb_gemm_tc_workspace_bytes(M, N, K) bytes), and the product itself only bulk-copies tiles and issues MMAs
+ * (256 x 256 tile of C per CTA, two accumulators in TMEM).  The library allocates nothing: the engine owns the buffers
+ * (1024-byte aligned) and registers them before any graph capture; buf = NULL unregisters the stream. */
+int scnb_gemm_tc_workspace(void* stream, void* buf, long long bytes);
+int scnb_gemm_tc_workspace_bytes(int M, int N, int K, long long* bytes_out);
+int scnb_gemm_tc_planes_count(long long* count_out);   /* products issued in the planes form so far */
 int scnb_colsum(const float* A, int M, int N, int lda, float* out, int accumulate, void* stream);
 int scnb_relu_bwd(const float* g, const float* y, float* out, long long n, void* stream);
 

@@ -50,6 +50,10 @@ SIGNATURES = {
     "scnb_csr_w1_bwd_optim": [I, P, P, P, I, I, I, P, P, P, P, P, P, P],
     "scnb_sgemm": [I, I, I, I, I, P, I, P, I, P, I, F, F, P, I, P, P],
     "scnb_gemm_tc_min_flops": [L],
+    "scnb_gemm_tc_min_flops_get": [P],
+    "scnb_gemm_tc_workspace": [P, P, L],
+    "scnb_gemm_tc_workspace_bytes": [I, I, I, P],
+    "scnb_gemm_tc_planes_count": [P],
     "scnb_colsum": [P, I, I, I, P, I, P],
     "scnb_relu_bwd": [P, P, P, L, P],
     "scnb_bn_eval_bwd": [P, P, I, I, I, P, P, P, P],

@@ -460,6 +460,53 @@ __device__ __forceinline__ void bnv_colsum8(F8& x, float (*red)[8]) {
   }
 }
 
+// Large batches (config 5: 16 384 rows): the rows of a segment are split over the CTAs of a thread-block CLUSTER
+// (cluster dims (1, 1, CL), cluster rank = blockIdx.z), so that a launch has CL times as many CTAs in flight on the same
+// 32-byte column group; the per-CTA column sums meet through distributed shared memory and are added in rank order
+// (deterministic).  One launch, no workspace.  With gridDim.z == 1 nothing changes.
+__device__ __forceinline__ void bnv_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// a, b: this CTA's 8 + 8 block sums (in every thread) -> the cluster's sums (in every thread).  xs: shared [32].
+__device__ __forceinline__ void bnv_cluster_sum16(F8& a, F8& b, float* xs) {
+  const int CL = (int)gridDim.z;
+  if (CL == 1) return;
+  const int t = threadIdx.x;
+  if (t < 16) {
+    float mine = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (t == j) mine = a.v[j];
+      if (t == 8 + j) mine = b.v[j];
+    }
+    xs[t] = mine;
+  }
+  bnv_cluster_sync();
+  if (t < 16) {
+    const uint32_t mine_addr = (uint32_t)__cvta_generic_to_shared(xs + t);
+    float acc = 0.f;
+    for (int p = 0; p < CL; ++p) {
+      uint32_t ra;
+      float v;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(mine_addr), "r"(p));
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+      acc += v;
+    }
+    xs[16 + t] = acc;
+  }
+  bnv_cluster_sync();            // nobody overwrites (or leaves with) xs[0..15] while a peer still reads it
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a.v[j] = xs[16 + j]; b.v[j] = xs[24 + j]; }
+  __syncthreads();
+}
+// this CTA's share [rb, re) of the rows [r0, r1) of a segment
+__device__ __forceinline__ void bnv_row_share(int r0, int r1, int& rb, int& re) {
+  const int CL = (int)gridDim.z;
+  const int chunk = (r1 - r0 + CL - 1) / CL;
+  rb = min(r1, r0 + (int)blockIdx.z * chunk);
+  re = min(r1, rb + chunk);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Cross-rank BatchNorm statistics through peer memory (data-parallel training, one process per GPU).
 // Every rank owns an exchange buffer that all ranks can address (CUDA IPC over NVLink / NVSwitch; bufs[r] is rank
@@ -545,8 +592,10 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_fwd_v8(const float* __restrict
   const uint32_t thr16 = (uint32_t)(p_drop * 65536.0f + 0.5f);
   const float drop_scale = 1.0f / (1.0f - p_drop);
   F8 mean, invstd;
-  const bool cached = (n <= 2 * BNV_T) && !partial_out && !ext_sums && !px.bufs;
+  const bool cached = (n <= 2 * BNV_T) && !partial_out && !ext_sums && !px.bufs && gridDim.z == 1;
   const bool has0 = t < n, has1 = t + BNV_T < n;
+  int rb, re;                      // this CTA's rows of the segment (all of them unless the launch is a cluster launch)
+  bnv_row_share(r0, r1, rb, re);
   F8 zc0, zc1;
   if (partial_out) {  // data-parallel pass 1: local sums only
     F8 a1, a2;
@@ -613,13 +662,19 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_fwd_v8(const float* __restrict
 #pragma unroll
       for (int j = 0; j < 8; ++j) mean.v[j] = (has0 ? zc0.v[j] : 0.f) + (has1 ? zc1.v[j] : 0.f);
     } else {
-      for (int r = r0 + t; r < r1; r += BNV_T) {
+      for (int r = rb + t; r < re; r += BNV_T) {
         const F8 z = ld8(Z + (size_t)r * H + c0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) mean.v[j] += z.v[j];
       }
     }
     bnv_colsum8(mean, red1);
+    {
+      F8 dummy;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dummy.v[j] = 0.f;
+      bnv_cluster_sum16(mean, dummy, xs);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) { mean.v[j] *= inv_n; var.v[j] = 0.f; }
     if (cached) {
@@ -629,19 +684,25 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_fwd_v8(const float* __restrict
         var.v[j] = fmaf(d0, d0, d1 * d1);
       }
     } else {
-      for (int r = r0 + t; r < r1; r += BNV_T) {
+      for (int r = rb + t; r < re; r += BNV_T) {
         const F8 z = ld8(Z + (size_t)r * H + c0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { const float d = z.v[j] - mean.v[j]; var.v[j] = fmaf(d, d, var.v[j]); }
       }
     }
     bnv_colsum8(var, red2);
+    {
+      F8 dummy;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dummy.v[j] = 0.f;
+      bnv_cluster_sum16(var, dummy, xs);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) var.v[j] *= inv_n;
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) invstd.v[j] = 1.0f / sqrtf(var.v[j] + BN_EPS);
-  if (stats && t < 8) {
+  if (stats && t < 8 && blockIdx.z == 0) {
     // dynamic register indexing would spill: select with a compile-time unrolled loop
     float m = 0.f, v = 0.f, is = 0.f;
 #pragma unroll
@@ -650,7 +711,7 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_fwd_v8(const float* __restrict
     stats[((size_t)s * 3 + 1) * H + c0 + t] = v;
     stats[((size_t)s * 3 + 2) * H + c0 + t] = is;
   }
-  for (int r = r0 + t; r < r1; r += BNV_T) {
+  for (int r = rb + t; r < re; r += BNV_T) {
     const size_t o = (size_t)r * H + c0;
     const F8 z = cached ? (r == r0 + t ? zc0 : zc1) : ld8(Z + o);
     uint32_t kb = 0xffu;
@@ -673,7 +734,7 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_fwd_v8(const float* __restrict
     F8 zero;
 #pragma unroll
     for (int j = 0; j < 8; ++j) zero.v[j] = 0.f;
-    for (int r = r1 + t; r < max_rows; r += BNV_T) {
+    for (int r = r1 + t + (int)blockIdx.z * BNV_T; r < max_rows; r += BNV_T * (int)gridDim.z) {
       st8(Aout + (size_t)r * H + c0, zero);
       if (pre_out) st8(pre_out + (size_t)r * H + c0, zero);
     }
@@ -711,7 +772,9 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_bwd_v8(const float* __restrict
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1.v[j] = s2.v[j] = 0.f;
   float inv_n = 1.0f / (float)max(n, 1);
-  const bool cached = (n <= 2 * BNV_T) && !ext_sums && !partial_out;
+  const bool cached = (n <= 2 * BNV_T) && !ext_sums && !partial_out && gridDim.z == 1;
+  int rb, re;                      // this CTA's rows of the segment (all of them unless the launch is a cluster launch)
+  bnv_row_share(r0, r1, rb, re);
   F8 dyc0, zhc0, dyc1, zhc1;
   if (ext_sums) {
 #pragma unroll
@@ -722,7 +785,7 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_bwd_v8(const float* __restrict
     inv_n = 1.0f / fmaxf(ext_cnt[s], 1.f);
   } else {
     int slot = 0;
-    for (int r = r0 + t; r < r1; r += BNV_T, ++slot) {
+    for (int r = rb + t; r < re; r += BNV_T, ++slot) {
       const size_t o = (size_t)r * H + c0;
       const F8 da = ld8(dA + o), z = ld8(Z + o);
       F8 av;
@@ -744,7 +807,8 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_bwd_v8(const float* __restrict
     }
     bnv_colsum8(s1, red1);
     bnv_colsum8(s2, red2);
-    if (t < 8) {
+    bnv_cluster_sum16(s1, s2, xs);
+    if (t < 8 && blockIdx.z == 0) {
       float a = 0.f, b2 = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) if (j == t) { a = s1.v[j]; b2 = s2.v[j]; }
@@ -779,7 +843,7 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_bwd_v8(const float* __restrict
       st8(dZ + (size_t)r * H + c0, out);
     }
   } else {
-    for (int r = r0 + t; r < r1; r += BNV_T) {
+    for (int r = rb + t; r < re; r += BNV_T) {
       const size_t o = (size_t)r * H + c0;
       const F8 da = ld8(dA + o), z = ld8(Z + o);
       F8 av;
@@ -802,13 +866,40 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_bwd_v8(const float* __restrict
     F8 zero;
 #pragma unroll
     for (int j = 0; j < 8; ++j) zero.v[j] = 0.f;
-    for (int r = r1 + t; r < max_rows; r += BNV_T) st8(dZ + (size_t)r * H + c0, zero);
+    for (int r = r1 + t + (int)blockIdx.z * BNV_T; r < max_rows; r += BNV_T * (int)gridDim.z) st8(dZ + (size_t)r * H + c0, zero);
   }
 }
 
 // The vector kernels need whole 32-byte column groups and 16-byte aligned rows (the dropout stream is
 // defined per 8-column group there, so forward and backward must take the same decision: it depends
 // only on H and on pointer alignment, which the caller keeps identical between the two calls).
+// cluster launch with dims (1, 1, grid.z)
+template <typename... P, typename... A>
+static inline cudaError_t bnv_launch_cluster(void (*kern)(P...), dim3 grid, cudaStream_t st, A... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(BNV_T);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 1;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = grid.z;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
+}
+// rows of a segment are split over a cluster from this many rows on (SCNB_BN_CLUSTER_ROWS overrides; 0 = never)
+static int bnv_cluster_size(int max_rows) {
+  static int thr = -1;
+  if (thr < 0) {
+    const char* e = getenv("SCNB_BN_CLUSTER_ROWS");
+    thr = e ? atoi(e) : 4096;
+  }
+  if (thr <= 0 || max_rows < thr) return 1;
+  return max_rows >= 2 * thr ? 8 : 4;
+}
+
 static bool bn_vec8_ok(int H, const void* a, const void* b, const void* c, const void* d, const void* e, const void* f,
                        const void* mask) {
   const uintptr_t bits = (uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d | (uintptr_t)e | (uintptr_t)f;
@@ -886,6 +977,15 @@ extern "C" int scnb_bn_act_fwd(const float* Z, float* A, float* pre_out, int H, 
   }
   if (bn_vec8_ok(H, Z, A, pre_out, gamma, beta, stats, keep_mask)) {
     dim3 gridv(H / 8, n_seg);
+    const int cl = (dp_partial_out || dp_sums) ? 1 : bnv_cluster_size(max_rows);
+    if (cl > 1) {
+      gridv.z = cl;
+      bnv_launch_cluster(k_bn_act_fwd_v8, gridv, (cudaStream_t)stream, Z, A, pre_out, H, n_seg, seg_off_dev, max_rows, gamma, beta, stats,
+                         keep_mask, rng, stream_id, p_drop, relu, dp_partial_out, dp_sums, ext_cnt,
+                         PeerX{nullptr, nullptr, 0, 1, 0, 0, 0}, (float*)nullptr);
+      SCNB_CHECK_LAUNCH("bn_act_fwd/v8 cluster");
+      return SCNB_OK;
+    }
     scnb_launch_pdl(k_bn_act_fwd_v8, gridv, dim3(BNV_T), 0, (cudaStream_t)stream, Z, A, pre_out, H, n_seg, seg_off_dev, max_rows, gamma, beta, stats,
                                                                keep_mask, rng, stream_id, p_drop, relu, dp_partial_out, dp_sums,
                                                                ext_cnt, PeerX{nullptr, nullptr, 0, 1, 0, 0, 0}, (float*)nullptr);
@@ -989,6 +1089,15 @@ extern "C" int scnb_bn_act_bwd(const float* dA, const float* Z, const float* A, 
   const float* ext_cnt = dp_sums ? dp_sums + (size_t)n_seg * 2 * H : nullptr;
   if (bn_vec8_ok(H, dA, Z, A, gamma, dZ, stats, keep_mask)) {
     dim3 gridv(H / 8, n_seg);
+    const int cl = (dp_partial_out || dp_sums) ? 1 : bnv_cluster_size(max_rows);
+    if (cl > 1) {
+      gridv.z = cl;
+      bnv_launch_cluster(k_bn_act_bwd_v8, gridv, (cudaStream_t)stream, dA, Z, A, H, n_seg, seg_off_dev, max_rows, gamma, stats, keep_mask,
+                         rng, stream_id, p_drop, relu, dZ, dgamma, dbeta, dp_partial_out, dp_sums, ext_cnt,
+                         PeerX{nullptr, nullptr, 0, 1, 0, 0, 0});
+      SCNB_CHECK_LAUNCH("bn_act_bwd/v8 cluster");
+      return SCNB_OK;
+    }
     scnb_launch_pdl(k_bn_act_bwd_v8, gridv, dim3(BNV_T), 0, (cudaStream_t)stream, dA, Z, A, H, n_seg, seg_off_dev, max_rows, gamma, stats, keep_mask,
                                                                rng, stream_id, p_drop, relu, dZ, dgamma, dbeta, dp_partial_out,
                                                                dp_sums, ext_cnt, PeerX{nullptr, nullptr, 0, 1, 0, 0, 0});

@@ -276,6 +276,275 @@ k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int lda, const float
   }
 }
 
+// =====================================================================================================================
+// Planes form (used when the caller has registered a workspace for the stream, scnb_gemm_tc_workspace): the fp32 -> bf16
+// hi / lo conversion is taken OFF the tensor pipe's critical resource.  In k_gemm_tc above eight warps convert 12 288
+// floats per k-tile between two named barriers while one thread issues 6 MMAs (768 cycles): the staging warps, not the
+// tensor cores, set the pace (ncu: tensor pipe 17 % active, profiles/r01_ncu_full_v11_gemm_tc.txt).  Here
+//   (1) k_gemm_operand_planes writes each operand ONCE as two bf16 planes in the layout the MMA wants: tiles
+//       [row tile of 256][k tile of 32], every tile a ready-made SWIZZLE_64B K-major shared-memory image of 16 KB
+//       (HBM-bound streaming pass; the transposed operands of the input- and weight-gradient products go through a
+//       shared-memory transposition so that both the reads and the writes are full lines);
+//   (2) k_gemm_planes owns a 256 x 256 tile of C (two 128-lane fp32 accumulators = all 512 TMEM columns): one thread
+//       brings a stage in with four 16 KB bulk copies (A_hi, A_lo, B_hi, B_lo), one thread issues 12 MMAs per stage
+//       (M = 128, N = 256, K = 16; acc += A_lo B_hi + A_hi B_lo + A_hi B_hi), eight warps only run the epilogue.
+//       64 KB per 1536 MMA cycles per SM = 12 TB/s of L2 -> SM traffic over the chip when every SM runs at the tensor
+//       peak -- the same operand bytes per flop as fp32 tiles, but no instruction issue between L2 and the tensor core.
+// =====================================================================================================================
+#define GP_BM 256
+#define GP_BN 256
+#define GP_KT 32
+#define GP_TILE_BYTES (256u * 64u)        // one plane of one 256 x 32 tile
+#define GP_THREADS 320                    // warp 0: loader, warp 1: TMEM owner + MMA issuer, warps 2-9: epilogue
+
+// P[r][k] (r: the operand's row on the MMA's M or N axis, k: the reduction index) as tiled planes.
+//   TRANS == false: P[r][k] = X[r * ld + k]   (k contiguous)      one thread per (row, 8-k chunk)
+//   TRANS == true : P[r][k] = X[k * ld + r]   (r contiguous)      one CTA per tile, transposed through shared memory
+// Rows >= R and k >= K are written as zeros (the GEMM always multiplies full tiles).
+template <bool TRANS>
+__global__ void __launch_bounds__(256) k_gemm_operand_planes(const float* __restrict__ X, int ld, int R, int K, int n_rt, int n_kt,
+                                                             uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+  if (!TRANS) {
+    const long long total = (long long)n_rt * 256 * n_kt * 4;
+    const bool vec = (ld % 4 == 0) && ((uintptr_t)X % 16 == 0);
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+      const int cpr = n_kt * 4;
+      const int r = (int)(e / cpr), cg = (int)(e - (long long)r * cpr);
+      const int k0 = cg * 8;
+      float x[8];
+      if (r < R && vec && k0 + 8 <= K) {
+        const float4 a = *reinterpret_cast<const float4*>(X + (size_t)r * ld + k0);
+        const float4 b = *reinterpret_cast<const float4*>(X + (size_t)r * ld + k0 + 4);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = (r < R && k0 + j < K) ? X[(size_t)r * ld + k0 + j] : 0.f;
+      }
+      uint4 h, l;
+      tg5_split8(x, h, l);
+      const uint32_t rr = (uint32_t)(r & 255);
+      const size_t off = ((size_t)(r >> 8) * n_kt + (size_t)(cg >> 2)) * (256 * 32) + (size_t)rr * 32 +
+                         (size_t)(swz_chunk<32>((uint32_t)(cg & 3), rr) >> 1);
+      *reinterpret_cast<uint4*>(hi + off) = h;
+      *reinterpret_cast<uint4*>(lo + off) = l;
+    }
+  } else {
+    __shared__ float wt[32][257];
+    const int kt = blockIdx.x, rt = blockIdx.y, t = threadIdx.x;
+    const int r = rt * 256 + t;
+#pragma unroll 8
+    for (int kk = 0; kk < 32; ++kk) {
+      const int k = kt * 32 + kk;
+      wt[kk][t] = (r < R && k < K) ? X[(size_t)k * ld + r] : 0.f;
+    }
+    __syncthreads();
+    const size_t tile = ((size_t)rt * n_kt + kt) * (256 * 32);
+    // thread (row rr, chunk c): consecutive threads take the four chunks of one row, so a warp writes 8 full 64-byte rows
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int task = t + 256 * u;
+      const uint32_t rr = (uint32_t)(task >> 2), c = (uint32_t)(task & 3);
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = wt[8 * c + j][rr];
+      uint4 h, l;
+      tg5_split8(x, h, l);
+      const size_t off = tile + (size_t)rr * 32 + (size_t)(swz_chunk<32>(c, rr) >> 1);
+      *reinterpret_cast<uint4*>(hi + off) = h;
+      *reinterpret_cast<uint4*>(lo + off) = l;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GP_THREADS, 1)
+k_gemm_planes(int M, int N, int n_kt, const uint8_t* __restrict__ a_hi, const uint8_t* __restrict__ a_lo,
+              const uint8_t* __restrict__ b_hi, const uint8_t* __restrict__ b_lo, float* __restrict__ C, int ldc, float alpha, float beta,
+              const float* __restrict__ bias, int relu, const float* __restrict__ gate, int kt_chunk, int stages) {
+  constexpr uint32_t STAGE_BYTES = 4u * GP_TILE_BYTES;   // A_hi | A_lo | B_hi | B_lo = 64 KB
+  extern __shared__ uint8_t tc_smem_raw[];
+  const uint32_t raw = smem_u32(tc_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = tc_smem_raw + (base - raw);
+  const uint32_t bars = base + (uint32_t)stages * STAGE_BYTES;
+  const uint32_t bar_full = bars, bar_empty = bars + 8u * stages, bar_acc = bars + 16u * stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (size_t)stages * STAGE_BYTES + 16 * stages + 8);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mt = blockIdx.x, nt = blockIdx.y;
+  const int kt0 = blockIdx.z * kt_chunk, kt1 = min(n_kt, kt0 + kt_chunk);
+  const int n_it = max(kt1 - kt0, 0);
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(bar_full + 8u * s, 1);
+      mbar_init(bar_empty + 8u * s, 1);
+    }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== loader: four 16 KB bulk copies per stage =====
+      const size_t a_off0 = ((size_t)mt * n_kt + kt0) * GP_TILE_BYTES, b_off0 = ((size_t)nt * n_kt + kt0) * GP_TILE_BYTES;
+      for (int i = 0; i < n_it; ++i) {
+        const int s = i % stages;
+        mbar_wait(bar_empty + 8u * s, ((uint32_t)(i / stages) & 1u) ^ 1u);
+        const uint32_t stage = base + (uint32_t)s * STAGE_BYTES;
+        const uint32_t bar = bar_full + 8u * s;
+        mbar_arrive_expect_tx(bar, STAGE_BYTES);
+        const size_t ao = a_off0 + (size_t)i * GP_TILE_BYTES, bo = b_off0 + (size_t)i * GP_TILE_BYTES;
+        bulk_g2s(stage, a_hi + ao, GP_TILE_BYTES, bar);
+        bulk_g2s(stage + GP_TILE_BYTES, a_lo + ao, GP_TILE_BYTES, bar);
+        bulk_g2s(stage + 2u * GP_TILE_BYTES, b_hi + bo, GP_TILE_BYTES, bar);
+        bulk_g2s(stage + 3u * GP_TILE_BYTES, b_lo + bo, GP_TILE_BYTES, bar);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(GP_BN >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+      for (int i = 0; i < n_it; ++i) {
+        const int s = i % stages;
+        mbar_wait(bar_full + 8u * s, (uint32_t)(i / stages) & 1u);
+        tc_fence_after();
+        const uint32_t stage = base + (uint32_t)s * STAGE_BYTES;
+        const uint64_t bh = umma_desc_kmajor<GP_KT>(stage + 2u * GP_TILE_BYTES), bl = umma_desc_kmajor<GP_KT>(stage + 3u * GP_TILE_BYTES);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint64_t ah = umma_desc_kmajor<GP_KT>(stage + (uint32_t)h * (TC_M * 64u));
+          const uint64_t al = umma_desc_kmajor<GP_KT>(stage + GP_TILE_BYTES + (uint32_t)h * (TC_M * 64u));
+          const uint32_t d = tmem_base + (uint32_t)(h * GP_BN);
+#pragma unroll
+          for (int k = 0; k < GP_KT / 16; ++k) {
+            const uint64_t ko = (uint64_t)(k * 2);
+            tc_mma_bf16(d, al + ko, bh + ko, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            tc_mma_bf16(d, ah + ko, bl + ko, idesc, 1u);
+            tc_mma_bf16(d, ah + ko, bh + ko, idesc, 1u);
+          }
+        }
+        tc_commit(bar_empty + 8u * s);
+      }
+      if (n_it > 0) tc_commit(bar_acc);
+    }
+  } else if (n_it > 0) {
+    // ===== epilogue: accumulator `half` holds rows [128 half, 128 half + 128) of the tile; TMEM lane = row =====
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int m = mt * GP_BM + half * TC_M + q * 32 + lane;
+    const int n0 = nt * GP_BN;
+    const bool split = gridDim.z > 1;
+    for (int cb = 0; cb < GP_BN && n0 + cb < N; cb += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * GP_BN + cb);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (m < M) {
+        float* out = C + (size_t)m * ldc + n0 + cb;
+        const float* gt = gate ? gate + (size_t)m * ldc + n0 + cb : nullptr;
+        if (split) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + cb + j < N) atomicAdd(out + j, alpha * __uint_as_float(v[j]));
+        } else if (n0 + cb + 32 <= N) {      // full 32-column group: 16-byte accesses (ldc % 4 == 0, C 16-byte aligned)
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(alpha * __uint_as_float(v[j]), alpha * __uint_as_float(v[j + 1]), alpha * __uint_as_float(v[j + 2]),
+                                   alpha * __uint_as_float(v[j + 3]));
+            if (beta != 0.f) {
+              const float4 c0 = *reinterpret_cast<const float4*>(out + j);
+              o.x += beta * c0.x; o.y += beta * c0.y; o.z += beta * c0.z; o.w += beta * c0.w;
+            }
+            if (bias) {
+              const float4 bb = *reinterpret_cast<const float4*>(bias + n0 + cb + j);
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            if (gt) {
+              const float4 g4 = *reinterpret_cast<const float4*>(gt + j);
+              if (!(g4.x > 0.f)) o.x = 0.f;
+              if (!(g4.y > 0.f)) o.y = 0.f;
+              if (!(g4.z > 0.f)) o.z = 0.f;
+              if (!(g4.w > 0.f)) o.w = 0.f;
+            }
+            *reinterpret_cast<float4*>(out + j) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + cb + j;
+            if (n < N) {
+              float x = alpha * __uint_as_float(v[j]);
+              if (beta != 0.f) x += beta * out[j];
+              if (bias) x += bias[n];
+              if (relu) x = fmaxf(x, 0.f);
+              if (gt && !(gt[j] > 0.f)) x = 0.f;
+              out[j] = x;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// Workspaces for the operand planes, one per stream that issues large products (registered by the engine before any
+// capture: the library itself allocates nothing).  A product on a stream without a (large enough) workspace keeps the
+// in-kernel staging form above.
+struct Tg5Workspace { cudaStream_t st; uint8_t* buf; long long bytes; };
+#define TG5_MAX_WS 64
+static Tg5Workspace g_tg5_ws[TG5_MAX_WS];
+static int g_tg5_n_ws = 0;
+extern "C" int scnb_gemm_tc_workspace(void* stream, void* buf, long long bytes) {
+  SCNB_CHECK_ARG(bytes >= 0 && ((uintptr_t)buf % 1024) == 0, "gemm_tc_workspace: the buffer must be 1024-byte aligned");
+  int free_slot = -1;
+  for (int i = 0; i < g_tg5_n_ws; ++i) {
+    if (g_tg5_ws[i].buf && g_tg5_ws[i].st == (cudaStream_t)stream) {
+      g_tg5_ws[i].buf = (uint8_t*)buf;
+      g_tg5_ws[i].bytes = buf ? bytes : 0;
+      return SCNB_OK;
+    }
+    if (!g_tg5_ws[i].buf && free_slot < 0) free_slot = i;
+  }
+  if (!buf) return SCNB_OK;                      // nothing registered for this stream
+  if (free_slot < 0) {
+    SCNB_CHECK_ARG(g_tg5_n_ws < TG5_MAX_WS, "gemm_tc_workspace: more than %d streams with a workspace", TG5_MAX_WS);
+    free_slot = g_tg5_n_ws++;
+  }
+  g_tg5_ws[free_slot] = Tg5Workspace{(cudaStream_t)stream, (uint8_t*)buf, bytes};
+  return SCNB_OK;
+}
+// bytes of workspace a product C[M, N] = op(A) op(B) over K needs
+static long long tg5_workspace_bytes(int M, int N, int K) {
+  const long long n_kt = (K + GP_KT - 1) / GP_KT;
+  return 2ll * GP_TILE_BYTES * n_kt * ((M + GP_BM - 1) / GP_BM + (N + GP_BN - 1) / GP_BN);
+}
+extern "C" int scnb_gemm_tc_workspace_bytes(int M, int N, int K, long long* bytes_out) {
+  SCNB_CHECK_ARG(M > 0 && N > 0 && K > 0 && bytes_out, "gemm_tc_workspace_bytes: bad arguments");
+  *bytes_out = tg5_workspace_bytes(M, N, K);
+  return SCNB_OK;
+}
+
 // Minimum size at which the tensor-core kernel takes over from the latency-oriented mma.sync kernel (SCNB_GEMM_TC_MIN_FLOPS
 // overrides; 0 disables).  The 1024 x 256 x 256 products of config 2 stay below it.
 static double g_tg5_min_flops = -1.0;
@@ -293,6 +562,66 @@ extern "C" int scnb_gemm_tc_min_flops(long long flops) {
   return SCNB_OK;
 }
 
+static long long g_tg5_planes_launches = 0;
+// number of products issued in the planes form so far (tests assert that the path they mean to cover really ran)
+extern "C" int scnb_gemm_tc_planes_count(long long* count_out) {
+  SCNB_CHECK_ARG(count_out, "gemm_tc_planes_count: null pointer");
+  *count_out = g_tg5_planes_launches;
+  return SCNB_OK;
+}
+extern "C" int scnb_gemm_tc_min_flops_get(long long* flops_out) {
+  SCNB_CHECK_ARG(flops_out, "gemm_tc_min_flops_get: null pointer");
+  *flops_out = (long long)tg5_min_flops();
+  return SCNB_OK;
+}
+
+// The planes form.  Returns 1 if launched, 0 if not applicable (no workspace on this stream, operands not aligned).
+static int tg5_planes_try(int lay, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, float alpha,
+                          float beta, const float* bias, int relu, const float* gate, cudaStream_t st) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("SCNB_GEMM_TC_PLANES"); off = (e && e[0] == '0') ? 1 : 0; }
+  if (off) return 0;
+  const Tg5Workspace* ws = nullptr;
+  for (int i = 0; i < g_tg5_n_ws; ++i)
+    if (g_tg5_ws[i].st == st && g_tg5_ws[i].buf) ws = &g_tg5_ws[i];
+  if (!ws || tg5_workspace_bytes(M, N, K) > ws->bytes) return 0;
+  if ((ldc % 4) || ((uintptr_t)C % 16) || (bias && ((uintptr_t)bias % 16)) || (gate && ((uintptr_t)gate % 16))) return 0;
+  const int n_kt = scnb_cdiv(K, GP_KT), n_mt = scnb_cdiv(M, GP_BM), n_nt = scnb_cdiv(N, GP_BN);
+  const size_t a_plane = (size_t)n_mt * n_kt * GP_TILE_BYTES, b_plane = (size_t)n_nt * n_kt * GP_TILE_BYTES;
+  uint8_t* a_hi = ws->buf;
+  uint8_t* a_lo = a_hi + a_plane;
+  uint8_t* b_hi = a_lo + a_plane;
+  uint8_t* b_lo = b_hi + b_plane;
+  auto planes = [&](bool trans, const float* X, int ld, int R, int n_rt, uint8_t* hi, uint8_t* lo) {
+    if (trans) {
+      k_gemm_operand_planes<true><<<dim3(n_kt, n_rt), 256, 0, st>>>(X, ld, R, K, n_rt, n_kt, (uint16_t*)hi, (uint16_t*)lo);
+    } else {
+      const long long total = (long long)n_rt * 256 * n_kt * 4;
+      const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+      k_gemm_operand_planes<false><<<blocks, 256, 0, st>>>(X, ld, R, K, n_rt, n_kt, (uint16_t*)hi, (uint16_t*)lo);
+    }
+  };
+  planes(lay == 2, A, lda, M, n_mt, a_hi, a_lo);
+  planes(lay != 0, B, ldb, N, n_nt, b_hi, b_lo);
+  int splits = 1;
+  const bool splittable = !bias && !relu && !gate && (beta == 1.f);
+  if (splittable)
+    while (splits < 64 && (long long)n_mt * n_nt * splits < 148 && n_kt / (splits * 2) >= 16) splits *= 2;
+  const int kt_chunk = scnb_cdiv(n_kt, splits);
+  splits = scnb_cdiv(n_kt, kt_chunk);
+  const int stages = 3;
+  const size_t smem = 1024 + (size_t)stages * 4 * GP_TILE_BYTES + 16 * stages + 16 + 16;
+  cudaError_t e = cudaFuncSetAttribute(k_gemm_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    scnb_set_error("sgemm/tcgen05 planes: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+    return SCNB_ERR_CUDA;
+  }
+  k_gemm_planes<<<dim3(n_mt, n_nt, splits), GP_THREADS, smem, st>>>(M, N, n_kt, a_hi, a_lo, b_hi, b_lo, C, ldc, alpha, beta, bias, relu, gate,
+                                                                    kt_chunk, stages);
+  ++g_tg5_planes_launches;
+  return 1;
+}
+
 // Returns 1 if launched, 0 if not applicable, <0 on error.
 int scnb_gemm_tc_try(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                      float alpha, float beta, const float* bias, int relu, const float* gate, cudaStream_t st) {
@@ -301,6 +630,10 @@ int scnb_gemm_tc_try(int transA, int transB, int M, int N, int K, const float* A
   const double flops = 2.0 * M * (double)N * K;
   if (tg5_min_flops() <= 0.0 || flops < tg5_min_flops()) return 0;
   if (M < TG5_BM || N < 64 || K < 64) return 0;
+  {
+    const int rc = tg5_planes_try(lay, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, bias, relu, gate, st);
+    if (rc != 0) return rc;
+  }
   // tile width: 256 columns; SCNB_GEMM_TC_BN = 32 / 64 / 128 narrows the tiles (tools/bench_gemm_small.py).  Measured on the
   // 1024 x 256 x 256 products of config 2 the narrow-tile form needs 16.7 us against 10.4 us of the mma.sync kernel (TMEM
   // allocation, a 4-stage pipeline and the fp32 -> bf16 staging are fixed costs per CTA), so those stay where they are.

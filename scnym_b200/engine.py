@@ -36,6 +36,14 @@ SID_IN_U = 1          # + k : input dropout of teacher view k
 SID_HID = 16          # + application index : hidden dropout of the student super-batch
 
 
+def _release_gemm_ws(handles):
+    try:
+        for h in handles:
+            call("scnb_gemm_tc_workspace", h, None, 0)
+    except Exception:
+        pass
+
+
 @dataclass
 class EngineConfig:
     # MixMatchLoss (losses.py:603-610) / fit_model defaults (main.py:511-524, api.py:71-105)
@@ -427,6 +435,7 @@ class TrainEngine(object):
         self._bn_running_done = False
         self._dz_planes_ready = False
         self._side = None
+        self._gemm_ws = None
         fus = lambda c: (self.H % 128 == 0 and self.H // 128 in (1, 2, 4, 8) and c * self.H * 4 <= 96 * 1024)
         self.fuse_classif = bool(cfg.fuse_heads and fus(self.C))
         self.fuse_dan = bool(cfg.fuse_heads and self.use_dan and fus(self.D))
@@ -528,12 +537,45 @@ class TrainEngine(object):
         (raw `.data` edits, another library): the next step rebuilds the bf16 operand planes of W1T before it runs."""
         self._planes_version = None
 
+    def _reserve_gemm_ws(self):
+        """Workspaces for the operand planes of the large hidden-layer products (tc_gemm.cu, planes form), one per stream
+        that issues them (main chain, weight-gradient branch, domain-adversary branch, teacher branch).  Only when the
+        step has products above the tcgen05 take-over size (config 5: 16 384 x 1024 x 1024); allocated here, once, before
+        any capture -- the library itself allocates nothing.  An engine without such products clears whatever a dead
+        engine may have left registered for a recycled stream handle."""
+        if self._gemm_ws is not None or not self.cfg.multi_stream or os.environ.get("SCNB_MAIN_PRIORITY", "1") == "0":
+            return
+        self._streams()
+        if getattr(self, "_hi", None) is None:
+            self._hi = torch.cuda.Stream(device=self.dev, priority=-1)
+        handles = [s.cuda_stream for s in (self._hi, self._side[0], self._side[1], self._side[2])]
+        mf = ctypes.c_longlong(0)
+        call("scnb_gemm_tc_min_flops_get", ctypes.byref(mf))
+        R, W = int(self.Rmax), int(max(self.widths))
+        self._gemm_ws = []
+        if not (mf.value > 0 and 2.0 * R * W * W >= mf.value and R >= 128 and W >= 64):
+            for h in handles:
+                call("scnb_gemm_tc_workspace", h, None, 0)
+            return
+        need = ctypes.c_longlong(0)
+        n_bytes = 0
+        for (m, n, k) in ((R, W, W), (W, W, R)):
+            call("scnb_gemm_tc_workspace_bytes", m, n, k, ctypes.byref(need))
+            n_bytes = max(n_bytes, int(need.value))
+        for h in handles:
+            buf = torch.empty(n_bytes + 1024, dtype=torch.uint8, device=self.dev)
+            self._gemm_ws.append(buf)
+            call("scnb_gemm_tc_workspace", h, buf.data_ptr() + (-buf.data_ptr()) % 1024, n_bytes)
+        import weakref
+        weakref.finalize(self, _release_gemm_ws, handles)
+
     def _sync_planes(self):
         """With `w1_emits_planes` the step itself keeps the operand planes current.  They are rebuilt here, eagerly, when
         something outside the engine's kernels may have written the first-layer weight since: `load_state_dict` (a
         post-hook on the model calls `invalidate_planes`), in-place torch ops on the Parameter or on the arena (a torch
         optimizer, `p.copy_()`: both version counters are tracked -- a Parameter re-pointed at an arena view keeps its
         OWN counter, the arena's does not move), every new epoch of sampler tables, and an explicit `invalidate_planes()`."""
+        self._reserve_gemm_ws()
         if not self.w1_emits_planes:
             return
         w1 = self.arena.params[0]
@@ -604,16 +646,18 @@ class TrainEngine(object):
                  ptr(self.inj_in_keep_L), ptr(self.inj_pois_L), ptr(self.inj_rowu_L), rng, SID_IN_L, self._gene_cnt_ptr(),
                  int(ctr_off), st)
 
-    def _prologue_next(self, stream, rng):
+    def _prologue_next(self, stream, rng, splits=True):
         """The whole prologue of the step that comes AFTER the counters' current value, into the current set of batch
-        buffers, on one stream: sampler hand-off (table row state[0] % n), gather (RNG counter + 1), MixUp plan, splits."""
+        buffers, on one stream: sampler hand-off (table row state[0] % n), gather (RNG counter + 1), MixUp plan, splits
+        (`splits=False`: the caller enqueues `_build_csc` itself, later in the step)."""
         st = stream.cuda_stream
         self._prep(st, phases=1)
         side = self._side[5] if (self.host_mapped and self._side is not None and stream is self._side[4]) else None
         if side is None:
             self._gather_batch(st, rng, ctr_off=1)
             self._plan(self._all_confident, st)
-            self._build_csc(self.nb, st)
+            if splits:
+                self._build_csc(self.nb, st)
             return
         # Rows fetched from host memory take ~100 us.  What does not need them runs next to the fetch on a branch of its
         # own (the MixUp plan: only the hand-off), and what needs only their gene indices (the gene-block split points)
@@ -692,11 +736,17 @@ class TrainEngine(object):
             sF.wait_event(self._ev_adv if os.environ.get("SCNB_PREFETCH_AT", "start") == "start" else self._ev_fl)
             cur = self.__dict__["_cur"]
             self.__dict__["_cur"] = 1 - cur
+            # SCNB_SPLITS_LATE=1 (experiment): the split points of the next batch (1024 short CTAs) are enqueued behind the
+            # heads instead of next to them
+            splits_late = (os.environ.get("SCNB_SPLITS_LATE", "0") == "1") and not self.host_mapped
             try:
-                self._prologue_next(sF, rng)
+                self._prologue_next(sF, rng, splits=not splits_late)
             finally:
                 self.__dict__["_cur"] = cur
-            self._ev_pf.record(sF)
+            if not splits_late:
+                self._ev_pf.record(sF)
+        else:
+            splits_late = False
         # -- teacher (eval mode, losses.py:660-737).  With pseudolabel_min_confidence <= 0 every unlabeled row is
         #    "confident", so the MixUp plan and the student forward do not depend on the teacher: it runs on its own
         #    branch and is joined in front of the losses.
@@ -823,6 +873,17 @@ class TrainEngine(object):
         call("scnb_colsum", ptr(self.dlogits), nb, C, C, self.Gp("model.classif.0.bias"), 1, sw)
         if self.use_dan and sD is not main:
             main.wait_event(self._ev_grl)
+        if splits_late:
+            sF = self._side[4]
+            self._ev_fl.record(main)
+            sF.wait_event(self._ev_fl)
+            cur = self.__dict__["_cur"]
+            self.__dict__["_cur"] = 1 - cur
+            try:
+                self._build_csc(self.nb, sF.cuda_stream)
+            finally:
+                self.__dict__["_cur"] = cur
+            self._ev_pf.record(sF)
         if sW is not main and hf:
             running_update()      # the statistics of the last application are written by the head kernels
         published = False
@@ -1451,6 +1512,7 @@ class TrainEngine(object):
         if self.cfg.use_cuda_graph and (self._graph is None or self._graph_key != (self.unsup_weight, self.dan_weight)):
             if self.mode == "mixmatch" and self.cfg.mean_teacher and self.teacher_bn is None:
                 self.teacher_bn = [(b["bn"].running_mean.clone(), b["bn"].running_var.clone()) for b in self._blk]
+            self._reserve_gemm_ws()
             self._capture((self.unsup_weight, self.dan_weight))
 
     def begin_step(self):

@@ -143,7 +143,10 @@ def _bn_ref(Z, segs, g, b, keep, p):
 
 
 @pytest.mark.parametrize("H,segs,maxr", [(64, [(0, 40), (40, 70), (70, 130)], 150), (37, [(0, 5), (5, 300)], 300),
-                                         (256, [(0, 256), (256, 512), (512, 1024)], 1024)])
+                                         (256, [(0, 256), (256, 512), (512, 1024)], 1024),
+                                         # large batches: the rows of a segment are split over a thread-block cluster
+                                         (256, [(0, 3000), (3000, 9001), (9001, 12000)], 12400),
+                                         (64, [(0, 4100), (4100, 5000)], 5003)])
 def test_bn_act_fwd_bwd(H, segs, maxr):
     from scnym_b200._lib import call, ptr
     torch.manual_seed(H)
@@ -710,12 +713,23 @@ def test_unmix_rows_planes_equals_unmix_then_planes(n, H):
     (0, 1024, 320, 1000, "bias_relu"), (0, 300, 256, 64, "plain"), (0, 2048, 1024, 1024, "bias"),
     (1, 1024, 320, 1000, "gate"), (1, 384, 64, 200, "alpha"),
     (2, 256, 512, 8192, "beta1"), (2, 1024, 1024, 4096, "beta1"), (2, 128, 72, 260, "plain")])
-def test_sgemm_tcgen05_path_matches_fp64(lay, M, N, K, extras):
-    """scnb_sgemm's tcgen05 kernel (bf16x3, operands split from fp32 in the kernel) for the three nn.Linear layouts
-    (forward, input gradient, weight gradient incl. the K split), ragged M / N / K and every epilogue option."""
+@pytest.mark.parametrize("planes", [False, True])
+def test_sgemm_tcgen05_path_matches_fp64(lay, M, N, K, extras, planes):
+    """scnb_sgemm's tcgen05 kernels (bf16x3) for the three nn.Linear layouts (forward, input gradient, weight gradient incl.
+    the K split), ragged M / N / K and every epilogue option: operands split from fp32 inside the kernel, and -- with a
+    workspace registered for the stream -- the planes form (operand planes written once, 256 x 256 tiles)."""
+    import ctypes
     from scnym_b200._lib import call, ptr
     call("scnb_gemm_tc_min_flops", 1)
+    ws = None
     try:
+        if planes:
+            need = ctypes.c_longlong(0)
+            call("scnb_gemm_tc_workspace_bytes", M, N, K, ctypes.byref(need))
+            ws = torch.full((need.value + 1024,), 0x7f, dtype=torch.uint8).cuda()   # garbage: every tile byte must be written
+            call("scnb_gemm_tc_workspace", _st(), ws.data_ptr() + (-ws.data_ptr()) % 1024, need.value)
+        n0 = ctypes.c_longlong(0)
+        call("scnb_gemm_tc_planes_count", ctypes.byref(n0))
         torch.manual_seed(lay * 100 + M)
         tA, tB = (lay == 2), (lay == 0)
         A = torch.randn((K, M) if tA else (M, K)).cuda()
@@ -739,6 +753,11 @@ def test_sgemm_tcgen05_path_matches_fp64(lay, M, N, K, extras):
             want = want.clamp_min(0)
         if gate is not None:
             want = want * (gate.double() > 0)
-        _chk(f"tc gemm lay {lay} {extras}", C.cpu(), want.float().cpu(), tol=3e-5)
+        _chk(f"tc gemm lay {lay} {extras} planes={planes}", C.cpu(), want.float().cpu(), tol=3e-5)
+        n1 = ctypes.c_longlong(0)
+        call("scnb_gemm_tc_planes_count", ctypes.byref(n1))
+        assert n1.value - n0.value == (1 if planes else 0)
     finally:
         call("scnb_gemm_tc_min_flops", 2_000_000_000)
+        if ws is not None:
+            call("scnb_gemm_tc_workspace", _st(), None, 0)

@@ -102,6 +102,10 @@ def test_config5_shape_step_matches_oracle():
         eng, _ = _run(dict(G=20000, L=512, U=512, C=16, H0=256, H=1024, n_layers=3, D_given=8, opt_name="adam", lr=1e-3,
                            wd=1e-4, seed=34, density=0.20, n_cells=1536))
         assert eng.n_app == 4 and eng.H == 1024
+        import ctypes
+        n = ctypes.c_longlong(0)
+        _lib.call("scnb_gemm_tc_planes_count", ctypes.byref(n))
+        assert eng._gemm_ws and n.value > 0      # the planes form of the tcgen05 products ran inside the engine
     finally:
         _lib.call("scnb_gemm_tc_min_flops", int(2e9))
 
