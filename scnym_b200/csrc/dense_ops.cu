@@ -441,21 +441,31 @@ __device__ __forceinline__ void st8(float* __restrict__ p, const F8& r) {
   *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
   *reinterpret_cast<float4*>(p + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
 }
-// sums over all rows of the CTA for each of the 8 columns; result in every thread
-__device__ __forceinline__ void bnv_colsum8(F8& x, float (*red)[8]) {
+// W column groups per CTA: thread t owns the 8 columns of group (t % W) and the rows (t / W) + k * (BNV_T / W); consecutive
+// lanes read consecutive 32-byte pieces of ONE row (W = 4: a full 128-byte line per 4 lanes).  W = 1 is the small-batch
+// form (a CTA = one column group, every thread a different row).
+// Sums over all rows of the CTA for each of the 8 columns of the thread's group; result in every thread.
+template <int W>
+__device__ __forceinline__ void bnv_colsum8(F8& x, float (*red)[W][8]) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) x.v[j] = warp_sum(x.v[j]);
+  for (int j = 0; j < 8; ++j) {
+    float v = x.v[j];
+#pragma unroll
+    for (int o = 16; o >= W; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);   // lanes with the same (lane % W)
+    x.v[j] = v;
+  }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) {
+  if (lane < W) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) red[wid][j] = x.v[j];
+    for (int j = 0; j < 8; ++j) red[wid][lane][j] = x.v[j];
   }
   __syncthreads();
+  const int cg = threadIdx.x % W;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < BNV_W; ++w) t += red[w][j];
+    for (int w = 0; w < BNV_W; ++w) t += red[w][cg][j];
     x.v[j] = t;
   }
 }
@@ -467,22 +477,19 @@ __device__ __forceinline__ void bnv_colsum8(F8& x, float (*red)[8]) {
 __device__ __forceinline__ void bnv_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// a, b: this CTA's 8 + 8 block sums (in every thread) -> the cluster's sums (in every thread).  xs: shared [32].
+// a, b: this CTA's 8 + 8 block sums of the thread's column group (in every thread) -> the cluster's sums.
+// xs: shared [32 * W].
+template <int W>
 __device__ __forceinline__ void bnv_cluster_sum16(F8& a, F8& b, float* xs) {
   const int CL = (int)gridDim.z;
   if (CL == 1) return;
   const int t = threadIdx.x;
-  if (t < 16) {
-    float mine = 0.f;
+  if (t < W) {                                   // thread t holds the sums of column group t
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (t == j) mine = a.v[j];
-      if (t == 8 + j) mine = b.v[j];
-    }
-    xs[t] = mine;
+    for (int j = 0; j < 8; ++j) { xs[t * 16 + j] = a.v[j]; xs[t * 16 + 8 + j] = b.v[j]; }
   }
   bnv_cluster_sync();
-  if (t < 16) {
+  if (t < 16 * W) {
     const uint32_t mine_addr = (uint32_t)__cvta_generic_to_shared(xs + t);
     float acc = 0.f;
     for (int p = 0; p < CL; ++p) {
@@ -492,11 +499,12 @@ __device__ __forceinline__ void bnv_cluster_sum16(F8& a, F8& b, float* xs) {
       asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
       acc += v;
     }
-    xs[16 + t] = acc;
+    xs[16 * W + t] = acc;
   }
-  bnv_cluster_sync();            // nobody overwrites (or leaves with) xs[0..15] while a peer still reads it
+  bnv_cluster_sync();            // nobody overwrites (or leaves with) xs[0 .. 16 W) while a peer still reads it
+  const int cg = t % W;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { a.v[j] = xs[16 + j]; b.v[j] = xs[24 + j]; }
+  for (int j = 0; j < 8; ++j) { a.v[j] = xs[16 * W + cg * 16 + j]; b.v[j] = xs[16 * W + cg * 16 + 8 + j]; }
   __syncthreads();
 }
 // this CTA's share [rb, re) of the rows [r0, r1) of a segment
@@ -565,6 +573,7 @@ __device__ __forceinline__ void peer_allreduce17(const PeerX& px, F8& a, F8& b, 
   __syncthreads();
 }
 
+template <int W>
 __global__ void __launch_bounds__(BNV_T) k_bn_act_fwd_v8(const float* __restrict__ Z, float* __restrict__ Aout,
                                                          float* __restrict__ pre_out, int H, int n_seg,
                                                          const int32_t* __restrict__ seg_off, int max_rows,
@@ -575,11 +584,14 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_fwd_v8(const float* __restrict
                                                          const float* __restrict__ ext_sums, const float* __restrict__ ext_cnt,
                                                          PeerX px, float* __restrict__ glob_out) {
   PDL_ENTRY();
-  __shared__ __align__(16) float red1[BNV_W][8];
-  __shared__ __align__(16) float red2[BNV_W][8];
-  __shared__ float xs[32];
+  __shared__ __align__(16) float red1[BNV_W][W][8];
+  __shared__ __align__(16) float red2[BNV_W][W][8];
+  __shared__ float xs[32 * W];
+  constexpr int RS = BNV_T / W;                  // rows per pass of the CTA
   const int t = threadIdx.x;
-  const int c0 = blockIdx.x * 8, s = blockIdx.y;
+  const int tr = t / W;                          // row lane of this thread
+  const int cgi = blockIdx.x * W + (t % W);      // its column group
+  const int c0 = cgi * 8, s = blockIdx.y;
   const int Hg = H >> 3;
   const int r0 = min(seg_off[s], max_rows), r1 = min(seg_off[s + 1], max_rows);
   const int n = r1 - r0;
@@ -592,7 +604,7 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_fwd_v8(const float* __restrict
   const uint32_t thr16 = (uint32_t)(p_drop * 65536.0f + 0.5f);
   const float drop_scale = 1.0f / (1.0f - p_drop);
   F8 mean, invstd;
-  const bool cached = (n <= 2 * BNV_T) && !partial_out && !ext_sums && !px.bufs && gridDim.z == 1;
+  const bool cached = (W == 1) && (n <= 2 * BNV_T) && !partial_out && !ext_sums && !px.bufs && gridDim.z == 1;
   const bool has0 = t < n, has1 = t + BNV_T < n;
   int rb, re;                      // this CTA's rows of the segment (all of them unless the launch is a cluster launch)
   bnv_row_share(r0, r1, rb, re);
@@ -606,8 +618,8 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_fwd_v8(const float* __restrict
 #pragma unroll
       for (int j = 0; j < 8; ++j) { a1.v[j] += z.v[j]; a2.v[j] = fmaf(z.v[j], z.v[j], a2.v[j]); }
     }
-    bnv_colsum8(a1, red1);
-    bnv_colsum8(a2, red2);
+    bnv_colsum8<W>(a1, red1);
+    bnv_colsum8<W>(a2, red2);
     if (t < 8) {
       partial_out[((size_t)s * 2 + 0) * H + c0 + t] = a1.v[t];
       partial_out[((size_t)s * 2 + 1) * H + c0 + t] = a2.v[t];
@@ -625,8 +637,8 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_fwd_v8(const float* __restrict
 #pragma unroll
       for (int j = 0; j < 8; ++j) { a1.v[j] += z.v[j]; a2.v[j] = fmaf(z.v[j], z.v[j], a2.v[j]); }
     }
-    bnv_colsum8(a1, red1);
-    bnv_colsum8(a2, red2);
+    bnv_colsum8<W>(a1, red1);
+    bnv_colsum8<W>(a2, red2);
     float rows = (float)n;
     peer_allreduce17(px, a1, a2, rows, xs);
     if (glob_out) {   // [seg][2][H] global sums + [seg] global rows: what the running-statistics update reads
@@ -662,18 +674,18 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_fwd_v8(const float* __restrict
 #pragma unroll
       for (int j = 0; j < 8; ++j) mean.v[j] = (has0 ? zc0.v[j] : 0.f) + (has1 ? zc1.v[j] : 0.f);
     } else {
-      for (int r = rb + t; r < re; r += BNV_T) {
+      for (int r = rb + tr; r < re; r += RS) {
         const F8 z = ld8(Z + (size_t)r * H + c0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) mean.v[j] += z.v[j];
       }
     }
-    bnv_colsum8(mean, red1);
+    bnv_colsum8<W>(mean, red1);
     {
       F8 dummy;
 #pragma unroll
       for (int j = 0; j < 8; ++j) dummy.v[j] = 0.f;
-      bnv_cluster_sum16(mean, dummy, xs);
+      bnv_cluster_sum16<W>(mean, dummy, xs);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) { mean.v[j] *= inv_n; var.v[j] = 0.f; }
@@ -684,38 +696,38 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_fwd_v8(const float* __restrict
         var.v[j] = fmaf(d0, d0, d1 * d1);
       }
     } else {
-      for (int r = rb + t; r < re; r += BNV_T) {
+      for (int r = rb + tr; r < re; r += RS) {
         const F8 z = ld8(Z + (size_t)r * H + c0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { const float d = z.v[j] - mean.v[j]; var.v[j] = fmaf(d, d, var.v[j]); }
       }
     }
-    bnv_colsum8(var, red2);
+    bnv_colsum8<W>(var, red2);
     {
       F8 dummy;
 #pragma unroll
       for (int j = 0; j < 8; ++j) dummy.v[j] = 0.f;
-      bnv_cluster_sum16(var, dummy, xs);
+      bnv_cluster_sum16<W>(var, dummy, xs);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) var.v[j] *= inv_n;
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) invstd.v[j] = 1.0f / sqrtf(var.v[j] + BN_EPS);
-  if (stats && t < 8 && blockIdx.z == 0) {
-    // dynamic register indexing would spill: select with a compile-time unrolled loop
+  if (stats && t < 8 * W && blockIdx.z == 0) {
+    // thread (group t % W, column t / W of the group); dynamic register indexing would spill: compile-time unrolled select
     float m = 0.f, v = 0.f, is = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) if (j == t) { m = mean.v[j]; v = var.v[j]; is = invstd.v[j]; }
-    stats[((size_t)s * 3 + 0) * H + c0 + t] = m;
-    stats[((size_t)s * 3 + 1) * H + c0 + t] = v;
-    stats[((size_t)s * 3 + 2) * H + c0 + t] = is;
+    for (int j = 0; j < 8; ++j) if (j == tr) { m = mean.v[j]; v = var.v[j]; is = invstd.v[j]; }
+    stats[((size_t)s * 3 + 0) * H + c0 + tr] = m;
+    stats[((size_t)s * 3 + 1) * H + c0 + tr] = v;
+    stats[((size_t)s * 3 + 2) * H + c0 + tr] = is;
   }
-  for (int r = rb + t; r < re; r += BNV_T) {
+  for (int r = rb + tr; r < re; r += RS) {
     const size_t o = (size_t)r * H + c0;
     const F8 z = cached ? (r == r0 + t ? zc0 : zc1) : ld8(Z + o);
     uint32_t kb = 0xffu;
-    if (p_drop > 0.f) kb = keep8(keep_mask, o, (uint64_t)r * Hg + blockIdx.x, seed, strm, thr16);
+    if (p_drop > 0.f) kb = keep8(keep_mask, o, (uint64_t)r * Hg + cgi, seed, strm, thr16);
     F8 y;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -734,13 +746,14 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_fwd_v8(const float* __restrict
     F8 zero;
 #pragma unroll
     for (int j = 0; j < 8; ++j) zero.v[j] = 0.f;
-    for (int r = r1 + t + (int)blockIdx.z * BNV_T; r < max_rows; r += BNV_T * (int)gridDim.z) {
+    for (int r = r1 + tr + (int)blockIdx.z * RS; r < max_rows; r += RS * (int)gridDim.z) {
       st8(Aout + (size_t)r * H + c0, zero);
       if (pre_out) st8(pre_out + (size_t)r * H + c0, zero);
     }
   }
 }
 
+template <int W>
 __global__ void __launch_bounds__(BNV_T) k_bn_act_bwd_v8(const float* __restrict__ dA, const float* __restrict__ Z,
                                                          const float* __restrict__ Aact, int H, int n_seg,
                                                          const int32_t* __restrict__ seg_off, int max_rows,
@@ -751,11 +764,14 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_bwd_v8(const float* __restrict
                                                          float* __restrict__ partial_out, const float* __restrict__ ext_sums,
                                                          const float* __restrict__ ext_cnt, PeerX px) {
   PDL_ENTRY();
-  __shared__ __align__(16) float red1[BNV_W][8];
-  __shared__ __align__(16) float red2[BNV_W][8];
-  __shared__ float xs[32];
+  __shared__ __align__(16) float red1[BNV_W][W][8];
+  __shared__ __align__(16) float red2[BNV_W][W][8];
+  __shared__ float xs[32 * W];
+  constexpr int RS = BNV_T / W;                  // rows per pass of the CTA
   const int t = threadIdx.x;
-  const int c0 = blockIdx.x * 8, s = blockIdx.y;
+  const int tr = t / W;                          // row lane of this thread
+  const int cgi = blockIdx.x * W + (t % W);      // its column group
+  const int c0 = cgi * 8, s = blockIdx.y;
   const int Hg = H >> 3;
   const int r0 = min(seg_off[s], max_rows), r1 = min(seg_off[s + 1], max_rows);
   const int n = r1 - r0;
@@ -772,7 +788,7 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_bwd_v8(const float* __restrict
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1.v[j] = s2.v[j] = 0.f;
   float inv_n = 1.0f / (float)max(n, 1);
-  const bool cached = (n <= 2 * BNV_T) && !ext_sums && !partial_out && gridDim.z == 1;
+  const bool cached = (W == 1) && (n <= 2 * BNV_T) && !ext_sums && !partial_out && gridDim.z == 1;
   int rb, re;                      // this CTA's rows of the segment (all of them unless the launch is a cluster launch)
   bnv_row_share(r0, r1, rb, re);
   F8 dyc0, zhc0, dyc1, zhc1;
@@ -785,13 +801,13 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_bwd_v8(const float* __restrict
     inv_n = 1.0f / fmaxf(ext_cnt[s], 1.f);
   } else {
     int slot = 0;
-    for (int r = rb + t; r < re; r += BNV_T, ++slot) {
+    for (int r = rb + tr; r < re; r += RS, ++slot) {
       const size_t o = (size_t)r * H + c0;
       const F8 da = ld8(dA + o), z = ld8(Z + o);
       F8 av;
       if (relu) av = ld8(Aact + o);
       uint32_t kb = 0xffu;
-      if (p_drop > 0.f) kb = keep8(keep_mask, o, (uint64_t)r * Hg + blockIdx.x, seed, strm, thr16);
+      if (p_drop > 0.f) kb = keep8(keep_mask, o, (uint64_t)r * Hg + cgi, seed, strm, thr16);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float dy = da.v[j];
@@ -805,20 +821,20 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_bwd_v8(const float* __restrict
         }
       }
     }
-    bnv_colsum8(s1, red1);
-    bnv_colsum8(s2, red2);
-    bnv_cluster_sum16(s1, s2, xs);
-    if (t < 8 && blockIdx.z == 0) {
+    bnv_colsum8<W>(s1, red1);
+    bnv_colsum8<W>(s2, red2);
+    bnv_cluster_sum16<W>(s1, s2, xs);
+    if (t < 8 * W && blockIdx.z == 0) {         // thread (group t % W, column t / W of the group)
       float a = 0.f, b2 = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) if (j == t) { a = s1.v[j]; b2 = s2.v[j]; }
+      for (int j = 0; j < 8; ++j) if (j == tr) { a = s1.v[j]; b2 = s2.v[j]; }
       if (n > 0) {
-        atomicAdd(dgamma + c0 + t, b2);
-        atomicAdd(dbeta + c0 + t, a);
+        atomicAdd(dgamma + c0 + tr, b2);
+        atomicAdd(dbeta + c0 + tr, a);
       }
       if (partial_out) {
-        partial_out[((size_t)s * 2 + 0) * H + c0 + t] = a;
-        partial_out[((size_t)s * 2 + 1) * H + c0 + t] = b2;
+        partial_out[((size_t)s * 2 + 0) * H + c0 + tr] = a;
+        partial_out[((size_t)s * 2 + 1) * H + c0 + tr] = b2;
       }
     }
     if (partial_out) {
@@ -843,13 +859,13 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_bwd_v8(const float* __restrict
       st8(dZ + (size_t)r * H + c0, out);
     }
   } else {
-    for (int r = rb + t; r < re; r += BNV_T) {
+    for (int r = rb + tr; r < re; r += RS) {
       const size_t o = (size_t)r * H + c0;
       const F8 da = ld8(dA + o), z = ld8(Z + o);
       F8 av;
       if (relu) av = ld8(Aact + o);
       uint32_t kb = 0xffu;
-      if (p_drop > 0.f) kb = keep8(keep_mask, o, (uint64_t)r * Hg + blockIdx.x, seed, strm, thr16);
+      if (p_drop > 0.f) kb = keep8(keep_mask, o, (uint64_t)r * Hg + cgi, seed, strm, thr16);
       F8 out;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -866,7 +882,7 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_bwd_v8(const float* __restrict
     F8 zero;
 #pragma unroll
     for (int j = 0; j < 8; ++j) zero.v[j] = 0.f;
-    for (int r = r1 + t + (int)blockIdx.z * BNV_T; r < max_rows; r += BNV_T * (int)gridDim.z) st8(dZ + (size_t)r * H + c0, zero);
+    for (int r = r1 + tr + (int)blockIdx.z * RS; r < max_rows; r += RS * (int)gridDim.z) st8(dZ + (size_t)r * H + c0, zero);
   }
 }
 
@@ -980,13 +996,19 @@ extern "C" int scnb_bn_act_fwd(const float* Z, float* A, float* pre_out, int H, 
     const int cl = (dp_partial_out || dp_sums) ? 1 : bnv_cluster_size(max_rows);
     if (cl > 1) {
       gridv.z = cl;
-      bnv_launch_cluster(k_bn_act_fwd_v8, gridv, (cudaStream_t)stream, Z, A, pre_out, H, n_seg, seg_off_dev, max_rows, gamma, beta, stats,
+      if (H % 32 == 0) {   // four column groups per CTA: every 4 lanes read a full 128-byte line of one row
+        gridv.x = H / 32;
+        bnv_launch_cluster(k_bn_act_fwd_v8<4>, gridv, (cudaStream_t)stream, Z, A, pre_out, H, n_seg, seg_off_dev, max_rows, gamma, beta, stats,
+                           keep_mask, rng, stream_id, p_drop, relu, dp_partial_out, dp_sums, ext_cnt,
+                           PeerX{nullptr, nullptr, 0, 1, 0, 0, 0}, (float*)nullptr);
+      } else
+      bnv_launch_cluster(k_bn_act_fwd_v8<1>, gridv, (cudaStream_t)stream, Z, A, pre_out, H, n_seg, seg_off_dev, max_rows, gamma, beta, stats,
                          keep_mask, rng, stream_id, p_drop, relu, dp_partial_out, dp_sums, ext_cnt,
                          PeerX{nullptr, nullptr, 0, 1, 0, 0, 0}, (float*)nullptr);
       SCNB_CHECK_LAUNCH("bn_act_fwd/v8 cluster");
       return SCNB_OK;
     }
-    scnb_launch_pdl(k_bn_act_fwd_v8, gridv, dim3(BNV_T), 0, (cudaStream_t)stream, Z, A, pre_out, H, n_seg, seg_off_dev, max_rows, gamma, beta, stats,
+    scnb_launch_pdl(k_bn_act_fwd_v8<1>, gridv, dim3(BNV_T), 0, (cudaStream_t)stream, Z, A, pre_out, H, n_seg, seg_off_dev, max_rows, gamma, beta, stats,
                                                                keep_mask, rng, stream_id, p_drop, relu, dp_partial_out, dp_sums,
                                                                ext_cnt, PeerX{nullptr, nullptr, 0, 1, 0, 0, 0}, (float*)nullptr);
     SCNB_CHECK_LAUNCH("bn_act_fwd/v8");
@@ -1092,13 +1114,19 @@ extern "C" int scnb_bn_act_bwd(const float* dA, const float* Z, const float* A, 
     const int cl = (dp_partial_out || dp_sums) ? 1 : bnv_cluster_size(max_rows);
     if (cl > 1) {
       gridv.z = cl;
-      bnv_launch_cluster(k_bn_act_bwd_v8, gridv, (cudaStream_t)stream, dA, Z, A, H, n_seg, seg_off_dev, max_rows, gamma, stats, keep_mask,
+      if (H % 32 == 0) {
+        gridv.x = H / 32;
+        bnv_launch_cluster(k_bn_act_bwd_v8<4>, gridv, (cudaStream_t)stream, dA, Z, A, H, n_seg, seg_off_dev, max_rows, gamma, stats, keep_mask,
+                           rng, stream_id, p_drop, relu, dZ, dgamma, dbeta, dp_partial_out, dp_sums, ext_cnt,
+                           PeerX{nullptr, nullptr, 0, 1, 0, 0, 0});
+      } else
+      bnv_launch_cluster(k_bn_act_bwd_v8<1>, gridv, (cudaStream_t)stream, dA, Z, A, H, n_seg, seg_off_dev, max_rows, gamma, stats, keep_mask,
                          rng, stream_id, p_drop, relu, dZ, dgamma, dbeta, dp_partial_out, dp_sums, ext_cnt,
                          PeerX{nullptr, nullptr, 0, 1, 0, 0, 0});
       SCNB_CHECK_LAUNCH("bn_act_bwd/v8 cluster");
       return SCNB_OK;
     }
-    scnb_launch_pdl(k_bn_act_bwd_v8, gridv, dim3(BNV_T), 0, (cudaStream_t)stream, dA, Z, A, H, n_seg, seg_off_dev, max_rows, gamma, stats, keep_mask,
+    scnb_launch_pdl(k_bn_act_bwd_v8<1>, gridv, dim3(BNV_T), 0, (cudaStream_t)stream, dA, Z, A, H, n_seg, seg_off_dev, max_rows, gamma, stats, keep_mask,
                                                                rng, stream_id, p_drop, relu, dZ, dgamma, dbeta, dp_partial_out,
                                                                dp_sums, ext_cnt, PeerX{nullptr, nullptr, 0, 1, 0, 0, 0});
     SCNB_CHECK_LAUNCH("bn_act_bwd/v8");
@@ -1153,7 +1181,7 @@ extern "C" int scnb_bn_act_fwd_peer(const float* Z, float* A, float* pre_out, in
                       buf_bytes, H, n_seg, &stride);
   if (rc != SCNB_OK) return rc;
   PeerX px{(const unsigned long long*)peer_bufs, (const long long*)epoch, rank, world, slot, peer_spin_limit(), stride};
-  k_bn_act_fwd_v8<<<dim3(H / 8, n_seg), BNV_T, 0, (cudaStream_t)stream>>>(Z, A, pre_out, H, n_seg, seg_off_dev, max_rows, gamma, beta, stats,
+  k_bn_act_fwd_v8<1><<<dim3(H / 8, n_seg), BNV_T, 0, (cudaStream_t)stream>>>(Z, A, pre_out, H, n_seg, seg_off_dev, max_rows, gamma, beta, stats,
                                                                          keep_mask, rng, stream_id, p_drop, relu, nullptr, nullptr,
                                                                          nullptr, px, global_sums_out);
   SCNB_CHECK_LAUNCH("bn_act_fwd_peer");
@@ -1174,7 +1202,7 @@ extern "C" int scnb_bn_act_bwd_peer(const float* dA, const float* Z, const float
                       buf_bytes, H, n_seg, &stride);
   if (rc != SCNB_OK) return rc;
   PeerX px{(const unsigned long long*)peer_bufs, (const long long*)epoch, rank, world, slot, peer_spin_limit(), stride};
-  k_bn_act_bwd_v8<<<dim3(H / 8, n_seg), BNV_T, 0, (cudaStream_t)stream>>>(dA, Z, A, H, n_seg, seg_off_dev, max_rows, gamma, stats, keep_mask, rng,
+  k_bn_act_bwd_v8<1><<<dim3(H / 8, n_seg), BNV_T, 0, (cudaStream_t)stream>>>(dA, Z, A, H, n_seg, seg_off_dev, max_rows, gamma, stats, keep_mask, rng,
                                                                          stream_id, p_drop, relu, dZ, dgamma, dbeta, nullptr, nullptr,
                                                                          nullptr, px);
   SCNB_CHECK_LAUNCH("bn_act_bwd_peer");

@@ -736,17 +736,20 @@ class TrainEngine(object):
             sF.wait_event(self._ev_adv if os.environ.get("SCNB_PREFETCH_AT", "start") == "start" else self._ev_fl)
             cur = self.__dict__["_cur"]
             self.__dict__["_cur"] = 1 - cur
-            # SCNB_SPLITS_LATE=1 (experiment): the split points of the next batch (1024 short CTAs) are enqueued behind the
-            # heads instead of next to them
-            splits_late = (os.environ.get("SCNB_SPLITS_LATE", "0") == "1") and not self.host_mapped
+            # The split points of the next batch (one short CTA per row) are enqueued BEHIND the heads (SCNB_SPLITS_LATE=1,
+            # default): launched next to them they delayed the cluster launch of the adversary head by 6 us (timeline:
+            # hs_dan_head started when row_gene_splits drained).  0: with the rest of the prologue; 2: next to the dW1 kernel
+            # (measured 0.1480 / 0.1466 / 0.1489 ms for 0 / 1 / 2)
+            splits_late = os.environ.get("SCNB_SPLITS_LATE", "1") if not self.host_mapped else "0"
+            splits_late = {"0": 0, "1": 1, "2": 2}.get(splits_late, 0)    # 1: behind the heads, 2: next to the dW1 kernel
             try:
-                self._prologue_next(sF, rng, splits=not splits_late)
+                self._prologue_next(sF, rng, splits=splits_late == 0)
             finally:
                 self.__dict__["_cur"] = cur
-            if not splits_late:
+            if splits_late == 0:
                 self._ev_pf.record(sF)
         else:
-            splits_late = False
+            splits_late = 0
         # -- teacher (eval mode, losses.py:660-737).  With pseudolabel_min_confidence <= 0 every unlabeled row is
         #    "confident", so the MixUp plan and the student forward do not depend on the teacher: it runs on its own
         #    branch and is joined in front of the losses.
@@ -873,7 +876,7 @@ class TrainEngine(object):
         call("scnb_colsum", ptr(self.dlogits), nb, C, C, self.Gp("model.classif.0.bias"), 1, sw)
         if self.use_dan and sD is not main:
             main.wait_event(self._ev_grl)
-        if splits_late:
+        def late_splits():
             sF = self._side[4]
             self._ev_fl.record(main)
             sF.wait_event(self._ev_fl)
@@ -884,6 +887,8 @@ class TrainEngine(object):
             finally:
                 self.__dict__["_cur"] = cur
             self._ev_pf.record(sF)
+        if splits_late == 1:
+            late_splits()
         if sW is not main and hf:
             running_update()      # the statistics of the last application are written by the head kernels
         published = False
@@ -907,6 +912,8 @@ class TrainEngine(object):
                  ptr(self.dz_lo), st)
         else:
             call("scnb_unmix_rows", ptr(dZ_first), H0, ptr(self.inv3), ptr(self.coef3), nb, ptr(self.dZ1), st)
+        if splits_late == 2:
+            late_splits()
         self._finish_step(main, sW, sD, self.dZ1, nb)
         if published:
             main.wait_event(self._ev_pub)
