@@ -210,6 +210,13 @@ int scnb_gemm_tc_min_flops_get(long long* flops_out);
 int scnb_gemm_tc_workspace(void* stream, void* buf, long long bytes);
 int scnb_gemm_tc_workspace_bytes(int M, int N, int K, long long* bytes_out);
 int scnb_gemm_tc_planes_count(long long* count_out);   /* products issued in the planes form so far */
+/* Planes written by the PRODUCER of a tensor: after scnb_gemm_tc_bind_planes(X, rows, cols, hi, lo) (cols a multiple of 32,
+ * planes of ceil(rows / 256) * 256 x cols bf16 each, 1024-byte aligned) scnb_bn_act_fwd (output A == X) and scnb_bn_act_bwd
+ * (output dZ == X) also write X as operand planes, and a product that reads X as its row-major A operand (lda == cols) skips
+ * the conversion pass; a weight-gradient product (transA) whose two operands are both bound reads those same planes as
+ * MN-major operands.  hi = lo = NULL unbinds.  scnb_gemm_tc_bound_count: operands taken from bound planes so far. */
+int scnb_gemm_tc_bind_planes(const float* X, int rows, int cols, void* hi, void* lo);
+int scnb_gemm_tc_bound_count(long long* count_out);
 int scnb_colsum(const float* A, int M, int N, int lda, float* out, int accumulate, void* stream);
 int scnb_relu_bwd(const float* g, const float* y, float* out, long long n, void* stream);
 

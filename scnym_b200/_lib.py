@@ -54,6 +54,8 @@ SIGNATURES = {
     "scnb_gemm_tc_workspace": [P, P, L],
     "scnb_gemm_tc_workspace_bytes": [I, I, I, P],
     "scnb_gemm_tc_planes_count": [P],
+    "scnb_gemm_tc_bind_planes": [P, I, I, P, P],
+    "scnb_gemm_tc_bound_count": [P],
     "scnb_colsum": [P, I, I, I, P, I, P],
     "scnb_relu_bwd": [P, P, P, L, P],
     "scnb_bn_eval_bwd": [P, P, I, I, I, P, P, P, P],

@@ -8,6 +8,7 @@
 // separate batch statistics; seg_off lives in device memory because the DAN segment length is
 // data dependent when pseudolabel thresholding is on.  Rows >= seg_off[n_seg] are written as 0.
 #include "common.cuh"
+#include "tc_common.cuh"
 #include <stdlib.h>
 
 #define BN_EPS 1e-5f
@@ -527,6 +528,35 @@ __device__ __forceinline__ void bnv_row_share(int r0, int r1, int& rb, int& re) 
 // exchange that ends a step separates reuses.
 //   packet(slot, parity, src, cta) : 32 words of 8 bytes = [sum_a[8] | sum_b[8] | rows | unused]
 // ---------------------------------------------------------------------------------------------
+// Operand planes of the tcgen05 hidden GEMMs (tc_gemm.cu, planes form) emitted by the PRODUCER of an activation / gradient
+// tensor: bf16 hi / lo planes tiled [rows / 256][cols / 32], every tile a SWIZZLE_64B K-major image of 256 x 32.  A thread
+// of the BatchNorm kernels owns 8 consecutive columns of a row = one 16-byte chunk of a plane row.  The engine binds plane
+// buffers to the tensors (scnb_gemm_tc_bind_planes); the GEMM that reads a bound tensor skips its conversion pass.
+struct PlaneSink {
+  uint16_t* hi;
+  uint16_t* lo;
+  int n_kt;        // cols / 32
+  int rows_pad;    // rows of the plane buffer (a multiple of 256): rows past the tensor's are written as zeros
+};
+bool scnb_planes_lookup(const float* X, int cols, int min_rows, uint16_t** hi, uint16_t** lo, int* rows_pad);   // tc_gemm.cu
+__device__ __forceinline__ void plane_store8(const PlaneSink& sk, int r, int cgi, const float (&x)[8]) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split_bf16x2(x[2 * j], x[2 * j + 1], h[j], l[j]);
+  const uint32_t rr = (uint32_t)(r & 255);
+  const size_t off = ((size_t)(r >> 8) * sk.n_kt + (size_t)(cgi >> 2)) * (256 * 32) + (size_t)rr * 32 +
+                     (size_t)(swz_chunk<32>((uint32_t)(cgi & 3), rr) >> 1);
+  *reinterpret_cast<uint4*>(sk.hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(sk.lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+static PlaneSink plane_sink_of(const float* X, int cols, int rows) {
+  PlaneSink sk{nullptr, nullptr, 0, 0};
+  uint16_t *hi = nullptr, *lo = nullptr;
+  int rp = 0;
+  if (cols % 32 == 0 && scnb_planes_lookup(X, cols, rows, &hi, &lo, &rp)) sk = PlaneSink{hi, lo, cols / 32, rp};
+  return sk;
+}
+
 struct PeerX {
   const unsigned long long* bufs;   // device array [world] of exchange-buffer base addresses (NULL: no exchange)
   const long long* epoch;           // device scalar: step number (> 0, changes every step)
@@ -582,7 +612,7 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_fwd_v8(const float* __restrict
                                                          const uint64_t* __restrict__ rng, uint32_t stream_id, float p_drop,
                                                          int relu, float* __restrict__ partial_out,
                                                          const float* __restrict__ ext_sums, const float* __restrict__ ext_cnt,
-                                                         PeerX px, float* __restrict__ glob_out) {
+                                                         PeerX px, float* __restrict__ glob_out, PlaneSink sink) {
   PDL_ENTRY();
   __shared__ __align__(16) float red1[BNV_W][W][8];
   __shared__ __align__(16) float red2[BNV_W][W][8];
@@ -741,6 +771,11 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_fwd_v8(const float* __restrict
       for (int j = 0; j < 8; ++j) y.v[j] = fmaxf(y.v[j], 0.f);
     }
     st8(Aout + o, y);
+    if (sink.hi) plane_store8(sink, r, cgi, y.v);
+  }
+  if (sink.hi && s == n_seg - 1) {
+    const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = r1 + tr + (int)blockIdx.z * RS; r < sink.rows_pad; r += RS * (int)gridDim.z) plane_store8(sink, r, cgi, zero8);
   }
   if (s == n_seg - 1) {  // inactive tail rows (data-dependent DAN segment length)
     F8 zero;
@@ -762,7 +797,7 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_bwd_v8(const float* __restrict
                                                          uint32_t stream_id, float p_drop, int relu, float* __restrict__ dZ,
                                                          float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                          float* __restrict__ partial_out, const float* __restrict__ ext_sums,
-                                                         const float* __restrict__ ext_cnt, PeerX px) {
+                                                         const float* __restrict__ ext_cnt, PeerX px, PlaneSink sink) {
   PDL_ENTRY();
   __shared__ __align__(16) float red1[BNV_W][W][8];
   __shared__ __align__(16) float red2[BNV_W][W][8];
@@ -857,6 +892,7 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_bwd_v8(const float* __restrict
         out.v[j] = g.v[j] * invstd.v[j] * (dy - s1.v[j] * inv_n - zh * (s2.v[j] * inv_n));
       }
       st8(dZ + (size_t)r * H + c0, out);
+      if (sink.hi) plane_store8(sink, r, cgi, out.v);
     }
   } else {
     for (int r = rb + tr; r < re; r += RS) {
@@ -876,7 +912,12 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_bwd_v8(const float* __restrict
         out.v[j] = g.v[j] * invstd.v[j] * (dy - s1.v[j] * inv_n - zh * (s2.v[j] * inv_n));
       }
       st8(dZ + o, out);
+      if (sink.hi) plane_store8(sink, r, cgi, out.v);
     }
+  }
+  if (sink.hi && s == n_seg - 1) {
+    const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = r1 + tr + (int)blockIdx.z * RS; r < sink.rows_pad; r += RS * (int)gridDim.z) plane_store8(sink, r, cgi, zero8);
   }
   if (s == n_seg - 1) {
     F8 zero;
@@ -976,6 +1017,10 @@ extern "C" int scnb_bn_act_fwd(const float* Z, float* A, float* pre_out, int H, 
   SCNB_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "bn_act_fwd: p_drop out of range");
   SCNB_CHECK_ARG(!(dp_partial_out && dp_sums), "bn_act_fwd: partial and reduced statistics are exclusive");
   const float* ext_cnt = dp_sums ? dp_sums + (size_t)n_seg * 2 * H : nullptr;
+  const PlaneSink sink = plane_sink_of(A, H, max_rows);
+#define PLANE_SINK_ARG sink
+  SCNB_CHECK_ARG(!sink.hi || (train && bn_vec8_ok(H, Z, A, pre_out, gamma, beta, stats, keep_mask)),
+                 "bn_act_fwd: operand planes are bound to this output, but this path (eval mode / unaligned) does not emit them");
   if (!train) {
     if (max_rows == 0) return SCNB_OK;
     const bool v4 = (H % 4 == 0) && ((((uintptr_t)Z | (uintptr_t)A | (uintptr_t)pre_out | (uintptr_t)gamma | (uintptr_t)beta |
@@ -1000,17 +1045,17 @@ extern "C" int scnb_bn_act_fwd(const float* Z, float* A, float* pre_out, int H, 
         gridv.x = H / 32;
         bnv_launch_cluster(k_bn_act_fwd_v8<4>, gridv, (cudaStream_t)stream, Z, A, pre_out, H, n_seg, seg_off_dev, max_rows, gamma, beta, stats,
                            keep_mask, rng, stream_id, p_drop, relu, dp_partial_out, dp_sums, ext_cnt,
-                           PeerX{nullptr, nullptr, 0, 1, 0, 0, 0}, (float*)nullptr);
+                           PeerX{nullptr, nullptr, 0, 1, 0, 0, 0}, (float*)nullptr, PLANE_SINK_ARG);
       } else
       bnv_launch_cluster(k_bn_act_fwd_v8<1>, gridv, (cudaStream_t)stream, Z, A, pre_out, H, n_seg, seg_off_dev, max_rows, gamma, beta, stats,
                          keep_mask, rng, stream_id, p_drop, relu, dp_partial_out, dp_sums, ext_cnt,
-                         PeerX{nullptr, nullptr, 0, 1, 0, 0, 0}, (float*)nullptr);
+                         PeerX{nullptr, nullptr, 0, 1, 0, 0, 0}, (float*)nullptr, PLANE_SINK_ARG);
       SCNB_CHECK_LAUNCH("bn_act_fwd/v8 cluster");
       return SCNB_OK;
     }
     scnb_launch_pdl(k_bn_act_fwd_v8<1>, gridv, dim3(BNV_T), 0, (cudaStream_t)stream, Z, A, pre_out, H, n_seg, seg_off_dev, max_rows, gamma, beta, stats,
                                                                keep_mask, rng, stream_id, p_drop, relu, dp_partial_out, dp_sums,
-                                                               ext_cnt, PeerX{nullptr, nullptr, 0, 1, 0, 0, 0}, (float*)nullptr);
+                                                               ext_cnt, PeerX{nullptr, nullptr, 0, 1, 0, 0, 0}, (float*)nullptr, PLANE_SINK_ARG);
     SCNB_CHECK_LAUNCH("bn_act_fwd/v8");
     return SCNB_OK;
   }
@@ -1020,6 +1065,7 @@ extern "C" int scnb_bn_act_fwd(const float* Z, float* A, float* pre_out, int H, 
                                                          relu, dp_partial_out, dp_sums, ext_cnt);
   SCNB_CHECK_LAUNCH("bn_act_fwd");
   return SCNB_OK;
+#undef PLANE_SINK_ARG
 }
 
 // Backward (train mode).  dA is the gradient w.r.t. the post-ReLU activation A.
@@ -1109,6 +1155,10 @@ extern "C" int scnb_bn_act_bwd(const float* dA, const float* Z, const float* A, 
   SCNB_CHECK_ARG(!(p_drop > 0.f) || keep_mask || rng, "bn_act_bwd: dropout needs keep_mask or rng state");
   SCNB_CHECK_ARG(!(dp_partial_out && dp_sums), "bn_act_bwd: partial and reduced sums are exclusive");
   const float* ext_cnt = dp_sums ? dp_sums + (size_t)n_seg * 2 * H : nullptr;
+  const PlaneSink sink = plane_sink_of(dZ, H, max_rows);
+#define PLANE_SINK_ARG sink
+  SCNB_CHECK_ARG(!sink.hi || bn_vec8_ok(H, dA, Z, A, gamma, dZ, stats, keep_mask),
+                 "bn_act_bwd: operand planes are bound to this output, but the unaligned path does not emit them");
   if (bn_vec8_ok(H, dA, Z, A, gamma, dZ, stats, keep_mask)) {
     dim3 gridv(H / 8, n_seg);
     const int cl = (dp_partial_out || dp_sums) ? 1 : bnv_cluster_size(max_rows);
@@ -1118,17 +1168,17 @@ extern "C" int scnb_bn_act_bwd(const float* dA, const float* Z, const float* A, 
         gridv.x = H / 32;
         bnv_launch_cluster(k_bn_act_bwd_v8<4>, gridv, (cudaStream_t)stream, dA, Z, A, H, n_seg, seg_off_dev, max_rows, gamma, stats, keep_mask,
                            rng, stream_id, p_drop, relu, dZ, dgamma, dbeta, dp_partial_out, dp_sums, ext_cnt,
-                           PeerX{nullptr, nullptr, 0, 1, 0, 0, 0});
+                           PeerX{nullptr, nullptr, 0, 1, 0, 0, 0}, PLANE_SINK_ARG);
       } else
       bnv_launch_cluster(k_bn_act_bwd_v8<1>, gridv, (cudaStream_t)stream, dA, Z, A, H, n_seg, seg_off_dev, max_rows, gamma, stats, keep_mask,
                          rng, stream_id, p_drop, relu, dZ, dgamma, dbeta, dp_partial_out, dp_sums, ext_cnt,
-                         PeerX{nullptr, nullptr, 0, 1, 0, 0, 0});
+                         PeerX{nullptr, nullptr, 0, 1, 0, 0, 0}, PLANE_SINK_ARG);
       SCNB_CHECK_LAUNCH("bn_act_bwd/v8 cluster");
       return SCNB_OK;
     }
     scnb_launch_pdl(k_bn_act_bwd_v8<1>, gridv, dim3(BNV_T), 0, (cudaStream_t)stream, dA, Z, A, H, n_seg, seg_off_dev, max_rows, gamma, stats, keep_mask,
                                                                rng, stream_id, p_drop, relu, dZ, dgamma, dbeta, dp_partial_out,
-                                                               dp_sums, ext_cnt, PeerX{nullptr, nullptr, 0, 1, 0, 0, 0});
+                                                               dp_sums, ext_cnt, PeerX{nullptr, nullptr, 0, 1, 0, 0, 0}, PLANE_SINK_ARG);
     SCNB_CHECK_LAUNCH("bn_act_bwd/v8");
     return SCNB_OK;
   }
@@ -1138,6 +1188,7 @@ extern "C" int scnb_bn_act_bwd(const float* dA, const float* Z, const float* A, 
                                                          ext_cnt);
   SCNB_CHECK_LAUNCH("bn_act_bwd");
   return SCNB_OK;
+#undef PLANE_SINK_ARG
 }
 
 // ---- data-parallel one-launch forms: statistics all-reduced through peer memory inside the kernel ----
@@ -1180,10 +1231,11 @@ extern "C" int scnb_bn_act_fwd_peer(const float* Z, float* A, float* pre_out, in
   int rc = peer_check("bn_act_fwd_peer", (const unsigned long long*)peer_bufs, rank, world, slot, n_slots, (const long long*)epoch,
                       buf_bytes, H, n_seg, &stride);
   if (rc != SCNB_OK) return rc;
+  SCNB_CHECK_ARG(!plane_sink_of(A, H, max_rows).hi, "bn_act_fwd_peer: operand planes are bound to this output; the peer form does not emit them");
   PeerX px{(const unsigned long long*)peer_bufs, (const long long*)epoch, rank, world, slot, peer_spin_limit(), stride};
   k_bn_act_fwd_v8<1><<<dim3(H / 8, n_seg), BNV_T, 0, (cudaStream_t)stream>>>(Z, A, pre_out, H, n_seg, seg_off_dev, max_rows, gamma, beta, stats,
                                                                          keep_mask, rng, stream_id, p_drop, relu, nullptr, nullptr,
-                                                                         nullptr, px, global_sums_out);
+                                                                         nullptr, px, global_sums_out, PlaneSink{nullptr, nullptr, 0, 0});
   SCNB_CHECK_LAUNCH("bn_act_fwd_peer");
   return SCNB_OK;
 }
@@ -1201,10 +1253,11 @@ extern "C" int scnb_bn_act_bwd_peer(const float* dA, const float* Z, const float
   int rc = peer_check("bn_act_bwd_peer", (const unsigned long long*)peer_bufs, rank, world, slot, n_slots, (const long long*)epoch,
                       buf_bytes, H, n_seg, &stride);
   if (rc != SCNB_OK) return rc;
+  SCNB_CHECK_ARG(!plane_sink_of(dZ, H, max_rows).hi, "bn_act_bwd_peer: operand planes are bound to this output; the peer form does not emit them");
   PeerX px{(const unsigned long long*)peer_bufs, (const long long*)epoch, rank, world, slot, peer_spin_limit(), stride};
   k_bn_act_bwd_v8<1><<<dim3(H / 8, n_seg), BNV_T, 0, (cudaStream_t)stream>>>(dA, Z, A, H, n_seg, seg_off_dev, max_rows, gamma, stats, keep_mask, rng,
                                                                          stream_id, p_drop, relu, dZ, dgamma, dbeta, nullptr, nullptr,
-                                                                         nullptr, px);
+                                                                         nullptr, px, PlaneSink{nullptr, nullptr, 0, 0});
   SCNB_CHECK_LAUNCH("bn_act_bwd_peer");
   return SCNB_OK;
 }

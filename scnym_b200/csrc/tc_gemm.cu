@@ -508,6 +508,147 @@ k_gemm_planes(int M, int N, int n_kt, const uint8_t* __restrict__ a_hi, const ui
   }
 }
 
+// Weight gradient C[M, N] (+)= alpha * sum_r P[r][m] Q[r][n] from the ROW-major planes of P [R][M] and Q [R][N] (the planes
+// their producers wrote for the forward / input-gradient products): both operands are MN-major for this product.  A
+// row-major tile (256 rows x 32 columns, 64-byte rows, SWIZZLE_64B by address) read with k = row, mn = column IS the
+// canonical MN-major SWIZZLE_64B layout ((8,4,m),(8,k)):((1,8,LBO),(32,SBO)) elements: 32 contiguous mn, the next 32 mn at LBO,
+// 8 k rows of 64 bytes, the next 8 at SBO = 512 bytes.  A stage holds 32 rows (k) of 8 + 8 column tiles (256 m, 256 n):
+// 32-row slabs of 2 KB per tile and plane (the swizzle repeats every 512 bytes, so a slab is a valid image), LBO = 2 KB.
+// CTA tile 256 x 256 (two accumulators), K split over gridDim.z with atomics.
+#define GPM_SLAB 2048u                       // 32 rows x 64 bytes of one tile
+#define GPM_OP_BYTES (8u * GPM_SLAB)         // one plane of one operand in a stage: 8 column tiles
+__device__ __forceinline__ uint64_t umma_desc_mnmajor64(uint32_t smem_addr, uint32_t lbo_bytes) {
+  const uint32_t lo = ((smem_addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+  const uint32_t hi = (512u >> 4) | (1u << 14) | (4u << 29);
+  return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+__global__ void __launch_bounds__(GP_THREADS, 1)
+k_gemm_planes_mn(int M, int N, int n_rt /* 256-row tiles of the operands */, int p_nkt, int q_nkt, const uint8_t* __restrict__ p_hi,
+                 const uint8_t* __restrict__ p_lo, const uint8_t* __restrict__ q_hi, const uint8_t* __restrict__ q_lo,
+                 float* __restrict__ C, int ldc, float alpha, int slabs_per_cta, int stages) {
+  constexpr uint32_t STAGE_BYTES = 4u * GPM_OP_BYTES;   // P_hi | P_lo | Q_hi | Q_lo = 64 KB
+  extern __shared__ uint8_t tc_smem_raw[];
+  const uint32_t raw = smem_u32(tc_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = tc_smem_raw + (base - raw);
+  const uint32_t bars = base + (uint32_t)stages * STAGE_BYTES;
+  const uint32_t bar_full = bars, bar_empty = bars + 8u * stages, bar_acc = bars + 16u * stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (size_t)stages * STAGE_BYTES + 16 * stages + 8);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mt = blockIdx.x, nt = blockIdx.y;                    // 256-column blocks of P and of Q
+  const int n_slabs = n_rt * 8;                                  // 32-row slabs over all rows
+  const int s0 = blockIdx.z * slabs_per_cta, s1 = min(n_slabs, s0 + slabs_per_cta);
+  const int n_it = max(s1 - s0, 0);
+  // column tiles of this CTA that exist (M, N multiples of 32; a partial 256-block multiplies zero-filled stage bytes)
+  const int p_tiles = min(8, p_nkt - mt * 8), q_tiles = min(8, q_nkt - nt * 8);
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(bar_full + 8u * s, 1);
+      mbar_init(bar_empty + 8u * s, 1);
+    }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (p_tiles < 8 || q_tiles < 8) {     // column tiles that do not exist stay zero in every stage
+    for (uint32_t o = (uint32_t)tid * 16u; o < (uint32_t)stages * STAGE_BYTES; o += GP_THREADS * 16u) st_shared_zero16(base + o);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== loader: a 2 KB slab per column tile and plane =====
+      for (int i = 0; i < n_it; ++i) {
+        const int s = i % stages;
+        mbar_wait(bar_empty + 8u * s, ((uint32_t)(i / stages) & 1u) ^ 1u);
+        const uint32_t stage = base + (uint32_t)s * STAGE_BYTES;
+        const uint32_t bar = bar_full + 8u * s;
+        mbar_arrive_expect_tx(bar, 2u * GPM_SLAB * (uint32_t)(p_tiles + q_tiles));
+        const int slab = s0 + i;
+        const int rt = slab >> 3;
+        const size_t in_tile = (size_t)(slab & 7) * GPM_SLAB;
+        for (int j = 0; j < p_tiles; ++j) {
+          const size_t off = ((size_t)rt * p_nkt + (size_t)(mt * 8 + j)) * GP_TILE_BYTES + in_tile;
+          bulk_g2s(stage + (uint32_t)j * GPM_SLAB, p_hi + off, GPM_SLAB, bar);
+          bulk_g2s(stage + GPM_OP_BYTES + (uint32_t)j * GPM_SLAB, p_lo + off, GPM_SLAB, bar);
+        }
+        for (int j = 0; j < q_tiles; ++j) {
+          const size_t off = ((size_t)rt * q_nkt + (size_t)(nt * 8 + j)) * GP_TILE_BYTES + in_tile;
+          bulk_g2s(stage + 2u * GPM_OP_BYTES + (uint32_t)j * GPM_SLAB, q_hi + off, GPM_SLAB, bar);
+          bulk_g2s(stage + 3u * GPM_OP_BYTES + (uint32_t)j * GPM_SLAB, q_lo + off, GPM_SLAB, bar);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer: both operands MN-major (idesc bits 15, 16) =====
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(GP_BN >> 3) << 17) |
+                             ((uint32_t)(TC_M >> 4) << 24);
+      for (int i = 0; i < n_it; ++i) {
+        const int s = i % stages;
+        mbar_wait(bar_full + 8u * s, (uint32_t)(i / stages) & 1u);
+        tc_fence_after();
+        const uint32_t stage = base + (uint32_t)s * STAGE_BYTES;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {          // 128 columns of P (4 column tiles) per accumulator
+          const uint32_t d = tmem_base + (uint32_t)(h * GP_BN);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {        // 16 rows per MMA: 1 KB further into every slab
+            const uint32_t ko = (uint32_t)k * 1024u;
+            const uint64_t ph = umma_desc_mnmajor64(stage + (uint32_t)h * 4u * GPM_SLAB + ko, GPM_SLAB);
+            const uint64_t pl = umma_desc_mnmajor64(stage + GPM_OP_BYTES + (uint32_t)h * 4u * GPM_SLAB + ko, GPM_SLAB);
+            const uint64_t qh = umma_desc_mnmajor64(stage + 2u * GPM_OP_BYTES + ko, GPM_SLAB);
+            const uint64_t ql = umma_desc_mnmajor64(stage + 3u * GPM_OP_BYTES + ko, GPM_SLAB);
+            tc_mma_bf16(d, pl, qh, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            tc_mma_bf16(d, ph, ql, idesc, 1u);
+            tc_mma_bf16(d, ph, qh, idesc, 1u);
+          }
+        }
+        tc_commit(bar_empty + 8u * s);
+      }
+      if (n_it > 0) tc_commit(bar_acc);
+    }
+  } else if (n_it > 0) {
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int m = mt * GP_BM + half * TC_M + q * 32 + lane;
+    const int n0 = nt * GP_BN;
+    for (int cb = 0; cb < GP_BN && n0 + cb < N; cb += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * GP_BN + cb);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (m < M) {
+        float* out = C + (size_t)m * ldc + n0 + cb;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + cb + j < N) atomicAdd(out + j, alpha * __uint_as_float(v[j]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // Workspaces for the operand planes, one per stream that issues large products (registered by the engine before any
 // capture: the library itself allocates nothing).  A product on a stream without a (large enough) workspace keeps the
 // in-kernel staging form above.
@@ -534,6 +675,45 @@ extern "C" int scnb_gemm_tc_workspace(void* stream, void* buf, long long bytes) 
   g_tg5_ws[free_slot] = Tg5Workspace{(cudaStream_t)stream, (uint8_t*)buf, bytes};
   return SCNB_OK;
 }
+// Plane buffers bound to fp32 tensors by the engine: the producer of the tensor (scnb_bn_act_fwd / scnb_bn_act_bwd) writes
+// the planes next to it, and a product that reads the tensor as a row-major operand [rows][cols] (lda == cols) takes them
+// as they are.  A weight-gradient product whose two operands are both bound reads the SAME planes as MN-major operands
+// (k_gemm_planes_mn) -- no transposed copies.  rows_pad x cols bf16 per plane, rows_pad a multiple of 256, cols of 32.
+struct Tg5Binding { const float* X; int rows, cols, rows_pad; uint16_t* hi; uint16_t* lo; };
+#define TG5_MAX_BIND 64
+static Tg5Binding g_tg5_bind[TG5_MAX_BIND];
+static int g_tg5_n_bind = 0;
+extern "C" int scnb_gemm_tc_bind_planes(const float* X, int rows, int cols, void* hi, void* lo) {
+  SCNB_CHECK_ARG(X && rows > 0 && cols > 0, "gemm_tc_bind_planes: bad arguments");
+  int free_slot = -1;
+  for (int i = 0; i < g_tg5_n_bind; ++i) {
+    if (g_tg5_bind[i].X == X) { free_slot = i; break; }
+    if (!g_tg5_bind[i].X && free_slot < 0) free_slot = i;
+  }
+  if (!hi || !lo) {                                           // unbind
+    if (free_slot >= 0 && g_tg5_bind[free_slot].X == X) g_tg5_bind[free_slot] = Tg5Binding{nullptr, 0, 0, 0, nullptr, nullptr};
+    return SCNB_OK;
+  }
+  SCNB_CHECK_ARG(cols % 32 == 0, "gemm_tc_bind_planes: cols must be a multiple of 32 (got %d)", cols);
+  SCNB_CHECK_ARG((((uintptr_t)hi | (uintptr_t)lo) % 1024) == 0, "gemm_tc_bind_planes: planes must be 1024-byte aligned");
+  if (free_slot < 0) {
+    SCNB_CHECK_ARG(g_tg5_n_bind < TG5_MAX_BIND, "gemm_tc_bind_planes: more than %d bound tensors", TG5_MAX_BIND);
+    free_slot = g_tg5_n_bind++;
+  }
+  g_tg5_bind[free_slot] = Tg5Binding{X, rows, cols, (rows + 255) / 256 * 256, (uint16_t*)hi, (uint16_t*)lo};
+  return SCNB_OK;
+}
+bool scnb_planes_lookup(const float* X, int cols, int min_rows, uint16_t** hi, uint16_t** lo, int* rows_pad) {
+  for (int i = 0; i < g_tg5_n_bind; ++i) {
+    const Tg5Binding& b = g_tg5_bind[i];
+    if (b.X == X && b.cols == cols && b.rows >= min_rows) {
+      *hi = b.hi; *lo = b.lo; *rows_pad = b.rows_pad;
+      return true;
+    }
+  }
+  return false;
+}
+
 // bytes of workspace a product C[M, N] = op(A) op(B) over K needs
 static long long tg5_workspace_bytes(int M, int N, int K) {
   const long long n_kt = (K + GP_KT - 1) / GP_KT;
@@ -563,6 +743,12 @@ extern "C" int scnb_gemm_tc_min_flops(long long flops) {
 }
 
 static long long g_tg5_planes_launches = 0;
+static long long g_tg5_bound_uses = 0;      // operands taken from planes their producer wrote (no conversion pass)
+extern "C" int scnb_gemm_tc_bound_count(long long* count_out) {
+  SCNB_CHECK_ARG(count_out, "gemm_tc_bound_count: null pointer");
+  *count_out = g_tg5_bound_uses;
+  return SCNB_OK;
+}
 // number of products issued in the planes form so far (tests assert that the path they mean to cover really ran)
 extern "C" int scnb_gemm_tc_planes_count(long long* count_out) {
   SCNB_CHECK_ARG(count_out, "gemm_tc_planes_count: null pointer");
@@ -581,6 +767,35 @@ static int tg5_planes_try(int lay, int M, int N, int K, const float* A, int lda,
   static int off = -1;
   if (off < 0) { const char* e = getenv("SCNB_GEMM_TC_PLANES"); off = (e && e[0] == '0') ? 1 : 0; }
   if (off) return 0;
+  static int bind_off = -1;
+  if (bind_off < 0) { const char* e = getenv("SCNB_GEMM_TC_BOUND"); bind_off = (e && e[0] == '0') ? 1 : 0; }
+  // weight gradient with both operands bound: the producers' row-major planes as MN-major operands, nothing to convert
+  if (lay == 2 && !bind_off && beta == 1.f && !bias && !relu && !gate && (M % 32 == 0) && (N % 32 == 0) && lda == M && ldb == N) {
+    uint16_t *ph, *pl, *qh, *ql;
+    int rp_a = 0, rp_b = 0;
+    if (scnb_planes_lookup(A, M, K, &ph, &pl, &rp_a) && scnb_planes_lookup(B, N, K, &qh, &ql, &rp_b)) {
+      const int n_rt = scnb_cdiv(K, 256);               // (rows past K are zeros in both operands' planes)
+      if (n_rt * 256 <= rp_a && n_rt * 256 <= rp_b) {
+        const int n_mt = scnb_cdiv(M, GP_BM), n_nt = scnb_cdiv(N, GP_BN), n_slabs = n_rt * 8;
+        int splits = 1;
+        while (splits < 64 && (long long)n_mt * n_nt * splits < 148 && n_slabs / (splits * 2) >= 16) splits *= 2;
+        const int per = scnb_cdiv(n_slabs, splits);
+        splits = scnb_cdiv(n_slabs, per);
+        const int stages = 3;
+        const size_t smem = 1024 + (size_t)stages * 4 * GPM_OP_BYTES + 16 * stages + 16 + 16;
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_planes_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+          scnb_set_error("sgemm/tcgen05 planes (MN-major): cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+          return SCNB_ERR_CUDA;
+        }
+        k_gemm_planes_mn<<<dim3(n_mt, n_nt, splits), GP_THREADS, smem, st>>>(M, N, n_rt, M / 32, N / 32, (const uint8_t*)ph, (const uint8_t*)pl,
+                                                                            (const uint8_t*)qh, (const uint8_t*)ql, C, ldc, alpha, per, stages);
+        ++g_tg5_planes_launches;
+        ++g_tg5_bound_uses;
+        return 1;
+      }
+    }
+  }
   const Tg5Workspace* ws = nullptr;
   for (int i = 0; i < g_tg5_n_ws; ++i)
     if (g_tg5_ws[i].st == st && g_tg5_ws[i].buf) ws = &g_tg5_ws[i];
@@ -592,6 +807,18 @@ static int tg5_planes_try(int lay, int M, int N, int K, const float* A, int lda,
   uint8_t* a_lo = a_hi + a_plane;
   uint8_t* b_hi = a_lo + a_plane;
   uint8_t* b_lo = b_hi + b_plane;
+  // a row-major A operand whose producer has already written its planes (scnb_gemm_tc_bind_planes)
+  bool a_bound = false;
+  if (lay != 2 && !bind_off && lda == K && K % 32 == 0) {
+    uint16_t *bh, *bl;
+    int rp = 0;
+    if (scnb_planes_lookup(A, K, M, &bh, &bl, &rp) && n_mt * GP_BM <= rp) {
+      a_hi = (uint8_t*)bh;
+      a_lo = (uint8_t*)bl;
+      a_bound = true;
+      ++g_tg5_bound_uses;
+    }
+  }
   auto planes = [&](bool trans, const float* X, int ld, int R, int n_rt, uint8_t* hi, uint8_t* lo) {
     if (trans) {
       k_gemm_operand_planes<true><<<dim3(n_kt, n_rt), 256, 0, st>>>(X, ld, R, K, n_rt, n_kt, (uint16_t*)hi, (uint16_t*)lo);
@@ -601,7 +828,7 @@ static int tg5_planes_try(int lay, int M, int N, int K, const float* A, int lda,
       k_gemm_operand_planes<false><<<blocks, 256, 0, st>>>(X, ld, R, K, n_rt, n_kt, (uint16_t*)hi, (uint16_t*)lo);
     }
   };
-  planes(lay == 2, A, lda, M, n_mt, a_hi, a_lo);
+  if (!a_bound) planes(lay == 2, A, lda, M, n_mt, a_hi, a_lo);
   planes(lay != 0, B, ldb, N, n_nt, b_hi, b_lo);
   int splits = 1;
   const bool splittable = !bias && !relu && !gate && (beta == 1.f);

@@ -709,6 +709,7 @@ extern "C" int scnb_linear_fwd_tc_planes(const void* a_hi, const void* a_lo, int
 
 #define W1TC_THREADS 320   // warp 0: dZ1 tile loader + L2 prefetch, warp 1: MMA issuer, warps 2-9: densify, then epilogue
 #define W1TC_DENSE 256     // densify / epilogue threads
+#define W1TC_PRE 8         // batch entries per densify thread held in registers one k-tile ahead
 #define W1TC_SINK_BYTES 16384u
 
 // D^T[c, g] = sum_r dZ1[r, c] * X[r, g]: the MMA's M axis is the H0 axis (two 128-lane accumulators for H0 = 256), its
@@ -893,10 +894,13 @@ k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict_
     int lo = 0, hi = 0, lo_n = 0, hi_n = 0;
     if (grp < n_it && grp * KT + rl < nb) { lo = sp0[grp * KT + rl]; hi = sp1[grp * KT + rl]; }
     if (grp + 2 < n_it && (grp + 2) * KT + rl < nb) { lo_n = sp0[(grp + 2) * KT + rl]; hi_n = sp1[(grp + 2) * KT + rl]; }
-    int gj[4];
-    float vj[4];
+    // W1TC_PRE entries per thread (4 x W1TC_PRE per batch row and gene block) are in registers before the stage is released;
+    // rows with more take the dependent loop below.  8 covers 20 % density (27 +- 5 entries per row and block of 136 genes:
+    // with 4 every k-tile of config 5 paid three dependent global round trips inside the refill)
+    int gj[W1TC_PRE];
+    float vj[W1TC_PRE];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < W1TC_PRE; ++j) {
       const int pj = lo + sub + 4 * j;
       gj[j] = pj < hi ? b_idx[pj] : -1;
       vj[j] = pj < hi ? b_val[pj] : 0.f;
@@ -909,10 +913,10 @@ k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict_
       const int rn2 = (i + 4) * KT + rl;
       int lo_n2 = 0, hi_n2 = 0;
       if (i + 4 < n_it && rn2 < nb) { lo_n2 = sp0[rn2]; hi_n2 = sp1[rn2]; }
-      int gn[4];
-      float vn[4];
+      int gn[W1TC_PRE];
+      float vn[W1TC_PRE];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {         // first entries of this group's next tile
+      for (int j = 0; j < W1TC_PRE; ++j) {         // first entries of this group's next tile
         const int pj = lo_n + sub + 4 * j;
         gn[j] = pj < hi_n ? b_idx[pj] : -1;
         vn[j] = pj < hi_n ? b_val[pj] : 0.f;
@@ -925,7 +929,7 @@ k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict_
       else asm volatile("bar.sync 2, 128;" ::: "memory");
       const uint32_t kcol = (uint32_t)rl;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < W1TC_PRE; ++j) {
         if (gj[j] >= 0 && vj[j] != 0.f) {
           const uint32_t g = (uint32_t)(gj[j] - g0);
           const __nv_bfloat16 h = __float2bfloat16_rn(vj[j]);
@@ -935,7 +939,7 @@ k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict_
           st_shared_u16(x_lo_base + off, __bfloat16_as_ushort(l));
         }
       }
-      for (int pj = lo + sub + 16; pj < hi; pj += 4) {   // rows with more than 16 entries in this gene block
+      for (int pj = lo + sub + 4 * W1TC_PRE; pj < hi; pj += 4) {   // rows with more than 4 * W1TC_PRE entries in this gene block
         const float v = b_val[pj];
         if (v != 0.f) {
           const uint32_t g = (uint32_t)(b_idx[pj] - g0);
@@ -951,7 +955,7 @@ k_w1_bwd_optim_tc(const int32_t* __restrict__ splits, const int32_t* __restrict_
       lo = lo_n; hi = hi_n;
       lo_n = lo_n2; hi_n = hi_n2;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { gj[j] = gn[j]; vj[j] = vn[j]; }
+      for (int j = 0; j < W1TC_PRE; ++j) { gj[j] = gn[j]; vj[j] = vn[j]; }
     }
     // ===== epilogue: warp (h, q) owns columns c = 128 h + 32 q + lane of W1T for all genes of the CTA =====
     const int q = warp & 3;                  // TMEM lane quarter this warp may read

@@ -36,10 +36,12 @@ SID_IN_U = 1          # + k : input dropout of teacher view k
 SID_HID = 16          # + application index : hidden dropout of the student super-batch
 
 
-def _release_gemm_ws(handles):
+def _release_gemm_ws(handles, bound=()):
     try:
         for h in handles:
             call("scnb_gemm_tc_workspace", h, None, 0)
+        for (p, r, w) in bound:
+            call("scnb_gemm_tc_bind_planes", p, r, w, None, None)
     except Exception:
         pass
 
@@ -566,8 +568,26 @@ class TrainEngine(object):
             buf = torch.empty(n_bytes + 1024, dtype=torch.uint8, device=self.dev)
             self._gemm_ws.append(buf)
             call("scnb_gemm_tc_workspace", h, buf.data_ptr() + (-buf.data_ptr()) % 1024, n_bytes)
+        # Operand planes written by the producers (dense_ops.cu PlaneSink): the BatchNorm forward writes As[a] also as the planes
+        # the next Linear's product reads, the BatchNorm backward writes dZs[a] also as the planes of the input-gradient
+        # product; the weight-gradient product reads both sets as MN-major operands.  (Unfused hidden path, one GPU.)
+        bound = []
+        if not self.hs_fused and self.comm is None and os.environ.get("SCNB_GEMM_TC_BOUND", "1") != "0":
+            Rp = (R + 255) // 256 * 256
+            todo = [self.As[a] for a in range(self.n_app - 1)] + [self.dZs[a] for a in range(1, self.n_app)]
+            for t in todo:
+                w = int(t.shape[1])
+                if w % 32 or int(t.shape[0]) < R or not t.is_contiguous():
+                    continue
+                pair = []
+                for _ in range(2):
+                    buf = torch.zeros(Rp * w * 2 + 1024, dtype=torch.uint8, device=self.dev)
+                    self._gemm_ws.append(buf)
+                    pair.append(buf.data_ptr() + (-buf.data_ptr()) % 1024)
+                call("scnb_gemm_tc_bind_planes", t.data_ptr(), R, w, pair[0], pair[1])
+                bound.append((t.data_ptr(), R, w))
         import weakref
-        weakref.finalize(self, _release_gemm_ws, handles)
+        weakref.finalize(self, _release_gemm_ws, handles, bound)
 
     def _sync_planes(self):
         """With `w1_emits_planes` the step itself keeps the operand planes current.  They are rebuilt here, eagerly, when

@@ -761,3 +761,120 @@ def test_sgemm_tcgen05_path_matches_fp64(lay, M, N, K, extras, planes):
         call("scnb_gemm_tc_min_flops", 2_000_000_000)
         if ws is not None:
             call("scnb_gemm_tc_workspace", _st(), None, 0)
+
+
+# ---- operand planes written by the producer of a tensor (tc_gemm.cu planes form, dense_ops.cu PlaneSink) ----------------
+def _planes_encode(X):
+    """fp32 [R, K] -> (hi, lo) bf16 planes tiled [R/256][K/32], each tile a SWIZZLE_64B K-major image of 256 x 32 (the layout
+    of k_gemm_operand_planes / PlaneSink): 16-byte chunk c of row r sits at chunk position c ^ ((r >> 1) & 3)."""
+    R, K = X.shape
+    Rp, Kp = (R + 255) // 256 * 256, (K + 31) // 32 * 32
+    Xp = torch.zeros(Rp, Kp, dtype=torch.float32, device=X.device)
+    Xp[:R, :K] = X
+    hi = Xp.to(torch.bfloat16)
+    lo = (Xp - hi.float()).to(torch.bfloat16)
+    rr = torch.arange(256, device=X.device)
+    pc = torch.arange(4, device=X.device)
+    src = (pc[None, :] ^ ((rr[:, None] >> 1) & 3))           # logical chunk stored at physical position pc of row rr
+
+    def tile(P):
+        T = P.view(Rp // 256, 256, Kp // 32, 4, 8).permute(0, 2, 1, 3, 4)          # [rt, kt, rr, c, j]
+        idx = src[None, None, :, :, None].expand(T.shape[0], T.shape[1], 256, 4, 8)
+        return torch.gather(T, 3, idx).contiguous().view(-1)
+    return tile(hi), tile(lo)
+
+
+def _aligned(n_elems, dtype):
+    buf = torch.zeros(n_elems + 1024, dtype=dtype).cuda()
+    off = ((-buf.data_ptr()) % 1024) // buf.element_size()
+    return buf, buf[off:off + n_elems]
+
+
+@pytest.mark.parametrize("H,segs,maxr", [(256, [(0, 3000), (3000, 9001), (9001, 12000)], 12400), (64, [(0, 300), (300, 520)], 600)])
+def test_bn_act_kernels_emit_operand_planes_of_bound_outputs(H, segs, maxr):
+    """scnb_bn_act_fwd / scnb_bn_act_bwd with planes bound to their outputs: the planes are the bf16 hi / lo split of the fp32
+    output, in the tiled layout, zero in the rows past the tensor's -- bit for bit."""
+    from scnym_b200._lib import call, ptr
+    torch.manual_seed(H + maxr)
+    Z = (torch.randn(maxr, H) * 2 + 0.5).cuda()
+    g, b = (torch.rand(H) + 0.5).cuda(), (torch.randn(H) * 0.1).cuda()
+    keep = (torch.rand(maxr, H) < 0.5).to(torch.uint8).cuda()
+    dA = torch.randn(maxr, H).cuda()
+    n_act = segs[-1][1]
+    seg = torch.tensor([s[0] for s in segs] + [n_act], dtype=torch.int32).cuda()
+    A, dZ = torch.full((maxr, H), 7.0).cuda(), torch.full((maxr, H), 7.0).cuda()
+    stats = torch.zeros(len(segs), 3, H).cuda()
+    Rp = (maxr + 255) // 256 * 256
+    bufs = [_aligned(Rp * H, torch.int16) for _ in range(4)]
+    for _, v in bufs:
+        v.fill_(0x7f7f)
+    try:
+        call("scnb_gemm_tc_bind_planes", ptr(A), maxr, H, ptr(bufs[0][1]), ptr(bufs[1][1]))
+        call("scnb_gemm_tc_bind_planes", ptr(dZ), maxr, H, ptr(bufs[2][1]), ptr(bufs[3][1]))
+        call("scnb_bn_act_fwd", ptr(Z), ptr(A), None, H, len(segs), ptr(seg), maxr, 1, ptr(g), ptr(b), None, None, ptr(stats),
+             ptr(keep), None, 0, 0.5, 1, None, None, _st())
+        dg, db = torch.zeros(H).cuda(), torch.zeros(H).cuda()
+        call("scnb_bn_act_bwd", ptr(dA), ptr(Z), ptr(A), H, len(segs), ptr(seg), maxr, ptr(g), ptr(stats), ptr(keep), None, 0,
+             0.5, 1, ptr(dZ), ptr(dg), ptr(db), None, None, _st())
+        torch.cuda.synchronize()
+        for name, X, (hi, lo) in (("A", A, (bufs[0][1], bufs[1][1])), ("dZ", dZ, (bufs[2][1], bufs[3][1]))):
+            assert float(X[n_act:].abs().sum()) == 0.0
+            want_hi, want_lo = _planes_encode(X)
+            assert torch.equal(hi.view(torch.bfloat16), want_hi), name + " hi plane"
+            assert torch.equal(lo.view(torch.bfloat16), want_lo), name + " lo plane"
+    finally:
+        call("scnb_gemm_tc_bind_planes", ptr(A), maxr, H, None, None)
+        call("scnb_gemm_tc_bind_planes", ptr(dZ), maxr, H, None, None)
+
+
+@pytest.mark.parametrize("lay,M,N,K", [(0, 1000, 320, 512), (1, 600, 96, 256), (2, 256, 512, 8192), (2, 1024, 1024, 4000),
+                                       (2, 128, 160, 700)])
+def test_sgemm_tcgen05_takes_bound_operand_planes(lay, M, N, K):
+    """Products whose operands already exist as planes (bound by scnb_gemm_tc_bind_planes): the row-major A operand of the
+    forward / input-gradient layouts is taken as it is, and the weight-gradient layout reads BOTH operands' row-major planes as
+    MN-major operands (k_gemm_planes_mn).  The bound planes are the only copy of the data that is right: the fp32 tensors handed
+    to scnb_sgemm for the bound operands hold garbage."""
+    import ctypes
+    from scnym_b200._lib import call, ptr
+    call("scnb_gemm_tc_min_flops", 1)
+    torch.manual_seed(lay * 1000 + M + K)
+    tA, tB = (lay == 2), (lay == 0)
+    A = torch.randn((K, M) if tA else (M, K)).cuda()
+    B = torch.randn((N, K) if tB else (K, N)).cuda()
+    C0 = torch.randn(M, N).cuda()
+    C = C0.clone()
+    beta = 1.0 if lay == 2 else 0.0
+    need = ctypes.c_longlong(0)
+    call("scnb_gemm_tc_workspace_bytes", M, N, K, ctypes.byref(need))
+    ws, wsv = _aligned(need.value, torch.uint8)
+    bound = [A, B] if lay == 2 else [A]
+    keepalive, fakes = [], []
+    try:
+        call("scnb_gemm_tc_workspace", _st(), ptr(wsv), need.value)
+        for X in bound:
+            hi, lo = _planes_encode(X)
+            bh, vh = _aligned(hi.numel(), torch.bfloat16)
+            bl, vl = _aligned(lo.numel(), torch.bfloat16)
+            vh.copy_(hi)
+            vl.copy_(lo)
+            keepalive += [bh, bl]
+            fake = torch.full_like(X, 1e30)          # what scnb_sgemm is handed: must never be read
+            fakes.append(fake)
+            call("scnb_gemm_tc_bind_planes", ptr(fake), X.shape[0], X.shape[1], ptr(vh), ptr(vl))
+        n0, n1 = ctypes.c_longlong(0), ctypes.c_longlong(0)
+        call("scnb_gemm_tc_bound_count", ctypes.byref(n0))
+        fa = fakes[0]
+        fb = fakes[1] if lay == 2 else B
+        call("scnb_sgemm", int(tA), int(tB), M, N, K, ptr(fa), fa.shape[1], ptr(fb), fb.shape[1], ptr(C), N, 1.0, beta, None, 0, None, _st())
+        torch.cuda.synchronize()
+        call("scnb_gemm_tc_bound_count", ctypes.byref(n1))
+        assert n1.value - n0.value == 1
+        opA = A.double().t() if tA else A.double()
+        opB = B.double().t() if tB else B.double()
+        want = opA @ opB + beta * C0.double()
+        _chk(f"tc gemm lay {lay} bound planes", C.cpu(), want.float().cpu(), tol=3e-5)
+    finally:
+        call("scnb_gemm_tc_min_flops", 2_000_000_000)
+        call("scnb_gemm_tc_workspace", _st(), None, 0)
+        for f in fakes:
+            call("scnb_gemm_tc_bind_planes", ptr(f), f.shape[0], f.shape[1], None, None)
