@@ -261,23 +261,61 @@ __global__ void __launch_bounds__(1024) k_colsum(const float* __restrict__ A, in
                                                  int accumulate) {
   PDL_ENTRY();
   __shared__ float red[32][33];
+  __shared__ float part[32];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
+  // tall matrices (config 5: 16 384 rows): the rows are split over the gridDim.y CTAs of a thread-block cluster and the
+  // partial sums meet in rank order through distributed shared memory (deterministic; one launch)
+  const int CL = (int)gridDim.y;
+  const int chunk = (M + CL - 1) / CL;
+  const int rb = min(M, (int)blockIdx.y * chunk), re = min(M, rb + chunk);
   float s = 0.f;
   if (c < N)
-    for (int r = ty; r < M; r += 32) s += A[(size_t)r * lda + c];
+    for (int r = rb + ty; r < re; r += 32) s += A[(size_t)r * lda + c];
   red[ty][tx] = s;
   __syncthreads();
+  float t = 0.f;
   if (ty == 0) {
-    float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) t += red[i][tx];
-    if (c < N) out[c] = accumulate ? out[c] + t : t;
   }
+  if (CL > 1) {
+    if (ty == 0) part[tx] = t;
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (ty == 0 && blockIdx.y == 0) {
+      const uint32_t mine = (uint32_t)__cvta_generic_to_shared(part + tx);
+      t = 0.f;
+      for (int p = 0; p < CL; ++p) {
+        uint32_t ra;
+        float v;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(mine), "r"(p));
+        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+        t += v;
+      }
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
+  if (ty == 0 && blockIdx.y == 0 && c < N) out[c] = accumulate ? out[c] + t : t;
 }
 
 extern "C" int scnb_colsum(const float* A, int M, int N, int lda, float* out, int accumulate, void* stream) {
   SCNB_CHECK_ARG(A && out && M >= 0 && N > 0, "colsum: bad arguments");
+  if (M >= 4096) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(scnb_cdiv(N, 32), 8);
+    cfg.blockDim = dim3(1024);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1;
+    at[0].val.clusterDim.y = 8;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k_colsum, A, M, N, lda, out, accumulate);
+    SCNB_CHECK_LAUNCH("colsum/cluster");
+    return SCNB_OK;
+  }
   scnb_launch_pdl(k_colsum, dim3(scnb_cdiv(N, 32)), dim3(1024), 0, (cudaStream_t)stream, A, M, N, lda, out, accumulate);
   SCNB_CHECK_LAUNCH("colsum");
   return SCNB_OK;

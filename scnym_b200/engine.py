@@ -1151,9 +1151,15 @@ class TrainEngine(object):
             # (the graph releases the children of a node one after the other, ~5 us apart: the dA product is issued first
             # and is the only child of its parent on the critical chain)
             ev = self._ev_dz[a]
-            if sW is not main:
+            # Large products (tcgen05, one 197 KB CTA per SM): two of them cannot share an SM, so the weight-gradient product
+            # is forked BEHIND the input-gradient product -- it then runs next to the HBM-bound BatchNorm backward of the
+            # layer below instead of fighting the chain's own product for the SMs
+            late_fork = bool(self._gemm_ws) and os.environ.get("SCNB_WGRAD_FORK", "late") == "late"
+            if sW is not main and not late_fork:
                 ev.record(main)
             call("scnb_sgemm", 0, 0, R, wp, w, ptr(dZ), w, self.P(blk[a]["W"]), wp, ptr(dA), wp, 1.0, 0.0, None, 0, None, st)
+            if sW is not main and late_fork:
+                ev.record(main)
             if sW is not main:
                 sW.wait_event(ev)
             call("scnb_sgemm", 1, 0, w, wp, R, ptr(dZ), w, ptr(self.As[a - 1]), wp, self.Gp(blk[a]["W"]), wp, 1.0, 1.0, None, 0,

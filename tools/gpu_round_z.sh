@@ -1,10 +1,11 @@
 #!/bin/bash
-# producer-written operand planes: kernel tests, config-5 parity, bench + timeline
+# full GPU tests + config 2 bench + config 5 bench (late / early weight-gradient fork) + timeline
 TAG=${1:-z}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_cuda_kernels.py tests/test_full_shape_parity.py -m gpu -q -p no:cacheprovider -k "bn_act or config5 or tcgen05 or planes" > gpurun_out/${TAG}_tests.log 2>&1
+timeout 1200 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/${TAG}_tests.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/${TAG}_tests.log
+timeout 600 python bench.py --steps 200 --warmup 20 --no-cpu-baseline --no-gpu-eager --no-predict --no-e2e > gpurun_out/${TAG}_bench_c2.json 2> gpurun_out/${TAG}_bench_c2.err
 timeout 600 python bench.py --config 5 --steps 20 --warmup 3 --no-cpu-baseline --no-gpu-eager --no-predict --no-e2e > gpurun_out/${TAG}_bench_c5.json 2> gpurun_out/${TAG}_bench_c5.err
-SCNB_GEMM_TC_BOUND=0 timeout 600 python bench.py --config 5 --steps 20 --warmup 3 --no-cpu-baseline --no-gpu-eager --no-predict --no-e2e > gpurun_out/${TAG}_bench_c5_unbound.json 2> gpurun_out/${TAG}_bench_c5_unbound.err
+SCNB_WGRAD_FORK=early timeout 600 python bench.py --config 5 --steps 20 --warmup 3 --no-cpu-baseline --no-gpu-eager --no-predict --no-e2e > gpurun_out/${TAG}_bench_c5_early.json 2> gpurun_out/${TAG}_bench_c5_early.err
 timeout 300 python tools/timeline.py --config 5 > gpurun_out/${TAG}_timeline_c5.txt 2>&1
-tail -15 gpurun_out/${TAG}_tests.log; head -c 300 gpurun_out/${TAG}_bench_c5.json; echo; head -c 300 gpurun_out/${TAG}_bench_c5_unbound.json; tail -3 gpurun_out/${TAG}_bench_c5.err
+tail -6 gpurun_out/${TAG}_tests.log; head -c 300 gpurun_out/${TAG}_bench_c2.json; echo;  head -c 300 gpurun_out/${TAG}_bench_c5.json; echo; head -c 300 gpurun_out/${TAG}_bench_c5_early.json; tail -3 gpurun_out/${TAG}_bench_c5.err
