@@ -732,6 +732,29 @@ __global__ void __launch_bounds__(BNV_T) k_bn_act_fwd_v8(const float* __restrict
       mean.v[j] = ext_sums[((size_t)s * 2 + 0) * H + c0 + j] / ng;
       var.v[j] = fmaxf(ext_sums[((size_t)s * 2 + 1) * H + c0 + j] / ng - mean.v[j] * mean.v[j], 0.f);
     }
+  } else if (W > 1 || gridDim.z > 1) {
+    // Large batches: ONE statistics pass over Z (sums of d = z - z0 and d^2, z0 = the segment's first row: a sample of the
+    // column, so E[d]^2 is of the order of the variance and the subtraction below does not cancel) instead of the two
+    // passes of the centred form -- Z is read twice per launch, not three times.
+    const float inv_n = 1.0f / (float)max(n, 1);
+    F8 z0, a1, a2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z0.v[j] = a1.v[j] = a2.v[j] = 0.f;
+    if (n > 0) z0 = ld8(Z + (size_t)r0 * H + c0);
+    for (int r = rb + tr; r < re; r += RS) {
+      const F8 z = ld8(Z + (size_t)r * H + c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = z.v[j] - z0.v[j]; a1.v[j] += d; a2.v[j] = fmaf(d, d, a2.v[j]); }
+    }
+    bnv_colsum8<W>(a1, red1);
+    bnv_colsum8<W>(a2, red2);
+    bnv_cluster_sum16<W>(a1, a2, xs);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float m = a1.v[j] * inv_n;
+      mean.v[j] = z0.v[j] + m;
+      var.v[j] = fmaxf(a2.v[j] * inv_n - m * m, 0.f);
+    }
   } else {
     const float inv_n = 1.0f / (float)max(n, 1);
 #pragma unroll

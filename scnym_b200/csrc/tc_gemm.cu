@@ -703,13 +703,19 @@ extern "C" int scnb_gemm_tc_bind_planes(const float* X, int rows, int cols, void
   g_tg5_bind[free_slot] = Tg5Binding{X, rows, cols, (rows + 255) / 256 * 256, (uint16_t*)hi, (uint16_t*)lo};
   return SCNB_OK;
 }
+// X may also start at a later row tile of a bound tensor (a row offset that is a multiple of 256: the planes of rows
+// [256 t, ...) are the tiles from t on) -- the adversary branch reads the rows behind the MixMatch segments of As[last].
 bool scnb_planes_lookup(const float* X, int cols, int min_rows, uint16_t** hi, uint16_t** lo, int* rows_pad) {
   for (int i = 0; i < g_tg5_n_bind; ++i) {
     const Tg5Binding& b = g_tg5_bind[i];
-    if (b.X == X && b.cols == cols && b.rows >= min_rows) {
-      *hi = b.hi; *lo = b.lo; *rows_pad = b.rows_pad;
-      return true;
-    }
+    if (!b.X || b.cols != cols || X < b.X) continue;
+    const size_t d = (size_t)(X - b.X);
+    if (d % ((size_t)256 * cols) != 0) continue;
+    const long long row0 = (long long)(d / cols);
+    if (row0 >= b.rows || b.rows - row0 < min_rows) continue;
+    const size_t off = (size_t)row0 * cols;        // bf16 elements: whole tiles
+    *hi = b.hi + off; *lo = b.lo + off; *rows_pad = b.rows_pad - (int)row0;
+    return true;
   }
   return false;
 }

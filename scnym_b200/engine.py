@@ -574,7 +574,7 @@ class TrainEngine(object):
         bound = []
         if not self.hs_fused and self.comm is None and os.environ.get("SCNB_GEMM_TC_BOUND", "1") != "0":
             Rp = (R + 255) // 256 * 256
-            todo = [self.As[a] for a in range(self.n_app - 1)] + [self.dZs[a] for a in range(1, self.n_app)]
+            todo = [self.As[a] for a in range(self.n_app)] + [self.dZs[a] for a in range(1, self.n_app)]
             for t in todo:
                 w = int(t.shape[1])
                 if w % 32 or int(t.shape[0]) < R or not t.is_contiguous():
@@ -1154,7 +1154,15 @@ class TrainEngine(object):
             # Large products (tcgen05, one 197 KB CTA per SM): two of them cannot share an SM, so the weight-gradient product
             # is forked BEHIND the input-gradient product -- it then runs next to the HBM-bound BatchNorm backward of the
             # layer below instead of fighting the chain's own product for the SMs
-            late_fork = bool(self._gemm_ws) and os.environ.get("SCNB_WGRAD_FORK", "late") == "late"
+            fork = os.environ.get("SCNB_WGRAD_FORK", "late") if self._gemm_ws else "early"
+            late_fork = fork == "late"
+            if fork == "chain" and sW is not main:
+                # (experiment) no fork at all: the weight-gradient product follows the input-gradient product on the chain
+                call("scnb_sgemm", 0, 0, R, wp, w, ptr(dZ), w, self.P(blk[a]["W"]), wp, ptr(dA), wp, 1.0, 0.0, None, 0, None, st)
+                call("scnb_sgemm", 1, 0, w, wp, R, ptr(dZ), w, ptr(self.As[a - 1]), wp, self.Gp(blk[a]["W"]), wp, 1.0, 1.0, None, 0,
+                     None, st)
+                call("scnb_colsum", ptr(dZ), R, w, w, self.Gp(blk[a]["b"]), 1, st)
+                continue
             if sW is not main and not late_fork:
                 ev.record(main)
             call("scnb_sgemm", 0, 0, R, wp, w, ptr(dZ), w, self.P(blk[a]["W"]), wp, ptr(dA), wp, 1.0, 0.0, None, 0, None, st)
