@@ -762,10 +762,16 @@ class TrainEngine(object):
             # (measured 0.1480 / 0.1466 / 0.1489 ms for 0 / 1 / 2)
             splits_late = os.environ.get("SCNB_SPLITS_LATE", "1") if not self.host_mapped else "0"
             splits_late = {"0": 0, "1": 1, "2": 2}.get(splits_late, 0)    # 1: behind the heads, 2: next to the dW1 kernel
-            try:
-                self._prologue_next(sF, rng, splits=splits_late == 0)
-            finally:
+            # SCNB_PREFETCH_AT=heads (experiment): the WHOLE prologue of the next step behind the heads
+            pf_deferred = os.environ.get("SCNB_PREFETCH_AT", "start") == "heads" and not self.host_mapped
+            if pf_deferred:
+                splits_late = 3
                 self.__dict__["_cur"] = cur
+            else:
+                try:
+                    self._prologue_next(sF, rng, splits=splits_late == 0)
+                finally:
+                    self.__dict__["_cur"] = cur
             if splits_late == 0:
                 self._ev_pf.record(sF)
         else:
@@ -909,6 +915,17 @@ class TrainEngine(object):
             self._ev_pf.record(sF)
         if splits_late == 1:
             late_splits()
+        if splits_late == 3:
+            sF = self._side[4]
+            self._ev_fl.record(main)
+            sF.wait_event(self._ev_fl)
+            cur = self.__dict__["_cur"]
+            self.__dict__["_cur"] = 1 - cur
+            try:
+                self._prologue_next(sF, rng, splits=True)
+            finally:
+                self.__dict__["_cur"] = cur
+            self._ev_pf.record(sF)
         if sW is not main and hf:
             running_update()      # the statistics of the last application are written by the head kernels
         published = False
