@@ -564,26 +564,26 @@ k_gemm_planes_mn(int M, int N, int n_rt /* 256-row tiles of the operands */, int
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {  // ===== loader: a 2 KB slab per column tile and plane =====
-      for (int i = 0; i < n_it; ++i) {
-        const int s = i % stages;
+    // ===== loader: a 2 KB slab per column tile and plane = up to 32 bulk copies per stage.  ONE per lane: a single thread
+    // issuing all 32 took longer than the 12 MMAs of a stage (the product ran at 40 % of the tensor peak) =====
+    // lane = 16 * operand + 8 * plane + column tile
+    const int op = lane >> 4, plane = (lane >> 3) & 1, j = lane & 7;
+    const bool mine = j < (op ? q_tiles : p_tiles);
+    const uint8_t* src = op ? (plane ? q_lo : q_hi) : (plane ? p_lo : p_hi);
+    const int nkt = op ? q_nkt : p_nkt, ct = (op ? nt : mt) * 8 + j;
+    const uint32_t dst_off = (uint32_t)(2 * op + plane) * GPM_OP_BYTES + (uint32_t)j * GPM_SLAB;
+    for (int i = 0; i < n_it; ++i) {
+      const int s = i % stages;
+      const uint32_t bar = bar_full + 8u * s;
+      if (lane == 0) {
         mbar_wait(bar_empty + 8u * s, ((uint32_t)(i / stages) & 1u) ^ 1u);
-        const uint32_t stage = base + (uint32_t)s * STAGE_BYTES;
-        const uint32_t bar = bar_full + 8u * s;
         mbar_arrive_expect_tx(bar, 2u * GPM_SLAB * (uint32_t)(p_tiles + q_tiles));
+      }
+      __syncwarp();
+      if (mine) {
         const int slab = s0 + i;
-        const int rt = slab >> 3;
-        const size_t in_tile = (size_t)(slab & 7) * GPM_SLAB;
-        for (int j = 0; j < p_tiles; ++j) {
-          const size_t off = ((size_t)rt * p_nkt + (size_t)(mt * 8 + j)) * GP_TILE_BYTES + in_tile;
-          bulk_g2s(stage + (uint32_t)j * GPM_SLAB, p_hi + off, GPM_SLAB, bar);
-          bulk_g2s(stage + GPM_OP_BYTES + (uint32_t)j * GPM_SLAB, p_lo + off, GPM_SLAB, bar);
-        }
-        for (int j = 0; j < q_tiles; ++j) {
-          const size_t off = ((size_t)rt * q_nkt + (size_t)(nt * 8 + j)) * GP_TILE_BYTES + in_tile;
-          bulk_g2s(stage + 2u * GPM_OP_BYTES + (uint32_t)j * GPM_SLAB, q_hi + off, GPM_SLAB, bar);
-          bulk_g2s(stage + 3u * GPM_OP_BYTES + (uint32_t)j * GPM_SLAB, q_lo + off, GPM_SLAB, bar);
-        }
+        const size_t off = ((size_t)(slab >> 3) * nkt + (size_t)ct) * GP_TILE_BYTES + (size_t)(slab & 7) * GPM_SLAB;
+        bulk_g2s(base + (uint32_t)s * STAGE_BYTES + dst_off, src + off, GPM_SLAB, bar);
       }
     }
   } else if (warp == 1) {

@@ -18,7 +18,9 @@ def main():
     ap.add_argument("--cells", type=int, default=20000)
     ap.add_argument("--predict", action="store_true")
     ap.add_argument("--single-stream", action="store_true")
+    ap.add_argument("--config", type=int, default=2)
     a = ap.parse_args()
+    bench.CFG, _ = bench.CONFIGS[a.config]
     dev = torch.device("cuda", 0)
     if a.predict:
         from scnym_b200.model import CellTypeCLF
