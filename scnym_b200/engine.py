@@ -1173,6 +1173,11 @@ class TrainEngine(object):
             # layer below instead of fighting the chain's own product for the SMs
             fork = os.environ.get("SCNB_WGRAD_FORK", "late") if self._gemm_ws else "early"
             late_fork = fork == "late"
+            # the LAST weight-gradient product (a == 1) has nothing left on the chain to hide behind except the dW1 kernel,
+            # which takes every SM: on the side branch it ran AFTER that kernel, a tail of ~120 us.  It goes on the chain in
+            # front of the dW1 kernel (SCNB_WGRAD_LAST=side restores the branch; 2.69 -> 2.66 ms)
+            if a == 1 and fork == "late" and os.environ.get("SCNB_WGRAD_LAST", "chain") == "chain":
+                fork = "chain"
             if fork == "chain" and sW is not main:
                 # (experiment) no fork at all: the weight-gradient product follows the input-gradient product on the chain
                 call("scnb_sgemm", 0, 0, R, wp, w, ptr(dZ), w, self.P(blk[a]["W"]), wp, ptr(dA), wp, 1.0, 0.0, None, 0, None, st)
