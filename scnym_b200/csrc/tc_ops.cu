@@ -347,11 +347,10 @@ k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ 
     // is paid once per window and off the critical path (a warp otherwise stalls on its slowest lane at
     // every entry).
     const int NONE = 0x7fffffff;
-    // TWO windows are in flight behind the current one (cn, cm): at 20 % density (config 5) a window of 8 entries lasts
-    // 1.25 gene tiles (~0.5 us), less than a global-memory round trip under load -- with one window ahead the refill
-    // stalled on its own prefetch and the first layer ran at half the tensor rate.
-    int cw[TC_W], cn[TC_W], cm[TC_W];
-    float vw[TC_W], vn[TC_W], vm[TC_W];
+    // (Two windows in flight behind the current one were measured: no gain at 20 % density -- config 5's first layer stays at
+    // 375 us -- and 5.6 % slower at 5 % density: predict's first layer 1.71 -> 1.81 ms per chunk.  One window ahead it is.)
+    int cw[TC_W], cn[TC_W];
+    float vw[TC_W], vn[TC_W];
 #pragma unroll
     for (int w = 0; w < TC_W; ++w) {
       cw[w] = p + w < pend ? idx[p + w] : NONE;
@@ -361,11 +360,6 @@ k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ 
     for (int w = 0; w < TC_W; ++w) {
       cn[w] = p + TC_W + w < pend ? idx[p + TC_W + w] : NONE;
       vn[w] = p + TC_W + w < pend ? val[p + TC_W + w] : 0.f;
-    }
-#pragma unroll
-    for (int w = 0; w < TC_W; ++w) {
-      cm[w] = p + 2 * TC_W + w < pend ? idx[p + 2 * TC_W + w] : NONE;
-      vm[w] = p + 2 * TC_W + w < pend ? val[p + 2 * TC_W + w] : 0.f;
     }
     // The head of the window is always cw[0] (consumed entries are shifted out), so every lane that still has an
     // entry for this tile executes the SAME store instruction: one shared-memory wavefront group per step of the
@@ -403,19 +397,17 @@ k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ 
           --cnt;
         }
         if (cnt > 0) break;                        // the head belongs to a later tile (or the row is finished)
-        // window exhausted: the prefetched ones move up, the one two windows ahead is requested now
+        // window exhausted: the prefetched one becomes current, the one after it is requested now
         p += TC_W;
 #pragma unroll
         for (int w = 0; w < TC_W; ++w) {
           cw[w] = cn[w];
           vw[w] = vn[w];
-          cn[w] = cm[w];
-          vn[w] = vm[w];
         }
 #pragma unroll
         for (int w = 0; w < TC_W; ++w) {
-          cm[w] = p + 2 * TC_W + w < pend ? idx[p + 2 * TC_W + w] : NONE;
-          vm[w] = p + 2 * TC_W + w < pend ? val[p + 2 * TC_W + w] : 0.f;
+          cn[w] = p + TC_W + w < pend ? idx[p + TC_W + w] : NONE;
+          vn[w] = p + TC_W + w < pend ? val[p + TC_W + w] : 0.f;
         }
         cnt = TC_W;
         if (cw[0] >= kend) break;
