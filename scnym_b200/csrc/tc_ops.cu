@@ -202,13 +202,27 @@ extern "C" int scnb_bn_eval_planes(const float* Z, int n_rows, int H, const floa
 // (N = 256 rows).  TMEM lanes are then columns of Z, so a warp of the epilogue adds 32 CONSECUTIVE floats of one row of Z
 // per instruction (one 128-byte line per atomic request) instead of 32 rows x 16 bytes: the 148 partial products of the
 // gene-axis split meet in L2 with a quarter of the atomic transactions.
+// Optional epilogue of the predict form: eval-mode BatchNorm -> ReLU of the first layer's output written straight as the bf16
+// hi / lo operand planes of the next Linear (the layout of scnb_bn_eval_planes), instead of fp32 Z: the 77 MB per chunk of Z
+// are neither written nor read back, and the separate BatchNorm launch disappears.  Same arithmetic, operation for operation,
+// as scnb_csr_linear_fwd_tc_i64 followed by scnb_bn_eval_planes (bit-identical planes).
+struct FwdBnPlanes {
+  const float* gamma;
+  const float* beta;
+  const float* rmean;
+  const float* rvar;
+  uint16_t* hi;
+  uint16_t* lo;
+  int relu;
+};
+
 template <typename IdxT, int HALVES, int KT, bool DENSE_A, bool TRN>
 __global__ void __launch_bounds__(64 + 128 * HALVES, 1)
 k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ idx, const float* __restrict__ val, int n_rows,
                    const uint8_t* __restrict__ planes_hi, const uint8_t* __restrict__ planes_lo, int N, int n_ktiles,
                    const float* __restrict__ bias, float* __restrict__ Z, int stages, int tmem_cols,
                    const uint8_t* __restrict__ a_hi_planes, const uint8_t* __restrict__ a_lo_planes,
-                   const int32_t* __restrict__ fwd_splits, long long* __restrict__ dbg) {
+                   const int32_t* __restrict__ fwd_splits, long long* __restrict__ dbg, FwdBnPlanes bnp) {
 #define FWDTC_GSTAMP(k) do { if (dbg) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[4 * (blockIdx.y * gridDim.x + blockIdx.x) + (k)] = (long long)t_; } } while (0)
   constexpr uint32_t ROWB = 2 * KT;                       // bytes per operand row (bf16)
   constexpr uint32_t A_HALF = TC_M * ROWB;                // one 128-row A block of one plane
@@ -455,6 +469,58 @@ k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ 
           }
         }
       }
+    } else if (n_it > 0 && bnp.hi) {
+      // ===== predict form, fused: Z + b -> BatchNorm(eval) -> ReLU -> operand planes of the next layer (no split over genes) =====
+      mbar_wait(bar_acc, 0);
+      tc_fence_after();
+      // per-column constants in the (now free) first stage: [mean | 1/sqrt(var + eps) | gamma | beta | bias], N floats each
+      float* cst = reinterpret_cast<float*>(sm);
+      for (int c = tid - 64; c < N; c += 128 * HALVES) {
+        cst[c] = bnp.rmean[c];
+        cst[N + c] = 1.0f / sqrtf(bnp.rvar[c] + 1e-5f);
+        cst[2 * N + c] = bnp.gamma[c];
+        cst[3 * N + c] = bnp.beta[c];
+        cst[4 * N + c] = bias ? bias[c] : 0.f;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * HALVES) : "memory");
+      const int n_kt_out = N >> 5;
+      const uint32_t rr = (uint32_t)(grow & 255);
+      const size_t tile_row = (size_t)(grow >> 8) * n_kt_out;
+      for (int cb = 0; cb < N; cb += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * N + cb);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const size_t tile = (tile_row + (size_t)(cb >> 5)) * (256 * 32) + (size_t)rr * 32;
+#pragma unroll
+        for (int jc = 0; jc < 4; ++jc) {
+          float y[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = cb + 8 * jc + j;
+            float z = __uint_as_float(v[8 * jc + j]);
+            z += cst[4 * N + c];
+            float yy = (z - cst[c]) * cst[N + c] * cst[2 * N + c] + cst[3 * N + c];
+            if (bnp.relu) yy = fmaxf(yy, 0.f);
+            y[j] = grow < n_rows ? yy : 0.f;       // rows past the chunk: zeros, as scnb_bn_eval_planes writes them
+          }
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) split_bf16x2(y[2 * j], y[2 * j + 1], h[j], l[j]);
+          const size_t off = tile + (size_t)(swz_chunk<32>((uint32_t)jc, rr & 127u) >> 1);
+          *reinterpret_cast<uint4*>(bnp.hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(bnp.lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+      }
     } else if (n_it > 0) {
       mbar_wait(bar_acc, 0);
       tc_fence_after();
@@ -531,7 +597,7 @@ static inline int fwd_tc_auto_splits(int n, int G, int rows_per_cta, int KT) {
 template <typename IdxT, int HALVES, int KT, bool DENSE_A, bool TRN = false>
 static int launch_dense_fwd_tc(const IdxT* indptr, const int32_t* idx, const float* val, int n, int G, int H0, const void* hi,
                                const void* lo, const float* b1, float* Z, int ksplits, cudaStream_t st, const void* a_hi = nullptr,
-                               const void* a_lo = nullptr, const int32_t* fwd_splits = nullptr) {
+                               const void* a_lo = nullptr, const int32_t* fwd_splits = nullptr, FwdBnPlanes bnp = FwdBnPlanes{}) {
   constexpr int ROWS = TC_M * HALVES;
   const int n_kt = scnb_cdiv(G, KT);
   const int row_tiles = scnb_cdiv(n, ROWS);
@@ -548,7 +614,7 @@ static int launch_dense_fwd_tc(const IdxT* indptr, const int32_t* idx, const flo
   const size_t smem = 1024 + stages * stage_bytes + 24 * stages + 16 + 16;
   if (TRN && (ksplits <= 1 || H0 % 128 != 0))   // the transposed accumulator only pays for (and is only built for) split-K sums
     return launch_dense_fwd_tc<IdxT, HALVES, KT, DENSE_A, false>(indptr, idx, val, n, G, H0, hi, lo, b1, Z, prezeroed ? -1 : ksplits, st,
-                                                                 a_hi, a_lo, fwd_splits);
+                                                                 a_hi, a_lo, fwd_splits, bnp);
   int tmem_cols = 32;
   while (tmem_cols < (TRN ? (H0 / 128) * ROWS : HALVES * H0)) tmem_cols *= 2;
   cudaError_t e = cudaFuncSetAttribute(k_csr_dense_fwd_tc<IdxT, HALVES, KT, DENSE_A, TRN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -575,7 +641,7 @@ static int launch_dense_fwd_tc(const IdxT* indptr, const int32_t* idx, const flo
   const bool stamp = dbg_on && !DENSE_A && n_cta <= 4096;
   k_csr_dense_fwd_tc<IdxT, HALVES, KT, DENSE_A, TRN><<<grid, 64 + 128 * HALVES, smem, st>>>(
       indptr, idx, val, n, (const uint8_t*)hi, (const uint8_t*)lo, H0, n_kt, b1, Z, stages, tmem_cols, (const uint8_t*)a_hi,
-      (const uint8_t*)a_lo, fwd_splits, stamp ? dbg : nullptr);
+      (const uint8_t*)a_lo, fwd_splits, stamp ? dbg : nullptr, bnp);
   SCNB_CHECK_LAUNCH("csr_linear_fwd_tc");
   if (stamp) {  // debugging aid only (synchronises): per-CTA wall-clock stamps (ns)
     static long long hc[4 * 4096];
@@ -675,6 +741,26 @@ extern "C" int scnb_csr_linear_fwd_tc_i64(const int64_t* indptr, const int32_t* 
   if (n == 0) return SCNB_OK;
   return launch_dense_fwd_tc<int64_t, 2, 32, false>(indptr, indices, data, n, G, H0, planes_hi, planes_lo, b1, Z, ksplits,
                                              (cudaStream_t)stream);
+}
+
+// scnb_csr_linear_fwd_tc_i64 + scnb_bn_eval_planes in one launch (FwdBnPlanes above): the first layer of batched predict
+// (scnym/model.py:211-216 in eval mode on CSR input) ending in the operand planes of the next Linear.  a_hi_out / a_lo_out:
+// ceil(n / 256) * 256 x H0 bf16 each.  Never splits the gene axis (the BatchNorm needs the complete sum).
+extern "C" int scnb_csr_linear_fwd_tc_bn_planes_i64(const int64_t* indptr, const int32_t* indices, const float* data, int n, int G, int H0,
+                                                    const void* planes_hi, const void* planes_lo, const float* b1, const float* gamma,
+                                                    const float* beta, const float* running_mean, const float* running_var, int relu,
+                                                    void* a_hi_out, void* a_lo_out, void* stream) {
+  SCNB_CHECK_ARG(indptr && indices && data && gamma && beta && running_mean && running_var && a_hi_out && a_lo_out,
+                 "csr_linear_fwd_tc_bn_planes_i64: null argument");
+  SCNB_CHECK_ARG(n >= 0 && G > 0 && planes_hi && planes_lo, "csr_linear_fwd_tc_bn_planes_i64: bad arguments");
+  SCNB_CHECK_ARG(H0 >= 32 && H0 <= 256 && H0 % 32 == 0, "csr_linear_fwd_tc_bn_planes_i64: H0 must be a multiple of 32 in [32, 256] (got %d)", H0);
+  SCNB_CHECK_ARG((((uintptr_t)planes_hi | (uintptr_t)planes_lo | (uintptr_t)a_hi_out | (uintptr_t)a_lo_out) % 16) == 0,
+                 "csr_linear_fwd_tc_bn_planes_i64: buffers must be 16-byte aligned");
+  if (n == 0) return SCNB_OK;
+  FwdBnPlanes bnp{gamma, beta, running_mean, running_var, (uint16_t*)a_hi_out, (uint16_t*)a_lo_out, relu};
+  // (Z is not written: the kernel needs a non-null pointer only for its unfused epilogue)
+  return launch_dense_fwd_tc<int64_t, 2, 32, false>(indptr, indices, data, n, G, H0, planes_hi, planes_lo, b1, (float*)a_hi_out, 1,
+                                                    (cudaStream_t)stream, nullptr, nullptr, nullptr, bnp);
 }
 
 // Y[n, N] = A[n, K] W[N, K]^T + b with both operands given as pre-tiled bf16 hi/lo planes

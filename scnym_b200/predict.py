@@ -87,6 +87,15 @@ class EvalRunner(object):
             n_blk = len(blocks)
             for a, (lin, bn, _) in enumerate(blocks):
                 w = self.widths[a]
+                if (a == 0 and self.use_tc and n_blk > 1 and self.tc_hidden[1] and w % 32 == 0
+                        and os.environ.get("SCNB_PREDICT_FUSE_BN", "1") != "0"):
+                    # first layer + eval BatchNorm + ReLU in one launch, ending in the next layer's operand planes
+                    hi, lo = self.planes[mi]
+                    ahi, alo = self.a_planes[1]
+                    call("scnb_csr_linear_fwd_tc_bn_planes_i64", ptr(ds.indptr[row0:]), ptr(ds.indices), ptr(ds.data), n, self.G, w,
+                         ptr(hi), ptr(lo), ptr(lin.bias), ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var), 1,
+                         ptr(ahi), ptr(alo), st)
+                    continue
                 if a == 0 and self.use_tc:
                     hi, lo = self.planes[mi]
                     call("scnb_csr_linear_fwd_tc_i64", ptr(ds.indptr[row0:]), ptr(ds.indices), ptr(ds.data), n, self.G, w,

@@ -878,3 +878,32 @@ def test_sgemm_tcgen05_takes_bound_operand_planes(lay, M, N, K):
         call("scnb_gemm_tc_workspace", _st(), None, 0)
         for f in fakes:
             call("scnb_gemm_tc_bind_planes", ptr(f), f.shape[0], f.shape[1], None, None)
+
+
+@pytest.mark.parametrize("n,G,H0", [(300, 1000, 128), (700, 2048, 256), (256, 640, 64), (1, 64, 32)])
+def test_first_layer_with_fused_bn_eval_planes_equals_the_two_launches(n, G, H0):
+    """scnb_csr_linear_fwd_tc_bn_planes_i64 (first layer -> eval BatchNorm -> ReLU -> operand planes, one launch) writes the
+    planes scnb_csr_linear_fwd_tc_i64 + scnb_bn_eval_planes write, bit for bit, zeros in the padding rows included."""
+    from oracle import scnym_oracle as O
+    from scnym_b200._lib import call, ptr
+    from scnym_b200.dataprep import DeviceCSR
+    ip, ii, dd, _ = O.synth_csr(n, G, 0.07, 3, seed=n + H0 + 1)
+    ds = DeviceCSR.from_arrays(ip, ii, dd, G)
+    torch.manual_seed(G + n)
+    WT, b1 = D(torch.randn(G, H0) * 0.1), D(torch.randn(H0))
+    g, b = D(torch.rand(H0) + 0.5), D(torch.randn(H0) * 0.1)
+    rm, rv = D(torch.randn(H0) * 0.2), D(torch.rand(H0) + 0.3)
+    n_kt = (G + 63) // 64
+    hi = torch.zeros(n_kt * H0 * 64, dtype=torch.int16).cuda()
+    lo = torch.zeros(n_kt * H0 * 64, dtype=torch.int16).cuda()
+    call("scnb_w1_planes", ptr(WT), G, H0, ptr(hi), ptr(lo), _st())
+    rows_pad = (n + 255) // 256 * 256
+    Z = torch.empty(n, H0).cuda()
+    a = [torch.full((rows_pad * H0,), 0x7f7f, dtype=torch.int16).cuda() for _ in range(4)]
+    call("scnb_csr_linear_fwd_tc_i64", ptr(ds.indptr), ptr(ds.indices), ptr(ds.data), n, G, H0, ptr(hi), ptr(lo), ptr(b1), ptr(Z), 1, _st())
+    call("scnb_bn_eval_planes", ptr(Z), n, H0, ptr(g), ptr(b), ptr(rm), ptr(rv), 1, None, None, ptr(a[0]), ptr(a[1]), _st())
+    call("scnb_csr_linear_fwd_tc_bn_planes_i64", ptr(ds.indptr), ptr(ds.indices), ptr(ds.data), n, G, H0, ptr(hi), ptr(lo), ptr(b1),
+         ptr(g), ptr(b), ptr(rm), ptr(rv), 1, ptr(a[2]), ptr(a[3]), _st())
+    torch.cuda.synchronize()
+    assert torch.equal(a[0], a[2]), "hi planes differ"
+    assert torch.equal(a[1], a[3]), "lo planes differ"
