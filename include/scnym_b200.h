@@ -173,8 +173,12 @@ int scnb_bn_eval_planes(const float* Z, int n_rows, int H, const float* gamma, c
                         void* stream);
 int scnb_linear_fwd_tc_planes(const void* a_hi, const void* a_lo, int n, int K, int N, const void* w_hi, const void* w_lo,
                               const float* bias, float* Y, void* stream);
-/* scnb_csr_linear_fwd_tc_i64 + scnb_bn_eval_planes in ONE launch: the first layer of batched predict (scnym/model.py:211-216,
- * eval mode) ends in the operand planes of the next Linear -- fp32 Z is neither written nor read back.  Bit-identical planes. */
+/* scnb_csr_linear_fwd_tc_i64 (or scnb_linear_fwd_tc_planes) + scnb_bn_eval_planes in ONE launch: a layer of batched predict
+ * (scnym/model.py:211-224, eval mode) ends in the operand planes of the next Linear -- fp32 Z is neither written nor read
+ * back.  Bit-identical planes. */
+int scnb_linear_fwd_tc_planes_bn_planes(const void* a_hi, const void* a_lo, int n, int K, int N, const void* w_hi, const void* w_lo,
+                                        const float* bias, const float* gamma, const float* beta, const float* running_mean,
+                                        const float* running_var, int relu, void* out_hi, void* out_lo, void* stream);
 int scnb_csr_linear_fwd_tc_bn_planes_i64(const int64_t* indptr, const int32_t* indices, const float* data, int n, int G, int H0,
                                          const void* planes_hi, const void* planes_lo, const float* b1, const float* gamma,
                                          const float* beta, const float* running_mean, const float* running_var, int relu,

@@ -777,6 +777,24 @@ extern "C" int scnb_linear_fwd_tc_planes(const void* a_hi, const void* a_lo, int
                                                    a_hi, a_lo);
 }
 
+// scnb_linear_fwd_tc_planes + scnb_bn_eval_planes in one launch: a hidden Linear of batched predict whose output goes through
+// the eval-mode BatchNorm -> ReLU straight into the operand planes of the NEXT Linear (FwdBnPlanes; bit-identical planes).
+extern "C" int scnb_linear_fwd_tc_planes_bn_planes(const void* a_hi, const void* a_lo, int n, int K, int N, const void* w_hi,
+                                                   const void* w_lo, const float* bias, const float* gamma, const float* beta,
+                                                   const float* running_mean, const float* running_var, int relu, void* out_hi,
+                                                   void* out_lo, void* stream) {
+  SCNB_CHECK_ARG(a_hi && a_lo && w_hi && w_lo && out_hi && out_lo && gamma && beta && running_mean && running_var && n >= 0 && K > 0 &&
+                     K % 32 == 0, "linear_fwd_tc_planes_bn_planes: bad arguments");
+  SCNB_CHECK_ARG(N >= 32 && N <= 256 && N % 32 == 0, "linear_fwd_tc_planes_bn_planes: N must be a multiple of 32 in [32, 256] (got %d)", N);
+  SCNB_CHECK_ARG((((uintptr_t)a_hi | (uintptr_t)a_lo | (uintptr_t)w_hi | (uintptr_t)w_lo | (uintptr_t)out_hi | (uintptr_t)out_lo) % 16) == 0,
+                 "linear_fwd_tc_planes_bn_planes: buffers must be 16-byte aligned");
+  SCNB_CHECK_ARG(out_hi != a_hi && out_lo != a_lo, "linear_fwd_tc_planes_bn_planes: the output planes must not alias the input planes");
+  if (n == 0) return SCNB_OK;
+  FwdBnPlanes bnp{gamma, beta, running_mean, running_var, (uint16_t*)out_hi, (uint16_t*)out_lo, relu};
+  return launch_dense_fwd_tc<int32_t, 2, 32, true>(nullptr, nullptr, nullptr, n, K, N, w_hi, w_lo, bias, (float*)out_hi, 1,
+                                                   (cudaStream_t)stream, a_hi, a_lo, nullptr, bnp);
+}
+
 // =============================================================================================
 // Tensor-core form of the fused first-layer gradient + optimizer kernel (K8+K9):
 //   dW1T[g, :] = sum_r X[r, g] * dZ1[r, :]      then   optimizer update of W1T[g, :], state1[g, :], state2[g, :]

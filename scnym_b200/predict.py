@@ -104,6 +104,13 @@ class EvalRunner(object):
                     wt = lin.weight_t()
                     call("scnb_csr_linear_fwd_i64", ptr(ds.indptr[row0:]), ptr(ds.indices), ptr(ds.data), n, ptr(wt),
                          ptr(lin.bias), w, ptr(self.Z[0]), st)
+                elif (self.tc_hidden[a] and a + 1 < n_blk and self.tc_hidden[a + 1] and w % 32 == 0
+                      and os.environ.get("SCNB_PREDICT_FUSE_BN", "1") != "0"):
+                    # hidden Linear + eval BatchNorm + ReLU in one launch, planes in, planes out
+                    (ahi, alo), (whi, wlo), (ohi, olo) = self.a_planes[a], self.w_planes[mi][a], self.a_planes[a + 1]
+                    call("scnb_linear_fwd_tc_planes_bn_planes", ptr(ahi), ptr(alo), n, self.widths[a - 1], w, ptr(whi), ptr(wlo),
+                         ptr(lin.bias), ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var), 1, ptr(ohi), ptr(olo), st)
+                    continue
                 elif self.tc_hidden[a]:
                     (ahi, alo), (whi, wlo) = self.a_planes[a], self.w_planes[mi][a]
                     call("scnb_linear_fwd_tc_planes", ptr(ahi), ptr(alo), n, self.widths[a - 1], w, ptr(whi), ptr(wlo),

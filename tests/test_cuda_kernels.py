@@ -907,3 +907,31 @@ def test_first_layer_with_fused_bn_eval_planes_equals_the_two_launches(n, G, H0)
     torch.cuda.synchronize()
     assert torch.equal(a[0], a[2]), "hi planes differ"
     assert torch.equal(a[1], a[3]), "lo planes differ"
+
+
+@pytest.mark.parametrize("n,K,N", [(300, 128, 128), (700, 256, 256), (256, 64, 96)])
+def test_hidden_linear_with_fused_bn_eval_planes_equals_the_two_launches(n, K, N):
+    """scnb_linear_fwd_tc_planes_bn_planes == scnb_linear_fwd_tc_planes + scnb_bn_eval_planes, bit for bit."""
+    from scnym_b200._lib import call, ptr
+    torch.manual_seed(n + K + N)
+    X = D(torch.randn(n, K))
+    W, bias = D(torch.randn(N, K) * 0.1), D(torch.randn(N))
+    g, b = D(torch.rand(N) + 0.5), D(torch.randn(N) * 0.1)
+    rm, rv = D(torch.randn(N) * 0.2), D(torch.rand(N) + 0.3)
+    ones, zeros = D(torch.ones(K)), D(torch.zeros(K))
+    rows_pad = (n + 255) // 256 * 256
+    i16 = lambda m: torch.full((m,), 0x7f7f, dtype=torch.int16).cuda()
+    a_hi, a_lo = i16(rows_pad * K), i16(rows_pad * K)
+    # input planes: identity "BatchNorm" (mean 0, var 1 - eps is not exactly representable: use the kernel on Z with gamma = sqrt(1 + eps))
+    call("scnb_bn_eval_planes", ptr(X), n, K, ptr(ones), ptr(zeros), ptr(zeros), ptr(ones), 0, None, None, ptr(a_hi), ptr(a_lo), _st())
+    w_hi, w_lo = i16(N * K), i16(N * K)
+    call("scnb_linear_planes", ptr(W), N, K, ptr(w_hi), ptr(w_lo), _st())
+    Y = torch.empty(n, N).cuda()
+    o = [i16(rows_pad * N) for _ in range(4)]
+    call("scnb_linear_fwd_tc_planes", ptr(a_hi), ptr(a_lo), n, K, N, ptr(w_hi), ptr(w_lo), ptr(bias), ptr(Y), _st())
+    call("scnb_bn_eval_planes", ptr(Y), n, N, ptr(g), ptr(b), ptr(rm), ptr(rv), 1, None, None, ptr(o[0]), ptr(o[1]), _st())
+    call("scnb_linear_fwd_tc_planes_bn_planes", ptr(a_hi), ptr(a_lo), n, K, N, ptr(w_hi), ptr(w_lo), ptr(bias), ptr(g), ptr(b), ptr(rm),
+         ptr(rv), 1, ptr(o[2]), ptr(o[3]), _st())
+    torch.cuda.synchronize()
+    assert torch.equal(o[0], o[2]), "hi planes differ"
+    assert torch.equal(o[1], o[3]), "lo planes differ"
