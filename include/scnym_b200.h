@@ -179,6 +179,12 @@ int scnb_linear_fwd_tc_planes(const void* a_hi, const void* a_lo, int n, int K, 
 int scnb_linear_fwd_tc_planes_bn_planes(const void* a_hi, const void* a_lo, int n, int K, int N, const void* w_hi, const void* w_lo,
                                         const float* bias, const float* gamma, const float* beta, const float* running_mean,
                                         const float* running_var, int relu, void* out_hi, void* out_lo, void* stream);
+/* ... and the LAST hidden Linear + BatchNorm + ReLU + classifier (scnym/model.py:218-229) in one launch: planes in, logits [n, C]
+ * (+= when accumulate: ensembles) and, optionally, the pre-ReLU BatchNorm output (the embedding, scnym/api.py:700) out.  C <= 16. */
+int scnb_linear_fwd_tc_planes_bn_head(const void* a_hi, const void* a_lo, int n, int K, int N, const void* w_hi, const void* w_lo,
+                                      const float* bias, const float* gamma, const float* beta, const float* running_mean,
+                                      const float* running_var, int relu, const float* Wc, const float* bc, int C, float* logits,
+                                      int accumulate, float* pre_out, void* stream);
 int scnb_csr_linear_fwd_tc_bn_planes_i64(const int64_t* indptr, const int32_t* indices, const float* data, int n, int G, int H0,
                                          const void* planes_hi, const void* planes_lo, const float* b1, const float* gamma,
                                          const float* beta, const float* running_mean, const float* running_var, int relu,

@@ -45,6 +45,7 @@ SIGNATURES = {
     "scnb_bn_eval_planes": [P, I, I, P, P, P, P, I, P, P, P, P, P],
     "scnb_linear_fwd_tc_planes": [P, P, I, I, I, P, P, P, P, P],
     "scnb_linear_fwd_tc_planes_bn_planes": [P, P, I, I, I, P, P, P, P, P, P, P, I, P, P, P],
+    "scnb_linear_fwd_tc_planes_bn_head": [P, P, I, I, I, P, P, P, P, P, P, P, I, P, P, I, P, I, P, P],
     "scnb_csr_linear_fwd_tc_bn_planes_i64": [P, P, P, I, I, I, P, P, P, P, P, P, P, I, P, P, P],
     "scnb_head_logits": [P, P, P, I, I, I, P, I, P],
     "scnb_csc_count": [P, P, I, P, P],

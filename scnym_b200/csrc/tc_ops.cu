@@ -216,13 +216,27 @@ struct FwdBnPlanes {
   int relu;
 };
 
+// ... or, for the LAST hidden layer, straight into the classifier: BatchNorm -> ReLU -> logits[r, :] (+)= A[r, :] Wc^T + bc
+// (scnym/model.py:229), the pre-ReLU BatchNorm output optionally kept as the embedding (scnym/api.py:700).  A thread owns a
+// row: it walks its accumulator 32 columns at a time and carries up to FWD_HEAD_CMAX running dot products; Wc sits in the
+// freed pipeline stages.  Neither Z nor A of the last layer ever exist in HBM.
+#define FWD_HEAD_CMAX 16
+struct FwdHead {
+  const float* Wc;      // [C, N]
+  const float* bc;      // [C] or NULL
+  float* logits;        // [n, C]
+  float* pre_out;       // [n, N] or NULL
+  int C;
+  int accumulate;       // logits += (ensembles: scnym/predict.py:178-192 sums the models' outputs)
+};
+
 template <typename IdxT, int HALVES, int KT, bool DENSE_A, bool TRN>
 __global__ void __launch_bounds__(64 + 128 * HALVES, 1)
 k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ idx, const float* __restrict__ val, int n_rows,
                    const uint8_t* __restrict__ planes_hi, const uint8_t* __restrict__ planes_lo, int N, int n_ktiles,
                    const float* __restrict__ bias, float* __restrict__ Z, int stages, int tmem_cols,
                    const uint8_t* __restrict__ a_hi_planes, const uint8_t* __restrict__ a_lo_planes,
-                   const int32_t* __restrict__ fwd_splits, long long* __restrict__ dbg, FwdBnPlanes bnp) {
+                   const int32_t* __restrict__ fwd_splits, long long* __restrict__ dbg, FwdBnPlanes bnp, FwdHead head) {
 #define FWDTC_GSTAMP(k) do { if (dbg) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[4 * (blockIdx.y * gridDim.x + blockIdx.x) + (k)] = (long long)t_; } } while (0)
   constexpr uint32_t ROWB = 2 * KT;                       // bytes per operand row (bf16)
   constexpr uint32_t A_HALF = TC_M * ROWB;                // one 128-row A block of one plane
@@ -469,6 +483,74 @@ k_csr_dense_fwd_tc(const IdxT* __restrict__ indptr, const int32_t* __restrict__ 
           }
         }
       }
+    } else if (n_it > 0 && head.logits) {
+      // ===== predict form, last hidden layer: Z + b -> BatchNorm(eval) [-> embedding] -> ReLU -> classifier logits =====
+      mbar_wait(bar_acc, 0);
+      tc_fence_after();
+      float* cst = reinterpret_cast<float*>(sm);          // [mean | 1/sqrt(var + eps) | gamma | beta | bias], N floats each
+      float* Ws = cst + 5 * N;                            // [C][N]
+      for (int c = tid - 64; c < N; c += 128 * HALVES) {
+        cst[c] = bnp.rmean[c];
+        cst[N + c] = 1.0f / sqrtf(bnp.rvar[c] + 1e-5f);
+        cst[2 * N + c] = bnp.gamma[c];
+        cst[3 * N + c] = bnp.beta[c];
+        cst[4 * N + c] = bias ? bias[c] : 0.f;
+      }
+      for (int e = tid - 64; e < head.C * N; e += 128 * HALVES) Ws[e] = head.Wc[e];
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * HALVES) : "memory");
+      float lg[FWD_HEAD_CMAX];
+#pragma unroll
+      for (int c = 0; c < FWD_HEAD_CMAX; ++c) lg[c] = 0.f;
+      for (int cb = 0; cb < N; cb += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * N + cb);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+          float a4[4], y4[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int c = cb + j4 + u;
+            float z = __uint_as_float(v[j4 + u]);
+            z += cst[4 * N + c];
+            y4[u] = (z - cst[c]) * cst[N + c] * cst[2 * N + c] + cst[3 * N + c];
+            a4[u] = bnp.relu ? fmaxf(y4[u], 0.f) : y4[u];
+          }
+          if (head.pre_out && grow < n_rows)
+            *reinterpret_cast<float4*>(head.pre_out + (size_t)grow * N + cb + j4) = make_float4(y4[0], y4[1], y4[2], y4[3]);
+#pragma unroll
+          for (int c = 0; c < FWD_HEAD_CMAX; ++c) {
+            if (c < head.C) {
+              const float4 w = *reinterpret_cast<const float4*>(Ws + (size_t)c * N + cb + j4);
+              lg[c] = fmaf(a4[0], w.x, lg[c]);
+              lg[c] = fmaf(a4[1], w.y, lg[c]);
+              lg[c] = fmaf(a4[2], w.z, lg[c]);
+              lg[c] = fmaf(a4[3], w.w, lg[c]);
+            }
+          }
+        }
+      }
+      if (grow < n_rows) {
+#pragma unroll
+        for (int c = 0; c < FWD_HEAD_CMAX; ++c) {
+          if (c < head.C) {
+            float o = lg[c] + (head.bc ? head.bc[c] : 0.f);
+            float* dst = head.logits + (size_t)grow * head.C + c;
+            if (head.accumulate) o += *dst;
+            *dst = o;
+          }
+        }
+      }
     } else if (n_it > 0 && bnp.hi) {
       // ===== predict form, fused: Z + b -> BatchNorm(eval) -> ReLU -> operand planes of the next layer (no split over genes) =====
       mbar_wait(bar_acc, 0);
@@ -597,7 +679,8 @@ static inline int fwd_tc_auto_splits(int n, int G, int rows_per_cta, int KT) {
 template <typename IdxT, int HALVES, int KT, bool DENSE_A, bool TRN = false>
 static int launch_dense_fwd_tc(const IdxT* indptr, const int32_t* idx, const float* val, int n, int G, int H0, const void* hi,
                                const void* lo, const float* b1, float* Z, int ksplits, cudaStream_t st, const void* a_hi = nullptr,
-                               const void* a_lo = nullptr, const int32_t* fwd_splits = nullptr, FwdBnPlanes bnp = FwdBnPlanes{}) {
+                               const void* a_lo = nullptr, const int32_t* fwd_splits = nullptr, FwdBnPlanes bnp = FwdBnPlanes{},
+                               FwdHead head = FwdHead{}) {
   constexpr int ROWS = TC_M * HALVES;
   const int n_kt = scnb_cdiv(G, KT);
   const int row_tiles = scnb_cdiv(n, ROWS);
@@ -614,7 +697,7 @@ static int launch_dense_fwd_tc(const IdxT* indptr, const int32_t* idx, const flo
   const size_t smem = 1024 + stages * stage_bytes + 24 * stages + 16 + 16;
   if (TRN && (ksplits <= 1 || H0 % 128 != 0))   // the transposed accumulator only pays for (and is only built for) split-K sums
     return launch_dense_fwd_tc<IdxT, HALVES, KT, DENSE_A, false>(indptr, idx, val, n, G, H0, hi, lo, b1, Z, prezeroed ? -1 : ksplits, st,
-                                                                 a_hi, a_lo, fwd_splits, bnp);
+                                                                 a_hi, a_lo, fwd_splits, bnp, head);
   int tmem_cols = 32;
   while (tmem_cols < (TRN ? (H0 / 128) * ROWS : HALVES * H0)) tmem_cols *= 2;
   cudaError_t e = cudaFuncSetAttribute(k_csr_dense_fwd_tc<IdxT, HALVES, KT, DENSE_A, TRN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -641,7 +724,7 @@ static int launch_dense_fwd_tc(const IdxT* indptr, const int32_t* idx, const flo
   const bool stamp = dbg_on && !DENSE_A && n_cta <= 4096;
   k_csr_dense_fwd_tc<IdxT, HALVES, KT, DENSE_A, TRN><<<grid, 64 + 128 * HALVES, smem, st>>>(
       indptr, idx, val, n, (const uint8_t*)hi, (const uint8_t*)lo, H0, n_kt, b1, Z, stages, tmem_cols, (const uint8_t*)a_hi,
-      (const uint8_t*)a_lo, fwd_splits, stamp ? dbg : nullptr, bnp);
+      (const uint8_t*)a_lo, fwd_splits, stamp ? dbg : nullptr, bnp, head);
   SCNB_CHECK_LAUNCH("csr_linear_fwd_tc");
   if (stamp) {  // debugging aid only (synchronises): per-CTA wall-clock stamps (ns)
     static long long hc[4 * 4096];
@@ -793,6 +876,25 @@ extern "C" int scnb_linear_fwd_tc_planes_bn_planes(const void* a_hi, const void*
   FwdBnPlanes bnp{gamma, beta, running_mean, running_var, (uint16_t*)out_hi, (uint16_t*)out_lo, relu};
   return launch_dense_fwd_tc<int32_t, 2, 32, true>(nullptr, nullptr, nullptr, n, K, N, w_hi, w_lo, bias, (float*)out_hi, 1,
                                                    (cudaStream_t)stream, a_hi, a_lo, nullptr, bnp);
+}
+
+// The LAST hidden Linear of batched predict, its eval-mode BatchNorm -> ReLU and the classifier in one launch (FwdHead above):
+// planes in, logits (and optionally the embedding) out.  C <= FWD_HEAD_CMAX.
+extern "C" int scnb_linear_fwd_tc_planes_bn_head(const void* a_hi, const void* a_lo, int n, int K, int N, const void* w_hi,
+                                                 const void* w_lo, const float* bias, const float* gamma, const float* beta,
+                                                 const float* running_mean, const float* running_var, int relu, const float* Wc,
+                                                 const float* bc, int C, float* logits, int accumulate, float* pre_out, void* stream) {
+  SCNB_CHECK_ARG(a_hi && a_lo && w_hi && w_lo && gamma && beta && running_mean && running_var && Wc && logits && n >= 0 && K > 0 &&
+                     K % 32 == 0, "linear_fwd_tc_planes_bn_head: bad arguments");
+  SCNB_CHECK_ARG(N >= 32 && N <= 256 && N % 32 == 0, "linear_fwd_tc_planes_bn_head: N must be a multiple of 32 in [32, 256] (got %d)", N);
+  SCNB_CHECK_ARG(C >= 1 && C <= FWD_HEAD_CMAX, "linear_fwd_tc_planes_bn_head: C must be in [1, %d] (got %d)", FWD_HEAD_CMAX, C);
+  SCNB_CHECK_ARG((((uintptr_t)a_hi | (uintptr_t)a_lo | (uintptr_t)w_hi | (uintptr_t)w_lo | (uintptr_t)Wc | (uintptr_t)pre_out) % 16) == 0,
+                 "linear_fwd_tc_planes_bn_head: buffers must be 16-byte aligned");
+  if (n == 0) return SCNB_OK;
+  FwdBnPlanes bnp{gamma, beta, running_mean, running_var, nullptr, nullptr, relu};
+  FwdHead head{Wc, bc, logits, pre_out, C, accumulate};
+  return launch_dense_fwd_tc<int32_t, 2, 32, true>(nullptr, nullptr, nullptr, n, K, N, w_hi, w_lo, bias, logits, 1, (cudaStream_t)stream,
+                                                   a_hi, a_lo, nullptr, bnp, head);
 }
 
 // =============================================================================================

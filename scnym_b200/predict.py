@@ -85,6 +85,7 @@ class EvalRunner(object):
         for mi, model in enumerate(self.models):
             blocks = model.block_modules()
             n_blk = len(blocks)
+            head_done = False
             for a, (lin, bn, _) in enumerate(blocks):
                 w = self.widths[a]
                 if (a == 0 and self.use_tc and n_blk > 1 and self.tc_hidden[1] and w % 32 == 0
@@ -111,6 +112,17 @@ class EvalRunner(object):
                     call("scnb_linear_fwd_tc_planes_bn_planes", ptr(ahi), ptr(alo), n, self.widths[a - 1], w, ptr(whi), ptr(wlo),
                          ptr(lin.bias), ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var), 1, ptr(ohi), ptr(olo), st)
                     continue
+                elif (self.tc_hidden[a] and a == n_blk - 1 and self.C <= 16
+                      and os.environ.get("SCNB_PREDICT_FUSE_BN", "1") != "0"):
+                    # last hidden Linear + eval BatchNorm (+ embedding) + ReLU + classifier in one launch: planes in, logits out
+                    (ahi, alo), (whi, wlo) = self.a_planes[a], self.w_planes[mi][a]
+                    clf = model.classif[0]
+                    pre = embed if (mi == 0 and embed is not None) else None
+                    call("scnb_linear_fwd_tc_planes_bn_head", ptr(ahi), ptr(alo), n, self.widths[a - 1], w, ptr(whi), ptr(wlo),
+                         ptr(lin.bias), ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var), 1, ptr(clf.weight),
+                         ptr(clf.bias), self.C, ptr(self.logits), 0 if mi == 0 else 1, ptr(pre), st)
+                    head_done = True
+                    continue
                 elif self.tc_hidden[a]:
                     (ahi, alo), (whi, wlo) = self.a_planes[a], self.w_planes[mi][a]
                     call("scnb_linear_fwd_tc_planes", ptr(ahi), ptr(alo), n, self.widths[a - 1], w, ptr(whi), ptr(wlo),
@@ -132,7 +144,9 @@ class EvalRunner(object):
                          ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var), None, None, None, 0, 0.0, 1, None, None, st)
             clf = model.classif[0]
             H = self.widths[-1]
-            if self.fuse_head:
+            if head_done:
+                pass
+            elif self.fuse_head:
                 call("scnb_head_logits", ptr(self.A[-1]), ptr(clf.weight), ptr(clf.bias), H, self.C, n, ptr(self.logits),
                      0 if mi == 0 else 1, st)
             else:

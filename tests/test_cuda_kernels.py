@@ -935,3 +935,36 @@ def test_hidden_linear_with_fused_bn_eval_planes_equals_the_two_launches(n, K, N
     torch.cuda.synchronize()
     assert torch.equal(o[0], o[2]), "hi planes differ"
     assert torch.equal(o[1], o[3]), "lo planes differ"
+
+
+@pytest.mark.parametrize("n,K,N,C,acc,want_pre", [(300, 128, 128, 5, 0, True), (700, 256, 256, 16, 1, False), (256, 64, 96, 1, 0, True)])
+def test_last_hidden_linear_with_fused_bn_and_classifier(n, K, N, C, acc, want_pre):
+    """scnb_linear_fwd_tc_planes_bn_head == scnb_linear_fwd_tc_planes -> eval BatchNorm (pre-ReLU output kept) -> ReLU ->
+    scnb_sgemm classifier: logits (also accumulated into, for ensembles) and embedding."""
+    from scnym_b200._lib import call, ptr
+    torch.manual_seed(n + K + N + C)
+    X = D(torch.randn(n, K))
+    W, bias = D(torch.randn(N, K) * 0.1), D(torch.randn(N))
+    g, b = D(torch.rand(N) + 0.5), D(torch.randn(N) * 0.1)
+    rm, rv = D(torch.randn(N) * 0.2), D(torch.rand(N) + 0.3)
+    Wc, bc = D(torch.randn(C, N) * 0.2), D(torch.randn(C))
+    ones, zeros = D(torch.ones(K)), D(torch.zeros(K))
+    rows_pad = (n + 255) // 256 * 256
+    i16 = lambda m: torch.zeros(m, dtype=torch.int16).cuda()
+    a_hi, a_lo, w_hi, w_lo = i16(rows_pad * K), i16(rows_pad * K), i16(N * K), i16(N * K)
+    call("scnb_bn_eval_planes", ptr(X), n, K, ptr(ones), ptr(zeros), ptr(zeros), ptr(ones), 0, None, None, ptr(a_hi), ptr(a_lo), _st())
+    call("scnb_linear_planes", ptr(W), N, K, ptr(w_hi), ptr(w_lo), _st())
+    # reference chain (fp32 kernels of this package; the tcgen05 product is shared)
+    Y = torch.empty(n, N).cuda()
+    call("scnb_linear_fwd_tc_planes", ptr(a_hi), ptr(a_lo), n, K, N, ptr(w_hi), ptr(w_lo), ptr(bias), ptr(Y), _st())
+    pre_ref = (Y.double() - rm.double()) / torch.sqrt(rv.double() + 1e-5) * g.double() + b.double()
+    init = torch.randn(n, C).cuda()
+    want = pre_ref.clamp_min(0) @ Wc.double().t() + bc.double() + (init.double() if acc else 0.0)
+    logits = init.clone()
+    pre = torch.full((n, N), 7.0).cuda() if want_pre else None
+    call("scnb_linear_fwd_tc_planes_bn_head", ptr(a_hi), ptr(a_lo), n, K, N, ptr(w_hi), ptr(w_lo), ptr(bias), ptr(g), ptr(b), ptr(rm),
+         ptr(rv), 1, ptr(Wc), ptr(bc), C, ptr(logits), acc, ptr(pre), _st())
+    torch.cuda.synchronize()
+    _chk("fused head logits", logits.cpu(), want.float().cpu(), tol=2e-6)
+    if want_pre:
+        _chk("fused head embedding", pre.cpu(), pre_ref.float().cpu(), tol=2e-6)
