@@ -457,7 +457,12 @@ k_gemm_planes(int M, int N, int n_kt, const uint8_t* __restrict__ a_hi, const ui
       if (m < M) {
         float* out = C + (size_t)m * ldc + n0 + cb;
         const float* gt = gate ? gate + (size_t)m * ldc + n0 + cb : nullptr;
-        if (split) {
+        if (split && n0 + cb + 32 <= N) {    // K split: 16-byte vector atomics (a quarter of the atomic operations)
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            atomicAdd(reinterpret_cast<float4*>(out + j), make_float4(alpha * __uint_as_float(v[j]), alpha * __uint_as_float(v[j + 1]),
+                                                                      alpha * __uint_as_float(v[j + 2]), alpha * __uint_as_float(v[j + 3])));
+        } else if (split) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (n0 + cb + j < N) atomicAdd(out + j, alpha * __uint_as_float(v[j]));
@@ -636,9 +641,16 @@ k_gemm_planes_mn(int M, int N, int n_rt /* 256-row tiles of the operands */, int
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (m < M) {
         float* out = C + (size_t)m * ldc + n0 + cb;
+        if (n0 + cb + 32 <= N) {               // 16-byte vector atomics (ldc % 4 == 0, C 16-byte aligned: checked by the launcher)
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n0 + cb + j < N) atomicAdd(out + j, alpha * __uint_as_float(v[j]));
+          for (int j = 0; j < 32; j += 4)
+            atomicAdd(reinterpret_cast<float4*>(out + j), make_float4(alpha * __uint_as_float(v[j]), alpha * __uint_as_float(v[j + 1]),
+                                                                      alpha * __uint_as_float(v[j + 2]), alpha * __uint_as_float(v[j + 3])));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + cb + j < N) atomicAdd(out + j, alpha * __uint_as_float(v[j]));
+        }
       }
     }
   }
@@ -776,7 +788,8 @@ static int tg5_planes_try(int lay, int M, int N, int K, const float* A, int lda,
   static int bind_off = -1;
   if (bind_off < 0) { const char* e = getenv("SCNB_GEMM_TC_BOUND"); bind_off = (e && e[0] == '0') ? 1 : 0; }
   // weight gradient with both operands bound: the producers' row-major planes as MN-major operands, nothing to convert
-  if (lay == 2 && !bind_off && beta == 1.f && !bias && !relu && !gate && (M % 32 == 0) && (N % 32 == 0) && lda == M && ldb == N) {
+  if (lay == 2 && !bind_off && beta == 1.f && !bias && !relu && !gate && (M % 32 == 0) && (N % 32 == 0) && lda == M && ldb == N &&
+      (ldc % 4 == 0) && ((uintptr_t)C % 16 == 0)) {
     uint16_t *ph, *pl, *qh, *ql;
     int rp_a = 0, rp_b = 0;
     if (scnb_planes_lookup(A, M, K, &ph, &pl, &rp_a) && scnb_planes_lookup(B, N, K, &qh, &ql, &rp_b)) {
