@@ -1426,10 +1426,48 @@ __global__ void __launch_bounds__(256) k_mix_rows(const float* __restrict__ Z, i
   }
 }
 
+// Tall super-batches (config 5: 16 384 rows): one WARP per row, 16 bytes per lane, the row's indices and gamma loaded by every
+// lane (broadcast) -- 8 rows per CTA instead of one: an eighth of the CTAs, each with its dependent index -> row loads of 8
+// rows in flight at once.  Same expressions as k_mix_rows (bit-identical output).
+__global__ void __launch_bounds__(256) k_mix_rows_w(const float* __restrict__ Z, int H, const int32_t* __restrict__ srcA,
+                                                    const int32_t* __restrict__ srcB, const float* __restrict__ gam,
+                                                    const int32_t* __restrict__ n_active, int max_rows, float* __restrict__ out) {
+  PDL_ENTRY();
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= max_rows) return;
+  const int na = n_active ? min(*n_active, max_rows) : max_rows;
+  float4* o = reinterpret_cast<float4*>(out + (size_t)i * H);
+  const int H4 = H >> 2;
+  if (i >= na) {
+    for (int h = lane; h < H4; h += 32) o[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const int a = srcA[i], b = srcB ? srcB[i] : a;
+  const float g = gam ? gam[i] : 1.f;
+  const float4* za = reinterpret_cast<const float4*>(Z + (size_t)a * H);
+  const float4* zb = reinterpret_cast<const float4*>(Z + (size_t)b * H);
+  if (a == b || g == 1.f) {
+    for (int h = lane; h < H4; h += 32) o[h] = za[h];
+  } else {
+    const float g1 = 1.f - g;
+    for (int h = lane; h < H4; h += 32) {
+      const float4 x = za[h], y = zb[h];
+      o[h] = make_float4(g * x.x + g1 * y.x, g * x.y + g1 * y.y, g * x.z + g1 * y.z, g * x.w + g1 * y.w);
+    }
+  }
+}
+
 extern "C" int scnb_mix_rows(const float* Z, int H, const int32_t* srcA, const int32_t* srcB, const float* gam,
                              const int32_t* n_active_dev, int max_rows, float* out, void* stream) {
   SCNB_CHECK_ARG(Z && srcA && out && H > 0 && max_rows >= 0, "mix_rows: bad arguments");
   if (max_rows == 0) return SCNB_OK;
+  if (max_rows >= 4096 && H % 4 == 0 && (((uintptr_t)Z | (uintptr_t)out) % 16) == 0) {
+    scnb_launch_pdl(k_mix_rows_w, dim3(scnb_cdiv(max_rows, 8)), dim3(256), 0, (cudaStream_t)stream, Z, H, srcA, srcB, gam, n_active_dev, max_rows,
+                    out);
+    SCNB_CHECK_LAUNCH("mix_rows/warp");
+    return SCNB_OK;
+  }
   scnb_launch_pdl(k_mix_rows, dim3(max_rows), dim3(256), 0, (cudaStream_t)stream, Z, H, srcA, srcB, gam, n_active_dev, max_rows, out);
   SCNB_CHECK_LAUNCH("mix_rows");
   return SCNB_OK;

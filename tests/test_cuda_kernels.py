@@ -968,3 +968,29 @@ def test_last_hidden_linear_with_fused_bn_and_classifier(n, K, N, C, acc, want_p
     _chk("fused head logits", logits.cpu(), want.float().cpu(), tol=2e-6)
     if want_pre:
         _chk("fused head embedding", pre.cpu(), pre_ref.float().cpu(), tol=2e-6)
+
+
+@pytest.mark.parametrize("R,H,na", [(5000, 256, 4500), (4096, 1024, 4096), (300, 64, 250)])
+def test_mix_rows_small_and_tall(R, H, na):
+    """scnb_mix_rows (hidden-space MixUp gather, losses.py:811-875 folded behind the first layer): the CTA-per-row form and,
+    from 4096 rows, the warp-per-row form; rows past the active count are zeros."""
+    from scnym_b200._lib import call, ptr
+    torch.manual_seed(R + H)
+    n_base = R // 2
+    Z = torch.randn(n_base, H).cuda()
+    a = torch.randint(0, n_base, (R,), dtype=torch.int32).cuda()
+    b = torch.randint(0, n_base, (R,), dtype=torch.int32).cuda()
+    b[::7] = a[::7]
+    g = torch.rand(R).cuda()
+    g[::5] = 1.0
+    cnt = torch.tensor([na], dtype=torch.int32).cuda()
+    out = torch.full((R, H), 7.0).cuda()
+    call("scnb_mix_rows", ptr(Z), H, ptr(a), ptr(b), ptr(g), ptr(cnt), R, ptr(out), _st())
+    torch.cuda.synchronize()
+    al, bl = a.long(), b.long()
+    want = g[:, None] * Z[al] + (1.0 - g)[:, None] * Z[bl]
+    same = (al == bl) | (g == 1.0)
+    want[same] = Z[al][same]
+    want[na:] = 0.0
+    _chk("mix_rows", out.cpu(), want.cpu(), tol=1e-6)
+    assert float(out[na:].abs().sum()) == 0.0
