@@ -1,5 +1,7 @@
 """Engine behaviours around the step: operand planes after external weight writes, optimizer state
 ownership, NaN rows in the argmax kernels."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -250,3 +252,56 @@ def test_fused_heads_match_the_split_chain_on_device_randomness(monkeypatch, H, 
         assert err < 2e-5, (k, err)
     for k in ("sup_loss", "unsup_loss") + (("dan_loss",) if use_dan else ()):
         assert abs(a["losses"][k] - b["losses"][k]) <= 2e-6 * max(1.0, abs(b["losses"][k])), (k, a["losses"][k], b["losses"][k])
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_val_epoch_loss_and_accuracy_match_the_oracle(tmp_path, weighted):
+    """`Trainer.val_epoch()` (scnym/trainer.py:259-327: eval-mode forward, cross-entropy per batch, the reference's running
+    `loss / batch size` bookkeeping, accuracy, best-weights file) on the device-resident fast path -- one fused predict pass
+    over the validation CSR + the row-wise CE kernel -- against the oracle's dense eval forward on the same weights:
+    epoch loss, accuracy and best loss; 1e-4 on the losses, the accuracy exact."""
+    import functools
+    from scipy import sparse
+    from oracle import scnym_oracle as O
+    from scnym_b200.dataprep import DeviceLoader, SingleCellDS
+    from scnym_b200.losses import cross_entropy
+    from scnym_b200.model import CellTypeCLF
+    from scnym_b200.trainer import Trainer
+    n, G, C, B = 777, 640, 6, 128                     # a ragged last batch of 9 rows
+    ip, ii, dd, y = O.synth_csr(n, G, 0.08, C, seed=5)
+    X = sparse.csr_matrix((np.asarray(dd), np.asarray(ii), np.asarray(ip)), shape=(n, G))
+    y = np.asarray(y).astype(np.int64)
+    torch.manual_seed(9)
+    model = CellTypeCLF(n_genes=G, n_cell_types=C, n_hidden=128, n_hidden_init=256, n_layers=2).cuda()
+    with torch.no_grad():                              # non-trivial running statistics
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.normal_(0.0, 0.3)
+                m.running_var.uniform_(0.5, 1.5)
+    cw = torch.linspace(0.5, 1.5, C) if weighted else None
+    crit = functools.partial(cross_entropy, class_weight=cw.cuda()) if weighted else cross_entropy
+    ds = SingleCellDS(X, y, num_classes=C)
+    loaders = {"train": DeviceLoader(ds, B, shuffle=True, drop_last=True), "val": DeviceLoader(ds, B)}
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    tr = Trainer(model, crit, opt, loaders, str(tmp_path), n_epochs=1, verbose=False)
+    tr.epoch = 0
+    tr.val_epoch()
+    # oracle: dense eval forward with the same weights, then the reference's bookkeeping
+    om = O.OracleModel({k: v.detach().cpu() for k, v in model.state_dict().items()}, n_layers=2)
+    Xd = O.csr_to_dense(ip, ii, dd, G, np.arange(n))
+    logits = om.forward(Xd, train=False)
+    onehot = torch.nn.functional.one_hot(torch.from_numpy(y), C).float()
+    running, n_b = 0.0, 0
+    for s in range(0, n, B):
+        lb = O.cross_entropy(logits[s:s + B], onehot[s:s + B], class_weight=cw)
+        running += float(lb) / min(B, n - s)
+        n_b += 1
+    want_loss = running / n_b
+    want_corrects = int((logits.argmax(1) == torch.from_numpy(y)).sum())
+    got_loss = float(tr.best_loss)                     # first validation pass: the best loss IS this epoch's loss
+    assert abs(got_loss - want_loss) <= 1e-4 * abs(want_loss), (got_loss, want_loss)
+    r_loss, r_nb, corrects, total = tr._eval_loader(loaders["val"])
+    assert r_nb == n_b and total == n
+    assert abs(r_loss / r_nb - want_loss) <= 1e-4 * abs(want_loss)
+    assert int(corrects) == want_corrects
+    assert os.path.exists(os.path.join(str(tmp_path), "00_best_model_weights.pkl"))
