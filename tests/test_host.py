@@ -132,3 +132,36 @@ def test_host_gather_rows_matches_numpy():
     assert h.scnb_host_gather_rows2(P(A[0]), P(A[1]), P(A[2]), P(ra), 64, P(oa[0]), P(oa[1]), P(oa[2]), 3,
                                     P(B[0]), P(B[1]), P(B[2]), P(rb), 48, P(ob[0]), P(ob[1]), P(ob[2]), 48 * 40, 2) != 0
     assert b"capacity" in h.scnb_last_error()
+
+
+def test_checkpoint_file_loads_into_the_reference_model_when_available(tmp_path):
+    """The weights file the trainers write (`00_best_model_weights.pkl`, scnym/trainer.py:404-417) is a plain state_dict in the
+    reference's own layout: the UNMODIFIED reference `CellTypeCLF` loads it with strict=True and its eval-mode forward equals
+    the oracle's on those weights (the gene-major storage of the first layer never shows in the file)."""
+    from oracle.ref_shim import reference_available, load_reference
+    if not reference_available():
+        pytest.skip("reference tree not present (GPU box)")
+    ref = load_reference(modules=("model",))
+    from oracle import scnym_oracle as O
+    from scnym_b200.model import CellTypeCLF
+    from scnym_b200.trainer import checkpoint_state
+    for nl in (1, 2, 3):
+        torch.manual_seed(11 + nl)
+        ours = CellTypeCLF(n_genes=90, n_cell_types=4, n_hidden=24, n_hidden_init=40, n_layers=nl)
+        with torch.no_grad():
+            for m in ours.modules():
+                if isinstance(m, torch.nn.BatchNorm1d):
+                    m.running_mean.normal_(0.0, 0.3)
+                    m.running_var.uniform_(0.5, 1.5)
+        path = str(tmp_path / f"00_best_model_weights_{nl}.pkl")
+        torch.save(checkpoint_state(ours), path)
+        sd = torch.load(path)
+        assert all(v.is_contiguous() for v in sd.values())
+        theirs = ref.model.CellTypeCLF(n_genes=90, n_cell_types=4, n_hidden=24, n_hidden_init=40, n_layers=nl)
+        theirs.load_state_dict(sd, strict=True)
+        theirs.eval()
+        X = torch.rand(17, 90) * 3.0
+        with torch.no_grad():
+            want = theirs(X)
+        got = O.OracleModel(sd, n_layers=nl).forward(X, train=False)
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
